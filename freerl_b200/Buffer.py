@@ -1,0 +1,101 @@
+"""Device-resident replay buffers with the reference's ``Buffer.py`` interface.
+
+Drop-in for ``from Buffer import Buffer`` (``SAC_file/Buffer.py:11-61`` = DQN/TD3/DDPG/MADDPG copies): same
+constructor ``Buffer(capacity, obs_dim, act_dim, device)``, ``add(obs, action, reward, next_obs, done)``,
+``sample(indices) -> (obs, actions, rewards[B,1], next_obs, dones[B,1])`` fresh fp32 tensors on ``device``,
+``len()``, ``_index`` / ``_size``.  Storage is ONE fp32 row per transition in HBM,
+``[obs | action | reward | done | next_obs | pad]`` (16-byte multiple), so a sampled transition is a single
+contiguous 16-B-vectorised read.  The float64->float32 cast the reference applies in ``sample`` happens at
+``add`` (same values: rounding a float64 once to fp32 is order-independent).
+
+Extension: ``add`` also accepts a batch (``obs`` of shape ``[N, obs_dim]`` …) for N vectorised envs; rows are
+written in env order exactly as N sequential single ``add`` calls would.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .nets import pad4
+
+
+class Buffer:
+    """replay buffer for each agent (device resident)"""
+
+    def __init__(self, capacity, obs_dim, act_dim, device):
+        self.capacity = capacity = int(capacity)
+        self.obs_dim, self.act_dim = int(obs_dim), int(act_dim)
+        self.device = _lib.require_device(device)
+        self.row_floats = pad4(2 * self.obs_dim + self.act_dim + 2)
+        self.storage = torch.zeros((max(capacity, 1), self.row_floats), dtype=torch.float32, device=self.device)
+        self._index = 0
+        self._size = 0
+        self._c = _lib.Replay(self.storage.data_ptr(), max(capacity, 1), self.row_floats, self.obs_dim, self.act_dim)
+
+    # ---- C descriptor ------------------------------------------------------------------------------
+    def c_struct(self):
+        return self._c
+
+    # ---- add ---------------------------------------------------------------------------------------
+    def _pack(self, obs, action, reward, next_obs, done):
+        od, ad = self.obs_dim, self.act_dim
+        obs = np.asarray(obs, dtype=np.float32).reshape(-1, od)
+        n = obs.shape[0]
+        rows = np.zeros((n, self.row_floats), np.float32)
+        rows[:, :od] = obs
+        rows[:, od:od + ad] = np.asarray(action, dtype=np.float32).reshape(n, ad)
+        rows[:, od + ad] = np.asarray(reward, dtype=np.float32).reshape(n)
+        rows[:, od + ad + 1] = np.asarray(done, dtype=np.float32).reshape(n)
+        rows[:, od + ad + 2:2 * od + ad + 2] = np.asarray(next_obs, dtype=np.float32).reshape(n, od)
+        return rows
+
+    def add(self, obs, action, reward, next_obs, done):
+        """add one experience (reference semantics) or a batch of N experiences (vectorised envs)"""
+        rows = torch.from_numpy(self._pack(obs, action, reward, next_obs, done)).to(self.device)
+        self.add_rows(rows)
+
+    def add_rows(self, rows):
+        """rows: device tensor [n, row_floats] already in storage layout"""
+        n = rows.shape[0]
+        if n > self.capacity:
+            rows = rows[n - self.capacity:]       # only the last `capacity` rows survive n sequential adds
+            self._index = (self._index + n - self.capacity) % self.capacity
+            n = self.capacity
+        first = min(n, self.capacity - self._index)
+        self.storage[self._index:self._index + first].copy_(rows[:first])
+        if first < n:
+            self.storage[:n - first].copy_(rows[first:])
+        self._index = (self._index + n) % self.capacity
+        self._size = min(self._size + n, self.capacity)
+
+    def add_device(self, obs, action, reward, next_obs, done):
+        """Batched add of fields already resident on the device (fp32 tensors) — packs SoA -> AoS rows with the
+        ``frl_replay_add_batch`` kernel.  ``done`` is a float tensor of 0/1."""
+        n = obs.shape[0]
+        assert n <= self.capacity
+        _lib.check(_lib.lib().frl_replay_add_batch(
+            ctypes.byref(self._c), self._index, _lib.ptr(obs), _lib.ptr(action), _lib.ptr(reward), _lib.ptr(next_obs),
+            _lib.ptr(done), n, _lib.stream_ptr(self.device)), "frl_replay_add_batch")
+        self._index = (self._index + n) % self.capacity
+        self._size = min(self._size + n, self.capacity)
+
+    # ---- sample ------------------------------------------------------------------------------------
+    def _indices_to_device(self, indices):
+        if isinstance(indices, torch.Tensor):
+            return indices.to(device=self.device, dtype=torch.int64).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(indices, dtype=np.int64)).to(self.device)
+
+    def sample(self, indices):
+        idx = self._indices_to_device(indices)
+        B = idx.numel()
+        f = lambda *s: torch.empty(s, dtype=torch.float32, device=self.device)
+        obs, actions, rewards = f(B, self.obs_dim), f(B, self.act_dim), f(B, 1)
+        next_obs, dones = f(B, self.obs_dim), f(B, 1)
+        _lib.check(_lib.lib().frl_replay_gather(
+            ctypes.byref(self._c), _lib.ptr(idx), B, _lib.ptr(obs), _lib.ptr(actions), _lib.ptr(rewards),
+            _lib.ptr(next_obs), _lib.ptr(dones), _lib.stream_ptr(self.device)), "frl_replay_gather")
+        return obs, actions, rewards, next_obs, dones
+
+    def __len__(self):
+        return self._size

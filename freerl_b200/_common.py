@@ -1,0 +1,94 @@
+"""Host-side helpers shared by the algorithm classes (index generation, scratch, batched inference)."""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def resolve_mode(mode):
+    """'parity' (default): indices from the numpy legacy global stream exactly like the reference
+    (``np.random.choice(total, B, replace=False)``) and noise tensors drawn with torch on ``device`` in the
+    reference's call order -> identical results on identical seeds.
+    'fast': on-device Philox sampling / noise (different random streams, same distributions) so a whole batch of
+    learn() calls is one kernel launch with no host work."""
+    mode = mode or os.environ.get("FREERL_B200_MODE", "parity")
+    if mode not in ("parity", "fast"):
+        raise ValueError("mode must be 'parity' or 'fast'")
+    return mode
+
+
+class DeviceScratch:
+    """Per-policy scratch the fused kernels need (gradient partials per CTA, norm partials, metrics)."""
+
+    def __init__(self, device, n_p_max):
+        sm = _lib.sm_count()
+        z = lambda *s: torch.zeros(s, dtype=torch.float32, device=device)
+        self.gpart = z(sm, n_p_max)
+        self.sumsq = z(sm)
+        self.stats = z(sm, 8)
+        self._out = None
+
+    def out(self, n_updates, device):
+        if self._out is None or self._out.shape[0] < n_updates:
+            self._out = torch.zeros((n_updates, 8), dtype=torch.float32, device=device)
+        return self._out
+
+
+_fast_seed_counter = [0]
+
+
+def default_seed():
+    """Seed for the on-device generators, derived from torch's CPU generator state so `torch.manual_seed`
+    still controls fast-mode runs."""
+    _fast_seed_counter[0] += 1
+    return (int(torch.initial_seed()) * 0x9E3779B97F4A7C15 + _fast_seed_counter[0]) & 0xFFFFFFFFFFFFFFFF
+
+
+def make_indices(mode, total_size, batch_size, n_updates, device, seed, counter):
+    """[n_updates, B] int64 device tensor of sampled transition indices (without replacement per update)."""
+    if mode == "parity":
+        idx = np.stack([np.random.choice(total_size, batch_size, replace=False) for _ in range(n_updates)])
+        return torch.from_numpy(idx.astype(np.int64, copy=False)).to(device)
+    out = torch.empty((n_updates, batch_size), dtype=torch.int64, device=device)
+    _lib.check(_lib.lib().frl_sample_uniform(_lib.ptr(out), int(total_size), int(batch_size), int(n_updates),
+                                             ctypes.c_uint64(seed), ctypes.c_uint64(counter), _lib.stream_ptr(device)),
+               "frl_sample_uniform")
+    return out
+
+
+def reference_randn(shape, device):
+    """What ``torch.distributions.Normal.rsample`` / ``torch.randn_like`` draw in the reference: a standard normal
+    tensor created directly on ``device`` (``torch.empty(shape).normal_()``)."""
+    return torch.empty(shape, dtype=torch.float32, device=device).normal_()
+
+
+def infer(net, obs, mode, device, out_cols, noise=None, seed=0, counter=0):
+    """Batched policy inference.  ``obs``: numpy / tensor [n, obs_dim] -> device tensor [n, out_cols]."""
+    if isinstance(obs, torch.Tensor):
+        x = obs.to(device=device, dtype=torch.float32).contiguous()
+    else:
+        x = torch.from_numpy(np.ascontiguousarray(obs, dtype=np.float32)).to(device)
+    n, obs_dim = x.shape
+    out = torch.empty((n, out_cols), dtype=torch.float32, device=device)
+    a = _lib.InferArgs()
+    a.net = net.c_struct()
+    a.obs, a.n, a.obs_dim, a.mode = x.data_ptr(), n, obs_dim, mode
+    a.noise = noise.data_ptr() if noise is not None else None
+    a.seed, a.counter = seed, counter & 0xFFFFFFFF
+    a.out, a.out_cols = out.data_ptr(), out_cols
+    _lib.check(_lib.lib().frl_policy_infer(ctypes.byref(a), _lib.stream_ptr(device)), "frl_policy_infer")
+    return out
+
+
+def as_obs_batch(obs, obs_dim):
+    """Reference ``select_action`` does ``reshape(1, -1)``; we accept [obs_dim] (single env, reference semantics)
+    or [N, obs_dim] (vectorised extension).  Returns (array [n, obs_dim], single: bool)."""
+    if isinstance(obs, torch.Tensor):
+        single = obs.dim() == 1
+        return obs.reshape(-1, obs_dim), single
+    arr = np.asarray(obs, dtype=np.float32)
+    single = arr.ndim <= 1
+    return arr.reshape(-1, obs_dim), single

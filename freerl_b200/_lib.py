@@ -1,0 +1,139 @@
+"""ctypes binding of ``libfreerl_b200.so`` (the C ABI declared in ``include/freerl_b200.h``).
+
+This is the reference-side binding a maintainer adds: plain ``ctypes``, raw device pointers
+(``tensor.data_ptr()``) and the current CUDA stream.  There is NO fallback: if the shared library is missing
+or reports a different ABI the import of any compute class raises.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+FRL_MAX_LAYERS = 6
+ABI_VERSION = 1
+
+
+class Layer(C.Structure):
+    _fields_ = [("in_", C.c_int), ("out", C.c_int), ("in_pad", C.c_int), ("out_pad", C.c_int),
+                ("w_off", C.c_int), ("b_off", C.c_int), ("wt_off", C.c_int)]
+
+
+class Net(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("pt", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("g", C.c_void_p),
+                ("n_p", C.c_int), ("n_pt", C.c_int), ("n_layers", C.c_int), ("x_off", C.c_int), ("x_len", C.c_int),
+                ("L", Layer * FRL_MAX_LAYERS)]
+
+
+class Replay(C.Structure):
+    _fields_ = [("storage", C.c_void_p), ("capacity", C.c_int64), ("row_floats", C.c_int), ("obs_dim", C.c_int),
+                ("act_dim", C.c_int)]
+
+
+class DqnArgs(C.Structure):
+    _fields_ = [("q", Net), ("q_target", Net), ("replay", Replay), ("indices", C.c_void_p), ("B", C.c_int),
+                ("n_updates", C.c_int), ("gamma", C.c_float), ("tau", C.c_float), ("lr", C.c_double),
+                ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("step0", C.c_int64),
+                ("gpart", C.c_void_p), ("stats", C.c_void_p), ("out", C.c_void_p)]
+
+
+class AcArgs(C.Structure):
+    _fields_ = [("actor", Net), ("actor_target", Net), ("critic", Net), ("critic_target", Net),
+                ("n_heads", C.c_int), ("actor_kind", C.c_int), ("replay", Replay), ("indices", C.c_void_p),
+                ("B", C.c_int), ("n_updates", C.c_int), ("noise_next", C.c_void_p), ("noise_new", C.c_void_p),
+                ("seed", C.c_uint64), ("gamma", C.c_float), ("tau", C.c_float),
+                ("lr_actor", C.c_double), ("lr_critic", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double),
+                ("eps", C.c_double), ("wd_critic", C.c_double), ("max_norm", C.c_float),
+                ("step_actor0", C.c_int64), ("step_critic0", C.c_int64), ("total_it0", C.c_int64),
+                ("policy_freq", C.c_int), ("target_smoothing", C.c_int), ("policy_noise", C.c_float),
+                ("noise_clip", C.c_float), ("max_action", C.c_float), ("policy_noise_scale", C.c_float),
+                ("alpha_state", C.c_void_p), ("adaptive_alpha", C.c_int), ("alpha_lr", C.c_double),
+                ("target_entropy", C.c_float), ("step_alpha0", C.c_int64),
+                ("gpart", C.c_void_p), ("sumsq", C.c_void_p), ("stats", C.c_void_p), ("out", C.c_void_p)]
+
+
+class InferArgs(C.Structure):
+    _fields_ = [("net", Net), ("obs", C.c_void_p), ("n", C.c_int), ("obs_dim", C.c_int), ("mode", C.c_int),
+                ("noise", C.c_void_p), ("seed", C.c_uint64), ("counter", C.c_uint32), ("out", C.c_void_p),
+                ("out_cols", C.c_int)]
+
+
+ACTOR_TANH, ACTOR_SAC = 0, 1
+INFER_ARGMAX, INFER_TANH, INFER_SAC_SAMPLE, INFER_SAC_MEAN, INFER_RAW = 0, 1, 2, 3, 4
+
+_lib = None
+
+
+def _declare(lib):
+    vp, i64, u64, ci = C.c_void_p, C.c_int64, C.c_uint64, C.c_int
+    lib.frl_last_error.restype = C.c_char_p
+    lib.frl_replay_add_batch.argtypes = [C.POINTER(Replay), i64, vp, vp, vp, vp, vp, ci, vp]
+    lib.frl_replay_gather.argtypes = [C.POINTER(Replay), vp, ci, vp, vp, vp, vp, vp, vp]
+    lib.frl_sample_uniform.argtypes = [vp, i64, ci, ci, u64, u64, vp]
+    lib.frl_net_sync_mirror.argtypes = [C.POINTER(Net), vp]
+    lib.frl_dqn_learn.argtypes = [C.POINTER(DqnArgs), vp]
+    lib.frl_ac_learn.argtypes = [C.POINTER(AcArgs), vp]
+    lib.frl_policy_infer.argtypes = [C.POINTER(InferArgs), vp]
+    for name in ("frl_replay_add_batch", "frl_replay_gather", "frl_sample_uniform", "frl_net_sync_mirror",
+                 "frl_dqn_learn", "frl_ac_learn", "frl_policy_infer", "frl_is_emulation", "frl_device_sm_count",
+                 "frl_abi_version"):
+        getattr(lib, name).restype = ci
+
+
+def library_path():
+    return os.environ.get("FREERL_B200_LIB", os.path.join(_HERE, "libfreerl_b200.so"))
+
+
+def lib():
+    """Load (once) and return the shared library.  Raises if it is absent — there is no CPU/eager fallback."""
+    global _lib
+    if _lib is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise RuntimeError(
+                "freerl_b200: CUDA extension %s not found. Build it with `python -c 'import __graft_entry__ as g; "
+                "g.build()'` (nvcc, sm_100a). There is no CPU fallback." % path)
+        l = C.CDLL(path)
+        _declare(l)
+        if l.frl_abi_version() != ABI_VERSION:
+            raise RuntimeError("freerl_b200: ABI mismatch in %s" % path)
+        _lib = l
+    return _lib
+
+
+def is_emulation():
+    return bool(lib().frl_is_emulation())
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError("%s failed (%d): %s" % (what, rc, lib().frl_last_error().decode()))
+
+
+def require_device(device):
+    """The product path runs on CUDA only.  (The host-emulation library used by the CPU unit tests reports
+    ``frl_is_emulation() == 1`` and is the only thing that may be driven with CPU tensors.)"""
+    device = torch.device(device)
+    if device.type != "cuda" and not is_emulation():
+        raise RuntimeError("freerl_b200 runs on CUDA devices only (got device=%s); there is no CPU path" % device)
+    return device
+
+
+def stream_ptr(device):
+    if device.type == "cuda":
+        return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    return C.c_void_p(0)
+
+
+def ptr(t):
+    return C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr())
+
+
+_sm_count = None
+
+
+def sm_count():
+    global _sm_count
+    if _sm_count is None:
+        _sm_count = int(lib().frl_device_sm_count())
+    return _sm_count

@@ -1,0 +1,339 @@
+// Fused actor-critic learn() for the deterministic / stochastic off-policy family:
+//   SAC  (SAC_file/SAC.py:222-271, Actor :60-97, Critic :103-127, Alpha :154-169, Agent.update_* :141-151)
+//   TD3  (TD3_file/TD3.py:189-244)      DDPG (DDPG_file/DDPG.py:203-233)
+// Per learn(): sampled rows are gathered straight from the device replay, target action / target Q / TD target,
+// twin-critic forward+backward, global-norm clip, Adam, then actor forward, critic forward with the UPDATED
+// critic, backward through critic into the actor, clip, Adam, Polyak of both targets, temperature step.
+// Six grid barriers per learn(); one launch runs n_updates sequential learns.
+#pragma once
+#include "algo_dqn.cuh"
+
+#define FRL_LOG_SQRT_2PI 0.91893853320467274178f
+#define FRL_LOG2F 0.69314718055994530942f
+
+FRL_DEV float softplus_t(float x) { return x > 20.f ? x : log1pf(expf(x)); }   // F.softplus(beta=1, threshold=20)
+
+struct AcAlgo {
+  typedef frl_ac_args_t Args;
+  static const int NSTAGES = 6;
+
+  FRL_SHD int max_layer_floats(const frl_net_t& n) {
+    int mx = 0;
+    for (int i = 0; i < n.n_layers; ++i) {
+      int f = n.L[i].in_pad * n.L[i].out_pad + n.L[i].out_pad;
+      if (f > mx) mx = f;
+    }
+    return mx;
+  }
+  FRL_SHD int wbuf_floats(const Args& a) {
+    int x = max_layer_floats(a.actor), y = max_layer_floats(a.critic);
+    return ((x > y ? x : y) + 31) & ~31;
+  }
+  FRL_SHD int user_floats(const Args& a) {
+    const int ldh = a.critic.L[0].out_pad, sa = a.critic.L[0].in_pad, ap = a.actor.L[2].out_pad;
+    return FRL_R * (a.replay.row_floats + 3 * sa + 8 * ldh + 6 * ap + 4 * 4 + 16) + 2 * FRL_NT + 128;
+  }
+  FRL_SHD int grid(const Args& a, int max_ctas) {
+    int tiles = (a.B + FRL_R - 1) / FRL_R;
+    return tiles < max_ctas ? tiles : max_ctas;
+  }
+  FRL_SHD int n_updates(const Args& a) { return a.n_updates; }
+
+  FRL_SDEV float noise_at(const float* ptr, const Args& a, int u, int row, int j, uint32_t stream) {
+    if (ptr) return ptr[((size_t)u * a.B + row) * a.replay.act_dim + j];
+    return frl_randn(a.seed, stream, (uint32_t)(a.total_it0 + u), (uint32_t)(row * a.replay.act_dim + j));
+  }
+
+  FRL_SDEV void stage(int s, int u, Cta& c, float* user, const Args& a) {
+    const frl_net_t& A = a.actor;
+    const frl_net_t& C = a.critic;
+    const frl_replay_t& rb = a.replay;
+    const int od = rb.obs_dim, ad = rb.act_dim, rf = rb.row_floats;
+    const int ldh = C.L[0].out_pad, sa = C.L[0].in_pad, ap = A.L[2].out_pad;
+    const int ntile = (a.B + FRL_R - 1) / FRL_R;
+    const int ncontrib = grid(a, c.ncta);
+    const float invB = 1.0f / (float)a.B;
+    const bool sac = a.actor_kind == FRL_ACTOR_SAC;
+    const bool policy_step = ((a.total_it0 + u + 1) % (a.policy_freq > 0 ? a.policy_freq : 1)) == 0;
+    // optimiser step counters: the critic steps every learn, the actor only on policy steps
+    const long n_policy_before = (a.policy_freq > 1) ? (long)((a.total_it0 + u) / a.policy_freq - a.total_it0 / a.policy_freq) : (long)u;
+    float alpha = 0.f;
+    if (sac) alpha = expf(a.alpha_state[0]);
+
+    SmemBump sb; sb.p = user;
+    float* raw = sb.take(FRL_R * rf);
+    float* XS = sb.take(FRL_R * sa);     // [obs | act]
+    float* XN = sb.take(FRL_R * sa);     // [next_obs | a']        (stage 3: [obs | pi(obs)])
+    float* dXP = sb.take(FRL_R * sa);    // dQ/d[obs|a]
+    float* H1 = sb.take(FRL_R * ldh);    // critic head activations (current head)
+    float* H2 = sb.take(FRL_R * ldh);
+    float* G1 = sb.take(FRL_R * ldh);    // second head activations (kept for backward)
+    float* G2 = sb.take(FRL_R * ldh);
+    float* A1 = sb.take(FRL_R * ldh);    // actor activations
+    float* A2 = sb.take(FRL_R * ldh);
+    float* D1 = sb.take(FRL_R * ldh);
+    float* D2 = sb.take(FRL_R * ldh);
+    float* MU = sb.take(FRL_R * ap);     // actor output (pre-tanh mean)
+    float* UU = sb.take(FRL_R * ap);     // SAC pre-tanh sample u
+    float* AC = sb.take(FRL_R * ap);     // squashed action
+    float* dMU = sb.take(FRL_R * ap);
+    float* dA = sb.take(FRL_R * ap);     // accumulated dL/da from the critic heads
+    float* EPS = sb.take(FRL_R * ap);
+    float* QA = sb.take(FRL_R * 4);      // head 0 output
+    float* QB = sb.take(FRL_R * 4);      // head 1 output
+    float* dQA = sb.take(FRL_R * 4);
+    float* dQB = sb.take(FRL_R * 4);
+    float* rowv = sb.take(FRL_R * 4);    // per-row scalars: y, logp, ...
+    float* red0 = sb.take(FRL_NT);
+    float* red1 = sb.take(FRL_NT);
+    const int gstride = C.n_p > A.n_p ? C.n_p : A.n_p;
+    float* gp = a.gpart + (size_t)c.cta * gstride;
+
+    if (s == 0) {
+      // ---------------- targets + critic forward/backward ----------------
+      float loss_acc = 0.f;
+      bool first = true;
+      for (int tile = c.cta; tile < ntile; tile += c.ncta) {
+        const int row0 = tile * FRL_R;
+        const int nvalid = (a.B - row0) < FRL_R ? (a.B - row0) : FRL_R;
+        stage_prefetch(c, layer_fwd_src(a.actor_target, 0), layer_fwd_bytes(a.actor_target.L[0]));
+        gather_rows<FRL_R>(c, rb, a.indices + (size_t)u * a.B + row0, nvalid, raw);
+        copy_cols<FRL_R>(XS, sa, 0, raw, rf, 0, od + ad, sa);
+        copy_cols<FRL_R>(XN, sa, 0, raw, rf, rb_col_nobs(rb), od, sa);
+        // a' = actor_target(next_obs)
+        mlp_fwd<FRL_R>(c, a.actor_target, 0, 3, XN, sa, A1, A2, ldh, MU, ap, FRL_ACT_NONE, fwd_hint(a.critic_target, 0));
+        FRL_PAR(t) {
+          if (t < FRL_R * ad) {
+            const int r = t / ad, j = t % ad;
+            const float mean = MU[r * ap + j];
+            float act;
+            if (sac) {
+              const float* ls_p = a.actor_target.p + a.actor_target.x_off;
+              const float ls = fminf(fmaxf(ls_p[j], -20.f), 2.f);
+              const float sd = expf(ls);
+              const float e = (r < nvalid) ? noise_at(a.noise_next, a, u, row0 + r, j, 1u) : 0.f;
+              const float uu = fadd(mean, fmul(e, sd));
+              const float diff = uu - mean;
+              float lp = -(diff * diff) / (2.f * (sd * sd)) - logf(sd) - FRL_LOG_SQRT_2PI;
+              lp -= 2.f * (FRL_LOG2F - uu - softplus_t(-2.f * uu));
+              UU[r * ap + j] = lp;                      // per-dim log-prob contribution
+              act = tanhf(uu);
+            } else if (a.target_smoothing) {
+              const float e = (r < nvalid) ? noise_at(a.noise_next, a, u, row0 + r, j, 1u) : 0.f;
+              float nz = fmul(a.policy_noise_scale, fmul(e, a.policy_noise));
+              nz = fminf(fmaxf(nz, -a.noise_clip), a.noise_clip);
+              float v = fadd(fmul(tanhf(mean), a.max_action), nz);
+              v = fminf(fmaxf(v, -a.max_action), a.max_action);
+              act = fdiv(v, a.max_action);
+            } else {
+              act = tanhf(mean);
+            }
+            XN[r * sa + od + j] = act;
+          }
+        }
+        FRL_SYNC();
+        // target Q heads
+        mlp_fwd<FRL_R>(c, a.critic_target, 0, 3, XN, sa, H1, H2, ldh, QA, 4, FRL_ACT_NONE,
+                       a.n_heads == 2 ? fwd_hint(a.critic_target, 3) : fwd_hint(C, 0));
+        if (a.n_heads == 2)
+          mlp_fwd<FRL_R>(c, a.critic_target, 3, 3, XN, sa, H1, H2, ldh, QB, 4, FRL_ACT_NONE, fwd_hint(C, 0));
+        FRL_PAR(t) {
+          if (t < FRL_R) {
+            const int r = t;
+            float nq = QA[r * 4];
+            if (a.n_heads == 2) nq = fminf(nq, QB[r * 4]);
+            const float rew = raw[r * rf + rb_col_rew(rb)], dn = raw[r * rf + rb_col_done(rb)];
+            float y;
+            if (sac) {
+              float lp = 0.f;
+              for (int j = 0; j < ad; ++j) lp += UU[r * ap + j];
+              // target = r + gamma*(1-d)*(minQ' + alpha*(-logp'))      (SAC.py:235)
+              y = fadd(rew, fmul(fmul(a.gamma, fadd(1.f, -dn)), fadd(nq, fmul(alpha, -lp))));
+            } else {
+              y = fadd(rew, fmul(fmul(a.gamma, nq), fadd(1.f, -dn)));     // TD3.py:209 / DDPG.py:212
+            }
+            rowv[r * 4 + 0] = y;
+          }
+        }
+        FRL_SYNC();
+        // critic heads on (s, a): forward keeps activations, then backward
+        mlp_fwd<FRL_R>(c, C, 0, 3, XS, sa, H1, H2, ldh, QA, 4, FRL_ACT_NONE, a.n_heads == 2 ? fwd_hint(C, 3) : bwd_hint(C, 2));
+        if (a.n_heads == 2) mlp_fwd<FRL_R>(c, C, 3, 3, XS, sa, G1, G2, ldh, QB, 4, FRL_ACT_NONE, bwd_hint(C, 2));
+        FRL_PAR(t) {
+          float l = 0.f;
+          if (t < FRL_R) {
+            const int r = t;
+            for (int j = 0; j < 4; ++j) { dQA[r * 4 + j] = 0.f; dQB[r * 4 + j] = 0.f; }
+            if (r < nvalid) {
+              const float y = rowv[r * 4];
+              const float d0 = QA[r * 4] - y;
+              dQA[r * 4] = 2.f * d0 * invB;
+              l = d0 * d0;
+              if (a.n_heads == 2) {
+                const float d1 = QB[r * 4] - y;
+                dQB[r * 4] = 2.f * d1 * invB;
+                l += d1 * d1;
+              }
+            }
+          }
+          red0[t] = l;
+        }
+        FRL_SYNC();
+        loss_acc += block_sum(c, red0);
+        mlp_bwd<FRL_R>(c, C, 0, 3, XS, sa, H1, H2, ldh, dQA, 4, D1, D2, nullptr, 0, gp, !first,
+                       a.n_heads == 2 ? bwd_hint(C, 5) : no_hint());
+        if (a.n_heads == 2) mlp_bwd<FRL_R>(c, C, 3, 3, XS, sa, G1, G2, ldh, dQB, 4, D1, D2, nullptr, 0, gp, !first, no_hint());
+        first = false;
+      }
+      FRL_PAR(t) { if (t == 0) a.stats[c.cta * 8 + 0] = loss_acc; }
+      FRL_SYNC();
+    } else if (s == 1) {
+      reduce_grads(c, C, a.gpart, gstride, ncontrib, a.sumsq);
+    } else if (s == 2) {
+      const AdamHP hp = make_adam_hp(a.lr_critic, a.beta1, a.beta2, a.eps, a.wd_critic, a.max_norm, (long)(a.step_critic0 + u + 1));
+      adam_update(c, C, a.sumsq, ncontrib, hp, policy_step ? &a.critic_target : nullptr, a.tau);
+      FRL_PAR(t) {
+        if (c.cta == 0 && t == 0) {
+          float l = 0.f, ss = 0.f;
+          for (int i = 0; i < ncontrib; ++i) { l += a.stats[i * 8 + 0]; ss += a.sumsq[i]; }
+          a.out[u * 8 + 0] = l * invB;
+          a.out[u * 8 + 4] = sqrtf(ss);
+          a.out[u * 8 + 2] = alpha;
+        }
+      }
+      FRL_SYNC();
+    } else if (s == 3) {
+      if (!policy_step) return;
+      // ---------------- actor forward, critic forward (updated weights), backward into the actor ----------------
+      float loss_acc = 0.f, ent_acc = 0.f;
+      bool first = true;
+      for (int tile = c.cta; tile < ntile; tile += c.ncta) {
+        const int row0 = tile * FRL_R;
+        const int nvalid = (a.B - row0) < FRL_R ? (a.B - row0) : FRL_R;
+        stage_prefetch(c, layer_fwd_src(A, 0), layer_fwd_bytes(A.L[0]));
+        gather_rows<FRL_R>(c, rb, a.indices + (size_t)u * a.B + row0, nvalid, raw);
+        copy_cols<FRL_R>(XN, sa, 0, raw, rf, 0, od, sa);
+        mlp_fwd<FRL_R>(c, A, 0, 3, XN, sa, A1, A2, ldh, MU, ap, FRL_ACT_NONE, fwd_hint(C, 0));
+        FRL_PAR(t) {
+          if (t < FRL_R * ap) {
+            const int r = t / ap, j = t % ap;
+            float act = 0.f, uu = 0.f, e = 0.f, lp = 0.f;
+            if (j < ad) {
+              const float mean = MU[r * ap + j];
+              if (sac) {
+                const float ls = fminf(fmaxf(A.p[A.x_off + j], -20.f), 2.f);
+                const float sd = expf(ls);
+                e = (r < nvalid) ? noise_at(a.noise_new, a, u, row0 + r, j, 2u) : 0.f;
+                uu = fadd(mean, fmul(e, sd));
+                const float diff = uu - mean;
+                lp = -(diff * diff) / (2.f * (sd * sd)) - logf(sd) - FRL_LOG_SQRT_2PI;
+                lp -= 2.f * (FRL_LOG2F - uu - softplus_t(-2.f * uu));
+                act = tanhf(uu);
+              } else {
+                act = tanhf(mean);
+              }
+              XN[r * sa + od + j] = act;
+            }
+            AC[r * ap + j] = act; UU[r * ap + j] = lp; EPS[r * ap + j] = e; dA[r * ap + j] = 0.f;
+          }
+        }
+        FRL_SYNC();
+        // Q heads at (s, pi(s)); dL/dQ_h = -(1/n_used)/B   (SAC: mean of both heads; TD3: Q1 only; DDPG: single)
+        const int heads_used = sac ? a.n_heads : 1;
+        const float dq = -invB / (float)heads_used;
+        float qsum_tile = 0.f;
+        for (int h = 0; h < heads_used; ++h) {
+          mlp_fwd<FRL_R>(c, C, 3 * h, 3, XN, sa, H1, H2, ldh, QA, 4, FRL_ACT_NONE, bwd_hint(C, 3 * h + 2));
+          FRL_PAR(t) {
+            float v = 0.f;
+            if (t < FRL_R) {
+              for (int j = 0; j < 4; ++j) dQA[t * 4 + j] = 0.f;
+              if (t < nvalid) { dQA[t * 4] = dq; v = QA[t * 4]; }
+            }
+            red0[t] = v;
+          }
+          FRL_SYNC();
+          qsum_tile += block_sum(c, red0);
+          mlp_bwd<FRL_R>(c, C, 3 * h, 3, XN, sa, H1, H2, ldh, dQA, 4, D1, D2, dXP, sa, nullptr, false,
+                         h + 1 < heads_used ? fwd_hint(C, 3 * (h + 1)) : bwd_hint(A, 2));
+          FRL_PAR(t) {
+            if (t < FRL_R * ad) { const int r = t / ad, j = t % ad; dA[r * ap + j] += dXP[r * sa + od + j]; }
+          }
+          FRL_SYNC();
+        }
+        // actor head backward: dL/dmean, dL/dlog_std, loss bookkeeping
+        FRL_PAR(t) {
+          float lsum = 0.f, esum = 0.f;
+          if (t < FRL_R) {
+            const int r = t;
+            float lp = 0.f;
+            for (int j = 0; j < ap; ++j) {
+              float g = 0.f;
+              if (j < ad && r < nvalid) {
+                const float act = AC[r * ap + j];
+                g = dA[r * ap + j] * (1.f - act * act);
+                if (sac) { g += alpha * invB * 2.f * act; lp += UU[r * ap + j]; }
+              }
+              dMU[r * ap + j] = g;
+            }
+            if (r < nvalid) { esum = -lp; lsum = alpha * lp; }     // actor_loss = mean(-Q_pi - alpha*entropy)
+          }
+          red0[t] = lsum; red1[t] = esum;
+        }
+        FRL_SYNC();
+        loss_acc += block_sum(c, red0) - qsum_tile / (float)heads_used;
+        ent_acc += block_sum(c, red1);
+        if (sac) {
+          // d/dlog_std_j = sum_r [ dL/du * std*eps - alpha/B ]   (zero outside the clamp range)
+          FRL_PAR(t) {
+            if (t < ad) {
+              const float lsr = A.p[A.x_off + t];
+              float g = 0.f;
+              if (lsr >= -20.f && lsr <= 2.f) {
+                const float sd = expf(lsr);
+                for (int r = 0; r < nvalid; ++r) g += dMU[r * ap + t] * sd * EPS[r * ap + t] - alpha * invB;
+              }
+              gp[A.x_off + t] = first ? g : gp[A.x_off + t] + g;
+            }
+          }
+          FRL_SYNC();
+        }
+        mlp_bwd<FRL_R>(c, A, 0, 3, XN, sa, A1, A2, ldh, dMU, ap, D1, D2, nullptr, 0, gp, !first, no_hint());
+        first = false;
+      }
+      FRL_PAR(t) { if (t == 0) { a.stats[c.cta * 8 + 1] = loss_acc; a.stats[c.cta * 8 + 2] = ent_acc; } }
+      FRL_SYNC();
+    } else if (s == 4) {
+      if (!policy_step) return;
+      reduce_grads(c, A, a.gpart, gstride, ncontrib, a.sumsq);
+    } else {
+      if (!policy_step) return;
+      const AdamHP hp = make_adam_hp(a.lr_actor, a.beta1, a.beta2, a.eps, 0.0, a.max_norm, (long)(a.step_actor0 + n_policy_before + 1));
+      adam_update(c, A, a.sumsq, ncontrib, hp, &a.actor_target, a.tau);
+      FRL_PAR(t) {
+        if (c.cta == 0 && t == 0) {
+          float l = 0.f, en = 0.f, ss = 0.f;
+          for (int i = 0; i < ncontrib; ++i) { l += a.stats[i * 8 + 1]; en += a.stats[i * 8 + 2]; ss += a.sumsq[i]; }
+          a.out[u * 8 + 1] = l * invB;
+          a.out[u * 8 + 5] = sqrtf(ss);
+          a.out[u * 8 + 6] = en * invB;
+          if (sac && a.adaptive_alpha) {
+            // alpha_loss = (exp(log_alpha) * (entropy - target_entropy).detach()).mean();  Adam(lr alpha_lr) on log_alpha
+            const float mean_term = en * invB - a.target_entropy;
+            const float al = expf(a.alpha_state[0]);
+            const float g = al * mean_term;
+            a.out[u * 8 + 3] = g;      // == alpha_loss value (alpha * mean(entropy - target))
+            const AdamHP ha = make_adam_hp(a.alpha_lr, a.beta1, a.beta2, a.eps, 0.0, 0.0, (long)(a.step_alpha0 + u + 1));
+            float m = a.alpha_state[1], v = a.alpha_state[2], w = a.alpha_state[0];
+            m = fmaf(ha.one_minus_b1, g - m, m);
+            v = fadd(fmul(v, ha.b2), fmul(fmul(ha.one_minus_b2, g), g));
+            const float denom = fadd(fdiv(fsqrt(v), ha.bc2_sqrt), ha.eps);
+            w = fadd(w, fdiv(fmul(ha.lr_over_bc1_neg, m), denom));
+            a.alpha_state[0] = w; a.alpha_state[1] = m; a.alpha_state[2] = v;
+          }
+        }
+      }
+      FRL_SYNC();
+    }
+  }
+};

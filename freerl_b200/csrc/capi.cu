@@ -1,0 +1,306 @@
+// freerl_b200 — C ABI implementation (see include/freerl_b200.h).
+// Compiled by nvcc for sm_100a (product: libfreerl_b200.so).  The same translation unit compiles with
+// `g++ -x c++ -DFRL_EMUL` into tests/emul/libfreerl_emul.so — a TEST-ONLY host emulation used by the CPU test
+// suite to check kernel indexing/arithmetic against the oracle; frl_is_emulation() tells them apart and the
+// product Python path refuses a library that reports 1.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "algo_ac.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+extern "C" void frl_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* frl_last_error(void) { return g_err; }
+extern "C" int frl_abi_version(void) { return 1; }
+
+#ifndef FRL_EMUL
+extern "C" int frl_is_emulation(void) { return 0; }
+int frl_device_max_ctas() {
+  static int cached = 0;
+  if (!cached) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 1;
+    cached = n;
+  }
+  return cached;
+}
+#else
+extern "C" int frl_is_emulation(void) { return 1; }
+#endif
+extern "C" int frl_device_sm_count(void) { return frl_device_max_ctas(); }
+
+// ------------------------------------------------------------------------------------------------
+// generic 1-D elementwise launcher (functor bodies are shared by the CUDA and the emulation build)
+// ------------------------------------------------------------------------------------------------
+#ifndef FRL_EMUL
+template <class F>
+__global__ void frl_for_kernel(long n, F f) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) f(i);
+}
+template <class F>
+static int frl_for(long n, const F& f, cudaStream_t s) {
+  if (n <= 0) return 0;
+  long blocks = (n + 255) / 256;
+  const long cap = (long)frl_device_max_ctas() * 16;     // grid-stride beyond 16 CTAs / SM
+  if (blocks > cap) blocks = cap;
+  frl_for_kernel<F><<<(unsigned)blocks, 256, 0, s>>>(n, f);
+  FRL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+#else
+template <class F>
+static int frl_for(long n, const F& f, cudaStream_t) {
+  for (long i = 0; i < n; ++i) f(i);
+  return 0;
+}
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// replay: batched add (SoA fields -> AoS rows at ring slots) and gather (AoS rows -> 5 dense tensors)
+// ------------------------------------------------------------------------------------------------
+struct AddBody {
+  frl_replay_t rb; int64_t index; const float *obs, *act, *rew, *nobs, *done; int n;
+  FRL_HDM void operator()(long i) const {
+    const int col = (int)(i % rb.row_floats);
+    const long r = i / rb.row_floats;
+    const int64_t slot = (index + r) % rb.capacity;
+    const int od = rb.obs_dim, ad = rb.act_dim;
+    float v = 0.f;
+    if (col < od) v = obs[r * od + col];
+    else if (col < od + ad) v = act[r * ad + (col - od)];
+    else if (col == od + ad) v = rew[r];
+    else if (col == od + ad + 1) v = done[r];
+    else if (col < 2 * od + ad + 2) v = nobs[r * od + (col - od - ad - 2)];
+    rb.storage[slot * rb.row_floats + col] = v;
+  }
+};
+
+extern "C" int frl_replay_add_batch(const frl_replay_t* rb, int64_t index, const float* obs, const float* act, const float* rew,
+                                    const float* next_obs, const float* done, int n, void* stream) {
+  if (!rb || !rb->storage || n < 0 || rb->row_floats % 4 || rb->row_floats < 2 * rb->obs_dim + rb->act_dim + 2) {
+    frl_set_error("frl_replay_add_batch: bad arguments");
+    return -1;
+  }
+  AddBody b = {*rb, index, obs, act, rew, next_obs, done, n};
+  return frl_for((long)n * rb->row_floats, b, (cudaStream_t)stream);
+}
+
+struct GatherBody {
+  frl_replay_t rb; const int64_t* idx; float *obs, *act, *rew, *nobs, *done;
+  FRL_HDM void operator()(long i) const {
+    const int col = (int)(i % rb.row_floats);
+    const long b = i / rb.row_floats;
+    const int od = rb.obs_dim, ad = rb.act_dim;
+    const float v = rb.storage[idx[b] * rb.row_floats + col];
+    if (col < od) obs[b * od + col] = v;
+    else if (col < od + ad) act[b * ad + (col - od)] = v;
+    else if (col == od + ad) rew[b] = v;
+    else if (col == od + ad + 1) done[b] = v;
+    else if (col < 2 * od + ad + 2) nobs[b * od + (col - od - ad - 2)] = v;
+  }
+};
+
+extern "C" int frl_replay_gather(const frl_replay_t* rb, const int64_t* indices, int B, float* obs, float* act, float* rew,
+                                 float* next_obs, float* done, void* stream) {
+  if (!rb || !rb->storage || B < 0) { frl_set_error("frl_replay_gather: bad arguments"); return -1; }
+  GatherBody b = {*rb, indices, obs, act, rew, next_obs, done};
+  return frl_for((long)B * rb->row_floats, b, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// uniform sampling without replacement on the device (fast mode; NOT the numpy legacy stream)
+// One CTA per update: draw B indices, then redraw any element that collides with a lower-indexed one
+// until all are distinct.
+// ------------------------------------------------------------------------------------------------
+struct SampleAlgo {
+  struct Args { int64_t* out; int64_t size; int B, n_updates; uint64_t seed, counter; };
+  static const int NSTAGES = 1;
+  FRL_SHD int wbuf_floats(const Args&) { return 32; }
+  FRL_SHD int user_floats(const Args& a) { return 2 * a.B + 64; }
+  FRL_SHD int grid(const Args& a, int) { return a.n_updates; }
+  FRL_SHD int n_updates(const Args&) { return 1; }
+  FRL_SDEV int64_t draw(const Args& a, int u, int i, int round) {
+    uint32_t o[4];
+    frl_philox((uint32_t)a.seed, (uint32_t)(a.seed >> 32), (uint32_t)i, (uint32_t)round, (uint32_t)(a.counter + u),
+               (uint32_t)((a.counter + u) >> 32) ^ 0x1d8e4e27u, o);
+    const uint64_t x = ((uint64_t)o[0] << 32) | o[1];
+#ifndef FRL_EMUL
+    return (int64_t)__umul64hi(x, (uint64_t)a.size);
+#else
+    return (int64_t)(((unsigned __int128)x * (unsigned __int128)a.size) >> 64);
+#endif
+  }
+  FRL_SDEV void stage(int, int, Cta& c, float* user, const Args& a) {
+    const int u = c.cta;
+    int* idx = (int*)user;            // sizes < 2^31 (checked by the host wrapper)
+    int* dup = idx + a.B;
+    FRL_PAR(t) { for (int i = t; i < a.B; i += FRL_NT) { idx[i] = (int)draw(a, u, i, 0); dup[i] = 0; } }
+    FRL_SYNC();
+    for (int round = 1; round < 64; ++round) {
+      FRL_PAR(t) {
+        for (int i = t; i < a.B; i += FRL_NT) {
+          int d = 0;
+          const int v = idx[i];
+          for (int j = 0; j < i; ++j) d |= (idx[j] == v);
+          dup[i] = d;
+        }
+      }
+      FRL_SYNC();
+      int any = 0;   // block-uniform after the reduction below
+      FRL_PAR(t) { if (t == 0) { int s = 0; for (int i = 0; i < a.B; ++i) s |= dup[i]; dup[a.B] = s; } }
+      FRL_SYNC();
+      any = dup[a.B];
+      if (!any) break;
+      FRL_PAR(t) { for (int i = t; i < a.B; i += FRL_NT) if (dup[i]) idx[i] = (int)draw(a, u, i, round); }
+      FRL_SYNC();
+    }
+    FRL_PAR(t) { for (int i = t; i < a.B; i += FRL_NT) a.out[(size_t)u * a.B + i] = idx[i]; }
+    FRL_SYNC();
+  }
+};
+
+extern "C" int frl_sample_uniform(int64_t* indices_out, int64_t size, int B, int n_updates, uint64_t seed, uint64_t counter,
+                                  void* stream) {
+  if (!indices_out || size <= 0 || size >= ((int64_t)1 << 31) || B <= 0 || B > size || B > 8192 || n_updates <= 0) {
+    frl_set_error("frl_sample_uniform: need 0 < B <= min(size, 8192), size < 2^31 (got size=%lld B=%d)", (long long)size, B);
+    return -1;
+  }
+  SampleAlgo::Args a = {indices_out, size, B, n_updates, seed, counter};
+  return frl_launch_tiles<SampleAlgo>(a, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// refresh the transposed mirror block from the trainable block (after load_state_dict / init)
+// ------------------------------------------------------------------------------------------------
+struct MirrorBody {
+  frl_net_t n;
+  FRL_HDM void operator()(long p) const {
+    for (int li = 0; li < n.n_layers; ++li) {
+      const frl_layer_t& L = n.L[li];
+      const int wsz = L.out_pad * L.in_pad;
+      if (p >= L.w_off && p < L.w_off + wsz) {
+        const int e = (int)p - L.w_off, j = e / L.in_pad, k = e % L.in_pad;
+        n.pt[L.wt_off + k * L.out_pad + j] = n.p[p];
+        return;
+      }
+      if (p >= L.b_off && p < L.b_off + L.out_pad) { n.pt[L.wt_off + wsz + ((int)p - L.b_off)] = n.p[p]; return; }
+    }
+  }
+};
+
+extern "C" int frl_net_sync_mirror(const frl_net_t* net, void* stream) {
+  if (!net || !net->p || !net->pt) { frl_set_error("frl_net_sync_mirror: null net"); return -1; }
+  MirrorBody b = {*net};
+  return frl_for(net->n_p, b, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched policy inference (select_action / evaluate_action for N vectorised envs)
+// ------------------------------------------------------------------------------------------------
+struct InferAlgo {
+  typedef frl_infer_args_t Args;
+  static const int NSTAGES = 1;
+  FRL_SHD int wbuf_floats(const Args& a) { return (AcAlgo::max_layer_floats(a.net) + 31) & ~31; }
+  FRL_SHD int user_floats(const Args& a) {
+    return FRL_R * (a.net.L[0].in_pad + 2 * a.net.L[0].out_pad + a.net.L[a.net.n_layers - 1].out_pad) + 64;
+  }
+  FRL_SHD int grid(const Args& a, int) { return (a.n + FRL_R - 1) / FRL_R; }
+  FRL_SHD int n_updates(const Args&) { return 1; }
+  FRL_SDEV void stage(int, int, Cta& c, float* user, const Args& a) {
+    const frl_net_t& n = a.net;
+    const int nl = n.n_layers, in_pad = n.L[0].in_pad, ldh = n.L[0].out_pad, op = n.L[nl - 1].out_pad, nout = n.L[nl - 1].out;
+    SmemBump sb; sb.p = user;
+    float* X = sb.take(FRL_R * in_pad);
+    float* H1 = sb.take(FRL_R * ldh);
+    float* H2 = sb.take(FRL_R * ldh);
+    float* O = sb.take(FRL_R * op);
+    const int row0 = c.cta * FRL_R;
+    const int nvalid = (a.n - row0) < FRL_R ? (a.n - row0) : FRL_R;
+    stage_prefetch(c, layer_fwd_src(n, 0), layer_fwd_bytes(n.L[0]));
+    FRL_PAR(t) {
+      for (int e = t; e < FRL_R * in_pad; e += FRL_NT) {
+        const int r = e / in_pad, j = e % in_pad;
+        X[e] = (r < nvalid && j < a.obs_dim) ? a.obs[(size_t)(row0 + r) * a.obs_dim + j] : 0.f;
+      }
+    }
+    FRL_SYNC();
+    mlp_fwd<FRL_R>(c, n, 0, nl, X, in_pad, H1, H2, ldh, O, op, FRL_ACT_NONE, no_hint());
+    FRL_PAR(t) {
+      if (a.mode == FRL_INFER_ARGMAX) {
+        if (t < nvalid) {
+          int best = 0; float bv = O[t * op];
+          for (int j = 1; j < nout; ++j) if (O[t * op + j] > bv) { bv = O[t * op + j]; best = j; }   // first max, like torch.argmax
+          a.out[(size_t)(row0 + t) * a.out_cols] = (float)best;
+        }
+      } else if (t < FRL_R * nout) {
+        const int r = t / nout, j = t % nout;
+        if (r < nvalid) {
+          float v = O[r * op + j];
+          if (a.mode == FRL_INFER_TANH || a.mode == FRL_INFER_SAC_MEAN) v = tanhf(v);
+          else if (a.mode == FRL_INFER_SAC_SAMPLE) {
+            const float ls = fminf(fmaxf(n.p[n.x_off + j], -20.f), 2.f);
+            const float e = a.noise ? a.noise[(size_t)(row0 + r) * nout + j]
+                                    : frl_randn(a.seed, 3u, a.counter, (uint32_t)((row0 + r) * nout + j));
+            v = tanhf(fadd(v, fmul(e, expf(ls))));
+          }
+          a.out[(size_t)(row0 + r) * a.out_cols + j] = v;
+        }
+      }
+    }
+    FRL_SYNC();
+  }
+};
+
+extern "C" int frl_policy_infer(const frl_infer_args_t* a, void* stream) {
+  if (!a || !a->obs || !a->out || a->n <= 0) { frl_set_error("frl_policy_infer: bad arguments"); return -1; }
+  return frl_launch_tiles<InferAlgo>(*a, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused learn() entry points
+// ------------------------------------------------------------------------------------------------
+static int check_net(const frl_net_t& n, bool trainable, const char* who) {
+  if (!n.p || !n.pt || n.n_layers < 1 || n.n_layers > FRL_MAX_LAYERS || (trainable && (!n.m || !n.v || !n.g))) {
+    frl_set_error("%s: malformed net descriptor", who);
+    return -1;
+  }
+  for (int i = 0; i < n.n_layers; ++i)
+    if (n.L[i].in_pad % 4 || n.L[i].out_pad % 4 || n.L[i].w_off % 4 || n.L[i].b_off % 4 || n.L[i].wt_off % 4) {
+      frl_set_error("%s: layer %d is not 16-byte aligned", who, i);
+      return -1;
+    }
+  return 0;
+}
+
+extern "C" int frl_dqn_learn(const frl_dqn_args_t* a, void* stream) {
+  if (!a || a->B <= 0 || a->n_updates <= 0 || !a->indices || !a->gpart || !a->stats || !a->out) {
+    frl_set_error("frl_dqn_learn: bad arguments");
+    return -1;
+  }
+  if (check_net(a->q, true, "frl_dqn_learn(q)") || check_net(a->q_target, false, "frl_dqn_learn(q_target)")) return -1;
+  return frl_launch<DqnAlgo>(*a, (cudaStream_t)stream);
+}
+
+extern "C" int frl_ac_learn(const frl_ac_args_t* a, void* stream) {
+  if (!a || a->B <= 0 || a->n_updates <= 0 || !a->indices || !a->gpart || !a->sumsq || !a->stats || !a->out) {
+    frl_set_error("frl_ac_learn: bad arguments");
+    return -1;
+  }
+  if (check_net(a->actor, true, "frl_ac_learn(actor)") || check_net(a->critic, true, "frl_ac_learn(critic)") ||
+      check_net(a->actor_target, false, "frl_ac_learn(actor_target)") || check_net(a->critic_target, false, "frl_ac_learn(critic_target)"))
+    return -1;
+  if (a->actor.n_layers != 3 || a->critic.n_layers != 3 * a->n_heads || (a->actor_kind == FRL_ACTOR_SAC && !a->alpha_state)) {
+    frl_set_error("frl_ac_learn: unsupported network shape / missing alpha state");
+    return -1;
+  }
+  return frl_launch<AcAlgo>(*a, (cudaStream_t)stream);
+}

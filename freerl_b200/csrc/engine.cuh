@@ -1,0 +1,509 @@
+// freerl_b200 — CTA-level training engine for small (hidden 128) MLPs on sm_100a.
+//
+// Building blocks used by every fused learn() kernel (DQN / SAC / TD3 / DDPG / PPO / multi-agent):
+//   * Stager      : double-buffered TMA (cp.async.bulk + mbarrier) staging of one weight matrix at a time
+//                   from HBM/L2 into shared memory, prefetching the next matrix while the current is used.
+//   * gemm_rk     : C[R][N] = epi(A[R][K] * B[K][N] + bias)   (forward with B = W^T, backward-dX with B = W)
+//                   4x4 register tiles, K split across threads, fixed-order shared-memory reduction.
+//   * gemm_outer  : dW[M][N] = sum_r dY[r][m] X[r][n]  written to this CTA's gradient partial in global.
+//   * reduce_grads / adam_update / polyak_update : cross-CTA fixed-order (deterministic, no float atomics)
+//                   gradient reduction, global-norm clip, torch-exact Adam, target Polyak; keep the
+//                   transposed weight mirrors in sync.
+// Activations live in shared memory as row-major [R][width_pad] tiles (width_pad % 4 == 0, pads zero).
+#pragma once
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// exact (non-contracted) fp32 helpers so optimiser math rounds like torch's op-by-op kernels
+// ------------------------------------------------------------------------------------------------
+#ifndef FRL_EMUL
+FRL_DEV float fmul(float a, float b) { return __fmul_rn(a, b); }
+FRL_DEV float fadd(float a, float b) { return __fadd_rn(a, b); }
+FRL_DEV float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+FRL_DEV float fsqrt(float a) { return __fsqrt_rn(a); }
+#else
+static inline float fmul(float a, float b) { volatile float r = a * b; return r; }
+static inline float fadd(float a, float b) { volatile float r = a + b; return r; }
+static inline float fdiv(float a, float b) { return a / b; }
+static inline float fsqrt(float a) { return sqrtf(a); }
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// CTA context
+// ------------------------------------------------------------------------------------------------
+struct Cta {
+  int cta, ncta;            // this CTA's index / grid size
+  float* smem;              // dynamic shared memory base (1024-B aligned)
+  // ---- stager (block-uniform state, replicated in every thread's registers) ----
+  float* wbuf[2];           // two weight staging buffers in smem
+  uint64_t* bar;            // two mbarriers in smem
+  uint32_t phase[2];
+  const float* pend_ptr;    // global source of the outstanding prefetch (or nullptr)
+  int pend_buf;
+  int next_buf;
+  float* red;               // [FRL_NT*16] reduction scratch in smem
+};
+
+// ------------------------------------------------------------------------------------------------
+// TMA staging
+// ------------------------------------------------------------------------------------------------
+#ifndef FRL_EMUL
+FRL_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+FRL_DEV void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+FRL_DEV void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+FRL_DEV void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+FRL_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "FRL_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra FRL_DONE_%=;\n\t"
+      "bra FRL_WAIT_%=;\n\t"
+      "FRL_DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+FRL_DEV void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+#endif
+
+// Carve the stager + scratch out of dynamic smem.  Returns the first free float after them.
+FRL_DEV float* cta_init(Cta& c, int cta, int ncta, float* smem, int wbuf_floats) {
+  c.cta = cta; c.ncta = ncta; c.smem = smem;
+  c.wbuf[0] = smem;
+  c.wbuf[1] = smem + wbuf_floats;
+  c.red = smem + 2 * wbuf_floats;
+  c.bar = (uint64_t*)(c.red + FRL_NT * 16);
+  c.phase[0] = c.phase[1] = 0;
+  c.pend_ptr = nullptr; c.pend_buf = 0; c.next_buf = 0;
+#ifndef FRL_EMUL
+  if (threadIdx.x == 0) {
+    mbar_init(&c.bar[0], 1);
+    mbar_init(&c.bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
+  }
+  __syncthreads();
+#endif
+  return (float*)(c.bar + 2);       // two 8-B mbarriers = 16 B, alignment preserved
+}
+
+// smem floats consumed by cta_init
+FRL_HD int cta_base_floats(int wbuf_floats) { return 2 * wbuf_floats + FRL_NT * 16 + 4; }
+
+FRL_DEV void stage_issue(Cta& c, int buf, const float* src, int bytes) {
+#ifndef FRL_EMUL
+  if (threadIdx.x == 0) {
+    fence_proxy_async();
+    mbar_expect_tx(&c.bar[buf], (uint32_t)bytes);
+    tma_bulk_g2s(c.wbuf[buf], src, (uint32_t)bytes, &c.bar[buf]);
+  }
+#else
+  memcpy(c.wbuf[buf], src, (size_t)bytes);
+#endif
+}
+
+FRL_DEV void stage_wait(Cta& c, int buf) {
+#ifndef FRL_EMUL
+  mbar_wait(&c.bar[buf], c.phase[buf]);
+#endif
+  c.phase[buf] ^= 1u;
+}
+
+// Start fetching `src` into the idle buffer.  Precondition: every thread is past its last read of that
+// buffer (all engine ops end with FRL_SYNC).  At most one prefetch is outstanding.
+FRL_DEV void stage_prefetch(Cta& c, const float* src, int bytes) {
+  if (src == nullptr || c.pend_ptr != nullptr) return;
+  stage_issue(c, c.next_buf, src, bytes);
+  c.pend_ptr = src;
+  c.pend_buf = c.next_buf;
+}
+
+// Returns the smem copy of `src` (waits for the matching prefetch, or fetches now).
+FRL_DEV const float* stage_acquire(Cta& c, const float* src, int bytes) {
+  if (c.pend_ptr != nullptr && c.pend_ptr != src) {   // stale hint: drain it to keep barrier phases aligned
+    stage_wait(c, c.pend_buf);
+    c.pend_ptr = nullptr;
+    c.next_buf = c.pend_buf ^ 1;
+    FRL_SYNC();
+  }
+  if (c.pend_ptr == nullptr) {
+    stage_issue(c, c.next_buf, src, bytes);
+    c.pend_buf = c.next_buf;
+  }
+  stage_wait(c, c.pend_buf);
+  c.pend_ptr = nullptr;
+  c.next_buf = c.pend_buf ^ 1;
+  return c.wbuf[c.pend_buf];
+}
+
+// Must be called when weights may have changed under a buffer we would otherwise trust (after grid sync).
+FRL_DEV void stage_reset(Cta& c) {
+  if (c.pend_ptr != nullptr) {
+    stage_wait(c, c.pend_buf);
+    c.pend_ptr = nullptr;
+    c.next_buf = c.pend_buf ^ 1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// float4 helpers
+// ------------------------------------------------------------------------------------------------
+FRL_DEV float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+FRL_DEV void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+FRL_DEV float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+FRL_DEV float apply_act(float v, int act) {
+  if (act == FRL_ACT_RELU) return v > 0.f ? v : 0.f;
+  if (act == FRL_ACT_TANH) return tanhf(v);
+  return v;
+}
+
+enum { EPI_BIAS_ACT = 0, EPI_RELU_MASK = 1 };
+
+// ------------------------------------------------------------------------------------------------
+// gemm_rk:  C[r][n] = epi( sum_k A[r][k] * Bs[k][n] (+ bias[n]) ),  r < R, n < N_pad, k < K_pad
+//   A  : smem, row-major, leading dim lda (multiple of 4), columns [0,K_pad) readable & finite
+//   Bs : smem, row-major [K_pad][N_pad] (rows >= logical K are zero)
+//   epi: EPI_BIAS_ACT  -> act(acc + bias[n])            (bias in smem, may be null)
+//        EPI_RELU_MASK -> acc * (mask[r][n] > 0)        (backward through ReLU; mask = stored activation)
+//   C  : smem, leading dim ldc.  Must not alias A.
+// ------------------------------------------------------------------------------------------------
+template <int R>
+FRL_DEV void gemm_rk(Cta& c, const float* A, int lda, int K_pad, const float* Bs, int N_pad, const float* bias,
+                     int epi, int act, const float* mask, int ldm, float* C, int ldc) {
+  const int nt = N_pad >> 2, rt = R / 4;
+  const int tiles = nt * rt;
+  const int nchunk = K_pad >> 2;
+  int ksplit = FRL_NT / tiles;
+  if (ksplit < 1) ksplit = 1;
+  if (ksplit > nchunk) ksplit = nchunk;
+  const int items = tiles * ksplit;
+  float* red = c.red;
+  FRL_PAR(t) {
+    for (int item = t; item < items; item += FRL_NT) {
+      const int tile = item % tiles, ks = item / tiles;
+      const int n0 = (tile % nt) * 4, r0 = (tile / nt) * 4;
+      const int kc0 = (ks * nchunk) / ksplit, kc1 = ((ks + 1) * nchunk) / ksplit;
+      float acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 2
+      for (int kc = kc0; kc < kc1; ++kc) {
+        const int k = kc * 4;
+        float4 b0 = ld4(Bs + (k + 0) * N_pad + n0);
+        float4 b1 = ld4(Bs + (k + 1) * N_pad + n0);
+        float4 b2 = ld4(Bs + (k + 2) * N_pad + n0);
+        float4 b3 = ld4(Bs + (k + 3) * N_pad + n0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4 a = ld4(A + (r0 + i) * lda + k);
+          acc[i][0] += a.x * b0.x; acc[i][1] += a.x * b0.y; acc[i][2] += a.x * b0.z; acc[i][3] += a.x * b0.w;
+          acc[i][0] += a.y * b1.x; acc[i][1] += a.y * b1.y; acc[i][2] += a.y * b1.z; acc[i][3] += a.y * b1.w;
+          acc[i][0] += a.z * b2.x; acc[i][1] += a.z * b2.y; acc[i][2] += a.z * b2.z; acc[i][3] += a.z * b2.w;
+          acc[i][0] += a.w * b3.x; acc[i][1] += a.w * b3.y; acc[i][2] += a.w * b3.z; acc[i][3] += a.w * b3.w;
+        }
+      }
+      if (ksplit == 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float v = acc[i][j];
+            if (epi == EPI_BIAS_ACT) v = apply_act(v + (bias ? bias[n0 + j] : 0.f), act);
+            else v = (mask[(r0 + i) * ldm + n0 + j] > 0.f) ? v : 0.f;
+            o[j] = v;
+          }
+          st4(C + (r0 + i) * ldc + n0, make_float4(o[0], o[1], o[2], o[3]));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          st4(red + (ks * R + r0 + i) * N_pad + n0, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+      }
+    }
+  }
+  FRL_SYNC();
+  if (ksplit > 1) {
+    FRL_PAR(t) {
+      for (int e = t; e < R * nt; e += FRL_NT) {
+        const int r = e / nt, n0 = (e % nt) * 4;
+        float4 s = ld4(red + r * N_pad + n0);
+        for (int ks = 1; ks < ksplit; ++ks) s = f4add(s, ld4(red + (ks * R + r) * N_pad + n0));
+        float o[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (epi == EPI_BIAS_ACT) o[j] = apply_act(o[j] + (bias ? bias[n0 + j] : 0.f), act);
+          else o[j] = (mask[r * ldm + n0 + j] > 0.f) ? o[j] : 0.f;
+        }
+        st4(C + r * ldc + n0, make_float4(o[0], o[1], o[2], o[3]));
+      }
+    }
+    FRL_SYNC();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// gemm_outer: G[m][n] (+)= sum_{r<R} dY[r][m] * X[r][n]   for m < M_pad, n < N_pad, written to GLOBAL
+//   G has leading dim N_pad (the trainable W layout [out_pad][in_pad]).  Columns n >= N_real are forced
+//   to zero (X pad columns may alias neighbouring fields).  Also the bias gradient gb[m] (+)= sum_r dY[r][m].
+// ------------------------------------------------------------------------------------------------
+template <int R>
+FRL_DEV void gemm_outer(Cta& c, const float* dY, int ldy, int M_pad, const float* X, int ldx, int N_pad, int N_real,
+                        float* G, float* gb, bool accumulate) {
+  const int mt = M_pad >> 2, nt = N_pad >> 2;
+  const int tiles = mt * nt;
+  FRL_PAR(t) {
+    for (int tile = t; tile < tiles; tile += FRL_NT) {
+      const int m0 = (tile / nt) * 4, n0 = (tile % nt) * 4;
+      float acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        float4 a = ld4(dY + r * ldy + m0);
+        float4 b = ld4(X + r * ldx + n0);
+        acc[0][0] += a.x * b.x; acc[0][1] += a.x * b.y; acc[0][2] += a.x * b.z; acc[0][3] += a.x * b.w;
+        acc[1][0] += a.y * b.x; acc[1][1] += a.y * b.y; acc[1][2] += a.y * b.z; acc[1][3] += a.y * b.w;
+        acc[2][0] += a.z * b.x; acc[2][1] += a.z * b.y; acc[2][2] += a.z * b.z; acc[2][3] += a.z * b.w;
+        acc[3][0] += a.w * b.x; acc[3][1] += a.w * b.y; acc[3][2] += a.w * b.z; acc[3][3] += a.w * b.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (n0 + j >= N_real) acc[i][j] = 0.f;
+        float* gp = G + (m0 + i) * N_pad + n0;
+        float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        if (accumulate) v = f4add(v, ld4(gp));
+        st4(gp, v);
+      }
+    }
+    // bias gradient
+    for (int m = t; m < M_pad; m += FRL_NT) {
+      float s = 0.f;
+#pragma unroll
+      for (int r = 0; r < R; ++r) s += dY[r * ldy + m];
+      if (accumulate) s += gb[m];
+      gb[m] = s;
+    }
+  }
+  FRL_SYNC();
+}
+
+// ------------------------------------------------------------------------------------------------
+// layer / MLP passes
+// ------------------------------------------------------------------------------------------------
+FRL_HD int layer_fwd_bytes(const frl_layer_t& L) { return (L.in_pad * L.out_pad + L.out_pad) * 4; }
+FRL_HD int layer_bwd_bytes(const frl_layer_t& L) { return (L.out_pad * L.in_pad) * 4; }
+FRL_DEV const float* layer_fwd_src(const frl_net_t& n, int li) { return n.pt + n.L[li].wt_off; }
+FRL_DEV const float* layer_bwd_src(const frl_net_t& n, int li) { return n.p + n.L[li].w_off; }
+
+struct Hint { const float* ptr; int bytes; };
+FRL_DEV Hint no_hint() { Hint h; h.ptr = nullptr; h.bytes = 0; return h; }
+FRL_DEV Hint fwd_hint(const frl_net_t& n, int li) { Hint h; h.ptr = layer_fwd_src(n, li); h.bytes = layer_fwd_bytes(n.L[li]); return h; }
+FRL_DEV Hint bwd_hint(const frl_net_t& n, int li) { Hint h; h.ptr = layer_bwd_src(n, li); h.bytes = layer_bwd_bytes(n.L[li]); return h; }
+
+// Y = act(X W^T + b).  `next` is what the caller will need after this layer (prefetched during the math).
+template <int R>
+FRL_DEV void layer_fwd(Cta& c, const frl_net_t& n, int li, const float* X, int ldx, float* Y, int ldy, int act, Hint next) {
+  const frl_layer_t& L = n.L[li];
+  const float* Bs = stage_acquire(c, layer_fwd_src(n, li), layer_fwd_bytes(L));
+  stage_prefetch(c, next.ptr, next.bytes);
+  gemm_rk<R>(c, X, ldx, L.in_pad, Bs, L.out_pad, Bs + L.in_pad * L.out_pad, EPI_BIAS_ACT, act, nullptr, 0, Y, ldy);
+}
+
+// dX = (dY W) * relu'(mask)   (mask == nullptr: no activation derivative)
+template <int R>
+FRL_DEV void layer_bwd_dx(Cta& c, const frl_net_t& n, int li, const float* dY, int ldy, const float* mask, int ldm,
+                          float* dX, int ldx, Hint next) {
+  const frl_layer_t& L = n.L[li];
+  const float* Bs = stage_acquire(c, layer_bwd_src(n, li), layer_bwd_bytes(L));
+  stage_prefetch(c, next.ptr, next.bytes);
+  if (mask) gemm_rk<R>(c, dY, ldy, L.out_pad, Bs, L.in_pad, nullptr, EPI_RELU_MASK, 0, mask, ldm, dX, ldx);
+  else gemm_rk<R>(c, dY, ldy, L.out_pad, Bs, L.in_pad, nullptr, EPI_BIAS_ACT, FRL_ACT_NONE, nullptr, 0, dX, ldx);
+}
+
+// MLP forward over layers [l0, l0+nl): hidden layers ReLU, last layer `act_out`.
+//   nl == 3: H1 = relu(l0 X), H2 = relu(l1 H1), OUT = act(l2 H2);   nl == 2: H1 = relu(l0 X), OUT = act(l1 H1).
+template <int R>
+FRL_DEV void mlp_fwd(Cta& c, const frl_net_t& n, int l0, int nl, const float* X, int ldx, float* H1, float* H2, int ldh,
+                     float* OUT, int ldo, int act_out, Hint next) {
+  if (nl == 3) {
+    layer_fwd<R>(c, n, l0 + 0, X, ldx, H1, ldh, FRL_ACT_RELU, fwd_hint(n, l0 + 1));
+    layer_fwd<R>(c, n, l0 + 1, H1, ldh, H2, ldh, FRL_ACT_RELU, fwd_hint(n, l0 + 2));
+    layer_fwd<R>(c, n, l0 + 2, H2, ldh, OUT, ldo, act_out, next);
+  } else {
+    layer_fwd<R>(c, n, l0 + 0, X, ldx, H1, ldh, FRL_ACT_RELU, fwd_hint(n, l0 + 1));
+    layer_fwd<R>(c, n, l0 + 1, H1, ldh, OUT, ldo, act_out, next);
+  }
+}
+
+// Backward of mlp_fwd given dOUT (gradient w.r.t. the last layer's pre-activation output).
+//   gp  : this CTA's gradient partial for net n (n_p floats, same layout as n.p) or nullptr (no dW wanted)
+//   dXo : if non-null receives dL/dX [R][in_pad of layer l0]
+//   D1/D2: scratch [R][ldh] for the hidden-layer gradients.
+template <int R>
+FRL_DEV void mlp_bwd(Cta& c, const frl_net_t& n, int l0, int nl, const float* X, int ldx, const float* H1, const float* H2,
+                     int ldh, const float* dOUT, int ldo, float* D1, float* D2, float* dXo, int lddx, float* gp,
+                     bool accumulate, Hint next) {
+  const float* dcur = dOUT;
+  int ldc = ldo;
+  for (int k = nl - 1; k >= 0; --k) {
+    const int li = l0 + k;
+    const frl_layer_t& L = n.L[li];
+    const float* Xin = (k == 0) ? X : (k == 1 ? H1 : H2);
+    const int ldin = (k == 0) ? ldx : ldh;
+    if (gp) gemm_outer<R>(c, dcur, ldc, L.out_pad, Xin, ldin, L.in_pad, L.in, gp + L.w_off, gp + L.b_off, accumulate);
+    if (k > 0) {
+      float* dn = (k == 2) ? D2 : D1;   // gradient wrt H2 (k==2) or H1 (k==1)
+      Hint h = (k - 1 > 0 || dXo) ? bwd_hint(n, li - 1) : next;
+      layer_bwd_dx<R>(c, n, li, dcur, ldc, Xin, ldin, dn, ldh, h);
+      dcur = dn; ldc = ldh;
+    } else if (dXo) {
+      layer_bwd_dx<R>(c, n, li, dcur, ldc, nullptr, 0, dXo, lddx, next);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// block-wide fixed-order sum of one float per thread (result broadcast to all threads via smem)
+// ------------------------------------------------------------------------------------------------
+FRL_DEV float block_sum(Cta& c, float* slot /*[FRL_NT] smem*/) {
+  for (int s = FRL_NT / 2; s > 0; s >>= 1) {
+    FRL_PAR(t) { if (t < s) slot[t] += slot[t + s]; }
+    FRL_SYNC();
+  }
+  return slot[0];
+}
+
+// ------------------------------------------------------------------------------------------------
+// cross-CTA gradient reduction (fixed order) + sum of squares partial per CTA
+//   gpart: [ncontrib][stride];  n.g <- sum_c gpart[c];  sumsq_part[cta] <- sum over this CTA's slice of g^2
+// ------------------------------------------------------------------------------------------------
+FRL_DEV void reduce_grads(Cta& c, const frl_net_t& n, const float* gpart, int stride, int ncontrib, float* sumsq_part) {
+  float* slot = c.red;
+  FRL_PAR(t) {
+    float local = 0.f;
+    for (int p = c.cta * FRL_NT + t; p < n.n_p; p += c.ncta * FRL_NT) {
+      float s = gpart[p];
+      for (int cc = 1; cc < ncontrib; ++cc) s += gpart[(size_t)cc * stride + p];
+      n.g[p] = s;
+      local += s * s;
+    }
+    slot[t] = local;
+  }
+  FRL_SYNC();
+  float tot = block_sum(c, slot);
+  FRL_PAR(t) { if (t == 0 && sumsq_part) sumsq_part[c.cta] = tot; }
+  FRL_SYNC();
+}
+
+struct AdamHP {
+  float lr_over_bc1_neg;   // -lr / (1 - b1^step)          (torch: value = -step_size)
+  float bc2_sqrt;          // sqrt(1 - b2^step)
+  float one_minus_b1;      // float(1 - b1)
+  float b2, one_minus_b2;
+  float eps;
+  float weight_decay;      // L2 (added to grad), 0 = off
+  float max_norm;          // clip_grad_norm_ max (<= 0: no clipping)
+};
+
+FRL_HD AdamHP make_adam_hp(double lr, double b1, double b2, double eps, double wd, double max_norm, long step) {
+  AdamHP h;
+  double bc1 = 1.0 - pow(b1, (double)step);
+  double bc2 = 1.0 - pow(b2, (double)step);
+  h.lr_over_bc1_neg = (float)(-(lr / bc1));
+  h.bc2_sqrt = (float)sqrt(bc2);
+  h.one_minus_b1 = (float)(1.0 - b1);
+  h.b2 = (float)b2;
+  h.one_minus_b2 = (float)(1.0 - b2);
+  h.eps = (float)eps;
+  h.weight_decay = (float)wd;
+  h.max_norm = (float)max_norm;
+  return h;
+}
+
+// where does parameter index p live in the transposed mirror?  (-1: no mirror, e.g. log_std)
+FRL_DEV int mirror_index(const frl_net_t& n, int p) {
+  for (int li = 0; li < n.n_layers; ++li) {
+    const frl_layer_t& L = n.L[li];
+    const int wsz = L.out_pad * L.in_pad;
+    if (p >= L.w_off && p < L.w_off + wsz) {
+      const int e = p - L.w_off, j = e / L.in_pad, k = e % L.in_pad;
+      return L.wt_off + k * L.out_pad + j;
+    }
+    if (p >= L.b_off && p < L.b_off + L.out_pad) return L.wt_off + L.in_pad * L.out_pad + (p - L.b_off);
+  }
+  return -1;
+}
+
+// torch.optim.Adam single-tensor math on this CTA's slice of the parameters, preceded by the global-norm
+// clip (coef from the per-CTA sum-of-squares partials written by reduce_grads), optionally followed by the
+// Polyak update of a target net with identical layout.  Keeps p / pt (and target p / pt) in sync.
+FRL_DEV void adam_update(Cta& c, const frl_net_t& n, const float* sumsq_part, int nparts, const AdamHP hp,
+                         const frl_net_t* tgt, float tau) {
+  float coef = 1.f;
+  if (hp.max_norm > 0.f && sumsq_part) {
+    float tot = 0.f;
+    for (int i = 0; i < nparts; ++i) tot += sumsq_part[i];
+    const float nrm = sqrtf(tot);
+    coef = hp.max_norm / (nrm + 1e-6f);
+    if (coef > 1.f) coef = 1.f;
+  }
+  const float omt = (float)(1.0 - (double)tau);
+  FRL_PAR(t) {
+    for (int p = c.cta * FRL_NT + t; p < n.n_p; p += c.ncta * FRL_NT) {
+      float g = n.g[p] * coef;
+      float w = n.p[p];
+      if (hp.weight_decay != 0.f) g = fmaf(w, hp.weight_decay, g);
+      float m = n.m[p], v = n.v[p];
+      m = fmaf(hp.one_minus_b1, g - m, m);                        // exp_avg.lerp_(grad, 1-b1)
+      v = fadd(fmul(v, hp.b2), fmul(fmul(hp.one_minus_b2, g), g));   // mul_(b2).addcmul_(g, g, 1-b2)
+      const float denom = fadd(fdiv(fsqrt(v), hp.bc2_sqrt), hp.eps);
+      w = fadd(w, fdiv(fmul(hp.lr_over_bc1_neg, m), denom));      // addcdiv_(m, denom, value=-step_size)
+      n.m[p] = m; n.v[p] = v; n.p[p] = w;
+      const int mi = mirror_index(n, p);
+      if (mi >= 0) n.pt[mi] = w;
+      if (tgt) {
+        float tw = fadd(fmul(tgt->p[p], omt), fmul(w, tau));
+        tgt->p[p] = tw;
+        if (mi >= 0) tgt->pt[mi] = tw;
+      }
+    }
+  }
+  FRL_SYNC();
+}
+
+FRL_DEV void polyak_update(Cta& c, const frl_net_t& src, const frl_net_t& tgt, float tau) {
+  const float omt = (float)(1.0 - (double)tau);
+  FRL_PAR(t) {
+    for (int p = c.cta * FRL_NT + t; p < src.n_p; p += c.ncta * FRL_NT) {
+      float tw = fadd(fmul(tgt.p[p], omt), fmul(src.p[p], tau));
+      tgt.p[p] = tw;
+      const int mi = mirror_index(src, p);
+      if (mi >= 0) tgt.pt[mi] = tw;
+    }
+  }
+  FRL_SYNC();
+}
+
+// zero-fill a smem tile [R][ld]
+FRL_DEV void tile_zero(float* T, int n) {
+  FRL_PAR(t) { for (int i = t; i < n; i += FRL_NT) T[i] = 0.f; }
+  FRL_SYNC();
+}

@@ -1,0 +1,137 @@
+// Persistent cooperative launcher shared by all fused learn() kernels.
+//
+// An "Algo" provides:   typedef Args;  static const int NSTAGES;
+//                       static int  wbuf_floats(const Args&);     // size of one weight staging buffer
+//                       static int  user_floats(const Args&);     // smem floats after the engine's own
+//                       static int  grid(const Args&, int max);   // CTAs wanted
+//                       static int  n_updates(const Args&);
+//                       static FRL_DEV void stage(int s, int u, Cta&, float* user, const Args&);
+// The kernel runs  for u: for s: stage(s,u); grid.sync()  — one launch performs n_updates sequential
+// learn() steps (stages are separated by grid-wide barriers because every optimiser step needs the
+// global gradient norm and the next phase needs the updated weights).
+#pragma once
+#include "engine.cuh"
+
+#ifndef FRL_EMUL
+namespace cg = cooperative_groups;
+
+template <class A>
+__global__ void __launch_bounds__(FRL_NT, 1) frl_persistent_kernel(const typename A::Args a) {
+  extern __shared__ __align__(1024) float frl_smem[];
+  Cta c;
+  float* user = cta_init(c, (int)blockIdx.x, (int)gridDim.x, frl_smem, A::wbuf_floats(a));
+  cg::grid_group grid = cg::this_grid();
+  const int U = A::n_updates(a);
+  for (int u = 0; u < U; ++u) {
+    for (int s = 0; s < A::NSTAGES; ++s) {
+      A::stage(s, u, c, user, a);
+      stage_reset(c);
+      fence_proxy_async();
+      grid.sync();
+    }
+  }
+}
+
+int frl_device_max_ctas();   // SM count of the current device (1 CTA / SM for the persistent kernels)
+
+template <class A>
+int frl_launch(const typename A::Args& a, cudaStream_t stream) {
+  const int smem_bytes = (cta_base_floats(A::wbuf_floats(a)) + A::user_floats(a)) * 4 + 64;
+  if (smem_bytes > 227 * 1024) {
+    frl_set_error("kernel needs %d B of shared memory (> 227 KB)", smem_bytes);
+    return -3;
+  }
+  static int configured_bytes = 0;
+  if (smem_bytes > configured_bytes) {
+    FRL_CUDA_OK(cudaFuncSetAttribute(frl_persistent_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    configured_bytes = smem_bytes;
+  }
+  const int grid = A::grid(a, frl_device_max_ctas());
+  typename A::Args args = a;
+  void* kargs[] = {(void*)&args};
+  FRL_CUDA_OK(cudaLaunchCooperativeKernel((void*)frl_persistent_kernel<A>, dim3(grid), dim3(FRL_NT), kargs, (size_t)smem_bytes, stream));
+  return 0;
+}
+
+// plain (non-cooperative) launch of a single-stage Algo over an arbitrary grid
+template <class A>
+__global__ void __launch_bounds__(FRL_NT, 1) frl_tile_kernel(const typename A::Args a) {
+  extern __shared__ __align__(1024) float frl_smem[];
+  Cta c;
+  float* user = cta_init(c, (int)blockIdx.x, (int)gridDim.x, frl_smem, A::wbuf_floats(a));
+  A::stage(0, 0, c, user, a);
+}
+
+template <class A>
+int frl_launch_tiles(const typename A::Args& a, cudaStream_t stream) {
+  const int smem_bytes = (cta_base_floats(A::wbuf_floats(a)) + A::user_floats(a)) * 4 + 64;
+  static int configured_bytes = 0;
+  if (smem_bytes > configured_bytes) {
+    FRL_CUDA_OK(cudaFuncSetAttribute(frl_tile_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    configured_bytes = smem_bytes;
+  }
+  const int grid = A::grid(a, 1 << 30);
+  frl_tile_kernel<A><<<grid, FRL_NT, smem_bytes, stream>>>(a);
+  FRL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+#else  // ---------------------------------------------------------------- host emulation (tests only)
+#include <stdlib.h>
+#include <vector>
+
+inline int frl_device_max_ctas() { return 148; }
+
+template <class A>
+int frl_launch(const typename A::Args& a, cudaStream_t) {
+  const int floats = cta_base_floats(A::wbuf_floats(a)) + A::user_floats(a) + 16;
+  const int grid = A::grid(a, frl_device_max_ctas());
+  std::vector<float*> mem(grid);
+  std::vector<Cta> ctas(grid);
+  std::vector<float*> user(grid);
+  for (int g = 0; g < grid; ++g) {
+    mem[g] = (float*)aligned_alloc(1024, ((size_t)floats * 4 + 1023) / 1024 * 1024);
+    for (int i = 0; i < floats; ++i) mem[g][i] = NAN;     // poison: reads of unwritten smem surface as NaN
+    user[g] = cta_init(ctas[g], g, grid, mem[g], A::wbuf_floats(a));
+  }
+  const int U = A::n_updates(a);
+  for (int u = 0; u < U; ++u)
+    for (int s = 0; s < A::NSTAGES; ++s)
+      for (int g = 0; g < grid; ++g) {
+        A::stage(s, u, ctas[g], user[g], a);
+        stage_reset(ctas[g]);
+      }
+  for (int g = 0; g < grid; ++g) free(mem[g]);
+  return 0;
+}
+
+template <class A>
+int frl_launch_tiles(const typename A::Args& a, cudaStream_t s) {
+  struct One : A { };
+  const int floats = cta_base_floats(A::wbuf_floats(a)) + A::user_floats(a) + 16;
+  const int grid = A::grid(a, 1 << 30);
+  float* mem = (float*)aligned_alloc(1024, ((size_t)floats * 4 + 1023) / 1024 * 1024);
+  for (int g = 0; g < grid; ++g) {
+    for (int i = 0; i < floats; ++i) mem[i] = NAN;
+    Cta c;
+    float* user = cta_init(c, g, grid, mem, A::wbuf_floats(a));
+    A::stage(0, 0, c, user, a);
+  }
+  free(mem);
+  (void)s;
+  return 0;
+}
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// tiny bump allocator over the user part of shared memory (16-B granularity)
+// ------------------------------------------------------------------------------------------------
+struct SmemBump {
+  float* p;
+  FRL_DEVM float* take(int floats) {
+    float* r = p;
+    p += (floats + 3) & ~3;
+    return r;
+  }
+};
+FRL_HD int pad4(int x) { return (x + 3) & ~3; }

@@ -1,0 +1,140 @@
+/* freerl_b200 — C ABI of the B200-native FreeRL training hot path.
+ *
+ * Drop-in boundary: the reference (wild-firefox/FreeRL) is pure Python/PyTorch; its "plugin interface" for this
+ * path is the set of Python classes/methods listed below.  A maintainer binds these entry points from Python with
+ * ctypes; freerl_b200/_lib.py is exactly that binding.  Every pointer argument marked "dev"
+ * is a raw CUDA device pointer (e.g. torch.Tensor.data_ptr()), borrowed for the duration of the stream operation.
+ * All functions return 0 on success, <0 on error (message via frl_last_error()); none throws across the boundary.
+ * No CPU fallback exists: every compute entry point launches sm_100a kernels on the given stream.
+ *
+ *   entry point               replaces (reference file:line)
+ *   ------------------------  ---------------------------------------------------------------------------------
+ *   frl_replay_add_batch      Buffer.add                     SAC_file/Buffer.py:28-38 (=DQN/TD3/DDPG/MADDPG copies)
+ *   frl_replay_gather         Buffer.sample(indices)         SAC_file/Buffer.py:40-57
+ *   frl_sample_uniform        np.random.choice(N,B,False)    DQN_file/DQN.py:97, SAC_file/SAC.py:213, TD3.py:183, DDPG.py:194
+ *   frl_dqn_learn             DQN.learn + update_target      DQN_file/DQN.py:104-128
+ *   frl_ac_learn              SAC.learn / TD3.learn / DDPG.learn   SAC_file/SAC.py:222-271, TD3_file/TD3.py:189-244,
+ *                                                            DDPG_file/DDPG.py:203-233 (+ Agent.update_*, Alpha)
+ *   frl_policy_infer          select_action / evaluate_action      DQN.py:70-88, SAC.py:192-204, TD3.py:163-174, DDPG.py:166-185
+ *   frl_net_sync_mirror       (state_dict load -> refresh transposed weight mirrors; no reference counterpart)
+ */
+#ifndef FREERL_B200_H
+#define FREERL_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRL_MAX_LAYERS 6
+
+/* One linear layer inside a parameter block.  W is stored [out_pad][in_pad] row-major (torch layout, zero padded to
+ * multiples of 4), bias [out_pad]; the transposed mirror WT [in_pad][out_pad] followed by a bias copy lives in `pt`. */
+typedef struct {
+  int in, out;
+  int in_pad, out_pad;
+  int w_off;   /* float offset of W   in p  */
+  int b_off;   /* float offset of b   in p  */
+  int wt_off;  /* float offset of WT (then bias copy) in pt */
+} frl_layer_t;
+
+/* A network = one parameter block (all tensors of one torch module, one optimiser) + its mirror.
+ * Twin critics are ONE net with 6 layers (head h uses layers 3h..3h+2), like the reference's Critic module. */
+typedef struct {
+  float* p;    /* dev [n_p]  parameters */
+  float* pt;   /* dev [n_pt] transposed mirrors (forward operand) */
+  float* m;    /* dev [n_p]  Adam exp_avg      (NULL for target nets) */
+  float* v;    /* dev [n_p]  Adam exp_avg_sq   (NULL for target nets) */
+  float* g;    /* dev [n_p]  reduced gradient  (NULL for target nets) */
+  int n_p, n_pt;
+  int n_layers;
+  int x_off, x_len;   /* extra vector parameter (SAC/PPO log_std); x_len = 0 if none */
+  frl_layer_t L[FRL_MAX_LAYERS];
+} frl_net_t;
+
+/* Device ring replay: `storage` is [capacity][row_floats] fp32, one row per transition laid out
+ * [obs(obs_dim) | action(act_dim) | reward | done | next_obs(obs_dim) | zero pad to a multiple of 4 floats]. */
+typedef struct {
+  float* storage;   /* dev */
+  int64_t capacity;
+  int row_floats, obs_dim, act_dim;
+} frl_replay_t;
+
+typedef struct {
+  frl_net_t q, q_target;
+  frl_replay_t replay;
+  const int64_t* indices;   /* dev [n_updates][B] */
+  int B, n_updates;
+  float gamma, tau;
+  double lr, beta1, beta2, eps;
+  int64_t step0;            /* optimiser steps taken before this call */
+  float* gpart;             /* dev scratch [frl_device_sm_count()][q.n_p] */
+  float* stats;             /* dev scratch [frl_device_sm_count()][8] */
+  float* out;               /* dev [n_updates][8]: out[u][0] = loss */
+} frl_dqn_args_t;
+
+enum { FRL_ACTOR_TANH = 0, FRL_ACTOR_SAC = 1 };
+
+typedef struct {
+  frl_net_t actor, actor_target, critic, critic_target;
+  int n_heads;              /* critic heads: 1 (DDPG, TD3 w/o clip_double) or 2 */
+  int actor_kind;           /* FRL_ACTOR_TANH | FRL_ACTOR_SAC */
+  frl_replay_t replay;
+  const int64_t* indices;   /* dev [n_updates][B] */
+  int B, n_updates;
+  const float* noise_next;  /* dev [n_updates][B][act_dim]: SAC eps of a', TD3 randn; NULL -> Philox(seed) */
+  const float* noise_new;   /* dev [n_updates][B][act_dim]: SAC eps of the new action; NULL -> Philox(seed) */
+  uint64_t seed;
+  float gamma, tau;
+  double lr_actor, lr_critic, beta1, beta2, eps, wd_critic;
+  float max_norm;           /* clip_grad_norm_ max (0.5 in the reference), <=0 disables */
+  int64_t step_actor0, step_critic0, total_it0;
+  int policy_freq;          /* TD3 twin_delay: actor + Polyak when (total_it0+u+1) % policy_freq == 0; 1 = always */
+  int target_smoothing;     /* TD3 policy_noise */
+  float policy_noise, noise_clip, max_action, policy_noise_scale;
+  /* SAC temperature: alpha_state = {log_alpha, exp_avg, exp_avg_sq, unused} on the device */
+  float* alpha_state;
+  int adaptive_alpha;
+  double alpha_lr;
+  float target_entropy;
+  int64_t step_alpha0;
+  float* gpart;             /* dev scratch [sm_count][max(actor.n_p, critic.n_p)] */
+  float* sumsq;             /* dev scratch [sm_count] */
+  float* stats;             /* dev scratch [sm_count][8] */
+  float* out;               /* dev [n_updates][8]: critic_loss, actor_loss, alpha, alpha_loss, critic_gnorm, actor_gnorm, mean_entropy, 0 */
+} frl_ac_args_t;
+
+enum { FRL_INFER_ARGMAX = 0, FRL_INFER_TANH = 1, FRL_INFER_SAC_SAMPLE = 2, FRL_INFER_SAC_MEAN = 3, FRL_INFER_RAW = 4 };
+
+typedef struct {
+  frl_net_t net;
+  const float* obs;         /* dev [n][obs_dim] */
+  int n, obs_dim;
+  int mode;                 /* FRL_INFER_* */
+  const float* noise;       /* dev [n][out] for SAC_SAMPLE (NULL -> Philox(seed, counter)) */
+  uint64_t seed;
+  uint32_t counter;
+  float* out;               /* dev [n][out_cols]: actions (ARGMAX: 1 column holding the index as float; RAW: net output) */
+  int out_cols;
+} frl_infer_args_t;
+
+const char* frl_last_error(void);
+int frl_is_emulation(void);          /* 0 for the CUDA library (the only one the product path accepts) */
+int frl_device_sm_count(void);
+int frl_abi_version(void);
+
+int frl_replay_add_batch(const frl_replay_t* rb, int64_t index, const float* obs, const float* act, const float* rew,
+                         const float* next_obs, const float* done, int n, void* stream);
+int frl_replay_gather(const frl_replay_t* rb, const int64_t* indices, int B, float* obs, float* act, float* rew,
+                      float* next_obs, float* done, void* stream);
+int frl_sample_uniform(int64_t* indices_out, int64_t size, int B, int n_updates, uint64_t seed, uint64_t counter,
+                       void* stream);
+int frl_net_sync_mirror(const frl_net_t* net, void* stream);
+int frl_dqn_learn(const frl_dqn_args_t* args, void* stream);
+int frl_ac_learn(const frl_ac_args_t* args, void* stream);
+int frl_policy_infer(const frl_infer_args_t* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -21,3 +21,40 @@ def golden():
     def load(name):
         return np.load(os.path.join(GOLDEN, name + ".npz"))
     return load
+
+
+EMUL_SO = os.path.join(ROOT, "tests", "emul", "libfreerl_emul.so")
+CSRC = os.path.join(ROOT, "freerl_b200", "csrc")
+
+
+def _build_emul():
+    """Host emulation of the kernels (g++ -DFRL_EMUL): TEST-ONLY, checks indexing / arithmetic of the CUDA
+    sources without a GPU.  The product path refuses it (frl_is_emulation() == 1 unless tests opt in)."""
+    import glob
+    import subprocess
+    srcs = glob.glob(os.path.join(CSRC, "*")) + [os.path.join(ROOT, "include", "freerl_b200.h")]
+    if os.path.exists(EMUL_SO) and all(os.path.getmtime(EMUL_SO) >= os.path.getmtime(s) for s in srcs):
+        return
+    os.makedirs(os.path.dirname(EMUL_SO), exist_ok=True)
+    subprocess.check_call(["g++", "-x", "c++", "-DFRL_EMUL", "-O2", "-g", "-std=c++17", "-ffp-contract=fast", "-mfma",
+                           "-shared", "-fPIC", "-Wno-unknown-pragmas", "-o", EMUL_SO, os.path.join(CSRC, "capi.cu")])
+
+
+@pytest.fixture()
+def emul(monkeypatch):
+    """Route freerl_b200 to the host-emulation library for this test (CPU tensors allowed)."""
+    _build_emul()
+    from freerl_b200 import _lib
+    monkeypatch.setenv("FREERL_B200_LIB", EMUL_SO)
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "_sm_count", None)
+    yield _lib
+    _lib._lib = None
+    _lib._sm_count = None
+
+
+@pytest.fixture()
+def dev(request):
+    """Device for parity tests: cuda under -m gpu, cpu (emulation) otherwise."""
+    import torch
+    return torch.device("cuda" if torch.cuda.is_available() else "cpu")

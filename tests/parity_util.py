@@ -1,0 +1,43 @@
+"""Shared helpers for CUDA-vs-oracle parity tests (run on the GPU under -m gpu, and on the host-emulation
+build of the same kernels under -m "not gpu")."""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+TOL = dict(rtol=1e-5, atol=2e-6)
+
+
+def net_from_golden(g, prefix):
+    out = OrderedDict()
+    for k in g.files:
+        if k.startswith(prefix):
+            out[k[len(prefix):]] = torch.from_numpy(g[k].copy())
+    assert out, prefix
+    return out
+
+
+def golden_batch(g, it):
+    return tuple(torch.from_numpy(g["batch/%d/%s" % (it, k)]) for k in ("obs", "act", "rew", "nobs", "done"))
+
+
+def load_into(module, sd):
+    module.load_state_dict({k: v.clone() for k, v in sd.items()})
+
+
+def assert_module_close(module, sd, what, tol=TOL):
+    got = module.state_dict()
+    for k, v in sd.items():
+        np.testing.assert_allclose(got[k].detach().cpu().numpy(), v.detach().cpu().numpy(), err_msg="%s/%s" % (what, k), **tol)
+
+
+def fill_buffer_from_batches(buf, g, n_iter):
+    """Store the golden batches as consecutive rows; returns index arrays selecting each batch."""
+    idxs, start = [], 0
+    for it in range(n_iter):
+        obs, act, rew, nobs, done = golden_batch(g, it)
+        buf.add(obs.numpy(), act.numpy(), rew.numpy().reshape(-1), nobs.numpy(), done.numpy().reshape(-1))
+        B = obs.shape[0]
+        idxs.append(np.arange(start, start + B))
+        start += B
+    return idxs
