@@ -286,8 +286,8 @@ struct AcAlgo {
         if (sac) {
           // d/dlog_std_j = sum_r [ dL/du * std*eps - alpha/B ]   (zero outside the clamp range)
           FRL_PAR(t) {
-            if (t < ad) {
-              const float lsr = A.p[A.x_off + t];
+            if (t < ap) {       // also clears the 16-B padding of the log_std slot in the shared partial buffer
+              const float lsr = (t < ad) ? A.p[A.x_off + t] : 1e30f;
               float g = 0.f;
               if (lsr >= -20.f && lsr <= 2.f) {
                 const float sd = expf(lsr);
