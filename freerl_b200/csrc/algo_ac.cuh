@@ -97,9 +97,10 @@ struct AcAlgo {
         const int row0 = tile * FRL_R;
         const int nvalid = (a.B - row0) < FRL_R ? (a.B - row0) : FRL_R;
         stage_prefetch(c, layer_fwd_src(a.actor_target, 0), layer_fwd_bytes(a.actor_target.L[0]));
-        gather_rows<FRL_R>(c, rb, a.indices + (size_t)u * a.B + row0, nvalid, raw);
+        gather_rows<FRL_R>(rb, a.indices + (size_t)u * a.B + row0, nvalid, raw);
         copy_cols<FRL_R>(XS, sa, 0, raw, rf, 0, od + ad, sa);
         copy_cols<FRL_R>(XN, sa, 0, raw, rf, rb_col_nobs(rb), od, sa);
+        stamp(c, 1);
         // a' = actor_target(next_obs)
         mlp_fwd<FRL_R>(c, a.actor_target, 0, 3, XN, sa, A1, A2, ldh, MU, ap, FRL_ACT_NONE, fwd_hint(a.critic_target, 0));
         FRL_PAR(t) {
@@ -132,6 +133,7 @@ struct AcAlgo {
           }
         }
         FRL_SYNC();
+        stamp(c, 2);
         // target Q heads
         mlp_fwd<FRL_R>(c, a.critic_target, 0, 3, XN, sa, H1, H2, ldh, QA, 4, FRL_ACT_NONE,
                        a.n_heads == 2 ? fwd_hint(a.critic_target, 3) : fwd_hint(C, 0));
@@ -156,6 +158,7 @@ struct AcAlgo {
           }
         }
         FRL_SYNC();
+        stamp(c, 3);
         // critic heads on (s, a): forward keeps activations, then backward
         mlp_fwd<FRL_R>(c, C, 0, 3, XS, sa, H1, H2, ldh, QA, 4, FRL_ACT_NONE, a.n_heads == 2 ? fwd_hint(C, 3) : bwd_hint(C, 2));
         if (a.n_heads == 2) mlp_fwd<FRL_R>(c, C, 3, 3, XS, sa, G1, G2, ldh, QB, 4, FRL_ACT_NONE, bwd_hint(C, 2));
@@ -179,19 +182,22 @@ struct AcAlgo {
           red0[t] = l;
         }
         FRL_SYNC();
-        loss_acc += block_sum(c, red0);
+        loss_acc += block_sum(red0);
+        stamp(c, 4);
         mlp_bwd<FRL_R>(c, C, 0, 3, XS, sa, H1, H2, ldh, dQA, 4, D1, D2, nullptr, 0, gp, !first,
                        a.n_heads == 2 ? bwd_hint(C, 5) : no_hint());
+        stamp(c, 5);
         if (a.n_heads == 2) mlp_bwd<FRL_R>(c, C, 3, 3, XS, sa, G1, G2, ldh, dQB, 4, D1, D2, nullptr, 0, gp, !first, no_hint());
+        stamp(c, 6);
         first = false;
       }
       FRL_PAR(t) { if (t == 0) a.stats[c.cta * 8 + 0] = loss_acc; }
       FRL_SYNC();
     } else if (s == 1) {
-      reduce_grads(c, C, a.gpart, gstride, ncontrib, a.sumsq);
+      reduce_grads(c.cta, c.ncta, c.red, C, a.gpart, gstride, ncontrib, a.sumsq);
     } else if (s == 2) {
-      const AdamHP hp = make_adam_hp(a.lr_critic, a.beta1, a.beta2, a.eps, a.wd_critic, a.max_norm, (long)(a.step_critic0 + u + 1));
-      adam_update(c, C, a.sumsq, ncontrib, hp, policy_step ? &a.critic_target : nullptr, a.tau);
+      const AdamSpec hp = {a.lr_critic, a.beta1, a.beta2, a.eps, a.wd_critic, (double)a.max_norm, (long)(a.step_critic0 + u + 1)};
+      adam_update(c.cta, c.ncta, c.red, C, a.sumsq, ncontrib, hp, policy_step ? &a.critic_target : nullptr, a.tau);
       FRL_PAR(t) {
         if (c.cta == 0 && t == 0) {
           float l = 0.f, ss = 0.f;
@@ -211,7 +217,7 @@ struct AcAlgo {
         const int row0 = tile * FRL_R;
         const int nvalid = (a.B - row0) < FRL_R ? (a.B - row0) : FRL_R;
         stage_prefetch(c, layer_fwd_src(A, 0), layer_fwd_bytes(A.L[0]));
-        gather_rows<FRL_R>(c, rb, a.indices + (size_t)u * a.B + row0, nvalid, raw);
+        gather_rows<FRL_R>(rb, a.indices + (size_t)u * a.B + row0, nvalid, raw);
         copy_cols<FRL_R>(XN, sa, 0, raw, rf, 0, od, sa);
         mlp_fwd<FRL_R>(c, A, 0, 3, XN, sa, A1, A2, ldh, MU, ap, FRL_ACT_NONE, fwd_hint(C, 0));
         FRL_PAR(t) {
@@ -253,7 +259,7 @@ struct AcAlgo {
             red0[t] = v;
           }
           FRL_SYNC();
-          qsum_tile += block_sum(c, red0);
+          qsum_tile += block_sum(red0);
           mlp_bwd<FRL_R>(c, C, 3 * h, 3, XN, sa, H1, H2, ldh, dQA, 4, D1, D2, dXP, sa, nullptr, false,
                          h + 1 < heads_used ? fwd_hint(C, 3 * (h + 1)) : bwd_hint(A, 2));
           FRL_PAR(t) {
@@ -281,8 +287,8 @@ struct AcAlgo {
           red0[t] = lsum; red1[t] = esum;
         }
         FRL_SYNC();
-        loss_acc += block_sum(c, red0) - qsum_tile / (float)heads_used;
-        ent_acc += block_sum(c, red1);
+        loss_acc += block_sum(red0) - qsum_tile / (float)heads_used;
+        ent_acc += block_sum(red1);
         if (sac) {
           // d/dlog_std_j = sum_r [ dL/du * std*eps - alpha/B ]   (zero outside the clamp range)
           FRL_PAR(t) {
@@ -305,11 +311,11 @@ struct AcAlgo {
       FRL_SYNC();
     } else if (s == 4) {
       if (!policy_step) return;
-      reduce_grads(c, A, a.gpart, gstride, ncontrib, a.sumsq);
+      reduce_grads(c.cta, c.ncta, c.red, A, a.gpart, gstride, ncontrib, a.sumsq);
     } else {
       if (!policy_step) return;
-      const AdamHP hp = make_adam_hp(a.lr_actor, a.beta1, a.beta2, a.eps, 0.0, a.max_norm, (long)(a.step_actor0 + n_policy_before + 1));
-      adam_update(c, A, a.sumsq, ncontrib, hp, &a.actor_target, a.tau);
+      const AdamSpec hp = {a.lr_actor, a.beta1, a.beta2, a.eps, 0.0, (double)a.max_norm, (long)(a.step_actor0 + n_policy_before + 1)};
+      adam_update(c.cta, c.ncta, c.red, A, a.sumsq, ncontrib, hp, &a.actor_target, a.tau);
       FRL_PAR(t) {
         if (c.cta == 0 && t == 0) {
           float l = 0.f, en = 0.f, ss = 0.f;

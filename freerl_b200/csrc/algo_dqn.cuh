@@ -4,7 +4,9 @@
 #pragma once
 #include "launch.cuh"
 
+#ifndef FRL_R
 #define FRL_R 8   // batch rows per CTA tile
+#endif
 
 // ---- replay row access ----------------------------------------------------------------------------------
 FRL_DEV int rb_col_act(const frl_replay_t& rb) { return rb.obs_dim; }
@@ -15,7 +17,7 @@ FRL_DEV int rb_col_nobs(const frl_replay_t& rb) { return rb.obs_dim + rb.act_dim
 // Gather R sampled rows (vectorised 16-B loads, one row = row_floats/4 lanes) into smem raw[R][row_floats].
 // Rows >= nvalid are zero-filled.
 template <int R>
-FRL_DEV void gather_rows(Cta& c, const frl_replay_t& rb, const int64_t* idx, int nvalid, float* raw) {
+FRL_NI_MISC void gather_rows(const frl_replay_t& rb, const int64_t* idx, int nvalid, float* raw) {
   const int q = rb.row_floats >> 2;
   FRL_PAR(t) {
     for (int e = t; e < R * q; e += FRL_NT) {
@@ -36,7 +38,7 @@ FRL_DEV void gather_rows(Cta& c, const frl_replay_t& rb, const int64_t* idx, int
 
 // dst[r][dcol0 + j] = src[r][scol0 + j] for j < n, then zero up to ncols_total_pad (if > 0)
 template <int R>
-FRL_DEV void copy_cols(float* dst, int ldd, int dcol0, const float* src, int lds, int scol0, int n, int zero_to) {
+FRL_NI_MISC void copy_cols(float* dst, int ldd, int dcol0, const float* src, int lds, int scol0, int n, int zero_to) {
   FRL_PAR(t) {
     const int w = (zero_to > dcol0 + n ? zero_to : dcol0 + n) - dcol0;
     for (int e = t; e < R * w; e += FRL_NT) {
@@ -93,7 +95,7 @@ struct DqnAlgo {
         const int row0 = tile * FRL_R;
         const int nvalid = (a.B - row0) < FRL_R ? (a.B - row0) : FRL_R;
         stage_prefetch(c, layer_fwd_src(a.q_target, 0), layer_fwd_bytes(a.q_target.L[0]));
-        gather_rows<FRL_R>(c, a.replay, a.indices + (size_t)u * a.B + row0, nvalid, raw);
+        gather_rows<FRL_R>(a.replay, a.indices + (size_t)u * a.B + row0, nvalid, raw);
         copy_cols<FRL_R>(Xo, in_pad, 0, raw, a.replay.row_floats, 0, a.replay.obs_dim, in_pad);
         copy_cols<FRL_R>(Xn, in_pad, 0, raw, a.replay.row_floats, rb_col_nobs(a.replay), a.replay.obs_dim, in_pad);
         // target net on next_obs, online net on obs
@@ -120,7 +122,7 @@ struct DqnAlgo {
           lossr[t] = l;
         }
         FRL_SYNC();
-        loss_acc += block_sum(c, lossr);
+        loss_acc += block_sum(lossr);
         mlp_bwd<FRL_R>(c, q, 0, nl, Xo, in_pad, H1, H1, ldh, dQ, op, D1, D1, nullptr, 0, gp, !first, no_hint());
         first = false;
       }
@@ -129,9 +131,9 @@ struct DqnAlgo {
     } else {
       // stage 1: cross-CTA reduce + Adam + Polyak on this CTA's parameter slice (no global norm needed)
       const int ncontrib = grid(a, c.ncta);
-      reduce_grads(c, q, a.gpart, q.n_p, ncontrib, nullptr);
-      const AdamHP hp = make_adam_hp(a.lr, a.beta1, a.beta2, a.eps, 0.0, 0.0, (long)(a.step0 + u + 1));
-      adam_update(c, q, nullptr, 0, hp, &a.q_target, a.tau);
+      reduce_grads(c.cta, c.ncta, c.red, q, a.gpart, q.n_p, ncontrib, nullptr);
+      const AdamSpec hp = {a.lr, a.beta1, a.beta2, a.eps, 0.0, 0.0, (long)(a.step0 + u + 1)};
+      adam_update(c.cta, c.ncta, c.red, q, nullptr, 0, hp, &a.q_target, a.tau);
       FRL_PAR(t) {
         if (c.cta == 0 && t == 0) {
           float l = 0.f;

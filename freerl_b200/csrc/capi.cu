@@ -38,6 +38,17 @@ extern "C" int frl_is_emulation(void) { return 1; }
 #endif
 extern "C" int frl_device_sm_count(void) { return frl_device_max_ctas(); }
 
+// debug: timestamps (id, globaltimer ns) from CTA 0 of the persistent kernels into a device int64 buffer [2*2000]
+extern "C" int frl_debug_set_timing(void* dev_buf) {
+#ifndef FRL_EMUL
+  long long* p = (long long*)dev_buf;
+  FRL_CUDA_OK(cudaMemcpyToSymbol(frl_dbg_ptr, &p, sizeof(p)));
+#else
+  (void)dev_buf;
+#endif
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // generic 1-D elementwise launcher (functor bodies are shared by the CUDA and the emulation build)
 // ------------------------------------------------------------------------------------------------

@@ -21,6 +21,8 @@
 #define FRL_DEV __device__ __forceinline__
 #define FRL_HD __host__ __device__ __forceinline__
 #define FRL_DEVM __device__ __forceinline__
+#define FRL_NOINL __device__ __noinline__
+#define FRL_INLINE_ALT __device__ __forceinline__
 #define FRL_SHD static __host__ __device__ __forceinline__
 #define FRL_HDM __host__ __device__ __forceinline__
 #define FRL_SDEV static __device__ __forceinline__
@@ -30,6 +32,8 @@
 #define FRL_DEV static inline
 #define FRL_HD static inline
 #define FRL_DEVM inline
+#define FRL_NOINL static
+#define FRL_INLINE_ALT static inline
 #define FRL_SHD static inline
 #define FRL_HDM inline
 #define FRL_SDEV static inline
@@ -41,7 +45,9 @@ static inline float4 make_float4(float x, float y, float z, float w) { float4 r 
 static inline float __ldg(const float* p) { return *p; }
 #endif
 
+#ifndef FRL_NT
 #define FRL_NT 256          // threads per CTA for every engine kernel
+#endif
 #include "../../include/freerl_b200.h"   // frl_layer_t / frl_net_t / argument structs (the C ABI)
 
 // Segment table entry for per-tensor optimiser semantics (cautious AdamW mask mean, c_adamw.py:116).

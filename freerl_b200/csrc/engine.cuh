@@ -13,6 +13,23 @@
 #pragma once
 #include "common.cuh"
 
+// bisect switches (debug): -DFRL_INL_GEMM / -DFRL_INL_MISC / -DFRL_INL_OPT force-inline a group again
+#ifdef FRL_INL_GEMM
+#define FRL_NI_GEMM FRL_INLINE_ALT
+#else
+#define FRL_NI_GEMM FRL_NOINL
+#endif
+#ifdef FRL_INL_MISC
+#define FRL_NI_MISC FRL_INLINE_ALT
+#else
+#define FRL_NI_MISC FRL_NOINL
+#endif
+#ifdef FRL_INL_OPT
+#define FRL_NI_OPT FRL_INLINE_ALT
+#else
+#define FRL_NI_OPT FRL_NOINL
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // exact (non-contracted) fp32 helpers so optimiser math rounds like torch's op-by-op kernels
 // ------------------------------------------------------------------------------------------------
@@ -35,14 +52,32 @@ struct Cta {
   int cta, ncta;            // this CTA's index / grid size
   float* smem;              // dynamic shared memory base (1024-B aligned)
   // ---- stager (block-uniform state, replicated in every thread's registers) ----
-  float* wbuf[2];           // two weight staging buffers in smem
+  float* wbuf0;             // two weight staging buffers in smem (scalars: no dynamically indexed
+  float* wbuf1;             //  arrays, they would push the whole context into local memory)
   uint64_t* bar;            // two mbarriers in smem
-  uint32_t phase[2];
+  uint32_t phase0, phase1;
   const float* pend_ptr;    // global source of the outstanding prefetch (or nullptr)
   int pend_buf;
   int next_buf;
   float* red;               // [FRL_NT*16] reduction scratch in smem
+  long long* dbg;           // optional timestamp sink (frl_debug_set_timing), CTA 0 / thread 0 only
+  int dbg_n;
 };
+
+// Debug timestamps: CTA 0 / thread 0 appends (id, clock) pairs.  Disabled (nullptr) in normal runs.
+#ifndef FRL_EMUL
+__device__ long long* frl_dbg_ptr = nullptr;
+FRL_DEV void stamp(Cta& c, int id) {
+  if (c.dbg && c.cta == 0 && threadIdx.x == 0 && c.dbg_n < 2000) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    c.dbg[2 * c.dbg_n] = id; c.dbg[2 * c.dbg_n + 1] = t;
+  }
+  if (c.dbg) c.dbg_n++;
+}
+#else
+FRL_DEV void stamp(Cta&, int) {}
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // TMA staging
@@ -79,13 +114,15 @@ FRL_DEV void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory
 // Carve the stager + scratch out of dynamic smem.  Returns the first free float after them.
 FRL_DEV float* cta_init(Cta& c, int cta, int ncta, float* smem, int wbuf_floats) {
   c.cta = cta; c.ncta = ncta; c.smem = smem;
-  c.wbuf[0] = smem;
-  c.wbuf[1] = smem + wbuf_floats;
+  c.wbuf0 = smem;
+  c.wbuf1 = smem + wbuf_floats;
   c.red = smem + 2 * wbuf_floats;
   c.bar = (uint64_t*)(c.red + FRL_NT * 16);
-  c.phase[0] = c.phase[1] = 0;
+  c.phase0 = c.phase1 = 0;
   c.pend_ptr = nullptr; c.pend_buf = 0; c.next_buf = 0;
+  c.dbg = nullptr; c.dbg_n = 0;
 #ifndef FRL_EMUL
+  c.dbg = frl_dbg_ptr;
   if (threadIdx.x == 0) {
     mbar_init(&c.bar[0], 1);
     mbar_init(&c.bar[1], 1);
@@ -104,19 +141,19 @@ FRL_DEV void stage_issue(Cta& c, int buf, const float* src, int bytes) {
 #ifndef FRL_EMUL
   if (threadIdx.x == 0) {
     fence_proxy_async();
-    mbar_expect_tx(&c.bar[buf], (uint32_t)bytes);
-    tma_bulk_g2s(c.wbuf[buf], src, (uint32_t)bytes, &c.bar[buf]);
+    mbar_expect_tx(c.bar + buf, (uint32_t)bytes);
+    tma_bulk_g2s(buf ? c.wbuf1 : c.wbuf0, src, (uint32_t)bytes, c.bar + buf);
   }
 #else
-  memcpy(c.wbuf[buf], src, (size_t)bytes);
+  memcpy(buf ? c.wbuf1 : c.wbuf0, src, (size_t)bytes);
 #endif
 }
 
 FRL_DEV void stage_wait(Cta& c, int buf) {
 #ifndef FRL_EMUL
-  mbar_wait(&c.bar[buf], c.phase[buf]);
+  mbar_wait(c.bar + buf, buf ? c.phase1 : c.phase0);
 #endif
-  c.phase[buf] ^= 1u;
+  if (buf) c.phase1 ^= 1u; else c.phase0 ^= 1u;
 }
 
 // Start fetching `src` into the idle buffer.  Precondition: every thread is past its last read of that
@@ -143,7 +180,7 @@ FRL_DEV const float* stage_acquire(Cta& c, const float* src, int bytes) {
   stage_wait(c, c.pend_buf);
   c.pend_ptr = nullptr;
   c.next_buf = c.pend_buf ^ 1;
-  return c.wbuf[c.pend_buf];
+  return c.pend_buf ? c.wbuf1 : c.wbuf0;
 }
 
 // Must be called when weights may have changed under a buffer we would otherwise trust (after grid sync).
@@ -160,6 +197,28 @@ FRL_DEV void stage_reset(Cta& c) {
 // ------------------------------------------------------------------------------------------------
 FRL_DEV float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 FRL_DEV void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// shared-memory flavours: explicit ld.shared / st.shared (the address-space is not always inferable once the
+// hot loops live in non-inlined functions; `__builtin_assume(__isShared(p))` proved fragile — the optimiser used it
+// to delete the K loop of the de-inlined gemm — so the space is spelled out in PTX instead).
+#ifndef FRL_EMUL
+FRL_DEV float4 lds4(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
+FRL_DEV void sts4(float* p, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+FRL_DEV float lds1(const float* p) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_u32(p)));
+  return v;
+}
+#else
+FRL_DEV float4 lds4(const float* p) { return ld4(p); }
+FRL_DEV void sts4(float* p, float4 v) { st4(p, v); }
+FRL_DEV float lds1(const float* p) { return *p; }
+#endif
 FRL_DEV float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
 FRL_DEV float apply_act(float v, int act) {
@@ -171,49 +230,95 @@ FRL_DEV float apply_act(float v, int act) {
 enum { EPI_BIAS_ACT = 0, EPI_RELU_MASK = 1 };
 
 // ------------------------------------------------------------------------------------------------
+// Shared-memory "word address" helpers.  The GEMM microkernels do all smem pointer arithmetic in 32-bit word
+// offsets relative to their operand bases (no 64-bit generic pointer math + cvta per access in the hot loop).
+// On the GPU an `sptr` is a 32-bit shared-space BYTE address; in the emulation it is a host pointer.
+// ------------------------------------------------------------------------------------------------
+#ifndef FRL_EMUL
+typedef uint32_t sptr;
+FRL_DEV sptr sp_of(const float* p) { return smem_u32(p); }
+FRL_DEV float4 sp_ld4(sptr base, int word) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(base + 4u * (uint32_t)word));
+  return v;
+}
+FRL_DEV float sp_ld1(sptr base, int word) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(base + 4u * (uint32_t)word));
+  return v;
+}
+FRL_DEV void sp_st4(sptr base, int word, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base + 4u * (uint32_t)word), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+#else
+typedef const float* sptr;
+FRL_DEV sptr sp_of(const float* p) { return p; }
+FRL_DEV float4 sp_ld4(sptr base, int word) { return ld4(base + word); }
+FRL_DEV float sp_ld1(sptr base, int word) { return base[word]; }
+FRL_DEV void sp_st4(sptr base, int word, float4 v) { st4(const_cast<float*>(base) + word, v); }
+#endif
+
+// unsigned divide helpers with a power-of-two fast path (shift >= 0) — the tile decode runs per thread per op
+FRL_DEV int ilog2_exact(int x) { int s = 0; while ((1 << s) < x) ++s; return ((1 << s) == x) ? s : -1; }
+FRL_DEV unsigned udiv(unsigned a, unsigned d, int shift) { return shift >= 0 ? (a >> shift) : (a / d); }
+
+// ------------------------------------------------------------------------------------------------
 // gemm_rk:  C[r][n] = epi( sum_k A[r][k] * Bs[k][n] (+ bias[n]) ),  r < R, n < N_pad, k < K_pad
 //   A  : smem, row-major, leading dim lda (multiple of 4), columns [0,K_pad) readable & finite
 //   Bs : smem, row-major [K_pad][N_pad] (rows >= logical K are zero)
 //   epi: EPI_BIAS_ACT  -> act(acc + bias[n])            (bias in smem, may be null)
 //        EPI_RELU_MASK -> acc * (mask[r][n] > 0)        (backward through ReLU; mask = stored activation)
 //   C  : smem, leading dim ldc.  Must not alias A.
+// (NOT inlined: one copy of the hot loop keeps the persistent kernels' instruction footprint inside the I-cache;
+//  the fully inlined build was 490 KB of SASS and spent most cycles in `no_instruction` stalls.)
 // ------------------------------------------------------------------------------------------------
 template <int R>
-FRL_DEV void gemm_rk(Cta& c, const float* A, int lda, int K_pad, const float* Bs, int N_pad, const float* bias,
-                     int epi, int act, const float* mask, int ldm, float* C, int ldc) {
-  const int nt = N_pad >> 2, rt = R / 4;
-  const int tiles = nt * rt;
-  const int nchunk = K_pad >> 2;
-  int ksplit = FRL_NT / tiles;
+FRL_NI_GEMM void gemm_rk(float* red, const float* A, int lda, int K_pad, const float* Bs, int N_pad, const float* bias,
+                         int epi, int act, const float* mask, int ldm, float* C, int ldc) {
+  const unsigned nt = (unsigned)N_pad >> 2, rt = R / 4;
+  const unsigned tiles = nt * rt;
+  const unsigned nchunk = (unsigned)K_pad >> 2;
+  unsigned ksplit = FRL_NT / tiles;
   if (ksplit < 1) ksplit = 1;
   if (ksplit > nchunk) ksplit = nchunk;
-  const int items = tiles * ksplit;
-  float* red = c.red;
+  const unsigned items = tiles * ksplit;
+  const int sh_tiles = ilog2_exact((int)tiles), sh_nt = ilog2_exact((int)nt);
+  const sptr sA = sp_of(A), sB = sp_of(Bs), sR = sp_of(red), sC = sp_of(C);
+  const bool has_bias = bias != nullptr;
+  const sptr sBias = sp_of(has_bias ? bias : Bs), sM = sp_of(mask ? mask : Bs);
   FRL_PAR(t) {
-    for (int item = t; item < items; item += FRL_NT) {
-      const int tile = item % tiles, ks = item / tiles;
-      const int n0 = (tile % nt) * 4, r0 = (tile / nt) * 4;
-      const int kc0 = (ks * nchunk) / ksplit, kc1 = ((ks + 1) * nchunk) / ksplit;
+    for (unsigned item = (unsigned)t; item < items; item += FRL_NT) {
+      const unsigned ks = udiv(item, tiles, sh_tiles), tile = item - ks * tiles;
+      const unsigned rti = udiv(tile, nt, sh_nt);
+      const int n0 = (int)(tile - rti * nt) * 4, r0 = (int)rti * 4;
+      const int kc0 = (int)((ks * nchunk) / ksplit), kc1 = (int)(((ks + 1) * nchunk) / ksplit);
       float acc[4][4];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      int wb = kc0 * 4 * N_pad + n0;          // word offset of Bs[k][n0]
+      int wa = r0 * lda + kc0 * 4;            // word offset of A[r0][k]
+      const int wb_step = 4 * N_pad;
 #pragma unroll 2
       for (int kc = kc0; kc < kc1; ++kc) {
-        const int k = kc * 4;
-        float4 b0 = ld4(Bs + (k + 0) * N_pad + n0);
-        float4 b1 = ld4(Bs + (k + 1) * N_pad + n0);
-        float4 b2 = ld4(Bs + (k + 2) * N_pad + n0);
-        float4 b3 = ld4(Bs + (k + 3) * N_pad + n0);
+        const float4 b0 = sp_ld4(sB, wb);
+        const float4 b1 = sp_ld4(sB, wb + N_pad);
+        const float4 b2 = sp_ld4(sB, wb + 2 * N_pad);
+        const float4 b3 = sp_ld4(sB, wb + 3 * N_pad);
+        float4 av[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) av[i] = sp_ld4(sA, wa + i * lda);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          float4 a = ld4(A + (r0 + i) * lda + k);
+          const float4 a = av[i];
           acc[i][0] += a.x * b0.x; acc[i][1] += a.x * b0.y; acc[i][2] += a.x * b0.z; acc[i][3] += a.x * b0.w;
           acc[i][0] += a.y * b1.x; acc[i][1] += a.y * b1.y; acc[i][2] += a.y * b1.z; acc[i][3] += a.y * b1.w;
           acc[i][0] += a.z * b2.x; acc[i][1] += a.z * b2.y; acc[i][2] += a.z * b2.z; acc[i][3] += a.z * b2.w;
           acc[i][0] += a.w * b3.x; acc[i][1] += a.w * b3.y; acc[i][2] += a.w * b3.z; acc[i][3] += a.w * b3.w;
         }
+        wb += wb_step;
+        wa += 4;
       }
       if (ksplit == 1) {
 #pragma unroll
@@ -222,33 +327,39 @@ FRL_DEV void gemm_rk(Cta& c, const float* A, int lda, int K_pad, const float* Bs
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             float v = acc[i][j];
-            if (epi == EPI_BIAS_ACT) v = apply_act(v + (bias ? bias[n0 + j] : 0.f), act);
-            else v = (mask[(r0 + i) * ldm + n0 + j] > 0.f) ? v : 0.f;
+            if (epi == EPI_BIAS_ACT) v = apply_act(v + (has_bias ? sp_ld1(sBias, n0 + j) : 0.f), act);
+            else v = (sp_ld1(sM, (r0 + i) * ldm + n0 + j) > 0.f) ? v : 0.f;
             o[j] = v;
           }
-          st4(C + (r0 + i) * ldc + n0, make_float4(o[0], o[1], o[2], o[3]));
+          sp_st4(sC, (r0 + i) * ldc + n0, make_float4(o[0], o[1], o[2], o[3]));
         }
       } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          st4(red + (ks * R + r0 + i) * N_pad + n0, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+          sp_st4(sR, ((int)ks * R + r0 + i) * N_pad + n0, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
       }
     }
   }
   FRL_SYNC();
   if (ksplit > 1) {
     FRL_PAR(t) {
-      for (int e = t; e < R * nt; e += FRL_NT) {
-        const int r = e / nt, n0 = (e % nt) * 4;
-        float4 s = ld4(red + r * N_pad + n0);
-        for (int ks = 1; ks < ksplit; ++ks) s = f4add(s, ld4(red + (ks * R + r) * N_pad + n0));
+      for (unsigned e = (unsigned)t; e < R * nt; e += FRL_NT) {
+        const unsigned r = udiv(e, nt, sh_nt);
+        const int n0 = (int)(e - r * nt) * 4;
+        int w = (int)r * N_pad + n0;
+        float4 s = sp_ld4(sR, w);
+        for (unsigned ks = 1; ks < ksplit; ++ks) { w += R * N_pad; s = f4add(s, sp_ld4(sR, w)); }
         float o[4] = {s.x, s.y, s.z, s.w};
+        if (epi == EPI_BIAS_ACT) {
+          if (has_bias) { const float4 bv = sp_ld4(sBias, n0); o[0] += bv.x; o[1] += bv.y; o[2] += bv.z; o[3] += bv.w; }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (epi == EPI_BIAS_ACT) o[j] = apply_act(o[j] + (bias ? bias[n0 + j] : 0.f), act);
-          else o[j] = (mask[r * ldm + n0 + j] > 0.f) ? o[j] : 0.f;
+          for (int j = 0; j < 4; ++j) o[j] = apply_act(o[j], act);
+        } else {
+          const float4 mv = sp_ld4(sM, (int)r * ldm + n0);
+          o[0] = mv.x > 0.f ? o[0] : 0.f; o[1] = mv.y > 0.f ? o[1] : 0.f;
+          o[2] = mv.z > 0.f ? o[2] : 0.f; o[3] = mv.w > 0.f ? o[3] : 0.f;
         }
-        st4(C + r * ldc + n0, make_float4(o[0], o[1], o[2], o[3]));
+        sp_st4(sC, (int)r * ldc + n0, make_float4(o[0], o[1], o[2], o[3]));
       }
     }
     FRL_SYNC();
@@ -261,13 +372,16 @@ FRL_DEV void gemm_rk(Cta& c, const float* A, int lda, int K_pad, const float* Bs
 //   to zero (X pad columns may alias neighbouring fields).  Also the bias gradient gb[m] (+)= sum_r dY[r][m].
 // ------------------------------------------------------------------------------------------------
 template <int R>
-FRL_DEV void gemm_outer(Cta& c, const float* dY, int ldy, int M_pad, const float* X, int ldx, int N_pad, int N_real,
-                        float* G, float* gb, bool accumulate) {
-  const int mt = M_pad >> 2, nt = N_pad >> 2;
-  const int tiles = mt * nt;
+FRL_NI_GEMM void gemm_outer(const float* dY, int ldy, int M_pad, const float* X, int ldx, int N_pad, int N_real,
+                            float* G, float* gb, bool accumulate) {
+  const unsigned mt = (unsigned)M_pad >> 2, nt = (unsigned)N_pad >> 2;
+  const unsigned tiles = mt * nt;
+  const int sh_nt = ilog2_exact((int)nt);
+  const sptr sY = sp_of(dY), sX = sp_of(X);
   FRL_PAR(t) {
-    for (int tile = t; tile < tiles; tile += FRL_NT) {
-      const int m0 = (tile / nt) * 4, n0 = (tile % nt) * 4;
+    for (unsigned tile = (unsigned)t; tile < tiles; tile += FRL_NT) {
+      const unsigned mi = udiv(tile, nt, sh_nt);
+      const int m0 = (int)mi * 4, n0 = (int)(tile - mi * nt) * 4;
       float acc[4][4];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -275,29 +389,30 @@ FRL_DEV void gemm_outer(Cta& c, const float* dY, int ldy, int M_pad, const float
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        float4 a = ld4(dY + r * ldy + m0);
-        float4 b = ld4(X + r * ldx + n0);
+        const float4 a = sp_ld4(sY, r * ldy + m0);
+        const float4 b = sp_ld4(sX, r * ldx + n0);
         acc[0][0] += a.x * b.x; acc[0][1] += a.x * b.y; acc[0][2] += a.x * b.z; acc[0][3] += a.x * b.w;
         acc[1][0] += a.y * b.x; acc[1][1] += a.y * b.y; acc[1][2] += a.y * b.z; acc[1][3] += a.y * b.w;
         acc[2][0] += a.z * b.x; acc[2][1] += a.z * b.y; acc[2][2] += a.z * b.z; acc[2][3] += a.z * b.w;
         acc[3][0] += a.w * b.x; acc[3][1] += a.w * b.y; acc[3][2] += a.w * b.z; acc[3][3] += a.w * b.w;
       }
+      float* gp = G + m0 * N_pad + n0;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           if (n0 + j >= N_real) acc[i][j] = 0.f;
-        float* gp = G + (m0 + i) * N_pad + n0;
         float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
         if (accumulate) v = f4add(v, ld4(gp));
         st4(gp, v);
+        gp += N_pad;
       }
     }
     // bias gradient
     for (int m = t; m < M_pad; m += FRL_NT) {
       float s = 0.f;
 #pragma unroll
-      for (int r = 0; r < R; ++r) s += dY[r * ldy + m];
+      for (int r = 0; r < R; ++r) s += sp_ld1(sY, r * ldy + m);
       if (accumulate) s += gb[m];
       gb[m] = s;
     }
@@ -322,9 +437,11 @@ FRL_DEV Hint bwd_hint(const frl_net_t& n, int li) { Hint h; h.ptr = layer_bwd_sr
 template <int R>
 FRL_DEV void layer_fwd(Cta& c, const frl_net_t& n, int li, const float* X, int ldx, float* Y, int ldy, int act, Hint next) {
   const frl_layer_t& L = n.L[li];
+  stamp(c, 10);
   const float* Bs = stage_acquire(c, layer_fwd_src(n, li), layer_fwd_bytes(L));
+  stamp(c, 11);
   stage_prefetch(c, next.ptr, next.bytes);
-  gemm_rk<R>(c, X, ldx, L.in_pad, Bs, L.out_pad, Bs + L.in_pad * L.out_pad, EPI_BIAS_ACT, act, nullptr, 0, Y, ldy);
+  gemm_rk<R>(c.red, X, ldx, L.in_pad, Bs, L.out_pad, Bs + L.in_pad * L.out_pad, EPI_BIAS_ACT, act, nullptr, 0, Y, ldy);
 }
 
 // dX = (dY W) * relu'(mask)   (mask == nullptr: no activation derivative)
@@ -334,8 +451,8 @@ FRL_DEV void layer_bwd_dx(Cta& c, const frl_net_t& n, int li, const float* dY, i
   const frl_layer_t& L = n.L[li];
   const float* Bs = stage_acquire(c, layer_bwd_src(n, li), layer_bwd_bytes(L));
   stage_prefetch(c, next.ptr, next.bytes);
-  if (mask) gemm_rk<R>(c, dY, ldy, L.out_pad, Bs, L.in_pad, nullptr, EPI_RELU_MASK, 0, mask, ldm, dX, ldx);
-  else gemm_rk<R>(c, dY, ldy, L.out_pad, Bs, L.in_pad, nullptr, EPI_BIAS_ACT, FRL_ACT_NONE, nullptr, 0, dX, ldx);
+  if (mask) gemm_rk<R>(c.red, dY, ldy, L.out_pad, Bs, L.in_pad, nullptr, EPI_RELU_MASK, 0, mask, ldm, dX, ldx);
+  else gemm_rk<R>(c.red, dY, ldy, L.out_pad, Bs, L.in_pad, nullptr, EPI_BIAS_ACT, FRL_ACT_NONE, nullptr, 0, dX, ldx);
 }
 
 // MLP forward over layers [l0, l0+nl): hidden layers ReLU, last layer `act_out`.
@@ -368,7 +485,7 @@ FRL_DEV void mlp_bwd(Cta& c, const frl_net_t& n, int l0, int nl, const float* X,
     const frl_layer_t& L = n.L[li];
     const float* Xin = (k == 0) ? X : (k == 1 ? H1 : H2);
     const int ldin = (k == 0) ? ldx : ldh;
-    if (gp) gemm_outer<R>(c, dcur, ldc, L.out_pad, Xin, ldin, L.in_pad, L.in, gp + L.w_off, gp + L.b_off, accumulate);
+    if (gp) gemm_outer<R>(dcur, ldc, L.out_pad, Xin, ldin, L.in_pad, L.in, gp + L.w_off, gp + L.b_off, accumulate);
     if (k > 0) {
       float* dn = (k == 2) ? D2 : D1;   // gradient wrt H2 (k==2) or H1 (k==1)
       Hint h = (k - 1 > 0 || dXo) ? bwd_hint(n, li - 1) : next;
@@ -383,7 +500,7 @@ FRL_DEV void mlp_bwd(Cta& c, const frl_net_t& n, int l0, int nl, const float* X,
 // ------------------------------------------------------------------------------------------------
 // block-wide fixed-order sum of one float per thread (result broadcast to all threads via smem)
 // ------------------------------------------------------------------------------------------------
-FRL_DEV float block_sum(Cta& c, float* slot /*[FRL_NT] smem*/) {
+FRL_NI_MISC float block_sum(float* slot /*[FRL_NT] smem*/) {
   for (int s = FRL_NT / 2; s > 0; s >>= 1) {
     FRL_PAR(t) { if (t < s) slot[t] += slot[t + s]; }
     FRL_SYNC();
@@ -395,21 +512,30 @@ FRL_DEV float block_sum(Cta& c, float* slot /*[FRL_NT] smem*/) {
 // cross-CTA gradient reduction (fixed order) + sum of squares partial per CTA
 //   gpart: [ncontrib][stride];  n.g <- sum_c gpart[c];  sumsq_part[cta] <- sum over this CTA's slice of g^2
 // ------------------------------------------------------------------------------------------------
-FRL_DEV void reduce_grads(Cta& c, const frl_net_t& n, const float* gpart, int stride, int ncontrib, float* sumsq_part) {
-  float* slot = c.red;
+FRL_NI_OPT void reduce_grads(int cta, int ncta, float* slot, const frl_net_t& n, const float* gpart, int stride, int ncontrib,
+                            float* sumsq_part) {
   FRL_PAR(t) {
     float local = 0.f;
-    for (int p = c.cta * FRL_NT + t; p < n.n_p; p += c.ncta * FRL_NT) {
-      float s = gpart[p];
-      for (int cc = 1; cc < ncontrib; ++cc) s += gpart[(size_t)cc * stride + p];
-      n.g[p] = s;
-      local += s * s;
+    // n_p and stride are multiples of 4: each thread owns groups of 4 consecutive parameters (16-B loads)
+    for (int p = (cta * FRL_NT + t) * 4; p < n.n_p; p += ncta * FRL_NT * 4) {
+      float4 s = ld4(gpart + p);
+      int cc = 1;
+      for (; cc + 8 <= ncontrib; cc += 8) {     // 8 independent loads in flight, summed in fixed order
+        float4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = ld4(gpart + (size_t)(cc + i) * stride + p);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s = f4add(s, v[i]);
+      }
+      for (; cc < ncontrib; ++cc) s = f4add(s, ld4(gpart + (size_t)cc * stride + p));
+      st4(n.g + p, s);
+      local += s.x * s.x + s.y * s.y + s.z * s.z + s.w * s.w;
     }
     slot[t] = local;
   }
   FRL_SYNC();
-  float tot = block_sum(c, slot);
-  FRL_PAR(t) { if (t == 0 && sumsq_part) sumsq_part[c.cta] = tot; }
+  float tot = block_sum(slot);
+  FRL_PAR(t) { if (t == 0 && sumsq_part) sumsq_part[cta] = tot; }
   FRL_SYNC();
 }
 
@@ -452,37 +578,83 @@ FRL_DEV int mirror_index(const frl_net_t& n, int p) {
   return -1;
 }
 
+// distance in the mirror between parameter p and p+1 (same tensor): W row (k, k+1) -> out_pad, bias -> 1
+FRL_DEV int mirror_stride(const frl_net_t& n, int p) {
+  for (int li = 0; li < n.n_layers; ++li) {
+    const frl_layer_t& L = n.L[li];
+    if (p >= L.w_off && p < L.w_off + L.out_pad * L.in_pad) return L.out_pad;
+  }
+  return 1;
+}
+
 // torch.optim.Adam single-tensor math on this CTA's slice of the parameters, preceded by the global-norm
 // clip (coef from the per-CTA sum-of-squares partials written by reduce_grads), optionally followed by the
 // Polyak update of a target net with identical layout.  Keeps p / pt (and target p / pt) in sync.
-FRL_DEV void adam_update(Cta& c, const frl_net_t& n, const float* sumsq_part, int nparts, const AdamHP hp,
-                         const frl_net_t* tgt, float tau) {
-  float coef = 1.f;
-  if (hp.max_norm > 0.f && sumsq_part) {
-    float tot = 0.f;
-    for (int i = 0; i < nparts; ++i) tot += sumsq_part[i];
-    const float nrm = sqrtf(tot);
-    coef = hp.max_norm / (nrm + 1e-6f);
-    if (coef > 1.f) coef = 1.f;
+struct AdamSpec { double lr, b1, b2, eps, wd, max_norm; long step; };
+
+FRL_NI_OPT void adam_update(int cta, int ncta, float* sh, const frl_net_t& n, const float* sumsq_part, int nparts,
+                           const AdamSpec sp, const frl_net_t* tgt, float tau) {
+  // (1) per-CTA scalars: bias corrections (double pow) by one thread, norm partials summed in fixed order from smem
+  FRL_PAR(t) {
+    if (sumsq_part) { for (int i = t; i < nparts; i += FRL_NT) sh[64 + i] = sumsq_part[i]; }
+    if (t == 0) {
+      const AdamHP h = make_adam_hp(sp.lr, sp.b1, sp.b2, sp.eps, sp.wd, sp.max_norm, sp.step);
+      sh[0] = h.lr_over_bc1_neg; sh[1] = h.bc2_sqrt; sh[2] = h.one_minus_b1; sh[3] = h.b2; sh[4] = h.one_minus_b2;
+      sh[5] = h.eps; sh[6] = h.weight_decay; sh[7] = h.max_norm;
+    }
   }
+  FRL_SYNC();
+  FRL_PAR(t) {
+    if (t == 0) {
+      float coef = 1.f;
+      if (sh[7] > 0.f && sumsq_part) {
+        float tot = 0.f;
+        for (int i = 0; i < nparts; ++i) tot += sh[64 + i];
+        coef = sh[7] / (sqrtf(tot) + 1e-6f);
+        if (coef > 1.f) coef = 1.f;
+      }
+      sh[8] = coef;
+    }
+  }
+  FRL_SYNC();
+  AdamHP hp;
+  hp.lr_over_bc1_neg = sh[0]; hp.bc2_sqrt = sh[1]; hp.one_minus_b1 = sh[2]; hp.b2 = sh[3]; hp.one_minus_b2 = sh[4];
+  hp.eps = sh[5]; hp.weight_decay = sh[6]; hp.max_norm = sh[7];
+  const float coef = sh[8];
   const float omt = (float)(1.0 - (double)tau);
   FRL_PAR(t) {
-    for (int p = c.cta * FRL_NT + t; p < n.n_p; p += c.ncta * FRL_NT) {
-      float g = n.g[p] * coef;
-      float w = n.p[p];
-      if (hp.weight_decay != 0.f) g = fmaf(w, hp.weight_decay, g);
-      float m = n.m[p], v = n.v[p];
-      m = fmaf(hp.one_minus_b1, g - m, m);                        // exp_avg.lerp_(grad, 1-b1)
-      v = fadd(fmul(v, hp.b2), fmul(fmul(hp.one_minus_b2, g), g));   // mul_(b2).addcmul_(g, g, 1-b2)
-      const float denom = fadd(fdiv(fsqrt(v), hp.bc2_sqrt), hp.eps);
-      w = fadd(w, fdiv(fmul(hp.lr_over_bc1_neg, m), denom));      // addcdiv_(m, denom, value=-step_size)
-      n.m[p] = m; n.v[p] = v; n.p[p] = w;
-      const int mi = mirror_index(n, p);
-      if (mi >= 0) n.pt[mi] = w;
-      if (tgt) {
-        float tw = fadd(fmul(tgt->p[p], omt), fmul(w, tau));
-        tgt->p[p] = tw;
-        if (mi >= 0) tgt->pt[mi] = tw;
+    // 4 consecutive parameters per thread (16-B loads/stores of p, m, v, g and the target); mirrors are scattered
+    for (int p4 = (cta * FRL_NT + t) * 4; p4 < n.n_p; p4 += ncta * FRL_NT * 4) {
+      const float4 g4 = ld4(n.g + p4), w4 = ld4(n.p + p4), m4 = ld4(n.m + p4), v4 = ld4(n.v + p4);
+      float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (tgt) t4 = ld4(tgt->p + p4);
+      float gg[4] = {g4.x, g4.y, g4.z, g4.w}, ww[4] = {w4.x, w4.y, w4.z, w4.w};
+      float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w}, tt[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float g = gg[i] * coef;
+        float w = ww[i];
+        if (hp.weight_decay != 0.f) g = fmaf(w, hp.weight_decay, g);
+        float m = mm[i], v = vv[i];
+        m = fmaf(hp.one_minus_b1, g - m, m);                           // exp_avg.lerp_(grad, 1-b1)
+        v = fadd(fmul(v, hp.b2), fmul(fmul(hp.one_minus_b2, g), g));   // mul_(b2).addcmul_(g, g, 1-b2)
+        const float denom = fadd(fdiv(fsqrt(v), hp.bc2_sqrt), hp.eps);
+        w = fadd(w, fdiv(fmul(hp.lr_over_bc1_neg, m), denom));         // addcdiv_(m, denom, value=-step_size)
+        mm[i] = m; vv[i] = v; ww[i] = w;
+        if (tgt) tt[i] = fadd(fmul(tt[i], omt), fmul(w, tau));
+      }
+      st4(n.m + p4, make_float4(mm[0], mm[1], mm[2], mm[3]));
+      st4(n.v + p4, make_float4(vv[0], vv[1], vv[2], vv[3]));
+      st4(n.p + p4, make_float4(ww[0], ww[1], ww[2], ww[3]));
+      if (tgt) st4(tgt->p + p4, make_float4(tt[0], tt[1], tt[2], tt[3]));
+      const int mi0 = mirror_index(n, p4);    // a group of 4 never straddles tensors (all offsets are multiples of 4)
+      if (mi0 >= 0) {
+        const int stride = mirror_stride(n, p4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          n.pt[mi0 + i * stride] = ww[i];
+          if (tgt) tgt->pt[mi0 + i * stride] = tt[i];
+        }
       }
     }
   }

@@ -16,7 +16,7 @@
 namespace cg = cooperative_groups;
 
 template <class A>
-__global__ void __launch_bounds__(FRL_NT, 1) frl_persistent_kernel(const typename A::Args a) {
+__global__ void __launch_bounds__(FRL_NT, 1) frl_persistent_kernel(const __grid_constant__ typename A::Args a) {
   extern __shared__ __align__(1024) float frl_smem[];
   Cta c;
   float* user = cta_init(c, (int)blockIdx.x, (int)gridDim.x, frl_smem, A::wbuf_floats(a));
@@ -26,8 +26,10 @@ __global__ void __launch_bounds__(FRL_NT, 1) frl_persistent_kernel(const typenam
     for (int s = 0; s < A::NSTAGES; ++s) {
       A::stage(s, u, c, user, a);
       stage_reset(c);
+      stamp(c, 100 + s);
       fence_proxy_async();
       grid.sync();
+      stamp(c, 200 + s);
     }
   }
 }
@@ -55,7 +57,7 @@ int frl_launch(const typename A::Args& a, cudaStream_t stream) {
 
 // plain (non-cooperative) launch of a single-stage Algo over an arbitrary grid
 template <class A>
-__global__ void __launch_bounds__(FRL_NT, 1) frl_tile_kernel(const typename A::Args a) {
+__global__ void __launch_bounds__(FRL_NT, 1) frl_tile_kernel(const __grid_constant__ typename A::Args a) {
   extern __shared__ __align__(1024) float frl_smem[];
   Cta c;
   float* user = cta_init(c, (int)blockIdx.x, (int)gridDim.x, frl_smem, A::wbuf_floats(a));
