@@ -99,3 +99,63 @@ class Buffer:
 
     def __len__(self):
         return self._size
+
+
+class Buffer_for_PPO:
+    """Device-resident rollout store with the reference interface (``PPO_file/Buffer.py:266-323`` =
+    ``MAPPO_file/Buffer.py:266-323``): ``Buffer_for_PPO(capacity, obs_dim, act_dim, device, trick=None)``,
+    ``add(obs, action, reward, next_obs, done, action_log_probs, adv_done)``, ``all()`` -> 7 fp32 tensors covering
+    the FULL capacity, ``clear()``, ``len()``.
+
+    Vectorised extension: ``add`` of N rows at once stores one time step of N envs; the rollout is then the
+    ``[T, N]`` time-major array the GAE kernel scans per env column (N = 1 reproduces the reference's flat order).
+    """
+
+    def __init__(self, capacity, obs_dim, act_dim, device, trick=None):
+        self.capacity = capacity = int(capacity)
+        self.obs_dim, self.act_dim = int(obs_dim), int(act_dim)
+        self.device = _lib.require_device(device)
+        self.logp_dim = 1 if (trick is not None and trick.get('decaystd')) else self.act_dim
+        c = max(capacity, 1)
+        z = lambda *s: torch.zeros(s, dtype=torch.float32, device=self.device)
+        self.obs, self.actions, self.rewards = z(c, self.obs_dim), z(c, self.act_dim), z(c)
+        self.next_obs, self.dones = z(c, self.obs_dim), z(c)
+        self.action_log_probs, self.adv_dones = z(c, self.logp_dim), z(c)
+        self._index = 0
+        self._size = 0
+        self.n_envs = 1
+
+    def add(self, obs, action, reward, next_obs, done, action_log_probs, adv_done):
+        od, ad = self.obs_dim, self.act_dim
+        o = np.asarray(obs, dtype=np.float32).reshape(-1, od)
+        n = o.shape[0]
+        if self._size == 0:
+            self.n_envs = n
+        packed = np.concatenate([
+            o, np.asarray(action, dtype=np.float32).reshape(n, ad), np.asarray(reward, dtype=np.float32).reshape(n, 1),
+            np.asarray(next_obs, dtype=np.float32).reshape(n, od), np.asarray(done, dtype=np.float32).reshape(n, 1),
+            np.asarray(action_log_probs, dtype=np.float32).reshape(n, self.logp_dim),
+            np.asarray(adv_done, dtype=np.float32).reshape(n, 1)], axis=1)
+        dev = torch.from_numpy(packed).to(self.device)
+        i = self._index
+        if i + n > self.capacity:
+            raise ValueError("Buffer_for_PPO: a vectorised add must not wrap (capacity %d, index %d, n %d)" % (self.capacity, i, n))
+        c0 = 0
+        for dst, w in ((self.obs, od), (self.actions, ad), (self.rewards, 1), (self.next_obs, od), (self.dones, 1),
+                       (self.action_log_probs, self.logp_dim), (self.adv_dones, 1)):
+            dst[i:i + n].copy_(dev[:, c0:c0 + w].reshape(dst[i:i + n].shape))
+            c0 += w
+        self._index = (i + n) % self.capacity
+        self._size = min(self._size + n, self.capacity)
+
+    def __len__(self):
+        return self._size
+
+    def clear(self):
+        self._index = 0
+        self._size = 0
+
+    def all(self):
+        """Views of the device arrays, shaped like the reference's return values (rewards / dones / adv_dones [cap,1])."""
+        return (self.obs, self.actions, self.rewards.reshape(-1, 1), self.next_obs, self.dones.reshape(-1, 1),
+                self.action_log_probs, self.adv_dones.reshape(-1, 1))

@@ -53,13 +53,26 @@ class AcArgs(C.Structure):
 
 
 class InferArgs(C.Structure):
-    _fields_ = [("net", Net), ("obs", C.c_void_p), ("n", C.c_int), ("obs_dim", C.c_int), ("mode", C.c_int),
+    _fields_ = [("net", Net), ("l0", C.c_int), ("nl", C.c_int), ("obs", C.c_void_p), ("n", C.c_int), ("obs_dim", C.c_int), ("mode", C.c_int),
                 ("noise", C.c_void_p), ("seed", C.c_uint64), ("counter", C.c_uint32), ("out", C.c_void_p),
                 ("out_cols", C.c_int)]
 
 
+class PpoArgs(C.Structure):
+    _fields_ = [("net", Net), ("continuous", C.c_int), ("obs", C.c_void_p), ("action", C.c_void_p),
+                ("logp_old", C.c_void_p), ("adv", C.c_void_p), ("v_target", C.c_void_p),
+                ("M", C.c_int), ("obs_dim", C.c_int), ("act_cols", C.c_int), ("logp_cols", C.c_int), ("n_adv", C.c_int),
+                ("indices", C.c_void_p), ("mb_rows", C.c_void_p), ("mb", C.c_int), ("n_updates", C.c_int),
+                ("clip_param", C.c_float), ("entropy_coef", C.c_float), ("max_norm_actor", C.c_float),
+                ("max_norm_critic", C.c_float), ("optimizer", C.c_int), ("lr", C.c_double), ("beta1", C.c_double),
+                ("beta2", C.c_double), ("eps", C.c_double), ("step0", C.c_int64), ("gpart", C.c_void_p),
+                ("sumsq", C.c_void_p), ("segcnt", C.c_void_p), ("stats", C.c_void_p), ("out", C.c_void_p)]
+
+
+OPT_CAUTIOUS_ADAMW, OPT_ADAM = 0, 1
+NSEG = 2 * FRL_MAX_LAYERS + 1
 ACTOR_TANH, ACTOR_SAC = 0, 1
-INFER_ARGMAX, INFER_TANH, INFER_SAC_SAMPLE, INFER_SAC_MEAN, INFER_RAW = 0, 1, 2, 3, 4
+INFER_ARGMAX, INFER_TANH, INFER_SAC_SAMPLE, INFER_SAC_MEAN, INFER_RAW, INFER_PPO_GAUSS, INFER_PPO_CAT = 0, 1, 2, 3, 4, 5, 6
 
 _lib = None
 
@@ -74,8 +87,10 @@ def _declare(lib):
     lib.frl_dqn_learn.argtypes = [C.POINTER(DqnArgs), vp]
     lib.frl_ac_learn.argtypes = [C.POINTER(AcArgs), vp]
     lib.frl_policy_infer.argtypes = [C.POINTER(InferArgs), vp]
+    lib.frl_gae.argtypes = [vp, vp, vp, vp, vp, ci, ci, C.c_double, C.c_double, vp, vp, vp]
+    lib.frl_ppo_update.argtypes = [C.POINTER(PpoArgs), vp]
     for name in ("frl_replay_add_batch", "frl_replay_gather", "frl_sample_uniform", "frl_net_sync_mirror",
-                 "frl_dqn_learn", "frl_ac_learn", "frl_policy_infer", "frl_is_emulation", "frl_device_sm_count",
+                 "frl_dqn_learn", "frl_ac_learn", "frl_policy_infer", "frl_gae", "frl_ppo_update", "frl_is_emulation", "frl_device_sm_count",
                  "frl_abi_version"):
         getattr(lib, name).restype = ci
 

@@ -1,0 +1,428 @@
+// Fused PPO minibatch update + GAE.
+//   PPO.learn minibatch loop      PPO_file/PPO.py:245-283   (clipped surrogate, entropy bonus, value MSE)
+//   Agent.update_ac_              PPO_file/PPO.py:145-152   (two backward()s, clip 0.5 actor / 0.5 critic, ONE optimiser step)
+//   c_adamw.AdamW.step            PPO_file/c_adamw.py:65-122 (cautious mask with PER-TENSOR mean, eps after sqrt)
+//   GAE                           PPO_file/PPO.py:222-233   (float64 reverse scan, zero tail, v_target = adv + V)
+// Actor (layers 0-2 [+ log_std]) and critic (layers 3-5) share ONE parameter block / optimiser state, like the
+// reference's merged `ac_optimizer`.  One persistent launch runs every minibatch of every epoch (n_updates steps).
+#pragma once
+#include "algo_ac.cuh"
+
+#define FRL_NSEG (2 * FRL_MAX_LAYERS + 1)
+#define FRL_HALF_LOG_2PI 0.91893853320467274178f
+
+// tensor (segment) id of parameter index p and that tensor's logical element count
+FRL_DEV int seg_of(const frl_net_t& n, int p, int* numel) {
+  for (int li = 0; li < n.n_layers; ++li) {
+    const frl_layer_t& L = n.L[li];
+    if (p >= L.w_off && p < L.w_off + L.out_pad * L.in_pad) { *numel = L.out * L.in; return 2 * li; }
+    if (p >= L.b_off && p < L.b_off + L.out_pad) { *numel = L.out; return 2 * li + 1; }
+  }
+  *numel = n.x_len;
+  return 2 * FRL_MAX_LAYERS;
+}
+
+struct PpoAlgo {
+  typedef frl_ppo_args_t Args;
+  static const int NSTAGES = 4;
+  FRL_SHD int wbuf_floats(const Args& a) { return (AcAlgo::max_layer_floats(a.net) + 31) & ~31; }
+  FRL_SHD int user_floats(const Args& a) {
+    const int ldh = a.net.L[0].out_pad, ip = a.net.L[0].in_pad, ap = a.net.L[2].out_pad;
+    return FRL_R * (ip + 6 * ldh + 4 * ap + 8 + 4 * a.n_adv + 8) + 2 * FRL_NT + 64 + FRL_NSEG + 3;
+  }
+  FRL_SHD int grid(const Args& a, int max_ctas) {
+    int tiles = (a.mb + FRL_R - 1) / FRL_R;
+    return tiles < max_ctas ? tiles : max_ctas;
+  }
+  FRL_SHD int n_updates(const Args& a) { return a.n_updates; }
+
+  FRL_SDEV bool is_critic(const frl_net_t& n, int p) { return p >= n.L[3].w_off && p < n.x_off; }
+
+  FRL_SDEV void stage(int s, int u, Cta& c, float* user, const Args& a) {
+    const frl_net_t& N = a.net;
+    const int ldh = N.L[0].out_pad, ip = N.L[0].in_pad, ap = N.L[2].out_pad, nout = N.L[2].out;
+    const int rows = a.mb_rows[u];
+    const int ntile = (rows + FRL_R - 1) / FRL_R;
+    const int ncontrib = ntile < c.ncta ? ntile : c.ncta;
+    SmemBump sb; sb.p = user;
+    float* X = sb.take(FRL_R * ip);
+    float* A1 = sb.take(FRL_R * ldh);
+    float* A2 = sb.take(FRL_R * ldh);
+    float* H1 = sb.take(FRL_R * ldh);
+    float* H2 = sb.take(FRL_R * ldh);
+    float* D1 = sb.take(FRL_R * ldh);
+    float* D2 = sb.take(FRL_R * ldh);
+    float* OA = sb.take(FRL_R * ap);
+    float* dOA = sb.take(FRL_R * ap);
+    float* ACT = sb.take(FRL_R * ap);
+    float* LPO = sb.take(FRL_R * ap);
+    float* V = sb.take(FRL_R * 4);
+    float* dV = sb.take(FRL_R * 4);
+    float* ADV = sb.take(FRL_R * a.n_adv);
+    float* VT = sb.take(FRL_R * a.n_adv);
+    float* red0 = sb.take(FRL_NT);
+    float* red1 = sb.take(FRL_NT);
+    int* segc = (int*)sb.take(FRL_NSEG + 3);
+    float* gp = a.gpart + (size_t)c.cta * N.n_p;
+
+    if (s == 0) {
+      if (c.cta >= ntile) return;
+      float la = 0.f, lc = 0.f, le = 0.f;
+      bool first = true;
+      const float inv_rows = 1.0f / (float)rows, inv_rn = 1.0f / (float)(rows * a.n_adv);
+      for (int tile = c.cta; tile < ntile; tile += c.ncta) {
+        const int row0 = tile * FRL_R;
+        const int nvalid = (rows - row0) < FRL_R ? (rows - row0) : FRL_R;
+        const int64_t* idx = a.indices + (size_t)u * a.mb + row0;
+        stage_prefetch(c, layer_fwd_src(N, 0), layer_fwd_bytes(N.L[0]));
+        FRL_PAR(t) {
+          for (int e = t; e < FRL_R * ip; e += FRL_NT) {
+            const int r = e / ip, j = e % ip;
+            X[e] = (r < nvalid && j < a.obs_dim) ? a.obs[(size_t)idx[r] * a.obs_dim + j] : 0.f;
+          }
+          for (int e = t; e < FRL_R * ap; e += FRL_NT) {
+            const int r = e / ap, j = e % ap;
+            ACT[e] = (r < nvalid && j < a.act_cols) ? a.action[(size_t)idx[r] * a.act_cols + j] : 0.f;
+            LPO[e] = (r < nvalid && j < a.logp_cols) ? a.logp_old[(size_t)idx[r] * a.logp_cols + j] : 0.f;
+          }
+          for (int e = t; e < FRL_R * a.n_adv; e += FRL_NT) {
+            const int r = e / a.n_adv, j = e % a.n_adv;
+            ADV[e] = (r < nvalid) ? a.adv[(size_t)idx[r] * a.n_adv + j] : 0.f;
+            VT[e] = (r < nvalid) ? a.v_target[(size_t)idx[r] * a.n_adv + j] : 0.f;
+          }
+        }
+        FRL_SYNC();
+        mlp_fwd<FRL_R>(c, N, 0, 3, X, ip, A1, A2, ldh, OA, ap, FRL_ACT_NONE, fwd_hint(N, 3));
+        mlp_fwd<FRL_R>(c, N, 3, 3, X, ip, H1, H2, ldh, V, 4, FRL_ACT_NONE, bwd_hint(N, 2));
+        // policy head: log-prob, entropy, ratio, clipped surrogate and its gradient w.r.t. the actor output
+        FRL_PAR(t) {
+          float sa = 0.f, se = 0.f;
+          if (t < FRL_R) {
+            const int r = t;
+            for (int j = 0; j < ap; ++j) dOA[r * ap + j] = 0.f;
+            if (r < nvalid) {
+              float lp_now = 0.f, lp_old = 0.f, ent = 0.f;
+              if (a.continuous) {
+                for (int j = 0; j < nout; ++j) {
+                  const float mean = tanhf(OA[r * ap + j]);
+                  const float ls = fminf(fmaxf(N.p[N.x_off + j], -20.f), 2.f);
+                  const float sd = expf(ls);
+                  const float diff = ACT[r * ap + j] - mean;
+                  lp_now += -(diff * diff) / (2.f * (sd * sd)) - logf(sd) - FRL_HALF_LOG_2PI;
+                  ent += 0.5f + FRL_HALF_LOG_2PI + logf(sd);
+                }
+                for (int j = 0; j < a.logp_cols; ++j) lp_old += LPO[r * ap + j];
+              } else {
+                float mx = OA[r * ap];
+                for (int j = 1; j < nout; ++j) mx = fmaxf(mx, OA[r * ap + j]);
+                float se_ = 0.f;
+                for (int j = 0; j < nout; ++j) se_ += expf(OA[r * ap + j] - mx);
+                const float lse = mx + logf(se_);
+                const int act = (int)ACT[r * ap];
+                lp_now = OA[r * ap + act] - lse;
+                for (int j = 0; j < nout; ++j) { const float lg = OA[r * ap + j] - lse; ent -= expf(lg) * lg; }
+                lp_old = LPO[r * ap];
+              }
+              const float ratio = expf(lp_now - lp_old);
+              // -min(r*A, clamp(r)*A) averaged over rows and advantage columns; gradient through the active branch
+              float dlp = 0.f, surr = 0.f;
+              const float lo = 1.f - a.clip_param, hi = 1.f + a.clip_param;
+              const float rc = fminf(fmaxf(ratio, lo), hi);
+              for (int k = 0; k < a.n_adv; ++k) {
+                const float A = ADV[r * a.n_adv + k];
+                const float s1 = ratio * A, s2 = rc * A;
+                surr += fminf(s1, s2);
+                const bool inside = ratio >= lo && ratio <= hi;
+                if (inside || s1 < s2) dlp += -A * ratio * inv_rn;      // ties (inside the clip range) pass the full gradient
+              }
+              sa = -surr * inv_rn;
+              se = ent;
+              // chain to the actor output
+              if (a.continuous) {
+                for (int j = 0; j < nout; ++j) {
+                  const float mean = tanhf(OA[r * ap + j]);
+                  const float ls = fminf(fmaxf(N.p[N.x_off + j], -20.f), 2.f);
+                  const float sd = expf(ls);
+                  const float diff = ACT[r * ap + j] - mean;
+                  dOA[r * ap + j] = dlp * (diff / (sd * sd)) * (1.f - mean * mean);
+                  LPO[r * ap + j] = dlp * ((diff * diff) / (sd * sd) - 1.f);      // d/dlog_std via log-prob (reuse LPO)
+                }
+              } else {
+                float mx = OA[r * ap];
+                for (int j = 1; j < nout; ++j) mx = fmaxf(mx, OA[r * ap + j]);
+                float se_ = 0.f;
+                for (int j = 0; j < nout; ++j) se_ += expf(OA[r * ap + j] - mx);
+                const float lse = mx + logf(se_);
+                const int act = (int)ACT[r * ap];
+                for (int j = 0; j < nout; ++j) {
+                  const float lg = OA[r * ap + j] - lse, pj = expf(lg);
+                  // d logp_a/dz_j = [j==a] - p_j ;  dH/dz_j = -p_j (lg + H)
+                  float g = dlp * ((j == act ? 1.f : 0.f) - pj);
+                  g += -a.entropy_coef * inv_rows * (-pj * (lg + ent));
+                  dOA[r * ap + j] = g;
+                }
+              }
+            } else if (a.continuous) {
+              for (int j = 0; j < ap; ++j) LPO[r * ap + j] = 0.f;
+            }
+          }
+          red0[t] = sa; red1[t] = se;
+        }
+        FRL_SYNC();
+        la += block_sum(red0);
+        le += block_sum(red1);
+        // value loss  mse(v_target, V)  (mean over rows x advantage columns)
+        FRL_PAR(t) {
+          float l = 0.f;
+          if (t < FRL_R) {
+            for (int j = 0; j < 4; ++j) dV[t * 4 + j] = 0.f;
+            if (t < nvalid) {
+              float g = 0.f;
+              for (int k = 0; k < a.n_adv; ++k) {
+                const float d = V[t * 4] - VT[t * a.n_adv + k];
+                g += 2.f * d * inv_rn;
+                l += d * d;
+              }
+              dV[t * 4] = g;
+            }
+          }
+          red0[t] = l;
+        }
+        FRL_SYNC();
+        lc += block_sum(red0);
+        if (a.continuous) {
+          // log_std gradient: log-prob path (stored in LPO) + entropy bonus  -c * mean_rows(sum_j 1)
+          FRL_PAR(t) {
+            if (t < ap) {
+              float g = 0.f;
+              if (t < nout) {
+                const float lsr = N.p[N.x_off + t];
+                if (lsr >= -20.f && lsr <= 2.f) {
+                  for (int r = 0; r < nvalid; ++r) g += LPO[r * ap + t] - a.entropy_coef * inv_rows;
+                }
+              }
+              gp[N.x_off + t] = first ? g : gp[N.x_off + t] + g;
+            }
+          }
+          FRL_SYNC();
+        }
+        mlp_bwd<FRL_R>(c, N, 0, 3, X, ip, A1, A2, ldh, dOA, ap, D1, D2, nullptr, 0, gp, !first, bwd_hint(N, 5));
+        mlp_bwd<FRL_R>(c, N, 3, 3, X, ip, H1, H2, ldh, dV, 4, D1, D2, nullptr, 0, gp, !first, no_hint());
+        first = false;
+      }
+      FRL_PAR(t) {
+        if (t == 0) { a.stats[c.cta * 8 + 0] = la; a.stats[c.cta * 8 + 1] = lc; a.stats[c.cta * 8 + 2] = le; }
+      }
+      FRL_SYNC();
+    } else if (s == 1) {
+      // fixed-order cross-CTA reduction with separate sum-of-squares for the actor and critic tensors
+      FRL_PAR(t) {
+        float la = 0.f, lc = 0.f;
+        for (int p = (c.cta * FRL_NT + t) * 4; p < N.n_p; p += c.ncta * FRL_NT * 4) {
+          float4 sgm = ld4(a.gpart + p);
+          for (int cc = 1; cc < ncontrib; ++cc) sgm = f4add(sgm, ld4(a.gpart + (size_t)cc * N.n_p + p));
+          st4(N.g + p, sgm);
+          const float q = sgm.x * sgm.x + sgm.y * sgm.y + sgm.z * sgm.z + sgm.w * sgm.w;
+          if (is_critic(N, p)) lc += q; else la += q;
+        }
+        red0[t] = la; red1[t] = lc;
+      }
+      FRL_SYNC();
+      const float ta = block_sum(red0), tc = block_sum(red1);
+      FRL_PAR(t) { if (t == 0) { a.sumsq[c.cta * 2] = ta; a.sumsq[c.cta * 2 + 1] = tc; } }
+      FRL_SYNC();
+    } else {
+      // optimiser scalars (one thread, broadcast through smem)
+      float* sh = c.red;
+      FRL_PAR(t) {
+        if (t == 0) {
+          float ta = 0.f, tc = 0.f;
+          for (int i = 0; i < c.ncta; ++i) { ta += a.sumsq[i * 2]; tc += a.sumsq[i * 2 + 1]; }
+          float ca = 1.f, cc = 1.f;
+          if (a.max_norm_actor > 0.f) ca = fminf(a.max_norm_actor / (sqrtf(ta) + 1e-6f), 1.f);
+          if (a.max_norm_critic > 0.f) cc = fminf(a.max_norm_critic / (sqrtf(tc) + 1e-6f), 1.f);
+          sh[0] = ca; sh[1] = cc;
+          const double step = (double)(a.step0 + u + 1);
+          const double bc1 = 1.0 - pow(a.beta1, step), bc2 = 1.0 - pow(a.beta2, step);
+          sh[2] = (float)(a.lr * sqrt(bc2) / bc1);         // c_adamw step_size
+          sh[3] = (float)(-(a.lr / bc1));                   // torch Adam: -lr/bc1
+          sh[4] = (float)sqrt(bc2);
+          if (s == 2 && c.cta == 0) {
+            float l0 = 0.f, l1 = 0.f, l2 = 0.f;
+            for (int i = 0; i < ncontrib; ++i) { l0 += a.stats[i * 8]; l1 += a.stats[i * 8 + 1]; l2 += a.stats[i * 8 + 2]; }
+            const float ent_mean = l2 / (float)rows;
+            a.out[u * 8 + 0] = l0 - a.entropy_coef * ent_mean;
+            a.out[u * 8 + 1] = l1 / (float)(rows * a.n_adv);
+            a.out[u * 8 + 2] = ent_mean;
+            a.out[u * 8 + 3] = sqrtf(ta);
+            a.out[u * 8 + 4] = sqrtf(tc);
+          }
+        }
+        if (t < FRL_NSEG) segc[t] = 0;
+      }
+      FRL_SYNC();
+      const float coef_a = sh[0], coef_c = sh[1], step_size = sh[2], adam_step = sh[3], bc2s = sh[4];
+      const float b1 = (float)a.beta1, b2 = (float)a.beta2, omb1 = (float)(1.0 - a.beta1), omb2 = (float)(1.0 - a.beta2);
+      const float eps = (float)a.eps;
+      if (a.optimizer == FRL_OPT_ADAM) {
+        if (s == 3) return;
+        FRL_PAR(t) {
+          for (int p = c.cta * FRL_NT + t; p < N.n_p; p += c.ncta * FRL_NT) {
+            const float g = N.g[p] * (is_critic(N, p) ? coef_c : coef_a);
+            float m = N.m[p], v = N.v[p], w = N.p[p];
+            m = fmaf(omb1, g - m, m);
+            v = fadd(fmul(v, b2), fmul(fmul(omb2, g), g));
+            const float denom = fadd(fdiv(fsqrt(v), bc2s), eps);
+            w = fadd(w, fdiv(fmul(adam_step, m), denom));
+            N.m[p] = m; N.v[p] = v; N.p[p] = w;
+            const int mi = mirror_index(N, p);
+            if (mi >= 0) N.pt[mi] = w;
+          }
+        }
+        FRL_SYNC();
+        return;
+      }
+      if (s == 2) {
+        // cautious AdamW, pass 1: moments + per-tensor count of (exp_avg * grad > 0)
+        FRL_PAR(t) {
+          for (int p = c.cta * FRL_NT + t; p < N.n_p; p += c.ncta * FRL_NT) {
+            const float g = N.g[p] * (is_critic(N, p) ? coef_c : coef_a);
+            float m = N.m[p], v = N.v[p];
+            m = fmaf(g, omb1, fmul(m, b1));                               // mul_(b1).add_(g, alpha=1-b1)
+            v = fadd(fmul(v, b2), fmul(fmul(omb2, g), g));                // mul_(b2).addcmul_(g, g, 1-b2)
+            N.m[p] = m; N.v[p] = v;
+            if (m * g > 0.f) {
+              int numel;
+              const int sg = seg_of(N, p, &numel);
+#ifndef FRL_EMUL
+              atomicAdd(&segc[sg], 1);
+#else
+              segc[sg] += 1;
+#endif
+            }
+          }
+        }
+        FRL_SYNC();
+        FRL_PAR(t) { if (t < FRL_NSEG) a.segcnt[c.cta * FRL_NSEG + t] = (float)segc[t]; }
+        FRL_SYNC();
+      } else {
+        // pass 2: p += -step * (m * mask / max(mean(mask), 1e-3)) / (sqrt(v) + eps)
+        float* segmean = red0;
+        FRL_PAR(t) {
+          if (t < FRL_NSEG) {
+            float cnt = 0.f;
+            for (int i = 0; i < c.ncta; ++i) cnt += a.segcnt[i * FRL_NSEG + t];
+            segmean[t] = cnt;
+          }
+        }
+        FRL_SYNC();
+        FRL_PAR(t) {
+          for (int p = c.cta * FRL_NT + t; p < N.n_p; p += c.ncta * FRL_NT) {
+            const float g = N.g[p] * (is_critic(N, p) ? coef_c : coef_a);
+            const float m = N.m[p], v = N.v[p];
+            float w = N.p[p];
+            int numel;
+            const int sg = seg_of(N, p, &numel);
+            if (numel > 0) {
+              const float mean = fmaxf(fdiv(segmean[sg], (float)numel), 1e-3f);
+              const float mask = (m * g > 0.f) ? fdiv(1.f, mean) : 0.f;
+              const float denom = fadd(fsqrt(v), eps);
+              const float ng = fdiv(fmul(m, mask), denom);
+              w = fmaf(ng, -step_size, w);
+            }
+            N.p[p] = w;
+            const int mi = mirror_index(N, p);
+            if (mi >= 0) N.pt[mi] = w;
+          }
+        }
+        FRL_SYNC();
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// GAE: one warp per env column, lanes own contiguous time chunks, float64 composition of the affine maps
+// A_t = b_t + a_t * A_{t+1}  via warp shuffles (segmented by construction: a_t = 0 where adv_done).
+// ------------------------------------------------------------------------------------------------
+struct GaeArgs {
+  const float *reward, *done, *adv_done, *vs, *vs_next;
+  int T, N;
+  double gamma, lmbda;
+  float *adv, *v_target;
+};
+
+struct GaeAlgo {
+  typedef GaeArgs Args;
+  static const int NSTAGES = 1;
+  FRL_SHD int wbuf_floats(const Args&) { return 32; }
+  FRL_SHD int user_floats(const Args&) { return 6 * (FRL_NT) + 64; }
+  FRL_SHD int grid(const Args& a, int) { const int wpb = FRL_NT / 32; return (a.N + wpb - 1) / wpb; }
+  FRL_SHD int n_updates(const Args&) { return 1; }
+  FRL_SDEV void stage(int, int, Cta& c, float* user, const Args& a) {
+    const int wpb = FRL_NT / 32;
+    double* sa = (double*)user;            // [FRL_NT] per-lane chunk product
+    double* sbv = sa + FRL_NT;             // [FRL_NT] per-lane chunk offset
+    const int chunk = (a.T + 31) / 32;
+    const float g32 = (float)a.gamma;
+    // pass 1: every lane folds its chunk [t0,t1) into (P, S):  A_{t0} = S + P * A_{t1}
+    FRL_PAR(t) {
+      const int col = c.cta * wpb + (t >> 5), lane = t & 31;
+      double P = 1.0, S = 0.0;
+      if (col < a.N) {
+        const int t0 = lane * chunk, t1 = (t0 + chunk < a.T) ? t0 + chunk : a.T;
+        for (int k = t1 - 1; k >= t0; --k) {
+          const size_t i = (size_t)k * a.N + col;
+          const float td = fadd(fadd(a.reward[i], fmul(fmul(g32, fadd(1.f, -a.done[i])), a.vs_next[i])), -a.vs[i]);
+          const double ak = a.gamma * a.lmbda * (1.0 - (double)a.adv_done[i]);
+          S = (double)td + ak * S;          // A_k = td_k + a_k * A_{k+1}
+          P = ak * P;
+        }
+      }
+      sa[t] = P; sbv[t] = S;
+    }
+    FRL_SYNC();
+    // pass 2: suffix composition of the per-lane affine maps across the 32 lanes of a column.
+    // GPU: Hillis-Steele suffix scan with warp shuffles ((P,S) o (P',S') = (P*P', S + P*S')), then the incoming value
+    // of lane l is the inclusive result of lane l+1.  (The emulation build walks the lanes sequentially.)
+    double* tailv = (double*)user + 2 * FRL_NT;
+#ifndef FRL_EMUL
+    {
+      const int t = (int)threadIdx.x, lane = t & 31;
+      double P = sa[t], S = sbv[t];
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const double P2 = __shfl_down_sync(0xffffffffu, P, off), S2 = __shfl_down_sync(0xffffffffu, S, off);
+        if (lane + off < 32) { S = S + P * S2; P = P * P2; }
+      }
+      const double nxt = __shfl_down_sync(0xffffffffu, S, 1);
+      tailv[t] = (lane == 31) ? 0.0 : nxt;
+    }
+#else
+    FRL_PAR(t) {
+      const int lane = t & 31, w0 = t & ~31;
+      double tail = 0.0;                    // A at the start of the chunk after this lane's
+      for (int l = 31; l > lane; --l) tail = sbv[w0 + l] + sa[w0 + l] * tail;
+      tailv[t] = tail;
+    }
+#endif
+    FRL_SYNC();
+    // pass 3: re-walk the chunk with the true incoming value and write adv / v_target
+    FRL_PAR(t) {
+      const int col = c.cta * wpb + (t >> 5), lane = t & 31;
+      if (col < a.N) {
+        const int t0 = lane * chunk, t1 = (t0 + chunk < a.T) ? t0 + chunk : a.T;
+        double A = tailv[t];
+        for (int k = t1 - 1; k >= t0; --k) {
+          const size_t i = (size_t)k * a.N + col;
+          const float td = fadd(fadd(a.reward[i], fmul(fmul(g32, fadd(1.f, -a.done[i])), a.vs_next[i])), -a.vs[i]);
+          A = (double)td + a.gamma * a.lmbda * A * (1.0 - (double)a.adv_done[i]);
+          const float af = (float)A;
+          a.adv[i] = af;
+          a.v_target[i] = fadd(af, a.vs[i]);
+        }
+      }
+    }
+    FRL_SYNC();
+  }
+};

@@ -6,7 +6,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 
-#include "algo_ac.cuh"
+#include "algo_ppo.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // error plumbing
@@ -220,15 +220,17 @@ extern "C" int frl_net_sync_mirror(const frl_net_t* net, void* stream) {
 struct InferAlgo {
   typedef frl_infer_args_t Args;
   static const int NSTAGES = 1;
+  FRL_SHD int nl_of(const Args& a) { return a.nl > 0 ? a.nl : a.net.n_layers; }
   FRL_SHD int wbuf_floats(const Args& a) { return (AcAlgo::max_layer_floats(a.net) + 31) & ~31; }
   FRL_SHD int user_floats(const Args& a) {
-    return FRL_R * (a.net.L[0].in_pad + 2 * a.net.L[0].out_pad + a.net.L[a.net.n_layers - 1].out_pad) + 64;
+    return FRL_R * (a.net.L[a.l0].in_pad + 2 * a.net.L[a.l0].out_pad + a.net.L[a.l0 + nl_of(a) - 1].out_pad) + 64;
   }
   FRL_SHD int grid(const Args& a, int) { return (a.n + FRL_R - 1) / FRL_R; }
   FRL_SHD int n_updates(const Args&) { return 1; }
   FRL_SDEV void stage(int, int, Cta& c, float* user, const Args& a) {
     const frl_net_t& n = a.net;
-    const int nl = n.n_layers, in_pad = n.L[0].in_pad, ldh = n.L[0].out_pad, op = n.L[nl - 1].out_pad, nout = n.L[nl - 1].out;
+    const int nl = nl_of(a), l0 = a.l0;
+    const int in_pad = n.L[l0].in_pad, ldh = n.L[l0].out_pad, op = n.L[l0 + nl - 1].out_pad, nout = n.L[l0 + nl - 1].out;
     SmemBump sb; sb.p = user;
     float* X = sb.take(FRL_R * in_pad);
     float* H1 = sb.take(FRL_R * ldh);
@@ -236,7 +238,7 @@ struct InferAlgo {
     float* O = sb.take(FRL_R * op);
     const int row0 = c.cta * FRL_R;
     const int nvalid = (a.n - row0) < FRL_R ? (a.n - row0) : FRL_R;
-    stage_prefetch(c, layer_fwd_src(n, 0), layer_fwd_bytes(n.L[0]));
+    stage_prefetch(c, layer_fwd_src(n, l0), layer_fwd_bytes(n.L[l0]));
     FRL_PAR(t) {
       for (int e = t; e < FRL_R * in_pad; e += FRL_NT) {
         const int r = e / in_pad, j = e % in_pad;
@@ -244,7 +246,7 @@ struct InferAlgo {
       }
     }
     FRL_SYNC();
-    mlp_fwd<FRL_R>(c, n, 0, nl, X, in_pad, H1, H2, ldh, O, op, FRL_ACT_NONE, no_hint());
+    mlp_fwd<FRL_R>(c, n, l0, nl, X, in_pad, H1, H2, ldh, O, op, FRL_ACT_NONE, no_hint());
     FRL_PAR(t) {
       if (a.mode == FRL_INFER_ARGMAX) {
         if (t < nvalid) {
@@ -252,16 +254,46 @@ struct InferAlgo {
           for (int j = 1; j < nout; ++j) if (O[t * op + j] > bv) { bv = O[t * op + j]; best = j; }   // first max, like torch.argmax
           a.out[(size_t)(row0 + t) * a.out_cols] = (float)best;
         }
+      } else if (a.mode == FRL_INFER_PPO_CAT) {
+        // Categorical(logits).sample() == argmax(softmax(logits) / q), q ~ Exp(1)  (torch.multinomial, 1 draw)
+        if (t < nvalid) {
+          float mx = O[t * op];
+          for (int j = 1; j < nout; ++j) mx = fmaxf(mx, O[t * op + j]);
+          float se = 0.f;
+          for (int j = 0; j < nout; ++j) se += expf(O[t * op + j] - mx);
+          const float lse = mx + logf(se);
+          int best = 0; float bv = -1.f;
+          for (int j = 0; j < nout; ++j) {
+            const float pj = expf(O[t * op + j] - lse);
+            float q = a.noise ? a.noise[(size_t)(row0 + t) * nout + j] : 0.f;
+            if (!a.noise) {
+              uint32_t o4[4];
+              frl_philox((uint32_t)a.seed, (uint32_t)(a.seed >> 32), (uint32_t)((row0 + t) * nout + j), a.counter, 4u, 0x5eed5eedu, o4);
+              q = -logf(frl_u01(o4[0]));
+            }
+            const float v = pj / q;
+            if (v > bv) { bv = v; best = j; }
+          }
+          a.out[(size_t)(row0 + t) * a.out_cols] = (float)best;
+          a.out[(size_t)(row0 + t) * a.out_cols + 1] = O[t * op + best] - lse;
+        }
       } else if (t < FRL_R * nout) {
         const int r = t / nout, j = t % nout;
         if (r < nvalid) {
           float v = O[r * op + j];
           if (a.mode == FRL_INFER_TANH || a.mode == FRL_INFER_SAC_MEAN) v = tanhf(v);
-          else if (a.mode == FRL_INFER_SAC_SAMPLE) {
+          else if (a.mode == FRL_INFER_SAC_SAMPLE || a.mode == FRL_INFER_PPO_GAUSS) {
             const float ls = fminf(fmaxf(n.p[n.x_off + j], -20.f), 2.f);
+            const float sd = expf(ls);
             const float e = a.noise ? a.noise[(size_t)(row0 + r) * nout + j]
                                     : frl_randn(a.seed, 3u, a.counter, (uint32_t)((row0 + r) * nout + j));
-            v = tanhf(fadd(v, fmul(e, expf(ls))));
+            if (a.mode == FRL_INFER_SAC_SAMPLE) v = tanhf(fadd(v, fmul(e, sd)));
+            else {
+              const float mean = tanhf(v);
+              v = fadd(fmul(e, sd), mean);                                   // Normal(mean, std).sample()
+              const float diff = v - mean;
+              a.out[(size_t)(row0 + r) * a.out_cols + nout + j] = -(diff * diff) / (2.f * (sd * sd)) - logf(sd) - FRL_HALF_LOG_2PI;
+            }
           }
           a.out[(size_t)(row0 + r) * a.out_cols + j] = v;
         }
@@ -272,7 +304,10 @@ struct InferAlgo {
 };
 
 extern "C" int frl_policy_infer(const frl_infer_args_t* a, void* stream) {
-  if (!a || !a->obs || !a->out || a->n <= 0) { frl_set_error("frl_policy_infer: bad arguments"); return -1; }
+  if (!a || !a->obs || !a->out || a->n <= 0 || a->l0 < 0 || a->l0 + (a->nl > 0 ? a->nl : a->net.n_layers) > a->net.n_layers) {
+    frl_set_error("frl_policy_infer: bad arguments");
+    return -1;
+  }
   return frl_launch_tiles<InferAlgo>(*a, (cudaStream_t)stream);
 }
 
@@ -314,4 +349,28 @@ extern "C" int frl_ac_learn(const frl_ac_args_t* a, void* stream) {
     return -1;
   }
   return frl_launch<AcAlgo>(*a, (cudaStream_t)stream);
+}
+
+extern "C" int frl_gae(const float* reward, const float* done, const float* adv_done, const float* vs, const float* vs_next, int T,
+                       int N, double gamma, double lmbda, float* adv_out, float* v_target_out, void* stream) {
+  if (!reward || !done || !adv_done || !vs || !vs_next || !adv_out || !v_target_out || T <= 0 || N <= 0) {
+    frl_set_error("frl_gae: bad arguments");
+    return -1;
+  }
+  GaeArgs a = {reward, done, adv_done, vs, vs_next, T, N, gamma, lmbda, adv_out, v_target_out};
+  return frl_launch_tiles<GaeAlgo>(a, (cudaStream_t)stream);
+}
+
+extern "C" int frl_ppo_update(const frl_ppo_args_t* a, void* stream) {
+  if (!a || a->mb <= 0 || a->n_updates <= 0 || !a->indices || !a->mb_rows || !a->gpart || !a->sumsq || !a->segcnt || !a->stats ||
+      !a->out || a->n_adv < 1) {
+    frl_set_error("frl_ppo_update: bad arguments");
+    return -1;
+  }
+  if (check_net(a->net, true, "frl_ppo_update(net)")) return -1;
+  if (a->net.n_layers != 6 || (a->continuous && a->net.x_len <= 0)) {
+    frl_set_error("frl_ppo_update: net must hold actor (layers 0-2) + critic (layers 3-5)");
+    return -1;
+  }
+  return frl_launch<PpoAlgo>(*a, (cudaStream_t)stream);
 }

@@ -17,6 +17,9 @@
  *                                                            DDPG_file/DDPG.py:203-233 (+ Agent.update_*, Alpha)
  *   frl_policy_infer          select_action / evaluate_action      DQN.py:70-88, SAC.py:192-204, TD3.py:163-174, DDPG.py:166-185
  *   frl_net_sync_mirror       (state_dict load -> refresh transposed weight mirrors; no reference counterpart)
+ *   frl_gae                   PPO.learn GAE loop             PPO_file/PPO.py:222-233 (MAPPO_file/MAPPO.py:362-383)
+ *   frl_ppo_update            PPO.learn minibatch loop + Agent.update_ac_ + c_adamw.AdamW.step
+ *                                                            PPO_file/PPO.py:245-283,145-152; PPO_file/c_adamw.py:65-122
  */
 #ifndef FREERL_B200_H
 #define FREERL_B200_H
@@ -104,10 +107,13 @@ typedef struct {
   float* out;               /* dev [n_updates][8]: critic_loss, actor_loss, alpha, alpha_loss, critic_gnorm, actor_gnorm, mean_entropy, 0 */
 } frl_ac_args_t;
 
-enum { FRL_INFER_ARGMAX = 0, FRL_INFER_TANH = 1, FRL_INFER_SAC_SAMPLE = 2, FRL_INFER_SAC_MEAN = 3, FRL_INFER_RAW = 4 };
+enum { FRL_INFER_ARGMAX = 0, FRL_INFER_TANH = 1, FRL_INFER_SAC_SAMPLE = 2, FRL_INFER_SAC_MEAN = 3, FRL_INFER_RAW = 4,
+       FRL_INFER_PPO_GAUSS = 5,   /* out = [action(act) | log_prob per dim(act)], noise = N(0,1) [n][act] */
+       FRL_INFER_PPO_CAT = 6 };   /* out = [action index | log_prob], noise = Exp(1) [n][n_actions] (torch.multinomial trick) */
 
 typedef struct {
   frl_net_t net;
+  int l0, nl;               /* layers [l0, l0+nl) of `net` form the MLP to evaluate (nl = 0: all layers) */
   const float* obs;         /* dev [n][obs_dim] */
   int n, obs_dim;
   int mode;                 /* FRL_INFER_* */
@@ -117,6 +123,33 @@ typedef struct {
   float* out;               /* dev [n][out_cols]: actions (ARGMAX: 1 column holding the index as float; RAW: net output) */
   int out_cols;
 } frl_infer_args_t;
+
+/* On-policy (PPO.py) minibatch update.  `net` holds actor (layers 0-2, + log_std extra when continuous) and critic
+ * (layers 3-5) in ONE parameter block with ONE optimiser, like the reference's merged `ac_optimizer`. */
+enum { FRL_OPT_CAUTIOUS_ADAMW = 0, FRL_OPT_ADAM = 1 };
+typedef struct {
+  frl_net_t net;
+  int continuous;           /* 1: Normal(tanh(mean), exp(clamp(log_std))), 0: Categorical(logits) */
+  const float* obs;         /* dev [M][obs_dim] rollout arrays (Buffer_for_PPO.all()) */
+  const float* action;      /* dev [M][act_cols]  (discrete: 1 column holding the index) */
+  const float* logp_old;    /* dev [M][logp_cols] */
+  const float* adv;         /* dev [M][n_adv] */
+  const float* v_target;    /* dev [M][n_adv] */
+  int M, obs_dim, act_cols, logp_cols, n_adv;
+  const int64_t* indices;   /* dev [n_updates][mb]: row indices of every minibatch (np.random.permutation slices) */
+  const int* mb_rows;       /* dev [n_updates]: valid rows of each minibatch (<= mb) */
+  int mb, n_updates;
+  float clip_param, entropy_coef;
+  float max_norm_actor, max_norm_critic;   /* <=0: no clipping */
+  int optimizer;            /* FRL_OPT_* */
+  double lr, beta1, beta2, eps;
+  int64_t step0;
+  float* gpart;             /* dev scratch [sm_count][net.n_p] */
+  float* sumsq;             /* dev scratch [sm_count][2] */
+  float* segcnt;            /* dev scratch [sm_count][2*FRL_MAX_LAYERS+1] cautious-mask counts per tensor */
+  float* stats;             /* dev scratch [sm_count][8] */
+  float* out;               /* dev [n_updates][8]: actor_loss, critic_loss, entropy, actor_gnorm, critic_gnorm */
+} frl_ppo_args_t;
 
 const char* frl_last_error(void);
 int frl_is_emulation(void);          /* 0 for the CUDA library (the only one the product path accepts) */
@@ -133,6 +166,11 @@ int frl_net_sync_mirror(const frl_net_t* net, void* stream);
 int frl_dqn_learn(const frl_dqn_args_t* args, void* stream);
 int frl_ac_learn(const frl_ac_args_t* args, void* stream);
 int frl_policy_infer(const frl_infer_args_t* args, void* stream);
+/* GAE over a [T][N] rollout (N env columns): td = r + gamma(1-done)v' - v (fp32); A_t = td_t + gamma*lmbda*(1-adv_done_t)A_{t+1}
+ * accumulated in float64 per column from a zero tail; adv (fp32) and v_target = adv + v. */
+int frl_gae(const float* reward, const float* done, const float* adv_done, const float* vs, const float* vs_next, int T, int N,
+            double gamma, double lmbda, float* adv_out, float* v_target_out, void* stream);
+int frl_ppo_update(const frl_ppo_args_t* args, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,54 @@
+"""freerl_b200.PPO (fused GAE + minibatch kernels) vs the oracle and the reference-generated goldens."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import algos
+from parity_util import assert_module_close, load_into, net_from_golden
+
+
+def _ppo(golden, device, name, is_continue):
+    from freerl_b200.PPO import PPO
+    g = golden(name)
+    act_dim = 2 if is_continue else 4
+    pol = PPO([8, act_dim], is_continue, 1e-3, 1e-3, 256, device)
+    load_into(pol.agent.actor, net_from_golden(g, "init/actor/"))
+    load_into(pol.agent.critic, net_from_golden(g, "init/critic/"))
+    orc = algos.PPOOracle(net_from_golden(g, "init/actor/"), net_from_golden(g, "init/critic/"), 1e-3, is_continue)
+    data = tuple(torch.from_numpy(g["data/" + k]) for k in ("obs", "act", "rew", "nobs", "done", "logp", "adv_done"))
+    d = [x.numpy() for x in data]
+    for t in range(256):
+        pol.add(d[0][t], d[1][t], float(d[2][t, 0]), d[3][t], bool(d[4][t, 0]), d[5][t], bool(d[6][t, 0]))
+    perms = [g["perm/%d" % k] for k in range(2)]
+    r = orc.learn(data, perms, 64, 0.99, 0.95, 0.2, 0.01)
+    pol.learn(64, 0.99, 0.95, 0.2, 2, 0.01, permutations=perms)
+    np.testing.assert_allclose(pol.last_adv.cpu().numpy(), r["adv"].numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(pol.last_v_target.cpu().numpy(), r["v_target"].numpy(), rtol=1e-5, atol=1e-6)
+    m = pol.last_metrics.cpu().numpy()
+    ref = np.array(r["losses"])
+    np.testing.assert_allclose(m[:, 0], ref[:, 0], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(m[:, 1], ref[:, 1], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(m[:, :2], g["losses"], rtol=5e-5, atol=5e-6)
+    tol = dict(rtol=2e-4, atol=2e-5)     # 8 chained cautious-AdamW steps: sign masks amplify last-ulp differences
+    assert_module_close(pol.agent.actor, orc.actor, "actor", tol)
+    assert_module_close(pol.agent.critic, orc.critic, "critic", tol)
+    assert_module_close(pol.agent.actor, net_from_golden(g, "final/actor/"), "actor vs reference", tol)
+    assert len(pol.buffer) == 0
+
+
+def test_ppo_continuous_emulated(golden, emul):
+    _ppo(golden, torch.device("cpu"), "ppo_cont", True)
+
+
+def test_ppo_discrete_emulated(golden, emul):
+    _ppo(golden, torch.device("cpu"), "ppo_disc", False)
+
+
+@pytest.mark.gpu
+def test_ppo_continuous_gpu(golden):
+    _ppo(golden, torch.device("cuda"), "ppo_cont", True)
+
+
+@pytest.mark.gpu
+def test_ppo_discrete_gpu(golden):
+    _ppo(golden, torch.device("cuda"), "ppo_disc", False)
