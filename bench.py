@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/s of the SAC training hot path (BASELINE.json config[1]) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (torchrun for N > 1)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port) on host cores
+
+Workload (config.workload = "sac_halfcheetah_256env_1Mreplay"): SAC with HalfCheetah-v4 dims (obs 17, act 6,
+hidden 128-128, twin critic), 256 vectorised synthetic envs per GPU, a pre-filled 1 000 000-transition device
+replay per GPU, batch 256, update-to-data ratio 1 (the reference trains once per env step, SAC_file/SAC.py:571-572).
+One "step" = one vector step: policy inference for 256 envs, 256 transitions added to the replay and 256 sequential
+learn() updates (ONE persistent kernel launch).  `value` keeps all inputs resident in HBM (synthetic env arrays come
+from a device pool); `e2e` drives the public Python API with HOST (numpy) buffers: select_action(host obs) -> host
+synthetic env -> add(host arrays) -> learn(…, n_updates=256) -> D2H read of the loss, with the H2D / D2H copies inside
+the timed region.  Replay rows are sampled uniformly from 176 MB (> the 126 MB L2), so batch gathers are HBM traffic.
+Multi-GPU: weak scaling, one process per GPU, env workers + replay sharded per GPU, no data-path collective; the
+replicas are kept one policy by a parameter all-reduce (NCCL) after every vector step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+OBS, ACT, NENV, CAP, BATCH = 17, 6, 256, 1_000_000, 256
+GAMMA, TAU = 0.99, 0.01
+PARAMS = 19596 + 39426                    # SAC actor + twin critic
+ALGO_BYTES_PER_LEARN = BATCH * 168 + PARAMS * 36 + 16       # sampled rows + param/Adam/target traffic
+ALGO_FLOPS_PER_LEARN = 0.70e6 * BATCH
+
+
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+class SyntheticVecEnv:
+    """obs ~ N(0,1) fp32 [N, obs_dim], reward ~ N(0,1), p_term = 0, truncation every 1000 steps.
+    Transitions come from a pre-generated host pool so the host cost per step is a memcpy, like a fast simulator."""
+
+    def __init__(self, n, seed, pool=64):
+        r = np.random.default_rng(seed)
+        self.obs_pool = r.standard_normal((pool, n, OBS), dtype=np.float32)
+        self.rew_pool = r.standard_normal((pool, n)).astype(np.float32)
+        self.n, self.t, self.pool = n, 0, pool
+        self.obs = self.obs_pool[0]
+
+    def step(self, action):
+        self.t += 1
+        nxt = self.obs_pool[self.t % self.pool]
+        rew = self.rew_pool[self.t % self.pool]
+        term = np.zeros(self.n, bool)
+        trunc = np.full(self.n, self.t % 1000 == 0)
+        return nxt, rew, term, trunc
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    p = os.path.join(ROOT, "profiles", "r1_sac_learn_ncu.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_learn")
+        except Exception:
+            return None
+    return None
+
+
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_arm(steps, warmup, transitions_per_step=4, fill=CAP, threads=None):
+    """The reference's own CPU implementation of the path (oracle port: numpy ring replay with
+    np.random.choice(len, 256, replace=False) + PyTorch-CPU SAC learn), all host threads.  A step = a bounded
+    sample: `transitions_per_step` single-env iterations of select_action + env + add + learn."""
+    import torch
+    from collections import OrderedDict
+    from oracle import algos, buffers
+    if threads:
+        torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    rng = np.random.default_rng(0)
+
+    def lin(i, o):
+        l = torch.nn.Linear(i, o)
+        return l.weight.detach().clone(), l.bias.detach().clone()
+    actor, critic = OrderedDict(), OrderedDict()
+    for n_, (i, o) in zip(("l1", "l2", "mean_layer"), ((OBS, 128), (128, 128), (128, ACT))):
+        actor[n_ + ".weight"], actor[n_ + ".bias"] = lin(i, o)
+    actor["log_std"] = torch.zeros(1, ACT)
+    actor.move_to_end("log_std", last=False)
+    for k in range(6):
+        i, o = ((OBS + ACT, 128), (128, 128), (128, 1))[k % 3]
+        critic["l%d.weight" % (k + 1)], critic["l%d.bias" % (k + 1)] = lin(i, o)
+    orc = algos.SACOracle(actor, critic, 1e-3, 1e-3, act_dim=ACT)
+    buf = buffers.RingReplay(CAP, OBS, ACT)
+    n = int(fill)
+    buf.obs[:n] = rng.standard_normal((n, OBS), dtype=np.float32)
+    buf.actions[:n] = rng.uniform(-1, 1, (n, ACT))
+    buf.rewards[:n] = rng.standard_normal(n)
+    buf.next_obs[:n] = rng.standard_normal((n, OBS), dtype=np.float32)
+    buf._size, buf._index = n, n % CAP
+    obs = rng.standard_normal(OBS).astype(np.float32)
+
+    def one_step():
+        nonlocal obs
+        for _ in range(transitions_per_step):
+            with torch.no_grad():
+                a, _ = algos.sac_actor(orc.actor, torch.as_tensor(obs).reshape(1, -1), torch.randn(1, ACT))
+            nxt = rng.standard_normal(OBS).astype(np.float32)
+            buf.add(obs, a.numpy()[0], float(rng.standard_normal()), nxt, False)
+            obs = nxt
+            idx = buffers.uniform_indices(len(buf), BATCH)
+            batch = tuple(torch.from_numpy(x) for x in buf.sample(idx))
+            orc.learn(batch, torch.randn(BATCH, ACT), torch.randn(BATCH, ACT), GAMMA, TAU)
+    for _ in range(warmup):
+        one_step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    dt = time.perf_counter() - t0
+    return steps * transitions_per_step / dt, dt * 1e3 / steps, torch.get_num_threads(), transitions_per_step
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": "sac_halfcheetah_256env_1Mreplay", "obs_dim": OBS, "act_dim": ACT, "hidden": [128, 128],
+              "envs_per_gpu": NENV, "replay_capacity_per_gpu": CAP, "batch": BATCH, "updates_per_env_step": 1,
+              "l2_note": "batches are uniform random rows of a 176 MB replay (> 126 MB L2)",
+              "parallelism": "dp%d (env+replay shards per GPU, parameter all-reduce per vector step)" % max(world, 1)}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        w = max(args.warmup, 1)
+        val, ms, cores, tps = cpu_reference_arm(args.steps, w)
+        print(json.dumps({
+            "impl": "reference", "metric": "env_steps_per_sec", "value": val, "unit": "env-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": w, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                             "sample": "%d single-env iterations (select_action + add + np.random.choice(1e6,256) + SAC learn B=256) per step" % tps},
+            "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from freerl_b200.SAC import SAC
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(args.warmup, 3)
+    K = args.steps
+    torch.manual_seed(1234 + rank)
+    np.random.seed(1234 + rank)
+    pol = SAC([OBS, ACT], True, 1e-3, 1e-3, CAP, dev, trick={}, mode="fast")
+    # pre-fill the per-GPU replay shard on the device
+    g = torch.Generator(device=dev)
+    g.manual_seed(99 + rank)
+    chunk = 250_000
+    for _ in range(CAP // chunk):
+        pol.buffer.add_device(torch.randn((chunk, OBS), device=dev, generator=g), torch.rand((chunk, ACT), device=dev, generator=g) * 2 - 1,
+                              torch.randn(chunk, device=dev, generator=g), torch.randn((chunk, OBS), device=dev, generator=g),
+                              (torch.rand(chunk, device=dev, generator=g) < 0.001).float())
+    POOL = 64
+    obs_pool = torch.randn((POOL, NENV, OBS), device=dev, generator=g)
+    rew_pool = torch.randn((POOL, NENV), device=dev, generator=g)
+    zeros = torch.zeros(NENV, device=dev)
+    from freerl_b200 import _common, _lib
+    params = [pol.agent._actor, pol.agent._critic, pol.agent._actor_t, pol.agent._critic_t]
+
+    def sync_params():
+        if world > 1:
+            for n_ in params:
+                dist.all_reduce(n_.p)
+                n_.p.div_(world)
+                n_.sync_mirror()
+
+    learn_ev = []
+
+    def device_step(t, timed):
+        obs = obs_pool[t % POOL]
+        act = _common.infer(pol.agent._actor, obs, _lib.INFER_SAC_SAMPLE, dev, ACT, seed=pol._seed, counter=t)
+        nxt, rew = obs_pool[(t + 1) % POOL], rew_pool[(t + 1) % POOL]
+        pol.buffer.add_device(obs, act, rew, nxt, zeros)
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        pol.learn(BATCH, GAMMA, TAU, n_updates=NENV)
+        if timed:
+            e1.record()
+            learn_ev.append((e0, e1))
+        sync_params()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_region(fn):
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for t in range(K):
+            fn(W + t, True)
+        t1.record()
+        barrier()
+        ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident value ------------------------------------------------------------------------
+    for t in range(W):
+        device_step(t, False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed_region(device_step)
+    clocks = sampler.stop() if rank == 0 else None
+    learn_ms = float(np.mean([a.elapsed_time(b) for a, b in learn_ev]))      # one launch = NENV sequential learns
+    value = world * NENV * K / (ms_total / 1e3)
+
+    # ---- end-to-end through the public API with host buffers ------------------------------------------
+    env = SyntheticVecEnv(NENV, 7 + rank)
+    state = {"obs": env.obs, "loss": 0.0}
+
+    def host_step(t, timed):
+        obs = state["obs"]
+        action = pol.select_action(obs)                              # H2D obs, kernel, D2H actions
+        nxt, rew, term, trunc = env.step(action)
+        pol.add(obs, action, rew, nxt, term)                         # H2D packed transitions
+        pol.learn(BATCH, GAMMA, TAU, n_updates=NENV)
+        state["loss"] = float(pol.last_metrics[NENV - 1, 0].item())  # D2H read of the step's result
+        state["obs"] = nxt
+        sync_params()
+    for t in range(W):
+        host_step(t, False)
+    ms_e2e = timed_region(host_step)
+    e2e = world * NENV * K / (ms_e2e / 1e3)
+    h2d = NENV * OBS * 4 + NENV * pol.buffer.row_floats * 4
+    d2h = NENV * ACT * 4 + 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = peaks()
+    achieved = ALGO_BYTES_PER_LEARN * NENV / (learn_ms / 1e3) / 1e9
+    out = {
+        "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": config,
+        "updates_per_sec": world * NENV * K / (ms_total / 1e3),
+        "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / K, "last_loss": state["loss"]},
+        "gpu_launches": 4 * K,      # per step: policy-infer, replay add_batch, uniform-sample, fused 256-update learn
+        "clocks": clocks,
+        "roofline": {"kernel": "frl_persistent_kernel<AcAlgo> (fused SAC learn x%d per launch)" % NENV, "bound": "hbm",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": ALGO_BYTES_PER_LEARN * NENV, "launch_ms": learn_ms,
+                     "traffic": ncu_traffic(),
+                     "achieved_tflops_fp32": ALGO_FLOPS_PER_LEARN * NENV / (learn_ms / 1e3) / 1e12,
+                     "note": "the fused update is FLOP/latency-bound at B=256 (SURVEY §7.3-1): params/Adam/targets are L2-resident"},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        val, ms, cores, tps = cpu_reference_arm(6, 1)
+        out["cpu_baseline"] = {"value": val, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                               "sample": "6 steps x %d single-env iterations of the oracle port (np.random.choice over the full 1e6 replay + SAC learn B=256)" % tps}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
