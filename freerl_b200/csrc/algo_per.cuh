@@ -1,0 +1,190 @@
+// Device sum-tree for prioritized replay, bit-exact with the reference's float64 array heap.
+//   SumTree            DQN_file/Buffer.py:134-194   (tree[2*cap-1] f64, leaf i at i+cap-1, NO power-of-two padding,
+//                                                   ancestors maintained by `+= change`, never re-summed)
+//   PER_Buffer         DQN_file/Buffer.py:66-132    (stratified sample, IS weights, update_priorities)
+// Bit-exactness: ancestors receive their `change`s in batch order.  Different nodes are independent, so the batch is
+// applied level by level: within a level every distinct node has one "leader" lane that adds the changes of all
+// batch items mapping to it IN BATCH ORDER (fp64 addition is not associative — order is what makes the last ulp match).
+#pragma once
+#include "launch.cuh"
+
+#ifndef FRL_EMUL
+FRL_DEV double dmul(double a, double b) { return __dmul_rn(a, b); }
+FRL_DEV double dadd(double a, double b) { return __dadd_rn(a, b); }
+FRL_DEV double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+#else
+static inline double dmul(double a, double b) { volatile double r = a * b; return r; }
+static inline double dadd(double a, double b) { volatile double r = a + b; return r; }
+static inline double ddiv(double a, double b) { return a / b; }
+#endif
+
+#define FRL_PER_MAXB 1024
+
+// ---- ordered batch update ------------------------------------------------------------------------------------
+struct TreeUpdateArgs {
+  double* tree; int64_t cap;
+  const int64_t* idx;        // [B] buffer indices
+  const float* pri32;        // [B] new priorities (fp32, widened exactly) or nullptr
+  const double* pri64;       // [1] a single fp64 priority for every item (PER add: max priority) or nullptr
+  double pri_const;          // used when both are null
+  int64_t idx0; int idx_is_range;   // idx_is_range: item i targets (idx0 + i) % cap (batched ring add)
+  int B;
+};
+
+struct TreeUpdateAlgo {
+  typedef TreeUpdateArgs Args;
+  static const int NSTAGES = 1;
+  FRL_SHD int wbuf_floats(const Args&) { return 32; }
+  FRL_SHD int user_floats(const Args& a) { return 2 * (2 * a.B + 2 * a.B) + 64; }     // node[B] (i64) + change[B] (f64)
+  FRL_SHD int grid(const Args&, int) { return 1; }
+  FRL_SHD int n_updates(const Args&) { return 1; }
+  FRL_SDEV void stage(int, int, Cta&, float* user, const Args& a) {
+    int64_t* node = (int64_t*)user;                 // current node of item i (-1: finished)
+    double* change = (double*)(node + a.B);
+    const int B = a.B;
+    // leaf phase: change_i = p_i - (value the leaf holds when item i is applied)
+    FRL_PAR(t) {
+      for (int i = t; i < B; i += FRL_NT) {
+        const int64_t bi = a.idx_is_range ? (a.idx0 + i) % a.cap : a.idx[i];
+        node[i] = bi + a.cap - 1;
+      }
+    }
+    FRL_SYNC();
+    FRL_PAR(t) {
+      for (int i = t; i < B; i += FRL_NT) {
+        const double p = a.pri32 ? (double)a.pri32[i] : (a.pri64 ? a.pri64[0] : a.pri_const);
+        int prev = -1;
+        for (int j = i - 1; j >= 0; --j) if (node[j] == node[i]) { prev = j; break; }
+        const double before = prev >= 0 ? (a.pri32 ? (double)a.pri32[prev] : p) : a.tree[node[i]];
+        change[i] = dadd(p, -before);
+      }
+    }
+    FRL_SYNC();
+    FRL_PAR(t) {
+      for (int i = t; i < B; i += FRL_NT) {
+        bool last = true;
+        for (int j = i + 1; j < B; ++j) if (node[j] == node[i]) { last = false; break; }
+        if (last) a.tree[node[i]] = a.pri32 ? (double)a.pri32[i] : (a.pri64 ? a.pri64[0] : a.pri_const);
+      }
+    }
+    FRL_SYNC();
+    // ancestor phases: one tree level per iteration
+    for (int level = 0; level < 64; ++level) {
+      FRL_PAR(t) {
+        for (int i = t; i < B; i += FRL_NT) node[i] = node[i] > 0 ? (node[i] - 1) / 2 : -1;
+      }
+      FRL_SYNC();
+      bool any = false;     // block-uniform: recomputed identically by every thread
+      for (int i = 0; i < B; ++i) any |= node[i] >= 0;
+      if (!any) break;
+      FRL_PAR(t) {
+        for (int i = t; i < B; i += FRL_NT) {
+          const int64_t nd = node[i];
+          if (nd < 0) continue;
+          bool leader = true;
+          for (int j = 0; j < i; ++j) if (node[j] == nd) { leader = false; break; }
+          if (!leader) continue;
+          double v = dadd(a.tree[nd], change[i]);
+          for (int j = i + 1; j < B; ++j) if (node[j] == nd) v = dadd(v, change[j]);
+          a.tree[nd] = v;
+        }
+      }
+      FRL_SYNC();
+    }
+  }
+};
+
+// ---- stratified sampling + importance weights --------------------------------------------------------------------
+struct TreeSampleArgs {
+  const double* tree; int64_t cap;
+  const double* u;           // [B] uniforms in [0,1) (numpy legacy random_sample in parity mode) or nullptr -> Philox
+  uint64_t seed, counter;
+  int B;
+  int64_t size;              // len(buffer)
+  double beta, prob_floor;
+  int64_t* out_idx;          // [B]
+  float* out_pri;            // [B] leaf priorities (fp32 container, Buffer.py:104)
+  float* out_w;              // [B] importance weights (fp32)
+};
+
+struct TreeSampleAlgo {
+  typedef TreeSampleArgs Args;
+  static const int NSTAGES = 1;
+  FRL_SHD int wbuf_floats(const Args&) { return 32; }
+  FRL_SHD int user_floats(const Args& a) { return 2 * a.B + 2 * FRL_NT + 64; }
+  FRL_SHD int grid(const Args&, int) { return 1; }
+  FRL_SHD int n_updates(const Args&) { return 1; }
+  FRL_SDEV void stage(int, int, Cta&, float* user, const Args& a) {
+    double* w = (double*)user;                      // [B]
+    double* redm = w + a.B;                         // [FRL_NT]
+    const int64_t nnodes = 2 * a.cap - 1;
+    const double total = a.tree[0];
+    const double seg = ddiv(total, (double)a.B);    // segment = sumtree.sum() / batch_size
+    FRL_PAR(t) {
+      double mx = 0.0;
+      for (int i = t; i < a.B; i += FRL_NT) {
+        double ui;
+        if (a.u) ui = a.u[i];
+        else {
+          uint32_t o[4];
+          frl_philox((uint32_t)a.seed, (uint32_t)(a.seed >> 32), (uint32_t)i, (uint32_t)a.counter, (uint32_t)(a.counter >> 32), 0x9e3779b9u, o);
+          ui = ((double)(((uint64_t)(o[0] >> 5) << 26) | (o[1] >> 6))) * (1.0 / 9007199254740992.0);
+        }
+        const double lo = dmul(seg, (double)i), hi = dmul(seg, (double)(i + 1));
+        double s = dadd(lo, dmul(dadd(hi, -lo), ui));       // np.random.uniform(a, b) = a + (b-a)*random_sample()
+        int64_t nd = 0;
+        while (2 * nd + 1 < nnodes) {                        // SumTree.get (Buffer.py:168-188)
+          const int64_t left = 2 * nd + 1;
+          const double tl = a.tree[left];
+          if (s <= tl) nd = left;
+          else { s = dadd(s, -tl); nd = left + 1; }
+        }
+        const float p32 = (float)a.tree[nd];
+        a.out_idx[i] = nd - a.cap + 1;
+        a.out_pri[i] = p32;
+        double prob = ddiv((double)p32, total);
+        if (prob < a.prob_floor) prob = a.prob_floor;
+        const double wi = pow(dmul((double)a.size, prob), -a.beta);
+        w[i] = wi;
+        mx = wi > mx ? wi : mx;
+      }
+      redm[t] = mx;
+    }
+    FRL_SYNC();
+    for (int s2 = FRL_NT / 2; s2 > 0; s2 >>= 1) {
+      FRL_PAR(t) { if (t < s2) redm[t] = redm[t] > redm[t + s2] ? redm[t] : redm[t + s2]; }
+      FRL_SYNC();
+    }
+    FRL_PAR(t) { for (int i = t; i < a.B; i += FRL_NT) a.out_w[i] = (float)ddiv(w[i], redm[0]); }
+    FRL_SYNC();
+  }
+};
+
+// ---- max over leaves (np.max(tree[-cap:])) ------------------------------------------------------------------------
+struct TreeMaxBody1 {
+  const double* tree; int64_t cap; double* part; int nblk;
+  FRL_HDM void operator()(long b) const {
+    const int64_t per = (cap + nblk - 1) / nblk;
+    const int64_t s = b * per, e = (s + per < cap) ? s + per : cap;
+    double m = -1e300;
+    for (int64_t i = s; i < e; ++i) { const double v = tree[cap - 1 + i]; m = v > m ? v : m; }
+    part[b] = m;
+  }
+};
+struct TreeMaxBody2 {
+  const double* part; int nblk; double* out;
+  FRL_HDM void operator()(long) const {
+    double m = -1e300;
+    for (int i = 0; i < nblk; ++i) m = part[i] > m ? part[i] : m;
+    out[0] = m;
+  }
+};
+
+// ---- priorities  (|td| + eps) ** alpha  on fp32 (numpy computes x ** 0.5 as sqrt — bit-exact for the default alpha) ----
+struct PriBody {
+  const float* td; float eps; float alpha; float* out;
+  FRL_HDM void operator()(long i) const {
+    const float x = fabsf(td[i]) + eps;
+    out[i] = (alpha == 0.5f) ? sqrtf(x) : (alpha == 1.0f ? x : (float)pow((double)x, (double)alpha));
+  }
+};

@@ -7,6 +7,7 @@
 #include <stdio.h>
 
 #include "algo_ppo.cuh"
+#include "algo_per.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // error plumbing
@@ -373,4 +374,43 @@ extern "C" int frl_ppo_update(const frl_ppo_args_t* a, void* stream) {
     return -1;
   }
   return frl_launch<PpoAlgo>(*a, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// prioritized replay: float64 sum-tree on the device
+// ------------------------------------------------------------------------------------------------
+extern "C" int frl_sumtree_update(double* tree, int64_t cap, const int64_t* idx, const float* pri32, const double* pri64_scalar,
+                                  double pri_const, int64_t idx0, int idx_is_range, int B, void* stream) {
+  if (!tree || cap <= 0 || B <= 0 || B > FRL_PER_MAXB || (!idx && !idx_is_range)) {
+    frl_set_error("frl_sumtree_update: bad arguments (B must be <= %d)", FRL_PER_MAXB);
+    return -1;
+  }
+  TreeUpdateArgs a = {tree, cap, idx, pri32, pri64_scalar, pri_const, idx0, idx_is_range, B};
+  return frl_launch_tiles<TreeUpdateAlgo>(a, (cudaStream_t)stream);
+}
+
+extern "C" int frl_sumtree_sample(const double* tree, int64_t cap, const double* u, uint64_t seed, uint64_t counter, int B, int64_t size,
+                                  double beta, double prob_floor, int64_t* out_idx, float* out_pri, float* out_w, void* stream) {
+  if (!tree || cap <= 0 || B <= 0 || B > 8192 || !out_idx || !out_pri || !out_w) {
+    frl_set_error("frl_sumtree_sample: bad arguments");
+    return -1;
+  }
+  TreeSampleArgs a = {tree, cap, u, seed, counter, B, size, beta, prob_floor, out_idx, out_pri, out_w};
+  return frl_launch_tiles<TreeSampleAlgo>(a, (cudaStream_t)stream);
+}
+
+extern "C" int frl_sumtree_max(const double* tree, int64_t cap, double* scratch, int nscratch, double* out, void* stream) {
+  if (!tree || cap <= 0 || !scratch || nscratch <= 0 || !out) { frl_set_error("frl_sumtree_max: bad arguments"); return -1; }
+  const int nblk = (int)(cap < nscratch ? cap : nscratch);
+  TreeMaxBody1 b1 = {tree, cap, scratch, nblk};
+  int rc = frl_for(nblk, b1, (cudaStream_t)stream);
+  if (rc) return rc;
+  TreeMaxBody2 b2 = {scratch, nblk, out};
+  return frl_for(1, b2, (cudaStream_t)stream);
+}
+
+extern "C" int frl_per_priorities(const float* td, int B, float eps, float alpha, float* out, void* stream) {
+  if (!td || !out || B <= 0) { frl_set_error("frl_per_priorities: bad arguments"); return -1; }
+  PriBody b = {td, eps, alpha, out};
+  return frl_for(B, b, (cudaStream_t)stream);
 }

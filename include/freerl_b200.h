@@ -17,6 +17,8 @@
  *                                                            DDPG_file/DDPG.py:203-233 (+ Agent.update_*, Alpha)
  *   frl_policy_infer          select_action / evaluate_action      DQN.py:70-88, SAC.py:192-204, TD3.py:163-174, DDPG.py:166-185
  *   frl_net_sync_mirror       (state_dict load -> refresh transposed weight mirrors; no reference counterpart)
+ *   frl_sumtree_update/_sample/_max, frl_per_priorities
+ *                             SumTree / PER_Buffer           DQN_file/Buffer.py:66-194
  *   frl_gae                   PPO.learn GAE loop             PPO_file/PPO.py:222-233 (MAPPO_file/MAPPO.py:362-383)
  *   frl_ppo_update            PPO.learn minibatch loop + Agent.update_ac_ + c_adamw.AdamW.step
  *                                                            PPO_file/PPO.py:245-283,145-152; PPO_file/c_adamw.py:65-122
@@ -171,6 +173,18 @@ int frl_policy_infer(const frl_infer_args_t* args, void* stream);
 int frl_gae(const float* reward, const float* done, const float* adv_done, const float* vs, const float* vs_next, int T, int N,
             double gamma, double lmbda, float* adv_out, float* v_target_out, void* stream);
 int frl_ppo_update(const frl_ppo_args_t* args, void* stream);
+
+/* Prioritized replay (DQN_file/Buffer.py:66-194): `tree` is the reference's float64 array heap [2*cap-1] on the device.
+ * frl_sumtree_update applies B leaf writes IN ORDER (ancestors get `+= change` in batch order => bit-exact with the
+ * sequential reference); targets are idx[i] or, with idx_is_range, (idx0+i) % cap; the new priority of item i is
+ * pri32[i] | *pri64_scalar | pri_const.  frl_sumtree_sample = PER_Buffer.sample (stratified descent on u[i] in [0,1),
+ * float32 priority container, float64 importance weights cast to fp32).  frl_sumtree_max = np.max(tree[-cap:]). */
+int frl_sumtree_update(double* tree, int64_t cap, const int64_t* idx, const float* pri32, const double* pri64_scalar,
+                       double pri_const, int64_t idx0, int idx_is_range, int B, void* stream);
+int frl_sumtree_sample(const double* tree, int64_t cap, const double* u, uint64_t seed, uint64_t counter, int B, int64_t size,
+                       double beta, double prob_floor, int64_t* out_idx, float* out_pri, float* out_w, void* stream);
+int frl_sumtree_max(const double* tree, int64_t cap, double* scratch, int nscratch, double* out, void* stream);
+int frl_per_priorities(const float* td, int B, float eps, float alpha, float* out, void* stream);
 
 #ifdef __cplusplus
 }
