@@ -69,6 +69,21 @@ class PpoArgs(C.Structure):
                 ("sumsq", C.c_void_p), ("segcnt", C.c_void_p), ("stats", C.c_void_p), ("out", C.c_void_p)]
 
 
+class NoisyMap(C.Structure):
+    _fields_ = [("mu_w", C.c_int), ("sg_w", C.c_int), ("mu_b", C.c_int), ("sg_b", C.c_int), ("row0", C.c_int),
+                ("eps_in", C.c_int), ("eps_out", C.c_int)]
+
+
+class RainbowArgs(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("p_target", C.c_void_p), ("n_train", C.c_int),
+                ("eff", Net * 3), ("map", NoisyMap * FRL_MAX_LAYERS), ("eps", C.c_void_p), ("eps_len", C.c_int),
+                ("n_actions", C.c_int), ("n_atoms", C.c_int), ("z", C.c_void_p), ("v_min", C.c_float), ("v_max", C.c_float),
+                ("delta_z", C.c_float), ("double_q", C.c_int), ("replay", Replay), ("indices", C.c_void_p),
+                ("is_weight", C.c_void_p), ("B", C.c_int), ("gamma", C.c_float), ("tau", C.c_float), ("lr", C.c_double),
+                ("beta1", C.c_double), ("beta2", C.c_double), ("eps_adam", C.c_double), ("step0", C.c_int64),
+                ("gpart", C.c_void_p), ("stats", C.c_void_p), ("error_out", C.c_void_p), ("out", C.c_void_p)]
+
+
 OPT_CAUTIOUS_ADAMW, OPT_ADAM = 0, 1
 NSEG = 2 * FRL_MAX_LAYERS + 1
 ACTOR_TANH, ACTOR_SAC = 0, 1
@@ -93,6 +108,10 @@ def _declare(lib):
     lib.frl_sumtree_sample.argtypes = [vp, i64, vp, u64, u64, ci, i64, C.c_double, C.c_double, vp, vp, vp, vp]
     lib.frl_sumtree_max.argtypes = [vp, i64, vp, ci, vp, vp]
     lib.frl_per_priorities.argtypes = [vp, ci, C.c_float, C.c_float, vp, vp]
+    lib.frl_rainbow_learn.argtypes = [C.POINTER(RainbowArgs), vp]
+    lib.frl_rainbow_act.argtypes = [C.POINTER(RainbowArgs), vp, ci, vp, vp]
+    lib.frl_rainbow_learn.restype = ci
+    lib.frl_rainbow_act.restype = ci
     for name in ("frl_replay_add_batch", "frl_replay_gather", "frl_sample_uniform", "frl_net_sync_mirror",
                  "frl_dqn_learn", "frl_ac_learn", "frl_policy_infer", "frl_gae", "frl_ppo_update", "frl_sumtree_update", "frl_sumtree_sample", "frl_sumtree_max",
                  "frl_per_priorities", "frl_is_emulation", "frl_device_sm_count",

@@ -1,0 +1,398 @@
+// Fused Rainbow learn(): Categorical (C51) + Dueling + NoisyLinear heads, Double-DQN action selection, PER weights,
+// n-step gamma.  Reference: DQN_file/DQN_with_tricks.py:81-160 (Categorical._predict / forward / projection_dist),
+// :242-284 (learn), DQN_file/Noisy_net.py:17-76 (factorised noise, resampled on EVERY forward).
+//
+// The trainable block holds the torch tensors (l1.weight/bias, V/A.{weight,bias}_{mu,sigma}); for each of the three
+// forwards of one learn() (online on s', target on s', online on s) a noise-applied "effective" linear net
+//   W = mu + sigma * (eps_out x eps_in),  b = bias_mu + bias_sigma * eps_out
+// is materialised in HBM (stage 0) in the engine's layouts, so the forward/backward passes are the ordinary TMA-staged
+// GEMMs.  The A head (n_actions*n_atoms outputs) is split into column blocks of <= 128 outputs.
+#pragma once
+#include "algo_ppo.cuh"
+
+struct RainbowAlgo {
+  typedef frl_rainbow_args_t Args;
+  static const int NSTAGES = 3;
+  FRL_SHD int wbuf_floats(const Args& a) { return (AcAlgo::max_layer_floats(a.eff[2]) + 31) & ~31; }
+  FRL_SHD int natot(const Args& a) { return (a.n_actions * a.n_atoms + 3) & ~3; }
+  FRL_SHD int user_floats(const Args& a) {
+    const int ldh = a.eff[2].L[0].out_pad, ip = a.eff[2].L[0].in_pad, zp = (a.n_atoms + 3) & ~3;
+    return FRL_R * (a.replay.row_floats + 2 * ip + 3 * ldh + 3 * zp + 2 * natot(a) + 4 * zp + 8) + FRL_NT + 64;
+  }
+  FRL_SHD int grid(const Args& a, int max_ctas) {
+    int tiles = (a.B + FRL_R - 1) / FRL_R;
+    return tiles < max_ctas ? tiles : max_ctas;
+  }
+  FRL_SHD int n_updates(const Args&) { return 1; }
+
+  // effective parameter e (index into eff-net block) of forward f <- trainable block + noise
+  FRL_SDEV void noisy_apply(const Args& a, int f, int cta, int ncta) {
+    const frl_net_t& E = a.eff[f];
+    const float* P = (f == 1) ? a.p_target : a.p;
+    const float* eps = a.eps + (size_t)f * a.eps_len;
+    FRL_PAR(t) {
+      for (int e = cta * FRL_NT + t; e < E.n_p; e += ncta * FRL_NT) {
+        float val = 0.f;
+        int mi = -1;
+        for (int li = 0; li < E.n_layers; ++li) {
+          const frl_layer_t& L = E.L[li];
+          const frl_noisy_map_t& M = a.map[li];
+          const int wsz = L.out_pad * L.in_pad;
+          if (e >= L.w_off && e < L.w_off + wsz) {
+            const int j = (e - L.w_off) / L.in_pad, k = (e - L.w_off) % L.in_pad;
+            if (j < L.out && k < L.in) {
+              const int src = (M.row0 + j) * L.in_pad + k;       // torch tensors are [out][in_pad] row-major in the block
+              val = P[M.mu_w + src];
+              if (M.sg_w >= 0) val = fadd(val, fmul(P[M.sg_w + src], fmul(eps[M.eps_out + M.row0 + j], eps[M.eps_in + k])));
+            }
+            mi = L.wt_off + k * L.out_pad + j;
+            break;
+          }
+          if (e >= L.b_off && e < L.b_off + L.out_pad) {
+            const int j = e - L.b_off;
+            if (j < L.out) {
+              val = P[M.mu_b + M.row0 + j];
+              if (M.sg_b >= 0) val = fadd(val, fmul(P[M.sg_b + M.row0 + j], eps[M.eps_out + M.row0 + j]));
+            }
+            mi = L.wt_off + wsz + j;
+            break;
+          }
+        }
+        E.p[e] = val;
+        if (mi >= 0) E.pt[mi] = val;
+      }
+    }
+    FRL_SYNC();
+  }
+
+  // logits -> per-action distribution + expected value; D holds [R][n_actions*n_atoms] (ld = nat), V [R][zp]
+  FRL_SDEV void head_probs(const Args& a, const float* V, int zp, float* A, int nat, float* qv /*[R][n_actions]*/) {
+    const int nA = a.n_actions, nZ = a.n_atoms;
+    FRL_PAR(t) {
+      if (t < FRL_R * nA) {
+        const int r = t / nA, ac = t % nA;
+        // logits[z] = V[z] + A[ac][z] - mean_a A[a][z];  softmax over z;  q = sum z * p
+        float mx = -1e30f;
+        for (int z = 0; z < nZ; ++z) {
+          float mean = 0.f;
+          for (int b = 0; b < nA; ++b) mean += A[r * nat + b * nZ + z];
+          mean = mean / (float)nA;
+          const float lg = V[r * zp + z] + A[r * nat + ac * nZ + z] - mean;
+          mx = fmaxf(mx, lg);
+        }
+        float se = 0.f;
+        for (int z = 0; z < nZ; ++z) {
+          float mean = 0.f;
+          for (int b = 0; b < nA; ++b) mean += A[r * nat + b * nZ + z];
+          mean = mean / (float)nA;
+          se += expf(V[r * zp + z] + A[r * nat + ac * nZ + z] - mean - mx);
+        }
+        float q = 0.f;
+        for (int z = 0; z < nZ; ++z) {
+          float mean = 0.f;
+          for (int b = 0; b < nA; ++b) mean += A[r * nat + b * nZ + z];
+          mean = mean / (float)nA;
+          const float p = expf(V[r * zp + z] + A[r * nat + ac * nZ + z] - mean - mx) / se;
+          q += p * a.z[z];
+        }
+        qv[r * nA + ac] = q;
+      }
+    }
+    FRL_SYNC();
+  }
+
+  // distribution of one chosen action per row -> P[r][z]
+  FRL_SDEV void dist_of(const Args& a, const float* V, int zp, const float* A, int nat, const int* act, float* P) {
+    const int nA = a.n_actions, nZ = a.n_atoms;
+    FRL_PAR(t) {
+      if (t < FRL_R) {
+        const int r = t, ac = act[r];
+        float mx = -1e30f;
+        for (int z = 0; z < nZ; ++z) {
+          float mean = 0.f;
+          for (int b = 0; b < nA; ++b) mean += A[r * nat + b * nZ + z];
+          mean = mean / (float)nA;
+          const float lg = V[r * zp + z] + A[r * nat + ac * nZ + z] - mean;
+          P[r * zp + z] = lg;
+          mx = fmaxf(mx, lg);
+        }
+        float se = 0.f;
+        for (int z = 0; z < nZ; ++z) { const float e = expf(P[r * zp + z] - mx); P[r * zp + z] = e; se += e; }
+        for (int z = 0; z < nZ; ++z) P[r * zp + z] = P[r * zp + z] / se;
+      }
+    }
+    FRL_SYNC();
+  }
+
+  // hidden -> V and A head outputs through effective net E (layers 1.. )
+  FRL_SDEV void heads_fwd(Cta& c, const frl_net_t& E, const float* H, int ldh, float* V, int zp, float* A, int nat, Hint next) {
+    layer_fwd<FRL_R>(c, E, 1, H, ldh, V, zp, FRL_ACT_NONE, fwd_hint(E, 2));
+    int col = 0;
+    for (int li = 2; li < E.n_layers; ++li) {
+      layer_fwd<FRL_R>(c, E, li, H, ldh, A + col, nat, FRL_ACT_NONE, li + 1 < E.n_layers ? fwd_hint(E, li + 1) : next);
+      col += E.L[li].out;
+    }
+  }
+
+  FRL_SDEV void stage(int s, int u, Cta& c, float* user, const Args& a) {
+    const frl_net_t& E3 = a.eff[2];
+    const int ldh = E3.L[0].out_pad, ip = E3.L[0].in_pad, zp = (a.n_atoms + 3) & ~3, nat = natot(a);
+    const int nA = a.n_actions, nZ = a.n_atoms, rf = a.replay.row_floats;
+    const int ntile = (a.B + FRL_R - 1) / FRL_R;
+    const int ncontrib = ntile < c.ncta ? ntile : c.ncta;
+    if (s == 0) {
+      for (int f = 0; f < 3; ++f) noisy_apply(a, f, c.cta, c.ncta);
+      return;
+    }
+    if (s == 1) {
+      SmemBump sb; sb.p = user;
+      float* raw = sb.take(FRL_R * rf);
+      float* Xo = sb.take(FRL_R * ip);
+      float* Xn = sb.take(FRL_R * ip);
+      float* H = sb.take(FRL_R * ldh);      // hidden of the gradient-carrying forward
+      float* Hn = sb.take(FRL_R * ldh);     // scratch hidden (next_obs passes)
+      float* dH = sb.take(FRL_R * ldh);
+      float* V = sb.take(FRL_R * zp);
+      float* dV = sb.take(FRL_R * zp);
+      float* Pm = sb.take(FRL_R * zp);      // projected target distribution m
+      float* A = sb.take(FRL_R * nat);
+      float* dA = sb.take(FRL_R * nat);
+      float* Pn = sb.take(FRL_R * zp);      // next_dist / current dist
+      float* Dt = sb.take(FRL_R * zp);      // scratch per-row
+      float* qv = sb.take(FRL_R * ((nA + 3) & ~3) + 4);
+      int* act = (int*)sb.take(FRL_R + 4);
+      float* red0 = sb.take(FRL_NT);
+      float* gp = a.gpart + (size_t)c.cta * E3.n_p;
+      float loss_acc = 0.f;
+      bool first = true;
+      if (c.cta >= ntile) return;
+      for (int tile = c.cta; tile < ntile; tile += c.ncta) {
+        const int row0 = tile * FRL_R;
+        const int nvalid = (a.B - row0) < FRL_R ? (a.B - row0) : FRL_R;
+        const frl_net_t& En = a.double_q ? a.eff[0] : a.eff[1];
+        stage_prefetch(c, layer_fwd_src(En, 0), layer_fwd_bytes(En.L[0]));
+        gather_rows<FRL_R>(a.replay, a.indices + (size_t)u * a.B + row0, nvalid, raw);
+        copy_cols<FRL_R>(Xo, ip, 0, raw, rf, 0, a.replay.obs_dim, ip);
+        copy_cols<FRL_R>(Xn, ip, 0, raw, rf, rb_col_nobs(a.replay), a.replay.obs_dim, ip);
+        // (1) next action: Double -> online net (forward #1), else the target's own argmax
+        if (a.double_q) {
+          layer_fwd<FRL_R>(c, a.eff[0], 0, Xn, ip, Hn, ldh, FRL_ACT_RELU, fwd_hint(a.eff[0], 1));
+          heads_fwd(c, a.eff[0], Hn, ldh, V, zp, A, nat, fwd_hint(a.eff[1], 0));
+          head_probs(a, V, zp, A, nat, qv);
+          FRL_PAR(t) {
+            if (t < FRL_R) { int best = 0; for (int b = 1; b < nA; ++b) if (qv[t * nA + b] > qv[t * nA + best]) best = b; act[t] = best; }
+          }
+          FRL_SYNC();
+        }
+        // (2) target net on next_obs (forward #2) -> next_dist of the chosen action
+        layer_fwd<FRL_R>(c, a.eff[1], 0, Xn, ip, Hn, ldh, FRL_ACT_RELU, fwd_hint(a.eff[1], 1));
+        heads_fwd(c, a.eff[1], Hn, ldh, V, zp, A, nat, fwd_hint(E3, 0));
+        if (!a.double_q) {
+          head_probs(a, V, zp, A, nat, qv);
+          FRL_PAR(t) {
+            if (t < FRL_R) { int best = 0; for (int b = 1; b < nA; ++b) if (qv[t * nA + b] > qv[t * nA + best]) best = b; act[t] = best; }
+          }
+          FRL_SYNC();
+        }
+        dist_of(a, V, zp, A, nat, act, Pn);
+        // (3) projection of the target distribution  (projection_dist, DQN_with_tricks.py:135-160)
+        FRL_PAR(t) {
+          if (t < FRL_R) {
+            const int r = t;
+            for (int z = 0; z < zp; ++z) Pm[r * zp + z] = 0.f;
+            if (r < nvalid) {
+              const float rew = raw[r * rf + rb_col_rew(a.replay)], dn = raw[r * rf + rb_col_done(a.replay)];
+              // index_add_ order: all l-contributions (z ascending), then all u-contributions
+              for (int pass = 0; pass < 2; ++pass)
+                for (int z = 0; z < nZ; ++z) {
+                  float tz = fadd(rew, fmul(fmul(a.gamma, a.z[z]), fadd(1.f, -dn)));
+                  tz = fminf(fmaxf(tz, a.v_min), a.v_max);
+                  const float b = fdiv(fadd(tz, -a.v_min), a.delta_z);
+                  const float lf = floorf(b), uf = ceilf(b);
+                  const int l = (int)lf, uu = (int)uf;
+                  const float nd = Pn[r * zp + z];
+                  if (pass == 0) Pm[r * zp + l] = fadd(Pm[r * zp + l], fmul(fadd((float)(uu + (l == uu ? 1 : 0)), -b), nd));
+                  else Pm[r * zp + uu] = fadd(Pm[r * zp + uu], fmul(fadd(b, -(float)l), nd));
+                }
+            }
+          }
+        }
+        FRL_SYNC();
+        // (4) online net on obs with the stored actions (forward #3, carries the gradient)
+        layer_fwd<FRL_R>(c, E3, 0, Xo, ip, H, ldh, FRL_ACT_RELU, fwd_hint(E3, 1));
+        heads_fwd(c, E3, H, ldh, V, zp, A, nat, bwd_hint(E3, 1));
+        FRL_PAR(t) { if (t < FRL_R) act[t] = (int)raw[t * rf + rb_col_act(a.replay)]; }
+        FRL_SYNC();
+        dist_of(a, V, zp, A, nat, act, Pn);
+        // (5) loss, PER error and d(loss)/d(logits of the taken action)
+        FRL_PAR(t) {
+          float l = 0.f;
+          if (t < FRL_R) {
+            const int r = t;
+            for (int z = 0; z < zp; ++z) dV[r * zp + z] = 0.f;
+            if (r < nvalid) {
+              const float w = a.is_weight ? a.is_weight[row0 + r] : 1.f;
+              float err = 0.f, dot = 0.f;
+              for (int z = 0; z < nZ; ++z) {
+                const float p = Pn[r * zp + z];
+                const float pc = fminf(fmaxf(p, 1e-5f), 1.f - 1e-5f);
+                err += Pm[r * zp + z] * logf(pc);
+                // dL/dp = -(m * w / B) / p inside the clamp range, 0 outside
+                const float gpz = (p >= 1e-5f && p <= 1.f - 1e-5f) ? -(Pm[r * zp + z] * w / (float)a.B) / pc : 0.f;
+                Dt[r * zp + z] = gpz;
+                dot += p * gpz;
+              }
+              for (int z = 0; z < nZ; ++z) dV[r * zp + z] = Pn[r * zp + z] * (Dt[r * zp + z] - dot);   // softmax backward
+              if (a.error_out) a.error_out[row0 + r] = err;
+              l = -err * w;
+            }
+          }
+          red0[t] = l;
+        }
+        FRL_SYNC();
+        loss_acc += block_sum(red0);
+        // dueling backward: dV[z] = dlogit[z];  dA[a'][z] = ([a'==a] - 1/nA) * dlogit[z]
+        FRL_PAR(t) {
+          for (int e = t; e < FRL_R * nat; e += FRL_NT) {
+            const int r = e / nat, j = e % nat;
+            float g = 0.f;
+            if (j < nA * nZ) {
+              const int ac = j / nZ, z = j % nZ;
+              g = ((ac == act[r] ? 1.f : 0.f) - 1.f / (float)nA) * dV[r * zp + z];
+            }
+            dA[e] = g;
+          }
+        }
+        FRL_SYNC();
+        // (6) backward through the heads into the hidden layer, then l1
+        gemm_outer<FRL_R>(dV, zp, E3.L[1].out_pad, H, ldh, E3.L[1].in_pad, E3.L[1].in, gp + E3.L[1].w_off, gp + E3.L[1].b_off, !first);
+        layer_bwd_dx<FRL_R>(c, E3, 1, dV, zp, nullptr, 0, dH, ldh, bwd_hint(E3, 2));
+        int col = 0;
+        for (int li = 2; li < E3.n_layers; ++li) {
+          const frl_layer_t& L = E3.L[li];
+          gemm_outer<FRL_R>(dA + col, nat, L.out_pad, H, ldh, L.in_pad, L.in, gp + L.w_off, gp + L.b_off, !first);
+          layer_bwd_dx<FRL_R>(c, E3, li, dA + col, nat, nullptr, 0, Hn, ldh, li + 1 < E3.n_layers ? bwd_hint(E3, li + 1) : no_hint());
+          FRL_PAR(t) { for (int e = t; e < FRL_R * ldh; e += FRL_NT) dH[e] += Hn[e]; }
+          FRL_SYNC();
+          col += L.out;
+        }
+        FRL_PAR(t) { for (int e = t; e < FRL_R * ldh; e += FRL_NT) dH[e] = H[e] > 0.f ? dH[e] : 0.f; }
+        FRL_SYNC();
+        gemm_outer<FRL_R>(dH, ldh, E3.L[0].out_pad, Xo, ip, E3.L[0].in_pad, E3.L[0].in, gp + E3.L[0].w_off, gp + E3.L[0].b_off, !first);
+        first = false;
+      }
+      FRL_PAR(t) { if (t == 0) a.stats[c.cta * 8] = loss_acc; }
+      FRL_SYNC();
+      return;
+    }
+    // stage 2: reduce effective-net gradients over CTAs, map to (mu, sigma), Adam + Polyak on the trainable block
+    float* sh = c.red;
+    FRL_PAR(t) {
+      if (t == 0) {
+        const AdamHP h = make_adam_hp(a.lr, a.beta1, a.beta2, a.eps_adam, 0.0, 0.0, (long)(a.step0 + u + 1));
+        sh[0] = h.lr_over_bc1_neg; sh[1] = h.bc2_sqrt; sh[2] = h.one_minus_b1; sh[3] = h.b2; sh[4] = h.one_minus_b2; sh[5] = h.eps;
+        if (c.cta == 0) {
+          float l = 0.f;
+          for (int i = 0; i < ncontrib; ++i) l += a.stats[i * 8];
+          a.out[u * 8] = l / (float)a.B;
+        }
+      }
+    }
+    FRL_SYNC();
+    const float* eps3 = a.eps + (size_t)2 * a.eps_len;
+    const float omt = (float)(1.0 - (double)a.tau);
+    FRL_PAR(t) {
+      for (int e = c.cta * FRL_NT + t; e < E3.n_p; e += c.ncta * FRL_NT) {
+        int dst_mu = -1, dst_sg = -1;
+        float noise = 0.f;
+        for (int li = 0; li < E3.n_layers; ++li) {
+          const frl_layer_t& L = E3.L[li];
+          const frl_noisy_map_t& M = a.map[li];
+          if (e >= L.w_off && e < L.w_off + L.out_pad * L.in_pad) {
+            const int j = (e - L.w_off) / L.in_pad, k = (e - L.w_off) % L.in_pad;
+            if (j < L.out && k < L.in) {
+              dst_mu = M.mu_w + (M.row0 + j) * L.in_pad + k;
+              if (M.sg_w >= 0) { dst_sg = M.sg_w + (M.row0 + j) * L.in_pad + k; noise = fmul(eps3[M.eps_out + M.row0 + j], eps3[M.eps_in + k]); }
+            }
+            break;
+          }
+          if (e >= L.b_off && e < L.b_off + L.out_pad) {
+            const int j = e - L.b_off;
+            if (j < L.out) {
+              dst_mu = M.mu_b + M.row0 + j;
+              if (M.sg_b >= 0) { dst_sg = M.sg_b + M.row0 + j; noise = eps3[M.eps_out + M.row0 + j]; }
+            }
+            break;
+          }
+        }
+        if (dst_mu < 0) continue;
+        float g = a.gpart[e];
+        for (int cc = 1; cc < ncontrib; ++cc) g += a.gpart[(size_t)cc * E3.n_p + e];
+        for (int which = 0; which < 2; ++which) {
+          const int d = which == 0 ? dst_mu : dst_sg;
+          if (d < 0) continue;
+          const float gg = which == 0 ? g : fmul(g, noise);
+          float m = a.m[d], v = a.v[d], w = a.p[d];
+          m = fmaf(sh[2], gg - m, m);
+          v = fadd(fmul(v, sh[3]), fmul(fmul(sh[4], gg), gg));
+          const float denom = fadd(fdiv(fsqrt(v), sh[1]), sh[5]);
+          w = fadd(w, fdiv(fmul(sh[0], m), denom));
+          a.m[d] = m; a.v[d] = v; a.p[d] = w;
+          a.p_target[d] = fadd(fmul(a.p_target[d], omt), fmul(w, a.tau));
+        }
+      }
+    }
+    FRL_SYNC();
+  }
+};
+
+// standalone noise application + greedy action (select_action of the Rainbow agent): effective net = eff[0]
+struct RainbowInferAlgo {
+  struct Args { frl_rainbow_args_t r; const float* obs; int n; float* out; };
+  static const int NSTAGES = 1;
+  FRL_SHD int wbuf_floats(const Args& a) { return RainbowAlgo::wbuf_floats(a.r); }
+  FRL_SHD int user_floats(const Args& a) { return RainbowAlgo::user_floats(a.r); }
+  FRL_SHD int grid(const Args& a, int) { return (a.n + FRL_R - 1) / FRL_R; }
+  FRL_SHD int n_updates(const Args&) { return 1; }
+  FRL_SDEV void stage(int, int, Cta& c, float* user, const Args& a) {
+    const frl_net_t& E = a.r.eff[0];
+    const int ldh = E.L[0].out_pad, ip = E.L[0].in_pad, zp = (a.r.n_atoms + 3) & ~3, nat = RainbowAlgo::natot(a.r), nA = a.r.n_actions;
+    SmemBump sb; sb.p = user;
+    float* X = sb.take(FRL_R * ip);
+    float* H = sb.take(FRL_R * ldh);
+    float* V = sb.take(FRL_R * zp);
+    float* A = sb.take(FRL_R * nat);
+    float* qv = sb.take(FRL_R * ((nA + 3) & ~3) + 4);
+    const int row0 = c.cta * FRL_R;
+    const int nvalid = (a.n - row0) < FRL_R ? (a.n - row0) : FRL_R;
+    stage_prefetch(c, layer_fwd_src(E, 0), layer_fwd_bytes(E.L[0]));
+    FRL_PAR(t) {
+      for (int e = t; e < FRL_R * ip; e += FRL_NT) {
+        const int r = e / ip, j = e % ip;
+        X[e] = (r < nvalid && j < a.r.replay.obs_dim) ? a.obs[(size_t)(row0 + r) * a.r.replay.obs_dim + j] : 0.f;
+      }
+    }
+    FRL_SYNC();
+    layer_fwd<FRL_R>(c, E, 0, X, ip, H, ldh, FRL_ACT_RELU, fwd_hint(E, 1));
+    RainbowAlgo::heads_fwd(c, E, H, ldh, V, zp, A, nat, no_hint());
+    RainbowAlgo::head_probs(a.r, V, zp, A, nat, qv);
+    FRL_PAR(t) {
+      if (t < nvalid) {
+        int best = 0;
+        for (int b = 1; b < nA; ++b) if (qv[t * nA + b] > qv[t * nA + best]) best = b;
+        a.out[row0 + t] = (float)best;
+      }
+    }
+    FRL_SYNC();
+  }
+};
+
+struct NoisyApplyAlgo {        // one effective net refresh as its own launch (select_action path)
+  struct Args { frl_rainbow_args_t r; int f; };
+  static const int NSTAGES = 1;
+  FRL_SHD int wbuf_floats(const Args&) { return 32; }
+  FRL_SHD int user_floats(const Args&) { return 64; }
+  FRL_SHD int grid(const Args& a, int) { return (a.r.eff[a.f].n_p + FRL_NT - 1) / FRL_NT; }
+  FRL_SHD int n_updates(const Args&) { return 1; }
+  FRL_SDEV void stage(int, int, Cta& c, float*, const Args& a) { RainbowAlgo::noisy_apply(a.r, a.f, c.cta, c.ncta); }
+};

@@ -8,6 +8,7 @@
 
 #include "algo_ppo.cuh"
 #include "algo_per.cuh"
+#include "algo_rainbow.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // error plumbing
@@ -413,4 +414,35 @@ extern "C" int frl_per_priorities(const float* td, int B, float eps, float alpha
   if (!td || !out || B <= 0) { frl_set_error("frl_per_priorities: bad arguments"); return -1; }
   PriBody b = {td, eps, alpha, out};
   return frl_for(B, b, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Rainbow
+// ------------------------------------------------------------------------------------------------
+static int check_rainbow(const frl_rainbow_args_t* a, const char* who) {
+  if (!a || !a->p || !a->p_target || !a->eps || !a->z || a->n_actions <= 0 || a->n_atoms <= 0) {
+    frl_set_error("%s: bad arguments", who);
+    return -1;
+  }
+  for (int f = 0; f < 3; ++f)
+    if (check_net(a->eff[f], false, who)) return -1;
+  return 0;
+}
+
+extern "C" int frl_rainbow_learn(const frl_rainbow_args_t* a, void* stream) {
+  if (check_rainbow(a, "frl_rainbow_learn")) return -1;
+  if (!a->m || !a->v || !a->indices || a->B <= 0 || !a->gpart || !a->stats || !a->out) {
+    frl_set_error("frl_rainbow_learn: bad arguments");
+    return -1;
+  }
+  return frl_launch<RainbowAlgo>(*a, (cudaStream_t)stream);
+}
+
+extern "C" int frl_rainbow_act(const frl_rainbow_args_t* a, const float* obs, int n, float* out, void* stream) {
+  if (check_rainbow(a, "frl_rainbow_act") || !obs || !out || n <= 0) { if (a) frl_set_error("frl_rainbow_act: bad arguments"); return -1; }
+  NoisyApplyAlgo::Args na = {*a, 0};
+  int rc = frl_launch_tiles<NoisyApplyAlgo>(na, (cudaStream_t)stream);
+  if (rc) return rc;
+  RainbowInferAlgo::Args ia = {*a, obs, n, out};
+  return frl_launch_tiles<RainbowInferAlgo>(ia, (cudaStream_t)stream);
 }

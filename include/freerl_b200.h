@@ -19,6 +19,7 @@
  *   frl_net_sync_mirror       (state_dict load -> refresh transposed weight mirrors; no reference counterpart)
  *   frl_sumtree_update/_sample/_max, frl_per_priorities
  *                             SumTree / PER_Buffer           DQN_file/Buffer.py:66-194
+ *   frl_rainbow_learn/_act    Rainbow DQN.learn / select_action   DQN_file/DQN_with_tricks.py:81-160,198-284; Noisy_net.py:17-76
  *   frl_gae                   PPO.learn GAE loop             PPO_file/PPO.py:222-233 (MAPPO_file/MAPPO.py:362-383)
  *   frl_ppo_update            PPO.learn minibatch loop + Agent.update_ac_ + c_adamw.AdamW.step
  *                                                            PPO_file/PPO.py:245-283,145-152; PPO_file/c_adamw.py:65-122
@@ -153,6 +154,41 @@ typedef struct {
   float* out;               /* dev [n_updates][8]: actor_loss, critic_loss, entropy, actor_gnorm, critic_gnorm */
 } frl_ppo_args_t;
 
+/* Rainbow (DQN_with_tricks.py): Categorical + Dueling + Noisy net.  The trainable block holds the torch tensors;
+ * eff[0..2] are noise-applied effective linear nets for the three forwards of a learn (online(s'), target(s'),
+ * online(s)); layer 0 = l1, layer 1 = V head, layers 2.. = column blocks (<=128 outputs) of the A head.
+ * map[li] tells where layer li's mu/sigma tensors live in the trainable block and which noise entries it uses. */
+typedef struct {
+  int mu_w, sg_w, mu_b, sg_b;   /* float offsets in the trainable block (sg_* = -1: plain nn.Linear) */
+  int row0;                     /* first output row of this block inside its torch tensor */
+  int eps_in, eps_out;          /* offsets of f(eps_in) / f(eps_out) inside one forward's noise vector */
+} frl_noisy_map_t;
+
+typedef struct {
+  float* p; float* m; float* v;      /* dev [n_train] online parameters + Adam state */
+  float* p_target;                   /* dev [n_train] target parameters */
+  int n_train;
+  frl_net_t eff[3];
+  frl_noisy_map_t map[FRL_MAX_LAYERS];
+  const float* eps;                  /* dev [3][eps_len]: transformed noise f(x)=sign(x)sqrt|x| per forward */
+  int eps_len;
+  int n_actions, n_atoms;
+  const float* z;                    /* dev [n_atoms] support (torch.linspace(v_min, v_max, n_atoms)) */
+  float v_min, v_max, delta_z;
+  int double_q;
+  frl_replay_t replay;
+  const int64_t* indices;            /* dev [B] */
+  const float* is_weight;            /* dev [B] PER importance weights or NULL */
+  int B;
+  float gamma, tau;                  /* gamma = n_step_gamma when N_Step */
+  double lr, beta1, beta2, eps_adam;
+  int64_t step0;
+  float* gpart;                      /* dev scratch [sm_count][eff[2].n_p] */
+  float* stats;                      /* dev scratch [sm_count][8] */
+  float* error_out;                  /* dev [B]: (m * log p).sum(1) per row (PER priorities) or NULL */
+  float* out;                        /* dev [8]: out[0] = loss */
+} frl_rainbow_args_t;
+
 const char* frl_last_error(void);
 int frl_is_emulation(void);          /* 0 for the CUDA library (the only one the product path accepts) */
 int frl_device_sm_count(void);
@@ -185,6 +221,9 @@ int frl_sumtree_sample(const double* tree, int64_t cap, const double* u, uint64_
                        double beta, double prob_floor, int64_t* out_idx, float* out_pri, float* out_w, void* stream);
 int frl_sumtree_max(const double* tree, int64_t cap, double* scratch, int nscratch, double* out, void* stream);
 int frl_per_priorities(const float* td, int B, float eps, float alpha, float* out, void* stream);
+int frl_rainbow_learn(const frl_rainbow_args_t* args, void* stream);
+/* select_action: refresh eff[0] from (p, eps[0]) and return argmax_a sum_z z*p(z|s,a) for n observations (out: [n] floats) */
+int frl_rainbow_act(const frl_rainbow_args_t* args, const float* obs, int n, float* out, void* stream);
 
 #ifdef __cplusplus
 }
