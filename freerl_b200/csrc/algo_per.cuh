@@ -9,13 +9,13 @@
 #include "launch.cuh"
 
 #ifndef FRL_EMUL
-FRL_DEV double dmul(double a, double b) { return __dmul_rn(a, b); }
-FRL_DEV double dadd(double a, double b) { return __dadd_rn(a, b); }
-FRL_DEV double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+FRL_DEV double f64mul(double a, double b) { return __dmul_rn(a, b); }
+FRL_DEV double f64add(double a, double b) { return __dadd_rn(a, b); }
+FRL_DEV double f64div(double a, double b) { return __ddiv_rn(a, b); }
 #else
-static inline double dmul(double a, double b) { volatile double r = a * b; return r; }
-static inline double dadd(double a, double b) { volatile double r = a + b; return r; }
-static inline double ddiv(double a, double b) { return a / b; }
+static inline double f64mul(double a, double b) { volatile double r = a * b; return r; }
+static inline double f64add(double a, double b) { volatile double r = a + b; return r; }
+static inline double f64div(double a, double b) { return a / b; }
 #endif
 
 #define FRL_PER_MAXB 1024
@@ -56,7 +56,7 @@ struct TreeUpdateAlgo {
         int prev = -1;
         for (int j = i - 1; j >= 0; --j) if (node[j] == node[i]) { prev = j; break; }
         const double before = prev >= 0 ? (a.pri32 ? (double)a.pri32[prev] : p) : a.tree[node[i]];
-        change[i] = dadd(p, -before);
+        change[i] = f64add(p, -before);
       }
     }
     FRL_SYNC();
@@ -84,8 +84,8 @@ struct TreeUpdateAlgo {
           bool leader = true;
           for (int j = 0; j < i; ++j) if (node[j] == nd) { leader = false; break; }
           if (!leader) continue;
-          double v = dadd(a.tree[nd], change[i]);
-          for (int j = i + 1; j < B; ++j) if (node[j] == nd) v = dadd(v, change[j]);
+          double v = f64add(a.tree[nd], change[i]);
+          for (int j = i + 1; j < B; ++j) if (node[j] == nd) v = f64add(v, change[j]);
           a.tree[nd] = v;
         }
       }
@@ -119,7 +119,7 @@ struct TreeSampleAlgo {
     double* redm = w + a.B;                         // [FRL_NT]
     const int64_t nnodes = 2 * a.cap - 1;
     const double total = a.tree[0];
-    const double seg = ddiv(total, (double)a.B);    // segment = sumtree.sum() / batch_size
+    const double seg = f64div(total, (double)a.B);    // segment = sumtree.sum() / batch_size
     FRL_PAR(t) {
       double mx = 0.0;
       for (int i = t; i < a.B; i += FRL_NT) {
@@ -130,21 +130,21 @@ struct TreeSampleAlgo {
           frl_philox((uint32_t)a.seed, (uint32_t)(a.seed >> 32), (uint32_t)i, (uint32_t)a.counter, (uint32_t)(a.counter >> 32), 0x9e3779b9u, o);
           ui = ((double)(((uint64_t)(o[0] >> 5) << 26) | (o[1] >> 6))) * (1.0 / 9007199254740992.0);
         }
-        const double lo = dmul(seg, (double)i), hi = dmul(seg, (double)(i + 1));
-        double s = dadd(lo, dmul(dadd(hi, -lo), ui));       // np.random.uniform(a, b) = a + (b-a)*random_sample()
+        const double lo = f64mul(seg, (double)i), hi = f64mul(seg, (double)(i + 1));
+        double s = f64add(lo, f64mul(f64add(hi, -lo), ui));       // np.random.uniform(a, b) = a + (b-a)*random_sample()
         int64_t nd = 0;
         while (2 * nd + 1 < nnodes) {                        // SumTree.get (Buffer.py:168-188)
           const int64_t left = 2 * nd + 1;
           const double tl = a.tree[left];
           if (s <= tl) nd = left;
-          else { s = dadd(s, -tl); nd = left + 1; }
+          else { s = f64add(s, -tl); nd = left + 1; }
         }
         const float p32 = (float)a.tree[nd];
         a.out_idx[i] = nd - a.cap + 1;
         a.out_pri[i] = p32;
-        double prob = ddiv((double)p32, total);
+        double prob = f64div((double)p32, total);
         if (prob < a.prob_floor) prob = a.prob_floor;
-        const double wi = pow(dmul((double)a.size, prob), -a.beta);
+        const double wi = pow(f64mul((double)a.size, prob), -a.beta);
         w[i] = wi;
         mx = wi > mx ? wi : mx;
       }
@@ -155,7 +155,7 @@ struct TreeSampleAlgo {
       FRL_PAR(t) { if (t < s2) redm[t] = redm[t] > redm[t + s2] ? redm[t] : redm[t + s2]; }
       FRL_SYNC();
     }
-    FRL_PAR(t) { for (int i = t; i < a.B; i += FRL_NT) a.out_w[i] = (float)ddiv(w[i], redm[0]); }
+    FRL_PAR(t) { for (int i = t; i < a.B; i += FRL_NT) a.out_w[i] = (float)f64div(w[i], redm[0]); }
     FRL_SYNC();
   }
 };
