@@ -1,0 +1,157 @@
+"""MADDPG with the reference's class API (``MADDPG_file/MADDPG.py:52-253``) on the fused B200 actor-critic kernel.
+
+``MADDPG(dim_info: dict, is_continue, actor_lr, critic_lr, buffer_size, device, trick, supplement)``;
+``select_action(obs: dict) -> dict``, ``evaluate_action``, ``add`` (dicts keyed by agent id), ``sample``,
+``learn(batch_size, gamma, tau)``, ``update_target``, ``save``/``load``.  Reference behaviour kept: one replay per
+agent sharing the sampled indices; a FRESH sample for every agent inside the learn loop (:211); centralised critic on
+``cat(all obs, all actions)``; next actions from every agent's TARGET actor; critic Adam with L2 weight_decay 1e-3
+and the uniform ``net_init`` when the supplements ask; Polyak of all agents only after the loop.
+``Batch_ObsNorm`` is not fused yet (raises).
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+from . import _common, _lib
+from .Buffer import Buffer
+from .DDPG import _reference_net_init
+from ._actor_critic import _ActorInit, _CriticInit
+from .nets import DeviceNet, alias_module, bind_module
+
+
+class Agent:
+    """``MADDPG.py:112-136``: per-agent actor (own obs) + centralised critic (all obs + all actions), targets, 2 Adams."""
+
+    def __init__(self, obs_dim, action_dim, dim_info, actor_lr, critic_lr, device, supplement):
+        joint = sum(sum(v) for v in dim_info.values())
+        a_dims = [(obs_dim, 128), (128, 128), (128, action_dim)]
+        c_dims = [(joint, 128), (128, 128), (128, 1)]
+        names = ("l1", "l2", "l3")
+        self._actor, self._critic = DeviceNet(a_dims, device, True), DeviceNet(c_dims, device, True)
+        self._actor_t, self._critic_t = DeviceNet(a_dims, device, False), DeviceNet(c_dims, device, False)
+        a_init = _ActorInit(obs_dim, action_dim, "l3")
+        if supplement['net_init']:
+            _reference_net_init(a_init, names)
+        c_init = _CriticInit(joint, 1)
+        if supplement['net_init']:
+            _reference_net_init(c_init, names)
+        self.actor = bind_module(self._actor, a_init, names)
+        self.critic = bind_module(self._critic, c_init, names)
+        self._actor_t.copy_from(self._actor)
+        self._critic_t.copy_from(self._critic)
+        self.actor_target = alias_module(self._actor_t, names)
+        self.critic_target = alias_module(self._critic_t, names)
+        self.actor_lr, self.critic_lr = actor_lr, critic_lr
+        self.weight_decay = 1e-3 if supplement['weight_decay'] else 0.0
+        self.actor_step = self.critic_step = 0
+
+
+class MADDPG:
+    def __init__(self, dim_info, is_continue, actor_lr, critic_lr, buffer_size, device, trick, supplement, mode=None):
+        self.device = _lib.require_device(device)
+        if len(dim_info) > _lib.FRL_MAX_AGENTS:
+            raise NotImplementedError("at most %d agents" % _lib.FRL_MAX_AGENTS)
+        if supplement.get('Batch_ObsNorm'):
+            raise NotImplementedError("Batch_ObsNorm is not available in the fused MADDPG kernel yet")
+        if not is_continue:
+            raise NotImplementedError("the reference implements continuous actions only (MADDPG.py:166)")
+        self.agents, self.buffers = {}, {}
+        for agent_id, (obs_dim, action_dim) in dim_info.items():
+            self.agents[agent_id] = Agent(obs_dim, action_dim, dim_info, actor_lr, critic_lr, self.device, supplement)
+            self.buffers[agent_id] = Buffer(buffer_size, obs_dim, act_dim=action_dim if is_continue else 1, device=self.device)
+        self.dim_info = dim_info
+        self.is_continue = is_continue
+        self.agent_x = list(self.agents.keys())[0]
+        self.regular = False
+        self.supplement = supplement
+        self.mode = _common.resolve_mode(mode)
+        self._seed = _common.default_seed()
+        self._n_learn = 0
+        n_p = max(max(a._actor.n_p, a._critic.n_p) for a in self.agents.values())
+        self._scratch = _common.DeviceScratch(self.device, n_p)
+        self.last_metrics = None
+
+    def select_action(self, obs):
+        actions = {}
+        for agent_id, o in obs.items():
+            od, ad = self.dim_info[agent_id]
+            x, single = _common.as_obs_batch(o, od)
+            a = _common.infer(self.agents[agent_id]._actor, x, _lib.INFER_TANH, self.device, ad).cpu().numpy()
+            actions[agent_id] = a[0] if single else a
+        return actions
+
+    def evaluate_action(self, obs):
+        return self.select_action(obs)
+
+    def add(self, obs, action, reward, next_obs, done):
+        for agent_id, buffer in self.buffers.items():
+            buffer.add(obs[agent_id], action[agent_id], reward[agent_id], next_obs[agent_id], done[agent_id])
+
+    def sample(self, batch_size):
+        total_size = len(self.buffers[self.agent_x])
+        indices = np.random.choice(total_size, batch_size, replace=False)
+        obs, action, reward, next_obs, done, next_action = {}, {}, {}, {}, {}, {}
+        for agent_id, buffer in self.buffers.items():
+            obs[agent_id], action[agent_id], reward[agent_id], next_obs[agent_id], done[agent_id] = buffer.sample(indices)
+            od, ad = self.dim_info[agent_id]
+            next_action[agent_id] = _common.infer(self.agents[agent_id]._actor_t, next_obs[agent_id], _lib.INFER_TANH, self.device, ad)
+        return obs, action, reward, next_obs, done, next_action
+
+    def learn(self, batch_size, gamma, tau, *, indices=None):
+        """``indices``: optional list (one per agent, agent order) of index arrays overriding the per-agent fresh samples."""
+        ids = list(self.agents.keys())
+        total = len(self.buffers[self.agent_x])
+        outs = []
+        for i, agent_id in enumerate(ids):
+            ag = self.agents[agent_id]
+            if indices is None:
+                idx = _common.make_indices(self.mode, total, batch_size, 1, self.device, self._seed, self._n_learn * len(ids) + i)
+            else:
+                idx = self.buffers[agent_id]._indices_to_device(indices[i]).reshape(1, -1)
+            B = idx.shape[1]
+            a = _lib.AcArgs()
+            a.actor, a.actor_target = ag._actor.c_struct(), ag._actor_t.c_struct()
+            a.critic, a.critic_target = ag._critic.c_struct(), ag._critic_t.c_struct()
+            a.n_heads, a.actor_kind = 1, _lib.ACTOR_TANH
+            a.replay = self.buffers[agent_id].c_struct()
+            a.indices, a.B, a.n_updates = idx.data_ptr(), B, 1
+            a.seed, a.gamma, a.tau = self._seed, gamma, tau
+            a.lr_actor, a.lr_critic = ag.actor_lr, ag.critic_lr
+            a.beta1, a.beta2, a.eps, a.wd_critic, a.max_norm = 0.9, 0.999, 1e-8, ag.weight_decay, 0.5
+            a.step_actor0, a.step_critic0, a.total_it0 = ag.actor_step, ag.critic_step, self._n_learn
+            a.policy_freq, a.target_smoothing, a.max_action, a.policy_noise_scale = 1, 0, 1.0, 1.0
+            out = torch.zeros((1, 8), dtype=torch.float32, device=self.device)
+            a.gpart, a.sumsq = self._scratch.gpart.data_ptr(), self._scratch.sumsq.data_ptr()
+            a.stats, a.out = self._scratch.stats.data_ptr(), out.data_ptr()
+            a.n_agents, a.agent_index, a.defer_polyak = len(ids), i, 1
+            for j, other in enumerate(ids):
+                a.ma_replay[j] = self.buffers[other].c_struct()
+                a.ma_actor_target[j] = self.agents[other]._actor_t.c_struct()
+            _lib.check(_lib.lib().frl_ac_learn(ctypes.byref(a), _lib.stream_ptr(self.device)), "frl_ac_learn")
+            ag.actor_step += 1
+            ag.critic_step += 1
+            outs.append((out, idx))
+        self.update_target(tau)
+        self._n_learn += 1
+        self.last_metrics = torch.cat([o for o, _ in outs])
+
+    def update_target(self, tau):
+        for ag in self.agents.values():
+            for src, tgt in ((ag._actor, ag._actor_t), (ag._critic, ag._critic_t)):
+                _lib.check(_lib.lib().frl_polyak(ctypes.byref(src.c_struct()), ctypes.byref(tgt.c_struct()), float(tau),
+                                                 _lib.stream_ptr(self.device)), "frl_polyak")
+
+    def save(self, model_path):
+        torch.save({name: {k: v.detach().clone().cpu() for k, v in agent.actor.state_dict().items()} for name, agent in self.agents.items()},
+                   os.path.join(model_path, 'MADDPG.pth'))
+
+    @staticmethod
+    def load(dim_info, is_continue, model_dir, trick=None, supplement=None, device=None):
+        device = device if device is not None else torch.device("cuda")
+        policy = MADDPG(dim_info, is_continue=is_continue, actor_lr=0, critic_lr=0, buffer_size=0, device=device, trick=trick, supplement=supplement)
+        data = torch.load(os.path.join(model_dir, 'MADDPG.pth'), map_location=device)
+        for agent_id, agent in policy.agents.items():
+            agent.actor.load_state_dict(data[agent_id])
+        return policy

@@ -11,6 +11,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 FRL_MAX_LAYERS = 6
+FRL_MAX_AGENTS = 6
 ABI_VERSION = 1
 
 
@@ -49,7 +50,9 @@ class AcArgs(C.Structure):
                 ("noise_clip", C.c_float), ("max_action", C.c_float), ("policy_noise_scale", C.c_float),
                 ("alpha_state", C.c_void_p), ("adaptive_alpha", C.c_int), ("alpha_lr", C.c_double),
                 ("target_entropy", C.c_float), ("step_alpha0", C.c_int64),
-                ("gpart", C.c_void_p), ("sumsq", C.c_void_p), ("stats", C.c_void_p), ("out", C.c_void_p)]
+                ("gpart", C.c_void_p), ("sumsq", C.c_void_p), ("stats", C.c_void_p), ("out", C.c_void_p),
+                ("n_agents", C.c_int), ("agent_index", C.c_int), ("ma_replay", Replay * FRL_MAX_AGENTS),
+                ("ma_actor_target", Net * FRL_MAX_AGENTS), ("defer_polyak", C.c_int)]
 
 
 class InferArgs(C.Structure):
@@ -99,6 +102,8 @@ def _declare(lib):
     lib.frl_replay_gather.argtypes = [C.POINTER(Replay), vp, ci, vp, vp, vp, vp, vp, vp]
     lib.frl_sample_uniform.argtypes = [vp, i64, ci, ci, u64, u64, vp]
     lib.frl_net_sync_mirror.argtypes = [C.POINTER(Net), vp]
+    lib.frl_polyak.argtypes = [C.POINTER(Net), C.POINTER(Net), C.c_float, vp]
+    lib.frl_polyak.restype = ci
     lib.frl_dqn_learn.argtypes = [C.POINTER(DqnArgs), vp]
     lib.frl_ac_learn.argtypes = [C.POINTER(AcArgs), vp]
     lib.frl_policy_infer.argtypes = [C.POINTER(InferArgs), vp]

@@ -29,9 +29,19 @@ struct AcAlgo {
     int x = max_layer_floats(a.actor), y = max_layer_floats(a.critic);
     return ((x > y ? x : y) + 31) & ~31;
   }
+  // ---- multi-agent helpers: where agent j's obs / action sit inside the joint critic input [obs_1..obs_N | act_1..act_N]
+  FRL_SHD int ma_n(const Args& a) { return a.n_agents > 1 ? a.n_agents : 1; }
+  FRL_SHD const frl_replay_t& rep(const Args& a, int j) { return a.n_agents > 1 ? a.ma_replay[j] : a.replay; }
+  FRL_SHD const frl_net_t& tnet(const Args& a, int j) { return a.n_agents > 1 ? a.ma_actor_target[j] : a.actor_target; }
+  FRL_SHD int obs_off(const Args& a, int j) { int o = 0; for (int k = 0; k < j; ++k) o += rep(a, k).obs_dim; return o; }
+  FRL_SHD int act_off(const Args& a, int j) { int o = obs_off(a, ma_n(a)); for (int k = 0; k < j; ++k) o += rep(a, k).act_dim; return o; }
+  FRL_SHD int raw_off(const Args& a, int j) { int o = 0; for (int k = 0; k < j; ++k) o += FRL_R * rep(a, k).row_floats; return o; }
+  FRL_SHD int max_aip(const Args& a) { int m = a.actor.L[0].in_pad; for (int j = 0; j < ma_n(a); ++j) { int v = tnet(a, j).L[0].in_pad; if (v > m) m = v; } return m; }
+  FRL_SHD int max_ap(const Args& a) { int m = a.actor.L[2].out_pad; for (int j = 0; j < ma_n(a); ++j) { int v = tnet(a, j).L[2].out_pad; if (v > m) m = v; } return m; }
+
   FRL_SHD int user_floats(const Args& a) {
-    const int ldh = a.critic.L[0].out_pad, sa = a.critic.L[0].in_pad, ap = a.actor.L[2].out_pad;
-    return FRL_R * (a.replay.row_floats + 3 * sa + 8 * ldh + 6 * ap + 4 * 4 + 16) + 2 * FRL_NT + 128;
+    const int ldh = a.critic.L[0].out_pad, sa = a.critic.L[0].in_pad, ap = max_ap(a);
+    return raw_off(a, ma_n(a)) + FRL_R * (max_aip(a) + 3 * sa + 8 * ldh + 6 * ap + 4 * 4 + 16) + 2 * FRL_NT + 128;
   }
   FRL_SHD int grid(const Args& a, int max_ctas) {
     int tiles = (a.B + FRL_R - 1) / FRL_R;
@@ -49,7 +59,9 @@ struct AcAlgo {
     const frl_net_t& C = a.critic;
     const frl_replay_t& rb = a.replay;
     const int od = rb.obs_dim, ad = rb.act_dim, rf = rb.row_floats;
-    const int ldh = C.L[0].out_pad, sa = C.L[0].in_pad, ap = A.L[2].out_pad;
+    const int ldh = C.L[0].out_pad, sa = C.L[0].in_pad, ap = max_ap(a);
+    const int NA = ma_n(a), ai = a.n_agents > 1 ? a.agent_index : 0;
+    const int aip = max_aip(a);
     const int ntile = (a.B + FRL_R - 1) / FRL_R;
     const int ncontrib = grid(a, c.ncta);
     const float invB = 1.0f / (float)a.B;
@@ -61,7 +73,9 @@ struct AcAlgo {
     if (sac) alpha = expf(a.alpha_state[0]);
 
     SmemBump sb; sb.p = user;
-    float* raw = sb.take(FRL_R * rf);
+    float* raw0 = sb.take(raw_off(a, NA));   // gathered rows of every agent's replay (same indices)
+    float* raw = raw0 + raw_off(a, ai);      // this agent's rows (reward / done come from here)
+    float* XA = sb.take(FRL_R * aip);        // actor input (one agent's obs / next_obs)
     float* XS = sb.take(FRL_R * sa);     // [obs | act]
     float* XN = sb.take(FRL_R * sa);     // [next_obs | a']        (stage 3: [obs | pi(obs)])
     float* dXP = sb.take(FRL_R * sa);    // dQ/d[obs|a]
@@ -96,43 +110,56 @@ struct AcAlgo {
       for (int tile = c.cta; tile < ntile; tile += c.ncta) {
         const int row0 = tile * FRL_R;
         const int nvalid = (a.B - row0) < FRL_R ? (a.B - row0) : FRL_R;
-        stage_prefetch(c, layer_fwd_src(a.actor_target, 0), layer_fwd_bytes(a.actor_target.L[0]));
-        gather_rows<FRL_R>(rb, a.indices + (size_t)u * a.B + row0, nvalid, raw);
-        copy_cols<FRL_R>(XS, sa, 0, raw, rf, 0, od + ad, sa);
-        copy_cols<FRL_R>(XN, sa, 0, raw, rf, rb_col_nobs(rb), od, sa);
-        stamp(c, 1);
-        // a' = actor_target(next_obs)
-        mlp_fwd<FRL_R>(c, a.actor_target, 0, 3, XN, sa, A1, A2, ldh, MU, ap, FRL_ACT_NONE, fwd_hint(a.critic_target, 0));
-        FRL_PAR(t) {
-          if (t < FRL_R * ad) {
-            const int r = t / ad, j = t % ad;
-            const float mean = MU[r * ap + j];
-            float act;
-            if (sac) {
-              const float* ls_p = a.actor_target.p + a.actor_target.x_off;
-              const float ls = fminf(fmaxf(ls_p[j], -20.f), 2.f);
-              const float sd = expf(ls);
-              const float e = (r < nvalid) ? noise_at(a.noise_next, a, u, row0 + r, j, 1u) : 0.f;
-              const float uu = fadd(mean, fmul(e, sd));
-              const float diff = uu - mean;
-              float lp = -(diff * diff) / (2.f * (sd * sd)) - logf(sd) - FRL_LOG_SQRT_2PI;
-              lp -= 2.f * (FRL_LOG2F - uu - softplus_t(-2.f * uu));
-              UU[r * ap + j] = lp;                      // per-dim log-prob contribution
-              act = tanhf(uu);
-            } else if (a.target_smoothing) {
-              const float e = (r < nvalid) ? noise_at(a.noise_next, a, u, row0 + r, j, 1u) : 0.f;
-              float nz = fmul(a.policy_noise_scale, fmul(e, a.policy_noise));
-              nz = fminf(fmaxf(nz, -a.noise_clip), a.noise_clip);
-              float v = fadd(fmul(tanhf(mean), a.max_action), nz);
-              v = fminf(fmaxf(v, -a.max_action), a.max_action);
-              act = fdiv(v, a.max_action);
-            } else {
-              act = tanhf(mean);
-            }
-            XN[r * sa + od + j] = act;
-          }
+        stage_prefetch(c, layer_fwd_src(tnet(a, 0), 0), layer_fwd_bytes(tnet(a, 0).L[0]));
+        for (int j = 0; j < NA; ++j) gather_rows<FRL_R>(rep(a, j), a.indices + (size_t)u * a.B + row0, nvalid, raw0 + raw_off(a, j));
+        copy_cols<FRL_R>(XN, sa, act_off(a, 0), raw0, 1, 0, 0, sa);                 // zero the action + pad columns of XN
+        for (int j = 0; j < NA; ++j) {
+          const frl_replay_t& rj = rep(a, j);
+          const float* rw = raw0 + raw_off(a, j);
+          copy_cols<FRL_R>(XS, sa, obs_off(a, j), rw, rj.row_floats, 0, rj.obs_dim, 0);
+          copy_cols<FRL_R>(XS, sa, act_off(a, j), rw, rj.row_floats, rb_col_act(rj), rj.act_dim, j == NA - 1 ? sa : 0);
+          copy_cols<FRL_R>(XN, sa, obs_off(a, j), rw, rj.row_floats, rb_col_nobs(rj), rj.obs_dim, 0);
         }
-        FRL_SYNC();
+        stamp(c, 1);
+        // a'_j = actor_target_j(next_obs_j) for every agent (single agent: j = 0)
+        for (int j = 0; j < NA; ++j) {
+          const frl_replay_t& rj = rep(a, j);
+          const frl_net_t& T = tnet(a, j);
+          const int adj = rj.act_dim, tip = T.L[0].in_pad, aoff = act_off(a, j);
+          copy_cols<FRL_R>(XA, tip, 0, raw0 + raw_off(a, j), rj.row_floats, rb_col_nobs(rj), rj.obs_dim, tip);
+          mlp_fwd<FRL_R>(c, T, 0, 3, XA, tip, A1, A2, ldh, MU, ap, FRL_ACT_NONE,
+                         j + 1 < NA ? fwd_hint(tnet(a, j + 1), 0) : fwd_hint(a.critic_target, 0));
+          FRL_PAR(t) {
+            if (t < FRL_R * adj) {
+              const int r = t / adj, jj = t % adj;
+              const float mean = MU[r * ap + jj];
+              float act;
+              if (sac) {
+                const float* ls_p = T.p + T.x_off;
+                const float ls = fminf(fmaxf(ls_p[jj], -20.f), 2.f);
+                const float sd = expf(ls);
+                const float e = (r < nvalid) ? noise_at(a.noise_next, a, u, row0 + r, jj, 1u) : 0.f;
+                const float uu = fadd(mean, fmul(e, sd));
+                const float diff = uu - mean;
+                float lp = -(diff * diff) / (2.f * (sd * sd)) - logf(sd) - FRL_LOG_SQRT_2PI;
+                lp -= 2.f * (FRL_LOG2F - uu - softplus_t(-2.f * uu));
+                UU[r * ap + jj] = lp;                      // per-dim log-prob contribution
+                act = tanhf(uu);
+              } else if (a.target_smoothing) {
+                const float e = (r < nvalid) ? noise_at(a.noise_next, a, u, row0 + r, jj, 1u) : 0.f;
+                float nz = fmul(a.policy_noise_scale, fmul(e, a.policy_noise));
+                nz = fminf(fmaxf(nz, -a.noise_clip), a.noise_clip);
+                float v = fadd(fmul(tanhf(mean), a.max_action), nz);
+                v = fminf(fmaxf(v, -a.max_action), a.max_action);
+                act = fdiv(v, a.max_action);
+              } else {
+                act = tanhf(mean);
+              }
+              XN[r * sa + aoff + jj] = act;
+            }
+          }
+          FRL_SYNC();
+        }
         stamp(c, 2);
         // target Q heads
         mlp_fwd<FRL_R>(c, a.critic_target, 0, 3, XN, sa, H1, H2, ldh, QA, 4, FRL_ACT_NONE,
@@ -197,7 +224,7 @@ struct AcAlgo {
       reduce_grads(c.cta, c.ncta, c.red, C, a.gpart, gstride, ncontrib, a.sumsq);
     } else if (s == 2) {
       const AdamSpec hp = {a.lr_critic, a.beta1, a.beta2, a.eps, a.wd_critic, (double)a.max_norm, (long)(a.step_critic0 + u + 1)};
-      adam_update(c.cta, c.ncta, c.red, C, a.sumsq, ncontrib, hp, policy_step ? &a.critic_target : nullptr, a.tau);
+      adam_update(c.cta, c.ncta, c.red, C, a.sumsq, ncontrib, hp, (policy_step && !a.defer_polyak) ? &a.critic_target : nullptr, a.tau);
       FRL_PAR(t) {
         if (c.cta == 0 && t == 0) {
           float l = 0.f, ss = 0.f;
@@ -217,9 +244,16 @@ struct AcAlgo {
         const int row0 = tile * FRL_R;
         const int nvalid = (a.B - row0) < FRL_R ? (a.B - row0) : FRL_R;
         stage_prefetch(c, layer_fwd_src(A, 0), layer_fwd_bytes(A.L[0]));
-        gather_rows<FRL_R>(rb, a.indices + (size_t)u * a.B + row0, nvalid, raw);
-        copy_cols<FRL_R>(XN, sa, 0, raw, rf, 0, od, sa);
-        mlp_fwd<FRL_R>(c, A, 0, 3, XN, sa, A1, A2, ldh, MU, ap, FRL_ACT_NONE, fwd_hint(C, 0));
+        for (int j = 0; j < NA; ++j) gather_rows<FRL_R>(rep(a, j), a.indices + (size_t)u * a.B + row0, nvalid, raw0 + raw_off(a, j));
+        for (int j = 0; j < NA; ++j) {
+          const frl_replay_t& rj = rep(a, j);
+          const float* rw = raw0 + raw_off(a, j);
+          copy_cols<FRL_R>(XN, sa, obs_off(a, j), rw, rj.row_floats, 0, rj.obs_dim, 0);
+          copy_cols<FRL_R>(XN, sa, act_off(a, j), rw, rj.row_floats, rb_col_act(rj), rj.act_dim, j == NA - 1 ? sa : 0);
+        }
+        const int aoff_i = act_off(a, ai), aipi = A.L[0].in_pad;
+        copy_cols<FRL_R>(XA, aipi, 0, raw, rf, 0, od, aipi);
+        mlp_fwd<FRL_R>(c, A, 0, 3, XA, aipi, A1, A2, ldh, MU, ap, FRL_ACT_NONE, fwd_hint(C, 0));
         FRL_PAR(t) {
           if (t < FRL_R * ap) {
             const int r = t / ap, j = t % ap;
@@ -238,7 +272,7 @@ struct AcAlgo {
               } else {
                 act = tanhf(mean);
               }
-              XN[r * sa + od + j] = act;
+              XN[r * sa + aoff_i + j] = act;
             }
             AC[r * ap + j] = act; UU[r * ap + j] = lp; EPS[r * ap + j] = e; dA[r * ap + j] = 0.f;
           }
@@ -263,7 +297,7 @@ struct AcAlgo {
           mlp_bwd<FRL_R>(c, C, 3 * h, 3, XN, sa, H1, H2, ldh, dQA, 4, D1, D2, dXP, sa, nullptr, false,
                          h + 1 < heads_used ? fwd_hint(C, 3 * (h + 1)) : bwd_hint(A, 2));
           FRL_PAR(t) {
-            if (t < FRL_R * ad) { const int r = t / ad, j = t % ad; dA[r * ap + j] += dXP[r * sa + od + j]; }
+            if (t < FRL_R * ad) { const int r = t / ad, j = t % ad; dA[r * ap + j] += dXP[r * sa + aoff_i + j]; }
           }
           FRL_SYNC();
         }
@@ -304,7 +338,7 @@ struct AcAlgo {
           }
           FRL_SYNC();
         }
-        mlp_bwd<FRL_R>(c, A, 0, 3, XN, sa, A1, A2, ldh, dMU, ap, D1, D2, nullptr, 0, gp, !first, no_hint());
+        mlp_bwd<FRL_R>(c, A, 0, 3, XA, aipi, A1, A2, ldh, dMU, ap, D1, D2, nullptr, 0, gp, !first, no_hint());
         first = false;
       }
       FRL_PAR(t) { if (t == 0) { a.stats[c.cta * 8 + 1] = loss_acc; a.stats[c.cta * 8 + 2] = ent_acc; } }
@@ -315,7 +349,7 @@ struct AcAlgo {
     } else {
       if (!policy_step) return;
       const AdamSpec hp = {a.lr_actor, a.beta1, a.beta2, a.eps, 0.0, (double)a.max_norm, (long)(a.step_actor0 + n_policy_before + 1)};
-      adam_update(c.cta, c.ncta, c.red, A, a.sumsq, ncontrib, hp, &a.actor_target, a.tau);
+      adam_update(c.cta, c.ncta, c.red, A, a.sumsq, ncontrib, hp, a.defer_polyak ? nullptr : &a.actor_target, a.tau);
       FRL_PAR(t) {
         if (c.cta == 0 && t == 0) {
           float l = 0.f, en = 0.f, ss = 0.f;

@@ -216,6 +216,30 @@ extern "C" int frl_net_sync_mirror(const frl_net_t* net, void* stream) {
   return frl_for(net->n_p, b, (cudaStream_t)stream);
 }
 
+struct PolyakBody {
+  frl_net_t src, tgt; float tau, omt;
+  FRL_DEVM void operator()(long p) const {
+    const float tw = fadd(fmul(tgt.p[p], omt), fmul(src.p[p], tau));
+    tgt.p[p] = tw;
+    for (int li = 0; li < src.n_layers; ++li) {
+      const frl_layer_t& L = src.L[li];
+      const int wsz = L.out_pad * L.in_pad;
+      if (p >= L.w_off && p < L.w_off + wsz) {
+        const int e = (int)p - L.w_off, j = e / L.in_pad, k = e % L.in_pad;
+        tgt.pt[L.wt_off + k * L.out_pad + j] = tw;
+        return;
+      }
+      if (p >= L.b_off && p < L.b_off + L.out_pad) { tgt.pt[L.wt_off + wsz + ((int)p - L.b_off)] = tw; return; }
+    }
+  }
+};
+
+extern "C" int frl_polyak(const frl_net_t* src, const frl_net_t* target, float tau, void* stream) {
+  if (!src || !target || !src->p || !target->p || !target->pt || src->n_p != target->n_p) { frl_set_error("frl_polyak: bad arguments"); return -1; }
+  PolyakBody b = {*src, *target, tau, (float)(1.0 - (double)tau)};
+  return frl_for(src->n_p, b, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------------------------------------
 // batched policy inference (select_action / evaluate_action for N vectorised envs)
 // ------------------------------------------------------------------------------------------------
@@ -346,6 +370,10 @@ extern "C" int frl_ac_learn(const frl_ac_args_t* a, void* stream) {
   if (check_net(a->actor, true, "frl_ac_learn(actor)") || check_net(a->critic, true, "frl_ac_learn(critic)") ||
       check_net(a->actor_target, false, "frl_ac_learn(actor_target)") || check_net(a->critic_target, false, "frl_ac_learn(critic_target)"))
     return -1;
+  if (a->n_agents > FRL_MAX_AGENTS || (a->n_agents > 1 && (a->agent_index < 0 || a->agent_index >= a->n_agents))) {
+    frl_set_error("frl_ac_learn: n_agents must be <= %d", FRL_MAX_AGENTS);
+    return -1;
+  }
   if (a->actor.n_layers != 3 || a->critic.n_layers != 3 * a->n_heads || (a->actor_kind == FRL_ACTOR_SAC && !a->alpha_state)) {
     frl_set_error("frl_ac_learn: unsupported network shape / missing alpha state");
     return -1;

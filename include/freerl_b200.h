@@ -33,6 +33,7 @@ extern "C" {
 #endif
 
 #define FRL_MAX_LAYERS 6
+#define FRL_MAX_AGENTS 6
 
 /* One linear layer inside a parameter block.  W is stored [out_pad][in_pad] row-major (torch layout, zero padded to
  * multiples of 4), bias [out_pad]; the transposed mirror WT [in_pad][out_pad] followed by a bias copy lives in `pt`. */
@@ -108,6 +109,13 @@ typedef struct {
   float* sumsq;             /* dev scratch [sm_count] */
   float* stats;             /* dev scratch [sm_count][8] */
   float* out;               /* dev [n_updates][8]: critic_loss, actor_loss, alpha, alpha_loss, critic_gnorm, actor_gnorm, mean_entropy, 0 */
+  /* ---- multi-agent (MADDPG, MADDPG_file/MADDPG.py:186-228): n_agents > 1 ----
+   * the critic sees cat(obs_1..obs_N, act_1..act_N); next actions come from every agent's target actor on its own
+   * next_obs; `replay`/`actor`/`actor_target` above belong to agent `agent_index`; all replays share the sampled indices. */
+  int n_agents, agent_index;
+  frl_replay_t ma_replay[FRL_MAX_AGENTS];
+  frl_net_t ma_actor_target[FRL_MAX_AGENTS];
+  int defer_polyak;         /* 1: do not touch the targets (MADDPG updates all targets after the agent loop) */
 } frl_ac_args_t;
 
 enum { FRL_INFER_ARGMAX = 0, FRL_INFER_TANH = 1, FRL_INFER_SAC_SAMPLE = 2, FRL_INFER_SAC_MEAN = 3, FRL_INFER_RAW = 4,
@@ -201,6 +209,8 @@ int frl_replay_gather(const frl_replay_t* rb, const int64_t* indices, int B, flo
 int frl_sample_uniform(int64_t* indices_out, int64_t size, int B, int n_updates, uint64_t seed, uint64_t counter,
                        void* stream);
 int frl_net_sync_mirror(const frl_net_t* net, void* stream);
+/* theta' <- theta'(1-tau) + theta*tau on parameter block + mirror (update_target, e.g. MADDPG.py:230-237) */
+int frl_polyak(const frl_net_t* src, const frl_net_t* target, float tau, void* stream);
 int frl_dqn_learn(const frl_dqn_args_t* args, void* stream);
 int frl_ac_learn(const frl_ac_args_t* args, void* stream);
 int frl_policy_infer(const frl_infer_args_t* args, void* stream);

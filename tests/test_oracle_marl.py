@@ -1,0 +1,38 @@
+"""MADDPG oracle replayed against the reference-generated fixture."""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from oracle.marl import MADDPGOracle
+
+IDS = ["agent_0", "agent_1", "agent_2"]
+
+
+def maddpg_nets(g, which, kind):
+    out = OrderedDict()
+    for k in IDS:
+        pre = "%s/%s/%s/" % (which, k, kind)
+        out[k] = OrderedDict((n[len(pre):], torch.from_numpy(g[n].copy())) for n in g.files if n.startswith(pre))
+    return out
+
+
+def maddpg_batch(g, idx):
+    f = lambda x: torch.from_numpy(np.asarray(x, dtype=np.float32))
+    return {k: (f(g["buf/%s/obs" % k][idx]), f(g["buf/%s/act" % k][idx]), f(g["buf/%s/rew" % k][idx]).reshape(-1, 1),
+                f(g["buf/%s/nobs" % k][idx]), f(g["buf/%s/done" % k][idx]).reshape(-1, 1)) for k in IDS}
+
+
+def test_maddpg_oracle_vs_reference(golden):
+    g = golden("maddpg")
+    orc = MADDPGOracle(maddpg_nets(g, "init", "actor"), maddpg_nets(g, "init", "critic"), 1e-3, 1e-3)
+    ls = []
+    for it in range(2):
+        r = orc.learn([maddpg_batch(g, g["idx/%d/%d" % (it, j)]) for j in range(3)], 0.95, 0.01)
+        for cl, al in r:
+            ls += [cl, al]
+    np.testing.assert_allclose(np.array(ls), g["losses"], rtol=2e-5, atol=1e-7)
+    for k in IDS:
+        for kind, nets in (("actor", orc.actor), ("critic", orc.critic), ("actor_target", orc.actor_target), ("critic_target", orc.critic_target)):
+            for n, v in nets[k].items():
+                np.testing.assert_allclose(v.detach().numpy(), g["final/%s/%s/%s" % (k, kind, n)], rtol=2e-5, atol=2e-6)
