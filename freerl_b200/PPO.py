@@ -54,14 +54,17 @@ class Agent:
     """``PPO.py:109-152``: actor + critic with ONE merged optimiser -> ONE device parameter block (layers 0-2 actor,
     3-5 critic, extra = log_std)."""
 
-    def __init__(self, obs_dim, action_dim, actor_lr, critic_lr, is_continue, device, critic_in=None):
+    def __init__(self, obs_dim, action_dim, actor_lr, critic_lr, is_continue, device, critic_in=None, init_hook=None):
         head = "mean_layer" if is_continue else "l3"
         critic_in = obs_dim if critic_in is None else critic_in
         dims = [(obs_dim, 128), (128, 128), (128, action_dim), (critic_in, 128), (128, 128), (128, 1)]
         self._net = DeviceNet(dims, device, True, x_len=action_dim if is_continue else 0)
         a_init = _ActorInit(obs_dim, action_dim, head)          # same RNG consumption as Actor / Actor_discrete
+        if init_hook:
+            init_hook(a_init, ("l1", "l2", head), "actor")          # re-initialisation inside the module constructor
         c_init = _CriticInit(critic_in)
-        self._post_init(a_init, c_init)
+        if init_hook:
+            init_hook(c_init, ("l1", "l2", "l3"), "critic")
         with torch.no_grad():
             for li, lay in enumerate((a_init.l1, a_init.l2, getattr(a_init, head), c_init.l1, c_init.l2, c_init.l3)):
                 self._net.weight(li).copy_(lay.weight.to(device))
@@ -72,9 +75,6 @@ class Agent:
         self.critic = _shim(self._net, (3, 4, 5), ("l1", "l2", "l3"))
         self.lr = actor_lr                                       # AdamW(actor+critic params, lr=actor_lr)  PPO.py:121
         self.step = 0
-
-    def _post_init(self, a_init, c_init):
-        pass
 
 
 class PPO:

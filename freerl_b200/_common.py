@@ -65,7 +65,7 @@ def reference_randn(shape, device):
     return torch.empty(shape, dtype=torch.float32, device=device).normal_()
 
 
-def infer(net, obs, mode, device, out_cols, noise=None, seed=0, counter=0, l0=0, nl=0):
+def infer(net, obs, mode, device, out_cols, noise=None, seed=0, counter=0, l0=0, nl=0, layer_norm=False):
     """Batched policy inference.  ``obs``: numpy / tensor [n, obs_dim] -> device tensor [n, out_cols]."""
     if isinstance(obs, torch.Tensor):
         x = obs.to(device=device, dtype=torch.float32).contiguous()
@@ -76,6 +76,7 @@ def infer(net, obs, mode, device, out_cols, noise=None, seed=0, counter=0, l0=0,
     a = _lib.InferArgs()
     a.net = net.c_struct()
     a.l0, a.nl = l0, nl
+    a.layer_norm = int(layer_norm)
     a.obs, a.n, a.obs_dim, a.mode = x.data_ptr(), n, obs_dim, mode
     a.noise = noise.data_ptr() if noise is not None else None
     a.seed, a.counter = seed, counter & 0xFFFFFFFF

@@ -58,7 +58,7 @@ class AcArgs(C.Structure):
 class InferArgs(C.Structure):
     _fields_ = [("net", Net), ("l0", C.c_int), ("nl", C.c_int), ("obs", C.c_void_p), ("n", C.c_int), ("obs_dim", C.c_int), ("mode", C.c_int),
                 ("noise", C.c_void_p), ("seed", C.c_uint64), ("counter", C.c_uint32), ("out", C.c_void_p),
-                ("out_cols", C.c_int)]
+                ("out_cols", C.c_int), ("layer_norm", C.c_int)]
 
 
 class PpoArgs(C.Structure):
@@ -68,7 +68,9 @@ class PpoArgs(C.Structure):
                 ("indices", C.c_void_p), ("mb_rows", C.c_void_p), ("mb", C.c_int), ("n_updates", C.c_int),
                 ("clip_param", C.c_float), ("entropy_coef", C.c_float), ("max_norm_actor", C.c_float),
                 ("max_norm_critic", C.c_float), ("optimizer", C.c_int), ("lr", C.c_double), ("beta1", C.c_double),
-                ("beta2", C.c_double), ("eps", C.c_double), ("step0", C.c_int64), ("gpart", C.c_void_p),
+                ("beta2", C.c_double), ("eps", C.c_double), ("step0", C.c_int64),
+                ("layer_norm", C.c_int), ("critic_obs", C.c_void_p), ("critic_obs_dim", C.c_int), ("value_loss", C.c_int),
+                ("huber_delta", C.c_float), ("gpart", C.c_void_p),
                 ("sumsq", C.c_void_p), ("segcnt", C.c_void_p), ("stats", C.c_void_p), ("out", C.c_void_p)]
 
 
@@ -115,6 +117,8 @@ def _declare(lib):
     lib.frl_per_priorities.argtypes = [vp, ci, C.c_float, C.c_float, vp, vp]
     lib.frl_rainbow_learn.argtypes = [C.POINTER(RainbowArgs), vp]
     lib.frl_rainbow_act.argtypes = [C.POINTER(RainbowArgs), vp, ci, vp, vp]
+    lib.frl_adv_norm.argtypes = [vp, ci, C.c_float, vp, vp]
+    lib.frl_adv_norm.restype = ci
     lib.frl_rainbow_learn.restype = ci
     lib.frl_rainbow_act.restype = ci
     for name in ("frl_replay_add_batch", "frl_replay_gather", "frl_sample_uniform", "frl_net_sync_mirror",

@@ -22,13 +22,113 @@ FRL_DEV int seg_of(const frl_net_t& n, int p, int* numel) {
   return 2 * FRL_MAX_LAYERS;
 }
 
+// ---- F.layer_norm(x, x.size()[1:]) without affine, eps 1e-5 (MAPPO.py:145-151), rows of a [R][ld] smem tile ----------
+template <int R>
+FRL_NI_MISC void ln_fwd(const float* X, int ld, int n, float* Y, float* rstd, float* scratch /*[R*32*2]*/) {
+  FRL_PAR(t) {
+    if (t < R * 32) {
+      const int r = t >> 5, l = t & 31;
+      float s = 0.f;
+      for (int k = l; k < n; k += 32) s += X[r * ld + k];
+      scratch[t] = s;
+    }
+  }
+  FRL_SYNC();
+  FRL_PAR(t) {
+    if (t < R * 32) {
+      const int r = t >> 5, l = t & 31;
+      float mean = 0.f;
+      for (int i = 0; i < 32; ++i) mean += scratch[r * 32 + i];
+      mean = mean / (float)n;
+      float s = 0.f;
+      for (int k = l; k < n; k += 32) { const float d = X[r * ld + k] - mean; s += d * d; }
+      scratch[R * 32 + t] = s;
+    }
+  }
+  FRL_SYNC();
+  FRL_PAR(t) {
+    if (t < R * 32) {
+      const int r = t >> 5, l = t & 31;
+      float mean = 0.f, var = 0.f;
+      for (int i = 0; i < 32; ++i) { mean += scratch[r * 32 + i]; var += scratch[R * 32 + r * 32 + i]; }
+      mean = mean / (float)n;
+      var = var / (float)n;
+      const float rs = 1.0f / sqrtf(var + 1e-5f);
+      for (int k = l; k < ld; k += 32) Y[r * ld + k] = (k < n) ? (X[r * ld + k] - mean) * rs : 0.f;
+      if (l == 0) rstd[r] = rs;
+    }
+  }
+  FRL_SYNC();
+}
+
+// dX = rstd * (dY - mean(dY) - Y * mean(dY*Y)), then optionally masked by relu'(H) (H = the pre-LN activation)
+template <int R>
+FRL_NI_MISC void ln_bwd(const float* dY, const float* Y, const float* rstd, const float* H, int ld, int n, float* dX,
+                        float* scratch /*[R*32*2]*/) {
+  FRL_PAR(t) {
+    if (t < R * 32) {
+      const int r = t >> 5, l = t & 31;
+      float s1 = 0.f, s2 = 0.f;
+      for (int k = l; k < n; k += 32) { const float g = dY[r * ld + k]; s1 += g; s2 += g * Y[r * ld + k]; }
+      scratch[t] = s1; scratch[R * 32 + t] = s2;
+    }
+  }
+  FRL_SYNC();
+  FRL_PAR(t) {
+    if (t < R * 32) {
+      const int r = t >> 5, l = t & 31;
+      float m1 = 0.f, m2 = 0.f;
+      for (int i = 0; i < 32; ++i) { m1 += scratch[r * 32 + i]; m2 += scratch[R * 32 + r * 32 + i]; }
+      m1 = m1 / (float)n; m2 = m2 / (float)n;
+      for (int k = l; k < ld; k += 32) {
+        float v = 0.f;
+        if (k < n) {
+          v = rstd[r] * (dY[r * ld + k] - m1 - Y[r * ld + k] * m2);
+          if (H && !(H[r * ld + k] > 0.f)) v = 0.f;
+        }
+        dX[r * ld + k] = v;
+      }
+    }
+  }
+  FRL_SYNC();
+}
+
+// activations kept by one 3-layer net pass (layer-norm variant keeps both the ReLU outputs and their normalised copies)
+struct NetBufs { float *X0, *H1, *H1n, *H2, *H2n, *rs1, *rs2, *scratch; };
+
+template <int R>
+FRL_DEV void net_fwd(Cta& c, const frl_net_t& N, int l0, bool ln, const float* Xin, int ip, int n_in, const NetBufs& b, int ldh,
+                     float* OUT, int ldo, Hint next) {
+  if (!ln) { mlp_fwd<R>(c, N, l0, 3, Xin, ip, b.H1, b.H2, ldh, OUT, ldo, FRL_ACT_NONE, next); return; }
+  ln_fwd<R>(Xin, ip, n_in, b.X0, b.rs1, b.scratch);                       // feature_norm (rstd not needed later)
+  layer_fwd<R>(c, N, l0, b.X0, ip, b.H1, ldh, FRL_ACT_RELU, fwd_hint(N, l0 + 1));
+  ln_fwd<R>(b.H1, ldh, N.L[l0].out, b.H1n, b.rs1, b.scratch);
+  layer_fwd<R>(c, N, l0 + 1, b.H1n, ldh, b.H2, ldh, FRL_ACT_RELU, fwd_hint(N, l0 + 2));
+  ln_fwd<R>(b.H2, ldh, N.L[l0 + 1].out, b.H2n, b.rs2, b.scratch);
+  layer_fwd<R>(c, N, l0 + 2, b.H2n, ldh, OUT, ldo, FRL_ACT_NONE, next);
+}
+
+template <int R>
+FRL_DEV void net_bwd(Cta& c, const frl_net_t& N, int l0, bool ln, const float* Xin, int ip, const NetBufs& b, int ldh, const float* dOUT,
+                     int ldo, float* D1, float* D2, float* gp, bool accumulate, Hint next) {
+  if (!ln) { mlp_bwd<R>(c, N, l0, 3, Xin, ip, b.H1, b.H2, ldh, dOUT, ldo, D1, D2, nullptr, 0, gp, accumulate, next); return; }
+  const frl_layer_t &L0 = N.L[l0], &L1 = N.L[l0 + 1], &L2 = N.L[l0 + 2];
+  gemm_outer<R>(dOUT, ldo, L2.out_pad, b.H2n, ldh, L2.in_pad, L2.in, gp + L2.w_off, gp + L2.b_off, accumulate);
+  layer_bwd_dx<R>(c, N, l0 + 2, dOUT, ldo, nullptr, 0, D2, ldh, bwd_hint(N, l0 + 1));
+  ln_bwd<R>(D2, b.H2n, b.rs2, b.H2, ldh, L1.out, D1, b.scratch);          // D1 = dL/d(pre-ReLU of layer l0+1)
+  gemm_outer<R>(D1, ldh, L1.out_pad, b.H1n, ldh, L1.in_pad, L1.in, gp + L1.w_off, gp + L1.b_off, accumulate);
+  layer_bwd_dx<R>(c, N, l0 + 1, D1, ldh, nullptr, 0, D2, ldh, next);
+  ln_bwd<R>(D2, b.H1n, b.rs1, b.H1, ldh, L0.out, D1, b.scratch);
+  gemm_outer<R>(D1, ldh, L0.out_pad, b.X0, ip, L0.in_pad, L0.in, gp + L0.w_off, gp + L0.b_off, accumulate);
+}
+
 struct PpoAlgo {
   typedef frl_ppo_args_t Args;
   static const int NSTAGES = 4;
   FRL_SHD int wbuf_floats(const Args& a) { return (AcAlgo::max_layer_floats(a.net) + 31) & ~31; }
   FRL_SHD int user_floats(const Args& a) {
-    const int ldh = a.net.L[0].out_pad, ip = a.net.L[0].in_pad, ap = a.net.L[2].out_pad;
-    return FRL_R * (ip + 6 * ldh + 4 * ap + 8 + 4 * a.n_adv + 8) + 2 * FRL_NT + 64 + FRL_NSEG + 3;
+    const int ldh = a.net.L[0].out_pad, ip = a.net.L[0].in_pad, cip = a.net.L[3].in_pad, ap = a.net.L[2].out_pad;
+    return FRL_R * (2 * ip + 2 * cip + 10 * ldh + 4 * ap + 8 + 4 * a.n_adv + 8 + 4 + 64) + 2 * FRL_NT + 64 + FRL_NSEG + 3;
   }
   FRL_SHD int grid(const Args& a, int max_ctas) {
     int tiles = (a.mb + FRL_R - 1) / FRL_R;
@@ -45,11 +145,18 @@ struct PpoAlgo {
     const int ntile = (rows + FRL_R - 1) / FRL_R;
     const int ncontrib = ntile < c.ncta ? ntile : c.ncta;
     SmemBump sb; sb.p = user;
+    const int cip = N.L[3].in_pad;
+    const bool ln = a.layer_norm != 0;
     float* X = sb.take(FRL_R * ip);
-    float* A1 = sb.take(FRL_R * ldh);
-    float* A2 = sb.take(FRL_R * ldh);
-    float* H1 = sb.take(FRL_R * ldh);
-    float* H2 = sb.take(FRL_R * ldh);
+    float* XC = sb.take(FRL_R * cip);       // critic input tile (joint obs for MAPPO, else a copy of X)
+    NetBufs ba, bc;
+    ba.X0 = sb.take(FRL_R * ip);  bc.X0 = sb.take(FRL_R * cip);
+    ba.H1 = sb.take(FRL_R * ldh); ba.H2 = sb.take(FRL_R * ldh);
+    bc.H1 = sb.take(FRL_R * ldh); bc.H2 = sb.take(FRL_R * ldh);
+    ba.H1n = sb.take(FRL_R * ldh); ba.H2n = sb.take(FRL_R * ldh);
+    bc.H1n = sb.take(FRL_R * ldh); bc.H2n = sb.take(FRL_R * ldh);
+    ba.rs1 = sb.take(FRL_R); ba.rs2 = sb.take(FRL_R); bc.rs1 = sb.take(FRL_R); bc.rs2 = sb.take(FRL_R);
+    ba.scratch = bc.scratch = sb.take(FRL_R * 64);
     float* D1 = sb.take(FRL_R * ldh);
     float* D2 = sb.take(FRL_R * ldh);
     float* OA = sb.take(FRL_R * ap);
@@ -80,6 +187,15 @@ struct PpoAlgo {
             const int r = e / ip, j = e % ip;
             X[e] = (r < nvalid && j < a.obs_dim) ? a.obs[(size_t)idx[r] * a.obs_dim + j] : 0.f;
           }
+          for (int e = t; e < FRL_R * cip; e += FRL_NT) {
+            const int r = e / cip, j = e % cip;
+            float v = 0.f;
+            if (r < nvalid) {
+              if (a.critic_obs) { if (j < a.critic_obs_dim) v = a.critic_obs[(size_t)idx[r] * a.critic_obs_dim + j]; }
+              else if (j < a.obs_dim) v = a.obs[(size_t)idx[r] * a.obs_dim + j];
+            }
+            XC[e] = v;
+          }
           for (int e = t; e < FRL_R * ap; e += FRL_NT) {
             const int r = e / ap, j = e % ap;
             ACT[e] = (r < nvalid && j < a.act_cols) ? a.action[(size_t)idx[r] * a.act_cols + j] : 0.f;
@@ -92,8 +208,9 @@ struct PpoAlgo {
           }
         }
         FRL_SYNC();
-        mlp_fwd<FRL_R>(c, N, 0, 3, X, ip, A1, A2, ldh, OA, ap, FRL_ACT_NONE, fwd_hint(N, 3));
-        mlp_fwd<FRL_R>(c, N, 3, 3, X, ip, H1, H2, ldh, V, 4, FRL_ACT_NONE, bwd_hint(N, 2));
+        const int c_in = a.critic_obs ? a.critic_obs_dim : a.obs_dim;
+        net_fwd<FRL_R>(c, N, 0, ln, X, ip, a.obs_dim, ba, ldh, OA, ap, fwd_hint(N, 3));
+        net_fwd<FRL_R>(c, N, 3, ln, XC, cip, c_in, bc, ldh, V, 4, bwd_hint(N, 2));
         // policy head: log-prob, entropy, ratio, clipped surrogate and its gradient w.r.t. the actor output
         FRL_PAR(t) {
           float sa = 0.f, se = 0.f;
@@ -180,8 +297,15 @@ struct PpoAlgo {
               float g = 0.f;
               for (int k = 0; k < a.n_adv; ++k) {
                 const float d = V[t * 4] - VT[t * a.n_adv + k];
-                g += 2.f * d * inv_rn;
-                l += d * d;
+                if (a.value_loss == 1) {
+                  // huber(e = v_target - V, delta): e^2/2 inside, delta(|e| - delta/2) outside  (MAPPO.py:273-276)
+                  const float e = -d, ae = fabsf(e), dl = a.huber_delta;
+                  l += (ae <= dl) ? 0.5f * e * e : dl * (ae - 0.5f * dl);
+                  g += -((ae <= dl) ? e : (e > 0.f ? dl : -dl)) * inv_rn;
+                } else {
+                  g += 2.f * d * inv_rn;
+                  l += d * d;
+                }
               }
               dV[t * 4] = g;
             }
@@ -206,8 +330,8 @@ struct PpoAlgo {
           }
           FRL_SYNC();
         }
-        mlp_bwd<FRL_R>(c, N, 0, 3, X, ip, A1, A2, ldh, dOA, ap, D1, D2, nullptr, 0, gp, !first, bwd_hint(N, 5));
-        mlp_bwd<FRL_R>(c, N, 3, 3, X, ip, H1, H2, ldh, dV, 4, D1, D2, nullptr, 0, gp, !first, no_hint());
+        net_bwd<FRL_R>(c, N, 0, ln, X, ip, ba, ldh, dOA, ap, D1, D2, gp, !first, bwd_hint(N, 5));
+        net_bwd<FRL_R>(c, N, 3, ln, XC, cip, bc, ldh, dV, 4, D1, D2, gp, !first, no_hint());
         first = false;
       }
       FRL_PAR(t) {

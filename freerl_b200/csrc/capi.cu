@@ -249,7 +249,7 @@ struct InferAlgo {
   FRL_SHD int nl_of(const Args& a) { return a.nl > 0 ? a.nl : a.net.n_layers; }
   FRL_SHD int wbuf_floats(const Args& a) { return (AcAlgo::max_layer_floats(a.net) + 31) & ~31; }
   FRL_SHD int user_floats(const Args& a) {
-    return FRL_R * (a.net.L[a.l0].in_pad + 2 * a.net.L[a.l0].out_pad + a.net.L[a.l0 + nl_of(a) - 1].out_pad) + 64;
+    return FRL_R * (2 * a.net.L[a.l0].in_pad + 4 * a.net.L[a.l0].out_pad + a.net.L[a.l0 + nl_of(a) - 1].out_pad + 2 + 64) + 64;
   }
   FRL_SHD int grid(const Args& a, int) { return (a.n + FRL_R - 1) / FRL_R; }
   FRL_SHD int n_updates(const Args&) { return 1; }
@@ -262,6 +262,10 @@ struct InferAlgo {
     float* H1 = sb.take(FRL_R * ldh);
     float* H2 = sb.take(FRL_R * ldh);
     float* O = sb.take(FRL_R * op);
+    NetBufs nb;
+    nb.H1 = H1; nb.H2 = H2;
+    nb.X0 = sb.take(FRL_R * in_pad); nb.H1n = sb.take(FRL_R * ldh); nb.H2n = sb.take(FRL_R * ldh);
+    nb.rs1 = sb.take(FRL_R); nb.rs2 = sb.take(FRL_R); nb.scratch = sb.take(FRL_R * 64);
     const int row0 = c.cta * FRL_R;
     const int nvalid = (a.n - row0) < FRL_R ? (a.n - row0) : FRL_R;
     stage_prefetch(c, layer_fwd_src(n, l0), layer_fwd_bytes(n.L[l0]));
@@ -272,7 +276,8 @@ struct InferAlgo {
       }
     }
     FRL_SYNC();
-    mlp_fwd<FRL_R>(c, n, l0, nl, X, in_pad, H1, H2, ldh, O, op, FRL_ACT_NONE, no_hint());
+    if (a.layer_norm && nl == 3) net_fwd<FRL_R>(c, n, l0, true, X, in_pad, a.obs_dim, nb, ldh, O, op, no_hint());
+    else mlp_fwd<FRL_R>(c, n, l0, nl, X, in_pad, H1, H2, ldh, O, op, FRL_ACT_NONE, no_hint());
     FRL_PAR(t) {
       if (a.mode == FRL_INFER_ARGMAX) {
         if (t < nvalid) {
@@ -473,4 +478,35 @@ extern "C" int frl_rainbow_act(const frl_rainbow_args_t* a, const float* obs, in
   if (rc) return rc;
   RainbowInferAlgo::Args ia = {*a, obs, n, out};
   return frl_launch_tiles<RainbowInferAlgo>(ia, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// joint advantage normalisation (single CTA, fixed-order reductions)
+// ------------------------------------------------------------------------------------------------
+struct AdvNormAlgo {
+  struct Args { const float* x; int n; float eps; float* out; };
+  static const int NSTAGES = 1;
+  FRL_SHD int wbuf_floats(const Args&) { return 32; }
+  FRL_SHD int user_floats(const Args&) { return FRL_NT + 64; }
+  FRL_SHD int grid(const Args&, int) { return 1; }
+  FRL_SHD int n_updates(const Args&) { return 1; }
+  FRL_SDEV void stage(int, int, Cta&, float* user, const Args& a) {
+    float* slot = user;
+    FRL_PAR(t) { float s = 0.f; for (int i = t; i < a.n; i += FRL_NT) s += a.x[i]; slot[t] = s; }
+    FRL_SYNC();
+    const float mean = block_sum(slot) / (float)a.n;
+    FRL_SYNC();
+    FRL_PAR(t) { float s = 0.f; for (int i = t; i < a.n; i += FRL_NT) { const float d = a.x[i] - mean; s += d * d; } slot[t] = s; }
+    FRL_SYNC();
+    const float var = block_sum(slot) / (float)(a.n - 1);       // torch.std(): unbiased
+    const float sd = sqrtf(var);
+    FRL_PAR(t) { for (int i = t; i < a.n; i += FRL_NT) a.out[i] = (a.x[i] - mean) / (sd + a.eps); }
+    FRL_SYNC();
+  }
+};
+
+extern "C" int frl_adv_norm(const float* x, int n, float eps, float* out, void* stream) {
+  if (!x || !out || n < 2) { frl_set_error("frl_adv_norm: bad arguments"); return -1; }
+  AdvNormAlgo::Args a = {x, n, eps, out};
+  return frl_launch_tiles<AdvNormAlgo>(a, (cudaStream_t)stream);
 }

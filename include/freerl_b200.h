@@ -133,6 +133,7 @@ typedef struct {
   uint32_t counter;
   float* out;               /* dev [n][out_cols]: actions (ARGMAX: 1 column holding the index as float; RAW: net output) */
   int out_cols;
+  int layer_norm;           /* MAPPO nets: F.layer_norm on the input and after each hidden ReLU */
 } frl_infer_args_t;
 
 /* On-policy (PPO.py) minibatch update.  `net` holds actor (layers 0-2, + log_std extra when continuous) and critic
@@ -155,6 +156,12 @@ typedef struct {
   int optimizer;            /* FRL_OPT_* */
   double lr, beta1, beta2, eps;
   int64_t step0;
+  /* ---- MAPPO options (MAPPO_file/MAPPO.py:127-218, 357-482) ---- */
+  int layer_norm;           /* F.layer_norm (no affine, eps 1e-5) on the input and after each hidden ReLU, actor and critic */
+  const float* critic_obs;  /* dev [M][critic_obs_dim] joint observation for the centralised critic (NULL: critic sees `obs`) */
+  int critic_obs_dim;
+  int value_loss;           /* 0: mse(v_target, V);  1: huber(v_target - V, huber_delta).mean()  (MAPPO.py:273-276,426-433) */
+  float huber_delta;
   float* gpart;             /* dev scratch [sm_count][net.n_p] */
   float* sumsq;             /* dev scratch [sm_count][2] */
   float* segcnt;            /* dev scratch [sm_count][2*FRL_MAX_LAYERS+1] cautious-mask counts per tensor */
@@ -219,6 +226,8 @@ int frl_policy_infer(const frl_infer_args_t* args, void* stream);
 int frl_gae(const float* reward, const float* done, const float* adv_done, const float* vs, const float* vs_next, int T, int N,
             double gamma, double lmbda, float* adv_out, float* v_target_out, void* stream);
 int frl_ppo_update(const frl_ppo_args_t* args, void* stream);
+/* joint advantage normalisation (MAPPO.py:385-386): out = (x - mean(x)) / (std_unbiased(x) + eps) over n floats (in place ok) */
+int frl_adv_norm(const float* x, int n, float eps, float* out, void* stream);
 
 /* Prioritized replay (DQN_file/Buffer.py:66-194): `tree` is the reference's float64 array heap [2*cap-1] on the device.
  * frl_sumtree_update applies B leaf writes IN ORDER (ancestors get `+= change` in batch order => bit-exact with the

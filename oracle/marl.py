@@ -52,3 +52,118 @@ class MADDPGOracle:
             polyak(self.actor_target[k], self.actor[k], tau)
             polyak(self.critic_target[k], self.critic[k], tau)
         return out
+
+
+# --------------------------------------------------------------------------------------------------
+# MAPPO  (MAPPO_file/MAPPO.py:106-482)
+# --------------------------------------------------------------------------------------------------
+def _ln(x):
+    return F.layer_norm(x, x.size()[1:])
+
+
+def mappo_body(net, x, names, trick):
+    """``Actor.forward`` / ``Critic.forward`` body (MAPPO.py:143-160, 204-218): optional feature_norm on the input and
+    LayerNorm (no affine) after each hidden ReLU."""
+    a, b, c = names
+    if trick['feature_norm']:
+        x = _ln(x)
+    x = F.relu(F.linear(x, net[a + ".weight"], net[a + ".bias"]))
+    if trick['LayerNorm']:
+        x = _ln(x)
+    x = F.relu(F.linear(x, net[b + ".weight"], net[b + ".bias"]))
+    if trick['LayerNorm']:
+        x = _ln(x)
+    return F.linear(x, net[c + ".weight"], net[c + ".bias"])
+
+
+def huber_loss(e, d):
+    a = (abs(e) <= d).float()
+    b = (abs(e) > d).float()
+    return a * e ** 2 / 2 + b * d * (abs(e) - d / 2)
+
+
+class MAPPOOracle:
+    """Continuous-action MAPPO with separated nets.  Quirks kept: ``surr = ratio[mb,1] * adv[index][mb,N]`` (every agent's
+    ratio multiplies ALL agents' advantages), ``v_s.repeat(1,N)`` against ``v_target[mb,N]``, value clip around ``v_s``
+    + huber with ``max(original, clipped)``, merged Adam(eps 1e-5, lr = actor_lr) over actor+critic, NO grad clip,
+    joint advantage normalisation with the unbiased std."""
+
+    def __init__(self, actors, critics, lr, trick):
+        self.ids = list(actors.keys())
+        self.actor = OrderedDict((k, _leaf(v)) for k, v in actors.items())
+        self.critic = OrderedDict((k, _leaf(v)) for k, v in critics.items())
+        self.trick = trick
+        self.opt = {k: AdamState(list(self.actor[k].values()) + list(self.critic[k].values()), lr, eps=1e-5) for k in self.ids}
+
+    def actor_dist(self, k, obs):
+        mean = torch.tanh(mappo_body(self.actor[k], obs, ("l1", "l2", "mean_layer"), self.trick))
+        std = torch.exp(torch.clamp(self.actor[k]["log_std"].expand_as(mean), -20, 2))
+        return mean, std
+
+    def values(self, k, joint):
+        return mappo_body(self.critic[k], joint, ("l1", "l2", "l3"), self.trick)
+
+    def advantages(self, data, gamma, lmbda):
+        """data: dict agent -> (obs, action, reward, next_obs, done, logp, adv_done) tensors over the horizon."""
+        ids = self.ids
+        with torch.no_grad():
+            joint = torch.cat([data[k][0] for k in ids], dim=1)
+            joint_n = torch.cat([data[k][3] for k in ids], dim=1)
+            vs = torch.cat([self.values(k, joint) for k in ids], dim=1)
+            vs_ = torch.cat([self.values(k, joint_n) for k in ids], dim=1)
+            reward = torch.cat([data[k][2] for k in ids], dim=1)
+            done = torch.cat([data[k][4] for k in ids], dim=1)
+            adv_dones = torch.cat([data[k][6] for k in ids], dim=1)
+            td = reward + gamma * (1.0 - done) * vs_ - vs
+            H = td.shape[0]
+            adv = torch.zeros(H, len(ids))
+            gae = 0
+            for i in reversed(range(H)):
+                gae = td[i] + gamma * lmbda * gae * (1.0 - adv_dones[i])
+                adv[i] = gae
+            v_target = adv + vs
+            if self.trick['adv_norm']:
+                adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+        return adv, v_target
+
+    def learn(self, data, permutations, minibatch_size, gamma, lmbda, clip_param, entropy_coefficient, huber_delta):
+        """permutations: dict agent -> list (K epochs) of index permutations"""
+        ids = self.ids
+        adv, v_target = self.advantages(data, gamma, lmbda)
+        H = adv.shape[0]
+        losses = []
+        for k in ids:
+            obs, action, logp_old = data[k][0], data[k][1], data[k][5]
+            for perm in permutations[k]:
+                for s in range(0, H, minibatch_size):
+                    index = perm[s:s + minibatch_size]
+                    mean, std = self.actor_dist(k, obs[index])
+                    dist = torch.distributions.Normal(mean, std)
+                    ent = dist.entropy().sum(dim=1, keepdim=True)
+                    logp = dist.log_prob(action[index])
+                    ratios = torch.exp(logp.sum(dim=1, keepdim=True) - logp_old[index].sum(dim=1, keepdim=True))
+                    surr1 = ratios * adv[index]
+                    surr2 = torch.clamp(ratios, 1 - clip_param, 1 + clip_param) * adv[index]
+                    actor_loss = -torch.min(surr1, surr2).mean() - entropy_coefficient * ent.mean()
+                    joint = torch.cat([data[j][0][index] for j in ids], dim=1)
+                    v_s = self.values(k, joint).repeat(1, len(ids))
+                    vt = v_target[index]
+                    if self.trick['ValueClip']:
+                        vt_clip = torch.clamp(vt, v_s - clip_param, v_s + clip_param)
+                        if self.trick['huber_loss']:
+                            l_clip = huber_loss(vt_clip - v_s, huber_delta).mean()
+                            l_orig = huber_loss(vt - v_s, huber_delta).mean()
+                        else:
+                            l_clip = F.mse_loss(vt_clip, v_s)
+                            l_orig = F.mse_loss(vt, v_s)
+                        critic_loss = torch.max(l_orig, l_clip)
+                    elif self.trick['huber_loss']:
+                        critic_loss = huber_loss(vt - v_s, huber_delta).mean()
+                    else:
+                        critic_loss = F.mse_loss(vt, v_s)
+                    ap, cp = list(self.actor[k].values()), list(self.critic[k].values())
+                    ga = torch.autograd.grad(actor_loss, ap)
+                    gc = torch.autograd.grad(critic_loss, cp)
+                    adam_step(ap + cp, list(ga) + list(gc), self.opt[k])
+                    losses.append((actor_loss.item(), critic_loss.item()))
+        return {"adv": adv, "v_target": v_target, "losses": losses}

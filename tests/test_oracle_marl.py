@@ -36,3 +36,24 @@ def test_maddpg_oracle_vs_reference(golden):
         for kind, nets in (("actor", orc.actor), ("critic", orc.critic), ("actor_target", orc.actor_target), ("critic_target", orc.critic_target)):
             for n, v in nets[k].items():
                 np.testing.assert_allclose(v.detach().numpy(), g["final/%s/%s/%s" % (k, kind, n)], rtol=2e-5, atol=2e-6)
+
+
+from oracle.marl import MAPPOOracle  # noqa: E402
+from oracle.make_golden_marl import MAPPO_TRICK  # noqa: E402
+
+
+def mappo_data(g):
+    return {k: tuple(torch.from_numpy(g["data/%s/%s" % (k, n)]) for n in ("obs", "act", "rew", "nobs", "done", "logp", "adv_done"))
+            for k in IDS}
+
+
+def test_mappo_oracle_vs_reference(golden):
+    g = golden("mappo")
+    orc = MAPPOOracle(maddpg_nets(g, "init", "actor"), maddpg_nets(g, "init", "critic"), 1e-3, MAPPO_TRICK)
+    perms = {k: [g["perm/%s/%d" % (k, e)] for e in range(2)] for k in IDS}
+    r = orc.learn(mappo_data(g), perms, 32, 0.95, 0.95, 0.2, 0.01, 10.0)
+    np.testing.assert_allclose(np.array(r["losses"]), g["losses"], rtol=2e-5, atol=1e-6)
+    for k in IDS:
+        for kind, nets in (("actor", orc.actor), ("critic", orc.critic)):
+            for n, v in nets[k].items():
+                np.testing.assert_allclose(v.detach().numpy(), g["final/%s/%s/%s" % (k, kind, n)], rtol=2e-5, atol=2e-6)
