@@ -181,13 +181,23 @@ class MAPPO:
             a.huber_delta = float(huber_delta) if huber_delta is not None else 0.0
             a.gpart, a.sumsq, a.segcnt = self._gpart.data_ptr(), self._sumsq.data_ptr(), self._segcnt.data_ptr()
             a.stats, a.out = self._stats.data_ptr(), out.data_ptr()
-            _lib.check(_lib.lib().frl_ppo_update(ctypes.byref(a), _lib.stream_ptr(self.device)), "frl_ppo_update")
+            self._launch_update(a, ag._net, n_updates)
             ag.step += n_updates
             outs.append(out)
             self._keep = (idx_d, rows_d, joint, adv, v_target)
         self.last_metrics = torch.cat(outs)
         for buffer in self.buffers.values():
             buffer.clear()
+
+    def enable_data_parallel(self, group=None):
+        """see PPO.enable_data_parallel; additionally the joint advantage normalisation all-reduces (sum, sum of squares, count)."""
+        import torch.distributed as dist
+        self._dp = (dist, group, dist.get_world_size(group))
+        for ag in self.agents.values():
+            dist.broadcast(ag._net.p, src=0, group=group)
+            ag._net.sync_mirror()
+
+    _launch_update = __import__("freerl_b200.PPO", fromlist=["PPO"]).PPO._launch_update
 
     def save(self, model_dir):
         torch.save({name: {k: v.detach().clone().cpu() for k, v in agent.actor.state_dict().items()} for name, agent in self.agents.items()},

@@ -194,10 +194,43 @@ class PPO:
         a.step0 = ag.step
         a.gpart, a.sumsq, a.segcnt = self._gpart.data_ptr(), self._sumsq.data_ptr(), self._segcnt.data_ptr()
         a.stats, a.out = self._stats.data_ptr(), out.data_ptr()
-        _lib.check(_lib.lib().frl_ppo_update(ctypes.byref(a), _lib.stream_ptr(self.device)), "frl_ppo_update")
+        self._launch_update(a, ag._net, n_updates)
         ag.step += n_updates
         self.last_metrics = out
         self._keep = (idx, rows, adv, v_target)
+
+    # ---- data parallel (one process per GPU) ---------------------------------------------------------
+    def enable_data_parallel(self, group=None):
+        """Synchronous data-parallel training over ``torch.distributed`` (NCCL over NVLink on the GPU box): every rank
+        holds its own env shard / rollout and an identical replica of the networks; each minibatch is the union of the
+        ranks' equal-size sub-minibatches.  Per optimiser step ONE flat gradient buffer (net.g, 36 k floats) is
+        all-reduced between the in-kernel cross-CTA reduction and the clip + (cautious-)AdamW stages, then scaled by
+        1/world (mean of equal-size means) so all replicas apply bit-identical updates."""
+        import torch.distributed as dist
+        self._dp = (dist, group, dist.get_world_size(group))
+        for t in (self.agent._net.p,):
+            dist.broadcast(t, src=0, group=group)
+        self.agent._net.sync_mirror()
+
+    def _launch_update(self, a, net, n_updates):
+        dp = getattr(self, "_dp", None)
+        if dp is None or dp[2] == 1:
+            _lib.check(_lib.lib().frl_ppo_update(ctypes.byref(a), _lib.stream_ptr(self.device)), "frl_ppo_update")
+            return
+        dist, group, world = dp
+        idx0, rows0, out0, step0 = a.indices, a.mb_rows, a.out, a.step0
+        a.n_updates = 1
+        a.grad_scale = 1.0 / world
+        for u in range(n_updates):
+            a.indices = idx0 + u * a.mb * 8
+            a.mb_rows = rows0 + u * 4
+            a.out = out0 + u * 8 * 4
+            a.step0 = step0 + u
+            a.stage_lo, a.stage_hi = 0, 2
+            _lib.check(_lib.lib().frl_ppo_update(ctypes.byref(a), _lib.stream_ptr(self.device)), "frl_ppo_update")
+            dist.all_reduce(net.g, group=group)                       # flat gradient buffer, sum over ranks
+            a.stage_lo, a.stage_hi = 2, 5
+            _lib.check(_lib.lib().frl_ppo_update(ctypes.byref(a), _lib.stream_ptr(self.device)), "frl_ppo_update")
 
     def learn(self, minibatch_size, gamma, lmbda, clip_param, K_epochs, entropy_coefficient, *, permutations=None):
         adv, v_target = self.compute_gae(gamma, lmbda)

@@ -70,7 +70,8 @@ class PpoArgs(C.Structure):
                 ("max_norm_critic", C.c_float), ("optimizer", C.c_int), ("lr", C.c_double), ("beta1", C.c_double),
                 ("beta2", C.c_double), ("eps", C.c_double), ("step0", C.c_int64),
                 ("layer_norm", C.c_int), ("critic_obs", C.c_void_p), ("critic_obs_dim", C.c_int), ("value_loss", C.c_int),
-                ("huber_delta", C.c_float), ("gpart", C.c_void_p),
+                ("huber_delta", C.c_float), ("stage_lo", C.c_int), ("stage_hi", C.c_int), ("grad_scale", C.c_float),
+                ("gpart", C.c_void_p),
                 ("sumsq", C.c_void_p), ("segcnt", C.c_void_p), ("stats", C.c_void_p), ("out", C.c_void_p)]
 
 

@@ -124,7 +124,7 @@ FRL_DEV void net_bwd(Cta& c, const frl_net_t& N, int l0, bool ln, const float* X
 
 struct PpoAlgo {
   typedef frl_ppo_args_t Args;
-  static const int NSTAGES = 4;
+  static const int NSTAGES = 5;
   FRL_SHD int wbuf_floats(const Args& a) { return (AcAlgo::max_layer_floats(a.net) + 31) & ~31; }
   FRL_SHD int user_floats(const Args& a) {
     const int ldh = a.net.L[0].out_pad, ip = a.net.L[0].in_pad, cip = a.net.L[3].in_pad, ap = a.net.L[2].out_pad;
@@ -141,6 +141,7 @@ struct PpoAlgo {
   FRL_SDEV void stage(int s, int u, Cta& c, float* user, const Args& a) {
     const frl_net_t& N = a.net;
     const int ldh = N.L[0].out_pad, ip = N.L[0].in_pad, ap = N.L[2].out_pad, nout = N.L[2].out;
+    if (a.stage_hi > 0 && (s < a.stage_lo || s >= a.stage_hi)) return;
     const int rows = a.mb_rows[u];
     const int ntile = (rows + FRL_R - 1) / FRL_R;
     const int ncontrib = ntile < c.ncta ? ntile : c.ncta;
@@ -339,13 +340,23 @@ struct PpoAlgo {
       }
       FRL_SYNC();
     } else if (s == 1) {
-      // fixed-order cross-CTA reduction with separate sum-of-squares for the actor and critic tensors
+      // fixed-order cross-CTA reduction of the gradient partials -> net.g
       FRL_PAR(t) {
-        float la = 0.f, lc = 0.f;
         for (int p = (c.cta * FRL_NT + t) * 4; p < N.n_p; p += c.ncta * FRL_NT * 4) {
           float4 sgm = ld4(a.gpart + p);
           for (int cc = 1; cc < ncontrib; ++cc) sgm = f4add(sgm, ld4(a.gpart + (size_t)cc * N.n_p + p));
           st4(N.g + p, sgm);
+        }
+      }
+      FRL_SYNC();
+    } else if (s == 2) {
+      // (data-parallel: net.g now holds the all-reduced SUM over ranks) scale, then separate actor / critic sum-of-squares
+      const float gs = a.grad_scale > 0.f ? a.grad_scale : 1.f;
+      FRL_PAR(t) {
+        float la = 0.f, lc = 0.f;
+        for (int p = (c.cta * FRL_NT + t) * 4; p < N.n_p; p += c.ncta * FRL_NT * 4) {
+          float4 sgm = ld4(N.g + p);
+          if (gs != 1.f) { sgm.x *= gs; sgm.y *= gs; sgm.z *= gs; sgm.w *= gs; st4(N.g + p, sgm); }
           const float q = sgm.x * sgm.x + sgm.y * sgm.y + sgm.z * sgm.z + sgm.w * sgm.w;
           if (is_critic(N, p)) lc += q; else la += q;
         }
@@ -371,7 +382,7 @@ struct PpoAlgo {
           sh[2] = (float)(a.lr * sqrt(bc2) / bc1);         // c_adamw step_size
           sh[3] = (float)(-(a.lr / bc1));                   // torch Adam: -lr/bc1
           sh[4] = (float)sqrt(bc2);
-          if (s == 2 && c.cta == 0) {
+          if (s == 3 && c.cta == 0) {
             float l0 = 0.f, l1 = 0.f, l2 = 0.f;
             for (int i = 0; i < ncontrib; ++i) { l0 += a.stats[i * 8]; l1 += a.stats[i * 8 + 1]; l2 += a.stats[i * 8 + 2]; }
             const float ent_mean = l2 / (float)rows;
@@ -389,7 +400,7 @@ struct PpoAlgo {
       const float b1 = (float)a.beta1, b2 = (float)a.beta2, omb1 = (float)(1.0 - a.beta1), omb2 = (float)(1.0 - a.beta2);
       const float eps = (float)a.eps;
       if (a.optimizer == FRL_OPT_ADAM) {
-        if (s == 3) return;
+        if (s == 4) return;
         FRL_PAR(t) {
           for (int p = c.cta * FRL_NT + t; p < N.n_p; p += c.ncta * FRL_NT) {
             const float g = N.g[p] * (is_critic(N, p) ? coef_c : coef_a);
@@ -406,7 +417,7 @@ struct PpoAlgo {
         FRL_SYNC();
         return;
       }
-      if (s == 2) {
+      if (s == 3) {
         // cautious AdamW, pass 1: moments + per-tensor count of (exp_avg * grad > 0)
         FRL_PAR(t) {
           for (int p = c.cta * FRL_NT + t; p < N.n_p; p += c.ncta * FRL_NT) {

@@ -162,6 +162,10 @@ typedef struct {
   int critic_obs_dim;
   int value_loss;           /* 0: mse(v_target, V);  1: huber(v_target - V, huber_delta).mean()  (MAPPO.py:273-276,426-433) */
   float huber_delta;
+  /* ---- data-parallel split (one process per GPU): stages are 0 fwd/bwd, 1 cross-CTA reduce -> net.g, 2 grad scale + norms,
+   * 3/4 optimiser.  A DP step launches [0,2), all-reduces net.g over NCCL, then launches [2,5) with grad_scale = 1/world. */
+  int stage_lo, stage_hi;   /* run stages in [stage_lo, stage_hi); 0,0 = all */
+  float grad_scale;         /* multiplies the reduced gradient before clipping (0 = 1.0) */
   float* gpart;             /* dev scratch [sm_count][net.n_p] */
   float* sumsq;             /* dev scratch [sm_count][2] */
   float* segcnt;            /* dev scratch [sm_count][2*FRL_MAX_LAYERS+1] cautious-mask counts per tensor */
