@@ -126,6 +126,7 @@ class MADDPG:
             a.gpart, a.sumsq = self._scratch.gpart.data_ptr(), self._scratch.sumsq.data_ptr()
             a.stats, a.out = self._scratch.stats.data_ptr(), out.data_ptr()
             a.n_agents, a.agent_index, a.defer_polyak = len(ids), i, 1
+            a.xchg = self._scratch.xchg(B, self.device).data_ptr()
             for j, other in enumerate(ids):
                 a.ma_replay[j] = self.buffers[other].c_struct()
                 a.ma_actor_target[j] = self.agents[other]._actor_t.c_struct()

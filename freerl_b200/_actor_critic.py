@@ -122,6 +122,7 @@ class ACBase:
         out = self._scratch.out(n_updates, self.device)
         a.gpart, a.sumsq = self._scratch.gpart.data_ptr(), self._scratch.sumsq.data_ptr()
         a.stats, a.out = self._scratch.stats.data_ptr(), out.data_ptr()
+        a.xchg = self._scratch.xchg(B, self.device).data_ptr()
         return a, idx, B, out
 
     def _launch(self, a, keep, n_updates, out):

@@ -30,6 +30,12 @@ class DeviceScratch:
         self.sumsq = z(sm)
         self.stats = z(sm, 8)
         self._out = None
+        self._xchg = None
+
+    def xchg(self, B, device):
+        if self._xchg is None or self._xchg.numel() < 3 * B:
+            self._xchg = torch.zeros(3 * B, dtype=torch.float32, device=device)
+        return self._xchg
 
     def out(self, n_updates, device):
         if self._out is None or self._out.shape[0] < n_updates:

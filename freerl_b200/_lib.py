@@ -52,7 +52,7 @@ class AcArgs(C.Structure):
                 ("target_entropy", C.c_float), ("step_alpha0", C.c_int64),
                 ("gpart", C.c_void_p), ("sumsq", C.c_void_p), ("stats", C.c_void_p), ("out", C.c_void_p),
                 ("n_agents", C.c_int), ("agent_index", C.c_int), ("ma_replay", Replay * FRL_MAX_AGENTS),
-                ("ma_actor_target", Net * FRL_MAX_AGENTS), ("defer_polyak", C.c_int)]
+                ("ma_actor_target", Net * FRL_MAX_AGENTS), ("defer_polyak", C.c_int), ("xchg", C.c_void_p)]
 
 
 class InferArgs(C.Structure):

@@ -1,10 +1,17 @@
-// Fused actor-critic learn() for the deterministic / stochastic off-policy family:
-//   SAC  (SAC_file/SAC.py:222-271, Actor :60-97, Critic :103-127, Alpha :154-169, Agent.update_* :141-151)
-//   TD3  (TD3_file/TD3.py:189-244)      DDPG (DDPG_file/DDPG.py:203-233)
-// Per learn(): sampled rows are gathered straight from the device replay, target action / target Q / TD target,
-// twin-critic forward+backward, global-norm clip, Adam, then actor forward, critic forward with the UPDATED
-// critic, backward through critic into the actor, clip, Adam, Polyak of both targets, temperature step.
-// Six grid barriers per learn(); one launch runs n_updates sequential learns.
+// Fused actor-critic learn() for the off-policy family:
+//   SAC    SAC_file/SAC.py:222-271 (Actor :60-97, Critic :103-127, Alpha :154-169, Agent.update_* :141-151)
+//   TD3    TD3_file/TD3.py:189-244          DDPG   DDPG_file/DDPG.py:203-233
+//   MADDPG MADDPG_file/MADDPG.py:186-237    (n_agents > 1: centralised critic on cat(all obs, all actions))
+// One persistent cooperative launch runs n_updates sequential learns; 7 grid-wide stages per learn:
+//   0 targets        gather rows, a' = actor_target(s') (every agent), target critic head[role] -> exchange buffer
+//   1 critic         y from both heads' target values, critic head[role] forward + backward -> gradient partials
+//   2 reduce         fixed-order cross-CTA reduction (per head: only that role's CTAs) + sum of squares
+//   3 optimiser      clip_grad_norm_ + Adam (+ critic-target Polyak)
+//   4 actor          actor forward, critic head[role] forward + dQ/da with the UPDATED critic, actor backward
+//   5 reduce         actor gradient
+//   6 optimiser      clip + Adam + actor-target Polyak + temperature step
+// CTA roles: a twin critic is split head-per-CTA (cta = tile_slot * n_heads + role), which doubles the SMs in use and
+// cuts the sequential layer ops per CTA from 45 to 28; the target action / actor forward are recomputed per role.
 #pragma once
 #include "algo_dqn.cuh"
 
@@ -13,9 +20,44 @@
 
 FRL_DEV float softplus_t(float x) { return x > 20.f ? x : log1pf(expf(x)); }   // F.softplus(beta=1, threshold=20)
 
+// Cross-CTA reduction of gradient partials.  Partial of CTA k lives at gpart + k*stride.  With split_heads the critic
+// block's head h (layers 3h..3h+2) only receives the partials of the CTAs with role h (k = h, h+nrole, ...); otherwise
+// every parameter sums `cnt` partials starting at CTA 0 with the given CTA step.
+FRL_NI_OPT void reduce_grads_roles(int cta, int ncta, float* slot, const frl_net_t& n, const float* gpart, int stride, int nslots,
+                                   int nrole, int split_heads, int cta_step, float* sumsq_part) {
+  FRL_PAR(t) {
+    float local = 0.f;
+    for (int p = (cta * FRL_NT + t) * 4; p < n.n_p; p += ncta * FRL_NT * 4) {
+      int first = 0, step = cta_step, cnt = nslots * (nrole / cta_step);
+      if (split_heads) {
+        int h = 0;
+        for (int li = 3; li < n.n_layers; li += 3) if (p >= n.L[li].w_off) h = li / 3;
+        first = h; step = nrole; cnt = nslots;
+      }
+      float4 s = ld4(gpart + (size_t)first * stride + p);
+      int k = 1;
+      for (; k + 8 <= cnt; k += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = ld4(gpart + (size_t)(first + (k + i) * step) * stride + p);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s = f4add(s, v[i]);
+      }
+      for (; k < cnt; ++k) s = f4add(s, ld4(gpart + (size_t)(first + k * step) * stride + p));
+      st4(n.g + p, s);
+      local += s.x * s.x + s.y * s.y + s.z * s.z + s.w * s.w;
+    }
+    slot[t] = local;
+  }
+  FRL_SYNC();
+  float tot = block_sum(slot);
+  FRL_PAR(t) { if (t == 0 && sumsq_part) sumsq_part[cta] = tot; }
+  FRL_SYNC();
+}
+
 struct AcAlgo {
   typedef frl_ac_args_t Args;
-  static const int NSTAGES = 6;
+  static const int NSTAGES = 7;
 
   FRL_SHD int max_layer_floats(const frl_net_t& n) {
     int mx = 0;
@@ -41,12 +83,13 @@ struct AcAlgo {
 
   FRL_SHD int user_floats(const Args& a) {
     const int ldh = a.critic.L[0].out_pad, sa = a.critic.L[0].in_pad, ap = max_ap(a);
-    return raw_off(a, ma_n(a)) + FRL_R * (max_aip(a) + 3 * sa + 8 * ldh + 6 * ap + 4 * 4 + 16) + 2 * FRL_NT + 128;
+    return raw_off(a, ma_n(a)) + FRL_R * (max_aip(a) + 3 * sa + 6 * ldh + 6 * ap + 3 * 4 + 16) + 2 * FRL_NT + 128;
   }
-  FRL_SHD int grid(const Args& a, int max_ctas) {
-    int tiles = (a.B + FRL_R - 1) / FRL_R;
-    return tiles < max_ctas ? tiles : max_ctas;
+  FRL_SHD int nslots_of(const Args& a, int max_ctas) {
+    const int tiles = (a.B + FRL_R - 1) / FRL_R, cap = max_ctas / (a.n_heads > 0 ? a.n_heads : 1);
+    return tiles < cap ? tiles : (cap > 0 ? cap : 1);
   }
+  FRL_SHD int grid(const Args& a, int max_ctas) { return nslots_of(a, max_ctas) * a.n_heads; }
   FRL_SHD int n_updates(const Args& a) { return a.n_updates; }
 
   FRL_SDEV float noise_at(const float* ptr, const Args& a, int u, int row, int j, uint32_t stream) {
@@ -62,13 +105,14 @@ struct AcAlgo {
     const int ldh = C.L[0].out_pad, sa = C.L[0].in_pad, ap = max_ap(a);
     const int NA = ma_n(a), ai = a.n_agents > 1 ? a.agent_index : 0;
     const int aip = max_aip(a);
+    const int nrole = a.n_heads, role = c.cta % nrole, slot = c.cta / nrole, nslots = c.ncta / nrole;
+    const int l0 = 3 * role;                                   // this CTA's critic head = layers l0..l0+2
     const int ntile = (a.B + FRL_R - 1) / FRL_R;
-    const int ncontrib = grid(a, c.ncta);
     const float invB = 1.0f / (float)a.B;
     const bool sac = a.actor_kind == FRL_ACTOR_SAC;
     const bool policy_step = ((a.total_it0 + u + 1) % (a.policy_freq > 0 ? a.policy_freq : 1)) == 0;
-    // optimiser step counters: the critic steps every learn, the actor only on policy steps
     const long n_policy_before = (a.policy_freq > 1) ? (long)((a.total_it0 + u) / a.policy_freq - a.total_it0 / a.policy_freq) : (long)u;
+    const int heads_used = sac ? a.n_heads : 1;                // actor loss: SAC mean of both heads, TD3 Q1 only, DDPG single
     float alpha = 0.f;
     if (sac) alpha = expf(a.alpha_state[0]);
 
@@ -76,38 +120,31 @@ struct AcAlgo {
     float* raw0 = sb.take(raw_off(a, NA));   // gathered rows of every agent's replay (same indices)
     float* raw = raw0 + raw_off(a, ai);      // this agent's rows (reward / done come from here)
     float* XA = sb.take(FRL_R * aip);        // actor input (one agent's obs / next_obs)
-    float* XS = sb.take(FRL_R * sa);     // [obs | act]
-    float* XN = sb.take(FRL_R * sa);     // [next_obs | a']        (stage 3: [obs | pi(obs)])
-    float* dXP = sb.take(FRL_R * sa);    // dQ/d[obs|a]
-    float* H1 = sb.take(FRL_R * ldh);    // critic head activations (current head)
+    float* XS = sb.take(FRL_R * sa);         // [obs | act]
+    float* XN = sb.take(FRL_R * sa);         // [next_obs | a']   (stage 4: [obs | pi(obs)])
+    float* dXP = sb.take(FRL_R * sa);        // dQ/d[obs|a]
+    float* H1 = sb.take(FRL_R * ldh);        // critic head activations
     float* H2 = sb.take(FRL_R * ldh);
-    float* G1 = sb.take(FRL_R * ldh);    // second head activations (kept for backward)
-    float* G2 = sb.take(FRL_R * ldh);
-    float* A1 = sb.take(FRL_R * ldh);    // actor activations
+    float* A1 = sb.take(FRL_R * ldh);        // actor activations
     float* A2 = sb.take(FRL_R * ldh);
     float* D1 = sb.take(FRL_R * ldh);
     float* D2 = sb.take(FRL_R * ldh);
-    float* MU = sb.take(FRL_R * ap);     // actor output (pre-tanh mean)
-    float* UU = sb.take(FRL_R * ap);     // SAC pre-tanh sample u
-    float* AC = sb.take(FRL_R * ap);     // squashed action
+    float* MU = sb.take(FRL_R * ap);         // actor output (pre-tanh mean)
+    float* UU = sb.take(FRL_R * ap);         // SAC per-dim log-prob terms
+    float* AC = sb.take(FRL_R * ap);         // squashed action
     float* dMU = sb.take(FRL_R * ap);
-    float* dA = sb.take(FRL_R * ap);     // accumulated dL/da from the critic heads
     float* EPS = sb.take(FRL_R * ap);
-    float* QA = sb.take(FRL_R * 4);      // head 0 output
-    float* QB = sb.take(FRL_R * 4);      // head 1 output
+    float* QA = sb.take(FRL_R * 4);          // head output
     float* dQA = sb.take(FRL_R * 4);
-    float* dQB = sb.take(FRL_R * 4);
-    float* rowv = sb.take(FRL_R * 4);    // per-row scalars: y, logp, ...
+    float* rowv = sb.take(FRL_R * 4);        // per-row scalars
     float* red0 = sb.take(FRL_NT);
     float* red1 = sb.take(FRL_NT);
     const int gstride = C.n_p > A.n_p ? C.n_p : A.n_p;
     float* gp = a.gpart + (size_t)c.cta * gstride;
 
     if (s == 0) {
-      // ---------------- targets + critic forward/backward ----------------
-      float loss_acc = 0.f;
-      bool first = true;
-      for (int tile = c.cta; tile < ntile; tile += c.ncta) {
+      // ---------------- target action(s) + this role's target critic head ----------------
+      for (int tile = slot; tile < ntile; tile += nslots) {
         const int row0 = tile * FRL_R;
         const int nvalid = (a.B - row0) < FRL_R ? (a.B - row0) : FRL_R;
         stage_prefetch(c, layer_fwd_src(tnet(a, 0), 0), layer_fwd_bytes(tnet(a, 0).L[0]));
@@ -115,20 +152,15 @@ struct AcAlgo {
         copy_cols<FRL_R>(XN, sa, act_off(a, 0), raw0, 1, 0, 0, sa);                 // zero the action + pad columns of XN
         for (int j = 0; j < NA; ++j) {
           const frl_replay_t& rj = rep(a, j);
-          const float* rw = raw0 + raw_off(a, j);
-          copy_cols<FRL_R>(XS, sa, obs_off(a, j), rw, rj.row_floats, 0, rj.obs_dim, 0);
-          copy_cols<FRL_R>(XS, sa, act_off(a, j), rw, rj.row_floats, rb_col_act(rj), rj.act_dim, j == NA - 1 ? sa : 0);
-          copy_cols<FRL_R>(XN, sa, obs_off(a, j), rw, rj.row_floats, rb_col_nobs(rj), rj.obs_dim, 0);
+          copy_cols<FRL_R>(XN, sa, obs_off(a, j), raw0 + raw_off(a, j), rj.row_floats, rb_col_nobs(rj), rj.obs_dim, 0);
         }
-        stamp(c, 1);
-        // a'_j = actor_target_j(next_obs_j) for every agent (single agent: j = 0)
-        for (int j = 0; j < NA; ++j) {
+        for (int j = 0; j < NA; ++j) {                                               // a'_j = actor_target_j(next_obs_j)
           const frl_replay_t& rj = rep(a, j);
           const frl_net_t& T = tnet(a, j);
           const int adj = rj.act_dim, tip = T.L[0].in_pad, aoff = act_off(a, j);
           copy_cols<FRL_R>(XA, tip, 0, raw0 + raw_off(a, j), rj.row_floats, rb_col_nobs(rj), rj.obs_dim, tip);
           mlp_fwd<FRL_R>(c, T, 0, 3, XA, tip, A1, A2, ldh, MU, ap, FRL_ACT_NONE,
-                         j + 1 < NA ? fwd_hint(tnet(a, j + 1), 0) : fwd_hint(a.critic_target, 0));
+                         j + 1 < NA ? fwd_hint(tnet(a, j + 1), 0) : fwd_hint(a.critic_target, l0));
           FRL_PAR(t) {
             if (t < FRL_R * adj) {
               const int r = t / adj, jj = t % adj;
@@ -160,87 +192,97 @@ struct AcAlgo {
           }
           FRL_SYNC();
         }
-        stamp(c, 2);
-        // target Q heads
-        mlp_fwd<FRL_R>(c, a.critic_target, 0, 3, XN, sa, H1, H2, ldh, QA, 4, FRL_ACT_NONE,
-                       a.n_heads == 2 ? fwd_hint(a.critic_target, 3) : fwd_hint(C, 0));
-        if (a.n_heads == 2)
-          mlp_fwd<FRL_R>(c, a.critic_target, 3, 3, XN, sa, H1, H2, ldh, QB, 4, FRL_ACT_NONE, fwd_hint(C, 0));
+        mlp_fwd<FRL_R>(c, a.critic_target, l0, 3, XN, sa, H1, H2, ldh, QA, 4, FRL_ACT_NONE, no_hint());
+        // exchange: xchg[row][role] = Q'_role ; xchg[B*nrole + row] = sum_j log pi(a'|s')  (SAC, role 0)
+        FRL_PAR(t) {
+          if (t < nvalid) {
+            a.xchg[(size_t)(row0 + t) * nrole + role] = QA[t * 4];
+            if (sac && role == 0) {
+              float lp = 0.f;
+              for (int j = 0; j < ad; ++j) lp += UU[t * ap + j];
+              a.xchg[(size_t)a.B * nrole + row0 + t] = lp;
+            }
+          }
+        }
+        FRL_SYNC();
+      }
+    } else if (s == 1) {
+      // ---------------- TD target, this role's critic head forward + backward ----------------
+      float loss_acc = 0.f;
+      bool first = true;
+      for (int tile = slot; tile < ntile; tile += nslots) {
+        const int row0 = tile * FRL_R;
+        const int nvalid = (a.B - row0) < FRL_R ? (a.B - row0) : FRL_R;
+        stage_prefetch(c, layer_fwd_src(C, l0), layer_fwd_bytes(C.L[l0]));
+        for (int j = 0; j < NA; ++j) gather_rows<FRL_R>(rep(a, j), a.indices + (size_t)u * a.B + row0, nvalid, raw0 + raw_off(a, j));
+        for (int j = 0; j < NA; ++j) {
+          const frl_replay_t& rj = rep(a, j);
+          const float* rw = raw0 + raw_off(a, j);
+          copy_cols<FRL_R>(XS, sa, obs_off(a, j), rw, rj.row_floats, 0, rj.obs_dim, 0);
+          copy_cols<FRL_R>(XS, sa, act_off(a, j), rw, rj.row_floats, rb_col_act(rj), rj.act_dim, j == NA - 1 ? sa : 0);
+        }
         FRL_PAR(t) {
           if (t < FRL_R) {
             const int r = t;
-            float nq = QA[r * 4];
-            if (a.n_heads == 2) nq = fminf(nq, QB[r * 4]);
-            const float rew = raw[r * rf + rb_col_rew(rb)], dn = raw[r * rf + rb_col_done(rb)];
-            float y;
-            if (sac) {
-              float lp = 0.f;
-              for (int j = 0; j < ad; ++j) lp += UU[r * ap + j];
-              // target = r + gamma*(1-d)*(minQ' + alpha*(-logp'))      (SAC.py:235)
-              y = fadd(rew, fmul(fmul(a.gamma, fadd(1.f, -dn)), fadd(nq, fmul(alpha, -lp))));
-            } else {
-              y = fadd(rew, fmul(fmul(a.gamma, nq), fadd(1.f, -dn)));     // TD3.py:209 / DDPG.py:212
+            float y = 0.f;
+            if (r < nvalid) {
+              float nq = a.xchg[(size_t)(row0 + r) * nrole];
+              if (nrole == 2) nq = fminf(nq, a.xchg[(size_t)(row0 + r) * nrole + 1]);
+              const float rew = raw[r * rf + rb_col_rew(rb)], dn = raw[r * rf + rb_col_done(rb)];
+              if (sac) {
+                const float lp = a.xchg[(size_t)a.B * nrole + row0 + r];
+                // target = r + gamma*(1-d)*(minQ' + alpha*(-logp'))      (SAC.py:235)
+                y = fadd(rew, fmul(fmul(a.gamma, fadd(1.f, -dn)), fadd(nq, fmul(alpha, -lp))));
+              } else {
+                y = fadd(rew, fmul(fmul(a.gamma, nq), fadd(1.f, -dn)));     // TD3.py:209 / DDPG.py:212 / MADDPG.py:214
+              }
             }
             rowv[r * 4 + 0] = y;
           }
         }
         FRL_SYNC();
-        stamp(c, 3);
-        // critic heads on (s, a): forward keeps activations, then backward
-        mlp_fwd<FRL_R>(c, C, 0, 3, XS, sa, H1, H2, ldh, QA, 4, FRL_ACT_NONE, a.n_heads == 2 ? fwd_hint(C, 3) : bwd_hint(C, 2));
-        if (a.n_heads == 2) mlp_fwd<FRL_R>(c, C, 3, 3, XS, sa, G1, G2, ldh, QB, 4, FRL_ACT_NONE, bwd_hint(C, 2));
+        mlp_fwd<FRL_R>(c, C, l0, 3, XS, sa, H1, H2, ldh, QA, 4, FRL_ACT_NONE, bwd_hint(C, l0 + 2));
         FRL_PAR(t) {
           float l = 0.f;
           if (t < FRL_R) {
             const int r = t;
-            for (int j = 0; j < 4; ++j) { dQA[r * 4 + j] = 0.f; dQB[r * 4 + j] = 0.f; }
+            for (int j = 0; j < 4; ++j) dQA[r * 4 + j] = 0.f;
             if (r < nvalid) {
-              const float y = rowv[r * 4];
-              const float d0 = QA[r * 4] - y;
+              const float d0 = QA[r * 4] - rowv[r * 4];
               dQA[r * 4] = 2.f * d0 * invB;
               l = d0 * d0;
-              if (a.n_heads == 2) {
-                const float d1 = QB[r * 4] - y;
-                dQB[r * 4] = 2.f * d1 * invB;
-                l += d1 * d1;
-              }
             }
           }
           red0[t] = l;
         }
         FRL_SYNC();
         loss_acc += block_sum(red0);
-        stamp(c, 4);
-        mlp_bwd<FRL_R>(c, C, 0, 3, XS, sa, H1, H2, ldh, dQA, 4, D1, D2, nullptr, 0, gp, !first,
-                       a.n_heads == 2 ? bwd_hint(C, 5) : no_hint());
-        stamp(c, 5);
-        if (a.n_heads == 2) mlp_bwd<FRL_R>(c, C, 3, 3, XS, sa, G1, G2, ldh, dQB, 4, D1, D2, nullptr, 0, gp, !first, no_hint());
-        stamp(c, 6);
+        mlp_bwd<FRL_R>(c, C, l0, 3, XS, sa, H1, H2, ldh, dQA, 4, D1, D2, nullptr, 0, gp, !first, no_hint());
         first = false;
       }
       FRL_PAR(t) { if (t == 0) a.stats[c.cta * 8 + 0] = loss_acc; }
       FRL_SYNC();
-    } else if (s == 1) {
-      reduce_grads(c.cta, c.ncta, c.red, C, a.gpart, gstride, ncontrib, a.sumsq);
     } else if (s == 2) {
+      reduce_grads_roles(c.cta, c.ncta, c.red, C, a.gpart, gstride, nslots, nrole, 1, 1, a.sumsq);
+    } else if (s == 3) {
       const AdamSpec hp = {a.lr_critic, a.beta1, a.beta2, a.eps, a.wd_critic, (double)a.max_norm, (long)(a.step_critic0 + u + 1)};
-      adam_update(c.cta, c.ncta, c.red, C, a.sumsq, ncontrib, hp, (policy_step && !a.defer_polyak) ? &a.critic_target : nullptr, a.tau);
+      adam_update(c.cta, c.ncta, c.red, C, a.sumsq, c.ncta, hp, (policy_step && !a.defer_polyak) ? &a.critic_target : nullptr, a.tau);
       FRL_PAR(t) {
         if (c.cta == 0 && t == 0) {
-          float l = 0.f, ss = 0.f;
-          for (int i = 0; i < ncontrib; ++i) { l += a.stats[i * 8 + 0]; ss += a.sumsq[i]; }
+          const float l = strided_sum(a.stats, 8, c.ncta), ss = strided_sum(a.sumsq, 1, c.ncta);
           a.out[u * 8 + 0] = l * invB;
           a.out[u * 8 + 4] = sqrtf(ss);
           a.out[u * 8 + 2] = alpha;
         }
       }
       FRL_SYNC();
-    } else if (s == 3) {
+    } else if (s == 4) {
       if (!policy_step) return;
-      // ---------------- actor forward, critic forward (updated weights), backward into the actor ----------------
+      // ---------------- actor forward, this role's critic head forward + dQ/da (updated critic), actor backward ----------------
       float loss_acc = 0.f, ent_acc = 0.f;
       bool first = true;
-      for (int tile = c.cta; tile < ntile; tile += c.ncta) {
+      const bool active = role < heads_used;
+      for (int tile = slot; tile < ntile && active; tile += nslots) {
         const int row0 = tile * FRL_R;
         const int nvalid = (a.B - row0) < FRL_R ? (a.B - row0) : FRL_R;
         stage_prefetch(c, layer_fwd_src(A, 0), layer_fwd_bytes(A.L[0]));
@@ -253,18 +295,18 @@ struct AcAlgo {
         }
         const int aoff_i = act_off(a, ai), aipi = A.L[0].in_pad;
         copy_cols<FRL_R>(XA, aipi, 0, raw, rf, 0, od, aipi);
-        mlp_fwd<FRL_R>(c, A, 0, 3, XA, aipi, A1, A2, ldh, MU, ap, FRL_ACT_NONE, fwd_hint(C, 0));
+        mlp_fwd<FRL_R>(c, A, 0, 3, XA, aipi, A1, A2, ldh, MU, ap, FRL_ACT_NONE, fwd_hint(C, l0));
         FRL_PAR(t) {
           if (t < FRL_R * ap) {
             const int r = t / ap, j = t % ap;
-            float act = 0.f, uu = 0.f, e = 0.f, lp = 0.f;
+            float act = 0.f, e = 0.f, lp = 0.f;
             if (j < ad) {
               const float mean = MU[r * ap + j];
               if (sac) {
                 const float ls = fminf(fmaxf(A.p[A.x_off + j], -20.f), 2.f);
                 const float sd = expf(ls);
                 e = (r < nvalid) ? noise_at(a.noise_new, a, u, row0 + r, j, 2u) : 0.f;
-                uu = fadd(mean, fmul(e, sd));
+                const float uu = fadd(mean, fmul(e, sd));
                 const float diff = uu - mean;
                 lp = -(diff * diff) / (2.f * (sd * sd)) - logf(sd) - FRL_LOG_SQRT_2PI;
                 lp -= 2.f * (FRL_LOG2F - uu - softplus_t(-2.f * uu));
@@ -274,34 +316,25 @@ struct AcAlgo {
               }
               XN[r * sa + aoff_i + j] = act;
             }
-            AC[r * ap + j] = act; UU[r * ap + j] = lp; EPS[r * ap + j] = e; dA[r * ap + j] = 0.f;
+            AC[r * ap + j] = act; UU[r * ap + j] = lp; EPS[r * ap + j] = e;
           }
         }
         FRL_SYNC();
-        // Q heads at (s, pi(s)); dL/dQ_h = -(1/n_used)/B   (SAC: mean of both heads; TD3: Q1 only; DDPG: single)
-        const int heads_used = sac ? a.n_heads : 1;
+        // Q_role(s, pi(s)); dL/dQ = -(1/heads_used)/B
         const float dq = -invB / (float)heads_used;
-        float qsum_tile = 0.f;
-        for (int h = 0; h < heads_used; ++h) {
-          mlp_fwd<FRL_R>(c, C, 3 * h, 3, XN, sa, H1, H2, ldh, QA, 4, FRL_ACT_NONE, bwd_hint(C, 3 * h + 2));
-          FRL_PAR(t) {
-            float v = 0.f;
-            if (t < FRL_R) {
-              for (int j = 0; j < 4; ++j) dQA[t * 4 + j] = 0.f;
-              if (t < nvalid) { dQA[t * 4] = dq; v = QA[t * 4]; }
-            }
-            red0[t] = v;
+        mlp_fwd<FRL_R>(c, C, l0, 3, XN, sa, H1, H2, ldh, QA, 4, FRL_ACT_NONE, bwd_hint(C, l0 + 2));
+        FRL_PAR(t) {
+          float v = 0.f;
+          if (t < FRL_R) {
+            for (int j = 0; j < 4; ++j) dQA[t * 4 + j] = 0.f;
+            if (t < nvalid) { dQA[t * 4] = dq; v = QA[t * 4]; }
           }
-          FRL_SYNC();
-          qsum_tile += block_sum(red0);
-          mlp_bwd<FRL_R>(c, C, 3 * h, 3, XN, sa, H1, H2, ldh, dQA, 4, D1, D2, dXP, sa, nullptr, false,
-                         h + 1 < heads_used ? fwd_hint(C, 3 * (h + 1)) : bwd_hint(A, 2));
-          FRL_PAR(t) {
-            if (t < FRL_R * ad) { const int r = t / ad, j = t % ad; dA[r * ap + j] += dXP[r * sa + aoff_i + j]; }
-          }
-          FRL_SYNC();
+          red0[t] = v;
         }
-        // actor head backward: dL/dmean, dL/dlog_std, loss bookkeeping
+        FRL_SYNC();
+        const float qsum_tile = block_sum(red0);
+        mlp_bwd<FRL_R>(c, C, l0, 3, XN, sa, H1, H2, ldh, dQA, 4, D1, D2, dXP, sa, nullptr, false, bwd_hint(A, 2));
+        // actor head backward (the log-prob / entropy terms are added once, by role 0)
         FRL_PAR(t) {
           float lsum = 0.f, esum = 0.f;
           if (t < FRL_R) {
@@ -311,12 +344,12 @@ struct AcAlgo {
               float g = 0.f;
               if (j < ad && r < nvalid) {
                 const float act = AC[r * ap + j];
-                g = dA[r * ap + j] * (1.f - act * act);
-                if (sac) { g += alpha * invB * 2.f * act; lp += UU[r * ap + j]; }
+                g = dXP[r * sa + aoff_i + j] * (1.f - act * act);
+                if (sac && role == 0) { g += alpha * invB * 2.f * act; lp += UU[r * ap + j]; }
               }
               dMU[r * ap + j] = g;
             }
-            if (r < nvalid) { esum = -lp; lsum = alpha * lp; }     // actor_loss = mean(-Q_pi - alpha*entropy)
+            if (r < nvalid && role == 0) { esum = -lp; lsum = alpha * lp; }     // actor_loss = mean(-Q_pi - alpha*entropy)
           }
           red0[t] = lsum; red1[t] = esum;
         }
@@ -324,14 +357,14 @@ struct AcAlgo {
         loss_acc += block_sum(red0) - qsum_tile / (float)heads_used;
         ent_acc += block_sum(red1);
         if (sac) {
-          // d/dlog_std_j = sum_r [ dL/du * std*eps - alpha/B ]   (zero outside the clamp range)
+          // d/dlog_std_j = sum_r [ dL/du * std*eps ] (+ role 0: -alpha/B per row); zero outside the clamp range
           FRL_PAR(t) {
             if (t < ap) {       // also clears the 16-B padding of the log_std slot in the shared partial buffer
               const float lsr = (t < ad) ? A.p[A.x_off + t] : 1e30f;
               float g = 0.f;
               if (lsr >= -20.f && lsr <= 2.f) {
                 const float sd = expf(lsr);
-                for (int r = 0; r < nvalid; ++r) g += dMU[r * ap + t] * sd * EPS[r * ap + t] - alpha * invB;
+                for (int r = 0; r < nvalid; ++r) g += dMU[r * ap + t] * sd * EPS[r * ap + t] - (role == 0 ? alpha * invB : 0.f);
               }
               gp[A.x_off + t] = first ? g : gp[A.x_off + t] + g;
             }
@@ -343,17 +376,17 @@ struct AcAlgo {
       }
       FRL_PAR(t) { if (t == 0) { a.stats[c.cta * 8 + 1] = loss_acc; a.stats[c.cta * 8 + 2] = ent_acc; } }
       FRL_SYNC();
-    } else if (s == 4) {
+    } else if (s == 5) {
       if (!policy_step) return;
-      reduce_grads(c.cta, c.ncta, c.red, A, a.gpart, gstride, ncontrib, a.sumsq);
+      // actor gradient: every ACTIVE role contributes to every actor parameter (TD3's idle head-2 CTAs are skipped)
+      reduce_grads_roles(c.cta, c.ncta, c.red, A, a.gpart, gstride, nslots, nrole, 0, heads_used == nrole ? 1 : nrole, a.sumsq);
     } else {
       if (!policy_step) return;
       const AdamSpec hp = {a.lr_actor, a.beta1, a.beta2, a.eps, 0.0, (double)a.max_norm, (long)(a.step_actor0 + n_policy_before + 1)};
-      adam_update(c.cta, c.ncta, c.red, A, a.sumsq, ncontrib, hp, a.defer_polyak ? nullptr : &a.actor_target, a.tau);
+      adam_update(c.cta, c.ncta, c.red, A, a.sumsq, c.ncta, hp, a.defer_polyak ? nullptr : &a.actor_target, a.tau);
       FRL_PAR(t) {
         if (c.cta == 0 && t == 0) {
-          float l = 0.f, en = 0.f, ss = 0.f;
-          for (int i = 0; i < ncontrib; ++i) { l += a.stats[i * 8 + 1]; en += a.stats[i * 8 + 2]; ss += a.sumsq[i]; }
+          const float l = strided_sum(a.stats + 1, 8, c.ncta), en = strided_sum(a.stats + 2, 8, c.ncta), ss = strided_sum(a.sumsq, 1, c.ncta);
           a.out[u * 8 + 1] = l * invB;
           a.out[u * 8 + 5] = sqrtf(ss);
           a.out[u * 8 + 6] = en * invB;

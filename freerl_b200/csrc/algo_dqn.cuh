@@ -136,8 +136,7 @@ struct DqnAlgo {
       adam_update(c.cta, c.ncta, c.red, q, nullptr, 0, hp, &a.q_target, a.tau);
       FRL_PAR(t) {
         if (c.cta == 0 && t == 0) {
-          float l = 0.f;
-          for (int i = 0; i < ncontrib; ++i) l += a.stats[i * 8 + 0];
+          const float l = strided_sum(a.stats, 8, ncontrib);
           a.out[u * 8 + 0] = l / (float)a.B;
         }
       }

@@ -371,8 +371,7 @@ struct PpoAlgo {
       float* sh = c.red;
       FRL_PAR(t) {
         if (t == 0) {
-          float ta = 0.f, tc = 0.f;
-          for (int i = 0; i < c.ncta; ++i) { ta += a.sumsq[i * 2]; tc += a.sumsq[i * 2 + 1]; }
+          const float ta = strided_sum(a.sumsq, 2, c.ncta), tc = strided_sum(a.sumsq + 1, 2, c.ncta);
           float ca = 1.f, cc = 1.f;
           if (a.max_norm_actor > 0.f) ca = fminf(a.max_norm_actor / (sqrtf(ta) + 1e-6f), 1.f);
           if (a.max_norm_critic > 0.f) cc = fminf(a.max_norm_critic / (sqrtf(tc) + 1e-6f), 1.f);
@@ -383,8 +382,7 @@ struct PpoAlgo {
           sh[3] = (float)(-(a.lr / bc1));                   // torch Adam: -lr/bc1
           sh[4] = (float)sqrt(bc2);
           if (s == 3 && c.cta == 0) {
-            float l0 = 0.f, l1 = 0.f, l2 = 0.f;
-            for (int i = 0; i < ncontrib; ++i) { l0 += a.stats[i * 8]; l1 += a.stats[i * 8 + 1]; l2 += a.stats[i * 8 + 2]; }
+            const float l0 = strided_sum(a.stats, 8, ncontrib), l1 = strided_sum(a.stats + 1, 8, ncontrib), l2 = strided_sum(a.stats + 2, 8, ncontrib);
             const float ent_mean = l2 / (float)rows;
             a.out[u * 8 + 0] = l0 - a.entropy_coef * ent_mean;
             a.out[u * 8 + 1] = l1 / (float)(rows * a.n_adv);
@@ -445,9 +443,7 @@ struct PpoAlgo {
         float* segmean = red0;
         FRL_PAR(t) {
           if (t < FRL_NSEG) {
-            float cnt = 0.f;
-            for (int i = 0; i < c.ncta; ++i) cnt += a.segcnt[i * FRL_NSEG + t];
-            segmean[t] = cnt;
+            segmean[t] = strided_sum(a.segcnt + t, FRL_NSEG, c.ncta);
           }
         }
         FRL_SYNC();

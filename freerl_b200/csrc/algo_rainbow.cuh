@@ -292,8 +292,7 @@ struct RainbowAlgo {
         const AdamHP h = make_adam_hp(a.lr, a.beta1, a.beta2, a.eps_adam, 0.0, 0.0, (long)(a.step0 + u + 1));
         sh[0] = h.lr_over_bc1_neg; sh[1] = h.bc2_sqrt; sh[2] = h.one_minus_b1; sh[3] = h.b2; sh[4] = h.one_minus_b2; sh[5] = h.eps;
         if (c.cta == 0) {
-          float l = 0.f;
-          for (int i = 0; i < ncontrib; ++i) l += a.stats[i * 8];
+          const float l = strided_sum(a.stats, 8, ncontrib);
           a.out[u * 8] = l / (float)a.B;
         }
       }

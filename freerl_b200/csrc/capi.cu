@@ -368,7 +368,8 @@ extern "C" int frl_dqn_learn(const frl_dqn_args_t* a, void* stream) {
 }
 
 extern "C" int frl_ac_learn(const frl_ac_args_t* a, void* stream) {
-  if (!a || a->B <= 0 || a->n_updates <= 0 || !a->indices || !a->gpart || !a->sumsq || !a->stats || !a->out) {
+  if (!a || a->B <= 0 || a->n_updates <= 0 || !a->indices || !a->gpart || !a->sumsq || !a->stats || !a->out || !a->xchg ||
+      a->n_heads < 1 || a->n_heads > 2) {
     frl_set_error("frl_ac_learn: bad arguments");
     return -1;
   }

@@ -497,6 +497,22 @@ FRL_DEV void mlp_bwd(Cta& c, const frl_net_t& n, int l0, int nl, const float* X,
   }
 }
 
+// fixed-order sum of n values at src[i*stride], 16 independent loads in flight (the naive loop serialises one L2 round
+// trip per element: ~10 us for 32 partials when a single thread does it while its CTA waits at the next barrier)
+FRL_DEV float strided_sum(const float* src, int stride, int n) {
+  float tot = 0.f;
+  int i = 0;
+  for (; i + 16 <= n; i += 16) {
+    float v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = src[(size_t)(i + k) * stride];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) tot += v[k];
+  }
+  for (; i < n; ++i) tot += src[(size_t)i * stride];
+  return tot;
+}
+
 // ------------------------------------------------------------------------------------------------
 // block-wide fixed-order sum of one float per thread (result broadcast to all threads via smem)
 // ------------------------------------------------------------------------------------------------

@@ -116,6 +116,7 @@ typedef struct {
   frl_replay_t ma_replay[FRL_MAX_AGENTS];
   frl_net_t ma_actor_target[FRL_MAX_AGENTS];
   int defer_polyak;         /* 1: do not touch the targets (MADDPG updates all targets after the agent loop) */
+  float* xchg;              /* dev scratch [3*B]: target-Q exchange between the per-head CTA roles */
 } frl_ac_args_t;
 
 enum { FRL_INFER_ARGMAX = 0, FRL_INFER_TANH = 1, FRL_INFER_SAC_SAMPLE = 2, FRL_INFER_SAC_MEAN = 3, FRL_INFER_RAW = 4,
