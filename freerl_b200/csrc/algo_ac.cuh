@@ -36,12 +36,19 @@ FRL_NI_OPT void reduce_grads_roles(int cta, int ncta, float* slot, const frl_net
       }
       float4 s = ld4(gpart + (size_t)first * stride + p);
       int k = 1;
-      for (; k + 8 <= cnt; k += 8) {
-        float4 v[8];
+      for (; k + 16 <= cnt; k += 16) {
+        float4 v[16];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = ld4(gpart + (size_t)(first + (k + i) * step) * stride + p);
+        for (int i = 0; i < 16; ++i) v[i] = ld4(gpart + (size_t)(first + (k + i) * step) * stride + p);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s = f4add(s, v[i]);
+        for (int i = 0; i < 16; ++i) s = f4add(s, v[i]);
+      }
+      for (; k + 4 <= cnt; k += 4) {
+        float4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = ld4(gpart + (size_t)(first + (k + i) * step) * stride + p);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s = f4add(s, v[i]);
       }
       for (; k < cnt; ++k) s = f4add(s, ld4(gpart + (size_t)(first + k * step) * stride + p));
       st4(n.g + p, s);

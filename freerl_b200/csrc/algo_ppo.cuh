@@ -377,7 +377,7 @@ struct PpoAlgo {
           if (a.max_norm_critic > 0.f) cc = fminf(a.max_norm_critic / (sqrtf(tc) + 1e-6f), 1.f);
           sh[0] = ca; sh[1] = cc;
           const double step = (double)(a.step0 + u + 1);
-          const double bc1 = 1.0 - pow(a.beta1, step), bc2 = 1.0 - pow(a.beta2, step);
+          const double bc1 = -expm1(step * log(a.beta1)), bc2 = -expm1(step * log(a.beta2));
           sh[2] = (float)(a.lr * sqrt(bc2) / bc1);         // c_adamw step_size
           sh[3] = (float)(-(a.lr / bc1));                   // torch Adam: -lr/bc1
           sh[4] = (float)sqrt(bc2);

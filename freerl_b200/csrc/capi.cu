@@ -511,3 +511,45 @@ extern "C" int frl_adv_norm(const float* x, int n, float eps, float* out, void* 
   AdvNormAlgo::Args a = {x, n, eps, out};
   return frl_launch_tiles<AdvNormAlgo>(a, (cudaStream_t)stream);
 }
+
+// ------------------------------------------------------------------------------------------------
+// debug micro-benchmark of one layer op (not part of the product API; used by tools_opbench.py)
+//   mode 0: gemm_rk on already-staged weights   1: layer_fwd with TMA every iteration, no prefetch
+//   mode 2: layer_fwd with prefetch of the next iteration's weights (alternating layers li and li2)
+// ------------------------------------------------------------------------------------------------
+struct OpBenchAlgo {
+  struct Args { frl_net_t net; int li, li2, iters, mode, ncta; float* sink; };
+  static const int NSTAGES = 1;
+  FRL_SHD int wbuf_floats(const Args& a) { return (AcAlgo::max_layer_floats(a.net) + 31) & ~31; }
+  FRL_SHD int user_floats(const Args& a) { return FRL_R * 3 * 256 + 64; }
+  FRL_SHD int grid(const Args& a, int) { return a.ncta; }
+  FRL_SHD int n_updates(const Args&) { return 1; }
+  FRL_SDEV void stage(int, int, Cta& c, float* user, const Args& a) {
+    const frl_layer_t& L = a.net.L[a.li];
+    float* X = user;
+    float* Y = user + FRL_R * 256;
+    FRL_PAR(t) { for (int e = t; e < FRL_R * 256; e += FRL_NT) { X[e] = 0.001f * (float)(e % 97); Y[e] = 0.f; } }
+    FRL_SYNC();
+    if (a.mode == 0) {
+      const float* Bs = stage_acquire(c, layer_fwd_src(a.net, a.li), layer_fwd_bytes(L));
+      for (int it = 0; it < a.iters; ++it)
+        gemm_rk<FRL_R>(c.red, X, L.in_pad, L.in_pad, Bs, L.out_pad, Bs + L.in_pad * L.out_pad, EPI_BIAS_ACT, FRL_ACT_RELU, nullptr, 0, Y, L.out_pad);
+    } else if (a.mode == 1) {
+      for (int it = 0; it < a.iters; ++it)
+        layer_fwd<FRL_R>(c, a.net, a.li, X, L.in_pad, Y, L.out_pad, FRL_ACT_RELU, no_hint());
+    } else {
+      for (int it = 0; it < a.iters; ++it) {
+        const int cur = (it & 1) ? a.li2 : a.li, nxt = (it & 1) ? a.li : a.li2;
+        layer_fwd<FRL_R>(c, a.net, cur, X, a.net.L[cur].in_pad, Y, a.net.L[cur].out_pad, FRL_ACT_RELU,
+                         it + 1 < a.iters ? fwd_hint(a.net, nxt) : no_hint());
+      }
+    }
+    FRL_PAR(t) { if (t == 0) a.sink[c.cta] = Y[0]; }
+    FRL_SYNC();
+  }
+};
+
+extern "C" int frl_debug_opbench(const frl_net_t* net, int li, int li2, int iters, int mode, int ncta, float* sink, void* stream) {
+  OpBenchAlgo::Args a = {*net, li, li2, iters, mode, ncta, sink};
+  return frl_launch_tiles<OpBenchAlgo>(a, (cudaStream_t)stream);
+}

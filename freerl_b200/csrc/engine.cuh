@@ -45,6 +45,10 @@ static inline float fdiv(float a, float b) { return a / b; }
 static inline float fsqrt(float a) { return sqrtf(a); }
 #endif
 
+#ifndef FRL_TMA_CHUNK
+#define FRL_TMA_CHUNK 16384
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // CTA context
 // ------------------------------------------------------------------------------------------------
@@ -77,6 +81,19 @@ FRL_DEV void stamp(Cta& c, int id) {
 }
 #else
 FRL_DEV void stamp(Cta&, int) {}
+#endif
+
+// fine-grained op tracing (debug builds only: -DFRL_TRACE): (id, clock64) pairs from CTA 0 / thread `who`
+#if defined(FRL_TRACE) && !defined(FRL_EMUL)
+__device__ int frl_trace_n = 0;
+FRL_DEV void trace(int id, int who = 0) {
+  if (frl_dbg_ptr && blockIdx.x == 0 && (int)threadIdx.x == who) {
+    const int k = atomicAdd(&frl_trace_n, 1);
+    if (k < 2000) { frl_dbg_ptr[2 * k] = id; frl_dbg_ptr[2 * k + 1] = clock64(); }
+  }
+}
+#else
+#define trace(...) ((void)0)
 #endif
 
 // ------------------------------------------------------------------------------------------------
@@ -142,7 +159,12 @@ FRL_DEV void stage_issue(Cta& c, int buf, const float* src, int bytes) {
   if (threadIdx.x == 0) {
     fence_proxy_async();
     mbar_expect_tx(c.bar + buf, (uint32_t)bytes);
-    tma_bulk_g2s(buf ? c.wbuf1 : c.wbuf0, src, (uint32_t)bytes, c.bar + buf);
+    char* dst = (char*)(buf ? c.wbuf1 : c.wbuf0);
+    const char* sp = (const char*)src;
+    for (int off = 0; off < bytes; off += FRL_TMA_CHUNK) {      // several bulk copies in flight on one mbarrier
+      const int nb = (bytes - off) < FRL_TMA_CHUNK ? (bytes - off) : FRL_TMA_CHUNK;
+      tma_bulk_g2s(dst + off, sp + off, (uint32_t)nb, c.bar + buf);
+    }
   }
 #else
   memcpy(buf ? c.wbuf1 : c.wbuf0, src, (size_t)bytes);
@@ -258,9 +280,16 @@ FRL_DEV float sp_ld1(sptr base, int word) { return base[word]; }
 FRL_DEV void sp_st4(sptr base, int word, float4 v) { st4(const_cast<float*>(base) + word, v); }
 #endif
 
-// unsigned divide helpers with a power-of-two fast path (shift >= 0) — the tile decode runs per thread per op
-FRL_DEV int ilog2_exact(int x) { int s = 0; while ((1 << s) < x) ++s; return ((1 << s) == x) ? s : -1; }
-FRL_DEV unsigned udiv(unsigned a, unsigned d, int shift) { return shift >= 0 ? (a >> shift) : (a / d); }
+// integer helpers — the GEMM index decode deliberately avoids runtime integer division: on the measured critical path a
+// handful of MUFU.RCP-based divisions per thread cost ~0.5 us per op (28 ops per learn).
+FRL_DEV unsigned floor_log2(unsigned x) {
+#ifndef FRL_EMUL
+  return 31u - (unsigned)__clz((int)x);
+#else
+  unsigned s = 0; while ((2u << s) <= x) ++s; return s;
+#endif
+}
+FRL_DEV unsigned ceil_pow2_log(unsigned x) { const unsigned f = floor_log2(x); return ((1u << f) == x) ? f : f + 1; }
 
 // ------------------------------------------------------------------------------------------------
 // gemm_rk:  C[r][n] = epi( sum_k A[r][k] * Bs[k][n] (+ bias[n]) ),  r < R, n < N_pad, k < K_pad
@@ -269,29 +298,33 @@ FRL_DEV unsigned udiv(unsigned a, unsigned d, int shift) { return shift >= 0 ? (
 //   epi: EPI_BIAS_ACT  -> act(acc + bias[n])            (bias in smem, may be null)
 //        EPI_RELU_MASK -> acc * (mask[r][n] > 0)        (backward through ReLU; mask = stored activation)
 //   C  : smem, leading dim ldc.  Must not alias A.
+// Work item = (k-split ks, tile); the tile count is padded to a power of two so item -> (ks, tile) is shift/mask, and a
+// tile is (n-tile, row-tile) with the row-tile in the low bit(s).  4x4 register tiles, K split `ksplit` (power of two)
+// ways across the CTA, fixed-order reduction of the split partials through shared memory.
 // (NOT inlined: one copy of the hot loop keeps the persistent kernels' instruction footprint inside the I-cache;
 //  the fully inlined build was 490 KB of SASS and spent most cycles in `no_instruction` stalls.)
 // ------------------------------------------------------------------------------------------------
 template <int R>
 FRL_NI_GEMM void gemm_rk(float* red, const float* A, int lda, int K_pad, const float* Bs, int N_pad, const float* bias,
                          int epi, int act, const float* mask, int ldm, float* C, int ldc) {
-  const unsigned nt = (unsigned)N_pad >> 2, rt = R / 4;
-  const unsigned tiles = nt * rt;
+  constexpr unsigned RT = R / 4, RT_SH = (RT == 1 ? 0 : (RT == 2 ? 1 : 2));
+  const unsigned nt = (unsigned)N_pad >> 2;
+  const unsigned tiles = nt * RT;
+  const unsigned sh_t = ceil_pow2_log(tiles), tiles_p2 = 1u << sh_t;
   const unsigned nchunk = (unsigned)K_pad >> 2;
-  unsigned ksplit = FRL_NT / tiles;
-  if (ksplit < 1) ksplit = 1;
-  if (ksplit > nchunk) ksplit = nchunk;
-  const unsigned items = tiles * ksplit;
-  const int sh_tiles = ilog2_exact((int)tiles), sh_nt = ilog2_exact((int)nt);
+  unsigned sh_k = 0;                                            // ksplit = 2^sh_k <= min(NT / tiles_p2, nchunk, 8)
+  while (sh_k < 3 && (tiles_p2 << (sh_k + 1)) <= FRL_NT && (2u << sh_k) <= nchunk) ++sh_k;
+  const unsigned ksplit = 1u << sh_k;
+  const unsigned items = tiles_p2 << sh_k;
   const sptr sA = sp_of(A), sB = sp_of(Bs), sR = sp_of(red), sC = sp_of(C);
   const bool has_bias = bias != nullptr;
   const sptr sBias = sp_of(has_bias ? bias : Bs), sM = sp_of(mask ? mask : Bs);
   FRL_PAR(t) {
     for (unsigned item = (unsigned)t; item < items; item += FRL_NT) {
-      const unsigned ks = udiv(item, tiles, sh_tiles), tile = item - ks * tiles;
-      const unsigned rti = udiv(tile, nt, sh_nt);
-      const int n0 = (int)(tile - rti * nt) * 4, r0 = (int)rti * 4;
-      const int kc0 = (int)((ks * nchunk) / ksplit), kc1 = (int)(((ks + 1) * nchunk) / ksplit);
+      const unsigned ks = item >> sh_t, tile = item & (tiles_p2 - 1);
+      if (tile >= tiles) continue;
+      const int n0 = (int)(tile >> RT_SH) * 4, r0 = (int)(tile & (RT - 1)) * 4;
+      const int kc0 = (int)((ks * nchunk) >> sh_k), kc1 = (int)(((ks + 1) * nchunk) >> sh_k);
       float acc[4][4];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -343,23 +376,30 @@ FRL_NI_GEMM void gemm_rk(float* red, const float* A, int lda, int K_pad, const f
   FRL_SYNC();
   if (ksplit > 1) {
     FRL_PAR(t) {
-      for (unsigned e = (unsigned)t; e < R * nt; e += FRL_NT) {
-        const unsigned r = udiv(e, nt, sh_nt);
-        const int n0 = (int)(e - r * nt) * 4;
-        int w = (int)r * N_pad + n0;
-        float4 s = sp_ld4(sR, w);
-        for (unsigned ks = 1; ks < ksplit; ++ks) { w += R * N_pad; s = f4add(s, sp_ld4(sR, w)); }
-        float o[4] = {s.x, s.y, s.z, s.w};
-        if (epi == EPI_BIAS_ACT) {
-          if (has_bias) { const float4 bv = sp_ld4(sBias, n0); o[0] += bv.x; o[1] += bv.y; o[2] += bv.z; o[3] += bv.w; }
+      // element e -> (row r, column group j): e = r * nt + j; one division per thread, then an incremental walk
+      const unsigned ne = R * nt;
+      if ((unsigned)t < ne) {
+        unsigned r = (unsigned)t / nt, j = (unsigned)t - r * nt;
+        const unsigned dr = FRL_NT / nt, dj = FRL_NT - dr * nt;
+        for (unsigned e = (unsigned)t; e < ne; e += FRL_NT) {
+          const int n0 = (int)j * 4;
+          int w = (int)r * N_pad + n0;
+          float4 s = sp_ld4(sR, w);
+          for (unsigned ks = 1; ks < ksplit; ++ks) { w += R * N_pad; s = f4add(s, sp_ld4(sR, w)); }
+          float o[4] = {s.x, s.y, s.z, s.w};
+          if (epi == EPI_BIAS_ACT) {
+            if (has_bias) { const float4 bv = sp_ld4(sBias, n0); o[0] += bv.x; o[1] += bv.y; o[2] += bv.z; o[3] += bv.w; }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) o[j] = apply_act(o[j], act);
-        } else {
-          const float4 mv = sp_ld4(sM, (int)r * ldm + n0);
-          o[0] = mv.x > 0.f ? o[0] : 0.f; o[1] = mv.y > 0.f ? o[1] : 0.f;
-          o[2] = mv.z > 0.f ? o[2] : 0.f; o[3] = mv.w > 0.f ? o[3] : 0.f;
+            for (int q = 0; q < 4; ++q) o[q] = apply_act(o[q], act);
+          } else {
+            const float4 mv = sp_ld4(sM, (int)r * ldm + n0);
+            o[0] = mv.x > 0.f ? o[0] : 0.f; o[1] = mv.y > 0.f ? o[1] : 0.f;
+            o[2] = mv.z > 0.f ? o[2] : 0.f; o[3] = mv.w > 0.f ? o[3] : 0.f;
+          }
+          sp_st4(sC, (int)r * ldc + n0, make_float4(o[0], o[1], o[2], o[3]));
+          r += dr; j += dj;
+          if (j >= nt) { j -= nt; ++r; }
         }
-        sp_st4(sC, (int)r * ldc + n0, make_float4(o[0], o[1], o[2], o[3]));
       }
     }
     FRL_SYNC();
@@ -376,36 +416,41 @@ FRL_NI_GEMM void gemm_outer(const float* dY, int ldy, int M_pad, const float* X,
                             float* G, float* gb, bool accumulate) {
   const unsigned mt = (unsigned)M_pad >> 2, nt = (unsigned)N_pad >> 2;
   const unsigned tiles = mt * nt;
-  const int sh_nt = ilog2_exact((int)nt);
   const sptr sY = sp_of(dY), sX = sp_of(X);
   FRL_PAR(t) {
-    for (unsigned tile = (unsigned)t; tile < tiles; tile += FRL_NT) {
-      const unsigned mi = udiv(tile, nt, sh_nt);
-      const int m0 = (int)mi * 4, n0 = (int)(tile - mi * nt) * 4;
-      float acc[4][4];
+    if ((unsigned)t < tiles) {
+      // tile -> (mi, ni): one division per thread, then an incremental walk (tile += FRL_NT)
+      unsigned mi = (unsigned)t / nt, ni = (unsigned)t - mi * nt;
+      const unsigned dm = FRL_NT / nt, dn = FRL_NT - dm * nt;
+      for (unsigned tile = (unsigned)t; tile < tiles; tile += FRL_NT) {
+        const int m0 = (int)mi * 4, n0 = (int)ni * 4;
+        float acc[4][4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+          for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const float4 a = sp_ld4(sY, r * ldy + m0);
-        const float4 b = sp_ld4(sX, r * ldx + n0);
-        acc[0][0] += a.x * b.x; acc[0][1] += a.x * b.y; acc[0][2] += a.x * b.z; acc[0][3] += a.x * b.w;
-        acc[1][0] += a.y * b.x; acc[1][1] += a.y * b.y; acc[1][2] += a.y * b.z; acc[1][3] += a.y * b.w;
-        acc[2][0] += a.z * b.x; acc[2][1] += a.z * b.y; acc[2][2] += a.z * b.z; acc[2][3] += a.z * b.w;
-        acc[3][0] += a.w * b.x; acc[3][1] += a.w * b.y; acc[3][2] += a.w * b.z; acc[3][3] += a.w * b.w;
-      }
-      float* gp = G + m0 * N_pad + n0;
+        for (int r = 0; r < R; ++r) {
+          const float4 a = sp_ld4(sY, r * ldy + m0);
+          const float4 b = sp_ld4(sX, r * ldx + n0);
+          acc[0][0] += a.x * b.x; acc[0][1] += a.x * b.y; acc[0][2] += a.x * b.z; acc[0][3] += a.x * b.w;
+          acc[1][0] += a.y * b.x; acc[1][1] += a.y * b.y; acc[1][2] += a.y * b.z; acc[1][3] += a.y * b.w;
+          acc[2][0] += a.z * b.x; acc[2][1] += a.z * b.y; acc[2][2] += a.z * b.z; acc[2][3] += a.z * b.w;
+          acc[3][0] += a.w * b.x; acc[3][1] += a.w * b.y; acc[3][2] += a.w * b.z; acc[3][3] += a.w * b.w;
+        }
+        float* gp = G + m0 * N_pad + n0;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 4; ++i) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (n0 + j >= N_real) acc[i][j] = 0.f;
-        float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-        if (accumulate) v = f4add(v, ld4(gp));
-        st4(gp, v);
-        gp += N_pad;
+          for (int j = 0; j < 4; ++j)
+            if (n0 + j >= N_real) acc[i][j] = 0.f;
+          float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+          if (accumulate) v = f4add(v, ld4(gp));
+          st4(gp, v);
+          gp += N_pad;
+        }
+        mi += dm; ni += dn;
+        if (ni >= nt) { ni -= nt; ++mi; }
       }
     }
     // bias gradient
@@ -437,9 +482,7 @@ FRL_DEV Hint bwd_hint(const frl_net_t& n, int li) { Hint h; h.ptr = layer_bwd_sr
 template <int R>
 FRL_DEV void layer_fwd(Cta& c, const frl_net_t& n, int li, const float* X, int ldx, float* Y, int ldy, int act, Hint next) {
   const frl_layer_t& L = n.L[li];
-  stamp(c, 10);
   const float* Bs = stage_acquire(c, layer_fwd_src(n, li), layer_fwd_bytes(L));
-  stamp(c, 11);
   stage_prefetch(c, next.ptr, next.bytes);
   gemm_rk<R>(c.red, X, ldx, L.in_pad, Bs, L.out_pad, Bs + L.in_pad * L.out_pad, EPI_BIAS_ACT, act, nullptr, 0, Y, ldy);
 }
@@ -567,8 +610,9 @@ struct AdamHP {
 
 FRL_HD AdamHP make_adam_hp(double lr, double b1, double b2, double eps, double wd, double max_norm, long step) {
   AdamHP h;
-  double bc1 = 1.0 - pow(b1, (double)step);
-  double bc2 = 1.0 - pow(b2, (double)step);
+  // 1 - b^step = -expm1(step * log(b)); double pow() on the single thread that computes this was a visible cost
+  double bc1 = -expm1((double)step * log(b1));
+  double bc2 = -expm1((double)step * log(b2));
   h.lr_over_bc1_neg = (float)(-(lr / bc1));
   h.bc2_sqrt = (float)sqrt(bc2);
   h.one_minus_b1 = (float)(1.0 - b1);
