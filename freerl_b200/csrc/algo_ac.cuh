@@ -155,7 +155,7 @@ struct AcAlgo {
         const int row0 = tile * FRL_R;
         const int nvalid = (a.B - row0) < FRL_R ? (a.B - row0) : FRL_R;
         stage_prefetch(c, layer_fwd_src(tnet(a, 0), 0), layer_fwd_bytes(tnet(a, 0).L[0]));
-        for (int j = 0; j < NA; ++j) gather_rows<FRL_R>(rep(a, j), a.indices + (size_t)u * a.B + row0, nvalid, raw0 + raw_off(a, j));
+        for (int j = 0; j < NA; ++j) gather_rows<FRL_R>(rep(a, j).storage, rep(a, j).row_floats, a.indices + (size_t)u * a.B + row0, nvalid, raw0 + raw_off(a, j));
         copy_cols<FRL_R>(XN, sa, act_off(a, 0), raw0, 1, 0, 0, sa);                 // zero the action + pad columns of XN
         for (int j = 0; j < NA; ++j) {
           const frl_replay_t& rj = rep(a, j);
@@ -221,7 +221,7 @@ struct AcAlgo {
         const int row0 = tile * FRL_R;
         const int nvalid = (a.B - row0) < FRL_R ? (a.B - row0) : FRL_R;
         stage_prefetch(c, layer_fwd_src(C, l0), layer_fwd_bytes(C.L[l0]));
-        for (int j = 0; j < NA; ++j) gather_rows<FRL_R>(rep(a, j), a.indices + (size_t)u * a.B + row0, nvalid, raw0 + raw_off(a, j));
+        for (int j = 0; j < NA; ++j) gather_rows<FRL_R>(rep(a, j).storage, rep(a, j).row_floats, a.indices + (size_t)u * a.B + row0, nvalid, raw0 + raw_off(a, j));
         for (int j = 0; j < NA; ++j) {
           const frl_replay_t& rj = rep(a, j);
           const float* rw = raw0 + raw_off(a, j);
@@ -293,7 +293,7 @@ struct AcAlgo {
         const int row0 = tile * FRL_R;
         const int nvalid = (a.B - row0) < FRL_R ? (a.B - row0) : FRL_R;
         stage_prefetch(c, layer_fwd_src(A, 0), layer_fwd_bytes(A.L[0]));
-        for (int j = 0; j < NA; ++j) gather_rows<FRL_R>(rep(a, j), a.indices + (size_t)u * a.B + row0, nvalid, raw0 + raw_off(a, j));
+        for (int j = 0; j < NA; ++j) gather_rows<FRL_R>(rep(a, j).storage, rep(a, j).row_floats, a.indices + (size_t)u * a.B + row0, nvalid, raw0 + raw_off(a, j));
         for (int j = 0; j < NA; ++j) {
           const frl_replay_t& rj = rep(a, j);
           const float* rw = raw0 + raw_off(a, j);

@@ -17,20 +17,20 @@ FRL_DEV int rb_col_nobs(const frl_replay_t& rb) { return rb.obs_dim + rb.act_dim
 // Gather R sampled rows (vectorised 16-B loads, one row = row_floats/4 lanes) into smem raw[R][row_floats].
 // Rows >= nvalid are zero-filled.
 template <int R>
-FRL_NI_MISC void gather_rows(const frl_replay_t& rb, const int64_t* idx, int nvalid, float* raw) {
-  const int q = rb.row_floats >> 2;
+FRL_NI_MISC void gather_rows(const float* storage, int row_floats, const int64_t* idx, int nvalid, float* raw) {
+  const int q = row_floats >> 2;
   FRL_PAR(t) {
     for (int e = t; e < R * q; e += FRL_NT) {
       const int r = e / q, j = e % q;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r < nvalid) {
 #ifndef FRL_EMUL
-        v = __ldg(reinterpret_cast<const float4*>(rb.storage + (size_t)idx[r] * rb.row_floats) + j);
+        v = __ldg(reinterpret_cast<const float4*>(storage + (size_t)idx[r] * row_floats) + j);
 #else
-        v = ld4(rb.storage + (size_t)idx[r] * rb.row_floats + 4 * j);
+        v = ld4(storage + (size_t)idx[r] * row_floats + 4 * j);
 #endif
       }
-      st4(raw + r * rb.row_floats + 4 * j, v);
+      st4(raw + r * row_floats + 4 * j, v);
     }
   }
   FRL_SYNC();
@@ -95,7 +95,7 @@ struct DqnAlgo {
         const int row0 = tile * FRL_R;
         const int nvalid = (a.B - row0) < FRL_R ? (a.B - row0) : FRL_R;
         stage_prefetch(c, layer_fwd_src(a.q_target, 0), layer_fwd_bytes(a.q_target.L[0]));
-        gather_rows<FRL_R>(a.replay, a.indices + (size_t)u * a.B + row0, nvalid, raw);
+        gather_rows<FRL_R>(a.replay.storage, a.replay.row_floats, a.indices + (size_t)u * a.B + row0, nvalid, raw);
         copy_cols<FRL_R>(Xo, in_pad, 0, raw, a.replay.row_floats, 0, a.replay.obs_dim, in_pad);
         copy_cols<FRL_R>(Xn, in_pad, 0, raw, a.replay.row_floats, rb_col_nobs(a.replay), a.replay.obs_dim, in_pad);
         // target net on next_obs, online net on obs

@@ -171,7 +171,7 @@ struct RainbowAlgo {
         const int nvalid = (a.B - row0) < FRL_R ? (a.B - row0) : FRL_R;
         const frl_net_t& En = a.double_q ? a.eff[0] : a.eff[1];
         stage_prefetch(c, layer_fwd_src(En, 0), layer_fwd_bytes(En.L[0]));
-        gather_rows<FRL_R>(a.replay, a.indices + (size_t)u * a.B + row0, nvalid, raw);
+        gather_rows<FRL_R>(a.replay.storage, a.replay.row_floats, a.indices + (size_t)u * a.B + row0, nvalid, raw);
         copy_cols<FRL_R>(Xo, ip, 0, raw, rf, 0, a.replay.obs_dim, ip);
         copy_cols<FRL_R>(Xn, ip, 0, raw, rf, rb_col_nobs(a.replay), a.replay.obs_dim, ip);
         // (1) next action: Double -> online net (forward #1), else the target's own argmax

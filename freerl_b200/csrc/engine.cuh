@@ -24,7 +24,7 @@
 #else
 #define FRL_NI_MISC FRL_NOINL
 #endif
-#ifdef FRL_INL_OPT
+#ifndef FRL_NOINL_OPT   // optimiser-stage helpers read the net descriptors: inlined so those are constant-bank (kernel parameter) loads
 #define FRL_NI_OPT FRL_INLINE_ALT
 #else
 #define FRL_NI_OPT FRL_NOINL
