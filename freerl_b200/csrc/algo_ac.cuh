@@ -25,38 +25,55 @@ FRL_DEV float softplus_t(float x) { return x > 20.f ? x : log1pf(expf(x)); }   /
 // every parameter sums `cnt` partials starting at CTA 0 with the given CTA step.
 FRL_NI_OPT void reduce_grads_roles(int cta, int ncta, float* slot, const frl_net_t& n, const float* gpart, int stride, int nslots,
                                    int nrole, int split_heads, int cta_step, float* sumsq_part) {
-  FRL_PAR(t) {
-    float local = 0.f;
-    for (int p = (cta * FRL_NT + t) * 4; p < n.n_p; p += ncta * FRL_NT * 4) {
-      int first = 0, step = cta_step, cnt = nslots * (nrole / cta_step);
-      if (split_heads) {
-        int h = 0;
-        for (int li = 3; li < n.n_layers; li += 3) if (p >= n.L[li].w_off) h = li / 3;
-        first = h; step = nrole; cnt = nslots;
-      }
-      float4 s = ld4(gpart + (size_t)first * stride + p);
-      int k = 1;
-      for (; k + 16 <= cnt; k += 16) {
-        float4 v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = ld4(gpart + (size_t)(first + (k + i) * step) * stride + p);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) s = f4add(s, v[i]);
-      }
-      for (; k + 4 <= cnt; k += 4) {
-        float4 v[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = ld4(gpart + (size_t)(first + (k + i) * step) * stride + p);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) s = f4add(s, v[i]);
-      }
-      for (; k < cnt; ++k) s = f4add(s, ld4(gpart + (size_t)(first + k * step) * stride + p));
-      st4(n.g + p, s);
-      local += s.x * s.x + s.y * s.y + s.z * s.z + s.w * s.w;
-    }
-    slot[t] = local;
-  }
+  // Two threads per 16-B parameter group, each summing half of the partials with all its loads in flight (the partials
+  // were just written by other SMs: every dependent L2 round trip costs ~0.7 us), halves combined in fixed order.
+  float* pair = slot + FRL_NT;                       // [FRL_NT][4]
+  const int ngroups = n.n_p >> 2;
+  FRL_PAR(t) { slot[t] = 0.f; }
   FRL_SYNC();
+  for (int base = cta * (FRL_NT / 2); base < ngroups; base += ncta * (FRL_NT / 2)) {
+    FRL_PAR(t) {
+      const int g = base + (t >> 1), half = t & 1, p = g * 4;
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (g < ngroups) {
+        int first = 0, step = cta_step, cnt = nslots * (nrole / cta_step);
+        if (split_heads) {
+          int h = 0;
+          for (int li = 3; li < n.n_layers; li += 3) if (p >= n.L[li].w_off) h = li / 3;
+          first = h; step = nrole; cnt = nslots;
+        }
+        const int mid = (cnt + 1) >> 1;
+        int k = half ? mid : 0;
+        const int k1 = half ? cnt : mid;
+        for (; k + 16 <= k1; k += 16) {
+          float4 v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = ld4(gpart + (size_t)(first + (k + i) * step) * stride + p);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) s = f4add(s, v[i]);
+        }
+        for (; k + 4 <= k1; k += 4) {
+          float4 v[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[i] = ld4(gpart + (size_t)(first + (k + i) * step) * stride + p);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) s = f4add(s, v[i]);
+        }
+        for (; k < k1; ++k) s = f4add(s, ld4(gpart + (size_t)(first + k * step) * stride + p));
+      }
+      st4(pair + 4 * t, s);
+    }
+    FRL_SYNC();
+    FRL_PAR(t) {
+      const int g = base + (t >> 1);
+      if (!(t & 1) && g < ngroups) {
+        const float4 s = f4add(ld4(pair + 4 * t), ld4(pair + 4 * t + 4));
+        st4(n.g + g * 4, s);
+        slot[t] += s.x * s.x + s.y * s.y + s.z * s.z + s.w * s.w;
+      }
+    }
+    FRL_SYNC();
+  }
   float tot = block_sum(slot);
   FRL_PAR(t) { if (t == 0 && sumsq_part) sumsq_part[cta] = tot; }
   FRL_SYNC();
@@ -274,15 +291,14 @@ struct AcAlgo {
     } else if (s == 3) {
       const AdamSpec hp = {a.lr_critic, a.beta1, a.beta2, a.eps, a.wd_critic, (double)a.max_norm, (long)(a.step_critic0 + u + 1)};
       adam_update(c.cta, c.ncta, c.red, C, a.sumsq, c.ncta, hp, (policy_step && !a.defer_polyak) ? &a.critic_target : nullptr, a.tau);
-      FRL_PAR(t) {
-        if (c.cta == 0 && t == 0) {
-          const float l = strided_sum(a.stats, 8, c.ncta), ss = strided_sum(a.sumsq, 1, c.ncta);
-          a.out[u * 8 + 0] = l * invB;
-          a.out[u * 8 + 4] = sqrtf(ss);
-          a.out[u * 8 + 2] = alpha;
+      if (c.cta == 0) {                      // metrics (block-uniform branch)
+        float o[3];
+        cta_sums(c.red, a.stats, 8, a.sumsq, 1, nullptr, 0, c.ncta, o);
+        FRL_PAR(t) {
+          if (t == 0) { a.out[u * 8 + 0] = o[0] * invB; a.out[u * 8 + 4] = sqrtf(o[1]); a.out[u * 8 + 2] = alpha; }
         }
+        FRL_SYNC();
       }
-      FRL_SYNC();
     } else if (s == 4) {
       if (!policy_step) return;
       // ---------------- actor forward, this role's critic head forward + dQ/da (updated critic), actor backward ----------------
@@ -391,9 +407,11 @@ struct AcAlgo {
       if (!policy_step) return;
       const AdamSpec hp = {a.lr_actor, a.beta1, a.beta2, a.eps, 0.0, (double)a.max_norm, (long)(a.step_actor0 + n_policy_before + 1)};
       adam_update(c.cta, c.ncta, c.red, A, a.sumsq, c.ncta, hp, a.defer_polyak ? nullptr : &a.actor_target, a.tau);
+      float o3[3] = {0.f, 0.f, 0.f};
+      if (c.cta == 0) cta_sums(c.red, a.stats + 1, 8, a.stats + 2, 8, a.sumsq, 1, c.ncta, o3);
       FRL_PAR(t) {
         if (c.cta == 0 && t == 0) {
-          const float l = strided_sum(a.stats + 1, 8, c.ncta), en = strided_sum(a.stats + 2, 8, c.ncta), ss = strided_sum(a.sumsq, 1, c.ncta);
+          const float l = o3[0], en = o3[1], ss = o3[2];
           a.out[u * 8 + 1] = l * invB;
           a.out[u * 8 + 5] = sqrtf(ss);
           a.out[u * 8 + 6] = en * invB;

@@ -556,6 +556,28 @@ FRL_DEV float strided_sum(const float* src, int stride, int n) {
   return tot;
 }
 
+// Sums of up to three strided series of n <= FRL_NT values each, loaded by n threads IN PARALLEL (one L2 round trip; a
+// single thread walking 64 partials costs ~0.7 us per dependent round trip) and added in fixed order.  sh: >= 3n+4 floats.
+FRL_DEV void cta_sums(float* sh, const float* p0, int s0, const float* p1, int s1, const float* p2, int s2, int n, float out[3]) {
+  FRL_PAR(t) {
+    if (t < n) {
+      sh[t] = p0[(size_t)t * s0];
+      sh[n + t] = p1 ? p1[(size_t)t * s1] : 0.f;
+      sh[2 * n + t] = p2 ? p2[(size_t)t * s2] : 0.f;
+    }
+  }
+  FRL_SYNC();
+  FRL_PAR(t) {
+    if (t < 3) {
+      float acc = 0.f;
+      for (int i = 0; i < n; ++i) acc += sh[t * n + i];
+      sh[3 * n + t] = acc;
+    }
+  }
+  FRL_SYNC();
+  out[0] = sh[3 * n]; out[1] = sh[3 * n + 1]; out[2] = sh[3 * n + 2];
+}
+
 // ------------------------------------------------------------------------------------------------
 // block-wide fixed-order sum of one float per thread (result broadcast to all threads via smem)
 // ------------------------------------------------------------------------------------------------
