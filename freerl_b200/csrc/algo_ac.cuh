@@ -86,15 +86,35 @@ struct AcAlgo {
   FRL_SHD int max_layer_floats(const frl_net_t& n) {
     int mx = 0;
     for (int i = 0; i < n.n_layers; ++i) {
-      int f = n.L[i].in_pad * n.L[i].out_pad + n.L[i].out_pad;
+      int f = wt_floats(n.L[i]);
       if (f > mx) mx = f;
     }
     return mx;
   }
-  FRL_SHD int wbuf_floats(const Args& a) {
+  // floats of the largest 3-layer head image (heads are contiguous in the mirror)
+  FRL_SHD int max_head_floats(const frl_net_t& n) {
+    int mx = 0;
+    for (int h = 0; h + 3 <= n.n_layers; h += 3) {
+      int f = wt_floats(n.L[h]) + wt_floats(n.L[h + 1]) + wt_floats(n.L[h + 2]);
+      if (f > mx) mx = f;
+    }
+    return mx;
+  }
+  FRL_SHD int stream_floats(const Args& a) {
     int x = max_layer_floats(a.actor), y = max_layer_floats(a.critic);
+    for (int j = 0; j < ma_n(a); ++j) { int v = max_layer_floats(tnet(a, j)); if (v > x) x = v; }
     return ((x > y ? x : y) + 31) & ~31;
   }
+  FRL_SHD int head_floats(const Args& a) {
+    int x = max_head_floats(a.actor), y = max_head_floats(a.critic);
+    for (int j = 0; j < ma_n(a); ++j) { int v = max_head_floats(tnet(a, j)); if (v > x) x = v; }
+    return ((x > y ? x : y) + 31) & ~31;
+  }
+  // Resident mode (two whole heads in smem, weights kept across stages) whenever it fits; else per-layer streaming.
+  FRL_SHD bool resident(const Args& a) {
+    return (size_t)(cta_base_floats(head_floats(a)) + user_floats(a)) * 4 + 64 <= (size_t)227 * 1024;
+  }
+  FRL_SHD int wbuf_floats(const Args& a) { return resident(a) ? head_floats(a) : stream_floats(a); }
   // ---- multi-agent helpers: where agent j's obs / action sit inside the joint critic input [obs_1..obs_N | act_1..act_N]
   FRL_SHD int ma_n(const Args& a) { return a.n_agents > 1 ? a.n_agents : 1; }
   FRL_SHD const frl_replay_t& rep(const Args& a, int j) { return a.n_agents > 1 ? a.ma_replay[j] : a.replay; }
@@ -107,7 +127,7 @@ struct AcAlgo {
 
   FRL_SHD int user_floats(const Args& a) {
     const int ldh = a.critic.L[0].out_pad, sa = a.critic.L[0].in_pad, ap = max_ap(a);
-    return raw_off(a, ma_n(a)) + FRL_R * (max_aip(a) + 3 * sa + 6 * ldh + 6 * ap + 3 * 4 + 16) + 2 * FRL_NT + 128;
+    return raw_off(a, ma_n(a)) + FRL_R * (max_aip(a) + 3 * sa + 6 * ldh + 6 * ap + 3 * 4 + 16) + 2 * FRL_NT + 128 + PLAN_FLOATS;
   }
   FRL_SHD int nslots_of(const Args& a, int max_ctas) {
     const int tiles = (a.B + FRL_R - 1) / FRL_R, cap = max_ctas / (a.n_heads > 0 ? a.n_heads : 1);
@@ -118,7 +138,25 @@ struct AcAlgo {
 
   FRL_SDEV float noise_at(const float* ptr, const Args& a, int u, int row, int j, uint32_t stream) {
     if (ptr) return ptr[((size_t)u * a.B + row) * a.replay.act_dim + j];
-    return frl_randn(a.seed, stream, (uint32_t)(a.total_it0 + u), (uint32_t)(row * a.replay.act_dim + j));
+    return randn_ni(a.seed, stream, (uint32_t)(a.total_it0 + u), (uint32_t)(row * a.replay.act_dim + j));
+  }
+
+  // Launch-invariant geometry, computed once (thread 0, first stage call) into shared memory: evaluating the multi-agent
+  // offset helpers inline at every use had grown to ~1/4 of the kernel's instructions.
+  struct Plan {
+    int NA, ai, ap, aip, res, gstride;
+    int obs_off[FRL_MAX_AGENTS + 1], act_off[FRL_MAX_AGENTS + 1], raw_off[FRL_MAX_AGENTS + 1];
+  };
+  static const int PLAN_FLOATS = 32;
+  FRL_SDEV void fill_plan(Plan& P, const Args& a) {
+    P.NA = ma_n(a); P.ai = a.n_agents > 1 ? a.agent_index : 0;
+    P.ap = max_ap(a); P.aip = max_aip(a); P.res = resident(a) ? 1 : 0;
+    P.gstride = a.critic.n_p > a.actor.n_p ? a.critic.n_p : a.actor.n_p;
+    int o = 0, r = 0;
+    for (int j = 0; j < P.NA; ++j) { P.obs_off[j] = o; P.raw_off[j] = r; o += rep(a, j).obs_dim; r += FRL_R * rep(a, j).row_floats; }
+    P.obs_off[P.NA] = o; P.raw_off[P.NA] = r;
+    for (int j = 0; j < P.NA; ++j) { P.act_off[j] = o; o += rep(a, j).act_dim; }
+    P.act_off[P.NA] = o;
   }
 
   FRL_SDEV void stage(int s, int u, Cta& c, float* user, const Args& a) {
@@ -126,9 +164,15 @@ struct AcAlgo {
     const frl_net_t& C = a.critic;
     const frl_replay_t& rb = a.replay;
     const int od = rb.obs_dim, ad = rb.act_dim, rf = rb.row_floats;
-    const int ldh = C.L[0].out_pad, sa = C.L[0].in_pad, ap = max_ap(a);
-    const int NA = ma_n(a), ai = a.n_agents > 1 ? a.agent_index : 0;
-    const int aip = max_aip(a);
+    Plan& P = *reinterpret_cast<Plan*>(user);
+    user += PLAN_FLOATS;
+    if (s == 0 && u == 0) {
+      FRL_PAR(t) { if (t == 0) fill_plan(P, a); }
+      FRL_SYNC();
+    }
+    const int ldh = C.L[0].out_pad, sa = C.L[0].in_pad, ap = P.ap;
+    const int NA = P.NA, ai = P.ai;
+    const int aip = P.aip;
     const int nrole = a.n_heads, role = c.cta % nrole, slot = c.cta / nrole, nslots = c.ncta / nrole;
     const int l0 = 3 * role;                                   // this CTA's critic head = layers l0..l0+2
     const int ntile = (a.B + FRL_R - 1) / FRL_R;
@@ -139,10 +183,11 @@ struct AcAlgo {
     const int heads_used = sac ? a.n_heads : 1;                // actor loss: SAC mean of both heads, TD3 Q1 only, DDPG single
     float alpha = 0.f;
     if (sac) alpha = expf(a.alpha_state[0]);
+    const bool res = P.res != 0;
 
     SmemBump sb; sb.p = user;
-    float* raw0 = sb.take(raw_off(a, NA));   // gathered rows of every agent's replay (same indices)
-    float* raw = raw0 + raw_off(a, ai);      // this agent's rows (reward / done come from here)
+    float* raw0 = sb.take(P.raw_off[NA]);   // gathered rows of every agent's replay (same indices)
+    float* raw = raw0 + P.raw_off[ai];      // this agent's rows (reward / done come from here)
     float* XA = sb.take(FRL_R * aip);        // actor input (one agent's obs / next_obs)
     float* XS = sb.take(FRL_R * sa);         // [obs | act]
     float* XN = sb.take(FRL_R * sa);         // [next_obs | a']   (stage 4: [obs | pi(obs)])
@@ -163,7 +208,7 @@ struct AcAlgo {
     float* rowv = sb.take(FRL_R * 4);        // per-row scalars
     float* red0 = sb.take(FRL_NT);
     float* red1 = sb.take(FRL_NT);
-    const int gstride = C.n_p > A.n_p ? C.n_p : A.n_p;
+    const int gstride = P.gstride;
     float* gp = a.gpart + (size_t)c.cta * gstride;
 
     if (s == 0) {
@@ -171,20 +216,52 @@ struct AcAlgo {
       for (int tile = slot; tile < ntile; tile += nslots) {
         const int row0 = tile * FRL_R;
         const int nvalid = (a.B - row0) < FRL_R ? (a.B - row0) : FRL_R;
-        stage_prefetch(c, layer_fwd_src(tnet(a, 0), 0), layer_fwd_bytes(tnet(a, 0).L[0]));
-        for (int j = 0; j < NA; ++j) gather_rows<FRL_R>(rep(a, j).storage, rep(a, j).row_floats, a.indices + (size_t)u * a.B + row0, nvalid, raw0 + raw_off(a, j));
-        copy_cols<FRL_R>(XN, sa, act_off(a, 0), raw0, 1, 0, 0, sa);                 // zero the action + pad columns of XN
+        // resident plan: actor targets alternate between the slots (next one prefetched behind the current forward), the
+        // target critic head goes to the slot the last actor does not use; once that actor is done its slot takes the
+        // online critic head stage 1 needs.  Heads still resident from the previous learn / tile are not fetched again.
+        const bool last_tile = tile + nslots >= ntile;
+        int at0 = -1, cts = -1;
+        if (res) {
+          const int ctk = res_find(c, a.critic_target, l0);
+          at0 = ctk >= 0 ? (ctk ^ 1) : 1;
+          res_fetch(c, at0, tnet(a, 0), 0, 3);
+          if (NA == 1) res_fetch(c, at0 ^ 1, a.critic_target, l0, 3);
+        } else {
+          stage_prefetch(c, layer_fwd_src(tnet(a, 0), 0), layer_fwd_bytes(tnet(a, 0).L[0]));
+        }
+        trace(10);
+        for (int j = 0; j < NA; ++j) gather_rows<FRL_R>(rep(a, j).storage, rep(a, j).row_floats, a.indices + (size_t)u * a.B + row0, nvalid, raw0 + P.raw_off[j]);
+        trace(11);
+        put_cols<FRL_R>(XN, sa, P.act_off[0], raw0, 1, 0, 0, sa - P.act_off[0]);   // zero the action + pad columns of XN
         for (int j = 0; j < NA; ++j) {
           const frl_replay_t& rj = rep(a, j);
-          copy_cols<FRL_R>(XN, sa, obs_off(a, j), raw0 + raw_off(a, j), rj.row_floats, rb_col_nobs(rj), rj.obs_dim, 0);
+          put_cols<FRL_R>(XN, sa, P.obs_off[j], raw0 + P.raw_off[j], rj.row_floats, rb_col_nobs(rj), rj.obs_dim, rj.obs_dim);
         }
+        {
+          const frl_replay_t& r0 = rep(a, 0);
+          const int tip0 = tnet(a, 0).L[0].in_pad;
+          put_cols<FRL_R>(XA, tip0, 0, raw0, r0.row_floats, rb_col_nobs(r0), r0.obs_dim, tip0);
+        }
+        FRL_SYNC();
         for (int j = 0; j < NA; ++j) {                                               // a'_j = actor_target_j(next_obs_j)
           const frl_replay_t& rj = rep(a, j);
           const frl_net_t& T = tnet(a, j);
-          const int adj = rj.act_dim, tip = T.L[0].in_pad, aoff = act_off(a, j);
-          copy_cols<FRL_R>(XA, tip, 0, raw0 + raw_off(a, j), rj.row_floats, rb_col_nobs(rj), rj.obs_dim, tip);
+          const int adj = rj.act_dim, tip = T.L[0].in_pad, aoff = P.act_off[j];
+          int sl = -1;
+          if (res) {
+            sl = at0 ^ (j & 1);
+            res_fetch(c, sl, T, 0, 3);
+            if (j + 1 < NA) res_fetch(c, sl ^ 1, tnet(a, j + 1), 0, 3);
+            else if (NA > 1) res_fetch(c, sl ^ 1, a.critic_target, l0, 3);
+            cts = sl ^ 1;
+          }
+          if (j > 0) {
+            put_cols<FRL_R>(XA, tip, 0, raw0 + P.raw_off[j], rj.row_floats, rb_col_nobs(rj), rj.obs_dim, tip);
+            FRL_SYNC();
+          }
+          trace(12);
           mlp_fwd<FRL_R>(c, T, 0, 3, XA, tip, A1, A2, ldh, MU, ap, FRL_ACT_NONE,
-                         j + 1 < NA ? fwd_hint(tnet(a, j + 1), 0) : fwd_hint(a.critic_target, l0));
+                         j + 1 < NA ? fwd_hint(tnet(a, j + 1), 0) : fwd_hint(a.critic_target, l0), sl);
           FRL_PAR(t) {
             if (t < FRL_R * adj) {
               const int r = t / adj, jj = t % adj;
@@ -214,9 +291,12 @@ struct AcAlgo {
               XN[r * sa + aoff + jj] = act;
             }
           }
+          trace(13);
           FRL_SYNC();
+          trace(14);
         }
-        mlp_fwd<FRL_R>(c, a.critic_target, l0, 3, XN, sa, H1, H2, ldh, QA, 4, FRL_ACT_NONE, no_hint());
+        if (res && last_tile) res_fetch(c, cts ^ 1, C, l0, 3);
+        mlp_fwd<FRL_R>(c, a.critic_target, l0, 3, XN, sa, H1, H2, ldh, QA, 4, FRL_ACT_NONE, no_hint(), cts);
         // exchange: xchg[row][role] = Q'_role ; xchg[B*nrole + row] = sum_j log pi(a'|s')  (SAC, role 0)
         FRL_PAR(t) {
           if (t < nvalid) {
@@ -228,6 +308,7 @@ struct AcAlgo {
             }
           }
         }
+        trace(15);
         FRL_SYNC();
       }
     } else if (s == 1) {
@@ -237,13 +318,21 @@ struct AcAlgo {
       for (int tile = slot; tile < ntile; tile += nslots) {
         const int row0 = tile * FRL_R;
         const int nvalid = (a.B - row0) < FRL_R ? (a.B - row0) : FRL_R;
-        stage_prefetch(c, layer_fwd_src(C, l0), layer_fwd_bytes(C.L[l0]));
-        for (int j = 0; j < NA; ++j) gather_rows<FRL_R>(rep(a, j).storage, rep(a, j).row_floats, a.indices + (size_t)u * a.B + row0, nvalid, raw0 + raw_off(a, j));
+        int cs = -1;
+        if (res) {
+          cs = res_find(c, C, l0);
+          if (cs < 0) cs = 0;
+          res_fetch(c, cs, C, l0, 3);
+          if (policy_step && role < heads_used && tile + nslots >= ntile) res_fetch(c, cs ^ 1, A, 0, 3);   // stage 4's actor
+        } else {
+          stage_prefetch(c, layer_fwd_src(C, l0), layer_fwd_bytes(C.L[l0]));
+        }
+        for (int j = 0; j < NA; ++j) gather_rows<FRL_R>(rep(a, j).storage, rep(a, j).row_floats, a.indices + (size_t)u * a.B + row0, nvalid, raw0 + P.raw_off[j]);
         for (int j = 0; j < NA; ++j) {
           const frl_replay_t& rj = rep(a, j);
-          const float* rw = raw0 + raw_off(a, j);
-          copy_cols<FRL_R>(XS, sa, obs_off(a, j), rw, rj.row_floats, 0, rj.obs_dim, 0);
-          copy_cols<FRL_R>(XS, sa, act_off(a, j), rw, rj.row_floats, rb_col_act(rj), rj.act_dim, j == NA - 1 ? sa : 0);
+          const float* rw = raw0 + P.raw_off[j];
+          put_cols<FRL_R>(XS, sa, P.obs_off[j], rw, rj.row_floats, 0, rj.obs_dim, rj.obs_dim);
+          put_cols<FRL_R>(XS, sa, P.act_off[j], rw, rj.row_floats, rb_col_act(rj), rj.act_dim, j == NA - 1 ? sa - P.act_off[j] : rj.act_dim);
         }
         FRL_PAR(t) {
           if (t < FRL_R) {
@@ -265,7 +354,7 @@ struct AcAlgo {
           }
         }
         FRL_SYNC();
-        mlp_fwd<FRL_R>(c, C, l0, 3, XS, sa, H1, H2, ldh, QA, 4, FRL_ACT_NONE, bwd_hint(C, l0 + 2));
+        mlp_fwd<FRL_R>(c, C, l0, 3, XS, sa, H1, H2, ldh, QA, 4, FRL_ACT_NONE, bwd_hint(C, l0 + 2), cs);
         FRL_PAR(t) {
           float l = 0.f;
           if (t < FRL_R) {
@@ -281,7 +370,7 @@ struct AcAlgo {
         }
         FRL_SYNC();
         loss_acc += block_sum(red0);
-        mlp_bwd<FRL_R>(c, C, l0, 3, XS, sa, H1, H2, ldh, dQA, 4, D1, D2, nullptr, 0, gp, !first, no_hint());
+        mlp_bwd<FRL_R>(c, C, l0, 3, XS, sa, H1, H2, ldh, dQA, 4, D1, D2, nullptr, 0, gp, !first, no_hint(), cs);
         first = false;
       }
       FRL_PAR(t) { if (t == 0) a.stats[c.cta * 8 + 0] = loss_acc; }
@@ -291,6 +380,8 @@ struct AcAlgo {
     } else if (s == 3) {
       const AdamSpec hp = {a.lr_critic, a.beta1, a.beta2, a.eps, a.wd_critic, (double)a.max_norm, (long)(a.step_critic0 + u + 1)};
       adam_update(c.cta, c.ncta, c.red, C, a.sumsq, c.ncta, hp, (policy_step && !a.defer_polyak) ? &a.critic_target : nullptr, a.tau);
+      res_invalidate(c, C);
+      if (policy_step && !a.defer_polyak) res_invalidate(c, a.critic_target);
       if (c.cta == 0) {                      // metrics (block-uniform branch)
         float o[3];
         cta_sums(c.red, a.stats, 8, a.sumsq, 1, nullptr, 0, c.ncta, o);
@@ -308,17 +399,27 @@ struct AcAlgo {
       for (int tile = slot; tile < ntile && active; tile += nslots) {
         const int row0 = tile * FRL_R;
         const int nvalid = (a.B - row0) < FRL_R ? (a.B - row0) : FRL_R;
-        stage_prefetch(c, layer_fwd_src(A, 0), layer_fwd_bytes(A.L[0]));
-        for (int j = 0; j < NA; ++j) gather_rows<FRL_R>(rep(a, j).storage, rep(a, j).row_floats, a.indices + (size_t)u * a.B + row0, nvalid, raw0 + raw_off(a, j));
+        int as = -1, cs = -1;
+        if (res) {
+          as = res_find(c, A, 0);
+          if (as < 0) as = 0;
+          res_fetch(c, as, A, 0, 3);
+          cs = as ^ 1;
+          res_fetch(c, cs, C, l0, 3);            // the critic head as updated by stage 3, behind the actor forward
+        } else {
+          stage_prefetch(c, layer_fwd_src(A, 0), layer_fwd_bytes(A.L[0]));
+        }
+        for (int j = 0; j < NA; ++j) gather_rows<FRL_R>(rep(a, j).storage, rep(a, j).row_floats, a.indices + (size_t)u * a.B + row0, nvalid, raw0 + P.raw_off[j]);
         for (int j = 0; j < NA; ++j) {
           const frl_replay_t& rj = rep(a, j);
-          const float* rw = raw0 + raw_off(a, j);
-          copy_cols<FRL_R>(XN, sa, obs_off(a, j), rw, rj.row_floats, 0, rj.obs_dim, 0);
-          copy_cols<FRL_R>(XN, sa, act_off(a, j), rw, rj.row_floats, rb_col_act(rj), rj.act_dim, j == NA - 1 ? sa : 0);
+          const float* rw = raw0 + P.raw_off[j];
+          put_cols<FRL_R>(XN, sa, P.obs_off[j], rw, rj.row_floats, 0, rj.obs_dim, rj.obs_dim);
+          put_cols<FRL_R>(XN, sa, P.act_off[j], rw, rj.row_floats, rb_col_act(rj), rj.act_dim, j == NA - 1 ? sa - P.act_off[j] : rj.act_dim);
         }
-        const int aoff_i = act_off(a, ai), aipi = A.L[0].in_pad;
-        copy_cols<FRL_R>(XA, aipi, 0, raw, rf, 0, od, aipi);
-        mlp_fwd<FRL_R>(c, A, 0, 3, XA, aipi, A1, A2, ldh, MU, ap, FRL_ACT_NONE, fwd_hint(C, l0));
+        const int aoff_i = P.act_off[ai], aipi = A.L[0].in_pad;
+        put_cols<FRL_R>(XA, aipi, 0, raw, rf, 0, od, aipi);
+        FRL_SYNC();
+        mlp_fwd<FRL_R>(c, A, 0, 3, XA, aipi, A1, A2, ldh, MU, ap, FRL_ACT_NONE, fwd_hint(C, l0), as);
         FRL_PAR(t) {
           if (t < FRL_R * ap) {
             const int r = t / ap, j = t % ap;
@@ -345,7 +446,7 @@ struct AcAlgo {
         FRL_SYNC();
         // Q_role(s, pi(s)); dL/dQ = -(1/heads_used)/B
         const float dq = -invB / (float)heads_used;
-        mlp_fwd<FRL_R>(c, C, l0, 3, XN, sa, H1, H2, ldh, QA, 4, FRL_ACT_NONE, bwd_hint(C, l0 + 2));
+        mlp_fwd<FRL_R>(c, C, l0, 3, XN, sa, H1, H2, ldh, QA, 4, FRL_ACT_NONE, bwd_hint(C, l0 + 2), cs);
         FRL_PAR(t) {
           float v = 0.f;
           if (t < FRL_R) {
@@ -356,7 +457,9 @@ struct AcAlgo {
         }
         FRL_SYNC();
         const float qsum_tile = block_sum(red0);
-        mlp_bwd<FRL_R>(c, C, l0, 3, XN, sa, H1, H2, ldh, dQA, 4, D1, D2, dXP, sa, nullptr, false, bwd_hint(A, 2));
+        mlp_bwd<FRL_R>(c, C, l0, 3, XN, sa, H1, H2, ldh, dQA, 4, D1, D2, dXP, sa, nullptr, false, bwd_hint(A, 2), cs);
+        // the critic slot is free again: start on the target head the next learn's stage 0 opens with (Polyak'd in stage 3)
+        if (res && tile + nslots >= ntile && u + 1 < a.n_updates) res_fetch(c, cs, a.critic_target, l0, 3);
         // actor head backward (the log-prob / entropy terms are added once, by role 0)
         FRL_PAR(t) {
           float lsum = 0.f, esum = 0.f;
@@ -394,7 +497,7 @@ struct AcAlgo {
           }
           FRL_SYNC();
         }
-        mlp_bwd<FRL_R>(c, A, 0, 3, XA, aipi, A1, A2, ldh, dMU, ap, D1, D2, nullptr, 0, gp, !first, no_hint());
+        mlp_bwd<FRL_R>(c, A, 0, 3, XA, aipi, A1, A2, ldh, dMU, ap, D1, D2, nullptr, 0, gp, !first, no_hint(), as);
         first = false;
       }
       FRL_PAR(t) { if (t == 0) { a.stats[c.cta * 8 + 1] = loss_acc; a.stats[c.cta * 8 + 2] = ent_acc; } }
@@ -407,6 +510,8 @@ struct AcAlgo {
       if (!policy_step) return;
       const AdamSpec hp = {a.lr_actor, a.beta1, a.beta2, a.eps, 0.0, (double)a.max_norm, (long)(a.step_actor0 + n_policy_before + 1)};
       adam_update(c.cta, c.ncta, c.red, A, a.sumsq, c.ncta, hp, a.defer_polyak ? nullptr : &a.actor_target, a.tau);
+      res_invalidate(c, A);
+      if (!a.defer_polyak) res_invalidate(c, a.actor_target);
       float o3[3] = {0.f, 0.f, 0.f};
       if (c.cta == 0) cta_sums(c.red, a.stats + 1, 8, a.stats + 2, 8, a.sumsq, 1, c.ncta, o3);
       FRL_PAR(t) {
@@ -421,7 +526,7 @@ struct AcAlgo {
             const float al = expf(a.alpha_state[0]);
             const float g = al * mean_term;
             a.out[u * 8 + 3] = g;      // == alpha_loss value (alpha * mean(entropy - target))
-            const AdamHP ha = make_adam_hp(a.alpha_lr, a.beta1, a.beta2, a.eps, 0.0, 0.0, (long)(a.step_alpha0 + u + 1));
+            const AdamHP ha = adam_hp_ni(a.alpha_lr, a.beta1, a.beta2, a.eps, 0.0, 0.0, (long)(a.step_alpha0 + u + 1));
             float m = a.alpha_state[1], v = a.alpha_state[2], w = a.alpha_state[0];
             m = fmaf(ha.one_minus_b1, g - m, m);
             v = fadd(fmul(v, ha.b2), fmul(fmul(ha.one_minus_b2, g), g));

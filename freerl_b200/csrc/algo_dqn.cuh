@@ -49,13 +49,25 @@ FRL_NI_MISC void copy_cols(float* dst, int ldd, int dcol0, const float* src, int
   FRL_SYNC();
 }
 
+// put_cols: dst[r][dcol0 + j] = (j < n) ? src[r][scol0 + j] : 0  for j < w, r < R.  One thread per column (no index
+// division) and NO barrier: several of these fill disjoint tiles from the gathered rows inside one phase.
+template <int R>
+FRL_DEV void put_cols(float* dst, int ldd, int dcol0, const float* src, int lds, int scol0, int n, int w) {
+  FRL_PAR(t) {
+    for (int j = t; j < w; j += FRL_NT) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) dst[r * ldd + dcol0 + j] = (j < n) ? src[r * lds + scol0 + j] : 0.f;
+    }
+  }
+}
+
 struct DqnAlgo {
   typedef frl_dqn_args_t Args;
   static const int NSTAGES = 2;
   FRL_SHD int wbuf_floats(const Args& a) {
     int mx = 0;
     for (int i = 0; i < a.q.n_layers; ++i) {
-      int f = a.q.L[i].in_pad * a.q.L[i].out_pad + a.q.L[i].out_pad;
+      int f = wt_floats(a.q.L[i]);
       if (f > mx) mx = f;
     }
     return (mx + 31) & ~31;

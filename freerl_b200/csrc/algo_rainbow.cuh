@@ -45,7 +45,7 @@ struct RainbowAlgo {
               val = P[M.mu_w + src];
               if (M.sg_w >= 0) val = fadd(val, fmul(P[M.sg_w + src], fmul(eps[M.eps_out + M.row0 + j], eps[M.eps_in + k])));
             }
-            mi = L.wt_off + k * L.out_pad + j;
+            mi = L.wt_off + k * wt_ld(L) + j;
             break;
           }
           if (e >= L.b_off && e < L.b_off + L.out_pad) {
@@ -54,7 +54,7 @@ struct RainbowAlgo {
               val = P[M.mu_b + M.row0 + j];
               if (M.sg_b >= 0) val = fadd(val, fmul(P[M.sg_b + M.row0 + j], eps[M.eps_out + M.row0 + j]));
             }
-            mi = L.wt_off + wsz + j;
+            mi = L.wt_off + wt_bias(L) + j;
             break;
           }
         }

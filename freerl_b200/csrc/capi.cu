@@ -202,10 +202,10 @@ struct MirrorBody {
       const int wsz = L.out_pad * L.in_pad;
       if (p >= L.w_off && p < L.w_off + wsz) {
         const int e = (int)p - L.w_off, j = e / L.in_pad, k = e % L.in_pad;
-        n.pt[L.wt_off + k * L.out_pad + j] = n.p[p];
+        n.pt[L.wt_off + k * wt_ld(L) + j] = n.p[p];
         return;
       }
-      if (p >= L.b_off && p < L.b_off + L.out_pad) { n.pt[L.wt_off + wsz + ((int)p - L.b_off)] = n.p[p]; return; }
+      if (p >= L.b_off && p < L.b_off + L.out_pad) { n.pt[L.wt_off + wt_bias(L) + ((int)p - L.b_off)] = n.p[p]; return; }
     }
   }
 };
@@ -226,10 +226,10 @@ struct PolyakBody {
       const int wsz = L.out_pad * L.in_pad;
       if (p >= L.w_off && p < L.w_off + wsz) {
         const int e = (int)p - L.w_off, j = e / L.in_pad, k = e % L.in_pad;
-        tgt.pt[L.wt_off + k * L.out_pad + j] = tw;
+        tgt.pt[L.wt_off + k * wt_ld(L) + j] = tw;
         return;
       }
-      if (p >= L.b_off && p < L.b_off + L.out_pad) { tgt.pt[L.wt_off + wsz + ((int)p - L.b_off)] = tw; return; }
+      if (p >= L.b_off && p < L.b_off + L.out_pad) { tgt.pt[L.wt_off + wt_bias(L) + ((int)p - L.b_off)] = tw; return; }
     }
   }
 };
@@ -533,7 +533,7 @@ struct OpBenchAlgo {
     if (a.mode == 0) {
       const float* Bs = stage_acquire(c, layer_fwd_src(a.net, a.li), layer_fwd_bytes(L));
       for (int it = 0; it < a.iters; ++it)
-        gemm_rk<FRL_R>(c.red, X, L.in_pad, L.in_pad, Bs, L.out_pad, Bs + L.in_pad * L.out_pad, EPI_BIAS_ACT, FRL_ACT_RELU, nullptr, 0, Y, L.out_pad);
+        gemm_rk<FRL_R>(c.red, X, L.in_pad, L.in_pad, Bs, wt_ld(L), L.out_pad, Bs + wt_bias(L), EPI_BIAS_ACT, FRL_ACT_RELU, nullptr, 0, Y, L.out_pad);
     } else if (a.mode == 1) {
       for (int it = 0; it < a.iters; ++it)
         layer_fwd<FRL_R>(c, a.net, a.li, X, L.in_pad, Y, L.out_pad, FRL_ACT_RELU, no_hint());

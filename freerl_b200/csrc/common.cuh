@@ -78,9 +78,16 @@ FRL_HD float frl_u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 167
 FRL_HD void frl_boxmuller(uint32_t a, uint32_t b, float* n0, float* n1) {
   float u1 = frl_u01(a), u2 = frl_u01(b);
   float r = sqrtf(-2.0f * logf(u1));
+#if defined(__CUDA_ARCH__)
+  float sn, cs;
+  sincospif(2.0f * u2, &sn, &cs);     // exact-range reduction in units of pi: none of cosf()'s large-argument slow path
+  *n0 = r * cs;
+  *n1 = r * sn;
+#else
   float th = 6.28318530717958647692f * u2;
   *n0 = r * cosf(th);
   *n1 = r * sinf(th);
+#endif
 }
 
 // N(0,1) for element (stream, idx) of draw `ctr`

@@ -24,14 +24,17 @@ __global__ void __launch_bounds__(FRL_NT, 1) frl_persistent_kernel(const __grid_
   const int U = A::n_updates(a);
   for (int u = 0; u < U; ++u) {
     for (int s = 0; s < A::NSTAGES; ++s) {
+      trace(1000 + s);
       A::stage(s, u, c, user, a);
       stage_reset(c);
+      trace(1100 + s);
       stamp(c, 100 + s);
       fence_proxy_async();
       grid.sync();
       stamp(c, 200 + s);
     }
   }
+  res_drain(c);      // no bulk copy may be in flight when the CTA retires
 }
 
 int frl_device_max_ctas();   // SM count of the current device (1 CTA / SM for the persistent kernels)
@@ -103,7 +106,7 @@ int frl_launch(const typename A::Args& a, cudaStream_t) {
         A::stage(s, u, ctas[g], user[g], a);
         stage_reset(ctas[g]);
       }
-  for (int g = 0; g < grid; ++g) free(mem[g]);
+  for (int g = 0; g < grid; ++g) { res_drain(ctas[g]); free(mem[g]); }
   return 0;
 }
 

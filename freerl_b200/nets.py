@@ -17,6 +17,11 @@ def pad4(x):
     return (x + 3) & ~3
 
 
+def wt_ld(out_pad):
+    """row stride of the transposed mirror (engine.cuh::wt_ld): padded so that stride/4 is odd"""
+    return out_pad if (out_pad >> 2) & 1 else out_pad + 4
+
+
 class DeviceNet:
     def __init__(self, layer_dims, device, trainable=True, x_len=0):
         """``layer_dims``: list of (in, out) in layer order (twin critics: 6 layers, head h = layers 3h..3h+2)."""
@@ -27,7 +32,7 @@ class DeviceNet:
             ip, op = pad4(i), pad4(o)
             d = dict(in_=i, out=o, in_pad=ip, out_pad=op, w_off=off, b_off=off + op * ip, wt_off=toff)
             off += op * ip + op
-            toff += ip * op + op
+            toff += ip * wt_ld(op) + op
             self.layers.append(d)
         self.x_off, self.x_len = off, x_len
         off += pad4(x_len)

@@ -14,11 +14,13 @@ for _ in range(3):
     pol.learn(256, 0.99, 0.01, n_updates=4)
 buf = torch.zeros(4000, dtype=torch.int64, device=dev)
 _lib.lib().frl_debug_set_timing(ctypes.c_void_p(buf.data_ptr()))
-pol.learn(256, 0.99, 0.01, n_updates=1)
+pol.learn(256, 0.99, 0.01, n_updates=2)
 torch.cuda.synchronize()
 b = buf.cpu().numpy().reshape(-1, 2)
 b = b[b[:, 1] > 0]
 b = b[np.argsort(b[:, 1], kind='stable')]
-t0 = b[0, 1]; prev = t0
-for i, (k, t) in enumerate(b[:150]):
-    print('%4d id=%3d  t=%8d clk  dt=%6d' % (i, k, t - t0, t - prev)); prev = t
+starts = [i for i, (k, t) in enumerate(b) if k == 1000]
+i0 = starts[1] if len(starts) > 1 else 0
+t0 = b[i0, 1]; prev = t0
+for i, (k, t) in enumerate(b[i0:i0 + 420]):
+    print('%4d id=%4d  t=%8d clk  dt=%6d' % (i, k, t - t0, t - prev)); prev = t
