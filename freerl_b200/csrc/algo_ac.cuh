@@ -82,6 +82,7 @@ FRL_NI_OPT void reduce_grads_roles(int cta, int ncta, float* slot, const frl_net
 struct AcAlgo {
   typedef frl_ac_args_t Args;
   static const int NSTAGES = 7;
+  FRL_SHD bool writes_params(int s) { return s == 3 || s == 6; }   // the two Adam / Polyak stages
 
   FRL_SHD int max_layer_floats(const frl_net_t& n) {
     int mx = 0;
@@ -176,6 +177,7 @@ struct AcAlgo {
     const int nrole = a.n_heads, role = c.cta % nrole, slot = c.cta / nrole, nslots = c.ncta / nrole;
     const int l0 = 3 * role;                                   // this CTA's critic head = layers l0..l0+2
     const int ntile = (a.B + FRL_R - 1) / FRL_R;
+    const bool one_tile = ntile <= nslots;
     const float invB = 1.0f / (float)a.B;
     const bool sac = a.actor_kind == FRL_ACTOR_SAC;
     const bool policy_step = ((a.total_it0 + u + 1) % (a.policy_freq > 0 ? a.policy_freq : 1)) == 0;
@@ -327,7 +329,8 @@ struct AcAlgo {
         } else {
           stage_prefetch(c, layer_fwd_src(C, l0), layer_fwd_bytes(C.L[l0]));
         }
-        for (int j = 0; j < NA; ++j) gather_rows<FRL_R>(rep(a, j).storage, rep(a, j).row_floats, a.indices + (size_t)u * a.B + row0, nvalid, raw0 + P.raw_off[j]);
+        // one tile per CTA: the rows gathered by stage 0 of this learn are still in shared memory
+        if (!one_tile) for (int j = 0; j < NA; ++j) gather_rows<FRL_R>(rep(a, j).storage, rep(a, j).row_floats, a.indices + (size_t)u * a.B + row0, nvalid, raw0 + P.raw_off[j]);
         for (int j = 0; j < NA; ++j) {
           const frl_replay_t& rj = rep(a, j);
           const float* rw = raw0 + P.raw_off[j];
@@ -409,7 +412,7 @@ struct AcAlgo {
         } else {
           stage_prefetch(c, layer_fwd_src(A, 0), layer_fwd_bytes(A.L[0]));
         }
-        for (int j = 0; j < NA; ++j) gather_rows<FRL_R>(rep(a, j).storage, rep(a, j).row_floats, a.indices + (size_t)u * a.B + row0, nvalid, raw0 + P.raw_off[j]);
+        if (!one_tile) for (int j = 0; j < NA; ++j) gather_rows<FRL_R>(rep(a, j).storage, rep(a, j).row_floats, a.indices + (size_t)u * a.B + row0, nvalid, raw0 + P.raw_off[j]);
         for (int j = 0; j < NA; ++j) {
           const frl_replay_t& rj = rep(a, j);
           const float* rw = raw0 + P.raw_off[j];

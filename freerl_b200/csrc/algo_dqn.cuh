@@ -64,6 +64,7 @@ FRL_DEV void put_cols(float* dst, int ldd, int dcol0, const float* src, int lds,
 struct DqnAlgo {
   typedef frl_dqn_args_t Args;
   static const int NSTAGES = 2;
+  FRL_SHD bool writes_params(int) { return true; }
   FRL_SHD int wbuf_floats(const Args& a) {
     int mx = 0;
     for (int i = 0; i < a.q.n_layers; ++i) {

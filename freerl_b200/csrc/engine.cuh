@@ -800,12 +800,30 @@ FRL_DEV void cta_sums(float* sh, const float* p0, int s0, const float* p1, int s
 // ------------------------------------------------------------------------------------------------
 // block-wide fixed-order sum of one float per thread (result broadcast to all threads via smem)
 // ------------------------------------------------------------------------------------------------
+// Fixed association: a shuffle tree inside each warp (lane i += lane i+off, off = 16..1), then the warp totals in warp
+// order.  3 barriers instead of the 9 of a shared-memory tree; the emulation applies the same tree to the array.
 FRL_NI_MISC float block_sum(float* slot /*[FRL_NT] smem*/) {
-  for (int s = FRL_NT / 2; s > 0; s >>= 1) {
-    FRL_PAR(t) { if (t < s) slot[t] += slot[t + s]; }
-    FRL_SYNC();
+#ifndef FRL_EMUL
+  float v = slot[threadIdx.x];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) slot[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < FRL_NT / 32; ++w) tot += slot[w];
+  __syncthreads();
+  return tot;
+#else
+  float tot = 0.f;
+  for (int w = 0; w < FRL_NT / 32; ++w) {
+    for (int off = 16; off > 0; off >>= 1)
+      for (int i = 0; i < off; ++i) slot[w * 32 + i] += slot[w * 32 + i + off];
+    tot += slot[w * 32];
   }
-  return slot[0];
+  return tot;
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -6,6 +6,7 @@
 //                       static int  grid(const Args&, int max);   // CTAs wanted
 //                       static int  n_updates(const Args&);
 //                       static FRL_DEV void stage(int s, int u, Cta&, float* user, const Args&);
+//                       static bool writes_params(int s);         // stage s rewrites weights a later TMA copy reads
 // The kernel runs  for u: for s: stage(s,u); grid.sync()  — one launch performs n_updates sequential
 // learn() steps (stages are separated by grid-wide barriers because every optimiser step needs the
 // global gradient norm and the next phase needs the updated weights).
@@ -29,7 +30,7 @@ __global__ void __launch_bounds__(FRL_NT, 1) frl_persistent_kernel(const __grid_
       stage_reset(c);
       trace(1100 + s);
       stamp(c, 100 + s);
-      fence_proxy_async();
+      if (A::writes_params(s)) fence_proxy_async();   // generic-proxy weight writes -> later TMA (async-proxy) reads
       grid.sync();
       stamp(c, 200 + s);
     }

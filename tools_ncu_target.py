@@ -10,6 +10,6 @@ n = 100000
 pol.add(rng.standard_normal((n, 17), dtype=np.float32), rng.uniform(-1, 1, (n, 6)).astype(np.float32),
         rng.standard_normal(n).astype(np.float32), rng.standard_normal((n, 17), dtype=np.float32), rng.random(n) < 0.01)
 for _ in range(6):
-    pol.learn(256, 0.99, 0.01, n_updates=2)
+    pol.learn(256, 0.99, 0.01, n_updates=8)
 torch.cuda.synchronize()
 print(pol.last_metrics[-1])
