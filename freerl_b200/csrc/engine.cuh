@@ -333,6 +333,17 @@ FRL_DEV unsigned floor_log2(unsigned x) {
 #endif
 }
 FRL_DEV unsigned ceil_pow2_log(unsigned x) { const unsigned f = floor_log2(x); return ((1u << f) == x) ? f : f + 1; }
+// log2 of the reduction split: the largest s <= 3 with (2^sh_tiles << s) <= FRL_NT and 2^s <= nchunk (closed form, no loop)
+template <unsigned N> struct FrlLog2 { static const unsigned value = 1 + FrlLog2<N / 2>::value; };
+template <> struct FrlLog2<1> { static const unsigned value = 0; };
+FRL_DEV unsigned split_log(unsigned sh_tiles, unsigned nchunk) {
+  constexpr unsigned NTL = FrlLog2<FRL_NT>::value;
+  unsigned s = sh_tiles >= NTL ? 0u : NTL - sh_tiles;
+  const unsigned fk = nchunk ? floor_log2(nchunk) : 0u;
+  if (fk < s) s = fk;
+  return s < 3u ? s : 3u;
+}
+FRL_DEV unsigned div_fast(unsigned t, unsigned d) { return t / d; }   // (a power-of-two shift fast path measured 0.5 us / learn slower)
 
 // ------------------------------------------------------------------------------------------------
 // gemm_rk:  C[r][n] = epi( sum_k A[r][k] * Bs[k][n] (+ bias[n]) ),  r < R, n < N_pad, k < K_pad
@@ -356,8 +367,8 @@ FRL_DEV void gemm_finish(sptr sR, unsigned ksplit, int N_pad, int epi, int act, 
     // element e -> (row r, column group j): e = r * nt + j; one division per thread, then an incremental walk
     const unsigned ne = R * nt;
     if ((unsigned)t < ne) {
-      unsigned r = (unsigned)t / nt, j = (unsigned)t - r * nt;
-      const unsigned dr = FRL_NT / nt, dj = FRL_NT - dr * nt;
+      unsigned r = div_fast((unsigned)t, nt), j = (unsigned)t - r * nt;
+      const unsigned dr = div_fast(FRL_NT, nt), dj = FRL_NT - dr * nt;
       for (unsigned e = (unsigned)t; e < ne; e += FRL_NT) {
         const int n0 = (int)j * 4;
         int w = (int)r * N_pad + n0;
@@ -390,13 +401,14 @@ FRL_NI_GEMM void gemm_rk(float* red, const float* A, int lda, int K_pad, const f
   const unsigned tiles = nt * RT;
   const unsigned sh_t = ceil_pow2_log(tiles), tiles_p2 = 1u << sh_t;
   const unsigned nchunk = (unsigned)K_pad >> 2;
-  unsigned sh_k = 0;                                            // ksplit = 2^sh_k <= min(NT / tiles_p2, nchunk, 8)
-  while (sh_k < 3 && (tiles_p2 << (sh_k + 1)) <= FRL_NT && (2u << sh_k) <= nchunk) ++sh_k;
+  const unsigned sh_k = split_log(sh_t, nchunk);                // ksplit = 2^sh_k <= min(NT / tiles_p2, nchunk, 8)
   const unsigned ksplit = 1u << sh_k;
   const unsigned items = tiles_p2 << sh_k;
   const sptr sA = sp_of(A), sB = sp_of(Bs), sR = sp_of(red), sC = sp_of(C);
   const bool has_bias = bias != nullptr;
   const sptr sBias = sp_of(has_bias ? bias : Bs), sM = sp_of(mask ? mask : Bs);
+  // (A dedicated one-warp-per-row + shuffle-tree path for the narrow N_pad <= 8 heads was measured 2.7 us / learn SLOWER
+  //  than this generic tiling on B200, inlined or not, and was dropped.)
   trace(50);
   FRL_PAR(t) {
     for (unsigned item = (unsigned)t; item < items; item += FRL_NT) {
@@ -475,8 +487,7 @@ FRL_NI_GEMM void gemm_nt(float* red, const float* A, int lda, int N_red, const f
   const unsigned sh_kl = ceil_pow2_log(KL), klp2 = 1u << sh_kl;
   const unsigned tiles_p2 = klp2 << RT_SH;
   const unsigned nchunk = (unsigned)N_red >> 2;
-  unsigned sh_n = 0;
-  while (sh_n < 3 && (tiles_p2 << (sh_n + 1)) <= FRL_NT && (2u << sh_n) <= nchunk) ++sh_n;
+  const unsigned sh_n = split_log(sh_kl + RT_SH, nchunk);
   const unsigned nsplit = 1u << sh_n;
   const unsigned items = tiles_p2 << sh_n;
   const sptr sA = sp_of(A), sB = sp_of(Bs), sR = sp_of(red), sC = sp_of(C);
@@ -552,8 +563,8 @@ FRL_NI_GEMM void gemm_outer(const float* dY, int ldy, int M_pad, const float* X,
   FRL_PAR(t) {
     if ((unsigned)t < tiles) {
       // tile -> (mi, ni): one division per thread, then an incremental walk (tile += FRL_NT)
-      unsigned mi = (unsigned)t / nt, ni = (unsigned)t - mi * nt;
-      const unsigned dm = FRL_NT / nt, dn = FRL_NT - dm * nt;
+      unsigned mi = div_fast((unsigned)t, nt), ni = (unsigned)t - mi * nt;
+      const unsigned dm = div_fast(FRL_NT, nt), dn = FRL_NT - dm * nt;
       for (unsigned tile = (unsigned)t; tile < tiles; tile += FRL_NT) {
         const int m0 = (int)mi * 4, n0 = (int)ni * 4;
         float acc[4][4];
