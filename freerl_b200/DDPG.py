@@ -1,7 +1,7 @@
 """DDPG with the reference's class API (``DDPG_file/DDPG.py:58-245``) on the fused B200 kernel.
 
 Supplements kept: ``weight_decay`` (critic Adam with L2 1e-3, DDPG.py:131-134) and ``net_init`` (uniform
-re-initialisation, note ``fan_in = weight.size(0)`` = out-features, DDPG.py:58-68).  ``Batch_ObsNorm`` is not fused yet.
+re-initialisation, note ``fan_in = weight.size(0)`` = out-features, DDPG.py:58-68).  ``Batch_ObsNorm`` (the default supplement, DDPG.py:446) runs inside the kernel (``freerl_b200/normalization.py``).
 """
 import os
 
@@ -33,18 +33,20 @@ class DDPG(ACBase):
         self.trick = trick
         self.supplement = supplement if supplement is not None else {
             "weight_decay": False, "OUNoise": False, "ObsNorm": False, "net_init": False, "Batch_ObsNorm": False}
-        if self.supplement.get("Batch_ObsNorm"):
-            raise NotImplementedError("Batch_ObsNorm is not available in the fused DDPG kernel yet")
         post = _reference_net_init if self.supplement.get("net_init") else None
-        self._setup(dim_info, is_continue, actor_lr, critic_lr, buffer_size, device, mode, post_init=post)
+        self._setup(dim_info, is_continue, actor_lr, critic_lr, buffer_size, device, mode, post_init=post,
+                    batch_obs_norm=self.supplement.get("Batch_ObsNorm", False))
 
     def select_action(self, obs):
         x, single = _common.as_obs_batch(obs, self.obs_dim)
-        a = _common.infer(self.agent._actor, x, _lib.INFER_TANH, self.device, self.action_dim).cpu().numpy()
+        a = _common.infer(self.agent._actor, x, _lib.INFER_TANH, self.device, self.action_dim, obs_norm=self._obs_norm()).cpu().numpy()
         return a[0] if single else a
 
     def evaluate_action(self, obs):
-        return self.select_action(obs)
+        """The reference's evaluate_action does NOT apply Batch_ObsNorm (DDPG.py:175-183); kept."""
+        x, single = _common.as_obs_batch(obs, self.obs_dim)
+        a = _common.infer(self.agent._actor, x, _lib.INFER_TANH, self.device, self.action_dim).cpu().numpy()
+        return a[0] if single else a
 
     def learn(self, batch_size, gamma, tau, *, n_updates=1, indices=None):
         a, idx, B, out = self._base_args(batch_size, gamma, tau, n_updates, indices)

@@ -6,7 +6,7 @@
 agent sharing the sampled indices; a FRESH sample for every agent inside the learn loop (:211); centralised critic on
 ``cat(all obs, all actions)``; next actions from every agent's TARGET actor; critic Adam with L2 weight_decay 1e-3
 and the uniform ``net_init`` when the supplements ask; Polyak of all agents only after the loop.
-``Batch_ObsNorm`` is not fused yet (raises).
+``Batch_ObsNorm`` (default supplement, MADDPG.py:437): per-agent statistics updated by EVERY agent's sample, in-kernel.
 """
 import ctypes
 import os
@@ -19,6 +19,7 @@ from .Buffer import Buffer
 from .DDPG import _reference_net_init
 from ._actor_critic import _ActorInit, _CriticInit
 from .nets import DeviceNet, alias_module, bind_module
+from .normalization import Normalization_batch_size
 
 
 class Agent:
@@ -53,8 +54,6 @@ class MADDPG:
         self.device = _lib.require_device(device)
         if len(dim_info) > _lib.FRL_MAX_AGENTS:
             raise NotImplementedError("at most %d agents" % _lib.FRL_MAX_AGENTS)
-        if supplement.get('Batch_ObsNorm'):
-            raise NotImplementedError("Batch_ObsNorm is not available in the fused MADDPG kernel yet")
         if not is_continue:
             raise NotImplementedError("the reference implements continuous actions only (MADDPG.py:166)")
         self.agents, self.buffers = {}, {}
@@ -63,6 +62,10 @@ class MADDPG:
             self.buffers[agent_id] = Buffer(buffer_size, obs_dim, act_dim=action_dim if is_continue else 1, device=self.device)
         self.dim_info = dim_info
         self.is_continue = is_continue
+        self._bon = bool(supplement.get('Batch_ObsNorm'))
+        if self._bon:
+            self.batch_size_obs_norm = {agent_id: Normalization_batch_size(shape=dim_info[agent_id][0], device=self.device)
+                                        for agent_id in dim_info.keys()}
         self.agent_x = list(self.agents.keys())[0]
         self.regular = False
         self.supplement = supplement
@@ -73,17 +76,18 @@ class MADDPG:
         self._scratch = _common.DeviceScratch(self.device, n_p)
         self.last_metrics = None
 
-    def select_action(self, obs):
+    def select_action(self, obs, evaluate=False):
         actions = {}
         for agent_id, o in obs.items():
             od, ad = self.dim_info[agent_id]
             x, single = _common.as_obs_batch(o, od)
-            a = _common.infer(self.agents[agent_id]._actor, x, _lib.INFER_TANH, self.device, ad).cpu().numpy()
+            norm = self.batch_size_obs_norm[agent_id] if (self._bon and not evaluate) else None   # MADDPG.py:162-163 vs :176-180
+            a = _common.infer(self.agents[agent_id]._actor, x, _lib.INFER_TANH, self.device, ad, obs_norm=norm).cpu().numpy()
             actions[agent_id] = a[0] if single else a
         return actions
 
     def evaluate_action(self, obs):
-        return self.select_action(obs)
+        return self.select_action(obs, evaluate=True)
 
     def add(self, obs, action, reward, next_obs, done):
         for agent_id, buffer in self.buffers.items():
@@ -96,6 +100,9 @@ class MADDPG:
         for agent_id, buffer in self.buffers.items():
             obs[agent_id], action[agent_id], reward[agent_id], next_obs[agent_id], done[agent_id] = buffer.sample(indices)
             od, ad = self.dim_info[agent_id]
+            if self._bon:
+                obs[agent_id] = self.batch_size_obs_norm[agent_id](obs[agent_id], update=True)
+                next_obs[agent_id] = self.batch_size_obs_norm[agent_id](next_obs[agent_id], update=False)
             next_action[agent_id] = _common.infer(self.agents[agent_id]._actor_t, next_obs[agent_id], _lib.INFER_TANH, self.device, ad)
         return obs, action, reward, next_obs, done, next_action
 
@@ -130,9 +137,16 @@ class MADDPG:
             for j, other in enumerate(ids):
                 a.ma_replay[j] = self.buffers[other].c_struct()
                 a.ma_actor_target[j] = self.agents[other]._actor_t.c_struct()
+                if self._bon:
+                    a.obs_norm[j] = self.batch_size_obs_norm[other].data_ptr()
+            if self._bon:
+                a.obs_norm_n0 = self.batch_size_obs_norm[self.agent_x].running_ms.n
             _lib.check(_lib.lib().frl_ac_learn(ctypes.byref(a), _lib.stream_ptr(self.device)), "frl_ac_learn")
             ag.actor_step += 1
             ag.critic_step += 1
+            if self._bon:                     # every agent's sample() updates every agent's statistics (MADDPG.py:192-196)
+                for nm in self.batch_size_obs_norm.values():
+                    nm.running_ms.n += 1
             outs.append((out, idx))
         self.update_target(tau)
         self._n_learn += 1

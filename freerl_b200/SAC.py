@@ -44,9 +44,8 @@ class SAC(ACBase):
 
     def __init__(self, dim_info, is_continue, actor_lr, critic_lr, buffer_size, device, trick=None, mode=None):
         self.trick = trick if trick is not None else {}
-        if self.trick.get("Batch_ObsNorm"):
-            raise NotImplementedError("Batch_ObsNorm is not available in the fused SAC kernel yet")
-        self._setup(dim_info, is_continue, actor_lr, critic_lr, buffer_size, device, mode)
+        self._setup(dim_info, is_continue, actor_lr, critic_lr, buffer_size, device, mode,
+                    batch_obs_norm=self.trick.get("Batch_ObsNorm", False))
         self.adaptive_alpha = True
         print('adaptive_alpha:', self.adaptive_alpha)
         self.alphas = Alpha(self.action_dim, self.device, alpha=0.01, requires_grad=self.adaptive_alpha, is_continue=is_continue)
@@ -61,7 +60,7 @@ class SAC(ACBase):
             noise = torch.as_tensor(noise, dtype=torch.float32).to(self.device).reshape(n, self.action_dim).contiguous()
         self._n_act += 1
         a = _common.infer(self.agent._actor, x, _lib.INFER_SAC_SAMPLE, self.device, self.action_dim, noise=noise,
-                          seed=self._seed, counter=self._n_act).cpu().numpy()
+                          seed=self._seed, counter=self._n_act, obs_norm=self._obs_norm()).cpu().numpy()
         return a[0] if single else a
 
     def evaluate_action(self, obs):

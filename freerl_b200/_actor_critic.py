@@ -8,6 +8,7 @@ import torch.nn as nn
 from . import _common, _lib
 from .Buffer import Buffer
 from .nets import DeviceNet, alias_module, bind_module
+from .normalization import Normalization_batch_size
 
 
 class _ActorInit(nn.Module):
@@ -70,9 +71,13 @@ class ACBase:
     n_heads = 2
     sac = False
 
-    def _setup(self, dim_info, is_continue, actor_lr, critic_lr, buffer_size, device, mode, post_init=None):
+    def _setup(self, dim_info, is_continue, actor_lr, critic_lr, buffer_size, device, mode, post_init=None,
+               batch_obs_norm=False):
         obs_dim, action_dim = dim_info
         self.device = _lib.require_device(device)
+        self._bon = bool(batch_obs_norm)
+        if self._bon:
+            self.batch_size_obs_norm = Normalization_batch_size(shape=obs_dim, device=self.device)
         self.obs_dim, self.action_dim = obs_dim, action_dim
         self.is_continue = is_continue
         self.agent = ACAgent(obs_dim, action_dim, actor_lr, critic_lr, self.device, self.n_heads, self.sac, post_init)
@@ -92,7 +97,14 @@ class ACBase:
         total_size = len(self.buffer)
         batch_size = min(total_size, batch_size)
         indices = np.random.choice(total_size, batch_size, replace=False)
-        return self.buffer.sample(indices)
+        obs, actions, rewards, next_obs, dones = self.buffer.sample(indices)
+        if self._bon:
+            obs = self.batch_size_obs_norm(obs)
+            next_obs = self.batch_size_obs_norm(next_obs, update=False)
+        return obs, actions, rewards, next_obs, dones
+
+    def _obs_norm(self):
+        return self.batch_size_obs_norm if self._bon else None
 
     # ---- kernel call -------------------------------------------------------------------------------
     def _base_args(self, batch_size, gamma, tau, n_updates, indices):
@@ -123,12 +135,17 @@ class ACBase:
         a.gpart, a.sumsq = self._scratch.gpart.data_ptr(), self._scratch.sumsq.data_ptr()
         a.stats, a.out = self._scratch.stats.data_ptr(), out.data_ptr()
         a.xchg = self._scratch.xchg(B, self.device).data_ptr()
+        if self._bon:                                      # running statistics folded in by the kernel, once per learn
+            a.obs_norm[0] = self.batch_size_obs_norm.data_ptr()
+            a.obs_norm_n0 = self.batch_size_obs_norm.running_ms.n
         return a, idx, B, out
 
     def _launch(self, a, keep, n_updates, out):
         _lib.check(_lib.lib().frl_ac_learn(ctypes.byref(a), _lib.stream_ptr(self.device)), "frl_ac_learn")
         self.last_metrics = out[:n_updates]
         self._keepalive = keep
+        if self._bon:
+            self.batch_size_obs_norm.running_ms.n += n_updates
 
     def _noise(self, given, n_updates, B):
         """parity mode: draw [n_updates, B, act] like the reference would, one tensor per learn, in order."""

@@ -71,7 +71,7 @@ def reference_randn(shape, device):
     return torch.empty(shape, dtype=torch.float32, device=device).normal_()
 
 
-def infer(net, obs, mode, device, out_cols, noise=None, seed=0, counter=0, l0=0, nl=0, layer_norm=False):
+def infer(net, obs, mode, device, out_cols, noise=None, seed=0, counter=0, l0=0, nl=0, layer_norm=False, obs_norm=None):
     """Batched policy inference.  ``obs``: numpy / tensor [n, obs_dim] -> device tensor [n, out_cols]."""
     if isinstance(obs, torch.Tensor):
         x = obs.to(device=device, dtype=torch.float32).contiguous()
@@ -87,6 +87,7 @@ def infer(net, obs, mode, device, out_cols, noise=None, seed=0, counter=0, l0=0,
     a.noise = noise.data_ptr() if noise is not None else None
     a.seed, a.counter = seed, counter & 0xFFFFFFFF
     a.out, a.out_cols = out.data_ptr(), out_cols
+    a.obs_norm = obs_norm.data_ptr() if obs_norm is not None else None      # Batch_ObsNorm, update=False
     _lib.check(_lib.lib().frl_policy_infer(ctypes.byref(a), _lib.stream_ptr(device)), "frl_policy_infer")
     return out
 

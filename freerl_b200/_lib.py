@@ -12,7 +12,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 FRL_MAX_LAYERS = 6
 FRL_MAX_AGENTS = 6
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class Layer(C.Structure):
@@ -52,13 +52,14 @@ class AcArgs(C.Structure):
                 ("target_entropy", C.c_float), ("step_alpha0", C.c_int64),
                 ("gpart", C.c_void_p), ("sumsq", C.c_void_p), ("stats", C.c_void_p), ("out", C.c_void_p),
                 ("n_agents", C.c_int), ("agent_index", C.c_int), ("ma_replay", Replay * FRL_MAX_AGENTS),
-                ("ma_actor_target", Net * FRL_MAX_AGENTS), ("defer_polyak", C.c_int), ("xchg", C.c_void_p)]
+                ("ma_actor_target", Net * FRL_MAX_AGENTS), ("defer_polyak", C.c_int), ("xchg", C.c_void_p),
+                ("obs_norm", C.c_void_p * FRL_MAX_AGENTS), ("obs_norm_n0", C.c_int64)]
 
 
 class InferArgs(C.Structure):
     _fields_ = [("net", Net), ("l0", C.c_int), ("nl", C.c_int), ("obs", C.c_void_p), ("n", C.c_int), ("obs_dim", C.c_int), ("mode", C.c_int),
                 ("noise", C.c_void_p), ("seed", C.c_uint64), ("counter", C.c_uint32), ("out", C.c_void_p),
-                ("out_cols", C.c_int), ("layer_norm", C.c_int)]
+                ("out_cols", C.c_int), ("layer_norm", C.c_int), ("obs_norm", C.c_void_p)]
 
 
 class PpoArgs(C.Structure):

@@ -2,8 +2,10 @@
 //   SAC    SAC_file/SAC.py:222-271 (Actor :60-97, Critic :103-127, Alpha :154-169, Agent.update_* :141-151)
 //   TD3    TD3_file/TD3.py:189-244          DDPG   DDPG_file/DDPG.py:203-233
 //   MADDPG MADDPG_file/MADDPG.py:186-237    (n_agents > 1: centralised critic on cat(all obs, all actions))
-// One persistent cooperative launch runs n_updates sequential learns; 7 grid-wide stages per learn:
-//   0 targets        gather rows, a' = actor_target(s') (every agent), target critic head[role] -> exchange buffer
+// One persistent cooperative launch runs n_updates sequential learns; 7 grid-wide stages per learn (the actor stages 4-6
+// and their barriers are skipped on TD3's off steps):
+//   0 targets        [Batch_ObsNorm: fold the batch mean of obs into the running statistics, normalise obs / next_obs]
+//            gather rows, a' = actor_target(s') (every agent), target critic head[role] -> exchange buffer
 //   1 critic         y from both heads' target values, critic head[role] forward + backward -> gradient partials
 //   2 reduce         fixed-order cross-CTA reduction (per head: only that role's CTAs) + sum of squares
 //   3 optimiser      clip_grad_norm_ + Adam (+ critic-target Polyak)
@@ -83,6 +85,12 @@ struct AcAlgo {
   typedef frl_ac_args_t Args;
   static const int NSTAGES = 7;
   FRL_SHD bool writes_params(int s) { return s == 3 || s == 6; }   // the two Adam / Polyak stages
+  FRL_SHD bool is_policy_step(const Args& a, int u) { return ((a.total_it0 + u + 1) % (a.policy_freq > 0 ? a.policy_freq : 1)) == 0; }
+  FRL_SHD bool stage_enabled(int s, int u, const Args& a) {
+    if (s >= 4) return is_policy_step(a, u);                // TD3 twin_delay: no actor stages (nor their barriers) on off steps
+    return true;
+  }
+  FRL_SHD int norm_floats(const Args& a) { return a.obs_norm[0] ? ((3 * obs_off(a, ma_n(a)) + 3) & ~3) : 0; }
 
   FRL_SHD int max_layer_floats(const frl_net_t& n) {
     int mx = 0;
@@ -128,7 +136,7 @@ struct AcAlgo {
 
   FRL_SHD int user_floats(const Args& a) {
     const int ldh = a.critic.L[0].out_pad, sa = a.critic.L[0].in_pad, ap = max_ap(a);
-    return raw_off(a, ma_n(a)) + FRL_R * (max_aip(a) + 3 * sa + 6 * ldh + 6 * ap + 3 * 4 + 16) + 2 * FRL_NT + 128 + PLAN_FLOATS;
+    return raw_off(a, ma_n(a)) + FRL_R * (max_aip(a) + 3 * sa + 6 * ldh + 6 * ap + 3 * 4 + 16) + 2 * FRL_NT + 128 + PLAN_FLOATS + norm_floats(a);
   }
   FRL_SHD int nslots_of(const Args& a, int max_ctas) {
     const int tiles = (a.B + FRL_R - 1) / FRL_R, cap = max_ctas / (a.n_heads > 0 ? a.n_heads : 1);
@@ -160,7 +168,135 @@ struct AcAlgo {
     P.act_off[P.NA] = o;
   }
 
+  // Batch_ObsNorm: (x - mean) / (std + 1e-8) on the obs and next_obs columns of the gathered rows, in place.
+  FRL_SDEV void norm_rows(const Args& a, const Plan& P, const float* NORM, float* raw0, int nvalid) {
+    const int tot = P.obs_off[P.NA];
+    FRL_PAR(t) {
+      for (int e = t; e < 2 * tot; e += FRL_NT) {
+        const int col = e < tot ? e : e - tot;
+        int j = 0;
+        while (j + 1 < P.NA && col >= P.obs_off[j + 1]) ++j;
+        const frl_replay_t& rj = rep(a, j);
+        const int k = col - P.obs_off[j];
+        const float mean = NORM[3 * P.obs_off[j] + k], den = fadd(NORM[3 * P.obs_off[j] + 2 * rj.obs_dim + k], 1e-8f);
+        float* x = raw0 + P.raw_off[j] + (e < tot ? 0 : rb_col_nobs(rj)) + k;
+        for (int r = 0; r < nvalid; ++r) x[r * rj.row_floats] = fdiv(fadd(x[r * rj.row_floats], -mean), den);
+      }
+    }
+    FRL_SYNC();
+  }
+
+  // Batch_ObsNorm statistics of one learn: x_bar = mean over the B sampled rows of every obs column, folded into the running
+  // {mean, S, std} (RunningMeanStd_batch_size.update, SAC.py:399-411).  Every CTA computes the same numbers redundantly from
+  // global memory (the rows are L2 hits: the batch gather touches them in the same stage); CTA 0 publishes the new state in
+  // stage 1, after the barrier that ends everyone's reads of the old one.
+  // Summation ORDER follows torch's CPU `x.mean(dim=0)` = sum_out / B (aten/src/ATen/native/cpu/SumKernel.cpp cascade_sum,
+  // AVX2 build as run in this container, SURVEY 7.3-3 "parity is defined against the oracle as run here"):
+  //   * columns inside a full group of 32 (obs_dim >= 8) or of 4 (obs_dim < 8) take `multi_row_sum`: rows in order, 16-row
+  //     blocks cascading into levels every 16 / 256 blocks, remainder rows in level 0, levels added low to high;
+  //   * the other columns take `row_sum`: four interleaved lanes of floor(B/4) rows (row = k + 4 i), each lane summed like
+  //     above, then the B % 4 leftover rows added to lane 0, then the lanes in order.
+  // The normalisation divides by std = sqrt(S/n) of batch-MEAN differences, so a different association shows up as 1e-3
+  // relative loss differences at n = 2; with the same association the statistics are bit-identical.
+  FRL_SDEV bool bon_col_seq(int od, int k) { return od >= 8 ? k < (od & ~31) : k < (od & ~3); }
+  FRL_SDEV void bon_update(Cta& c, const Args& a, const Plan& P, float* NORM, float* scratch, int u) {
+    const int NA = P.NA, tot = P.obs_off[NA], npair = tot * 4, B = a.B;
+    const int64_t* idx = a.indices + (size_t)u * B;
+    // scratch: part[npair][nbp] block sums | lvl[npair][4] cascade levels      (6 * FRL_R * ldh floats available)
+    const int avail = 6 * FRL_R * a.critic.L[0].out_pad - npair * 4;
+    int nbp = avail / npair;
+    if (nbp > 16) nbp = 16;
+    float* part = scratch;
+    float* lvl = scratch + npair * nbp;
+    FRL_PAR(t) { for (int i = t; i < npair * 4; i += FRL_NT) lvl[i] = 0.f; }
+    const int max_blocks = B >> 4;
+    for (int b0 = 0; b0 < max_blocks; b0 += nbp) {
+      FRL_SYNC();
+      FRL_PAR(t) {
+        for (int it = t; it < npair * nbp; it += FRL_NT) {
+          const int pair = it / nbp, bl = b0 + it % nbp, col = pair >> 2, k = pair & 3;
+          int j = 0;
+          while (j + 1 < NA && col >= P.obs_off[j + 1]) ++j;
+          const frl_replay_t& rj = rep(a, j);
+          const bool seq = bon_col_seq(rj.obs_dim, col - P.obs_off[j]);
+          const int lane_rows = seq ? (k == 0 ? B : 0) : (B >> 2), first = seq ? 0 : k, stride = seq ? 1 : 4;
+          if (bl >= (lane_rows >> 4)) continue;
+          const float* base = rj.storage + (col - P.obs_off[j]);
+          int64_t ix[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) ix[q] = idx[first + stride * (16 * bl + q)];
+          float v[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] = base[(size_t)ix[q] * rj.row_floats];
+          float sm = v[0];
+#pragma unroll
+          for (int q = 1; q < 16; ++q) sm += v[q];
+          part[pair * nbp + it % nbp] = sm;
+        }
+      }
+      FRL_SYNC();
+      FRL_PAR(t) {
+        for (int pair = t; pair < npair; pair += FRL_NT) {
+          const int col = pair >> 2, k = pair & 3;
+          int j = 0;
+          while (j + 1 < NA && col >= P.obs_off[j + 1]) ++j;
+          const bool seq = bon_col_seq(rep(a, j).obs_dim, col - P.obs_off[j]);
+          const int nblk = (seq ? (k == 0 ? B : 0) : (B >> 2)) >> 4;
+          float a1 = lvl[pair * 4 + 1], a2 = lvl[pair * 4 + 2], a3 = lvl[pair * 4 + 3];
+          for (int q = 0; q < nbp && b0 + q < nblk; ++q) {
+            const int i = (b0 + q + 1) << 4;               // lane rows consumed so far
+            a1 += part[pair * nbp + q];
+            if ((i & 0xF0) == 0) { a2 += a1; a1 = 0.f; if ((i & 0xF00) == 0) { a3 += a2; a2 = 0.f; } }
+          }
+          lvl[pair * 4 + 1] = a1; lvl[pair * 4 + 2] = a2; lvl[pair * 4 + 3] = a3;
+        }
+      }
+    }
+    FRL_SYNC();
+    FRL_PAR(t) {                // remainder rows of each lane (< 16), the levels low to high, row_sum's leftover rows
+      for (int pair = t; pair < npair; pair += FRL_NT) {
+        const int col = pair >> 2, k = pair & 3;
+        int j = 0;
+        while (j + 1 < NA && col >= P.obs_off[j + 1]) ++j;
+        const frl_replay_t& rj = rep(a, j);
+        const bool seq = bon_col_seq(rj.obs_dim, col - P.obs_off[j]);
+        const int lane_rows = seq ? (k == 0 ? B : 0) : (B >> 2), first = seq ? 0 : k, stride = seq ? 1 : 4;
+        const float* base = rj.storage + (col - P.obs_off[j]);
+        float a0 = 0.f;
+        for (int r = lane_rows & ~15; r < lane_rows; ++r) a0 += base[(size_t)idx[first + stride * r] * rj.row_floats];
+        float res = ((a0 + lvl[pair * 4 + 1]) + lvl[pair * 4 + 2]) + lvl[pair * 4 + 3];
+        if (!seq && k == 0) for (int r = B & ~3; r < B; ++r) res += base[(size_t)idx[r] * rj.row_floats];
+        lvl[pair * 4] = res;
+      }
+    }
+    FRL_SYNC();
+    const long n = (long)(a.obs_norm_n0 + u + 1);
+    FRL_PAR(t) {
+      for (int col = t; col < tot; col += FRL_NT) {
+        int j = 0;
+        while (j + 1 < NA && col >= P.obs_off[j + 1]) ++j;
+        const int k = col - P.obs_off[j], odj = rep(a, j).obs_dim;
+        const float sum = ((lvl[col * 16] + lvl[col * 16 + 4]) + lvl[col * 16 + 8]) + lvl[col * 16 + 12];
+        const float xb = fdiv(sum, (float)B);
+        const float* st = a.obs_norm[j];
+        float mean, S = st[odj + k], sd;
+        if (n == 1) { mean = xb; sd = xb; }                    // first call: mean = std = x_bar (reference quirk)
+        else {
+          const float old = st[k];
+          mean = fadd(old, fdiv(fadd(xb, -old), (float)n));
+          S = fadd(S, fmul(fadd(xb, -old), fadd(xb, -mean)));
+          sd = fsqrt(fdiv(S, (float)n));
+        }
+        float* o = NORM + 3 * P.obs_off[j];
+        o[k] = mean; o[odj + k] = S; o[2 * odj + k] = sd;
+      }
+    }
+    FRL_SYNC();
+    (void)c;
+  }
+
   FRL_SDEV void stage(int s, int u, Cta& c, float* user, const Args& a) {
+    const bool bon = a.obs_norm[0] != nullptr;
     const frl_net_t& A = a.actor;
     const frl_net_t& C = a.critic;
     const frl_replay_t& rb = a.replay;
@@ -171,6 +307,8 @@ struct AcAlgo {
       FRL_PAR(t) { if (t == 0) fill_plan(P, a); }
       FRL_SYNC();
     }
+    float* NORM = user;                        // [agent j at 3*obs_off[j]] {mean, S, std} of this learn (Batch_ObsNorm)
+    user += norm_floats(a);
     const int ldh = C.L[0].out_pad, sa = C.L[0].in_pad, ap = P.ap;
     const int NA = P.NA, ai = P.ai;
     const int aip = P.aip;
@@ -180,7 +318,7 @@ struct AcAlgo {
     const bool one_tile = ntile <= nslots;
     const float invB = 1.0f / (float)a.B;
     const bool sac = a.actor_kind == FRL_ACTOR_SAC;
-    const bool policy_step = ((a.total_it0 + u + 1) % (a.policy_freq > 0 ? a.policy_freq : 1)) == 0;
+    const bool policy_step = is_policy_step(a, u);
     const long n_policy_before = (a.policy_freq > 1) ? (long)((a.total_it0 + u) / a.policy_freq - a.total_it0 / a.policy_freq) : (long)u;
     const int heads_used = sac ? a.n_heads : 1;                // actor loss: SAC mean of both heads, TD3 Q1 only, DDPG single
     float alpha = 0.f;
@@ -214,6 +352,9 @@ struct AcAlgo {
     float* gp = a.gpart + (size_t)c.cta * gstride;
 
     if (s == 0) {
+      if (bon) {
+        bon_update(c, a, P, NORM, H1, u);    // H1..D2 (6 contiguous [R][ldh] tiles) are free scratch here
+      }
       // ---------------- target action(s) + this role's target critic head ----------------
       for (int tile = slot; tile < ntile; tile += nslots) {
         const int row0 = tile * FRL_R;
@@ -233,6 +374,7 @@ struct AcAlgo {
         }
         trace(10);
         for (int j = 0; j < NA; ++j) gather_rows<FRL_R>(rep(a, j).storage, rep(a, j).row_floats, a.indices + (size_t)u * a.B + row0, nvalid, raw0 + P.raw_off[j]);
+        if (bon) norm_rows(a, P, NORM, raw0, nvalid);
         trace(11);
         put_cols<FRL_R>(XN, sa, P.act_off[0], raw0, 1, 0, 0, sa - P.act_off[0]);   // zero the action + pad columns of XN
         for (int j = 0; j < NA; ++j) {
@@ -317,6 +459,18 @@ struct AcAlgo {
       // ---------------- TD target, this role's critic head forward + backward ----------------
       float loss_acc = 0.f;
       bool first = true;
+      if (bon && c.cta == 0) {
+        FRL_PAR(t) {
+          if (t < P.obs_off[NA]) {
+            int j = 0;
+            while (j + 1 < NA && t >= P.obs_off[j + 1]) ++j;
+            const int k = t - P.obs_off[j], odj = rep(a, j).obs_dim;
+            const float* o = NORM + 3 * P.obs_off[j];
+            float* st = a.obs_norm[j];
+            st[k] = o[k]; st[odj + k] = o[odj + k]; st[2 * odj + k] = o[2 * odj + k];
+          }
+        }
+      }
       for (int tile = slot; tile < ntile; tile += nslots) {
         const int row0 = tile * FRL_R;
         const int nvalid = (a.B - row0) < FRL_R ? (a.B - row0) : FRL_R;
@@ -330,7 +484,10 @@ struct AcAlgo {
           stage_prefetch(c, layer_fwd_src(C, l0), layer_fwd_bytes(C.L[l0]));
         }
         // one tile per CTA: the rows gathered by stage 0 of this learn are still in shared memory
-        if (!one_tile) for (int j = 0; j < NA; ++j) gather_rows<FRL_R>(rep(a, j).storage, rep(a, j).row_floats, a.indices + (size_t)u * a.B + row0, nvalid, raw0 + P.raw_off[j]);
+        if (!one_tile) {
+          for (int j = 0; j < NA; ++j) gather_rows<FRL_R>(rep(a, j).storage, rep(a, j).row_floats, a.indices + (size_t)u * a.B + row0, nvalid, raw0 + P.raw_off[j]);
+          if (bon) norm_rows(a, P, NORM, raw0, nvalid);
+        }
         for (int j = 0; j < NA; ++j) {
           const frl_replay_t& rj = rep(a, j);
           const float* rw = raw0 + P.raw_off[j];
@@ -412,7 +569,10 @@ struct AcAlgo {
         } else {
           stage_prefetch(c, layer_fwd_src(A, 0), layer_fwd_bytes(A.L[0]));
         }
-        if (!one_tile) for (int j = 0; j < NA; ++j) gather_rows<FRL_R>(rep(a, j).storage, rep(a, j).row_floats, a.indices + (size_t)u * a.B + row0, nvalid, raw0 + P.raw_off[j]);
+        if (!one_tile) {
+          for (int j = 0; j < NA; ++j) gather_rows<FRL_R>(rep(a, j).storage, rep(a, j).row_floats, a.indices + (size_t)u * a.B + row0, nvalid, raw0 + P.raw_off[j]);
+          if (bon) norm_rows(a, P, NORM, raw0, nvalid);
+        }
         for (int j = 0; j < NA; ++j) {
           const frl_replay_t& rj = rep(a, j);
           const float* rw = raw0 + P.raw_off[j];

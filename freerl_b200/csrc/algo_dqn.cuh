@@ -65,6 +65,7 @@ struct DqnAlgo {
   typedef frl_dqn_args_t Args;
   static const int NSTAGES = 2;
   FRL_SHD bool writes_params(int) { return true; }
+  FRL_SHD bool stage_enabled(int, int, const Args&) { return true; }
   FRL_SHD int wbuf_floats(const Args& a) {
     int mx = 0;
     for (int i = 0; i < a.q.n_layers; ++i) {

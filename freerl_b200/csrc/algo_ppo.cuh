@@ -126,6 +126,7 @@ struct PpoAlgo {
   typedef frl_ppo_args_t Args;
   static const int NSTAGES = 5;
   FRL_SHD bool writes_params(int) { return true; }
+  FRL_SHD bool stage_enabled(int, int, const Args&) { return true; }
   FRL_SHD int wbuf_floats(const Args& a) { return (AcAlgo::max_layer_floats(a.net) + 31) & ~31; }
   FRL_SHD int user_floats(const Args& a) {
     const int ldh = a.net.L[0].out_pad, ip = a.net.L[0].in_pad, cip = a.net.L[3].in_pad, ap = a.net.L[2].out_pad;

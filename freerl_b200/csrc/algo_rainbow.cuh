@@ -14,6 +14,7 @@ struct RainbowAlgo {
   typedef frl_rainbow_args_t Args;
   static const int NSTAGES = 3;
   FRL_SHD bool writes_params(int) { return true; }
+  FRL_SHD bool stage_enabled(int, int, const Args&) { return true; }
   FRL_SHD int wbuf_floats(const Args& a) { return (AcAlgo::max_layer_floats(a.eff[2]) + 31) & ~31; }
   FRL_SHD int natot(const Args& a) { return (a.n_actions * a.n_atoms + 3) & ~3; }
   FRL_SHD int user_floats(const Args& a) {

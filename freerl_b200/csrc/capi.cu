@@ -22,7 +22,7 @@ extern "C" void frl_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 extern "C" const char* frl_last_error(void) { return g_err; }
-extern "C" int frl_abi_version(void) { return 1; }
+extern "C" int frl_abi_version(void) { return 2; }
 
 #ifndef FRL_EMUL
 extern "C" int frl_is_emulation(void) { return 0; }
@@ -272,7 +272,10 @@ struct InferAlgo {
     FRL_PAR(t) {
       for (int e = t; e < FRL_R * in_pad; e += FRL_NT) {
         const int r = e / in_pad, j = e % in_pad;
-        X[e] = (r < nvalid && j < a.obs_dim) ? a.obs[(size_t)(row0 + r) * a.obs_dim + j] : 0.f;
+        float x = (r < nvalid && j < a.obs_dim) ? a.obs[(size_t)(row0 + r) * a.obs_dim + j] : 0.f;
+        if (a.obs_norm && r < nvalid && j < a.obs_dim)       // Batch_ObsNorm with update=False (e.g. DDPG.py:168-169)
+          x = fdiv(fadd(x, -a.obs_norm[j]), fadd(a.obs_norm[2 * a.obs_dim + j], 1e-8f));
+        X[e] = x;
       }
     }
     FRL_SYNC();

@@ -7,6 +7,7 @@
 //                       static int  n_updates(const Args&);
 //                       static FRL_DEV void stage(int s, int u, Cta&, float* user, const Args&);
 //                       static bool writes_params(int s);         // stage s rewrites weights a later TMA copy reads
+//                       static bool stage_enabled(int s, int u, const Args&);   // false: skip stage s of update u and its barrier
 // The kernel runs  for u: for s: stage(s,u); grid.sync()  — one launch performs n_updates sequential
 // learn() steps (stages are separated by grid-wide barriers because every optimiser step needs the
 // global gradient norm and the next phase needs the updated weights).
@@ -25,6 +26,7 @@ __global__ void __launch_bounds__(FRL_NT, 1) frl_persistent_kernel(const __grid_
   const int U = A::n_updates(a);
   for (int u = 0; u < U; ++u) {
     for (int s = 0; s < A::NSTAGES; ++s) {
+      if (!A::stage_enabled(s, u, a)) continue;      // block-uniform AND grid-uniform: stage and its barrier are skipped together
       trace(1000 + s);
       A::stage(s, u, c, user, a);
       stage_reset(c);
@@ -102,11 +104,13 @@ int frl_launch(const typename A::Args& a, cudaStream_t) {
   }
   const int U = A::n_updates(a);
   for (int u = 0; u < U; ++u)
-    for (int s = 0; s < A::NSTAGES; ++s)
+    for (int s = 0; s < A::NSTAGES; ++s) {
+      if (!A::stage_enabled(s, u, a)) continue;
       for (int g = 0; g < grid; ++g) {
         A::stage(s, u, ctas[g], user[g], a);
         stage_reset(ctas[g]);
       }
+    }
   for (int g = 0; g < grid; ++g) { res_drain(ctas[g]); free(mem[g]); }
   return 0;
 }

@@ -117,6 +117,12 @@ typedef struct {
   frl_net_t ma_actor_target[FRL_MAX_AGENTS];
   int defer_polyak;         /* 1: do not touch the targets (MADDPG updates all targets after the agent loop) */
   float* xchg;              /* dev scratch [3*B]: target-Q exchange between the per-head CTA roles */
+  /* ---- Batch_ObsNorm (SAC.py:390-421, DDPG.py:372-403, MADDPG.py:366-397): running statistics over BATCH MEANS.
+   * obs_norm[j] = dev [3][obs_dim_j] floats {mean, S, std} of agent j (single-agent: j = 0); NULL = trick off.
+   * Every learn first folds mean_rows(obs) into the state (n = obs_norm_n0 + u + 1; n == 1 sets mean = std = x_bar like
+   * the reference), then feeds (x - mean) / (std + 1e-8) for obs AND next_obs to every network. */
+  float* obs_norm[FRL_MAX_AGENTS];
+  int64_t obs_norm_n0;      /* updates folded in before this call */
 } frl_ac_args_t;
 
 enum { FRL_INFER_ARGMAX = 0, FRL_INFER_TANH = 1, FRL_INFER_SAC_SAMPLE = 2, FRL_INFER_SAC_MEAN = 3, FRL_INFER_RAW = 4,
@@ -135,6 +141,7 @@ typedef struct {
   float* out;               /* dev [n][out_cols]: actions (ARGMAX: 1 column holding the index as float; RAW: net output) */
   int out_cols;
   int layer_norm;           /* MAPPO nets: F.layer_norm on the input and after each hidden ReLU */
+  const float* obs_norm;    /* dev [3][obs_dim] {mean, S, std} Batch_ObsNorm state applied with update=False, or NULL */
 } frl_infer_args_t;
 
 /* On-policy (PPO.py) minibatch update.  `net` holds actor (layers 0-2, + log_std extra when continuous) and critic

@@ -209,7 +209,8 @@ class DQNOracle:
 # --------------------------------------------------------------------------------------------------
 class SACOracle:
     def __init__(self, actor, critic, actor_lr, critic_lr, act_dim, alpha0=0.01, alpha_lr=1e-4,
-                 adaptive_alpha=True):
+                 adaptive_alpha=True, obs_norm=None):
+        self.obs_norm = obs_norm          # BatchObsNorm or None (trick Batch_ObsNorm, applied in sample(): SAC.py:215-217)
         self.actor, self.critic = _leaf(actor), _leaf(critic)
         self.actor_target, self.critic_target = clone_net(actor), clone_net(critic)
         self.opt_a = AdamState(list(self.actor.values()), actor_lr)
@@ -223,6 +224,9 @@ class SACOracle:
 
     def learn(self, batch, eps_next, eps_new, gamma, tau):
         obs, act, rew, nobs, done = batch
+        if self.obs_norm is not None:
+            obs = self.obs_norm(obs)
+            nobs = self.obs_norm(nobs, update=False)
         alpha = self.alpha.detach()
         with torch.no_grad():
             na, nlogp = sac_actor(self.actor_target, nobs, eps_next)         # uses the ACTOR TARGET (SAC.py:227)
@@ -265,7 +269,8 @@ class SACOracle:
 # --------------------------------------------------------------------------------------------------
 class TD3Oracle:
     def __init__(self, actor, critic, actor_lr, critic_lr, clip_double=True, policy_noise=True, twin_delay=True,
-                 critic_weight_decay=0.0):
+                 critic_weight_decay=0.0, obs_norm=None):
+        self.obs_norm = obs_norm          # BatchObsNorm or None (DDPG.py:196-198)
         self.actor, self.critic = _leaf(actor), _leaf(critic)
         self.actor_target, self.critic_target = clone_net(actor), clone_net(critic)
         self.opt_a = AdamState(list(self.actor.values()), actor_lr)
@@ -277,6 +282,9 @@ class TD3Oracle:
               policy_noise_scale=1.0):
         self.total_it += 1
         obs, act, rew, nobs, done = batch
+        if self.obs_norm is not None:
+            obs = self.obs_norm(obs)
+            nobs = self.obs_norm(nobs, update=False)
         with torch.no_grad():
             if self.policy_noise:
                 noise = (policy_noise_scale * (randn * policy_noise)).clamp(-noise_clip, noise_clip)
@@ -322,9 +330,9 @@ class DDPGOracle(TD3Oracle):
     """DDPG = single critic, no target smoothing, actor every step; critic Adam has L2 weight_decay 1e-3
     when ``supplement['weight_decay']`` (``DDPG_file/DDPG.py:131-134``)."""
 
-    def __init__(self, actor, critic, actor_lr, critic_lr, weight_decay=True):
+    def __init__(self, actor, critic, actor_lr, critic_lr, weight_decay=True, obs_norm=None):
         super().__init__(actor, critic, actor_lr, critic_lr, clip_double=False, policy_noise=False,
-                         twin_delay=False, critic_weight_decay=1e-3 if weight_decay else 0.0)
+                         twin_delay=False, critic_weight_decay=1e-3 if weight_decay else 0.0, obs_norm=obs_norm)
 
     def learn(self, batch, gamma, tau):
         return super().learn(batch, None, gamma, tau)

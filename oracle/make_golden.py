@@ -29,12 +29,16 @@ def sd_np(module, prefix):
     return {prefix + k: v.detach().cpu().numpy().copy() for k, v in module.state_dict().items()}
 
 
-def fill(policy, n, obs_dim, act_dim, rng, discrete_actions=None):
+def fill(policy, n, obs_dim, act_dim, rng, discrete_actions=None, offset=None):
     for _ in range(n):
         o = rng.standard_normal(obs_dim).astype(np.float32)
+        if offset is not None:          # Batch_ObsNorm fixtures: observations with a non-zero mean, like real envs
+            o = o + offset
         a = rng.integers(0, discrete_actions) if discrete_actions else rng.uniform(-1, 1, act_dim).astype(np.float32)
         r = float(rng.standard_normal())
         o2 = rng.standard_normal(obs_dim).astype(np.float32)
+        if offset is not None:
+            o2 = o2 + offset
         d = bool(rng.random() < 0.1)
         policy.add(o, a, r, o2, d)
 
@@ -63,12 +67,13 @@ def rng_restore(s):
 
 
 def gen_offpolicy(name, make_policy, learn_call, n_learn, B, obs_dim, act_dim, noise_draws, nets, discrete=None,
-                  extra=None, seed=3):
+                  extra=None, seed=3, bon=False):
     np.random.seed(seed)
     torch.manual_seed(seed)
     policy = make_policy()
     rng = np.random.default_rng(seed)
-    fill(policy, 400, obs_dim, act_dim, rng, discrete)
+    offset = rng.uniform(1.0, 3.0, obs_dim).astype(np.float32) if bon else None
+    fill(policy, 400, obs_dim, act_dim, rng, discrete, offset)
     tap = LossTap(policy.agent, [n for n in ("update_critic", "update_actor", "update_Qnet") if hasattr(policy.agent, n)])
     rec = {}
     for nm, getter in nets.items():
@@ -92,6 +97,14 @@ def gen_offpolicy(name, make_policy, learn_call, n_learn, B, obs_dim, act_dim, n
         rec["loss/%03d/%s" % (i, n)] = np.array(vals, np.float64)
     if extra:
         rec.update(extra(policy))
+    if bon:     # Batch_ObsNorm running statistics after the learns + one normalised select_action
+        ms = policy.batch_size_obs_norm.running_ms
+        rec["final/norm/mean"], rec["final/norm/std"] = ms.mean.numpy().copy(), ms.std.numpy().copy()
+        rec["final/norm/n"] = np.array(ms.n)
+        o = rng.standard_normal(obs_dim).astype(np.float32) + offset
+        rec["act/obs"] = o
+        if name.startswith("ddpg"):
+            rec["act/action"] = np.asarray(policy.select_action(o))
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
     print(name, "ok:", len(rec), "arrays;", [(n, v) for n, v in tap.log[:3]])
 
@@ -111,6 +124,28 @@ def gen_sac():
                   {"actor": lambda p: p.agent.actor, "critic": lambda p: p.agent.critic,
                    "actor_target": lambda p: p.agent.actor_target, "critic_target": lambda p: p.agent.critic_target},
                   extra=lambda p: {"final/log_alpha": np.array(p.alphas.log_alpha.item(), np.float64)})
+
+
+def gen_sac_bon():
+    """SAC with trick Batch_ObsNorm (SAC.py:181-182, 215-217)."""
+    m = refload.load("SAC_file", "SAC")
+    trick = {"ObsNorm": False, "Batch_ObsNorm": True, "OUNoise": True, "GaussNoise": False}
+    gen_offpolicy("sac_bon", lambda: m.SAC([17, 6], True, 1e-3, 1e-3, 1000, torch.device("cpu"), trick=trick),
+                  lambda p, B: p.learn(B, 0.99, 0.01), 4, 64, 17, 6, 2,
+                  {"actor": lambda p: p.agent.actor, "critic": lambda p: p.agent.critic,
+                   "actor_target": lambda p: p.agent.actor_target, "critic_target": lambda p: p.agent.critic_target},
+                  extra=lambda p: {"final/log_alpha": np.array(p.alphas.log_alpha.item(), np.float64)}, seed=21, bon=True)
+
+
+def gen_ddpg_bon():
+    """DDPG with its DEFAULT supplements (DDPG.py:446): weight_decay, net_init, Batch_ObsNorm all on."""
+    m = refload.load("DDPG_file", "DDPG")
+    sup = {"weight_decay": True, "OUNoise": True, "ObsNorm": False, "net_init": True, "Batch_ObsNorm": True}
+    gen_offpolicy("ddpg_bon", lambda: m.DDPG([17, 6], True, 1e-3, 1e-3, 1000, torch.device("cpu"), trick=None, supplement=sup),
+                  lambda p, B: p.learn(B, 0.99, 0.01), 4, 64, 17, 6, 0,
+                  {"actor": lambda p: p.agent.actor, "critic": lambda p: p.agent.critic,
+                   "actor_target": lambda p: p.agent.actor_target, "critic_target": lambda p: p.agent.critic_target},
+                  seed=22, bon=True)
 
 
 def gen_td3():
@@ -252,6 +287,9 @@ if __name__ == "__main__":
         gen_td3()
     if "ddpg" in which:
         gen_ddpg()
+    if "bon" in which:
+        gen_sac_bon()
+        gen_ddpg_bon()
     if "ppo" in which:
         gen_ppo(True)
         gen_ppo(False)

@@ -15,9 +15,11 @@ from .algos import (AdamState, adam_step, clip_grad_norm, clone_net, mlp2, polya
 
 
 class MADDPGOracle:
-    def __init__(self, actors, critics, actor_lr, critic_lr, weight_decay=True):
-        """actors / critics: OrderedDict agent_id -> net dict"""
+    def __init__(self, actors, critics, actor_lr, critic_lr, weight_decay=True, obs_norms=None):
+        """actors / critics: OrderedDict agent_id -> net dict; obs_norms: agent_id -> algos.BatchObsNorm (supplement
+        Batch_ObsNorm: EVERY agent's statistics are updated by EVERY agent's sample(), MADDPG.py:192-196)"""
         self.ids = list(actors.keys())
+        self.obs_norms = obs_norms
         self.actor = OrderedDict((k, _leaf(v)) for k, v in actors.items())
         self.critic = OrderedDict((k, _leaf(v)) for k, v in critics.items())
         self.actor_target = OrderedDict((k, clone_net(v)) for k, v in actors.items())
@@ -29,6 +31,9 @@ class MADDPGOracle:
         """batches: list (one per agent, in agent order) of dict agent_id -> (obs, act, rew, nobs, done)"""
         out = []
         for aid, batch in zip(self.ids, batches):
+            if self.obs_norms is not None:
+                batch = {k: (self.obs_norms[k](b[0], update=True), b[1], b[2], self.obs_norms[k](b[3], update=False), b[4])
+                         for k, b in batch.items()}
             obs = [batch[k][0] for k in self.ids]
             act = [batch[k][1] for k in self.ids]
             nobs = [batch[k][3] for k in self.ids]

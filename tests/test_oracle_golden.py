@@ -84,6 +84,39 @@ def test_ddpg(golden):
         assert_net(getattr(o, n), g, "final/%s/" % n)
 
 
+def test_sac_batch_obs_norm(golden):
+    g = golden("sac_bon")
+    bon = algos.BatchObsNorm(17)
+    o = algos.SACOracle(net(g, "init/actor/"), net(g, "init/critic/"), 1e-3, 1e-3, act_dim=6, obs_norm=bon)
+    lc, la = losses(g, "update_critic"), losses(g, "update_actor")
+    for it in range(4):
+        r = o.learn(batch(g, it), torch.from_numpy(g["noise/%d/0" % it]), torch.from_numpy(g["noise/%d/1" % it]), 0.99, 0.01)
+        np.testing.assert_allclose(r["critic_loss"], lc[it][0], rtol=1e-6)
+        np.testing.assert_allclose(r["actor_loss"], la[it][0], rtol=1e-5)
+    for n in ("actor", "critic", "actor_target", "critic_target"):
+        assert_net(getattr(o, n), g, "final/%s/" % n)
+    assert bon.n == int(g["final/norm/n"]) == 4
+    np.testing.assert_array_equal(bon.mean.numpy(), g["final/norm/mean"])
+    np.testing.assert_array_equal(bon.std.numpy(), g["final/norm/std"])
+
+
+def test_ddpg_batch_obs_norm(golden):
+    g = golden("ddpg_bon")
+    bon = algos.BatchObsNorm(17)
+    o = algos.DDPGOracle(net(g, "init/actor/"), net(g, "init/critic/"), 1e-3, 1e-3, weight_decay=True, obs_norm=bon)
+    lc, la = losses(g, "update_critic"), losses(g, "update_actor")
+    for it in range(4):
+        r = o.learn(batch(g, it), 0.99, 0.01)
+        np.testing.assert_allclose(r["critic_loss"], lc[it][0], rtol=1e-6)
+        np.testing.assert_allclose(r["actor_loss"], la[it][0], rtol=1e-5)
+    for n in ("actor", "critic", "actor_target", "critic_target"):
+        assert_net(getattr(o, n), g, "final/%s/" % n)
+    np.testing.assert_array_equal(bon.std.numpy(), g["final/norm/std"])
+    # select_action with update=False (DDPG.py:166-173)
+    a = algos.tanh_actor(o.actor, bon(torch.from_numpy(g["act/obs"]).reshape(1, -1), update=False))
+    np.testing.assert_allclose(a.detach().numpy()[0], g["act/action"], rtol=1e-5, atol=1e-6)
+
+
 def _ppo(golden, name, is_continue):
     g = golden(name)
     o = algos.PPOOracle(net(g, "init/actor/"), net(g, "init/critic/"), 1e-3, is_continue)

@@ -17,6 +17,11 @@ def maddpg_nets(g, which, kind):
     return out
 
 
+def maddpg_norms():
+    from oracle.algos import BatchObsNorm
+    return {k: BatchObsNorm(18) for k in IDS}
+
+
 def maddpg_batch(g, idx):
     f = lambda x: torch.from_numpy(np.asarray(x, dtype=np.float32))
     return {k: (f(g["buf/%s/obs" % k][idx]), f(g["buf/%s/act" % k][idx]), f(g["buf/%s/rew" % k][idx]).reshape(-1, 1),
@@ -34,6 +39,24 @@ def test_maddpg_oracle_vs_reference(golden):
     np.testing.assert_allclose(np.array(ls), g["losses"], rtol=2e-5, atol=1e-7)
     for k in IDS:
         for kind, nets in (("actor", orc.actor), ("critic", orc.critic), ("actor_target", orc.actor_target), ("critic_target", orc.critic_target)):
+            for n, v in nets[k].items():
+                np.testing.assert_allclose(v.detach().numpy(), g["final/%s/%s/%s" % (k, kind, n)], rtol=2e-5, atol=2e-6)
+
+
+def test_maddpg_batch_obs_norm_oracle_vs_reference(golden):
+    g = golden("maddpg_bon")
+    norms = maddpg_norms()
+    orc = MADDPGOracle(maddpg_nets(g, "init", "actor"), maddpg_nets(g, "init", "critic"), 1e-3, 1e-3, obs_norms=norms)
+    ls = []
+    for it in range(2):
+        r = orc.learn([maddpg_batch(g, g["idx/%d/%d" % (it, j)]) for j in range(3)], 0.95, 0.01)
+        for cl, al in r:
+            ls += [cl, al]
+    np.testing.assert_allclose(np.array(ls), g["losses"], rtol=2e-5, atol=1e-7)
+    for k in IDS:
+        assert norms[k].n == int(g["final/norm/%s/n" % k]) == 6          # 2 learns x 3 agents' samples
+        np.testing.assert_array_equal(norms[k].std.numpy(), g["final/norm/%s/std" % k])
+        for kind, nets in (("actor", orc.actor), ("critic", orc.critic), ("actor_target", orc.actor_target)):
             for n, v in nets[k].items():
                 np.testing.assert_allclose(v.detach().numpy(), g["final/%s/%s/%s" % (k, kind, n)], rtol=2e-5, atol=2e-6)
 

@@ -85,6 +85,101 @@ def _ddpg(golden, device):
         assert_module_close(getattr(pol.agent, n), net_from_golden(g, "final/%s/" % n), "final " + n)
 
 
+def _bon(golden, device, alg):
+    """Batch_ObsNorm inside the fused kernel (running statistics over batch means, SAC.py:390-421) vs oracle + golden.
+    The statistics are BIT-IDENTICAL to torch's (the kernel reproduces the association of torch's CPU mean(dim=0)); that
+    matters because the normalisation divides by std = sqrt(S/n) of batch-mean differences (a different summation order
+    moves the n = 2 losses by 1e-3)."""
+    from freerl_b200.DDPG import DDPG
+    from freerl_b200.SAC import SAC
+    g = golden(alg + "_bon")
+    bon = algos.BatchObsNorm(17)
+    if alg == "sac":
+        trick = {"ObsNorm": False, "Batch_ObsNorm": True, "OUNoise": True, "GaussNoise": False}
+        pol = SAC([17, 6], True, 1e-3, 1e-3, 1000, device, trick=trick)
+        orc = algos.SACOracle(net_from_golden(g, "init/actor/"), net_from_golden(g, "init/critic/"), 1e-3, 1e-3, act_dim=6, obs_norm=bon)
+    else:
+        sup = {"weight_decay": True, "OUNoise": True, "ObsNorm": False, "net_init": True, "Batch_ObsNorm": True}
+        pol = DDPG([17, 6], True, 1e-3, 1e-3, 1000, device, trick=None, supplement=sup)
+        orc = algos.DDPGOracle(net_from_golden(g, "init/actor/"), net_from_golden(g, "init/critic/"), 1e-3, 1e-3, weight_decay=True, obs_norm=bon)
+    _load(pol, g)
+    idxs = fill_buffer_from_batches(pol.buffer, g, 4)
+    tol = dict(rtol=2e-5, atol=2e-6)
+    for it in range(4):
+        if alg == "sac":
+            n0, n1 = g["noise/%d/0" % it], g["noise/%d/1" % it]
+            r = orc.learn(golden_batch(g, it), torch.from_numpy(n0), torch.from_numpy(n1), 0.99, 0.01)
+            pol.learn(64, 0.99, 0.01, indices=idxs[it][None], noise_next=n0[None], noise_new=n1[None])
+        else:
+            r = orc.learn(golden_batch(g, it), 0.99, 0.01)
+            pol.learn(64, 0.99, 0.01, indices=idxs[it][None])
+        m = pol.last_metrics[0].cpu().numpy()
+        assert _rel(m[0], r["critic_loss"]) < 1e-5, (it, m[0], r["critic_loss"])
+        assert _rel(m[1], r["actor_loss"]) < 2e-5, (it, m[1], r["actor_loss"])
+        ms = pol.batch_size_obs_norm.running_ms
+        assert ms.n == it + 1
+        np.testing.assert_array_equal(ms.mean.cpu().numpy(), bon.mean.numpy())
+        np.testing.assert_array_equal(ms.std.cpu().numpy(), bon.std.numpy())
+        for n in NETS:
+            assert_module_close(getattr(pol.agent, n), getattr(orc, n), "%s after learn %d" % (n, it), tol)
+    for n in NETS:
+        assert_module_close(getattr(pol.agent, n), net_from_golden(g, "final/%s/" % n), "final " + n, tol)
+    np.testing.assert_array_equal(pol.batch_size_obs_norm.running_ms.std.cpu().numpy(), g["final/norm/std"])
+    if alg == "ddpg":
+        np.testing.assert_allclose(pol.select_action(g["act/obs"]), g["act/action"], rtol=1e-5, atol=2e-6)
+
+
+def _bon_sizes(device):
+    """Ragged batch sizes (lane remainders, < 16 rows, > 256 rows) and both summation paths of torch's outer sum (obs 19:
+    interleaved `row_sum` lanes; obs 6: columns 0-3 plain `multi_row_sum`, 4-5 `row_sum` — the same split under AVX2 and
+    AVX-512 builds of torch): running statistics bit-identical to torch's."""
+    from freerl_b200.DDPG import DDPG
+    sup = {"weight_decay": False, "OUNoise": False, "ObsNorm": False, "net_init": False, "Batch_ObsNorm": True}
+    rng = np.random.default_rng(5)
+    for B, od in ((7, 19), (100, 19), (300, 19), (7, 6), (37, 6), (300, 6)):
+        torch.manual_seed(B)
+        pol = DDPG([od, 3], True, 1e-3, 1e-3, 512, device, trick=None, supplement=sup)
+        obs = (rng.standard_normal((400, od)) + rng.uniform(1, 3, od)).astype(np.float32)
+        pol.add(obs, rng.uniform(-1, 1, (400, 3)).astype(np.float32), rng.standard_normal(400).astype(np.float32),
+                obs[::-1].copy(), rng.random(400) < 0.1)
+        bon = algos.BatchObsNorm(od)
+        for it in range(3):
+            idx = rng.permutation(400)[:B]
+            bon(torch.from_numpy(obs[idx]))
+            pol.learn(B, 0.99, 0.01, indices=idx[None])
+            ms = pol.batch_size_obs_norm.running_ms
+            np.testing.assert_array_equal(ms.mean.cpu().numpy(), bon.mean.numpy(), err_msg="B=%d it=%d" % (B, it))
+            np.testing.assert_array_equal(ms.std.cpu().numpy(), bon.std.numpy(), err_msg="B=%d it=%d" % (B, it))
+            assert np.isfinite(pol.last_metrics.cpu().numpy()).all()
+
+
+def test_bon_sizes_emulated(emul):
+    _bon_sizes(torch.device("cpu"))
+
+
+@pytest.mark.gpu
+def test_bon_sizes_gpu():
+    _bon_sizes(torch.device("cuda"))
+
+
+def test_sac_bon_emulated(golden, emul):
+    _bon(golden, torch.device("cpu"), "sac")
+
+
+def test_ddpg_bon_emulated(golden, emul):
+    _bon(golden, torch.device("cpu"), "ddpg")
+
+
+@pytest.mark.gpu
+def test_sac_bon_gpu(golden):
+    _bon(golden, torch.device("cuda"), "sac")
+
+
+@pytest.mark.gpu
+def test_ddpg_bon_gpu(golden):
+    _bon(golden, torch.device("cuda"), "ddpg")
+
+
 def test_sac_emulated(golden, emul):
     _sac(golden, torch.device("cpu"))
 
