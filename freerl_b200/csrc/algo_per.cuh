@@ -68,29 +68,32 @@ struct TreeUpdateAlgo {
       }
     }
     FRL_SYNC();
-    // ancestor phases: one tree level per iteration
-    for (int level = 0; level < 64; ++level) {
-      FRL_PAR(t) {
-        for (int i = t; i < B; i += FRL_NT) node[i] = node[i] > 0 ? (node[i] - 1) / 2 : -1;
-      }
-      FRL_SYNC();
-      bool any = false;     // block-uniform: recomputed identically by every thread
-      for (int i = 0; i < B; ++i) any |= node[i] >= 0;
-      if (!any) break;
-      FRL_PAR(t) {
-        for (int i = t; i < B; i += FRL_NT) {
-          const int64_t nd = node[i];
-          if (nd < 0) continue;
-          bool leader = true;
-          for (int j = 0; j < i; ++j) if (node[j] == nd) { leader = false; break; }
-          if (!leader) continue;
-          double v = f64add(a.tree[nd], change[i]);
-          for (int j = i + 1; j < B; ++j) if (node[j] == nd) v = f64add(v, change[j]);
-          a.tree[nd] = v;
-        }
-      }
-      FRL_SYNC();
+    // Ancestors.  With key = heap index + 1 the parent of a node is key >> 1, so the ancestor of item i at level L is
+    // (key_i >> L) - 1 and two items meet at level L iff their keys agree after the shift.  A node's new value depends only
+    // on its old value and the batch-ordered changes of the items below it, never on other levels: every (item, level)
+    // pair is processed independently in ONE phase (no per-level barrier, all tree loads in flight together).  The pair is
+    // the node's "leader" when no earlier item shares the node; the leader adds the changes of all its items IN BATCH
+    // ORDER (fp64 addition is not associative: the order is what makes the last ulp match the sequential reference).
+    FRL_PAR(t) {
+      for (int i = t; i < B; i += FRL_NT) node[i] = node[i] + 1;       // node[] now holds the leaf KEY
     }
+    FRL_SYNC();
+    int maxlev = 0;
+    { uint64_t k = (uint64_t)(2 * a.cap - 1); while (k > 1) { k >>= 1; ++maxlev; } }   // depth of the deepest leaf
+    FRL_PAR(t) {
+      for (int it = t; it < B * maxlev; it += FRL_NT) {
+        const int L = it / B + 1, i = it - (L - 1) * B;               // consecutive threads: consecutive items of one level
+        const int64_t k = node[i] >> L;
+        if (k < 1) continue;
+        bool leader = true;
+        for (int j = 0; j < i; ++j) if ((node[j] >> L) == k) { leader = false; break; }
+        if (!leader) continue;
+        double v = f64add(a.tree[k - 1], change[i]);
+        for (int j = i + 1; j < B; ++j) if ((node[j] >> L) == k) v = f64add(v, change[j]);
+        a.tree[k - 1] = v;
+      }
+    }
+    FRL_SYNC();
   }
 };
 
@@ -161,22 +164,35 @@ struct TreeSampleAlgo {
 };
 
 // ---- max over leaves (np.max(tree[-cap:])) ------------------------------------------------------------------------
-struct TreeMaxBody1 {
-  const double* tree; int64_t cap; double* part; int nblk;
-  FRL_HDM void operator()(long b) const {
-    const int64_t per = (cap + nblk - 1) / nblk;
-    const int64_t s = b * per, e = (s + per < cap) ? s + per : cap;
-    double m = -1e300;
-    for (int64_t i = s; i < e; ++i) { const double v = tree[cap - 1 + i]; m = v > m ? v : m; }
-    part[b] = m;
-  }
-};
-struct TreeMaxBody2 {
-  const double* part; int nblk; double* out;
-  FRL_HDM void operator()(long) const {
-    double m = -1e300;
-    for (int i = 0; i < nblk; ++i) m = part[i] > m ? part[i] : m;
-    out[0] = m;
+// phase 0: CTA-strided coalesced sweep over the leaves -> part[cta];  phase 1 (one CTA): max of the partials -> out.
+// (max is order independent, so any partition gives np.max's result exactly.)
+struct TreeMaxArgs { const double* tree; int64_t cap; double* part; int nblk; double* out; int phase; };
+struct TreeMaxAlgo {
+  typedef TreeMaxArgs Args;
+  static const int NSTAGES = 1;
+  FRL_SHD int wbuf_floats(const Args&) { return 32; }
+  FRL_SHD int user_floats(const Args&) { return 2 * FRL_NT + 64; }
+  FRL_SHD int grid(const Args& a, int) { return a.phase == 0 ? a.nblk : 1; }
+  FRL_SHD int n_updates(const Args&) { return 1; }
+  FRL_SDEV void stage(int, int, Cta& c, float* user, const Args& a) {
+    double* red = (double*)user;
+    FRL_PAR(t) {
+      double m = -1e300;
+      if (a.phase == 0) {
+        const double* leaves = a.tree + (a.cap - 1);
+        for (int64_t i = (int64_t)c.cta * FRL_NT + t; i < a.cap; i += (int64_t)a.nblk * FRL_NT) { const double v = leaves[i]; m = v > m ? v : m; }
+      } else {
+        for (int i = t; i < a.nblk; i += FRL_NT) { const double v = a.part[i]; m = v > m ? v : m; }
+      }
+      red[t] = m;
+    }
+    FRL_SYNC();
+    for (int s2 = FRL_NT / 2; s2 > 0; s2 >>= 1) {
+      FRL_PAR(t) { if (t < s2) red[t] = red[t] > red[t + s2] ? red[t] : red[t + s2]; }
+      FRL_SYNC();
+    }
+    FRL_PAR(t) { if (t == 0) { if (a.phase == 0) a.part[c.cta] = red[0]; else a.out[0] = red[0]; } }
+    FRL_SYNC();
   }
 };
 

@@ -80,20 +80,32 @@ static int frl_for(long n, const F& f, cudaStream_t) {
 // ------------------------------------------------------------------------------------------------
 // replay: batched add (SoA fields -> AoS rows at ring slots) and gather (AoS rows -> 5 dense tensors)
 // ------------------------------------------------------------------------------------------------
+// One thread per 16-byte quad of a row: the AoS side is a single float4 access (rows are 16-B multiples), the SoA side
+// (five dense tensors with odd widths such as obs_dim 17) takes scalar accesses that a warp still coalesces.
+FRL_HD float soa_read(const frl_replay_t& rb, long r, int col, const float* obs, const float* act, const float* rew,
+                      const float* nobs, const float* done) {
+  const int od = rb.obs_dim, ad = rb.act_dim;
+  if (col < od) return obs[r * od + col];
+  if (col < od + ad) return act[r * ad + (col - od)];
+  if (col == od + ad) return rew[r];
+  if (col == od + ad + 1) return done[r];
+  if (col < 2 * od + ad + 2) return nobs[r * od + (col - od - ad - 2)];
+  return 0.f;
+}
 struct AddBody {
   frl_replay_t rb; int64_t index; const float *obs, *act, *rew, *nobs, *done; int n;
   FRL_HDM void operator()(long i) const {
-    const int col = (int)(i % rb.row_floats);
-    const long r = i / rb.row_floats;
-    const int64_t slot = (index + r) % rb.capacity;
-    const int od = rb.obs_dim, ad = rb.act_dim;
-    float v = 0.f;
-    if (col < od) v = obs[r * od + col];
-    else if (col < od + ad) v = act[r * ad + (col - od)];
-    else if (col == od + ad) v = rew[r];
-    else if (col == od + ad + 1) v = done[r];
-    else if (col < 2 * od + ad + 2) v = nobs[r * od + (col - od - ad - 2)];
-    rb.storage[slot * rb.row_floats + col] = v;
+    const int nq = rb.row_floats >> 2;
+    const long r = (i >> 31) ? i / nq : (long)((unsigned)i / (unsigned)nq);     // 32-bit division whenever it is enough
+    const int c0 = (int)(i - r * nq) * 4;
+    int64_t slot = index + r;
+    if (slot >= rb.capacity) slot %= rb.capacity;
+    float4 v;
+    v.x = soa_read(rb, r, c0, obs, act, rew, nobs, done);
+    v.y = soa_read(rb, r, c0 + 1, obs, act, rew, nobs, done);
+    v.z = soa_read(rb, r, c0 + 2, obs, act, rew, nobs, done);
+    v.w = soa_read(rb, r, c0 + 3, obs, act, rew, nobs, done);
+    *reinterpret_cast<float4*>(rb.storage + slot * rb.row_floats + c0) = v;
   }
 };
 
@@ -104,21 +116,25 @@ extern "C" int frl_replay_add_batch(const frl_replay_t* rb, int64_t index, const
     return -1;
   }
   AddBody b = {*rb, index, obs, act, rew, next_obs, done, n};
-  return frl_for((long)n * rb->row_floats, b, (cudaStream_t)stream);
+  return frl_for((long)n * (rb->row_floats >> 2), b, (cudaStream_t)stream);
 }
 
 struct GatherBody {
   frl_replay_t rb; const int64_t* idx; float *obs, *act, *rew, *nobs, *done;
-  FRL_HDM void operator()(long i) const {
-    const int col = (int)(i % rb.row_floats);
-    const long b = i / rb.row_floats;
+  FRL_HDM void put(long b, int col, float v) const {
     const int od = rb.obs_dim, ad = rb.act_dim;
-    const float v = rb.storage[idx[b] * rb.row_floats + col];
     if (col < od) obs[b * od + col] = v;
     else if (col < od + ad) act[b * ad + (col - od)] = v;
     else if (col == od + ad) rew[b] = v;
     else if (col == od + ad + 1) done[b] = v;
     else if (col < 2 * od + ad + 2) nobs[b * od + (col - od - ad - 2)] = v;
+  }
+  FRL_HDM void operator()(long i) const {
+    const int nq = rb.row_floats >> 2;
+    const long b = (i >> 31) ? i / nq : (long)((unsigned)i / (unsigned)nq);
+    const int c0 = (int)(i - b * nq) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(rb.storage + idx[b] * rb.row_floats + c0);
+    put(b, c0, v.x); put(b, c0 + 1, v.y); put(b, c0 + 2, v.z); put(b, c0 + 3, v.w);
   }
 };
 
@@ -126,7 +142,7 @@ extern "C" int frl_replay_gather(const frl_replay_t* rb, const int64_t* indices,
                                  float* next_obs, float* done, void* stream) {
   if (!rb || !rb->storage || B < 0) { frl_set_error("frl_replay_gather: bad arguments"); return -1; }
   GatherBody b = {*rb, indices, obs, act, rew, next_obs, done};
-  return frl_for((long)B * rb->row_floats, b, (cudaStream_t)stream);
+  return frl_for((long)B * (rb->row_floats >> 2), b, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -397,7 +413,9 @@ extern "C" int frl_gae(const float* reward, const float* done, const float* adv_
     return -1;
   }
   GaeArgs a = {reward, done, adv_done, vs, vs_next, T, N, gamma, lmbda, adv_out, v_target_out};
-  return frl_launch_tiles<GaeAlgo>(a, (cudaStream_t)stream);
+  if (N >= 32) return frl_launch_tiles<GaeTileAlgo>(a, (cudaStream_t)stream);      // vectorised envs: coalesced column tiles
+  return frl_launch_tiles<GaeAlgo>(a, (cudaStream_t)stream);                       // few columns: one warp per column
+
 }
 
 extern "C" int frl_ppo_update(const frl_ppo_args_t* a, void* stream) {
@@ -439,12 +457,15 @@ extern "C" int frl_sumtree_sample(const double* tree, int64_t cap, const double*
 
 extern "C" int frl_sumtree_max(const double* tree, int64_t cap, double* scratch, int nscratch, double* out, void* stream) {
   if (!tree || cap <= 0 || !scratch || nscratch <= 0 || !out) { frl_set_error("frl_sumtree_max: bad arguments"); return -1; }
-  const int nblk = (int)(cap < nscratch ? cap : nscratch);
-  TreeMaxBody1 b1 = {tree, cap, scratch, nblk};
-  int rc = frl_for(nblk, b1, (cudaStream_t)stream);
+  int64_t want = (cap + FRL_NT * 8 - 1) / (FRL_NT * 8);            // ~8 leaves per thread
+  const int64_t lim = (int64_t)4 * frl_device_max_ctas() < nscratch ? (int64_t)4 * frl_device_max_ctas() : nscratch;
+  if (want > lim) want = lim;
+  if (want < 1) want = 1;
+  TreeMaxArgs a = {tree, cap, scratch, (int)want, out, 0};
+  int rc = frl_launch_tiles<TreeMaxAlgo>(a, (cudaStream_t)stream);
   if (rc) return rc;
-  TreeMaxBody2 b2 = {scratch, nblk, out};
-  return frl_for(1, b2, (cudaStream_t)stream);
+  a.phase = 1;
+  return frl_launch_tiles<TreeMaxAlgo>(a, (cudaStream_t)stream);
 }
 
 extern "C" int frl_per_priorities(const float* td, int B, float eps, float alpha, float* out, void* stream) {
@@ -485,33 +506,100 @@ extern "C" int frl_rainbow_act(const frl_rainbow_args_t* a, const float* obs, in
 }
 
 // ------------------------------------------------------------------------------------------------
-// joint advantage normalisation (single CTA, fixed-order reductions)
+// joint advantage normalisation: out = (x - mean) / (std_unbiased + eps).  Two grid-wide launches: float64 partial
+// (sum, sum of squares) per CTA over float4 grid-stride loads, then every CTA folds the partials in fixed order and
+// normalises its slice.  (float64 accumulation like torch's CPU mean/std accumulators; deterministic.)
 // ------------------------------------------------------------------------------------------------
+FRL_NI_MISC double block_sum_f64(double* slot /*[FRL_NT] smem*/) {
+  for (int s2 = FRL_NT / 2; s2 > 0; s2 >>= 1) {
+    FRL_PAR(t) { if (t < s2) slot[t] += slot[t + s2]; }
+    FRL_SYNC();
+  }
+  const double r = slot[0];
+  FRL_SYNC();
+  return r;
+}
+struct AdvNormArgs { const float* x; int n; float eps; float* out; double* part; int phase; int ncta; };
 struct AdvNormAlgo {
-  struct Args { const float* x; int n; float eps; float* out; };
+  typedef AdvNormArgs Args;
   static const int NSTAGES = 1;
   FRL_SHD int wbuf_floats(const Args&) { return 32; }
-  FRL_SHD int user_floats(const Args&) { return FRL_NT + 64; }
-  FRL_SHD int grid(const Args&, int) { return 1; }
+  FRL_SHD int user_floats(const Args&) { return 4 * FRL_NT + 64; }
+  FRL_SHD int grid(const Args& a, int) { return a.ncta; }
   FRL_SHD int n_updates(const Args&) { return 1; }
-  FRL_SDEV void stage(int, int, Cta&, float* user, const Args& a) {
-    float* slot = user;
-    FRL_PAR(t) { float s = 0.f; for (int i = t; i < a.n; i += FRL_NT) s += a.x[i]; slot[t] = s; }
-    FRL_SYNC();
-    const float mean = block_sum(slot) / (float)a.n;
-    FRL_SYNC();
-    FRL_PAR(t) { float s = 0.f; for (int i = t; i < a.n; i += FRL_NT) { const float d = a.x[i] - mean; s += d * d; } slot[t] = s; }
-    FRL_SYNC();
-    const float var = block_sum(slot) / (float)(a.n - 1);       // torch.std(): unbiased
-    const float sd = sqrtf(var);
-    FRL_PAR(t) { for (int i = t; i < a.n; i += FRL_NT) a.out[i] = (a.x[i] - mean) / (sd + a.eps); }
-    FRL_SYNC();
+  FRL_SDEV void stage(int, int, Cta& c, float* user, const Args& a) {
+    double* s1 = (double*)user;
+    double* s2 = s1 + FRL_NT;
+    const int n4 = ((((size_t)a.x | (size_t)a.out) & 15) == 0) ? (a.n >> 2) : 0;       // float4 body when 16-B aligned
+    if (a.phase == 0) {
+      FRL_PAR(t) {
+        double s = 0.0, q = 0.0;
+        for (int i = c.cta * FRL_NT + t; i < n4; i += c.ncta * FRL_NT) {
+          const float4 v = ld4(a.x + 4 * (size_t)i);
+          s += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
+          q += ((double)v.x * v.x + (double)v.y * v.y) + ((double)v.z * v.z + (double)v.w * v.w);
+        }
+        for (int i = 4 * n4 + c.cta * FRL_NT + t; i < a.n; i += c.ncta * FRL_NT) { const double v = a.x[i]; s += v; q += v * v; }
+        s1[t] = s; s2[t] = q;
+      }
+      FRL_SYNC();
+      const double S = block_sum_f64(s1), Q = block_sum_f64(s2);
+      FRL_PAR(t) { if (t == 0) { a.part[2 * c.cta] = S; a.part[2 * c.cta + 1] = Q; } }
+      FRL_SYNC();
+    } else {
+      FRL_PAR(t) {
+        double s = 0.0, q = 0.0;
+        for (int i = t; i < c.ncta; i += FRL_NT) { s += a.part[2 * i]; q += a.part[2 * i + 1]; }
+        s1[t] = s; s2[t] = q;
+      }
+      FRL_SYNC();
+      const double S = block_sum_f64(s1), Q = block_sum_f64(s2);
+      const double mean = S / (double)a.n;
+      double var = (Q - S * mean) / (double)(a.n - 1);                                 // torch.std(): unbiased
+      if (var < 0.0) var = 0.0;
+      const float mf = (float)mean, den = (float)sqrt(var) + a.eps;
+      FRL_PAR(t) {
+        for (int i = c.cta * FRL_NT + t; i < n4; i += c.ncta * FRL_NT) {
+          float4 v = ld4(a.x + 4 * (size_t)i);
+          v.x = fdiv(v.x - mf, den); v.y = fdiv(v.y - mf, den); v.z = fdiv(v.z - mf, den); v.w = fdiv(v.w - mf, den);
+          st4(a.out + 4 * (size_t)i, v);
+        }
+        for (int i = 4 * n4 + c.cta * FRL_NT + t; i < a.n; i += c.ncta * FRL_NT) a.out[i] = fdiv(a.x[i] - mf, den);
+      }
+      FRL_SYNC();
+    }
   }
 };
 
+// per-device scratch for the two-launch reductions (allocated once; 16 B per CTA)
+static double* frl_reduce_scratch(int doubles) {
+  static double* buf = nullptr;
+  static int cap = 0;
+  if (doubles > cap) {
+#ifndef FRL_EMUL
+    if (buf) cudaFree(buf);
+    if (cudaMalloc((void**)&buf, (size_t)doubles * sizeof(double)) != cudaSuccess) { buf = nullptr; cap = 0; return nullptr; }
+#else
+    free(buf);
+    buf = (double*)malloc((size_t)doubles * sizeof(double));
+#endif
+    cap = doubles;
+  }
+  return buf;
+}
+
 extern "C" int frl_adv_norm(const float* x, int n, float eps, float* out, void* stream) {
   if (!x || !out || n < 2) { frl_set_error("frl_adv_norm: bad arguments"); return -1; }
-  AdvNormAlgo::Args a = {x, n, eps, out};
+  int ncta = (n / 4 + FRL_NT - 1) / FRL_NT;
+  const int cap = 4 * frl_device_max_ctas();
+  if (ncta > cap) ncta = cap;
+  if (ncta < 1) ncta = 1;
+  double* part = frl_reduce_scratch(2 * cap > 4096 ? 2 * cap : 4096);
+  if (!part) { frl_set_error("frl_adv_norm: scratch allocation failed"); return -2; }
+  AdvNormArgs a = {x, n, eps, out, part, 0, ncta};
+  int rc = frl_launch_tiles<AdvNormAlgo>(a, (cudaStream_t)stream);
+  if (rc) return rc;
+  a.phase = 1;
   return frl_launch_tiles<AdvNormAlgo>(a, (cudaStream_t)stream);
 }
 

@@ -1,0 +1,55 @@
+"""frl_gae / frl_adv_norm through the C ABI vs the oracle's float64 reverse scan (PPO_file/PPO.py:222-233) on vectorised
+[T, N] rollouts: the coalesced column-tile kernel (N >= 32, with and without the shared-memory stash), the
+warp-per-column kernel (N < 32), ragged T / N, and segment resets at adv_done."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import algos
+
+
+def _gae_case(_lib, device, T, N, seed):
+    rng = np.random.default_rng(seed)
+    rew = rng.standard_normal((T, N)).astype(np.float32)
+    vs = rng.standard_normal((T, N)).astype(np.float32)
+    vn = rng.standard_normal((T, N)).astype(np.float32)
+    done = (rng.random((T, N)) < 0.03).astype(np.float32)
+    adone = np.maximum(done, (rng.random((T, N)) < 0.02).astype(np.float32))
+    gamma, lmbda = 0.99, 0.95
+    td = (torch.from_numpy(rew) + gamma * (1.0 - torch.from_numpy(done)) * torch.from_numpy(vn) - torch.from_numpy(vs)).numpy()
+    want = np.stack([algos.gae_reference(td[:, j].astype(np.float64), adone[:, j].astype(np.float64), gamma, lmbda) for j in range(N)], axis=1)
+    d = lambda x: torch.from_numpy(x).to(device)
+    r_, dn_, ad_, vs_, vn_ = d(rew), d(done), d(adone), d(vs), d(vn)
+    adv, vt = torch.empty((T, N), device=device), torch.empty((T, N), device=device)
+    _lib.check(_lib.lib().frl_gae(_lib.ptr(r_), _lib.ptr(dn_), _lib.ptr(ad_), _lib.ptr(vs_), _lib.ptr(vn_), T, N, gamma, lmbda,
+                                  _lib.ptr(adv), _lib.ptr(vt), _lib.stream_ptr(device)), "frl_gae")
+    np.testing.assert_allclose(adv.cpu().numpy(), want.astype(np.float32), rtol=2e-6, atol=2e-6, err_msg="T=%d N=%d" % (T, N))
+    np.testing.assert_allclose(vt.cpu().numpy(), want.astype(np.float32) + vs, rtol=2e-6, atol=2e-6)
+
+
+def _run(_lib, device):
+    for T, N, seed in ((128, 64, 0), (50, 33, 1), (7, 32, 2), (600, 40, 3), (1, 70, 4), (257, 3, 5), (40, 1, 6)):
+        _gae_case(_lib, device, T, N, seed)
+    # advantage normalisation: ragged / unaligned sizes vs torch (MAPPO.py:385-386: (adv - adv.mean()) / (adv.std() + 1e-8))
+    rng = np.random.default_rng(9)
+    for n in (3, 768, 1025, 70001):
+        x = torch.from_numpy((rng.standard_normal(n + 1) * 3 + 1).astype(np.float32))
+        for off in (0, 1):
+            xs = x[off:off + n]
+            xd = x.to(device)[off:off + n]
+            out = torch.empty(n + 1, device=device)[off:off + n]
+            _lib.check(_lib.lib().frl_adv_norm(_lib.ptr(xd), n, ctypes.c_float(1e-8), _lib.ptr(out), _lib.stream_ptr(device)), "frl_adv_norm")
+            want = (xs - xs.mean()) / (xs.std() + 1e-8)
+            np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=1e-5, atol=2e-6, err_msg="n=%d off=%d" % (n, off))
+
+
+def test_gae_adv_norm_emulated(emul):
+    _run(emul, torch.device("cpu"))
+
+
+@pytest.mark.gpu
+def test_gae_adv_norm_gpu():
+    from freerl_b200 import _lib
+    _run(_lib, torch.device("cuda"))
