@@ -120,12 +120,13 @@ def _declare(lib):
     lib.frl_rainbow_learn.argtypes = [C.POINTER(RainbowArgs), vp]
     lib.frl_rainbow_act.argtypes = [C.POINTER(RainbowArgs), vp, ci, vp, vp]
     lib.frl_adv_norm.argtypes = [vp, ci, C.c_float, vp, vp]
+    lib.frl_wt_ld.argtypes = [ci]
     lib.frl_adv_norm.restype = ci
     lib.frl_rainbow_learn.restype = ci
     lib.frl_rainbow_act.restype = ci
     for name in ("frl_replay_add_batch", "frl_replay_gather", "frl_sample_uniform", "frl_net_sync_mirror",
                  "frl_dqn_learn", "frl_ac_learn", "frl_policy_infer", "frl_gae", "frl_ppo_update", "frl_sumtree_update", "frl_sumtree_sample", "frl_sumtree_max",
-                 "frl_per_priorities", "frl_is_emulation", "frl_device_sm_count",
+                 "frl_per_priorities", "frl_is_emulation", "frl_device_sm_count", "frl_wt_ld",
                  "frl_abi_version"):
         getattr(lib, name).restype = ci
 

@@ -135,7 +135,7 @@ struct AcAlgo {
   FRL_SHD int max_ap(const Args& a) { int m = a.actor.L[2].out_pad; for (int j = 0; j < ma_n(a); ++j) { int v = tnet(a, j).L[2].out_pad; if (v > m) m = v; } return m; }
 
   FRL_SHD int user_floats(const Args& a) {
-    const int ldh = a.critic.L[0].out_pad, sa = a.critic.L[0].in_pad, ap = max_ap(a);
+    const int ldh = act_ld(a.critic.L[0].out_pad), sa = act_ld(a.critic.L[0].in_pad), ap = max_ap(a);
     return raw_off(a, ma_n(a)) + FRL_R * (max_aip(a) + 3 * sa + 6 * ldh + 6 * ap + 3 * 4 + 16) + 2 * FRL_NT + 128 + PLAN_FLOATS + norm_floats(a);
   }
   FRL_SHD int nslots_of(const Args& a, int max_ctas) {
@@ -203,7 +203,7 @@ struct AcAlgo {
     const int NA = P.NA, tot = P.obs_off[NA], npair = tot * 4, B = a.B;
     const int64_t* idx = a.indices + (size_t)u * B;
     // scratch: part[npair][nbp] block sums | lvl[npair][4] cascade levels      (6 * FRL_R * ldh floats available)
-    const int avail = 6 * FRL_R * a.critic.L[0].out_pad - npair * 4;
+    const int avail = 6 * FRL_R * act_ld(a.critic.L[0].out_pad) - npair * 4;
     int nbp = avail / npair;
     if (nbp > 16) nbp = 16;
     float* part = scratch;
@@ -309,7 +309,7 @@ struct AcAlgo {
     }
     float* NORM = user;                        // [agent j at 3*obs_off[j]] {mean, S, std} of this learn (Batch_ObsNorm)
     user += norm_floats(a);
-    const int ldh = C.L[0].out_pad, sa = C.L[0].in_pad, ap = P.ap;
+    const int ldh = act_ld(C.L[0].out_pad), sa = act_ld(C.L[0].in_pad), ap = P.ap;   // strides (bank-conflict free), not widths
     const int NA = P.NA, ai = P.ai;
     const int aip = P.aip;
     const int nrole = a.n_heads, role = c.cta % nrole, slot = c.cta / nrole, nslots = c.ncta / nrole;

@@ -75,7 +75,7 @@ struct DqnAlgo {
     return (mx + 31) & ~31;
   }
   FRL_SHD int user_floats(const Args& a) {
-    const int ldh = a.q.L[0].out_pad, in_pad = a.q.L[0].in_pad, op = a.q.L[a.q.n_layers - 1].out_pad;
+    const int ldh = act_ld(a.q.L[0].out_pad), in_pad = a.q.L[0].in_pad, op = a.q.L[a.q.n_layers - 1].out_pad;
     return FRL_R * (a.replay.row_floats + 2 * in_pad + 3 * ldh + 3 * op + 8) + FRL_NT + 64;
   }
   FRL_SHD int grid(const Args& a, int max_ctas) {
@@ -87,7 +87,7 @@ struct DqnAlgo {
   FRL_SDEV void stage(int s, int u, Cta& c, float* user, const Args& a) {
     const frl_net_t& q = a.q;
     const int nl = q.n_layers;
-    const int ldh = q.L[0].out_pad, in_pad = q.L[0].in_pad, op = q.L[nl - 1].out_pad, nact = q.L[nl - 1].out;
+    const int ldh = act_ld(q.L[0].out_pad), in_pad = q.L[0].in_pad, op = q.L[nl - 1].out_pad, nact = q.L[nl - 1].out;
     if (s == 0) {
       SmemBump sb; sb.p = user;
       float* raw = sb.take(FRL_R * a.replay.row_floats);

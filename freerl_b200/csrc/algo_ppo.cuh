@@ -129,7 +129,7 @@ struct PpoAlgo {
   FRL_SHD bool stage_enabled(int, int, const Args&) { return true; }
   FRL_SHD int wbuf_floats(const Args& a) { return (AcAlgo::max_layer_floats(a.net) + 31) & ~31; }
   FRL_SHD int user_floats(const Args& a) {
-    const int ldh = a.net.L[0].out_pad, ip = a.net.L[0].in_pad, cip = a.net.L[3].in_pad, ap = a.net.L[2].out_pad;
+    const int ldh = act_ld(a.net.L[0].out_pad), ip = a.net.L[0].in_pad, cip = a.net.L[3].in_pad, ap = a.net.L[2].out_pad;
     return FRL_R * (2 * ip + 2 * cip + 10 * ldh + 4 * ap + 8 + 4 * a.n_adv + 8 + 4 + 64) + 2 * FRL_NT + 64 + FRL_NSEG + 3;
   }
   FRL_SHD int grid(const Args& a, int max_ctas) {
@@ -142,7 +142,7 @@ struct PpoAlgo {
 
   FRL_SDEV void stage(int s, int u, Cta& c, float* user, const Args& a) {
     const frl_net_t& N = a.net;
-    const int ldh = N.L[0].out_pad, ip = N.L[0].in_pad, ap = N.L[2].out_pad, nout = N.L[2].out;
+    const int ldh = act_ld(N.L[0].out_pad), ip = N.L[0].in_pad, ap = N.L[2].out_pad, nout = N.L[2].out;
     if (a.stage_hi > 0 && (s < a.stage_lo || s >= a.stage_hi)) return;
     const int rows = a.mb_rows[u];
     const int ntile = (rows + FRL_R - 1) / FRL_R;

@@ -18,7 +18,7 @@ struct RainbowAlgo {
   FRL_SHD int wbuf_floats(const Args& a) { return (AcAlgo::max_layer_floats(a.eff[2]) + 31) & ~31; }
   FRL_SHD int natot(const Args& a) { return (a.n_actions * a.n_atoms + 3) & ~3; }
   FRL_SHD int user_floats(const Args& a) {
-    const int ldh = a.eff[2].L[0].out_pad, ip = a.eff[2].L[0].in_pad, zp = (a.n_atoms + 3) & ~3;
+    const int ldh = act_ld(a.eff[2].L[0].out_pad), ip = a.eff[2].L[0].in_pad, zp = (a.n_atoms + 3) & ~3;
     return FRL_R * (a.replay.row_floats + 2 * ip + 3 * ldh + 3 * zp + 2 * natot(a) + 4 * zp + 8) + FRL_NT + 64;
   }
   FRL_SHD int grid(const Args& a, int max_ctas) {
@@ -138,7 +138,7 @@ struct RainbowAlgo {
 
   FRL_SDEV void stage(int s, int u, Cta& c, float* user, const Args& a) {
     const frl_net_t& E3 = a.eff[2];
-    const int ldh = E3.L[0].out_pad, ip = E3.L[0].in_pad, zp = (a.n_atoms + 3) & ~3, nat = natot(a);
+    const int ldh = act_ld(E3.L[0].out_pad), ip = E3.L[0].in_pad, zp = (a.n_atoms + 3) & ~3, nat = natot(a);
     const int nA = a.n_actions, nZ = a.n_atoms, rf = a.replay.row_floats;
     const int ntile = (a.B + FRL_R - 1) / FRL_R;
     const int ncontrib = ntile < c.ncta ? ntile : c.ncta;
@@ -357,7 +357,7 @@ struct RainbowInferAlgo {
   FRL_SHD int n_updates(const Args&) { return 1; }
   FRL_SDEV void stage(int, int, Cta& c, float* user, const Args& a) {
     const frl_net_t& E = a.r.eff[0];
-    const int ldh = E.L[0].out_pad, ip = E.L[0].in_pad, zp = (a.r.n_atoms + 3) & ~3, nat = RainbowAlgo::natot(a.r), nA = a.r.n_actions;
+    const int ldh = act_ld(E.L[0].out_pad), ip = E.L[0].in_pad, zp = (a.r.n_atoms + 3) & ~3, nat = RainbowAlgo::natot(a.r), nA = a.r.n_actions;
     SmemBump sb; sb.p = user;
     float* X = sb.take(FRL_R * ip);
     float* H = sb.take(FRL_R * ldh);

@@ -39,6 +39,7 @@ int frl_device_max_ctas() {
 extern "C" int frl_is_emulation(void) { return 1; }
 #endif
 extern "C" int frl_device_sm_count(void) { return frl_device_max_ctas(); }
+extern "C" int frl_wt_ld(int out_pad) { return wt_ld_of(out_pad); }
 
 // debug: timestamps (id, globaltimer ns) from CTA 0 of the persistent kernels into a device int64 buffer [2*2000]
 extern "C" int frl_debug_set_timing(void* dev_buf) {
@@ -265,14 +266,14 @@ struct InferAlgo {
   FRL_SHD int nl_of(const Args& a) { return a.nl > 0 ? a.nl : a.net.n_layers; }
   FRL_SHD int wbuf_floats(const Args& a) { return (AcAlgo::max_layer_floats(a.net) + 31) & ~31; }
   FRL_SHD int user_floats(const Args& a) {
-    return FRL_R * (2 * a.net.L[a.l0].in_pad + 4 * a.net.L[a.l0].out_pad + a.net.L[a.l0 + nl_of(a) - 1].out_pad + 2 + 64) + 64;
+    return FRL_R * (2 * a.net.L[a.l0].in_pad + 4 * act_ld(a.net.L[a.l0].out_pad) + a.net.L[a.l0 + nl_of(a) - 1].out_pad + 2 + 64) + 64;
   }
   FRL_SHD int grid(const Args& a, int) { return (a.n + FRL_R - 1) / FRL_R; }
   FRL_SHD int n_updates(const Args&) { return 1; }
   FRL_SDEV void stage(int, int, Cta& c, float* user, const Args& a) {
     const frl_net_t& n = a.net;
     const int nl = nl_of(a), l0 = a.l0;
-    const int in_pad = n.L[l0].in_pad, ldh = n.L[l0].out_pad, op = n.L[l0 + nl - 1].out_pad, nout = n.L[l0 + nl - 1].out;
+    const int in_pad = n.L[l0].in_pad, ldh = act_ld(n.L[l0].out_pad), op = n.L[l0 + nl - 1].out_pad, nout = n.L[l0 + nl - 1].out;
     SmemBump sb; sb.p = user;
     float* X = sb.take(FRL_R * in_pad);
     float* H1 = sb.take(FRL_R * ldh);

@@ -13,6 +13,17 @@
 #pragma once
 #include "common.cuh"
 
+// The product build runs the GEMMs as fp32 FFMA on the CUDA cores (8 x 128 x 128 per op: far below the "genuine dense
+// >= 256 x 256" bar the north star sets for tensor cores, and fp32 keeps the 1e-5 parity budget with room to spare).
+// -DFRL_MMA_3XTF32 builds the experimental tensor-core flavour instead (mma.sync m16n8k8, error-compensated 3xTF32).
+// Measured on B200 (fused SAC learn, B = 256, 64 CTAs): 92.7 us / learn vs 90.1 us for FFMA — the legacy mma.sync path
+// issues slowly on sm_100a and the hi/lo operand split costs as many instructions as it saves — with 2-4x the rounding
+// noise (one Adam-conditioned parameter in 2944 left the 1e-5 band in the TD3 parity test).  Kept as a recorded negative
+// result, not shipped.
+#if !defined(FRL_EMUL) && defined(FRL_MMA_3XTF32)
+#define FRL_MMA 1
+#endif
+
 // bisect switches (debug): -DFRL_INL_GEMM / -DFRL_INL_MISC / -DFRL_INL_OPT force-inline a group again
 #ifdef FRL_INL_GEMM
 #define FRL_NI_GEMM FRL_INLINE_ALT
@@ -56,12 +67,22 @@ static inline float fsqrt(float a) { return sqrtf(a); }
 #endif
 
 // ------------------------------------------------------------------------------------------------
-// Transposed-mirror layout (`pt`): per layer WT[in_pad][wt_ld] followed by bias[out_pad].  The row stride is padded so
-// that wt_ld/4 is odd: rows k, k+1, ... then start in different 16-B bank groups and the backward pass can read the SAME
-// image "transposed" (dX[r][k] = sum_n dY[r][n] * WT[k][n]) without shared-memory bank conflicts — one staged copy of a
-// layer serves forward and backward.
+// Transposed-mirror layout (`pt`): per layer WT[in_pad][wt_ld] followed by bias[out_pad]; ONE staged copy of a layer
+// serves forward (Y = X WT) and backward (dX = dY WT^T, read "transposed").
+//   FFMA build: the row stride is padded so that wt_ld / 4 is odd — rows k, k+1, ... start in different 16-B bank
+//     groups and the backward float4 reads of consecutive rows are free of bank conflicts; activation tiles are dense.
+//   3xTF32 build: wt_ld = 8 (mod 32) and activation strides = 4 (mod 32) make the scalar fragment loads (lane 4g + t
+//     reads row t / column g style patterns) conflict free.
+// The host asks the library for the stride (frl_wt_ld), so both layouts work with the same Python code.
 // ------------------------------------------------------------------------------------------------
-FRL_HD int wt_ld(const frl_layer_t& L) { return ((L.out_pad >> 2) & 1) ? L.out_pad : L.out_pad + 4; }
+#ifdef FRL_MMA
+FRL_HD int wt_ld_of(int out_pad) { return out_pad + ((40 - (out_pad & 31)) & 31); }
+FRL_HD int act_ld(int width) { return width + ((36 - (width & 31)) & 31); }
+#else
+FRL_HD int wt_ld_of(int out_pad) { return ((out_pad >> 2) & 1) ? out_pad : out_pad + 4; }
+FRL_HD int act_ld(int width) { return width; }
+#endif
+FRL_HD int wt_ld(const frl_layer_t& L) { return wt_ld_of(L.out_pad); }
 FRL_HD int wt_bias(const frl_layer_t& L) { return L.in_pad * wt_ld(L); }               // offset of the bias inside the layer image
 FRL_HD int wt_floats(const frl_layer_t& L) { return L.in_pad * wt_ld(L) + L.out_pad; }
 
@@ -393,6 +414,7 @@ FRL_DEV void gemm_finish(sptr sR, unsigned ksplit, int N_pad, int epi, int act, 
   FRL_SYNC();
 }
 
+#ifndef FRL_MMA
 template <int R>
 FRL_NI_GEMM void gemm_rk(float* red, const float* A, int lda, int K_pad, const float* Bs, int ldb, int N_pad, const float* bias,
                          int epi, int act, const float* mask, int ldm, float* C, int ldc) {
@@ -609,6 +631,215 @@ FRL_NI_GEMM void gemm_outer(const float* dY, int ldy, int M_pad, const float* X,
   FRL_SYNC();
   trace(72);
 }
+
+#endif   // !FRL_MMA
+
+// ------------------------------------------------------------------------------------------------
+// Tensor-core flavours of the three microkernels (CUDA build; -DFRL_NO_MMA keeps the FFMA ones above).
+// The batch tile has R = 8 rows, so every product is shaped  [16 x 8] += [16 x 8k] * [8k x 8]  with the 128-wide feature
+// dimension as M, the 8 batch rows as N and the reduction as K: exactly mma.sync m16n8k8 with NO padding waste, one
+// m-tile (16 output features) per warp, the whole reduction inside the warp — no K-split, no cross-warp reduction pass,
+// one barrier per op.  Operands are fp32 in shared memory; each is split on the fly into tf32 hi + lo parts and the
+// product is formed as hi*hi + (hi*lo + lo*hi) in three fp32 accumulators ("3xTF32": per-product error ~2^-21, the same
+// order as the reordering noise of an fp32 FFMA chain; a plain tf32 product would miss the 1e-5 parity budget).
+//   A fragment (row-major 16x8): a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4);   g = lane / 4, t = lane % 4
+//   B fragment (8x8):            b0 (k = t, n = g)   b1 (k = t+4, n = g)
+//   C fragment (16x8):           c0 (g, 2t)  c1 (g, 2t+1)  c2 (g+8, 2t)  c3 (g+8, 2t+1)
+// ------------------------------------------------------------------------------------------------
+#ifdef FRL_MMA
+FRL_DEV void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
+  // hi = x rounded to tf32's 10 mantissa bits (round half away, on the integer pipe: cvt.rna.tf32.f32 runs at 1/8 rate and
+  // was the bottleneck of the whole k-step); lo = x - hi is exact, the tensor core reads its top 10 mantissa bits.
+  hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+// d += a * b  (tf32 operands, fp32 accumulate).  Not volatile: a pure function of its operands, free to be scheduled.
+FRL_DEV void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// Shared-memory load WITHOUT volatile / memory clobber: inside the (non-inlined) GEMM microkernels nothing writes the
+// operands between function entry and the closing barrier, so the compiler may hoist and software-pipeline these freely
+// (the volatile flavour pins every load behind the previous k-step's math: 200+ clk per k-step instead of ~60).
+FRL_DEV float lds_op(uint32_t byte_addr) {
+  float v;
+  asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(byte_addr));
+  return v;
+}
+// One k-step of the 3xTF32 product.  The tensor core adds into its fp32 accumulator with truncation; chained over the
+// 16 k-steps of a 128-deep reduction that bias reaches ~1e-6 relative.  So the dominant hi*hi term (exact products) is
+// produced against a ZERO accumulator and folded into `acc` with round-to-nearest FADDs, like an FFMA chain; only the
+// 2^-11-times-smaller cross terms are chained inside the tensor core (two chains, to halve the dependent latency).
+FRL_DEV void mma3(float (&acc)[4], float (&s1)[4], float (&s2)[4], const float (&af)[4], const float (&bf)[2]) {
+  uint32_t ah[4], al[4], bh[2], bl[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) tf32_split(af[i], ah[i], al[i]);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) tf32_split(bf[i], bh[i], bl[i]);
+  // every MMA starts from a zero accumulator: no HMMA -> HMMA dependency (its latency is ~100 clk on this path; chained,
+  // a lone warp spent 120 clk per k-step), the sums are carried by round-to-nearest FADDs
+  float d[4] = {0.f, 0.f, 0.f, 0.f}, e1[4] = {0.f, 0.f, 0.f, 0.f}, e2[4] = {0.f, 0.f, 0.f, 0.f};
+  mma_tf32(d, ah, bh);
+  mma_tf32(e1, ah, bl);
+  mma_tf32(e2, al, bh);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { acc[i] += d[i]; s1[i] += e1[i]; s2[i] += e2[i]; }
+}
+
+// out[q] for the m-tile `mt` of C[r][m] = sum_k W(m, k) X[r][k]: rows m0 = 16 mt + g, m1 = m0 + 8 (clamped to M - 1 for the
+// loads), batch rows 2t, 2t + 1.  W(m, k) lives at byte wB + 4 (m wsm + k wsk)  (forward: wsm = 1, wsk = ldb; backward on
+// the same image: wsm = ldb, wsk = 1), X[r][k] at xB + 4 (r ldx + k).  Kred % 4 == 0; a trailing half step is zero filled.
+FRL_DEV void mma_tile(uint32_t wB, int wsm, int wsk, uint32_t xB, int ldx, int M, int Kred, int mt, int g, int t, float (&out)[4]) {
+  const int m0 = mt * 16 + g, m1 = m0 + 8;
+  const int m0c = m0 < M ? m0 : M - 1, m1c = m1 < M ? m1 : M - 1;
+  uint32_t pa0 = wB + 4u * (uint32_t)(m0c * wsm + t * wsk), pa1 = wB + 4u * (uint32_t)(m1c * wsm + t * wsk);
+  uint32_t pb = xB + 4u * (uint32_t)(g * ldx + t);
+  const uint32_t k4 = 16u * (uint32_t)wsk, k8 = 32u * (uint32_t)wsk;
+  const int nfull = Kred >> 3;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+  for (int ks = 0; ks < nfull; ++ks) {
+    const float af[4] = {lds_op(pa0), lds_op(pa1), lds_op(pa0 + k4), lds_op(pa1 + k4)};
+    const float bf[2] = {lds_op(pb), lds_op(pb + 16u)};
+    pa0 += k8; pa1 += k8; pb += 32u;
+    mma3(acc, s1, s2, af, bf);
+  }
+  if (Kred & 4) {
+    const float af[4] = {lds_op(pa0), lds_op(pa1), 0.f, 0.f};
+    const float bf[2] = {lds_op(pb), 0.f};
+    mma3(acc, s1, s2, af, bf);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) out[q] = acc[q] + (s1[q] + s2[q]);
+}
+
+// C[r][n] = epi( sum_k A[r][k] * Bs[k][n] (+ bias[n]) )    (same contract as the FFMA gemm_rk; `red` unused)
+template <int R>
+FRL_NI_GEMM void gemm_rk(float* red, const float* A, int lda, int K_pad, const float* Bs, int ldb, int N_pad, const float* bias,
+                         int epi, int act, const float* mask, int ldm, float* C, int ldc) {
+  static_assert(R == 8, "the tensor-core path maps the batch tile onto the n = 8 side of m16n8k8");
+  (void)red;
+  const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const sptr sA = sp_of(A), sB = sp_of(Bs), sC = sp_of(C);
+  const bool has_bias = bias != nullptr;
+  const sptr sBias = sp_of(has_bias ? bias : Bs), sM = sp_of(mask ? mask : Bs);
+  const int mtiles = (N_pad + 15) >> 4;
+  trace(50);
+  for (int mt = warp; mt < mtiles; mt += FRL_NT / 32) {
+    float v4[4];
+    mma_tile(sB, 1, ldb, sA, lda, N_pad, K_pad, mt, g, t, v4);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int o = mt * 16 + g + ((q & 2) ? 8 : 0), r = 2 * t + (q & 1);
+      if (o < N_pad) {
+        float v = v4[q];
+        if (epi == EPI_BIAS_ACT) v = apply_act(v + (has_bias ? sp_ld1(sBias, o) : 0.f), act);
+        else v = (sp_ld1(sM, r * ldm + o) > 0.f) ? v : 0.f;
+        sp_st1(sC, r * ldc + o, v);
+      }
+    }
+  }
+  trace(51);
+  FRL_SYNC();
+  trace(53);
+}
+
+// C[r][k] = epi( sum_n A[r][n] * Bs[k][n] )   (backward dX on the forward image; same contract as the FFMA gemm_nt)
+template <int R>
+FRL_NI_GEMM void gemm_nt(float* red, const float* A, int lda, int N_red, const float* Bs, int ldb, int K_out, int epi,
+                         const float* mask, int ldm, float* C, int ldc) {
+  static_assert(R == 8, "tensor-core path: R == 8");
+  (void)red;
+  const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const sptr sA = sp_of(A), sB = sp_of(Bs), sC = sp_of(C), sM = sp_of(mask ? mask : Bs);
+  const int mtiles = (K_out + 15) >> 4;
+  trace(60);
+  for (int mt = warp; mt < mtiles; mt += FRL_NT / 32) {
+    float v4[4];
+    mma_tile(sB, ldb, 1, sA, lda, K_out, N_red, mt, g, t, v4);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = mt * 16 + g + ((q & 2) ? 8 : 0), r = 2 * t + (q & 1);
+      if (i < K_out) {
+        float v = v4[q];
+        if (epi == EPI_RELU_MASK) v = (sp_ld1(sM, r * ldm + i) > 0.f) ? v : 0.f;
+        sp_st1(sC, r * ldc + i, v);
+      }
+    }
+  }
+  trace(61);
+  FRL_SYNC();
+  trace(63);
+}
+
+// G[m][n] (+)= sum_{r<8} dY[r][m] * X[r][n]  to GLOBAL (one k-step per 16x8 tile), bias gradient gb[m] (+)= sum_r dY[r][m]
+template <int R>
+FRL_NI_GEMM void gemm_outer(const float* dY, int ldy, int M_pad, const float* X, int ldx, int N_pad, int N_real,
+                            float* G, float* gb, bool accumulate) {
+  static_assert(R == 8, "tensor-core path: R == 8");
+  const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const sptr sY = sp_of(dY), sX = sp_of(X);
+  const int mtiles = (M_pad + 15) >> 4, ntiles = (N_pad + 7) >> 3;
+  // a warp owns an (m-tile, n-tile parity) strip so that narrow layers (one or two m-tiles) still use all 8 warps
+  const int nstrips = mtiles >= FRL_NT / 32 ? 1 : ((FRL_NT / 32) / mtiles);
+  trace(70);
+  for (int u = warp; u < mtiles * nstrips; u += FRL_NT / 32) {
+    const int mt = u / nstrips, strip = u - mt * nstrips;
+    const int m0 = mt * 16 + g, m1 = m0 + 8;
+    const int m0c = m0 < M_pad ? m0 : M_pad - 1, m1c = m1 < M_pad ? m1 : M_pad - 1;
+    uint32_t ah[4], al[4];
+    tf32_split(lds_op(sY + 4u * (uint32_t)(t * ldy + m0c)), ah[0], al[0]);
+    tf32_split(lds_op(sY + 4u * (uint32_t)(t * ldy + m1c)), ah[1], al[1]);
+    tf32_split(lds_op(sY + 4u * (uint32_t)((t + 4) * ldy + m0c)), ah[2], al[2]);
+    tf32_split(lds_op(sY + 4u * (uint32_t)((t + 4) * ldy + m1c)), ah[3], al[3]);
+    float xn0, xn1;
+    {
+      const int n = strip * 8 + g, nc = n < N_pad ? n : N_pad - 1;
+      xn0 = lds_op(sX + 4u * (uint32_t)(t * ldx + nc)); xn1 = lds_op(sX + 4u * (uint32_t)((t + 4) * ldx + nc));
+    }
+#pragma unroll 2
+    for (int nt = strip; nt < ntiles; nt += nstrips) {
+      const float x0 = xn0, x1 = xn1;
+      if (nt + nstrips < ntiles) {            // next tile's fragment before this tile's math
+        const int n = (nt + nstrips) * 8 + g, nc = n < N_pad ? n : N_pad - 1;
+        xn0 = lds_op(sX + 4u * (uint32_t)(t * ldx + nc)); xn1 = lds_op(sX + 4u * (uint32_t)((t + 4) * ldx + nc));
+      }
+      uint32_t bh[2], bl[2];
+      tf32_split(x0, bh[0], bl[0]);
+      tf32_split(x1, bh[1], bl[1]);
+      float hh[4] = {0.f, 0.f, 0.f, 0.f}, lo[4] = {0.f, 0.f, 0.f, 0.f};
+      mma_tf32(hh, ah, bh);
+      mma_tf32(lo, ah, bl);
+      mma_tf32(lo, al, bh);
+      const int c0 = nt * 8 + 2 * t;            // columns c0, c0 + 1 of rows m0 (hh[0..1]) and m1 (hh[2..3])
+      if (c0 < N_pad) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int m = h ? m1 : m0;
+          if (m < M_pad) {
+            float2 v = make_float2(c0 < N_real ? hh[2 * h] + lo[2 * h] : 0.f, c0 + 1 < N_real ? hh[2 * h + 1] + lo[2 * h + 1] : 0.f);
+            float2* dst = reinterpret_cast<float2*>(G + (size_t)m * N_pad + c0);
+            if (accumulate) { const float2 o = *dst; v.x += o.x; v.y += o.y; }
+            *dst = v;
+          }
+        }
+      }
+    }
+  }
+  // bias gradient (exact fp32 row sums)
+  for (int m = (int)threadIdx.x; m < M_pad; m += FRL_NT) {
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < R; ++r) s += sp_ld1(sY, r * ldy + m);
+    if (accumulate) s += gb[m];
+    gb[m] = s;
+  }
+  trace(71);
+  FRL_SYNC();
+  trace(72);
+}
+#endif   // FRL_MMA
 
 // ------------------------------------------------------------------------------------------------
 // layer / MLP passes

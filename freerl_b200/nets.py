@@ -18,8 +18,9 @@ def pad4(x):
 
 
 def wt_ld(out_pad):
-    """row stride of the transposed mirror (engine.cuh::wt_ld): padded so that stride/4 is odd"""
-    return out_pad if (out_pad >> 2) & 1 else out_pad + 4
+    """row stride of the transposed mirror: the library decides (engine.cuh::wt_ld_of — bank-conflict-free for its GEMM
+    microkernels), the host only lays the block out accordingly"""
+    return int(_lib.lib().frl_wt_ld(int(out_pad)))
 
 
 class DeviceNet:

@@ -22,7 +22,8 @@ def _ppo(golden, device, name, is_continue):
     perms = [g["perm/%d" % k] for k in range(2)]
     r = orc.learn(data, perms, 64, 0.99, 0.95, 0.2, 0.01)
     pol.learn(64, 0.99, 0.95, 0.2, 2, 0.01, permutations=perms)
-    np.testing.assert_allclose(pol.last_adv.cpu().numpy(), r["adv"].numpy(), rtol=1e-5, atol=1e-6)
+    # advantages are differences of value estimates of magnitude ~5 (one fp32 ulp = 4.8e-7): atol = 4 ulp of |V|
+    np.testing.assert_allclose(pol.last_adv.cpu().numpy(), r["adv"].numpy(), rtol=1e-5, atol=2e-6)
     np.testing.assert_allclose(pol.last_v_target.cpu().numpy(), r["v_target"].numpy(), rtol=1e-5, atol=1e-6)
     m = pol.last_metrics.cpu().numpy()
     ref = np.array(r["losses"])
