@@ -156,6 +156,8 @@ class _NStepMixin:
     def _push(self, obs, action, reward, next_obs, done, obs_dim):
         o = np.asarray(obs).reshape(-1, obs_dim)
         n = o.shape[0]
+        if n > 1 and len(self._deques) == 1 and len(self.n_step_deque) == 0:
+            return self._push_vec(o, action, reward, next_obs, done, obs_dim)
         while len(self._deques) < n:
             self._deques.append(deque(maxlen=self.n_step))
         a = np.asarray(action).reshape(n, -1)
@@ -172,6 +174,26 @@ class _NStepMixin:
             return None
         return (np.stack([x[0] for x in out]), np.stack([x[1] for x in out]), np.array([x[2] for x in out], np.float64),
                 np.stack([x[3] for x in out]), np.array([x[4] for x in out]))
+
+
+    def _push_vec(self, o, action, reward, next_obs, done, obs_dim):
+        """N vectorised envs stepping in lock-step: one window of the last n_step BATCHES, folded for all envs at once in
+        numpy float64 with the reference's expression order (r + gamma * R * (1 - d): identical bits to N python folds)."""
+        n = o.shape[0]
+        win = self.__dict__.setdefault("_vec_window", deque(maxlen=self.n_step))
+        if win and win[0][0].shape[0] != n:
+            raise ValueError("vectorised n-step adds must keep the same number of envs")
+        win.append((o, np.asarray(action).reshape(n, -1), np.asarray(reward, dtype=np.float64).reshape(n),
+                    np.asarray(next_obs).reshape(n, obs_dim), np.asarray(done).reshape(n).astype(bool)))
+        if len(win) < self.n_step:
+            return None
+        R, nobs, dn = win[-1][2].copy(), win[-1][3].copy(), win[-1][4].copy()
+        for i in range(self.n_step - 2, -1, -1):
+            _, _, r, n_o, d = win[i]
+            R = r + self.gamma * R * (1 - d)
+            nobs[d] = n_o[d]
+            dn = dn | d
+        return win[0][0], win[0][1], R, nobs, dn
 
 
 class N_Step_Buffer(Buffer, _NStepMixin):

@@ -100,3 +100,35 @@ def test_per_golden_gpu(golden):
 def test_per_random_gpu():
     _random_vs_oracle(torch.device("cuda"), 100000, 256, 4)   # reference-style 1e5 (non power of two), B = 256
     _random_vs_oracle(torch.device("cuda"), 1 << 14, 256, 3)
+
+
+def test_vectorised_nstep_fold_matches_per_env_folds():
+    """N lock-stepped envs folded at once (numpy float64) == N reference-style python folds, bit for bit."""
+    from collections import deque
+    from freerl_b200.per import _NStepMixin, _fold
+
+    class W(_NStepMixin):
+        pass
+    rng = np.random.default_rng(0)
+    w = W()
+    w._init_nstep(0.9, 3)
+    ref_win = [deque(maxlen=3) for _ in range(5)]
+    emitted = 0
+    for _ in range(9):
+        o, ac = rng.standard_normal((5, 2)), rng.integers(0, 3, (5, 1))
+        r, o2, d = rng.standard_normal(5), rng.standard_normal((5, 2)), rng.random(5) < 0.3
+        out = w._push(o, ac, r, o2, d, 2)
+        ref = []
+        for e in range(5):
+            ref_win[e].append((o[e], ac[e], float(r[e]), o2[e], bool(d[e])))
+            if len(ref_win[e]) == 3:
+                ref.append(_fold(ref_win[e], 0.9))
+        if out is None:
+            assert not ref
+            continue
+        emitted += 1
+        np.testing.assert_array_equal(out[0], np.stack([x[0] for x in ref]))
+        np.testing.assert_array_equal(out[2], np.array([x[2] for x in ref]))
+        np.testing.assert_array_equal(out[3], np.stack([x[3] for x in ref]))
+        np.testing.assert_array_equal(out[4], np.array([x[4] for x in ref]))
+    assert emitted == 7
