@@ -107,10 +107,12 @@ def peaks():
 
 
 def ncu_traffic():
-    p = os.path.join(ROOT, "profiles", "r1_sac_learn_ncu.json")
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE bench launch (256 learns) from the committed `ncu --set full`
+    capture of this same command (profiles/r1c_bench_sac_learn_ncu_full.json); None when no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "r1c_bench_sac_learn_ncu_full.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("dram_bytes_per_learn")
+            return json.load(open(p)).get("dram_bytes_per_launch")
         except Exception:
             return None
     return None
@@ -192,7 +194,7 @@ def main():
         if rank != 0:
             return
         w = max(args.warmup, 1)
-        val, ms, cores, tps = cpu_reference_arm(args.steps, w)
+        val, ms, cores, tps = cpu_reference_arm(args.steps, w, transitions_per_step=16)
         print(json.dumps({
             "impl": "reference", "metric": "env_steps_per_sec", "value": val, "unit": "env-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": w, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -213,7 +215,9 @@ def main():
     K = args.steps
     torch.manual_seed(1234 + rank)
     np.random.seed(1234 + rank)
-    pol = SAC([OBS, ACT], True, 1e-3, 1e-3, CAP, dev, trick={}, mode="fast")
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):      # the reference-style constructor prints; stdout carries ONE JSON line
+        pol = SAC([OBS, ACT], True, 1e-3, 1e-3, CAP, dev, trick={}, mode="fast")
     # pre-fill the per-GPU replay shard on the device
     g = torch.Generator(device=dev)
     g.manual_seed(99 + rank)
@@ -324,9 +328,9 @@ def main():
                      "note": "the fused update is FLOP/latency-bound at B=256 (SURVEY §7.3-1): params/Adam/targets are L2-resident"},
     }
     if not args.no_cpu_baseline and world == 1:
-        val, ms, cores, tps = cpu_reference_arm(6, 1)
+        val, ms, cores, tps = cpu_reference_arm(150, 1)
         out["cpu_baseline"] = {"value": val, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                               "sample": "6 steps x %d single-env iterations of the oracle port (np.random.choice over the full 1e6 replay + SAC learn B=256)" % tps}
+                               "sample": "150 steps x %d single-env iterations of the oracle port (np.random.choice over the full 1e6 replay + SAC learn B=256)" % tps}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -142,7 +142,16 @@ struct AcAlgo {
     const int tiles = (a.B + FRL_R - 1) / FRL_R, cap = max_ctas / (a.n_heads > 0 ? a.n_heads : 1);
     return tiles < cap ? tiles : (cap > 0 ? cap : 1);
   }
-  FRL_SHD int grid(const Args& a, int max_ctas) { return nslots_of(a, max_ctas) * a.n_heads; }
+  // Worker CTAs (row tile x critic head) run the GEMM stages; with FRL_AC_GRID > 0 the grid is padded with HELPER CTAs
+  // (up to FRL_AC_GRID, capped by the SM count) that only take part in the cross-CTA reduce / Adam / Polyak stages, whose
+  // parameter sweep is partitioned over ALL CTAs.
+#ifndef FRL_AC_GRID
+#define FRL_AC_GRID 96
+#endif
+  FRL_SHD int grid(const Args& a, int max_ctas) {
+    const int w = nslots_of(a, max_ctas) * a.n_heads, cap = FRL_AC_GRID < max_ctas ? FRL_AC_GRID : max_ctas;
+    return w > cap ? w : cap;
+  }
   FRL_SHD int n_updates(const Args& a) { return a.n_updates; }
 
   FRL_SDEV float noise_at(const float* ptr, const Args& a, int u, int row, int j, uint32_t stream) {
@@ -312,9 +321,11 @@ struct AcAlgo {
     const int ldh = act_ld(C.L[0].out_pad), sa = act_ld(C.L[0].in_pad), ap = P.ap;   // strides (bank-conflict free), not widths
     const int NA = P.NA, ai = P.ai;
     const int aip = P.aip;
-    const int nrole = a.n_heads, role = c.cta % nrole, slot = c.cta / nrole, nslots = c.ncta / nrole;
-    const int l0 = 3 * role;                                   // this CTA's critic head = layers l0..l0+2
     const int ntile = (a.B + FRL_R - 1) / FRL_R;
+    const int nrole = a.n_heads, role = c.cta % nrole, nslots = nslots_of(a, c.ncta);
+    const bool helper = c.cta >= nslots * nrole;               // reduce / optimiser stages only
+    const int slot = helper ? ntile : c.cta / nrole;           // helpers own no row tile: every tile loop is empty
+    const int l0 = 3 * role;                                   // this CTA's critic head = layers l0..l0+2
     const bool one_tile = ntile <= nslots;
     const float invB = 1.0f / (float)a.B;
     const bool sac = a.actor_kind == FRL_ACTOR_SAC;
@@ -352,7 +363,7 @@ struct AcAlgo {
     float* gp = a.gpart + (size_t)c.cta * gstride;
 
     if (s == 0) {
-      if (bon) {
+      if (bon && !helper) {
         bon_update(c, a, P, NORM, H1, u);    // H1..D2 (6 contiguous [R][ldh] tiles) are free scratch here
       }
       // ---------------- target action(s) + this role's target critic head ----------------
