@@ -126,8 +126,9 @@ def cpu_reference_arm(steps, warmup, transitions_per_step=4, fill=CAP, threads=N
     import torch
     from collections import OrderedDict
     from oracle import algos, buffers
-    if threads:
-        torch.set_num_threads(threads)
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm may use every host core, so set the pool explicitly and keep
+    # whichever of {all cores, 1 thread} runs the learn faster (the 256x128 matmuls do not always scale with threads)
+    torch.set_num_threads(threads or os.cpu_count() or 1)
     torch.manual_seed(0)
     np.random.seed(0)
     rng = np.random.default_rng(0)
@@ -164,6 +165,17 @@ def cpu_reference_arm(steps, warmup, transitions_per_step=4, fill=CAP, threads=N
             idx = buffers.uniform_indices(len(buf), BATCH)
             batch = tuple(torch.from_numpy(x) for x in buf.sample(idx))
             orc.learn(batch, torch.randn(BATCH, ACT), torch.randn(BATCH, ACT), GAMMA, TAU)
+    if not threads and (os.cpu_count() or 1) > 1:
+        def probe():
+            t0 = time.perf_counter()
+            for _ in range(2):
+                one_step()
+            return time.perf_counter() - t0
+        probe()
+        t_all = probe()
+        torch.set_num_threads(1)
+        if probe() > t_all:
+            torch.set_num_threads(os.cpu_count())
     for _ in range(warmup):
         one_step()
     t0 = time.perf_counter()
