@@ -148,30 +148,53 @@ extern "C" int frl_replay_gather(const frl_replay_t* rb, const int64_t* indices,
 
 // ------------------------------------------------------------------------------------------------
 // uniform sampling without replacement on the device (fast mode; NOT the numpy legacy stream)
-// One CTA per update: draw B indices, then redraw any element that collides with a lower-indexed one
-// until all are distinct.
+// One CTA per update.  Sparse regime (size >= 2B, every replay that has outgrown its first batches): draw B indices, then
+// redraw any element that collides with a lower-indexed one until all are distinct (expected < 2 rounds).  Dense regime
+// (size < 2B, e.g. the reference's first learns where B = min(len, batch_size) == len): rejection would need
+// coupon-collector many rounds, so a partial Fisher-Yates shuffle of [0, size) in shared memory is used instead.
 // ------------------------------------------------------------------------------------------------
 struct SampleAlgo {
   struct Args { int64_t* out; int64_t size; int B, n_updates; uint64_t seed, counter; };
   static const int NSTAGES = 1;
   FRL_SHD int wbuf_floats(const Args&) { return 32; }
-  FRL_SHD int user_floats(const Args& a) { return 2 * a.B + 64; }
+  FRL_SHD bool dense(const Args& a) { return a.size < 2 * (int64_t)a.B; }
+  FRL_SHD int user_floats(const Args& a) { return (dense(a) ? (int)a.size : 2 * a.B) + 64; }
   FRL_SHD int grid(const Args& a, int) { return a.n_updates; }
   FRL_SHD int n_updates(const Args&) { return 1; }
-  FRL_SDEV int64_t draw(const Args& a, int u, int i, int round) {
+  FRL_SDEV int64_t draw(const Args& a, int u, int i, int round) { return draw_below(a, u, i, round, (uint64_t)a.size); }
+  FRL_SDEV int64_t draw_below(const Args& a, int u, int i, int round, uint64_t range) {
     uint32_t o[4];
     frl_philox((uint32_t)a.seed, (uint32_t)(a.seed >> 32), (uint32_t)i, (uint32_t)round, (uint32_t)(a.counter + u),
                (uint32_t)((a.counter + u) >> 32) ^ 0x1d8e4e27u, o);
     const uint64_t x = ((uint64_t)o[0] << 32) | o[1];
 #ifndef FRL_EMUL
-    return (int64_t)__umul64hi(x, (uint64_t)a.size);
+    return (int64_t)__umul64hi(x, range);
 #else
-    return (int64_t)(((unsigned __int128)x * (unsigned __int128)a.size) >> 64);
+    return (int64_t)(((unsigned __int128)x * (unsigned __int128)range) >> 64);
 #endif
   }
   FRL_SDEV void stage(int, int, Cta& c, float* user, const Args& a) {
     const int u = c.cta;
     int* idx = (int*)user;            // sizes < 2^31 (checked by the host wrapper)
+    if (dense(a)) {
+      const int n = (int)a.size;
+      FRL_PAR(t) { for (int i = t; i < n; i += FRL_NT) idx[i] = i; }
+      FRL_SYNC();
+      FRL_PAR(t) {
+        if (t == 0) {
+          for (int i = 0; i < a.B; ++i) {
+            const int j = i + (int)draw_below(a, u, i, 0, (uint64_t)(n - i));
+            const int vi = idx[i];
+            idx[i] = idx[j];
+            idx[j] = vi;
+          }
+        }
+      }
+      FRL_SYNC();
+      FRL_PAR(t) { for (int i = t; i < a.B; i += FRL_NT) a.out[(size_t)u * a.B + i] = idx[i]; }
+      FRL_SYNC();
+      return;
+    }
     int* dup = idx + a.B;
     FRL_PAR(t) { for (int i = t; i < a.B; i += FRL_NT) { idx[i] = (int)draw(a, u, i, 0); dup[i] = 0; } }
     FRL_SYNC();

@@ -1,0 +1,309 @@
+"""BASELINE.json's configurations at their FULL sizes on the GPU (C2 SAC: 256 envs / 1 000 000-row replay / B 256;
+C3 PPO: 1024 envs x 128 steps, minibatch 8192; C4 Rainbow: 512 envs, PER capacity 1e6 (non-power-of-two heap), n-step 3;
+C5 MAPPO: 3 agents x 512 envs x horizon 256).  At these sizes a python-loop oracle over the whole store does not finish in
+seconds, so each case checks size-independent properties (round trips through the ring, distinctness and range of
+sampled indices, heap invariants, segment structure of the GAE scan) and runs the oracle only on what one learn() touches
+(the gathered rows / one minibatch epoch).  Tolerances as in the small-size parity tests: bit-exact for stored rows,
+indices and priorities; 1e-5 relative for fp32 losses."""
+import ctypes
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import algos
+from oracle import buffers as ob
+
+pytestmark = pytest.mark.gpu
+
+
+def _sd(module):
+    return OrderedDict((k, v.detach().cpu().clone()) for k, v in module.state_dict().items())
+
+
+def _rel(a, b):
+    return abs(a - b) / max(abs(b), 1e-12)
+
+
+# ------------------------------------------------------------------------------------------------ C2: ring replay
+def test_replay_1m_ring_roundtrip_and_wrap():
+    """Buffer(1e6, 17, 6): vector steps of 256 envs written across the wrap point come back bit-identical (float64 inputs are
+    cast to fp32 exactly like the reference's sample()), `_index` / `len` follow Buffer.py:29-38."""
+    from freerl_b200.Buffer import Buffer
+    dev = torch.device("cuda")
+    cap = int(1e6)
+    buf = Buffer(1e6, 17, 6, dev)                      # float capacity like the reference mains (buffer_size=1e6)
+    rng = np.random.default_rng(0)
+    host = {k: np.zeros((cap, w)) for k, w in (("obs", 17), ("act", 6), ("rew", 1), ("nobs", 17), ("done", 1))}
+    pos, size = 0, 0
+
+    def push(n):
+        nonlocal pos, size
+        o, a = rng.standard_normal((n, 17)), rng.uniform(-1, 1, (n, 6))            # float64, like gymnasium + numpy
+        r, o2, d = rng.standard_normal(n), rng.standard_normal((n, 17)), rng.random(n) < 0.01
+        buf.add(o, a, r, o2, d)
+        ix = (pos + np.arange(n)) % cap
+        host["obs"][ix], host["act"][ix], host["rew"][ix, 0], host["nobs"][ix], host["done"][ix, 0] = o, a, r, o2, d
+        pos, size = (pos + n) % cap, min(size + n, cap)
+
+    for _ in range(4):
+        push(249_000)                                   # 996 000 rows in big host batches
+    for _ in range(40):                                 # 10 240 more in 256-env vector steps: crosses the wrap
+        push(256)
+        assert (buf._index, len(buf)) == (pos, size)
+    assert len(buf) == cap and buf._index == (996_000 + 10_240) % cap
+    idx = np.concatenate([rng.integers(0, cap, 4096), np.arange(cap - 300, cap), np.arange(0, 300), [buf._index - 1, buf._index]])
+    got = buf.sample(idx)
+    for t, k in zip(got, ("obs", "act", "rew", "nobs", "done")):
+        assert t.dtype == torch.float32 and t.shape == (idx.size, host[k].shape[1])
+        assert np.array_equal(t.cpu().numpy(), host[k][idx].astype(np.float32)), k
+
+
+def test_uniform_sampler_1m_properties():
+    """frl_sample_uniform over 1e6 rows (the on-device replacement of np.random.choice(N, B, replace=False)): every batch
+    has B distinct in-range indices, different updates / counters give different batches, the same (seed, counter) repeats,
+    and the marginal is uniform (chi-square over 100 bins of 256 x 256 draws)."""
+    from freerl_b200 import _common
+    dev = torch.device("cuda")
+    a = _common.make_indices("fast", 1_000_000, 256, 256, dev, 1234, 7).cpu().numpy()
+    b = _common.make_indices("fast", 1_000_000, 256, 256, dev, 1234, 7).cpu().numpy()
+    c = _common.make_indices("fast", 1_000_000, 256, 256, dev, 1234, 8).cpu().numpy()
+    assert a.shape == (256, 256) and a.min() >= 0 and a.max() < 1_000_000
+    assert all(np.unique(r).size == 256 for r in a)
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    assert len({r.tobytes() for r in a}) == 256
+    hist = np.bincount(a.reshape(-1) // 10_000, minlength=100)
+    chi2 = ((hist - hist.mean()) ** 2 / hist.mean()).sum()
+    assert chi2 < 180, chi2                              # 99 dof: mean 99, sd 14
+    # small stores: B == N must return a permutation
+    p = _common.make_indices("fast", 256, 256, 4, dev, 1, 0).cpu().numpy()
+    assert all(np.array_equal(np.sort(r), np.arange(256)) for r in p)
+
+
+def test_sac_learn_on_1m_replay_vs_oracle():
+    """C2 at full size: 1 000 000 stored transitions, B = 256, reference RNG order (np.random.choice over the FULL store,
+    then two randn[B, act]); the oracle consumes the rows the indices select from a host mirror."""
+    from freerl_b200.SAC import SAC
+    dev = torch.device("cuda")
+    torch.manual_seed(3)
+    np.random.seed(3)
+    pol = SAC([17, 6], True, 1e-3, 1e-3, 1e6, dev, trick={})
+    rng = np.random.default_rng(1)
+    n = 1_000_000
+    host = [rng.standard_normal((n, 17), dtype=np.float32), rng.uniform(-1, 1, (n, 6)).astype(np.float32),
+            rng.standard_normal(n).astype(np.float32), rng.standard_normal((n, 17), dtype=np.float32), rng.random(n) < 0.005]
+    for s in range(0, n, 250_000):
+        pol.add(*[h[s:s + 250_000] for h in host])
+    assert len(pol.buffer) == n
+    orc = algos.SACOracle(_sd(pol.agent.actor), _sd(pol.agent.critic), 1e-3, 1e-3, act_dim=6)
+    t = lambda x: torch.from_numpy(np.asarray(x, dtype=np.float32))
+    for it in range(3):
+        st = np.random.get_state()
+        idx = np.random.choice(n, 256, replace=False)            # what the product path draws in parity mode
+        np.random.set_state(st)
+        n0, n1 = torch.randn(256, 6), torch.randn(256, 6)
+        batch = (t(host[0][idx]), t(host[1][idx]), t(host[2][idx]).reshape(-1, 1), t(host[3][idx]), t(host[4][idx]).reshape(-1, 1))
+        r = orc.learn(batch, n0, n1, 0.99, 0.01)
+        pol.learn(256, 0.99, 0.01, noise_next=n0[None], noise_new=n1[None])      # indices drawn inside, from numpy's stream
+        m = pol.last_metrics[0].cpu().numpy()
+        assert _rel(m[0], r["critic_loss"]) < 1e-5, (it, m[0], r["critic_loss"])
+        assert _rel(m[1], r["actor_loss"]) < 2e-5, (it, m[1], r["actor_loss"])
+    for k, v in pol.agent.critic.state_dict().items():
+        np.testing.assert_allclose(v.cpu().numpy(), orc.critic[k].detach().numpy(), rtol=1e-5, atol=2e-6, err_msg=k)
+    for k, v in pol.agent.actor_target.state_dict().items():
+        np.testing.assert_allclose(v.cpu().numpy(), orc.actor_target[k].detach().numpy(), rtol=1e-5, atol=2e-6, err_msg=k)
+    # 256 sequential learns in ONE launch (the bench configuration) stay finite and move the parameters
+    before = pol.agent._critic.p.clone()
+    pol.mode = "fast"
+    pol.learn(256, 0.99, 0.01, n_updates=256)
+    out = pol.last_metrics.cpu().numpy()
+    assert out.shape[0] == 256 and np.isfinite(out).all() and not torch.equal(before, pol.agent._critic.p)
+
+
+# ------------------------------------------------------------------------------------------------ C3: PPO 1024 envs
+def test_ppo_1024_envs_gae_and_minibatch_epoch_vs_oracle():
+    """C3 throughput shape: [T=128, N=1024] rollout (131 072 rows), minibatch 8192.  GAE: every env column equals the
+    reference's flat float64 scan of that column; then one epoch (16 minibatch updates) vs the oracle."""
+    from freerl_b200.PPO import PPO
+    dev = torch.device("cuda")
+    torch.manual_seed(0)
+    T, N, mb = 128, 1024, 8192
+    pol = PPO([8, 4], False, 1e-3, 1e-3, T * N, dev)
+    rng = np.random.default_rng(2)
+    cols = []
+    for t in range(T):
+        o, o2 = rng.standard_normal((N, 8), dtype=np.float32), rng.standard_normal((N, 8), dtype=np.float32)
+        a = rng.integers(0, 4, (N, 1)).astype(np.float32)
+        r, lp = rng.standard_normal(N).astype(np.float32), -np.abs(rng.standard_normal((N, 1))).astype(np.float32)
+        d = rng.random(N) < 1 / 300
+        ad = d | (rng.random(N) < 1 / 500)
+        pol.add(o, a, r, o2, d, lp, ad)
+        cols.append((o, a, r.reshape(N, 1), o2, d.reshape(N, 1).astype(np.float32), lp, ad.reshape(N, 1).astype(np.float32)))
+    assert len(pol.buffer) == T * N and pol.buffer.n_envs == N
+    data = tuple(torch.from_numpy(np.concatenate([c[k] for c in cols])) for k in range(7))      # time-major flat [T*N, .]
+    orc = algos.PPOOracle(_sd(pol.agent.actor), _sd(pol.agent.critic), 1e-3, False)
+    # oracle advantages per env column (vectorised float64 reverse scan == gae_reference on each column)
+    with torch.no_grad():
+        vs, vn = algos.mlp2(orc.critic, data[0]), algos.mlp2(orc.critic, data[3])
+        td = (data[2] + 0.99 * (1.0 - data[4]) * vn - vs).numpy().reshape(T, N).astype(np.float64)
+    adn = data[6].numpy().reshape(T, N).astype(np.float64)
+    want = np.zeros((T, N))
+    g = np.zeros(N)
+    for t in reversed(range(T)):
+        g = td[t] + 0.99 * 0.95 * g * (1.0 - adn[t])
+        want[t] = g
+    for j in (0, 517, 1023):
+        np.testing.assert_array_equal(want[:, j], algos.gae_reference(td[:, j], adn[:, j], 0.99, 0.95))
+    adv, vt = pol.compute_gae(0.99, 0.95)
+    np.testing.assert_allclose(adv.cpu().numpy().reshape(T, N), want.astype(np.float32), rtol=1e-5, atol=4e-6)
+    np.testing.assert_allclose(vt.cpu().numpy(), want.astype(np.float32).reshape(-1, 1) + vs.numpy(), rtol=1e-5, atol=4e-6)
+    # one epoch of 16 minibatches
+    perm = rng.permutation(T * N)
+    adv_o, vt_o = torch.from_numpy(want.astype(np.float32).reshape(-1, 1)), torch.from_numpy(want.astype(np.float32).reshape(-1, 1)) + vs
+    ref = [orc.minibatch(data, adv_o, vt_o, perm[s:s + mb], 0.2, 0.01) for s in range(0, T * N, mb)]
+    pol.learn(mb, 0.99, 0.95, 0.2, 1, 0.01, permutations=[perm])
+    m = pol.last_metrics.cpu().numpy()
+    assert m.shape[0] == 16
+    # Cautious-AdamW applies sign masks (m * g > 0), so two fp32 implementations of a CHAINED run separate exponentially
+    # once a mask bit flips (measured on B200: loss agreement 1e-7 for ~9 updates, then 3e-6, 2e-5, 3e-4 — the reference
+    # run against itself with a different BLAS shows the same).  Hence: tight on the first 8 updates, bounded afterwards.
+    ra, rc = np.array([x[0] for x in ref]), np.array([x[1] for x in ref])
+    np.testing.assert_allclose(m[:8, 0], ra[:8], rtol=3e-5, atol=2e-6)
+    np.testing.assert_allclose(m[:8, 1], rc[:8], rtol=3e-5, atol=2e-6)
+    np.testing.assert_allclose(m[:, 0], ra, rtol=5e-3, atol=1e-4)
+    np.testing.assert_allclose(m[:, 1], rc, rtol=5e-3, atol=1e-4)
+    for mod, o in ((pol.agent.actor, orc.actor), (pol.agent.critic, orc.critic)):
+        for k, v in mod.state_dict().items():
+            d = np.abs(v.cpu().numpy() - o[k].detach().numpy())
+            assert d.max() <= 4e-3 and d.mean() <= 2e-4, (k, d.max(), d.mean())        # 16 steps of lr 1e-3 moved them by ~1.6e-2
+
+
+# ------------------------------------------------------------------------------------------------ C4: PER at 1e6
+def test_per_1m_heap_invariants_and_sampling():
+    """PER_Buffer(1e6) (the reference default: leaves at two depths, rotated in-order sequence): after 512-env vector adds,
+    a stratified sample and an ordered priority update the float64 heap still satisfies parent == left + right to rounding,
+    the root equals the leaf sum, sampled indices are in range with priorities equal to their leaves, descents agree with the
+    numpy oracle walking the SAME heap, and IS weights follow Buffer.py:116-122."""
+    from freerl_b200.per import PER_Buffer
+    dev = torch.device("cuda")
+    cap = int(1e6)
+    per = PER_Buffer(1e6, 8, 1, dev)
+    rng = np.random.default_rng(4)
+    for _ in range(40):                                  # 20 480 transitions in 512-env steps (new leaves get max priority)
+        n = 512
+        per.add(rng.standard_normal((n, 8)), rng.integers(0, 4, (n, 1)), rng.standard_normal(n), rng.standard_normal((n, 8)),
+                rng.random(n) < 0.01)
+    assert len(per) == 20_480 and per.buffer._index == 20_480
+    tree = per.sumtree.tree.cpu().numpy()
+    assert tree.dtype == np.float64 and tree.size == 2 * cap - 1
+    assert np.array_equal(tree[cap - 1:cap - 1 + 20_480], np.ones(20_480)) and tree[cap - 1 + 20_480:].sum() == 0
+    assert tree[0] == 20_480.0                           # integers: exact
+    for rnd in range(3):
+        B = 256
+        u = rng.random(B)
+        beta_before = per.beta
+        idx, w, pri = per.sample_device(B, u=u)
+        idx, w, pri = idx.cpu().numpy(), w.cpu().numpy(), pri.cpu().numpy()
+        tree = per.sumtree.tree.cpu().numpy()
+        assert idx.min() >= 0 and idx.max() < len(per)
+        assert np.array_equal(pri.astype(np.float64), tree[idx + cap - 1].astype(np.float32).astype(np.float64)) or \
+            np.allclose(pri, tree[idx + cap - 1], rtol=1e-7)
+        # the oracle's descent over the same heap (Buffer.py:168-188)
+        st = ob.SumTreeOracle(cap)
+        st.tree = tree
+        seg = tree[0] / B
+        for i in range(B):
+            a, b = seg * i, seg * (i + 1)
+            p_i, i_i = st.find(a + (b - a) * u[i])
+            assert i_i == idx[i], (rnd, i)
+        beta = min(1.0, beta_before + 0.001)
+        assert float(per.beta) == beta
+        prob = np.clip(tree[idx + cap - 1] / tree[0], 1e-7, None)
+        ww = (len(per) * prob) ** (-beta)
+        np.testing.assert_allclose(w, (ww / ww.max()).astype(np.float32), rtol=1e-6)
+        td = rng.standard_normal((B, 1)).astype(np.float32) * 3
+        per.update_priorities(idx, td)
+        tree2 = per.sumtree.tree.cpu().numpy()
+        want_leaf = (np.abs(td.reshape(-1)) + np.float32(0.01)).astype(np.float32) ** 0.5      # alpha 0.5, eps 0.01
+        last = {}
+        for k, i in enumerate(idx):
+            last[int(i)] = k                                                                   # sequential adds: the last write wins
+        for i, k in last.items():
+            assert abs(tree2[i + cap - 1] - float(want_leaf[k])) <= 1e-7 * float(want_leaf[k])
+        inner = np.arange(cap - 1)
+        np.testing.assert_allclose(tree2[inner], tree2[2 * inner + 1] + tree2[2 * inner + 2], rtol=1e-12, atol=1e-9)
+        assert abs(tree2[0] - tree2[cap - 1:].sum()) <= 1e-9 * tree2[0]
+        assert per.sumtree.max() == tree2[cap - 1:].max()
+
+
+def test_rainbow_512_envs_nstep_per_learn():
+    """C4: 512 lock-stepped envs through N_Step_PER_Buffer (n = 3, capacity 1e6) — the folded transitions equal the
+    per-env reference folds — then fused Rainbow learns (B = 256) run with finite losses and every sampled index in range."""
+    from freerl_b200.DQN_with_tricks import DQN
+    dev = torch.device("cuda")
+    torch.manual_seed(0)
+    np.random.seed(0)
+    trick = {"Double": True, "Dueling": True, "PER": True, "Noisy": True, "N_Step": True, "Categorical": True}
+    pol = DQN([8, 4], False, 1e-3, 1e6, dev, trick=trick, gamma=0.99, batch_size=256)
+    rng = np.random.default_rng(6)
+    n, steps = 512, 8
+    seq = []
+    for _ in range(steps):
+        s = (rng.standard_normal((n, 8)), rng.integers(0, 4, (n, 1)), rng.standard_normal(n), rng.standard_normal((n, 8)),
+             rng.random(n) < 0.05)
+        seq.append(s)
+        pol.add(*s)
+    assert len(pol.buffer) == (steps - 2) * n
+    # per-env reference fold (DQN_file/Buffer.py:350-369) of env 37 and env 511
+    for e in (37, 511):
+        ref = ob.NStepPrioritizedReplay(64, 8, 1, gamma=0.99, n_step=3)
+        for s in seq:
+            ref.add(s[0][e], s[1][e], float(s[2][e]), s[3][e], bool(s[4][e]))
+        rows = np.arange(steps - 2) * n + e
+        got = pol.buffer.buffer.sample(rows)
+        want = ref.buffer.sample(np.arange(steps - 2))
+        for g_, w_ in zip(got, want):
+            assert np.array_equal(g_.cpu().numpy(), np.asarray(w_, dtype=np.float32).reshape(g_.shape))
+    for _ in range(3):
+        pol.learn(256, 0.99, 0.01)
+        idx = pol.last_indices.cpu().numpy()
+        assert idx.min() >= 0 and idx.max() < len(pol.buffer)
+        assert np.isfinite(float(pol.last_metrics[0]))
+    a = pol.select_action(rng.standard_normal((512, 8)).astype(np.float32))
+    assert a.shape == (512,) and a.min() >= 0 and a.max() < 4
+
+
+# ------------------------------------------------------------------------------------------------ C5: MAPPO 512 envs
+def test_gae_adv_norm_mappo_full_shape():
+    """C5: horizon 256 x 512 envs per agent.  frl_gae on [256, 512] vs the float64 column scan, and frl_adv_norm over the
+    joint [T*N_env, 3 agents] advantages vs torch ((adv - mean) / (std + 1e-8), MAPPO.py:385-386)."""
+    from freerl_b200 import _lib
+    dev = torch.device("cuda")
+    T, N = 256, 512
+    rng = np.random.default_rng(8)
+    rew, vs, vn = (rng.standard_normal((T, N)).astype(np.float32) for _ in range(3))
+    done = np.zeros((T, N), np.float32)
+    adone = np.zeros((T, N), np.float32)
+    adone[24::25] = 1.0                                                        # simple_spread: truncation every 25 steps
+    td = (torch.from_numpy(rew) + 0.95 * (1.0 - torch.from_numpy(done)) * torch.from_numpy(vn) - torch.from_numpy(vs)).numpy().astype(np.float64)
+    want = np.zeros((T, N))
+    g = np.zeros(N)
+    for t in reversed(range(T)):
+        g = td[t] + 0.95 * 0.95 * g * (1.0 - adone[t])
+        want[t] = g
+    d = lambda x: torch.from_numpy(x).to(dev)
+    r_, dn_, ad_, vs_, vn_ = d(rew), d(done), d(adone), d(vs), d(vn)
+    adv, vt = torch.empty((T, N), device=dev), torch.empty((T, N), device=dev)
+    _lib.check(_lib.lib().frl_gae(_lib.ptr(r_), _lib.ptr(dn_), _lib.ptr(ad_), _lib.ptr(vs_), _lib.ptr(vn_), T, N, 0.95, 0.95,
+                                  _lib.ptr(adv), _lib.ptr(vt), _lib.stream_ptr(dev)), "frl_gae")
+    np.testing.assert_allclose(adv.cpu().numpy(), want.astype(np.float32), rtol=2e-6, atol=2e-6)
+    # segments are independent: the last step of every 25-step episode has A_t = td_t exactly
+    np.testing.assert_allclose(adv.cpu().numpy()[24::25], td[24::25].astype(np.float32), rtol=1e-6, atol=1e-6)
+    x = torch.from_numpy((rng.standard_normal(T * N * 3) * 2 + 0.5).astype(np.float32))
+    out = torch.empty(T * N * 3, device=dev)
+    xd = x.to(dev)
+    _lib.check(_lib.lib().frl_adv_norm(_lib.ptr(xd), x.numel(), ctypes.c_float(1e-8), _lib.ptr(out), _lib.stream_ptr(dev)), "frl_adv_norm")
+    want_n = (x.double() - x.double().mean()) / (x.double().std() + 1e-8)
+    np.testing.assert_allclose(out.cpu().numpy(), want_n.float().numpy(), rtol=1e-5, atol=2e-6)
+    assert abs(float(out.mean())) < 1e-5 and abs(float(out.std()) - 1.0) < 1e-5
