@@ -1,9 +1,14 @@
 """Rainbow DQN with the reference's class API (``DQN_file/DQN_with_tricks.py:40-308``) on the fused B200 kernels.
 
 ``DQN(dim_info, is_continue, Qnet_lr, buffer_size, device, trick=None, gamma=None, batch_size=None)`` with the six
-tricks ``Double / Dueling / PER / Noisy / N_Step / Categorical``.  This build fuses the distributional core
-(Categorical + Dueling + Noisy — the ``DQN_Rainbow_`` configuration) and lets ``Double``, ``PER`` and
-``N_Step`` be switched; other sub-combinations of the three network tricks raise ``NotImplementedError``.
+tricks ``Double / Dueling / PER / Noisy / N_Step / Categorical``.  Two fused paths:
+
+* distributional core (Categorical + Dueling + Noisy — the ``DQN_Rainbow_`` configuration, the script's default trick set,
+  SURVEY App. A) with ``Double``, ``PER`` and ``N_Step`` switchable -> ``frl_rainbow_learn``;
+* the non-distributional branch (``DQN_with_tricks.py:261-283``): ``MLP`` or ``Dueling`` value net with any of ``Double``,
+  ``PER``, ``N_Step`` -> ``frl_dqn_learn`` with its trick flags.
+
+``Noisy`` without ``Categorical`` and ``Categorical`` without ``Dueling`` + ``Noisy`` raise ``NotImplementedError``.
 
 Reference behaviour kept: ``NoisyLinear`` resamples factorised noise from the torch CPU generator on EVERY forward
 (V then A, ``randn(in)`` then ``randn(out)``) — three forwards per ``learn`` (online(s') for Double, target(s'),
@@ -142,10 +147,168 @@ class Agent:
             mod.A.weight_epsilon.copy_(torch.ger(aout, ain).to(dev)); mod.A.bias_epsilon.copy_(aout.to(dev))
 
 
+TRICKS = ("Double", "Dueling", "PER", "Noisy", "N_Step", "Categorical")
+
+
 class DQN:
+    """Dispatches on the trick set like the reference's ``Agent.__init__`` (``DQN_with_tricks.py:163-172``)."""
+
+    def __new__(cls, dim_info=None, is_continue=None, Qnet_lr=None, buffer_size=None, device=None, trick=None, *args, **kw):
+        if cls is DQN:
+            cls = _RainbowDQN if (trick or {}).get("Categorical") else _ValueDQN
+        return object.__new__(cls)
+
+    @staticmethod
+    def load(dim_info, is_continue, model_dir, trick=None, device=None, gamma=0.99, batch_size=256):
+        """The reference's ``load`` omits gamma/batch_size and crashes for Categorical/N_Step (SURVEY §8b); here they default."""
+        device = device if device is not None else torch.device("cuda")
+        policy = DQN(dim_info, is_continue, 0, 0, device=device, trick=trick, gamma=gamma, batch_size=batch_size)
+        policy.agent.Qnet.load_state_dict(torch.load(os.path.join(model_dir, "DQN.pt"), map_location=device))
+        if (trick or {}).get('Noisy'):
+            for module in policy.agent.Qnet.children():
+                if isinstance(module, _NoisyShim):
+                    module.is_train = False
+        return policy
+
+
+class _ValueModule(nn.Module):
+    def forward(self, *a, **k):
+        raise RuntimeError("freerl_b200 modules are parameter containers; use select_action()")
+
+
+def _value_shim(net, dueling):
+    """state_dict schema of the reference's ``MLP`` (l1, l2) / ``Dueling`` (l1, V, A): the dueling head is ONE device layer
+    whose rows are [V | A_0..A_{n-1}]"""
+    mod = _ValueModule()
+    mod.l1 = _LinearShim(net.weight(0), net.bias(0))
+    if dueling:
+        mod.V = _LinearShim(net.weight(1)[0:1], net.bias(1)[0:1])
+        mod.A = _LinearShim(net.weight(1)[1:], net.bias(1)[1:])
+    else:
+        mod.l2 = _LinearShim(net.weight(1), net.bias(1))
+    mod.register_load_state_dict_post_hook(lambda module, incompatible: net.sync_mirror())
+    return mod
+
+
+class _ValueAgent:
+    def __init__(self, obs_dim, action_dim, Qnet_lr, device, dueling):
+        head = (1 + action_dim) if dueling else action_dim
+        dims = [(obs_dim, HIDDEN), (HIDDEN, head)]
+        self._q = DeviceNet(dims, device, trainable=True)
+        self._qt = DeviceNet(dims, device, trainable=False)
+        l1 = nn.Linear(obs_dim, HIDDEN)                         # reference construction order (RNG consumption)
+        with torch.no_grad():
+            self._q.weight(0).copy_(l1.weight)
+            self._q.bias(0).copy_(l1.bias)
+            if dueling:
+                V, A = nn.Linear(HIDDEN, 1), nn.Linear(HIDDEN, action_dim)
+                self._q.weight(1)[0:1].copy_(V.weight); self._q.bias(1)[0:1].copy_(V.bias)
+                self._q.weight(1)[1:].copy_(A.weight); self._q.bias(1)[1:].copy_(A.bias)
+            else:
+                l2 = nn.Linear(HIDDEN, action_dim)
+                self._q.weight(1).copy_(l2.weight); self._q.bias(1).copy_(l2.bias)
+        self._q.sync_mirror()
+        self._qt.copy_from(self._q)                             # deepcopy(self.Qnet)
+        self.Qnet, self.Qnet_target = _value_shim(self._q, dueling), _value_shim(self._qt, dueling)
+        self.lr, self.step = Qnet_lr, 0
+
+
+def _make_buffer(trick, buffer_size, obs_dim, act_dim, device, gamma, mode):
+    """``DQN_with_tricks.py:186-193``"""
+    if trick['PER'] and trick['N_Step']:
+        return N_Step_PER_Buffer(buffer_size, obs_dim, act_dim=act_dim, device=device, gamma=gamma, mode=mode)
+    if trick['PER']:
+        return PER_Buffer(buffer_size, obs_dim, act_dim=act_dim, device=device, mode=mode)
+    if trick['N_Step']:
+        return N_Step_Buffer(buffer_size, obs_dim, act_dim=act_dim, device=device, gamma=gamma)
+    return Buffer(buffer_size, obs_dim, act_dim=act_dim, device=device)
+
+
+class _ValueDQN(DQN):
+    """Non-distributional branch: MLP / Dueling value net + Double / PER / N-step (``DQN_with_tricks.py:261-283``)."""
+
     def __init__(self, dim_info, is_continue, Qnet_lr, buffer_size, device, trick=None, gamma=None, batch_size=None, mode=None):
         obs_dim, action_dim = dim_info
         self.device = _lib.require_device(device)
+        trick = dict({k: False for k in TRICKS}, **(trick or {}))
+        if trick['Noisy']:
+            raise NotImplementedError("freerl_b200: NoisyLinear is fused only in the Categorical (Rainbow) kernel")
+        self.trick = trick
+        self.agent = _ValueAgent(obs_dim, action_dim, Qnet_lr, self.device, bool(trick['Dueling']))
+        self.buffer = _make_buffer(trick, buffer_size, obs_dim, action_dim if is_continue else 1, self.device, gamma, mode)
+        self.is_continue = is_continue
+        self.obs_dim, self.action_dim = obs_dim, action_dim
+        self.mode = _common.resolve_mode(mode)
+        self._scratch = _common.DeviceScratch(self.device, self.agent._q.n_p)
+        self._seed = _common.default_seed()
+        self._n_learn = 0
+        self.last_metrics = None
+
+    def select_action(self, obs):
+        if self.is_continue:
+            raise RuntimeError("DQN is not suitable for continuous action spaces (use dis_to_con)")
+        x, single = _common.as_obs_batch(obs, self.obs_dim)
+        mode = _lib.INFER_ARGMAX_DUELING if self.trick['Dueling'] else _lib.INFER_ARGMAX
+        a = _common.infer(self.agent._q, x, mode, self.device, 1).reshape(-1).to(torch.int64).cpu().numpy()
+        return a[0] if single else a
+
+    def evaluate_action(self, obs):
+        return self.select_action(obs)
+
+    def add(self, obs, action, reward, next_obs, done):
+        self.buffer.add(obs, action, reward, next_obs, done)
+
+    sample = None      # bound below (same body as the distributional class)
+
+    def learn(self, batch_size, gamma, tau, *, u=None, indices=None):
+        total = len(self.buffer)
+        B = min(batch_size, total)
+        per = bool(self.trick['PER'])
+        if per:
+            idx, w, _ = self.buffer.sample_device(B, u=u)
+        else:
+            w = None
+            idx = _common.make_indices(self.mode, total, B, 1, self.device, self._seed, self._n_learn).reshape(-1) if indices is None \
+                else self.buffer._indices_to_device(indices).reshape(-1)
+            B = idx.numel()
+        if self.trick['N_Step']:
+            gamma = self.buffer.n_step_gamma
+        ag = self.agent
+        td = torch.empty((B, 1), dtype=torch.float32, device=self.device)
+        a = _lib.DqnArgs()
+        a.q, a.q_target = ag._q.c_struct(), ag._qt.c_struct()
+        a.replay = (self.buffer.buffer if per else self.buffer).c_struct()
+        a.indices, a.B, a.n_updates = idx.data_ptr(), B, 1
+        a.gamma, a.tau = gamma, tau
+        a.lr, a.beta1, a.beta2, a.eps = ag.lr, 0.9, 0.999, 1e-8
+        a.step0 = ag.step
+        out = self._scratch.out(1, self.device)
+        a.gpart, a.stats, a.out = self._scratch.gpart.data_ptr(), self._scratch.stats.data_ptr(), out.data_ptr()
+        a.double_q, a.dueling = int(bool(self.trick['Double'])), int(bool(self.trick['Dueling']))
+        a.is_weight = w.data_ptr() if w is not None else None
+        a.td_error = td.data_ptr()
+        _lib.check(_lib.lib().frl_dqn_learn(ctypes.byref(a), _lib.stream_ptr(self.device)), "frl_dqn_learn")
+        ag.step += 1
+        self._n_learn += 1
+        if per:
+            self.buffer.update_priorities(idx, td)                  # td_error [B,1] like the reference (:278)
+        self.last_metrics = out[0]
+        self.last_error, self.last_indices = td, idx
+
+    def update_target(self, tau):
+        t, s_ = self.agent._qt, self.agent._q
+        t.p.mul_(1.0 - tau).add_(s_.p * tau)
+        t.sync_mirror()
+
+    def save(self, model_dir):
+        torch.save({k: v.detach().clone().cpu() for k, v in self.agent.Qnet.state_dict().items()}, os.path.join(model_dir, "DQN.pt"))
+
+
+class _RainbowDQN(DQN):
+    def __init__(self, dim_info, is_continue, Qnet_lr, buffer_size, device, trick=None, gamma=None, batch_size=None, mode=None):
+        obs_dim, action_dim = dim_info
+        self.device = _lib.require_device(device)
+        trick = dict({k: False for k in TRICKS}, **(trick or {}))
         self.trick = trick
         self.agent = Agent(obs_dim, action_dim, Qnet_lr, self.device, trick=trick, batch_size=batch_size)
         act_dim = action_dim if is_continue else 1
@@ -293,14 +456,5 @@ class DQN:
         self.agent._refresh_buffers()
         torch.save({k: v.detach().clone().cpu() for k, v in self.agent.Qnet.state_dict().items()}, os.path.join(model_dir, "DQN.pt"))
 
-    @staticmethod
-    def load(dim_info, is_continue, model_dir, trick=None, device=None, gamma=0.99, batch_size=256):
-        """The reference's ``load`` omits gamma/batch_size and crashes for Categorical/N_Step (SURVEY §8b); here they default."""
-        device = device if device is not None else torch.device("cuda")
-        policy = DQN(dim_info, is_continue, 0, 0, device=device, trick=trick, gamma=gamma, batch_size=batch_size)
-        policy.agent.Qnet.load_state_dict(torch.load(os.path.join(model_dir, "DQN.pt"), map_location=device))
-        if trick['Noisy']:
-            for module in policy.agent.Qnet.children():
-                if isinstance(module, _NoisyShim):
-                    module.is_train = False
-        return policy
+
+_ValueDQN.sample = _RainbowDQN.sample

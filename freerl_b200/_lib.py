@@ -35,7 +35,8 @@ class DqnArgs(C.Structure):
     _fields_ = [("q", Net), ("q_target", Net), ("replay", Replay), ("indices", C.c_void_p), ("B", C.c_int),
                 ("n_updates", C.c_int), ("gamma", C.c_float), ("tau", C.c_float), ("lr", C.c_double),
                 ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("step0", C.c_int64),
-                ("gpart", C.c_void_p), ("stats", C.c_void_p), ("out", C.c_void_p)]
+                ("gpart", C.c_void_p), ("stats", C.c_void_p), ("out", C.c_void_p),
+                ("double_q", C.c_int), ("dueling", C.c_int), ("is_weight", C.c_void_p), ("td_error", C.c_void_p)]
 
 
 class AcArgs(C.Structure):
@@ -95,6 +96,7 @@ OPT_CAUTIOUS_ADAMW, OPT_ADAM = 0, 1
 NSEG = 2 * FRL_MAX_LAYERS + 1
 ACTOR_TANH, ACTOR_SAC = 0, 1
 INFER_ARGMAX, INFER_TANH, INFER_SAC_SAMPLE, INFER_SAC_MEAN, INFER_RAW, INFER_PPO_GAUSS, INFER_PPO_CAT = 0, 1, 2, 3, 4, 5, 6
+INFER_ARGMAX_DUELING = 7
 
 _lib = None
 

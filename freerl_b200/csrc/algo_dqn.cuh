@@ -76,7 +76,7 @@ struct DqnAlgo {
   }
   FRL_SHD int user_floats(const Args& a) {
     const int ldh = act_ld(a.q.L[0].out_pad), in_pad = a.q.L[0].in_pad, op = a.q.L[a.q.n_layers - 1].out_pad;
-    return FRL_R * (a.replay.row_floats + 2 * in_pad + 3 * ldh + 3 * op + 8) + FRL_NT + 64;
+    return FRL_R * (a.replay.row_floats + 2 * in_pad + 3 * ldh + 4 * op + 8) + FRL_NT + 64;
   }
   FRL_SHD int grid(const Args& a, int max_ctas) {
     int tiles = (a.B + FRL_R - 1) / FRL_R;
@@ -87,7 +87,9 @@ struct DqnAlgo {
   FRL_SDEV void stage(int s, int u, Cta& c, float* user, const Args& a) {
     const frl_net_t& q = a.q;
     const int nl = q.n_layers;
-    const int ldh = act_ld(q.L[0].out_pad), in_pad = q.L[0].in_pad, op = q.L[nl - 1].out_pad, nact = q.L[nl - 1].out;
+    const int ldh = act_ld(q.L[0].out_pad), in_pad = q.L[0].in_pad, op = q.L[nl - 1].out_pad;
+    const int c0 = a.dueling ? 1 : 0;                          // first action column of the head ([V | A] when dueling)
+    const int nact = q.L[nl - 1].out - c0;
     if (s == 0) {
       SmemBump sb; sb.p = user;
       float* raw = sb.take(FRL_R * a.replay.row_floats);
@@ -99,12 +101,24 @@ struct DqnAlgo {
       float* Q = sb.take(FRL_R * op);
       float* Qt = sb.take(FRL_R * op);
       float* dQ = sb.take(FRL_R * op);
+      float* Qn = sb.take(FRL_R * op);               // Double: online net on next_obs
       float* lossr = sb.take(FRL_NT);
       float* gp = a.gpart + (size_t)c.cta * q.n_p;
       const int ntile = (a.B + FRL_R - 1) / FRL_R;
       const float invB = 1.0f / (float)a.B;
       float loss_acc = 0.f;   // block-uniform (only thread 0's copy is used on the GPU)
       bool first = true;
+      // PER: the reference multiplies is_weight [B] with td_error^2 [B,1] -> mean over [B,B] = mean(w) * mean(td^2)
+      float wmean = 1.f;
+      if (a.is_weight) {
+        FRL_PAR(t) {
+          float sw = 0.f;
+          for (int i = t; i < a.B; i += FRL_NT) sw += a.is_weight[i];
+          lossr[t] = sw;
+        }
+        FRL_SYNC();
+        wmean = block_sum(lossr) * invB;
+      }
       for (int tile = c.cta; tile < ntile; tile += c.ncta) {
         const int row0 = tile * FRL_R;
         const int nvalid = (a.B - row0) < FRL_R ? (a.B - row0) : FRL_R;
@@ -114,6 +128,7 @@ struct DqnAlgo {
         copy_cols<FRL_R>(Xn, in_pad, 0, raw, a.replay.row_floats, rb_col_nobs(a.replay), a.replay.obs_dim, in_pad);
         // target net on next_obs, online net on obs
         mlp_fwd<FRL_R>(c, a.q_target, 0, nl, Xn, in_pad, Ht, Ht, ldh, Qt, op, FRL_ACT_NONE, fwd_hint(q, 0));
+        if (a.double_q) mlp_fwd<FRL_R>(c, q, 0, nl, Xn, in_pad, Ht, Ht, ldh, Qn, op, FRL_ACT_NONE, fwd_hint(q, 0));
         mlp_fwd<FRL_R>(c, q, 0, nl, Xo, in_pad, H1, H1, ldh, Q, op, FRL_ACT_NONE, nl > 1 ? bwd_hint(q, nl - 1) : no_hint());
         // TD target, loss, dL/dQ  (DQN.py:110-116)
         FRL_PAR(t) {
@@ -122,14 +137,46 @@ struct DqnAlgo {
             const int r = t;
             for (int j = 0; j < op; ++j) dQ[r * op + j] = 0.f;
             if (r < nvalid) {
-              float mx = Qt[r * op];
-              for (int j = 1; j < nact; ++j) mx = fmaxf(mx, Qt[r * op + j]);
+              // Dueling: Q_j = (V + A_j) - mean(A)  (DQN_with_tricks.py:79); plain head: Q_j = head_j
+              float mt = 0.f, mn = 0.f, mo = 0.f;
+              if (a.dueling) {
+                float st = 0.f, sn = 0.f, so = 0.f;
+                for (int j = 0; j < nact; ++j) {
+                  st = fadd(st, Qt[r * op + 1 + j]);
+                  so = fadd(so, Q[r * op + 1 + j]);
+                  if (a.double_q) sn = fadd(sn, Qn[r * op + 1 + j]);
+                }
+                mt = fdiv(st, (float)nact); mo = fdiv(so, (float)nact); mn = fdiv(sn, (float)nact);
+              }
+              const float vt = a.dueling ? Qt[r * op] : 0.f, vo = a.dueling ? Q[r * op] : 0.f, vn = (a.dueling && a.double_q) ? Qn[r * op] : 0.f;
+              float nq;
+              if (a.double_q) {                       // first max of the online net's Q(s'), like torch.argmax
+                int best = 0;
+                float bv = a.dueling ? fadd(fadd(vn, Qn[r * op + 1]), -mn) : Qn[r * op];
+                for (int j = 1; j < nact; ++j) {
+                  const float qv = a.dueling ? fadd(fadd(vn, Qn[r * op + 1 + j]), -mn) : Qn[r * op + j];
+                  if (qv > bv) { bv = qv; best = j; }
+                }
+                nq = a.dueling ? fadd(fadd(vt, Qt[r * op + 1 + best]), -mt) : Qt[r * op + best];
+              } else {
+                nq = a.dueling ? fadd(fadd(vt, Qt[r * op + 1]), -mt) : Qt[r * op];
+                for (int j = 1; j < nact; ++j) nq = fmaxf(nq, a.dueling ? fadd(fadd(vt, Qt[r * op + 1 + j]), -mt) : Qt[r * op + j]);
+              }
               const float rew = raw[r * a.replay.row_floats + rb_col_rew(a.replay)];
               const float dn = raw[r * a.replay.row_floats + rb_col_done(a.replay)];
-              const float y = fadd(rew, fmul(fmul(a.gamma, mx), fadd(1.f, -dn)));
+              const float y = fadd(rew, fmul(fmul(a.gamma, nq), fadd(1.f, -dn)));
               const int act = (int)raw[r * a.replay.row_floats + rb_col_act(a.replay)];
-              const float diff = Q[r * op + act] - y;
-              dQ[r * op + act] = 2.f * diff * invB;
+              const float cur = a.dueling ? fadd(fadd(vo, Q[r * op + 1 + act]), -mo) : Q[r * op + act];
+              const float diff = cur - y;
+              const float gq = 2.f * diff * invB * wmean;
+              if (a.dueling) {                        // dV = g, dA_j = g * (delta_ja - 1/n)
+                dQ[r * op] = gq;
+                const float gm = gq / (float)nact;
+                for (int j = 0; j < nact; ++j) dQ[r * op + 1 + j] = (j == act ? gq : 0.f) - gm;
+              } else {
+                dQ[r * op + act] = gq;
+              }
+              if (a.td_error) a.td_error[(size_t)u * a.B + row0 + r] = diff;
               l = diff * diff;
             }
           }
@@ -140,7 +187,7 @@ struct DqnAlgo {
         mlp_bwd<FRL_R>(c, q, 0, nl, Xo, in_pad, H1, H1, ldh, dQ, op, D1, D1, nullptr, 0, gp, !first, no_hint());
         first = false;
       }
-      FRL_PAR(t) { if (t == 0) a.stats[c.cta * 8 + 0] = loss_acc; }
+      FRL_PAR(t) { if (t == 0) { a.stats[c.cta * 8 + 0] = loss_acc; a.stats[c.cta * 8 + 1] = wmean; } }
       FRL_SYNC();
     } else {
       // stage 1: cross-CTA reduce + Adam + Polyak on this CTA's parameter slice (no global norm needed)
@@ -151,7 +198,7 @@ struct DqnAlgo {
       FRL_PAR(t) {
         if (c.cta == 0 && t == 0) {
           const float l = strided_sum(a.stats, 8, ncontrib);
-          a.out[u * 8 + 0] = l / (float)a.B;
+          a.out[u * 8 + 0] = l / (float)a.B * a.stats[1];
         }
       }
       FRL_SYNC();

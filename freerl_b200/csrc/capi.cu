@@ -328,6 +328,19 @@ struct InferAlgo {
           for (int j = 1; j < nout; ++j) if (O[t * op + j] > bv) { bv = O[t * op + j]; best = j; }   // first max, like torch.argmax
           a.out[(size_t)(row0 + t) * a.out_cols] = (float)best;
         }
+      } else if (a.mode == FRL_INFER_ARGMAX_DUELING) {
+        if (t < nvalid) {
+          const int na = nout - 1;
+          float sA = 0.f;
+          for (int j = 0; j < na; ++j) sA = fadd(sA, O[t * op + 1 + j]);
+          const float mean = fdiv(sA, (float)na), V = O[t * op];
+          int best = 0; float bv = fadd(fadd(V, O[t * op + 1]), -mean);
+          for (int j = 1; j < na; ++j) {
+            const float qv = fadd(fadd(V, O[t * op + 1 + j]), -mean);
+            if (qv > bv) { bv = qv; best = j; }
+          }
+          a.out[(size_t)(row0 + t) * a.out_cols] = (float)best;
+        }
       } else if (a.mode == FRL_INFER_PPO_CAT) {
         // Categorical(logits).sample() == argmax(softmax(logits) / q), q ~ Exp(1)  (torch.multinomial, 1 draw)
         if (t < nvalid) {

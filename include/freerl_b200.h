@@ -78,6 +78,11 @@ typedef struct {
   float* gpart;             /* dev scratch [frl_device_sm_count()][q.n_p] */
   float* stats;             /* dev scratch [frl_device_sm_count()][8] */
   float* out;               /* dev [n_updates][8]: out[u][0] = loss */
+  /* non-distributional tricks of DQN_file/DQN_with_tricks.py:261-283 (all 0 / NULL = plain DQN.py) */
+  int double_q;             /* Double: a* = argmax_a Q(s') of the ONLINE net, evaluated by the target net (:263-265) */
+  int dueling;              /* Dueling (:60-79): last layer rows = [V | A_0..A_{n-1}] (out = 1 + n_actions), Q = V + A - mean(A) */
+  const float* is_weight;   /* PER (:276-278): dev [B] IS weights; loss = mean over the [B,B] product w_j * td_i^2 */
+  float* td_error;          /* dev [n_updates][B] or NULL: Q(s,a) - y per sampled row (the PER priorities' input) */
 } frl_dqn_args_t;
 
 enum { FRL_ACTOR_TANH = 0, FRL_ACTOR_SAC = 1 };
@@ -125,6 +130,8 @@ typedef struct {
   int64_t obs_norm_n0;      /* updates folded in before this call */
 } frl_ac_args_t;
 
+/* FRL_INFER_ARGMAX_DUELING (7): argmax_a of V + A_a - mean(A) for a [V | A] head (Dueling.forward, DQN_with_tricks.py:75-79) */
+enum { FRL_INFER_ARGMAX_DUELING = 7 };
 enum { FRL_INFER_ARGMAX = 0, FRL_INFER_TANH = 1, FRL_INFER_SAC_SAMPLE = 2, FRL_INFER_SAC_MEAN = 3, FRL_INFER_RAW = 4,
        FRL_INFER_PPO_GAUSS = 5,   /* out = [action(act) | log_prob per dim(act)], noise = N(0,1) [n][act] */
        FRL_INFER_PPO_CAT = 6 };   /* out = [action index | log_prob], noise = Exp(1) [n][n_actions] (torch.multinomial trick) */

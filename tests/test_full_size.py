@@ -166,8 +166,8 @@ def test_ppo_1024_envs_gae_and_minibatch_epoch_vs_oracle():
     m = pol.last_metrics.cpu().numpy()
     assert m.shape[0] == 16
     # Cautious-AdamW applies sign masks (m * g > 0), so two fp32 implementations of a CHAINED run separate exponentially
-    # once a mask bit flips (measured on B200: loss agreement 1e-7 for ~9 updates, then 3e-6, 2e-5, 3e-4 — the reference
-    # run against itself with a different BLAS shows the same).  Hence: tight on the first 8 updates, bounded afterwards.
+    # once a mask bit flips (measured on B200: loss agreement 1e-7 for ~9 updates, then 3e-6, 2e-5, 3e-4).
+    # Hence: tight on the first 8 updates, bounded afterwards.
     ra, rc = np.array([x[0] for x in ref]), np.array([x[1] for x in ref])
     np.testing.assert_allclose(m[:8, 0], ra[:8], rtol=3e-5, atol=2e-6)
     np.testing.assert_allclose(m[:8, 1], rc[:8], rtol=3e-5, atol=2e-6)
