@@ -191,6 +191,7 @@ class PPO:
         a.max_norm_actor = a.max_norm_critic = self.max_norm
         a.optimizer = self.optimizer
         a.lr, a.beta1, a.beta2, a.eps = ag.lr, 0.9, 0.999, self.adam_eps
+        a.lr_critic = float(getattr(ag, "lr_critic", 0.0))        # separate actor / critic Adams (PPO_advance); 0 = merged
         a.step0 = ag.step
         a.gpart, a.sumsq, a.segcnt = self._gpart.data_ptr(), self._sumsq.data_ptr(), self._segcnt.data_ptr()
         a.stats, a.out = self._stats.data_ptr(), out.data_ptr()

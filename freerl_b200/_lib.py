@@ -74,7 +74,8 @@ class PpoArgs(C.Structure):
                 ("layer_norm", C.c_int), ("critic_obs", C.c_void_p), ("critic_obs_dim", C.c_int), ("value_loss", C.c_int),
                 ("huber_delta", C.c_float), ("stage_lo", C.c_int), ("stage_hi", C.c_int), ("grad_scale", C.c_float),
                 ("gpart", C.c_void_p),
-                ("sumsq", C.c_void_p), ("segcnt", C.c_void_p), ("stats", C.c_void_p), ("out", C.c_void_p)]
+                ("sumsq", C.c_void_p), ("segcnt", C.c_void_p), ("stats", C.c_void_p), ("out", C.c_void_p),
+                ("lr_critic", C.c_double)]
 
 
 class NoisyMap(C.Structure):

@@ -383,6 +383,7 @@ struct PpoAlgo {
           sh[2] = (float)(a.lr * sqrt(bc2) / bc1);         // c_adamw step_size
           sh[3] = (float)(-(a.lr / bc1));                   // torch Adam: -lr/bc1
           sh[4] = (float)sqrt(bc2);
+          sh[5] = (float)(-((a.lr_critic > 0.0 ? a.lr_critic : a.lr) / bc1));
           if (s == 3 && c.cta == 0) {
             const float l0 = strided_sum(a.stats, 8, ncontrib), l1 = strided_sum(a.stats + 1, 8, ncontrib), l2 = strided_sum(a.stats + 2, 8, ncontrib);
             const float ent_mean = l2 / (float)rows;
@@ -396,19 +397,20 @@ struct PpoAlgo {
         if (t < FRL_NSEG) segc[t] = 0;
       }
       FRL_SYNC();
-      const float coef_a = sh[0], coef_c = sh[1], step_size = sh[2], adam_step = sh[3], bc2s = sh[4];
+      const float coef_a = sh[0], coef_c = sh[1], step_size = sh[2], adam_step = sh[3], bc2s = sh[4], adam_step_c = sh[5];
       const float b1 = (float)a.beta1, b2 = (float)a.beta2, omb1 = (float)(1.0 - a.beta1), omb2 = (float)(1.0 - a.beta2);
       const float eps = (float)a.eps;
       if (a.optimizer == FRL_OPT_ADAM) {
         if (s == 4) return;
         FRL_PAR(t) {
           for (int p = c.cta * FRL_NT + t; p < N.n_p; p += c.ncta * FRL_NT) {
-            const float g = N.g[p] * (is_critic(N, p) ? coef_c : coef_a);
+            const bool crit = is_critic(N, p);
+            const float g = N.g[p] * (crit ? coef_c : coef_a);
             float m = N.m[p], v = N.v[p], w = N.p[p];
             m = fmaf(omb1, g - m, m);
             v = fadd(fmul(v, b2), fmul(fmul(omb2, g), g));
             const float denom = fadd(fdiv(fsqrt(v), bc2s), eps);
-            w = fadd(w, fdiv(fmul(adam_step, m), denom));
+            w = fadd(w, fdiv(fmul(crit ? adam_step_c : adam_step, m), denom));
             N.m[p] = m; N.v[p] = v; N.p[p] = w;
             const int mi = mirror_index(N, p);
             if (mi >= 0) N.pt[mi] = w;

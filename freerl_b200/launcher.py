@@ -22,6 +22,7 @@ _ALGOS = {            # script file name -> (class name in the script, our modul
     "TD3.py": ("TD3", "freerl_b200.TD3", "TD3"),
     "DDPG.py": ("DDPG", "freerl_b200.DDPG", "DDPG"),
     "PPO.py": ("PPO", "freerl_b200.PPO", "PPO"),
+    "PPO_advance/PPO.py": ("PPO", "freerl_b200.PPO_advance", "PPO"),      # keyed by <dir>/<file> where names collide
     "MADDPG.py": ("MADDPG", "freerl_b200.MADDPG", "MADDPG"),
     "MAPPO.py": ("MAPPO", "freerl_b200.MAPPO", "MAPPO"),
 }
@@ -47,9 +48,10 @@ def _is_main_guard(node):
 def run_reference_script(script_path, argv=(), results_root="./freerl_runs", extra_rebinds=None):
     script_path = os.path.abspath(script_path)
     fname = os.path.basename(script_path)
-    if fname not in _ALGOS:
+    qual = os.path.basename(os.path.dirname(script_path)) + "/" + fname
+    if qual not in _ALGOS and fname not in _ALGOS:
         raise ValueError("no freerl_b200 class for %s (supported: %s)" % (fname, sorted(_ALGOS)))
-    cls_name, mod_name, our_name = _ALGOS[fname]
+    cls_name, mod_name, our_name = _ALGOS.get(qual) or _ALGOS[fname]
     sys.modules["Buffer"] = buffer_module()
     try:
         importlib.import_module("gymnasium")

@@ -186,6 +186,8 @@ typedef struct {
   float* segcnt;            /* dev scratch [sm_count][2*FRL_MAX_LAYERS+1] cautious-mask counts per tensor */
   float* stats;             /* dev scratch [sm_count][8] */
   float* out;               /* dev [n_updates][8]: actor_loss, critic_loss, entropy, actor_gnorm, critic_gnorm */
+  double lr_critic;         /* FRL_OPT_ADAM only: learning rate of the critic layers (separate actor / critic Adams of
+                             * PPO_advance/PPO.py:118-119); 0 = use `lr` for both (merged optimiser) */
 } frl_ppo_args_t;
 
 /* Rainbow (DQN_with_tricks.py): Categorical + Dueling + Noisy net.  The trainable block holds the torch tensors;

@@ -413,3 +413,40 @@ class PPOOracle:
                 losses.append(self.minibatch(data, adv, v_target, perm[s:s + minibatch_size], clip_param,
                                              entropy_coefficient))
         return {"adv": adv, "v_target": v_target, "losses": losses}
+
+
+class PPOAdvanceOracle(PPOOracle):
+    """``PPO_advance/PPO.py:118-119,122-133,198-260``: the standard PPO — separate ``torch.optim.Adam`` (eps 1e-8) for actor
+    (``actor_lr``) and critic (``critic_lr``), ``clip_grad_norm_(0.5)`` each, actor step then critic step per minibatch;
+    the discrete actor returns ``softmax`` probabilities fed to ``Categorical(probs=...)`` (``:89,236``)."""
+
+    def __init__(self, actor, critic, actor_lr, critic_lr, is_continue):
+        self.actor, self.critic = _leaf(actor), _leaf(critic)
+        self.is_continue = is_continue
+        self.opt_a = AdamState(list(self.actor.values()), actor_lr)
+        self.opt_c = AdamState(list(self.critic.values()), critic_lr)
+
+    def minibatch(self, data, adv, v_target, index, clip_param, entropy_coefficient):
+        obs, action, reward, next_obs, done, logp_old, adv_dones = data
+        if self.is_continue:
+            mean, std = ppo_actor_cont(self.actor, obs[index])
+            dist = torch.distributions.Normal(mean, std)
+            ent = dist.entropy().sum(dim=1, keepdim=True)
+            logp = dist.log_prob(action[index])
+        else:
+            dist = torch.distributions.Categorical(probs=torch.softmax(mlp2(self.actor, obs[index]), dim=1))
+            ent = dist.entropy().reshape(-1, 1)
+            logp = dist.log_prob(action[index].reshape(-1)).reshape(-1, 1)
+        ratios = torch.exp(logp.sum(dim=1, keepdim=True) - logp_old[index].sum(dim=1, keepdim=True))
+        surr1 = ratios * adv[index]
+        surr2 = torch.clamp(ratios, 1 - clip_param, 1 + clip_param) * adv[index]
+        actor_loss = -torch.min(surr1, surr2).mean() - entropy_coefficient * ent.mean()
+        ap = list(self.actor.values())
+        ga, _ = clip_grad_norm(torch.autograd.grad(actor_loss, ap), 0.5)
+        adam_step(ap, list(ga), self.opt_a)
+        v_s = mlp2(self.critic, obs[index])
+        critic_loss = F.mse_loss(v_target[index], v_s)
+        cp = list(self.critic.values())
+        gc, _ = clip_grad_norm(torch.autograd.grad(critic_loss, cp), 0.5)
+        adam_step(cp, list(gc), self.opt_c)
+        return actor_loss.item(), critic_loss.item()

@@ -136,6 +136,25 @@ def test_ppo_discrete(golden):
     _ppo(golden, "ppo_disc", False)
 
 
+def _ppo_advance(golden, name, is_continue):
+    """PPO_advance/PPO.py (separate Adams, probs head) replayed through oracle.algos.PPOAdvanceOracle"""
+    g = golden(name)
+    o = algos.PPOAdvanceOracle(net(g, "init/actor/"), net(g, "init/critic/"), 1e-3, 5e-4, is_continue)
+    data = tuple(torch.from_numpy(g["data/" + k]) for k in ("obs", "act", "rew", "nobs", "done", "logp", "adv_done"))
+    r = o.learn(data, [g["perm/%d" % k] for k in range(2)], 64, 0.99, 0.95, 0.2, 0.01)
+    np.testing.assert_allclose(np.array(r["losses"]), g["losses"], rtol=2e-5, atol=1e-6)
+    assert_net(o.actor, g, "final/actor/")
+    assert_net(o.critic, g, "final/critic/")
+
+
+def test_ppo_advance_continuous(golden):
+    _ppo_advance(golden, "ppo_adv_cont", True)
+
+
+def test_ppo_advance_discrete(golden):
+    _ppo_advance(golden, "ppo_adv_disc", False)
+
+
 def test_buffers_per_and_tree(golden):
     g = golden("buffers")
     for cap in (5, 8, 37, 100):

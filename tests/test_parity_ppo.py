@@ -53,3 +53,54 @@ def test_ppo_continuous_gpu(golden):
 @pytest.mark.gpu
 def test_ppo_discrete_gpu(golden):
     _ppo(golden, torch.device("cuda"), "ppo_disc", False)
+
+
+def _ppo_advance(golden, device, name, is_continue):
+    """freerl_b200.PPO_advance (two Adams as one per-network-lr sweep, probs head) vs oracle + PPO_advance/PPO.py golden"""
+    from freerl_b200.PPO_advance import PPO
+    g = golden(name)
+    act_dim = 2 if is_continue else 4
+    pol = PPO([8, act_dim], is_continue, 1e-3, 5e-4, 256, device, trick={"adv_norm": False})
+    load_into(pol.agent.actor, net_from_golden(g, "init/actor/"))
+    load_into(pol.agent.critic, net_from_golden(g, "init/critic/"))
+    orc = algos.PPOAdvanceOracle(net_from_golden(g, "init/actor/"), net_from_golden(g, "init/critic/"), 1e-3, 5e-4, is_continue)
+    data = tuple(torch.from_numpy(g["data/" + k]) for k in ("obs", "act", "rew", "nobs", "done", "logp", "adv_done"))
+    d = [x.numpy() for x in data]
+    for t in range(256):
+        pol.add(d[0][t], d[1][t], float(d[2][t, 0]), d[3][t], bool(d[4][t, 0]), d[5][t], bool(d[6][t, 0]))
+    perms = [g["perm/%d" % k] for k in range(2)]
+    r = orc.learn(data, perms, 64, 0.99, 0.95, 0.2, 0.01)
+    pol.learn(64, 0.99, 0.95, 0.2, 2, 0.01, permutations=perms)
+    m = pol.last_metrics.cpu().numpy()
+    ref = np.array(r["losses"])
+    np.testing.assert_allclose(m[:, 0], ref[:, 0], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(m[:, 1], ref[:, 1], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(m[:, :2], g["losses"], rtol=5e-5, atol=5e-6)
+    tol = dict(rtol=2e-5, atol=3e-6)      # plain Adam: no sign masks, 8 chained steps stay inside the fp32 band
+    assert_module_close(pol.agent.actor, orc.actor, "actor", tol)
+    assert_module_close(pol.agent.critic, orc.critic, "critic", tol)
+    assert_module_close(pol.agent.actor, net_from_golden(g, "final/actor/"), "actor vs reference", tol)
+    assert_module_close(pol.agent.critic, net_from_golden(g, "final/critic/"), "critic vs reference", tol)
+    ev = pol.evaluate_action(g["act/obs"])
+    if is_continue:
+        np.testing.assert_allclose(ev, g["act/eval"], rtol=1e-5, atol=2e-6)
+    else:
+        assert np.array_equal(ev, g["act/eval"])
+
+
+def test_ppo_advance_continuous_emulated(golden, emul):
+    _ppo_advance(golden, torch.device("cpu"), "ppo_adv_cont", True)
+
+
+def test_ppo_advance_discrete_emulated(golden, emul):
+    _ppo_advance(golden, torch.device("cpu"), "ppo_adv_disc", False)
+
+
+@pytest.mark.gpu
+def test_ppo_advance_continuous_gpu(golden):
+    _ppo_advance(golden, torch.device("cuda"), "ppo_adv_cont", True)
+
+
+@pytest.mark.gpu
+def test_ppo_advance_discrete_gpu(golden):
+    _ppo_advance(golden, torch.device("cuda"), "ppo_adv_disc", False)
