@@ -25,31 +25,34 @@ from .normalization import Normalization_batch_size
 class Agent:
     """``MADDPG.py:112-136``: per-agent actor (own obs) + centralised critic (all obs + all actions), targets, 2 Adams."""
 
-    def __init__(self, obs_dim, action_dim, dim_info, actor_lr, critic_lr, device, supplement):
+    def __init__(self, obs_dim, action_dim, dim_info, actor_lr, critic_lr, device, supplement, n_heads=1):
         joint = sum(sum(v) for v in dim_info.values())
         a_dims = [(obs_dim, 128), (128, 128), (128, action_dim)]
-        c_dims = [(joint, 128), (128, 128), (128, 1)]
+        c_dims = [(joint, 128), (128, 128), (128, 1)] * n_heads         # twin: Critic_TD3 l1-l3 / l4-l6 (MATD3_simple.py:87-115)
         names = ("l1", "l2", "l3")
+        c_names = names if n_heads == 1 else ("l1", "l2", "l3", "l4", "l5", "l6")
         self._actor, self._critic = DeviceNet(a_dims, device, True), DeviceNet(c_dims, device, True)
         self._actor_t, self._critic_t = DeviceNet(a_dims, device, False), DeviceNet(c_dims, device, False)
         a_init = _ActorInit(obs_dim, action_dim, "l3")
         if supplement['net_init']:
             _reference_net_init(a_init, names)
-        c_init = _CriticInit(joint, 1)
+        c_init = _CriticInit(joint, n_heads)
         if supplement['net_init']:
-            _reference_net_init(c_init, names)
+            _reference_net_init(c_init, c_names)
         self.actor = bind_module(self._actor, a_init, names)
-        self.critic = bind_module(self._critic, c_init, names)
+        self.critic = bind_module(self._critic, c_init, c_names)
         self._actor_t.copy_from(self._actor)
         self._critic_t.copy_from(self._critic)
         self.actor_target = alias_module(self._actor_t, names)
-        self.critic_target = alias_module(self._critic_t, names)
+        self.critic_target = alias_module(self._critic_t, c_names)
         self.actor_lr, self.critic_lr = actor_lr, critic_lr
         self.weight_decay = 1e-3 if supplement['weight_decay'] else 0.0
         self.actor_step = self.critic_step = 0
 
 
 class MADDPG:
+    n_heads = 1          # MATD3 (clip_double): 2
+
     def __init__(self, dim_info, is_continue, actor_lr, critic_lr, buffer_size, device, trick, supplement, mode=None):
         self.device = _lib.require_device(device)
         if len(dim_info) > _lib.FRL_MAX_AGENTS:
@@ -58,7 +61,7 @@ class MADDPG:
             raise NotImplementedError("the reference implements continuous actions only (MADDPG.py:166)")
         self.agents, self.buffers = {}, {}
         for agent_id, (obs_dim, action_dim) in dim_info.items():
-            self.agents[agent_id] = Agent(obs_dim, action_dim, dim_info, actor_lr, critic_lr, self.device, supplement)
+            self.agents[agent_id] = Agent(obs_dim, action_dim, dim_info, actor_lr, critic_lr, self.device, supplement, self.n_heads)
             self.buffers[agent_id] = Buffer(buffer_size, obs_dim, act_dim=action_dim if is_continue else 1, device=self.device)
         self.dim_info = dim_info
         self.is_continue = is_continue
@@ -108,6 +111,11 @@ class MADDPG:
 
     def learn(self, batch_size, gamma, tau, *, indices=None):
         """``indices``: optional list (one per agent, agent order) of index arrays overriding the per-agent fresh samples."""
+        self._learn(batch_size, gamma, tau, indices, None)
+
+    def _learn(self, batch_size, gamma, tau, indices, td3):
+        """One learn() over all agents.  ``td3`` (MATD3 only): dict(policy_step, policy_freq, total_it, smoothing, policy_noise,
+        noise_clip, max_action, policy_noise_scale, noise) with ``noise[i][j]`` = device randn [B, act_j] of agent j inside agent i's sample."""
         ids = list(self.agents.keys())
         total = len(self.buffers[self.agent_x])
         outs = []
@@ -121,7 +129,7 @@ class MADDPG:
             a = _lib.AcArgs()
             a.actor, a.actor_target = ag._actor.c_struct(), ag._actor_t.c_struct()
             a.critic, a.critic_target = ag._critic.c_struct(), ag._critic_t.c_struct()
-            a.n_heads, a.actor_kind = 1, _lib.ACTOR_TANH
+            a.n_heads, a.actor_kind = self.n_heads, _lib.ACTOR_TANH
             a.replay = self.buffers[agent_id].c_struct()
             a.indices, a.B, a.n_updates = idx.data_ptr(), B, 1
             a.seed, a.gamma, a.tau = self._seed, gamma, tau
@@ -129,6 +137,17 @@ class MADDPG:
             a.beta1, a.beta2, a.eps, a.wd_critic, a.max_norm = 0.9, 0.999, 1e-8, ag.weight_decay, 0.5
             a.step_actor0, a.step_critic0, a.total_it0 = ag.actor_step, ag.critic_step, self._n_learn
             a.policy_freq, a.target_smoothing, a.max_action, a.policy_noise_scale = 1, 0, 1.0, 1.0
+            policy_step = True
+            if td3 is not None:
+                # the kernel runs the actor stages when (total_it0 + 1) % policy_freq == 0 (total_it counts learn() calls)
+                policy_step = bool(td3["policy_step"])
+                a.policy_freq, a.total_it0 = td3["policy_freq"], td3["total_it"] - 1
+                a.target_smoothing = int(td3["smoothing"])
+                a.policy_noise, a.noise_clip = td3["policy_noise"], td3["noise_clip"]
+                a.max_action, a.policy_noise_scale = td3["max_action"], td3["policy_noise_scale"]
+                if td3["noise"] is not None:
+                    for j in range(len(ids)):
+                        a.ma_noise_next[j] = td3["noise"][i][j].data_ptr()
             out = torch.zeros((1, 8), dtype=torch.float32, device=self.device)
             a.gpart, a.sumsq = self._scratch.gpart.data_ptr(), self._scratch.sumsq.data_ptr()
             a.stats, a.out = self._scratch.stats.data_ptr(), out.data_ptr()
@@ -142,13 +161,14 @@ class MADDPG:
             if self._bon:
                 a.obs_norm_n0 = self.batch_size_obs_norm[self.agent_x].running_ms.n
             _lib.check(_lib.lib().frl_ac_learn(ctypes.byref(a), _lib.stream_ptr(self.device)), "frl_ac_learn")
-            ag.actor_step += 1
+            ag.actor_step += 1 if policy_step else 0
             ag.critic_step += 1
             if self._bon:                     # every agent's sample() updates every agent's statistics (MADDPG.py:192-196)
                 for nm in self.batch_size_obs_norm.values():
                     nm.running_ms.n += 1
             outs.append((out, idx))
-        self.update_target(tau)
+        if td3 is None or td3["policy_step"]:
+            self.update_target(tau)
         self._n_learn += 1
         self.last_metrics = torch.cat([o for o, _ in outs])
 

@@ -54,7 +54,8 @@ class AcArgs(C.Structure):
                 ("gpart", C.c_void_p), ("sumsq", C.c_void_p), ("stats", C.c_void_p), ("out", C.c_void_p),
                 ("n_agents", C.c_int), ("agent_index", C.c_int), ("ma_replay", Replay * FRL_MAX_AGENTS),
                 ("ma_actor_target", Net * FRL_MAX_AGENTS), ("defer_polyak", C.c_int), ("xchg", C.c_void_p),
-                ("obs_norm", C.c_void_p * FRL_MAX_AGENTS), ("obs_norm_n0", C.c_int64)]
+                ("obs_norm", C.c_void_p * FRL_MAX_AGENTS), ("obs_norm_n0", C.c_int64),
+                ("ma_noise_next", C.c_void_p * FRL_MAX_AGENTS)]
 
 
 class InferArgs(C.Structure):

@@ -434,7 +434,14 @@ struct AcAlgo {
                 UU[r * ap + jj] = lp;                      // per-dim log-prob contribution
                 act = tanhf(uu);
               } else if (a.target_smoothing) {
-                const float e = (r < nvalid) ? noise_at(a.noise_next, a, u, row0 + r, jj, 1u) : 0.f;
+                float e = 0.f;
+                if (r < nvalid) {
+                  if (a.n_agents > 1)        // MATD3: every agent's target action has its own randn_like draw
+                    e = a.ma_noise_next[j] ? a.ma_noise_next[j][(size_t)(row0 + r) * adj + jj]
+                                           : randn_ni(a.seed, 16u + (uint32_t)j, (uint32_t)(a.total_it0 * NA + ai), (uint32_t)((row0 + r) * adj + jj));
+                  else
+                    e = noise_at(a.noise_next, a, u, row0 + r, jj, 1u);
+                }
                 float nz = fmul(a.policy_noise_scale, fmul(e, a.policy_noise));
                 nz = fminf(fmaxf(nz, -a.noise_clip), a.noise_clip);
                 float v = fadd(fmul(tanhf(mean), a.max_action), nz);

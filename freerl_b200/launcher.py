@@ -24,6 +24,9 @@ _ALGOS = {            # script file name -> (class name in the script, our modul
     "PPO.py": ("PPO", "freerl_b200.PPO", "PPO"),
     "PPO_advance/PPO.py": ("PPO", "freerl_b200.PPO_advance", "PPO"),      # keyed by <dir>/<file> where names collide
     "MADDPG.py": ("MADDPG", "freerl_b200.MADDPG", "MADDPG"),
+    "MADDPG_simple.py": ("MADDPG", "freerl_b200.MADDPG_simple", "MADDPG"),
+    "MATD3_simple.py": ("MATD3", "freerl_b200.MATD3_simple", "MATD3"),
+    "DDPG_simple.py": ("DDPG", "freerl_b200.DDPG_simple", "DDPG"),
     "MAPPO.py": ("MAPPO", "freerl_b200.MAPPO", "MAPPO"),
 }
 

@@ -128,6 +128,8 @@ typedef struct {
    * the reference), then feeds (x - mean) / (std + 1e-8) for obs AND next_obs to every network. */
   float* obs_norm[FRL_MAX_AGENTS];
   int64_t obs_norm_n0;      /* updates folded in before this call */
+  const float* ma_noise_next[FRL_MAX_AGENTS];   /* n_agents > 1 with target_smoothing (MATD3_simple.py:203-205): dev [B][act_dim_j]
+                                                 * randn of agent j's target action for THIS agent's sample; NULL -> Philox(seed) */
 } frl_ac_args_t;
 
 /* FRL_INFER_ARGMAX_DUELING (7): argmax_a of V + A_a - mean(A) for a [V | A] head (Dueling.forward, DQN_with_tricks.py:75-79) */

@@ -59,6 +59,57 @@ class MADDPGOracle:
         return out
 
 
+class MATD3Oracle(MADDPGOracle):
+    """``MADDPG_file/MATD3_simple.py:151-262``: MADDPG with twin centralised critics (``Critic_TD3``: l1-l3 / l4-l6),
+    target policy smoothing on EVERY agent's next action (``:203-205``, one ``randn_like`` per agent per sample), clipped
+    double-Q targets, ``Q1`` only in the actor loss, and actor + Polyak updates only when ``total_it % policy_freq == 0``
+    (``total_it`` counts learn() calls, not agent updates).  No weight decay, default torch init."""
+
+    def __init__(self, actors, critics, actor_lr, critic_lr):
+        super().__init__(actors, critics, actor_lr, critic_lr, weight_decay=False)
+        self.total_it = 0
+
+    @staticmethod
+    def _twin(net, x):
+        return mlp2(net, x, ("l1", "l2", "l3")), mlp2(net, x, ("l4", "l5", "l6"))
+
+    def learn(self, batches, noises, gamma, tau, policy_noise_scale, policy_noise, noise_clip, max_action, policy_freq):
+        """batches[i]: dict agent_id -> (obs, act, rew, nobs, done) of agent i's fresh sample; noises[i][j]: randn [B, act_j]"""
+        self.total_it += 1
+        out = []
+        for (aid, batch), nz in zip(zip(self.ids, batches), noises):
+            obs = [batch[k][0] for k in self.ids]
+            act = [batch[k][1] for k in self.ids]
+            nobs = [batch[k][3] for k in self.ids]
+            with torch.no_grad():
+                nact = []
+                for j, k in enumerate(self.ids):
+                    noise = (policy_noise_scale * (nz[j] * policy_noise)).clamp(-noise_clip, noise_clip)
+                    nact.append((tanh_actor(self.actor_target[k], batch[k][3]) * max_action + noise).clamp(-max_action, max_action) / max_action)
+                q1, q2 = self._twin(self.critic_target[aid], torch.cat(nobs + nact, dim=1))
+                target = batch[aid][2] + gamma * torch.min(q1, q2) * (1 - batch[aid][4])
+            c1, c2 = self._twin(self.critic[aid], torch.cat(obs + act, dim=1))
+            critic_loss = F.mse_loss(c1, target) + F.mse_loss(c2, target)
+            cp = list(self.critic[aid].values())
+            g, _ = clip_grad_norm(torch.autograd.grad(critic_loss, cp), 0.5)
+            adam_step(cp, g, self.opt_c[aid])
+            rec = [critic_loss.item(), None]
+            if self.total_it % policy_freq == 0:
+                new_a = tanh_actor(self.actor[aid], batch[aid][0])
+                act2 = [new_a if k == aid else batch[k][1] for k in self.ids]
+                actor_loss = -mlp2(self.critic[aid], torch.cat(obs + act2, dim=1), ("l1", "l2", "l3")).mean()
+                ap = list(self.actor[aid].values())
+                ga, _ = clip_grad_norm(torch.autograd.grad(actor_loss, ap), 0.5)
+                adam_step(ap, ga, self.opt_a[aid])
+                rec[1] = actor_loss.item()
+            out.append(tuple(rec))
+        if self.total_it % policy_freq == 0:
+            for k in self.ids:
+                polyak(self.actor_target[k], self.actor[k], tau)
+                polyak(self.critic_target[k], self.critic[k], tau)
+        return out
+
+
 # --------------------------------------------------------------------------------------------------
 # MAPPO  (MAPPO_file/MAPPO.py:106-482)
 # --------------------------------------------------------------------------------------------------

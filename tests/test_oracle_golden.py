@@ -136,6 +136,19 @@ def test_ppo_discrete(golden):
     _ppo(golden, "ppo_disc", False)
 
 
+def test_ddpg_simple(golden):
+    """DDPG_file/DDPG_simple.py = DDPG without supplements, replayed through DDPGOracle(weight_decay=False)"""
+    g = golden("ddpg_simple")
+    o = algos.DDPGOracle(net(g, "init/actor/"), net(g, "init/critic/"), 1e-3, 1e-3, weight_decay=False)
+    lc, la = losses(g, "update_critic"), losses(g, "update_actor")
+    for it in range(3):
+        r = o.learn(batch(g, it), 0.99, 0.01)
+        np.testing.assert_allclose(r["critic_loss"], lc[it][0], rtol=1e-6)
+        np.testing.assert_allclose(r["actor_loss"], la[it][0], rtol=1e-5)
+    for n in ("actor", "critic", "actor_target", "critic_target"):
+        assert_net(getattr(o, n), g, "final/%s/" % n)
+
+
 def _ppo_advance(golden, name, is_continue):
     """PPO_advance/PPO.py (separate Adams, probs head) replayed through oracle.algos.PPOAdvanceOracle"""
     g = golden(name)

@@ -80,3 +80,41 @@ def test_mappo_oracle_vs_reference(golden):
         for kind, nets in (("actor", orc.actor), ("critic", orc.critic)):
             for n, v in nets[k].items():
                 np.testing.assert_allclose(v.detach().numpy(), g["final/%s/%s/%s" % (k, kind, n)], rtol=2e-5, atol=2e-6)
+
+
+def _final_close(orc, g):
+    for k in IDS:
+        for kind, nets in (("actor", orc.actor), ("critic", orc.critic), ("actor_target", orc.actor_target), ("critic_target", orc.critic_target)):
+            for n, v in nets[k].items():
+                np.testing.assert_allclose(v.detach().numpy(), g["final/%s/%s/%s" % (k, kind, n)], rtol=2e-5, atol=2e-6, err_msg="%s %s %s" % (k, kind, n))
+
+
+def test_maddpg_simple_oracle_vs_reference(golden):
+    """MADDPG_simple.py = MADDPG without supplements (no weight decay, default init)"""
+    g = golden("maddpg_simple")
+    orc = MADDPGOracle(maddpg_nets(g, "init", "actor"), maddpg_nets(g, "init", "critic"), 1e-3, 1e-3, weight_decay=False)
+    ls = []
+    for it in range(2):
+        r = orc.learn([maddpg_batch(g, g["idx/%d/%d" % (it, j)]) for j in range(3)], 0.95, 0.01)
+        for cl, al in r:
+            ls += [cl, al]
+    np.testing.assert_allclose(np.array(ls), g["losses"][:, 1], rtol=2e-5, atol=1e-7)
+    _final_close(orc, g)
+
+
+def matd3_noises(g, it):
+    return [[torch.from_numpy(g["noise/%d/%d/%d" % (it, i, j)]) for j in range(3)] for i in range(3)]
+
+
+def test_matd3_oracle_vs_reference(golden):
+    from oracle.marl import MATD3Oracle
+    g = golden("matd3")
+    orc = MATD3Oracle(maddpg_nets(g, "init", "actor"), maddpg_nets(g, "init", "critic"), 1e-3, 1e-3)
+    ls = []
+    for it in range(3):
+        r = orc.learn([maddpg_batch(g, g["idx/%d/%d" % (it, j)]) for j in range(3)], matd3_noises(g, it), 0.95, 0.01, 1.0, 0.1, 0.5, 1.0, 2)
+        for cl, al in r:
+            ls += [cl] + ([al] if al is not None else [])
+    assert len(ls) == g["losses"].shape[0] == 12                      # 9 critic + 3 actor updates (policy_freq 2)
+    np.testing.assert_allclose(np.array(ls), g["losses"][:, 1], rtol=2e-5, atol=1e-7)
+    _final_close(orc, g)
