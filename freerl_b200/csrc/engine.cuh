@@ -67,6 +67,35 @@ static inline float fsqrt(float a) { return sqrtf(a); }
 #endif
 
 // ------------------------------------------------------------------------------------------------
+// Packed fp32x2 FMA (Blackwell `fma.rn.f32x2`, SASS FFMA2): two IEEE fp32 FMAs per issued instruction — the same rounding
+// as two FFMAs, so results are bit-identical to the scalar loops they replace.  The GEMM microkernels are FMA-issue bound
+// (3-register FFMA issues every 2nd cycle per SM sub-partition), so halving the instruction count is what buys time.
+//   fma2_bcast: (d0, d1) += a * (b0, b1)        scalar multiplicand broadcast by the instruction itself (Ra.F32 form)
+//   fma2_elem : (d0, d1) += (a0, a1) * (b0, b1) element-wise pairs (both operands natural register pairs of an LDS.128)
+// -DFRL_NO_FFMA2 keeps the scalar FFMA loops (A/B timing); the host emulation is scalar.
+// ------------------------------------------------------------------------------------------------
+#if !defined(FRL_EMUL) && !defined(FRL_NO_FFMA2)
+FRL_DEV void fma2_bcast(float& d0, float& d1, float a, float b0, float b1) {
+  unsigned long long B, C;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(B) : "f"(b0), "f"(b1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(C) : "f"(d0), "f"(d1));
+  asm("{\n\t.reg .b64 aa;\n\tmov.b64 aa, {%1, %1};\n\tfma.rn.f32x2 %0, aa, %2, %0;\n\t}" : "+l"(C) : "f"(a), "l"(B));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(C));
+}
+FRL_DEV void fma2_elem(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  unsigned long long A, B, C;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(B) : "f"(b0), "f"(b1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(C) : "f"(d0), "f"(d1));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(C) : "l"(A), "l"(B));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(C));
+}
+#else
+FRL_DEV void fma2_bcast(float& d0, float& d1, float a, float b0, float b1) { d0 += a * b0; d1 += a * b1; }
+FRL_DEV void fma2_elem(float& d0, float& d1, float a0, float a1, float b0, float b1) { d0 += a0 * b0; d1 += a1 * b1; }
+#endif
+
+// ------------------------------------------------------------------------------------------------
 // Transposed-mirror layout (`pt`): per layer WT[in_pad][wt_ld] followed by bias[out_pad]; ONE staged copy of a layer
 // serves forward (Y = X WT) and backward (dX = dY WT^T, read "transposed").
 //   FFMA build: the row stride is padded so that wt_ld / 4 is odd — rows k, k+1, ... start in different 16-B bank
@@ -458,10 +487,10 @@ FRL_NI_GEMM void gemm_rk(float* red, const float* A, int lda, int K_pad, const f
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float4 a = av[i];
-          acc[i][0] += a.x * b0.x; acc[i][1] += a.x * b0.y; acc[i][2] += a.x * b0.z; acc[i][3] += a.x * b0.w;
-          acc[i][0] += a.y * b1.x; acc[i][1] += a.y * b1.y; acc[i][2] += a.y * b1.z; acc[i][3] += a.y * b1.w;
-          acc[i][0] += a.z * b2.x; acc[i][1] += a.z * b2.y; acc[i][2] += a.z * b2.z; acc[i][3] += a.z * b2.w;
-          acc[i][0] += a.w * b3.x; acc[i][1] += a.w * b3.y; acc[i][2] += a.w * b3.z; acc[i][3] += a.w * b3.w;
+          fma2_bcast(acc[i][0], acc[i][1], a.x, b0.x, b0.y); fma2_bcast(acc[i][2], acc[i][3], a.x, b0.z, b0.w);
+          fma2_bcast(acc[i][0], acc[i][1], a.y, b1.x, b1.y); fma2_bcast(acc[i][2], acc[i][3], a.y, b1.z, b1.w);
+          fma2_bcast(acc[i][0], acc[i][1], a.z, b2.x, b2.y); fma2_bcast(acc[i][2], acc[i][3], a.z, b2.z, b2.w);
+          fma2_bcast(acc[i][0], acc[i][1], a.w, b3.x, b3.y); fma2_bcast(acc[i][2], acc[i][3], a.w, b3.z, b3.w);
         }
         wb += wb_step;
         wa += 4;
@@ -521,11 +550,13 @@ FRL_NI_GEMM void gemm_nt(float* red, const float* A, int lda, int N_red, const f
       if (kl >= KL) continue;
       const int r0 = (int)rt * 4;
       const int nc0 = (int)((ns * nchunk) >> sh_n), nc1 = (int)(((ns + 1) * nchunk) >> sh_n);
-      float acc[4][4];
+      // two interleaved partial sums per output (even / odd reduction index): the pairs (a.x, a.y) * (b.x, b.y) are natural
+      // register pairs of the LDS.128 operands, so each FFMA2 retires two products; folded as lo + hi at the end
+      float acc[4][4], acc_hi[4][4];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) { acc[i][j] = 0.f; acc_hi[i][j] = 0.f; }
       int wa = r0 * lda + nc0 * 4;                  // A[r0][n]
       int wb = (int)kl * ldb + nc0 * 4;             // Bs[kl][n]
       const int kstep = (int)KL * ldb;
@@ -540,11 +571,15 @@ FRL_NI_GEMM void gemm_nt(float* red, const float* A, int lda, int N_red, const f
         for (int i = 0; i < 4; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            acc[i][j] += av[i].x * bv[j].x; acc[i][j] += av[i].y * bv[j].y;
-            acc[i][j] += av[i].z * bv[j].z; acc[i][j] += av[i].w * bv[j].w;
+            fma2_elem(acc[i][j], acc_hi[i][j], av[i].x, av[i].y, bv[j].x, bv[j].y);
+            fma2_elem(acc[i][j], acc_hi[i][j], av[i].z, av[i].w, bv[j].z, bv[j].w);
           }
         wa += 4; wb += 4;
       }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += acc_hi[i][j];
       if (nsplit == 1) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -598,10 +633,10 @@ FRL_NI_GEMM void gemm_outer(const float* dY, int ldy, int M_pad, const float* X,
         for (int r = 0; r < R; ++r) {
           const float4 a = sp_ld4(sY, r * ldy + m0);
           const float4 b = sp_ld4(sX, r * ldx + n0);
-          acc[0][0] += a.x * b.x; acc[0][1] += a.x * b.y; acc[0][2] += a.x * b.z; acc[0][3] += a.x * b.w;
-          acc[1][0] += a.y * b.x; acc[1][1] += a.y * b.y; acc[1][2] += a.y * b.z; acc[1][3] += a.y * b.w;
-          acc[2][0] += a.z * b.x; acc[2][1] += a.z * b.y; acc[2][2] += a.z * b.z; acc[2][3] += a.z * b.w;
-          acc[3][0] += a.w * b.x; acc[3][1] += a.w * b.y; acc[3][2] += a.w * b.z; acc[3][3] += a.w * b.w;
+          fma2_bcast(acc[0][0], acc[0][1], a.x, b.x, b.y); fma2_bcast(acc[0][2], acc[0][3], a.x, b.z, b.w);
+          fma2_bcast(acc[1][0], acc[1][1], a.y, b.x, b.y); fma2_bcast(acc[1][2], acc[1][3], a.y, b.z, b.w);
+          fma2_bcast(acc[2][0], acc[2][1], a.z, b.x, b.y); fma2_bcast(acc[2][2], acc[2][3], a.z, b.z, b.w);
+          fma2_bcast(acc[3][0], acc[3][1], a.w, b.x, b.y); fma2_bcast(acc[3][2], acc[3][3], a.w, b.z, b.w);
         }
         float* gp = G + m0 * N_pad + n0;
 #pragma unroll
