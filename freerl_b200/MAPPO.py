@@ -46,8 +46,6 @@ class Agent(_PPOAgent):
 class MAPPO:
     def __init__(self, dim_info, is_continue, actor_lr, critic_lr, horizon, device, trick=None, mode=None):
         self.device = _lib.require_device(device)
-        if not is_continue:
-            raise NotImplementedError("the fused MAPPO path implements the reference's continuous-action configuration")
         if bool(trick['LayerNorm']) != bool(trick['feature_norm']):
             raise NotImplementedError("LayerNorm and feature_norm must be switched together")
         self.agents, self.buffers = {}, {}
@@ -72,6 +70,8 @@ class MAPPO:
 
     # ---- acting ------------------------------------------------------------------------------------
     def select_action(self, obs, *, noise=None):
+        if not self.is_continue:
+            return self._select_action_discrete(obs, noise)
         actions, action_log_pis = {}, {}
         self._n_act += 1
         for i, (agent_id, o) in enumerate(obs.items()):
@@ -95,9 +95,34 @@ class MAPPO:
         for agent_id, o in obs.items():
             od, ad = self.dim_info[agent_id]
             x, single = _common.as_obs_batch(o, od)
-            a = _common.infer(self.agents[agent_id]._net, x, _lib.INFER_TANH, self.device, ad, l0=0, nl=3, layer_norm=self.layer_norm).cpu().numpy()
+            if self.is_continue:
+                a = _common.infer(self.agents[agent_id]._net, x, _lib.INFER_TANH, self.device, ad, l0=0, nl=3, layer_norm=self.layer_norm).cpu().numpy()
+            else:                                     # np.argmax(a_prob)  (MAPPO.py:335)
+                a = _common.infer(self.agents[agent_id]._net, x, _lib.INFER_ARGMAX, self.device, 1, l0=0, nl=3,
+                                  layer_norm=self.layer_norm).reshape(-1).to(torch.int64).cpu().numpy()
             actions[agent_id] = a[0] if single else a
         return actions
+
+    def _select_action_discrete(self, obs, noise):
+        """``Categorical(probs=actor(obs)).sample()`` + ``log_prob`` per agent (MAPPO.py:316-318): torch.multinomial draws
+        q ~ Exp(1) per class and takes argmax(p / q)"""
+        actions, action_log_pis = {}, {}
+        self._n_act += 1
+        for i, (agent_id, o) in enumerate(obs.items()):
+            od, ad = self.dim_info[agent_id]
+            x, single = _common.as_obs_batch(o, od)
+            n = x.shape[0]
+            nz = None
+            if noise is not None:
+                nz = torch.as_tensor(noise[agent_id], dtype=torch.float32).to(self.device).reshape(n, ad).contiguous()
+            elif self.mode == "parity":
+                nz = torch.empty((n, ad), dtype=torch.float32, device=self.device).exponential_(1)
+            out = _common.infer(self.agents[agent_id]._net, x, _lib.INFER_PPO_CAT, self.device, 2, noise=nz, seed=self._seed,
+                                counter=self._n_act * 16 + i, l0=0, nl=3, layer_norm=self.layer_norm).cpu().numpy()
+            a, lp = out[:, 0].astype(np.int64), out[:, 1]
+            actions[agent_id] = a[0] if single else a
+            action_log_pis[agent_id] = lp[0] if single else lp
+        return actions, action_log_pis
 
     # ---- buffer ------------------------------------------------------------------------------------
     def add(self, obs, action, reward, next_obs, done, action_log_pi, adv_dones):
@@ -165,7 +190,7 @@ class MAPPO:
             n_updates = idx.shape[0]
             out = torch.zeros((n_updates, 8), dtype=torch.float32, device=self.device)
             a = _lib.PpoArgs()
-            a.net, a.continuous = ag._net.c_struct(), 1
+            a.net, a.continuous = ag._net.c_struct(), int(self.is_continue)
             a.obs, a.action, a.logp_old = b.obs.data_ptr(), b.actions.data_ptr(), b.action_log_probs.data_ptr()
             a.adv, a.v_target = adv.data_ptr(), v_target.data_ptr()
             a.M, a.obs_dim, a.act_cols, a.logp_cols, a.n_adv = b.capacity, b.obs_dim, b.act_dim, b.logp_dim, N

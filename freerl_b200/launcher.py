@@ -28,6 +28,7 @@ _ALGOS = {            # script file name -> (class name in the script, our modul
     "MATD3_simple.py": ("MATD3", "freerl_b200.MATD3_simple", "MATD3"),
     "DDPG_simple.py": ("DDPG", "freerl_b200.DDPG_simple", "DDPG"),
     "MAPPO.py": ("MAPPO", "freerl_b200.MAPPO", "MAPPO"),
+    "IPPO.py": ("IPPO", "freerl_b200.IPPO", "IPPO"),
 }
 
 

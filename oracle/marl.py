@@ -144,11 +144,12 @@ class MAPPOOracle:
     + huber with ``max(original, clipped)``, merged Adam(eps 1e-5, lr = actor_lr) over actor+critic, NO grad clip,
     joint advantage normalisation with the unbiased std."""
 
-    def __init__(self, actors, critics, lr, trick):
+    def __init__(self, actors, critics, lr, trick, is_continue=True):
         self.ids = list(actors.keys())
         self.actor = OrderedDict((k, _leaf(v)) for k, v in actors.items())
         self.critic = OrderedDict((k, _leaf(v)) for k, v in critics.items())
         self.trick = trick
+        self.is_continue = is_continue         # False: Actor_discrete -> Categorical(probs=softmax(l3))  (MAPPO.py:163-186, 405-407)
         self.opt = {k: AdamState(list(self.actor[k].values()) + list(self.critic[k].values()), lr, eps=1e-5) for k in self.ids}
 
     def actor_dist(self, k, obs):
@@ -193,10 +194,16 @@ class MAPPOOracle:
             for perm in permutations[k]:
                 for s in range(0, H, minibatch_size):
                     index = perm[s:s + minibatch_size]
-                    mean, std = self.actor_dist(k, obs[index])
-                    dist = torch.distributions.Normal(mean, std)
-                    ent = dist.entropy().sum(dim=1, keepdim=True)
-                    logp = dist.log_prob(action[index])
+                    if self.is_continue:
+                        mean, std = self.actor_dist(k, obs[index])
+                        dist = torch.distributions.Normal(mean, std)
+                        ent = dist.entropy().sum(dim=1, keepdim=True)
+                        logp = dist.log_prob(action[index])
+                    else:
+                        probs = torch.softmax(mappo_body(self.actor[k], obs[index], ("l1", "l2", "l3"), self.trick), dim=1)
+                        dist = torch.distributions.Categorical(probs=probs)
+                        ent = dist.entropy().reshape(-1, 1)
+                        logp = dist.log_prob(action[index].reshape(-1)).reshape(-1, 1)
                     ratios = torch.exp(logp.sum(dim=1, keepdim=True) - logp_old[index].sum(dim=1, keepdim=True))
                     surr1 = ratios * adv[index]
                     surr2 = torch.clamp(ratios, 1 - clip_param, 1 + clip_param) * adv[index]
@@ -223,3 +230,87 @@ class MAPPOOracle:
                     adam_step(ap + cp, list(ga) + list(gc), self.opt[k])
                     losses.append((actor_loss.item(), critic_loss.item()))
         return {"adv": adv, "v_target": v_target, "losses": losses}
+
+
+# --------------------------------------------------------------------------------------------------
+# IPPO  (MAPPO_file/IPPO.py:100-330)
+# --------------------------------------------------------------------------------------------------
+class IPPOOracle:
+    """``IPPO.py:249-316``: every agent is an independent PPO on ITS OWN observation — decentralised critic (``Critic`` takes the
+    agent's obs_dim, ``:146-156``), per-agent flat GAE in float64 numpy and per-agent ``adv_norm`` (``:255-270``), the MAPPO
+    network body (feature_norm / LayerNorm), separate ``Adam(eps=1e-5)`` for actor (``actor_lr``) and critic (``critic_lr``) with
+    ``clip_grad_norm_(0.5)`` each (``:165-184``), ValueClip + huber value loss; the discrete actor returns softmax
+    probabilities for ``Categorical(probs=...)`` (``:118-129``)."""
+
+    def __init__(self, actors, critics, actor_lr, critic_lr, trick, is_continue):
+        self.ids = list(actors.keys())
+        self.actor = OrderedDict((k, _leaf(v)) for k, v in actors.items())
+        self.critic = OrderedDict((k, _leaf(v)) for k, v in critics.items())
+        self.trick, self.is_continue = trick, is_continue
+        eps = 1e-5 if trick['adam_eps'] else 1e-8
+        self.opt_a = {k: AdamState(list(self.actor[k].values()), actor_lr, eps=eps) for k in self.ids}
+        self.opt_c = {k: AdamState(list(self.critic[k].values()), critic_lr, eps=eps) for k in self.ids}
+
+    def dist(self, k, obs):
+        if self.is_continue:
+            mean = torch.tanh(mappo_body(self.actor[k], obs, ("l1", "l2", "mean_layer"), self.trick))
+            std = torch.exp(torch.clamp(self.actor[k]["log_std"].expand_as(mean), -20, 2))
+            return torch.distributions.Normal(mean, std)
+        return torch.distributions.Categorical(probs=torch.softmax(mappo_body(self.actor[k], obs, ("l1", "l2", "l3"), self.trick), dim=-1))
+
+    def advantages(self, k, data, gamma, lmbda):
+        from .algos import gae_reference
+        obs, action, reward, next_obs, done, logp_old, adv_dones = data
+        with torch.no_grad():
+            vs = mappo_body(self.critic[k], obs, ("l1", "l2", "l3"), self.trick)
+            vs_ = mappo_body(self.critic[k], next_obs, ("l1", "l2", "l3"), self.trick)
+            td = reward + gamma * (1.0 - done) * vs_ - vs
+            adv = gae_reference(td.reshape(-1).numpy(), adv_dones.reshape(-1).numpy(), gamma, lmbda)
+            adv = torch.as_tensor(adv, dtype=torch.float32).reshape(-1, 1)
+            v_target = adv + vs
+            if self.trick['adv_norm']:
+                adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+        return adv, v_target
+
+    def learn(self, data, permutations, minibatch_size, gamma, lmbda, clip_param, entropy_coefficient, huber_delta):
+        """data: dict agent -> 7 tensors; permutations: dict agent -> list (K epochs) of index permutations"""
+        out = {"losses": [], "adv": {}, "v_target": {}}
+        for k in self.ids:
+            obs, action, logp_old = data[k][0], data[k][1], data[k][5]
+            adv, v_target = self.advantages(k, data[k], gamma, lmbda)
+            out["adv"][k], out["v_target"][k] = adv, v_target
+            H = adv.shape[0]
+            for perm in permutations[k]:
+                for s in range(0, H, minibatch_size):
+                    index = perm[s:s + minibatch_size]
+                    dist = self.dist(k, obs[index])
+                    if self.is_continue:
+                        ent = dist.entropy().sum(dim=1, keepdim=True)
+                        logp = dist.log_prob(action[index])
+                    else:
+                        ent = dist.entropy().reshape(-1, 1)
+                        logp = dist.log_prob(action[index].reshape(-1)).reshape(-1, 1)
+                    ratios = torch.exp(logp.sum(dim=1, keepdim=True) - logp_old[index].sum(dim=1, keepdim=True))
+                    surr1 = ratios * adv[index]
+                    surr2 = torch.clamp(ratios, 1 - clip_param, 1 + clip_param) * adv[index]
+                    actor_loss = -torch.min(surr1, surr2).mean() - entropy_coefficient * ent.mean()
+                    ap = list(self.actor[k].values())
+                    ga, _ = clip_grad_norm(torch.autograd.grad(actor_loss, ap), 0.5)
+                    adam_step(ap, list(ga), self.opt_a[k])
+                    v_s = mappo_body(self.critic[k], obs[index], ("l1", "l2", "l3"), self.trick)
+                    vt = v_target[index]
+                    if self.trick['ValueClip']:
+                        vt_clip = torch.clamp(vt, v_s - clip_param, v_s + clip_param)
+                        if self.trick['huber_loss']:
+                            critic_loss = torch.max(huber_loss(vt - v_s, huber_delta).mean(), huber_loss(vt_clip - v_s, huber_delta).mean())
+                        else:
+                            critic_loss = torch.max(F.mse_loss(vt, v_s), F.mse_loss(vt_clip, v_s))
+                    elif self.trick['huber_loss']:
+                        critic_loss = huber_loss(vt - v_s, huber_delta).mean()
+                    else:
+                        critic_loss = F.mse_loss(vt, v_s)
+                    cp = list(self.critic[k].values())
+                    gc, _ = clip_grad_norm(torch.autograd.grad(critic_loss, cp), 0.5)
+                    adam_step(cp, list(gc), self.opt_c[k])
+                    out["losses"].append((actor_loss.item(), critic_loss.item()))
+        return out

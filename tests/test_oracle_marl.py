@@ -82,6 +82,18 @@ def test_mappo_oracle_vs_reference(golden):
                 np.testing.assert_allclose(v.detach().numpy(), g["final/%s/%s/%s" % (k, kind, n)], rtol=2e-5, atol=2e-6)
 
 
+def test_mappo_discrete_oracle_vs_reference(golden):
+    g = golden("mappo_disc")
+    orc = MAPPOOracle(maddpg_nets(g, "init", "actor"), maddpg_nets(g, "init", "critic"), 1e-3, MAPPO_TRICK, is_continue=False)
+    perms = {k: [g["perm/%s/%d" % (k, e)] for e in range(2)] for k in IDS}
+    r = orc.learn(mappo_data(g), perms, 32, 0.95, 0.95, 0.2, 0.01, 10.0)
+    np.testing.assert_allclose(np.array(r["losses"]), g["losses"], rtol=2e-5, atol=1e-6)
+    for k in IDS:
+        for kind, nets in (("actor", orc.actor), ("critic", orc.critic)):
+            for n, v in nets[k].items():
+                np.testing.assert_allclose(v.detach().numpy(), g["final/%s/%s/%s" % (k, kind, n)], rtol=2e-5, atol=2e-6)
+
+
 def _final_close(orc, g):
     for k in IDS:
         for kind, nets in (("actor", orc.actor), ("critic", orc.critic), ("actor_target", orc.actor_target), ("critic_target", orc.critic_target)):
@@ -118,3 +130,32 @@ def test_matd3_oracle_vs_reference(golden):
     assert len(ls) == g["losses"].shape[0] == 12                      # 9 critic + 3 actor updates (policy_freq 2)
     np.testing.assert_allclose(np.array(ls), g["losses"][:, 1], rtol=2e-5, atol=1e-7)
     _final_close(orc, g)
+
+
+IPPO_TRICK = {'adv_norm': True, 'ObsNorm': True, 'reward_norm': False, 'reward_scaling': True, 'orthogonal_init': True,
+              'adam_eps': True, 'lr_decay': False, 'ValueClip': True, 'huber_loss': True, 'LayerNorm': True, 'feature_norm': True}
+
+
+def ippo_data(g):
+    return {k: tuple(torch.from_numpy(g["data/%s/%s" % (k, n)]) for n in ("obs", "act", "rew", "nobs", "done", "logp", "adv_done")) for k in IDS}
+
+
+def _ippo_oracle(golden, name, is_continue):
+    from oracle.marl import IPPOOracle
+    g = golden(name)
+    orc = IPPOOracle(maddpg_nets(g, "init", "actor"), maddpg_nets(g, "init", "critic"), 1e-3, 5e-4, IPPO_TRICK, is_continue)
+    perms = {k: [g["perm/%s/%d" % (k, e)] for e in range(2)] for k in IDS}
+    r = orc.learn(ippo_data(g), perms, 32, 0.95, 0.95, 0.2, 0.01, 10.0)
+    np.testing.assert_allclose(np.array(r["losses"]), g["losses"], rtol=3e-5, atol=1e-6)
+    for k in IDS:
+        for kind, nets in (("actor", orc.actor), ("critic", orc.critic)):
+            for n, v in nets[k].items():
+                np.testing.assert_allclose(v.detach().numpy(), g["final/%s/%s/%s" % (k, kind, n)], rtol=2e-5, atol=2e-6, err_msg="%s %s %s" % (k, kind, n))
+
+
+def test_ippo_continuous_oracle_vs_reference(golden):
+    _ippo_oracle(golden, "ippo_cont", True)
+
+
+def test_ippo_discrete_oracle_vs_reference(golden):
+    _ippo_oracle(golden, "ippo_disc", False)

@@ -9,16 +9,16 @@ from parity_util import assert_module_close, load_into
 from test_oracle_marl import IDS, maddpg_nets, mappo_data
 
 
-def _run(golden, device):
+def _run(golden, device, is_continue=True):
     from freerl_b200.MAPPO import MAPPO
-    g = golden("mappo")
+    g = golden("mappo" if is_continue else "mappo_disc")
     dim_info = {k: [18, 5] for k in IDS}
-    pol = MAPPO(dim_info, True, 1e-3, 1e-3, 64, device, dict(MAPPO_TRICK))
+    pol = MAPPO(dim_info, is_continue, 1e-3, 1e-3, 64, device, dict(MAPPO_TRICK))
     ia, ic = maddpg_nets(g, "init", "actor"), maddpg_nets(g, "init", "critic")
     for k in IDS:
         load_into(pol.agents[k].actor, ia[k])
         load_into(pol.agents[k].critic, ic[k])
-    orc = MAPPOOracle(ia, ic, 1e-3, MAPPO_TRICK)
+    orc = MAPPOOracle(ia, ic, 1e-3, MAPPO_TRICK, is_continue=is_continue)
     data = mappo_data(g)
     d = {k: [x.numpy() for x in data[k]] for k in IDS}
     for t in range(64):
@@ -41,13 +41,90 @@ def _run(golden, device):
         assert_module_close(pol.agents[k].critic, orc.critic[k], "critic " + k, tol)
         assert_module_close(pol.agents[k].actor, maddpg_nets(g, "final", "actor")[k], "actor vs reference " + k, tol)
     acts, lps = pol.select_action({k: d[k][0][0] for k in IDS})
-    assert acts["agent_0"].shape == (5,) and lps["agent_0"].shape == (5,)
+    if is_continue:
+        assert acts["agent_0"].shape == (5,) and lps["agent_0"].shape == (5,)
+    else:
+        assert 0 <= int(acts["agent_0"]) < 5 and float(lps["agent_0"]) <= 0.0
+        ev = pol.evaluate_action({k: d[k][0][:4] for k in IDS})
+        assert ev["agent_1"].shape == (4,)
 
 
 def test_mappo_emulated(golden, emul):
     _run(golden, torch.device("cpu"))
 
 
+def test_mappo_discrete_emulated(golden, emul):
+    _run(golden, torch.device("cpu"), is_continue=False)
+
+
+@pytest.mark.gpu
+def test_mappo_discrete_gpu(golden):
+    _run(golden, torch.device("cuda"), is_continue=False)
+
+
 @pytest.mark.gpu
 def test_mappo_gpu(golden):
     _run(golden, torch.device("cuda"))
+
+
+def _ippo(golden, device, name, is_continue):
+    """freerl_b200.IPPO (independent per-agent PPO on the fused kernels) vs oracle + MAPPO_file/IPPO.py golden"""
+    from freerl_b200.IPPO import IPPO
+    from oracle.marl import IPPOOracle
+    from test_oracle_marl import IDS, IPPO_TRICK, ippo_data, maddpg_nets
+    from parity_util import assert_module_close, load_into
+    g = golden(name)
+    pol = IPPO({k: [18, 5] for k in IDS}, is_continue, 1e-3, 5e-4, 64, device, dict(IPPO_TRICK))
+    ia, ic = maddpg_nets(g, "init", "actor"), maddpg_nets(g, "init", "critic")
+    for k in IDS:
+        load_into(pol.agents[k].actor, ia[k])
+        load_into(pol.agents[k].critic, ic[k])
+    orc = IPPOOracle(ia, ic, 1e-3, 5e-4, IPPO_TRICK, is_continue)
+    data = ippo_data(g)
+    for t in range(64):
+        d = {n: {k: data[k][i][t].numpy() for k in IDS} for i, n in enumerate(("obs", "act", "rew", "nobs", "done", "logp", "adv_done"))}
+        pol.add(d["obs"], d["act"], {k: float(v[0]) for k, v in d["rew"].items()}, d["nobs"], {k: bool(v[0]) for k, v in d["done"].items()},
+                d["logp"], {k: bool(v[0]) for k, v in d["adv_done"].items()})
+    perms = {k: [g["perm/%s/%d" % (k, e)] for e in range(2)] for k in IDS}
+    r = orc.learn(data, perms, 32, 0.95, 0.95, 0.2, 0.01, 10.0)
+    pol.learn(32, 0.95, 0.95, 0.2, 2, 0.01, 10.0, permutations=perms)
+    for k in IDS:
+        np.testing.assert_allclose(pol.last_adv[k].cpu().numpy(), r["adv"][k].numpy(), rtol=2e-5, atol=5e-6)
+        np.testing.assert_allclose(pol.last_v_target[k].cpu().numpy(), r["v_target"][k].numpy(), rtol=1e-5, atol=2e-6)
+    m = pol.last_metrics.cpu().numpy()
+    ref = np.array(r["losses"])
+    np.testing.assert_allclose(m[:, 0], ref[:, 0], rtol=3e-5, atol=3e-6)
+    np.testing.assert_allclose(m[:, 1], ref[:, 1], rtol=3e-5, atol=3e-6)
+    np.testing.assert_allclose(m[:, :2], g["losses"], rtol=1e-4, atol=1e-5)
+    tol = dict(rtol=5e-5, atol=5e-6)
+    for k in IDS:
+        assert_module_close(pol.agents[k].actor, orc.actor[k], "actor " + k, tol)
+        assert_module_close(pol.agents[k].critic, orc.critic[k], "critic " + k, tol)
+        assert_module_close(pol.agents[k].actor, maddpg_nets(g, "final", "actor")[k], "final actor " + k, tol)
+        assert_module_close(pol.agents[k].critic, maddpg_nets(g, "final", "critic")[k], "final critic " + k, tol)
+    ev = pol.evaluate_action({k: g["act/%s/obs" % k] for k in IDS})
+    for k in IDS:
+        if is_continue:
+            np.testing.assert_allclose(ev[k], g["act/%s/eval" % k], rtol=1e-5, atol=2e-6)
+        else:
+            assert int(ev[k]) == int(g["act/%s/eval" % k])
+    a, lp = pol.select_action({k: g["act/%s/obs" % k] for k in IDS})
+    assert set(a) == set(IDS) and (np.asarray(lp["agent_0"]).shape == ((5,) if is_continue else ()))
+
+
+def test_ippo_continuous_emulated(golden, emul):
+    _ippo(golden, torch.device("cpu"), "ippo_cont", True)
+
+
+def test_ippo_discrete_emulated(golden, emul):
+    _ippo(golden, torch.device("cpu"), "ippo_disc", False)
+
+
+@pytest.mark.gpu
+def test_ippo_continuous_gpu(golden):
+    _ippo(golden, torch.device("cuda"), "ippo_cont", True)
+
+
+@pytest.mark.gpu
+def test_ippo_discrete_gpu(golden):
+    _ippo(golden, torch.device("cuda"), "ippo_disc", False)
