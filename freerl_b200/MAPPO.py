@@ -163,53 +163,66 @@ class MAPPO:
             _lib.check(_lib.lib().frl_adv_norm(_lib.ptr(adv), adv.numel(), 1e-8, _lib.ptr(adv), _lib.stream_ptr(self.device)), "frl_adv_norm")
         return adv, v_target, joint
 
+    # optimiser of MAPPO.update_ac (MAPPO.py:230-247): ONE Adam(eps 1e-5) over actor + critic, lr = actor_lr, no clip_grad_norm_
+    max_norm = 0.0
+    adam_eps = 1e-5
+
+    def _permutations(self, ag, K_epochs, given):
+        H = self.horizon
+        if given is not None:
+            return given
+        if self.mode == "parity":
+            return [np.random.permutation(H) for _ in range(K_epochs)]                  # MAPPO.py:395
+        g = torch.Generator(device="cpu")
+        g.manual_seed((self._seed + ag.step) & 0x7FFFFFFF)
+        return [torch.randperm(H, generator=g).numpy() for _ in range(K_epochs)]
+
+    def _agent_update(self, agent_id, adv, v_target, joint, minibatch_size, K_epochs, clip_param, entropy_coefficient, huber_delta, perms):
+        """All K_epochs x minibatches of ONE agent in one persistent launch (adv / v_target: [M, n_adv] device tensors)."""
+        ag, b = self.agents[agent_id], self.buffers[agent_id]
+        H = self.horizon
+        nmb = (H + minibatch_size - 1) // minibatch_size
+        idx = np.zeros((K_epochs * nmb, minibatch_size), np.int64)
+        rows = np.zeros(K_epochs * nmb, np.int32)
+        for e, perm in enumerate(perms):
+            for j in range(nmb):
+                sl = np.asarray(perm[j * minibatch_size:(j + 1) * minibatch_size])
+                idx[e * nmb + j, :sl.size] = sl
+                rows[e * nmb + j] = sl.size
+        idx_d, rows_d = torch.from_numpy(idx).to(self.device), torch.from_numpy(rows).to(self.device)
+        n_updates = idx.shape[0]
+        out = torch.zeros((n_updates, 8), dtype=torch.float32, device=self.device)
+        a = _lib.PpoArgs()
+        a.net, a.continuous = ag._net.c_struct(), int(self.is_continue)
+        a.obs, a.action, a.logp_old = b.obs.data_ptr(), b.actions.data_ptr(), b.action_log_probs.data_ptr()
+        a.adv, a.v_target = adv.data_ptr(), v_target.data_ptr()
+        a.M, a.obs_dim, a.act_cols, a.logp_cols, a.n_adv = b.capacity, b.obs_dim, b.act_dim, b.logp_dim, adv.shape[1]
+        a.indices, a.mb_rows, a.mb, a.n_updates = idx_d.data_ptr(), rows_d.data_ptr(), minibatch_size, n_updates
+        a.clip_param, a.entropy_coef = clip_param, entropy_coefficient
+        a.max_norm_actor = a.max_norm_critic = self.max_norm
+        a.optimizer = _lib.OPT_ADAM
+        a.lr, a.beta1, a.beta2, a.eps = ag.lr, 0.9, 0.999, self.adam_eps
+        a.lr_critic = float(getattr(ag, "lr_critic", 0.0))
+        a.step0 = ag.step
+        a.layer_norm = int(self.layer_norm)
+        a.critic_obs, a.critic_obs_dim = joint.data_ptr(), joint.shape[1]
+        a.value_loss = 1 if self.trick['huber_loss'] else 0
+        a.huber_delta = float(huber_delta) if huber_delta is not None else 0.0
+        a.gpart, a.sumsq, a.segcnt = self._gpart.data_ptr(), self._sumsq.data_ptr(), self._segcnt.data_ptr()
+        a.stats, a.out = self._stats.data_ptr(), out.data_ptr()
+        self._launch_update(a, ag._net, n_updates)
+        ag.step += n_updates
+        self._keep = (idx_d, rows_d, joint, adv, v_target)
+        return out
+
     def learn(self, minibatch_size, gamma, lmbda, clip_param, K_epochs, entropy_coefficient, huber_delta=None, *, permutations=None):
         adv, v_target, joint = self.compute_advantages(gamma, lmbda)
         self.last_adv, self.last_v_target = adv, v_target
-        H, N = self.horizon, self.num_agents
-        nmb = (H + minibatch_size - 1) // minibatch_size
         outs = []
         for agent_id, ag in self.agents.items():
-            b = self.buffers[agent_id]
-            if permutations is not None:
-                perms = permutations[agent_id]
-            elif self.mode == "parity":
-                perms = [np.random.permutation(H) for _ in range(K_epochs)]              # MAPPO.py:395
-            else:
-                g = torch.Generator(device="cpu")
-                g.manual_seed((self._seed + ag.step) & 0x7FFFFFFF)
-                perms = [torch.randperm(H, generator=g).numpy() for _ in range(K_epochs)]
-            idx = np.zeros((K_epochs * nmb, minibatch_size), np.int64)
-            rows = np.zeros(K_epochs * nmb, np.int32)
-            for e, perm in enumerate(perms):
-                for j in range(nmb):
-                    sl = np.asarray(perm[j * minibatch_size:(j + 1) * minibatch_size])
-                    idx[e * nmb + j, :sl.size] = sl
-                    rows[e * nmb + j] = sl.size
-            idx_d, rows_d = torch.from_numpy(idx).to(self.device), torch.from_numpy(rows).to(self.device)
-            n_updates = idx.shape[0]
-            out = torch.zeros((n_updates, 8), dtype=torch.float32, device=self.device)
-            a = _lib.PpoArgs()
-            a.net, a.continuous = ag._net.c_struct(), int(self.is_continue)
-            a.obs, a.action, a.logp_old = b.obs.data_ptr(), b.actions.data_ptr(), b.action_log_probs.data_ptr()
-            a.adv, a.v_target = adv.data_ptr(), v_target.data_ptr()
-            a.M, a.obs_dim, a.act_cols, a.logp_cols, a.n_adv = b.capacity, b.obs_dim, b.act_dim, b.logp_dim, N
-            a.indices, a.mb_rows, a.mb, a.n_updates = idx_d.data_ptr(), rows_d.data_ptr(), minibatch_size, n_updates
-            a.clip_param, a.entropy_coef = clip_param, entropy_coefficient
-            a.max_norm_actor = a.max_norm_critic = 0.0                                # no clip_grad_norm_ in MAPPO.update_ac
-            a.optimizer = _lib.OPT_ADAM
-            a.lr, a.beta1, a.beta2, a.eps = ag.lr, 0.9, 0.999, 1e-5
-            a.step0 = ag.step
-            a.layer_norm = int(self.layer_norm)
-            a.critic_obs, a.critic_obs_dim = joint.data_ptr(), joint.shape[1]
-            a.value_loss = 1 if self.trick['huber_loss'] else 0
-            a.huber_delta = float(huber_delta) if huber_delta is not None else 0.0
-            a.gpart, a.sumsq, a.segcnt = self._gpart.data_ptr(), self._sumsq.data_ptr(), self._segcnt.data_ptr()
-            a.stats, a.out = self._stats.data_ptr(), out.data_ptr()
-            self._launch_update(a, ag._net, n_updates)
-            ag.step += n_updates
-            outs.append(out)
-            self._keep = (idx_d, rows_d, joint, adv, v_target)
+            perms = self._permutations(ag, K_epochs, None if permutations is None else permutations[agent_id])
+            outs.append(self._agent_update(agent_id, adv, v_target, joint, minibatch_size, K_epochs, clip_param, entropy_coefficient,
+                                           huber_delta, perms))
         self.last_metrics = torch.cat(outs)
         for buffer in self.buffers.values():
             buffer.clear()

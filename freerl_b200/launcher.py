@@ -29,6 +29,7 @@ _ALGOS = {            # script file name -> (class name in the script, our modul
     "DDPG_simple.py": ("DDPG", "freerl_b200.DDPG_simple", "DDPG"),
     "MAPPO.py": ("MAPPO", "freerl_b200.MAPPO", "MAPPO"),
     "IPPO.py": ("IPPO", "freerl_b200.IPPO", "IPPO"),
+    "HAPPO.py": ("HAPPO", "freerl_b200.HAPPO", "HAPPO"),
 }
 
 

@@ -314,3 +314,73 @@ class IPPOOracle:
                     adam_step(cp, list(gc), self.opt_c[k])
                     out["losses"].append((actor_loss.item(), critic_loss.item()))
         return out
+
+
+# --------------------------------------------------------------------------------------------------
+# HAPPO  (MAPPO_file/HAPPO.py:263-458)
+# --------------------------------------------------------------------------------------------------
+class HAPPOOracle(MAPPOOracle):
+    """``HAPPO.py:338-447`` (continuous actions): MAPPO's joint-observation critics, joint GAE and joint ``adv_norm``, but the
+    agents are visited sequentially in ``torch.randperm`` order and agent m's surrogate is weighted row-wise by
+    ``factor = prod_{agents before m} exp(logp_new - logp_old)`` evaluated on the FULL horizon with that agent's actor before /
+    after its own epochs (``:367-377, 437-445``; float32 numpy).  Separate ``Adam`` for actor / critic (eps 1e-5 with
+    ``adam_eps``), ``clip_grad_norm_(0.5)`` each, actor step then critic step (``:236-253``)."""
+
+    def __init__(self, actors, critics, actor_lr, critic_lr, trick):
+        super().__init__(actors, critics, actor_lr, trick, is_continue=True)
+        eps = 1e-5 if trick['adam_eps'] else 1e-8
+        self.opt_a = {k: AdamState(list(self.actor[k].values()), actor_lr, eps=eps) for k in self.ids}
+        self.opt_c = {k: AdamState(list(self.critic[k].values()), critic_lr, eps=eps) for k in self.ids}
+
+    def full_logp(self, k, obs, action):
+        with torch.no_grad():
+            mean, std = self.actor_dist(k, obs)
+            return torch.distributions.Normal(mean, std).log_prob(action).sum(dim=1, keepdim=True)
+
+    def learn(self, data, order, permutations, minibatch_size, gamma, lmbda, clip_param, entropy_coefficient, huber_delta):
+        import numpy as np
+        ids = self.ids
+        adv, v_target = self.advantages(data, gamma, lmbda)
+        H = adv.shape[0]
+        factor = np.ones((H, 1), dtype=np.float32)
+        losses = []
+        for pos, ai in enumerate(order):
+            k = ids[int(ai)]
+            obs, action, logp_old = data[k][0], data[k][1], data[k][5]
+            if pos != len(ids) - 1:
+                old_full = self.full_logp(k, obs, action)
+            factor_t = torch.as_tensor(factor, dtype=torch.float32).reshape(-1, 1)
+            for perm in permutations[k]:
+                for s in range(0, H, minibatch_size):
+                    index = perm[s:s + minibatch_size]
+                    mean, std = self.actor_dist(k, obs[index])
+                    dist = torch.distributions.Normal(mean, std)
+                    ent = dist.entropy().sum(dim=1, keepdim=True)
+                    logp = dist.log_prob(action[index])
+                    ratios = torch.exp(logp.sum(dim=1, keepdim=True) - logp_old[index].sum(dim=1, keepdim=True))
+                    surr1 = ratios * adv[index]
+                    surr2 = torch.clamp(ratios, 1 - clip_param, 1 + clip_param) * adv[index]
+                    actor_loss = -(factor_t[index] * torch.min(surr1, surr2)).mean() - entropy_coefficient * ent.mean()
+                    ap = list(self.actor[k].values())
+                    ga, _ = clip_grad_norm(torch.autograd.grad(actor_loss, ap), 0.5)
+                    adam_step(ap, list(ga), self.opt_a[k])
+                    joint = torch.cat([data[j][0][index] for j in ids], dim=1)
+                    v_s = self.values(k, joint).repeat(1, len(ids))
+                    vt = v_target[index]
+                    if self.trick['huber_loss']:        # ValueClip: max(original, clipped) == original (see freerl_b200/IPPO.py)
+                        critic_loss = huber_loss(vt - v_s, huber_delta).mean()
+                        if self.trick['ValueClip']:
+                            vt_clip = torch.clamp(vt, v_s - clip_param, v_s + clip_param)
+                            critic_loss = torch.max(critic_loss, huber_loss(vt_clip - v_s, huber_delta).mean())
+                    else:
+                        critic_loss = F.mse_loss(vt, v_s)
+                        if self.trick['ValueClip']:
+                            critic_loss = torch.max(critic_loss, F.mse_loss(torch.clamp(vt, v_s - clip_param, v_s + clip_param), v_s))
+                    cp = list(self.critic[k].values())
+                    gc, _ = clip_grad_norm(torch.autograd.grad(critic_loss, cp), 0.5)
+                    adam_step(cp, list(gc), self.opt_c[k])
+                    losses.append((actor_loss.item(), critic_loss.item()))
+            if pos != len(ids) - 1:
+                new_full = self.full_logp(k, obs, action)
+                factor = factor * torch.exp(new_full - old_full).reshape(-1, 1).numpy()
+        return {"adv": adv, "v_target": v_target, "losses": losses, "factor": factor}

@@ -159,3 +159,17 @@ def test_ippo_continuous_oracle_vs_reference(golden):
 
 def test_ippo_discrete_oracle_vs_reference(golden):
     _ippo_oracle(golden, "ippo_disc", False)
+
+
+def test_happo_oracle_vs_reference(golden):
+    from oracle.marl import HAPPOOracle
+    g = golden("happo")
+    assert list(g["order"]) != [0, 1, 2]                       # the fixture exercises a non-trivial agent order
+    orc = HAPPOOracle(maddpg_nets(g, "init", "actor"), maddpg_nets(g, "init", "critic"), 1e-3, 5e-4, MAPPO_TRICK)
+    perms = {k: [g["perm/%s/%d" % (k, e)] for e in range(2)] for k in IDS}
+    r = orc.learn(mappo_data(g), g["order"], perms, 32, 0.95, 0.95, 0.2, 0.01, 10.0)
+    np.testing.assert_allclose(np.array(r["losses"]), g["losses"], rtol=3e-5, atol=1e-6)
+    for k in IDS:
+        for kind, nets in (("actor", orc.actor), ("critic", orc.critic)):
+            for n, v in nets[k].items():
+                np.testing.assert_allclose(v.detach().numpy(), g["final/%s/%s/%s" % (k, kind, n)], rtol=2e-5, atol=2e-6, err_msg="%s %s %s" % (k, kind, n))

@@ -128,3 +128,46 @@ def test_ippo_continuous_gpu(golden):
 @pytest.mark.gpu
 def test_ippo_discrete_gpu(golden):
     _ippo(golden, torch.device("cuda"), "ippo_disc", False)
+
+
+def _happo(golden, device):
+    """freerl_b200.HAPPO (sequential agents, factor folded into the advantages) vs oracle + MAPPO_file/HAPPO.py golden"""
+    from freerl_b200.HAPPO import HAPPO
+    from oracle.marl import HAPPOOracle
+    g = golden("happo")
+    pol = HAPPO({k: [18, 5] for k in IDS}, True, 1e-3, 5e-4, 64, device, dict(MAPPO_TRICK))
+    ia, ic = maddpg_nets(g, "init", "actor"), maddpg_nets(g, "init", "critic")
+    for k in IDS:
+        load_into(pol.agents[k].actor, ia[k])
+        load_into(pol.agents[k].critic, ic[k])
+    orc = HAPPOOracle(ia, ic, 1e-3, 5e-4, MAPPO_TRICK)
+    data = mappo_data(g)
+    d = {k: [x.numpy() for x in data[k]] for k in IDS}
+    for t in range(64):
+        pol.add({k: d[k][0][t] for k in IDS}, {k: d[k][1][t] for k in IDS}, {k: float(d[k][2][t, 0]) for k in IDS},
+                {k: d[k][3][t] for k in IDS}, {k: bool(d[k][4][t, 0]) for k in IDS}, {k: d[k][5][t] for k in IDS},
+                {k: bool(d[k][6][t, 0]) for k in IDS})
+    perms = {k: [g["perm/%s/%d" % (k, e)] for e in range(2)] for k in IDS}
+    r = orc.learn(data, g["order"], perms, 32, 0.95, 0.95, 0.2, 0.01, 10.0)
+    pol.learn(32, 0.95, 0.95, 0.2, 2, 0.01, 10.0, permutations=perms, order=g["order"])
+    np.testing.assert_allclose(pol.last_factor.cpu().numpy(), r["factor"], rtol=5e-5, atol=1e-6)
+    m = pol.last_metrics.cpu().numpy()
+    ref = np.array(r["losses"])
+    np.testing.assert_allclose(m[:, 0], ref[:, 0], rtol=5e-5, atol=3e-6)
+    np.testing.assert_allclose(m[:, 1], ref[:, 1], rtol=3e-5, atol=3e-6)
+    np.testing.assert_allclose(m[:, :2], g["losses"], rtol=1e-4, atol=1e-5)
+    tol = dict(rtol=1e-4, atol=1e-5)
+    for k in IDS:
+        assert_module_close(pol.agents[k].actor, orc.actor[k], "actor " + k, tol)
+        assert_module_close(pol.agents[k].critic, orc.critic[k], "critic " + k, tol)
+        assert_module_close(pol.agents[k].actor, maddpg_nets(g, "final", "actor")[k], "final actor " + k, tol)
+        assert_module_close(pol.agents[k].critic, maddpg_nets(g, "final", "critic")[k], "final critic " + k, tol)
+
+
+def test_happo_emulated(golden, emul):
+    _happo(golden, torch.device("cpu"))
+
+
+@pytest.mark.gpu
+def test_happo_gpu(golden):
+    _happo(golden, torch.device("cuda"))
