@@ -63,6 +63,13 @@ def run_reference_script(script_path, argv=(), results_root="./freerl_runs", ext
     except Exception:
         from . import envshim
         sys.modules["gymnasium"] = envshim.as_module()
+    try:
+        importlib.import_module("pettingzoo.mpe")
+    except Exception:
+        from . import envshim
+        sys.modules.update(envshim.mpe_modules())
+    for helper in ("Noisy_net", "normalization", "c_adamw", "util"):      # same module names, different contents per directory
+        sys.modules.pop(helper, None)
     sdir = os.path.dirname(script_path)
     if sdir not in sys.path:
         sys.path.insert(0, sdir)                 # sibling helpers (Noisy_net, c_adamw, normalization) stay the reference's own

@@ -34,3 +34,50 @@ def test_reference_sac_and_ppo_scripts_unchanged(tmp_path, emul):
                                        ["--env_name", "Pendulum-v1", "--max_episodes", "2", "--horizon", "128", "--minibatch_size", "32",
                                         "--K_epochs", "2", "--device", "cpu"], results_root=str(tmp_path))
     assert ns["policy"].agent.step == 3 * 2 * 4 or ns["policy"].agent.step > 0
+
+
+def test_reference_multi_agent_scripts_unchanged(tmp_path, emul):
+    """MADDPG.py / MATD3_simple.py (off-policy, dict-in / dict-out PettingZoo loop) and MAPPO.py / IPPO.py / HAPPO.py (on-policy)
+    run unchanged on the synthetic MPE shim; learn() runs on the fused kernels (optimiser step counters move)."""
+    from freerl_b200 import launcher
+    off = ["--env_name", "simple_spread_v3", "--N", "3", "--max_episodes", "4", "--start_steps", "60", "--batch_size", "32",
+           "--buffer_size", "2000", "--device", "cpu"]
+    ns = launcher.run_reference_script(os.path.join(REF, "MADDPG_file", "MADDPG.py"), off, results_root=str(tmp_path))
+    pol = ns["policy"]
+    assert type(pol).__module__ == "freerl_b200.MADDPG" and all(a.critic_step > 0 for a in pol.agents.values())
+    assert os.path.exists(os.path.join(ns["model_dir"], "MADDPG.pth"))
+    ns = launcher.run_reference_script(os.path.join(REF, "MADDPG_file", "MATD3_simple.py"), off, results_root=str(tmp_path))
+    pol = ns["policy"]
+    assert type(pol).__module__ == "freerl_b200.MATD3_simple" and pol.total_it > 0
+    on = ["--env_name", "simple_spread_v3", "--N", "3", "--max_episodes", "6", "--horizon", "50", "--minibatch_size", "25",
+          "--K_epochs", "2", "--device", "cpu"]
+    for sub, cls in (("MAPPO.py", "MAPPO"), ("IPPO.py", "IPPO"), ("HAPPO.py", "HAPPO")):
+        extra = ["--continuous_actions", "True"] if sub != "MAPPO.py" else []
+        ns = launcher.run_reference_script(os.path.join(REF, "MAPPO_file", sub), on + extra, results_root=str(tmp_path))
+        pol = ns["policy"]
+        assert type(pol).__module__ == "freerl_b200." + cls and all(a.step > 0 for a in pol.agents.values()), sub
+
+
+def test_reference_single_agent_siblings_unchanged(tmp_path, emul):
+    """TD3.py, Rainbow DQN_with_tricks.py (default trick set), DDPG_simple.py, MADDPG_simple.py and PPO_advance/PPO.py unchanged."""
+    from freerl_b200 import launcher
+    ns = launcher.run_reference_script(os.path.join(REF, "TD3_file", "TD3.py"),
+                                       ["--env_name", "Pendulum-v1", "--max_episodes", "1", "--start_steps", "60", "--batch_size", "32",
+                                        "--buffer_size", "1000", "--device", "cpu"], results_root=str(tmp_path))
+    assert ns["policy"].total_it > 0 and ns["policy"].agent.actor_step == ns["policy"].total_it // 2
+    ns = launcher.run_reference_script(os.path.join(REF, "DQN_file", "DQN_with_tricks.py"),
+                                       ["--env_name", "CartPole-v1", "--max_episodes", "2", "--start_steps", "40", "--batch_size", "16",
+                                        "--buffer_size", "512", "--device", "cpu"], results_root=str(tmp_path))
+    assert type(ns["policy"]).__name__ == "_RainbowDQN" and ns["policy"].agent.step > 0
+    ns = launcher.run_reference_script(os.path.join(REF, "DDPG_file", "DDPG_simple.py"),
+                                       ["--env_name", "Pendulum-v1", "--max_episodes", "1", "--start_steps", "60", "--batch_size", "32",
+                                        "--buffer_size", "1000", "--device", "cpu"], results_root=str(tmp_path))
+    assert type(ns["policy"]).__module__ == "freerl_b200.DDPG_simple" and ns["policy"].agent.critic_step > 0
+    ns = launcher.run_reference_script(os.path.join(REF, "MADDPG_file", "MADDPG_simple.py"),
+                                       ["--env_name", "simple_spread_v3", "--N", "3", "--max_episodes", "4", "--start_steps", "60",
+                                        "--batch_size", "32", "--buffer_size", "2000", "--device", "cpu"], results_root=str(tmp_path))
+    assert type(ns["policy"]).__module__ == "freerl_b200.MADDPG_simple"
+    ns = launcher.run_reference_script(os.path.join(REF, "PPO_advance", "PPO.py"),
+                                       ["--env_name", "CartPole-v1", "--max_episodes", "3", "--horizon", "64", "--minibatch_size", "32",
+                                        "--K_epochs", "2", "--device", "cpu"], results_root=str(tmp_path))
+    assert type(ns["policy"]).__module__ == "freerl_b200.PPO_advance" and ns["policy"].agent.step > 0
