@@ -141,7 +141,11 @@ class Agent:
 
     def _refresh_buffers(self):
         for key, mod in (("online", self.Qnet), ("target", self.Qnet_target)):
-            vin, vout, ain, aout = [f_noise(x) for x in self._last_eps[key]]
+            last = self._last_eps[key]
+            if len(last) == 2 and isinstance(last[0], str):          # fast mode: ("f", already transformed device slices)
+                vin, vout, ain, aout = [x.detach().cpu() for x in last[1]]
+            else:
+                vin, vout, ain, aout = [f_noise(x) for x in last]
             dev = mod.V.weight_epsilon.device
             mod.V.weight_epsilon.copy_(torch.ger(vout, vin).to(dev)); mod.V.bias_epsilon.copy_(vout.to(dev))
             mod.A.weight_epsilon.copy_(torch.ger(aout, ain).to(dev)); mod.A.bias_epsilon.copy_(aout.to(dev))
@@ -342,6 +346,15 @@ class _RainbowDQN(DQN):
         ag = self.agent
         return (torch.randn(HIDDEN), torch.randn(ag.n_atoms), torch.randn(HIDDEN), torch.randn(ag.nA * ag.n_atoms))
 
+    def _device_eps(self):
+        """fast mode: the transformed noise f(eps) = sign(eps) sqrt|eps| of all three forwards drawn ON the device (no host
+        round trip); returns per-forward 4-tuples of slices for the weight_epsilon bookkeeping"""
+        ag, e, o = self.agent, self._eps, self.agent.eps_off
+        e.normal_()
+        torch.mul(torch.sign(e), torch.sqrt(torch.abs(e)), out=e)
+        return [(e[f, o["V_in"]:o["V_in"] + HIDDEN], e[f, o["V_out"]:o["V_out"] + ag.n_atoms], e[f, o["A_in"]:o["A_in"] + HIDDEN],
+                 e[f, o["A_out"]:o["A_out"] + ag.nA * ag.n_atoms]) for f in range(3)]
+
     def _pack_eps(self, raws):
         """raws: list of 3 (or fewer) 4-tuples -> device [3, eps_len] of transformed noise"""
         ag = self.agent
@@ -388,10 +401,13 @@ class _RainbowDQN(DQN):
         x, single = _common.as_obs_batch(obs, self.obs_dim)
         xd = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(self.device) if not isinstance(x, torch.Tensor) else x.to(self.device).float().contiguous()
         train = getattr(self.agent.Qnet.V, "is_train", True)
-        raw = noise if noise is not None else (self._draw_forward_noise() if train else tuple(torch.zeros(n) for n in (HIDDEN, self.agent.n_atoms, HIDDEN, self.agent.nA * self.agent.n_atoms)))
-        if train:
-            self.agent._last_eps["online"] = tuple(torch.as_tensor(r) for r in raw)
-        self._pack_eps([raw, None, None])
+        if noise is None and train and self.mode == "fast":
+            self.agent._last_eps["online"] = ("f", self._device_eps()[0])
+        else:
+            raw = noise if noise is not None else (self._draw_forward_noise() if train else tuple(torch.zeros(n) for n in (HIDDEN, self.agent.n_atoms, HIDDEN, self.agent.nA * self.agent.n_atoms)))
+            if train:
+                self.agent._last_eps["online"] = tuple(torch.as_tensor(r) for r in raw)
+            self._pack_eps([raw, None, None])
         out = torch.empty(xd.shape[0], dtype=torch.float32, device=self.device)
         a = self._args()
         _lib.check(_lib.lib().frl_rainbow_act(ctypes.byref(a), _lib.ptr(xd), xd.shape[0], _lib.ptr(out), _lib.stream_ptr(self.device)),
@@ -427,13 +443,15 @@ class _RainbowDQN(DQN):
                 else self.buffer._indices_to_device(indices).reshape(-1)
         if self.trick['N_Step']:
             gamma = self.buffer.n_step_gamma
-        if noise is None:
-            noise = [self._draw_forward_noise() if self.trick['Double'] else None, self._draw_forward_noise(), self._draw_forward_noise()]
-        if noise[0] is not None:
-            pass
-        self.agent._last_eps["online"] = tuple(torch.as_tensor(r) for r in noise[2])
-        self.agent._last_eps["target"] = tuple(torch.as_tensor(r) for r in noise[1])
-        self._pack_eps(noise)
+        if noise is None and self.mode == "fast":
+            sl = self._device_eps()
+            self.agent._last_eps["online"], self.agent._last_eps["target"] = ("f", sl[2]), ("f", sl[1])
+        else:
+            if noise is None:
+                noise = [self._draw_forward_noise() if self.trick['Double'] else None, self._draw_forward_noise(), self._draw_forward_noise()]
+            self.agent._last_eps["online"] = tuple(torch.as_tensor(r) for r in noise[2])
+            self.agent._last_eps["target"] = tuple(torch.as_tensor(r) for r in noise[1])
+            self._pack_eps(noise)
         err = torch.empty(B, dtype=torch.float32, device=self.device)
         a = self._args()
         a.indices, a.B = idx.data_ptr(), B

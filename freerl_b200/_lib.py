@@ -117,7 +117,7 @@ def _declare(lib):
     lib.frl_policy_infer.argtypes = [C.POINTER(InferArgs), vp]
     lib.frl_gae.argtypes = [vp, vp, vp, vp, vp, ci, ci, C.c_double, C.c_double, vp, vp, vp]
     lib.frl_ppo_update.argtypes = [C.POINTER(PpoArgs), vp]
-    lib.frl_sumtree_update.argtypes = [vp, i64, vp, vp, vp, C.c_double, i64, ci, ci, vp]
+    lib.frl_sumtree_update.argtypes = [vp, i64, vp, vp, vp, C.c_double, i64, ci, ci, vp, vp]
     lib.frl_sumtree_sample.argtypes = [vp, i64, vp, u64, u64, ci, i64, C.c_double, C.c_double, vp, vp, vp, vp]
     lib.frl_sumtree_max.argtypes = [vp, i64, vp, ci, vp, vp]
     lib.frl_per_priorities.argtypes = [vp, ci, C.c_float, C.c_float, vp, vp]

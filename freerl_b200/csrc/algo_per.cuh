@@ -21,6 +21,14 @@ static inline double f64div(double a, double b) { return a / b; }
 #define FRL_PER_MAXB 1024
 
 // ---- ordered batch update ------------------------------------------------------------------------------------
+// Two stages of one cooperative launch over `depth` CTAs.  Stage 0 (CTA 0): leaf phase — change_i = p_i - (value the leaf
+// holds when item i is applied), leaves written, keys + changes published in `scratch`.  Stage 1: one CTA per tree LEVEL.
+// With key = heap index + 1 the parent of a node is key >> 1, so the ancestor of item i at level L is (key_i >> L) - 1 and
+// two items meet at level L iff their keys agree after the shift.  A node's new value depends only on its old value and
+// the batch-ordered changes of the items below it, never on other levels, so the levels run concurrently on different
+// SMs.  Inside a level, item i is the node's "leader" when no earlier item shares the node; the leader adds the changes of
+// all its items IN BATCH ORDER (fp64 addition is not associative: the order is what makes the last ulp match the
+// sequential reference).  Keys are 32-bit (capacity < 2^30) and scanned four at a time from shared memory.
 struct TreeUpdateArgs {
   double* tree; int64_t cap;
   const int64_t* idx;        // [B] buffer indices
@@ -29,71 +37,90 @@ struct TreeUpdateArgs {
   double pri_const;          // used when both are null
   int64_t idx0; int idx_is_range;   // idx_is_range: item i targets (idx0 + i) % cap (batched ring add)
   int B;
+  double* scratch;           // dev [FRL_PER_MAXB] changes (f64) followed by [FRL_PER_MAXB] keys (u32)
 };
 
 struct TreeUpdateAlgo {
   typedef TreeUpdateArgs Args;
-  static const int NSTAGES = 1;
+  static const int NSTAGES = 2;
+  FRL_SHD bool writes_params(int) { return false; }
+  FRL_SHD bool stage_enabled(int, int, const Args&) { return true; }
   FRL_SHD int wbuf_floats(const Args&) { return 32; }
-  FRL_SHD int user_floats(const Args& a) { return 2 * (2 * a.B + 2 * a.B) + 64; }     // node[B] (i64) + change[B] (f64)
-  FRL_SHD int grid(const Args&, int) { return 1; }
+  FRL_SHD int bp(const Args& a) { return (a.B + 3) & ~3; }
+  FRL_SHD int user_floats(const Args& a) { return 4 * bp(a) + 64; }                   // keys (u32) + shifted keys (u32) + changes (f64)
+  FRL_SHD int depth(const Args& a) { int m = 0; uint64_t k = (uint64_t)(2 * a.cap - 1); while (k > 1) { k >>= 1; ++m; } return m; }
+  FRL_SHD int grid(const Args& a, int max_ctas) { const int m = depth(a); return m < 1 ? 1 : (m < max_ctas ? m : max_ctas); }
   FRL_SHD int n_updates(const Args&) { return 1; }
-  FRL_SDEV void stage(int, int, Cta&, float* user, const Args& a) {
-    int64_t* node = (int64_t*)user;                 // current node of item i (-1: finished)
-    double* change = (double*)(node + a.B);
-    const int B = a.B;
-    // leaf phase: change_i = p_i - (value the leaf holds when item i is applied)
-    FRL_PAR(t) {
-      for (int i = t; i < B; i += FRL_NT) {
-        const int64_t bi = a.idx_is_range ? (a.idx0 + i) % a.cap : a.idx[i];
-        node[i] = bi + a.cap - 1;
+  FRL_SDEV double pri_of(const Args& a, int i) { return a.pri32 ? (double)a.pri32[i] : (a.pri64 ? a.pri64[0] : a.pri_const); }
+  // any j in [lo, hi) with ks[j] == k ?   (hi - lo may be anything; ks is padded to a multiple of 4 with never-matching zeros)
+  FRL_SDEV bool any_equal(const uint32_t* ks, int lo, int hi, uint32_t k) {
+    bool hit = false;
+    int j = lo;
+    for (; j < hi && (j & 3); ++j) hit |= (ks[j] == k);
+    for (; j + 4 <= hi; j += 4) {
+      const uint4 q = *reinterpret_cast<const uint4*>(ks + j);
+      hit |= (q.x == k) | (q.y == k) | (q.z == k) | (q.w == k);
+    }
+    for (; j < hi; ++j) hit |= (ks[j] == k);
+    return hit;
+  }
+  FRL_SDEV void stage(int s, int, Cta& c, float* user, const Args& a) {
+    const int B = a.B, Bp = bp(a);
+    uint32_t* key = (uint32_t*)user;                // leaf KEY (= heap index + 1) of item i
+    uint32_t* ks = key + Bp;                        // key >> L of the level in flight
+    double* change = (double*)(ks + Bp);
+    uint32_t* gkey = (uint32_t*)(a.scratch + FRL_PER_MAXB);
+    if (s == 0) {
+      if (c.cta != 0) return;
+      FRL_PAR(t) {
+        for (int i = t; i < Bp; i += FRL_NT) {
+          const int64_t bi = a.idx_is_range ? (a.idx0 + i) % a.cap : (i < B ? a.idx[i] : 0);
+          key[i] = i < B ? (uint32_t)(bi + a.cap) : 0u;
+        }
       }
-    }
-    FRL_SYNC();
-    FRL_PAR(t) {
-      for (int i = t; i < B; i += FRL_NT) {
-        const double p = a.pri32 ? (double)a.pri32[i] : (a.pri64 ? a.pri64[0] : a.pri_const);
-        int prev = -1;
-        for (int j = i - 1; j >= 0; --j) if (node[j] == node[i]) { prev = j; break; }
-        const double before = prev >= 0 ? (a.pri32 ? (double)a.pri32[prev] : p) : a.tree[node[i]];
-        change[i] = f64add(p, -before);
+      FRL_SYNC();
+      // change_i = p_i - before_i; before_i = priority of the previous item on the same leaf, else the stored leaf
+      FRL_PAR(t) {
+        for (int i = t; i < B; i += FRL_NT) {
+          const uint32_t k = key[i];
+          int prev = -1;
+          for (int j = 0; j < i; ++j) prev = (key[j] == k) ? j : prev;
+          const double p = pri_of(a, i);
+          const double before = prev >= 0 ? pri_of(a, prev) : a.tree[(int64_t)k - 1];
+          const double ch = f64add(p, -before);
+          a.scratch[i] = ch;
+          gkey[i] = k;
+        }
       }
-    }
-    FRL_SYNC();
-    FRL_PAR(t) {
-      for (int i = t; i < B; i += FRL_NT) {
-        bool last = true;
-        for (int j = i + 1; j < B; ++j) if (node[j] == node[i]) { last = false; break; }
-        if (last) a.tree[node[i]] = a.pri32 ? (double)a.pri32[i] : (a.pri64 ? a.pri64[0] : a.pri_const);
+      FRL_SYNC();                                   // every `before` read precedes every leaf write
+      FRL_PAR(t) {
+        for (int i = t; i < B; i += FRL_NT)
+          if (!any_equal(key, i + 1, B, key[i])) a.tree[(int64_t)key[i] - 1] = pri_of(a, i);      // the last write wins
       }
+      FRL_SYNC();
+      return;
     }
-    FRL_SYNC();
-    // Ancestors.  With key = heap index + 1 the parent of a node is key >> 1, so the ancestor of item i at level L is
-    // (key_i >> L) - 1 and two items meet at level L iff their keys agree after the shift.  A node's new value depends only
-    // on its old value and the batch-ordered changes of the items below it, never on other levels: every (item, level)
-    // pair is processed independently in ONE phase (no per-level barrier, all tree loads in flight together).  The pair is
-    // the node's "leader" when no earlier item shares the node; the leader adds the changes of all its items IN BATCH
-    // ORDER (fp64 addition is not associative: the order is what makes the last ulp match the sequential reference).
-    FRL_PAR(t) {
-      for (int i = t; i < B; i += FRL_NT) node[i] = node[i] + 1;       // node[] now holds the leaf KEY
-    }
-    FRL_SYNC();
-    int maxlev = 0;
-    { uint64_t k = (uint64_t)(2 * a.cap - 1); while (k > 1) { k >>= 1; ++maxlev; } }   // depth of the deepest leaf
-    FRL_PAR(t) {
-      for (int it = t; it < B * maxlev; it += FRL_NT) {
-        const int L = it / B + 1, i = it - (L - 1) * B;               // consecutive threads: consecutive items of one level
-        const int64_t k = node[i] >> L;
-        if (k < 1) continue;
-        bool leader = true;
-        for (int j = 0; j < i; ++j) if ((node[j] >> L) == k) { leader = false; break; }
-        if (!leader) continue;
-        double v = f64add(a.tree[k - 1], change[i]);
-        for (int j = i + 1; j < B; ++j) if ((node[j] >> L) == k) v = f64add(v, change[j]);
-        a.tree[k - 1] = v;
+    const int maxlev = depth(a);
+    for (int L = c.cta + 1; L <= maxlev; L += c.ncta) {
+      FRL_PAR(t) {
+        for (int i = t; i < Bp; i += FRL_NT) {
+          ks[i] = i < B ? (gkey[i] >> L) : 0u;
+          if (i < B) change[i] = a.scratch[i];
+        }
       }
+      FRL_SYNC();
+      FRL_PAR(t) {
+        for (int i = t; i < B; i += FRL_NT) {
+          const uint32_t k = ks[i];
+          if (k < 1u) continue;                     // this leaf sits above level L (two leaf depths when cap is not 2^k)
+          if (any_equal(ks, 0, i, k)) continue;     // an earlier item leads this node
+          double v = f64add(a.tree[(int64_t)k - 1], change[i]);
+          for (int j = i + 1; j < B; ++j) if (ks[j] == k) v = f64add(v, change[j]);
+          a.tree[(int64_t)k - 1] = v;
+        }
+      }
+      FRL_SYNC();
     }
-    FRL_SYNC();
   }
 };
 

@@ -221,11 +221,47 @@ struct SampleAlgo {
   }
 };
 
+// Large batches (B > 8192, e.g. one 65 536-row update per vector step): out[u][i] = P_u(i), i < B, where P_u is a keyed
+// BIJECTION of [0, size) — a 6-round balanced Feistel network on 2h >= log2(size) bits with cycle walking (re-encrypt until the
+// value falls below `size`; < 4 expected rounds).  Distinct by construction, O(1) per element, one thread per element.
+FRL_HD uint64_t frl_mix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+struct FeistelBody {
+  int64_t* out; uint64_t size; int B; uint64_t seed, counter; int half_bits;
+  FRL_HDM void operator()(long e) const {
+    const long u = e / B;
+    const uint64_t i = (uint64_t)(e - u * B);
+    const uint64_t key = frl_mix64(seed ^ frl_mix64(counter + (uint64_t)u + 0x9E3779B97F4A7C15ull));
+    const uint64_t mask = (1ull << half_bits) - 1;
+    uint64_t x = i;
+    do {
+      uint64_t L = x >> half_bits, R = x & mask;
+      for (int r = 0; r < 6; ++r) {
+        const uint64_t f = frl_mix64(R ^ (key + (uint64_t)r * 0xD1B54A32D192ED03ull)) & mask;
+        const uint64_t nl = R;
+        R = L ^ f;
+        L = nl;
+      }
+      x = (L << half_bits) | R;
+    } while (x >= size);
+    out[e] = (int64_t)x;
+  }
+};
+
 extern "C" int frl_sample_uniform(int64_t* indices_out, int64_t size, int B, int n_updates, uint64_t seed, uint64_t counter,
                                   void* stream) {
-  if (!indices_out || size <= 0 || size >= ((int64_t)1 << 31) || B <= 0 || B > size || B > 8192 || n_updates <= 0) {
-    frl_set_error("frl_sample_uniform: need 0 < B <= min(size, 8192), size < 2^31 (got size=%lld B=%d)", (long long)size, B);
+  if (!indices_out || size <= 0 || size >= ((int64_t)1 << 31) || B <= 0 || B > size || n_updates <= 0) {
+    frl_set_error("frl_sample_uniform: need 0 < B <= size < 2^31 (got size=%lld B=%d)", (long long)size, B);
     return -1;
+  }
+  if (B > 8192) {
+    int bits = 1;
+    while (((int64_t)1 << bits) < size) ++bits;
+    FeistelBody b = {indices_out, (uint64_t)size, B, seed, counter, (bits + 1) / 2};
+    return frl_for((long)B * n_updates, b, (cudaStream_t)stream);
   }
   SampleAlgo::Args a = {indices_out, size, B, n_updates, seed, counter};
   return frl_launch_tiles<SampleAlgo>(a, (cudaStream_t)stream);
@@ -473,13 +509,13 @@ extern "C" int frl_ppo_update(const frl_ppo_args_t* a, void* stream) {
 // prioritized replay: float64 sum-tree on the device
 // ------------------------------------------------------------------------------------------------
 extern "C" int frl_sumtree_update(double* tree, int64_t cap, const int64_t* idx, const float* pri32, const double* pri64_scalar,
-                                  double pri_const, int64_t idx0, int idx_is_range, int B, void* stream) {
-  if (!tree || cap <= 0 || B <= 0 || B > FRL_PER_MAXB || (!idx && !idx_is_range)) {
-    frl_set_error("frl_sumtree_update: bad arguments (B must be <= %d)", FRL_PER_MAXB);
+                                  double pri_const, int64_t idx0, int idx_is_range, int B, double* scratch, void* stream) {
+  if (!tree || cap <= 0 || cap >= ((int64_t)1 << 30) || B <= 0 || B > FRL_PER_MAXB || (!idx && !idx_is_range) || !scratch) {
+    frl_set_error("frl_sumtree_update: bad arguments (B <= %d, capacity < 2^30, scratch of %d doubles)", FRL_PER_MAXB, 2 * FRL_PER_MAXB);
     return -1;
   }
-  TreeUpdateArgs a = {tree, cap, idx, pri32, pri64_scalar, pri_const, idx0, idx_is_range, B};
-  return frl_launch_tiles<TreeUpdateAlgo>(a, (cudaStream_t)stream);
+  TreeUpdateArgs a = {tree, cap, idx, pri32, pri64_scalar, pri_const, idx0, idx_is_range, B, scratch};
+  return frl_launch<TreeUpdateAlgo>(a, (cudaStream_t)stream);
 }
 
 extern "C" int frl_sumtree_sample(const double* tree, int64_t cap, const double* u, uint64_t seed, uint64_t counter, int B, int64_t size,

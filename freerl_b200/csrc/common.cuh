@@ -41,6 +41,7 @@
 #define FRL_SYNC() ((void)0)
 typedef void* cudaStream_t;
 struct float4 { float x, y, z, w; };
+struct uint4 { unsigned x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { float4 r = {x, y, z, w}; return r; }
 static inline float __ldg(const float* p) { return *p; }
 #endif

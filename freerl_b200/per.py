@@ -30,7 +30,7 @@ class SumTree:
         B = int(B if B is not None else idx.numel())
         _lib.check(_lib.lib().frl_sumtree_update(
             _lib.ptr(self.tree), self.capacity, _lib.ptr(idx), _lib.ptr(pri32), _lib.ptr(pri64), float(pri_const), int(idx0),
-            int(is_range), B, _lib.stream_ptr(self.device)), "frl_sumtree_update")
+            int(is_range), B, _lib.ptr(self._scratch), _lib.stream_ptr(self.device)), "frl_sumtree_update")
 
     def add(self, buffer_index, priority):
         """set one leaf (reference ``SumTree.add``)"""

@@ -256,10 +256,11 @@ int frl_adv_norm(const float* x, int n, float eps, float* out, void* stream);
 /* Prioritized replay (DQN_file/Buffer.py:66-194): `tree` is the reference's float64 array heap [2*cap-1] on the device.
  * frl_sumtree_update applies B leaf writes IN ORDER (ancestors get `+= change` in batch order => bit-exact with the
  * sequential reference); targets are idx[i] or, with idx_is_range, (idx0+i) % cap; the new priority of item i is
- * pri32[i] | *pri64_scalar | pri_const.  frl_sumtree_sample = PER_Buffer.sample (stratified descent on u[i] in [0,1),
+ * pri32[i] | *pri64_scalar | pri_const; B <= 1024 per call, capacity < 2^30; one cooperative launch, one CTA per tree level.  frl_sumtree_sample = PER_Buffer.sample (stratified descent on u[i] in [0,1),
  * float32 priority container, float64 importance weights cast to fp32).  frl_sumtree_max = np.max(tree[-cap:]). */
 int frl_sumtree_update(double* tree, int64_t cap, const int64_t* idx, const float* pri32, const double* pri64_scalar,
-                       double pri_const, int64_t idx0, int idx_is_range, int B, void* stream);
+                       double pri_const, int64_t idx0, int idx_is_range, int B, double* scratch /* dev, >= 2048 doubles */,
+                       void* stream);
 int frl_sumtree_sample(const double* tree, int64_t cap, const double* u, uint64_t seed, uint64_t counter, int B, int64_t size,
                        double beta, double prob_floor, int64_t* out_idx, float* out_pri, float* out_w, void* stream);
 int frl_sumtree_max(const double* tree, int64_t cap, double* scratch, int nscratch, double* out, void* stream);

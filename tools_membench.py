@@ -102,14 +102,15 @@ def main():
     # ---- PER sum-tree (cap 1e6 like the reference default, non power of two) ----
     capt = 1_000_000
     tree = torch.zeros(2 * capt - 1, dtype=torch.float64, device=dev)
+    tscr = torch.zeros(4096, dtype=torch.float64, device=dev)
     pri = torch.rand(capt, device=dev, generator=g) + 0.01
     # build by ordered range update in chunks (also the timed "add" path)
     B = 256
-    ms = timeit(lambda: L.frl_sumtree_update(_lib.ptr(tree), capt, None, _lib.ptr(pri), None, 0.0, 0, 1, B, st), reps=20)
-    rec("frl_sumtree_update B=256 cap=1e6 (ordered)", ms, B * 20 * 16, "B x ceil(log2 cap)=20 levels x (8 B read + 8 B write); serial by design (bit-exact)")
+    ms = timeit(lambda: L.frl_sumtree_update(_lib.ptr(tree), capt, None, _lib.ptr(pri), None, 0.0, 0, 1, B, _lib.ptr(tscr), st), reps=20)
+    rec("frl_sumtree_update B=256 cap=1e6 (ordered)", ms, B * 20 * 16, "B x ceil(log2 cap)=20 levels x (8 B read + 8 B write); one CTA per tree level, batch-ordered fp64 chains (bit-exact)")
     for i0 in range(0, capt, 1024):
         nb = min(1024, capt - i0)
-        L.frl_sumtree_update(_lib.ptr(tree), capt, None, _lib.ptr(pri[i0:]), None, 0.0, i0, 1, nb, st)
+        L.frl_sumtree_update(_lib.ptr(tree), capt, None, _lib.ptr(pri[i0:]), None, 0.0, i0, 1, nb, _lib.ptr(tscr), st)
     oi = torch.empty(B, dtype=torch.int64, device=dev); op = torch.empty(B, device=dev); ow = torch.empty(B, device=dev)
     ms = timeit(lambda: L.frl_sumtree_sample(_lib.ptr(tree), capt, None, ctypes.c_uint64(3), ctypes.c_uint64(0), B, capt, 0.4, 1e-7,
                                              _lib.ptr(oi), _lib.ptr(op), _lib.ptr(ow), st), reps=20)
