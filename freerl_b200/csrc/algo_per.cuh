@@ -22,13 +22,15 @@ static inline double f64div(double a, double b) { return a / b; }
 
 // ---- ordered batch update ------------------------------------------------------------------------------------
 // Two stages of one cooperative launch over `depth` CTAs.  Stage 0 (CTA 0): leaf phase — change_i = p_i - (value the leaf
-// holds when item i is applied), leaves written, keys + changes published in `scratch`.  Stage 1: one CTA per tree LEVEL.
-// With key = heap index + 1 the parent of a node is key >> 1, so the ancestor of item i at level L is (key_i >> L) - 1 and
-// two items meet at level L iff their keys agree after the shift.  A node's new value depends only on its old value and
-// the batch-ordered changes of the items below it, never on other levels, so the levels run concurrently on different
-// SMs.  Inside a level, item i is the node's "leader" when no earlier item shares the node; the leader adds the changes of
-// all its items IN BATCH ORDER (fp64 addition is not associative: the order is what makes the last ulp match the
-// sequential reference).  Keys are 32-bit (capacity < 2^30) and scanned four at a time from shared memory.
+// holds when item i is applied), leaves written, keys + changes published in `scratch`.  Stage 1: one CTA per tree DEPTH.
+// With key = heap index + 1 the parent of a node is key >> 1 and a node's depth is floor(log2(key)), so the ancestor of item
+// i at depth d is (key_i >> (depth_i - d)) - 1; two items meet at depth d iff these agree.  (Grouping by DEPTH, not by
+// distance from the leaf: with a non-power-of-two capacity the leaves sit at two depths and e.g. the root is 16 levels above
+// one leaf and 17 above another — every node must have exactly one owner.)  A node's new value depends only on its old
+// value and the batch-ordered changes of the items below it, never on other depths, so the depths run concurrently on
+// different SMs.  Inside a depth, item i is the node's "leader" when no earlier item shares the node; the leader adds the
+// changes of all its items IN BATCH ORDER (fp64 addition is not associative: the order is what makes the last ulp match
+// the sequential reference).  Keys are 32-bit (capacity < 2^30) and scanned four at a time from shared memory.
 struct TreeUpdateArgs {
   double* tree; int64_t cap;
   const int64_t* idx;        // [B] buffer indices
@@ -51,6 +53,13 @@ struct TreeUpdateAlgo {
   FRL_SHD int depth(const Args& a) { int m = 0; uint64_t k = (uint64_t)(2 * a.cap - 1); while (k > 1) { k >>= 1; ++m; } return m; }
   FRL_SHD int grid(const Args& a, int max_ctas) { const int m = depth(a); return m < 1 ? 1 : (m < max_ctas ? m : max_ctas); }
   FRL_SHD int n_updates(const Args&) { return 1; }
+  FRL_SDEV int ilog2(uint32_t x) {
+#ifndef FRL_EMUL
+    return 31 - __clz((int)x);
+#else
+    return 31 - __builtin_clz(x);
+#endif
+  }
   FRL_SDEV double pri_of(const Args& a, int i) { return a.pri32 ? (double)a.pri32[i] : (a.pri64 ? a.pri64[0] : a.pri_const); }
   // any j in [lo, hi) with ks[j] == k ?   (hi - lo may be anything; ks is padded to a multiple of 4 with never-matching zeros)
   FRL_SDEV bool any_equal(const uint32_t* ks, int lo, int hi, uint32_t k) {
@@ -100,19 +109,25 @@ struct TreeUpdateAlgo {
       FRL_SYNC();
       return;
     }
-    const int maxlev = depth(a);
-    for (int L = c.cta + 1; L <= maxlev; L += c.ncta) {
+    const int maxdepth = depth(a);                  // depth of the deepest leaf; ancestors live at depths 0 .. maxdepth - 1
+    for (int d = c.cta; d < maxdepth; d += c.ncta) {
       FRL_PAR(t) {
         for (int i = t; i < Bp; i += FRL_NT) {
-          ks[i] = i < B ? (gkey[i] >> L) : 0u;
-          if (i < B) change[i] = a.scratch[i];
+          uint32_t k = 0u;
+          if (i < B) {
+            const uint32_t key_i = gkey[i];
+            const int di = ilog2(key_i);
+            if (di > d) k = key_i >> (di - d);     // 0: this item's leaf is at or above depth d (never matches)
+            change[i] = a.scratch[i];
+          }
+          ks[i] = k;
         }
       }
       FRL_SYNC();
       FRL_PAR(t) {
         for (int i = t; i < B; i += FRL_NT) {
           const uint32_t k = ks[i];
-          if (k < 1u) continue;                     // this leaf sits above level L (two leaf depths when cap is not 2^k)
+          if (k < 1u) continue;                     // this item has no ancestor at depth d
           if (any_equal(ks, 0, i, k)) continue;     // an earlier item leads this node
           double v = f64add(a.tree[(int64_t)k - 1], change[i]);
           for (int j = i + 1; j < B; ++j) if (ks[j] == k) v = f64add(v, change[j]);

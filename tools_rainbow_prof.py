@@ -45,3 +45,19 @@ a = pol._args()
 us, _ = wall(lambda: _lib.check(_lib.lib().frl_rainbow_act(ctypes.byref(a), _lib.ptr(xd), 512, _lib.ptr(out), _lib.stream_ptr(dev)), "x"), 20); print("  act: frl_rainbow_act      %8.1f us" % us)
 us, _ = wall(lambda: out.to(torch.int64).cpu().numpy(), 20); print("  act: D2H                  %8.1f us" % us)
 us, _ = wall(lambda: pol._device_eps(), 20); print("  device eps (fast mode)    %8.1f us" % us)
+# ---- select_action, step by step with a sync after each step ----
+import freerl_b200._common as _c
+def step_by_step():
+    t = []
+    def lap(): torch.cuda.synchronize(); t.append(time.perf_counter())
+    lap()
+    xx, single = _c.as_obs_batch(x, 8); lap()
+    xd2 = torch.from_numpy(np.ascontiguousarray(xx, dtype=np.float32)).to(dev); lap()
+    pol.agent._last_eps["online"] = ("f", pol._device_eps()[0]); lap()
+    o2 = torch.empty(512, dtype=torch.float32, device=dev); aa = pol._args(); lap()
+    _lib.check(_lib.lib().frl_rainbow_act(ctypes.byref(aa), _lib.ptr(xd2), 512, _lib.ptr(o2), _lib.stream_ptr(dev)), "x"); lap()
+    act = o2.to(torch.int64).cpu().numpy(); lap()
+    return [(b - a) * 1e6 for a, b in zip(t, t[1:])]
+for _ in range(3): r = step_by_step()
+print("  act steps (us): as_obs %.0f | H2D %.0f | device eps %.0f | args %.0f | kernels %.0f | D2H %.0f" % tuple(r))
+us, _ = wall(lambda: pol.select_action(x), 50); print("select_action(512) again   %8.1f us" % us)
