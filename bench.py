@@ -243,14 +243,11 @@ def main():
     rew_pool = torch.randn((POOL, NENV), device=dev, generator=g)
     zeros = torch.zeros(NENV, device=dev)
     from freerl_b200 import _common, _lib
-    params = [pol.agent._actor, pol.agent._critic, pol.agent._actor_t, pol.agent._critic_t]
+    if world > 1:
+        pol.enable_replica_sync()             # broadcast rank 0's parameters; sync_replicas() averages them afterwards
 
     def sync_params():
-        if world > 1:
-            for n_ in params:
-                dist.all_reduce(n_.p)
-                n_.p.div_(world)
-                n_.sync_mirror()
+        pol.sync_replicas()                   # no-op at world 1
 
     learn_ev = []
 

@@ -161,3 +161,36 @@ class ACBase:
         for t, s in ((self.agent._critic_t, self.agent._critic), (self.agent._actor_t, self.agent._actor)):
             t.p.mul_(1.0 - tau).add_(s.p * tau)
             t.sync_mirror()
+
+    # ---- multi-GPU: replicas with sharded env workers / replay (off-policy) ---------------------------
+    def enable_replica_sync(self, group=None):
+        """One process per GPU, each with its own env shard and replay shard (no data-path collective).  The replicas stay ONE
+        policy by averaging parameters over ``torch.distributed`` (NCCL over NVLink on the GPU box): rank 0's parameters are
+        broadcast now, ``sync_replicas()`` averages them afterwards (call it every K learns; the bench uses K = one vector step).
+        Adam moments stay local — each replica's optimiser sees its own shard's gradients, the standard local-SGD scheme."""
+        import torch.distributed as dist
+        self._rs = (dist, group, dist.get_world_size(group))
+        for n_ in self._replica_nets():
+            dist.broadcast(n_.p, src=0, group=group)
+            n_.sync_mirror()
+        if self.sac:
+            dist.broadcast(self.alphas.state, src=0, group=group)
+
+    def _replica_nets(self):
+        ag = self.agent
+        return (ag._actor, ag._critic, ag._actor_t, ag._critic_t)
+
+    def sync_replicas(self):
+        """parameter average over the replicas (all-reduce sum, scale by 1/world, refresh the transposed mirrors)"""
+        rs = getattr(self, "_rs", None)
+        if rs is None or rs[2] == 1:
+            return
+        dist, group, world = rs
+        for n_ in self._replica_nets():
+            dist.all_reduce(n_.p, group=group)
+            n_.p.div_(world)
+            n_.sync_mirror()
+        if self.sac:                      # log_alpha (the Adam moments of alpha stay local like the others)
+            la = self.alphas.state[:1]
+            dist.all_reduce(la, group=group)
+            la.div_(world)

@@ -74,3 +74,47 @@ def test_ppo_data_parallel_gloo(tmp_path, emul):
         np.testing.assert_allclose(r0[k], v.detach().numpy(), rtol=2e-4, atol=2e-5, err_msg=k)
     for k, v in orc.critic.items():
         np.testing.assert_allclose(r0["critic." + k], v.detach().numpy(), rtol=2e-4, atol=2e-5, err_msg=k)
+
+
+REPLICA_WORKER = r'''
+import os, sys
+import numpy as np, torch
+import torch.distributed as dist
+sys.path.insert(0, os.environ["FRL_ROOT"])
+from freerl_b200.SAC import SAC
+dist.init_process_group("gloo")
+rank = dist.get_rank()
+torch.manual_seed(10 + rank); np.random.seed(10 + rank)           # different initial replicas on purpose
+pol = SAC([5, 2], True, 1e-3, 1e-3, 512, torch.device("cpu"), trick={}, mode="fast")
+rng = np.random.default_rng(rank)                                  # different replay shards
+pol.add(rng.standard_normal((200, 5)), rng.uniform(-1, 1, (200, 2)), rng.standard_normal(200), rng.standard_normal((200, 5)), rng.random(200) < 0.1)
+pol.enable_replica_sync()
+p0 = pol.agent._critic.p.clone()
+pol.learn(32, 0.99, 0.01, n_updates=3)
+local = {n: getattr(pol.agent, n).p.clone() for n in ("_actor", "_critic", "_actor_t", "_critic_t")}
+la_local = pol.alphas.state[0].clone()
+pol.sync_replicas()
+np.savez(os.path.join(os.environ["FRL_OUT"], "rep%d.npz" % rank), start=p0.numpy(), la_local=la_local.numpy(), la=pol.alphas.state[0].numpy(),
+         **{"local" + n: v.numpy() for n, v in local.items()}, **{"synced" + n: getattr(pol.agent, n).p.numpy() for n in local},
+         mirror=pol.agent._critic.pt.numpy())
+dist.destroy_process_group()
+'''
+
+
+def test_offpolicy_replica_sync_gloo(tmp_path, emul):
+    """SAC replicas with different shards: enable_replica_sync() starts both from rank 0's parameters, local learns diverge,
+    sync_replicas() leaves both with the mean of the two (parameters, targets, log_alpha) and refreshed mirrors."""
+    (tmp_path / "worker.py").write_text(REPLICA_WORKER)
+    env = dict(os.environ, FRL_ROOT=ROOT, FRL_OUT=str(tmp_path), FREERL_B200_LIB=os.environ["FREERL_B200_LIB"], OMP_NUM_THREADS="2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", str(tmp_path / "worker.py")]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    a, b = np.load(tmp_path / "rep0.npz"), np.load(tmp_path / "rep1.npz")
+    assert np.array_equal(a["start"], b["start"])                                   # broadcast from rank 0
+    for n in ("_actor", "_critic", "_actor_t", "_critic_t"):
+        assert not np.array_equal(a["local" + n], b["local" + n])                   # shards differ -> replicas diverged
+        assert np.array_equal(a["synced" + n], b["synced" + n])
+        np.testing.assert_allclose(a["synced" + n], (a["local" + n] + b["local" + n]) / 2, rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(a["la"], (a["la_local"] + b["la_local"]) / 2, rtol=1e-6)
+    assert np.array_equal(a["mirror"], b["mirror"])
