@@ -677,7 +677,7 @@ extern "C" int frl_adv_norm(const float* x, int n, float eps, float* out, void* 
 }
 
 // ------------------------------------------------------------------------------------------------
-// debug micro-benchmark of one layer op (not part of the product API; used by tools_opbench.py)
+// debug micro-benchmark of one layer op (not part of the product API; used by tools/opbench.py)
 //   mode 0: gemm_rk on already-staged weights   1: layer_fwd with TMA every iteration, no prefetch
 //   mode 2: layer_fwd with prefetch of the next iteration's weights (alternating layers li and li2)
 // ------------------------------------------------------------------------------------------------

@@ -79,15 +79,18 @@ class PER_Buffer:
     # ---- add: new transitions get the current max priority (1.0 for the very first) ------------------------------
     def _add_priorities(self, n):
         tree = self.sumtree
-        if len(self.buffer) == 0:
-            tree._update(None, pri_const=1.0, idx0=self.buffer._index, is_range=True, B=n)
-        else:
-            tree._update(None, pri64=tree.max_device(), idx0=self.buffer._index, is_range=True, B=n)
+        empty = len(self.buffer) == 0
+        pmax = None if empty else tree.max_device()          # max priority BEFORE the batch (new leaves do not raise it)
+        for s in range(0, n, 1024):                           # the ordered update kernel takes <= 1024 leaves per launch
+            m = min(1024, n - s)
+            i0 = (self.buffer._index + s) % self.capacity
+            if empty:
+                tree._update(None, pri_const=1.0, idx0=i0, is_range=True, B=m)
+            else:
+                tree._update(None, pri64=pmax, idx0=i0, is_range=True, B=m)
 
     def add(self, obs, action, reward, next_obs, done):
         n = int(np.asarray(obs).reshape(-1, self.buffer.obs_dim).shape[0])
-        for s in range(0, n, 1024):
-            pass
         self._add_priorities(n)
         self.buffer.add(obs, action, reward, next_obs, done)
 

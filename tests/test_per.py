@@ -132,3 +132,19 @@ def test_vectorised_nstep_fold_matches_per_env_folds():
         np.testing.assert_array_equal(out[3], np.stack([x[3] for x in ref]))
         np.testing.assert_array_equal(out[4], np.array([x[4] for x in ref]))
     assert emitted == 7
+
+
+def test_per_vectorised_add_larger_than_one_launch(emul):
+    """a 2500-row vectorised add (3 update launches) == 2500 sequential reference adds, bit for bit"""
+    from freerl_b200.per import PER_Buffer
+    rng = np.random.default_rng(3)
+    cap = 3000
+    ours, orc = PER_Buffer(cap, 3, 1, torch.device("cpu")), ob.PrioritizedReplay(cap, 3, 1)
+    for n in (2500, 1200):                                    # the second add wraps the ring
+        o, a = rng.standard_normal((n, 3)).astype(np.float32), rng.integers(0, 3, (n, 1))
+        r, o2, d = rng.standard_normal(n), rng.standard_normal((n, 3)).astype(np.float32), rng.random(n) < 0.1
+        ours.add(o, a, r, o2, d)
+        for j in range(n):
+            orc.add(o[j], a[j], r[j], o2[j], d[j])
+        assert np.array_equal(ours.sumtree.tree.cpu().numpy(), orc.sumtree.tree)
+        assert (ours.buffer._index, len(ours)) == (orc.buffer._index, len(orc))

@@ -1,7 +1,7 @@
 """learn() throughput of every BASELINE.json configuration at its SURVEY §8(d) shape on one B200 — NOT the bench (bench.py
 measures config 2 end to end); this is the secondary table DESIGN.md §3 quotes for the other algorithm kernels.
 
-    python tools_configbench.py [--json profiles/rX_configs.json]
+    python tools/configbench.py [--json profiles/rX_configs.json]
 
 C1 DQN CartPole (obs 4, 2 actions, B 256) · C2 SAC (obs 17, act 6, B 256, 1M replay) · C3 PPO (1024 envs x T 128 = 131 072
 rows, minibatch 8192, K 10 = 160 updates / learn) · C4 Rainbow (obs 8, 4 actions, 51 atoms, PER + n-step, B 256, capacity 1e6)
@@ -17,7 +17,7 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 dev = torch.device("cuda")
 

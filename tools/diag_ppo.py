@@ -1,5 +1,5 @@
 import os, sys
-sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
+sys.path.insert(0, '.'); sys.path.insert(0, 'tests')  # run from the repo root: python tools/diag_ppo.py
 import numpy as np, torch
 from collections import OrderedDict
 dev = torch.device(os.environ.get("DEV", "cpu"))

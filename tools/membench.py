@@ -1,7 +1,7 @@
 """Micro-benchmarks of the memory-bound members of the hot path (replay add / gather, GAE scan, advantage
 normalisation, PER sum-tree, Polyak sweep, batched policy inference) against the measured HBM peak.
 
-    python tools_membench.py [--json profiles/rX_membench.json]
+    python tools/membench.py [--json profiles/rX_membench.json]
 
 Every kernel is timed with CUDA events on the launching stream over `reps` launches after warm-up; working sets are
 rotated through buffers larger than the 126 MB L2 where the kernel is meant to stream from HBM.  `GB/s` = ALGORITHMIC
@@ -15,7 +15,7 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from freerl_b200 import _common, _lib          # noqa: E402
 from freerl_b200.Buffer import Buffer          # noqa: E402

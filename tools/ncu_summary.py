@@ -1,6 +1,6 @@
 """Turn `ncu -i X.ncu-rep --page raw --csv` output into the small JSON summary committed under profiles/.
 
-    python tools_ncu_summary.py raw.csv out.json "<command that was profiled>"
+    python tools/ncu_summary.py raw.csv out.json "<command that was profiled>"
 """
 import csv
 import json
