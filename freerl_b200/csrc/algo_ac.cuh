@@ -81,16 +81,25 @@ FRL_NI_OPT void reduce_grads_roles(int cta, int ncta, float* slot, const frl_net
   FRL_SYNC();
 }
 
-struct AcAlgo {
+// SPEC selects a compile-time specialisation of the same source (the generic kernel is 320 KB of SASS — more than the
+// instruction cache holds, and a learn walks most of it; the specialisations drop the multi-agent loops, Batch_ObsNorm and
+// the branches of the other actor kind):  0 generic (multi-agent / Batch_ObsNorm / anything) · 1 single-agent SAC (twin
+// critic, no Batch_ObsNorm) · 2 single-agent deterministic actor (TD3 / DDPG, no Batch_ObsNorm).  Same arithmetic, same order.
+template <int SPEC>
+struct AcAlgoT {
   typedef frl_ac_args_t Args;
   static const int NSTAGES = 7;
+  FRL_SHD bool multi(const Args& a) { return SPEC == 0 && a.n_agents > 1; }
+  FRL_SHD bool has_bon(const Args& a) { return SPEC == 0 && a.obs_norm[0] != nullptr; }
+  FRL_SHD bool is_sac(const Args& a) { return SPEC == 1 ? true : (SPEC == 2 ? false : a.actor_kind == FRL_ACTOR_SAC); }
+  FRL_SHD int heads(const Args& a) { return SPEC == 1 ? 2 : a.n_heads; }
   FRL_SHD bool writes_params(int s) { return s == 3 || s == 6; }   // the two Adam / Polyak stages
   FRL_SHD bool is_policy_step(const Args& a, int u) { return ((a.total_it0 + u + 1) % (a.policy_freq > 0 ? a.policy_freq : 1)) == 0; }
   FRL_SHD bool stage_enabled(int s, int u, const Args& a) {
     if (s >= 4) return is_policy_step(a, u);                // TD3 twin_delay: no actor stages (nor their barriers) on off steps
     return true;
   }
-  FRL_SHD int norm_floats(const Args& a) { return a.obs_norm[0] ? ((3 * obs_off(a, ma_n(a)) + 3) & ~3) : 0; }
+  FRL_SHD int norm_floats(const Args& a) { return has_bon(a) ? ((3 * obs_off(a, ma_n(a)) + 3) & ~3) : 0; }
 
   FRL_SHD int max_layer_floats(const frl_net_t& n) {
     int mx = 0;
@@ -125,9 +134,9 @@ struct AcAlgo {
   }
   FRL_SHD int wbuf_floats(const Args& a) { return resident(a) ? head_floats(a) : stream_floats(a); }
   // ---- multi-agent helpers: where agent j's obs / action sit inside the joint critic input [obs_1..obs_N | act_1..act_N]
-  FRL_SHD int ma_n(const Args& a) { return a.n_agents > 1 ? a.n_agents : 1; }
-  FRL_SHD const frl_replay_t& rep(const Args& a, int j) { return a.n_agents > 1 ? a.ma_replay[j] : a.replay; }
-  FRL_SHD const frl_net_t& tnet(const Args& a, int j) { return a.n_agents > 1 ? a.ma_actor_target[j] : a.actor_target; }
+  FRL_SHD int ma_n(const Args& a) { return multi(a) ? a.n_agents : 1; }
+  FRL_SHD const frl_replay_t& rep(const Args& a, int j) { return multi(a) ? a.ma_replay[j] : a.replay; }
+  FRL_SHD const frl_net_t& tnet(const Args& a, int j) { return multi(a) ? a.ma_actor_target[j] : a.actor_target; }
   FRL_SHD int obs_off(const Args& a, int j) { int o = 0; for (int k = 0; k < j; ++k) o += rep(a, k).obs_dim; return o; }
   FRL_SHD int act_off(const Args& a, int j) { int o = obs_off(a, ma_n(a)); for (int k = 0; k < j; ++k) o += rep(a, k).act_dim; return o; }
   FRL_SHD int raw_off(const Args& a, int j) { int o = 0; for (int k = 0; k < j; ++k) o += FRL_R * rep(a, k).row_floats; return o; }
@@ -139,7 +148,7 @@ struct AcAlgo {
     return raw_off(a, ma_n(a)) + FRL_R * (max_aip(a) + 3 * sa + 6 * ldh + 6 * ap + 3 * 4 + 16) + 2 * FRL_NT + 128 + PLAN_FLOATS + norm_floats(a);
   }
   FRL_SHD int nslots_of(const Args& a, int max_ctas) {
-    const int tiles = (a.B + FRL_R - 1) / FRL_R, cap = max_ctas / (a.n_heads > 0 ? a.n_heads : 1);
+    const int tiles = (a.B + FRL_R - 1) / FRL_R, cap = max_ctas / (heads(a) > 0 ? heads(a) : 1);
     return tiles < cap ? tiles : (cap > 0 ? cap : 1);
   }
   // Worker CTAs (row tile x critic head) run the GEMM stages; with FRL_AC_GRID > 0 the grid is padded with HELPER CTAs
@@ -149,7 +158,7 @@ struct AcAlgo {
 #define FRL_AC_GRID 96
 #endif
   FRL_SHD int grid(const Args& a, int max_ctas) {
-    const int w = nslots_of(a, max_ctas) * a.n_heads, cap = FRL_AC_GRID < max_ctas ? FRL_AC_GRID : max_ctas;
+    const int w = nslots_of(a, max_ctas) * heads(a), cap = FRL_AC_GRID < max_ctas ? FRL_AC_GRID : max_ctas;
     return w > cap ? w : cap;
   }
   FRL_SHD int n_updates(const Args& a) { return a.n_updates; }
@@ -167,7 +176,7 @@ struct AcAlgo {
   };
   static const int PLAN_FLOATS = 32;
   FRL_SDEV void fill_plan(Plan& P, const Args& a) {
-    P.NA = ma_n(a); P.ai = a.n_agents > 1 ? a.agent_index : 0;
+    P.NA = ma_n(a); P.ai = multi(a) ? a.agent_index : 0;
     P.ap = max_ap(a); P.aip = max_aip(a); P.res = resident(a) ? 1 : 0;
     P.gstride = a.critic.n_p > a.actor.n_p ? a.critic.n_p : a.actor.n_p;
     int o = 0, r = 0;
@@ -305,7 +314,7 @@ struct AcAlgo {
   }
 
   FRL_SDEV void stage(int s, int u, Cta& c, float* user, const Args& a) {
-    const bool bon = a.obs_norm[0] != nullptr;
+    const bool bon = has_bon(a);
     const frl_net_t& A = a.actor;
     const frl_net_t& C = a.critic;
     const frl_replay_t& rb = a.replay;
@@ -319,19 +328,20 @@ struct AcAlgo {
     float* NORM = user;                        // [agent j at 3*obs_off[j]] {mean, S, std} of this learn (Batch_ObsNorm)
     user += norm_floats(a);
     const int ldh = act_ld(C.L[0].out_pad), sa = act_ld(C.L[0].in_pad), ap = P.ap;   // strides (bank-conflict free), not widths
-    const int NA = P.NA, ai = P.ai;
+    const int NA = SPEC != 0 ? 1 : P.NA, ai = SPEC != 0 ? 0 : P.ai;
     const int aip = P.aip;
     const int ntile = (a.B + FRL_R - 1) / FRL_R;
-    const int nrole = a.n_heads, role = c.cta % nrole, nslots = nslots_of(a, c.ncta);
+    const int nrole = heads(a), role = c.cta % nrole, nslots = nslots_of(a, c.ncta);
     const bool helper = c.cta >= nslots * nrole;               // reduce / optimiser stages only
     const int slot = helper ? ntile : c.cta / nrole;           // helpers own no row tile: every tile loop is empty
     const int l0 = 3 * role;                                   // this CTA's critic head = layers l0..l0+2
     const bool one_tile = ntile <= nslots;
     const float invB = 1.0f / (float)a.B;
-    const bool sac = a.actor_kind == FRL_ACTOR_SAC;
+    const bool sac = is_sac(a);
+    const bool smoothing = SPEC != 1 && a.target_smoothing;
     const bool policy_step = is_policy_step(a, u);
     const long n_policy_before = (a.policy_freq > 1) ? (long)((a.total_it0 + u) / a.policy_freq - a.total_it0 / a.policy_freq) : (long)u;
-    const int heads_used = sac ? a.n_heads : 1;                // actor loss: SAC mean of both heads, TD3 Q1 only, DDPG single
+    const int heads_used = sac ? nrole : 1;                // actor loss: SAC mean of both heads, TD3 Q1 only, DDPG single
     float alpha = 0.f;
     if (sac) alpha = expf(a.alpha_state[0]);
     const bool res = P.res != 0;
@@ -433,10 +443,10 @@ struct AcAlgo {
                 lp -= 2.f * (FRL_LOG2F - uu - softplus_t(-2.f * uu));
                 UU[r * ap + jj] = lp;                      // per-dim log-prob contribution
                 act = tanhf(uu);
-              } else if (a.target_smoothing) {
+              } else if (smoothing) {
                 float e = 0.f;
                 if (r < nvalid) {
-                  if (a.n_agents > 1)        // MATD3: every agent's target action has its own randn_like draw
+                  if (multi(a))              // MATD3: every agent's target action has its own randn_like draw
                     e = a.ma_noise_next[j] ? a.ma_noise_next[j][(size_t)(row0 + r) * adj + jj]
                                            : randn_ni(a.seed, 16u + (uint32_t)j, (uint32_t)(a.total_it0 * NA + ai), (uint32_t)((row0 + r) * adj + jj));
                   else
@@ -721,3 +731,4 @@ struct AcAlgo {
     }
   }
 };
+typedef AcAlgoT<0> AcAlgo;            // generic instantiation (also provides the static sizing helpers other kernels borrow)

@@ -476,6 +476,11 @@ extern "C" int frl_ac_learn(const frl_ac_args_t* a, void* stream) {
     frl_set_error("frl_ac_learn: unsupported network shape / missing alpha state");
     return -1;
   }
+  // compile-time specialisations of the same kernel source for the two single-agent families (smaller instruction footprint)
+  if (a->n_agents <= 1 && !a->obs_norm[0]) {
+    if (a->actor_kind == FRL_ACTOR_SAC && a->n_heads == 2) return frl_launch<AcAlgoT<1> >(*a, (cudaStream_t)stream);
+    if (a->actor_kind == FRL_ACTOR_TANH) return frl_launch<AcAlgoT<2> >(*a, (cudaStream_t)stream);
+  }
   return frl_launch<AcAlgo>(*a, (cudaStream_t)stream);
 }
 
