@@ -108,8 +108,8 @@ def peaks():
 
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of ONE bench launch (256 learns) from the committed `ncu --set full`
-    capture of this same command (profiles/r1c_bench_sac_learn_ncu_full.json); None when no capture is committed."""
-    p = os.path.join(ROOT, "profiles", "r1c_bench_sac_learn_ncu_full.json")
+    capture of this same command (profiles/r1e_bench_sac_learn_ncu_full.json); None when no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "r1e_bench_sac_learn_ncu_full.json")
     if os.path.exists(p):
         try:
             return json.load(open(p)).get("dram_bytes_per_launch")
