@@ -148,3 +148,31 @@ def test_per_vectorised_add_larger_than_one_launch(emul):
             orc.add(o[j], a[j], r[j], o2[j], d[j])
         assert np.array_equal(ours.sumtree.tree.cpu().numpy(), orc.sumtree.tree)
         assert (ours.buffer._index, len(ours)) == (orc.buffer._index, len(orc))
+
+
+def _sumtree_property(device):
+    """Random capacities (leaves at one or two depths), random batches WITH duplicate leaves, priorities spanning 12 orders of
+    magnitude (so fp64 sums are NOT exact and the batch order matters): the device heap equals the sequential reference
+    `tree[idx] += change` walk bit for bit after every batch."""
+    from freerl_b200.per import SumTree
+    rng = np.random.default_rng(11)
+    for cap in (1, 2, 3, 5, 6, 7, 8, 9, 31, 33, 100, 257, 1000, 4097):
+        ours, orc = SumTree(cap, device), ob.SumTreeOracle(cap)
+        for _ in range(4):
+            B = int(rng.integers(1, min(300, 4 * cap) + 1))
+            idx = rng.integers(0, cap, B)
+            pri = (10.0 ** rng.uniform(-6, 6, B)).astype(np.float32)
+            for i, p in zip(idx, pri):
+                orc.set_leaf(int(i), float(p))                       # float(np.float32) widens exactly, like the kernel
+            ours._update(torch.from_numpy(idx.astype(np.int64)).to(device), pri32=torch.from_numpy(pri).to(device))
+            assert np.array_equal(ours.tree.cpu().numpy(), orc.tree), (cap, B)
+        assert ours.max() == orc.max_leaf() and ours.sum() == orc.total()
+
+
+def test_sumtree_ordered_update_property_emulated(emul):
+    _sumtree_property(torch.device("cpu"))
+
+
+@pytest.mark.gpu
+def test_sumtree_ordered_update_property_gpu():
+    _sumtree_property(torch.device("cuda"))
