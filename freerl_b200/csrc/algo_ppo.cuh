@@ -122,7 +122,10 @@ FRL_DEV void net_bwd(Cta& c, const frl_net_t& N, int l0, bool ln, const float* X
   gemm_outer<R>(D1, ldh, L0.out_pad, b.X0, ip, L0.in_pad, L0.in, gp + L0.w_off, gp + L0.b_off, accumulate);
 }
 
-struct PpoAlgo {
+// R = batch rows per CTA tile: 8 for the reference-sized minibatches (more CTAs per minibatch), 16 for large minibatches
+// (>= 1024 rows: twice the FMAs per staged weight and per barrier; chosen by frl_ppo_update when the tile fits in shared memory).
+template <int R>
+struct PpoAlgoT {
   typedef frl_ppo_args_t Args;
   static const int NSTAGES = 5;
   FRL_SHD bool writes_params(int) { return true; }
@@ -130,10 +133,12 @@ struct PpoAlgo {
   FRL_SHD int wbuf_floats(const Args& a) { return (AcAlgo::max_layer_floats(a.net) + 31) & ~31; }
   FRL_SHD int user_floats(const Args& a) {
     const int ldh = act_ld(a.net.L[0].out_pad), ip = a.net.L[0].in_pad, cip = a.net.L[3].in_pad, ap = a.net.L[2].out_pad;
-    return FRL_R * (2 * ip + 2 * cip + 10 * ldh + 4 * ap + 8 + 4 * a.n_adv + 8 + 4 + 64) + 2 * FRL_NT + 64 + FRL_NSEG + 3;
+    // the LayerNorm variant keeps the normalised copies of the input and of both hidden activations, per net
+    const int ln_extra = a.layer_norm ? (ip + cip + 4 * ldh) : 0;
+    return R * (ip + cip + ln_extra + 6 * ldh + 4 * ap + 8 + 4 * a.n_adv + 8 + 4 + 64) + 2 * FRL_NT + 64 + FRL_NSEG + 3;
   }
   FRL_SHD int grid(const Args& a, int max_ctas) {
-    int tiles = (a.mb + FRL_R - 1) / FRL_R;
+    int tiles = (a.mb + R - 1) / R;
     return tiles < max_ctas ? tiles : max_ctas;
   }
   FRL_SHD int n_updates(const Args& a) { return a.n_updates; }
@@ -145,31 +150,34 @@ struct PpoAlgo {
     const int ldh = act_ld(N.L[0].out_pad), ip = N.L[0].in_pad, ap = N.L[2].out_pad, nout = N.L[2].out;
     if (a.stage_hi > 0 && (s < a.stage_lo || s >= a.stage_hi)) return;
     const int rows = a.mb_rows[u];
-    const int ntile = (rows + FRL_R - 1) / FRL_R;
+    const int ntile = (rows + R - 1) / R;
     const int ncontrib = ntile < c.ncta ? ntile : c.ncta;
     SmemBump sb; sb.p = user;
     const int cip = N.L[3].in_pad;
     const bool ln = a.layer_norm != 0;
-    float* X = sb.take(FRL_R * ip);
-    float* XC = sb.take(FRL_R * cip);       // critic input tile (joint obs for MAPPO, else a copy of X)
+    float* X = sb.take(R * ip);
+    float* XC = sb.take(R * cip);       // critic input tile (joint obs for MAPPO, else a copy of X)
     NetBufs ba, bc;
-    ba.X0 = sb.take(FRL_R * ip);  bc.X0 = sb.take(FRL_R * cip);
-    ba.H1 = sb.take(FRL_R * ldh); ba.H2 = sb.take(FRL_R * ldh);
-    bc.H1 = sb.take(FRL_R * ldh); bc.H2 = sb.take(FRL_R * ldh);
-    ba.H1n = sb.take(FRL_R * ldh); ba.H2n = sb.take(FRL_R * ldh);
-    bc.H1n = sb.take(FRL_R * ldh); bc.H2n = sb.take(FRL_R * ldh);
-    ba.rs1 = sb.take(FRL_R); ba.rs2 = sb.take(FRL_R); bc.rs1 = sb.take(FRL_R); bc.rs2 = sb.take(FRL_R);
-    ba.scratch = bc.scratch = sb.take(FRL_R * 64);
-    float* D1 = sb.take(FRL_R * ldh);
-    float* D2 = sb.take(FRL_R * ldh);
-    float* OA = sb.take(FRL_R * ap);
-    float* dOA = sb.take(FRL_R * ap);
-    float* ACT = sb.take(FRL_R * ap);
-    float* LPO = sb.take(FRL_R * ap);
-    float* V = sb.take(FRL_R * 4);
-    float* dV = sb.take(FRL_R * 4);
-    float* ADV = sb.take(FRL_R * a.n_adv);
-    float* VT = sb.take(FRL_R * a.n_adv);
+    ba.H1 = sb.take(R * ldh); ba.H2 = sb.take(R * ldh);
+    bc.H1 = sb.take(R * ldh); bc.H2 = sb.take(R * ldh);
+    ba.X0 = bc.X0 = ba.H1n = ba.H2n = bc.H1n = bc.H2n = nullptr;
+    if (a.layer_norm) {
+      ba.X0 = sb.take(R * ip);  bc.X0 = sb.take(R * cip);
+      ba.H1n = sb.take(R * ldh); ba.H2n = sb.take(R * ldh);
+      bc.H1n = sb.take(R * ldh); bc.H2n = sb.take(R * ldh);
+    }
+    ba.rs1 = sb.take(R); ba.rs2 = sb.take(R); bc.rs1 = sb.take(R); bc.rs2 = sb.take(R);
+    ba.scratch = bc.scratch = sb.take(R * 64);
+    float* D1 = sb.take(R * ldh);
+    float* D2 = sb.take(R * ldh);
+    float* OA = sb.take(R * ap);
+    float* dOA = sb.take(R * ap);
+    float* ACT = sb.take(R * ap);
+    float* LPO = sb.take(R * ap);
+    float* V = sb.take(R * 4);
+    float* dV = sb.take(R * 4);
+    float* ADV = sb.take(R * a.n_adv);
+    float* VT = sb.take(R * a.n_adv);
     float* red0 = sb.take(FRL_NT);
     float* red1 = sb.take(FRL_NT);
     int* segc = (int*)sb.take(FRL_NSEG + 3);
@@ -181,16 +189,16 @@ struct PpoAlgo {
       bool first = true;
       const float inv_rows = 1.0f / (float)rows, inv_rn = 1.0f / (float)(rows * a.n_adv);
       for (int tile = c.cta; tile < ntile; tile += c.ncta) {
-        const int row0 = tile * FRL_R;
-        const int nvalid = (rows - row0) < FRL_R ? (rows - row0) : FRL_R;
+        const int row0 = tile * R;
+        const int nvalid = (rows - row0) < R ? (rows - row0) : R;
         const int64_t* idx = a.indices + (size_t)u * a.mb + row0;
         stage_prefetch(c, layer_fwd_src(N, 0), layer_fwd_bytes(N.L[0]));
         FRL_PAR(t) {
-          for (int e = t; e < FRL_R * ip; e += FRL_NT) {
+          for (int e = t; e < R * ip; e += FRL_NT) {
             const int r = e / ip, j = e % ip;
             X[e] = (r < nvalid && j < a.obs_dim) ? a.obs[(size_t)idx[r] * a.obs_dim + j] : 0.f;
           }
-          for (int e = t; e < FRL_R * cip; e += FRL_NT) {
+          for (int e = t; e < R * cip; e += FRL_NT) {
             const int r = e / cip, j = e % cip;
             float v = 0.f;
             if (r < nvalid) {
@@ -199,12 +207,12 @@ struct PpoAlgo {
             }
             XC[e] = v;
           }
-          for (int e = t; e < FRL_R * ap; e += FRL_NT) {
+          for (int e = t; e < R * ap; e += FRL_NT) {
             const int r = e / ap, j = e % ap;
             ACT[e] = (r < nvalid && j < a.act_cols) ? a.action[(size_t)idx[r] * a.act_cols + j] : 0.f;
             LPO[e] = (r < nvalid && j < a.logp_cols) ? a.logp_old[(size_t)idx[r] * a.logp_cols + j] : 0.f;
           }
-          for (int e = t; e < FRL_R * a.n_adv; e += FRL_NT) {
+          for (int e = t; e < R * a.n_adv; e += FRL_NT) {
             const int r = e / a.n_adv, j = e % a.n_adv;
             ADV[e] = (r < nvalid) ? a.adv[(size_t)idx[r] * a.n_adv + j] : 0.f;
             VT[e] = (r < nvalid) ? a.v_target[(size_t)idx[r] * a.n_adv + j] : 0.f;
@@ -212,12 +220,12 @@ struct PpoAlgo {
         }
         FRL_SYNC();
         const int c_in = a.critic_obs ? a.critic_obs_dim : a.obs_dim;
-        net_fwd<FRL_R>(c, N, 0, ln, X, ip, a.obs_dim, ba, ldh, OA, ap, fwd_hint(N, 3));
-        net_fwd<FRL_R>(c, N, 3, ln, XC, cip, c_in, bc, ldh, V, 4, bwd_hint(N, 2));
+        net_fwd<R>(c, N, 0, ln, X, ip, a.obs_dim, ba, ldh, OA, ap, fwd_hint(N, 3));
+        net_fwd<R>(c, N, 3, ln, XC, cip, c_in, bc, ldh, V, 4, bwd_hint(N, 2));
         // policy head: log-prob, entropy, ratio, clipped surrogate and its gradient w.r.t. the actor output
         FRL_PAR(t) {
           float sa = 0.f, se = 0.f;
-          if (t < FRL_R) {
+          if (t < R) {
             const int r = t;
             for (int j = 0; j < ap; ++j) dOA[r * ap + j] = 0.f;
             if (r < nvalid) {
@@ -294,7 +302,7 @@ struct PpoAlgo {
         // value loss  mse(v_target, V)  (mean over rows x advantage columns)
         FRL_PAR(t) {
           float l = 0.f;
-          if (t < FRL_R) {
+          if (t < R) {
             for (int j = 0; j < 4; ++j) dV[t * 4 + j] = 0.f;
             if (t < nvalid) {
               float g = 0.f;
@@ -333,8 +341,8 @@ struct PpoAlgo {
           }
           FRL_SYNC();
         }
-        net_bwd<FRL_R>(c, N, 0, ln, X, ip, ba, ldh, dOA, ap, D1, D2, gp, !first, bwd_hint(N, 5));
-        net_bwd<FRL_R>(c, N, 3, ln, XC, cip, bc, ldh, dV, 4, D1, D2, gp, !first, no_hint());
+        net_bwd<R>(c, N, 0, ln, X, ip, ba, ldh, dOA, ap, D1, D2, gp, !first, bwd_hint(N, 5));
+        net_bwd<R>(c, N, 3, ln, XC, cip, bc, ldh, dV, 4, D1, D2, gp, !first, no_hint());
         first = false;
       }
       FRL_PAR(t) {
@@ -475,6 +483,7 @@ struct PpoAlgo {
     }
   }
 };
+typedef PpoAlgoT<8> PpoAlgo;
 
 // ------------------------------------------------------------------------------------------------
 // GAE: one warp per env column, lanes own contiguous time chunks, float64 composition of the affine maps

@@ -507,6 +507,12 @@ extern "C" int frl_ppo_update(const frl_ppo_args_t* a, void* stream) {
     frl_set_error("frl_ppo_update: net must hold actor (layers 0-2) + critic (layers 3-5)");
     return -1;
   }
+  // 16-row tiles for large minibatches when they fit in shared memory (checked with the launcher's own formula)
+  if (a->mb >= 1024) {
+    typedef PpoAlgoT<16> P16;
+    const int smem_bytes = (cta_base_floats(P16::wbuf_floats(*a)) + P16::user_floats(*a)) * 4 + 64;
+    if (smem_bytes <= 227 * 1024) return frl_launch<P16>(*a, (cudaStream_t)stream);
+  }
   return frl_launch<PpoAlgo>(*a, (cudaStream_t)stream);
 }
 

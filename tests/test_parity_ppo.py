@@ -104,3 +104,57 @@ def test_ppo_advance_continuous_gpu(golden):
 @pytest.mark.gpu
 def test_ppo_advance_discrete_gpu(golden):
     _ppo_advance(golden, torch.device("cuda"), "ppo_adv_disc", False)
+
+
+def _ppo_large_minibatch(device, is_continue):
+    """minibatch >= 1024 rows takes the 16-row-tile instantiation of the PPO kernel (frl_ppo_update picks it when the tile fits
+    in shared memory): [T=16, N=128] vectorised rollout, minibatch 1024, one epoch (2 updates) vs the oracle."""
+    from collections import OrderedDict
+    from freerl_b200.PPO import PPO
+    torch.manual_seed(4)
+    T, N, mb = 16, 128, 1024
+    ad = 2 if is_continue else 4
+    pol = PPO([8, ad], is_continue, 1e-3, 1e-3, T * N, device)
+    rng = np.random.default_rng(12)
+    cols = []
+    for t in range(T):
+        o, o2 = rng.standard_normal((N, 8), dtype=np.float32), rng.standard_normal((N, 8), dtype=np.float32)
+        act, lp = pol.select_action(o)
+        act = np.asarray(act, dtype=np.float32).reshape(N, -1)
+        lp = np.asarray(lp, dtype=np.float32).reshape(N, -1)
+        r = rng.standard_normal(N).astype(np.float32)
+        d = rng.random(N) < 0.02
+        adn = d | (rng.random(N) < 0.02)
+        pol.add(o, act, r, o2, d, lp, adn)
+        cols.append((o, act, r.reshape(N, 1), o2, d.reshape(N, 1).astype(np.float32), lp, adn.reshape(N, 1).astype(np.float32)))
+    data = tuple(torch.from_numpy(np.concatenate([c[k] for c in cols])) for k in range(7))
+    sd = lambda m: OrderedDict((k, v.detach().cpu().clone()) for k, v in m.state_dict().items())
+    orc = algos.PPOOracle(sd(pol.agent.actor), sd(pol.agent.critic), 1e-3, is_continue)
+    with torch.no_grad():
+        vs, vn = algos.mlp2(orc.critic, data[0]), algos.mlp2(orc.critic, data[3])
+        td = (data[2] + 0.99 * (1.0 - data[4]) * vn - vs).numpy().reshape(T, N).astype(np.float64)
+    adn = data[6].numpy().reshape(T, N).astype(np.float64)
+    want, g = np.zeros((T, N)), np.zeros(N)
+    for t in reversed(range(T)):
+        g = td[t] + 0.99 * 0.95 * g * (1.0 - adn[t])
+        want[t] = g
+    adv_o = torch.from_numpy(want.astype(np.float32).reshape(-1, 1))
+    perm = rng.permutation(T * N)
+    ref = [orc.minibatch(data, adv_o, adv_o + vs, perm[s:s + mb], 0.2, 0.01) for s in range(0, T * N, mb)]
+    pol.learn(mb, 0.99, 0.95, 0.2, 1, 0.01, permutations=[perm])
+    m = pol.last_metrics.cpu().numpy()
+    np.testing.assert_allclose(m[:, 0], [x[0] for x in ref], rtol=3e-5, atol=2e-6)
+    np.testing.assert_allclose(m[:, 1], [x[1] for x in ref], rtol=3e-5, atol=2e-6)
+    tol = dict(rtol=2e-4, atol=2e-5)
+    assert_module_close(pol.agent.actor, orc.actor, "actor", tol)
+    assert_module_close(pol.agent.critic, orc.critic, "critic", tol)
+
+
+def test_ppo_large_minibatch_emulated(emul):
+    _ppo_large_minibatch(torch.device("cpu"), True)
+
+
+@pytest.mark.gpu
+def test_ppo_large_minibatch_gpu():
+    _ppo_large_minibatch(torch.device("cuda"), True)
+    _ppo_large_minibatch(torch.device("cuda"), False)
