@@ -12,7 +12,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 FRL_MAX_LAYERS = 6
 FRL_MAX_AGENTS = 6
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class Layer(C.Structure):
@@ -151,7 +151,14 @@ def lib():
         l = C.CDLL(path)
         _declare(l)
         if l.frl_abi_version() != ABI_VERSION:
-            raise RuntimeError("freerl_b200: ABI mismatch in %s" % path)
+            raise RuntimeError("freerl_b200: ABI mismatch in %s (library %d, binding %d): rebuild the extension"
+                               % (path, l.frl_abi_version(), ABI_VERSION))
+        l.frl_struct_size.restype = C.c_int
+        l.frl_struct_size.argtypes = [C.c_int]
+        for which, mirror in enumerate((Layer, Net, Replay, DqnArgs, AcArgs, InferArgs, PpoArgs, NoisyMap, RainbowArgs)):
+            if l.frl_struct_size(which) != C.sizeof(mirror):
+                raise RuntimeError("freerl_b200: ctypes mirror %s is %d bytes, the library's struct is %d"
+                                   % (mirror.__name__, C.sizeof(mirror), l.frl_struct_size(which)))
         _lib = l
     return _lib
 

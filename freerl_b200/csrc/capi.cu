@@ -22,7 +22,22 @@ extern "C" void frl_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 extern "C" const char* frl_last_error(void) { return g_err; }
-extern "C" int frl_abi_version(void) { return 2; }
+extern "C" int frl_abi_version(void) { return 3; }
+// sizeof() of the argument structs, so a binding can verify its mirror of the layout before the first call
+extern "C" int frl_struct_size(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(frl_layer_t);
+    case 1: return (int)sizeof(frl_net_t);
+    case 2: return (int)sizeof(frl_replay_t);
+    case 3: return (int)sizeof(frl_dqn_args_t);
+    case 4: return (int)sizeof(frl_ac_args_t);
+    case 5: return (int)sizeof(frl_infer_args_t);
+    case 6: return (int)sizeof(frl_ppo_args_t);
+    case 7: return (int)sizeof(frl_noisy_map_t);
+    case 8: return (int)sizeof(frl_rainbow_args_t);
+    default: return -1;
+  }
+}
 
 #ifndef FRL_EMUL
 extern "C" int frl_is_emulation(void) { return 0; }

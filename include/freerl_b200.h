@@ -232,6 +232,10 @@ int frl_is_emulation(void);          /* 0 for the CUDA library (the only one the
 int frl_device_sm_count(void);
 int frl_wt_ld(int out_pad);          /* row stride (floats) of a transposed-mirror layer image with this padded width */
 int frl_abi_version(void);
+/* sizeof the argument structs as compiled: 0 frl_layer_t, 1 frl_net_t, 2 frl_replay_t, 3 frl_dqn_args_t, 4 frl_ac_args_t,
+ * 5 frl_infer_args_t, 6 frl_ppo_args_t, 7 frl_noisy_map_t, 8 frl_rainbow_args_t; -1 otherwise.  A binding checks its mirror
+ * of the layout against these before the first call (freerl_b200/_lib.py does, at load time). */
+int frl_struct_size(int which);
 
 int frl_replay_add_batch(const frl_replay_t* rb, int64_t index, const float* obs, const float* act, const float* rew,
                          const float* next_obs, const float* done, int n, void* stream);
