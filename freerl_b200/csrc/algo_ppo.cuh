@@ -377,23 +377,32 @@ struct PpoAlgoT {
       FRL_PAR(t) { if (t == 0) { a.sumsq[c.cta * 2] = ta; a.sumsq[c.cta * 2 + 1] = tc; } }
       FRL_SYNC();
     } else {
-      // optimiser scalars (one thread, broadcast through smem)
+      // optimiser scalars (broadcast through smem).  The per-CTA partials are fetched by one thread EACH and folded in CTA
+      // order from shared memory (same association as a serial walk; a single thread walking 148 partials in global memory
+      // cost 7 us per sum while its CTA, and with it the whole grid, waited at the next barrier).
       float* sh = c.red;
+      float nrm[3], met[3] = {0.f, 0.f, 0.f};
+      cta_sums(sh, a.sumsq, 2, a.sumsq + 1, 2, nullptr, 0, c.ncta, nrm);
+      if (s == 3 && c.cta == 0) cta_sums(sh, a.stats, 8, a.stats + 1, 8, a.stats + 2, 8, ncontrib, met);
       FRL_PAR(t) {
         if (t == 0) {
-          const float ta = strided_sum(a.sumsq, 2, c.ncta), tc = strided_sum(a.sumsq + 1, 2, c.ncta);
+          const float ta = nrm[0], tc = nrm[1];
           float ca = 1.f, cc = 1.f;
           if (a.max_norm_actor > 0.f) ca = fminf(a.max_norm_actor / (sqrtf(ta) + 1e-6f), 1.f);
           if (a.max_norm_critic > 0.f) cc = fminf(a.max_norm_critic / (sqrtf(tc) + 1e-6f), 1.f);
           sh[0] = ca; sh[1] = cc;
-          const double step = (double)(a.step0 + u + 1);
-          const double bc1 = -expm1(step * log(a.beta1)), bc2 = -expm1(step * log(a.beta2));
+          double p1 = 1.0, p2 = 1.0, q1 = a.beta1, q2 = a.beta2;          // beta^step by squaring (as make_adam_hp)
+          for (unsigned long e = (unsigned long)(a.step0 + u + 1); e; e >>= 1) {
+            if (e & 1) { p1 *= q1; p2 *= q2; }
+            q1 *= q1; q2 *= q2;
+          }
+          const double bc1 = 1.0 - p1, bc2 = 1.0 - p2;
           sh[2] = (float)(a.lr * sqrt(bc2) / bc1);         // c_adamw step_size
           sh[3] = (float)(-(a.lr / bc1));                   // torch Adam: -lr/bc1
           sh[4] = (float)sqrt(bc2);
           sh[5] = (float)(-((a.lr_critic > 0.0 ? a.lr_critic : a.lr) / bc1));
           if (s == 3 && c.cta == 0) {
-            const float l0 = strided_sum(a.stats, 8, ncontrib), l1 = strided_sum(a.stats + 1, 8, ncontrib), l2 = strided_sum(a.stats + 2, 8, ncontrib);
+            const float l0 = met[0], l1 = met[1], l2 = met[2];
             const float ent_mean = l2 / (float)rows;
             a.out[u * 8 + 0] = l0 - a.entropy_coef * ent_mean;
             a.out[u * 8 + 1] = l1 / (float)(rows * a.n_adv);
