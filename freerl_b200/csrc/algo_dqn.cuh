@@ -195,13 +195,12 @@ struct DqnAlgo {
       reduce_grads(c.cta, c.ncta, c.red, q, a.gpart, q.n_p, ncontrib, nullptr);
       const AdamSpec hp = {a.lr, a.beta1, a.beta2, a.eps, 0.0, 0.0, (long)(a.step0 + u + 1)};
       adam_update(c.cta, c.ncta, c.red, q, nullptr, 0, hp, &a.q_target, a.tau);
-      FRL_PAR(t) {
-        if (c.cta == 0 && t == 0) {
-          const float l = strided_sum(a.stats, 8, ncontrib);
-          a.out[u * 8 + 0] = l / (float)a.B * a.stats[1];
-        }
+      if (c.cta == 0) {                     // loss metric: partials fetched in parallel, folded in CTA order (block-uniform branch)
+        float o[3];
+        cta_sums(c.red, a.stats, 8, nullptr, 0, nullptr, 0, ncontrib, o);
+        FRL_PAR(t) { if (t == 0) a.out[u * 8 + 0] = o[0] / (float)a.B * a.stats[1]; }
+        FRL_SYNC();
       }
-      FRL_SYNC();
     }
   }
 };

@@ -289,14 +289,16 @@ struct RainbowAlgo {
     }
     // stage 2: reduce effective-net gradients over CTAs, map to (mu, sigma), Adam + Polyak on the trainable block
     float* sh = c.red;
+    if (c.cta == 0) {                       // loss metric: partials fetched in parallel, folded in CTA order (block-uniform branch)
+      float o[3];
+      cta_sums(sh, a.stats, 8, nullptr, 0, nullptr, 0, ncontrib, o);
+      FRL_PAR(t) { if (t == 0) a.out[u * 8] = o[0] / (float)a.B; }
+      FRL_SYNC();
+    }
     FRL_PAR(t) {
       if (t == 0) {
         const AdamHP h = make_adam_hp(a.lr, a.beta1, a.beta2, a.eps_adam, 0.0, 0.0, (long)(a.step0 + u + 1));
         sh[0] = h.lr_over_bc1_neg; sh[1] = h.bc2_sqrt; sh[2] = h.one_minus_b1; sh[3] = h.b2; sh[4] = h.one_minus_b2; sh[5] = h.eps;
-        if (c.cta == 0) {
-          const float l = strided_sum(a.stats, 8, ncontrib);
-          a.out[u * 8] = l / (float)a.B;
-        }
       }
     }
     FRL_SYNC();
