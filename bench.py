@@ -194,6 +194,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries ONE JSON line: keep the real stdout aside and point fd 1 at stderr, so prints from libraries (NCCL's
+    # version banner, reference-style constructors) cannot get in front of it
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -207,13 +212,14 @@ def main():
             return
         w = max(args.warmup, 1)
         val, ms, cores, tps = cpu_reference_arm(args.steps, w, transitions_per_step=16)
-        print(json.dumps({
+        line = json.dumps({
             "impl": "reference", "metric": "env_steps_per_sec", "value": val, "unit": "env-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": w, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": cores, "kind": "port",
                              "sample": "%d single-env iterations (select_action + add + np.random.choice(1e6,256) + SAC learn B=256) per step" % tps},
-            "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+            "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        print(line, file=json_out, flush=True)
         return
 
     import torch
@@ -340,7 +346,7 @@ def main():
         val, ms, cores, tps = cpu_reference_arm(150, 1)
         out["cpu_baseline"] = {"value": val, "unit": "env-steps/s", "cores": cores, "kind": "port",
                                "sample": "150 steps x %d single-env iterations of the oracle port (np.random.choice over the full 1e6 replay + SAC learn B=256)" % tps}
-    print(json.dumps(out))
+    print(json.dumps(out), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
