@@ -19,7 +19,7 @@ struct RainbowAlgo {
   FRL_SHD int natot(const Args& a) { return (a.n_actions * a.n_atoms + 3) & ~3; }
   FRL_SHD int user_floats(const Args& a) {
     const int ldh = act_ld(a.eff[2].L[0].out_pad), ip = a.eff[2].L[0].in_pad, zp = (a.n_atoms + 3) & ~3;
-    return FRL_R * (a.replay.row_floats + 2 * ip + 3 * ldh + 3 * zp + 2 * natot(a) + 4 * zp + 8) + FRL_NT + 64;
+    return FRL_R * (a.replay.row_floats + 2 * ip + 3 * ldh + 3 * zp + 2 * natot(a) + 7 * zp + 8) + 3 * FRL_NT + 64;
   }
   FRL_SHD int grid(const Args& a, int max_ctas) {
     int tiles = (a.B + FRL_R - 1) / FRL_R;
@@ -67,63 +67,108 @@ struct RainbowAlgo {
     FRL_SYNC();
   }
 
-  // logits -> per-action distribution + expected value; D holds [R][n_actions*n_atoms] (ld = nat), V [R][zp]
-  FRL_SDEV void head_probs(const Args& a, const float* V, int zp, float* A, int nat, float* qv /*[R][n_actions]*/) {
-    const int nA = a.n_actions, nZ = a.n_atoms;
+  // ---- per-row distribution helpers ------------------------------------------------------------------------------------
+  // The distributional head works on R rows x 51 atoms (x n_actions).  Every step below is spread over (row, atom) items or
+  // over `lanes` partial reductions per row — the first version walked each row with ONE thread (8 of 256 threads busy for
+  // ~5 us per softmax) and those serial walks were a third of the learn.
+  // Row i of a "row set" starts at X[(i / inner) * outer + (i % inner) * istride]  (dist of one action: inner 1, outer zp;
+  // all actions of the dueling head: inner n_actions, outer nat, istride n_atoms).
+  FRL_SDEV int row_base(int i, int inner, int outer, int istride) { return (i / inner) * outer + (i % inner) * istride; }
+  FRL_SDEV int row_lanes(int nrows) { int l = FRL_NT / (nrows > 0 ? nrows : 1); return l > 32 ? 32 : (l < 1 ? 1 : l); }
+
+  // in-place softmax over n entries of each row; sc: [FRL_NT + nrows] floats of scratch.  Rows beyond FRL_NT are not supported
+  // (n_actions * R <= FRL_NT is checked by the host wrapper through the layer-count limit).
+  FRL_SDEV void softmax_rows(float* X, int nrows, int n, int inner, int outer, int istride, float* sc) {
+    const int lanes = row_lanes(nrows);
     FRL_PAR(t) {
-      if (t < FRL_R * nA) {
-        const int r = t / nA, ac = t % nA;
-        // logits[z] = V[z] + A[ac][z] - mean_a A[a][z];  softmax over z;  q = sum z * p
-        float mx = -1e30f;
-        for (int z = 0; z < nZ; ++z) {
-          float mean = 0.f;
-          for (int b = 0; b < nA; ++b) mean += A[r * nat + b * nZ + z];
-          mean = mean / (float)nA;
-          const float lg = V[r * zp + z] + A[r * nat + ac * nZ + z] - mean;
-          mx = fmaxf(mx, lg);
-        }
+      if (t < nrows * lanes) {
+        const int i = t / lanes, l = t % lanes, b = row_base(i, inner, outer, istride);
+        float m = -1e30f;
+        for (int z = l; z < n; z += lanes) m = fmaxf(m, X[b + z]);
+        sc[t] = m;
+      }
+    }
+    FRL_SYNC();
+    FRL_PAR(t) {
+      if (t < nrows) { float m = sc[t * lanes]; for (int l = 1; l < lanes; ++l) m = fmaxf(m, sc[t * lanes + l]); sc[FRL_NT + t] = m; }
+    }
+    FRL_SYNC();
+    FRL_PAR(t) {
+      if (t < nrows * lanes) {
+        const int i = t / lanes, l = t % lanes, b = row_base(i, inner, outer, istride);
+        const float mx = sc[FRL_NT + i];
         float se = 0.f;
-        for (int z = 0; z < nZ; ++z) {
-          float mean = 0.f;
-          for (int b = 0; b < nA; ++b) mean += A[r * nat + b * nZ + z];
-          mean = mean / (float)nA;
-          se += expf(V[r * zp + z] + A[r * nat + ac * nZ + z] - mean - mx);
-        }
-        float q = 0.f;
-        for (int z = 0; z < nZ; ++z) {
-          float mean = 0.f;
-          for (int b = 0; b < nA; ++b) mean += A[r * nat + b * nZ + z];
-          mean = mean / (float)nA;
-          const float p = expf(V[r * zp + z] + A[r * nat + ac * nZ + z] - mean - mx) / se;
-          q += p * a.z[z];
-        }
-        qv[r * nA + ac] = q;
+        for (int z = l; z < n; z += lanes) { const float e = expf(X[b + z] - mx); X[b + z] = e; se += e; }
+        sc[t] = se;
+      }
+    }
+    FRL_SYNC();
+    FRL_PAR(t) {
+      if (t < nrows) { float se = sc[t * lanes]; for (int l = 1; l < lanes; ++l) se += sc[t * lanes + l]; sc[FRL_NT + t] = se; }
+    }
+    FRL_SYNC();
+    FRL_PAR(t) {
+      if (t < nrows * lanes) {
+        const int i = t / lanes, l = t % lanes, b = row_base(i, inner, outer, istride);
+        const float se = sc[FRL_NT + i];
+        for (int z = l; z < n; z += lanes) X[b + z] = X[b + z] / se;
       }
     }
     FRL_SYNC();
   }
 
-  // distribution of one chosen action per row -> P[r][z]
-  FRL_SDEV void dist_of(const Args& a, const float* V, int zp, const float* A, int nat, const int* act, float* P) {
+  // logits -> per-action expected value q[r][ac] = sum_z softmax_z(V + A[ac] - mean_a A)[z] * z_atom
+  //   mean: [R][zp] scratch, L: [R][nat] scratch (all-action logits / probabilities), sc: [2*FRL_NT] scratch
+  FRL_SDEV void head_probs(const Args& a, const float* V, int zp, const float* A, int nat, float* qv /*[R][n_actions]*/, float* mean,
+                           float* L, float* sc) {
     const int nA = a.n_actions, nZ = a.n_atoms;
     FRL_PAR(t) {
-      if (t < FRL_R) {
-        const int r = t, ac = act[r];
-        float mx = -1e30f;
-        for (int z = 0; z < nZ; ++z) {
-          float mean = 0.f;
-          for (int b = 0; b < nA; ++b) mean += A[r * nat + b * nZ + z];
-          mean = mean / (float)nA;
-          const float lg = V[r * zp + z] + A[r * nat + ac * nZ + z] - mean;
-          P[r * zp + z] = lg;
-          mx = fmaxf(mx, lg);
-        }
-        float se = 0.f;
-        for (int z = 0; z < nZ; ++z) { const float e = expf(P[r * zp + z] - mx); P[r * zp + z] = e; se += e; }
-        for (int z = 0; z < nZ; ++z) P[r * zp + z] = P[r * zp + z] / se;
+      for (int e = t; e < FRL_R * nZ; e += FRL_NT) {
+        const int r = e / nZ, z = e % nZ;
+        float m = 0.f;
+        for (int b = 0; b < nA; ++b) m += A[r * nat + b * nZ + z];
+        mean[r * zp + z] = m / (float)nA;
       }
     }
     FRL_SYNC();
+    FRL_PAR(t) {
+      for (int e = t; e < FRL_R * nA * nZ; e += FRL_NT) {
+        const int r = e / (nA * nZ), j = e % (nA * nZ), z = j % nZ;
+        L[r * nat + j] = V[r * zp + z] + A[r * nat + j] - mean[r * zp + z];
+      }
+    }
+    FRL_SYNC();
+    softmax_rows(L, FRL_R * nA, nZ, nA, nat, nZ, sc);
+    const int nrows = FRL_R * nA, lanes = row_lanes(nrows);
+    FRL_PAR(t) {
+      if (t < nrows * lanes) {
+        const int i = t / lanes, l = t % lanes, b = row_base(i, nA, nat, nZ);
+        float q = 0.f;
+        for (int z = l; z < nZ; z += lanes) q += L[b + z] * a.z[z];
+        sc[t] = q;
+      }
+    }
+    FRL_SYNC();
+    FRL_PAR(t) {
+      if (t < nrows) { float q = sc[t * lanes]; for (int l = 1; l < lanes; ++l) q += sc[t * lanes + l]; qv[t] = q; }     // t = r * nA + ac
+    }
+    FRL_SYNC();
+  }
+
+  // distribution of one chosen action per row -> P[r][z]   (sc: [2*FRL_NT] scratch)
+  FRL_SDEV void dist_of(const Args& a, const float* V, int zp, const float* A, int nat, const int* act, float* P, float* sc) {
+    const int nA = a.n_actions, nZ = a.n_atoms;
+    FRL_PAR(t) {
+      for (int e = t; e < FRL_R * nZ; e += FRL_NT) {
+        const int r = e / nZ, z = e % nZ;
+        float m = 0.f;
+        for (int b = 0; b < nA; ++b) m += A[r * nat + b * nZ + z];
+        m = m / (float)nA;
+        P[r * zp + z] = V[r * zp + z] + A[r * nat + act[r] * nZ + z] - m;
+      }
+    }
+    FRL_SYNC();
+    softmax_rows(P, FRL_R, nZ, 1, zp, 0, sc);
   }
 
   // hidden -> V and A head outputs through effective net E (layers 1.. )
@@ -164,6 +209,8 @@ struct RainbowAlgo {
       float* qv = sb.take(FRL_R * ((nA + 3) & ~3) + 4);
       int* act = (int*)sb.take(FRL_R + 4);
       float* red0 = sb.take(FRL_NT);
+      float* sc2 = sb.take(2 * FRL_NT);        // row-reduction scratch of the distribution helpers
+      float* proj = sb.take(3 * FRL_R * zp);   // projection scratch: l index, u index, l-weight per (row, source atom)
       float* gp = a.gpart + (size_t)c.cta * E3.n_p;
       float loss_acc = 0.f;
       bool first = true;
@@ -180,7 +227,7 @@ struct RainbowAlgo {
         if (a.double_q) {
           layer_fwd<FRL_R>(c, a.eff[0], 0, Xn, ip, Hn, ldh, FRL_ACT_RELU, fwd_hint(a.eff[0], 1));
           heads_fwd(c, a.eff[0], Hn, ldh, V, zp, A, nat, fwd_hint(a.eff[1], 0));
-          head_probs(a, V, zp, A, nat, qv);
+          head_probs(a, V, zp, A, nat, qv, Dt, dA, sc2);
           FRL_PAR(t) {
             if (t < FRL_R) { int best = 0; for (int b = 1; b < nA; ++b) if (qv[t * nA + b] > qv[t * nA + best]) best = b; act[t] = best; }
           }
@@ -190,69 +237,109 @@ struct RainbowAlgo {
         layer_fwd<FRL_R>(c, a.eff[1], 0, Xn, ip, Hn, ldh, FRL_ACT_RELU, fwd_hint(a.eff[1], 1));
         heads_fwd(c, a.eff[1], Hn, ldh, V, zp, A, nat, fwd_hint(E3, 0));
         if (!a.double_q) {
-          head_probs(a, V, zp, A, nat, qv);
+          head_probs(a, V, zp, A, nat, qv, Dt, dA, sc2);
           FRL_PAR(t) {
             if (t < FRL_R) { int best = 0; for (int b = 1; b < nA; ++b) if (qv[t * nA + b] > qv[t * nA + best]) best = b; act[t] = best; }
           }
           FRL_SYNC();
         }
-        dist_of(a, V, zp, A, nat, act, Pn);
-        // (3) projection of the target distribution  (projection_dist, DQN_with_tricks.py:135-160)
-        FRL_PAR(t) {
-          if (t < FRL_R) {
-            const int r = t;
-            for (int z = 0; z < zp; ++z) Pm[r * zp + z] = 0.f;
-            if (r < nvalid) {
-              const float rew = raw[r * rf + rb_col_rew(a.replay)], dn = raw[r * rf + rb_col_done(a.replay)];
-              // index_add_ order: all l-contributions (z ascending), then all u-contributions
-              for (int pass = 0; pass < 2; ++pass)
-                for (int z = 0; z < nZ; ++z) {
-                  float tz = fadd(rew, fmul(fmul(a.gamma, a.z[z]), fadd(1.f, -dn)));
-                  tz = fminf(fmaxf(tz, a.v_min), a.v_max);
-                  const float b = fdiv(fadd(tz, -a.v_min), a.delta_z);
-                  const float lf = floorf(b), uf = ceilf(b);
-                  const int l = (int)lf, uu = (int)uf;
-                  const float nd = Pn[r * zp + z];
-                  if (pass == 0) Pm[r * zp + l] = fadd(Pm[r * zp + l], fmul(fadd((float)(uu + (l == uu ? 1 : 0)), -b), nd));
-                  else Pm[r * zp + uu] = fadd(Pm[r * zp + uu], fmul(fadd(b, -(float)l), nd));
-                }
+        dist_of(a, V, zp, A, nat, act, Pn, sc2);
+        // (3) projection of the target distribution  (projection_dist, DQN_with_tricks.py:135-160), two parallel phases:
+        //     per source atom (r, z): l, u and the two weighted contributions; per target atom (r, j): gather, in the
+        //     reference's index_add_ order (all l-contributions with z ascending, then all u-contributions) — bit-identical
+        //     to the sequential scatter.  Scratch: lidx / uidx / wl in `proj`, wu in Dt (free until step 5).
+        {
+          int* lidx = (int*)proj;
+          int* uidx = lidx + FRL_R * zp;
+          float* wl = proj + 2 * FRL_R * zp;
+          float* wu = Dt;
+          FRL_PAR(t) {
+            for (int e = t; e < FRL_R * nZ; e += FRL_NT) {
+              const int r = e / nZ, z = e % nZ;
+              int l = -1, uu = -1;
+              float cl = 0.f, cu = 0.f;
+              if (r < nvalid) {
+                const float rew = raw[r * rf + rb_col_rew(a.replay)], dn = raw[r * rf + rb_col_done(a.replay)];
+                float tz = fadd(rew, fmul(fmul(a.gamma, a.z[z]), fadd(1.f, -dn)));
+                tz = fminf(fmaxf(tz, a.v_min), a.v_max);
+                const float b = fdiv(fadd(tz, -a.v_min), a.delta_z);
+                l = (int)floorf(b); uu = (int)ceilf(b);
+                const float nd = Pn[r * zp + z];
+                cl = fmul(fadd((float)(uu + (l == uu ? 1 : 0)), -b), nd);
+                cu = fmul(fadd(b, -(float)l), nd);
+              }
+              lidx[r * zp + z] = l; uidx[r * zp + z] = uu; wl[r * zp + z] = cl; wu[r * zp + z] = cu;
             }
           }
+          FRL_SYNC();
+          FRL_PAR(t) {
+            for (int e = t; e < FRL_R * zp; e += FRL_NT) {
+              const int r = e / zp, jz = e % zp;
+              float m = 0.f;
+              if (jz < nZ) {
+                for (int z = 0; z < nZ; ++z) if (lidx[r * zp + z] == jz) m = fadd(m, wl[r * zp + z]);
+                for (int z = 0; z < nZ; ++z) if (uidx[r * zp + z] == jz) m = fadd(m, wu[r * zp + z]);
+              }
+              Pm[e] = m;
+            }
+          }
+          FRL_SYNC();
         }
-        FRL_SYNC();
         // (4) online net on obs with the stored actions (forward #3, carries the gradient)
         layer_fwd<FRL_R>(c, E3, 0, Xo, ip, H, ldh, FRL_ACT_RELU, fwd_hint(E3, 1));
         heads_fwd(c, E3, H, ldh, V, zp, A, nat, bwd_hint(E3, 1));
         FRL_PAR(t) { if (t < FRL_R) act[t] = (int)raw[t * rf + rb_col_act(a.replay)]; }
         FRL_SYNC();
-        dist_of(a, V, zp, A, nat, act, Pn);
-        // (5) loss, PER error and d(loss)/d(logits of the taken action)
-        FRL_PAR(t) {
-          float l = 0.f;
-          if (t < FRL_R) {
-            const int r = t;
-            for (int z = 0; z < zp; ++z) dV[r * zp + z] = 0.f;
-            if (r < nvalid) {
-              const float w = a.is_weight ? a.is_weight[row0 + r] : 1.f;
+        dist_of(a, V, zp, A, nat, act, Pn, sc2);
+        // (5) loss, PER error and d(loss)/d(logits of the taken action): per (r, z) terms, `lanes` partial sums per row
+        {
+          const int lanes = row_lanes(FRL_R);
+          float* perr = sc2;                       // [R * lanes] partial sum_z m log p      (then [FRL_NT + r] = row total)
+          float* pdot = dA;                        // [R * lanes] partial sum_z p dL/dp      (then [R*lanes + r] = row total)
+          FRL_PAR(t) {
+            if (t < FRL_R * lanes) {
+              const int r = t / lanes, l = t % lanes;
               float err = 0.f, dot = 0.f;
-              for (int z = 0; z < nZ; ++z) {
-                const float p = Pn[r * zp + z];
-                const float pc = fminf(fmaxf(p, 1e-5f), 1.f - 1e-5f);
-                err += Pm[r * zp + z] * logf(pc);
-                // dL/dp = -(m * w / B) / p inside the clamp range, 0 outside
-                const float gpz = (p >= 1e-5f && p <= 1.f - 1e-5f) ? -(Pm[r * zp + z] * w / (float)a.B) / pc : 0.f;
-                Dt[r * zp + z] = gpz;
-                dot += p * gpz;
+              if (r < nvalid) {
+                const float w = a.is_weight ? a.is_weight[row0 + r] : 1.f;
+                for (int z = l; z < nZ; z += lanes) {
+                  const float p = Pn[r * zp + z];
+                  const float pc = fminf(fmaxf(p, 1e-5f), 1.f - 1e-5f);
+                  err += Pm[r * zp + z] * logf(pc);
+                  // dL/dp = -(m * w / B) / p inside the clamp range, 0 outside
+                  const float gpz = (p >= 1e-5f && p <= 1.f - 1e-5f) ? -(Pm[r * zp + z] * w / (float)a.B) / pc : 0.f;
+                  Dt[r * zp + z] = gpz;
+                  dot += p * gpz;
+                }
               }
-              for (int z = 0; z < nZ; ++z) dV[r * zp + z] = Pn[r * zp + z] * (Dt[r * zp + z] - dot);   // softmax backward
-              if (a.error_out) a.error_out[row0 + r] = err;
-              l = -err * w;
+              perr[t] = err; pdot[t] = dot;
             }
           }
-          red0[t] = l;
+          FRL_SYNC();
+          FRL_PAR(t) {
+            float l = 0.f;
+            if (t < FRL_R) {
+              float err = 0.f, dot = 0.f;
+              for (int k = 0; k < lanes; ++k) { err += perr[t * lanes + k]; dot += pdot[t * lanes + k]; }
+              pdot[FRL_R * lanes + t] = dot;
+              if (t < nvalid) {
+                const float w = a.is_weight ? a.is_weight[row0 + t] : 1.f;
+                if (a.error_out) a.error_out[row0 + t] = err;
+                l = -err * w;
+              }
+            }
+            red0[t] = l;
+          }
+          FRL_SYNC();
+          loss_acc += block_sum(red0);
+          FRL_PAR(t) {
+            for (int e = t; e < FRL_R * zp; e += FRL_NT) {
+              const int r = e / zp, z = e % zp;
+              dV[e] = (r < nvalid && z < nZ) ? Pn[e] * (Dt[e] - pdot[FRL_R * lanes + r]) : 0.f;      // softmax backward
+            }
+          }
+          FRL_SYNC();
         }
-        FRL_SYNC();
-        loss_acc += block_sum(red0);
         // dueling backward: dV[z] = dlogit[z];  dA[a'][z] = ([a'==a] - 1/nA) * dlogit[z]
         FRL_PAR(t) {
           for (int e = t; e < FRL_R * nat; e += FRL_NT) {
@@ -366,6 +453,9 @@ struct RainbowInferAlgo {
     float* V = sb.take(FRL_R * zp);
     float* A = sb.take(FRL_R * nat);
     float* qv = sb.take(FRL_R * ((nA + 3) & ~3) + 4);
+    float* mean = sb.take(FRL_R * zp);
+    float* L = sb.take(FRL_R * nat);
+    float* sc2 = sb.take(2 * FRL_NT);
     const int row0 = c.cta * FRL_R;
     const int nvalid = (a.n - row0) < FRL_R ? (a.n - row0) : FRL_R;
     stage_prefetch(c, layer_fwd_src(E, 0), layer_fwd_bytes(E.L[0]));
@@ -378,7 +468,7 @@ struct RainbowInferAlgo {
     FRL_SYNC();
     layer_fwd<FRL_R>(c, E, 0, X, ip, H, ldh, FRL_ACT_RELU, fwd_hint(E, 1));
     RainbowAlgo::heads_fwd(c, E, H, ldh, V, zp, A, nat, no_hint());
-    RainbowAlgo::head_probs(a.r, V, zp, A, nat, qv);
+    RainbowAlgo::head_probs(a.r, V, zp, A, nat, qv, mean, L, sc2);
     FRL_PAR(t) {
       if (t < nvalid) {
         int best = 0;

@@ -72,3 +72,57 @@ def test_rainbow_emulated(golden, emul):
 @pytest.mark.gpu
 def test_rainbow_gpu(golden):
     _run(golden, torch.device("cuda"))
+
+
+def _other_action_counts(device):
+    """n_actions 2 and 6 (different head widths / column-block splits / scratch sizes than the 4-action golden): fused learn vs
+    the oracle with explicit PER uniforms and NoisyLinear draws."""
+    from collections import OrderedDict
+    from freerl_b200.DQN_with_tricks import DQN
+    from oracle import buffers
+    rng = np.random.default_rng(21)
+    for nA in (2, 6):
+        torch.manual_seed(nA)
+        B, od = 24, 5
+        pol = DQN([od, nA], False, 1e-3, 200, device, trick=TRICK, gamma=0.97, batch_size=B)
+        q = OrderedDict((k, v.detach().cpu().clone()) for k, v in pol.agent.Qnet.state_dict().items())
+        orc = RainbowOracle(q, 1e-3, nA)
+        per = buffers.NStepPrioritizedReplay(200, od, 1, gamma=0.97, n_step=3)
+        for _ in range(90):
+            o, a_, r = rng.standard_normal(od).astype(np.float32), int(rng.integers(0, nA)), float(np.float32(rng.standard_normal()))
+            o2, d = rng.standard_normal(od).astype(np.float32), bool(rng.random() < 0.1)
+            pol.add(o, a_, r, o2, d)
+            per.add(o, a_, r, o2, d)
+        assert np.array_equal(pol.buffer.sumtree.tree.cpu().numpy(), per.sumtree.tree)
+        gamma_n = per.n_step_gamma
+        for it in range(2):
+            u = rng.random(B)
+            raw = [tuple(torch.randn(n) for n in (128, 51, 128, nA * 51)) for _ in range(3)]
+            seg = per.sumtree.total() / B
+            per.beta = np.min([1., per.beta + per.beta_increment])
+            idx, pri = np.zeros(B, np.int64), np.zeros(B, np.float32)
+            for i in range(B):
+                lo, hi = seg * i, seg * (i + 1)
+                pri[i], idx[i] = per.sumtree.find(lo + (hi - lo) * u[i])
+            prob = np.clip(pri / per.sumtree.total(), 1e-7, None)
+            w = (len(per) * prob) ** (-per.beta)
+            w = (w / w.max()).astype(np.float32)
+            batch = tuple(torch.from_numpy(x) for x in per.buffer.sample(idx))
+            r = orc.learn(batch, raw, gamma_n, 0.01, is_weight=torch.from_numpy(w), double_q=True)
+            per.update_priorities(idx, r["error"].numpy())
+            pol.learn(B, 0.97, 0.01, u=u, noise=[tuple(x.numpy() for x in f) for f in raw])
+            assert np.array_equal(pol.last_indices.cpu().numpy(), idx)
+            loss = float(pol.last_metrics[0])
+            assert abs(loss - r["loss"]) <= 1e-5 * abs(r["loss"]), (nA, it, loss, r["loss"])
+            np.testing.assert_allclose(pol.last_error.cpu().numpy(), r["error"].numpy(), rtol=1e-5, atol=1e-6)
+        from parity_util import assert_module_close           # outlier-aware (Adam-conditioned elements, see parity_util)
+        assert_module_close(pol.agent.Qnet, orc.q, "nA=%d" % nA)
+
+
+def test_rainbow_other_action_counts_emulated(emul):
+    _other_action_counts(torch.device("cpu"))
+
+
+@pytest.mark.gpu
+def test_rainbow_other_action_counts_gpu():
+    _other_action_counts(torch.device("cuda"))
