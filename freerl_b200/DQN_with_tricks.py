@@ -267,6 +267,8 @@ class _ValueDQN(DQN):
     def learn(self, batch_size, gamma, tau, *, u=None, indices=None):
         total = len(self.buffer)
         B = min(batch_size, total)
+        if B <= 0:
+            raise RuntimeError("learn() called on an empty replay (with N_Step the first n_step - 1 adds only fill the window)")
         per = bool(self.trick['PER'])
         if per:
             idx, w, _ = self.buffer.sample_device(B, u=u)
@@ -349,9 +351,13 @@ class _RainbowDQN(DQN):
     def _device_eps(self):
         """fast mode: the transformed noise f(eps) = sign(eps) sqrt|eps| of all three forwards drawn ON the device (no host
         round trip); returns per-forward 4-tuples of slices for the weight_epsilon bookkeeping"""
-        ag, e, o = self.agent, self._eps, self.agent.eps_off
+        e = self._eps
         e.normal_()
         torch.mul(torch.sign(e), torch.sqrt(torch.abs(e)), out=e)
+        return self._eps_slices()
+
+    def _eps_slices(self):
+        ag, e, o = self.agent, self._eps, self.agent.eps_off
         return [(e[f, o["V_in"]:o["V_in"] + HIDDEN], e[f, o["V_out"]:o["V_out"] + ag.n_atoms], e[f, o["A_in"]:o["A_in"] + HIDDEN],
                  e[f, o["A_out"]:o["A_out"] + ag.nA * ag.n_atoms]) for f in range(3)]
 
@@ -434,6 +440,8 @@ class _RainbowDQN(DQN):
     def learn(self, batch_size, gamma, tau, *, u=None, noise=None, indices=None):
         total = len(self.buffer)
         B = min(batch_size, total)
+        if B <= 0:
+            raise RuntimeError("learn() called on an empty replay (with N_Step the first n_step - 1 adds only fill the window)")
         per = bool(self.trick['PER'])
         if per:
             idx, w, _ = self.buffer.sample_device(B, u=u)
@@ -443,8 +451,9 @@ class _RainbowDQN(DQN):
                 else self.buffer._indices_to_device(indices).reshape(-1)
         if self.trick['N_Step']:
             gamma = self.buffer.n_step_gamma
-        if noise is None and self.mode == "fast":
-            sl = self._device_eps()
+        gen = noise is None and self.mode == "fast"
+        if gen:                                  # the kernel draws the noise itself (Philox) and leaves it in self._eps
+            sl = self._eps_slices()
             self.agent._last_eps["online"], self.agent._last_eps["target"] = ("f", sl[2]), ("f", sl[1])
         else:
             if noise is None:
@@ -458,6 +467,7 @@ class _RainbowDQN(DQN):
         a.is_weight = w.data_ptr() if w is not None else None
         a.gamma, a.tau = gamma, tau
         a.error_out = err.data_ptr()
+        a.noise_gen, a.noise_seed, a.noise_counter = int(gen), self._seed, self._n_learn
         _lib.check(_lib.lib().frl_rainbow_learn(ctypes.byref(a), _lib.stream_ptr(self.device)), "frl_rainbow_learn")
         self.agent.step += 1
         self._n_learn += 1

@@ -91,7 +91,8 @@ class RainbowArgs(C.Structure):
                 ("delta_z", C.c_float), ("double_q", C.c_int), ("replay", Replay), ("indices", C.c_void_p),
                 ("is_weight", C.c_void_p), ("B", C.c_int), ("gamma", C.c_float), ("tau", C.c_float), ("lr", C.c_double),
                 ("beta1", C.c_double), ("beta2", C.c_double), ("eps_adam", C.c_double), ("step0", C.c_int64),
-                ("gpart", C.c_void_p), ("stats", C.c_void_p), ("error_out", C.c_void_p), ("out", C.c_void_p)]
+                ("gpart", C.c_void_p), ("stats", C.c_void_p), ("error_out", C.c_void_p), ("out", C.c_void_p),
+                ("noise_gen", C.c_int), ("noise_seed", C.c_uint64), ("noise_counter", C.c_uint64)]
 
 
 OPT_CAUTIOUS_ADAMW, OPT_ADAM = 0, 1

@@ -28,10 +28,10 @@ struct RainbowAlgo {
   FRL_SHD int n_updates(const Args&) { return 1; }
 
   // effective parameter e (index into eff-net block) of forward f <- trainable block + noise
-  FRL_SDEV void noisy_apply(const Args& a, int f, int cta, int ncta) {
+  FRL_SDEV void noisy_apply(const Args& a, int f, int cta, int ncta, const float* eps_all = nullptr) {
     const frl_net_t& E = a.eff[f];
     const float* P = (f == 1) ? a.p_target : a.p;
-    const float* eps = a.eps + (size_t)f * a.eps_len;
+    const float* eps = (eps_all ? eps_all : a.eps) + (size_t)f * a.eps_len;
     FRL_PAR(t) {
       for (int e = cta * FRL_NT + t; e < E.n_p; e += ncta * FRL_NT) {
         float val = 0.f;
@@ -188,7 +188,24 @@ struct RainbowAlgo {
     const int ntile = (a.B + FRL_R - 1) / FRL_R;
     const int ncontrib = ntile < c.ncta ? ntile : c.ncta;
     if (s == 0) {
-      for (int f = 0; f < 3; ++f) noisy_apply(a, f, c.cta, c.ncta);
+      const float* eps_all = nullptr;
+      if (a.noise_gen) {
+        // fast mode: every CTA derives the same 3 x eps_len factorised-noise vector in shared memory (counter-based, so no
+        // exchange and no extra barrier); CTA 0 publishes it for the host-side weight_epsilon bookkeeping
+        float* se = user;
+        FRL_PAR(t) {
+          for (int e = t; e < 3 * a.eps_len; e += FRL_NT) {
+            const int f = e / a.eps_len, i = e - f * a.eps_len;
+            const float x = frl_randn(a.noise_seed, 40u + (uint32_t)f, (uint32_t)a.noise_counter, (uint32_t)i);
+            const float fe = (x < 0.f ? -1.f : (x > 0.f ? 1.f : 0.f)) * sqrtf(fabsf(x));
+            se[e] = fe;
+            if (c.cta == 0) const_cast<float*>(a.eps)[e] = fe;
+          }
+        }
+        FRL_SYNC();
+        eps_all = se;
+      }
+      for (int f = 0; f < 3; ++f) noisy_apply(a, f, c.cta, c.ncta, eps_all);
       return;
     }
     if (s == 1) {

@@ -225,6 +225,11 @@ typedef struct {
   float* stats;                      /* dev scratch [sm_count][8] */
   float* error_out;                  /* dev [B]: (m * log p).sum(1) per row (PER priorities) or NULL */
   float* out;                        /* dev [8]: out[0] = loss */
+  /* fast mode: when noise_gen != 0 the kernel draws the factorised noise itself — eps[f][i] = sign(x) sqrt|x| with
+   * x = Philox-normal(noise_seed, stream f, noise_counter, i) — for the three forwards of this learn and writes it to `eps`
+   * (the NoisyLinear epsilon bookkeeping reads it back); otherwise `eps` is an input (reference order, torch CPU generator). */
+  int noise_gen;
+  uint64_t noise_seed, noise_counter;
 } frl_rainbow_args_t;
 
 const char* frl_last_error(void);

@@ -126,3 +126,28 @@ def test_rainbow_other_action_counts_emulated(emul):
 @pytest.mark.gpu
 def test_rainbow_other_action_counts_gpu():
     _other_action_counts(torch.device("cuda"))
+
+
+def test_rainbow_fast_mode_in_kernel_noise(emul):
+    """fast mode: the kernel draws the factorised noise f(eps) = sign(eps) sqrt|eps| itself (Philox): fresh per learn, with the
+    moments of the transform (E|f| = 0.822, E f^2 = E|eps| = 0.798), published for the weight_epsilon bookkeeping."""
+    from freerl_b200.DQN_with_tricks import DQN
+    torch.manual_seed(0)
+    pol = DQN([8, 4], False, 1e-3, 256, torch.device("cpu"), trick=TRICK, gamma=0.99, batch_size=16, mode="fast")
+    rng = np.random.default_rng(0)
+    for _ in range(6):                      # 16 lock-stepped envs; the 3-step window emits from the third add on
+        pol.add(rng.standard_normal((16, 8)), rng.integers(0, 4, (16, 1)), rng.standard_normal(16), rng.standard_normal((16, 8)), rng.random(16) < 0.1)
+    assert len(pol.buffer) == 64
+    pol.learn(16, 0.99, 0.01)
+    e1 = pol._eps.clone()
+    pol.learn(16, 0.99, 0.01)
+    e2 = pol._eps.clone()
+    used = pol.agent.eps_off["A_out"] + pol.agent.nA * pol.agent.n_atoms
+    a, b = e1[:, :used].numpy(), e2[:, :used].numpy()
+    assert not np.array_equal(a, b) and not np.array_equal(a[0], a[1])
+    assert abs(np.abs(a).mean() - 0.822) < 0.03 and abs((a ** 2).mean() - 0.798) < 0.04 and abs(a.mean()) < 0.05
+    assert np.isfinite(float(pol.last_metrics[0]))
+    pol.agent._refresh_buffers()                                                   # bookkeeping reads the published noise
+    we = pol.agent.Qnet.V.weight_epsilon.cpu().numpy()
+    o = pol.agent.eps_off
+    np.testing.assert_allclose(we, np.outer(b[2, o["V_out"]:o["V_out"] + 51], b[2, o["V_in"]:o["V_in"] + 128]), rtol=1e-6)
