@@ -57,9 +57,9 @@ def test_sac_learns_point_env():
         rets.append(float(r.mean()))
         if step >= 20:
             pol.learn(256, 0.95, 0.01, n_updates=16)
-    early, late = np.mean(rets[20:70]), np.mean(rets[-100:])
+    random_phase, late = np.mean(rets[:20]), np.mean(rets[-100:])     # the first 20 steps act uniformly at random (~ -0.6)
     assert np.isfinite(pol.last_metrics.cpu().numpy()).all()
-    assert late > early + 0.15 and late > -0.35, (early, late)          # a random policy sits near -0.67
+    assert late > random_phase + 0.3 and late > -0.2, (random_phase, late)   # measured on B200: -0.19 after 50 steps, -0.08 at the end
 
 
 def test_dqn_learns_point_env():
