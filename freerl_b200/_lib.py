@@ -119,6 +119,7 @@ def _declare(lib):
     lib.frl_gae.argtypes = [vp, vp, vp, vp, vp, ci, ci, C.c_double, C.c_double, vp, vp, vp]
     lib.frl_ppo_update.argtypes = [C.POINTER(PpoArgs), vp]
     lib.frl_sumtree_update.argtypes = [vp, i64, vp, vp, vp, C.c_double, i64, ci, ci, vp, vp]
+    lib.frl_sumtree_update_td.argtypes = [vp, i64, vp, vp, C.c_float, C.c_float, ci, vp, vp]
     lib.frl_sumtree_sample.argtypes = [vp, i64, vp, u64, u64, ci, i64, C.c_double, C.c_double, vp, vp, vp, vp]
     lib.frl_sumtree_max.argtypes = [vp, i64, vp, ci, vp, vp]
     lib.frl_per_priorities.argtypes = [vp, ci, C.c_float, C.c_float, vp, vp]
@@ -130,7 +131,7 @@ def _declare(lib):
     lib.frl_rainbow_learn.restype = ci
     lib.frl_rainbow_act.restype = ci
     for name in ("frl_replay_add_batch", "frl_replay_gather", "frl_sample_uniform", "frl_net_sync_mirror",
-                 "frl_dqn_learn", "frl_ac_learn", "frl_policy_infer", "frl_gae", "frl_ppo_update", "frl_sumtree_update", "frl_sumtree_sample", "frl_sumtree_max",
+                 "frl_dqn_learn", "frl_ac_learn", "frl_policy_infer", "frl_gae", "frl_ppo_update", "frl_sumtree_update", "frl_sumtree_update_td", "frl_sumtree_sample", "frl_sumtree_max",
                  "frl_per_priorities", "frl_is_emulation", "frl_device_sm_count", "frl_wt_ld",
                  "frl_abi_version"):
         getattr(lib, name).restype = ci

@@ -40,7 +40,15 @@ struct TreeUpdateArgs {
   int64_t idx0; int idx_is_range;   // idx_is_range: item i targets (idx0 + i) % cap (batched ring add)
   int B;
   double* scratch;           // dev [FRL_PER_MAXB] changes (f64) followed by [FRL_PER_MAXB] keys (u32)
+  const float* td;           // [B] TD errors or nullptr: priority = (|td| + td_eps) ^ td_alpha in fp32 (PER_Buffer.update_priorities)
+  float td_eps, td_alpha;
 };
+
+// (|td| + eps) ^ alpha as the reference computes it: float32 array arithmetic (DQN_file/Buffer.py:126-129)
+FRL_HD float frl_td_priority(float td, float eps, float alpha) {
+  const float x = fabsf(td) + eps;
+  return (alpha == 0.5f) ? sqrtf(x) : (alpha == 1.0f ? x : (float)pow((double)x, (double)alpha));
+}
 
 struct TreeUpdateAlgo {
   typedef TreeUpdateArgs Args;
@@ -60,7 +68,10 @@ struct TreeUpdateAlgo {
     return 31 - __builtin_clz(x);
 #endif
   }
-  FRL_SDEV double pri_of(const Args& a, int i) { return a.pri32 ? (double)a.pri32[i] : (a.pri64 ? a.pri64[0] : a.pri_const); }
+  FRL_SDEV double pri_of(const Args& a, int i) {
+    if (a.td) return (double)frl_td_priority(a.td[i], a.td_eps, a.td_alpha);
+    return a.pri32 ? (double)a.pri32[i] : (a.pri64 ? a.pri64[0] : a.pri_const);
+  }
   // any j in [lo, hi) with ks[j] == k ?   (hi - lo may be anything; ks is padded to a multiple of 4 with never-matching zeros)
   FRL_SDEV bool any_equal(const uint32_t* ks, int lo, int hi, uint32_t k) {
     bool hit = false;
@@ -241,8 +252,5 @@ struct TreeMaxAlgo {
 // ---- priorities  (|td| + eps) ** alpha  on fp32 (numpy computes x ** 0.5 as sqrt — bit-exact for the default alpha) ----
 struct PriBody {
   const float* td; float eps; float alpha; float* out;
-  FRL_HDM void operator()(long i) const {
-    const float x = fabsf(td[i]) + eps;
-    out[i] = (alpha == 0.5f) ? sqrtf(x) : (alpha == 1.0f ? x : (float)pow((double)x, (double)alpha));
-  }
+  FRL_HDM void operator()(long i) const { out[i] = frl_td_priority(td[i], eps, alpha); }
 };

@@ -540,7 +540,19 @@ extern "C" int frl_sumtree_update(double* tree, int64_t cap, const int64_t* idx,
     frl_set_error("frl_sumtree_update: bad arguments (B <= %d, capacity < 2^30, scratch of %d doubles)", FRL_PER_MAXB, 2 * FRL_PER_MAXB);
     return -1;
   }
-  TreeUpdateArgs a = {tree, cap, idx, pri32, pri64_scalar, pri_const, idx0, idx_is_range, B, scratch};
+  TreeUpdateArgs a = {tree, cap, idx, pri32, pri64_scalar, pri_const, idx0, idx_is_range, B, scratch, nullptr, 0.f, 0.f};
+  return frl_launch<TreeUpdateAlgo>(a, (cudaStream_t)stream);
+}
+
+// PER_Buffer.update_priorities in ONE launch: priority_i = (|td_i| + eps) ^ alpha (fp32, like the reference's array arithmetic),
+// then the ordered leaf / ancestor update of frl_sumtree_update.
+extern "C" int frl_sumtree_update_td(double* tree, int64_t cap, const int64_t* idx, const float* td, float eps, float alpha, int B,
+                                     double* scratch, void* stream) {
+  if (!tree || cap <= 0 || cap >= ((int64_t)1 << 30) || B <= 0 || B > FRL_PER_MAXB || !idx || !td || !scratch) {
+    frl_set_error("frl_sumtree_update_td: bad arguments (B <= %d, capacity < 2^30, scratch of %d doubles)", FRL_PER_MAXB, 2 * FRL_PER_MAXB);
+    return -1;
+  }
+  TreeUpdateArgs a = {tree, cap, idx, nullptr, nullptr, 0.0, 0, 0, B, scratch, td, eps, alpha};
   return frl_launch<TreeUpdateAlgo>(a, (cudaStream_t)stream);
 }
 

@@ -123,12 +123,12 @@ class PER_Buffer:
             td = td_error.detach().to(device=self.device, dtype=torch.float32).reshape(-1).contiguous()
         else:
             td = torch.from_numpy(np.ascontiguousarray(td_error, dtype=np.float32).reshape(-1)).to(self.device)
-        pri = torch.empty_like(td)
-        _lib.check(_lib.lib().frl_per_priorities(_lib.ptr(td), td.numel(), float(self.epsilon), float(self.alpha), _lib.ptr(pri),
-                                                 _lib.stream_ptr(self.device)), "frl_per_priorities")
-        for s in range(0, idx.numel(), 1024):        # the kernel applies up to 1024 ordered updates per launch
+        for s in range(0, idx.numel(), 1024):        # one launch per <= 1024 ordered updates: priority transform + heap update
             e = min(s + 1024, idx.numel())
-            self.sumtree._update(idx[s:e].contiguous(), pri32=pri[s:e].contiguous())
+            _lib.check(_lib.lib().frl_sumtree_update_td(
+                _lib.ptr(self.sumtree.tree), self.capacity, _lib.ptr(idx[s:e].contiguous()), _lib.ptr(td[s:e].contiguous()),
+                float(self.epsilon), float(self.alpha), e - s, _lib.ptr(self.sumtree._scratch), _lib.stream_ptr(self.device)),
+                "frl_sumtree_update_td")
 
     def __len__(self):
         return len(self.buffer)

@@ -270,6 +270,9 @@ int frl_adv_norm(const float* x, int n, float eps, float* out, void* stream);
 int frl_sumtree_update(double* tree, int64_t cap, const int64_t* idx, const float* pri32, const double* pri64_scalar,
                        double pri_const, int64_t idx0, int idx_is_range, int B, double* scratch /* dev, >= 2048 doubles */,
                        void* stream);
+/* PER_Buffer.update_priorities (DQN_file/Buffer.py:126-129) in one launch: p_i = (|td_i| + eps)^alpha in fp32, then the ordered update */
+int frl_sumtree_update_td(double* tree, int64_t cap, const int64_t* idx, const float* td, float eps, float alpha, int B,
+                          double* scratch /* dev, >= 2048 doubles */, void* stream);
 int frl_sumtree_sample(const double* tree, int64_t cap, const double* u, uint64_t seed, uint64_t counter, int B, int64_t size,
                        double beta, double prob_floor, int64_t* out_idx, float* out_pri, float* out_w, void* stream);
 int frl_sumtree_max(const double* tree, int64_t cap, double* scratch, int nscratch, double* out, void* stream);
