@@ -73,23 +73,19 @@ class IPPO(_MAPPO):
             # agents share nothing, so the order is immaterial
             adv, v_target = self.compute_advantages_one(agent_id, gamma, lmbda)
             self.last_adv[agent_id], self.last_v_target[agent_id] = adv, v_target
-            if permutations is not None:
-                perms = permutations[agent_id]
-            elif self.mode == "parity":
-                perms = [np.random.permutation(H) for _ in range(K_epochs)]              # IPPO.py:274
+            if permutations is None and self.mode != "parity":          # fast mode: plan built on the device
+                idx_d, rows_d, n_updates = _common.device_minibatch_plan(H, minibatch_size, K_epochs, self.device, self._seed + ag.step)
             else:
-                g = torch.Generator(device="cpu")
-                g.manual_seed((self._seed + ag.step) & 0x7FFFFFFF)
-                perms = [torch.randperm(H, generator=g).numpy() for _ in range(K_epochs)]
-            idx = np.zeros((K_epochs * nmb, minibatch_size), np.int64)
-            rows = np.zeros(K_epochs * nmb, np.int32)
-            for e, perm in enumerate(perms):
-                for j in range(nmb):
-                    sl = np.asarray(perm[j * minibatch_size:(j + 1) * minibatch_size])
-                    idx[e * nmb + j, :sl.size] = sl
-                    rows[e * nmb + j] = sl.size
-            idx_d, rows_d = torch.from_numpy(idx).to(self.device), torch.from_numpy(rows).to(self.device)
-            n_updates = idx.shape[0]
+                perms = permutations[agent_id] if permutations is not None else [np.random.permutation(H) for _ in range(K_epochs)]  # IPPO.py:274
+                idx = np.zeros((K_epochs * nmb, minibatch_size), np.int64)
+                rows = np.zeros(K_epochs * nmb, np.int32)
+                for e, perm in enumerate(perms):
+                    for j in range(nmb):
+                        sl = np.asarray(perm[j * minibatch_size:(j + 1) * minibatch_size])
+                        idx[e * nmb + j, :sl.size] = sl
+                        rows[e * nmb + j] = sl.size
+                idx_d, rows_d = torch.from_numpy(idx).to(self.device), torch.from_numpy(rows).to(self.device)
+                n_updates = idx.shape[0]
             out = torch.zeros((n_updates, 8), dtype=torch.float32, device=self.device)
             a = _lib.PpoArgs()
             a.net, a.continuous = ag._net.c_struct(), int(self.is_continue)

@@ -173,24 +173,25 @@ class MAPPO:
             return given
         if self.mode == "parity":
             return [np.random.permutation(H) for _ in range(K_epochs)]                  # MAPPO.py:395
-        g = torch.Generator(device="cpu")
-        g.manual_seed((self._seed + ag.step) & 0x7FFFFFFF)
-        return [torch.randperm(H, generator=g).numpy() for _ in range(K_epochs)]
+        return None                              # fast mode: _agent_update builds the plan on the device
 
     def _agent_update(self, agent_id, adv, v_target, joint, minibatch_size, K_epochs, clip_param, entropy_coefficient, huber_delta, perms):
         """All K_epochs x minibatches of ONE agent in one persistent launch (adv / v_target: [M, n_adv] device tensors)."""
         ag, b = self.agents[agent_id], self.buffers[agent_id]
         H = self.horizon
         nmb = (H + minibatch_size - 1) // minibatch_size
-        idx = np.zeros((K_epochs * nmb, minibatch_size), np.int64)
-        rows = np.zeros(K_epochs * nmb, np.int32)
-        for e, perm in enumerate(perms):
-            for j in range(nmb):
-                sl = np.asarray(perm[j * minibatch_size:(j + 1) * minibatch_size])
-                idx[e * nmb + j, :sl.size] = sl
-                rows[e * nmb + j] = sl.size
-        idx_d, rows_d = torch.from_numpy(idx).to(self.device), torch.from_numpy(rows).to(self.device)
-        n_updates = idx.shape[0]
+        if perms is None:                       # fast mode: permutations and minibatch slicing on the device
+            idx_d, rows_d, n_updates = _common.device_minibatch_plan(H, minibatch_size, K_epochs, self.device, self._seed + ag.step)
+        else:
+            idx = np.zeros((K_epochs * nmb, minibatch_size), np.int64)
+            rows = np.zeros(K_epochs * nmb, np.int32)
+            for e, perm in enumerate(perms):
+                for j in range(nmb):
+                    sl = np.asarray(perm[j * minibatch_size:(j + 1) * minibatch_size])
+                    idx[e * nmb + j, :sl.size] = sl
+                    rows[e * nmb + j] = sl.size
+            idx_d, rows_d = torch.from_numpy(idx).to(self.device), torch.from_numpy(rows).to(self.device)
+            n_updates = idx.shape[0]
         out = torch.zeros((n_updates, 8), dtype=torch.float32, device=self.device)
         a = _lib.PpoArgs()
         a.net, a.continuous = ag._net.c_struct(), int(self.is_continue)

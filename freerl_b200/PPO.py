@@ -159,6 +159,8 @@ class PPO:
     def _minibatch_plan(self, minibatch_size, K_epochs, permutations):
         """Reference: per epoch ``np.random.permutation(horizon)`` sliced into minibatches (PPO.py:247-248)."""
         H = self.horizon
+        if permutations is None and self.mode != "parity":
+            return _common.device_minibatch_plan(H, minibatch_size, K_epochs, self.device, self._seed + self.agent.step)
         if permutations is None:
             if self.mode == "parity":
                 permutations = [np.random.permutation(H) for _ in range(K_epochs)]

@@ -101,3 +101,20 @@ def as_obs_batch(obs, obs_dim):
     arr = np.asarray(obs, dtype=np.float32)
     single = arr.ndim <= 1
     return arr.reshape(-1, obs_dim), single
+
+
+def device_minibatch_plan(H, minibatch_size, K_epochs, device, seed):
+    """fast mode: K_epochs random permutations of range(H) cut into minibatches, built ON the device (no host loops, no H2D of
+    the K * H index matrix).  Returns (indices int64 [K * nmb, mb], valid rows int32 [K * nmb], n_updates) like the host plan
+    of the reference loop (``np.random.permutation(horizon)`` sliced every ``minibatch_size``, PPO.py:247-248)."""
+    nmb = (H + minibatch_size - 1) // minibatch_size
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed) & 0x7FFFFFFF)
+    perms = torch.stack([torch.randperm(H, device=device, generator=g) for _ in range(K_epochs)])
+    pad = nmb * minibatch_size - H
+    if pad:
+        perms = torch.cat([perms, torch.zeros((K_epochs, pad), dtype=torch.int64, device=device)], dim=1)
+    idx = perms.reshape(K_epochs * nmb, minibatch_size).contiguous()
+    last = H - (nmb - 1) * minibatch_size
+    rows = torch.tensor(([minibatch_size] * (nmb - 1) + [last]) * K_epochs, dtype=torch.int32).to(device)
+    return idx, rows, K_epochs * nmb

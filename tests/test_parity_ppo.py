@@ -158,3 +158,34 @@ def test_ppo_large_minibatch_emulated(emul):
 def test_ppo_large_minibatch_gpu():
     _ppo_large_minibatch(torch.device("cuda"), True)
     _ppo_large_minibatch(torch.device("cuda"), False)
+
+
+def test_device_minibatch_plan(emul):
+    """fast-mode plan: every epoch is a permutation of range(H) cut into minibatches; the ragged last minibatch is padded and
+    its valid-row count says so; PPO / MAPPO fast-mode learns run on it."""
+    from freerl_b200 import _common
+    from freerl_b200.PPO import PPO
+    dev = torch.device("cpu")
+    for H, mb, K in ((100, 32, 3), (64, 64, 2), (7, 3, 1)):
+        idx, rows, n = _common.device_minibatch_plan(H, mb, K, dev, 5)
+        nmb = (H + mb - 1) // mb
+        assert n == K * nmb and idx.shape == (n, mb) and rows.dtype == torch.int32
+        idx, rows = idx.numpy(), rows.numpy()
+        for e in range(K):
+            got = np.concatenate([idx[e * nmb + j, :rows[e * nmb + j]] for j in range(nmb)])
+            assert np.array_equal(np.sort(got), np.arange(H)), (H, mb, e)
+        assert rows.sum() == K * H
+    a = _common.device_minibatch_plan(50, 16, 2, dev, 1)[0]
+    b = _common.device_minibatch_plan(50, 16, 2, dev, 2)[0]
+    assert not torch.equal(a, b)
+    torch.manual_seed(0)
+    pol = PPO([8, 2], True, 1e-3, 1e-3, 100, dev, mode="fast")
+    rng = np.random.default_rng(0)
+    for _ in range(100):
+        o = rng.standard_normal(8).astype(np.float32)
+        act, lp = pol.select_action(o)
+        pol.add(o, act, float(rng.standard_normal()), rng.standard_normal(8).astype(np.float32), False, lp, bool(rng.random() < 0.05))
+    before = pol.agent._net.p.clone()
+    pol.learn(32, 0.99, 0.95, 0.2, 2, 0.01)
+    m = pol.last_metrics.numpy()
+    assert m.shape[0] == 8 and np.isfinite(m).all() and not torch.equal(before, pol.agent._net.p)
