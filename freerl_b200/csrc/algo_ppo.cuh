@@ -582,78 +582,75 @@ struct GaeAlgo {
 
 // ------------------------------------------------------------------------------------------------
 // GAE for N >= 32 env columns: a CTA owns 32 adjacent columns (lane = column: every row access is one coalesced 128-B
-// line) and splits the time axis into 8 chunks (one warp each).  Pass 1 folds each chunk into its affine map
-// A_{t0} = S + P * A_{t1} (float64) and — when it fits — stashes (td, a_t, vs) in shared memory; the 8 maps of a column are
-// composed through shared memory; pass 2 re-walks the chunk from the stash (or re-reads it) and writes adv / v_target.
-// Algorithmic traffic: 20 B read + 8 B written per element (48 B when the rollout is too long for the stash).
+// line) and walks the time axis from the end in ROUNDS of 8 chunks (one warp each, <= GAE_LC steps per chunk).  In a round,
+// pass 1 reads the five inputs ONCE, folds each chunk into its affine map A_{t0} = S + P * A_{t1} (float64) and stashes
+// (td, 1 - adv_done, vs) in shared memory; the 8 maps of a column are composed through shared memory on top of the carry
+// from the previous (later-in-time) round; pass 2 re-walks the chunk from the stash and writes adv / v_target; the value
+// at the round's first step is the next round's carry.  The stash is 48 KB whatever T is, so four CTAs fit on an SM and the
+// algorithmic traffic (20 B read + 8 B written per element) is also the DRAM traffic.
 // ------------------------------------------------------------------------------------------------
+#define GAE_LC 16
 struct GaeTileAlgo {
   typedef GaeArgs Args;
-  static const int NSTAGES = 1;
+  static const int MIN_CTAS = 4;
   static const int NCHUNK = FRL_NT / 32;
-  FRL_SHD int chunk_len(const Args& a) { return (a.T + NCHUNK - 1) / NCHUNK; }
-  FRL_SHD bool stash(const Args& a) { return chunk_len(a) <= 56; }            // 3 floats x 256 threads x 56 steps = 168 KB
-  FRL_SHD int wbuf_floats(const Args&) { return 32; }
-  FRL_SHD int user_floats(const Args& a) { return 4 * FRL_NT + (stash(a) ? 3 * chunk_len(a) * FRL_NT : 0) + 64; }
-  FRL_SHD int grid(const Args& a, int) { return (a.N + 31) / 32; }
-  FRL_SHD int n_updates(const Args&) { return 1; }
-  FRL_SDEV void stage(int, int, Cta& c, float* user, const Args& a) {
-    double* sa = (double*)user;            // [FRL_NT] chunk product
+  FRL_SHD int chunk_len(const Args& a) { const int l = (a.T + NCHUNK - 1) / NCHUNK; return l < GAE_LC ? l : GAE_LC; }
+  FRL_SHD int smem_floats(const Args& a) { return 4 * FRL_NT + 128 + 3 * chunk_len(a) * FRL_NT; }
+  FRL_SHD int grid(const Args& a) { return (a.N + 31) / 32; }
+  FRL_SDEV void run(int cta, int, float* sm, const Args& a) {
+    double* sa = (double*)sm;              // [FRL_NT] chunk product
     double* sbv = sa + FRL_NT;             // [FRL_NT] chunk offset
-    float* st = user + 4 * FRL_NT;         // [3][Lc][FRL_NT] stash
-    const int Lc = chunk_len(a);
-    const bool keep = stash(a);
+    double* carry = sbv + FRL_NT;          // [2][32] value entering the round from later time steps (double-buffered)
+    float* st = sm + 4 * FRL_NT + 128;      // [3][Lc][FRL_NT] stash
+    const int Lc = chunk_len(a), R = Lc * NCHUNK;
     const float g32 = (float)a.gamma;
     const double gl = a.gamma * a.lmbda;
-    FRL_PAR(t) {
-      const int col = c.cta * 32 + (t & 31), w = t >> 5;
-      double P = 1.0, S = 0.0;
-      if (col < a.N) {
-        const int t0 = w * Lc, t1 = (t0 + Lc < a.T) ? t0 + Lc : a.T;
+    FRL_PAR(t) { if (t < 32) carry[t] = 0.0; }               // zero tail at t = T
+    const int rounds = (a.T + R - 1) / R;
+    for (int r = 0; r < rounds; ++r) {
+      // rounds are aligned to the END of the rollout: round r covers [hi - R, hi), the first one may be short at the front
+      const int hi = a.T - r * R, lo = hi - R > 0 ? hi - R : 0;
+      FRL_PAR(t) {
+        const int col = cta * 32 + (t & 31), w = t >> 5;
+        double P = 1.0, S = 0.0;
+        const int t0 = lo + w * Lc, t1 = (t0 + Lc < hi) ? t0 + Lc : hi;
+        if (col < a.N) {
 #pragma unroll 4
-        for (int k = t1 - 1; k >= t0; --k) {
-          const size_t i = (size_t)k * a.N + col;
-          const float v = a.vs[i];
-          const float td = fadd(fadd(a.reward[i], fmul(fmul(g32, fadd(1.f, -a.done[i])), a.vs_next[i])), -v);
-          const float om = 1.f - a.adv_done[i];
-          const double ak = gl * (double)om;
-          S = (double)td + ak * S;
-          P = ak * P;
-          if (keep) {
+          for (int k = t1 - 1; k >= t0; --k) {
+            const size_t i = (size_t)k * a.N + col;
+            const float v = a.vs[i];
+            const float td = fadd(fadd(a.reward[i], fmul(fmul(g32, fadd(1.f, -a.done[i])), a.vs_next[i])), -v);
+            const float om = 1.f - a.adv_done[i];
+            const double ak = gl * (double)om;
+            S = (double)td + ak * S;
+            P = ak * P;
             float* q = st + (size_t)(k - t0) * FRL_NT + t;
             q[0] = td; q[(size_t)Lc * FRL_NT] = om; q[(size_t)2 * Lc * FRL_NT] = v;
           }
         }
+        sa[t] = P; sbv[t] = S;
       }
-      sa[t] = P; sbv[t] = S;
-    }
-    FRL_SYNC();
-    FRL_PAR(t) {
-      const int col = c.cta * 32 + (t & 31), lane = t & 31, w = t >> 5;
-      if (col < a.N) {
-        double A = 0.0;                     // value entering this chunk from the later ones (zero tail at t = T)
-        for (int cc = NCHUNK - 1; cc > w; --cc) A = sbv[cc * 32 + lane] + sa[cc * 32 + lane] * A;
-        const int t0 = w * Lc, t1 = (t0 + Lc < a.T) ? t0 + Lc : a.T;
+      FRL_SYNC();
+      FRL_PAR(t) {
+        const int col = cta * 32 + (t & 31), lane = t & 31, w = t >> 5;
+        const int t0 = lo + w * Lc, t1 = (t0 + Lc < hi) ? t0 + Lc : hi;
+        if (col < a.N && t0 < t1) {
+          double A = carry[(r & 1) * 32 + lane];
+          for (int cc = NCHUNK - 1; cc > w; --cc) A = sbv[cc * 32 + lane] + sa[cc * 32 + lane] * A;
 #pragma unroll 4
-        for (int k = t1 - 1; k >= t0; --k) {
-          const size_t i = (size_t)k * a.N + col;
-          float td, om, v;
-          if (keep) {
+          for (int k = t1 - 1; k >= t0; --k) {
+            const size_t i = (size_t)k * a.N + col;
             const float* q = st + (size_t)(k - t0) * FRL_NT + t;
-            td = q[0]; om = q[(size_t)Lc * FRL_NT]; v = q[(size_t)2 * Lc * FRL_NT];
-          } else {
-            v = a.vs[i];
-            td = fadd(fadd(a.reward[i], fmul(fmul(g32, fadd(1.f, -a.done[i])), a.vs_next[i])), -v);
-            om = 1.f - a.adv_done[i];
+            const float td = q[0], om = q[(size_t)Lc * FRL_NT], v = q[(size_t)2 * Lc * FRL_NT];
+            A = (double)td + gl * (double)om * A;
+            const float af = (float)A;
+            a.adv[i] = af;
+            a.v_target[i] = fadd(af, v);
           }
-          A = (double)td + gl * (double)om * A;
-          const float af = (float)A;
-          a.adv[i] = af;
-          a.v_target[i] = fadd(af, v);
+          if (w == 0) carry[((r + 1) & 1) * 32 + lane] = A;     // value at the round's first step -> next round's carry
         }
       }
+      FRL_SYNC();
     }
-    FRL_SYNC();
   }
 };
-

@@ -94,34 +94,157 @@ static int frl_for(long n, const F& f, cudaStream_t) {
 #endif
 
 // ------------------------------------------------------------------------------------------------
+// plain tile launcher for the streaming helpers: A::run(cta, ncta, smem, args) with a caller-chosen grid and a small dynamic
+// shared-memory tile (no engine state, several CTAs per SM)
+// ------------------------------------------------------------------------------------------------
+#ifndef FRL_EMUL
+template <class A>
+__global__ void __launch_bounds__(FRL_NT, A::MIN_CTAS) frl_simple_kernel(const __grid_constant__ typename A::Args a) {
+  extern __shared__ __align__(1024) float frl_smem[];
+  A::run((int)blockIdx.x, (int)gridDim.x, frl_smem, a);
+}
+template <class A>
+static int frl_launch_simple(const typename A::Args& a, int grid, int smem_floats, cudaStream_t s) {
+  const int smem_bytes = smem_floats * 4;
+  if (smem_bytes > 227 * 1024) { frl_set_error("tile of %d B does not fit in shared memory", smem_bytes); return -3; }
+  static int configured_bytes = 48 * 1024;
+  if (smem_bytes > configured_bytes) {
+    FRL_CUDA_OK(cudaFuncSetAttribute(frl_simple_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    configured_bytes = smem_bytes;
+  }
+  frl_simple_kernel<A><<<grid, FRL_NT, smem_bytes, s>>>(a);
+  FRL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+#else
+template <class A>
+static int frl_launch_simple(const typename A::Args& a, int grid, int smem_floats, cudaStream_t) {
+  std::vector<float> sm((size_t)smem_floats + 4);
+  for (int g = 0; g < grid; ++g) {
+    for (size_t i = 0; i < sm.size(); ++i) sm[i] = NAN;
+    A::run(g, grid, sm.data(), a);
+  }
+  return 0;
+}
+#endif
+
+// ------------------------------------------------------------------------------------------------
 // replay: batched add (SoA fields -> AoS rows at ring slots) and gather (AoS rows -> 5 dense tensors)
 // ------------------------------------------------------------------------------------------------
-// One thread per 16-byte quad of a row: the AoS side is a single float4 access (rows are 16-B multiples), the SoA side
-// (five dense tensors with odd widths such as obs_dim 17) takes scalar accesses that a warp still coalesces.
-FRL_HD float soa_read(const frl_replay_t& rb, long r, int col, const float* obs, const float* act, const float* rew,
-                      const float* nobs, const float* done) {
-  const int od = rb.obs_dim, ad = rb.act_dim;
-  if (col < od) return obs[r * od + col];
-  if (col < od + ad) return act[r * ad + (col - od)];
-  if (col == od + ad) return rew[r];
-  if (col == od + ad + 1) return done[r];
-  if (col < 2 * od + ad + 2) return nobs[r * od + (col - od - ad - 2)];
-  return 0.f;
+// A CTA moves a tile of FRL_RT_ROWS transitions through shared memory, so that BOTH sides of the AoS <-> SoA transpose are
+// 16-byte coalesced accesses: the five dense tensors (odd widths such as obs_dim 17) are contiguous over a tile of rows and
+// go through float4 loads / stores whenever the tile start is 16-byte aligned (always for 64-row tiles of an aligned
+// tensor); the ring rows (16-byte multiples) are float4 on the storage side.  Every thread issues all loads of its share
+// of the tile before the barrier (~10 independent 16-byte requests per thread in flight), the grid is a multiple of the
+// SM count and tiles are taken grid-stride.
+#define FRL_RT_ROWS 64
+struct ReplayTileArgs {
+  frl_replay_t rb; int64_t index; const int64_t* idx;
+  const float *obs, *act, *rew, *nobs, *done;      // gather writes through these (cast away in the body)
+  int n;
+};
+static int replay_tile_grid(int n) {
+  const long tiles = ((long)n + FRL_RT_ROWS - 1) / FRL_RT_ROWS;
+  const long cap = (long)frl_device_max_ctas() * 8;
+  return (int)(tiles < cap ? tiles : cap);
 }
-struct AddBody {
-  frl_replay_t rb; int64_t index; const float *obs, *act, *rew, *nobs, *done; int n;
-  FRL_HDM void operator()(long i) const {
-    const int nq = rb.row_floats >> 2;
-    const long r = (i >> 31) ? i / nq : (long)((unsigned)i / (unsigned)nq);     // 32-bit division whenever it is enough
-    const int c0 = (int)(i - r * nq) * 4;
-    int64_t slot = index + r;
-    if (slot >= rb.capacity) slot %= rb.capacity;
-    float4 v;
-    v.x = soa_read(rb, r, c0, obs, act, rew, nobs, done);
-    v.y = soa_read(rb, r, c0 + 1, obs, act, rew, nobs, done);
-    v.z = soa_read(rb, r, c0 + 2, obs, act, rew, nobs, done);
-    v.w = soa_read(rb, r, c0 + 3, obs, act, rew, nobs, done);
-    *reinterpret_cast<float4*>(rb.storage + slot * rb.row_floats + c0) = v;
+// field f of a row: {obs, act, rew, done, next_obs} -> (width, column offset inside the ring row)
+FRL_HD void replay_field(const frl_replay_t& rb, int f, int* width, int* off) {
+  const int od = rb.obs_dim, ad = rb.act_dim;
+  if (f == 0) { *width = od; *off = 0; }
+  else if (f == 1) { *width = ad; *off = od; }
+  else if (f == 2) { *width = 1; *off = od + ad; }
+  else if (f == 3) { *width = 1; *off = od + ad + 1; }
+  else { *width = od; *off = od + ad + 2; }
+}
+struct ReplayAddTiles {
+  typedef ReplayTileArgs Args;
+  static const int MIN_CTAS = 8;
+  FRL_SDEV void run(int cta, int ncta, float* sm, const Args& a) {
+    const int RF = a.rb.row_floats, nq = RF >> 2, used = 2 * a.rb.obs_dim + a.rb.act_dim + 2;
+    const float* src[5] = {a.obs, a.act, a.rew, a.done, a.nobs};
+    const int ntiles = (a.n + FRL_RT_ROWS - 1) / FRL_RT_ROWS;
+    for (int tile = cta; tile < ntiles; tile += ncta) {
+      const int r0 = tile * FRL_RT_ROWS, nr = (a.n - r0 < FRL_RT_ROWS) ? a.n - r0 : FRL_RT_ROWS;
+      FRL_PAR(t) {
+        for (int f = 0; f < 5; ++f) {
+          int w, off;
+          replay_field(a.rb, f, &w, &off);
+          const float* p = src[f] + (size_t)r0 * w;
+          const int ne = nr * w, n4 = (((size_t)p & 15) == 0) ? (ne >> 2) : 0;
+          for (int q = t; q < n4; q += FRL_NT) {
+            const float4 v = ld4(p + 4 * q);
+            const float e4[4] = {v.x, v.y, v.z, v.w};
+            unsigned row = (unsigned)(4 * q) / (unsigned)w, col = (unsigned)(4 * q) - row * (unsigned)w;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              sm[row * RF + off + col] = e4[k];
+              if (++col == (unsigned)w) { col = 0; ++row; }
+            }
+          }
+          for (int e = 4 * n4 + t; e < ne; e += FRL_NT) {
+            const unsigned row = (unsigned)e / (unsigned)w, col = (unsigned)e - row * (unsigned)w;
+            sm[row * RF + off + col] = p[e];
+          }
+        }
+        for (int e = t; e < nr * (RF - used); e += FRL_NT) {        // zero the padding columns of the ring row
+          const int row = e / (RF - used), col = e - row * (RF - used);
+          sm[row * RF + used + col] = 0.f;
+        }
+      }
+      FRL_SYNC();
+      FRL_PAR(t) {
+        for (int q = t; q < nr * nq; q += FRL_NT) {
+          const int row = (unsigned)q / (unsigned)nq, c4 = (q - row * nq) * 4;
+          int64_t slot = a.index + r0 + row;
+          if (slot >= a.rb.capacity) slot %= a.rb.capacity;
+          st4(a.rb.storage + slot * RF + c4, lds4(sm + row * RF + c4));
+        }
+      }
+      FRL_SYNC();
+    }
+  }
+};
+struct ReplayGatherTiles {
+  typedef ReplayTileArgs Args;
+  static const int MIN_CTAS = 8;
+  FRL_SDEV void run(int cta, int ncta, float* sm, const Args& a) {
+    const int RF = a.rb.row_floats, nq = RF >> 2;
+    float* dst[5] = {(float*)a.obs, (float*)a.act, (float*)a.rew, (float*)a.done, (float*)a.nobs};
+    const int ntiles = (a.n + FRL_RT_ROWS - 1) / FRL_RT_ROWS;
+    for (int tile = cta; tile < ntiles; tile += ncta) {
+      const int r0 = tile * FRL_RT_ROWS, nr = (a.n - r0 < FRL_RT_ROWS) ? a.n - r0 : FRL_RT_ROWS;
+      FRL_PAR(t) {
+        for (int q = t; q < nr * nq; q += FRL_NT) {
+          const int row = (unsigned)q / (unsigned)nq, c4 = (q - row * nq) * 4;
+          sts4(sm + row * RF + c4, ld4(a.rb.storage + a.idx[r0 + row] * RF + c4));
+        }
+      }
+      FRL_SYNC();
+      FRL_PAR(t) {
+        for (int f = 0; f < 5; ++f) {
+          int w, off;
+          replay_field(a.rb, f, &w, &off);
+          float* p = dst[f] + (size_t)r0 * w;
+          const int ne = nr * w, n4 = (((size_t)p & 15) == 0) ? (ne >> 2) : 0;
+          for (int q = t; q < n4; q += FRL_NT) {
+            float e4[4];
+            unsigned row = (unsigned)(4 * q) / (unsigned)w, col = (unsigned)(4 * q) - row * (unsigned)w;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              e4[k] = sm[row * RF + off + col];
+              if (++col == (unsigned)w) { col = 0; ++row; }
+            }
+            st4(p + 4 * q, make_float4(e4[0], e4[1], e4[2], e4[3]));
+          }
+          for (int e = 4 * n4 + t; e < ne; e += FRL_NT) {
+            const unsigned row = (unsigned)e / (unsigned)w, col = (unsigned)e - row * (unsigned)w;
+            p[e] = sm[row * RF + off + col];
+          }
+        }
+      }
+      FRL_SYNC();
+    }
   }
 };
 
@@ -131,34 +254,17 @@ extern "C" int frl_replay_add_batch(const frl_replay_t* rb, int64_t index, const
     frl_set_error("frl_replay_add_batch: bad arguments");
     return -1;
   }
-  AddBody b = {*rb, index, obs, act, rew, next_obs, done, n};
-  return frl_for((long)n * (rb->row_floats >> 2), b, (cudaStream_t)stream);
+  if (n == 0) return 0;
+  ReplayTileArgs a = {*rb, index, nullptr, obs, act, rew, next_obs, done, n};
+  return frl_launch_simple<ReplayAddTiles>(a, replay_tile_grid(n), FRL_RT_ROWS * rb->row_floats, (cudaStream_t)stream);
 }
-
-struct GatherBody {
-  frl_replay_t rb; const int64_t* idx; float *obs, *act, *rew, *nobs, *done;
-  FRL_HDM void put(long b, int col, float v) const {
-    const int od = rb.obs_dim, ad = rb.act_dim;
-    if (col < od) obs[b * od + col] = v;
-    else if (col < od + ad) act[b * ad + (col - od)] = v;
-    else if (col == od + ad) rew[b] = v;
-    else if (col == od + ad + 1) done[b] = v;
-    else if (col < 2 * od + ad + 2) nobs[b * od + (col - od - ad - 2)] = v;
-  }
-  FRL_HDM void operator()(long i) const {
-    const int nq = rb.row_floats >> 2;
-    const long b = (i >> 31) ? i / nq : (long)((unsigned)i / (unsigned)nq);
-    const int c0 = (int)(i - b * nq) * 4;
-    const float4 v = *reinterpret_cast<const float4*>(rb.storage + idx[b] * rb.row_floats + c0);
-    put(b, c0, v.x); put(b, c0 + 1, v.y); put(b, c0 + 2, v.z); put(b, c0 + 3, v.w);
-  }
-};
 
 extern "C" int frl_replay_gather(const frl_replay_t* rb, const int64_t* indices, int B, float* obs, float* act, float* rew,
                                  float* next_obs, float* done, void* stream) {
   if (!rb || !rb->storage || B < 0) { frl_set_error("frl_replay_gather: bad arguments"); return -1; }
-  GatherBody b = {*rb, indices, obs, act, rew, next_obs, done};
-  return frl_for((long)B * (rb->row_floats >> 2), b, (cudaStream_t)stream);
+  if (B == 0) return 0;
+  ReplayTileArgs a = {*rb, 0, indices, obs, act, rew, next_obs, done, B};
+  return frl_launch_simple<ReplayGatherTiles>(a, replay_tile_grid(B), FRL_RT_ROWS * rb->row_floats, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -506,7 +612,8 @@ extern "C" int frl_gae(const float* reward, const float* done, const float* adv_
     return -1;
   }
   GaeArgs a = {reward, done, adv_done, vs, vs_next, T, N, gamma, lmbda, adv_out, v_target_out};
-  if (N >= 32) return frl_launch_tiles<GaeTileAlgo>(a, (cudaStream_t)stream);      // vectorised envs: coalesced column tiles
+  if (N >= 32)                                                                     // vectorised envs: coalesced column tiles
+    return frl_launch_simple<GaeTileAlgo>(a, GaeTileAlgo::grid(a), GaeTileAlgo::smem_floats(a), (cudaStream_t)stream);
   return frl_launch_tiles<GaeAlgo>(a, (cudaStream_t)stream);                       // few columns: one warp per column
 
 }
@@ -631,36 +738,50 @@ FRL_NI_MISC double block_sum_f64(double* slot /*[FRL_NT] smem*/) {
   return r;
 }
 struct AdvNormArgs { const float* x; int n; float eps; float* out; double* part; int phase; int ncta; };
+// Two launches (a grid-wide mean / std sits between them).  Launch 0: every thread streams float4 quads with four
+// independent loads in flight and accumulates sum / sum of squares in float64; per-CTA partials go to `part`.  Launch 1:
+// every CTA folds the partials in the same order (identical statistics on all CTAs), then streams the input a second time
+// — from the END, so that the part of `x` that launch 0 read last is still in L2 — and writes (x - mean) / (std + eps).
 struct AdvNormAlgo {
   typedef AdvNormArgs Args;
-  static const int NSTAGES = 1;
-  FRL_SHD int wbuf_floats(const Args&) { return 32; }
-  FRL_SHD int user_floats(const Args&) { return 4 * FRL_NT + 64; }
-  FRL_SHD int grid(const Args& a, int) { return a.ncta; }
-  FRL_SHD int n_updates(const Args&) { return 1; }
-  FRL_SDEV void stage(int, int, Cta& c, float* user, const Args& a) {
-    double* s1 = (double*)user;
+  static const int MIN_CTAS = 6;
+  FRL_SHD int smem_floats(const Args&) { return 4 * FRL_NT + 64; }
+  FRL_SDEV void run(int cta, int ncta, float* sm, const Args& a) {
+    double* s1 = (double*)sm;
     double* s2 = s1 + FRL_NT;
     const int n4 = ((((size_t)a.x | (size_t)a.out) & 15) == 0) ? (a.n >> 2) : 0;       // float4 body when 16-B aligned
+    const int stride = ncta * FRL_NT;
     if (a.phase == 0) {
       FRL_PAR(t) {
         double s = 0.0, q = 0.0;
-        for (int i = c.cta * FRL_NT + t; i < n4; i += c.ncta * FRL_NT) {
+        int i = cta * FRL_NT + t;
+        for (; i + 3 * stride < n4; i += 4 * stride) {
+          const float4 v0 = ld4(a.x + 4 * (size_t)i), v1 = ld4(a.x + 4 * (size_t)(i + stride));
+          const float4 v2 = ld4(a.x + 4 * (size_t)(i + 2 * stride)), v3 = ld4(a.x + 4 * (size_t)(i + 3 * stride));
+          const float4 vv[4] = {v0, v1, v2, v3};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 v = vv[k];
+            s += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
+            q += ((double)v.x * v.x + (double)v.y * v.y) + ((double)v.z * v.z + (double)v.w * v.w);
+          }
+        }
+        for (; i < n4; i += stride) {
           const float4 v = ld4(a.x + 4 * (size_t)i);
           s += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
           q += ((double)v.x * v.x + (double)v.y * v.y) + ((double)v.z * v.z + (double)v.w * v.w);
         }
-        for (int i = 4 * n4 + c.cta * FRL_NT + t; i < a.n; i += c.ncta * FRL_NT) { const double v = a.x[i]; s += v; q += v * v; }
+        for (int j = 4 * n4 + cta * FRL_NT + t; j < a.n; j += stride) { const double v = a.x[j]; s += v; q += v * v; }
         s1[t] = s; s2[t] = q;
       }
       FRL_SYNC();
       const double S = block_sum_f64(s1), Q = block_sum_f64(s2);
-      FRL_PAR(t) { if (t == 0) { a.part[2 * c.cta] = S; a.part[2 * c.cta + 1] = Q; } }
+      FRL_PAR(t) { if (t == 0) { a.part[2 * cta] = S; a.part[2 * cta + 1] = Q; } }
       FRL_SYNC();
     } else {
       FRL_PAR(t) {
         double s = 0.0, q = 0.0;
-        for (int i = t; i < c.ncta; i += FRL_NT) { s += a.part[2 * i]; q += a.part[2 * i + 1]; }
+        for (int i = t; i < ncta; i += FRL_NT) { s += a.part[2 * i]; q += a.part[2 * i + 1]; }
         s1[t] = s; s2[t] = q;
       }
       FRL_SYNC();
@@ -670,12 +791,24 @@ struct AdvNormAlgo {
       if (var < 0.0) var = 0.0;
       const float mf = (float)mean, den = (float)sqrt(var) + a.eps;
       FRL_PAR(t) {
-        for (int i = c.cta * FRL_NT + t; i < n4; i += c.ncta * FRL_NT) {
+        for (int j = 4 * n4 + cta * FRL_NT + t; j < a.n; j += stride) a.out[j] = fdiv(a.x[j] - mf, den);
+        int i = n4 - 1 - (cta * FRL_NT + t);
+        for (; i - 3 * stride >= 0; i -= 4 * stride) {
+          float4 vv[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) vv[k] = ld4(a.x + 4 * (size_t)(i - k * stride));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float4 v = vv[k];
+            v.x = fdiv(v.x - mf, den); v.y = fdiv(v.y - mf, den); v.z = fdiv(v.z - mf, den); v.w = fdiv(v.w - mf, den);
+            st4(a.out + 4 * (size_t)(i - k * stride), v);
+          }
+        }
+        for (; i >= 0; i -= stride) {
           float4 v = ld4(a.x + 4 * (size_t)i);
           v.x = fdiv(v.x - mf, den); v.y = fdiv(v.y - mf, den); v.z = fdiv(v.z - mf, den); v.w = fdiv(v.w - mf, den);
           st4(a.out + 4 * (size_t)i, v);
         }
-        for (int i = 4 * n4 + c.cta * FRL_NT + t; i < a.n; i += c.ncta * FRL_NT) a.out[i] = fdiv(a.x[i] - mf, den);
       }
       FRL_SYNC();
     }
@@ -701,17 +834,17 @@ static double* frl_reduce_scratch(int doubles) {
 
 extern "C" int frl_adv_norm(const float* x, int n, float eps, float* out, void* stream) {
   if (!x || !out || n < 2) { frl_set_error("frl_adv_norm: bad arguments"); return -1; }
-  int ncta = (n / 4 + FRL_NT - 1) / FRL_NT;
-  const int cap = 4 * frl_device_max_ctas();
+  int ncta = (n / 16 + FRL_NT - 1) / FRL_NT;      // >= 4 quads per thread before the grid grows
+  const int cap = 6 * frl_device_max_ctas();
   if (ncta > cap) ncta = cap;
   if (ncta < 1) ncta = 1;
   double* part = frl_reduce_scratch(2 * cap > 4096 ? 2 * cap : 4096);
   if (!part) { frl_set_error("frl_adv_norm: scratch allocation failed"); return -2; }
   AdvNormArgs a = {x, n, eps, out, part, 0, ncta};
-  int rc = frl_launch_tiles<AdvNormAlgo>(a, (cudaStream_t)stream);
+  int rc = frl_launch_simple<AdvNormAlgo>(a, ncta, AdvNormAlgo::smem_floats(a), (cudaStream_t)stream);
   if (rc) return rc;
   a.phase = 1;
-  return frl_launch_tiles<AdvNormAlgo>(a, (cudaStream_t)stream);
+  return frl_launch_simple<AdvNormAlgo>(a, ncta, AdvNormAlgo::smem_floats(a), (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------

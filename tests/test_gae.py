@@ -30,7 +30,7 @@ def _gae_case(_lib, device, T, N, seed):
 
 
 def _run(_lib, device):
-    for T, N, seed in ((128, 64, 0), (50, 33, 1), (7, 32, 2), (600, 40, 3), (1, 70, 4), (257, 3, 5), (40, 1, 6)):
+    for T, N, seed in ((128, 64, 0), (50, 33, 1), (7, 32, 2), (600, 40, 3), (1, 70, 4), (257, 3, 5), (40, 1, 6), (1030, 64, 7), (129, 32, 8)):
         _gae_case(_lib, device, T, N, seed)
     # advantage normalisation: ragged / unaligned sizes vs torch (MAPPO.py:385-386: (adv - adv.mean()) / (adv.std() + 1e-8))
     rng = np.random.default_rng(9)
