@@ -12,7 +12,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 FRL_MAX_LAYERS = 6
 FRL_MAX_AGENTS = 6
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class Layer(C.Structure):
@@ -84,6 +84,13 @@ class NoisyMap(C.Structure):
                 ("eps_in", C.c_int), ("eps_out", C.c_int)]
 
 
+class ExploreArgs(C.Structure):
+    _fields_ = [("kind", C.c_int), ("N", C.c_int), ("A", C.c_int), ("action", C.c_void_p), ("ou_state", C.c_void_p), ("z", C.c_void_p),
+                ("seed", C.c_uint64), ("counter", C.c_uint64), ("mu", C.c_double), ("theta", C.c_double), ("sigma", C.c_double),
+                ("dt", C.c_double), ("scale", C.c_double), ("gauss_scale", C.c_double), ("gauss_sigma", C.c_double),
+                ("max_action", C.c_double), ("clip", C.c_int), ("out64", C.c_void_p), ("out", C.c_void_p)]
+
+
 class RainbowArgs(C.Structure):
     _fields_ = [("p", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("p_target", C.c_void_p), ("n_train", C.c_int),
                 ("eff", Net * 3), ("map", NoisyMap * FRL_MAX_LAYERS), ("eps", C.c_void_p), ("eps_len", C.c_int),
@@ -126,6 +133,12 @@ def _declare(lib):
     lib.frl_rainbow_learn.argtypes = [C.POINTER(RainbowArgs), vp]
     lib.frl_rainbow_act.argtypes = [C.POINTER(RainbowArgs), vp, ci, vp, vp]
     lib.frl_adv_norm.argtypes = [vp, ci, C.c_float, vp, vp]
+    lib.frl_vecnorm.argtypes = [vp, i64, vp, ci, ci, ci, ci, vp, vp, vp]
+    lib.frl_reward_scaling.argtypes = [vp, i64, vp, vp, ci, C.c_double, ci, vp, vp, vp]
+    lib.frl_explore.argtypes = [C.POINTER(ExploreArgs), vp]
+    lib.frl_masked_reset.argtypes = [vp, vp, ci, ci, C.c_double, vp]
+    for name in ("frl_vecnorm", "frl_reward_scaling", "frl_explore", "frl_masked_reset"):
+        getattr(lib, name).restype = ci
     lib.frl_wt_ld.argtypes = [ci]
     lib.frl_adv_norm.restype = ci
     lib.frl_rainbow_learn.restype = ci
@@ -157,7 +170,7 @@ def lib():
                                % (path, l.frl_abi_version(), ABI_VERSION))
         l.frl_struct_size.restype = C.c_int
         l.frl_struct_size.argtypes = [C.c_int]
-        for which, mirror in enumerate((Layer, Net, Replay, DqnArgs, AcArgs, InferArgs, PpoArgs, NoisyMap, RainbowArgs)):
+        for which, mirror in enumerate((Layer, Net, Replay, DqnArgs, AcArgs, InferArgs, PpoArgs, NoisyMap, RainbowArgs, ExploreArgs)):
             if l.frl_struct_size(which) != C.sizeof(mirror):
                 raise RuntimeError("freerl_b200: ctypes mirror %s is %d bytes, the library's struct is %d"
                                    % (mirror.__name__, C.sizeof(mirror), l.frl_struct_size(which)))

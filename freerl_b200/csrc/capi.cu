@@ -9,6 +9,7 @@
 #include "algo_ppo.cuh"
 #include "algo_per.cuh"
 #include "algo_rainbow.cuh"
+#include "algo_vec.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // error plumbing
@@ -22,7 +23,7 @@ extern "C" void frl_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 extern "C" const char* frl_last_error(void) { return g_err; }
-extern "C" int frl_abi_version(void) { return 3; }
+extern "C" int frl_abi_version(void) { return 4; }
 // sizeof() of the argument structs, so a binding can verify its mirror of the layout before the first call
 extern "C" int frl_struct_size(int which) {
   switch (which) {
@@ -35,6 +36,7 @@ extern "C" int frl_struct_size(int which) {
     case 6: return (int)sizeof(frl_ppo_args_t);
     case 7: return (int)sizeof(frl_noisy_map_t);
     case 8: return (int)sizeof(frl_rainbow_args_t);
+    case 9: return (int)sizeof(frl_explore_args_t);
     default: return -1;
   }
 }
@@ -100,7 +102,8 @@ static int frl_for(long n, const F& f, cudaStream_t) {
 #ifndef FRL_EMUL
 template <class A>
 __global__ void __launch_bounds__(FRL_NT, A::MIN_CTAS) frl_simple_kernel(const __grid_constant__ typename A::Args a) {
-  extern __shared__ __align__(1024) float frl_smem[];
+  extern __shared__ __align__(16) float frl_smem_tile[];
+  float* frl_smem = frl_smem_tile;
   A::run((int)blockIdx.x, (int)gridDim.x, frl_smem, a);
 }
 template <class A>
@@ -845,6 +848,45 @@ extern "C" int frl_adv_norm(const float* x, int n, float eps, float* out, void* 
   if (rc) return rc;
   a.phase = 1;
   return frl_launch_simple<AdvNormAlgo>(a, ncta, AdvNormAlgo::smem_floats(a), (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-step train-loop work over N vectorised envs (algo_vec.cuh)
+// ------------------------------------------------------------------------------------------------
+static int elementwise_grid(long n) {
+  long g = (n + FRL_NT - 1) / FRL_NT;
+  const long cap = 4L * frl_device_max_ctas();
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+extern "C" int frl_vecnorm(double* state, int64_t n0, const void* x, int x_is_f64, int N, int D, int update, float* out, double* out64,
+                           void* stream) {
+  if (!state || !x || N < 0 || D <= 0 || n0 < 0 || (!out && !out64)) { frl_set_error("frl_vecnorm: bad arguments"); return -1; }
+  if (N == 0) return 0;
+  VecNormArgs a = {state, n0, x, x_is_f64, N, D, update, out, out64};
+  if (update) return frl_launch_simple<VecNormFold>(a, (D + FRL_NT - 1) / FRL_NT, 4, (cudaStream_t)stream);
+  return frl_launch_simple<VecNormApply>(a, elementwise_grid((long)N * D), 4, (cudaStream_t)stream);
+}
+extern "C" int frl_reward_scaling(double* state, int64_t n0, double* R, const void* x, int x_is_f64, double gamma, int N, float* out,
+                                  double* out64, void* stream) {
+  if (!state || !R || !x || N < 0 || n0 < 0 || (!out && !out64)) { frl_set_error("frl_reward_scaling: bad arguments"); return -1; }
+  if (N == 0) return 0;
+  RewardScaleArgs a = {state, n0, R, x, x_is_f64, gamma, N, out, out64};
+  return frl_launch_simple<RewardScaleFold>(a, 1, 4, (cudaStream_t)stream);
+}
+extern "C" int frl_explore(const frl_explore_args_t* a, void* stream) {
+  if (!a || !a->action || a->N < 0 || a->A <= 0 || (a->kind != 0 && a->kind != 1) || (a->kind == 0 && !a->ou_state) ||
+      (!a->out && !a->out64)) {
+    frl_set_error("frl_explore: bad arguments");
+    return -1;
+  }
+  if (a->N == 0) return 0;
+  return frl_launch_simple<ExploreAlgo>(*a, elementwise_grid((long)a->N * a->A), 4, (cudaStream_t)stream);
+}
+extern "C" int frl_masked_reset(double* state, const uint8_t* mask, int N, int W, double value, void* stream) {
+  if (!state || !mask || N < 0 || W <= 0) { frl_set_error("frl_masked_reset: bad arguments"); return -1; }
+  if (N == 0) return 0;
+  MaskedResetArgs a = {state, mask, N, W, value};
+  return frl_launch_simple<MaskedReset>(a, elementwise_grid((long)N * W), 4, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -59,12 +59,18 @@ FRL_DEV float fmul(float a, float b) { return __fmul_rn(a, b); }
 FRL_DEV float fadd(float a, float b) { return __fadd_rn(a, b); }
 FRL_DEV float fdiv(float a, float b) { return __fdiv_rn(a, b); }
 FRL_DEV float fsqrt(float a) { return __fsqrt_rn(a); }
+FRL_DEV double frl_dmul(double a, double b) { return __dmul_rn(a, b); }
+FRL_DEV double frl_dadd(double a, double b) { return __dadd_rn(a, b); }
 #else
 static inline float fmul(float a, float b) { volatile float r = a * b; return r; }
 static inline float fadd(float a, float b) { volatile float r = a + b; return r; }
 static inline float fdiv(float a, float b) { return a / b; }
 static inline float fsqrt(float a) { return sqrtf(a); }
+static inline double frl_dmul(double a, double b) { volatile double r = a * b; return r; }
+static inline double frl_dadd(double a, double b) { volatile double r = a + b; return r; }
 #endif
+FRL_DEV float xmul(float a, float b) { return fmul(a, b); }       // dtype-generic spellings for templated numpy-order arithmetic
+FRL_DEV double xmul(double a, double b) { return frl_dmul(a, b); }
 
 // ------------------------------------------------------------------------------------------------
 // Packed fp32x2 FMA (Blackwell `fma.rn.f32x2`, SASS FFMA2): two IEEE fp32 FMAs per issued instruction — the same rounding

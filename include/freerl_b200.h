@@ -20,6 +20,9 @@
  *   frl_sumtree_update/_sample/_max, frl_per_priorities
  *                             SumTree / PER_Buffer           DQN_file/Buffer.py:66-194
  *   frl_rainbow_learn/_act    Rainbow DQN.learn / select_action   DQN_file/DQN_with_tricks.py:81-160,198-284; Noisy_net.py:17-76
+ *   frl_vecnorm / frl_reward_scaling / frl_explore / frl_masked_reset
+ *                             Normalization, RewardScaling, OUNoise / Gaussian exploration of the train loops, for N envs
+ *                                                            PPO_file/normalization.py:17-101; SAC_file/SAC.py:334-355; DDPG_file/DDPG.py:519-522
  *   frl_gae                   PPO.learn GAE loop             PPO_file/PPO.py:222-233 (MAPPO_file/MAPPO.py:362-383)
  *   frl_ppo_update            PPO.learn minibatch loop + Agent.update_ac_ + c_adamw.AdamW.step
  *                                                            PPO_file/PPO.py:245-283,145-152; PPO_file/c_adamw.py:65-122
@@ -232,13 +235,31 @@ typedef struct {
   uint64_t noise_seed, noise_counter;
 } frl_rainbow_args_t;
 
+/* Exploration noise of the reference train loops for N vectorised envs (SAC_file/SAC.py:334-355 OUNoise; DDPG_file/DDPG.py:519-522):
+ *   kind 0: OU  dx = theta (mu - x) + sqrt(dt) sigma z; x += dx; action_ = clip(action*max_action + x*scale*max_action, +-max_action)
+ *   kind 1: Gaussian  action_ = clip(action*max_action + gauss_scale * (gauss_sigma*max_action*z), +-max_action)
+ * z: dev [N][A] float64 standard normals drawn by the caller in the reference's order, or NULL -> Philox(seed, counter). */
+typedef struct {
+  int kind, N, A;
+  const float* action;               /* dev [N][A] policy output in (-1, 1) */
+  double* ou_state;                  /* dev [N][A] OU state (kind 0), updated in place */
+  const double* z;
+  uint64_t seed, counter;
+  double mu, theta, sigma, dt, scale;/* OU; scale < 0 = the reference's scale=None */
+  double gauss_scale, gauss_sigma;
+  double max_action;
+  int clip;                          /* 0: no clip (OUNoise.noise() alone: action = 0, max_action = 1) */
+  double* out64;                     /* dev [N][A] float64 env action (numpy's result dtype) or NULL */
+  float* out;                        /* dev [N][A] fp32 copy or NULL */
+} frl_explore_args_t;
+
 const char* frl_last_error(void);
 int frl_is_emulation(void);          /* 0 for the CUDA library (the only one the product path accepts) */
 int frl_device_sm_count(void);
 int frl_wt_ld(int out_pad);          /* row stride (floats) of a transposed-mirror layer image with this padded width */
 int frl_abi_version(void);
 /* sizeof the argument structs as compiled: 0 frl_layer_t, 1 frl_net_t, 2 frl_replay_t, 3 frl_dqn_args_t, 4 frl_ac_args_t,
- * 5 frl_infer_args_t, 6 frl_ppo_args_t, 7 frl_noisy_map_t, 8 frl_rainbow_args_t; -1 otherwise.  A binding checks its mirror
+ * 5 frl_infer_args_t, 6 frl_ppo_args_t, 7 frl_noisy_map_t, 8 frl_rainbow_args_t, 9 frl_explore_args_t; -1 otherwise.  A binding checks its mirror
  * of the layout against these before the first call (freerl_b200/_lib.py does, at load time). */
 int frl_struct_size(int which);
 
@@ -280,6 +301,22 @@ int frl_per_priorities(const float* td, int B, float eps, float alpha, float* ou
 int frl_rainbow_learn(const frl_rainbow_args_t* args, void* stream);
 /* select_action: refresh eff[0] from (p, eps[0]) and return argmax_a sum_z z*p(z|s,a) for n observations (out: [n] floats) */
 int frl_rainbow_act(const frl_rainbow_args_t* args, const float* obs, int n, float* out, void* stream);
+
+
+/* ---- per-step work of the reference train loops over N vectorised envs ----
+ * frl_vecnorm = Normalization.__call__ (PPO_file/normalization.py:17-49): `state` = dev [3][D] float64 {mean, S, std}, n0 = updates
+ * folded so far (the caller adds N after an update call).  update != 0 folds rows 0..N-1 IN ORDER, each row normalised with the
+ * statistics that include it (bit-identical to calling the reference object once per row, float32 or float64 rows);
+ * update == 0 applies frozen statistics.  out (fp32) / out64 (float64): [N][D], either may be NULL. */
+int frl_vecnorm(double* state, int64_t n0, const void* x, int x_is_f64, int N, int D, int update, float* out, double* out64,
+                void* stream);
+/* RewardScaling.__call__ (normalization.py:87-97) for N envs: R[i] = gamma R[i] + x[i]; the shared running std is fed R[0..N-1]
+ * in order; out[i] = x[i] / (std + 1e-8).  state = dev [3] float64 {mean, S, std}. */
+int frl_reward_scaling(double* state, int64_t n0, double* R, const void* x, int x_is_f64, double gamma, int N, float* out,
+                       double* out64, void* stream);
+int frl_explore(const frl_explore_args_t* args, void* stream);
+/* state[i][:] = value where mask[i] != 0 (OUNoise.reset / RewardScaling.reset of the envs whose episode ended); state dev [N][W] float64 */
+int frl_masked_reset(double* state, const uint8_t* mask, int N, int W, double value, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,71 @@
+"""CPU restatement of the per-step helpers of the reference train loops, fed row by row.
+
+TEST INFRASTRUCTURE ONLY — only ``tests/`` may import this; the product path (``freerl_b200/vecloop.py``) runs CUDA kernels.
+Pinned by ``tests/golden/vecloop.npz``, generated from the unmodified reference classes by ``oracle/make_golden_vecloop.py``.
+"""
+import numpy as np
+
+
+class RunningMeanStd:
+    """``PPO_file/normalization.py:17-35`` (same code in ``MAPPO_file/normalization.py``, ``DDPG_file/DDPG.py:358-376``,
+    ``SAC_file/SAC.py:357-375``): Welford over single observations; the first call aliases mean = std = x (x's dtype)."""
+
+    def __init__(self, shape):
+        self.n = 0
+        self.mean = np.zeros(shape)
+        self.S = np.zeros(shape)
+        self.std = np.sqrt(self.S)
+
+    def update(self, x):
+        x = np.array(x)
+        self.n += 1
+        if self.n == 1:
+            self.mean = x
+            self.std = x
+        else:
+            old = self.mean.copy()
+            self.mean = old + (x - old) / self.n
+            self.S = self.S + (x - old) * (x - self.mean)
+            self.std = np.sqrt(self.S / self.n)
+
+
+def normalize_rows(ms, rows, update=True):
+    """``Normalization.__call__`` (``normalization.py:38-49``) applied to each row in order; returns the stacked float64 results."""
+    out = []
+    for x in rows:
+        if update:
+            ms.update(x)
+        out.append(np.asarray((x - ms.mean) / (ms.std + 1e-8), dtype=np.float64))
+    return np.stack(out)
+
+
+def reward_scaling_rows(ms, R, gamma, rewards):
+    """``RewardScaling.__call__`` (``normalization.py:87-97``) with one discounted return per env and a shared RunningMeanStd fed in
+    env order.  ``R`` is modified in place."""
+    out = np.empty(len(rewards))
+    for i, x in enumerate(rewards):
+        R[i] = gamma * R[i] + x
+        ms.update(R[i:i + 1].copy())
+        out[i] = (x / (ms.std + 1e-8))[0]
+    return out
+
+
+def ou_rows(state, z, mu=0.0, theta=0.15, sigma=0.1, dt=1e-2, scale=None):
+    """``OUNoise.noise`` (``SAC_file/SAC.py:347-355``) per env row with the given standard normals; ``state`` updated in place."""
+    out = np.empty_like(state)
+    for i in range(state.shape[0]):
+        x = state[i]
+        dx = theta * (mu - x) + np.sqrt(dt) * sigma * z[i]
+        state[i] = x + dx
+        out[i] = state[i] if scale is None else state[i] * scale
+    return out
+
+
+def explore_ou(action, noise, max_action):
+    """``DDPG_file/DDPG.py:520``"""
+    return np.clip(action * max_action + noise * max_action, -max_action, max_action)
+
+
+def explore_gauss(action, z, max_action, gauss_scale, gauss_sigma):
+    """``DDPG_file/DDPG.py:522``: ``np.random.normal(scale=s, size)`` is ``0.0 + s * z`` on the legacy stream."""
+    return np.clip(action * max_action + gauss_scale * (0.0 + (gauss_sigma * max_action) * z), -max_action, max_action)
