@@ -137,7 +137,9 @@ def _declare(lib):
     lib.frl_reward_scaling.argtypes = [vp, i64, vp, vp, ci, C.c_double, ci, vp, vp, vp]
     lib.frl_explore.argtypes = [C.POINTER(ExploreArgs), vp]
     lib.frl_masked_reset.argtypes = [vp, vp, ci, ci, C.c_double, vp]
-    for name in ("frl_vecnorm", "frl_reward_scaling", "frl_explore", "frl_masked_reset"):
+    lib.frl_epsilon_greedy.argtypes = [vp, ci, ci, C.c_double, vp, vp, u64, u64, vp, vp]
+    lib.frl_dis_to_con.argtypes = [vp, ci, ci, ci, ci, vp, vp, vp, vp, vp]
+    for name in ("frl_vecnorm", "frl_reward_scaling", "frl_explore", "frl_masked_reset", "frl_epsilon_greedy", "frl_dis_to_con"):
         getattr(lib, name).restype = ci
     lib.frl_wt_ld.argtypes = [ci]
     lib.frl_adv_norm.restype = ci

@@ -179,3 +179,63 @@ struct MaskedReset {
     }
   }
 };
+
+// epsilon-greedy of the DQN mains (DQN_file/DQN.py:307-310) for N envs: out[i] = u[i] < epsilon ? random action : greedy[i].
+// Parity mode passes the host-drawn u / random actions (the legacy stream consumes a randint only where u < epsilon, so the
+// host draws them in env order); fast mode (u == NULL) draws both from Philox(seed, counter, i).
+struct EpsGreedyArgs {
+  const int64_t* greedy; int N, n_actions; double epsilon;
+  const double* u; const int64_t* rnd; uint64_t seed, counter;
+  int64_t* out;
+};
+struct EpsGreedyAlgo {
+  typedef EpsGreedyArgs Args;
+  static const int MIN_CTAS = 4;
+  FRL_SDEV void run(int cta, int ncta, float*, const Args& a) {
+    FRL_PAR(t) {
+      for (int i = cta * FRL_NT + t; i < a.N; i += ncta * FRL_NT) {
+        double u;
+        int64_t r;
+        if (a.u) { u = a.u[i]; r = a.rnd ? a.rnd[i] : 0; }
+        else {
+          uint32_t o[4];
+          frl_philox((uint32_t)a.seed, (uint32_t)(a.seed >> 32), (uint32_t)i, (uint32_t)a.counter, (uint32_t)(a.counter >> 32), 0xe9511eedu, o);
+          u = ((double)(((uint64_t)o[0] << 21) ^ (uint64_t)(o[1] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);    // 53-bit (0,1)
+          r = (int64_t)(((uint64_t)o[2] * (uint64_t)a.n_actions) >> 32);
+        }
+        a.out[i] = (u < a.epsilon) ? r : a.greedy[i];
+      }
+    }
+  }
+};
+
+// dis_to_con (DQN_file/DQN.py:195-217) for N discrete actions -> [N][shape] continuous env actions.  float32 bounds, float64
+// arithmetic (np.int64 / int -> float64; * the float32 span -> float64), one-dimensional and per-dimension digit forms.
+struct DisToConArgs {
+  const int64_t* action; int N, n_actions, shape, per;      // per = int(n_actions ** (1 / shape)) computed by the host like the reference
+  const float *low, *high;                                  // dev [shape]
+  double* out64; float* out;
+};
+struct DisToConAlgo {
+  typedef DisToConArgs Args;
+  static const int MIN_CTAS = 4;
+  FRL_SDEV void run(int cta, int ncta, float*, const Args& a) {
+    FRL_PAR(t) {
+      for (int e = cta * FRL_NT + t; e < a.N * a.shape; e += ncta * FRL_NT) {
+        const int i = e / a.shape, j = e - i * a.shape;
+        const float span = a.high[j] - a.low[j];
+        double frac;
+        if (a.shape == 1) frac = (double)a.action[i] / (double)(a.n_actions - 1);
+        else {
+          int64_t p = 1;
+          for (int k = 0; k < j; ++k) p *= a.per;
+          int64_t q = a.action[i] / p;                       // floor division: actions are >= 0
+          frac = (double)(q % a.per) / (double)(a.per - 1);
+        }
+        const double v = frl_dadd((double)a.low[j], frl_dmul(frac, (double)span));
+        if (a.out64) a.out64[e] = v;
+        if (a.out) a.out[e] = (float)v;
+      }
+    }
+  }
+};

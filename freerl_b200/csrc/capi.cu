@@ -889,6 +889,24 @@ extern "C" int frl_masked_reset(double* state, const uint8_t* mask, int N, int W
   return frl_launch_simple<MaskedReset>(a, elementwise_grid((long)N * W), 4, (cudaStream_t)stream);
 }
 
+extern "C" int frl_epsilon_greedy(const int64_t* greedy, int N, int n_actions, double epsilon, const double* u, const int64_t* rnd,
+                                  uint64_t seed, uint64_t counter, int64_t* out, void* stream) {
+  if (!greedy || !out || N < 0 || n_actions <= 0 || (u && !rnd)) { frl_set_error("frl_epsilon_greedy: bad arguments"); return -1; }
+  if (N == 0) return 0;
+  EpsGreedyArgs a = {greedy, N, n_actions, epsilon, u, rnd, seed, counter, out};
+  return frl_launch_simple<EpsGreedyAlgo>(a, elementwise_grid(N), 4, (cudaStream_t)stream);
+}
+extern "C" int frl_dis_to_con(const int64_t* action, int N, int n_actions, int shape, int per, const float* low, const float* high,
+                              double* out64, float* out, void* stream) {
+  if (!action || !low || !high || N < 0 || shape <= 0 || (!out && !out64) || (shape == 1 ? n_actions < 2 : per < 2)) {
+    frl_set_error("frl_dis_to_con: bad arguments (needs >= 2 actions per dimension)");
+    return -1;
+  }
+  if (N == 0) return 0;
+  DisToConArgs a = {action, N, n_actions, shape, per, low, high, out64, out};
+  return frl_launch_simple<DisToConAlgo>(a, elementwise_grid((long)N * shape), 4, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------------------------------------
 // debug micro-benchmark of one layer op (not part of the product API; used by tools/opbench.py)
 //   mode 0: gemm_rk on already-staged weights   1: layer_fwd with TMA every iteration, no prefetch

@@ -187,3 +187,43 @@ def explore_gauss(action, max_action, gauss_scale, gauss_sigma, device="cuda", z
         a.out = _lib.ptr(out)
     _lib.check(_lib.lib().frl_explore(C.byref(a), _lib.stream_ptr(device)), "frl_explore")
     return out
+
+
+def epsilon_greedy(greedy, n_actions, epsilon, device="cuda", mode="parity", seed=0, counter=0):
+    """``if np.random.rand() < epsilon: action = np.random.randint(action_dim) else: action = policy.select_action(obs)``
+    (``DQN_file/DQN.py:307-310``) for N envs.  ``greedy``: the N greedy actions (int64).  Parity mode draws ``rand()`` — and a
+    ``randint`` only where it fires — on the host in env order, i.e. the legacy-stream consumption of N reference iterations;
+    fast mode draws on the device."""
+    device = _lib.require_device(device)
+    g = (greedy if isinstance(greedy, torch.Tensor) else torch.as_tensor(np.asarray(greedy, dtype=np.int64))).to(device).to(torch.int64).reshape(-1).contiguous()
+    n = g.numel()
+    out = torch.empty(n, dtype=torch.int64, device=device)
+    u = r = None
+    if mode == "parity":
+        uh, rh = np.empty(n), np.zeros(n, dtype=np.int64)
+        for i in range(n):
+            uh[i] = np.random.rand()
+            if uh[i] < epsilon:
+                rh[i] = np.random.randint(n_actions)
+        u, r = torch.from_numpy(uh).to(device), torch.from_numpy(rh).to(device)
+    _lib.check(_lib.lib().frl_epsilon_greedy(_lib.ptr(g), n, int(n_actions), float(epsilon), None if u is None else _lib.ptr(u),
+                                             None if r is None else _lib.ptr(r), C.c_uint64(int(seed)), C.c_uint64(int(counter)),
+                                             _lib.ptr(out), _lib.stream_ptr(device)), "frl_epsilon_greedy")
+    return out
+
+
+def dis_to_con(discrete_action, low, high, action_dim, device="cuda", out_dtype=torch.float64):
+    """``dis_to_con(discrete_action, env, action_dim)`` (``DQN_file/DQN.py:195-217``) for N actions: ``low`` / ``high`` are the Box
+    bounds (``env.action_space.low / high``, float32), result ``[N, len(low)]``."""
+    device = _lib.require_device(device)
+    a = (discrete_action if isinstance(discrete_action, torch.Tensor) else torch.as_tensor(np.asarray(discrete_action, dtype=np.int64)))
+    a = a.to(device).to(torch.int64).reshape(-1).contiguous()
+    lo = torch.as_tensor(np.asarray(low, dtype=np.float32).reshape(-1)).to(device)
+    hi = torch.as_tensor(np.asarray(high, dtype=np.float32).reshape(-1)).to(device)
+    shape = lo.numel()
+    per = int(action_dim ** (1 / shape)) if shape > 1 else 0
+    out = torch.empty((a.numel(), shape), dtype=out_dtype, device=device)
+    o64, o32 = (_lib.ptr(out), None) if out_dtype == torch.float64 else (None, _lib.ptr(out))
+    _lib.check(_lib.lib().frl_dis_to_con(_lib.ptr(a), a.numel(), int(action_dim), shape, per, _lib.ptr(lo), _lib.ptr(hi), o64, o32,
+                                         _lib.stream_ptr(device)), "frl_dis_to_con")
+    return out

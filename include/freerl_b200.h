@@ -317,6 +317,14 @@ int frl_reward_scaling(double* state, int64_t n0, double* R, const void* x, int 
 int frl_explore(const frl_explore_args_t* args, void* stream);
 /* state[i][:] = value where mask[i] != 0 (OUNoise.reset / RewardScaling.reset of the envs whose episode ended); state dev [N][W] float64 */
 int frl_masked_reset(double* state, const uint8_t* mask, int N, int W, double value, void* stream);
+/* epsilon-greedy of the DQN mains (DQN_file/DQN.py:307-310) for N envs: out[i] = u[i] < epsilon ? rnd[i] : greedy[i]; u == NULL draws
+ * u and the random action from Philox(seed, counter, i). */
+int frl_epsilon_greedy(const int64_t* greedy, int N, int n_actions, double epsilon, const double* u, const int64_t* rnd,
+                       uint64_t seed, uint64_t counter, int64_t* out, void* stream);
+/* dis_to_con (DQN_file/DQN.py:195-217): N discrete actions -> [N][shape] continuous actions between float32 bounds low/high (dev [shape]);
+ * per = int(n_actions ** (1 / shape)) as the reference computes it (unused for shape == 1). */
+int frl_dis_to_con(const int64_t* action, int N, int n_actions, int shape, int per, const float* low, const float* high,
+                   double* out64, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -69,3 +69,20 @@ def explore_ou(action, noise, max_action):
 def explore_gauss(action, z, max_action, gauss_scale, gauss_sigma):
     """``DDPG_file/DDPG.py:522``: ``np.random.normal(scale=s, size)`` is ``0.0 + s * z`` on the legacy stream."""
     return np.clip(action * max_action + gauss_scale * (0.0 + (gauss_sigma * max_action) * z), -max_action, max_action)
+
+
+def dis_to_con(discrete_action, low, high, action_dim):
+    """``DQN_file/DQN.py:195-217`` for one np.int64 action; ``low`` / ``high`` float32 arrays."""
+    if len(low) == 1:
+        return np.array([low[0] + (discrete_action / (action_dim - 1)) * (high[0] - low[0])])
+    per = int(action_dim ** (1 / len(low)))
+    idx = [discrete_action // (per ** i) % per for i in range(len(low))]
+    return np.array([low[i] + idx[i] / (per - 1) * (high[i] - low[i]) for i in range(len(low))])
+
+
+def epsilon_greedy(greedy, n_actions, epsilon):
+    """``DQN_file/DQN.py:307-310`` iterated over envs on numpy's legacy global stream."""
+    out = np.empty(len(greedy), dtype=np.int64)
+    for i, gA in enumerate(greedy):
+        out[i] = np.random.randint(n_actions) if np.random.rand() < epsilon else gA
+    return out

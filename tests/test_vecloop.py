@@ -36,6 +36,14 @@ def test_oracle_vecloop_matches_reference_fixture():
                               G["gauss_out"][t])
 
 
+    a1 = np.stack([ov.dis_to_con(a, np.array([-2.0], np.float32), np.array([2.0], np.float32), 11) for a in G["d2c1_a"]])
+    assert np.array_equal(a1.astype(np.float64), G["d2c1_out"])
+    a4 = np.stack([ov.dis_to_con(a, G["d2c4_low"], G["d2c4_high"], 81) for a in G["d2c4_a"]])
+    assert np.array_equal(a4.astype(np.float64), G["d2c4_out"])
+    np.random.seed(23)
+    assert np.array_equal(ov.epsilon_greedy(G["eg_greedy"], 4, 0.3), G["eg_out"])
+
+
 # ---- product (C ABI) vs fixture and oracle ------------------------------------------------------------------------
 def _np(t):
     return t.detach().cpu().numpy()
@@ -86,6 +94,16 @@ def _run(device):
     np.random.seed(7)
     ou3 = vl.OUNoise(3, sigma=0.2, dt=1e-2, scale=0.3, n_envs=N, device=device)
     assert np.array_equal(_np(ou3.noise()), G["ou_noise"][0])
+    # dis_to_con and epsilon-greedy of the DQN mains
+    assert np.array_equal(_np(vl.dis_to_con(G["d2c1_a"], [-2.0], [2.0], 11, device=device)), G["d2c1_out"])
+    assert np.array_equal(_np(vl.dis_to_con(G["d2c4_a"], G["d2c4_low"], G["d2c4_high"], 81, device=device)), G["d2c4_out"])
+    np.random.seed(23)
+    assert np.array_equal(_np(vl.epsilon_greedy(G["eg_greedy"], 4, 0.3, device=device)), G["eg_out"])
+    gr = np.zeros(20000, dtype=np.int64) + 7
+    fe = _np(vl.epsilon_greedy(gr, 4, 0.25, device=device, mode="fast", seed=5, counter=1))
+    fired = fe != 7
+    assert 0.22 < fired.mean() < 0.28 and set(np.unique(fe[fired])) == {0, 1, 2, 3}
+    assert np.array_equal(fe, _np(vl.epsilon_greedy(gr, 4, 0.25, device=device, mode="fast", seed=5, counter=1)))
     # larger random cases vs the oracle: 1024 envs (C3), wide observations (more than one CTA of columns), many steps
     rng = np.random.default_rng(5)
     for n_env, d, dt in ((1024, 8, np.float32), (64, 300, np.float64), (3, 54, np.float32)):
