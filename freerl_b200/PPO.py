@@ -86,7 +86,7 @@ class PPO:
         obs_dim, action_dim = dim_info
         self.device = _lib.require_device(device)
         self.obs_dim, self.action_dim = obs_dim, action_dim
-        self.agent = Agent(obs_dim, action_dim, actor_lr, critic_lr, is_continue, self.device)
+        self.agent = Agent(obs_dim, action_dim, actor_lr, critic_lr, is_continue, self.device, init_hook=getattr(self, "_init_hook", None))
         self.buffer = Buffer_for_PPO(horizon, obs_dim, act_dim=action_dim if is_continue else 1, device=self.device)
         self.is_continue = is_continue
         print('actor_type:continue') if self.is_continue else print('actor_type:discrete')

@@ -1,0 +1,71 @@
+"""PPO with the reference's trick switches and class API (``PPO_file/PPO_with_tricks.py:190-374``) on the fused PPO kernels.
+
+Upstream this file's ``learn()`` cannot run (``np.zeros(self.horizon, dtype=torch.float32)`` raises, ``:302``); what it is meant to
+compute — the plain-Adam PPO of ``PPO_advance/PPO.py`` plus switches — is what this class runs, pinned against the reference
+executed with that one call patched (``oracle/make_golden_ppo_tricks.py``):
+
+* ``adv_norm``        ``(adv - adv.mean()) / (adv.std() + 1e-8)`` over the horizon after GAE (``:314-315``) -> ``frl_adv_norm``
+* ``adam_eps``        both Adams with ``eps = 1e-5`` (``:198-200``)
+* ``lr_decay``        ``lr_decay(episode_num, max_episodes)``: linear decay of both learning rates (``:356-362``)
+* ``orthogonal_init`` orthogonal weights (gain 1, 0.01 on the action head), zero biases, applied inside each module constructor
+                      (``:71-77,90-93,166-169``)
+* ``ObsNorm`` / ``reward_norm`` / ``reward_scaling`` live in the train loop, not in the class (``:515-540``) -> ``freerl_b200.vecloop``
+
+Not provided (raise ``NotImplementedError``): ``tanh`` hidden activations, ``Batch_ObsNorm`` inside ``learn`` and the Beta policy
+(``beta=True``) — the PPO kernel has ReLU bodies and Gaussian / Categorical heads only.
+"""
+import os
+
+import torch
+from torch import nn
+
+from . import _lib
+from .PPO_advance import PPO as _PPOAdvance
+
+_TRICKS = ('adv_norm', 'ObsNorm', 'Batch_ObsNorm', 'reward_norm', 'reward_scaling', 'lr_decay', 'orthogonal_init', 'adam_eps', 'tanh')
+
+
+def orthogonal_init(layer, gain=1.0):
+    """``PPO_with_tricks.py:71-77``"""
+    nn.init.orthogonal_(layer.weight, gain=gain)
+    nn.init.constant_(layer.bias, 0)
+
+
+class PPO(_PPOAdvance):
+    def __init__(self, dim_info, is_continue, actor_lr, critic_lr, horizon, device, trick=None, beta=False, mode=None):
+        t = {k: False for k in _TRICKS}
+        t.update(trick or {})
+        if beta:
+            raise NotImplementedError("PPO_with_tricks: the Beta policy head (beta=True) is not implemented on the fused kernel")
+        for k in ('tanh', 'Batch_ObsNorm'):
+            if t[k]:
+                raise NotImplementedError("PPO_with_tricks: trick %r is not implemented on the fused kernel" % k)
+        self.adam_eps = 1e-5 if t['adam_eps'] else 1e-8
+        self.actor_dist = {'Beta': False}
+        print('actor_dist:Gaussian')
+        if t['orthogonal_init']:
+            def hook(module, names, which):
+                for n in names:
+                    orthogonal_init(getattr(module, n), gain=0.01 if (which == "actor" and n == "mean_layer") else 1.0)
+            self._init_hook = hook
+        super().__init__(dim_info, is_continue, actor_lr, critic_lr, horizon, device, trick=t, mode=mode)
+        self.actor_lr, self.critic_lr = actor_lr, critic_lr
+
+    def learn(self, minibatch_size, gamma, lmbda, clip_param, K_epochs, entropy_coefficient, *, permutations=None):
+        adv, v_target = self.compute_gae(gamma, lmbda)
+        if self.trick['adv_norm']:
+            _lib.check(_lib.lib().frl_adv_norm(_lib.ptr(adv), adv.numel(), 1e-8, _lib.ptr(adv), _lib.stream_ptr(self.device)), "frl_adv_norm")
+        self.last_adv, self.last_v_target = adv, v_target
+        self._update(adv, v_target, minibatch_size, K_epochs, clip_param, entropy_coefficient, permutations)
+        self.buffer.clear()
+
+    def lr_decay(self, episode_num, max_episodes):
+        self.agent.lr = self.actor_lr * (1 - episode_num / max_episodes)
+        self.agent.lr_critic = self.critic_lr * (1 - episode_num / max_episodes)
+
+    @staticmethod
+    def load(dim_info, is_continue, model_dir, trick=None, beta=False, device=None):
+        device = device if device is not None else torch.device("cuda")
+        policy = PPO(dim_info, is_continue, 0, 0, 0, device=device, trick=trick, beta=beta)
+        policy.agent.actor.load_state_dict(torch.load(os.path.join(model_dir, "PPO.pt"), map_location=device))
+        return policy

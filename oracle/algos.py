@@ -450,3 +450,26 @@ class PPOAdvanceOracle(PPOOracle):
         gc, _ = clip_grad_norm(torch.autograd.grad(critic_loss, cp), 0.5)
         adam_step(cp, list(gc), self.opt_c)
         return actor_loss.item(), critic_loss.item()
+
+
+class PPOTricksOracle(PPOAdvanceOracle):
+    """``PPO_file/PPO_with_tricks.py:190-362`` with the ``np.zeros(dtype=torch.float32)`` call (``:302``) read as float32 zeros:
+    ``PPOAdvanceOracle`` plus ``adam_eps`` (both Adams eps 1e-5, ``:198-200``), ``adv_norm`` (``:314-315``) and ``lr_decay``
+    (``:356-362``)."""
+
+    def __init__(self, actor, critic, actor_lr, critic_lr, is_continue, adam_eps=False, adv_norm=False):
+        super().__init__(actor, critic, actor_lr, critic_lr, is_continue)
+        self.actor_lr, self.critic_lr, self.adv_norm = actor_lr, critic_lr, adv_norm
+        if adam_eps:
+            self.opt_a.eps = self.opt_c.eps = 1e-5
+
+    def advantages(self, data, gamma, lmbda):
+        adv, v_target = super().advantages(data, gamma, lmbda)
+        if self.adv_norm:
+            adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+        return adv, v_target
+
+    def lr_decay(self, episode_num, max_episodes):
+        self.opt_a.lr = self.actor_lr * (1 - episode_num / max_episodes)
+        self.opt_c.lr = self.critic_lr * (1 - episode_num / max_episodes)
+

@@ -81,3 +81,13 @@ def test_reference_single_agent_siblings_unchanged(tmp_path, emul):
                                        ["--env_name", "CartPole-v1", "--max_episodes", "3", "--horizon", "64", "--minibatch_size", "32",
                                         "--K_epochs", "2", "--device", "cpu"], results_root=str(tmp_path))
     assert type(ns["policy"]).__module__ == "freerl_b200.PPO_advance" and ns["policy"].agent.step > 0
+
+
+def test_reference_ppo_with_tricks_script_unchanged(tmp_path, emul):
+    """PPO_file/PPO_with_tricks.py: upstream its learn() raises (np.zeros with a torch dtype, :302); with the class rebound to ours the
+    UNCHANGED script trains (default trick dict: everything off)."""
+    from freerl_b200 import launcher
+    ns = launcher.run_reference_script(os.path.join(REF, "PPO_file", "PPO_with_tricks.py"),
+                                       ["--env_name", "Pendulum-v1", "--max_episodes", "2", "--horizon", "128", "--minibatch_size", "32",
+                                        "--K_epochs", "2", "--device", "cpu"], results_root=str(tmp_path))
+    assert type(ns["policy"]).__module__ == "freerl_b200.PPO_with_tricks" and ns["policy"].agent.step > 0

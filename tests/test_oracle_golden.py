@@ -216,3 +216,26 @@ def test_choice_stream(golden):
     np.random.seed(0)
     assert np.array_equal(buffers.uniform_indices(1000, 8), g["choice/seed0_1000_8"])
     assert np.array_equal(buffers.uniform_indices(50, 50), g["choice/seed0_next_50_50"])
+
+
+def _ppo_tricks(golden, name, is_continue):
+    """PPO_file/PPO_with_tricks.py (adv_norm + orthogonal_init + adam_eps + lr_decay; np.zeros call patched at generation time) replayed
+    through oracle.algos.PPOTricksOracle: two learns with lr_decay(10, 100) after each"""
+    g = golden(name)
+    o = algos.PPOTricksOracle(net(g, "init/actor/"), net(g, "init/critic/"), 1e-3, 5e-4, is_continue, adam_eps=True, adv_norm=True)
+    losses_ = []
+    for r in range(2):
+        data = tuple(torch.from_numpy(g["data%d/%s" % (r, k)]) for k in ("obs", "act", "rew", "nobs", "done", "logp", "adv_done"))
+        losses_ += o.learn(data, [g["perm%d/%d" % (r, k)] for k in range(2)], 64, 0.99, 0.95, 0.2, 0.01)["losses"]
+        o.lr_decay(10, 100)
+        assert_net(o.actor, g, "after%d/actor/" % r)
+        assert_net(o.critic, g, "after%d/critic/" % r)
+    np.testing.assert_allclose(np.array(losses_), g["losses"], rtol=2e-5, atol=1e-6)
+
+
+def test_ppo_with_tricks_continuous(golden):
+    _ppo_tricks(golden, "ppo_tricks_cont", True)
+
+
+def test_ppo_with_tricks_discrete(golden):
+    _ppo_tricks(golden, "ppo_tricks_disc", False)

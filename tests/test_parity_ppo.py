@@ -106,6 +106,70 @@ def test_ppo_advance_discrete_gpu(golden):
     _ppo_advance(golden, torch.device("cuda"), "ppo_adv_disc", False)
 
 
+TRICKS = {'adv_norm': True, 'ObsNorm': False, 'Batch_ObsNorm': False, 'reward_norm': False, 'reward_scaling': False,
+          'lr_decay': True, 'orthogonal_init': True, 'adam_eps': True, 'tanh': False}
+
+
+def _ppo_tricks(golden, device, name, is_continue):
+    """freerl_b200.PPO_with_tricks (adv_norm via frl_adv_norm, Adam eps 1e-5, lr_decay, orthogonal init) vs oracle + the fixture
+    generated from PPO_file/PPO_with_tricks.py: two rollouts / learns with lr_decay(10, 100) in between"""
+    from freerl_b200.PPO_with_tricks import PPO
+    g = golden(name)
+    act_dim = 2 if is_continue else 4
+    pol = PPO([8, act_dim], is_continue, 1e-3, 5e-4, 256, device, trick=dict(TRICKS))
+    # orthogonal init went through the module constructors: zero biases, orthonormal rows / columns (gain 1; 0.01 on the Gaussian head)
+    sd = pol.agent.critic.state_dict()
+    w = sd["l2.weight"].cpu().double()
+    assert float(sd["l1.bias"].abs().max()) == 0.0 and torch.allclose(w @ w.T, torch.eye(128, dtype=torch.float64), atol=1e-4)
+    if is_continue:
+        wm = pol.agent.actor.state_dict()["mean_layer.weight"].cpu().double()
+        assert torch.allclose(wm @ wm.T, 1e-4 * torch.eye(act_dim, dtype=torch.float64), atol=1e-7)
+    load_into(pol.agent.actor, net_from_golden(g, "init/actor/"))
+    load_into(pol.agent.critic, net_from_golden(g, "init/critic/"))
+    orc = algos.PPOTricksOracle(net_from_golden(g, "init/actor/"), net_from_golden(g, "init/critic/"), 1e-3, 5e-4, is_continue,
+                                adam_eps=True, adv_norm=True)
+    tol = dict(rtol=3e-5, atol=4e-6)
+    for r in range(2):
+        data = tuple(torch.from_numpy(g["data%d/%s" % (r, k)]) for k in ("obs", "act", "rew", "nobs", "done", "logp", "adv_done"))
+        d = [x.numpy() for x in data]
+        for t in range(256):
+            pol.add(d[0][t], d[1][t], float(d[2][t, 0]), d[3][t], bool(d[4][t, 0]), d[5][t], bool(d[6][t, 0]))
+        perms = [g["perm%d/%d" % (r, k)] for k in range(2)]
+        ref = np.array(orc.learn(data, perms, 64, 0.99, 0.95, 0.2, 0.01)["losses"])
+        pol.learn(64, 0.99, 0.95, 0.2, 2, 0.01, permutations=perms)
+        m = pol.last_metrics.cpu().numpy()
+        np.testing.assert_allclose(m[:, :2], ref, rtol=3e-5, atol=3e-6)
+        np.testing.assert_allclose(m[:, :2], g["losses"][8 * r:8 * r + 8], rtol=6e-5, atol=6e-6)
+        orc.lr_decay(10, 100)
+        pol.lr_decay(10, 100)
+        assert_module_close(pol.agent.actor, orc.actor, "actor", tol)
+        assert_module_close(pol.agent.critic, orc.critic, "critic", tol)
+        assert_module_close(pol.agent.actor, net_from_golden(g, "after%d/actor/" % r), "actor vs reference", tol)
+        assert_module_close(pol.agent.critic, net_from_golden(g, "after%d/critic/" % r), "critic vs reference", tol)
+    with pytest.raises(NotImplementedError):
+        PPO([8, act_dim], is_continue, 1e-3, 5e-4, 256, device, trick=dict(TRICKS, tanh=True))
+    with pytest.raises(NotImplementedError):
+        PPO([8, act_dim], is_continue, 1e-3, 5e-4, 256, device, trick=dict(TRICKS), beta=True)
+
+
+def test_ppo_with_tricks_continuous_emulated(golden, emul):
+    _ppo_tricks(golden, torch.device("cpu"), "ppo_tricks_cont", True)
+
+
+def test_ppo_with_tricks_discrete_emulated(golden, emul):
+    _ppo_tricks(golden, torch.device("cpu"), "ppo_tricks_disc", False)
+
+
+@pytest.mark.gpu
+def test_ppo_with_tricks_continuous_gpu(golden):
+    _ppo_tricks(golden, torch.device("cuda"), "ppo_tricks_cont", True)
+
+
+@pytest.mark.gpu
+def test_ppo_with_tricks_discrete_gpu(golden):
+    _ppo_tricks(golden, torch.device("cuda"), "ppo_tricks_disc", False)
+
+
 def _ppo_large_minibatch(device, is_continue):
     """minibatch >= 1024 rows takes the 16-row-tile instantiation of the PPO kernel (frl_ppo_update picks it when the tile fits
     in shared memory): [T=16, N=128] vectorised rollout, minibatch 1024, one epoch (2 updates) vs the oracle."""
