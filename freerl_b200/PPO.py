@@ -81,6 +81,7 @@ class PPO:
     optimizer = _lib.OPT_CAUTIOUS_ADAMW
     adam_eps = 1e-6
     max_norm = 0.5
+    hidden_tanh = 0              # PPO_with_tricks' `tanh` switch, bit 0: actor, bit 1: critic use tanh instead of ReLU hidden activations
 
     def __init__(self, dim_info, is_continue, actor_lr, critic_lr, horizon, device, trick=None, mode=None):
         obs_dim, action_dim = dim_info
@@ -113,7 +114,7 @@ class PPO:
             elif noise is not None:
                 noise = torch.as_tensor(noise, dtype=torch.float32).to(self.device).reshape(n, self.action_dim).contiguous()
             out = _common.infer(net, x, _lib.INFER_PPO_GAUSS, self.device, 2 * self.action_dim, noise=noise, seed=self._seed,
-                                counter=self._n_act, l0=0, nl=3).cpu().numpy()
+                                counter=self._n_act, l0=0, nl=3, hidden_tanh=bool(self.hidden_tanh & 1)).cpu().numpy()
             action, logp = out[:, :self.action_dim], out[:, self.action_dim:]
             return (action[0], logp[0]) if single else (action, logp)
         if noise is None and self.mode == "parity":
@@ -122,7 +123,7 @@ class PPO:
         elif noise is not None:
             noise = torch.as_tensor(noise, dtype=torch.float32).to(self.device).reshape(n, self.action_dim).contiguous()
         out = _common.infer(net, x, _lib.INFER_PPO_CAT, self.device, 2, noise=noise, seed=self._seed, counter=self._n_act,
-                            l0=0, nl=3).cpu().numpy()
+                            l0=0, nl=3, hidden_tanh=bool(self.hidden_tanh & 1)).cpu().numpy()
         action, logp = out[:, 0].astype(np.int64), out[:, 1]
         return (action[0], logp[0]) if single else (action, logp)
 
@@ -130,9 +131,9 @@ class PPO:
         x, single = _common.as_obs_batch(obs, self.obs_dim)
         net = self.agent._net
         if self.is_continue:
-            a = _common.infer(net, x, _lib.INFER_TANH, self.device, self.action_dim, l0=0, nl=3).cpu().numpy()
+            a = _common.infer(net, x, _lib.INFER_TANH, self.device, self.action_dim, l0=0, nl=3, hidden_tanh=bool(self.hidden_tanh & 1)).cpu().numpy()
             return a[0] if single else a
-        a = _common.infer(net, x, _lib.INFER_ARGMAX, self.device, 1, l0=0, nl=3).reshape(-1).to(torch.int64).cpu().numpy()
+        a = _common.infer(net, x, _lib.INFER_ARGMAX, self.device, 1, l0=0, nl=3, hidden_tanh=bool(self.hidden_tanh & 1)).reshape(-1).to(torch.int64).cpu().numpy()
         return a[0] if single else a
 
     def add(self, obs, action, reward, next_obs, done, action_log_pi, adv_dones):
@@ -140,7 +141,7 @@ class PPO:
 
     # ---- learning ----------------------------------------------------------------------------------
     def _values(self, obs):
-        return _common.infer(self.agent._net, obs, _lib.INFER_RAW, self.device, 1, l0=3, nl=3)
+        return _common.infer(self.agent._net, obs, _lib.INFER_RAW, self.device, 1, l0=3, nl=3, hidden_tanh=bool(self.hidden_tanh & 2))
 
     def compute_gae(self, gamma, lmbda):
         """critic(obs), critic(next_obs) -> fused TD-delta + GAE scan (PPO.py:222-233) -> (adv, v_target) [M,1]."""
@@ -193,6 +194,7 @@ class PPO:
         a.max_norm_actor = a.max_norm_critic = self.max_norm
         a.optimizer = self.optimizer
         a.lr, a.beta1, a.beta2, a.eps = ag.lr, 0.9, 0.999, self.adam_eps
+        a.hidden_tanh = int(self.hidden_tanh)
         a.lr_critic = float(getattr(ag, "lr_critic", 0.0))        # separate actor / critic Adams (PPO_advance); 0 = merged
         a.step0 = ag.step
         a.gpart, a.sumsq, a.segcnt = self._gpart.data_ptr(), self._sumsq.data_ptr(), self._segcnt.data_ptr()

@@ -11,8 +11,10 @@ executed with that one call patched (``oracle/make_golden_ppo_tricks.py``):
                       (``:71-77,90-93,166-169``)
 * ``ObsNorm`` / ``reward_norm`` / ``reward_scaling`` live in the train loop, not in the class (``:515-540``) -> ``freerl_b200.vecloop``
 
-Not provided (raise ``NotImplementedError``): ``tanh`` hidden activations, ``Batch_ObsNorm`` inside ``learn`` and the Beta policy
-(``beta=True``) — the PPO kernel has ReLU bodies and Gaussian / Categorical heads only.
+* ``tanh``            tanh instead of ReLU hidden activations in actor and critic (``:95,172``; continuous actor and critic — the
+                      discrete actor takes no trick argument upstream and keeps ReLU and the default init, ``:106-118``) -> ``frl_ppo_args_t.hidden_tanh`` / ``frl_infer_args_t.hidden_tanh``
+
+Not provided (raise ``NotImplementedError``): ``Batch_ObsNorm`` inside ``learn`` and the Beta policy (``beta=True``).
 """
 import os
 
@@ -37,14 +39,17 @@ class PPO(_PPOAdvance):
         t.update(trick or {})
         if beta:
             raise NotImplementedError("PPO_with_tricks: the Beta policy head (beta=True) is not implemented on the fused kernel")
-        for k in ('tanh', 'Batch_ObsNorm'):
-            if t[k]:
-                raise NotImplementedError("PPO_with_tricks: trick %r is not implemented on the fused kernel" % k)
+        if t['Batch_ObsNorm']:
+            raise NotImplementedError("PPO_with_tricks: trick 'Batch_ObsNorm' is not implemented on the fused kernel")
+        # Actor_discrete takes no trick argument upstream (:106-118, :187): ReLU body and default init whatever the switches say
+        self.hidden_tanh = (3 if is_continue else 2) if t['tanh'] else 0
         self.adam_eps = 1e-5 if t['adam_eps'] else 1e-8
         self.actor_dist = {'Beta': False}
         print('actor_dist:Gaussian')
         if t['orthogonal_init']:
             def hook(module, names, which):
+                if which == "actor" and not is_continue:
+                    return
                 for n in names:
                     orthogonal_init(getattr(module, n), gain=0.01 if (which == "actor" and n == "mean_layer") else 1.0)
             self._init_hook = hook

@@ -71,7 +71,7 @@ def reference_randn(shape, device):
     return torch.empty(shape, dtype=torch.float32, device=device).normal_()
 
 
-def infer(net, obs, mode, device, out_cols, noise=None, seed=0, counter=0, l0=0, nl=0, layer_norm=False, obs_norm=None):
+def infer(net, obs, mode, device, out_cols, noise=None, seed=0, counter=0, l0=0, nl=0, layer_norm=False, obs_norm=None, hidden_tanh=False):
     """Batched policy inference.  ``obs``: numpy / tensor [n, obs_dim] -> device tensor [n, out_cols]."""
     if isinstance(obs, torch.Tensor):
         x = obs.to(device=device, dtype=torch.float32).contiguous()
@@ -83,6 +83,7 @@ def infer(net, obs, mode, device, out_cols, noise=None, seed=0, counter=0, l0=0,
     a.net = net.c_struct()
     a.l0, a.nl = l0, nl
     a.layer_norm = int(layer_norm)
+    a.hidden_tanh = int(hidden_tanh)
     a.obs, a.n, a.obs_dim, a.mode = x.data_ptr(), n, obs_dim, mode
     a.noise = noise.data_ptr() if noise is not None else None
     a.seed, a.counter = seed, counter & 0xFFFFFFFF

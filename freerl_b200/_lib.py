@@ -12,7 +12,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 FRL_MAX_LAYERS = 6
 FRL_MAX_AGENTS = 6
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class Layer(C.Structure):
@@ -61,7 +61,7 @@ class AcArgs(C.Structure):
 class InferArgs(C.Structure):
     _fields_ = [("net", Net), ("l0", C.c_int), ("nl", C.c_int), ("obs", C.c_void_p), ("n", C.c_int), ("obs_dim", C.c_int), ("mode", C.c_int),
                 ("noise", C.c_void_p), ("seed", C.c_uint64), ("counter", C.c_uint32), ("out", C.c_void_p),
-                ("out_cols", C.c_int), ("layer_norm", C.c_int), ("obs_norm", C.c_void_p)]
+                ("out_cols", C.c_int), ("layer_norm", C.c_int), ("obs_norm", C.c_void_p), ("hidden_tanh", C.c_int)]
 
 
 class PpoArgs(C.Structure):
@@ -76,7 +76,7 @@ class PpoArgs(C.Structure):
                 ("huber_delta", C.c_float), ("stage_lo", C.c_int), ("stage_hi", C.c_int), ("grad_scale", C.c_float),
                 ("gpart", C.c_void_p),
                 ("sumsq", C.c_void_p), ("segcnt", C.c_void_p), ("stats", C.c_void_p), ("out", C.c_void_p),
-                ("lr_critic", C.c_double)]
+                ("lr_critic", C.c_double), ("hidden_tanh", C.c_int)]
 
 
 class NoisyMap(C.Structure):

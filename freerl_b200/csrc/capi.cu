@@ -23,7 +23,7 @@ extern "C" void frl_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 extern "C" const char* frl_last_error(void) { return g_err; }
-extern "C" int frl_abi_version(void) { return 4; }
+extern "C" int frl_abi_version(void) { return 5; }
 // sizeof() of the argument structs, so a binding can verify its mirror of the layout before the first call
 extern "C" int frl_struct_size(int which) {
   switch (which) {
@@ -480,7 +480,7 @@ struct InferAlgo {
     }
     FRL_SYNC();
     if (a.layer_norm && nl == 3) net_fwd<FRL_R>(c, n, l0, true, X, in_pad, a.obs_dim, nb, ldh, O, op, no_hint());
-    else mlp_fwd<FRL_R>(c, n, l0, nl, X, in_pad, H1, H2, ldh, O, op, FRL_ACT_NONE, no_hint());
+    else mlp_fwd<FRL_R>(c, n, l0, nl, X, in_pad, H1, H2, ldh, O, op, FRL_ACT_NONE, no_hint(), -1, a.hidden_tanh ? FRL_ACT_TANH : FRL_ACT_RELU);
     FRL_PAR(t) {
       if (a.mode == FRL_INFER_ARGMAX) {
         if (t < nvalid) {
@@ -628,6 +628,7 @@ extern "C" int frl_ppo_update(const frl_ppo_args_t* a, void* stream) {
     return -1;
   }
   if (check_net(a->net, true, "frl_ppo_update(net)")) return -1;
+  if (a->hidden_tanh && a->layer_norm) { frl_set_error("frl_ppo_update: hidden_tanh is not available with layer_norm"); return -1; }
   if (a->net.n_layers != 6 || (a->continuous && a->net.x_len <= 0)) {
     frl_set_error("frl_ppo_update: net must hold actor (layers 0-2) + critic (layers 3-5)");
     return -1;

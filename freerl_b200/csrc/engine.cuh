@@ -344,7 +344,7 @@ FRL_DEV float apply_act(float v, int act) {
   return v;
 }
 
-enum { EPI_BIAS_ACT = 0, EPI_RELU_MASK = 1 };
+enum { EPI_BIAS_ACT = 0, EPI_RELU_MASK = 1, EPI_TANH_MASK = 2 };   // TANH_MASK: acc * (1 - mask^2), mask = stored tanh output
 
 // ------------------------------------------------------------------------------------------------
 // Shared-memory "word address" helpers.  The GEMM microkernels do all smem pointer arithmetic in 32-bit word
@@ -435,6 +435,10 @@ FRL_DEV void gemm_finish(sptr sR, unsigned ksplit, int N_pad, int epi, int act, 
           if (has_bias) { const float4 bv = sp_ld4(sBias, n0); o[0] += bv.x; o[1] += bv.y; o[2] += bv.z; o[3] += bv.w; }
 #pragma unroll
           for (int q = 0; q < 4; ++q) o[q] = apply_act(o[q], act);
+        } else if (epi == EPI_TANH_MASK) {
+          const float4 mv = sp_ld4(sM, (int)r * ldm + n0);
+          o[0] = o[0] * (1.f - mv.x * mv.x); o[1] = o[1] * (1.f - mv.y * mv.y);
+          o[2] = o[2] * (1.f - mv.z * mv.z); o[3] = o[3] * (1.f - mv.w * mv.w);
         } else {
           const float4 mv = sp_ld4(sM, (int)r * ldm + n0);
           o[0] = mv.x > 0.f ? o[0] : 0.f; o[1] = mv.y > 0.f ? o[1] : 0.f;
@@ -594,6 +598,7 @@ FRL_NI_GEMM void gemm_nt(float* red, const float* A, int lda, int N_red, const f
             const int k = (int)kl + j * (int)KL;
             float v = acc[i][j];
             if (epi == EPI_RELU_MASK) v = (sp_ld1(sM, (r0 + i) * ldm + k) > 0.f) ? v : 0.f;
+            else if (epi == EPI_TANH_MASK) { const float m = sp_ld1(sM, (r0 + i) * ldm + k); v = v * (1.f - m * m); }
             sp_st1(sC, (r0 + i) * ldc + k, v);
           }
       } else {
@@ -805,6 +810,7 @@ FRL_NI_GEMM void gemm_nt(float* red, const float* A, int lda, int N_red, const f
       if (i < K_out) {
         float v = v4[q];
         if (epi == EPI_RELU_MASK) v = (sp_ld1(sM, r * ldm + i) > 0.f) ? v : 0.f;
+        else if (epi == EPI_TANH_MASK) { const float m = sp_ld1(sM, r * ldm + i); v = v * (1.f - m * m); }
         sp_st1(sC, r * ldc + i, v);
       }
     }
@@ -984,8 +990,9 @@ FRL_DEV void layer_fwd_img(Cta& c, const frl_layer_t& L, const float* Bs, const 
 // dX = (dY W) * relu'(mask)   (mask == nullptr: no activation derivative) on the same forward image
 template <int R>
 FRL_DEV void layer_bwd_img(Cta& c, const frl_layer_t& L, const float* Bs, const float* dY, int ldy, const float* mask, int ldm,
-                           float* dX, int ldx) {
-  gemm_nt<R>(c.red, dY, ldy, L.out_pad, Bs, wt_ld(L), L.in_pad, mask ? EPI_RELU_MASK : EPI_BIAS_ACT, mask, ldm, dX, ldx);
+                           float* dX, int ldx, int hact = FRL_ACT_RELU) {
+  gemm_nt<R>(c.red, dY, ldy, L.out_pad, Bs, wt_ld(L), L.in_pad, mask ? (hact == FRL_ACT_TANH ? EPI_TANH_MASK : EPI_RELU_MASK) : EPI_BIAS_ACT,
+             mask, ldm, dX, ldx);
 }
 
 // Streaming flavours.  `next` is what the caller will need after this layer (prefetched during the math).
@@ -999,18 +1006,18 @@ FRL_DEV void layer_bwd_dx(Cta& c, const frl_net_t& n, int li, const float* dY, i
   layer_bwd_img<R>(c, n.L[li], wt_acquire(c, -1, n, li, 0, next), dY, ldy, mask, ldm, dX, ldx);
 }
 
-// MLP forward over layers [l0, l0+nl): hidden layers ReLU, last layer `act_out`.
+// MLP forward over layers [l0, l0+nl): hidden layers `hact` (ReLU unless a caller asks for tanh), last layer `act_out`.
 //   nl == 3: H1 = relu(l0 X), H2 = relu(l1 H1), OUT = act(l2 H2);   nl == 2: H1 = relu(l0 X), OUT = act(l1 H1).
 //   slot >= 0: the head is resident in that slot (res_fetch was issued by the caller); slot < 0: streaming.
 template <int R>
 FRL_NI_MLP void mlp_fwd(Cta& c, const frl_net_t& n, int l0, int nl, const float* X, int ldx, float* H1, float* H2, int ldh,
-                     float* OUT, int ldo, int act_out, Hint next, int slot = -1) {
+                     float* OUT, int ldo, int act_out, Hint next, int slot = -1, int hact = FRL_ACT_RELU) {
   if (nl == 3) {
-    layer_fwd_img<R>(c, n.L[l0], wt_acquire(c, slot, n, l0, 0, fwd_hint(n, l0 + 1)), X, ldx, H1, ldh, FRL_ACT_RELU);
-    layer_fwd_img<R>(c, n.L[l0 + 1], wt_acquire(c, slot, n, l0, 1, fwd_hint(n, l0 + 2)), H1, ldh, H2, ldh, FRL_ACT_RELU);
+    layer_fwd_img<R>(c, n.L[l0], wt_acquire(c, slot, n, l0, 0, fwd_hint(n, l0 + 1)), X, ldx, H1, ldh, hact);
+    layer_fwd_img<R>(c, n.L[l0 + 1], wt_acquire(c, slot, n, l0, 1, fwd_hint(n, l0 + 2)), H1, ldh, H2, ldh, hact);
     layer_fwd_img<R>(c, n.L[l0 + 2], wt_acquire(c, slot, n, l0, 2, next), H2, ldh, OUT, ldo, act_out);
   } else {
-    layer_fwd_img<R>(c, n.L[l0], wt_acquire(c, slot, n, l0, 0, fwd_hint(n, l0 + 1)), X, ldx, H1, ldh, FRL_ACT_RELU);
+    layer_fwd_img<R>(c, n.L[l0], wt_acquire(c, slot, n, l0, 0, fwd_hint(n, l0 + 1)), X, ldx, H1, ldh, hact);
     layer_fwd_img<R>(c, n.L[l0 + 1], wt_acquire(c, slot, n, l0, 1, next), H1, ldh, OUT, ldo, act_out);
   }
 }
@@ -1022,7 +1029,7 @@ FRL_NI_MLP void mlp_fwd(Cta& c, const frl_net_t& n, int l0, int nl, const float*
 template <int R>
 FRL_NI_MLP void mlp_bwd(Cta& c, const frl_net_t& n, int l0, int nl, const float* X, int ldx, const float* H1, const float* H2,
                      int ldh, const float* dOUT, int ldo, float* D1, float* D2, float* dXo, int lddx, float* gp,
-                     bool accumulate, Hint next, int slot = -1) {
+                     bool accumulate, Hint next, int slot = -1, int hact = FRL_ACT_RELU) {
   const float* dcur = dOUT;
   int ldc = ldo;
   for (int k = nl - 1; k >= 0; --k) {
@@ -1034,7 +1041,7 @@ FRL_NI_MLP void mlp_bwd(Cta& c, const frl_net_t& n, int l0, int nl, const float*
     if (k > 0) {
       float* dn = (k == 2) ? D2 : D1;   // gradient wrt H2 (k==2) or H1 (k==1)
       Hint h = (k - 1 > 0 || dXo) ? bwd_hint(n, li - 1) : next;
-      layer_bwd_img<R>(c, L, wt_acquire(c, slot, n, l0, k, h), dcur, ldc, Xin, ldin, dn, ldh);
+      layer_bwd_img<R>(c, L, wt_acquire(c, slot, n, l0, k, h), dcur, ldc, Xin, ldin, dn, ldh, hact);
       dcur = dn; ldc = ldh;
     } else if (dXo) {
       layer_bwd_img<R>(c, L, wt_acquire(c, slot, n, l0, k, next), dcur, ldc, nullptr, 0, dXo, lddx);

@@ -154,6 +154,7 @@ typedef struct {
   int out_cols;
   int layer_norm;           /* MAPPO nets: F.layer_norm on the input and after each hidden ReLU */
   const float* obs_norm;    /* dev [3][obs_dim] {mean, S, std} Batch_ObsNorm state applied with update=False, or NULL */
+  int hidden_tanh;          /* 1: tanh hidden activations (the `tanh` trick of PPO_file/PPO_with_tricks.py:95,172); 0: ReLU */
 } frl_infer_args_t;
 
 /* On-policy (PPO.py) minibatch update.  `net` holds actor (layers 0-2, + log_std extra when continuous) and critic
@@ -193,6 +194,7 @@ typedef struct {
   float* out;               /* dev [n_updates][8]: actor_loss, critic_loss, entropy, actor_gnorm, critic_gnorm */
   double lr_critic;         /* FRL_OPT_ADAM only: learning rate of the critic layers (separate actor / critic Adams of
                              * PPO_advance/PPO.py:118-119); 0 = use `lr` for both (merged optimiser) */
+  int hidden_tanh;          /* bit 0: actor, bit 1: critic use tanh hidden activations (PPO_with_tricks.py:95,172; not with layer_norm) */
 } frl_ppo_args_t;
 
 /* Rainbow (DQN_with_tricks.py): Categorical + Dueling + Noisy net.  The trainable block holds the torch tensors;

@@ -110,11 +110,12 @@ def _leaf(net):
 # --------------------------------------------------------------------------------------------------
 # network forward passes (functional)
 # --------------------------------------------------------------------------------------------------
-def mlp2(net, x, names=("l1", "l2", "l3")):
-    """relu(l1) -> relu(l2) -> l3 (linear), the 128-128 body every actor / critic uses."""
+def mlp2(net, x, names=("l1", "l2", "l3"), act=F.relu):
+    """relu(l1) -> relu(l2) -> l3 (linear), the 128-128 body every actor / critic uses (``act=torch.tanh``: the ``tanh`` switch of
+    ``PPO_file/PPO_with_tricks.py:95,172``)."""
     a, b, c = names
-    h = F.relu(F.linear(x, net[a + ".weight"], net[a + ".bias"]))
-    h = F.relu(F.linear(h, net[b + ".weight"], net[b + ".bias"]))
+    h = act(F.linear(x, net[a + ".weight"], net[a + ".bias"]))
+    h = act(F.linear(h, net[b + ".weight"], net[b + ".bias"]))
     return F.linear(h, net[c + ".weight"], net[c + ".bias"])
 
 
@@ -353,14 +354,17 @@ def gae_reference(td_delta, adv_dones, gamma, lmbda):
     return adv
 
 
-def ppo_actor_cont(net, obs):
+def ppo_actor_cont(net, obs, act=F.relu):
     """``PPO_file/PPO.py:58-76``: mean = tanh(mean_layer(.)), std = exp(clamp(log_std))."""
-    mean = torch.tanh(mlp2(net, obs, ("l1", "l2", "mean_layer")))
+    mean = torch.tanh(mlp2(net, obs, ("l1", "l2", "mean_layer"), act=act))
     std = torch.exp(torch.clamp(net["log_std"].expand_as(mean), -20, 2))
     return mean, std
 
 
 class PPOOracle:
+    act = staticmethod(F.relu)          # critic hidden activation (PPOTricksOracle(tanh=True) switches to torch.tanh)
+    act_actor = staticmethod(F.relu)    # actor hidden activation (tanh only for the continuous actor: Actor_discrete has no switch)
+
     def __init__(self, actor, critic, lr, is_continue):
         self.actor, self.critic = _leaf(actor), _leaf(critic)
         self.is_continue = is_continue
@@ -370,8 +374,8 @@ class PPOOracle:
     def advantages(self, data, gamma, lmbda):
         obs, action, reward, next_obs, done, logp_old, adv_dones = data
         with torch.no_grad():
-            vs = mlp2(self.critic, obs)
-            vs_ = mlp2(self.critic, next_obs)
+            vs = mlp2(self.critic, obs, act=self.act)
+            vs_ = mlp2(self.critic, next_obs, act=self.act)
             td = reward + gamma * (1.0 - done) * vs_ - vs
             adv = gae_reference(td.reshape(-1).numpy(), adv_dones.reshape(-1).numpy(), gamma, lmbda)
             adv = torch.as_tensor(adv, dtype=torch.float32).reshape(-1, 1)
@@ -429,12 +433,12 @@ class PPOAdvanceOracle(PPOOracle):
     def minibatch(self, data, adv, v_target, index, clip_param, entropy_coefficient):
         obs, action, reward, next_obs, done, logp_old, adv_dones = data
         if self.is_continue:
-            mean, std = ppo_actor_cont(self.actor, obs[index])
+            mean, std = ppo_actor_cont(self.actor, obs[index], act=self.act_actor)
             dist = torch.distributions.Normal(mean, std)
             ent = dist.entropy().sum(dim=1, keepdim=True)
             logp = dist.log_prob(action[index])
         else:
-            dist = torch.distributions.Categorical(probs=torch.softmax(mlp2(self.actor, obs[index]), dim=1))
+            dist = torch.distributions.Categorical(probs=torch.softmax(mlp2(self.actor, obs[index], act=self.act_actor), dim=1))
             ent = dist.entropy().reshape(-1, 1)
             logp = dist.log_prob(action[index].reshape(-1)).reshape(-1, 1)
         ratios = torch.exp(logp.sum(dim=1, keepdim=True) - logp_old[index].sum(dim=1, keepdim=True))
@@ -444,7 +448,7 @@ class PPOAdvanceOracle(PPOOracle):
         ap = list(self.actor.values())
         ga, _ = clip_grad_norm(torch.autograd.grad(actor_loss, ap), 0.5)
         adam_step(ap, list(ga), self.opt_a)
-        v_s = mlp2(self.critic, obs[index])
+        v_s = mlp2(self.critic, obs[index], act=self.act)
         critic_loss = F.mse_loss(v_target[index], v_s)
         cp = list(self.critic.values())
         gc, _ = clip_grad_norm(torch.autograd.grad(critic_loss, cp), 0.5)
@@ -457,8 +461,12 @@ class PPOTricksOracle(PPOAdvanceOracle):
     ``PPOAdvanceOracle`` plus ``adam_eps`` (both Adams eps 1e-5, ``:198-200``), ``adv_norm`` (``:314-315``) and ``lr_decay``
     (``:356-362``)."""
 
-    def __init__(self, actor, critic, actor_lr, critic_lr, is_continue, adam_eps=False, adv_norm=False):
+    def __init__(self, actor, critic, actor_lr, critic_lr, is_continue, adam_eps=False, adv_norm=False, tanh=False):
         super().__init__(actor, critic, actor_lr, critic_lr, is_continue)
+        if tanh:
+            self.act = torch.tanh
+            if is_continue:
+                self.act_actor = torch.tanh
         self.actor_lr, self.critic_lr, self.adv_norm = actor_lr, critic_lr, adv_norm
         if adam_eps:
             self.opt_a.eps = self.opt_c.eps = 1e-5

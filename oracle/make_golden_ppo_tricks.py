@@ -1,6 +1,6 @@
 """Golden fixtures for ``PPO_file/PPO_with_tricks.py`` with tricks adv_norm + orthogonal_init + adam_eps + lr_decay.
 
-    python -m oracle.make_golden_ppo_tricks     # writes tests/golden/ppo_tricks_{cont,disc}.npz
+    python -m oracle.make_golden_ppo_tricks     # writes tests/golden/ppo_tricks_{cont,disc}.npz and ppo_tricks_tanh_{cont,disc}.npz (the `tanh` switch on)
 
 The reference file is run UNMODIFIED except for one call it cannot execute: ``np.zeros(self.horizon, dtype=torch.float32)``
 (``:302``) raises ``TypeError`` under every NumPy.  The module's ``np`` name is rebound to a proxy whose ``zeros`` maps a torch dtype
@@ -33,14 +33,14 @@ class _NpProxy:
         return np.zeros(shape, dtype=dtype)
 
 
-def gen(is_continue):
+def gen(is_continue, tanh=False):
     m = refload.load("PPO_file", "PPO_with_tricks")
     m.np = _NpProxy()
     seed, horizon, mb, K = 13, 256, 64, 2
     obs_dim, act_dim = 8, (2 if is_continue else 4)
     np.random.seed(seed)
     torch.manual_seed(seed)
-    policy = m.PPO([obs_dim, act_dim], is_continue, 1e-3, 5e-4, horizon, torch.device("cpu"), trick=dict(TRICK))
+    policy = m.PPO([obs_dim, act_dim], is_continue, 1e-3, 5e-4, horizon, torch.device("cpu"), trick=dict(TRICK, tanh=tanh))
     rng = np.random.default_rng(seed)
     rec = {}
     rec.update(sd_np(policy.agent.actor, "init/actor/"))
@@ -69,7 +69,7 @@ def gen(is_continue):
         rec.update(sd_np(policy.agent.critic, "after%d/critic/" % r))
     log = [v[0] for _, v in tap.log]
     rec["losses"] = np.array(list(zip(log[0::2], log[1::2])), np.float64)          # (actor, critic) per minibatch, both learns
-    name = "ppo_tricks_cont" if is_continue else "ppo_tricks_disc"
+    name = ("ppo_tricks_tanh_" if tanh else "ppo_tricks_") + ("cont" if is_continue else "disc")
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
     print(name, "ok", rec["losses"][:2], rec["losses"].shape)
 
@@ -78,3 +78,5 @@ if __name__ == "__main__":
     torch.set_num_threads(1)
     gen(True)
     gen(False)
+    gen(True, tanh=True)
+    gen(False, tanh=True)

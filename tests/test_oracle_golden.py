@@ -218,11 +218,11 @@ def test_choice_stream(golden):
     assert np.array_equal(buffers.uniform_indices(50, 50), g["choice/seed0_next_50_50"])
 
 
-def _ppo_tricks(golden, name, is_continue):
+def _ppo_tricks(golden, name, is_continue, tanh=False):
     """PPO_file/PPO_with_tricks.py (adv_norm + orthogonal_init + adam_eps + lr_decay; np.zeros call patched at generation time) replayed
     through oracle.algos.PPOTricksOracle: two learns with lr_decay(10, 100) after each"""
     g = golden(name)
-    o = algos.PPOTricksOracle(net(g, "init/actor/"), net(g, "init/critic/"), 1e-3, 5e-4, is_continue, adam_eps=True, adv_norm=True)
+    o = algos.PPOTricksOracle(net(g, "init/actor/"), net(g, "init/critic/"), 1e-3, 5e-4, is_continue, adam_eps=True, adv_norm=True, tanh=tanh)
     losses_ = []
     for r in range(2):
         data = tuple(torch.from_numpy(g["data%d/%s" % (r, k)]) for k in ("obs", "act", "rew", "nobs", "done", "logp", "adv_done"))
@@ -239,3 +239,8 @@ def test_ppo_with_tricks_continuous(golden):
 
 def test_ppo_with_tricks_discrete(golden):
     _ppo_tricks(golden, "ppo_tricks_disc", False)
+
+
+def test_ppo_with_tricks_tanh(golden):
+    _ppo_tricks(golden, "ppo_tricks_tanh_cont", True, tanh=True)
+    _ppo_tricks(golden, "ppo_tricks_tanh_disc", False, tanh=True)       # Actor_discrete keeps ReLU, the critic switches

@@ -110,13 +110,13 @@ TRICKS = {'adv_norm': True, 'ObsNorm': False, 'Batch_ObsNorm': False, 'reward_no
           'lr_decay': True, 'orthogonal_init': True, 'adam_eps': True, 'tanh': False}
 
 
-def _ppo_tricks(golden, device, name, is_continue):
+def _ppo_tricks(golden, device, name, is_continue, tanh=False):
     """freerl_b200.PPO_with_tricks (adv_norm via frl_adv_norm, Adam eps 1e-5, lr_decay, orthogonal init) vs oracle + the fixture
     generated from PPO_file/PPO_with_tricks.py: two rollouts / learns with lr_decay(10, 100) in between"""
     from freerl_b200.PPO_with_tricks import PPO
     g = golden(name)
     act_dim = 2 if is_continue else 4
-    pol = PPO([8, act_dim], is_continue, 1e-3, 5e-4, 256, device, trick=dict(TRICKS))
+    pol = PPO([8, act_dim], is_continue, 1e-3, 5e-4, 256, device, trick=dict(TRICKS, tanh=tanh))
     # orthogonal init went through the module constructors: zero biases, orthonormal rows / columns (gain 1; 0.01 on the Gaussian head)
     sd = pol.agent.critic.state_dict()
     w = sd["l2.weight"].cpu().double()
@@ -127,7 +127,7 @@ def _ppo_tricks(golden, device, name, is_continue):
     load_into(pol.agent.actor, net_from_golden(g, "init/actor/"))
     load_into(pol.agent.critic, net_from_golden(g, "init/critic/"))
     orc = algos.PPOTricksOracle(net_from_golden(g, "init/actor/"), net_from_golden(g, "init/critic/"), 1e-3, 5e-4, is_continue,
-                                adam_eps=True, adv_norm=True)
+                                adam_eps=True, adv_norm=True, tanh=tanh)
     tol = dict(rtol=3e-5, atol=4e-6)
     for r in range(2):
         data = tuple(torch.from_numpy(g["data%d/%s" % (r, k)]) for k in ("obs", "act", "rew", "nobs", "done", "logp", "adv_done"))
@@ -147,7 +147,7 @@ def _ppo_tricks(golden, device, name, is_continue):
         assert_module_close(pol.agent.actor, net_from_golden(g, "after%d/actor/" % r), "actor vs reference", tol)
         assert_module_close(pol.agent.critic, net_from_golden(g, "after%d/critic/" % r), "critic vs reference", tol)
     with pytest.raises(NotImplementedError):
-        PPO([8, act_dim], is_continue, 1e-3, 5e-4, 256, device, trick=dict(TRICKS, tanh=True))
+        PPO([8, act_dim], is_continue, 1e-3, 5e-4, 256, device, trick=dict(TRICKS, Batch_ObsNorm=True))
     with pytest.raises(NotImplementedError):
         PPO([8, act_dim], is_continue, 1e-3, 5e-4, 256, device, trick=dict(TRICKS), beta=True)
 
@@ -158,6 +158,17 @@ def test_ppo_with_tricks_continuous_emulated(golden, emul):
 
 def test_ppo_with_tricks_discrete_emulated(golden, emul):
     _ppo_tricks(golden, torch.device("cpu"), "ppo_tricks_disc", False)
+
+
+def test_ppo_with_tricks_tanh_emulated(golden, emul):
+    _ppo_tricks(golden, torch.device("cpu"), "ppo_tricks_tanh_cont", True, tanh=True)
+    _ppo_tricks(golden, torch.device("cpu"), "ppo_tricks_tanh_disc", False, tanh=True)
+
+
+@pytest.mark.gpu
+def test_ppo_with_tricks_tanh_gpu(golden):
+    _ppo_tricks(golden, torch.device("cuda"), "ppo_tricks_tanh_cont", True, tanh=True)
+    _ppo_tricks(golden, torch.device("cuda"), "ppo_tricks_tanh_disc", False, tanh=True)
 
 
 @pytest.mark.gpu
