@@ -96,10 +96,10 @@ FRL_NI_MISC void ln_bwd(const float* dY, const float* Y, const float* rstd, cons
 // activations kept by one 3-layer net pass (layer-norm variant keeps both the ReLU outputs and their normalised copies)
 struct NetBufs { float *X0, *H1, *H1n, *H2, *H2n, *rs1, *rs2, *scratch; };
 
-template <int R>
+template <int R, int HM = 0>
 FRL_DEV void net_fwd(Cta& c, const frl_net_t& N, int l0, bool ln, const float* Xin, int ip, int n_in, const NetBufs& b, int ldh,
-                     float* OUT, int ldo, Hint next, int hact = FRL_ACT_RELU) {
-  if (!ln) { mlp_fwd<R>(c, N, l0, 3, Xin, ip, b.H1, b.H2, ldh, OUT, ldo, FRL_ACT_NONE, next, -1, hact); return; }
+                     float* OUT, int ldo, Hint next) {
+  if (!ln) { mlp_fwd<R, HM>(c, N, l0, 3, Xin, ip, b.H1, b.H2, ldh, OUT, ldo, FRL_ACT_NONE, next); return; }
   ln_fwd<R>(Xin, ip, n_in, b.X0, b.rs1, b.scratch);                       // feature_norm (rstd not needed later)
   layer_fwd<R>(c, N, l0, b.X0, ip, b.H1, ldh, FRL_ACT_RELU, fwd_hint(N, l0 + 1));
   ln_fwd<R>(b.H1, ldh, N.L[l0].out, b.H1n, b.rs1, b.scratch);
@@ -108,10 +108,10 @@ FRL_DEV void net_fwd(Cta& c, const frl_net_t& N, int l0, bool ln, const float* X
   layer_fwd<R>(c, N, l0 + 2, b.H2n, ldh, OUT, ldo, FRL_ACT_NONE, next);
 }
 
-template <int R>
+template <int R, int HM = 0>
 FRL_DEV void net_bwd(Cta& c, const frl_net_t& N, int l0, bool ln, const float* Xin, int ip, const NetBufs& b, int ldh, const float* dOUT,
-                     int ldo, float* D1, float* D2, float* gp, bool accumulate, Hint next, int hact = FRL_ACT_RELU) {
-  if (!ln) { mlp_bwd<R>(c, N, l0, 3, Xin, ip, b.H1, b.H2, ldh, dOUT, ldo, D1, D2, nullptr, 0, gp, accumulate, next, -1, hact); return; }
+                     int ldo, float* D1, float* D2, float* gp, bool accumulate, Hint next) {
+  if (!ln) { mlp_bwd<R, HM>(c, N, l0, 3, Xin, ip, b.H1, b.H2, ldh, dOUT, ldo, D1, D2, nullptr, 0, gp, accumulate, next); return; }
   const frl_layer_t &L0 = N.L[l0], &L1 = N.L[l0 + 1], &L2 = N.L[l0 + 2];
   gemm_outer<R>(dOUT, ldo, L2.out_pad, b.H2n, ldh, L2.in_pad, L2.in, gp + L2.w_off, gp + L2.b_off, accumulate);
   layer_bwd_dx<R>(c, N, l0 + 2, dOUT, ldo, nullptr, 0, D2, ldh, bwd_hint(N, l0 + 1));
@@ -124,7 +124,9 @@ FRL_DEV void net_bwd(Cta& c, const frl_net_t& N, int l0, bool ln, const float* X
 
 // R = batch rows per CTA tile: 8 for the reference-sized minibatches (more CTAs per minibatch), 16 for large minibatches
 // (>= 1024 rows: twice the FMAs per staged weight and per barrier; chosen by frl_ppo_update when the tile fits in shared memory).
-template <int R>
+// HM (compile time): the `tanh` switch of PPO_with_tricks.py — bit 0: actor, bit 1: critic hidden layers use tanh.  HM = 0 is the
+// kernel every other PPO-family class launches; the tanh instantiations exist for 8-row tiles only.
+template <int R, int HM = 0>
 struct PpoAlgoT {
   typedef frl_ppo_args_t Args;
   static const int NSTAGES = 5;
@@ -155,7 +157,6 @@ struct PpoAlgoT {
     SmemBump sb; sb.p = user;
     const int cip = N.L[3].in_pad;
     const bool ln = a.layer_norm != 0;
-    const int hact_a = (a.hidden_tanh & 1) ? FRL_ACT_TANH : FRL_ACT_RELU, hact_c = (a.hidden_tanh & 2) ? FRL_ACT_TANH : FRL_ACT_RELU;
     float* X = sb.take(R * ip);
     float* XC = sb.take(R * cip);       // critic input tile (joint obs for MAPPO, else a copy of X)
     NetBufs ba, bc;
@@ -221,8 +222,8 @@ struct PpoAlgoT {
         }
         FRL_SYNC();
         const int c_in = a.critic_obs ? a.critic_obs_dim : a.obs_dim;
-        net_fwd<R>(c, N, 0, ln, X, ip, a.obs_dim, ba, ldh, OA, ap, fwd_hint(N, 3), hact_a);
-        net_fwd<R>(c, N, 3, ln, XC, cip, c_in, bc, ldh, V, 4, bwd_hint(N, 2), hact_c);
+        net_fwd<R, (HM & 1)>(c, N, 0, ln, X, ip, a.obs_dim, ba, ldh, OA, ap, fwd_hint(N, 3));
+        net_fwd<R, ((HM >> 1) & 1)>(c, N, 3, ln, XC, cip, c_in, bc, ldh, V, 4, bwd_hint(N, 2));
         // policy head: log-prob, entropy, ratio, clipped surrogate and its gradient w.r.t. the actor output
         FRL_PAR(t) {
           float sa = 0.f, se = 0.f;
@@ -342,8 +343,8 @@ struct PpoAlgoT {
           }
           FRL_SYNC();
         }
-        net_bwd<R>(c, N, 0, ln, X, ip, ba, ldh, dOA, ap, D1, D2, gp, !first, bwd_hint(N, 5), hact_a);
-        net_bwd<R>(c, N, 3, ln, XC, cip, bc, ldh, dV, 4, D1, D2, gp, !first, no_hint(), hact_c);
+        net_bwd<R, (HM & 1)>(c, N, 0, ln, X, ip, ba, ldh, dOA, ap, D1, D2, gp, !first, bwd_hint(N, 5));
+        net_bwd<R, ((HM >> 1) & 1)>(c, N, 3, ln, XC, cip, bc, ldh, dV, 4, D1, D2, gp, !first, no_hint());
         first = false;
       }
       FRL_PAR(t) {

@@ -443,7 +443,8 @@ extern "C" int frl_polyak(const frl_net_t* src, const frl_net_t* target, float t
 // ------------------------------------------------------------------------------------------------
 // batched policy inference (select_action / evaluate_action for N vectorised envs)
 // ------------------------------------------------------------------------------------------------
-struct InferAlgo {
+template <int HM>      // HM = 1: tanh hidden activations (frl_infer_args_t.hidden_tanh); 0: the kernel every other caller launches
+struct InferAlgoT {
   typedef frl_infer_args_t Args;
   static const int NSTAGES = 1;
   FRL_SHD int nl_of(const Args& a) { return a.nl > 0 ? a.nl : a.net.n_layers; }
@@ -480,7 +481,7 @@ struct InferAlgo {
     }
     FRL_SYNC();
     if (a.layer_norm && nl == 3) net_fwd<FRL_R>(c, n, l0, true, X, in_pad, a.obs_dim, nb, ldh, O, op, no_hint());
-    else mlp_fwd<FRL_R>(c, n, l0, nl, X, in_pad, H1, H2, ldh, O, op, FRL_ACT_NONE, no_hint(), -1, a.hidden_tanh ? FRL_ACT_TANH : FRL_ACT_RELU);
+    else mlp_fwd<FRL_R, HM>(c, n, l0, nl, X, in_pad, H1, H2, ldh, O, op, FRL_ACT_NONE, no_hint());
     FRL_PAR(t) {
       if (a.mode == FRL_INFER_ARGMAX) {
         if (t < nvalid) {
@@ -550,10 +551,16 @@ struct InferAlgo {
   }
 };
 
+typedef InferAlgoT<0> InferAlgo;
+
 extern "C" int frl_policy_infer(const frl_infer_args_t* a, void* stream) {
   if (!a || !a->obs || !a->out || a->n <= 0 || a->l0 < 0 || a->l0 + (a->nl > 0 ? a->nl : a->net.n_layers) > a->net.n_layers) {
     frl_set_error("frl_policy_infer: bad arguments");
     return -1;
+  }
+  if (a->hidden_tanh) {
+    if (a->layer_norm) { frl_set_error("frl_policy_infer: hidden_tanh is not available with layer_norm"); return -1; }
+    return frl_launch_tiles<InferAlgoT<1> >(*a, (cudaStream_t)stream);
   }
   return frl_launch_tiles<InferAlgo>(*a, (cudaStream_t)stream);
 }
@@ -632,6 +639,11 @@ extern "C" int frl_ppo_update(const frl_ppo_args_t* a, void* stream) {
   if (a->net.n_layers != 6 || (a->continuous && a->net.x_len <= 0)) {
     frl_set_error("frl_ppo_update: net must hold actor (layers 0-2) + critic (layers 3-5)");
     return -1;
+  }
+  if (a->hidden_tanh) {          // tanh hidden activations (PPO_with_tricks): compile-time variants of the 8-row-tile kernel
+    if ((a->hidden_tanh & 3) == 3) return frl_launch<PpoAlgoT<8, 3> >(*a, (cudaStream_t)stream);
+    if (a->hidden_tanh & 2) return frl_launch<PpoAlgoT<8, 2> >(*a, (cudaStream_t)stream);
+    return frl_launch<PpoAlgoT<8, 1> >(*a, (cudaStream_t)stream);
   }
   // 16-row tiles for large minibatches when they fit in shared memory (checked with the launcher's own formula)
   if (a->mb >= 1024) {

@@ -338,13 +338,16 @@ FRL_DEV float lds1(const float* p) { return *p; }
 #endif
 FRL_DEV float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
+// (The GEMMs below are templated on HM only to give the tanh variants of the PPO update / inference their OWN instantiations: in
+// the HM = 0 ones no caller ever passes FRL_ACT_TANH, so the compiler's whole-program constant propagation drops the tanh branch
+// from the shared epilogues exactly as it did before the `tanh` switch existed.)
 FRL_DEV float apply_act(float v, int act) {
   if (act == FRL_ACT_RELU) return v > 0.f ? v : 0.f;
   if (act == FRL_ACT_TANH) return tanhf(v);
   return v;
 }
 
-enum { EPI_BIAS_ACT = 0, EPI_RELU_MASK = 1, EPI_TANH_MASK = 2 };   // TANH_MASK: acc * (1 - mask^2), mask = stored tanh output
+enum { EPI_BIAS_ACT = 0, EPI_RELU_MASK = 1 };
 
 // ------------------------------------------------------------------------------------------------
 // Shared-memory "word address" helpers.  The GEMM microkernels do all smem pointer arithmetic in 32-bit word
@@ -415,7 +418,10 @@ FRL_DEV unsigned div_fast(unsigned t, unsigned d) { return t / d; }   // (a powe
 //  the fully inlined build was 490 KB of SASS and spent most cycles in `no_instruction` stalls.)
 // ------------------------------------------------------------------------------------------------
 // fixed-order reduction of the K-split partials red[ks][R][N_pad] + epilogue -> C   (second phase of gemm_rk / gemm_nt)
-template <int R>
+// HM (compile time, default 0): what a MASK epilogue means — 0: relu'(mask) = mask > 0; 1: tanh'(mask) = 1 - mask^2 (the `tanh`
+// switch of PPO_file/PPO_with_tricks.py).  A template parameter, not a run-time one: the HM = 0 instantiations — every kernel
+// except the tanh variants of the PPO update / inference — compile to exactly the code they had before the switch existed.
+template <int R, int HM = 0>
 FRL_DEV void gemm_finish(sptr sR, unsigned ksplit, int N_pad, int epi, int act, bool has_bias, sptr sBias, sptr sM, int ldm,
                          sptr sC, int ldc) {
   const unsigned nt = (unsigned)N_pad >> 2;
@@ -435,7 +441,7 @@ FRL_DEV void gemm_finish(sptr sR, unsigned ksplit, int N_pad, int epi, int act, 
           if (has_bias) { const float4 bv = sp_ld4(sBias, n0); o[0] += bv.x; o[1] += bv.y; o[2] += bv.z; o[3] += bv.w; }
 #pragma unroll
           for (int q = 0; q < 4; ++q) o[q] = apply_act(o[q], act);
-        } else if (epi == EPI_TANH_MASK) {
+        } else if (HM) {
           const float4 mv = sp_ld4(sM, (int)r * ldm + n0);
           o[0] = o[0] * (1.f - mv.x * mv.x); o[1] = o[1] * (1.f - mv.y * mv.y);
           o[2] = o[2] * (1.f - mv.z * mv.z); o[3] = o[3] * (1.f - mv.w * mv.w);
@@ -454,7 +460,7 @@ FRL_DEV void gemm_finish(sptr sR, unsigned ksplit, int N_pad, int epi, int act, 
 }
 
 #ifndef FRL_MMA
-template <int R>
+template <int R, int HM = 0>
 FRL_NI_GEMM void gemm_rk(float* red, const float* A, int lda, int K_pad, const float* Bs, int ldb, int N_pad, const float* bias,
                          int epi, int act, const float* mask, int ldm, float* C, int ldc) {
   constexpr unsigned RT = R / 4, RT_SH = (RT == 1 ? 0 : (RT == 2 ? 1 : 2));
@@ -528,7 +534,7 @@ FRL_NI_GEMM void gemm_rk(float* red, const float* A, int lda, int K_pad, const f
   trace(51);
   FRL_SYNC();
   trace(52);
-  if (ksplit > 1) gemm_finish<R>(sR, ksplit, N_pad, epi, act, has_bias, sBias, sM, ldm, sC, ldc);
+  if (ksplit > 1) gemm_finish<R, HM>(sR, ksplit, N_pad, epi, act, has_bias, sBias, sM, ldm, sC, ldc);
   trace(53);
 }
 
@@ -540,7 +546,7 @@ FRL_NI_GEMM void gemm_rk(float* red, const float* A, int lda, int K_pad, const f
 //   2^sh_n ways across the CTA; the partials take the same fixed-order reduction + epilogue as gemm_rk.
 //   epi: EPI_RELU_MASK (mask = stored activation) or EPI_BIAS_ACT with act NONE / no bias (plain product).
 // ------------------------------------------------------------------------------------------------
-template <int R>
+template <int R, int HM = 0>
 FRL_NI_GEMM void gemm_nt(float* red, const float* A, int lda, int N_red, const float* Bs, int ldb, int K_out, int epi,
                          const float* mask, int ldm, float* C, int ldc) {
   constexpr unsigned RT = R / 4, RT_SH = (RT == 1 ? 0 : (RT == 2 ? 1 : 2));
@@ -597,8 +603,10 @@ FRL_NI_GEMM void gemm_nt(float* red, const float* A, int lda, int N_red, const f
           for (int j = 0; j < 4; ++j) {
             const int k = (int)kl + j * (int)KL;
             float v = acc[i][j];
-            if (epi == EPI_RELU_MASK) v = (sp_ld1(sM, (r0 + i) * ldm + k) > 0.f) ? v : 0.f;
-            else if (epi == EPI_TANH_MASK) { const float m = sp_ld1(sM, (r0 + i) * ldm + k); v = v * (1.f - m * m); }
+            if (epi == EPI_RELU_MASK) {
+              if (HM) { const float m = sp_ld1(sM, (r0 + i) * ldm + k); v = v * (1.f - m * m); }
+              else v = (sp_ld1(sM, (r0 + i) * ldm + k) > 0.f) ? v : 0.f;
+            }
             sp_st1(sC, (r0 + i) * ldc + k, v);
           }
       } else {
@@ -612,7 +620,7 @@ FRL_NI_GEMM void gemm_nt(float* red, const float* A, int lda, int N_red, const f
   trace(61);
   FRL_SYNC();
   trace(62);
-  if (nsplit > 1) gemm_finish<R>(sR, nsplit, K_out, epi, FRL_ACT_NONE, false, sB, sM, ldm, sC, ldc);
+  if (nsplit > 1) gemm_finish<R, HM>(sR, nsplit, K_out, epi, FRL_ACT_NONE, false, sB, sM, ldm, sC, ldc);
   trace(63);
 }
 
@@ -761,7 +769,7 @@ FRL_DEV void mma_tile(uint32_t wB, int wsm, int wsk, uint32_t xB, int ldx, int M
 }
 
 // C[r][n] = epi( sum_k A[r][k] * Bs[k][n] (+ bias[n]) )    (same contract as the FFMA gemm_rk; `red` unused)
-template <int R>
+template <int R, int HM = 0>
 FRL_NI_GEMM void gemm_rk(float* red, const float* A, int lda, int K_pad, const float* Bs, int ldb, int N_pad, const float* bias,
                          int epi, int act, const float* mask, int ldm, float* C, int ldc) {
   static_assert(R == 8, "the tensor-core path maps the batch tile onto the n = 8 side of m16n8k8");
@@ -792,7 +800,7 @@ FRL_NI_GEMM void gemm_rk(float* red, const float* A, int lda, int K_pad, const f
 }
 
 // C[r][k] = epi( sum_n A[r][n] * Bs[k][n] )   (backward dX on the forward image; same contract as the FFMA gemm_nt)
-template <int R>
+template <int R, int HM = 0>
 FRL_NI_GEMM void gemm_nt(float* red, const float* A, int lda, int N_red, const float* Bs, int ldb, int K_out, int epi,
                          const float* mask, int ldm, float* C, int ldc) {
   static_assert(R == 8, "tensor-core path: R == 8");
@@ -809,8 +817,10 @@ FRL_NI_GEMM void gemm_nt(float* red, const float* A, int lda, int N_red, const f
       const int i = mt * 16 + g + ((q & 2) ? 8 : 0), r = 2 * t + (q & 1);
       if (i < K_out) {
         float v = v4[q];
-        if (epi == EPI_RELU_MASK) v = (sp_ld1(sM, r * ldm + i) > 0.f) ? v : 0.f;
-        else if (epi == EPI_TANH_MASK) { const float m = sp_ld1(sM, r * ldm + i); v = v * (1.f - m * m); }
+        if (epi == EPI_RELU_MASK) {
+          if (HM) { const float m = sp_ld1(sM, r * ldm + i); v = v * (1.f - m * m); }
+          else v = (sp_ld1(sM, r * ldm + i) > 0.f) ? v : 0.f;
+        }
         sp_st1(sC, r * ldc + i, v);
       }
     }
@@ -983,16 +993,15 @@ FRL_DEV const float* wt_acquire(Cta& c, int slot, const frl_net_t& n, int l0, in
 }
 
 // Y = act(X W^T + b) on a staged layer image
-template <int R>
+template <int R, int HM = 0>
 FRL_DEV void layer_fwd_img(Cta& c, const frl_layer_t& L, const float* Bs, const float* X, int ldx, float* Y, int ldy, int act) {
-  gemm_rk<R>(c.red, X, ldx, L.in_pad, Bs, wt_ld(L), L.out_pad, Bs + wt_bias(L), EPI_BIAS_ACT, act, nullptr, 0, Y, ldy);
+  gemm_rk<R, HM>(c.red, X, ldx, L.in_pad, Bs, wt_ld(L), L.out_pad, Bs + wt_bias(L), EPI_BIAS_ACT, act, nullptr, 0, Y, ldy);
 }
 // dX = (dY W) * relu'(mask)   (mask == nullptr: no activation derivative) on the same forward image
-template <int R>
+template <int R, int HM = 0>
 FRL_DEV void layer_bwd_img(Cta& c, const frl_layer_t& L, const float* Bs, const float* dY, int ldy, const float* mask, int ldm,
-                           float* dX, int ldx, int hact = FRL_ACT_RELU) {
-  gemm_nt<R>(c.red, dY, ldy, L.out_pad, Bs, wt_ld(L), L.in_pad, mask ? (hact == FRL_ACT_TANH ? EPI_TANH_MASK : EPI_RELU_MASK) : EPI_BIAS_ACT,
-             mask, ldm, dX, ldx);
+                           float* dX, int ldx) {
+  gemm_nt<R, HM>(c.red, dY, ldy, L.out_pad, Bs, wt_ld(L), L.in_pad, mask ? EPI_RELU_MASK : EPI_BIAS_ACT, mask, ldm, dX, ldx);
 }
 
 // Streaming flavours.  `next` is what the caller will need after this layer (prefetched during the math).
@@ -1006,18 +1015,18 @@ FRL_DEV void layer_bwd_dx(Cta& c, const frl_net_t& n, int li, const float* dY, i
   layer_bwd_img<R>(c, n.L[li], wt_acquire(c, -1, n, li, 0, next), dY, ldy, mask, ldm, dX, ldx);
 }
 
-// MLP forward over layers [l0, l0+nl): hidden layers `hact` (ReLU unless a caller asks for tanh), last layer `act_out`.
+// MLP forward over layers [l0, l0+nl): hidden layers ReLU (HM = 1: tanh), last layer `act_out`.
 //   nl == 3: H1 = relu(l0 X), H2 = relu(l1 H1), OUT = act(l2 H2);   nl == 2: H1 = relu(l0 X), OUT = act(l1 H1).
 //   slot >= 0: the head is resident in that slot (res_fetch was issued by the caller); slot < 0: streaming.
-template <int R>
+template <int R, int HM = 0>
 FRL_NI_MLP void mlp_fwd(Cta& c, const frl_net_t& n, int l0, int nl, const float* X, int ldx, float* H1, float* H2, int ldh,
-                     float* OUT, int ldo, int act_out, Hint next, int slot = -1, int hact = FRL_ACT_RELU) {
+                     float* OUT, int ldo, int act_out, Hint next, int slot = -1) {
   if (nl == 3) {
-    layer_fwd_img<R>(c, n.L[l0], wt_acquire(c, slot, n, l0, 0, fwd_hint(n, l0 + 1)), X, ldx, H1, ldh, hact);
-    layer_fwd_img<R>(c, n.L[l0 + 1], wt_acquire(c, slot, n, l0, 1, fwd_hint(n, l0 + 2)), H1, ldh, H2, ldh, hact);
+    layer_fwd_img<R, HM>(c, n.L[l0], wt_acquire(c, slot, n, l0, 0, fwd_hint(n, l0 + 1)), X, ldx, H1, ldh, HM ? FRL_ACT_TANH : FRL_ACT_RELU);
+    layer_fwd_img<R, HM>(c, n.L[l0 + 1], wt_acquire(c, slot, n, l0, 1, fwd_hint(n, l0 + 2)), H1, ldh, H2, ldh, HM ? FRL_ACT_TANH : FRL_ACT_RELU);
     layer_fwd_img<R>(c, n.L[l0 + 2], wt_acquire(c, slot, n, l0, 2, next), H2, ldh, OUT, ldo, act_out);
   } else {
-    layer_fwd_img<R>(c, n.L[l0], wt_acquire(c, slot, n, l0, 0, fwd_hint(n, l0 + 1)), X, ldx, H1, ldh, hact);
+    layer_fwd_img<R, HM>(c, n.L[l0], wt_acquire(c, slot, n, l0, 0, fwd_hint(n, l0 + 1)), X, ldx, H1, ldh, HM ? FRL_ACT_TANH : FRL_ACT_RELU);
     layer_fwd_img<R>(c, n.L[l0 + 1], wt_acquire(c, slot, n, l0, 1, next), H1, ldh, OUT, ldo, act_out);
   }
 }
@@ -1026,10 +1035,10 @@ FRL_NI_MLP void mlp_fwd(Cta& c, const frl_net_t& n, int l0, int nl, const float*
 //   gp  : this CTA's gradient partial for net n (n_p floats, same layout as n.p) or nullptr (no dW wanted)
 //   dXo : if non-null receives dL/dX [R][in_pad of layer l0]
 //   D1/D2: scratch [R][ldh] for the hidden-layer gradients.
-template <int R>
+template <int R, int HM = 0>
 FRL_NI_MLP void mlp_bwd(Cta& c, const frl_net_t& n, int l0, int nl, const float* X, int ldx, const float* H1, const float* H2,
                      int ldh, const float* dOUT, int ldo, float* D1, float* D2, float* dXo, int lddx, float* gp,
-                     bool accumulate, Hint next, int slot = -1, int hact = FRL_ACT_RELU) {
+                     bool accumulate, Hint next, int slot = -1) {
   const float* dcur = dOUT;
   int ldc = ldo;
   for (int k = nl - 1; k >= 0; --k) {
@@ -1041,7 +1050,7 @@ FRL_NI_MLP void mlp_bwd(Cta& c, const frl_net_t& n, int l0, int nl, const float*
     if (k > 0) {
       float* dn = (k == 2) ? D2 : D1;   // gradient wrt H2 (k==2) or H1 (k==1)
       Hint h = (k - 1 > 0 || dXo) ? bwd_hint(n, li - 1) : next;
-      layer_bwd_img<R>(c, L, wt_acquire(c, slot, n, l0, k, h), dcur, ldc, Xin, ldin, dn, ldh, hact);
+      layer_bwd_img<R, HM>(c, L, wt_acquire(c, slot, n, l0, k, h), dcur, ldc, Xin, ldin, dn, ldh);
       dcur = dn; ldc = ldh;
     } else if (dXo) {
       layer_bwd_img<R>(c, L, wt_acquire(c, slot, n, l0, k, next), dcur, ldc, nullptr, 0, dXo, lddx);
