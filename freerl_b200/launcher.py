@@ -19,6 +19,7 @@ _ALGOS = {            # script file name -> (class name in the script, our modul
     "DQN.py": ("DQN", "freerl_b200.DQN", "DQN"),
     "DQN_with_tricks.py": ("DQN", "freerl_b200.DQN_with_tricks", "DQN"),
     "SAC.py": ("SAC", "freerl_b200.SAC", "SAC"),
+    "SAC_add_discrete.py": ("SAC", "freerl_b200.SAC_add_discrete", "SAC"),
     "TD3.py": ("TD3", "freerl_b200.TD3", "TD3"),
     "DDPG.py": ("DDPG", "freerl_b200.DDPG", "DDPG"),
     "PPO.py": ("PPO", "freerl_b200.PPO", "PPO"),
@@ -59,14 +60,15 @@ def run_reference_script(script_path, argv=(), results_root="./freerl_runs", ext
         raise ValueError("no freerl_b200 class for %s (supported: %s)" % (fname, sorted(_ALGOS)))
     cls_name, mod_name, our_name = _ALGOS.get(qual) or _ALGOS[fname]
     sys.modules["Buffer"] = buffer_module()
-    try:
-        importlib.import_module("gymnasium")
-    except Exception:
+    def usable(name, attr):      # importable AND a real package (an empty placeholder left in sys.modules by other tooling is not)
+        try:
+            return hasattr(importlib.import_module(name), attr)
+        except Exception:
+            return False
+    if not usable("gymnasium", "make"):
         from . import envshim
         sys.modules["gymnasium"] = envshim.as_module()
-    try:
-        importlib.import_module("pettingzoo.mpe")
-    except Exception:
+    if not usable("pettingzoo.mpe", "__path__"):
         from . import envshim
         sys.modules.update(envshim.mpe_modules())
     for helper in ("Noisy_net", "normalization", "c_adamw", "util"):      # same module names, different contents per directory

@@ -91,3 +91,34 @@ def test_reference_ppo_with_tricks_script_unchanged(tmp_path, emul):
                                        ["--env_name", "Pendulum-v1", "--max_episodes", "2", "--horizon", "128", "--minibatch_size", "32",
                                         "--K_epochs", "2", "--device", "cpu"], results_root=str(tmp_path))
     assert type(ns["policy"]).__module__ == "freerl_b200.PPO_with_tricks" and ns["policy"].agent.step > 0
+
+
+def test_sac_add_discrete_continuous_is_sac(tmp_path, emul):
+    """SAC_file/SAC_add_discrete.py with a continuous action space is SAC.py statement for statement: the unmodified reference class,
+    driven exactly like oracle/make_golden.py::gen_sac, reproduces tests/golden/sac.npz bit for bit — which is what justifies
+    freerl_b200.SAC_add_discrete.SAC delegating to the SAC kernel path.  Then the unchanged script runs through the launcher."""
+    import tempfile
+    from oracle import make_golden as mg, refload
+    m = refload.load("SAC_file", "SAC_add_discrete")
+    m.is_continue = True          # the actor branch reads the script's module-level global (SAC_add_discrete.py:328)
+    trick = {"ObsNorm": False, "Batch_ObsNorm": False, "OUNoise": True, "GaussNoise": False}
+    old_out, mg.OUT = mg.OUT, tempfile.mkdtemp(dir=str(tmp_path))
+    try:
+        mg.gen_offpolicy("sacd", lambda: m.SAC([17, 6], True, 1e-3, 1e-3, 1000, torch.device("cpu"), trick=trick),
+                         lambda p, B: p.learn(B, 0.99, 0.01), 3, 64, 17, 6, 2,
+                         {"actor": lambda p: p.agent.actor, "critic": lambda p: p.agent.critic,
+                          "actor_target": lambda p: p.agent.actor_target, "critic_target": lambda p: p.agent.critic_target},
+                         extra=lambda p: {"final/log_alpha": np.array(p.alphas.log_alpha.item(), np.float64)})
+        got = dict(np.load(os.path.join(mg.OUT, "sacd.npz")))
+    finally:
+        mg.OUT = old_out
+    want = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "sac.npz")))
+    assert sorted(got) == sorted(want) and all(np.array_equal(got[k], want[k]) for k in want)
+    from freerl_b200 import launcher
+    ns = launcher.run_reference_script(os.path.join(REF, "SAC_file", "SAC_add_discrete.py"),
+                                       ["--env_name", "Pendulum-v1", "--max_episodes", "1", "--start_steps", "60", "--random_steps", "20",
+                                        "--batch_size", "32", "--buffer_size", "2000", "--device", "cpu"], results_root=str(tmp_path))
+    assert type(ns["policy"]).__module__ == "freerl_b200.SAC_add_discrete" and ns["policy"].agent.critic_step > 0
+    from freerl_b200.SAC_add_discrete import SAC
+    with pytest.raises(NotImplementedError):
+        SAC([4, 2], False, 1e-3, 1e-3, 1000, torch.device("cpu"), trick=trick)
