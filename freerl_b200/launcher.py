@@ -24,7 +24,8 @@ _ALGOS = {            # script file name -> (class name in the script, our modul
     "DDPG.py": ("DDPG", "freerl_b200.DDPG", "DDPG"),
     "PPO.py": ("PPO", "freerl_b200.PPO", "PPO"),
     "PPO_advance/PPO.py": ("PPO", "freerl_b200.PPO_advance", "PPO"),      # keyed by <dir>/<file> where names collide
-    "PPO_with_tricks.py": ("PPO", "freerl_b200.PPO_with_tricks", "PPO"),
+    "PPO_cc.py": ("PPO", "freerl_b200.PPO_advance", "PPO"),               # same classes as PPO_advance/PPO.py (only the train loop differs)
+    "PPO_with_tricks.py": ("PPO", "freerl_b200.PPO_with_tricks", "PPO"),  # PPO_file/ and PPO_advance/ hold the same classes
     "MADDPG.py": ("MADDPG", "freerl_b200.MADDPG", "MADDPG"),
     "MADDPG_simple.py": ("MADDPG", "freerl_b200.MADDPG_simple", "MADDPG"),
     "MATD3_simple.py": ("MATD3", "freerl_b200.MATD3_simple", "MATD3"),

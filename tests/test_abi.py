@@ -51,3 +51,42 @@ def test_product_path_refuses_cpu_and_missing_library(monkeypatch, tmp_path):
     with pytest.raises(RuntimeError, match="not found"):
         _lib.lib()
     monkeypatch.setattr(_lib, "_lib", None)
+
+
+def test_entry_points_reject_bad_arguments_without_touching_the_gpu():
+    """Error behaviour of the boundary: every function returns an int status, never throws; bad arguments give a negative
+    code and a thread-local message from frl_last_error().  Argument validation runs before any CUDA call, so this is checked on the
+    REAL CUDA library on a machine without a GPU."""
+    so = os.path.join(ROOT, "freerl_b200", "libfreerl_b200.so")
+    lib = ctypes.CDLL(so)
+    from freerl_b200 import _lib
+    _lib._declare(lib)
+    N = None
+    calls = {
+        "frl_replay_add_batch": lambda: lib.frl_replay_add_batch(N, 0, N, N, N, N, N, 4, N),
+        "frl_replay_gather": lambda: lib.frl_replay_gather(N, N, 4, N, N, N, N, N, N),
+        "frl_gae": lambda: lib.frl_gae(N, N, N, N, N, 8, 8, 0.99, 0.95, N, N, N),
+        "frl_adv_norm": lambda: lib.frl_adv_norm(N, 100, ctypes.c_float(1e-8), N, N),
+        "frl_dqn_learn": lambda: lib.frl_dqn_learn(N, N),
+        "frl_ac_learn": lambda: lib.frl_ac_learn(N, N),
+        "frl_ppo_update": lambda: lib.frl_ppo_update(N, N),
+        "frl_policy_infer": lambda: lib.frl_policy_infer(N, N),
+        "frl_rainbow_learn": lambda: lib.frl_rainbow_learn(N, N),
+        "frl_sumtree_update": lambda: lib.frl_sumtree_update(N, 16, N, N, N, 0.0, 0, 0, 4, N, N),
+        "frl_sumtree_update_td": lambda: lib.frl_sumtree_update_td(N, 16, N, N, ctypes.c_float(0.01), ctypes.c_float(0.5), 4, N, N),
+        "frl_vecnorm": lambda: lib.frl_vecnorm(N, 0, N, 0, 4, 3, 1, N, N, N),
+        "frl_reward_scaling": lambda: lib.frl_reward_scaling(N, 0, N, N, 1, 0.99, 4, N, N, N),
+        "frl_explore": lambda: lib.frl_explore(N, N),
+        "frl_masked_reset": lambda: lib.frl_masked_reset(N, N, 4, 1, 0.0, N),
+        "frl_epsilon_greedy": lambda: lib.frl_epsilon_greedy(N, 4, 2, 0.1, N, N, 0, 0, N, N),
+        "frl_dis_to_con": lambda: lib.frl_dis_to_con(N, 4, 11, 1, 0, N, N, N, N, N),
+    }
+    for name, call in calls.items():
+        rc = call()
+        assert rc < 0, name
+        msg = lib.frl_last_error().decode()
+        assert name.replace("frl_", "").split("_")[0] in msg or name in msg, (name, msg)
+    # a struct with inconsistent fields is refused too (PPO tanh + layer_norm; unknown explore kind)
+    a = _lib.ExploreArgs()
+    a.kind, a.N, a.A = 7, 4, 2
+    assert lib.frl_explore(ctypes.byref(a), None) < 0 and "frl_explore" in lib.frl_last_error().decode()

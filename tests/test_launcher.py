@@ -91,6 +91,11 @@ def test_reference_ppo_with_tricks_script_unchanged(tmp_path, emul):
                                        ["--env_name", "Pendulum-v1", "--max_episodes", "2", "--horizon", "128", "--minibatch_size", "32",
                                         "--K_epochs", "2", "--device", "cpu"], results_root=str(tmp_path))
     assert type(ns["policy"]).__module__ == "freerl_b200.PPO_with_tricks" and ns["policy"].agent.step > 0
+    for d, f, mod in (("PPO_advance", "PPO_with_tricks.py", "freerl_b200.PPO_with_tricks"), ("PPO_advance", "PPO_cc.py", "freerl_b200.PPO_advance")):
+        ns = launcher.run_reference_script(os.path.join(REF, d, f),
+                                           ["--env_name", "Pendulum-v1", "--max_episodes", "2", "--horizon", "128", "--minibatch_size", "32",
+                                            "--K_epochs", "2", "--device", "cpu"], results_root=str(tmp_path))
+        assert type(ns["policy"]).__module__ == mod and ns["policy"].agent.step > 0, f
 
 
 def test_sac_add_discrete_continuous_is_sac(tmp_path, emul):
