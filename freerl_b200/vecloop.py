@@ -6,7 +6,8 @@ Same class names and call signatures as the reference's helpers, with a leading 
   ``DDPG_file/DDPG.py:358-388``, ``SAC_file/SAC.py:357-388``): ``norm(x[N, shape], update=True)``.
 * ``RewardScaling(shape=1, gamma)``             — ``PPO_file/normalization.py:87-101``: ``rs(reward[N])``, ``rs.reset(done_mask)``.
 * ``OUNoise(action_dim, ...)``                  — ``SAC_file/SAC.py:334-355``: ``ou.noise()`` → ``[N, action_dim]``, ``ou.reset(done_mask)``.
-* ``explore_ou`` / ``explore_gauss``            — the action post-processing of ``DDPG_file/DDPG.py:519-522``.
+* ``OUNoise.explore`` / ``explore_gauss``       — the action post-processing of ``DDPG_file/DDPG.py:519-522``.
+* ``epsilon_greedy`` / ``dis_to_con``           — ``DQN_file/DQN.py:307-310`` and ``:195-217``.
 
 The reference owns ONE statistics object and calls it once per env step.  Here the rows of a vector step are folded in env
 order inside one kernel launch (``frl_vecnorm`` / ``frl_reward_scaling``), so statistics and outputs equal — bit for bit —

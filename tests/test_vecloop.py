@@ -131,3 +131,30 @@ def test_vecloop_emulated(emul):
 @pytest.mark.gpu
 def test_vecloop_gpu():
     _run(torch.device("cuda"))
+
+
+def test_vecloop_random_interleavings_emulated(emul):
+    """Random env counts / widths / dtypes with update and evaluation calls interleaved, against the oracle fed row by row."""
+    from freerl_b200 import vecloop as vl
+    device = torch.device("cpu")
+    rng = np.random.default_rng(77)
+    for trial in range(12):
+        d, dt = int(rng.integers(1, 40)), (np.float32 if trial % 2 else np.float64)
+        nm, ms = vl.Normalization(d, device), ov.RunningMeanStd(d)
+        for step in range(int(rng.integers(2, 7))):
+            n_env = int(rng.choice([1, 2, 5, 33, 130]))
+            x = (rng.standard_normal((n_env, d)) * rng.uniform(0.1, 5) + rng.uniform(-3, 3)).astype(dt)
+            upd = bool(rng.random() < 0.7) or step == 0
+            assert np.array_equal(_np(nm(x, update=upd, out_dtype=torch.float64)), ov.normalize_rows(ms, x, update=upd)), (trial, step, upd)
+        assert nm.running_ms.n == ms.n
+        assert np.array_equal(_np(nm.running_ms.mean), np.asarray(ms.mean, np.float64).reshape(-1))
+        assert np.array_equal(_np(nm.running_ms.std), np.asarray(ms.std, np.float64).reshape(-1))
+    for trial in range(6):
+        n_env, gamma = int(rng.choice([1, 3, 64])), float(rng.uniform(0.9, 0.999))
+        rs, ms, R = vl.RewardScaling(1, gamma, n_envs=n_env, device=device), ov.RunningMeanStd(1), np.zeros(n_env)
+        for step in range(8):
+            x = rng.standard_normal(n_env) * 3
+            assert np.array_equal(_np(rs(x, out_dtype=torch.float64)), ov.reward_scaling_rows(ms, R, gamma, x))
+            done = rng.random(n_env) < 0.3
+            rs.reset(done)
+            R[done] = 0.0
