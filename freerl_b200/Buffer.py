@@ -82,9 +82,19 @@ class Buffer:
 
     # ---- sample ------------------------------------------------------------------------------------
     def _indices_to_device(self, indices):
+        """Host (numpy / list) indices get numpy's fancy-indexing semantics before they reach the device: negative values count
+        from the end of the store, anything outside ``[-capacity, capacity)`` raises ``IndexError`` (``SAC_file/Buffer.py:41-45``
+        indexes ``self.obs[indices]``).  Device tensors are taken as they are — the caller owns their range."""
         if isinstance(indices, torch.Tensor):
             return indices.to(device=self.device, dtype=torch.int64).contiguous()
-        return torch.from_numpy(np.ascontiguousarray(indices, dtype=np.int64)).to(self.device)
+        idx = np.ascontiguousarray(indices, dtype=np.int64)
+        if idx.size:
+            lo, hi = int(idx.min()), int(idx.max())
+            if lo < -self.capacity or hi >= self.capacity:
+                raise IndexError("index %d is out of bounds for axis 0 with size %d" % (lo if lo < -self.capacity else hi, self.capacity))
+            if lo < 0:
+                idx = np.where(idx < 0, idx + self.capacity, idx)
+        return torch.from_numpy(idx).to(self.device)
 
     def sample(self, indices):
         idx = self._indices_to_device(indices)

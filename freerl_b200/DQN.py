@@ -75,6 +75,8 @@ class DQN:
     def learn(self, batch_size, gamma, tau, *, n_updates=1, indices=None):
         """One (or ``n_updates`` sequential) DQN update(s).  ``indices`` ([n_updates, B] int64) overrides sampling."""
         total = len(self.buffer)
+        if total == 0:
+            raise RuntimeError("learn() called on an empty replay buffer")
         B = min(total, batch_size)
         if indices is None:
             idx = _common.make_indices(self.mode, total, B, n_updates, self.device, self._seed, self._n_learn)

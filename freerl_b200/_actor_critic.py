@@ -109,6 +109,8 @@ class ACBase:
     # ---- kernel call -------------------------------------------------------------------------------
     def _base_args(self, batch_size, gamma, tau, n_updates, indices):
         total = len(self.buffer)
+        if total == 0:
+            raise RuntimeError("learn() called on an empty replay buffer")
         B = min(total, batch_size)
         if indices is None:
             idx = _common.make_indices(self.mode, total, B, n_updates, self.device, self._seed, self._n_learn)

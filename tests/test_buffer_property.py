@@ -44,3 +44,29 @@ def test_ring_replay_property_emulated(emul):
 @pytest.mark.gpu
 def test_ring_replay_property_gpu():
     _run(torch.device("cuda"), 1)
+
+
+def test_host_index_semantics_and_empty_replay_emulated(emul):
+    """numpy fancy-indexing semantics for host indices (negative = from the end of the store, out of range raises IndexError like
+    ``self.obs[indices]`` in SAC_file/Buffer.py:41-45) and a clear error for learn() on an empty replay."""
+    from freerl_b200.Buffer import Buffer
+    from freerl_b200.DQN import DQN
+    from freerl_b200.SAC import SAC
+    dev = torch.device("cpu")
+    cap, od, ad = 12, 3, 2
+    ours, orc = Buffer(cap, od, ad, dev), ob.RingReplay(cap, od, ad)
+    rng = np.random.default_rng(3)
+    for _ in range(cap):
+        t = (rng.standard_normal(od), rng.uniform(-1, 1, ad), float(rng.standard_normal()), rng.standard_normal(od), bool(rng.random() < 0.5))
+        ours.add(*t); orc.add(*t)
+    idx = np.array([-1, -cap, 0, cap - 1, -3])
+    for g, w in zip(ours.sample(idx), orc.sample(idx)):
+        assert np.array_equal(g.cpu().numpy(), np.asarray(w, dtype=np.float32).reshape(g.shape))
+    for bad in ([cap], [-cap - 1], [0, 5, 10 ** 9]):
+        with pytest.raises(IndexError):
+            ours.sample(np.array(bad))
+    assert all(t.shape[0] == 0 for t in ours.sample(np.array([], dtype=np.int64)))
+    with pytest.raises(RuntimeError, match="empty replay"):
+        SAC([3, 2], True, 1e-3, 1e-3, 100, dev, trick={}).learn(8, 0.99, 0.01)
+    with pytest.raises(RuntimeError, match="empty replay"):
+        DQN([4, 2], False, 1e-3, 100, dev).learn(8, 0.99, 0.01)
