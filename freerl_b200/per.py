@@ -123,8 +123,9 @@ class PER_Buffer:
             td = td_error.detach().to(device=self.device, dtype=torch.float32).reshape(-1).contiguous()
         else:
             td = torch.from_numpy(np.ascontiguousarray(td_error, dtype=np.float32).reshape(-1)).to(self.device)
-        for s in range(0, idx.numel(), 1024):        # one launch per <= 1024 ordered updates: priority transform + heap update
-            e = min(s + 1024, idx.numel())
+        n = min(idx.numel(), td.numel())             # `for idx, priority in zip(indices, priorities)` (DQN_file/Buffer.py:128): the shorter wins
+        for s in range(0, n, 1024):                  # one launch per <= 1024 ordered updates: priority transform + heap update
+            e = min(s + 1024, n)
             _lib.check(_lib.lib().frl_sumtree_update_td(
                 _lib.ptr(self.sumtree.tree), self.capacity, _lib.ptr(idx[s:e].contiguous()), _lib.ptr(td[s:e].contiguous()),
                 float(self.epsilon), float(self.alpha), e - s, _lib.ptr(self.sumtree._scratch), _lib.stream_ptr(self.device)),
