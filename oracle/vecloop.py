@@ -7,26 +7,30 @@ import numpy as np
 
 
 class RunningMeanStd:
-    """``PPO_file/normalization.py:17-35`` (same code in ``MAPPO_file/normalization.py``, ``DDPG_file/DDPG.py:358-376``,
-    ``SAC_file/SAC.py:357-375``): Welford over single observations; the first call aliases mean = std = x (x's dtype)."""
+    """Welford statistics over single observations as ``PPO_file/normalization.py:17-35`` keeps them (same code in
+    ``MAPPO_file/normalization.py``, ``DDPG_file/DDPG.py:358-376``, ``SAC_file/SAC.py:357-375``).  Restated as one fold step:
+
+    * call 1 ALIASES the observation: ``mean`` and ``std`` both become ``x`` itself (so they carry x's dtype — float32 observations
+      give a float32 mean from then on — and the first normalised output is exactly 0);
+    * call n > 1: ``mean += (x - mean) / n`` in mean's dtype (python-int ``n`` is a weak scalar under NumPy 2), the float64
+      accumulator ``S += (x - mean_old) * (x - mean_new)``, ``std = sqrt(S / n)`` (float64).
+    """
 
     def __init__(self, shape):
-        self.n = 0
-        self.mean = np.zeros(shape)
-        self.S = np.zeros(shape)
+        self.n, self.mean, self.S = 0, np.zeros(shape), np.zeros(shape)
         self.std = np.sqrt(self.S)
 
     def update(self, x):
         x = np.array(x)
         self.n += 1
         if self.n == 1:
-            self.mean = x
-            self.std = x
-        else:
-            old = self.mean.copy()
-            self.mean = old + (x - old) / self.n
-            self.S = self.S + (x - old) * (x - self.mean)
-            self.std = np.sqrt(self.S / self.n)
+            self.mean = self.std = x
+            return
+        before = self.mean.copy()
+        step = (x - before) / self.n
+        self.mean = before + step
+        self.S = self.S + (x - before) * (x - self.mean)
+        self.std = np.sqrt(self.S / self.n)
 
 
 def normalize_rows(ms, rows, update=True):
