@@ -1,0 +1,82 @@
+"""On-disk formats: a model saved by freerl_b200 loads with the UNMODIFIED reference class's own ``load()`` and acts
+the same, and the other way round — which is what keeps the reference's ``evaluate.py`` / ``MA_evaluate.py`` tools usable on our runs.
+Needs the reference tree (build container only); the product side runs on the host emulation here."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+REF = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "DQN_file")), reason="reference tree not present")
+
+SAC_TRICK = {"ObsNorm": False, "Batch_ObsNorm": False, "OUNoise": True, "GaussNoise": False}
+TD3_TRICK = {"Batch_ObsNorm": False}
+CASES = [
+    # name, reference dir, module, class, our module, dim_info, is_continue, ctor args after (dim_info, is_continue), kwargs, file
+    ("dqn", "DQN_file", "DQN", "DQN", "freerl_b200.DQN", [4, 3], False, (1e-3, 100), {}, "DQN.pt"),
+    ("sac", "SAC_file", "SAC", "SAC", "freerl_b200.SAC", [5, 2], True, (1e-3, 1e-3, 100), {"trick": SAC_TRICK}, "SAC.pt"),
+    ("ppo_cont", "PPO_file", "PPO", "PPO", "freerl_b200.PPO", [6, 2], True, (1e-3, 1e-3, 32), {"trick": {"adv_norm": False}}, "PPO.pt"),
+    ("ppo_disc", "PPO_file", "PPO", "PPO", "freerl_b200.PPO", [6, 3], False, (1e-3, 1e-3, 32), {"trick": {"adv_norm": False}}, "PPO.pt"),
+    ("ppo_advance", "PPO_advance", "PPO", "PPO", "freerl_b200.PPO_advance", [6, 2], True, (1e-3, 1e-3, 32), {"trick": {"adv_norm": False}}, "PPO.pt"),
+    ("td3", "TD3_file", "TD3", "TD3", "freerl_b200.TD3", [5, 2], True, (1e-3, 1e-3, 100),
+     {"trick": None, "realize": {"clip_double": True, "policy_noise": True, "twin_delay": True}}, "TD3.pt"),
+]
+
+
+def _acts(policy, obs):
+    return np.stack([np.asarray(policy.evaluate_action(o), dtype=np.float64).reshape(-1) for o in obs])
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_saved_models_interoperate_with_the_reference(case, tmp_path, emul):
+    import importlib
+    from oracle import refload
+    name, rdir, rmod, cls, ours_mod, dim_info, is_continue, args, kw, fname = case
+    ref = getattr(refload.load(rdir, rmod), cls)
+    ours = getattr(importlib.import_module(ours_mod), cls)
+    dev = torch.device("cpu")
+    obs = np.random.default_rng(1).standard_normal((6, dim_info[0])).astype(np.float32)
+    # ours -> disk -> reference.load()
+    torch.manual_seed(5)
+    a = ours(dim_info, is_continue, *args, dev, **kw)
+    d1 = tmp_path / "ours"; d1.mkdir()
+    a.save(str(d1))
+    assert os.path.exists(d1 / fname)
+    r = ref.load(dim_info, is_continue, str(d1), **kw)
+    np.testing.assert_allclose(_acts(r, obs), _acts(a, obs), rtol=1e-5, atol=2e-6)
+    # reference -> disk -> ours.load()
+    torch.manual_seed(6)
+    r2 = ref(dim_info, is_continue, *args, dev, **kw)
+    d2 = tmp_path / "ref"; d2.mkdir()
+    r2.save(str(d2))
+    b = ours.load(dim_info, is_continue, str(d2), device=dev, **kw)
+    np.testing.assert_allclose(_acts(b, obs), _acts(r2, obs), rtol=1e-5, atol=2e-6)
+    # same keys, shapes and dtypes on disk
+    s1, s2 = torch.load(d1 / fname), torch.load(d2 / fname)
+    assert list(s1) == list(s2) and all(s1[k].shape == s2[k].shape and s1[k].dtype == s2[k].dtype for k in s1)
+
+
+def test_maddpg_checkpoint_interoperates_with_the_reference(tmp_path, emul):
+    """MADDPG.pth = {agent_id: actor state_dict} (MADDPG_file/MADDPG.py:240-253), both directions."""
+    from freerl_b200.MADDPG import MADDPG
+    from oracle import refload
+    ref = refload.load("MADDPG_file", "MADDPG").MADDPG
+    sup = {"weight_decay": False, "OUNoise": False, "ObsNorm": False, "net_init": False, "Batch_ObsNorm": False}
+    dim_info = {"agent_%d" % i: [7, 3] for i in range(3)}
+    dev = torch.device("cpu")
+    rng = np.random.default_rng(2)
+    obs = [{k: rng.standard_normal(7).astype(np.float32) for k in dim_info} for _ in range(4)]
+    acts = lambda pol: np.stack([np.concatenate([np.asarray(v, np.float64).reshape(-1) for v in pol.evaluate_action(o).values()]) for o in obs])
+    torch.manual_seed(3)
+    a = MADDPG(dim_info, True, 1e-3, 1e-3, 100, dev, trick=None, supplement=dict(sup))
+    d1 = tmp_path / "ours"; d1.mkdir()
+    a.save(str(d1))
+    r = ref.load(dim_info, True, str(d1), trick=None, supplement=dict(sup))
+    np.testing.assert_allclose(acts(r), acts(a), rtol=1e-5, atol=2e-6)
+    torch.manual_seed(4)
+    r2 = ref(dim_info, True, 1e-3, 1e-3, 100, dev, trick=None, supplement=dict(sup))
+    d2 = tmp_path / "ref"; d2.mkdir()
+    r2.save(str(d2))
+    b = MADDPG.load(dim_info, True, str(d2), trick=None, supplement=dict(sup), device=dev)
+    np.testing.assert_allclose(acts(b), acts(r2), rtol=1e-5, atol=2e-6)
