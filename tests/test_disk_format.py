@@ -80,3 +80,37 @@ def test_maddpg_checkpoint_interoperates_with_the_reference(tmp_path, emul):
     r2.save(str(d2))
     b = MADDPG.load(dim_info, True, str(d2), trick=None, supplement=dict(sup), device=dev)
     np.testing.assert_allclose(acts(b), acts(r2), rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("algo", ["MAPPO", "IPPO", "HAPPO"])
+def test_mappo_family_checkpoints_interoperate_with_the_reference(algo, tmp_path, emul):
+    """MAPPO.pth / IPPO.pth / HAPPO.pth = {agent_id: actor state_dict} (e.g. MAPPO_file/MAPPO.py:494-507), both directions."""
+    import importlib
+    from oracle import refload
+    from oracle.make_golden_marl import MAPPO_TRICK
+    refmod = refload.load("MAPPO_file", algo)
+    ref = getattr(refmod, algo)
+
+    def fresh():      # IPPO / HAPPO number their critics with a class-level counter (IPPO.py:131-134): one policy per process upstream
+        if hasattr(refmod.Critic, "id_num"):
+            refmod.Critic.id_num = 0
+    ours = getattr(importlib.import_module("freerl_b200." + algo), algo)
+    dim_info = {"agent_%d" % i: [9, 3] for i in range(3)}
+    dev = torch.device("cpu")
+    rng = np.random.default_rng(4)
+    obs = [{k: rng.standard_normal(9).astype(np.float32) for k in dim_info} for _ in range(4)]
+    acts = lambda pol: np.stack([np.concatenate([np.asarray(v, np.float64).reshape(-1) for v in pol.evaluate_action(o).values()]) for o in obs])
+    torch.manual_seed(7)
+    a = ours(dim_info, True, 1e-3, 1e-3, 32, dev, dict(MAPPO_TRICK))
+    d1 = tmp_path / "ours"; d1.mkdir()
+    a.save(str(d1))
+    fresh()
+    r = ref.load(dim_info, True, str(d1), trick=dict(MAPPO_TRICK))
+    np.testing.assert_allclose(acts(r), acts(a), rtol=1e-5, atol=2e-6)
+    torch.manual_seed(8)
+    fresh()
+    r2 = ref(dim_info, True, 1e-3, 1e-3, 32, dev, dict(MAPPO_TRICK))
+    d2 = tmp_path / "ref"; d2.mkdir()
+    r2.save(str(d2))
+    b = ours.load(dim_info, True, str(d2), trick=dict(MAPPO_TRICK), device=dev)
+    np.testing.assert_allclose(acts(b), acts(r2), rtol=1e-5, atol=2e-6)
