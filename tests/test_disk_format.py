@@ -114,3 +114,28 @@ def test_mappo_family_checkpoints_interoperate_with_the_reference(algo, tmp_path
     r2.save(str(d2))
     b = ours.load(dim_info, True, str(d2), trick=dict(MAPPO_TRICK), device=dev)
     np.testing.assert_allclose(acts(b), acts(r2), rtol=1e-5, atol=2e-6)
+
+
+def test_rainbow_checkpoint_schema_matches_the_reference(tmp_path, emul):
+    """Rainbow DQN.pt (DQN_file/DQN_with_tricks.py:297-298): NoisyLinear parameters AND the weight_epsilon / bias_epsilon buffers.
+    Upstream ``DQN.load`` cannot run (it omits gamma / batch_size), so the file written by us is loaded with a strict
+    ``load_state_dict`` into a reference network built by the reference constructor, and the reverse through ours."""
+    from freerl_b200.DQN_with_tricks import DQN
+    from oracle import refload
+    ref = refload.load("DQN_file", "DQN_with_tricks").DQN
+    trick = {"Double": True, "Dueling": True, "PER": True, "Noisy": True, "N_Step": True, "Categorical": True}
+    dev = torch.device("cpu")
+    torch.manual_seed(9)
+    a = DQN([8, 4], False, 1e-3, 64, dev, trick=dict(trick), gamma=0.99, batch_size=32)
+    d1 = tmp_path / "ours"; d1.mkdir()
+    a.save(str(d1))
+    r = ref([8, 4], False, 1e-3, 64, dev, trick=dict(trick), gamma=0.99, batch_size=32)
+    sd = torch.load(d1 / "DQN.pt")
+    r.agent.Qnet.load_state_dict(sd, strict=True)
+    assert list(sd) == list(r.agent.Qnet.state_dict())
+    obs = np.random.default_rng(3).standard_normal((5, 8)).astype(np.float32)
+    assert [int(a.evaluate_action(o)) for o in obs] == [int(r.evaluate_action(o)) for o in obs]
+    d2 = tmp_path / "ref"; d2.mkdir()
+    r.save(str(d2))
+    b = DQN.load([8, 4], False, str(d2), trick=dict(trick), device=dev, gamma=0.99, batch_size=32)
+    assert [int(b.evaluate_action(o)) for o in obs] == [int(r.evaluate_action(o)) for o in obs]
