@@ -29,6 +29,10 @@ class HAPPO(_MAPPO):
             ag.lr_critic = critic_lr
         self.adam_eps = 1e-5 if trick['adam_eps'] else 1e-8
         self.agent_ids = list(self.agents.keys())
+        self.actor_lr, self.critic_lr = actor_lr, critic_lr
+
+    def lr_decay(self, episode_num, max_episodes):
+        self._lr_decay_two_optimisers(episode_num, max_episodes)
 
     def _full_logp(self, agent_id):
         """sum_j log N(action_j | mean_j, std_j) of the STORED actions over the whole horizon with the agent's current actor"""

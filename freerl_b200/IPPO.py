@@ -39,6 +39,7 @@ class IPPO(_MAPPO):
         for agent_id, (obs_dim, action_dim) in dim_info.items():
             self.agents[agent_id] = Agent(obs_dim, action_dim, actor_lr, critic_lr, is_continue, self.device, trick)
             self.buffers[agent_id] = Buffer_for_PPO(horizon, obs_dim, act_dim=action_dim if is_continue else 1, device=self.device)
+        self.actor_lr, self.critic_lr = actor_lr, critic_lr
         self.dim_info = dim_info
         self.is_continue = is_continue
         print('actor_type:continue') if self.is_continue else print('actor_type:discrete')
@@ -56,6 +57,9 @@ class IPPO(_MAPPO):
         self.last_metrics = None
 
     # select_action / evaluate_action: inherited from MAPPO (Gaussian and Categorical heads, same network body)
+
+    def lr_decay(self, episode_num, max_episodes):
+        self._lr_decay_two_optimisers(episode_num, max_episodes)
 
     # ---- learning ----------------------------------------------------------------------------------
     def compute_advantages(self, gamma, lmbda):

@@ -238,6 +238,19 @@ class MAPPO:
 
     _launch_update = __import__("freerl_b200.PPO", fromlist=["PPO"]).PPO._launch_update
 
+    def lr_decay(self, episode_num, max_episodes):
+        """MAPPO.py:484-491 walks ``agent.actor_optimizer`` / ``agent.critic_optimizer``, which its merged-optimiser Agent does not
+        have: upstream this raises AttributeError as soon as the ``lr_decay`` trick is on.  Kept as an error (not papered over);
+        IPPO / HAPPO, whose agents do have the two optimisers, override it."""
+        raise AttributeError("'Agent' object has no attribute 'actor_optimizer' (reference defect, MAPPO.py:488: lr_decay is not "
+                             "usable with MAPPO's merged optimiser)")
+
+    def _lr_decay_two_optimisers(self, episode_num, max_episodes):
+        """IPPO.py:324-331 / HAPPO.py:460-467: both learning rates decay linearly with the episode count."""
+        for ag in self.agents.values():
+            ag.lr = self.actor_lr * (1 - episode_num / max_episodes)
+            ag.lr_critic = self.critic_lr * (1 - episode_num / max_episodes)
+
     def save(self, model_dir):
         torch.save({name: {k: v.detach().clone().cpu() for k, v in agent.actor.state_dict().items()} for name, agent in self.agents.items()},
                    os.path.join(model_dir, 'MAPPO.pth'))

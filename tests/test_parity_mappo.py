@@ -171,3 +171,19 @@ def test_happo_emulated(golden, emul):
 @pytest.mark.gpu
 def test_happo_gpu(golden):
     _happo(golden, torch.device("cuda"))
+
+
+def test_lr_decay_of_the_mappo_family_emulated(emul):
+    """IPPO.py:324-331 / HAPPO.py:460-467 decay both learning rates linearly (the next learn reads them from the agents);
+    MAPPO.py:484-491 cannot run upstream (its merged-optimiser Agent has no actor_optimizer) and raises here too."""
+    from freerl_b200.HAPPO import HAPPO
+    from freerl_b200.IPPO import IPPO
+    from freerl_b200.MAPPO import MAPPO
+    dim_info, dev = {k: [18, 5] for k in IDS}, torch.device("cpu")
+    for cls in (IPPO, HAPPO):
+        pol = cls(dim_info, True, 1e-3, 5e-4, 64, dev, dict(MAPPO_TRICK))
+        pol.lr_decay(25, 100)
+        for ag in pol.agents.values():
+            assert ag.lr == 1e-3 * 0.75 and ag.lr_critic == 5e-4 * 0.75
+    with pytest.raises(AttributeError, match="actor_optimizer"):
+        MAPPO(dim_info, True, 1e-3, 5e-4, 64, dev, dict(MAPPO_TRICK)).lr_decay(25, 100)
