@@ -37,6 +37,13 @@ class SumTree:
         idx = torch.tensor([int(buffer_index)], dtype=torch.int64, device=self.device)
         self._update(idx, pri_const=float(np.asarray(priority).reshape(-1)[0]))
 
+    def update(self, idx, priority):
+        """reference ``SumTree.update`` (``DQN_file/Buffer.py:157-166``): ``idx`` is a TREE index of a leaf (``buffer_index + capacity - 1``)"""
+        idx = int(idx)
+        if not self.capacity - 1 <= idx < 2 * self.capacity - 1:
+            raise IndexError("SumTree.update: tree index %d is not a leaf (leaves are [%d, %d))" % (idx, self.capacity - 1, 2 * self.capacity - 1))
+        self.add(idx - self.capacity + 1, priority)
+
     def get(self, s):
         """reference ``SumTree.get`` for one value (host round trip; the batched path is ``PER_Buffer.sample``)"""
         tree = self.tree.cpu().numpy()

@@ -176,3 +176,22 @@ def test_sumtree_ordered_update_property_emulated(emul):
 @pytest.mark.gpu
 def test_sumtree_ordered_update_property_gpu():
     _sumtree_property(torch.device("cuda"))
+
+
+def test_sumtree_update_by_tree_index_emulated(emul):
+    """``SumTree.update(tree_idx, p)`` (DQN_file/Buffer.py:157-166) next to ``add(buffer_idx, p)``: same heap as the oracle's."""
+    from freerl_b200.per import SumTree
+    from oracle import buffers as ob
+    cap = 11
+    ours, orc = SumTree(cap, torch.device("cpu")), ob.SumTree(cap)
+    rng = np.random.default_rng(0)
+    for _ in range(30):
+        leaf, p = int(rng.integers(0, cap)), float(rng.random() * 3)
+        if rng.random() < 0.5:
+            ours.update(leaf + cap - 1, p)
+        else:
+            ours.add(leaf, p)
+        orc.set_leaf(leaf, p)
+    assert np.array_equal(ours.tree.cpu().numpy(), orc.tree)
+    with pytest.raises(IndexError):
+        ours.update(0, 1.0)          # the root is not a leaf: the reference would corrupt the heap silently
