@@ -183,7 +183,7 @@ def test_sumtree_update_by_tree_index_emulated(emul):
     from freerl_b200.per import SumTree
     from oracle import buffers as ob
     cap = 11
-    ours, orc = SumTree(cap, torch.device("cpu")), ob.SumTree(cap)
+    ours, orc = SumTree(cap, torch.device("cpu")), ob.SumTreeOracle(cap)
     rng = np.random.default_rng(0)
     for _ in range(30):
         leaf, p = int(rng.integers(0, cap)), float(rng.random() * 3)
