@@ -37,6 +37,29 @@ class Buffer:
     def c_struct(self):
         return self._c
 
+    # ---- the reference's five arrays as views of the row store (SAC_file/Buffer.py:18-22) --------------------------
+    # device fp32 views, not host float64 arrays: element [i] is what ``sample([i])`` returns; writing through them edits the store
+    @property
+    def obs(self):
+        return self.storage[:, :self.obs_dim]
+
+    @property
+    def actions(self):
+        return self.storage[:, self.obs_dim:self.obs_dim + self.act_dim]
+
+    @property
+    def rewards(self):
+        return self.storage[:, self.obs_dim + self.act_dim]
+
+    @property
+    def dones(self):
+        return self.storage[:, self.obs_dim + self.act_dim + 1]
+
+    @property
+    def next_obs(self):
+        o = self.obs_dim + self.act_dim + 2
+        return self.storage[:, o:o + self.obs_dim]
+
     # ---- add ---------------------------------------------------------------------------------------
     def _pack(self, obs, action, reward, next_obs, done):
         od, ad = self.obs_dim, self.act_dim

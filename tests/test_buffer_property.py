@@ -59,6 +59,9 @@ def test_host_index_semantics_and_empty_replay_emulated(emul):
     for _ in range(cap):
         t = (rng.standard_normal(od), rng.uniform(-1, 1, ad), float(rng.standard_normal()), rng.standard_normal(od), bool(rng.random() < 0.5))
         ours.add(*t); orc.add(*t)
+    # the reference's array attributes are views of the row store
+    for name, want in (("obs", orc.obs), ("actions", orc.actions), ("rewards", orc.rewards), ("next_obs", orc.next_obs), ("dones", orc.dones)):
+        assert np.array_equal(getattr(ours, name).cpu().numpy(), np.asarray(want, dtype=np.float32)), name
     idx = np.array([-1, -cap, 0, cap - 1, -3])
     for g, w in zip(ours.sample(idx), orc.sample(idx)):
         assert np.array_equal(g.cpu().numpy(), np.asarray(w, dtype=np.float32).reshape(g.shape))
