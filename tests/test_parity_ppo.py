@@ -166,12 +166,6 @@ def test_ppo_with_tricks_tanh_emulated(golden, emul):
 
 
 @pytest.mark.gpu
-def test_ppo_with_tricks_tanh_gpu(golden):
-    _ppo_tricks(golden, torch.device("cuda"), "ppo_tricks_tanh_cont", True, tanh=True)
-    _ppo_tricks(golden, torch.device("cuda"), "ppo_tricks_tanh_disc", False, tanh=True)
-
-
-@pytest.mark.gpu
 def test_ppo_with_tricks_continuous_gpu(golden):
     _ppo_tricks(golden, torch.device("cuda"), "ppo_tricks_cont", True)
 
