@@ -53,3 +53,11 @@ def test_gae_adv_norm_emulated(emul):
 def test_gae_adv_norm_gpu():
     from freerl_b200 import _lib
     _run(_lib, torch.device("cuda"))
+
+
+def test_gae_round_boundaries_emulated(emul):
+    """The column-tile kernel walks the horizon in rounds of 8 chunks x 16 steps aligned to the END of the rollout: horizons around the
+    round size (128) and its multiples, chunk-length boundaries (T <= 128: ceil(T / 8) steps per chunk) and ragged column tiles."""
+    for seed, (T, N) in enumerate(((127, 32), (128, 33), (129, 64), (255, 40), (256, 32), (257, 65), (16, 32), (17, 47), (9, 32), (8, 96),
+                                   (383, 32), (640, 34))):
+        _gae_case(emul, torch.device("cpu"), T, N, 100 + seed)
