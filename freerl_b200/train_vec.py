@@ -1,0 +1,164 @@
+"""Vectorised off-policy train loop: N gymnasium envs stepped on the host cores, everything else on the device.
+
+    python -m freerl_b200.train_vec --algo SAC --env_name HalfCheetah-v4 --n_envs 256 --total_steps 1000000 --device cuda
+
+The same loop as the reference mains (``SAC_file/SAC.py:497-590``, ``TD3_file/TD3.py``, ``DQN_file/DQN.py:287-349``) with a leading env
+axis — one ``select_action`` (batched inference kernel) per vector step, one ``add`` of N transitions, then ``n_envs *
+updates_per_step`` sequential learns fused into ONE persistent launch (``learn(..., n_updates=K)``, update-to-data ratio 1 like the
+reference's one learn per env step).  The per-step helpers of the reference mains run as device ops over the N envs
+(``freerl_b200.vecloop``: OU / Gaussian exploration, ε-greedy, observation normalisation).  Uses the real ``gymnasium`` when it is
+importable, else the synthetic shape-only shim (``freerl_b200.envshim``) — which is also what ``bench.py`` steps.
+
+This is the B200-native counterpart of the reference ``__main__`` blocks for users who want vectorised envs; the unchanged reference
+scripts themselves run through ``freerl_b200.launcher``.
+"""
+import argparse
+import os
+import time
+
+import numpy as np
+import torch
+
+from . import vecloop
+
+
+def _gym():
+    try:
+        import gymnasium
+        if hasattr(gymnasium, "make"):
+            return gymnasium
+    except Exception:
+        pass
+    from . import envshim
+    return envshim.as_module()
+
+
+def build_policy(algo, obs_dim, act_dim, n_actions, args, device):
+    if algo == "SAC":
+        from .SAC import SAC
+        return SAC([obs_dim, act_dim], True, args.actor_lr, args.critic_lr, args.buffer_size, device,
+                   trick={"ObsNorm": False, "Batch_ObsNorm": False, "OUNoise": False, "GaussNoise": False}, mode=args.mode)
+    if algo == "TD3":
+        from .TD3 import TD3
+        return TD3([obs_dim, act_dim], True, args.actor_lr, args.critic_lr, args.buffer_size, device, trick=None,
+                   realize={"clip_double": True, "policy_noise": True, "twin_delay": True}, mode=args.mode)
+    if algo == "DQN":
+        from .DQN import DQN
+        return DQN([obs_dim, n_actions], False, args.actor_lr, args.buffer_size, device, mode=args.mode)
+    raise ValueError("algo must be SAC, TD3 or DQN")
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--algo", default="SAC", choices=["SAC", "TD3", "DQN"])
+    ap.add_argument("--env_name", default="HalfCheetah-v4")
+    ap.add_argument("--n_envs", type=int, default=256)
+    ap.add_argument("--total_steps", type=int, default=100_000, help="env steps summed over the envs")
+    ap.add_argument("--random_steps", type=int, default=5_000)
+    ap.add_argument("--start_steps", type=int, default=5_000, help="env steps collected before the first learn")
+    ap.add_argument("--updates_per_step", type=float, default=1.0, help="learns per env step (the reference: 1)")
+    ap.add_argument("--batch_size", type=int, default=256)
+    ap.add_argument("--buffer_size", type=int, default=1_000_000)
+    ap.add_argument("--gamma", type=float, default=0.99)
+    ap.add_argument("--tau", type=float, default=0.01)
+    ap.add_argument("--actor_lr", type=float, default=1e-3)
+    ap.add_argument("--critic_lr", type=float, default=1e-3)
+    ap.add_argument("--epsilon", type=float, default=0.1, help="DQN epsilon-greedy")
+    ap.add_argument("--gauss_sigma", type=float, default=0.1, help="TD3 exploration noise (DDPG.py:522 form)")
+    ap.add_argument("--policy_noise", type=float, default=0.1, help="TD3 target smoothing (TD3.py:343-345)")
+    ap.add_argument("--noise_clip", type=float, default=0.5)
+    ap.add_argument("--policy_freq", type=int, default=2)
+    ap.add_argument("--obs_norm", action="store_true", help="running observation normalisation over all envs (vecloop.Normalization)")
+    ap.add_argument("--mode", default="fast", choices=["fast", "parity"])
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--device", default="cuda")
+    ap.add_argument("--save_dir", default=None)
+    ap.add_argument("--log_every", type=int, default=50, help="vector steps between progress lines (0: quiet)")
+    args = ap.parse_args(argv)
+
+    gym = _gym()
+    device = torch.device(args.device)
+    np.random.seed(args.seed)
+    torch.manual_seed(args.seed)
+    N = args.n_envs
+    envs = [gym.make(args.env_name) for _ in range(N)]
+    space = envs[0].action_space
+    obs_dim = envs[0].observation_space.shape[0]
+    discrete = not hasattr(space, "high")
+    if discrete != (args.algo == "DQN"):
+        raise ValueError("%s needs a %s action space (%s has the other kind)" % (args.algo, "discrete" if args.algo == "DQN" else "continuous", args.env_name))
+    act_dim = 1 if discrete else space.shape[0]
+    n_actions = space.n if discrete else 0
+    max_action = None if discrete else float(space.high[0])
+    for i, e in enumerate(envs):
+        e.action_space.seed(seed=args.seed + i)
+    policy = build_policy(args.algo, obs_dim, act_dim, n_actions, args, device)
+    norm = vecloop.Normalization(obs_dim, device) if args.obs_norm else None
+
+    def observe(rows):
+        rows = np.stack(rows).astype(np.float32)
+        return norm(rows).cpu().numpy() if norm is not None else rows
+
+    obs = observe([e.reset(seed=args.seed + i)[0] for i, e in enumerate(envs)])
+    ep_ret, returns = np.zeros(N), []
+    steps, vec_step, n_learn, t0 = 0, 0, 0, time.perf_counter()
+    carry = 0.0
+    while steps < args.total_steps:
+        if steps < args.random_steps:
+            if discrete:
+                action = np.array([e.action_space.sample() for e in envs], dtype=np.int64)
+            else:
+                action = np.stack([e.action_space.sample() for e in envs]) / max_action
+        else:
+            action = policy.select_action(obs)                                           # one batched inference launch for the N envs
+            if discrete:
+                action = vecloop.epsilon_greedy(action, n_actions, args.epsilon, device=device, mode=args.mode, seed=args.seed,
+                                                counter=vec_step).cpu().numpy()
+        if discrete:
+            action_ = action
+        elif args.algo == "TD3" and steps >= args.random_steps:
+            action_ = vecloop.explore_gauss(action, max_action, 1.0, args.gauss_sigma, device=device, mode=args.mode, seed=args.seed,
+                                            counter=vec_step).cpu().numpy()
+        else:
+            action_ = np.clip(action * max_action, -max_action, max_action)
+        out = [e.step(a if not discrete else int(a)) for e, a in zip(envs, action_)]
+        next_raw = [o[0] for o in out]
+        reward = np.array([o[1] for o in out], dtype=np.float64)
+        terminated = np.array([o[2] for o in out], dtype=bool)
+        done = terminated | np.array([o[3] for o in out], dtype=bool)
+        ep_ret += reward
+        for i in np.nonzero(done)[0]:                                                    # the stored next_obs is the terminal one; reset after
+            returns.append(ep_ret[i]); ep_ret[i] = 0.0
+        next_obs = observe(next_raw)
+        policy.add(obs, np.asarray(action).reshape(N, act_dim), reward, next_obs, terminated)
+        obs = next_obs
+        if done.any():                                                                   # only the reset envs' first observations are new rows
+            idx = np.nonzero(done)[0]
+            obs = next_obs.copy()
+            obs[idx] = observe([envs[i].reset(seed=args.seed + int(i))[0] for i in idx])
+        steps += N
+        vec_step += 1
+        if steps >= args.start_steps:
+            carry += N * args.updates_per_step
+            k = int(carry)
+            if k > 0:
+                if args.algo == "TD3":                                                   # k sequential learns, one persistent launch
+                    policy.learn(args.batch_size, args.gamma, args.tau, args.policy_noise, args.noise_clip, max_action, args.policy_freq,
+                                 1.0, n_updates=k)
+                else:
+                    policy.learn(args.batch_size, args.gamma, args.tau, n_updates=k)
+                carry -= k
+                n_learn += k
+        if args.log_every and vec_step % args.log_every == 0:
+            dt = time.perf_counter() - t0
+            print("steps %d  learns %d  %.0f env-steps/s  mean return(last 20) %s" % (
+                steps, n_learn, steps / dt, "%.2f" % np.mean(returns[-20:]) if returns else "n/a"), flush=True)
+    if args.save_dir:
+        os.makedirs(args.save_dir, exist_ok=True)
+        policy.save(args.save_dir)
+        np.save(os.path.join(args.save_dir, "%s_seed_%d.npy" % (args.algo, args.seed)), np.array(returns))
+    return {"policy": policy, "steps": steps, "learns": n_learn, "returns": returns}
+
+
+if __name__ == "__main__":
+    main()
