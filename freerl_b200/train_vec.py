@@ -1,4 +1,5 @@
-"""Vectorised off-policy train loop: N gymnasium envs stepped on the host cores, everything else on the device.
+"""Vectorised train loops (off-policy SAC / TD3 / DQN, on-policy PPO): N gymnasium envs stepped on the host cores, everything else
+on the device.
 
     python -m freerl_b200.train_vec --algo SAC --env_name HalfCheetah-v4 --n_envs 256 --total_steps 1000000 --device cuda
 
@@ -8,6 +9,9 @@ updates_per_step`` sequential learns fused into ONE persistent launch (``learn(.
 reference's one learn per env step).  The per-step helpers of the reference mains run as device ops over the N envs
 (``freerl_b200.vecloop``: OU / Gaussian exploration, ε-greedy, observation normalisation).  Uses the real ``gymnasium`` when it is
 importable, else the synthetic shape-only shim (``freerl_b200.envshim``) — which is also what ``bench.py`` steps.
+
+``--algo PPO`` is the on-policy loop of ``PPO_file/PPO.py:388-447``: rollouts of ``horizon`` vector steps ([horizon, N] rows in the
+rollout store, GAE scanned per env column), then ``K_epochs`` of minibatches in one persistent launch.
 
 This is the B200-native counterpart of the reference ``__main__`` blocks for users who want vectorised envs; the unchanged reference
 scripts themselves run through ``freerl_b200.launcher``.
@@ -48,9 +52,48 @@ def build_policy(algo, obs_dim, act_dim, n_actions, args, device):
     raise ValueError("algo must be SAC, TD3 or DQN")
 
 
+def _ppo_loop(args, envs, obs_dim, action_dim, discrete, device):
+    from .PPO import PPO
+    N, T = args.n_envs, args.horizon
+    max_action = None if discrete else float(envs[0].action_space.high[0])
+    policy = PPO([obs_dim, action_dim], not discrete, args.actor_lr, args.critic_lr, T * N, device, trick={"adv_norm": False}, mode=args.mode)
+    norm = vecloop.Normalization(obs_dim, device) if args.obs_norm else None
+    observe = (lambda rows: norm(np.stack(rows).astype(np.float32)).cpu().numpy()) if norm is not None else (lambda rows: np.stack(rows).astype(np.float32))
+    obs = observe([e.reset(seed=args.seed + i)[0] for i, e in enumerate(envs)])
+    ep_ret, returns, steps, n_learn, t0 = np.zeros(N), [], 0, 0, time.perf_counter()
+    while steps < args.total_steps:
+        for _ in range(T):
+            action, logp = policy.select_action(obs)                                     # [N] ids or [N, act] in (-1, 1)
+            out = [e.step(int(a) if discrete else np.clip(a * max_action, -max_action, max_action)) for e, a in zip(envs, action)]
+            next_raw = [o[0] for o in out]
+            reward = np.array([o[1] for o in out], dtype=np.float64)
+            terminated = np.array([o[2] for o in out], dtype=bool)
+            done = terminated | np.array([o[3] for o in out], dtype=bool)
+            ep_ret += reward
+            for i in np.nonzero(done)[0]:
+                returns.append(ep_ret[i]); ep_ret[i] = 0.0
+            next_obs = observe(next_raw)
+            policy.add(obs, action, reward, next_obs, terminated, logp, done)
+            obs = next_obs
+            if done.any():
+                idx = np.nonzero(done)[0]
+                obs = next_obs.copy()
+                obs[idx] = observe([envs[i].reset(seed=args.seed + int(i))[0] for i in idx])
+            steps += N
+        policy.learn(min(args.minibatch_size, T * N), args.gamma, args.lmbda, args.clip_param, args.K_epochs, args.entropy_coefficient)
+        n_learn += 1
+        if args.log_every:
+            print("steps %d  rollouts %d  %.0f env-steps/s  mean return(last 20) %s" % (
+                steps, n_learn, steps / (time.perf_counter() - t0), "%.2f" % np.mean(returns[-20:]) if returns else "n/a"), flush=True)
+    if args.save_dir:
+        os.makedirs(args.save_dir, exist_ok=True)
+        policy.save(args.save_dir)
+    return {"policy": policy, "steps": steps, "learns": n_learn, "returns": returns}
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser()
-    ap.add_argument("--algo", default="SAC", choices=["SAC", "TD3", "DQN"])
+    ap.add_argument("--algo", default="SAC", choices=["SAC", "TD3", "DQN", "PPO"])
     ap.add_argument("--env_name", default="HalfCheetah-v4")
     ap.add_argument("--n_envs", type=int, default=256)
     ap.add_argument("--total_steps", type=int, default=100_000, help="env steps summed over the envs")
@@ -68,6 +111,12 @@ def main(argv=None):
     ap.add_argument("--policy_noise", type=float, default=0.1, help="TD3 target smoothing (TD3.py:343-345)")
     ap.add_argument("--noise_clip", type=float, default=0.5)
     ap.add_argument("--policy_freq", type=int, default=2)
+    ap.add_argument("--horizon", type=int, default=128, help="PPO: vector steps per rollout (rollout rows = horizon * n_envs)")
+    ap.add_argument("--minibatch_size", type=int, default=8192)
+    ap.add_argument("--K_epochs", type=int, default=10)
+    ap.add_argument("--lmbda", type=float, default=0.95)
+    ap.add_argument("--clip_param", type=float, default=0.2)
+    ap.add_argument("--entropy_coefficient", type=float, default=0.01)
     ap.add_argument("--obs_norm", action="store_true", help="running observation normalisation over all envs (vecloop.Normalization)")
     ap.add_argument("--mode", default="fast", choices=["fast", "parity"])
     ap.add_argument("--seed", type=int, default=0)
@@ -85,10 +134,12 @@ def main(argv=None):
     space = envs[0].action_space
     obs_dim = envs[0].observation_space.shape[0]
     discrete = not hasattr(space, "high")
-    if discrete != (args.algo == "DQN"):
+    if args.algo != "PPO" and discrete != (args.algo == "DQN"):
         raise ValueError("%s needs a %s action space (%s has the other kind)" % (args.algo, "discrete" if args.algo == "DQN" else "continuous", args.env_name))
     act_dim = 1 if discrete else space.shape[0]
     n_actions = space.n if discrete else 0
+    if args.algo == "PPO":
+        return _ppo_loop(args, envs, obs_dim, space.n if discrete else space.shape[0], discrete, device)
     max_action = None if discrete else float(space.high[0])
     for i, e in enumerate(envs):
         e.action_space.seed(seed=args.seed + i)
