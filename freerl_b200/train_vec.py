@@ -1,4 +1,4 @@
-"""Vectorised train loops (off-policy SAC / TD3 / DQN, on-policy PPO): N gymnasium envs stepped on the host cores, everything else
+"""Vectorised train loops (off-policy SAC / TD3 / DQN / Rainbow, on-policy PPO): N gymnasium envs stepped on the host cores, everything else
 on the device.
 
     python -m freerl_b200.train_vec --algo SAC --env_name HalfCheetah-v4 --n_envs 256 --total_steps 1000000 --device cuda
@@ -49,7 +49,12 @@ def build_policy(algo, obs_dim, act_dim, n_actions, args, device):
     if algo == "DQN":
         from .DQN import DQN
         return DQN([obs_dim, n_actions], False, args.actor_lr, args.buffer_size, device, mode=args.mode)
-    raise ValueError("algo must be SAC, TD3 or DQN")
+    if algo == "RAINBOW":     # DQN_with_tricks.py with every trick on (PER + Noisy + C51 + N-step + Double + Dueling), BASELINE config C4
+        from .DQN_with_tricks import DQN
+        trick = {"Double": True, "Dueling": True, "PER": True, "Noisy": True, "N_Step": True, "Categorical": True}
+        return DQN([obs_dim, n_actions], False, args.actor_lr, args.buffer_size, device, trick=trick, gamma=args.gamma,
+                   batch_size=args.batch_size, mode=args.mode)
+    raise ValueError("algo must be SAC, TD3, DQN or RAINBOW")
 
 
 def _ppo_loop(args, envs, obs_dim, action_dim, discrete, device):
@@ -93,7 +98,7 @@ def _ppo_loop(args, envs, obs_dim, action_dim, discrete, device):
 
 def main(argv=None):
     ap = argparse.ArgumentParser()
-    ap.add_argument("--algo", default="SAC", choices=["SAC", "TD3", "DQN", "PPO"])
+    ap.add_argument("--algo", default="SAC", choices=["SAC", "TD3", "DQN", "RAINBOW", "PPO"])
     ap.add_argument("--env_name", default="HalfCheetah-v4")
     ap.add_argument("--n_envs", type=int, default=256)
     ap.add_argument("--total_steps", type=int, default=100_000, help="env steps summed over the envs")
@@ -134,8 +139,8 @@ def main(argv=None):
     space = envs[0].action_space
     obs_dim = envs[0].observation_space.shape[0]
     discrete = not hasattr(space, "high")
-    if args.algo != "PPO" and discrete != (args.algo == "DQN"):
-        raise ValueError("%s needs a %s action space (%s has the other kind)" % (args.algo, "discrete" if args.algo == "DQN" else "continuous", args.env_name))
+    if args.algo != "PPO" and discrete != (args.algo in ("DQN", "RAINBOW")):
+        raise ValueError("%s needs a %s action space (%s has the other kind)" % (args.algo, "discrete" if args.algo in ("DQN", "RAINBOW") else "continuous", args.env_name))
     act_dim = 1 if discrete else space.shape[0]
     n_actions = space.n if discrete else 0
     if args.algo == "PPO":
@@ -162,7 +167,7 @@ def main(argv=None):
                 action = np.stack([e.action_space.sample() for e in envs]) / max_action
         else:
             action = policy.select_action(obs)                                           # one batched inference launch for the N envs
-            if discrete:
+            if args.algo == "DQN":                                                       # Rainbow explores through its NoisyLinear layers
                 action = vecloop.epsilon_greedy(action, n_actions, args.epsilon, device=device, mode=args.mode, seed=args.seed,
                                                 counter=vec_step).cpu().numpy()
         if discrete:
@@ -196,6 +201,9 @@ def main(argv=None):
                 if args.algo == "TD3":                                                   # k sequential learns, one persistent launch
                     policy.learn(args.batch_size, args.gamma, args.tau, args.policy_noise, args.noise_clip, max_action, args.policy_freq,
                                  1.0, n_updates=k)
+                elif args.algo == "RAINBOW":                                             # PER priorities feed back between learns: one launch each
+                    for _ in range(k):
+                        policy.learn(args.batch_size, args.gamma, args.tau)
                 else:
                     policy.learn(args.batch_size, args.gamma, args.tau, n_updates=k)
                 carry -= k

@@ -17,6 +17,8 @@ def _run(device, tmp_path):
     assert r["learns"] == 52 and r["policy"].total_it == 52
     r = train_vec.main(["--algo", "DQN", "--env_name", "CartPole-v1"] + common)
     assert r["learns"] == 104 and len(r["returns"]) >= 0
+    r = train_vec.main(["--algo", "RAINBOW", "--env_name", "CartPole-v1", "--updates_per_step", "0.25"] + common)
+    assert r["learns"] == 26 and len(r["policy"].buffer) > 100          # the n-step windows hold back the newest steps of every env
     for env in ("Pendulum-v1", "CartPole-v1"):                                             # Gaussian and Categorical heads
         r = train_vec.main(["--algo", "PPO", "--env_name", env, "--n_envs", "8", "--horizon", "16", "--total_steps", "256", "--minibatch_size", "32",
                             "--K_epochs", "2", "--log_every", "0", "--device", str(device)])
