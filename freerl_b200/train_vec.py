@@ -1,4 +1,4 @@
-"""Vectorised train loops (off-policy SAC / TD3 / DQN / Rainbow, on-policy PPO): N gymnasium envs stepped on the host cores, everything else
+"""Vectorised train loops (off-policy SAC / TD3 / DQN / Rainbow, on-policy PPO / MAPPO): N gymnasium or PettingZoo-MPE envs stepped on the host cores, everything else
 on the device.
 
     python -m freerl_b200.train_vec --algo SAC --env_name HalfCheetah-v4 --n_envs 256 --total_steps 1000000 --device cuda
@@ -96,9 +96,67 @@ def _ppo_loop(args, envs, obs_dim, action_dim, discrete, device):
     return {"policy": policy, "steps": steps, "learns": n_learn, "returns": returns}
 
 
+def _mpe(name, **kw):
+    try:
+        import importlib
+        mod = importlib.import_module("pettingzoo.mpe." + name)
+        if hasattr(mod, "parallel_env") and not getattr(importlib.import_module("pettingzoo"), "__freerl_b200_shim__", False):
+            return mod.parallel_env(**kw)
+    except Exception:
+        pass
+    from . import envshim
+    return envshim.mpe_modules()["pettingzoo.mpe." + name].parallel_env(**kw)
+
+
+def _mappo_loop(args, device):
+    """``MAPPO_file/MAPPO.py:640-742`` over N parallel envs (BASELINE config C5: simple_spread_v3, 3 agents, continuous actions)."""
+    from .MAPPO import MAPPO
+    N, T = args.n_envs, args.horizon
+    envs = [_mpe(args.env_name, max_cycles=25, continuous_actions=True, **({"N": args.n_agents} if args.n_agents else {})) for _ in range(N)]
+    first = [e.reset(seed=args.seed + i)[0] for i, e in enumerate(envs)]
+    ids = list(envs[0].agents)
+    dim_info = {a: [envs[0].observation_space(a).shape[0], envs[0].action_space(a).shape[0]] for a in ids}
+    trick = {'adv_norm': True, 'ObsNorm': False, 'reward_norm': False, 'reward_scaling': False, 'orthogonal_init': True, 'adam_eps': True,
+             'lr_decay': False, 'ValueClip': False, 'huber_loss': False, 'LayerNorm': True, 'feature_norm': True}
+    policy = MAPPO(dim_info, True, args.actor_lr, args.critic_lr, T * N, device, trick, mode=args.mode)
+    stack = lambda dicts: {a: np.stack([d[a] for d in dicts]).astype(np.float32) for a in ids}
+    obs = stack(first)
+    ep_ret, returns, steps, n_learn, t0 = np.zeros(N), [], 0, 0, time.perf_counter()
+    while steps < args.total_steps:
+        for _ in range(T):
+            action, logp = policy.select_action(obs)                                     # per agent [N, act] in (-1, 1)
+            act_env = {a: (np.clip(action[a], -1.0, 1.0).astype(np.float32) + 1) / 2 for a in ids}          # MAPPO.py:682-683: -> [0, 1]
+            out = [e.step({a: act_env[a][i] for a in ids}) for i, e in enumerate(envs)]
+            next_obs = stack([o[0] for o in out])
+            reward = {a: np.array([o[1][a] for o in out], dtype=np.float64) for a in ids}
+            term = {a: np.array([o[2][a] for o in out], dtype=bool) for a in ids}
+            done = {a: term[a] | np.array([o[3][a] for o in out], dtype=bool) for a in ids}
+            policy.add(obs, action, reward, next_obs, term, logp, done)
+            ep_ret += sum(reward[a] for a in ids)
+            obs = next_obs
+            over = np.array([not e.agents for e in envs]) | np.any([done[a] for a in ids], axis=0)
+            if over.any():
+                obs = {a: next_obs[a].copy() for a in ids}
+                for i in np.nonzero(over)[0]:
+                    returns.append(ep_ret[i]); ep_ret[i] = 0.0
+                    o0 = envs[i].reset(seed=args.seed + int(i))[0]
+                    for a in ids:
+                        obs[a][i] = o0[a]
+            steps += N
+        policy.learn(min(args.minibatch_size, T * N), args.gamma, args.lmbda, args.clip_param, args.K_epochs, args.entropy_coefficient)
+        n_learn += 1
+        if args.log_every:
+            print("steps %d  rollouts %d  %.0f env-steps/s  mean return(last 20) %s" % (
+                steps, n_learn, steps / (time.perf_counter() - t0), "%.2f" % np.mean(returns[-20:]) if returns else "n/a"), flush=True)
+    if args.save_dir:
+        os.makedirs(args.save_dir, exist_ok=True)
+        policy.save(args.save_dir)
+    return {"policy": policy, "steps": steps, "learns": n_learn, "returns": returns}
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser()
-    ap.add_argument("--algo", default="SAC", choices=["SAC", "TD3", "DQN", "RAINBOW", "PPO"])
+    ap.add_argument("--algo", default="SAC", choices=["SAC", "TD3", "DQN", "RAINBOW", "PPO", "MAPPO"])
     ap.add_argument("--env_name", default="HalfCheetah-v4")
     ap.add_argument("--n_envs", type=int, default=256)
     ap.add_argument("--total_steps", type=int, default=100_000, help="env steps summed over the envs")
@@ -122,6 +180,7 @@ def main(argv=None):
     ap.add_argument("--lmbda", type=float, default=0.95)
     ap.add_argument("--clip_param", type=float, default=0.2)
     ap.add_argument("--entropy_coefficient", type=float, default=0.01)
+    ap.add_argument("--n_agents", type=int, default=0, help="MAPPO: N of the MPE env (0: its default)")
     ap.add_argument("--obs_norm", action="store_true", help="running observation normalisation over all envs (vecloop.Normalization)")
     ap.add_argument("--mode", default="fast", choices=["fast", "parity"])
     ap.add_argument("--seed", type=int, default=0)
@@ -130,10 +189,12 @@ def main(argv=None):
     ap.add_argument("--log_every", type=int, default=50, help="vector steps between progress lines (0: quiet)")
     args = ap.parse_args(argv)
 
-    gym = _gym()
     device = torch.device(args.device)
     np.random.seed(args.seed)
     torch.manual_seed(args.seed)
+    if args.algo == "MAPPO":
+        return _mappo_loop(args, device)
+    gym = _gym()
     N = args.n_envs
     envs = [gym.make(args.env_name) for _ in range(N)]
     space = envs[0].action_space

@@ -23,6 +23,9 @@ def _run(device, tmp_path):
         r = train_vec.main(["--algo", "PPO", "--env_name", env, "--n_envs", "8", "--horizon", "16", "--total_steps", "256", "--minibatch_size", "32",
                             "--K_epochs", "2", "--log_every", "0", "--device", str(device)])
         assert r["steps"] == 256 and r["learns"] == 2 and r["policy"].agent.step == 2 * 2 * 4
+    r = train_vec.main(["--algo", "MAPPO", "--env_name", "simple_spread_v3", "--n_agents", "3", "--n_envs", "4", "--horizon", "30", "--total_steps", "240",
+                        "--minibatch_size", "60", "--K_epochs", "2", "--log_every", "0", "--device", str(device)])
+    assert r["steps"] == 240 and r["learns"] == 2 and len(r["returns"]) == 4 * 2          # max_cycles 25: two finished episodes per env
     with pytest.raises(ValueError, match="action space"):
         train_vec.main(["--algo", "DQN", "--env_name", "Pendulum-v1"] + common)
 
