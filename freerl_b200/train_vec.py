@@ -2,6 +2,7 @@
 on the device.
 
     python -m freerl_b200.train_vec --algo SAC --env_name HalfCheetah-v4 --n_envs 256 --total_steps 1000000 --device cuda
+    torchrun --nproc-per-node 8 --master-addr 127.0.0.1 -m freerl_b200.train_vec --algo SAC --n_envs 256 …     # 8 x 256 envs, replica sync
 
 The same loop as the reference mains (``SAC_file/SAC.py:497-590``, ``TD3_file/TD3.py``, ``DQN_file/DQN.py:287-349``) with a leading env
 axis — one ``select_action`` (batched inference kernel) per vector step, one ``add`` of N transitions, then ``n_envs *
@@ -189,6 +190,20 @@ def main(argv=None):
     ap.add_argument("--log_every", type=int, default=50, help="vector steps between progress lines (0: quiet)")
     args = ap.parse_args(argv)
 
+    # one process per GPU (torchrun): every rank steps its own n_envs envs into its own replay shard — no data-path collective —
+    # and the SAC / TD3 replicas are kept one policy by a parameter average per vector step (ACBase.sync_replicas)
+    world, rank, dist = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), None
+    if world > 1:
+        if args.algo not in ("SAC", "TD3"):
+            raise ValueError("multi-process train_vec supports SAC and TD3 (replica sync); PPO data parallelism: PPO.enable_data_parallel")
+        import torch.distributed as dist
+        if args.device.startswith("cuda"):
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+            args.device = "cuda:%d" % int(os.environ.get("LOCAL_RANK", "0"))
+        if not dist.is_initialized():
+            dist.init_process_group("nccl" if args.device.startswith("cuda") else "gloo")
+        args.seed += 1000 * rank
+        args.log_every = args.log_every if rank == 0 else 0
     device = torch.device(args.device)
     np.random.seed(args.seed)
     torch.manual_seed(args.seed)
@@ -210,6 +225,8 @@ def main(argv=None):
     for i, e in enumerate(envs):
         e.action_space.seed(seed=args.seed + i)
     policy = build_policy(args.algo, obs_dim, act_dim, n_actions, args, device)
+    if world > 1:
+        policy.enable_replica_sync()                                                     # start every replica from rank 0's parameters
     norm = vecloop.Normalization(obs_dim, device) if args.obs_norm else None
 
     def observe(rows):
@@ -269,15 +286,17 @@ def main(argv=None):
                     policy.learn(args.batch_size, args.gamma, args.tau, n_updates=k)
                 carry -= k
                 n_learn += k
+                if world > 1:
+                    policy.sync_replicas()
         if args.log_every and vec_step % args.log_every == 0:
             dt = time.perf_counter() - t0
             print("steps %d  learns %d  %.0f env-steps/s  mean return(last 20) %s" % (
                 steps, n_learn, steps / dt, "%.2f" % np.mean(returns[-20:]) if returns else "n/a"), flush=True)
-    if args.save_dir:
+    if args.save_dir and rank == 0:
         os.makedirs(args.save_dir, exist_ok=True)
         policy.save(args.save_dir)
         np.save(os.path.join(args.save_dir, "%s_seed_%d.npy" % (args.algo, args.seed)), np.array(returns))
-    return {"policy": policy, "steps": steps, "learns": n_learn, "returns": returns}
+    return {"policy": policy, "steps": steps, "learns": n_learn, "returns": returns, "rank": rank, "world": world}
 
 
 if __name__ == "__main__":

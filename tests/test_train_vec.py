@@ -32,3 +32,35 @@ def _run(device, tmp_path):
 
 def test_train_vec_emulated(emul, tmp_path):
     _run(torch.device("cpu"), tmp_path)
+
+
+WORKER = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["FRL_ROOT"])
+from freerl_b200 import train_vec
+r = train_vec.main(["--algo", "SAC", "--env_name", "Pendulum-v1", "--n_envs", "4", "--total_steps", "96", "--random_steps", "16", "--start_steps", "32",
+                    "--batch_size", "8", "--buffer_size", "300", "--log_every", "0", "--device", "cpu"])
+pol = r["policy"]
+np.savez(os.path.join(os.environ["FRL_OUT"], "tv%d.npz" % r["rank"]), actor=pol.agent._actor.p.numpy(), critic=pol.agent._critic.p.numpy(),
+         first_obs=pol.buffer.obs[0].numpy(), learns=r["learns"], world=r["world"])
+dist.destroy_process_group()
+'''
+
+
+def test_train_vec_two_processes_gloo(tmp_path, emul):
+    """torchrun x 2 (gloo, host emulation): each rank steps its own envs into its own replay shard (different data), the replicas
+    end every vector step with the same averaged parameters."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    (tmp_path / "worker.py").write_text(WORKER)
+    env = dict(os.environ, FRL_ROOT=root, FRL_OUT=str(tmp_path), FREERL_B200_LIB=os.environ["FREERL_B200_LIB"], OMP_NUM_THREADS="2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", str(tmp_path / "worker.py")]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    a, b = np.load(tmp_path / "tv0.npz"), np.load(tmp_path / "tv1.npz")
+    assert int(a["world"]) == 2 and int(a["learns"]) == int(b["learns"]) == 68
+    assert not np.array_equal(a["first_obs"], b["first_obs"])                       # different env shards
+    assert np.array_equal(a["actor"], b["actor"]) and np.array_equal(a["critic"], b["critic"])
