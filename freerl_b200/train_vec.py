@@ -58,11 +58,13 @@ def build_policy(algo, obs_dim, act_dim, n_actions, args, device):
     raise ValueError("algo must be SAC, TD3, DQN or RAINBOW")
 
 
-def _ppo_loop(args, envs, obs_dim, action_dim, discrete, device):
+def _ppo_loop(args, envs, obs_dim, action_dim, discrete, device, world=1, rank=0):
     from .PPO import PPO
     N, T = args.n_envs, args.horizon
     max_action = None if discrete else float(envs[0].action_space.high[0])
     policy = PPO([obs_dim, action_dim], not discrete, args.actor_lr, args.critic_lr, T * N, device, trick={"adv_norm": False}, mode=args.mode)
+    if world > 1:      # synchronous data parallel: every minibatch step all-reduces ONE flat gradient buffer, replicas stay bit-identical
+        policy.enable_data_parallel()
     norm = vecloop.Normalization(obs_dim, device) if args.obs_norm else None
     observe = (lambda rows: norm(np.stack(rows).astype(np.float32)).cpu().numpy()) if norm is not None else (lambda rows: np.stack(rows).astype(np.float32))
     obs = observe([e.reset(seed=args.seed + i)[0] for i, e in enumerate(envs)])
@@ -91,10 +93,10 @@ def _ppo_loop(args, envs, obs_dim, action_dim, discrete, device):
         if args.log_every:
             print("steps %d  rollouts %d  %.0f env-steps/s  mean return(last 20) %s" % (
                 steps, n_learn, steps / (time.perf_counter() - t0), "%.2f" % np.mean(returns[-20:]) if returns else "n/a"), flush=True)
-    if args.save_dir:
+    if args.save_dir and rank == 0:
         os.makedirs(args.save_dir, exist_ok=True)
         policy.save(args.save_dir)
-    return {"policy": policy, "steps": steps, "learns": n_learn, "returns": returns}
+    return {"policy": policy, "steps": steps, "learns": n_learn, "returns": returns, "rank": rank, "world": world}
 
 
 def _mpe(name, **kw):
@@ -194,8 +196,8 @@ def main(argv=None):
     # and the SAC / TD3 replicas are kept one policy by a parameter average per vector step (ACBase.sync_replicas)
     world, rank, dist = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), None
     if world > 1:
-        if args.algo not in ("SAC", "TD3"):
-            raise ValueError("multi-process train_vec supports SAC and TD3 (replica sync); PPO data parallelism: PPO.enable_data_parallel")
+        if args.algo not in ("SAC", "TD3", "PPO"):
+            raise ValueError("multi-process train_vec supports SAC / TD3 (replica sync) and PPO (gradient all-reduce)")
         import torch.distributed as dist
         if args.device.startswith("cuda"):
             torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
@@ -220,7 +222,7 @@ def main(argv=None):
     act_dim = 1 if discrete else space.shape[0]
     n_actions = space.n if discrete else 0
     if args.algo == "PPO":
-        return _ppo_loop(args, envs, obs_dim, space.n if discrete else space.shape[0], discrete, device)
+        return _ppo_loop(args, envs, obs_dim, space.n if discrete else space.shape[0], discrete, device, world, rank)
     max_action = None if discrete else float(space.high[0])
     for i, e in enumerate(envs):
         e.action_space.seed(seed=args.seed + i)

@@ -41,8 +41,11 @@ from freerl_b200 import train_vec
 r = train_vec.main(["--algo", "SAC", "--env_name", "Pendulum-v1", "--n_envs", "4", "--total_steps", "96", "--random_steps", "16", "--start_steps", "32",
                     "--batch_size", "8", "--buffer_size", "300", "--log_every", "0", "--device", "cpu"])
 pol = r["policy"]
+q = train_vec.main(["--algo", "PPO", "--env_name", "Pendulum-v1", "--n_envs", "4", "--horizon", "16", "--total_steps", "128", "--minibatch_size", "16",
+                    "--K_epochs", "2", "--log_every", "0", "--device", "cpu"])
 np.savez(os.path.join(os.environ["FRL_OUT"], "tv%d.npz" % r["rank"]), actor=pol.agent._actor.p.numpy(), critic=pol.agent._critic.p.numpy(),
-         first_obs=pol.buffer.obs[0].numpy(), learns=r["learns"], world=r["world"])
+         first_obs=pol.buffer.obs[0].numpy(), learns=r["learns"], world=r["world"], ppo=q["policy"].agent._net.p.numpy(),
+         ppo_steps=q["policy"].agent.step)
 dist.destroy_process_group()
 '''
 
@@ -64,3 +67,5 @@ def test_train_vec_two_processes_gloo(tmp_path, emul):
     assert int(a["world"]) == 2 and int(a["learns"]) == int(b["learns"]) == 68
     assert not np.array_equal(a["first_obs"], b["first_obs"])                       # different env shards
     assert np.array_equal(a["actor"], b["actor"]) and np.array_equal(a["critic"], b["critic"])
+    # PPO: gradient all-reduce inside every minibatch step -> bit-identical replicas although the rollouts differ
+    assert int(a["ppo_steps"]) == 2 * 2 * 4 and np.array_equal(a["ppo"], b["ppo"])
