@@ -142,7 +142,22 @@ class ACBase:
             a.obs_norm_n0 = self.batch_size_obs_norm.running_ms.n
         return a, idx, B, out
 
+    def _fx_scratch(self, a):
+        """Scratch of the small-batch schedule (``csrc/algo_acfx.cuh``): exchange blocks sized by the library for these shapes
+        (0 floats = not eligible -> the generic kernel runs) and the barrier / flag words.  Call once every argument is set."""
+        need = int(_lib.lib().frl_ac_ws_floats(ctypes.byref(a)))
+        if need <= 0:
+            return
+        ws = getattr(self, "_fx_ws", None)
+        if ws is None or ws.numel() < need:
+            self._fx_ws = ws = torch.zeros(need, dtype=torch.float32, device=self.device)
+            self._fx_sync = torch.zeros(1024, dtype=torch.int32, device=self.device)
+        a.ws, a.sync = ws.data_ptr(), self._fx_sync.data_ptr()
+
     def _launch(self, a, keep, n_updates, out):
+        if a.n_agents <= 1:
+            self._fx_scratch(a)
+        self.last_path = int(_lib.lib().frl_ac_path(ctypes.byref(a)))       # 1: small-batch schedule, 0: generic kernel
         _lib.check(_lib.lib().frl_ac_learn(ctypes.byref(a), _lib.stream_ptr(self.device)), "frl_ac_learn")
         self.last_metrics = out[:n_updates]
         self._keepalive = keep

@@ -12,7 +12,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 FRL_MAX_LAYERS = 6
 FRL_MAX_AGENTS = 6
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class Layer(C.Structure):
@@ -55,7 +55,7 @@ class AcArgs(C.Structure):
                 ("n_agents", C.c_int), ("agent_index", C.c_int), ("ma_replay", Replay * FRL_MAX_AGENTS),
                 ("ma_actor_target", Net * FRL_MAX_AGENTS), ("defer_polyak", C.c_int), ("xchg", C.c_void_p),
                 ("obs_norm", C.c_void_p * FRL_MAX_AGENTS), ("obs_norm_n0", C.c_int64),
-                ("ma_noise_next", C.c_void_p * FRL_MAX_AGENTS)]
+                ("ma_noise_next", C.c_void_p * FRL_MAX_AGENTS), ("ws", C.c_void_p), ("sync", C.c_void_p)]
 
 
 class InferArgs(C.Structure):
@@ -122,6 +122,10 @@ def _declare(lib):
     lib.frl_polyak.restype = ci
     lib.frl_dqn_learn.argtypes = [C.POINTER(DqnArgs), vp]
     lib.frl_ac_learn.argtypes = [C.POINTER(AcArgs), vp]
+    lib.frl_ac_ws_floats.argtypes = [C.POINTER(AcArgs)]
+    lib.frl_ac_ws_floats.restype = C.c_longlong
+    lib.frl_ac_path.argtypes = [C.POINTER(AcArgs)]
+    lib.frl_ac_path.restype = ci
     lib.frl_policy_infer.argtypes = [C.POINTER(InferArgs), vp]
     lib.frl_gae.argtypes = [vp, vp, vp, vp, vp, ci, ci, C.c_double, C.c_double, vp, vp, vp]
     lib.frl_ppo_update.argtypes = [C.POINTER(PpoArgs), vp]

@@ -13,7 +13,11 @@ import collections
 import numpy as np
 import torch
 
-_SKIP_PREFIX = ("last_", "_last_eps", "_keep", "_c", "_dp", "_rs")
+# transient members, by EXACT name (a prefix rule would silently drop any future `_c…` / `_keep…` state from checkpoints):
+# results of the last call, keep-alive references of in-flight launches, cached C descriptors, process-group handles, and the
+# scratch of the small-batch actor-critic schedule (rewritten by every launch)
+_SKIP = frozenset(("last_adv", "last_error", "last_factor", "last_indices", "last_metrics", "last_path", "last_v_target", "_last_eps",
+                   "_keep", "_keep_noise", "_keepalive", "_c", "_dp", "_rs", "_fx_ws", "_fx_sync"))
 _SCALARS = (int, float, bool, str, type(None), np.integer, np.floating, np.bool_)
 
 
@@ -30,7 +34,7 @@ def _walk(obj, path, out, seen, frozen=False):
     if isinstance(obj, torch.nn.Module) or callable(obj) and not hasattr(obj, "__dict__"):
         return
     if isinstance(obj, collections.deque):
-        out[path] = obj                      # n-step windows: numpy payloads, stored whole
+        out[path] = obj                      # n-step windows: numpy payloads, stored whole (aliases share one object, see save)
         return
     if isinstance(obj, dict):
         seen.add(id(obj))
@@ -48,7 +52,7 @@ def _walk(obj, path, out, seen, frozen=False):
         return
     seen.add(id(obj))
     for k, v in vars(obj).items():
-        if k.startswith(_SKIP_PREFIX) and k not in ("_critic", "_critic_t", "_counter"):
+        if k in _SKIP:
             continue
         _walk(v, "%s.%s" % (path, k), out, seen)
 
@@ -62,11 +66,13 @@ def state_of(policy):
 def save_checkpoint(policy, path):
     st = state_of(policy)
     blob = {"format": "freerl_b200.checkpoint/1", "class": "%s.%s" % (type(policy).__module__, type(policy).__name__), "state": {}}
+    deque_ids = {}
     for k, v in st.items():
         if isinstance(v, torch.Tensor):
             blob["state"][k] = ("tensor", v.detach().cpu().clone())
         elif isinstance(v, collections.deque):
-            blob["state"][k] = ("deque", (list(v), v.maxlen))
+            first = deque_ids.setdefault(id(v), k)
+            blob["state"][k] = ("deque", (list(v), v.maxlen)) if first == k else ("alias", first)
         else:
             blob["state"][k] = ("value", v)
     blob["rng"] = {"numpy": np.random.get_state(), "torch": torch.get_rng_state(),
@@ -75,22 +81,24 @@ def save_checkpoint(policy, path):
 
 
 def _assign(policy, path, value):
-    """set `policy<path> = value` for a path made of .attr and [key] steps"""
+    """set `policy<path> = value` for a path made of .attr and [key] steps (keys are str / int literals)"""
     import re
+    from ast import literal_eval as _lit
     steps = re.findall(r"\.([A-Za-z_]\w*)|\[([^\]]+)\]", path[len("policy"):])
     obj = policy
     for attr, key in steps[:-1]:
-        obj = getattr(obj, attr) if attr else obj[eval(key)]
+        obj = getattr(obj, attr) if attr else obj[_lit(key)]
     attr, key = steps[-1]
     if attr:
         setattr(obj, attr, value)
-    elif isinstance(obj, list) and eval(key) == len(obj):
+    elif isinstance(obj, list) and _lit(key) == len(obj):
         obj.append(value)                    # e.g. one n-step window per vectorised env, created lazily
     else:
-        obj[eval(key)] = value
+        obj[_lit(key)] = value
 
 
 def load_checkpoint(policy, path, restore_rng=True):
+    """Checkpoints are TRUSTED files (pickled numpy payloads and RNG states): only load what this package wrote."""
     blob = torch.load(path, weights_only=False)
     if blob.get("format") != "freerl_b200.checkpoint/1":
         raise ValueError("not a freerl_b200 checkpoint: %s" % path)
@@ -101,6 +109,7 @@ def load_checkpoint(policy, path, restore_rng=True):
     missing = [k for k, (kind, _) in blob["state"].items() if kind == "tensor" and k not in cur]
     if missing:
         raise ValueError("policy was constructed differently from the checkpointed one (no %s)" % missing[0])
+    restored = {}
     for k, (kind, v) in blob["state"].items():
         if kind == "tensor":
             dst = cur[k]
@@ -111,7 +120,10 @@ def load_checkpoint(policy, path, restore_rng=True):
                 raise ValueError("shape mismatch at %s: %s vs %s" % (k, tuple(dst.shape), tuple(v.shape)))
             dst.copy_(v.to(dst.device))
         elif kind == "deque":
-            _assign(policy, k, collections.deque(v[0], maxlen=v[1]))
+            restored[k] = collections.deque(v[0], maxlen=v[1])
+            _assign(policy, k, restored[k])
+        elif kind == "alias":                # a second name of a deque saved above: the same object again
+            _assign(policy, k, restored[v])
         else:
             _assign(policy, k, v)
     if restore_rng:

@@ -1,0 +1,1204 @@
+// Small-batch fused actor-critic learn() — the latency-optimised schedule for the reference's own batch sizes (B <= 256).
+//   SAC   SAC_file/SAC.py:222-271      TD3   TD3_file/TD3.py:189-244      DDPG   DDPG_file/DDPG.py:203-233
+// Same arithmetic as algo_ac.cuh (single agent, hidden 128-128, no Batch_ObsNorm); what changes is WHERE the work runs.  The
+// r1 trace of the generic kernel (profiles/r2a_trace_generic.txt) showed a learn as a chain of 28 layer ops of ~3.4 k clk each
+// — 1.9 k in the FMA loop, 0.9 k in the shared-memory K-split pass, 0.6 k of scalar index math between ops — plus 12 k clk of
+// per-tile outer products, 2 x 11 k clk of reduce / Adam stages and 7 cooperative-groups grid barriers of 2.5 k clk.  Here:
+//   * CTA sets.  For every 8-row tile t and critic head h there is a TARGET CTA T(t,h) and an ONLINE CTA C(t,h); weights stay
+//     resident in shared memory (T: actor_target + target head h; C: actor + online head h) and are re-fetched by TMA only
+//     after the optimiser stage that rewrites them.  T and C run concurrently in phase A: T computes a' and Q'_h(s',a') and
+//     publishes them with a release flag, C meanwhile runs the online critic forward on (s,a) and the actor forward pi(s),
+//     then picks up the targets (acquire spin), forms y and backpropagates.  The chain per learn drops from 28 ops to 16.
+//   * dW out of the chain.  Worker CTAs only write the layer inputs X_l and pre-activation gradients dY_l of their tile to a
+//     blocked exchange buffer in L2; the weight gradient dW_l = dY_l^T X_l over ALL rows is one batched GEMM stage whose
+//     16x16 / 16x32 output tiles are spread over all 148 SMs (operands arrive as contiguous TMA bulk copies).  The CTA that
+//     produced a tile keeps it in shared memory across the norm barrier and applies clip + Adam + Polyak + mirror refresh to
+//     exactly those elements: no per-CTA partial gradients, no separate cross-CTA reduce stage, fixed summation order.
+//   * GEMM microkernels with static 128-wide shapes: each warp owns 16 output columns, lanes split K 8 ways and combine with a
+//     3-step shuffle reduce-scatter (no shared-memory K-split pass, one barrier per op).
+//   * Hand-rolled grid barrier (red.release + ld.acquire spin on one L2 word) instead of cooperative-groups grid.sync.
+// Stages per learn:  0 phase A (targets || online critic + actor forward, critic backward)   1 dW(critic) + sum of squares
+//   2 clip + Adam(critic) + Polyak   3 phase C (Q(s,pi(s)), dQ/da, actor backward)   4 dW(actor)   5 Adam(actor) + Polyak + alpha
+#pragma once
+#include "algo_ac.cuh"
+
+#define FX_LDW 132            // wt_ld_of(128): row stride of a 128-wide layer image
+#define FX_MAXB 256           // exchange operands of one dW job must fit one weight slot
+#define FX_SPIN_LIMIT (1u << 24)
+
+// ------------------------------------------------------------------------------------------------------------------------
+// cross-CTA signalling (GPU: release / acquire on L2 words; emulation: CTAs of a stage run in index order)
+// ------------------------------------------------------------------------------------------------------------------------
+#ifndef FRL_EMUL
+FRL_DEV void fx_flag_set(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+FRL_DEV unsigned fx_flag_ld(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+FRL_DEV void fx_flag_wait(const unsigned* p, unsigned v) {
+  unsigned spins = 0;
+  while ((int)(fx_flag_ld(p) - v) < 0) {
+    if (++spins > FX_SPIN_LIMIT) __trap();        // never hang the device on a protocol bug
+  }
+}
+FRL_DEV float fx_ldcg(const float* p) { return __ldcg(p); }
+FRL_DEV float shx(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+// grid-wide barrier: every CTA adds 1 to *ctr (zeroed by the host before the launch) and waits for `target` arrivals
+FRL_DEV void fx_grid_barrier(unsigned* ctr, unsigned target) {
+  __syncthreads();
+  trace(90);
+  if (threadIdx.x == 0) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+    trace(91);
+    unsigned spins = 0;
+    while ((int)(fx_flag_ld(ctr) - target) < 0) {
+      if (++spins > FX_SPIN_LIMIT) __trap();
+    }
+    trace(92);
+  }
+  __syncthreads();
+  trace(93);
+}
+#else
+#include <stdlib.h>
+#include <stdio.h>
+static inline void fx_flag_set(unsigned* p, unsigned v) { *p = v; }
+static inline void fx_flag_wait(const unsigned* p, unsigned v) {
+  if ((int)(*p - v) < 0) { fprintf(stderr, "frl emulation: AcFx flag protocol violated (%u < %u)\n", *p, v); abort(); }
+}
+static inline float fx_ldcg(const float* p) { return *p; }
+// per-thread scratch standing in for the register files of one CTA when a warp shuffle has to be emulated
+static thread_local float fx_emu_a[FRL_NT][64];
+static thread_local float fx_emu_b[FRL_NT][64];
+// one reduce-scatter step on NV values per thread: thread t keeps half (t & m ? 1 : 0) and adds its partner's copy of that half
+static inline void fx_emu_rs(float (*src)[64], float (*dst)[64], int NV, int m) {
+  for (int t = 0; t < FRL_NT; ++t) {
+    const int h = (t & m) ? NV / 2 : 0;
+    for (int i = 0; i < NV / 2; ++i) dst[t][i] = fadd(src[t][h + i], src[t ^ m][h + i]);
+  }
+}
+// butterfly sum step: every thread adds its partner's value
+static inline void fx_emu_bf(float (*src)[64], float (*dst)[64], int NV, int m) {
+  for (int t = 0; t < FRL_NT; ++t)
+    for (int i = 0; i < NV; ++i) dst[t][i] = fadd(src[t][i], src[t ^ m][i]);
+}
+#endif
+
+// ------------------------------------------------------------------------------------------------------------------------
+// microkernels on one 8-row tile, 256 threads.  Activation tiles are [8][128] (hidden) or [8][ld] (inputs), zero padded.
+// ------------------------------------------------------------------------------------------------------------------------
+
+// Y[8][128] = act(X[8][4 nch] * WT[4 nch][128] + bias)         (layer 0: nch = in_pad / 4 <= 8; layer 1: nch = 32)
+//   warp w owns columns 16w..16w+15; lane (kq = lane / 4, cg = lane % 4) accumulates all 8 rows x 4 columns over the K chunks
+//   kq, kq + 8, ...; the 8 K-partials are combined by a reduce-scatter over lane bits 4, 3, 2 that leaves row kq with lane kq.
+//   Bank behaviour: a quarter warp reads two consecutive 16-B chunks of X (broadcast) and rows 4c+q of two chunks 16 B x 4
+//   wide whose row offset differs by 4 * 132 = 16 (mod 32) words — conflict free.
+template <int NCH_STATIC>
+FRL_NI_GEMM void fx_fwd(const float* X, int ldx, int nch_rt, const float* W, const float* bias, int relu, float* Y) {
+  const int nch = NCH_STATIC > 0 ? NCH_STATIC : nch_rt;
+  trace(50);
+  FRL_PAR(t) {
+    const int w = t >> 5, l = t & 31, cg = l & 3, kq = l >> 2, col = 16 * w + 4 * cg;
+    const sptr sX = sp_of(X), sW = sp_of(W);
+    float acc[8][4];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[r][j] = 0.f;
+    constexpr int NIT = NCH_STATIC > 0 ? (NCH_STATIC + 7) / 8 : 1;      // layer 0 has in_pad <= 32: one pass
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int c = kq + 8 * it;
+      if (NCH_STATIC <= 0 && c >= nch) break;
+      const int wb = 4 * c * FX_LDW + col;
+      const float4 b0 = sp_ld4(sW, wb), b1 = sp_ld4(sW, wb + FX_LDW), b2 = sp_ld4(sW, wb + 2 * FX_LDW), b3 = sp_ld4(sW, wb + 3 * FX_LDW);
+      float4 av[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) av[r] = sp_ld4(sX, r * ldx + 4 * c);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        fma2_bcast(acc[r][0], acc[r][1], av[r].x, b0.x, b0.y); fma2_bcast(acc[r][2], acc[r][3], av[r].x, b0.z, b0.w);
+        fma2_bcast(acc[r][0], acc[r][1], av[r].y, b1.x, b1.y); fma2_bcast(acc[r][2], acc[r][3], av[r].y, b1.z, b1.w);
+        fma2_bcast(acc[r][0], acc[r][1], av[r].z, b2.x, b2.y); fma2_bcast(acc[r][2], acc[r][3], av[r].z, b2.z, b2.w);
+        fma2_bcast(acc[r][0], acc[r][1], av[r].w, b3.x, b3.y); fma2_bcast(acc[r][2], acc[r][3], av[r].w, b3.z, b3.w);
+      }
+    }
+#ifndef FRL_EMUL
+    const bool h4 = (l & 16) != 0, h3 = (l & 8) != 0, h2 = (l & 4) != 0;
+    float v1[4][4], v2[2][4], v3[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float keep = h4 ? acc[i + 4][j] : acc[i][j], send = h4 ? acc[i][j] : acc[i + 4][j];
+        v1[i][j] = keep + shx(send, 16);
+      }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float keep = h3 ? v1[i + 2][j] : v1[i][j], send = h3 ? v1[i][j] : v1[i + 2][j];
+        v2[i][j] = keep + shx(send, 8);
+      }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float keep = h2 ? v2[1][j] : v2[0][j], send = h2 ? v2[0][j] : v2[1][j];
+      v3[j] = keep + shx(send, 4);
+    }
+    const float4 bv = sp_ld4(sp_of(bias), col);
+    float o[4] = {v3[0] + bv.x, v3[1] + bv.y, v3[2] + bv.z, v3[3] + bv.w};
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = o[j] > 0.f ? o[j] : 0.f;
+    }
+    sp_st4(sp_of(Y), kq * 128 + col, make_float4(o[0], o[1], o[2], o[3]));
+#else
+    for (int r = 0; r < 8; ++r)
+      for (int j = 0; j < 4; ++j) fx_emu_a[t][r * 4 + j] = acc[r][j];
+#endif
+  }
+#ifdef FRL_EMUL
+  fx_emu_rs(fx_emu_a, fx_emu_b, 32, 16);
+  fx_emu_rs(fx_emu_b, fx_emu_a, 16, 8);
+  fx_emu_rs(fx_emu_a, fx_emu_b, 8, 4);
+  FRL_PAR(t) {
+    const int w = t >> 5, l = t & 31, cg = l & 3, kq = l >> 2, col = 16 * w + 4 * cg;
+    for (int j = 0; j < 4; ++j) {
+      float o = fx_emu_b[t][j] + bias[col + j];
+      if (relu) o = o > 0.f ? o : 0.f;
+      Y[kq * 128 + col + j] = o;
+    }
+  }
+#endif
+  trace(51);
+  FRL_SYNC();
+  trace(53);
+}
+
+// dX[8][128] = (dY[8][128] * W[128][128]) * relu'(mask)  on the forward image WT[k][n] (row k holds column k of W):
+//   dX[r][k] = sum_n dY[r][n] WT[k][n].  Warp w owns outputs k = 16w..16w+15; lane (cg = lane / 8, nq = lane % 8) accumulates
+//   8 rows x 4 outputs (k = 16w + 4cg + i) over the n chunks nq, nq + 8, ... with even / odd n in separate accumulators (both
+//   operands are natural register pairs of the 16-B loads -> FFMA2); reduce-scatter over lane bits 2, 1, 0 leaves row nq.
+//   A quarter warp reads one 128-B row segment of WT and one of dY: conflict free.
+FRL_NI_GEMM void fx_bwd(const float* dY, const float* W, const float* mask, float* dX) {
+  trace(60);
+  FRL_PAR(t) {
+    const int w = t >> 5, l = t & 31, nq = l & 7, cg = l >> 3, k0 = 16 * w + 4 * cg;
+    const sptr sY = sp_of(dY), sW = sp_of(W);
+    float acc[8][4], ach[8][4];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { acc[r][i] = 0.f; ach[r][i] = 0.f; }
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int c = nq + 8 * it;
+      float4 bv[4], av[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) bv[i] = sp_ld4(sW, (k0 + i) * FX_LDW + 4 * c);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) av[r] = sp_ld4(sY, r * 128 + 4 * c);
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          fma2_elem(acc[r][i], ach[r][i], av[r].x, av[r].y, bv[i].x, bv[i].y);
+          fma2_elem(acc[r][i], ach[r][i], av[r].z, av[r].w, bv[i].z, bv[i].w);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[r][i] += ach[r][i];
+#ifndef FRL_EMUL
+    const bool h2 = (l & 4) != 0, h1 = (l & 2) != 0, h0 = (l & 1) != 0;
+    float v1[4][4], v2[2][4], v3[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float keep = h2 ? acc[i + 4][j] : acc[i][j], send = h2 ? acc[i][j] : acc[i + 4][j];
+        v1[i][j] = keep + shx(send, 4);
+      }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float keep = h1 ? v1[i + 2][j] : v1[i][j], send = h1 ? v1[i][j] : v1[i + 2][j];
+        v2[i][j] = keep + shx(send, 2);
+      }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float keep = h0 ? v2[1][j] : v2[0][j], send = h0 ? v2[0][j] : v2[1][j];
+      v3[j] = keep + shx(send, 1);
+    }
+    const float4 mv = sp_ld4(sp_of(mask), nq * 128 + k0);
+    sp_st4(sp_of(dX), nq * 128 + k0,
+           make_float4(mv.x > 0.f ? v3[0] : 0.f, mv.y > 0.f ? v3[1] : 0.f, mv.z > 0.f ? v3[2] : 0.f, mv.w > 0.f ? v3[3] : 0.f));
+#else
+    for (int r = 0; r < 8; ++r)
+      for (int i = 0; i < 4; ++i) fx_emu_a[t][r * 4 + i] = acc[r][i];
+#endif
+  }
+#ifdef FRL_EMUL
+  fx_emu_rs(fx_emu_a, fx_emu_b, 32, 4);
+  fx_emu_rs(fx_emu_b, fx_emu_a, 16, 2);
+  fx_emu_rs(fx_emu_a, fx_emu_b, 8, 1);
+  FRL_PAR(t) {
+    const int w = t >> 5, l = t & 31, nq = l & 7, cg = l >> 3, k0 = 16 * w + 4 * cg;
+    for (int j = 0; j < 4; ++j) dX[nq * 128 + k0 + j] = mask[nq * 128 + k0 + j] > 0.f ? fx_emu_b[t][j] : 0.f;
+  }
+#endif
+  trace(61);
+  FRL_SYNC();
+  trace(63);
+}
+
+// narrow head forward:  Y[8][ldy] (columns < NO) = X[8][128] * WT[128][ld] + bias,  NO = 4 or 8 (the layer's out_pad).
+//   warp r = row, lane l owns k = l, l + 32, l + 64, l + 96 (consecutive lanes read consecutive 16-B / 48-B rows of WT);
+//   the 32 K-partials of each output are summed by a 5-step butterfly (every lane ends with the same total).
+FRL_NI_GEMM void fx_fwd_narrow(const float* X, const float* W, const float* bias, int NO, int ld, float* Y, int ldy) {
+  trace(54);
+  FRL_PAR(t) {
+    const int r = t >> 5, l = t & 31;
+    const sptr sX = sp_of(X), sW = sp_of(W);
+    float p[8];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) p[n] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int k = l + 32 * q;
+      const float a = sp_ld1(sX, r * 128 + k);
+      const float4 b0 = sp_ld4(sW, k * ld);
+      p[0] += a * b0.x; p[1] += a * b0.y; p[2] += a * b0.z; p[3] += a * b0.w;
+      if (NO > 4) {
+        const float4 b1 = sp_ld4(sW, k * ld + 4);
+        p[4] += a * b1.x; p[5] += a * b1.y; p[6] += a * b1.z; p[7] += a * b1.w;
+      }
+    }
+#ifndef FRL_EMUL
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1)
+#pragma unroll
+      for (int n = 0; n < 8; ++n) p[n] += shx(p[n], m);
+    if (l < NO) {
+      float v = p[0];
+#pragma unroll
+      for (int n = 1; n < 8; ++n) v = (l == n) ? p[n] : v;
+      Y[r * ldy + l] = v + bias[l];
+    }
+#else
+    for (int n = 0; n < 8; ++n) fx_emu_a[t][n] = p[n];
+#endif
+  }
+#ifdef FRL_EMUL
+  fx_emu_bf(fx_emu_a, fx_emu_b, 8, 16);
+  fx_emu_bf(fx_emu_b, fx_emu_a, 8, 8);
+  fx_emu_bf(fx_emu_a, fx_emu_b, 8, 4);
+  fx_emu_bf(fx_emu_b, fx_emu_a, 8, 2);
+  fx_emu_bf(fx_emu_a, fx_emu_b, 8, 1);
+  FRL_PAR(t) {
+    const int r = t >> 5, l = t & 31;
+    if (l < NO) Y[r * ldy + l] = fx_emu_b[t][l] + bias[l];
+  }
+#endif
+  trace(55);
+  FRL_SYNC();
+}
+
+// narrow head backward:  dH[8][128] = (dOut[8][ldo](columns < NO) * W) * relu'(mask):  dH[r][k] = sum_n dOut[r][n] WT[k][n]
+FRL_NI_GEMM void fx_bwd_narrow(const float* dOut, int ldo, const float* W, int NO, int ld, const float* mask, float* dH) {
+  trace(64);
+  // thread = (output column k, rows 4 hi .. 4 hi + 3): consecutive lanes read consecutive 16-B (NO = 4) / 48-B (NO = 8) rows of WT
+  // and write consecutive words of dH — no bank conflicts; the dOut rows are warp-wide broadcasts
+  FRL_PAR(t) {
+    const int k = t & 127, hi = t >> 7;
+    const sptr sW = sp_of(W), sO = sp_of(dOut), sM = sp_of(mask), sH = sp_of(dH);
+    const float4 w0 = sp_ld4(sW, k * ld);
+    float4 w1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (NO > 4) w1 = sp_ld4(sW, k * ld + 4);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = 4 * hi + i;
+      const float4 d0 = sp_ld4(sO, r * ldo);
+      float s = 0.f;
+      s += d0.x * w0.x; s += d0.y * w0.y; s += d0.z * w0.z; s += d0.w * w0.w;
+      if (NO > 4) {
+        const float4 d1 = sp_ld4(sO, r * ldo + 4);
+        s += d1.x * w1.x; s += d1.y * w1.y; s += d1.z * w1.z; s += d1.w * w1.w;
+      }
+      sp_st1(sH, r * 128 + k, sp_ld1(sM, r * 128 + k) > 0.f ? s : 0.f);
+    }
+  }
+  trace(65);
+  FRL_SYNC();
+}
+
+// gradient wrt NA (<= 8) input columns c0.. of layer 0 (dQ/da):  dXa[r][j] = sum_n D1[r][n] WT0[c0 + j][n]
+FRL_NI_GEMM void fx_bwd_cols(const float* D1, const float* W0, int c0, int NA, float* dXa /*[8][8]*/) {
+  trace(66);
+  FRL_PAR(t) {
+    const int r = t >> 5, l = t & 31, j = l & 7, nq = l >> 3;
+    float p = 0.f;
+    if (j < NA) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 a = ld4(D1 + r * 128 + 32 * nq + 4 * i), b = ld4(W0 + (c0 + j) * FX_LDW + 32 * nq + 4 * i);
+        p += a.x * b.x; p += a.y * b.y; p += a.z * b.z; p += a.w * b.w;
+      }
+    }
+#ifndef FRL_EMUL
+    p += shx(p, 8);
+    p += shx(p, 16);
+    if (nq == 0) dXa[r * 8 + j] = p;
+#else
+    fx_emu_a[t][0] = p;
+#endif
+  }
+#ifdef FRL_EMUL
+  fx_emu_bf(fx_emu_a, fx_emu_b, 1, 8);
+  fx_emu_bf(fx_emu_b, fx_emu_a, 1, 16);
+  FRL_PAR(t) {
+    const int r = t >> 5, l = t & 31;
+    if ((l >> 3) == 0) dXa[r * 8 + (l & 7)] = fx_emu_a[t][0];
+  }
+#endif
+  trace(67);
+  FRL_SYNC();
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// exchange buffer: layer inputs X and pre-activation gradients dY of every tile, blocked [block of 16 columns][row][16] so
+// that the operands of one dW job are contiguous (1-D TMA bulk copies)
+// ------------------------------------------------------------------------------------------------------------------------
+FRL_HD int fx_xb(const frl_net_t& n, int li) { return (n.L[li].in_pad + 15) >> 4; }
+FRL_HD int fx_yb(const frl_net_t& n, int li) { return (n.L[li].out_pad + 15) >> 4; }
+FRL_HD int fx_xblocks(const frl_net_t& n, int upto) { int b = 0; for (int i = 0; i < upto; ++i) b += fx_xb(n, i); return b; }
+FRL_HD int fx_yblocks(const frl_net_t& n, int upto) { int b = 0; for (int i = 0; i < upto; ++i) b += fx_yb(n, i); return b; }
+
+// copy a tile T[8][ld] (columns [0, 16 nblk)) into blocks blk0.. of an exchange region: rows row0..row0+7
+FRL_DEV void fx_put_blocks(float* region, int blk0, int nblk, int Rmax, int row0, const float* T, int ld, int width) {
+  FRL_PAR(t) {
+    const int sh = nblk == 8 ? 5 : (nblk == 2 ? 3 : (nblk == 1 ? 2 : -1));        // log2(4 nblk) for the block counts in use
+    for (int e = t; e < 8 * nblk * 4; e += FRL_NT) {
+      const int r = sh >= 0 ? (e >> sh) : e / (nblk * 4), q = e - r * (nblk * 4), b = q >> 2, c4 = (q & 3) * 4, col = b * 16 + c4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col + 3 < width) v = ld4(T + r * ld + col);
+      else {
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int i = 0; i < 4; ++i) if (col + i < width) o[i] = T[r * ld + col + i];
+        v = make_float4(o[0], o[1], o[2], o[3]);
+      }
+      st4(region + ((size_t)(blk0 + b) * Rmax + row0 + r) * 16 + c4, v);
+    }
+  }
+}
+
+struct FxJob {
+  int li;         // absolute layer index (-1: the extras job, e.g. SAC log_std)
+  int n0, k0;     // first output row / input column
+  int NB, KB;     // tile height / width (NB * KB in {256, 512})
+};
+
+struct AcFx {
+  typedef frl_ac_args_t Args;
+  static const int NSTAGES = 6;
+  FRL_SHD int heads(const Args& a) { return a.n_heads; }
+  FRL_SHD bool is_sac(const Args& a) { return a.actor_kind == FRL_ACTOR_SAC; }
+  FRL_SHD int ntile(const Args& a) { return (a.B + 7) >> 3; }
+  FRL_SHD int rmax(const Args& a) { return ntile(a) * 8; }
+  // (the 64-bit modulo is a ~500-clk subroutine on the GPU: not paid when every step is a policy step)
+  FRL_SHD bool is_policy_step(const Args& a, int u) { return a.policy_freq <= 1 ? true : ((a.total_it0 + u + 1) % a.policy_freq) == 0; }
+  FRL_SHD bool stage_enabled(int s, int u, const Args& a) { return s >= 3 ? is_policy_step(a, u) : true; }
+  FRL_SHD bool writes_params(int) { return true; }     // every stage publishes something a later TMA copy reads
+  FRL_SHD int n_updates(const Args& a) { return a.n_updates; }
+  FRL_SHD int heads_used(const Args& a) { return is_sac(a) ? a.n_heads : 1; }
+
+  FRL_SHD int head_floats(const frl_net_t& n, int l0) { return wt_floats(n.L[l0]) + wt_floats(n.L[l0 + 1]) + wt_floats(n.L[l0 + 2]); }
+  FRL_SHD int wbuf_floats(const Args& a) {
+    int x = head_floats(a.actor, 0), y = head_floats(a.critic, 0);
+    return ((x > y ? x : y) + 31) & ~31;
+  }
+  // shared memory after the engine's own (two slots + c.red + mbarriers): see the SmemBump sequence in stage()
+  static const int GST_SLOTS = 2;                    // dW jobs one CTA may own (jobs <= GST_SLOTS * grid)
+  FRL_SHD int user_floats(const Args& a) {
+    return 8 * a.replay.row_floats + 3 * 8 * 32 + 64 + 6 * 1024 + 5 * 64 + 3 * 32 + 2 * FRL_NT + GST_SLOTS * 528 + 128 + GST_SLOTS * 16 + 16 + 64;
+  }
+  FRL_SHD int grid(const Args&, int max_ctas) { return max_ctas; }
+
+  // ---- exchange / workspace layout (floats) ----
+  struct Ws {
+    size_t cx, cy, ax, ay0, ay1, xq, xlp, lsg, stats, sumsq, total;
+  };
+  FRL_SHD Ws ws_layout(const Args& a, int ncta) {
+    Ws w;
+    const size_t R16 = (size_t)rmax(a) * 16;
+    size_t o = 0;
+    w.cx = o; o += (size_t)fx_xblocks(a.critic, a.critic.n_layers) * R16;
+    w.cy = o; o += (size_t)fx_yblocks(a.critic, a.critic.n_layers) * R16;
+    w.ax = o; o += (size_t)fx_xblocks(a.actor, 3) * R16;
+    w.ay0 = o; o += (size_t)fx_yblocks(a.actor, 3) * R16;
+    w.ay1 = o; o += (size_t)fx_yblocks(a.actor, 3) * R16;
+    w.xq = o; o += (size_t)rmax(a) * 2;
+    w.xlp = o; o += (size_t)rmax(a);
+    w.lsg = o; o += (size_t)ncta * 8;
+    w.stats = o; o += (size_t)ncta * 8;
+    w.sumsq = o; o += 512;
+    w.total = (o + 3) & ~(size_t)3;
+    return w;
+  }
+
+  // ---- dW jobs of a net: layer li % 3 == 0 -> 16 x 32 tiles, 1 -> 16 x 16, 2 -> out_pad x (256 / out_pad); + extras ----
+  FRL_SHD void job_shape(const frl_net_t& n, int li, int* NB, int* KB) {
+    const int k = li % 3;
+    if (k == 0) { *NB = 16; *KB = 32; }
+    else if (k == 1) { *NB = 16; *KB = 16; }
+    else { *NB = n.L[li].out_pad >= 16 ? 16 : (n.L[li].out_pad >= 8 ? 8 : 4); *KB = *NB == 16 ? 16 : (*NB == 8 ? 32 : 64); }
+  }
+  FRL_SHD int lg2(int x) { return x >= 64 ? 6 : (x >= 32 ? 5 : (x >= 16 ? 4 : (x >= 8 ? 3 : 2))); }      // tile sides are 4 .. 64
+  FRL_SHD int layer_jobs(const frl_net_t& n, int li) {
+    int NB, KB;
+    job_shape(n, li, &NB, &KB);
+    return ((n.L[li].out_pad + NB - 1) >> lg2(NB)) * ((n.L[li].in_pad + KB - 1) >> lg2(KB));
+  }
+  FRL_SHD int net_jobs(const frl_net_t& n) {
+    int j = 0;
+    for (int li = 0; li < n.n_layers; ++li) j += layer_jobs(n, li);
+    return j + (n.x_len > 0 ? 1 : 0);
+  }
+  FRL_SHD FxJob job_of(const frl_net_t& n, int j) {
+    FxJob J;
+    for (int li = 0; li < n.n_layers; ++li) {
+      const int cnt = layer_jobs(n, li);
+      if (j < cnt) {
+        job_shape(n, li, &J.NB, &J.KB);
+        const int kbc = (n.L[li].in_pad + J.KB - 1) >> lg2(J.KB);
+        const int jn = kbc == 1 ? j : (kbc == 8 ? j >> 3 : (kbc == 2 ? j >> 1 : j / kbc));
+        J.li = li; J.n0 = jn * J.NB; J.k0 = (j - jn * kbc) * J.KB;
+        return J;
+      }
+      j -= cnt;
+    }
+    J.li = -1; J.n0 = J.k0 = 0; J.NB = J.KB = 0;
+    return J;
+  }
+
+  // host-side eligibility (capi.cu): everything else takes the generic kernel of algo_ac.cuh
+  FRL_SHD bool shape_ok(const frl_net_t& n, int l0, int max_out) {
+    return n.L[l0].out_pad == 128 && n.L[l0 + 1].in_pad == 128 && n.L[l0 + 1].out_pad == 128 && n.L[l0 + 2].in_pad == 128 &&
+           n.L[l0].in_pad <= 32 && n.L[l0 + 2].out_pad <= max_out;
+  }
+  static bool eligible(const Args& a, int max_ctas) {
+    if (a.n_agents > 1 || a.obs_norm[0] || !a.ws || !a.sync || a.defer_polyak) return false;
+    if (wt_ld_of(128) != FX_LDW) return false;
+    if (a.B > FX_MAXB || a.replay.act_dim > 8 || a.n_heads < 1 || a.n_heads > 2) return false;
+    if (a.actor.n_layers != 3 || a.critic.n_layers != 3 * a.n_heads) return false;
+    if (!shape_ok(a.actor, 0, 8) || !shape_ok(a.actor_target, 0, 8)) return false;
+    for (int h = 0; h < a.n_heads; ++h)
+      if (!shape_ok(a.critic, 3 * h, 4) || !shape_ok(a.critic_target, 3 * h, 4)) return false;
+    if (a.actor.L[2].out_pad < 4 || a.critic.L[2].out_pad != 4) return false;
+    if (is_sac(a) && a.n_heads != 2) return false;
+    if (2 * ntile(a) * a.n_heads > max_ctas) return false;
+    if (net_jobs(a.critic) > 512 || net_jobs(a.actor) > 512) return false;
+    if (net_jobs(a.critic) > GST_SLOTS * max_ctas || net_jobs(a.actor) > GST_SLOTS * max_ctas) return false;
+    const size_t smem = (size_t)(cta_base_floats(wbuf_floats(a)) + user_floats(a)) * 4 + 64 + sizeof(Args) + 64;
+    return smem <= (size_t)227 * 1024;
+  }
+
+  FRL_SDEV float noise_at(const float* ptr, const Args& a, int u, int row, int j, uint32_t stream) {
+    if (ptr) return ptr[((size_t)u * a.B + row) * a.replay.act_dim + j];
+    return randn_ni(a.seed, stream, (uint32_t)(a.total_it0 + u), (uint32_t)(row * a.replay.act_dim + j));
+  }
+
+  // thread 0: bulk copies of `nblk` exchange blocks (rows [0, R)) into consecutive [R][16] arrays at dst, on mbarrier bar[0]
+  FRL_SDEV void job_issue(Cta& c, float* dst, const float* region, int blk0, int nblk, int Rmax, int R, bool arm, int total_blocks) {
+#ifndef FRL_EMUL
+    if (threadIdx.x == 0) {
+      trace(24);
+      if (arm) {
+        fence_proxy_async();
+        trace(25);
+        mbar_expect_tx(c.bar, (uint32_t)total_blocks * (uint32_t)R * 64u);
+        trace(26);
+      }
+      for (int b = 0; b < nblk; ++b) tma_bulk_g2s(dst + (size_t)b * R * 16, region + (size_t)(blk0 + b) * Rmax * 16, (uint32_t)R * 64u, c.bar);
+      trace(27);
+    }
+#else
+    (void)c; (void)arm; (void)total_blocks;
+    for (int b = 0; b < nblk; ++b) memcpy(dst + (size_t)b * R * 16, region + (size_t)(blk0 + b) * Rmax * 16, (size_t)R * 64);
+#endif
+  }
+
+  // dW tile of one job:  G[n][k] = sum_R DY[R][n0 + n] X[R][k0 + k]   (+ second DY operand added element-wise; + bias sums)
+  //   operands in shared memory: DY0 / DY1 as [R][16] (columns n0 % 16 ..), X as KB / 16 arrays [R][16]
+  //   lanes: TL = NB KB / 16 register tiles of 4 x 4 per warp pass, 32 / TL row sub-splits inside the warp, 8 warps split the
+  //   rows further (row = split, split + S, ...); warp partials are combined in fixed order through c.red.
+  FRL_SDEV void job_compute(Cta& c, const FxJob& J, int R, const float* DY0, const float* DY1, const float* Xs, int ncol0, float* gst,
+                            float* gbst, float* redb) {
+    const int TL = (J.NB * J.KB) >> 4, ktl = J.KB >> 2, RSW = 32 / TL, S = 8 * RSW;
+    trace(70);
+    FRL_PAR(t) {
+      const int w = t >> 5, l = t & 31, tl = l % TL, rs = l / TL, nt = tl / ktl, kt = tl - nt * ktl;
+      const sptr xa = sp_of(Xs + (size_t)(kt >> 2) * R * 16 + 4 * (kt & 3));
+      const sptr ya = sp_of(DY0 + ncol0 + 4 * nt);
+      const bool two = DY1 != nullptr;
+      const sptr yb = sp_of((two ? DY1 : DY0) + ncol0 + 4 * nt);
+      float acc[4][4], ab[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        ab[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      }
+#pragma unroll 4
+      for (int r = w * RSW + rs; r < R; r += S) {
+        float4 av = sp_ld4(ya, r * 16);
+        if (two) av = f4add(av, sp_ld4(yb, r * 16));
+        const float4 bv = sp_ld4(xa, r * 16);
+        fma2_bcast(acc[0][0], acc[0][1], av.x, bv.x, bv.y); fma2_bcast(acc[0][2], acc[0][3], av.x, bv.z, bv.w);
+        fma2_bcast(acc[1][0], acc[1][1], av.y, bv.x, bv.y); fma2_bcast(acc[1][2], acc[1][3], av.y, bv.z, bv.w);
+        fma2_bcast(acc[2][0], acc[2][1], av.z, bv.x, bv.y); fma2_bcast(acc[2][2], acc[2][3], av.z, bv.z, bv.w);
+        fma2_bcast(acc[3][0], acc[3][1], av.w, bv.x, bv.y); fma2_bcast(acc[3][2], acc[3][3], av.w, bv.z, bv.w);
+        ab[0] += av.x; ab[1] += av.y; ab[2] += av.z; ab[3] += av.w;
+      }
+#ifndef FRL_EMUL
+      if (RSW == 2) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          ab[i] += shx(ab[i], 16);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] += shx(acc[i][j], 16);
+        }
+      }
+      if (rs == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) st4(c.red + w * 512 + (4 * nt + i) * J.KB + 4 * kt, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+        if (kt == 0) st4(redb + w * 16 + 4 * nt, make_float4(ab[0], ab[1], ab[2], ab[3]));
+      }
+#else
+      for (int i = 0; i < 4; ++i) {
+        for (int j = 0; j < 4; ++j) fx_emu_a[t][i * 4 + j] = acc[i][j];
+        fx_emu_a[t][16 + i] = ab[i];
+      }
+#endif
+    }
+#ifdef FRL_EMUL
+    if (RSW == 2) fx_emu_bf(fx_emu_a, fx_emu_b, 20, 16);
+    FRL_PAR(t) {
+      const int w = t >> 5, l = t & 31, tl = l % TL, rs = l / TL, nt = tl / ktl, kt = tl - nt * ktl;
+      float (*src)[64] = RSW == 2 ? fx_emu_b : fx_emu_a;
+      if (rs == 0) {
+        for (int i = 0; i < 4; ++i)
+          for (int j = 0; j < 4; ++j) c.red[w * 512 + (4 * nt + i) * J.KB + 4 * kt + j] = src[t][i * 4 + j];
+        if (kt == 0) for (int i = 0; i < 4; ++i) redb[w * 16 + 4 * nt + i] = src[t][16 + i];
+      }
+    }
+#endif
+    trace(71);
+    FRL_SYNC();
+    FRL_PAR(t) {
+      for (int e = t; e < J.NB * J.KB; e += FRL_NT) {
+        float s = c.red[e];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) s += c.red[w * 512 + e];
+        gst[e] = s;
+      }
+      if (t < J.NB) {
+        float s = redb[t];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) s += redb[w * 16 + t];
+        gbst[t] = s;
+      }
+    }
+    trace(72);
+    FRL_SYNC();
+  }
+
+  // ---- one optimiser element (torch.optim.Adam single-tensor math, same rounding order as engine.cuh::adam_update) ----
+  FRL_SDEV void adam_elem(const AdamHP& hp, float coef, float gin, float* p, float* m, float* v, float* w_out) {
+    float g = gin * coef;
+    float w = *p;
+    if (hp.weight_decay != 0.f) g = fmaf(w, hp.weight_decay, g);
+    float mm = *m, vv = *v;
+    mm = fmaf(hp.one_minus_b1, g - mm, mm);
+    vv = fadd(fmul(vv, hp.b2), fmul(fmul(hp.one_minus_b2, g), g));
+    const float denom = fadd(fdiv(fsqrt(vv), hp.bc2_sqrt), hp.eps);
+    w = fadd(w, fdiv(fmul(hp.lr_over_bc1_neg, mm), denom));
+    *p = w; *m = mm; *v = vv; *w_out = w;
+  }
+
+  // dW + sum of squares of this CTA's jobs of net n (stage 1 / 4).  `scr` = the weight slot that is dead in this stage.
+  FRL_SDEV void dw_stage(Cta& c, const Args& a, const frl_net_t& n, const float* xreg, const float* yreg0, const float* yreg1,
+                         float* scr, float* gst, float* gbst, float* redb, float* red0, float* sumsq, const float* lsg, int nls,
+                         const AdamSpec sp, float* hpst, int njobs) {
+    const int Rm = rmax(a), R = Rm;
+    // bias corrections of the optimiser stage that follows (double-precision powers, ~1.5 k clk on one thread): computed here,
+    // by a thread that has nothing to do while the operands are in flight, and kept in shared memory
+    FRL_PAR(t) {
+      if (t == FRL_NT - 1) {
+        const AdamHP h = adam_hp_ni(sp.lr, sp.b1, sp.b2, sp.eps, sp.wd, sp.max_norm, sp.step);
+        hpst[0] = h.lr_over_bc1_neg; hpst[1] = h.bc2_sqrt; hpst[2] = h.one_minus_b1; hpst[3] = h.b2; hpst[4] = h.one_minus_b2;
+        hpst[5] = h.eps; hpst[6] = h.weight_decay; hpst[7] = h.max_norm;
+      }
+    }
+    int slot = 0;
+    for (int j = c.cta; j < njobs; j += c.ncta, ++slot) {
+      const FxJob J = job_of(n, j);
+      float ss = 0.f;
+      if (J.li < 0) {
+        // extras (SAC log_std): fixed-order sum of the per-CTA partials written in phase C
+        FRL_PAR(t) {
+          float l = 0.f;
+          if (t < n.x_len) {
+            float s = 0.f;
+            for (int k = 0; k < nls; ++k) s += fx_ldcg(lsg + (size_t)k * 8 + t);
+            gst[slot * 528 + t] = s;
+            l = s * s;
+          }
+          red0[t] = l;
+        }
+        FRL_SYNC();
+        ss = block_sum(red0);
+      } else {
+        const int yb0 = fx_yblocks(n, J.li) + (J.n0 >> 4), xb0 = fx_xblocks(n, J.li) + (J.k0 >> 4);
+        const int xbn_all = fx_xb(n, J.li) - (J.k0 >> 4), xbn = (J.KB >> 4) < xbn_all ? (J.KB >> 4) : xbn_all;
+        const int nyb = yreg1 ? 2 : 1;
+        float* DY0 = scr;
+        float* DY1 = yreg1 ? scr + (size_t)R * 16 : nullptr;
+        float* Xs = scr + (size_t)nyb * R * 16;
+        // (blocks beyond the layer's last X block are not loaded: their register tiles multiply stale but finite slot data
+        //  into outputs that the optimiser masks out as k >= in_pad)
+        job_issue(c, DY0, yreg0, yb0, 1, Rm, R, true, nyb + xbn);
+        if (yreg1) job_issue(c, DY1, yreg1, yb0, 1, Rm, R, false, 0);
+        job_issue(c, Xs, xreg, xb0, xbn, Rm, R, false, 0);
+        trace(73);
+        stage_wait(c, 0);
+        trace(74);
+        if (xbn < (J.KB >> 4)) {                  // zero the missing X blocks so no NaN garbage enters the sums
+          FRL_PAR(t) { for (int e = t; e < ((J.KB >> 4) - xbn) * R * 16; e += FRL_NT) Xs[(size_t)xbn * R * 16 + e] = 0.f; }
+          FRL_SYNC();
+        }
+        job_compute(c, J, R, DY0, DY1, Xs, J.n0 & 15, gst + slot * 528, gbst + slot * 16, redb);
+        FRL_PAR(t) {
+          float l = 0.f;
+          const frl_layer_t& L = n.L[J.li];
+          const int ksh = J.KB == 16 ? 4 : (J.KB == 32 ? 5 : 6);
+          for (int e = t; e < J.NB * J.KB; e += FRL_NT) {
+            const int nn = e >> ksh, kk = e - (nn << ksh);
+            if (J.n0 + nn < L.out_pad && J.k0 + kk < L.in_pad) { const float g = gst[slot * 528 + e]; l += g * g; }
+          }
+          if (J.k0 == 0 && t < J.NB && J.n0 + t < L.out_pad) { const float g = gbst[slot * 16 + t]; l += g * g; }
+          red0[t] = l;
+        }
+        FRL_SYNC();
+        ss = block_sum(red0);
+      }
+      FRL_PAR(t) { if (t == 0) sumsq[j] = ss; }
+    }
+    FRL_SYNC();
+  }
+
+  // clip + Adam (+ Polyak of tgt) on the elements of this CTA's jobs (stage 2 / 5).  Returns the total squared norm.
+  FRL_SDEV float opt_stage(Cta& c, const frl_net_t& n, const frl_net_t* tgt, float tau, const float* hpst, const float* gst,
+                           const float* gbst, const float* sumsq, float* sh, int njobs) {
+    trace(80);
+    // total squared gradient norm: the per-job partials (<= 512) folded in a fixed order (strided per-thread sums, then the
+    // block tree), so every CTA computes the same number
+    FRL_PAR(t) {
+      float v = 0.f;
+      for (int i = t; i < njobs; i += FRL_NT) v += fx_ldcg(sumsq + i);
+      sh[t] = v;
+    }
+    FRL_SYNC();
+    const float total = block_sum(sh);
+    trace(82);
+    AdamHP hp;
+    hp.lr_over_bc1_neg = hpst[0]; hp.bc2_sqrt = hpst[1]; hp.one_minus_b1 = hpst[2]; hp.b2 = hpst[3]; hp.one_minus_b2 = hpst[4];
+    hp.eps = hpst[5]; hp.weight_decay = hpst[6]; hp.max_norm = hpst[7];
+    float coef = 1.f;
+    if (hp.max_norm > 0.f) {
+      coef = hp.max_norm / (sqrtf(total) + 1e-6f);
+      if (coef > 1.f) coef = 1.f;
+    }
+    const float omt = (float)(1.0 - (double)tau);
+    int slot = 0;
+    for (int j = c.cta; j < njobs; j += c.ncta, ++slot) {
+      const FxJob J = job_of(n, j);
+      const int ksh = J.KB == 16 ? 4 : (J.KB == 32 ? 5 : 6);
+      FRL_PAR(t) {
+        if (J.li < 0) {
+          if (t < n.x_len) {
+            float w;
+            adam_elem(hp, coef, gst[slot * 528 + t], n.p + n.x_off + t, n.m + n.x_off + t, n.v + n.x_off + t, &w);
+            if (tgt) tgt->p[n.x_off + t] = fadd(fmul(tgt->p[n.x_off + t], omt), fmul(w, tau));
+          }
+        } else {
+          const frl_layer_t& L = n.L[J.li];
+          const int ldw = wt_ld(L);
+          for (int e = t; e < J.NB * J.KB; e += FRL_NT) {
+            const int nn = e >> ksh, kk = e - (nn << ksh), row = J.n0 + nn, col = J.k0 + kk;
+            if (row < L.out_pad && col < L.in_pad) {
+              const int pi = L.w_off + row * L.in_pad + col, mi = L.wt_off + col * ldw + row;
+              float w;
+              adam_elem(hp, coef, gst[slot * 528 + e], n.p + pi, n.m + pi, n.v + pi, &w);
+              n.pt[mi] = w;
+              if (tgt) {
+                const float tw = fadd(fmul(tgt->p[pi], omt), fmul(w, tau));
+                tgt->p[pi] = tw; tgt->pt[mi] = tw;
+              }
+            }
+          }
+          if (J.k0 == 0 && t < J.NB && J.n0 + t < L.out_pad) {
+            const int pi = L.b_off + J.n0 + t, mi = L.wt_off + wt_bias(L) + J.n0 + t;
+            float w;
+            adam_elem(hp, coef, gbst[slot * 16 + t], n.p + pi, n.m + pi, n.v + pi, &w);
+            n.pt[mi] = w;
+            if (tgt) {
+              const float tw = fadd(fmul(tgt->p[pi], omt), fmul(w, tau));
+              tgt->p[pi] = tw; tgt->pt[mi] = tw;
+            }
+          }
+        }
+      }
+    }
+    trace(83);
+    FRL_SYNC();
+    return total;
+  }
+
+  FRL_SDEV void stage(int s, int u, Cta& c, float* user, const Args& a) {
+    const frl_net_t& A = a.actor;
+    const frl_net_t& C = a.critic;
+    const frl_replay_t& rb = a.replay;
+    const int od = rb.obs_dim, ad = rb.act_dim, rf = rb.row_floats;
+    const int NH = a.n_heads, nt_ = ntile(a), Rm = nt_ * 8, nwork = nt_ * NH;
+    const bool sac = is_sac(a);
+    const int hu = heads_used(a);
+    const bool policy_step = is_policy_step(a, u);
+    const int role = c.cta < nwork ? 0 : (c.cta < 2 * nwork ? 1 : 2);        // 0 target set, 1 online set, 2 helper
+    const int wi = role == 0 ? c.cta : c.cta - nwork;                        // worker index inside its set
+    const int tile = wi / NH, h = wi - tile * NH, l0 = 3 * h;
+    const int row0 = tile * 8;
+    const int nvalid = (a.B - row0) < 8 ? (a.B - row0) : 8;
+    const float invB = 1.0f / (float)a.B;
+    const int aip = A.L[0].in_pad, cip = C.L[0].in_pad, ap = A.L[2].out_pad, ald = wt_ld(A.L[2]), cld = wt_ld(C.L[2]);
+    float alpha = 0.f;
+    if (sac) alpha = expf(fx_ldcg(a.alpha_state));      // written by CTA 0 in stage 5: read through L2
+    const Ws W = ws_layout(a, c.ncta);
+    float* ws = a.ws;
+    unsigned* flags = a.sync + 32;
+    const unsigned epoch = (unsigned)u + 1u;
+
+    trace(1);
+    SmemBump sb; sb.p = user;
+    float* raw = sb.take(8 * rf);
+    float* XA = sb.take(8 * 32);             // actor input  [8][aip]
+    float* XS = sb.take(8 * 32);             // critic input [8][cip] = [obs | act]
+    float* XN = sb.take(8 * 32);             // [next_obs | a'] (target set) or [obs | pi(obs)] (phase C)
+    float* dXa = sb.take(64);                // dQ/da [8][8]
+    float* H1 = sb.take(1024);
+    float* H2 = sb.take(1024);
+    float* A1 = sb.take(1024);               // actor activations: live from phase A to phase C on the online set
+    float* A2 = sb.take(1024);
+    float* D1 = sb.take(1024);
+    float* D2 = sb.take(1024);
+    float* MU = sb.take(64);
+    float* UU = sb.take(64);
+    float* AC = sb.take(64);
+    float* dMU = sb.take(64);
+    float* EPS = sb.take(64);
+    float* QA = sb.take(32);
+    float* dQA = sb.take(32);
+    float* rowv = sb.take(32);
+    float* red0 = sb.take(FRL_NT);
+    float* red1 = sb.take(FRL_NT);
+    float* gst = sb.take(GST_SLOTS * 528);   // gradient tile(s) of this CTA's dW job(s): kept from the dW stage to the optimiser stage
+    float* redb = sb.take(128);
+    float* gbst = sb.take(GST_SLOTS * 16);
+    float* hpst = sb.take(16);               // optimiser scalars: written in the dW stage, read in the optimiser stage
+    const int njobs_c = net_jobs(C), njobs_a = net_jobs(A);
+
+    if (s == 0) {
+      if (role == 2) return;
+      const int64_t* idx = a.indices + (size_t)u * a.B + row0;
+      if (role == 0) {
+        // ------------------------------- target set: a' = actor_target(s'), Q'_h(s', a') -------------------------------
+        const frl_net_t& AT = a.actor_target;
+        const frl_net_t& CT = a.critic_target;
+        res_fetch(c, 0, AT, 0, 3);
+        res_fetch(c, 1, CT, l0, 3);
+        trace(10);
+        gather_rows<8>(rb.storage, rf, idx, nvalid, raw);
+        trace(11);
+        put_cols<8>(XA, aip, 0, raw, rf, rb_col_nobs(rb), od, aip);
+        put_cols<8>(XN, cip, 0, raw, rf, rb_col_nobs(rb), od, cip);
+        FRL_SYNC();
+        trace(12);
+        fx_fwd<0>(XA, aip, aip >> 2, res_layer(c, 0, AT, 0, 0), res_layer(c, 0, AT, 0, 0) + wt_bias(AT.L[0]), 1, H1);
+        fx_fwd<32>(H1, 128, 32, res_layer(c, 0, AT, 0, 1), res_layer(c, 0, AT, 0, 1) + wt_bias(AT.L[1]), 1, H2);
+        fx_fwd_narrow(H2, res_layer(c, 0, AT, 0, 2), res_layer(c, 0, AT, 0, 2) + wt_bias(AT.L[2]), ap, ald, MU, 8);
+        const bool smoothing = !sac && a.target_smoothing;
+        FRL_PAR(t) {
+          if (t < 8 * ad) {
+            const int r = t / ad, jj = t - r * ad;
+            const float mean = MU[r * 8 + jj];
+            float act;
+            if (sac) {
+              const float ls = fminf(fmaxf(fx_ldcg(AT.p + AT.x_off + jj), -20.f), 2.f);
+              const float sd = expf(ls);
+              const float e = (r < nvalid) ? noise_at(a.noise_next, a, u, row0 + r, jj, 1u) : 0.f;
+              const float uu = fadd(mean, fmul(e, sd));
+              const float diff = uu - mean;
+              float lp = -(diff * diff) / (2.f * (sd * sd)) - logf(sd) - FRL_LOG_SQRT_2PI;
+              lp -= 2.f * (FRL_LOG2F - uu - softplus_t(-2.f * uu));
+              UU[r * 8 + jj] = lp;
+              act = tanhf(uu);
+            } else if (smoothing) {
+              const float e = (r < nvalid) ? noise_at(a.noise_next, a, u, row0 + r, jj, 1u) : 0.f;
+              float nz = fmul(a.policy_noise_scale, fmul(e, a.policy_noise));
+              nz = fminf(fmaxf(nz, -a.noise_clip), a.noise_clip);
+              float v = fadd(fmul(tanhf(mean), a.max_action), nz);
+              v = fminf(fmaxf(v, -a.max_action), a.max_action);
+              act = fdiv(v, a.max_action);
+            } else {
+              act = tanhf(mean);
+            }
+            XN[r * cip + od + jj] = act;
+          }
+        }
+        FRL_SYNC();
+        trace(13);
+        fx_fwd<0>(XN, cip, cip >> 2, res_layer(c, 1, CT, l0, 0), res_layer(c, 1, CT, l0, 0) + wt_bias(CT.L[l0]), 1, H1);
+        fx_fwd<32>(H1, 128, 32, res_layer(c, 1, CT, l0, 1), res_layer(c, 1, CT, l0, 1) + wt_bias(CT.L[l0 + 1]), 1, H2);
+        fx_fwd_narrow(H2, res_layer(c, 1, CT, l0, 2), res_layer(c, 1, CT, l0, 2) + wt_bias(CT.L[l0 + 2]), 4, cld, QA, 4);
+        FRL_PAR(t) {
+          if (t < 8) {
+            ws[W.xq + (size_t)(row0 + t) * 2 + h] = QA[t * 4];
+            if (sac && h == 0) {
+              float lp = 0.f;
+              for (int j = 0; j < ad; ++j) lp += UU[t * 8 + j];
+              ws[W.xlp + row0 + t] = lp;
+            }
+          }
+        }
+        FRL_SYNC();
+        FRL_PAR(t) { if (t == 0) fx_flag_set(flags + wi, epoch); }
+        trace(15);
+        return;
+      }
+      // ------------------------------- online set: Q_h(s, a), pi(s); then y, loss, critic backward -------------------------------
+      res_fetch(c, 1, C, l0, 3);
+      const bool do_actor = policy_step && h < hu;
+      if (do_actor) res_fetch(c, 0, A, 0, 3);
+      trace(10);
+      gather_rows<8>(rb.storage, rf, idx, nvalid, raw);
+      trace(11);
+      put_cols<8>(XS, cip, 0, raw, rf, 0, od + ad, cip);        // [obs | act] are adjacent in a replay row
+      put_cols<8>(XA, aip, 0, raw, rf, 0, od, aip);
+      FRL_SYNC();
+      trace(12);
+      fx_fwd<0>(XS, cip, cip >> 2, res_layer(c, 1, C, l0, 0), res_layer(c, 1, C, l0, 0) + wt_bias(C.L[l0]), 1, H1);
+      fx_fwd<32>(H1, 128, 32, res_layer(c, 1, C, l0, 1), res_layer(c, 1, C, l0, 1) + wt_bias(C.L[l0 + 1]), 1, H2);
+      fx_fwd_narrow(H2, res_layer(c, 1, C, l0, 2), res_layer(c, 1, C, l0, 2) + wt_bias(C.L[l0 + 2]), 4, cld, QA, 4);
+      if (do_actor) {
+        trace(16);
+        fx_fwd<0>(XA, aip, aip >> 2, res_layer(c, 0, A, 0, 0), res_layer(c, 0, A, 0, 0) + wt_bias(A.L[0]), 1, A1);
+        fx_fwd<32>(A1, 128, 32, res_layer(c, 0, A, 0, 1), res_layer(c, 0, A, 0, 1) + wt_bias(A.L[1]), 1, A2);
+        fx_fwd_narrow(A2, res_layer(c, 0, A, 0, 2), res_layer(c, 0, A, 0, 2) + wt_bias(A.L[2]), ap, ald, MU, 8);
+        FRL_PAR(t) {
+          if (t < 64) {
+            const int r = t >> 3, j = t & 7;
+            float act = 0.f, e = 0.f, lp = 0.f;
+            if (j < ad) {
+              const float mean = MU[r * 8 + j];
+              if (sac) {
+                const float ls = fminf(fmaxf(fx_ldcg(A.p + A.x_off + j), -20.f), 2.f);
+                const float sd = expf(ls);
+                e = (r < nvalid) ? noise_at(a.noise_new, a, u, row0 + r, j, 2u) : 0.f;
+                const float uu = fadd(mean, fmul(e, sd));
+                const float diff = uu - mean;
+                lp = -(diff * diff) / (2.f * (sd * sd)) - logf(sd) - FRL_LOG_SQRT_2PI;
+                lp -= 2.f * (FRL_LOG2F - uu - softplus_t(-2.f * uu));
+                act = tanhf(uu);
+              } else {
+                act = tanhf(mean);
+              }
+            }
+            AC[t] = act; UU[t] = lp; EPS[t] = e;
+          }
+        }
+        FRL_SYNC();
+      }
+      // targets of this tile from the target set (both heads)
+      trace(17);
+      FRL_PAR(t) {
+        if (t < 8) {
+          const int r = t;
+          float y = 0.f;
+          for (int hh = 0; hh < NH; ++hh) fx_flag_wait(flags + tile * NH + hh, epoch);
+          if (r < nvalid) {
+            float nq = fx_ldcg(ws + W.xq + (size_t)(row0 + r) * 2);
+            if (NH == 2) nq = fminf(nq, fx_ldcg(ws + W.xq + (size_t)(row0 + r) * 2 + 1));
+            const float rew = raw[r * rf + rb_col_rew(rb)], dn = raw[r * rf + rb_col_done(rb)];
+            if (sac) {
+              const float lp = fx_ldcg(ws + W.xlp + row0 + r);
+              y = fadd(rew, fmul(fmul(a.gamma, fadd(1.f, -dn)), fadd(nq, fmul(alpha, -lp))));      // SAC.py:235
+            } else {
+              y = fadd(rew, fmul(fmul(a.gamma, nq), fadd(1.f, -dn)));                              // TD3.py:209 / DDPG.py:212
+            }
+          }
+          rowv[r] = y;
+        }
+      }
+      FRL_SYNC();
+      trace(18);
+      FRL_PAR(t) {
+        float l = 0.f;
+        if (t < 8) {
+          for (int j = 0; j < 4; ++j) dQA[t * 4 + j] = 0.f;
+          if (t < nvalid) {
+            const float d0 = QA[t * 4] - rowv[t];
+            dQA[t * 4] = 2.f * d0 * invB;
+            l = d0 * d0;
+          }
+        }
+        red0[t] = l;
+      }
+      FRL_SYNC();
+      const float loss_c = block_sum(red0);
+      fx_bwd_narrow(dQA, 4, res_layer(c, 1, C, l0, 2), 4, cld, H2, D2);
+      fx_bwd(D2, res_layer(c, 1, C, l0, 1), H1, D1);
+      // layer inputs and pre-activation gradients of this tile -> exchange blocks of head h's layers l0..l0+2
+      float* cx = ws + W.cx;
+      float* cy = ws + W.cy;
+      fx_put_blocks(cx, fx_xblocks(C, l0), fx_xb(C, l0), Rm, row0, XS, cip, cip);
+      fx_put_blocks(cx, fx_xblocks(C, l0 + 1), 8, Rm, row0, H1, 128, 128);
+      fx_put_blocks(cx, fx_xblocks(C, l0 + 2), 8, Rm, row0, H2, 128, 128);
+      fx_put_blocks(cy, fx_yblocks(C, l0), 8, Rm, row0, D1, 128, 128);
+      fx_put_blocks(cy, fx_yblocks(C, l0 + 1), 8, Rm, row0, D2, 128, 128);
+      fx_put_blocks(cy, fx_yblocks(C, l0 + 2), 1, Rm, row0, dQA, 4, 4);
+      FRL_PAR(t) { if (t == 0) ws[W.stats + (size_t)wi * 8 + 0] = loss_c; }
+      FRL_SYNC();
+      trace(19);
+    } else if (s == 1) {
+      res_invalidate(c, C);
+      res_invalidate(c, a.critic_target);
+      res_drain_slot(c, 1);
+      if (c.stag1 != nullptr) c.stag1 = nullptr;      // slot 1 is scratch in stages 1 / 2 whatever it held
+      const AdamSpec hp = {a.lr_critic, a.beta1, a.beta2, a.eps, a.wd_critic, (double)a.max_norm, (long)(a.step_critic0 + u + 1)};
+      dw_stage(c, a, C, ws + W.cx, ws + W.cy, nullptr, c.wbuf1, gst, gbst, redb, red0, ws + W.sumsq, nullptr, 0, hp, hpst, njobs_c);
+    } else if (s == 2) {
+      const float tot = opt_stage(c, C, policy_step ? &a.critic_target : nullptr, a.tau, hpst, gst, gbst, ws + W.sumsq, c.red, njobs_c);
+      if (c.cta == 0) {
+        FRL_PAR(t) { red0[t] = t < nwork ? fx_ldcg(ws + W.stats + (size_t)t * 8) : 0.f; }
+        FRL_SYNC();
+        const float ls = block_sum(red0);
+        FRL_PAR(t) {
+          if (t == 0) { a.out[u * 8 + 0] = ls * invB; a.out[u * 8 + 4] = sqrtf(tot); a.out[u * 8 + 2] = alpha; }
+        }
+        FRL_SYNC();
+      }
+    } else if (s == 3) {
+      // ------------------------------- phase C: Q_h(s, pi(s)) with the updated critic, dQ/da, actor backward -------------------------------
+      if (role == 0) { res_fetch(c, 1, a.critic_target, l0, 3); return; }      // prefetch for the next learn
+      if (role != 1) return;
+      res_fetch(c, 1, C, l0, 3);
+      if (h >= hu) return;
+      put_cols<8>(XN, cip, 0, XS, cip, 0, od, od);
+      FRL_PAR(t) {
+        if (t < 8 * (cip - od)) {
+          const int r = t / (cip - od), j = t - r * (cip - od);
+          XN[r * cip + od + j] = j < ad ? AC[r * 8 + j] : 0.f;
+        }
+      }
+      FRL_SYNC();
+      trace(30);
+      fx_fwd<0>(XN, cip, cip >> 2, res_layer(c, 1, C, l0, 0), res_layer(c, 1, C, l0, 0) + wt_bias(C.L[l0]), 1, H1);
+      fx_fwd<32>(H1, 128, 32, res_layer(c, 1, C, l0, 1), res_layer(c, 1, C, l0, 1) + wt_bias(C.L[l0 + 1]), 1, H2);
+      fx_fwd_narrow(H2, res_layer(c, 1, C, l0, 2), res_layer(c, 1, C, l0, 2) + wt_bias(C.L[l0 + 2]), 4, cld, QA, 4);
+      const float dq = -invB / (float)hu;
+      FRL_PAR(t) {
+        float v = 0.f;
+        if (t < 8) {
+          for (int j = 0; j < 4; ++j) dQA[t * 4 + j] = 0.f;
+          if (t < nvalid) { dQA[t * 4] = dq; v = QA[t * 4]; }
+        }
+        red0[t] = v;
+      }
+      FRL_SYNC();
+      const float qsum = block_sum(red0);
+      trace(31);
+      fx_bwd_narrow(dQA, 4, res_layer(c, 1, C, l0, 2), 4, cld, H2, D2);
+      fx_bwd(D2, res_layer(c, 1, C, l0, 1), H1, D1);
+      fx_bwd_cols(D1, res_layer(c, 1, C, l0, 0), od, ad, dXa);
+      trace(32);
+      FRL_PAR(t) {
+        float lsum = 0.f, esum = 0.f;
+        if (t < 8) {
+          const int r = t;
+          float lp = 0.f;
+          for (int j = 0; j < 8; ++j) {
+            float g = 0.f;
+            if (j < ad && r < nvalid) {
+              const float act = AC[r * 8 + j];
+              g = dXa[r * 8 + j] * (1.f - act * act);
+              if (sac && h == 0) { g += alpha * invB * 2.f * act; lp += UU[r * 8 + j]; }
+            }
+            dMU[r * 8 + j] = g;
+          }
+          if (r < nvalid && h == 0) { esum = -lp; lsum = alpha * lp; }        // actor_loss = mean(-Q_pi - alpha * entropy)
+        }
+        red0[t] = lsum; red1[t] = esum;
+      }
+      FRL_SYNC();
+      const float loss_a = block_sum(red0) - qsum / (float)hu;
+      const float ent = block_sum(red1);
+      if (sac) {
+        // d/dlog_std_j = sum_r dL/du std eps (+ head 0: -alpha / B per row); zero outside the clamp range
+        FRL_PAR(t) {
+          if (t < 8) {
+            const float lsr = (t < ad) ? fx_ldcg(A.p + A.x_off + t) : 1e30f;
+            float g = 0.f;
+            if (lsr >= -20.f && lsr <= 2.f) {
+              const float sd = expf(lsr);
+              for (int r = 0; r < nvalid; ++r) g += dMU[r * 8 + t] * sd * EPS[r * 8 + t] - (h == 0 ? alpha * invB : 0.f);
+            }
+            ws[W.lsg + (size_t)wi * 8 + t] = g;
+          }
+        }
+      }
+      trace(33);
+      fx_bwd_narrow(dMU, 8, res_layer(c, 0, A, 0, 2), ap, ald, A2, D2);
+      fx_bwd(D2, res_layer(c, 0, A, 0, 1), A1, D1);
+      trace(34);
+      float* ay = ws + (h == 0 ? W.ay0 : W.ay1);
+      if (h == 0) {
+        float* ax = ws + W.ax;
+        fx_put_blocks(ax, fx_xblocks(A, 0), fx_xb(A, 0), Rm, row0, XA, aip, aip);
+        fx_put_blocks(ax, fx_xblocks(A, 1), 8, Rm, row0, A1, 128, 128);
+        fx_put_blocks(ax, fx_xblocks(A, 2), 8, Rm, row0, A2, 128, 128);
+      }
+      fx_put_blocks(ay, fx_yblocks(A, 0), 8, Rm, row0, D1, 128, 128);
+      fx_put_blocks(ay, fx_yblocks(A, 1), 8, Rm, row0, D2, 128, 128);
+      fx_put_blocks(ay, fx_yblocks(A, 2), 1, Rm, row0, dMU, 8, ap);
+      FRL_PAR(t) { if (t == 0) { ws[W.stats + (size_t)wi * 8 + 1] = loss_a; ws[W.stats + (size_t)wi * 8 + 2] = ent; } }
+      FRL_SYNC();
+      trace(39);
+    } else if (s == 4) {
+      res_invalidate(c, A);
+      res_invalidate(c, a.actor_target);
+      res_drain_slot(c, 0);
+      if (c.stag0 != nullptr) c.stag0 = nullptr;      // slot 0 is scratch in stages 4 / 5
+      const long n_policy_before = (a.policy_freq > 1) ? (long)((a.total_it0 + u) / a.policy_freq - a.total_it0 / a.policy_freq) : (long)u;
+      const AdamSpec hp = {a.lr_actor, a.beta1, a.beta2, a.eps, 0.0, (double)a.max_norm, (long)(a.step_actor0 + n_policy_before + 1)};
+      dw_stage(c, a, A, ws + W.ax, ws + W.ay0, hu == 2 ? ws + W.ay1 : nullptr, c.wbuf0, gst, gbst, redb, red0, ws + W.sumsq,
+               ws + W.lsg, nwork, hp, hpst, njobs_a);
+    } else {
+      const float tot = opt_stage(c, A, &a.actor_target, a.tau, hpst, gst, gbst, ws + W.sumsq, c.red, njobs_a);
+      if (c.cta == 0) {
+        FRL_PAR(t) {
+          const bool on = t < nwork && (t % NH) < hu;
+          red0[t] = on ? fx_ldcg(ws + W.stats + (size_t)t * 8 + 1) : 0.f;
+          red1[t] = on ? fx_ldcg(ws + W.stats + (size_t)t * 8 + 2) : 0.f;
+        }
+        FRL_SYNC();
+        const float l = block_sum(red0);
+        const float en = block_sum(red1);
+        FRL_PAR(t) {
+          if (t == 0) {
+            a.out[u * 8 + 1] = l * invB;
+            a.out[u * 8 + 5] = sqrtf(tot);
+            a.out[u * 8 + 6] = en * invB;
+            if (sac && a.adaptive_alpha) {
+              // alpha_loss = (exp(log_alpha) * (entropy - target_entropy).detach()).mean();  Adam(lr alpha_lr) on log_alpha
+              const float mean_term = en * invB - a.target_entropy;
+              const float al = expf(a.alpha_state[0]);
+              const float g = al * mean_term;
+              a.out[u * 8 + 3] = g;
+              const AdamHP ha = adam_hp_ni(a.alpha_lr, a.beta1, a.beta2, a.eps, 0.0, 0.0, (long)(a.step_alpha0 + u + 1));
+              float m = a.alpha_state[1], v = a.alpha_state[2], w = a.alpha_state[0];
+              m = fmaf(ha.one_minus_b1, g - m, m);
+              v = fadd(fmul(v, ha.b2), fmul(fmul(ha.one_minus_b2, g), g));
+              const float denom = fadd(fdiv(fsqrt(v), ha.bc2_sqrt), ha.eps);
+              w = fadd(w, fdiv(fmul(ha.lr_over_bc1_neg, m), denom));
+              a.alpha_state[0] = w; a.alpha_state[1] = m; a.alpha_state[2] = v;
+            }
+          }
+        }
+        FRL_SYNC();
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------------------------
+// launcher: cooperative launch (co-residency guarantee), hand-rolled grid barrier
+// ------------------------------------------------------------------------------------------------------------------------
+#ifndef FRL_EMUL
+template <class A>
+__global__ void __launch_bounds__(FRL_NT, 1) frl_fx_kernel(const __grid_constant__ typename A::Args a) {
+  extern __shared__ __align__(1024) float frl_smem[];
+  // The argument block (network / replay descriptors, ~3 KB) is copied to shared memory once: read from the constant bank, its
+  // scattered fields cost a constant-cache miss each at the head of every stage (measured: 2 - 5 k clk of scalar preamble per
+  // stage, profiles/r2d_trace_64.txt), and every stage of every learn re-reads them.
+  __shared__ __align__(16) typename A::Args sa;
+  {
+    const int* src = reinterpret_cast<const int*>(&a);
+    int* dst = reinterpret_cast<int*>(&sa);
+    for (int i = (int)threadIdx.x; i < (int)(sizeof(typename A::Args) / 4); i += FRL_NT) dst[i] = src[i];
+  }
+  Cta c;
+  float* user = cta_init(c, (int)blockIdx.x, (int)gridDim.x, frl_smem, A::wbuf_floats(a));      // ends with __syncthreads
+  const int U = A::n_updates(a);
+  unsigned* const ctr = a.sync;
+  unsigned target = 0;
+  for (int u = 0; u < U; ++u) {
+    for (int s = 0; s < A::NSTAGES; ++s) {
+      if (!A::stage_enabled(s, u, sa)) continue;
+      trace(1000 + s);
+      A::stage(s, u, c, user, sa);
+      trace(1100 + s);
+      stamp(c, 100 + s);
+      // (no proxy fence here: the thread that issues a TMA copy of data other CTAs wrote runs fence.proxy.async after this
+      //  barrier's acquire, which puts the fence on the causality path between the generic writes and the bulk read)
+      target += gridDim.x;
+      fx_grid_barrier(ctr, target);
+      stamp(c, 200 + s);
+    }
+  }
+  res_drain(c);
+}
+
+template <class A>
+int frl_launch_fx(const typename A::Args& a, cudaStream_t stream) {
+  const int smem_bytes = (cta_base_floats(A::wbuf_floats(a)) + A::user_floats(a)) * 4 + 64;      // + the static copy of the arguments
+  int dev = 0;
+  FRL_CUDA_OK(cudaGetDevice(&dev));
+  static int configured_bytes[64] = {0};
+  if (dev < 0 || dev >= 64) { frl_set_error("device ordinal %d out of range", dev); return -3; }
+  if (smem_bytes > configured_bytes[dev]) {
+    FRL_CUDA_OK(cudaFuncSetAttribute(frl_fx_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    configured_bytes[dev] = smem_bytes;
+  }
+  const int grid = A::grid(a, frl_device_max_ctas());
+  int per_sm = 0;
+  FRL_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frl_fx_kernel<A>, FRL_NT, (size_t)smem_bytes));
+  if (per_sm * frl_device_max_ctas() < grid) {
+    frl_set_error("cooperative launch of %d CTAs does not fit the device (%d per SM)", grid, per_sm);
+    return -3;
+  }
+  FRL_CUDA_OK(cudaMemsetAsync(a.sync, 0, 4096, stream));       // barrier counter + hand-off flags
+  typename A::Args args = a;
+  void* kargs[] = {(void*)&args};
+  FRL_CUDA_OK(cudaLaunchCooperativeKernel((void*)frl_fx_kernel<A>, dim3(grid), dim3(FRL_NT), kargs, (size_t)smem_bytes, stream));
+  return 0;
+}
+#else
+template <class A>
+int frl_launch_fx(const typename A::Args& a, cudaStream_t s) {
+  memset(a.sync, 0, 4096);
+  return frl_launch<A>(a, s);
+}
+#endif

@@ -5,8 +5,11 @@
 // product Python path refuses a library that reports 1.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "algo_ppo.cuh"
+#include "algo_acfx.cuh"
 #include "algo_per.cuh"
 #include "algo_rainbow.cuh"
 #include "algo_vec.cuh"
@@ -23,7 +26,7 @@ extern "C" void frl_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 extern "C" const char* frl_last_error(void) { return g_err; }
-extern "C" int frl_abi_version(void) { return 5; }
+extern "C" int frl_abi_version(void) { return 6; }
 // sizeof() of the argument structs, so a binding can verify its mirror of the layout before the first call
 extern "C" int frl_struct_size(int which) {
   switch (which) {
@@ -65,6 +68,16 @@ extern "C" int frl_debug_set_timing(void* dev_buf) {
   FRL_CUDA_OK(cudaMemcpyToSymbol(frl_dbg_ptr, &p, sizeof(p)));
 #else
   (void)dev_buf;
+#endif
+  return 0;
+}
+
+// debug (-DFRL_TRACE builds only): which CTA of the persistent kernels writes the op trace
+extern "C" int frl_debug_set_trace_cta(int cta) {
+#if !defined(FRL_EMUL) && defined(FRL_TRACE)
+  FRL_CUDA_OK(cudaMemcpyToSymbol(frl_trace_cta, &cta, sizeof(cta)));
+#else
+  (void)cta;
 #endif
   return 0;
 }
@@ -590,6 +603,23 @@ extern "C" int frl_dqn_learn(const frl_dqn_args_t* a, void* stream) {
   return frl_launch<DqnAlgo>(*a, (cudaStream_t)stream);
 }
 
+// FREERL_B200_AC_PATH=generic forces the generic kernel (A/B timing, tests of the fallback)
+extern "C" int frl_ac_path(const frl_ac_args_t* a) {
+  if (!a) return 0;
+  const char* e = getenv("FREERL_B200_AC_PATH");
+  if (e && !strcmp(e, "generic")) return 0;
+  return AcFx::eligible(*a, frl_device_max_ctas()) ? 1 : 0;
+}
+extern "C" long long frl_ac_ws_floats(const frl_ac_args_t* a) {
+  if (!a) return 0;
+  frl_ac_args_t b = *a;                 // eligibility of the shapes, whatever the scratch pointers are right now
+  float dummy_ws = 0.f;
+  unsigned dummy_sync = 0;
+  b.ws = &dummy_ws; b.sync = &dummy_sync;
+  if (!AcFx::eligible(b, frl_device_max_ctas())) return 0;
+  return (long long)AcFx::ws_layout(b, frl_device_max_ctas()).total;
+}
+
 extern "C" int frl_ac_learn(const frl_ac_args_t* a, void* stream) {
   if (!a || a->B <= 0 || a->n_updates <= 0 || !a->indices || !a->gpart || !a->sumsq || !a->stats || !a->out || !a->xchg ||
       a->n_heads < 1 || a->n_heads > 2) {
@@ -607,6 +637,8 @@ extern "C" int frl_ac_learn(const frl_ac_args_t* a, void* stream) {
     frl_set_error("frl_ac_learn: unsupported network shape / missing alpha state");
     return -1;
   }
+  // the reference's own batch sizes (B <= 256), single agent, hidden 128-128: the small-batch schedule of algo_acfx.cuh
+  if (frl_ac_path(a)) return frl_launch_fx<AcFx>(*a, (cudaStream_t)stream);
   // compile-time specialisations of the same kernel source for the two single-agent families (smaller instruction footprint)
   if (a->n_agents <= 1 && !a->obs_norm[0]) {
     if (a->actor_kind == FRL_ACTOR_SAC && a->n_heads == 2) return frl_launch<AcAlgoT<1> >(*a, (cudaStream_t)stream);

@@ -152,6 +152,7 @@ struct Cta {
 // Debug timestamps: CTA 0 / thread 0 appends (id, clock) pairs.  Disabled (nullptr) in normal runs.
 #if !defined(FRL_EMUL) && defined(FRL_TRACE)
 __device__ long long* frl_dbg_ptr = nullptr;
+__device__ int frl_trace_cta = 0;           // which CTA writes the op trace (frl_debug_set_trace_cta)
 FRL_DEV void stamp(Cta&, int) {}            // the op trace owns the sink in -DFRL_TRACE builds
 #elif !defined(FRL_EMUL)
 __device__ long long* frl_dbg_ptr = nullptr;
@@ -171,7 +172,7 @@ FRL_DEV void stamp(Cta&, int) {}
 #if defined(FRL_TRACE) && !defined(FRL_EMUL)
 __shared__ int frl_trace_n;         // per-CTA event counter in smem: a probe costs ~50 clk (a global atomic cost ~1000)
 FRL_DEV void trace(int id, int who = 0) {
-  if (frl_dbg_ptr && blockIdx.x == 0 && (int)threadIdx.x == who) {
+  if (frl_dbg_ptr && (int)blockIdx.x == frl_trace_cta && (int)threadIdx.x == who) {
     const int k = frl_trace_n;
     frl_trace_n = k + 1;
     if (k < 2000) { frl_dbg_ptr[2 * k] = id; frl_dbg_ptr[2 * k + 1] = clock64(); }
@@ -937,12 +938,16 @@ FRL_DEV void res_drain_slot(Cta& c, int s) {
 // thread 0: one bulk copy + mbarrier per layer (kept out of line: eight call sites)
 FRL_NI_MISC void res_issue(float* dst, uint64_t* bars, const frl_net_t& n, int l0, int nl) {
 #ifndef FRL_EMUL
+  trace(20);
   fence_proxy_async();
+  trace(21);
   for (int k = 0; k < nl; ++k) {
     const frl_layer_t& L = n.L[l0 + k];
     const uint32_t bytes = (uint32_t)wt_floats(L) * 4u;
     mbar_expect_tx(bars + k, bytes);
+    trace(22);
     tma_bulk_g2s(dst + (L.wt_off - n.L[l0].wt_off), n.pt + L.wt_off, bytes, bars + k);
+    trace(23);
   }
 #else
   (void)bars;

@@ -133,6 +133,11 @@ typedef struct {
   int64_t obs_norm_n0;      /* updates folded in before this call */
   const float* ma_noise_next[FRL_MAX_AGENTS];   /* n_agents > 1 with target_smoothing (MATD3_simple.py:203-205): dev [B][act_dim_j]
                                                  * randn of agent j's target action for THIS agent's sample; NULL -> Philox(seed) */
+  /* ---- small-batch schedule (csrc/algo_acfx.cuh; single agent, hidden 128-128, B <= 256): taken when both are given ----
+   * ws   = dev scratch of frl_ac_ws_floats(args) floats (activation / gradient exchange blocks, partial sums);
+   * sync = dev scratch of 1024 uint32 (grid-barrier counter + hand-off flags; the library zeroes it at every launch). */
+  float* ws;
+  unsigned* sync;
 } frl_ac_args_t;
 
 /* FRL_INFER_ARGMAX_DUELING (7): argmax_a of V + A_a - mean(A) for a [V | A] head (Dueling.forward, DQN_with_tricks.py:75-79) */
@@ -276,6 +281,10 @@ int frl_net_sync_mirror(const frl_net_t* net, void* stream);
 int frl_polyak(const frl_net_t* src, const frl_net_t* target, float tau, void* stream);
 int frl_dqn_learn(const frl_dqn_args_t* args, void* stream);
 int frl_ac_learn(const frl_ac_args_t* args, void* stream);
+/* floats of `ws` the small-batch schedule needs for these shapes (0: not eligible, frl_ac_learn takes the generic kernel);
+ * frl_ac_path: 1 if frl_ac_learn(args) would run the small-batch schedule, 0 for the generic kernel */
+long long frl_ac_ws_floats(const frl_ac_args_t* args);
+int frl_ac_path(const frl_ac_args_t* args);
 int frl_policy_infer(const frl_infer_args_t* args, void* stream);
 /* GAE over a [T][N] rollout (N env columns): td = r + gamma(1-done)v' - v (fp32); A_t = td_t + gamma*lmbda*(1-adv_done_t)A_{t+1}
  * accumulated in float64 per column from a zero tail; adv (fp32) and v_target = adv + v. */

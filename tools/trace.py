@@ -13,6 +13,9 @@ pol.add(rng.standard_normal((n, 17), dtype=np.float32), rng.uniform(-1, 1, (n, 6
 for _ in range(3):
     pol.learn(256, 0.99, 0.01, n_updates=4)
 buf = torch.zeros(4000, dtype=torch.int64, device=dev)
+cta = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+_lib.lib().frl_debug_set_trace_cta(cta)
+print('trace of CTA', cta)
 _lib.lib().frl_debug_set_timing(ctypes.c_void_p(buf.data_ptr()))
 pol.learn(256, 0.99, 0.01, n_updates=2)
 torch.cuda.synchronize()
