@@ -94,8 +94,12 @@ static inline void fx_emu_bf(float (*src)[64], float (*dst)[64], int NV, int m) 
 //   kq, kq + 8, ...; the 8 K-partials are combined by a reduce-scatter over lane bits 4, 3, 2 that leaves row kq with lane kq.
 //   Bank behaviour: a quarter warp reads two consecutive 16-B chunks of X (broadcast) and rows 4c+q of two chunks 16 B x 4
 //   wide whose row offset differs by 4 * 132 = 16 (mod 32) words — conflict free.
+//   xg != nullptr: the output tile is also written to the exchange blocks it belongs to (xg = region + (blk0 Rmax + row0) 16,
+//   rm16 = 16 Rmax): element (r, col) -> xg[(col / 16) rm16 + 16 r + col % 16] — the fire-and-forget global store of the
+//   epilogue replaces a separate smem -> global pass.
 template <int NCH_STATIC>
-FRL_NI_GEMM void fx_fwd(const float* X, int ldx, int nch_rt, const float* W, const float* bias, int relu, float* Y) {
+FRL_NI_GEMM void fx_fwd(const float* X, int ldx, int nch_rt, const float* W, const float* bias, int relu, float* Y, float* xg = nullptr,
+                        int rm16 = 0) {
   const int nch = NCH_STATIC > 0 ? NCH_STATIC : nch_rt;
   trace(50);
   FRL_PAR(t) {
@@ -153,6 +157,7 @@ FRL_NI_GEMM void fx_fwd(const float* X, int ldx, int nch_rt, const float* W, con
       for (int j = 0; j < 4; ++j) o[j] = o[j] > 0.f ? o[j] : 0.f;
     }
     sp_st4(sp_of(Y), kq * 128 + col, make_float4(o[0], o[1], o[2], o[3]));
+    if (xg) st4(xg + (size_t)w * rm16 + kq * 16 + 4 * cg, make_float4(o[0], o[1], o[2], o[3]));
 #else
     for (int r = 0; r < 8; ++r)
       for (int j = 0; j < 4; ++j) fx_emu_a[t][r * 4 + j] = acc[r][j];
@@ -168,6 +173,7 @@ FRL_NI_GEMM void fx_fwd(const float* X, int ldx, int nch_rt, const float* W, con
       float o = fx_emu_b[t][j] + bias[col + j];
       if (relu) o = o > 0.f ? o : 0.f;
       Y[kq * 128 + col + j] = o;
+      if (xg) xg[(size_t)w * rm16 + kq * 16 + 4 * cg + j] = o;
     }
   }
 #endif
@@ -181,7 +187,7 @@ FRL_NI_GEMM void fx_fwd(const float* X, int ldx, int nch_rt, const float* W, con
 //   8 rows x 4 outputs (k = 16w + 4cg + i) over the n chunks nq, nq + 8, ... with even / odd n in separate accumulators (both
 //   operands are natural register pairs of the 16-B loads -> FFMA2); reduce-scatter over lane bits 2, 1, 0 leaves row nq.
 //   A quarter warp reads one 128-B row segment of WT and one of dY: conflict free.
-FRL_NI_GEMM void fx_bwd(const float* dY, const float* W, const float* mask, float* dX) {
+FRL_NI_GEMM void fx_bwd(const float* dY, const float* W, const float* mask, float* dX, float* xg = nullptr, int rm16 = 0) {
   trace(60);
   FRL_PAR(t) {
     const int w = t >> 5, l = t & 31, nq = l & 7, cg = l >> 3, k0 = 16 * w + 4 * cg;
@@ -234,8 +240,9 @@ FRL_NI_GEMM void fx_bwd(const float* dY, const float* W, const float* mask, floa
       v3[j] = keep + shx(send, 1);
     }
     const float4 mv = sp_ld4(sp_of(mask), nq * 128 + k0);
-    sp_st4(sp_of(dX), nq * 128 + k0,
-           make_float4(mv.x > 0.f ? v3[0] : 0.f, mv.y > 0.f ? v3[1] : 0.f, mv.z > 0.f ? v3[2] : 0.f, mv.w > 0.f ? v3[3] : 0.f));
+    const float4 ov = make_float4(mv.x > 0.f ? v3[0] : 0.f, mv.y > 0.f ? v3[1] : 0.f, mv.z > 0.f ? v3[2] : 0.f, mv.w > 0.f ? v3[3] : 0.f);
+    sp_st4(sp_of(dX), nq * 128 + k0, ov);
+    if (xg) st4(xg + (size_t)w * rm16 + nq * 16 + 4 * cg, ov);
 #else
     for (int r = 0; r < 8; ++r)
       for (int i = 0; i < 4; ++i) fx_emu_a[t][r * 4 + i] = acc[r][i];
@@ -247,7 +254,11 @@ FRL_NI_GEMM void fx_bwd(const float* dY, const float* W, const float* mask, floa
   fx_emu_rs(fx_emu_a, fx_emu_b, 8, 1);
   FRL_PAR(t) {
     const int w = t >> 5, l = t & 31, nq = l & 7, cg = l >> 3, k0 = 16 * w + 4 * cg;
-    for (int j = 0; j < 4; ++j) dX[nq * 128 + k0 + j] = mask[nq * 128 + k0 + j] > 0.f ? fx_emu_b[t][j] : 0.f;
+    for (int j = 0; j < 4; ++j) {
+      const float o = mask[nq * 128 + k0 + j] > 0.f ? fx_emu_b[t][j] : 0.f;
+      dX[nq * 128 + k0 + j] = o;
+      if (xg) xg[(size_t)w * rm16 + nq * 16 + 4 * cg + j] = o;
+    }
   }
 #endif
   trace(61);
@@ -308,7 +319,8 @@ FRL_NI_GEMM void fx_fwd_narrow(const float* X, const float* W, const float* bias
 }
 
 // narrow head backward:  dH[8][128] = (dOut[8][ldo](columns < NO) * W) * relu'(mask):  dH[r][k] = sum_n dOut[r][n] WT[k][n]
-FRL_NI_GEMM void fx_bwd_narrow(const float* dOut, int ldo, const float* W, int NO, int ld, const float* mask, float* dH) {
+FRL_NI_GEMM void fx_bwd_narrow(const float* dOut, int ldo, const float* W, int NO, int ld, const float* mask, float* dH,
+                               float* xg = nullptr, int rm16 = 0) {
   trace(64);
   // thread = (output column k, rows 4 hi .. 4 hi + 3): consecutive lanes read consecutive 16-B (NO = 4) / 48-B (NO = 8) rows of WT
   // and write consecutive words of dH — no bank conflicts; the dOut rows are warp-wide broadcasts
@@ -328,7 +340,9 @@ FRL_NI_GEMM void fx_bwd_narrow(const float* dOut, int ldo, const float* W, int N
         const float4 d1 = sp_ld4(sO, r * ldo + 4);
         s += d1.x * w1.x; s += d1.y * w1.y; s += d1.z * w1.z; s += d1.w * w1.w;
       }
-      sp_st1(sH, r * 128 + k, sp_ld1(sM, r * 128 + k) > 0.f ? s : 0.f);
+      const float o = sp_ld1(sM, r * 128 + k) > 0.f ? s : 0.f;
+      sp_st1(sH, r * 128 + k, o);
+      if (xg) xg[(size_t)(k >> 4) * rm16 + r * 16 + (k & 15)] = o;
     }
   }
   trace(65);
@@ -401,6 +415,76 @@ struct FxJob {
   int NB, KB;     // tile height / width (NB * KB in {256, 512})
 };
 
+// what stage() needs from the argument block, derived once per launch (AcFx::build_plan) and kept in shared memory
+struct FxJobP { int li, n0, k0, NB, KB, ksh, yb0, xb0, xbn, pad; };      // li = -2: no job in this slot; -1: the extras job
+struct FxPlan {
+  int role, wi, tile, h, l0, row0, nvalid, njobs_c, njobs_a;
+  int cxb[3], cyb[3], axb[3], ayb[3];                                    // first exchange block of this CTA's critic head / the actor layers
+  int w_cx, w_cy, w_ax, w_ay0, w_ay1, w_xq, w_xlp, w_lsg, w_stats, w_sumsq;
+  FxJobP jc[2], ja[2];
+};
+#define FX_PLAN_FLOATS 80
+static_assert(sizeof(FxPlan) <= FX_PLAN_FLOATS * 4, "FxPlan outgrew its shared-memory reservation");
+
+// Start fetching the 3-layer head (l0..l0+2 of net n, contiguous in the mirror) into slot s unless it is already resident:
+// layer 0 on the slot's first mbarrier (small: the first op can start early), layers 1 + 2 as ONE copy on the second.  The two
+// copies are issued by the leaders of two different warps (`lead`, `lead + 32`) — each issue is a proxy fence (~1 k clk) plus
+// ~0.7 k clk of expect_tx / UBLKCP latency, and a stage that needs two heads gives them four different warps.
+FRL_DEV void fx_fetch(Cta& c, int s, const frl_net_t& n, int l0, int lead) {
+  const float* key = res_key(n, l0);
+  if ((s ? c.stag1 : c.stag0) == key) return;
+  res_drain_slot(c, s);
+  if (s) c.stag1 = key; else c.stag0 = key;
+  float* dst = s ? c.wbuf1 : c.wbuf0;
+  const int f0 = wt_floats(n.L[l0]), f12 = wt_floats(n.L[l0 + 1]) + wt_floats(n.L[l0 + 2]);
+#ifndef FRL_EMUL
+  uint64_t* bars = c.bar + 2 + s * 3;
+  if ((int)threadIdx.x == lead) {
+    fence_proxy_async();
+    mbar_expect_tx(bars, (uint32_t)f0 * 4u);
+    tma_bulk_g2s(dst, key, (uint32_t)f0 * 4u, bars);
+  } else if ((int)threadIdx.x == lead + 32) {
+    fence_proxy_async();
+    mbar_expect_tx(bars + 1, (uint32_t)f12 * 4u);
+    tma_bulk_g2s(dst + f0, key + f0, (uint32_t)f12 * 4u, bars + 1);
+  }
+#else
+  (void)lead;
+  memcpy(dst, key, (size_t)(f0 + f12) * 4);
+#endif
+  c.spend |= 3u << (s * 3);
+}
+// smem image of layer l0 + k of the head fetched into slot s by fx_fetch (waits for its copy if still outstanding)
+FRL_DEV const float* fx_layer(Cta& c, int s, const frl_net_t& n, int l0, int k) {
+  const uint32_t bit = 1u << (s * 3 + (k ? 1 : 0));
+  if (c.spend & bit) {
+#ifndef FRL_EMUL
+    mbar_wait(c.bar + 2 + s * 3 + (k ? 1 : 0), (c.sphase >> (s * 3 + (k ? 1 : 0))) & 1u);
+#endif
+    c.sphase ^= bit; c.spend &= ~bit;
+  }
+  return (s ? c.wbuf1 : c.wbuf0) + (n.L[l0 + k].wt_off - n.L[l0].wt_off);
+}
+
+// Sum of slot[0..31], written by the lanes of warp 0 in the phase just before (no block barrier needed): the shuffle tree of
+// block_sum's first level, so a phase whose other warps contribute zeros gets block_sum's bits.  GPU: valid in thread 0 only.
+FRL_DEV float fx_tree32(float* slot) {
+#ifndef FRL_EMUL
+  float v = 0.f;
+  if (threadIdx.x < 32) {
+    __syncwarp();
+    v = slot[threadIdx.x];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+  }
+  return v;
+#else
+  for (int off = 16; off > 0; off >>= 1)
+    for (int i = 0; i < off; ++i) slot[i] += slot[i + off];
+  return slot[0];
+#endif
+}
+
 struct AcFx {
   typedef frl_ac_args_t Args;
   static const int NSTAGES = 6;
@@ -423,7 +507,8 @@ struct AcFx {
   // shared memory after the engine's own (two slots + c.red + mbarriers): see the SmemBump sequence in stage()
   static const int GST_SLOTS = 2;                    // dW jobs one CTA may own (jobs <= GST_SLOTS * grid)
   FRL_SHD int user_floats(const Args& a) {
-    return 8 * a.replay.row_floats + 3 * 8 * 32 + 64 + 6 * 1024 + 5 * 64 + 3 * 32 + 2 * FRL_NT + GST_SLOTS * 528 + 128 + GST_SLOTS * 16 + 16 + 64;
+    return FX_PLAN_FLOATS + 8 * a.replay.row_floats + 3 * 8 * 32 + 64 + 6 * 1024 + 5 * 64 + 2 * 32 + 2 * FRL_NT + GST_SLOTS * 528 + 128 +
+           GST_SLOTS * 16 + 16 + 4 + 64;
   }
   FRL_SHD int grid(const Args&, int max_ctas) { return max_ctas; }
 
@@ -486,6 +571,8 @@ struct AcFx {
 
   // host-side eligibility (capi.cu): everything else takes the generic kernel of algo_ac.cuh
   FRL_SHD bool shape_ok(const frl_net_t& n, int l0, int max_out) {
+    // (fx_fetch copies layers l0+1, l0+2 as one block: the head's layer images must be contiguous in the mirror)
+    if (n.L[l0 + 1].wt_off != n.L[l0].wt_off + wt_floats(n.L[l0]) || n.L[l0 + 2].wt_off != n.L[l0 + 1].wt_off + wt_floats(n.L[l0 + 1])) return false;
     return n.L[l0].out_pad == 128 && n.L[l0 + 1].in_pad == 128 && n.L[l0 + 1].out_pad == 128 && n.L[l0 + 2].in_pad == 128 &&
            n.L[l0].in_pad <= 32 && n.L[l0 + 2].out_pad <= max_out;
   }
@@ -511,23 +598,63 @@ struct AcFx {
     return randn_ni(a.seed, stream, (uint32_t)(a.total_it0 + u), (uint32_t)(row * a.replay.act_dim + j));
   }
 
-  // thread 0: bulk copies of `nblk` exchange blocks (rows [0, R)) into consecutive [R][16] arrays at dst, on mbarrier bar[0]
-  FRL_SDEV void job_issue(Cta& c, float* dst, const float* region, int blk0, int nblk, int Rmax, int R, bool arm, int total_blocks) {
+  // ---- per-CTA plan: what stage() derives from the argument block (roles, workspace offsets, exchange block numbers, the dW
+  //      jobs this CTA owns), computed ONCE by thread 0 and kept in shared memory.  Recomputing it per stage cost 2 - 5 k clk of
+  //      redundant scalar code at the head of each of the 6 stages of every learn (profiles/r2e_trace_fx_cta64.txt). ----
+  FRL_SDEV void plan_jobs(FxJobP* out, const frl_net_t& n, int njobs, const Cta& c) {
+    for (int slot = 0; slot < GST_SLOTS; ++slot) {
+      FxJobP& Q = out[slot];
+      const int j = c.cta + slot * c.ncta;
+      Q.li = -2; Q.n0 = Q.k0 = Q.NB = Q.KB = Q.ksh = Q.yb0 = Q.xb0 = Q.xbn = Q.pad = 0;
+      if (j >= njobs) continue;
+      const FxJob J = job_of(n, j);
+      Q.li = J.li; Q.n0 = J.n0; Q.k0 = J.k0; Q.NB = J.NB; Q.KB = J.KB;
+      if (J.li < 0) continue;
+      Q.ksh = J.KB == 16 ? 4 : (J.KB == 32 ? 5 : 6);
+      Q.yb0 = fx_yblocks(n, J.li) + (J.n0 >> 4);
+      Q.xb0 = fx_xblocks(n, J.li) + (J.k0 >> 4);
+      const int xbn_all = fx_xb(n, J.li) - (J.k0 >> 4);
+      Q.xbn = (J.KB >> 4) < xbn_all ? (J.KB >> 4) : xbn_all;
+    }
+  }
+  FRL_SDEV void build_plan(FxPlan& P, const Cta& c, const Args& a) {
+    const int NH = a.n_heads, nwork = ntile(a) * NH;
+    P.role = c.cta < nwork ? 0 : (c.cta < 2 * nwork ? 1 : 2);
+    P.wi = P.role == 0 ? c.cta : c.cta - nwork;
+    P.tile = P.wi / NH; P.h = P.wi - P.tile * NH; P.l0 = 3 * P.h; P.row0 = P.tile * 8;
+    P.nvalid = (a.B - P.row0) < 8 ? (a.B - P.row0) : 8;
+    P.njobs_c = net_jobs(a.critic); P.njobs_a = net_jobs(a.actor);
+    for (int k = 0; k < 3; ++k) {
+      P.cxb[k] = fx_xblocks(a.critic, P.l0 + k); P.cyb[k] = fx_yblocks(a.critic, P.l0 + k);
+      P.axb[k] = fx_xblocks(a.actor, k); P.ayb[k] = fx_yblocks(a.actor, k);
+    }
+    const Ws W = ws_layout(a, c.ncta);
+    P.w_cx = (int)W.cx; P.w_cy = (int)W.cy; P.w_ax = (int)W.ax; P.w_ay0 = (int)W.ay0; P.w_ay1 = (int)W.ay1; P.w_xq = (int)W.xq;
+    P.w_xlp = (int)W.xlp; P.w_lsg = (int)W.lsg; P.w_stats = (int)W.stats; P.w_sumsq = (int)W.sumsq;
+    plan_jobs(P.jc, a.critic, P.njobs_c, c);
+    plan_jobs(P.ja, a.actor, P.njobs_a, c);
+  }
+
+  // Operands of one dW job -> the scratch slot, as 1-D bulk copies of whole exchange blocks ([R][16] each) on mbarrier bar[0]:
+  // copy 0 = dY block of yreg0, [copy 1 = the same block of yreg1], then the job's X blocks.  Warp q's leader issues copy q
+  // (each issue is ~300 clk of uniform-datapath latency plus the proxy fence; spread over warps they overlap).
+  FRL_SDEV void job_issue(Cta& c, const FxJobP& J, float* scr, const float* xreg, const float* yreg0, const float* yreg1, int Rm) {
+    const int nyb = yreg1 ? 2 : 1, ncopies = nyb + J.xbn;
+    const size_t blk = (size_t)Rm * 16;
 #ifndef FRL_EMUL
-    if (threadIdx.x == 0) {
-      trace(24);
-      if (arm) {
-        fence_proxy_async();
-        trace(25);
-        mbar_expect_tx(c.bar, (uint32_t)total_blocks * (uint32_t)R * 64u);
-        trace(26);
-      }
-      for (int b = 0; b < nblk; ++b) tma_bulk_g2s(dst + (size_t)b * R * 16, region + (size_t)(blk0 + b) * Rmax * 16, (uint32_t)R * 64u, c.bar);
-      trace(27);
+    const int tid = (int)threadIdx.x, q = tid >> 5;
+    if ((tid & 31) == 0 && q < ncopies) {
+      fence_proxy_async();
+      if (q == 0) mbar_expect_tx(c.bar, (uint32_t)ncopies * (uint32_t)Rm * 64u);
+      const float* src = q == 0 ? yreg0 + (size_t)J.yb0 * blk : (q < nyb ? yreg1 + (size_t)J.yb0 * blk : xreg + (size_t)(J.xb0 + q - nyb) * blk);
+      tma_bulk_g2s(scr + (size_t)q * blk, src, (uint32_t)Rm * 64u, c.bar);
     }
 #else
-    (void)c; (void)arm; (void)total_blocks;
-    for (int b = 0; b < nblk; ++b) memcpy(dst + (size_t)b * R * 16, region + (size_t)(blk0 + b) * Rmax * 16, (size_t)R * 64);
+    for (int q = 0; q < ncopies; ++q) {
+      const float* src = q == 0 ? yreg0 + (size_t)J.yb0 * blk : (q < nyb ? yreg1 + (size_t)J.yb0 * blk : xreg + (size_t)(J.xb0 + q - nyb) * blk);
+      memcpy(scr + (size_t)q * blk, src, blk * 4);
+    }
+    (void)c;
 #endif
   }
 
@@ -535,8 +662,9 @@ struct AcFx {
   //   operands in shared memory: DY0 / DY1 as [R][16] (columns n0 % 16 ..), X as KB / 16 arrays [R][16]
   //   lanes: TL = NB KB / 16 register tiles of 4 x 4 per warp pass, 32 / TL row sub-splits inside the warp, 8 warps split the
   //   rows further (row = split, split + S, ...); warp partials are combined in fixed order through c.red.
-  FRL_SDEV void job_compute(Cta& c, const FxJob& J, int R, const float* DY0, const float* DY1, const float* Xs, int ncol0, float* gst,
-                            float* gbst, float* redb) {
+  //   Returns (every thread) this thread's share of the tile's sum of squares over the real (unpadded) elements.
+  FRL_SDEV float job_compute(Cta& c, const FxJobP& J, const frl_layer_t& L, int R, const float* DY0, const float* DY1, const float* Xs,
+                             int ncol0, float* gst, float* gbst, float* redb, float* sq /*[FRL_NT]*/) {
     const int TL = (J.NB * J.KB) >> 4, ktl = J.KB >> 2, RSW = 32 / TL, S = 8 * RSW;
     trace(70);
     FRL_PAR(t) {
@@ -598,42 +726,46 @@ struct AcFx {
 #endif
     trace(71);
     FRL_SYNC();
+    // warp partials in warp order -> the gradient tile (kept in shared memory for the optimiser stage) + this thread's squares
     FRL_PAR(t) {
+      float l = 0.f;
       for (int e = t; e < J.NB * J.KB; e += FRL_NT) {
         float s = c.red[e];
 #pragma unroll
         for (int w = 1; w < 8; ++w) s += c.red[w * 512 + e];
         gst[e] = s;
+        const int nn = e >> J.ksh, kk = e - (nn << J.ksh);
+        if (J.n0 + nn < L.out_pad && J.k0 + kk < L.in_pad) l += s * s;
       }
       if (t < J.NB) {
         float s = redb[t];
 #pragma unroll
         for (int w = 1; w < 8; ++w) s += redb[w * 16 + t];
         gbst[t] = s;
+        if (J.k0 == 0 && J.n0 + t < L.out_pad) l += s * s;
       }
+      sq[t] = l;
     }
     trace(72);
     FRL_SYNC();
+    return block_sum(sq);
   }
 
   // ---- one optimiser element (torch.optim.Adam single-tensor math, same rounding order as engine.cuh::adam_update) ----
-  FRL_SDEV void adam_elem(const AdamHP& hp, float coef, float gin, float* p, float* m, float* v, float* w_out) {
+  FRL_SDEV void adam_val(const AdamHP& hp, float coef, float gin, float& w, float& mm, float& vv) {
     float g = gin * coef;
-    float w = *p;
     if (hp.weight_decay != 0.f) g = fmaf(w, hp.weight_decay, g);
-    float mm = *m, vv = *v;
     mm = fmaf(hp.one_minus_b1, g - mm, mm);
     vv = fadd(fmul(vv, hp.b2), fmul(fmul(hp.one_minus_b2, g), g));
     const float denom = fadd(fdiv(fsqrt(vv), hp.bc2_sqrt), hp.eps);
     w = fadd(w, fdiv(fmul(hp.lr_over_bc1_neg, mm), denom));
-    *p = w; *m = mm; *v = vv; *w_out = w;
   }
 
   // dW + sum of squares of this CTA's jobs of net n (stage 1 / 4).  `scr` = the weight slot that is dead in this stage.
-  FRL_SDEV void dw_stage(Cta& c, const Args& a, const frl_net_t& n, const float* xreg, const float* yreg0, const float* yreg1,
-                         float* scr, float* gst, float* gbst, float* redb, float* red0, float* sumsq, const float* lsg, int nls,
-                         const AdamSpec sp, float* hpst, int njobs) {
-    const int Rm = rmax(a), R = Rm;
+  FRL_SDEV void dw_stage(Cta& c, const Args& a, const frl_net_t& n, const FxJobP* jobs, const float* xreg, const float* yreg0,
+                         const float* yreg1, float* scr, float* gst, float* gbst, float* redb, float* red0, float* sumsq_out,
+                         const float* lsg, int nls, const AdamSpec sp, float* hpst) {
+    const int Rm = rmax(a);
     // bias corrections of the optimiser stage that follows (double-precision powers, ~1.5 k clk on one thread): computed here,
     // by a thread that has nothing to do while the operands are in flight, and kept in shared memory
     FRL_PAR(t) {
@@ -643,9 +775,10 @@ struct AcFx {
         hpst[5] = h.eps; hpst[6] = h.weight_decay; hpst[7] = h.max_norm;
       }
     }
-    int slot = 0;
-    for (int j = c.cta; j < njobs; j += c.ncta, ++slot) {
-      const FxJob J = job_of(n, j);
+    float ss_cta = 0.f;
+    for (int slot = 0; slot < GST_SLOTS; ++slot) {
+      const FxJobP J = jobs[slot];
+      if (J.li == -2) break;
       float ss = 0.f;
       if (J.li < 0) {
         // extras (SAC log_std): fixed-order sum of the per-CTA partials written in phase C
@@ -662,53 +795,37 @@ struct AcFx {
         FRL_SYNC();
         ss = block_sum(red0);
       } else {
-        const int yb0 = fx_yblocks(n, J.li) + (J.n0 >> 4), xb0 = fx_xblocks(n, J.li) + (J.k0 >> 4);
-        const int xbn_all = fx_xb(n, J.li) - (J.k0 >> 4), xbn = (J.KB >> 4) < xbn_all ? (J.KB >> 4) : xbn_all;
         const int nyb = yreg1 ? 2 : 1;
         float* DY0 = scr;
-        float* DY1 = yreg1 ? scr + (size_t)R * 16 : nullptr;
-        float* Xs = scr + (size_t)nyb * R * 16;
-        // (blocks beyond the layer's last X block are not loaded: their register tiles multiply stale but finite slot data
-        //  into outputs that the optimiser masks out as k >= in_pad)
-        job_issue(c, DY0, yreg0, yb0, 1, Rm, R, true, nyb + xbn);
-        if (yreg1) job_issue(c, DY1, yreg1, yb0, 1, Rm, R, false, 0);
-        job_issue(c, Xs, xreg, xb0, xbn, Rm, R, false, 0);
+        float* DY1 = yreg1 ? scr + (size_t)Rm * 16 : nullptr;
+        float* Xs = scr + (size_t)nyb * Rm * 16;
+        // (blocks beyond the layer's last X block are not loaded; they are zeroed below so no stale NaN enters the sums)
+        trace(24);
+        job_issue(c, J, scr, xreg, yreg0, yreg1, Rm);
         trace(73);
-        stage_wait(c, 0);
-        trace(74);
-        if (xbn < (J.KB >> 4)) {                  // zero the missing X blocks so no NaN garbage enters the sums
-          FRL_PAR(t) { for (int e = t; e < ((J.KB >> 4) - xbn) * R * 16; e += FRL_NT) Xs[(size_t)xbn * R * 16 + e] = 0.f; }
+        if (J.xbn < (J.KB >> 4)) {
+          FRL_PAR(t) { for (int e = t; e < ((J.KB >> 4) - J.xbn) * Rm * 16; e += FRL_NT) Xs[(size_t)J.xbn * Rm * 16 + e] = 0.f; }
           FRL_SYNC();
         }
-        job_compute(c, J, R, DY0, DY1, Xs, J.n0 & 15, gst + slot * 528, gbst + slot * 16, redb);
-        FRL_PAR(t) {
-          float l = 0.f;
-          const frl_layer_t& L = n.L[J.li];
-          const int ksh = J.KB == 16 ? 4 : (J.KB == 32 ? 5 : 6);
-          for (int e = t; e < J.NB * J.KB; e += FRL_NT) {
-            const int nn = e >> ksh, kk = e - (nn << ksh);
-            if (J.n0 + nn < L.out_pad && J.k0 + kk < L.in_pad) { const float g = gst[slot * 528 + e]; l += g * g; }
-          }
-          if (J.k0 == 0 && t < J.NB && J.n0 + t < L.out_pad) { const float g = gbst[slot * 16 + t]; l += g * g; }
-          red0[t] = l;
-        }
-        FRL_SYNC();
-        ss = block_sum(red0);
+        stage_wait(c, 0);
+        trace(74);
+        ss = job_compute(c, J, n.L[J.li], Rm, DY0, DY1, Xs, J.n0 & 15, gst + slot * 528, gbst + slot * 16, redb, red0);
       }
-      FRL_PAR(t) { if (t == 0) sumsq[j] = ss; }
+      ss_cta += ss;
     }
+    FRL_PAR(t) { if (t == 0) *sumsq_out = ss_cta; }
     FRL_SYNC();
   }
 
   // clip + Adam (+ Polyak of tgt) on the elements of this CTA's jobs (stage 2 / 5).  Returns the total squared norm.
   FRL_SDEV float opt_stage(Cta& c, const frl_net_t& n, const frl_net_t* tgt, float tau, const float* hpst, const float* gst,
-                           const float* gbst, const float* sumsq, float* sh, int njobs) {
+                           const float* gbst, const float* sumsq, float* sh, const FxJobP* jobs) {
     trace(80);
-    // total squared gradient norm: the per-job partials (<= 512) folded in a fixed order (strided per-thread sums, then the
-    // block tree), so every CTA computes the same number
+    // total squared gradient norm: one partial per CTA, folded in a fixed order (strided per-thread sums, then the block
+    // tree), so every CTA computes the same number
     FRL_PAR(t) {
       float v = 0.f;
-      for (int i = t; i < njobs; i += FRL_NT) v += fx_ldcg(sumsq + i);
+      for (int i = t; i < c.ncta; i += FRL_NT) v += fx_ldcg(sumsq + i);
       sh[t] = v;
     }
     FRL_SYNC();
@@ -723,41 +840,56 @@ struct AcFx {
       if (coef > 1.f) coef = 1.f;
     }
     const float omt = (float)(1.0 - (double)tau);
-    int slot = 0;
-    for (int j = c.cta; j < njobs; j += c.ncta, ++slot) {
-      const FxJob J = job_of(n, j);
-      const int ksh = J.KB == 16 ? 4 : (J.KB == 32 ? 5 : 6);
+    for (int slot = 0; slot < GST_SLOTS; ++slot) {
+      const FxJobP J = jobs[slot];
+      if (J.li == -2) break;
       FRL_PAR(t) {
         if (J.li < 0) {
           if (t < n.x_len) {
-            float w;
-            adam_elem(hp, coef, gst[slot * 528 + t], n.p + n.x_off + t, n.m + n.x_off + t, n.v + n.x_off + t, &w);
+            float w = n.p[n.x_off + t], mm = n.m[n.x_off + t], vv = n.v[n.x_off + t];
+            adam_val(hp, coef, gst[slot * 528 + t], w, mm, vv);
+            n.p[n.x_off + t] = w; n.m[n.x_off + t] = mm; n.v[n.x_off + t] = vv;
             if (tgt) tgt->p[n.x_off + t] = fadd(fmul(tgt->p[n.x_off + t], omt), fmul(w, tau));
           }
         } else {
+          // up to two tile elements + one bias element per thread; every load is issued before the first dependent use so the
+          // L2 round trips of p / m / v / target overlap (they were serialised behind the stores of the previous element)
           const frl_layer_t& L = n.L[J.li];
           const int ldw = wt_ld(L);
-          for (int e = t; e < J.NB * J.KB; e += FRL_NT) {
-            const int nn = e >> ksh, kk = e - (nn << ksh), row = J.n0 + nn, col = J.k0 + kk;
-            if (row < L.out_pad && col < L.in_pad) {
-              const int pi = L.w_off + row * L.in_pad + col, mi = L.wt_off + col * ldw + row;
-              float w;
-              adam_elem(hp, coef, gst[slot * 528 + e], n.p + pi, n.m + pi, n.v + pi, &w);
-              n.pt[mi] = w;
-              if (tgt) {
-                const float tw = fadd(fmul(tgt->p[pi], omt), fmul(w, tau));
-                tgt->p[pi] = tw; tgt->pt[mi] = tw;
+          int pi[3], mi[3];
+          float gg[3], pw[3], pm[3], pv[3], tp[3];
+          bool ok[3];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int e = t + q * FRL_NT;
+            ok[q] = false; pi[q] = mi[q] = 0; gg[q] = 0.f;
+            if (e < J.NB * J.KB) {
+              const int nn = e >> J.ksh, kk = e - (nn << J.ksh), row = J.n0 + nn, col = J.k0 + kk;
+              if (row < L.out_pad && col < L.in_pad) {
+                ok[q] = true; pi[q] = L.w_off + row * L.in_pad + col; mi[q] = L.wt_off + col * ldw + row; gg[q] = gst[slot * 528 + e];
               }
             }
           }
-          if (J.k0 == 0 && t < J.NB && J.n0 + t < L.out_pad) {
-            const int pi = L.b_off + J.n0 + t, mi = L.wt_off + wt_bias(L) + J.n0 + t;
-            float w;
-            adam_elem(hp, coef, gbst[slot * 16 + t], n.p + pi, n.m + pi, n.v + pi, &w);
-            n.pt[mi] = w;
-            if (tgt) {
-              const float tw = fadd(fmul(tgt->p[pi], omt), fmul(w, tau));
-              tgt->p[pi] = tw; tgt->pt[mi] = tw;
+          ok[2] = J.k0 == 0 && t < J.NB && J.n0 + t < L.out_pad;
+          pi[2] = L.b_off + J.n0 + t; mi[2] = L.wt_off + wt_bias(L) + J.n0 + t; gg[2] = ok[2] ? gbst[slot * 16 + t] : 0.f;
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            pw[q] = pm[q] = pv[q] = tp[q] = 0.f;
+            if (ok[q]) {
+              pw[q] = n.p[pi[q]]; pm[q] = n.m[pi[q]]; pv[q] = n.v[pi[q]];
+              if (tgt) tp[q] = tgt->p[pi[q]];
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            if (ok[q]) {
+              adam_val(hp, coef, gg[q], pw[q], pm[q], pv[q]);
+              n.p[pi[q]] = pw[q]; n.m[pi[q]] = pm[q]; n.v[pi[q]] = pv[q];
+              n.pt[mi[q]] = pw[q];
+              if (tgt) {
+                const float tw = fadd(fmul(tp[q], omt), fmul(pw[q], tau));
+                tgt->p[pi[q]] = tw; tgt->pt[mi[q]] = tw;
+              }
             }
           }
         }
@@ -772,28 +904,10 @@ struct AcFx {
     const frl_net_t& A = a.actor;
     const frl_net_t& C = a.critic;
     const frl_replay_t& rb = a.replay;
-    const int od = rb.obs_dim, ad = rb.act_dim, rf = rb.row_floats;
-    const int NH = a.n_heads, nt_ = ntile(a), Rm = nt_ * 8, nwork = nt_ * NH;
-    const bool sac = is_sac(a);
-    const int hu = heads_used(a);
-    const bool policy_step = is_policy_step(a, u);
-    const int role = c.cta < nwork ? 0 : (c.cta < 2 * nwork ? 1 : 2);        // 0 target set, 1 online set, 2 helper
-    const int wi = role == 0 ? c.cta : c.cta - nwork;                        // worker index inside its set
-    const int tile = wi / NH, h = wi - tile * NH, l0 = 3 * h;
-    const int row0 = tile * 8;
-    const int nvalid = (a.B - row0) < 8 ? (a.B - row0) : 8;
-    const float invB = 1.0f / (float)a.B;
-    const int aip = A.L[0].in_pad, cip = C.L[0].in_pad, ap = A.L[2].out_pad, ald = wt_ld(A.L[2]), cld = wt_ld(C.L[2]);
-    float alpha = 0.f;
-    if (sac) alpha = expf(fx_ldcg(a.alpha_state));      // written by CTA 0 in stage 5: read through L2
-    const Ws W = ws_layout(a, c.ncta);
-    float* ws = a.ws;
-    unsigned* flags = a.sync + 32;
-    const unsigned epoch = (unsigned)u + 1u;
-
     trace(1);
     SmemBump sb; sb.p = user;
-    float* raw = sb.take(8 * rf);
+    FxPlan* Pp = reinterpret_cast<FxPlan*>(sb.take(FX_PLAN_FLOATS));
+    float* raw = sb.take(8 * rb.row_floats);
     float* XA = sb.take(8 * 32);             // actor input  [8][aip]
     float* XS = sb.take(8 * 32);             // critic input [8][cip] = [obs | act]
     float* XN = sb.take(8 * 32);             // [next_obs | a'] (target set) or [obs | pi(obs)] (phase C)
@@ -811,14 +925,30 @@ struct AcFx {
     float* EPS = sb.take(64);
     float* QA = sb.take(32);
     float* dQA = sb.take(32);
-    float* rowv = sb.take(32);
     float* red0 = sb.take(FRL_NT);
     float* red1 = sb.take(FRL_NT);
     float* gst = sb.take(GST_SLOTS * 528);   // gradient tile(s) of this CTA's dW job(s): kept from the dW stage to the optimiser stage
     float* redb = sb.take(128);
     float* gbst = sb.take(GST_SLOTS * 16);
     float* hpst = sb.take(16);               // optimiser scalars: written in the dW stage, read in the optimiser stage
-    const int njobs_c = net_jobs(C), njobs_a = net_jobs(A);
+    float* alpha_s = sb.take(4);             // exp(log_alpha) of this learn: read in phase A (y), reused in phase C
+    if (s == 0 && u == 0) {
+      FRL_PAR(t) { if (t == 0) build_plan(*Pp, c, a); }
+      FRL_SYNC();
+    }
+    const FxPlan& P = *Pp;
+    const int od = rb.obs_dim, ad = rb.act_dim, rf = rb.row_floats;
+    const int NH = a.n_heads, Rm = rmax(a), rm16 = Rm * 16, nwork = ntile(a) * NH;
+    const bool sac = is_sac(a);
+    const int hu = heads_used(a);
+    const bool policy_step = is_policy_step(a, u);
+    const int role = P.role, wi = P.wi, tile = P.tile, h = P.h, l0 = P.l0, row0 = P.row0, nvalid = P.nvalid;
+    const float invB = 1.0f / (float)a.B;
+    const int aip = A.L[0].in_pad, cip = C.L[0].in_pad, ap = A.L[2].out_pad, ald = wt_ld(A.L[2]), cld = wt_ld(C.L[2]);
+    float* ws = a.ws;
+    unsigned* flags = a.sync + 32;
+    const unsigned epoch = (unsigned)u + 1u;
+    const bool metrics_cta = c.cta == c.ncta - 1;        // the last CTA owns the lightest jobs: it also folds the metrics
 
     if (s == 0) {
       if (role == 2) return;
@@ -827,8 +957,8 @@ struct AcFx {
         // ------------------------------- target set: a' = actor_target(s'), Q'_h(s', a') -------------------------------
         const frl_net_t& AT = a.actor_target;
         const frl_net_t& CT = a.critic_target;
-        res_fetch(c, 0, AT, 0, 3);
-        res_fetch(c, 1, CT, l0, 3);
+        fx_fetch(c, 0, AT, 0, 0);
+        fx_fetch(c, 1, CT, l0, 64);
         trace(10);
         gather_rows<8>(rb.storage, rf, idx, nvalid, raw);
         trace(11);
@@ -836,9 +966,12 @@ struct AcFx {
         put_cols<8>(XN, cip, 0, raw, rf, rb_col_nobs(rb), od, cip);
         FRL_SYNC();
         trace(12);
-        fx_fwd<0>(XA, aip, aip >> 2, res_layer(c, 0, AT, 0, 0), res_layer(c, 0, AT, 0, 0) + wt_bias(AT.L[0]), 1, H1);
-        fx_fwd<32>(H1, 128, 32, res_layer(c, 0, AT, 0, 1), res_layer(c, 0, AT, 0, 1) + wt_bias(AT.L[1]), 1, H2);
-        fx_fwd_narrow(H2, res_layer(c, 0, AT, 0, 2), res_layer(c, 0, AT, 0, 2) + wt_bias(AT.L[2]), ap, ald, MU, 8);
+        const float* w0 = fx_layer(c, 0, AT, 0, 0);
+        fx_fwd<0>(XA, aip, aip >> 2, w0, w0 + wt_bias(AT.L[0]), 1, H1);
+        const float* w1 = fx_layer(c, 0, AT, 0, 1);
+        fx_fwd<32>(H1, 128, 32, w1, w1 + wt_bias(AT.L[1]), 1, H2);
+        const float* w2 = fx_layer(c, 0, AT, 0, 2);
+        fx_fwd_narrow(H2, w2, w2 + wt_bias(AT.L[2]), ap, ald, MU, 8);
         const bool smoothing = !sac && a.target_smoothing;
         FRL_PAR(t) {
           if (t < 8 * ad) {
@@ -870,16 +1003,19 @@ struct AcFx {
         }
         FRL_SYNC();
         trace(13);
-        fx_fwd<0>(XN, cip, cip >> 2, res_layer(c, 1, CT, l0, 0), res_layer(c, 1, CT, l0, 0) + wt_bias(CT.L[l0]), 1, H1);
-        fx_fwd<32>(H1, 128, 32, res_layer(c, 1, CT, l0, 1), res_layer(c, 1, CT, l0, 1) + wt_bias(CT.L[l0 + 1]), 1, H2);
-        fx_fwd_narrow(H2, res_layer(c, 1, CT, l0, 2), res_layer(c, 1, CT, l0, 2) + wt_bias(CT.L[l0 + 2]), 4, cld, QA, 4);
+        const float* q0 = fx_layer(c, 1, CT, l0, 0);
+        fx_fwd<0>(XN, cip, cip >> 2, q0, q0 + wt_bias(CT.L[l0]), 1, H1);
+        const float* q1 = fx_layer(c, 1, CT, l0, 1);
+        fx_fwd<32>(H1, 128, 32, q1, q1 + wt_bias(CT.L[l0 + 1]), 1, H2);
+        const float* q2 = fx_layer(c, 1, CT, l0, 2);
+        fx_fwd_narrow(H2, q2, q2 + wt_bias(CT.L[l0 + 2]), 4, cld, QA, 4);
         FRL_PAR(t) {
           if (t < 8) {
-            ws[W.xq + (size_t)(row0 + t) * 2 + h] = QA[t * 4];
+            ws[P.w_xq + (size_t)(row0 + t) * 2 + h] = QA[t * 4];
             if (sac && h == 0) {
               float lp = 0.f;
               for (int j = 0; j < ad; ++j) lp += UU[t * 8 + j];
-              ws[W.xlp + row0 + t] = lp;
+              ws[P.w_xlp + row0 + t] = lp;
             }
           }
         }
@@ -889,9 +1025,11 @@ struct AcFx {
         return;
       }
       // ------------------------------- online set: Q_h(s, a), pi(s); then y, loss, critic backward -------------------------------
-      res_fetch(c, 1, C, l0, 3);
+      float* cx = ws + P.w_cx;
+      float* cy = ws + P.w_cy;
+      fx_fetch(c, 1, C, l0, 0);
       const bool do_actor = policy_step && h < hu;
-      if (do_actor) res_fetch(c, 0, A, 0, 3);
+      if (do_actor) fx_fetch(c, 0, A, 0, 64);
       trace(10);
       gather_rows<8>(rb.storage, rf, idx, nvalid, raw);
       trace(11);
@@ -899,14 +1037,25 @@ struct AcFx {
       put_cols<8>(XA, aip, 0, raw, rf, 0, od, aip);
       FRL_SYNC();
       trace(12);
-      fx_fwd<0>(XS, cip, cip >> 2, res_layer(c, 1, C, l0, 0), res_layer(c, 1, C, l0, 0) + wt_bias(C.L[l0]), 1, H1);
-      fx_fwd<32>(H1, 128, 32, res_layer(c, 1, C, l0, 1), res_layer(c, 1, C, l0, 1) + wt_bias(C.L[l0 + 1]), 1, H2);
-      fx_fwd_narrow(H2, res_layer(c, 1, C, l0, 2), res_layer(c, 1, C, l0, 2) + wt_bias(C.L[l0 + 2]), 4, cld, QA, 4);
+      // layer inputs X and pre-activation gradients dY of this tile go to the exchange blocks of head h's layers l0..l0+2 as they
+      // are produced (the 128-wide ones from the GEMM epilogues)
+      fx_put_blocks(cx, P.cxb[0], fx_xb(C, l0), Rm, row0, XS, cip, cip);
+      const float* w0 = fx_layer(c, 1, C, l0, 0);
+      fx_fwd<0>(XS, cip, cip >> 2, w0, w0 + wt_bias(C.L[l0]), 1, H1, cx + ((size_t)P.cxb[1] * Rm + row0) * 16, rm16);
+      const float* w1 = fx_layer(c, 1, C, l0, 1);
+      fx_fwd<32>(H1, 128, 32, w1, w1 + wt_bias(C.L[l0 + 1]), 1, H2, cx + ((size_t)P.cxb[2] * Rm + row0) * 16, rm16);
+      const float* w2 = fx_layer(c, 1, C, l0, 2);
+      fx_fwd_narrow(H2, w2, w2 + wt_bias(C.L[l0 + 2]), 4, cld, QA, 4);
       if (do_actor) {
         trace(16);
-        fx_fwd<0>(XA, aip, aip >> 2, res_layer(c, 0, A, 0, 0), res_layer(c, 0, A, 0, 0) + wt_bias(A.L[0]), 1, A1);
-        fx_fwd<32>(A1, 128, 32, res_layer(c, 0, A, 0, 1), res_layer(c, 0, A, 0, 1) + wt_bias(A.L[1]), 1, A2);
-        fx_fwd_narrow(A2, res_layer(c, 0, A, 0, 2), res_layer(c, 0, A, 0, 2) + wt_bias(A.L[2]), ap, ald, MU, 8);
+        float* ax = (h == 0) ? ws + P.w_ax : nullptr;           // head 0's CTA publishes the actor's layer inputs
+        if (ax) fx_put_blocks(ax, P.axb[0], fx_xb(A, 0), Rm, row0, XA, aip, aip);
+        const float* p0 = fx_layer(c, 0, A, 0, 0);
+        fx_fwd<0>(XA, aip, aip >> 2, p0, p0 + wt_bias(A.L[0]), 1, A1, ax ? ax + ((size_t)P.axb[1] * Rm + row0) * 16 : nullptr, rm16);
+        const float* p1 = fx_layer(c, 0, A, 0, 1);
+        fx_fwd<32>(A1, 128, 32, p1, p1 + wt_bias(A.L[1]), 1, A2, ax ? ax + ((size_t)P.axb[2] * Rm + row0) * 16 : nullptr, rm16);
+        const float* p2 = fx_layer(c, 0, A, 0, 2);
+        fx_fwd_narrow(A2, p2, p2 + wt_bias(A.L[2]), ap, ald, MU, 8);
         FRL_PAR(t) {
           if (t < 64) {
             const int r = t >> 3, j = t & 7;
@@ -929,58 +1078,45 @@ struct AcFx {
             AC[t] = act; UU[t] = lp; EPS[t] = e;
           }
         }
-        FRL_SYNC();
+        // (no barrier: the next phase touches none of AC / UU / EPS, and several barriers precede their first reader in phase C)
       }
-      // targets of this tile from the target set (both heads)
+      // targets of this tile from the target set (both heads) -> y, loss, dL/dQ in one phase (threads 0..7 = the tile's rows)
       trace(17);
-      FRL_PAR(t) {
-        if (t < 8) {
-          const int r = t;
-          float y = 0.f;
-          for (int hh = 0; hh < NH; ++hh) fx_flag_wait(flags + tile * NH + hh, epoch);
-          if (r < nvalid) {
-            float nq = fx_ldcg(ws + W.xq + (size_t)(row0 + r) * 2);
-            if (NH == 2) nq = fminf(nq, fx_ldcg(ws + W.xq + (size_t)(row0 + r) * 2 + 1));
-            const float rew = raw[r * rf + rb_col_rew(rb)], dn = raw[r * rf + rb_col_done(rb)];
-            if (sac) {
-              const float lp = fx_ldcg(ws + W.xlp + row0 + r);
-              y = fadd(rew, fmul(fmul(a.gamma, fadd(1.f, -dn)), fadd(nq, fmul(alpha, -lp))));      // SAC.py:235
-            } else {
-              y = fadd(rew, fmul(fmul(a.gamma, nq), fadd(1.f, -dn)));                              // TD3.py:209 / DDPG.py:212
-            }
-          }
-          rowv[r] = y;
-        }
-      }
-      FRL_SYNC();
-      trace(18);
       FRL_PAR(t) {
         float l = 0.f;
         if (t < 8) {
+          const int r = t;
+          const float al = sac ? expf(fx_ldcg(a.alpha_state)) : 0.f;      // rewritten in stage 5 of the previous learn: read through L2
+          for (int hh = 0; hh < NH; ++hh) fx_flag_wait(flags + tile * NH + hh, epoch);
+          float y = 0.f;
+          if (r < nvalid) {
+            float nq = fx_ldcg(ws + P.w_xq + (size_t)(row0 + r) * 2);
+            if (NH == 2) nq = fminf(nq, fx_ldcg(ws + P.w_xq + (size_t)(row0 + r) * 2 + 1));
+            const float rew = raw[r * rf + rb_col_rew(rb)], dn = raw[r * rf + rb_col_done(rb)];
+            if (sac) {
+              const float lp = fx_ldcg(ws + P.w_xlp + row0 + r);
+              y = fadd(rew, fmul(fmul(a.gamma, fadd(1.f, -dn)), fadd(nq, fmul(al, -lp))));      // SAC.py:235
+            } else {
+              y = fadd(rew, fmul(fmul(a.gamma, nq), fadd(1.f, -dn)));                            // TD3.py:209 / DDPG.py:212
+            }
+          }
           for (int j = 0; j < 4; ++j) dQA[t * 4 + j] = 0.f;
-          if (t < nvalid) {
-            const float d0 = QA[t * 4] - rowv[t];
+          if (r < nvalid) {
+            const float d0 = QA[t * 4] - y;
             dQA[t * 4] = 2.f * d0 * invB;
             l = d0 * d0;
           }
+          if (t == 0) alpha_s[0] = al;
         }
-        red0[t] = l;
+        if (t < 32) red0[t] = l;
       }
+      const float loss_c = fx_tree32(red0);
       FRL_SYNC();
-      const float loss_c = block_sum(red0);
-      fx_bwd_narrow(dQA, 4, res_layer(c, 1, C, l0, 2), 4, cld, H2, D2);
-      fx_bwd(D2, res_layer(c, 1, C, l0, 1), H1, D1);
-      // layer inputs and pre-activation gradients of this tile -> exchange blocks of head h's layers l0..l0+2
-      float* cx = ws + W.cx;
-      float* cy = ws + W.cy;
-      fx_put_blocks(cx, fx_xblocks(C, l0), fx_xb(C, l0), Rm, row0, XS, cip, cip);
-      fx_put_blocks(cx, fx_xblocks(C, l0 + 1), 8, Rm, row0, H1, 128, 128);
-      fx_put_blocks(cx, fx_xblocks(C, l0 + 2), 8, Rm, row0, H2, 128, 128);
-      fx_put_blocks(cy, fx_yblocks(C, l0), 8, Rm, row0, D1, 128, 128);
-      fx_put_blocks(cy, fx_yblocks(C, l0 + 1), 8, Rm, row0, D2, 128, 128);
-      fx_put_blocks(cy, fx_yblocks(C, l0 + 2), 1, Rm, row0, dQA, 4, 4);
-      FRL_PAR(t) { if (t == 0) ws[W.stats + (size_t)wi * 8 + 0] = loss_c; }
-      FRL_SYNC();
+      trace(18);
+      fx_put_blocks(cy, P.cyb[2], 1, Rm, row0, dQA, 4, 4);
+      fx_bwd_narrow(dQA, 4, w2, 4, cld, H2, D2, cy + ((size_t)P.cyb[1] * Rm + row0) * 16, rm16);
+      fx_bwd(D2, w1, H1, D1, cy + ((size_t)P.cyb[0] * Rm + row0) * 16, rm16);
+      FRL_PAR(t) { if (t == 0) ws[P.w_stats + (size_t)wi * 8 + 0] = loss_c; }
       trace(19);
     } else if (s == 1) {
       res_invalidate(c, C);
@@ -988,24 +1124,29 @@ struct AcFx {
       res_drain_slot(c, 1);
       if (c.stag1 != nullptr) c.stag1 = nullptr;      // slot 1 is scratch in stages 1 / 2 whatever it held
       const AdamSpec hp = {a.lr_critic, a.beta1, a.beta2, a.eps, a.wd_critic, (double)a.max_norm, (long)(a.step_critic0 + u + 1)};
-      dw_stage(c, a, C, ws + W.cx, ws + W.cy, nullptr, c.wbuf1, gst, gbst, redb, red0, ws + W.sumsq, nullptr, 0, hp, hpst, njobs_c);
+      dw_stage(c, a, C, P.jc, ws + P.w_cx, ws + P.w_cy, nullptr, c.wbuf1, gst, gbst, redb, red0, ws + P.w_sumsq + c.cta, nullptr, 0, hp,
+               hpst);
     } else if (s == 2) {
-      const float tot = opt_stage(c, C, policy_step ? &a.critic_target : nullptr, a.tau, hpst, gst, gbst, ws + W.sumsq, c.red, njobs_c);
-      if (c.cta == 0) {
-        FRL_PAR(t) { red0[t] = t < nwork ? fx_ldcg(ws + W.stats + (size_t)t * 8) : 0.f; }
+      const float tot = opt_stage(c, C, policy_step ? &a.critic_target : nullptr, a.tau, hpst, gst, gbst, ws + P.w_sumsq, c.red, P.jc);
+      if (metrics_cta) {
+        FRL_PAR(t) { red0[t] = t < nwork ? fx_ldcg(ws + P.w_stats + (size_t)t * 8) : 0.f; }
         FRL_SYNC();
         const float ls = block_sum(red0);
         FRL_PAR(t) {
-          if (t == 0) { a.out[u * 8 + 0] = ls * invB; a.out[u * 8 + 4] = sqrtf(tot); a.out[u * 8 + 2] = alpha; }
+          if (t == 0) {
+            a.out[u * 8 + 0] = ls * invB; a.out[u * 8 + 4] = sqrtf(tot);
+            a.out[u * 8 + 2] = sac ? expf(fx_ldcg(a.alpha_state)) : 0.f;
+          }
         }
         FRL_SYNC();
       }
     } else if (s == 3) {
       // ------------------------------- phase C: Q_h(s, pi(s)) with the updated critic, dQ/da, actor backward -------------------------------
-      if (role == 0) { res_fetch(c, 1, a.critic_target, l0, 3); return; }      // prefetch for the next learn
+      if (role == 0) { fx_fetch(c, 1, a.critic_target, l0, 0); return; }      // prefetch for the next learn
       if (role != 1) return;
-      res_fetch(c, 1, C, l0, 3);
+      fx_fetch(c, 1, C, l0, 0);
       if (h >= hu) return;
+      const float alpha = sac ? alpha_s[0] : 0.f;
       put_cols<8>(XN, cip, 0, XS, cip, 0, od, od);
       FRL_PAR(t) {
         if (t < 8 * (cip - od)) {
@@ -1015,9 +1156,12 @@ struct AcFx {
       }
       FRL_SYNC();
       trace(30);
-      fx_fwd<0>(XN, cip, cip >> 2, res_layer(c, 1, C, l0, 0), res_layer(c, 1, C, l0, 0) + wt_bias(C.L[l0]), 1, H1);
-      fx_fwd<32>(H1, 128, 32, res_layer(c, 1, C, l0, 1), res_layer(c, 1, C, l0, 1) + wt_bias(C.L[l0 + 1]), 1, H2);
-      fx_fwd_narrow(H2, res_layer(c, 1, C, l0, 2), res_layer(c, 1, C, l0, 2) + wt_bias(C.L[l0 + 2]), 4, cld, QA, 4);
+      const float* w0 = fx_layer(c, 1, C, l0, 0);
+      fx_fwd<0>(XN, cip, cip >> 2, w0, w0 + wt_bias(C.L[l0]), 1, H1);
+      const float* w1 = fx_layer(c, 1, C, l0, 1);
+      fx_fwd<32>(H1, 128, 32, w1, w1 + wt_bias(C.L[l0 + 1]), 1, H2);
+      const float* w2 = fx_layer(c, 1, C, l0, 2);
+      fx_fwd_narrow(H2, w2, w2 + wt_bias(C.L[l0 + 2]), 4, cld, QA, 4);
       const float dq = -invB / (float)hu;
       FRL_PAR(t) {
         float v = 0.f;
@@ -1025,14 +1169,14 @@ struct AcFx {
           for (int j = 0; j < 4; ++j) dQA[t * 4 + j] = 0.f;
           if (t < nvalid) { dQA[t * 4] = dq; v = QA[t * 4]; }
         }
-        red0[t] = v;
+        if (t < 32) red0[t] = v;
       }
+      const float qsum = fx_tree32(red0);
       FRL_SYNC();
-      const float qsum = block_sum(red0);
       trace(31);
-      fx_bwd_narrow(dQA, 4, res_layer(c, 1, C, l0, 2), 4, cld, H2, D2);
-      fx_bwd(D2, res_layer(c, 1, C, l0, 1), H1, D1);
-      fx_bwd_cols(D1, res_layer(c, 1, C, l0, 0), od, ad, dXa);
+      fx_bwd_narrow(dQA, 4, w2, 4, cld, H2, D2);
+      fx_bwd(D2, w1, H1, D1);
+      fx_bwd_cols(D1, w0, od, ad, dXa);
       trace(32);
       FRL_PAR(t) {
         float lsum = 0.f, esum = 0.f;
@@ -1050,11 +1194,11 @@ struct AcFx {
           }
           if (r < nvalid && h == 0) { esum = -lp; lsum = alpha * lp; }        // actor_loss = mean(-Q_pi - alpha * entropy)
         }
-        red0[t] = lsum; red1[t] = esum;
+        if (t < 32) { red0[t] = lsum; red1[t] = esum; }
       }
+      const float loss_a = fx_tree32(red0) - qsum / (float)hu;
+      const float ent = fx_tree32(red1);
       FRL_SYNC();
-      const float loss_a = block_sum(red0) - qsum / (float)hu;
-      const float ent = block_sum(red1);
       if (sac) {
         // d/dlog_std_j = sum_r dL/du std eps (+ head 0: -alpha / B per row); zero outside the clamp range
         FRL_PAR(t) {
@@ -1065,26 +1209,19 @@ struct AcFx {
               const float sd = expf(lsr);
               for (int r = 0; r < nvalid; ++r) g += dMU[r * 8 + t] * sd * EPS[r * 8 + t] - (h == 0 ? alpha * invB : 0.f);
             }
-            ws[W.lsg + (size_t)wi * 8 + t] = g;
+            ws[P.w_lsg + (size_t)wi * 8 + t] = g;
           }
         }
       }
       trace(33);
-      fx_bwd_narrow(dMU, 8, res_layer(c, 0, A, 0, 2), ap, ald, A2, D2);
-      fx_bwd(D2, res_layer(c, 0, A, 0, 1), A1, D1);
+      float* ay = ws + (h == 0 ? P.w_ay0 : P.w_ay1);
+      fx_put_blocks(ay, P.ayb[2], 1, Rm, row0, dMU, 8, ap);
+      const float* p2 = fx_layer(c, 0, A, 0, 2);
+      const float* p1 = fx_layer(c, 0, A, 0, 1);
+      fx_bwd_narrow(dMU, 8, p2, ap, ald, A2, D2, ay + ((size_t)P.ayb[1] * Rm + row0) * 16, rm16);
+      fx_bwd(D2, p1, A1, D1, ay + ((size_t)P.ayb[0] * Rm + row0) * 16, rm16);
       trace(34);
-      float* ay = ws + (h == 0 ? W.ay0 : W.ay1);
-      if (h == 0) {
-        float* ax = ws + W.ax;
-        fx_put_blocks(ax, fx_xblocks(A, 0), fx_xb(A, 0), Rm, row0, XA, aip, aip);
-        fx_put_blocks(ax, fx_xblocks(A, 1), 8, Rm, row0, A1, 128, 128);
-        fx_put_blocks(ax, fx_xblocks(A, 2), 8, Rm, row0, A2, 128, 128);
-      }
-      fx_put_blocks(ay, fx_yblocks(A, 0), 8, Rm, row0, D1, 128, 128);
-      fx_put_blocks(ay, fx_yblocks(A, 1), 8, Rm, row0, D2, 128, 128);
-      fx_put_blocks(ay, fx_yblocks(A, 2), 1, Rm, row0, dMU, 8, ap);
-      FRL_PAR(t) { if (t == 0) { ws[W.stats + (size_t)wi * 8 + 1] = loss_a; ws[W.stats + (size_t)wi * 8 + 2] = ent; } }
-      FRL_SYNC();
+      FRL_PAR(t) { if (t == 0) { ws[P.w_stats + (size_t)wi * 8 + 1] = loss_a; ws[P.w_stats + (size_t)wi * 8 + 2] = ent; } }
       trace(39);
     } else if (s == 4) {
       res_invalidate(c, A);
@@ -1093,15 +1230,15 @@ struct AcFx {
       if (c.stag0 != nullptr) c.stag0 = nullptr;      // slot 0 is scratch in stages 4 / 5
       const long n_policy_before = (a.policy_freq > 1) ? (long)((a.total_it0 + u) / a.policy_freq - a.total_it0 / a.policy_freq) : (long)u;
       const AdamSpec hp = {a.lr_actor, a.beta1, a.beta2, a.eps, 0.0, (double)a.max_norm, (long)(a.step_actor0 + n_policy_before + 1)};
-      dw_stage(c, a, A, ws + W.ax, ws + W.ay0, hu == 2 ? ws + W.ay1 : nullptr, c.wbuf0, gst, gbst, redb, red0, ws + W.sumsq,
-               ws + W.lsg, nwork, hp, hpst, njobs_a);
+      dw_stage(c, a, A, P.ja, ws + P.w_ax, ws + P.w_ay0, hu == 2 ? ws + P.w_ay1 : nullptr, c.wbuf0, gst, gbst, redb, red0,
+               ws + P.w_sumsq + c.cta, ws + P.w_lsg, nwork, hp, hpst);
     } else {
-      const float tot = opt_stage(c, A, &a.actor_target, a.tau, hpst, gst, gbst, ws + W.sumsq, c.red, njobs_a);
-      if (c.cta == 0) {
+      const float tot = opt_stage(c, A, &a.actor_target, a.tau, hpst, gst, gbst, ws + P.w_sumsq, c.red, P.ja);
+      if (metrics_cta) {
         FRL_PAR(t) {
           const bool on = t < nwork && (t % NH) < hu;
-          red0[t] = on ? fx_ldcg(ws + W.stats + (size_t)t * 8 + 1) : 0.f;
-          red1[t] = on ? fx_ldcg(ws + W.stats + (size_t)t * 8 + 2) : 0.f;
+          red0[t] = on ? fx_ldcg(ws + P.w_stats + (size_t)t * 8 + 1) : 0.f;
+          red1[t] = on ? fx_ldcg(ws + P.w_stats + (size_t)t * 8 + 2) : 0.f;
         }
         FRL_SYNC();
         const float l = block_sum(red0);

@@ -15,6 +15,11 @@ def _load(pol, g):
         load_into(getattr(pol.agent, n), net_from_golden(g, "init/%s/" % src))
 
 
+def EXPECT_PATH():
+    import os
+    return 0 if os.environ.get("FREERL_B200_AC_PATH") == "generic" else 1
+
+
 def _rel(a, b):
     return abs(a - b) / max(abs(b), 1e-12)
 
@@ -31,6 +36,7 @@ def _sac(golden, device):
         n0, n1 = g["noise/%d/0" % it], g["noise/%d/1" % it]
         r = orc.learn(golden_batch(g, it), torch.from_numpy(n0), torch.from_numpy(n1), 0.99, 0.01)
         pol.learn(64, 0.99, 0.01, indices=idxs[it][None], noise_next=n0[None], noise_new=n1[None])
+        assert pol.last_path == EXPECT_PATH()      # the small-batch schedule (csrc/algo_acfx.cuh) unless the env forces the generic kernel
         m = pol.last_metrics[0].cpu().numpy()
         assert _rel(m[0], r["critic_loss"]) < 1e-5, (m[0], r["critic_loss"])
         assert _rel(m[1], r["actor_loss"]) < 2e-5, (m[1], r["actor_loss"])
@@ -55,6 +61,7 @@ def _td3(golden, device):
         nz = g["noise/%d/0" % it]
         r = orc.learn(golden_batch(g, it), torch.from_numpy(nz), 0.99, 0.01, 0.1, 0.5, 1.0, 2, 1.0)
         pol.learn(64, 0.99, 0.01, 0.1, 0.5, 1.0, 2, 1.0, indices=idxs[it][None], noise=nz[None])
+        assert pol.last_path == EXPECT_PATH()
         m = pol.last_metrics[0].cpu().numpy()
         assert _rel(m[0], r["critic_loss"]) < 1e-5
         if "actor_loss" in r:
@@ -76,6 +83,7 @@ def _ddpg(golden, device):
     for it in range(3):
         r = orc.learn(golden_batch(g, it), 0.99, 0.01)
         pol.learn(64, 0.99, 0.01, indices=idxs[it][None])
+        assert pol.last_path == EXPECT_PATH()
         m = pol.last_metrics[0].cpu().numpy()
         assert _rel(m[0], r["critic_loss"]) < 1e-5
         assert _rel(m[1], r["actor_loss"]) < 2e-5
@@ -205,3 +213,70 @@ def test_td3_gpu(golden):
 @pytest.mark.gpu
 def test_ddpg_gpu(golden):
     _ddpg(golden, torch.device("cuda"))
+
+
+# ---- the generic kernel (csrc/algo_ac.cuh) stays covered: same checks with the small-batch schedule switched off ----
+def test_sac_generic_kernel_emulated(golden, emul, monkeypatch):
+    monkeypatch.setenv("FREERL_B200_AC_PATH", "generic")
+    _sac(golden, torch.device("cpu"))
+
+
+@pytest.mark.gpu
+def test_sac_td3_generic_kernel_gpu(golden, monkeypatch):
+    monkeypatch.setenv("FREERL_B200_AC_PATH", "generic")
+    _sac(golden, torch.device("cuda"))
+    _td3(golden, torch.device("cuda"))
+
+
+# ---- one launch of K fused learns == K launches of one learn, BIT FOR BIT (same indices / noise): a stale-weights or
+#      stale-exchange bug between the fused updates of the persistent kernel would show up here ----
+def _fused_equals_sequential(device, alg, B, K):
+    from freerl_b200.SAC import SAC
+    from freerl_b200.TD3 import TD3
+    rng = np.random.default_rng(11)
+    n = 2048
+    obs, nobs = rng.standard_normal((n, 17), dtype=np.float32), rng.standard_normal((n, 17), dtype=np.float32)
+    act, rew = rng.uniform(-1, 1, (n, 6)).astype(np.float32), rng.standard_normal(n).astype(np.float32)
+    done = rng.random(n) < 0.05
+    idx = np.stack([rng.permutation(n)[:B] for _ in range(K)])
+    nz0 = rng.standard_normal((K, B, 6)).astype(np.float32)
+    nz1 = rng.standard_normal((K, B, 6)).astype(np.float32)
+    pols = []
+    for fused in (True, False):
+        torch.manual_seed(3)
+        if alg == "sac":
+            pol = SAC([17, 6], True, 1e-3, 1e-3, 4096, device, trick={})
+        else:
+            pol = TD3([17, 6], True, 1e-3, 1e-3, 4096, device, trick=None,
+                      realize={"clip_double": True, "policy_noise": True, "twin_delay": True})
+        pol.add(obs, act, rew, nobs, done)
+        metrics = []
+        for k0 in ([0] if fused else range(K)):
+            sl = slice(0, K) if fused else slice(k0, k0 + 1)
+            nu = K if fused else 1
+            if alg == "sac":
+                pol.learn(B, 0.99, 0.01, indices=idx[sl], noise_next=nz0[sl], noise_new=nz1[sl], n_updates=nu)
+            else:
+                pol.learn(B, 0.99, 0.01, 0.1, 0.5, 1.0, 2, 1.0, indices=idx[sl], noise=nz0[sl], n_updates=nu)
+            assert pol.last_path == EXPECT_PATH()
+            metrics.append(pol.last_metrics.cpu().numpy().copy())
+        pols.append((pol, np.concatenate(metrics)))
+    (pa, ma), (pb, mb) = pols
+    cols = [0, 4] if alg == "td3" else [0, 1, 2, 4, 5, 6]      # TD3 off-steps leave the actor columns unwritten
+    np.testing.assert_array_equal(ma[:, cols], mb[:, cols])
+    for nname in NETS:
+        for (k, va), (_, vb) in zip(getattr(pa.agent, nname).state_dict().items(), getattr(pb.agent, nname).state_dict().items()):
+            np.testing.assert_array_equal(va.cpu().numpy(), vb.cpu().numpy(), err_msg="%s.%s" % (nname, k))
+    if alg == "sac":
+        assert float(pa.alphas.log_alpha) == float(pb.alphas.log_alpha)
+
+
+def test_fused_equals_sequential_emulated(emul):
+    _fused_equals_sequential(torch.device("cpu"), "sac", 40, 3)
+    _fused_equals_sequential(torch.device("cpu"), "td3", 40, 4)
+
+
+@pytest.mark.gpu
+def test_fused_equals_sequential_gpu():
+    _fused_equals_sequential(torch.device("cuda"), "sac", 256, 8)
+    _fused_equals_sequential(torch.device("cuda"), "td3", 256, 8)
