@@ -151,7 +151,7 @@ class ACBase:
         ws = getattr(self, "_fx_ws", None)
         if ws is None or ws.numel() < need:
             self._fx_ws = ws = torch.zeros(need, dtype=torch.float32, device=self.device)
-            self._fx_sync = torch.zeros(1024, dtype=torch.int32, device=self.device)
+            self._fx_sync = torch.zeros(4096, dtype=torch.int32, device=self.device)
         a.ws, a.sync = ws.data_ptr(), self._fx_sync.data_ptr()
 
     def _launch(self, a, keep, n_updates, out):

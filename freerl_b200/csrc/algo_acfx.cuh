@@ -21,10 +21,16 @@
 //   2 clip + Adam(critic) + Polyak   3 phase C (Q(s,pi(s)), dQ/da, actor backward)   4 dW(actor)   5 Adam(actor) + Polyak + alpha
 #pragma once
 #include "algo_ac.cuh"
+#ifdef FRL_EMUL
+#include <stdlib.h>
+#include <stdio.h>
+#endif
 
 #define FX_LDW 132            // wt_ld_of(128): row stride of a 128-wide layer image
 #define FX_MAXB 256           // exchange operands of one dW job must fit one weight slot
 #define FX_SPIN_LIMIT (1u << 24)
+#define FX_SYNC_WORDS 4096    // uint32 words of frl_ac_args_t.sync: [0] grid-barrier counter, [64, 2048) 3 x 64-bit hand-off packets per
+                              // batch row, [2048, 4096) one 64-bit gradient-norm packet per CTA for the critic and the actor
 
 // ------------------------------------------------------------------------------------------------------------------------
 // cross-CTA signalling (GPU: release / acquire on L2 words; emulation: CTAs of a stage run in index order)
@@ -43,6 +49,40 @@ FRL_DEV void fx_flag_wait(const unsigned* p, unsigned v) {
   }
 }
 FRL_DEV float fx_ldcg(const float* p) { return __ldcg(p); }
+// Hand-off packets: one 64-bit word = (epoch << 32 | float bits).  An aligned 8-byte store is single-copy atomic, so a reader that
+// sees the epoch it waits for has the value of THAT store — no release / acquire pair, no separate flag word, and a consumer can
+// poll all the packets it needs with independent loads in flight (one L2 round trip when the producer is already done).
+FRL_DEV void fx_pk_put(unsigned long long* p, unsigned epoch, float v) {
+  const unsigned long long w = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(v);
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+FRL_DEV unsigned long long fx_pk_ld(const unsigned long long* p) {
+  unsigned long long w;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+  return w;
+}
+FRL_DEV float fx_pk_wait1(const unsigned long long* p, unsigned epoch) {
+  unsigned spins = 0;
+  for (;;) {
+    const unsigned long long a = fx_pk_ld(p);
+    if ((unsigned)(a >> 32) == epoch) return __uint_as_float((unsigned)a);
+    if (++spins > FX_SPIN_LIMIT) __trap();
+  }
+}
+FRL_DEV void fx_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// wait until the (up to three) packets carry `epoch`; returns their values.  Unused slots: pass nullptr.
+FRL_DEV void fx_pk_wait3(const unsigned long long* p0, const unsigned long long* p1, const unsigned long long* p2, unsigned epoch,
+                         float* v0, float* v1, float* v2) {
+  unsigned spins = 0;
+  for (;;) {
+    const unsigned long long a = fx_pk_ld(p0), b = p1 ? fx_pk_ld(p1) : a, d = p2 ? fx_pk_ld(p2) : a;
+    if ((unsigned)(a >> 32) == epoch && (unsigned)(b >> 32) == epoch && (unsigned)(d >> 32) == epoch) {
+      *v0 = __uint_as_float((unsigned)a); *v1 = __uint_as_float((unsigned)b); *v2 = __uint_as_float((unsigned)d);
+      return;
+    }
+    if (++spins > FX_SPIN_LIMIT) __trap();
+  }
+}
 FRL_DEV float shx(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 // grid-wide barrier: every CTA adds 1 to *ctr (zeroed by the host before the launch) and waits for `target` arrivals
 FRL_DEV void fx_grid_barrier(unsigned* ctr, unsigned target) {
@@ -61,13 +101,30 @@ FRL_DEV void fx_grid_barrier(unsigned* ctr, unsigned target) {
   trace(93);
 }
 #else
-#include <stdlib.h>
-#include <stdio.h>
 static inline void fx_flag_set(unsigned* p, unsigned v) { *p = v; }
 static inline void fx_flag_wait(const unsigned* p, unsigned v) {
   if ((int)(*p - v) < 0) { fprintf(stderr, "frl emulation: AcFx flag protocol violated (%u < %u)\n", *p, v); abort(); }
 }
 static inline float fx_ldcg(const float* p) { return *p; }
+static inline void fx_pk_put(unsigned long long* p, unsigned epoch, float v) {
+  unsigned b; memcpy(&b, &v, 4);
+  *p = ((unsigned long long)epoch << 32) | b;
+}
+static inline float fx_pk_wait1(const unsigned long long* p, unsigned epoch) {
+  if ((unsigned)(*p >> 32) != epoch) { fprintf(stderr, "frl emulation: AcFx packet protocol violated\n"); abort(); }
+  const unsigned b = (unsigned)*p; float v; memcpy(&v, &b, 4);
+  return v;
+}
+static inline void fx_prefetch_l1(const void*) {}
+static inline void fx_pk_wait3(const unsigned long long* p0, const unsigned long long* p1, const unsigned long long* p2, unsigned epoch,
+                               float* v0, float* v1, float* v2) {
+  const unsigned long long* ps[3] = {p0, p1 ? p1 : p0, p2 ? p2 : p0};
+  float* vs[3] = {v0, v1, v2};
+  for (int i = 0; i < 3; ++i) {
+    if ((unsigned)(*ps[i] >> 32) != epoch) { fprintf(stderr, "frl emulation: AcFx packet protocol violated\n"); abort(); }
+    const unsigned b = (unsigned)*ps[i]; memcpy(vs[i], &b, 4);
+  }
+}
 // per-thread scratch standing in for the register files of one CTA when a warp shuffle has to be emulated
 static thread_local float fx_emu_a[FRL_NT][64];
 static thread_local float fx_emu_b[FRL_NT][64];
@@ -415,15 +472,47 @@ struct FxJob {
   int NB, KB;     // tile height / width (NB * KB in {256, 512})
 };
 
+// Sampled rows of one tile -> raw[8][row_floats] without passing through registers (LDGSTS): issued one optimiser stage ahead of
+// the phase that consumes them, so the index load, the DRAM latency of the random rows and the smem write are off the chain.
+FRL_DEV void fx_gather_async(const float* storage, int row_floats, const int64_t* idx, int nvalid, float* raw) {
+  const int q = row_floats >> 2;
+  FRL_PAR(t) {
+    for (int e = t; e < 8 * q; e += FRL_NT) {
+      const int r = e / q, j = e - r * q;
+      float* dst = raw + r * row_floats + 4 * j;
+      if (r < nvalid) {
+        const float* src = storage + (size_t)idx[r] * row_floats + 4 * j;
+#ifndef FRL_EMUL
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+#else
+        memcpy(dst, src, 16);
+#endif
+      } else {
+        st4(dst, make_float4(0.f, 0.f, 0.f, 0.f));
+      }
+    }
+#ifndef FRL_EMUL
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+  }
+}
+FRL_DEV void fx_gather_wait() {
+#ifndef FRL_EMUL
+  asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+  FRL_SYNC();
+}
+
 // what stage() needs from the argument block, derived once per launch (AcFx::build_plan) and kept in shared memory
 struct FxJobP { int li, n0, k0, NB, KB, ksh, yb0, xb0, xbn, pad; };      // li = -2: no job in this slot; -1: the extras job
 struct FxPlan {
   int role, wi, tile, h, l0, row0, nvalid, njobs_c, njobs_a;
   int cxb[3], cyb[3], axb[3], ayb[3];                                    // first exchange block of this CTA's critic head / the actor layers
-  int w_cx, w_cy, w_ax, w_ay0, w_ay1, w_xq, w_xlp, w_lsg, w_stats, w_sumsq;
+  int w_cx, w_cy, w_ax, w_ay0, w_ay1, w_lsg, w_stats, w_sumsq;
+  int coff[3], cboff[3], aoff[3], aboff[3];                              // layer image / bias offsets inside a resident head slot (floats)
   FxJobP jc[2], ja[2];
 };
-#define FX_PLAN_FLOATS 80
+#define FX_PLAN_FLOATS 96
 static_assert(sizeof(FxPlan) <= FX_PLAN_FLOATS * 4, "FxPlan outgrew its shared-memory reservation");
 
 // Start fetching the 3-layer head (l0..l0+2 of net n, contiguous in the mirror) into slot s unless it is already resident:
@@ -466,6 +555,17 @@ FRL_DEV const float* fx_layer(Cta& c, int s, const frl_net_t& n, int l0, int k) 
   return (s ? c.wbuf1 : c.wbuf0) + (n.L[l0 + k].wt_off - n.L[l0].wt_off);
 }
 
+// wait (if still outstanding) for layer k of the head fx_fetch put into slot s
+FRL_DEV void fx_wait(Cta& c, int s, int k) {
+  const uint32_t bit = 1u << (s * 3 + (k ? 1 : 0));
+  if (c.spend & bit) {
+#ifndef FRL_EMUL
+    mbar_wait(c.bar + 2 + s * 3 + (k ? 1 : 0), (c.sphase >> (s * 3 + (k ? 1 : 0))) & 1u);
+#endif
+    c.sphase ^= bit; c.spend &= ~bit;
+  }
+}
+
 // Sum of slot[0..31], written by the lanes of warp 0 in the phase just before (no block barrier needed): the shuffle tree of
 // block_sum's first level, so a phase whose other warps contribute zeros gets block_sum's bits.  GPU: valid in thread 0 only.
 FRL_DEV float fx_tree32(float* slot) {
@@ -497,6 +597,8 @@ struct AcFx {
   FRL_SHD bool stage_enabled(int s, int u, const Args& a) { return s >= 3 ? is_policy_step(a, u) : true; }
   FRL_SHD bool writes_params(int) { return true; }     // every stage publishes something a later TMA copy reads
   FRL_SHD int n_updates(const Args& a) { return a.n_updates; }
+  // the optimiser stages open with an all-gather of norm packets, which orders them after every CTA's dW stage by itself
+  FRL_SHD bool barrier_after(int s) { return s != 1 && s != 4; }
   FRL_SHD int heads_used(const Args& a) { return is_sac(a) ? a.n_heads : 1; }
 
   FRL_SHD int head_floats(const frl_net_t& n, int l0) { return wt_floats(n.L[l0]) + wt_floats(n.L[l0 + 1]) + wt_floats(n.L[l0 + 2]); }
@@ -508,13 +610,13 @@ struct AcFx {
   static const int GST_SLOTS = 2;                    // dW jobs one CTA may own (jobs <= GST_SLOTS * grid)
   FRL_SHD int user_floats(const Args& a) {
     return FX_PLAN_FLOATS + 8 * a.replay.row_floats + 3 * 8 * 32 + 64 + 6 * 1024 + 5 * 64 + 2 * 32 + 2 * FRL_NT + GST_SLOTS * 528 + 128 +
-           GST_SLOTS * 16 + 16 + 4 + 64;
+           GST_SLOTS * 16 + 16 + 4 + 8 + 64 + 64;
   }
   FRL_SHD int grid(const Args&, int max_ctas) { return max_ctas; }
 
   // ---- exchange / workspace layout (floats) ----
   struct Ws {
-    size_t cx, cy, ax, ay0, ay1, xq, xlp, lsg, stats, sumsq, total;
+    size_t cx, cy, ax, ay0, ay1, lsg, stats, sumsq, total;
   };
   FRL_SHD Ws ws_layout(const Args& a, int ncta) {
     Ws w;
@@ -525,8 +627,6 @@ struct AcFx {
     w.ax = o; o += (size_t)fx_xblocks(a.actor, 3) * R16;
     w.ay0 = o; o += (size_t)fx_yblocks(a.actor, 3) * R16;
     w.ay1 = o; o += (size_t)fx_yblocks(a.actor, 3) * R16;
-    w.xq = o; o += (size_t)rmax(a) * 2;
-    w.xlp = o; o += (size_t)rmax(a);
     w.lsg = o; o += (size_t)ncta * 8;
     w.stats = o; o += (size_t)ncta * 8;
     w.sumsq = o; o += 512;
@@ -585,6 +685,12 @@ struct AcFx {
     for (int h = 0; h < a.n_heads; ++h)
       if (!shape_ok(a.critic, 3 * h, 4) || !shape_ok(a.critic_target, 3 * h, 4)) return false;
     if (a.actor.L[2].out_pad < 4 || a.critic.L[2].out_pad != 4) return false;
+    for (int k = 0; k < 3; ++k) {       // the plan's slot offsets serve the nets and their targets alike
+      if (a.actor_target.L[k].wt_off - a.actor_target.L[0].wt_off != a.actor.L[k].wt_off - a.actor.L[0].wt_off) return false;
+      for (int h = 0; h < a.n_heads; ++h)
+        if (a.critic_target.L[3 * h + k].wt_off - a.critic_target.L[3 * h].wt_off != a.critic.L[3 * h + k].wt_off - a.critic.L[3 * h].wt_off) return false;
+    }
+    if (64 + 6 * rmax(a) > 2048 || max_ctas > 512) return false;
     if (is_sac(a) && a.n_heads != 2) return false;
     if (2 * ntile(a) * a.n_heads > max_ctas) return false;
     if (net_jobs(a.critic) > 512 || net_jobs(a.actor) > 512) return false;
@@ -629,8 +735,12 @@ struct AcFx {
       P.axb[k] = fx_xblocks(a.actor, k); P.ayb[k] = fx_yblocks(a.actor, k);
     }
     const Ws W = ws_layout(a, c.ncta);
-    P.w_cx = (int)W.cx; P.w_cy = (int)W.cy; P.w_ax = (int)W.ax; P.w_ay0 = (int)W.ay0; P.w_ay1 = (int)W.ay1; P.w_xq = (int)W.xq;
-    P.w_xlp = (int)W.xlp; P.w_lsg = (int)W.lsg; P.w_stats = (int)W.stats; P.w_sumsq = (int)W.sumsq;
+    P.w_cx = (int)W.cx; P.w_cy = (int)W.cy; P.w_ax = (int)W.ax; P.w_ay0 = (int)W.ay0; P.w_ay1 = (int)W.ay1;
+    P.w_lsg = (int)W.lsg; P.w_stats = (int)W.stats; P.w_sumsq = (int)W.sumsq;
+    for (int k = 0; k < 3; ++k) {
+      P.coff[k] = a.critic.L[P.l0 + k].wt_off - a.critic.L[P.l0].wt_off; P.cboff[k] = P.coff[k] + wt_bias(a.critic.L[P.l0 + k]);
+      P.aoff[k] = a.actor.L[k].wt_off - a.actor.L[0].wt_off; P.aboff[k] = P.aoff[k] + wt_bias(a.actor.L[k]);
+    }
     plan_jobs(P.jc, a.critic, P.njobs_c, c);
     plan_jobs(P.ja, a.actor, P.njobs_a, c);
   }
@@ -763,8 +873,8 @@ struct AcFx {
 
   // dW + sum of squares of this CTA's jobs of net n (stage 1 / 4).  `scr` = the weight slot that is dead in this stage.
   FRL_SDEV void dw_stage(Cta& c, const Args& a, const frl_net_t& n, const FxJobP* jobs, const float* xreg, const float* yreg0,
-                         const float* yreg1, float* scr, float* gst, float* gbst, float* redb, float* red0, float* sumsq_out,
-                         const float* lsg, int nls, const AdamSpec sp, float* hpst) {
+                         const float* yreg1, float* scr, float* gst, float* gbst, float* redb, float* red0,
+                         unsigned long long* ss_pk, unsigned epoch, const float* lsg, int nls, const AdamSpec sp, float* hpst) {
     const int Rm = rmax(a);
     // bias corrections of the optimiser stage that follows (double-precision powers, ~1.5 k clk on one thread): computed here,
     // by a thread that has nothing to do while the operands are in flight, and kept in shared memory
@@ -813,19 +923,40 @@ struct AcFx {
       }
       ss_cta += ss;
     }
-    FRL_PAR(t) { if (t == 0) *sumsq_out = ss_cta; }
+    // this CTA's share of the squared gradient norm, as an epoch-tagged packet: publishing it IS the arrival at the norm
+    // all-gather the optimiser stage opens with (no grid barrier between the two stages on the GPU)
+    FRL_PAR(t) { if (t == 0) fx_pk_put(ss_pk, epoch, ss_cta); }
     FRL_SYNC();
   }
 
   // clip + Adam (+ Polyak of tgt) on the elements of this CTA's jobs (stage 2 / 5).  Returns the total squared norm.
   FRL_SDEV float opt_stage(Cta& c, const frl_net_t& n, const frl_net_t* tgt, float tau, const float* hpst, const float* gst,
-                           const float* gbst, const float* sumsq, float* sh, const FxJobP* jobs) {
+                           const float* gbst, const unsigned long long* ss_pk, unsigned epoch, float* sh, const FxJobP* jobs) {
     trace(80);
-    // total squared gradient norm: one partial per CTA, folded in a fixed order (strided per-thread sums, then the block
-    // tree), so every CTA computes the same number
+    // the optimiser operands of this CTA's first job start moving towards L1 while the norm packets are polled
+    {
+      const FxJobP J = jobs[0];
+      if (J.li >= 0) {
+        const frl_layer_t& L = n.L[J.li];
+        FRL_PAR(t) {
+          // one 16-element row segment of the tile per thread (NB KB / 16 <= 32 segments), for p, m, v and the target
+          const int segs = (J.NB * J.KB) >> 4, seg = t & 31, which = t >> 5;
+          if (seg < segs && which < 4) {
+            const int nn = (seg << 4) >> J.ksh, kk = (seg << 4) - (nn << J.ksh), row = J.n0 + nn, col = J.k0 + kk;
+            if (row < L.out_pad && col < L.in_pad) {
+              const int pi = L.w_off + row * L.in_pad + col;
+              const float* base = which == 0 ? n.p : (which == 1 ? n.m : (which == 2 ? n.v : (tgt ? tgt->p : nullptr)));
+              if (base) fx_prefetch_l1(base + pi);
+            }
+          }
+        }
+      }
+    }
+    // total squared gradient norm: one packet per CTA (written at the end of its dW stage), folded in a fixed order (strided
+    // per-thread sums, then the block tree), so every CTA computes the same number
     FRL_PAR(t) {
       float v = 0.f;
-      for (int i = t; i < c.ncta; i += FRL_NT) v += fx_ldcg(sumsq + i);
+      for (int i = t; i < c.ncta; i += FRL_NT) v += fx_pk_wait1(ss_pk + i, epoch);
       sh[t] = v;
     }
     FRL_SYNC();
@@ -932,6 +1063,8 @@ struct AcFx {
     float* gbst = sb.take(GST_SLOTS * 16);
     float* hpst = sb.take(16);               // optimiser scalars: written in the dW stage, read in the optimiser stage
     float* alpha_s = sb.take(4);             // exp(log_alpha) of this learn: read in phase A (y), reused in phase C
+    float* LS = sb.take(8);                  // the actor's log_std as phase A read it (it changes in stage 5 only): reused in phase C
+    float* NZ = sb.take(64);                 // this tile's sampling noise [8][8], drawn / loaded at the head of phase A
     if (s == 0 && u == 0) {
       FRL_PAR(t) { if (t == 0) build_plan(*Pp, c, a); }
       FRL_SYNC();
@@ -942,12 +1075,16 @@ struct AcFx {
     const bool sac = is_sac(a);
     const int hu = heads_used(a);
     const bool policy_step = is_policy_step(a, u);
-    const int role = P.role, wi = P.wi, tile = P.tile, h = P.h, l0 = P.l0, row0 = P.row0, nvalid = P.nvalid;
+    const int role = P.role, wi = P.wi, h = P.h, l0 = P.l0, row0 = P.row0, nvalid = P.nvalid;
     const float invB = 1.0f / (float)a.B;
     const int aip = A.L[0].in_pad, cip = C.L[0].in_pad, ap = A.L[2].out_pad, ald = wt_ld(A.L[2]), cld = wt_ld(C.L[2]);
     float* ws = a.ws;
-    unsigned* flags = a.sync + 32;
+    // hand-off packets of the target set (zeroed with the barrier word at every launch): per batch row {Q'_0, Q'_1, log pi(a'|s')}
+    unsigned long long* pk = reinterpret_cast<unsigned long long*>(a.sync + 64);
+    unsigned long long* sspk = reinterpret_cast<unsigned long long*>(a.sync + 2048);      // norm packets: [0, 512) critic, [512, 1024) actor
     const unsigned epoch = (unsigned)u + 1u;
+    float* const slot0 = c.wbuf0;
+    float* const slot1 = c.wbuf1;
     const bool metrics_cta = c.cta == c.ncta - 1;        // the last CTA owns the lightest jobs: it also folds the metrics
 
     if (s == 0) {
@@ -957,31 +1094,41 @@ struct AcFx {
         // ------------------------------- target set: a' = actor_target(s'), Q'_h(s', a') -------------------------------
         const frl_net_t& AT = a.actor_target;
         const frl_net_t& CT = a.critic_target;
-        fx_fetch(c, 0, AT, 0, 0);
-        fx_fetch(c, 1, CT, l0, 64);
+        fx_fetch(c, 0, AT, 0, 128);                // (issued by warps 4 - 7: warps 0 - 2 have the row gather to do)
+        fx_fetch(c, 1, CT, l0, 192);
         trace(10);
-        gather_rows<8>(rb.storage, rf, idx, nvalid, raw);
+        if (u == 0) fx_gather_async(rb.storage, rf, idx, nvalid, raw);      // later learns: prefetched in stage 2 of the previous one
+        const bool smoothing = !sac && a.target_smoothing;
+        // sampling noise and log_std do not depend on the forward passes: warps 4, 5 and 7 fetch / draw them now (a Philox +
+        // Box-Muller draw or an L2 round trip each) instead of inside the sampling phase on the critical chain
+        FRL_PAR(t) {
+          const int q = t - 128;
+          if (q >= 0 && q < 8 * ad) {
+            const int r = q / ad, jj = q - r * ad;
+            NZ[r * 8 + jj] = ((sac || smoothing) && r < nvalid) ? noise_at(a.noise_next, a, u, row0 + r, jj, 1u) : 0.f;
+          }
+          if (sac && t >= 224 && t < 224 + ad) LS[t - 224] = fx_ldcg(AT.p + AT.x_off + t - 224);
+        }
+        fx_gather_wait();
         trace(11);
         put_cols<8>(XA, aip, 0, raw, rf, rb_col_nobs(rb), od, aip);
         put_cols<8>(XN, cip, 0, raw, rf, rb_col_nobs(rb), od, cip);
         FRL_SYNC();
         trace(12);
-        const float* w0 = fx_layer(c, 0, AT, 0, 0);
-        fx_fwd<0>(XA, aip, aip >> 2, w0, w0 + wt_bias(AT.L[0]), 1, H1);
-        const float* w1 = fx_layer(c, 0, AT, 0, 1);
-        fx_fwd<32>(H1, 128, 32, w1, w1 + wt_bias(AT.L[1]), 1, H2);
-        const float* w2 = fx_layer(c, 0, AT, 0, 2);
-        fx_fwd_narrow(H2, w2, w2 + wt_bias(AT.L[2]), ap, ald, MU, 8);
-        const bool smoothing = !sac && a.target_smoothing;
+        fx_wait(c, 0, 0);
+        fx_fwd<0>(XA, aip, aip >> 2, slot0 + P.aoff[0], slot0 + P.aboff[0], 1, H1);
+        fx_wait(c, 0, 1);
+        fx_fwd<32>(H1, 128, 32, slot0 + P.aoff[1], slot0 + P.aboff[1], 1, H2);
+        fx_fwd_narrow(H2, slot0 + P.aoff[2], slot0 + P.aboff[2], ap, ald, MU, 8);
         FRL_PAR(t) {
           if (t < 8 * ad) {
             const int r = t / ad, jj = t - r * ad;
             const float mean = MU[r * 8 + jj];
             float act;
             if (sac) {
-              const float ls = fminf(fmaxf(fx_ldcg(AT.p + AT.x_off + jj), -20.f), 2.f);
+              const float ls = fminf(fmaxf(LS[jj], -20.f), 2.f);
               const float sd = expf(ls);
-              const float e = (r < nvalid) ? noise_at(a.noise_next, a, u, row0 + r, jj, 1u) : 0.f;
+              const float e = NZ[r * 8 + jj];
               const float uu = fadd(mean, fmul(e, sd));
               const float diff = uu - mean;
               float lp = -(diff * diff) / (2.f * (sd * sd)) - logf(sd) - FRL_LOG_SQRT_2PI;
@@ -989,7 +1136,7 @@ struct AcFx {
               UU[r * 8 + jj] = lp;
               act = tanhf(uu);
             } else if (smoothing) {
-              const float e = (r < nvalid) ? noise_at(a.noise_next, a, u, row0 + r, jj, 1u) : 0.f;
+              const float e = NZ[r * 8 + jj];
               float nz = fmul(a.policy_noise_scale, fmul(e, a.policy_noise));
               nz = fminf(fmaxf(nz, -a.noise_clip), a.noise_clip);
               float v = fadd(fmul(tanhf(mean), a.max_action), nz);
@@ -1003,35 +1150,42 @@ struct AcFx {
         }
         FRL_SYNC();
         trace(13);
-        const float* q0 = fx_layer(c, 1, CT, l0, 0);
-        fx_fwd<0>(XN, cip, cip >> 2, q0, q0 + wt_bias(CT.L[l0]), 1, H1);
-        const float* q1 = fx_layer(c, 1, CT, l0, 1);
-        fx_fwd<32>(H1, 128, 32, q1, q1 + wt_bias(CT.L[l0 + 1]), 1, H2);
-        const float* q2 = fx_layer(c, 1, CT, l0, 2);
-        fx_fwd_narrow(H2, q2, q2 + wt_bias(CT.L[l0 + 2]), 4, cld, QA, 4);
+        fx_wait(c, 1, 0);
+        fx_fwd<0>(XN, cip, cip >> 2, slot1 + P.coff[0], slot1 + P.cboff[0], 1, H1);
+        fx_wait(c, 1, 1);
+        fx_fwd<32>(H1, 128, 32, slot1 + P.coff[1], slot1 + P.cboff[1], 1, H2);
+        fx_fwd_narrow(H2, slot1 + P.coff[2], slot1 + P.cboff[2], 4, cld, QA, 4);
         FRL_PAR(t) {
           if (t < 8) {
-            ws[P.w_xq + (size_t)(row0 + t) * 2 + h] = QA[t * 4];
+            fx_pk_put(pk + (size_t)(row0 + t) * 3 + h, epoch, QA[t * 4]);
             if (sac && h == 0) {
               float lp = 0.f;
               for (int j = 0; j < ad; ++j) lp += UU[t * 8 + j];
-              ws[P.w_xlp + row0 + t] = lp;
+              fx_pk_put(pk + (size_t)(row0 + t) * 3 + 2, epoch, lp);
             }
           }
         }
-        FRL_SYNC();
-        FRL_PAR(t) { if (t == 0) fx_flag_set(flags + wi, epoch); }
         trace(15);
         return;
       }
       // ------------------------------- online set: Q_h(s, a), pi(s); then y, loss, critic backward -------------------------------
       float* cx = ws + P.w_cx;
       float* cy = ws + P.w_cy;
-      fx_fetch(c, 1, C, l0, 0);
+      fx_fetch(c, 1, C, l0, 128);
       const bool do_actor = policy_step && h < hu;
-      if (do_actor) fx_fetch(c, 0, A, 0, 64);
+      if (do_actor) fx_fetch(c, 0, A, 0, 192);
       trace(10);
-      gather_rows<8>(rb.storage, rf, idx, nvalid, raw);
+      if (u == 0) fx_gather_async(rb.storage, rf, idx, nvalid, raw);
+      FRL_PAR(t) {
+        const int q = t - 128;
+        if (do_actor && sac && q >= 0 && q < 64) {
+          const int r = q >> 3, j = q & 7;
+          NZ[q] = (j < ad && r < nvalid) ? noise_at(a.noise_new, a, u, row0 + r, j, 2u) : 0.f;
+        }
+        if (do_actor && sac && t >= 224 && t < 224 + ad) LS[t - 224] = fx_ldcg(A.p + A.x_off + t - 224);
+        if (t == 255) alpha_s[0] = sac ? expf(fx_ldcg(a.alpha_state)) : 0.f;      // rewritten in stage 5 of the previous learn: read through L2
+      }
+      fx_gather_wait();
       trace(11);
       put_cols<8>(XS, cip, 0, raw, rf, 0, od + ad, cip);        // [obs | act] are adjacent in a replay row
       put_cols<8>(XA, aip, 0, raw, rf, 0, od, aip);
@@ -1040,22 +1194,23 @@ struct AcFx {
       // layer inputs X and pre-activation gradients dY of this tile go to the exchange blocks of head h's layers l0..l0+2 as they
       // are produced (the 128-wide ones from the GEMM epilogues)
       fx_put_blocks(cx, P.cxb[0], fx_xb(C, l0), Rm, row0, XS, cip, cip);
-      const float* w0 = fx_layer(c, 1, C, l0, 0);
-      fx_fwd<0>(XS, cip, cip >> 2, w0, w0 + wt_bias(C.L[l0]), 1, H1, cx + ((size_t)P.cxb[1] * Rm + row0) * 16, rm16);
-      const float* w1 = fx_layer(c, 1, C, l0, 1);
-      fx_fwd<32>(H1, 128, 32, w1, w1 + wt_bias(C.L[l0 + 1]), 1, H2, cx + ((size_t)P.cxb[2] * Rm + row0) * 16, rm16);
-      const float* w2 = fx_layer(c, 1, C, l0, 2);
-      fx_fwd_narrow(H2, w2, w2 + wt_bias(C.L[l0 + 2]), 4, cld, QA, 4);
+      const float* w0 = slot1 + P.coff[0];
+      const float* w1 = slot1 + P.coff[1];
+      const float* w2 = slot1 + P.coff[2];
+      fx_wait(c, 1, 0);
+      fx_fwd<0>(XS, cip, cip >> 2, w0, slot1 + P.cboff[0], 1, H1, cx + ((size_t)P.cxb[1] * Rm + row0) * 16, rm16);
+      fx_wait(c, 1, 1);
+      fx_fwd<32>(H1, 128, 32, w1, slot1 + P.cboff[1], 1, H2, cx + ((size_t)P.cxb[2] * Rm + row0) * 16, rm16);
+      fx_fwd_narrow(H2, w2, slot1 + P.cboff[2], 4, cld, QA, 4);
       if (do_actor) {
         trace(16);
         float* ax = (h == 0) ? ws + P.w_ax : nullptr;           // head 0's CTA publishes the actor's layer inputs
         if (ax) fx_put_blocks(ax, P.axb[0], fx_xb(A, 0), Rm, row0, XA, aip, aip);
-        const float* p0 = fx_layer(c, 0, A, 0, 0);
-        fx_fwd<0>(XA, aip, aip >> 2, p0, p0 + wt_bias(A.L[0]), 1, A1, ax ? ax + ((size_t)P.axb[1] * Rm + row0) * 16 : nullptr, rm16);
-        const float* p1 = fx_layer(c, 0, A, 0, 1);
-        fx_fwd<32>(A1, 128, 32, p1, p1 + wt_bias(A.L[1]), 1, A2, ax ? ax + ((size_t)P.axb[2] * Rm + row0) * 16 : nullptr, rm16);
-        const float* p2 = fx_layer(c, 0, A, 0, 2);
-        fx_fwd_narrow(A2, p2, p2 + wt_bias(A.L[2]), ap, ald, MU, 8);
+        fx_wait(c, 0, 0);
+        fx_fwd<0>(XA, aip, aip >> 2, slot0 + P.aoff[0], slot0 + P.aboff[0], 1, A1, ax ? ax + ((size_t)P.axb[1] * Rm + row0) * 16 : nullptr, rm16);
+        fx_wait(c, 0, 1);
+        fx_fwd<32>(A1, 128, 32, slot0 + P.aoff[1], slot0 + P.aboff[1], 1, A2, ax ? ax + ((size_t)P.axb[2] * Rm + row0) * 16 : nullptr, rm16);
+        fx_fwd_narrow(A2, slot0 + P.aoff[2], slot0 + P.aboff[2], ap, ald, MU, 8);
         FRL_PAR(t) {
           if (t < 64) {
             const int r = t >> 3, j = t & 7;
@@ -1063,9 +1218,9 @@ struct AcFx {
             if (j < ad) {
               const float mean = MU[r * 8 + j];
               if (sac) {
-                const float ls = fminf(fmaxf(fx_ldcg(A.p + A.x_off + j), -20.f), 2.f);
+                const float ls = fminf(fmaxf(LS[j], -20.f), 2.f);
                 const float sd = expf(ls);
-                e = (r < nvalid) ? noise_at(a.noise_new, a, u, row0 + r, j, 2u) : 0.f;
+                e = NZ[t];
                 const float uu = fadd(mean, fmul(e, sd));
                 const float diff = uu - mean;
                 lp = -(diff * diff) / (2.f * (sd * sd)) - logf(sd) - FRL_LOG_SQRT_2PI;
@@ -1086,15 +1241,15 @@ struct AcFx {
         float l = 0.f;
         if (t < 8) {
           const int r = t;
-          const float al = sac ? expf(fx_ldcg(a.alpha_state)) : 0.f;      // rewritten in stage 5 of the previous learn: read through L2
-          for (int hh = 0; hh < NH; ++hh) fx_flag_wait(flags + tile * NH + hh, epoch);
+          const float al = alpha_s[0];
           float y = 0.f;
           if (r < nvalid) {
-            float nq = fx_ldcg(ws + P.w_xq + (size_t)(row0 + r) * 2);
-            if (NH == 2) nq = fminf(nq, fx_ldcg(ws + P.w_xq + (size_t)(row0 + r) * 2 + 1));
+            const unsigned long long* pr = pk + (size_t)(row0 + r) * 3;
+            float nq, nq1, lp;
+            fx_pk_wait3(pr, NH == 2 ? pr + 1 : nullptr, sac ? pr + 2 : nullptr, epoch, &nq, &nq1, &lp);
+            if (NH == 2) nq = fminf(nq, nq1);
             const float rew = raw[r * rf + rb_col_rew(rb)], dn = raw[r * rf + rb_col_done(rb)];
             if (sac) {
-              const float lp = fx_ldcg(ws + P.w_xlp + row0 + r);
               y = fadd(rew, fmul(fmul(a.gamma, fadd(1.f, -dn)), fadd(nq, fmul(al, -lp))));      // SAC.py:235
             } else {
               y = fadd(rew, fmul(fmul(a.gamma, nq), fadd(1.f, -dn)));                            // TD3.py:209 / DDPG.py:212
@@ -1106,7 +1261,6 @@ struct AcFx {
             dQA[t * 4] = 2.f * d0 * invB;
             l = d0 * d0;
           }
-          if (t == 0) alpha_s[0] = al;
         }
         if (t < 32) red0[t] = l;
       }
@@ -1118,17 +1272,31 @@ struct AcFx {
       fx_bwd(D2, w1, H1, D1, cy + ((size_t)P.cyb[0] * Rm + row0) * 16, rm16);
       FRL_PAR(t) { if (t == 0) ws[P.w_stats + (size_t)wi * 8 + 0] = loss_c; }
       trace(19);
-    } else if (s == 1) {
-      res_invalidate(c, C);
-      res_invalidate(c, a.critic_target);
-      res_drain_slot(c, 1);
-      if (c.stag1 != nullptr) c.stag1 = nullptr;      // slot 1 is scratch in stages 1 / 2 whatever it held
-      const AdamSpec hp = {a.lr_critic, a.beta1, a.beta2, a.eps, a.wd_critic, (double)a.max_norm, (long)(a.step_critic0 + u + 1)};
-      dw_stage(c, a, C, P.jc, ws + P.w_cx, ws + P.w_cy, nullptr, c.wbuf1, gst, gbst, redb, red0, ws + P.w_sumsq + c.cta, nullptr, 0, hp,
-               hpst);
-    } else if (s == 2) {
-      const float tot = opt_stage(c, C, policy_step ? &a.critic_target : nullptr, a.tau, hpst, gst, gbst, ws + P.w_sumsq, c.red, P.jc);
-      if (metrics_cta) {
+    } else if (s == 1 || s == 4) {
+      // dW of the critic (1) / the actor (4): ONE inlined copy of the stage body serves both (the kernel is ~180 KB of SASS and a
+      // learn walks most of it once: instruction fetch is a visible part of every short phase)
+      const bool cr = s == 1;
+      const frl_net_t& N = cr ? C : A;
+      res_invalidate(c, N);
+      res_invalidate(c, cr ? a.critic_target : a.actor_target);
+      res_drain_slot(c, cr ? 1 : 0);
+      if (cr) c.stag1 = nullptr; else c.stag0 = nullptr;      // the slot is scratch in this stage and the next whatever it held
+      long step;
+      if (cr) step = (long)(a.step_critic0 + u + 1);
+      else {
+        const long n_policy_before = (a.policy_freq > 1) ? (long)((a.total_it0 + u) / a.policy_freq - a.total_it0 / a.policy_freq) : (long)u;
+        step = (long)(a.step_actor0 + n_policy_before + 1);
+      }
+      const AdamSpec hp = {cr ? a.lr_critic : a.lr_actor, a.beta1, a.beta2, a.eps, cr ? a.wd_critic : 0.0, (double)a.max_norm, step};
+      dw_stage(c, a, N, cr ? P.jc : P.ja, ws + (cr ? P.w_cx : P.w_ax), ws + (cr ? P.w_cy : P.w_ay0), (!cr && hu == 2) ? ws + P.w_ay1 : nullptr,
+               cr ? c.wbuf1 : c.wbuf0, gst, gbst, redb, red0, sspk + (cr ? 0 : 512) + c.cta, epoch, ws + P.w_lsg, cr ? 0 : nwork, hp, hpst);
+    } else if (s == 2 || s == 5) {
+      const bool cr = s == 2;
+      if (cr && role != 2 && u + 1 < a.n_updates)          // rows of the NEXT learn's tile (raw is dead after phase A)
+        fx_gather_async(rb.storage, rf, a.indices + (size_t)(u + 1) * a.B + row0, nvalid, raw);
+      const float tot = opt_stage(c, cr ? C : A, cr ? (policy_step ? &a.critic_target : nullptr) : &a.actor_target, a.tau, hpst, gst, gbst,
+                                  sspk + (cr ? 0 : 512), epoch, c.red, cr ? P.jc : P.ja);
+      if (metrics_cta && cr) {
         FRL_PAR(t) { red0[t] = t < nwork ? fx_ldcg(ws + P.w_stats + (size_t)t * 8) : 0.f; }
         FRL_SYNC();
         const float ls = block_sum(red0);
@@ -1140,11 +1308,43 @@ struct AcFx {
         }
         FRL_SYNC();
       }
+      if (metrics_cta && !cr) {
+        FRL_PAR(t) {
+          const bool on = t < nwork && (t % NH) < hu;
+          red0[t] = on ? fx_ldcg(ws + P.w_stats + (size_t)t * 8 + 1) : 0.f;
+          red1[t] = on ? fx_ldcg(ws + P.w_stats + (size_t)t * 8 + 2) : 0.f;
+        }
+        FRL_SYNC();
+        const float l = block_sum(red0);
+        const float en = block_sum(red1);
+        FRL_PAR(t) {
+          if (t == 0) {
+            a.out[u * 8 + 1] = l * invB;
+            a.out[u * 8 + 5] = sqrtf(tot);
+            a.out[u * 8 + 6] = en * invB;
+            if (sac && a.adaptive_alpha) {
+              // alpha_loss = (exp(log_alpha) * (entropy - target_entropy).detach()).mean();  Adam(lr alpha_lr) on log_alpha
+              const float mean_term = en * invB - a.target_entropy;
+              const float al = expf(a.alpha_state[0]);
+              const float g = al * mean_term;
+              a.out[u * 8 + 3] = g;
+              const AdamHP ha = adam_hp_ni(a.alpha_lr, a.beta1, a.beta2, a.eps, 0.0, 0.0, (long)(a.step_alpha0 + u + 1));
+              float m = a.alpha_state[1], v = a.alpha_state[2], w = a.alpha_state[0];
+              m = fmaf(ha.one_minus_b1, g - m, m);
+              v = fadd(fmul(v, ha.b2), fmul(fmul(ha.one_minus_b2, g), g));
+              const float denom = fadd(fdiv(fsqrt(v), ha.bc2_sqrt), ha.eps);
+              w = fadd(w, fdiv(fmul(ha.lr_over_bc1_neg, m), denom));
+              a.alpha_state[0] = w; a.alpha_state[1] = m; a.alpha_state[2] = v;
+            }
+          }
+        }
+        FRL_SYNC();
+      }
     } else if (s == 3) {
       // ------------------------------- phase C: Q_h(s, pi(s)) with the updated critic, dQ/da, actor backward -------------------------------
-      if (role == 0) { fx_fetch(c, 1, a.critic_target, l0, 0); return; }      // prefetch for the next learn
+      if (role == 0) { fx_fetch(c, 1, a.critic_target, l0, 128); return; }      // prefetch for the next learn
       if (role != 1) return;
-      fx_fetch(c, 1, C, l0, 0);
+      fx_fetch(c, 1, C, l0, 128);
       if (h >= hu) return;
       const float alpha = sac ? alpha_s[0] : 0.f;
       put_cols<8>(XN, cip, 0, XS, cip, 0, od, od);
@@ -1156,12 +1356,14 @@ struct AcFx {
       }
       FRL_SYNC();
       trace(30);
-      const float* w0 = fx_layer(c, 1, C, l0, 0);
-      fx_fwd<0>(XN, cip, cip >> 2, w0, w0 + wt_bias(C.L[l0]), 1, H1);
-      const float* w1 = fx_layer(c, 1, C, l0, 1);
-      fx_fwd<32>(H1, 128, 32, w1, w1 + wt_bias(C.L[l0 + 1]), 1, H2);
-      const float* w2 = fx_layer(c, 1, C, l0, 2);
-      fx_fwd_narrow(H2, w2, w2 + wt_bias(C.L[l0 + 2]), 4, cld, QA, 4);
+      const float* w0 = slot1 + P.coff[0];
+      const float* w1 = slot1 + P.coff[1];
+      const float* w2 = slot1 + P.coff[2];
+      fx_wait(c, 1, 0);
+      fx_fwd<0>(XN, cip, cip >> 2, w0, slot1 + P.cboff[0], 1, H1);
+      fx_wait(c, 1, 1);
+      fx_fwd<32>(H1, 128, 32, w1, slot1 + P.cboff[1], 1, H2);
+      fx_fwd_narrow(H2, w2, slot1 + P.cboff[2], 4, cld, QA, 4);
       const float dq = -invB / (float)hu;
       FRL_PAR(t) {
         float v = 0.f;
@@ -1203,7 +1405,7 @@ struct AcFx {
         // d/dlog_std_j = sum_r dL/du std eps (+ head 0: -alpha / B per row); zero outside the clamp range
         FRL_PAR(t) {
           if (t < 8) {
-            const float lsr = (t < ad) ? fx_ldcg(A.p + A.x_off + t) : 1e30f;
+            const float lsr = (t < ad) ? LS[t] : 1e30f;
             float g = 0.f;
             if (lsr >= -20.f && lsr <= 2.f) {
               const float sd = expf(lsr);
@@ -1216,56 +1418,13 @@ struct AcFx {
       trace(33);
       float* ay = ws + (h == 0 ? P.w_ay0 : P.w_ay1);
       fx_put_blocks(ay, P.ayb[2], 1, Rm, row0, dMU, 8, ap);
-      const float* p2 = fx_layer(c, 0, A, 0, 2);
-      const float* p1 = fx_layer(c, 0, A, 0, 1);
+      const float* p2 = slot0 + P.aoff[2];
+      const float* p1 = slot0 + P.aoff[1];
       fx_bwd_narrow(dMU, 8, p2, ap, ald, A2, D2, ay + ((size_t)P.ayb[1] * Rm + row0) * 16, rm16);
       fx_bwd(D2, p1, A1, D1, ay + ((size_t)P.ayb[0] * Rm + row0) * 16, rm16);
       trace(34);
       FRL_PAR(t) { if (t == 0) { ws[P.w_stats + (size_t)wi * 8 + 1] = loss_a; ws[P.w_stats + (size_t)wi * 8 + 2] = ent; } }
       trace(39);
-    } else if (s == 4) {
-      res_invalidate(c, A);
-      res_invalidate(c, a.actor_target);
-      res_drain_slot(c, 0);
-      if (c.stag0 != nullptr) c.stag0 = nullptr;      // slot 0 is scratch in stages 4 / 5
-      const long n_policy_before = (a.policy_freq > 1) ? (long)((a.total_it0 + u) / a.policy_freq - a.total_it0 / a.policy_freq) : (long)u;
-      const AdamSpec hp = {a.lr_actor, a.beta1, a.beta2, a.eps, 0.0, (double)a.max_norm, (long)(a.step_actor0 + n_policy_before + 1)};
-      dw_stage(c, a, A, P.ja, ws + P.w_ax, ws + P.w_ay0, hu == 2 ? ws + P.w_ay1 : nullptr, c.wbuf0, gst, gbst, redb, red0,
-               ws + P.w_sumsq + c.cta, ws + P.w_lsg, nwork, hp, hpst);
-    } else {
-      const float tot = opt_stage(c, A, &a.actor_target, a.tau, hpst, gst, gbst, ws + P.w_sumsq, c.red, P.ja);
-      if (metrics_cta) {
-        FRL_PAR(t) {
-          const bool on = t < nwork && (t % NH) < hu;
-          red0[t] = on ? fx_ldcg(ws + P.w_stats + (size_t)t * 8 + 1) : 0.f;
-          red1[t] = on ? fx_ldcg(ws + P.w_stats + (size_t)t * 8 + 2) : 0.f;
-        }
-        FRL_SYNC();
-        const float l = block_sum(red0);
-        const float en = block_sum(red1);
-        FRL_PAR(t) {
-          if (t == 0) {
-            a.out[u * 8 + 1] = l * invB;
-            a.out[u * 8 + 5] = sqrtf(tot);
-            a.out[u * 8 + 6] = en * invB;
-            if (sac && a.adaptive_alpha) {
-              // alpha_loss = (exp(log_alpha) * (entropy - target_entropy).detach()).mean();  Adam(lr alpha_lr) on log_alpha
-              const float mean_term = en * invB - a.target_entropy;
-              const float al = expf(a.alpha_state[0]);
-              const float g = al * mean_term;
-              a.out[u * 8 + 3] = g;
-              const AdamHP ha = adam_hp_ni(a.alpha_lr, a.beta1, a.beta2, a.eps, 0.0, 0.0, (long)(a.step_alpha0 + u + 1));
-              float m = a.alpha_state[1], v = a.alpha_state[2], w = a.alpha_state[0];
-              m = fmaf(ha.one_minus_b1, g - m, m);
-              v = fadd(fmul(v, ha.b2), fmul(fmul(ha.one_minus_b2, g), g));
-              const float denom = fadd(fdiv(fsqrt(v), ha.bc2_sqrt), ha.eps);
-              w = fadd(w, fdiv(fmul(ha.lr_over_bc1_neg, m), denom));
-              a.alpha_state[0] = w; a.alpha_state[1] = m; a.alpha_state[2] = v;
-            }
-          }
-        }
-        FRL_SYNC();
-      }
     }
   }
 };
@@ -1300,8 +1459,10 @@ __global__ void __launch_bounds__(FRL_NT, 1) frl_fx_kernel(const __grid_constant
       stamp(c, 100 + s);
       // (no proxy fence here: the thread that issues a TMA copy of data other CTAs wrote runs fence.proxy.async after this
       //  barrier's acquire, which puts the fence on the causality path between the generic writes and the bulk read)
-      target += gridDim.x;
-      fx_grid_barrier(ctr, target);
+      if (A::barrier_after(s)) {
+        target += gridDim.x;
+        fx_grid_barrier(ctr, target);
+      }
       stamp(c, 200 + s);
     }
   }
@@ -1326,7 +1487,7 @@ int frl_launch_fx(const typename A::Args& a, cudaStream_t stream) {
     frl_set_error("cooperative launch of %d CTAs does not fit the device (%d per SM)", grid, per_sm);
     return -3;
   }
-  FRL_CUDA_OK(cudaMemsetAsync(a.sync, 0, 4096, stream));       // barrier counter + hand-off flags
+  FRL_CUDA_OK(cudaMemsetAsync(a.sync, 0, FX_SYNC_WORDS * 4, stream));       // barrier counter + hand-off packets
   typename A::Args args = a;
   void* kargs[] = {(void*)&args};
   FRL_CUDA_OK(cudaLaunchCooperativeKernel((void*)frl_fx_kernel<A>, dim3(grid), dim3(FRL_NT), kargs, (size_t)smem_bytes, stream));
@@ -1335,7 +1496,7 @@ int frl_launch_fx(const typename A::Args& a, cudaStream_t stream) {
 #else
 template <class A>
 int frl_launch_fx(const typename A::Args& a, cudaStream_t s) {
-  memset(a.sync, 0, 4096);
+  memset(a.sync, 0, FX_SYNC_WORDS * 4);
   return frl_launch<A>(a, s);
 }
 #endif

@@ -135,7 +135,7 @@ typedef struct {
                                                  * randn of agent j's target action for THIS agent's sample; NULL -> Philox(seed) */
   /* ---- small-batch schedule (csrc/algo_acfx.cuh; single agent, hidden 128-128, B <= 256): taken when both are given ----
    * ws   = dev scratch of frl_ac_ws_floats(args) floats (activation / gradient exchange blocks, partial sums);
-   * sync = dev scratch of 1024 uint32 (grid-barrier counter + hand-off flags; the library zeroes it at every launch). */
+   * sync = dev scratch of 4096 uint32 (grid-barrier counter + hand-off packets; the library zeroes it at every launch). */
   float* ws;
   unsigned* sync;
 } frl_ac_args_t;
