@@ -7,8 +7,8 @@
 Workload (config.workload = "sac_halfcheetah_256env_1Mreplay"): SAC with HalfCheetah-v4 dims (obs 17, act 6,
 hidden 128-128, twin critic), 256 vectorised synthetic envs per GPU, a pre-filled 1 000 000-transition device
 replay per GPU, batch 256, update-to-data ratio 1 (the reference trains once per env step, SAC_file/SAC.py:571-572).
-One "step" = one vector step: policy inference for 256 envs, 256 transitions added to the replay and 256 sequential
-learn() updates (ONE persistent kernel launch).  `value` keeps all inputs resident in HBM (synthetic env arrays come
+One "step" = VSTEPS (8) vector steps (so that the driver's 20 timed steps last about two seconds); a vector step = policy
+inference for 256 envs, 256 transitions added to the replay and 256 sequential learn() updates (ONE persistent kernel launch).  `value` keeps all inputs resident in HBM (synthetic env arrays come
 from a device pool); `e2e` drives the public Python API with HOST (numpy) buffers: select_action(host obs) -> host
 synthetic env -> add(host arrays) -> learn(…, n_updates=256) -> D2H read of the loss, with the H2D / D2H copies inside
 the timed region.  Replay rows are sampled uniformly from 176 MB (> the 126 MB L2), so batch gathers are HBM traffic.
@@ -29,6 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 OBS, ACT, NENV, CAP, BATCH = 17, 6, 256, 1_000_000, 256
+VSTEPS = 8                                # vector steps per bench step
 GAMMA, TAU = 0.99, 0.01
 PARAMS = 19596 + 39426                    # SAC actor + twin critic
 ALGO_BYTES_PER_LEARN = BATCH * 168 + PARAMS * 36 + 16       # sampled rows + param/Adam/target traffic
@@ -106,10 +107,14 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+NCU_CAPTURE = "profiles/r2_bench_sac_learn_ncu_full.json"
+
+
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of ONE bench launch (256 learns) from the committed `ncu --set full`
-    capture of this same command (profiles/r1e_bench_sac_learn_ncu_full.json); None when no capture is committed."""
-    p = os.path.join(ROOT, "profiles", "r1e_bench_sac_learn_ncu_full.json")
+    capture of this same command and kernel build (NCU_CAPTURE; a profiler cannot run inside the timed bench, so the
+    number is a stored measurement and `traffic_source` says which); None when no capture is committed."""
+    p = os.path.join(ROOT, NCU_CAPTURE)
     if os.path.exists(p):
         try:
             return json.load(open(p)).get("dram_bytes_per_launch")
@@ -119,10 +124,13 @@ def ncu_traffic():
 
 
 # --------------------------------------------------------------------------------------------------
-def cpu_reference_arm(steps, warmup, transitions_per_step=4, fill=CAP, threads=None):
+def cpu_reference_arm(steps, warmup, transitions_per_step=4, fill=CAP, threads=None, device="cpu", choice=True):
     """The reference's own CPU implementation of the path (oracle port: numpy ring replay with
     np.random.choice(len, 256, replace=False) + PyTorch-CPU SAC learn), all host threads.  A step = a bounded
-    sample: `transitions_per_step` single-env iterations of select_action + env + add + learn."""
+    sample: `transitions_per_step` single-env iterations of select_action + env + add + learn.
+    device="cuda": the SAME torch code with the networks on the GPU (the like-for-like "stock PyTorch on this B200" arm:
+    numpy replay on the host, batch copied H2D per learn, as the reference does with --device cuda); choice=False replaces
+    np.random.choice(1e6, 256, replace=False) — a full permutation per sample, 60 % of the CPU arm — by rng.integers."""
     import torch
     from collections import OrderedDict
     from oracle import algos, buffers
@@ -144,6 +152,10 @@ def cpu_reference_arm(steps, warmup, transitions_per_step=4, fill=CAP, threads=N
     for k in range(6):
         i, o = ((OBS + ACT, 128), (128, 128), (128, 1))[k % 3]
         critic["l%d.weight" % (k + 1)], critic["l%d.bias" % (k + 1)] = lin(i, o)
+    tdev = torch.device(device)
+    if tdev.type == "cuda":
+        actor = OrderedDict((k, v.to(tdev)) for k, v in actor.items())
+        critic = OrderedDict((k, v.to(tdev)) for k, v in critic.items())
     orc = algos.SACOracle(actor, critic, 1e-3, 1e-3, act_dim=ACT)
     buf = buffers.RingReplay(CAP, OBS, ACT)
     n = int(fill)
@@ -158,14 +170,14 @@ def cpu_reference_arm(steps, warmup, transitions_per_step=4, fill=CAP, threads=N
         nonlocal obs
         for _ in range(transitions_per_step):
             with torch.no_grad():
-                a, _ = algos.sac_actor(orc.actor, torch.as_tensor(obs).reshape(1, -1), torch.randn(1, ACT))
+                a, _ = algos.sac_actor(orc.actor, torch.as_tensor(obs).reshape(1, -1).to(tdev), torch.randn(1, ACT, device=tdev))
             nxt = rng.standard_normal(OBS).astype(np.float32)
-            buf.add(obs, a.numpy()[0], float(rng.standard_normal()), nxt, False)
+            buf.add(obs, a.cpu().numpy()[0], float(rng.standard_normal()), nxt, False)
             obs = nxt
-            idx = buffers.uniform_indices(len(buf), BATCH)
-            batch = tuple(torch.from_numpy(x) for x in buf.sample(idx))
-            orc.learn(batch, torch.randn(BATCH, ACT), torch.randn(BATCH, ACT), GAMMA, TAU)
-    if not threads and (os.cpu_count() or 1) > 1:
+            idx = buffers.uniform_indices(len(buf), BATCH) if choice else rng.integers(0, len(buf), BATCH)
+            batch = tuple(torch.from_numpy(x).to(tdev) for x in buf.sample(idx))
+            orc.learn(batch, torch.randn(BATCH, ACT, device=tdev), torch.randn(BATCH, ACT, device=tdev), GAMMA, TAU)
+    if not threads and (os.cpu_count() or 1) > 1 and tdev.type == "cpu":
         def probe():
             t0 = time.perf_counter()
             for _ in range(2):
@@ -186,6 +198,52 @@ def cpu_reference_arm(steps, warmup, transitions_per_step=4, fill=CAP, threads=N
 
 
 # --------------------------------------------------------------------------------------------------
+def ppo_dp_block(dev, rank, world, dist, learns=3):
+    """BASELINE config 3 on every rank: PPO (LunarLander dims: obs 8, 4 actions), 1024 envs x 128 steps per GPU, minibatch
+    8192 rows per GPU, K = 10 epochs = 160 optimiser steps per learn.  At world > 1 the replicas train data-parallel
+    (PPO.enable_data_parallel: the flat gradient is summed across ranks between the in-kernel reduction and the clip /
+    optimiser stages of every step), weak scaling: the union minibatch is world x 8192 rows.  Timed with CUDA events,
+    max over ranks."""
+    import contextlib
+    import torch
+    from freerl_b200.PPO import PPO
+    T, N, mb, K = 128, 1024, 8192, 10
+    rng = np.random.default_rng(100 + rank)
+    with contextlib.redirect_stdout(sys.stderr):
+        pol = PPO([8, 4], False, 1e-3, 1e-3, T * N, dev, mode="fast")
+    if world > 1:
+        pol.enable_data_parallel()
+    data = [(rng.standard_normal((N, 8), dtype=np.float32), rng.integers(0, 4, (N, 1)).astype(np.float32), rng.standard_normal(N).astype(np.float32),
+             rng.standard_normal((N, 8), dtype=np.float32), rng.random(N) < 1 / 300, -np.abs(rng.standard_normal((N, 1))).astype(np.float32) * 0.1 - 1.3)
+            for _ in range(T)]
+    for o, a, r, o2, d, lp in data:
+        pol.add(o, a, r, o2, d, lp, d)
+
+    def learn():
+        pol.buffer._index, pol.buffer._size, pol.buffer.n_envs = 0, T * N, N      # the rollout stays resident (learn() clears it)
+        pol.learn(mb, 0.99, 0.95, 0.2, K, 0.01)
+    learn()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(learns):
+        learn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / learns], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    updates = K * (T * N // mb)
+    return {"workload": "ppo_lunarlander_1024env_x128_mb8192_k10", "ms_per_learn": ms, "updates_per_learn": updates,
+            "updates_per_sec": updates / ms * 1e3, "env_steps_per_sec": world * T * N / ms * 1e3, "us_per_update": ms * 1e3 / updates,
+            "scaling": "weak", "collective": "none (1 rank)" if world == 1 else getattr(pol, "dp_collective", "nccl all_reduce of net.g per optimiser step"),
+            "loss_finite": bool(torch.isfinite(pol.last_metrics).all().item())}
+
+
+# --------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -193,6 +251,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip reference_cuda / extra.configs / ppo_dp (profiling runs)")
     args = ap.parse_args()
     # stdout carries ONE JSON line: keep the real stdout aside and point fd 1 at stderr, so prints from libraries (NCCL's
     # version banner, reference-style constructors) cannot get in front of it
@@ -204,6 +263,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     config = {"workload": "sac_halfcheetah_256env_1Mreplay", "obs_dim": OBS, "act_dim": ACT, "hidden": [128, 128],
               "envs_per_gpu": NENV, "replay_capacity_per_gpu": CAP, "batch": BATCH, "updates_per_env_step": 1,
+              "vector_steps_per_step": VSTEPS,
               "l2_note": "batches are uniform random rows of a 176 MB replay (> 126 MB L2)",
               "parallelism": "dp%d (env+replay shards per GPU, parameter all-reduce per vector step)" % max(world, 1)}
 
@@ -258,6 +318,10 @@ def main():
     learn_ev = []
 
     def device_step(t, timed):
+        for v in range(VSTEPS):
+            device_vstep(t * VSTEPS + v, timed)
+
+    def device_vstep(t, timed):
         obs = obs_pool[t % POOL]
         act = _common.infer(pol.agent._actor, obs, _lib.INFER_SAC_SAMPLE, dev, ACT, seed=pol._seed, counter=t)
         nxt, rew = obs_pool[(t + 1) % POOL], rew_pool[(t + 1) % POOL]
@@ -295,16 +359,22 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    launches0 = int(_lib.lib().frl_launch_count())
     ms_total = timed_region(device_step)
+    launches = int(_lib.lib().frl_launch_count()) - launches0               # counted by the library at its launch sites
     clocks = sampler.stop() if rank == 0 else None
     learn_ms = float(np.mean([a.elapsed_time(b) for a, b in learn_ev]))      # one launch = NENV sequential learns
-    value = world * NENV * K / (ms_total / 1e3)
+    value = world * NENV * VSTEPS * K / (ms_total / 1e3)
 
     # ---- end-to-end through the public API with host buffers ------------------------------------------
     env = SyntheticVecEnv(NENV, 7 + rank)
     state = {"obs": env.obs, "loss": 0.0}
 
     def host_step(t, timed):
+        for v in range(VSTEPS):
+            host_vstep()
+
+    def host_vstep():
         obs = state["obs"]
         action = pol.select_action(obs)                              # H2D obs, kernel, D2H actions
         nxt, rew, term, trunc = env.step(action)
@@ -316,9 +386,17 @@ def main():
     for t in range(W):
         host_step(t, False)
     ms_e2e = timed_region(host_step)
-    e2e = world * NENV * K / (ms_e2e / 1e3)
-    h2d = NENV * OBS * 4 + NENV * pol.buffer.row_floats * 4
-    d2h = NENV * ACT * 4 + 4
+    e2e = world * NENV * VSTEPS * K / (ms_e2e / 1e3)
+    h2d = VSTEPS * (NENV * OBS * 4 + NENV * pol.buffer.row_floats * 4)
+    d2h = VSTEPS * (NENV * ACT * 4 + 4)
+
+    # ---- on-policy data parallel (config 3 shape) at this N: every rank runs it, rank 0 reports ------------------------
+    ppo_dp = None
+    if not args.no_extras:
+        try:
+            ppo_dp = ppo_dp_block(dev, rank, world, dist)
+        except Exception as e:                                   # the headline line must survive a failure of an extra
+            ppo_dp = {"error": "%s: %s" % (type(e).__name__, e)}
 
     if rank != 0:
         if world > 1:
@@ -330,15 +408,15 @@ def main():
         "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": config,
-        "updates_per_sec": world * NENV * K / (ms_total / 1e3),
+        "updates_per_sec": world * NENV * VSTEPS * K / (ms_total / 1e3),
         "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / K, "last_loss": state["loss"]},
-        "gpu_launches": 4 * K,      # per step: policy-infer, replay add_batch, uniform-sample, fused 256-update learn
+        "gpu_launches": launches,   # frl_launch_count() delta over the timed region (per vector step: policy-infer, replay add_batch, fused 256-update learn)
         "clocks": clocks,
-        "roofline": {"kernel": "frl_persistent_kernel<AcAlgo> (fused SAC learn x%d per launch)" % NENV, "bound": "hbm",
+        "roofline": {"kernel": "frl_fx_kernel<AcFx> (fused SAC learn x%d per launch)" % NENV, "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ALGO_BYTES_PER_LEARN * NENV, "launch_ms": learn_ms,
-                     "traffic": ncu_traffic(),
+                     "traffic": ncu_traffic(), "traffic_source": NCU_CAPTURE + " (stored ncu --set full capture of this command; not measured in this run)",
                      "achieved_tflops_fp32": ALGO_FLOPS_PER_LEARN * NENV / (learn_ms / 1e3) / 1e12,
                      "note": "the fused update is FLOP/latency-bound at B=256 (SURVEY §7.3-1): params/Adam/targets are L2-resident"},
     }
@@ -346,6 +424,24 @@ def main():
         val, ms, cores, tps = cpu_reference_arm(150, 1)
         out["cpu_baseline"] = {"value": val, "unit": "env-steps/s", "cores": cores, "kind": "port",
                                "sample": "150 steps x %d single-env iterations of the oracle port (np.random.choice over the full 1e6 replay + SAC learn B=256)" % tps}
+    if ppo_dp is not None:
+        out["ppo_dp"] = ppo_dp
+    if not args.no_extras and world == 1:
+        extra = {}
+        try:       # stock PyTorch on this same B200: the oracle port's torch code with the networks on cuda
+            v1, _, _, tps = cpu_reference_arm(12, 2, transitions_per_step=16, device="cuda")
+            v2, _, _, _ = cpu_reference_arm(12, 2, transitions_per_step=16, device="cuda", choice=False)
+            out["reference_cuda"] = {"value": v1, "value_without_np_random_choice": v2, "unit": "env-steps/s", "kind": "port",
+                                     "sample": "12 steps x %d single-env iterations; numpy replay on the host, networks + learn on cuda:0" % tps}
+        except Exception as e:
+            out["reference_cuda"] = {"error": "%s: %s" % (type(e).__name__, e)}
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import configbench
+            extra["configs"] = configbench.run(("C1", "C3", "C4", "C5"), log=lambda *a: print(*a, file=sys.stderr))
+        except Exception as e:
+            extra["configs_error"] = "%s: %s" % (type(e).__name__, e)
+        out["extra"] = extra
     print(json.dumps(out), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -107,6 +107,7 @@ class IPPO(_MAPPO):
             a.value_loss = 1 if self.trick['huber_loss'] else 0
             a.huber_delta = float(huber_delta) if huber_delta is not None else 0.0
             a.gpart, a.sumsq, a.segcnt = self._gpart.data_ptr(), self._sumsq.data_ptr(), self._segcnt.data_ptr()
+            a.umma_ws = _common.umma_ws_ptr(self.device, int(a.mb))
             a.stats, a.out = self._stats.data_ptr(), out.data_ptr()
             self._launch_update(a, ag._net, n_updates)
             ag.step += n_updates

@@ -198,6 +198,7 @@ class PPO:
         a.lr_critic = float(getattr(ag, "lr_critic", 0.0))        # separate actor / critic Adams (PPO_advance); 0 = merged
         a.step0 = ag.step
         a.gpart, a.sumsq, a.segcnt = self._gpart.data_ptr(), self._sumsq.data_ptr(), self._segcnt.data_ptr()
+        a.umma_ws = _common.umma_ws_ptr(self.device, int(a.mb))
         a.stats, a.out = self._stats.data_ptr(), out.data_ptr()
         self._launch_update(a, ag._net, n_updates)
         ag.step += n_updates

@@ -119,3 +119,22 @@ def device_minibatch_plan(H, minibatch_size, K_epochs, device, seed):
     last = H - (nmb - 1) * minibatch_size
     rows = torch.tensor(([minibatch_size] * (nmb - 1) + [last]) * K_epochs, dtype=torch.int32).to(device)
     return idx, rows, K_epochs * nmb
+
+
+_UMMA_WS = {}
+
+
+def umma_ws_ptr(device, minibatch_size):
+    """Device scratch of the tensor-core PPO / MAPPO path (``frl_ppo_args_t.umma_ws``, csrc/algo_ppo_umma.cuh): split weights +
+    per-CTA activation scratch, one allocation per device shared by every policy (launches on a device are stream-ordered).
+    0 when the minibatch is below the 1024-row threshold (the library then takes the FFMA tile kernels)."""
+    from . import _lib
+    if minibatch_size < 1024 or os.environ.get("FREERL_B200_NO_UMMA"):      # the switch exists for A/B timing (tools/configbench.py)
+        return 0
+    n = int(_lib.lib().frl_ppo_umma_ws_floats())
+    if n <= 0:
+        return 0
+    key = str(device)
+    if key not in _UMMA_WS:
+        _UMMA_WS[key] = torch.zeros(n, dtype=torch.float32, device=device)
+    return _UMMA_WS[key].data_ptr()

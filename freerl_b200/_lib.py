@@ -12,7 +12,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 FRL_MAX_LAYERS = 6
 FRL_MAX_AGENTS = 6
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 
 class Layer(C.Structure):
@@ -76,7 +76,7 @@ class PpoArgs(C.Structure):
                 ("huber_delta", C.c_float), ("stage_lo", C.c_int), ("stage_hi", C.c_int), ("grad_scale", C.c_float),
                 ("gpart", C.c_void_p),
                 ("sumsq", C.c_void_p), ("segcnt", C.c_void_p), ("stats", C.c_void_p), ("out", C.c_void_p),
-                ("lr_critic", C.c_double), ("hidden_tanh", C.c_int)]
+                ("lr_critic", C.c_double), ("hidden_tanh", C.c_int), ("umma_ws", C.c_void_p)]
 
 
 class NoisyMap(C.Structure):
@@ -146,6 +146,10 @@ def _declare(lib):
     for name in ("frl_vecnorm", "frl_reward_scaling", "frl_explore", "frl_masked_reset", "frl_epsilon_greedy", "frl_dis_to_con"):
         getattr(lib, name).restype = ci
     lib.frl_wt_ld.argtypes = [ci]
+    lib.frl_ppo_umma_ws_floats.restype = C.c_longlong
+    lib.frl_launch_count.restype = C.c_longlong
+    lib.frl_launch_count.argtypes = []
+    lib.frl_ppo_umma_ws_floats.argtypes = []
     lib.frl_adv_norm.restype = ci
     lib.frl_rainbow_learn.restype = ci
     lib.frl_rainbow_act.restype = ci

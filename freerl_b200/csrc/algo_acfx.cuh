@@ -1491,6 +1491,7 @@ int frl_launch_fx(const typename A::Args& a, cudaStream_t stream) {
   typename A::Args args = a;
   void* kargs[] = {(void*)&args};
   FRL_CUDA_OK(cudaLaunchCooperativeKernel((void*)frl_fx_kernel<A>, dim3(grid), dim3(FRL_NT), kargs, (size_t)smem_bytes, stream));
+  ++frl_launch_counter;
   return 0;
 }
 #else

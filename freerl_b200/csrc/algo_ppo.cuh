@@ -10,6 +10,7 @@
 
 #define FRL_NSEG (2 * FRL_MAX_LAYERS + 1)
 #define FRL_HALF_LOG_2PI 0.91893853320467274178f
+#include "algo_ppo_umma.cuh"
 
 // tensor (segment) id of parameter index p and that tensor's logical element count
 FRL_DEV int seg_of(const frl_net_t& n, int p, int* numel) {
@@ -126,20 +127,28 @@ FRL_DEV void net_bwd(Cta& c, const frl_net_t& N, int l0, bool ln, const float* X
 // (>= 1024 rows: twice the FMAs per staged weight and per barrier; chosen by frl_ppo_update when the tile fits in shared memory).
 // HM (compile time): the `tanh` switch of PPO_with_tricks.py — bit 0: actor, bit 1: critic hidden layers use tanh.  HM = 0 is the
 // kernel every other PPO-family class launches; the tanh instantiations exist for 8-row tiles only.
-template <int R, int HM = 0>
+// UM = 1 (GPU only): the tensor-core variant of algo_ppo_umma.cuh — one more stage in front (split the weights into hi / lo TF32
+// operands), stage "fwd/bwd" runs on tcgen05 over 128-row tiles, the reduce / clip / optimiser stages below are shared.
+template <int R, int HM = 0, int UM = 0>
 struct PpoAlgoT {
   typedef frl_ppo_args_t Args;
-  static const int NSTAGES = 5;
+  static const int NSTAGES = UM ? 6 : 5;
   FRL_SHD bool writes_params(int) { return true; }
   FRL_SHD bool stage_enabled(int, int, const Args&) { return true; }
-  FRL_SHD int wbuf_floats(const Args& a) { return (AcAlgo::max_layer_floats(a.net) + 31) & ~31; }
+  FRL_SHD int wbuf_floats(const Args& a) { return UM ? 32 : ((AcAlgo::max_layer_floats(a.net) + 31) & ~31); }      // UM: no weight stager, its ring lives in `user`
   FRL_SHD int user_floats(const Args& a) {
+#ifndef FRL_EMUL
+    if (UM) return UM_USER_FLOATS;
+#endif
     const int ldh = act_ld(a.net.L[0].out_pad), ip = a.net.L[0].in_pad, cip = a.net.L[3].in_pad, ap = a.net.L[2].out_pad;
     // the LayerNorm variant keeps the normalised copies of the input and of both hidden activations, per net
     const int ln_extra = a.layer_norm ? (ip + cip + 4 * ldh) : 0;
     return R * (ip + cip + ln_extra + 6 * ldh + 4 * ap + 8 + 4 * a.n_adv + 8 + 4 + 64) + 2 * FRL_NT + 64 + FRL_NSEG + 3;
   }
   FRL_SHD int grid(const Args& a, int max_ctas) {
+#ifndef FRL_EMUL
+    if (UM) return um_grid(a, max_ctas);
+#endif
     int tiles = (a.mb + R - 1) / R;
     return tiles < max_ctas ? tiles : max_ctas;
   }
@@ -150,10 +159,24 @@ struct PpoAlgoT {
   FRL_SDEV void stage(int s, int u, Cta& c, float* user, const Args& a) {
     const frl_net_t& N = a.net;
     const int ldh = act_ld(N.L[0].out_pad), ip = N.L[0].in_pad, ap = N.L[2].out_pad, nout = N.L[2].out;
+#ifndef FRL_EMUL
+    if (UM) {
+      // logical stages (the data-parallel split of stage_lo / stage_hi counts them): split + fwd/bwd = 0, then 1 .. 4 as below
+      const int logical = s == 0 ? 0 : s - 1;
+      if (a.stage_hi > 0 && (logical < a.stage_lo || logical >= a.stage_hi)) return;
+      if (s == 0) { um_split(c, a); return; }
+      if (s == 1) { ppo_umma_stage(c, user, a, u); return; }
+      s = s - 1;
+    } else
+#endif
     if (a.stage_hi > 0 && (s < a.stage_lo || s >= a.stage_hi)) return;
     const int rows = a.mb_rows[u];
     const int ntile = (rows + R - 1) / R;
+#ifndef FRL_EMUL
+    const int ncontrib = UM ? um_ncontrib(rows, c.ncta) : (ntile < c.ncta ? ntile : c.ncta);
+#else
     const int ncontrib = ntile < c.ncta ? ntile : c.ncta;
+#endif
     SmemBump sb; sb.p = user;
     const int cip = N.L[3].in_pad;
     const bool ln = a.layer_norm != 0;
@@ -352,15 +375,34 @@ struct PpoAlgoT {
       }
       FRL_SYNC();
     } else if (s == 1) {
-      // fixed-order cross-CTA reduction of the gradient partials -> net.g
-      FRL_PAR(t) {
-        for (int p = (c.cta * FRL_NT + t) * 4; p < N.n_p; p += c.ncta * FRL_NT * 4) {
-          float4 sgm = ld4(a.gpart + p);
-          for (int cc = 1; cc < ncontrib; ++cc) sgm = f4add(sgm, ld4(a.gpart + (size_t)cc * N.n_p + p));
-          st4(N.g + p, sgm);
+      // fixed-order cross-CTA reduction of the gradient partials -> net.g.  Eight threads share one float4 column: each folds a
+      // contiguous eighth of the partials (independent L2 loads in flight instead of one thread walking up to 148 of them), then
+      // the eight sub-sums are folded in lane order through shared memory — the association is fixed by (ncontrib, 8) alone.
+      const int nq = N.n_p >> 2, per = (ncontrib + 7) >> 3;
+      float* r4 = c.red;                                     // [FRL_NT] float4
+      for (int q0 = c.cta * (FRL_NT / 8); q0 < nq; q0 += c.ncta * (FRL_NT / 8)) {
+        FRL_PAR(t) {
+          const int sub = t & 7, q = q0 + (t >> 3);
+          float4 sgm = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (q < nq) {
+            const int c0 = sub * per, c1 = (c0 + per) < ncontrib ? (c0 + per) : ncontrib;
+            const float* src = a.gpart + (size_t)c0 * N.n_p + 4 * q;
+#pragma unroll 4
+            for (int cc = c0; cc < c1; ++cc, src += N.n_p) sgm = f4add(sgm, ld4(src));
+          }
+          st4(r4 + 4 * t, sgm);
         }
+        FRL_SYNC();
+        FRL_PAR(t) {
+          const int q = q0 + (t >> 3);
+          if ((t & 7) == 0 && q < nq) {
+            float4 sgm = ld4(r4 + 4 * t);
+            for (int l = 1; l < 8; ++l) sgm = f4add(sgm, ld4(r4 + 4 * (t + l)));
+            st4(N.g + 4 * q, sgm);
+          }
+        }
+        FRL_SYNC();
       }
-      FRL_SYNC();
     } else if (s == 2) {
       // (data-parallel: net.g now holds the all-reduced SUM over ranks) scale, then separate actor / critic sum-of-squares
       const float gs = a.grad_scale > 0.f ? a.grad_scale : 1.f;

@@ -1,0 +1,590 @@
+// Large-minibatch PPO / MAPPO forward + backward on the 5th-generation tensor cores (tcgen05.mma kind::tf32, 3xTF32 error
+// compensation, fp32 accumulators in TMEM) — stage "fwd/bwd" of frl_ppo_update when a minibatch has >= 1024 rows and both
+// networks are in -> 128 -> 128 -> out MLPs (C3 PPO LunarLander: 8192-row minibatches; C5 MAPPO: 131 072-row full batches).
+//   PPO.learn minibatch loop   PPO_file/PPO.py:245-283     Agent.update_ac_   PPO_file/PPO.py:145-152
+//   MAPPO.learn                MAPPO_file/MAPPO.py:392-436 (LayerNorm nets: MAPPO.py:127-218)
+//
+// Work split: the first half of the grid owns the actor, the second half the critic; a CTA walks 128-row tiles of the
+// minibatch.  Per tile ("phase A") the activations never touch shared memory:
+//     x (registers) -> TMEM (hi | lo columns) --MMA(W1)--> TMEM acc --tcgen05.ld, +b, ReLU [, LayerNorm]--> TMEM (hi | lo) --MMA(W2)--> ...
+// the A operand of every forward / backward-dX GEMM is read from TMEM, the B operand (pre-split hi / lo weights in UMMA
+// layout Q, written once per update by the split stage) streams through a 4 x 32 KB shared-memory ring of bulk copies that
+// runs one GEMM ahead of the epilogues.  The epilogues also leave hi / lo copies of x, h1, h2 and of the three dZ in a
+// per-CTA global scratch (L2-resident, UMMA layout S); "phase B" streams them back in 32-row chunks and forms
+//     dW2 += dZ2^T h1 (kept in TMEM across all tiles of the CTA),  dW1 += dZ1^T x,  dW3^T += h2^T dZ3,  db1 / db2 = dZ^T 1
+// with MN-major operands.  One gradient partial per (net, CTA) goes to gpart; the reduce / clip / optimiser stages of
+// algo_ppo.cuh are unchanged.  Algorithmic bytes per 128-row tile and net: ~0.3 MB of weights + ~0.6 MB of scratch written
+// and read back, all L2 hits; HBM sees the gathered rollout rows only.
+#pragma once
+#ifndef FRL_EMUL
+#include "umma.cuh"
+
+#define UM_SLOT_F 8192                  // floats per ring slot: hi 16 KB | lo 16 KB
+#define UM_WS_LAYER 65536               // split-weight block per layer: fwd hi | fwd lo | bwd hi | bwd lo, 16384 floats each
+#define UM_WS_CTA 155648                // per-CTA activation scratch (floats): X 2x8192, H1 H2 DZ1 DZ2 2x16384 each, DZ3 2x4096
+#define UM_USER_FLOATS 47616            // shared memory the fwd/bwd stage carves from `user` (incl. 1 KB alignment slack)
+
+FRL_HD int um_pad16(int x) { return (x + 15) & ~15; }
+FRL_HD int um_pad32(int x) { return (x + 31) & ~31; }
+
+// host + device: can this update take the tensor-core path?
+FRL_HD bool um_eligible(const frl_ppo_args_t& a) {
+  if (!a.umma_ws || a.mb < 1024 || a.hidden_tanh || a.layer_norm || a.net.n_layers != 6) return false;
+  for (int r = 0; r < 2; ++r) {
+    const frl_layer_t &L0 = a.net.L[3 * r], &L1 = a.net.L[3 * r + 1], &L2 = a.net.L[3 * r + 2];
+    if (L0.out != 128 || L1.in != 128 || L1.out != 128 || L2.in != 128 || L0.in > 64 || L2.out > 16) return false;
+    if (L1.in_pad != 128 || L2.in_pad != 128) return false;
+  }
+  return a.n_adv <= 16 && a.act_cols <= 16 && a.logp_cols <= 16;
+}
+FRL_HD int um_grid(const frl_ppo_args_t& a, int max_ctas) {
+  const int want = 2 * ((a.mb + 127) / 128), cap = max_ctas & ~1;
+  return want < cap ? want : cap;
+}
+// gradient partials (and loss partials) that stage "reduce" has to sum for a minibatch of `rows` rows
+FRL_HD int um_ncontrib(int rows, int ncta) {
+  const int ntile = (rows + 127) / 128, nper = ncta >> 1;
+  return ntile < nper ? ntile : nper;
+}
+
+// ---- stage "split": fp32 weights -> hi / lo TF32 pairs in UMMA layout Q, forward (W[n][k]: rows n, K = k) and backward-dX
+// (W^T[k][n]: rows k, K = n) operands of every layer -------------------------------------------------------------------
+__device__ __noinline__ void um_split(const Cta& c, const frl_ppo_args_t& a) {
+  const frl_net_t& N = a.net;
+  const int tid = (int)threadIdx.x;
+  for (int li = 0; li < 6; ++li) {
+    const frl_layer_t& L = N.L[li];
+    const int j = li % 3;
+    float* ws = a.umma_ws + (size_t)li * UM_WS_LAYER;
+    const int Rf = j == 2 ? 16 : 128, Cf = j == 0 ? um_pad16(L.in) : 128;
+    for (int e = c.cta * FRL_NT + tid; e < Rf * Cf; e += c.ncta * FRL_NT) {
+      const int n = e / Cf, k = e % Cf;
+      const float x = (n < L.out && k < L.in) ? N.p[L.w_off + n * L.in_pad + k] : 0.f;
+      const float hi = um_hi(x);
+      const int o = um_q_off(n, k, Rf);
+      ws[o] = hi;
+      ws[16384 + o] = x - hi;
+    }
+    if (j != 0) {
+      const int Cb = j == 2 ? 16 : 128;            // rows k = 128 input features, K = n (output features, padded)
+      for (int e = c.cta * FRL_NT + tid; e < 128 * Cb; e += c.ncta * FRL_NT) {
+        const int n = e / 128, k = e % 128;
+        const float x = (n < L.out && k < L.in) ? N.p[L.w_off + n * L.in_pad + k] : 0.f;
+        const float hi = um_hi(x);
+        const int o = um_q_off(k, n, 128);
+        ws[32768 + o] = hi;
+        ws[49152 + o] = x - hi;
+      }
+    }
+  }
+}
+
+// 16 consecutive columns of row `r` -> layout S scratch (two 8-float groups, float4 stores)
+UM_DEV void um_s_store16(float* bh, float* bl, int r, int c0, int C, const float* hi, const float* lo) {
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const int o = um_s_off(r, c0 + 8 * g, C);
+    st4(bh + o, make_float4(hi[8 * g], hi[8 * g + 1], hi[8 * g + 2], hi[8 * g + 3]));
+    st4(bh + o + 4, make_float4(hi[8 * g + 4], hi[8 * g + 5], hi[8 * g + 6], hi[8 * g + 7]));
+    st4(bl + o, make_float4(lo[8 * g], lo[8 * g + 1], lo[8 * g + 2], lo[8 * g + 3]));
+    st4(bl + o + 4, make_float4(lo[8 * g + 4], lo[8 * g + 5], lo[8 * g + 6], lo[8 * g + 7]));
+  }
+}
+
+// ring + barriers, driven by thread 0 only
+struct UmPipe {
+  float* ring;
+  uint64_t *full, *empty, *acc;
+  uint32_t tm;
+  uint32_t head, tail;
+};
+UM_DEV void um_fill(UmPipe& p, const float* hi, const float* lo, uint32_t bytes) {
+  const uint32_t s = p.head & 3u, use = p.head >> 2;
+  if (use > 0) um_mbar_wait(&p.empty[s], (use - 1) & 1u);
+  um_mbar_expect_tx(&p.full[s], lo ? 2 * bytes : bytes);
+  um_bulk_g2s(p.ring + s * UM_SLOT_F, hi, bytes, &p.full[s]);
+  if (lo) um_bulk_g2s(p.ring + s * UM_SLOT_F + 4096, lo, bytes, &p.full[s]);
+  p.head++;
+}
+// D[128 x R] (TMEM column dcol) (+)= A (TMEM hi at column 128 + acol, lo at 256 + acol; kc K-columns) . B (next ring slot, layout Q with R rows)
+UM_DEV void um_consume_ts(UmPipe& p, uint32_t dcol, uint32_t acol, int R, int kc, bool first) {
+  const uint32_t s = p.tail & 3u, use = p.tail >> 2;
+  um_mbar_wait(&p.full[s], use & 1u);
+  um_fence_after();
+  const uint32_t sb = um_smem_u32(p.ring + s * UM_SLOT_F);
+  const uint64_t bh = um_desc_q(sb, R), bl = um_desc_q(sb + 16384u, R);
+  const uint32_t idesc = um_idesc_tf32(128, R, 0, 0);
+  for (int ks = 0; ks < kc / 8; ++ks) {
+    const uint64_t adv = (uint64_t)((uint32_t)(ks * 32 * R) >> 4);
+    um_mma_ts(p.tm + dcol, p.tm + 256 + acol + ks * 8, bh + adv, idesc, (first && ks == 0) ? 0u : 1u);
+    um_mma_ts(p.tm + dcol, p.tm + 128 + acol + ks * 8, bl + adv, idesc, 1u);
+    um_mma_ts(p.tm + dcol, p.tm + 128 + acol + ks * 8, bh + adv, idesc, 1u);
+  }
+  um_commit(&p.empty[s]);
+  p.tail++;
+}
+// one 32-row chunk of a dW GEMM: A = ring slot (layout S, CA columns, M = 128 of them), B = next slot (layout S, CB columns,
+// first NB used) -> D[128 x NB] at TMEM column dcol; optionally also D1[128 x 16] at column ocol = A^T . ones (bias gradient)
+UM_DEV void um_consume_ss(UmPipe& p, uint32_t dcol, int CA, int CB, int NB, bool first, int ocol, bool first_o, uint32_t ones_addr) {
+  const uint32_t sa = p.tail & 3u, ua = p.tail >> 2, sb_ = (p.tail + 1) & 3u, ub = (p.tail + 1) >> 2;
+  um_mbar_wait(&p.full[sa], ua & 1u);
+  um_mbar_wait(&p.full[sb_], ub & 1u);
+  um_fence_after();
+  const uint32_t aa = um_smem_u32(p.ring + sa * UM_SLOT_F), ba = um_smem_u32(p.ring + sb_ * UM_SLOT_F);
+  const uint64_t ah = um_desc_s(aa, CA), al = um_desc_s(aa + 16384u, CA), bh = um_desc_s(ba, CB), bl = um_desc_s(ba + 16384u, CB);
+  const uint64_t on = um_desc_s(ones_addr, 32);
+  const uint32_t idesc = um_idesc_tf32(128, NB, 1, 1), idesc1 = um_idesc_tf32(128, 16, 1, 1);
+  for (int ks = 0; ks < 4; ++ks) {
+    const uint64_t aadv = (uint64_t)((uint32_t)(ks * 32 * CA) >> 4), badv = (uint64_t)((uint32_t)(ks * 32 * CB) >> 4);
+    const uint32_t acc0 = (first && ks == 0) ? 0u : 1u;
+    um_mma_ss(p.tm + dcol, al + aadv, bh + badv, idesc, acc0);
+    um_mma_ss(p.tm + dcol, ah + aadv, bl + badv, idesc, 1u);
+    um_mma_ss(p.tm + dcol, ah + aadv, bh + badv, idesc, 1u);
+    if (ocol >= 0) {
+      const uint64_t oadv = (uint64_t)((uint32_t)(ks * 32 * 32) >> 4);
+      um_mma_ss(p.tm + ocol, al + aadv, on + oadv, idesc1, (first_o && ks == 0) ? 0u : 1u);
+      um_mma_ss(p.tm + ocol, ah + aadv, on + oadv, idesc1, 1u);
+    }
+  }
+  um_commit(&p.empty[sa]);
+  um_commit(&p.empty[sb_]);
+  p.tail += 2;
+}
+
+// ---- stage "fwd/bwd" -----------------------------------------------------------------------------------------------
+__device__ __noinline__ void ppo_umma_stage(Cta& c, float* user, const frl_ppo_args_t& a, int u) {
+  const frl_net_t& N = a.net;
+  const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31, q = warp & 3, hh = warp >> 2;
+  const int row = q * 32 + lane;
+  const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+  const int rows = a.mb_rows[u];
+  const int ntile = (rows + 127) / 128, nper = c.ncta >> 1;
+  const int role = c.cta >= nper ? 1 : 0;                  // 0 = actor CTA, 1 = critic CTA
+  const int ci = role ? c.cta - nper : c.cta;
+  if (ci >= um_ncontrib(rows, c.ncta) || c.cta >= 2 * nper) return;
+  const int l0 = 3 * role;
+  const frl_layer_t &L0 = N.L[l0], &L1 = N.L[l0 + 1], &L2 = N.L[l0 + 2];
+  const int in = L0.in, nout = L2.out;
+  const int K0 = um_pad16(in), Cx = um_pad32(in);
+
+  float* ring = (float*)(((uintptr_t)user + 1023) & ~(uintptr_t)1023);
+  float* ones = ring + 4 * UM_SLOT_F;          // [32 x 32] layout S, column 0 = 1
+  float* accW1 = ones + 1024;                  // [64][128]  dW1[n][k] at [k][n]
+  float* accW3 = accW1 + 64 * 128;             // [16][128]  dW3[n][k] at [n][k]
+  float* accB = accW3 + 16 * 128;              // [2][128]   db1 | db2
+  float* accX = accB + 256;                    // [32]       db3[16] | dlog_std[16]
+  float* bias = accX + 32;                     // [3][128]
+  float* cs = bias + 384;                      // [128][17] column-sum scratch
+  float* red = cs + 128 * 17;                  // [256]
+  uint64_t* bars = (uint64_t*)(red + 256);     // full[4] | empty[4] | acc
+  uint32_t* tslot = (uint32_t*)(bars + 9);
+
+  for (int i = tid; i < 64 * 128 + 16 * 128 + 256 + 32; i += FRL_NT) accW1[i] = 0.f;
+  for (int i = tid; i < 1024; i += FRL_NT) ones[i] = 0.f;
+  for (int i = tid; i < 384; i += FRL_NT) {
+    const frl_layer_t& L = N.L[l0 + i / 128];
+    bias[i] = (i % 128) < L.out ? N.p[L.b_off + (i % 128)] : 0.f;
+  }
+  __syncthreads();
+  if (tid < 32) ones[um_s_off(tid, 0, 32)] = 1.f;
+  if (tid == 0) {
+    for (int i = 0; i < 9; ++i) um_mbar_init(&bars[i], 1);
+    um_fence_mbar_init();
+  }
+  um_fence_proxy_async();
+  if (warp == 0) um_tmem_alloc<512>(tslot);
+  um_fence_before();
+  __syncthreads();
+  um_fence_after();
+
+  stamp(c, 300);
+  UmPipe p;
+  p.ring = ring; p.full = bars; p.empty = bars + 4; p.acc = bars + 8; p.tm = *tslot; p.head = p.tail = 0;
+  const uint32_t tm = p.tm;
+  uint32_t accn = 0;                           // accumulator-barrier uses so far (all threads keep the count)
+  const uint32_t ones_addr = um_smem_u32(ones);
+
+  const float* wsl = a.umma_ws;
+  float* act = a.umma_ws + (size_t)6 * UM_WS_LAYER + (size_t)c.cta * UM_WS_CTA;
+  float *Xh = act, *Xl = act + 8192, *H1h = act + 16384, *H1l = act + 32768, *H2h = act + 49152, *H2l = act + 65536;
+  float *D1h = act + 81920, *D1l = act + 98304, *D2h = act + 114688, *D2l = act + 131072, *D3h = act + 147456, *D3l = act + 151552;
+#define UM_W(li, w) (wsl + (size_t)(li) * UM_WS_LAYER + (size_t)(w) * 16384)
+
+  float la = 0.f, lc = 0.f, le = 0.f;
+  const float inv_rows = 1.0f / (float)rows, inv_rn = 1.0f / (float)(rows * a.n_adv);
+  int it = 0;
+  for (int tile = ci; tile < ntile; tile += nper, ++it) {
+    const int row0 = tile * 128;
+    const int nvalid = (rows - row0) < 128 ? (rows - row0) : 128;
+    const bool valid = row < nvalid;
+    const int64_t gi = valid ? a.indices[(size_t)u * a.mb + row0 + row] : 0;
+    if (tid == 0)
+      for (int c0 = 0; c0 < K0; c0 += 32) {
+        const int kc = (K0 - c0) < 32 ? (K0 - c0) : 32;
+        um_fill(p, UM_W(l0, 0) + c0 * 128, UM_W(l0, 1) + c0 * 128, (uint32_t)kc * 512u);
+      }
+    // ---- inputs: x -> TMEM A columns + scratch X ----
+    if (hh == 0) {
+      const float* src = (role && a.critic_obs) ? a.critic_obs + (size_t)gi * a.critic_obs_dim : a.obs + (size_t)gi * a.obs_dim;
+      for (int c0 = 0; c0 < K0; c0 += 16) {
+        float hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float x = (valid && c0 + i < in) ? src[c0 + i] : 0.f;
+          hi[i] = um_hi(x);
+          lo[i] = x - hi[i];
+        }
+        um_st16(tm + lane_base + 128 + c0, hi);
+        um_st16(tm + lane_base + 256 + c0, lo);
+        um_s_store16(Xh, Xl, row, c0, Cx, hi, lo);
+      }
+    }
+    um_wait_st();
+    um_fence_before();
+    __syncthreads();
+    stamp(c, 301);
+    // ---- layer 1: acc = x W1^T ----
+    if (tid == 0) {
+      um_fence_after();
+      for (int c0 = 0; c0 < K0; c0 += 32) um_consume_ts(p, 0, c0, 128, (K0 - c0) < 32 ? (K0 - c0) : 32, c0 == 0);
+      um_commit(p.acc);
+    }
+    um_mbar_wait(p.acc, accn & 1u); ++accn;
+    um_fence_after();
+    if (tid == 0)
+      for (int c0 = 0; c0 < 128; c0 += 32) um_fill(p, UM_W(l0 + 1, 0) + c0 * 128, UM_W(l0 + 1, 1) + c0 * 128, 16384u);
+    uint64_t mask1 = 0, mask2 = 0;
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      const int c0 = hh * 64 + j * 16;
+      float v[16], hi[16], lo[16];
+      um_ld16(tm + lane_base + c0, v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float x = v[i] + bias[c0 + i];
+        if (x > 0.f) mask1 |= 1ull << (j * 16 + i); else x = 0.f;
+        hi[i] = um_hi(x);
+        lo[i] = x - hi[i];
+      }
+      um_st16(tm + lane_base + 128 + c0, hi);
+      um_st16(tm + lane_base + 256 + c0, lo);
+      um_s_store16(H1h, H1l, row, c0, 128, hi, lo);
+    }
+    um_wait_st();
+    um_fence_before();
+    __syncthreads();
+    stamp(c, 302);
+    // ---- layer 2: acc = h1 W2^T ----
+    if (tid == 0) {
+      um_fence_after();
+      for (int c0 = 0; c0 < 128; c0 += 32) um_consume_ts(p, 0, c0, 128, 32, c0 == 0);
+      um_commit(p.acc);
+    }
+    um_mbar_wait(p.acc, accn & 1u); ++accn;
+    um_fence_after();
+    if (tid == 0) um_fill(p, UM_W(l0 + 2, 0), UM_W(l0 + 2, 1), 8192u);          // W3 forward: [16 x 128] layout Q
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      const int c0 = hh * 64 + j * 16;
+      float v[16], hi[16], lo[16];
+      um_ld16(tm + lane_base + c0, v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float x = v[i] + bias[128 + c0 + i];
+        if (x > 0.f) mask2 |= 1ull << (j * 16 + i); else x = 0.f;
+        hi[i] = um_hi(x);
+        lo[i] = x - hi[i];
+      }
+      um_st16(tm + lane_base + 128 + c0, hi);
+      um_st16(tm + lane_base + 256 + c0, lo);
+      um_s_store16(H2h, H2l, row, c0, 128, hi, lo);
+    }
+    um_wait_st();
+    um_fence_before();
+    __syncthreads();
+    stamp(c, 303);
+    // ---- layer 3: acc[:, 0:16] = h2 W3^T ----
+    if (tid == 0) {
+      um_fence_after();
+      um_consume_ts(p, 0, 0, 16, 128, true);
+      um_commit(p.acc);
+    }
+    um_mbar_wait(p.acc, accn & 1u); ++accn;
+    um_fence_after();
+    if (tid == 0) um_fill(p, UM_W(l0 + 2, 2), UM_W(l0 + 2, 3), 8192u);          // W3 backward: [128 x 16] layout Q
+    // ---- heads: losses and dL/d(output) per row (PPO.py:256-279) ----
+    float lsg[16];                             // d/dlog_std through the log-prob, per action dim (continuous actor)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) lsg[i] = 0.f;
+    if (hh == 0) {
+      float v[16], dz[16];
+      um_ld16(tm + lane_base, v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { v[i] += bias[256 + i]; dz[i] = 0.f; }
+      if (valid && role == 0) {
+        float lp_now = 0.f, lp_old = 0.f, ent = 0.f, lse = 0.f;
+        int act = 0;
+        if (a.continuous) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < nout) {
+              const float mean = tanhf(v[j]);
+              const float ls = fminf(fmaxf(N.p[N.x_off + j], -20.f), 2.f);
+              const float sd = expf(ls);
+              const float diff = a.action[(size_t)gi * a.act_cols + j] - mean;
+              lp_now += -(diff * diff) / (2.f * (sd * sd)) - logf(sd) - FRL_HALF_LOG_2PI;
+              ent += 0.5f + FRL_HALF_LOG_2PI + logf(sd);
+            }
+          for (int j = 0; j < a.logp_cols; ++j) lp_old += a.logp_old[(size_t)gi * a.logp_cols + j];
+        } else {
+          float mx = v[0];
+#pragma unroll
+          for (int j = 1; j < 16; ++j) if (j < nout) mx = fmaxf(mx, v[j]);
+          float se_ = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) if (j < nout) se_ += expf(v[j] - mx);
+          lse = mx + logf(se_);
+          act = (int)a.action[(size_t)gi * a.act_cols];
+          float oa_act = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (j == act) oa_act = v[j];
+            if (j < nout) { const float lg = v[j] - lse; ent -= expf(lg) * lg; }
+          }
+          lp_now = oa_act - lse;
+          lp_old = a.logp_old[(size_t)gi * a.logp_cols];
+        }
+        const float ratio = expf(lp_now - lp_old);
+        float dlp = 0.f, surr = 0.f;
+        const float lo_ = 1.f - a.clip_param, hi_ = 1.f + a.clip_param;
+        const float rc = fminf(fmaxf(ratio, lo_), hi_);
+        for (int k = 0; k < a.n_adv; ++k) {
+          const float A = a.adv[(size_t)gi * a.n_adv + k];
+          const float s1 = ratio * A, s2 = rc * A;
+          surr += fminf(s1, s2);
+          const bool inside = ratio >= lo_ && ratio <= hi_;
+          if (inside || s1 < s2) dlp += -A * ratio * inv_rn;
+        }
+        la += -surr * inv_rn;
+        le += ent;
+        if (a.continuous) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < nout) {
+              const float mean = tanhf(v[j]);
+              const float lsr = N.p[N.x_off + j];
+              const float ls = fminf(fmaxf(lsr, -20.f), 2.f);
+              const float sd = expf(ls);
+              const float diff = a.action[(size_t)gi * a.act_cols + j] - mean;
+              dz[j] = dlp * (diff / (sd * sd)) * (1.f - mean * mean);
+              if (lsr >= -20.f && lsr <= 2.f) lsg[j] = dlp * ((diff * diff) / (sd * sd) - 1.f) - a.entropy_coef * inv_rows;
+            }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < nout) {
+              const float lg = v[j] - lse, pj = expf(lg);
+              float g = dlp * ((j == act ? 1.f : 0.f) - pj);
+              g += -a.entropy_coef * inv_rows * (-pj * (lg + ent));
+              dz[j] = g;
+            }
+        }
+      } else if (valid) {
+        float g = 0.f, l = 0.f;
+        for (int k = 0; k < a.n_adv; ++k) {
+          const float d = v[0] - a.v_target[(size_t)gi * a.n_adv + k];
+          if (a.value_loss == 1) {
+            const float e = -d, ae = fabsf(e), dl = a.huber_delta;
+            l += (ae <= dl) ? 0.5f * e * e : dl * (ae - 0.5f * dl);
+            g += -((ae <= dl) ? e : (e > 0.f ? dl : -dl)) * inv_rn;
+          } else {
+            g += 2.f * d * inv_rn;
+            l += d * d;
+          }
+        }
+        lc += l;
+        dz[0] = g;
+      }
+      float hi[16], lo[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { hi[i] = um_hi(dz[i]); lo[i] = dz[i] - hi[i]; cs[row * 17 + i] = dz[i]; }
+      um_st16(tm + lane_base + 128, hi);
+      um_st16(tm + lane_base + 256, lo);
+      um_s_store16(D3h, D3l, row, 0, 32, hi, lo);
+    }
+    um_wait_st();
+    um_fence_before();
+    __syncthreads();
+    stamp(c, 304);
+    // ---- dH2 = dZ3 W3 (K = 16) ----
+    if (tid == 0) {
+      um_fence_after();
+      um_consume_ts(p, 0, 0, 128, 16, true);
+      um_commit(p.acc);
+    }
+    if (tid < 16) {                            // db3: column sums of dZ3 in row order
+      float s = 0.f;
+      for (int r = 0; r < 128; ++r) s += cs[r * 17 + tid];
+      accX[tid] += s;
+    }
+    __syncthreads();
+    if (role == 0 && a.continuous) {
+      if (hh == 0) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) cs[row * 17 + i] = lsg[i];
+      }
+      __syncthreads();
+      if (tid < 16) {
+        float s = 0.f;
+        for (int r = 0; r < 128; ++r) s += cs[r * 17 + tid];
+        accX[16 + tid] += s;
+      }
+    }
+    um_mbar_wait(p.acc, accn & 1u); ++accn;
+    um_fence_after();
+    if (tid == 0)
+      for (int c0 = 0; c0 < 128; c0 += 32) um_fill(p, UM_W(l0 + 1, 2) + c0 * 128, UM_W(l0 + 1, 3) + c0 * 128, 16384u);
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      const int c0 = hh * 64 + j * 16;
+      float v[16], hi[16], lo[16];
+      um_ld16(tm + lane_base + c0, v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float x = ((mask2 >> (j * 16 + i)) & 1ull) ? v[i] : 0.f;
+        hi[i] = um_hi(x);
+        lo[i] = x - hi[i];
+      }
+      um_st16(tm + lane_base + 128 + c0, hi);
+      um_st16(tm + lane_base + 256 + c0, lo);
+      um_s_store16(D2h, D2l, row, c0, 128, hi, lo);
+    }
+    um_wait_st();
+    um_fence_before();
+    um_fence_proxy_async();
+    __syncthreads();
+    stamp(c, 305);
+    // ---- dH1 = dZ2 W2 ----
+    if (tid == 0) {
+      um_fence_after();
+      for (int c0 = 0; c0 < 128; c0 += 32) um_consume_ts(p, 0, c0, 128, 32, c0 == 0);
+      um_commit(p.acc);
+    }
+    um_mbar_wait(p.acc, accn & 1u); ++accn;
+    um_fence_after();
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      const int c0 = hh * 64 + j * 16;
+      float v[16], hi[16], lo[16];
+      um_ld16(tm + lane_base + c0, v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float x = ((mask1 >> (j * 16 + i)) & 1ull) ? v[i] : 0.f;
+        hi[i] = um_hi(x);
+        lo[i] = x - hi[i];
+      }
+      um_s_store16(D1h, D1l, row, c0, 128, hi, lo);
+    }
+    um_fence_before();
+    um_fence_proxy_async();                    // scratch written by the generic proxy -> bulk-copy (async proxy) reads
+    __syncthreads();
+    stamp(c, 306);
+    // ---- phase B: dW3^T = h2^T dZ3 | dW2 = dZ2^T h1, db2 | dW1 = dZ1^T x, db1   (12 steps of 32 rows, two slots each) ----
+    if (tid == 0) {
+      um_fence_after();
+      for (int st = 0; st <= 12; ++st) {
+        if (st < 12) {
+          const int g = st >> 2, j = st & 3;
+          const float *ah, *al, *bh, *bl;
+          uint32_t ab = 16384u, bb;
+          if (g == 0) { ah = H2h; al = H2l; bh = D3h + j * 1024; bl = D3l + j * 1024; bb = 4096u; }
+          else if (g == 1) { ah = D2h; al = D2l; bh = H1h + j * 4096; bl = H1l + j * 4096; bb = 16384u; }
+          else { ah = D1h; al = D1l; bh = Xh + j * 32 * Cx; bl = Xl + j * 32 * Cx; bb = (uint32_t)(128 * Cx); }
+          um_fill(p, ah + j * 4096, al + j * 4096, ab);
+          um_fill(p, bh, bl, bb);
+        }
+        if (st > 0) {
+          const int g = (st - 1) >> 2, j = (st - 1) & 3;
+          if (g == 0) um_consume_ss(p, 0, 128, 32, 16, j == 0, -1, false, ones_addr);
+          else if (g == 1) um_consume_ss(p, 384, 128, 128, 128, j == 0 && it == 0, 16, j == 0, ones_addr);
+          else um_consume_ss(p, 64, 128, Cx, K0, j == 0, 32, j == 0, ones_addr);
+        }
+      }
+      um_commit(p.acc);
+    }
+    um_mbar_wait(p.acc, accn & 1u); ++accn;
+    um_fence_after();
+    if (hh == 0) {
+      float v[16];
+      um_ld16(tm + lane_base, v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) accW3[i * 128 + row] += v[i];
+      um_ld16(tm + lane_base + 16, v);
+      accB[128 + row] += v[0];
+      um_ld16(tm + lane_base + 32, v);
+      accB[row] += v[0];
+      for (int c0 = 0; c0 < K0; c0 += 16) {
+        um_ld16(tm + lane_base + 64 + c0, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) accW1[(c0 + i) * 128 + row] += v[i];
+      }
+    }
+    um_fence_before();
+    __syncthreads();
+    stamp(c, 307);
+  }
+
+  // ---- gradient partial of this (net, CTA) -> gpart slot ci; padded entries are written as zeros ----
+  um_fence_after();
+  float* gp = a.gpart + (size_t)ci * N.n_p;
+#pragma unroll 1
+  for (int j = 0; j < 4; ++j) {
+    const int c0 = hh * 64 + j * 16;
+    float v[16];
+    um_ld16(tm + lane_base + 384 + c0, v);
+    if (row < L1.out_pad) {
+#pragma unroll
+      for (int i = 0; i < 16; i += 4)
+        st4(gp + L1.w_off + row * 128 + c0 + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+    }
+  }
+  for (int e = tid; e < L0.out_pad * L0.in_pad; e += FRL_NT) {
+    const int n = e / L0.in_pad, k = e % L0.in_pad;
+    gp[L0.w_off + e] = (n < L0.out && k < L0.in) ? accW1[k * 128 + n] : 0.f;
+  }
+  for (int e = tid; e < L2.out_pad * L2.in_pad; e += FRL_NT) {
+    const int n = e / L2.in_pad, k = e % L2.in_pad;
+    gp[L2.w_off + e] = (n < L2.out && k < L2.in) ? accW3[n * 128 + k] : 0.f;
+  }
+  if (tid < L0.out_pad) gp[L0.b_off + tid] = tid < L0.out ? accB[tid] : 0.f;
+  if (tid < L1.out_pad) gp[L1.b_off + tid] = tid < L1.out ? accB[128 + tid] : 0.f;
+  if (tid < L2.out_pad) gp[L2.b_off + tid] = tid < L2.out ? accX[tid] : 0.f;
+  if (role == 0 && a.continuous && tid < L2.out_pad) gp[N.x_off + tid] = tid < nout ? accX[16 + tid] : 0.f;
+  // loss partials, folded in thread order
+  __syncthreads();
+  red[tid] = role ? lc : la;
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f;
+    for (int i = 0; i < FRL_NT; ++i) s += red[i];
+    a.stats[ci * 8 + (role ? 1 : 0)] = s;
+  }
+  __syncthreads();
+  if (role == 0) {
+    red[tid] = le;
+    __syncthreads();
+    if (tid == 0) {
+      float s = 0.f;
+      for (int i = 0; i < FRL_NT; ++i) s += red[i];
+      a.stats[ci * 8 + 2] = s;
+    }
+  }
+  um_fence_before();
+  __syncthreads();
+  stamp(c, 308);
+  if (warp == 0) um_tmem_dealloc<512>(tm);
+  if (tid == 0)
+    for (int i = 0; i < 9; ++i) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(um_smem_u32(&bars[i])) : "memory");
+#undef UM_W
+}
+#endif  // !FRL_EMUL

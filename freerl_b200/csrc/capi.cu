@@ -26,7 +26,7 @@ extern "C" void frl_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 extern "C" const char* frl_last_error(void) { return g_err; }
-extern "C" int frl_abi_version(void) { return 6; }
+extern "C" int frl_abi_version(void) { return 7; }
 // sizeof() of the argument structs, so a binding can verify its mirror of the layout before the first call
 extern "C" int frl_struct_size(int which) {
   switch (which) {
@@ -58,6 +58,9 @@ int frl_device_max_ctas() {
 #else
 extern "C" int frl_is_emulation(void) { return 1; }
 #endif
+long long frl_launch_counter = 0;
+// kernels launched by the library since it was loaded (host-side count at the five launch sites; 0 forever = nothing ran on the GPU)
+extern "C" long long frl_launch_count(void) { return frl_launch_counter; }
 extern "C" int frl_device_sm_count(void) { return frl_device_max_ctas(); }
 extern "C" int frl_wt_ld(int out_pad) { return wt_ld_of(out_pad); }
 
@@ -98,6 +101,7 @@ static int frl_for(long n, const F& f, cudaStream_t s) {
   if (blocks > cap) blocks = cap;
   frl_for_kernel<F><<<(unsigned)blocks, 256, 0, s>>>(n, f);
   FRL_CUDA_OK(cudaGetLastError());
+  ++frl_launch_counter;
   return 0;
 }
 #else
@@ -123,13 +127,10 @@ template <class A>
 static int frl_launch_simple(const typename A::Args& a, int grid, int smem_floats, cudaStream_t s) {
   const int smem_bytes = smem_floats * 4;
   if (smem_bytes > 227 * 1024) { frl_set_error("tile of %d B does not fit in shared memory", smem_bytes); return -3; }
-  static int configured_bytes = 48 * 1024;
-  if (smem_bytes > configured_bytes) {
-    FRL_CUDA_OK(cudaFuncSetAttribute(frl_simple_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    configured_bytes = smem_bytes;
-  }
+  FRL_SMEM_OPT_IN(frl_simple_kernel<A>, smem_bytes, 48 * 1024);
   frl_simple_kernel<A><<<grid, FRL_NT, smem_bytes, s>>>(a);
   FRL_CUDA_OK(cudaGetLastError());
+  ++frl_launch_counter;
   return 0;
 }
 #else
@@ -660,6 +661,15 @@ extern "C" int frl_gae(const float* reward, const float* done, const float* adv_
 
 }
 
+// floats of frl_ppo_args_t.umma_ws: 6 split-weight blocks + one activation scratch per CTA of the largest grid
+extern "C" long long frl_ppo_umma_ws_floats(void) {
+#ifndef FRL_EMUL
+  return (long long)6 * UM_WS_LAYER + (long long)frl_device_max_ctas() * UM_WS_CTA;
+#else
+  return 0;
+#endif
+}
+
 extern "C" int frl_ppo_update(const frl_ppo_args_t* a, void* stream) {
   if (!a || a->mb <= 0 || a->n_updates <= 0 || !a->indices || !a->mb_rows || !a->gpart || !a->sumsq || !a->segcnt || !a->stats ||
       !a->out || a->n_adv < 1) {
@@ -677,6 +687,13 @@ extern "C" int frl_ppo_update(const frl_ppo_args_t* a, void* stream) {
     if (a->hidden_tanh & 2) return frl_launch<PpoAlgoT<8, 2> >(*a, (cudaStream_t)stream);
     return frl_launch<PpoAlgoT<8, 1> >(*a, (cudaStream_t)stream);
   }
+#ifndef FRL_EMUL
+  // tensor-core path (tcgen05, 128-row tiles) for large minibatches over in->128->128->out networks when the caller gave the scratch
+  if (um_eligible(*a)) {
+    if (((uintptr_t)a->umma_ws & 511) != 0) { frl_set_error("frl_ppo_update: umma_ws must be 512-B aligned"); return -1; }
+    return frl_launch<PpoAlgoT<8, 0, 1> >(*a, (cudaStream_t)stream);
+  }
+#endif
   // 16-row tiles for large minibatches when they fit in shared memory (checked with the launcher's own formula)
   if (a->mb >= 1024) {
     typedef PpoAlgoT<16> P16;

@@ -41,6 +41,20 @@ __global__ void __launch_bounds__(FRL_NT, 1) frl_persistent_kernel(const __grid_
 }
 
 int frl_device_max_ctas();   // SM count of the current device (1 CTA / SM for the persistent kernels)
+extern long long frl_launch_counter;       // kernels launched by this library so far (frl_launch_count(), read by bench.py)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: remember the opt-in per device ordinal
+#define FRL_SMEM_OPT_IN(kernel, smem_bytes, floor_bytes)                                                        \
+  do {                                                                                                          \
+    static int configured_bytes[64] = {0};                                                                      \
+    int dev_ = 0;                                                                                               \
+    FRL_CUDA_OK(cudaGetDevice(&dev_));                                                                          \
+    if (dev_ < 0 || dev_ >= 64) { frl_set_error("device ordinal %d out of range", dev_); return -3; }           \
+    if ((smem_bytes) > (floor_bytes) && (smem_bytes) > configured_bytes[dev_]) {                                \
+      FRL_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (smem_bytes)));     \
+      configured_bytes[dev_] = (smem_bytes);                                                                    \
+    }                                                                                                           \
+  } while (0)
 
 template <class A>
 int frl_launch(const typename A::Args& a, cudaStream_t stream) {
@@ -49,15 +63,18 @@ int frl_launch(const typename A::Args& a, cudaStream_t stream) {
     frl_set_error("kernel needs %d B of shared memory (> 227 KB)", smem_bytes);
     return -3;
   }
-  static int configured_bytes = 0;
-  if (smem_bytes > configured_bytes) {
-    FRL_CUDA_OK(cudaFuncSetAttribute(frl_persistent_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    configured_bytes = smem_bytes;
-  }
+  FRL_SMEM_OPT_IN(frl_persistent_kernel<A>, smem_bytes, 0);
   const int grid = A::grid(a, frl_device_max_ctas());
+  int per_sm = 0;      // a cooperative grid must be co-resident
+  FRL_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frl_persistent_kernel<A>, FRL_NT, (size_t)smem_bytes));
+  if (per_sm * frl_device_max_ctas() < grid) {
+    frl_set_error("cooperative launch of %d CTAs does not fit the device (%d per SM)", grid, per_sm);
+    return -3;
+  }
   typename A::Args args = a;
   void* kargs[] = {(void*)&args};
   FRL_CUDA_OK(cudaLaunchCooperativeKernel((void*)frl_persistent_kernel<A>, dim3(grid), dim3(FRL_NT), kargs, (size_t)smem_bytes, stream));
+  ++frl_launch_counter;
   return 0;
 }
 
@@ -73,14 +90,11 @@ __global__ void __launch_bounds__(FRL_NT, 1) frl_tile_kernel(const __grid_consta
 template <class A>
 int frl_launch_tiles(const typename A::Args& a, cudaStream_t stream) {
   const int smem_bytes = (cta_base_floats(A::wbuf_floats(a)) + A::user_floats(a)) * 4 + 64;
-  static int configured_bytes = 0;
-  if (smem_bytes > configured_bytes) {
-    FRL_CUDA_OK(cudaFuncSetAttribute(frl_tile_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    configured_bytes = smem_bytes;
-  }
+  FRL_SMEM_OPT_IN(frl_tile_kernel<A>, smem_bytes, 0);
   const int grid = A::grid(a, 1 << 30);
   frl_tile_kernel<A><<<grid, FRL_NT, smem_bytes, stream>>>(a);
   FRL_CUDA_OK(cudaGetLastError());
+  ++frl_launch_counter;
   return 0;
 }
 

@@ -79,11 +79,13 @@ UM_DEV void um_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" 
 UM_DEV void um_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 UM_DEV void um_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// one warp: allocate ncols (power of two >= 32) TMEM columns, base address -> *slot (shared memory)
-template <int NCOLS>
+// one warp: allocate ncols (power of two >= 32) TMEM columns, base address -> *slot (shared memory).  RELINQUISH = true gives up
+// the CTA's right to allocate again (lets another CTA of the SM allocate); a persistent kernel that allocates once per update
+// (one CTA per SM) must keep the permit.
+template <int NCOLS, bool RELINQUISH = false>
 UM_DEV void um_tmem_alloc(uint32_t* slot) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(um_smem_u32(slot)), "n"(NCOLS) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (RELINQUISH) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 }
 template <int NCOLS>
 UM_DEV void um_tmem_dealloc(uint32_t taddr) {

@@ -200,6 +200,9 @@ typedef struct {
   double lr_critic;         /* FRL_OPT_ADAM only: learning rate of the critic layers (separate actor / critic Adams of
                              * PPO_advance/PPO.py:118-119); 0 = use `lr` for both (merged optimiser) */
   int hidden_tanh;          /* bit 0: actor, bit 1: critic use tanh hidden activations (PPO_with_tricks.py:95,172; not with layer_norm) */
+  /* ---- tensor-core path (csrc/algo_ppo_umma.cuh): taken for minibatches of >= 1024 rows over in->128->128->out networks when
+   * umma_ws = dev scratch of frl_ppo_umma_ws_floats() floats (512-B aligned; split weights + per-CTA activation scratch) is given */
+  float* umma_ws;
 } frl_ppo_args_t;
 
 /* Rainbow (DQN_with_tricks.py): Categorical + Dueling + Noisy net.  The trainable block holds the torch tensors;
@@ -263,6 +266,8 @@ typedef struct {
 const char* frl_last_error(void);
 int frl_is_emulation(void);          /* 0 for the CUDA library (the only one the product path accepts) */
 int frl_device_sm_count(void);
+long long frl_launch_count(void);    /* kernels launched by the library since load (bench.py's gpu_launches) */
+long long frl_ppo_umma_ws_floats(void);   /* size of frl_ppo_args_t.umma_ws (0 from the test-only emulation) */
 int frl_wt_ld(int out_pad);          /* row stride (floats) of a transposed-mirror layer image with this padded width */
 int frl_abi_version(void);
 /* sizeof the argument structs as compiled: 0 frl_layer_t, 1 frl_net_t, 2 frl_replay_t, 3 frl_dqn_args_t, 4 frl_ac_args_t,

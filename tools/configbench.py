@@ -35,17 +35,15 @@ def timeit(fn, reps, warm=2):
     return e0.elapsed_time(e1) / reps
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--json", default=None)
-    args = ap.parse_args()
+def run(which=("C1", "C2", "C3", "C4", "C5"), log=print):
+    """Time the learn() of the named configurations; returns the list of row dicts (bench.py puts it under extra.configs)."""
     rows = []
     rng = np.random.default_rng(0)
 
     def rec(name, ms, updates, transitions, note):
         rows.append({"config": name, "ms_per_learn_call": ms, "updates_per_call": updates, "updates_per_sec": updates / ms * 1e3,
                      "us_per_update": ms * 1e3 / updates, "transitions_per_sec": transitions / ms * 1e3, "note": note})
-        print("%-34s %9.3f ms/call  %6d updates  %9.1f us/update  %10.0f updates/s  %s" % (name, ms, updates, ms * 1e3 / updates, updates / ms * 1e3, note))
+        log("%-34s %9.3f ms/call  %6d updates  %9.1f us/update  %10.0f updates/s  %s" % (name, ms, updates, ms * 1e3 / updates, updates / ms * 1e3, note))
 
     with contextlib.redirect_stdout(sys.stderr):
         from freerl_b200.DQN import DQN
@@ -54,6 +52,20 @@ def main():
         from freerl_b200.PPO import PPO
         from freerl_b200.SAC import SAC
 
+    if "C1" in which:
+        _c1(rec, rng, DQN)
+    if "C2" in which:
+        _c2(rec, rng, SAC)
+    if "C3" in which:
+        _c3(rec, rng, PPO)
+    if "C4" in which:
+        _c4(rec, rng, Rainbow)
+    if "C5" in which:
+        _c5(rec, rng, MAPPO)
+    return rows
+
+
+def _c1(rec, rng, DQN):
     # ---- C1: DQN CartPole dims ----
     with contextlib.redirect_stdout(sys.stderr):
         pol = DQN([4, 2], False, 1e-3, 1e6, dev, mode="fast")
@@ -62,6 +74,8 @@ def main():
     ms = timeit(lambda: pol.learn(256, 0.99, 0.01, n_updates=256), 5)
     rec("C1 DQN CartPole B=256", ms, 256, 256 * 256, "256 sequential learns per launch")
 
+
+def _c2(rec, rng, SAC):
     # ---- C2: SAC (the bench workload's kernel) ----
     with contextlib.redirect_stdout(sys.stderr):
         pol = SAC([17, 6], True, 1e-3, 1e-3, 1e6, dev, trick={}, mode="fast")
@@ -75,6 +89,8 @@ def main():
     rec("C2 SAC B=65536 (1 update/vec step)", ms, 1, 65536, "SURVEY 8d alternative: one big-batch update per vector step")
     del pol
 
+
+def _c3(rec, rng, PPO):
     # ---- C3: PPO 1024 envs ----
     T, N, mb, K = 128, 1024, 8192, 10
     with contextlib.redirect_stdout(sys.stderr):
@@ -97,6 +113,8 @@ def main():
     rec("C3 PPO critic(obs), critic(obs') + GAE", adv_ms, 1, T * N, "2 batched value inferences + frl_gae over [128, 1024]")
     del pol
 
+
+def _c4(rec, rng, Rainbow):
     # ---- C4: Rainbow ----
     trick = {"Double": True, "Dueling": True, "PER": True, "Noisy": True, "N_Step": True, "Categorical": True}
     with contextlib.redirect_stdout(sys.stderr):
@@ -110,6 +128,8 @@ def main():
     rec("C4 Rainbow add of 512 envs (n-step + PER)", add_ms, 1, 512, "host n-step fold + H2D + tree max + 512 ordered leaf updates")
     del pol
 
+
+def _c5(rec, rng, MAPPO):
     # ---- C5: MAPPO ----
     from oracle.make_golden_marl import MAPPO_TRICK          # the trick dict only (no reference code involved)
     H, E, K5 = 256, 512, 15
@@ -131,7 +151,14 @@ def main():
     ms = timeit(mappo_learn, 2, warm=1)
     rec("C5 MAPPO 3 agents, 512 envs x 256, K 15", ms, 3 * K5, H * E, "joint GAE + adv-norm + 15 full-batch updates per agent (minibatch = horizon x envs)")
 
-    out = {"device": torch.cuda.get_device_name(0), "rows": rows}
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--json", default=None)
+    ap.add_argument("--only", default="C1,C2,C3,C4,C5")
+    args = ap.parse_args()
+    rows = run(tuple(args.only.split(",")))
+    out = {"device": torch.cuda.get_device_name(0), "rows": rows, "umma": not os.environ.get("FREERL_B200_NO_UMMA")}
     if args.json:
         json.dump(out, open(args.json, "w"), indent=1)
 
