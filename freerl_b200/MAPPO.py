@@ -160,7 +160,19 @@ class MAPPO:
         adv = torch.stack(advs, dim=1).contiguous()           # [M, N]
         v_target = torch.stack(vts, dim=1).contiguous()
         if self.trick['adv_norm']:
-            _lib.check(_lib.lib().frl_adv_norm(_lib.ptr(adv), adv.numel(), 1e-8, _lib.ptr(adv), _lib.stream_ptr(self.device)), "frl_adv_norm")
+            dp = getattr(self, "_dp", None)
+            if dp is not None and dp[2] > 1:
+                # data parallel: the reference normalises over the WHOLE rollout (MAPPO.py:386-388), i.e. over the union of the ranks'
+                # shards — all-reduce (sum, sum of squares, count) in float64, then normalise with the global mean / unbiased std
+                dist, group, _ = dp
+                a64 = adv.double()
+                st = torch.stack([a64.sum(), (a64 * a64).sum(), torch.tensor(float(adv.numel()), dtype=torch.float64, device=self.device)])
+                dist.all_reduce(st, group=group)
+                n, mean = st[2], st[0] / st[2]
+                std = ((st[1] - n * mean * mean) / (n - 1)).clamp_min(0.0).sqrt()
+                adv = ((a64 - mean) / (std + 1e-8)).float().contiguous()
+            else:
+                _lib.check(_lib.lib().frl_adv_norm(_lib.ptr(adv), adv.numel(), 1e-8, _lib.ptr(adv), _lib.stream_ptr(self.device)), "frl_adv_norm")
         return adv, v_target, joint
 
     # optimiser of MAPPO.update_ac (MAPPO.py:230-247): ONE Adam(eps 1e-5) over actor + critic, lr = actor_lr, no clip_grad_norm_
@@ -229,13 +241,7 @@ class MAPPO:
         for buffer in self.buffers.values():
             buffer.clear()
 
-    def enable_data_parallel(self, group=None):
-        """see PPO.enable_data_parallel; additionally the joint advantage normalisation all-reduces (sum, sum of squares, count)."""
-        import torch.distributed as dist
-        self._dp = (dist, group, dist.get_world_size(group))
-        for ag in self.agents.values():
-            dist.broadcast(ag._net.p, src=0, group=group)
-            ag._net.sync_mirror()
+    enable_data_parallel = __import__("freerl_b200.PPO", fromlist=["PPO"]).PPO.enable_data_parallel      # one exchange block for all agents
 
     _launch_update = __import__("freerl_b200.PPO", fromlist=["PPO"]).PPO._launch_update
 

@@ -206,17 +206,27 @@ class PPO:
         self._keep = (idx, rows, adv, v_target)
 
     # ---- data parallel (one process per GPU) ---------------------------------------------------------
-    def enable_data_parallel(self, group=None):
-        """Synchronous data-parallel training over ``torch.distributed`` (NCCL over NVLink on the GPU box): every rank
-        holds its own env shard / rollout and an identical replica of the networks; each minibatch is the union of the
-        ranks' equal-size sub-minibatches.  Per optimiser step ONE flat gradient buffer (net.g, 36 k floats) is
-        all-reduced between the in-kernel cross-CTA reduction and the clip + (cautious-)AdamW stages, then scaled by
-        1/world (mean of equal-size means) so all replicas apply bit-identical updates."""
+    def enable_data_parallel(self, group=None, peer=None):
+        """Synchronous data-parallel training over ``torch.distributed`` (one process per GPU): every rank holds its own env shard /
+        rollout and an identical replica of the networks; each minibatch is the union of the ranks' equal-size sub-minibatches.
+        Per optimiser step the flat gradient (net.g, 36 k floats) is summed over the ranks between the in-kernel cross-CTA
+        reduction and the clip + (cautious-)AdamW stages and scaled by 1/world, so all replicas apply bit-identical updates
+        (SURVEY §8e).  ``peer=True`` (default on CUDA): the sum runs INSIDE the one persistent launch over peer-mapped NVLink
+        memory (``_common.DpPeers`` / the exchange stage of csrc/algo_ppo.cuh) — no NCCL call per step; ``peer=False`` (and the
+        test-only host emulation): the host splits every step into launch [0,2) -> ``dist.all_reduce(net.g)`` -> launch [2,5)."""
         import torch.distributed as dist
-        self._dp = (dist, group, dist.get_world_size(group))
-        for t in (self.agent._net.p,):
-            dist.broadcast(t, src=0, group=group)
-        self.agent._net.sync_mirror()
+        world = dist.get_world_size(group)
+        self._dp = (dist, group, world)
+        nets = [ag._net for ag in self.agents.values()] if hasattr(self, "agents") else [self.agent._net]
+        for net in nets:
+            dist.broadcast(net.p, src=0, group=group)
+            net.sync_mirror()
+        if peer is None:
+            peer = (self.device.type == "cuda" and world > 1 and not _lib.lib().frl_is_emulation()
+                    and os.environ.get("FREERL_B200_DP_PEER", "1") != "0")
+        self._dp_peers = _common.DpPeers(dist, group, self.device, max(n.n_p for n in nets)) if (peer and world > 1) else None
+        self.dp_collective = ("in-kernel peer-memory sum (NVLink P2P loads, flag hand-off), one launch per learn" if self._dp_peers
+                              else "dist.all_reduce(net.g) between two launches per optimiser step")
 
     def _launch_update(self, a, net, n_updates):
         dp = getattr(self, "_dp", None)
@@ -224,9 +234,14 @@ class PPO:
             _lib.check(_lib.lib().frl_ppo_update(ctypes.byref(a), _lib.stream_ptr(self.device)), "frl_ppo_update")
             return
         dist, group, world = dp
+        a.grad_scale = 1.0 / world
+        peers = getattr(self, "_dp_peers", None)
+        if peers is not None:                       # every optimiser step of the learn in ONE launch, gradients summed over NVLink
+            peers.fill(a, net.n_p, n_updates)
+            _lib.check(_lib.lib().frl_ppo_update(ctypes.byref(a), _lib.stream_ptr(self.device)), "frl_ppo_update")
+            return
         idx0, rows0, out0, step0 = a.indices, a.mb_rows, a.out, a.step0
         a.n_updates = 1
-        a.grad_scale = 1.0 / world
         for u in range(n_updates):
             a.indices = idx0 + u * a.mb * 8
             a.mb_rows = rows0 + u * 4

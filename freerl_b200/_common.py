@@ -138,3 +138,46 @@ def umma_ws_ptr(device, minibatch_size):
     if key not in _UMMA_WS:
         _UMMA_WS[key] = torch.zeros(n, dtype=torch.float32, device=device)
     return _UMMA_WS[key].data_ptr()
+
+
+class DpPeers:
+    """Peer-memory blocks of the in-kernel data-parallel gradient exchange (``frl_dp_peers_t``, include/freerl_b200.h): every rank
+    allocates ``[flags 256 B | g: 2 x n_floats]`` with ``frl_dp_alloc``, the CUDA IPC handles travel through ``all_gather_object`` and
+    each rank maps the others' blocks (``frl_dp_open``).  One block serves every network of a policy (sized for the largest): the
+    exchanges of successive launches are numbered by one epoch counter that all ranks advance identically."""
+
+    def __init__(self, dist, group, device, n_floats):
+        import ctypes
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > _lib.FRL_DP_MAX_RANKS:
+            raise ValueError("peer-memory data parallel supports up to %d ranks per node" % _lib.FRL_DP_MAX_RANKS)
+        self.n_floats = int(n_floats)
+        self.bytes = 256 + 2 * self.n_floats * 4
+        lib = _lib.lib()
+        ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+        with torch.cuda.device(device):
+            _lib.check(lib.frl_dp_alloc(self.bytes, ctypes.byref(ptr), handle), "frl_dp_alloc")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, (bytes(handle.raw), self.bytes), group=group)
+            self.base = [0] * self.world
+            for r, (h, nbytes) in enumerate(handles):
+                if nbytes != self.bytes:
+                    raise RuntimeError("rank %d allocated a different exchange block" % r)
+                if r == self.rank:
+                    self.base[r] = ptr.value
+                else:
+                    q = ctypes.c_void_p()
+                    _lib.check(lib.frl_dp_open(h, ctypes.byref(q)), "frl_dp_open")
+                    self.base[r] = q.value
+        self.epoch = 0
+        dist.barrier(group=group)
+
+    def fill(self, a, n_floats, n_updates):
+        """Point ``a.dp`` (a ``PpoArgs``) at the blocks for a launch of ``n_updates`` exchanges of ``n_floats`` gradients each."""
+        if n_floats > self.n_floats:
+            raise ValueError("network larger than the exchange block")
+        for r in range(self.world):
+            a.dp.flags[r] = self.base[r]
+            a.dp.g[r] = self.base[r] + 256
+        a.dp.rank, a.dp.world, a.dp.epoch0 = self.rank, self.world, self.epoch & 0xFFFFFFFF
+        self.epoch += n_updates

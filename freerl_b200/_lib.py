@@ -12,7 +12,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 FRL_MAX_LAYERS = 6
 FRL_MAX_AGENTS = 6
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 
 class Layer(C.Structure):
@@ -64,6 +64,14 @@ class InferArgs(C.Structure):
                 ("out_cols", C.c_int), ("layer_norm", C.c_int), ("obs_norm", C.c_void_p), ("hidden_tanh", C.c_int)]
 
 
+FRL_DP_MAX_RANKS = 8
+
+
+class DpPeers(C.Structure):
+    _fields_ = [("g", C.c_void_p * FRL_DP_MAX_RANKS), ("flags", C.c_void_p * FRL_DP_MAX_RANKS), ("rank", C.c_int), ("world", C.c_int),
+                ("epoch0", C.c_uint)]
+
+
 class PpoArgs(C.Structure):
     _fields_ = [("net", Net), ("continuous", C.c_int), ("obs", C.c_void_p), ("action", C.c_void_p),
                 ("logp_old", C.c_void_p), ("adv", C.c_void_p), ("v_target", C.c_void_p),
@@ -76,7 +84,7 @@ class PpoArgs(C.Structure):
                 ("huber_delta", C.c_float), ("stage_lo", C.c_int), ("stage_hi", C.c_int), ("grad_scale", C.c_float),
                 ("gpart", C.c_void_p),
                 ("sumsq", C.c_void_p), ("segcnt", C.c_void_p), ("stats", C.c_void_p), ("out", C.c_void_p),
-                ("lr_critic", C.c_double), ("hidden_tanh", C.c_int), ("umma_ws", C.c_void_p)]
+                ("lr_critic", C.c_double), ("hidden_tanh", C.c_int), ("umma_ws", C.c_void_p), ("dp", DpPeers)]
 
 
 class NoisyMap(C.Structure):
@@ -148,6 +156,14 @@ def _declare(lib):
     lib.frl_wt_ld.argtypes = [ci]
     lib.frl_ppo_umma_ws_floats.restype = C.c_longlong
     lib.frl_launch_count.restype = C.c_longlong
+    lib.frl_debug_randn.argtypes = [u64, C.c_uint32, C.c_uint32, C.c_longlong, vp, vp]
+    lib.frl_debug_randn.restype = ci
+    lib.frl_dp_alloc.argtypes = [C.c_longlong, C.POINTER(C.c_void_p), C.c_char_p]
+    lib.frl_dp_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.frl_dp_close.argtypes = [vp]
+    lib.frl_dp_free.argtypes = [vp]
+    for name in ("frl_dp_alloc", "frl_dp_open", "frl_dp_close", "frl_dp_free"):
+        getattr(lib, name).restype = ci
     lib.frl_launch_count.argtypes = []
     lib.frl_ppo_umma_ws_floats.argtypes = []
     lib.frl_adv_norm.restype = ci

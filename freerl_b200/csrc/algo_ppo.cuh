@@ -123,6 +123,45 @@ FRL_DEV void net_bwd(Cta& c, const frl_net_t& N, int l0, bool ln, const float* X
   gemm_outer<R>(D1, ldh, L0.out_pad, b.X0, ip, L0.in_pad, L0.in, gp + L0.w_off, gp + L0.b_off, accumulate);
 }
 
+#ifndef FRL_EMUL
+// Exchange stage of the data-parallel peers (frl_dp_peers_t): publish the epoch to every peer, wait for every peer's epoch,
+// sum the world's gradient blocks in rank order into net.g.  All peers run the same launch; a peer that never arrives is
+// reported after ~2 s through out[u][7] = -1 instead of hanging the cooperative grid.
+FRL_DEV void dp_exchange(Cta& c, const frl_ppo_args_t& a, int u) {
+  const frl_net_t& N = a.net;
+  const unsigned epoch = a.dp.epoch0 + (unsigned)u + 1u;
+  const int world = a.dp.world, rank = a.dp.rank, tid = (int)threadIdx.x;
+  if (c.cta == 0 && tid < world && tid != rank) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.dp.flags[tid] + rank), "r"(epoch) : "memory");
+  }
+  if (tid < world && tid != rank) {
+    const unsigned* f = a.dp.flags[rank] + tid;
+    long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+      unsigned v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if ((int)(v - epoch) >= 0) break;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 2000000000ll) { if (c.cta == 0) a.out[u * 8 + 7] = -1.f; break; }
+    }
+  }
+  __syncthreads();
+  const size_t par = (size_t)(epoch & 1u) * N.n_p;
+  for (int p = (c.cta * FRL_NT + tid) * 4; p < N.n_p; p += c.ncta * FRL_NT * 4) {
+    float4 sgm = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < world; ++r) {
+      float4 v;
+      asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(a.dp.g[r] + par + p) : "memory");
+      sgm = f4add(sgm, v);
+    }
+    st4(N.g + p, sgm);
+  }
+  __syncthreads();
+}
+#endif
+
 // R = batch rows per CTA tile: 8 for the reference-sized minibatches (more CTAs per minibatch), 16 for large minibatches
 // (>= 1024 rows: twice the FMAs per staged weight and per barrier; chosen by frl_ppo_update when the tile fits in shared memory).
 // HM (compile time): the `tanh` switch of PPO_with_tricks.py — bit 0: actor, bit 1: critic hidden layers use tanh.  HM = 0 is the
@@ -132,9 +171,12 @@ FRL_DEV void net_bwd(Cta& c, const frl_net_t& N, int l0, bool ln, const float* X
 template <int R, int HM = 0, int UM = 0>
 struct PpoAlgoT {
   typedef frl_ppo_args_t Args;
-  static const int NSTAGES = UM ? 6 : 5;
+  static const int NSTAGES = UM ? 7 : 6;      // [split,] fwd/bwd, reduce, exchange (data-parallel peers only), norms, optimiser x 2
+  static const int XCHG = UM ? 3 : 2;         // physical index of the exchange stage
   FRL_SHD bool writes_params(int) { return true; }
-  FRL_SHD bool stage_enabled(int, int, const Args&) { return true; }
+  // the exchange stage exists for data-parallel peers only; the weight split of the tensor-core variant runs on the first update of
+  // a launch (the optimiser stages keep the split copies current afterwards)
+  FRL_SHD bool stage_enabled(int s, int u, const Args& a) { return (s != XCHG || a.dp.world > 1) && !(UM && s == 0 && u > 0); }
   FRL_SHD int wbuf_floats(const Args& a) { return UM ? 32 : ((AcAlgo::max_layer_floats(a.net) + 31) & ~31); }      // UM: no weight stager, its ring lives in `user`
   FRL_SHD int user_floats(const Args& a) {
 #ifndef FRL_EMUL
@@ -159,17 +201,22 @@ struct PpoAlgoT {
   FRL_SDEV void stage(int s, int u, Cta& c, float* user, const Args& a) {
     const frl_net_t& N = a.net;
     const int ldh = act_ld(N.L[0].out_pad), ip = N.L[0].in_pad, ap = N.L[2].out_pad, nout = N.L[2].out;
+    // physical -> logical stage (stage_lo / stage_hi of the host-driven data-parallel split count the logical ones):
+    //   [split +] fwd/bwd = 0, reduce = 1, (exchange), norms = 2, optimiser = 3, 4
+    if (s == XCHG) {
 #ifndef FRL_EMUL
-    if (UM) {
-      // logical stages (the data-parallel split of stage_lo / stage_hi counts them): split + fwd/bwd = 0, then 1 .. 4 as below
-      const int logical = s == 0 ? 0 : s - 1;
-      if (a.stage_hi > 0 && (logical < a.stage_lo || logical >= a.stage_hi)) return;
-      if (s == 0) { um_split(c, a); return; }
-      if (s == 1) { ppo_umma_stage(c, user, a, u); return; }
-      s = s - 1;
-    } else
+      dp_exchange(c, a, u);
 #endif
+      return;
+    }
+    const int phys = s;
+    s = phys > XCHG ? phys - 1 : phys;
+    if (UM) s = s == 0 ? 0 : s - 1;
     if (a.stage_hi > 0 && (s < a.stage_lo || s >= a.stage_hi)) return;
+#ifndef FRL_EMUL
+    if (UM && phys == 0) { um_split(c, a); return; }
+    if (UM && phys == 1) { ppo_umma_stage(c, user, a, u); return; }
+#endif
     const int rows = a.mb_rows[u];
     const int ntile = (rows + R - 1) / R;
 #ifndef FRL_EMUL
@@ -380,6 +427,8 @@ struct PpoAlgoT {
       // the eight sub-sums are folded in lane order through shared memory — the association is fixed by (ncontrib, 8) alone.
       const int nq = N.n_p >> 2, per = (ncontrib + 7) >> 3;
       float* r4 = c.red;                                     // [FRL_NT] float4
+      // data-parallel peers: the rank's sum goes to its exchange block g[epoch & 1]; the exchange stage writes net.g
+      float* gdst = a.dp.world > 1 ? a.dp.g[a.dp.rank] + (size_t)((a.dp.epoch0 + (unsigned)u + 1u) & 1u) * N.n_p : N.g;
       for (int q0 = c.cta * (FRL_NT / 8); q0 < nq; q0 += c.ncta * (FRL_NT / 8)) {
         FRL_PAR(t) {
           const int sub = t & 7, q = q0 + (t >> 3);
@@ -398,11 +447,14 @@ struct PpoAlgoT {
           if ((t & 7) == 0 && q < nq) {
             float4 sgm = ld4(r4 + 4 * t);
             for (int l = 1; l < 8; ++l) sgm = f4add(sgm, ld4(r4 + 4 * (t + l)));
-            st4(N.g + 4 * q, sgm);
+            st4(gdst + 4 * q, sgm);
           }
         }
         FRL_SYNC();
       }
+#ifndef FRL_EMUL
+      if (a.dp.world > 1) __threadfence_system();            // the peers read this block over NVLink after the exchange flag
+#endif
     } else if (s == 2) {
       // (data-parallel: net.g now holds the all-reduced SUM over ranks) scale, then separate actor / critic sum-of-squares
       const float gs = a.grad_scale > 0.f ? a.grad_scale : 1.f;
@@ -475,6 +527,9 @@ struct PpoAlgoT {
             N.m[p] = m; N.v[p] = v; N.p[p] = w;
             const int mi = mirror_index(N, p);
             if (mi >= 0) N.pt[mi] = w;
+#ifndef FRL_EMUL
+            if (UM) um_split_one(a, p, w);
+#endif
           }
         }
         FRL_SYNC();
@@ -529,6 +584,9 @@ struct PpoAlgoT {
             N.p[p] = w;
             const int mi = mirror_index(N, p);
             if (mi >= 0) N.pt[mi] = w;
+#ifndef FRL_EMUL
+            if (UM) um_split_one(a, p, w);
+#endif
           }
         }
         FRL_SYNC();

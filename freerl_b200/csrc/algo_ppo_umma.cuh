@@ -22,14 +22,14 @@
 #define UM_SLOT_F 8192                  // floats per ring slot: hi 16 KB | lo 16 KB
 #define UM_WS_LAYER 65536               // split-weight block per layer: fwd hi | fwd lo | bwd hi | bwd lo, 16384 floats each
 #define UM_WS_CTA 155648                // per-CTA activation scratch (floats): X 2x8192, H1 H2 DZ1 DZ2 2x16384 each, DZ3 2x4096
-#define UM_USER_FLOATS 47616            // shared memory the fwd/bwd stage carves from `user` (incl. 1 KB alignment slack)
+#define UM_USER_FLOATS 50432            // shared memory the fwd/bwd stage carves from `user` (incl. 1 KB alignment slack)
 
 FRL_HD int um_pad16(int x) { return (x + 15) & ~15; }
 FRL_HD int um_pad32(int x) { return (x + 31) & ~31; }
 
 // host + device: can this update take the tensor-core path?
 FRL_HD bool um_eligible(const frl_ppo_args_t& a) {
-  if (!a.umma_ws || a.mb < 1024 || a.hidden_tanh || a.layer_norm || a.net.n_layers != 6) return false;
+  if (!a.umma_ws || a.mb < 1024 || a.hidden_tanh || a.net.n_layers != 6) return false;
   for (int r = 0; r < 2; ++r) {
     const frl_layer_t &L0 = a.net.L[3 * r], &L1 = a.net.L[3 * r + 1], &L2 = a.net.L[3 * r + 2];
     if (L0.out != 128 || L1.in != 128 || L1.out != 128 || L2.in != 128 || L0.in > 64 || L2.out > 16) return false;
@@ -79,6 +79,31 @@ __device__ __noinline__ void um_split(const Cta& c, const frl_ppo_args_t& a) {
   }
 }
 
+// one updated parameter -> its hi / lo copies in the split-weight blocks (called by the optimiser stages, so only the first update of
+// a launch needs the split stage)
+UM_DEV void um_split_one(const frl_ppo_args_t& a, int p, float w) {
+  const frl_net_t& N = a.net;
+  for (int li = 0; li < 6; ++li) {
+    const frl_layer_t& L = N.L[li];
+    if (p >= L.w_off && p < L.w_off + L.out_pad * L.in_pad) {
+      const int e = p - L.w_off, n = e / L.in_pad, k = e % L.in_pad;
+      if (n >= L.out || k >= L.in) return;
+      const int j = li % 3;
+      float* ws = a.umma_ws + (size_t)li * UM_WS_LAYER;
+      const float hi = um_hi(w), lo = w - hi;
+      const int o = um_q_off(n, k, j == 2 ? 16 : 128);
+      ws[o] = hi;
+      ws[16384 + o] = lo;
+      if (j != 0) {
+        const int ob = um_q_off(k, n, 128);
+        ws[32768 + ob] = hi;
+        ws[49152 + ob] = lo;
+      }
+      return;
+    }
+  }
+}
+
 // 16 consecutive columns of row `r` -> layout S scratch (two 8-float groups, float4 stores)
 UM_DEV void um_s_store16(float* bh, float* bl, int r, int c0, int C, const float* hi, const float* lo) {
 #pragma unroll
@@ -124,31 +149,187 @@ UM_DEV void um_consume_ts(UmPipe& p, uint32_t dcol, uint32_t acol, int R, int kc
   p.tail++;
 }
 // one 32-row chunk of a dW GEMM: A = ring slot (layout S, CA columns, M = 128 of them), B = next slot (layout S, CB columns,
-// first NB used) -> D[128 x NB] at TMEM column dcol; optionally also D1[128 x 16] at column ocol = A^T . ones (bias gradient)
-UM_DEV void um_consume_ss(UmPipe& p, uint32_t dcol, int CA, int CB, int NB, bool first, int ocol, bool first_o, uint32_t ones_addr) {
+// first NB used) -> D[128 x NB] at TMEM column dcol
+UM_DEV void um_consume_ss(UmPipe& p, uint32_t dcol, int CA, int CB, int NB, bool first) {
   const uint32_t sa = p.tail & 3u, ua = p.tail >> 2, sb_ = (p.tail + 1) & 3u, ub = (p.tail + 1) >> 2;
   um_mbar_wait(&p.full[sa], ua & 1u);
   um_mbar_wait(&p.full[sb_], ub & 1u);
   um_fence_after();
   const uint32_t aa = um_smem_u32(p.ring + sa * UM_SLOT_F), ba = um_smem_u32(p.ring + sb_ * UM_SLOT_F);
   const uint64_t ah = um_desc_s(aa, CA), al = um_desc_s(aa + 16384u, CA), bh = um_desc_s(ba, CB), bl = um_desc_s(ba + 16384u, CB);
-  const uint64_t on = um_desc_s(ones_addr, 32);
-  const uint32_t idesc = um_idesc_tf32(128, NB, 1, 1), idesc1 = um_idesc_tf32(128, 16, 1, 1);
+  const uint32_t idesc = um_idesc_tf32(128, NB, 1, 1);
   for (int ks = 0; ks < 4; ++ks) {
     const uint64_t aadv = (uint64_t)((uint32_t)(ks * 32 * CA) >> 4), badv = (uint64_t)((uint32_t)(ks * 32 * CB) >> 4);
-    const uint32_t acc0 = (first && ks == 0) ? 0u : 1u;
-    um_mma_ss(p.tm + dcol, al + aadv, bh + badv, idesc, acc0);
+    um_mma_ss(p.tm + dcol, al + aadv, bh + badv, idesc, (first && ks == 0) ? 0u : 1u);
     um_mma_ss(p.tm + dcol, ah + aadv, bl + badv, idesc, 1u);
     um_mma_ss(p.tm + dcol, ah + aadv, bh + badv, idesc, 1u);
-    if (ocol >= 0) {
-      const uint64_t oadv = (uint64_t)((uint32_t)(ks * 32 * 32) >> 4);
-      um_mma_ss(p.tm + ocol, al + aadv, on + oadv, idesc1, (first_o && ks == 0) ? 0u : 1u);
-      um_mma_ss(p.tm + ocol, ah + aadv, on + oadv, idesc1, 1u);
-    }
   }
   um_commit(&p.empty[sa]);
   um_commit(&p.empty[sb_]);
   p.tail += 2;
+}
+
+// per-thread view of the stage: which TMEM lanes / columns the thread owns, the row-statistics exchange buffer
+struct UmThr {
+  uint32_t tm, lane_base;
+  int row, hh, tid;
+  float* xs;            // [4][2][128] partial row sums of the two half-row threads
+};
+
+// Forward epilogue of a hidden layer: acc -> +bias -> ReLU [-> F.layer_norm over the 128 features, MAPPO.py:145-151] -> TMEM A
+// operand (hi | lo) + layout-S scratch.  Returns the ReLU mask of the thread's 64 columns; *rstd = 1 / sqrt(var + 1e-5) of the row.
+UM_DEV uint64_t um_hidden_fwd(const UmThr& th, const float* bias, bool ln, float* Sh, float* Sl, float* rstd, const float* W3s = nullptr,
+                              int nout = 0, float* lgp = nullptr) {
+  uint64_t mask = 0;
+  float mean = 0.f, rs = 1.f;
+  if (ln) {
+    float s = 0.f;
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      const int c0 = th.hh * 64 + j * 16;
+      float v[16];
+      um_ld16(th.tm + th.lane_base + c0, v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) s += fmaxf(v[i] + bias[c0 + i], 0.f);
+    }
+    th.xs[th.hh * 128 + th.row] = s;
+    __syncthreads();
+    mean = (th.xs[th.row] + th.xs[128 + th.row]) * (1.0f / 128.f);
+    float q = 0.f;
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      const int c0 = th.hh * 64 + j * 16;
+      float v[16];
+      um_ld16(th.tm + th.lane_base + c0, v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { const float d = fmaxf(v[i] + bias[c0 + i], 0.f) - mean; q += d * d; }
+    }
+    th.xs[256 + th.hh * 128 + th.row] = q;
+    __syncthreads();
+    rs = 1.0f / sqrtf((th.xs[256 + th.row] + th.xs[384 + th.row]) * (1.0f / 128.f) + 1e-5f);
+  }
+#pragma unroll 1
+  for (int j = 0; j < 4; ++j) {
+    const int c0 = th.hh * 64 + j * 16;
+    float v[16], hi[16], lo[16];
+    um_ld16(th.tm + th.lane_base + c0, v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float x = v[i] + bias[c0 + i];
+      if (x > 0.f) mask |= 1ull << (j * 16 + i); else x = 0.f;
+      if (ln) x = (x - mean) * rs;
+      hi[i] = um_hi(x);
+      lo[i] = x - hi[i];
+      v[i] = x;
+    }
+    um_st16(th.tm + th.lane_base + 128 + c0, hi);
+    um_st16(th.tm + th.lane_base + 256 + c0, lo);
+    um_s_store16(Sh, Sl, th.row, c0, 128, hi, lo);
+    if (W3s) {                                 // output layer on the CUDA cores (out <= 16): partial dot products over this thread's columns
+#pragma unroll
+      for (int n = 0; n < 16; ++n)
+        if (n < nout) {
+          float acc = lgp[n];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc = fmaf(v[i], W3s[n * 128 + c0 + i], acc);
+          lgp[n] = acc;
+        }
+    }
+  }
+  *rstd = rs;
+  return mask;
+}
+
+// Backward epilogue of a hidden layer: acc = dL/d(layer output) -> [layer-norm backward with Y = the normalised activations read
+// back from the scratch (hi + lo is the exact fp32 value): dX = rstd (dY - mean(dY) - Y mean(dY Y))] -> ReLU mask -> dZ, written
+// to the layout-S scratch and (to_tmem) as the next GEMM's A operand.
+// Column sums of a [32 lanes x 16] register tile by recursive halving (16 shuffles): afterwards every lane holds the sum over the
+// warp's 32 rows of column um_colsum_col(lane).
+UM_DEV float um_colsum16(const float* x, int lane) {
+  float a8[8], a4[4], a2[2], a1;
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a8[i] = (b4 ? x[8 + i] : x[i]) + __shfl_xor_sync(0xffffffffu, b4 ? x[i] : x[8 + i], 16);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) a4[i] = (b3 ? a8[4 + i] : a8[i]) + __shfl_xor_sync(0xffffffffu, b3 ? a8[i] : a8[4 + i], 8);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) a2[i] = (b2 ? a4[2 + i] : a4[i]) + __shfl_xor_sync(0xffffffffu, b2 ? a4[i] : a4[2 + i], 4);
+  a1 = (b1 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, b1 ? a2[0] : a2[1], 2);
+  return a1 + __shfl_xor_sync(0xffffffffu, a1, 1);
+}
+UM_DEV int um_colsum_col(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1); }
+
+// dY of 16 columns: from the TMEM accumulator, or (W3s given) = dz . W3 on the CUDA cores
+UM_DEV void um_dy16(const UmThr& th, int c0, const float* W3s, const float* dz, int nout, float* v) {
+  if (!W3s) { um_ld16(th.tm + th.lane_base + c0, v); return; }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = 0.f;
+#pragma unroll
+  for (int n = 0; n < 16; ++n)
+    if (n < nout) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = fmaf(dz[n], W3s[n * 128 + c0 + i], v[i]);
+    }
+}
+
+UM_DEV void um_hidden_bwd(const UmThr& th, uint64_t mask, bool ln, float rs, const float* Yh, const float* Yl, float* Dh, float* Dl,
+                          bool to_tmem, float* dbp, const float* W3s = nullptr, const float* dz = nullptr, int nout = 0) {
+  float m1 = 0.f, m2 = 0.f;
+  if (ln) {
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      const int c0 = th.hh * 64 + j * 16;
+      float v[16];
+      um_dy16(th, c0, W3s, dz, nout, v);
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const int o = um_s_off(th.row, c0 + 8 * g, 128);
+        const float4 a0 = ld4(Yh + o), a1 = ld4(Yh + o + 4), b0 = ld4(Yl + o), b1 = ld4(Yl + o + 4);
+        const float y[8] = {a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w, a1.x + b1.x, a1.y + b1.y, a1.z + b1.z, a1.w + b1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s1 += v[8 * g + i]; s2 += v[8 * g + i] * y[i]; }
+      }
+    }
+    th.xs[512 + th.hh * 128 + th.row] = s1;
+    th.xs[768 + th.hh * 128 + th.row] = s2;
+    __syncthreads();
+    m1 = (th.xs[512 + th.row] + th.xs[640 + th.row]) * (1.0f / 128.f);
+    m2 = (th.xs[768 + th.row] + th.xs[896 + th.row]) * (1.0f / 128.f);
+  }
+#pragma unroll 1
+  for (int j = 0; j < 4; ++j) {
+    const int c0 = th.hh * 64 + j * 16;
+    float v[16], hi[16], lo[16];
+    um_dy16(th, c0, W3s, dz, nout, v);
+    if (ln) {
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const int o = um_s_off(th.row, c0 + 8 * g, 128);
+        const float4 a0 = ld4(Yh + o), a1 = ld4(Yh + o + 4), b0 = ld4(Yl + o), b1 = ld4(Yl + o + 4);
+        const float y[8] = {a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w, a1.x + b1.x, a1.y + b1.y, a1.z + b1.z, a1.w + b1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[8 * g + i] = rs * (v[8 * g + i] - m1 - y[i] * m2);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float x = ((mask >> (j * 16 + i)) & 1ull) ? v[i] : 0.f;
+      hi[i] = um_hi(x);
+      lo[i] = x - hi[i];
+      v[i] = x;
+    }
+    {                                          // bias gradient: column sums over the warp's 32 rows, accumulated per TMEM lane quarter
+      const int lane = th.tid & 31;
+      const float cs_ = um_colsum16(v, lane);
+      if ((lane & 1) == 0) dbp[((th.tid >> 5) & 3) * 128 + c0 + um_colsum_col(lane)] += cs_;
+    }
+    if (to_tmem) {
+      um_st16(th.tm + th.lane_base + 128 + c0, hi);
+      um_st16(th.tm + th.lane_base + 256 + c0, lo);
+    }
+    um_s_store16(Dh, Dl, th.row, c0, 128, hi, lo);
+  }
 }
 
 // ---- stage "fwd/bwd" -----------------------------------------------------------------------------------------------
@@ -168,25 +349,26 @@ __device__ __noinline__ void ppo_umma_stage(Cta& c, float* user, const frl_ppo_a
   const int K0 = um_pad16(in), Cx = um_pad32(in);
 
   float* ring = (float*)(((uintptr_t)user + 1023) & ~(uintptr_t)1023);
-  float* ones = ring + 4 * UM_SLOT_F;          // [32 x 32] layout S, column 0 = 1
-  float* accW1 = ones + 1024;                  // [64][128]  dW1[n][k] at [k][n]
+  float* W3s = ring + 4 * UM_SLOT_F;           // [16][128] fp32 output-layer weights (rows >= out are zero)
+  float* accW1 = W3s + 2048;                   // [64][128]  dW1[n][k] at [k][n]
   float* accW3 = accW1 + 64 * 128;             // [16][128]  dW3[n][k] at [n][k]
-  float* accB = accW3 + 16 * 128;              // [2][128]   db1 | db2
-  float* accX = accB + 256;                    // [32]       db3[16] | dlog_std[16]
+  float* accB = accW3 + 16 * 128;              // [2][4][128] db1 | db2 partial sums per TMEM lane quarter
+  float* accX = accB + 1024;                   // [32]       db3[16] | dlog_std[16]
   float* bias = accX + 32;                     // [3][128]
   float* cs = bias + 384;                      // [128][17] column-sum scratch
   float* red = cs + 128 * 17;                  // [256]
-  uint64_t* bars = (uint64_t*)(red + 256);     // full[4] | empty[4] | acc
+  float* xs = red + 256;                       // [4][2][128] row-statistics exchange (LayerNorm)
+  uint64_t* bars = (uint64_t*)(xs + 1024);     // full[4] | empty[4] | acc
   uint32_t* tslot = (uint32_t*)(bars + 9);
 
-  for (int i = tid; i < 64 * 128 + 16 * 128 + 256 + 32; i += FRL_NT) accW1[i] = 0.f;
-  for (int i = tid; i < 1024; i += FRL_NT) ones[i] = 0.f;
+  for (int i = tid; i < 64 * 128 + 16 * 128 + 1024 + 32; i += FRL_NT) accW1[i] = 0.f;
+  for (int i = tid; i < 2048; i += FRL_NT) W3s[i] = (i >> 7) < nout ? N.p[L2.w_off + (i >> 7) * L2.in_pad + (i & 127)] : 0.f;
   for (int i = tid; i < 384; i += FRL_NT) {
     const frl_layer_t& L = N.L[l0 + i / 128];
     bias[i] = (i % 128) < L.out ? N.p[L.b_off + (i % 128)] : 0.f;
   }
+  float* dzs = c.red;                          // [128][17] dZ3 rows (engine scratch, unused by this stage otherwise)
   __syncthreads();
-  if (tid < 32) ones[um_s_off(tid, 0, 32)] = 1.f;
   if (tid == 0) {
     for (int i = 0; i < 9; ++i) um_mbar_init(&bars[i], 1);
     um_fence_mbar_init();
@@ -202,7 +384,9 @@ __device__ __noinline__ void ppo_umma_stage(Cta& c, float* user, const frl_ppo_a
   p.ring = ring; p.full = bars; p.empty = bars + 4; p.acc = bars + 8; p.tm = *tslot; p.head = p.tail = 0;
   const uint32_t tm = p.tm;
   uint32_t accn = 0;                           // accumulator-barrier uses so far (all threads keep the count)
-  const uint32_t ones_addr = um_smem_u32(ones);
+  const bool ln = a.layer_norm != 0;
+  UmThr th;
+  th.tm = tm; th.lane_base = lane_base; th.row = row; th.hh = hh; th.tid = tid; th.xs = xs;
 
   const float* wsl = a.umma_ws;
   float* act = a.umma_ws + (size_t)6 * UM_WS_LAYER + (size_t)c.cta * UM_WS_CTA;
@@ -226,11 +410,20 @@ __device__ __noinline__ void ppo_umma_stage(Cta& c, float* user, const frl_ppo_a
     // ---- inputs: x -> TMEM A columns + scratch X ----
     if (hh == 0) {
       const float* src = (role && a.critic_obs) ? a.critic_obs + (size_t)gi * a.critic_obs_dim : a.obs + (size_t)gi * a.obs_dim;
+      float mean = 0.f, rs = 1.f;
+      if (ln && valid) {                       // feature_norm: F.layer_norm over the `in` input features (MAPPO.py:145)
+        float s_ = 0.f, q_ = 0.f;
+        for (int k = 0; k < in; ++k) s_ += src[k];
+        mean = s_ / (float)in;
+        for (int k = 0; k < in; ++k) { const float d = src[k] - mean; q_ += d * d; }
+        rs = 1.0f / sqrtf(q_ / (float)in + 1e-5f);
+      }
       for (int c0 = 0; c0 < K0; c0 += 16) {
         float hi[16], lo[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float x = (valid && c0 + i < in) ? src[c0 + i] : 0.f;
+          float x = (valid && c0 + i < in) ? src[c0 + i] : 0.f;
+          if (ln && valid && c0 + i < in) x = (x - mean) * rs;
           hi[i] = um_hi(x);
           lo[i] = x - hi[i];
         }
@@ -253,23 +446,8 @@ __device__ __noinline__ void ppo_umma_stage(Cta& c, float* user, const frl_ppo_a
     um_fence_after();
     if (tid == 0)
       for (int c0 = 0; c0 < 128; c0 += 32) um_fill(p, UM_W(l0 + 1, 0) + c0 * 128, UM_W(l0 + 1, 1) + c0 * 128, 16384u);
-    uint64_t mask1 = 0, mask2 = 0;
-#pragma unroll 1
-    for (int j = 0; j < 4; ++j) {
-      const int c0 = hh * 64 + j * 16;
-      float v[16], hi[16], lo[16];
-      um_ld16(tm + lane_base + c0, v);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float x = v[i] + bias[c0 + i];
-        if (x > 0.f) mask1 |= 1ull << (j * 16 + i); else x = 0.f;
-        hi[i] = um_hi(x);
-        lo[i] = x - hi[i];
-      }
-      um_st16(tm + lane_base + 128 + c0, hi);
-      um_st16(tm + lane_base + 256 + c0, lo);
-      um_s_store16(H1h, H1l, row, c0, 128, hi, lo);
-    }
+    float rs1 = 1.f, rs2 = 1.f;
+    const uint64_t mask1 = um_hidden_fwd(th, bias, ln, H1h, H1l, &rs1);
     um_wait_st();
     um_fence_before();
     __syncthreads();
@@ -282,45 +460,28 @@ __device__ __noinline__ void ppo_umma_stage(Cta& c, float* user, const frl_ppo_a
     }
     um_mbar_wait(p.acc, accn & 1u); ++accn;
     um_fence_after();
-    if (tid == 0) um_fill(p, UM_W(l0 + 2, 0), UM_W(l0 + 2, 1), 8192u);          // W3 forward: [16 x 128] layout Q
-#pragma unroll 1
-    for (int j = 0; j < 4; ++j) {
-      const int c0 = hh * 64 + j * 16;
-      float v[16], hi[16], lo[16];
-      um_ld16(tm + lane_base + c0, v);
+    if (tid == 0)                              // W2 backward operand for dH1, one GEMM ahead
+      for (int c0 = 0; c0 < 128; c0 += 32) um_fill(p, UM_W(l0 + 1, 2) + c0 * 128, UM_W(l0 + 1, 3) + c0 * 128, 16384u);
+    // layer-2 epilogue; the output layer (out <= 16 columns) runs on the CUDA cores from the registers of the same pass
+    float lgp[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float x = v[i] + bias[128 + c0 + i];
-        if (x > 0.f) mask2 |= 1ull << (j * 16 + i); else x = 0.f;
-        hi[i] = um_hi(x);
-        lo[i] = x - hi[i];
-      }
-      um_st16(tm + lane_base + 128 + c0, hi);
-      um_st16(tm + lane_base + 256 + c0, lo);
-      um_s_store16(H2h, H2l, row, c0, 128, hi, lo);
+    for (int i = 0; i < 16; ++i) lgp[i] = 0.f;
+    const uint64_t mask2 = um_hidden_fwd(th, bias + 128, ln, H2h, H2l, &rs2, W3s, nout, lgp);
+    if (hh == 1) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) cs[row * 17 + i] = lgp[i];
     }
     um_wait_st();
-    um_fence_before();
     __syncthreads();
     stamp(c, 303);
-    // ---- layer 3: acc[:, 0:16] = h2 W3^T ----
-    if (tid == 0) {
-      um_fence_after();
-      um_consume_ts(p, 0, 0, 16, 128, true);
-      um_commit(p.acc);
-    }
-    um_mbar_wait(p.acc, accn & 1u); ++accn;
-    um_fence_after();
-    if (tid == 0) um_fill(p, UM_W(l0 + 2, 2), UM_W(l0 + 2, 3), 8192u);          // W3 backward: [128 x 16] layout Q
     // ---- heads: losses and dL/d(output) per row (PPO.py:256-279) ----
     float lsg[16];                             // d/dlog_std through the log-prob, per action dim (continuous actor)
 #pragma unroll
     for (int i = 0; i < 16; ++i) lsg[i] = 0.f;
     if (hh == 0) {
       float v[16], dz[16];
-      um_ld16(tm + lane_base, v);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) { v[i] += bias[256 + i]; dz[i] = 0.f; }
+      for (int i = 0; i < 16; ++i) { v[i] = (lgp[i] + cs[row * 17 + i]) + bias[256 + i]; dz[i] = 0.f; }
       if (valid && role == 0) {
         float lp_now = 0.f, lp_old = 0.f, ent = 0.f, lse = 0.f;
         int act = 0;
@@ -407,57 +568,47 @@ __device__ __noinline__ void ppo_umma_stage(Cta& c, float* user, const frl_ppo_a
       }
       float hi[16], lo[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) { hi[i] = um_hi(dz[i]); lo[i] = dz[i] - hi[i]; cs[row * 17 + i] = dz[i]; }
-      um_st16(tm + lane_base + 128, hi);
-      um_st16(tm + lane_base + 256, lo);
+      for (int i = 0; i < 16; ++i) { hi[i] = um_hi(dz[i]); lo[i] = dz[i] - hi[i]; dzs[row * 17 + i] = dz[i]; }
       um_s_store16(D3h, D3l, row, 0, 32, hi, lo);
     }
-    um_wait_st();
-    um_fence_before();
     __syncthreads();
     stamp(c, 304);
-    // ---- dH2 = dZ3 W3 (K = 16) ----
-    if (tid == 0) {
-      um_fence_after();
-      um_consume_ts(p, 0, 0, 128, 16, true);
-      um_commit(p.acc);
-    }
-    if (tid < 16) {                            // db3: column sums of dZ3 in row order
+    {                                          // db3: column sums of dZ3 — 16 segments of 8 rows, then the segments in order
       float s = 0.f;
-      for (int r = 0; r < 128; ++r) s += cs[r * 17 + tid];
-      accX[tid] += s;
+      for (int r = 0; r < 8; ++r) s += dzs[((tid >> 4) * 8 + r) * 17 + (tid & 15)];
+      red[tid] = s;
     }
     __syncthreads();
+    if (tid < 16) {
+      float s = 0.f;
+      for (int g = 0; g < 16; ++g) s += red[g * 16 + tid];
+      accX[tid] += s;
+    }
     if (role == 0 && a.continuous) {
+      __syncthreads();
       if (hh == 0) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) cs[row * 17 + i] = lsg[i];
       }
       __syncthreads();
+      {
+        float s = 0.f;
+        for (int r = 0; r < 8; ++r) s += cs[((tid >> 4) * 8 + r) * 17 + (tid & 15)];
+        red[tid] = s;
+      }
+      __syncthreads();
       if (tid < 16) {
         float s = 0.f;
-        for (int r = 0; r < 128; ++r) s += cs[r * 17 + tid];
+        for (int g = 0; g < 16; ++g) s += red[g * 16 + tid];
         accX[16 + tid] += s;
       }
     }
-    um_mbar_wait(p.acc, accn & 1u); ++accn;
-    um_fence_after();
-    if (tid == 0)
-      for (int c0 = 0; c0 < 128; c0 += 32) um_fill(p, UM_W(l0 + 1, 2) + c0 * 128, UM_W(l0 + 1, 3) + c0 * 128, 16384u);
-#pragma unroll 1
-    for (int j = 0; j < 4; ++j) {
-      const int c0 = hh * 64 + j * 16;
-      float v[16], hi[16], lo[16];
-      um_ld16(tm + lane_base + c0, v);
+    // dH2 = dZ3 W3 on the CUDA cores, straight into the layer-2 backward epilogue
+    {
+      float dz[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float x = ((mask2 >> (j * 16 + i)) & 1ull) ? v[i] : 0.f;
-        hi[i] = um_hi(x);
-        lo[i] = x - hi[i];
-      }
-      um_st16(tm + lane_base + 128 + c0, hi);
-      um_st16(tm + lane_base + 256 + c0, lo);
-      um_s_store16(D2h, D2l, row, c0, 128, hi, lo);
+      for (int i = 0; i < 16; ++i) dz[i] = dzs[row * 17 + i];
+      um_hidden_bwd(th, mask2, ln, rs2, H2h, H2l, D2h, D2l, true, accB + 512, W3s, dz, nout);
     }
     um_wait_st();
     um_fence_before();
@@ -472,19 +623,7 @@ __device__ __noinline__ void ppo_umma_stage(Cta& c, float* user, const frl_ppo_a
     }
     um_mbar_wait(p.acc, accn & 1u); ++accn;
     um_fence_after();
-#pragma unroll 1
-    for (int j = 0; j < 4; ++j) {
-      const int c0 = hh * 64 + j * 16;
-      float v[16], hi[16], lo[16];
-      um_ld16(tm + lane_base + c0, v);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float x = ((mask1 >> (j * 16 + i)) & 1ull) ? v[i] : 0.f;
-        hi[i] = um_hi(x);
-        lo[i] = x - hi[i];
-      }
-      um_s_store16(D1h, D1l, row, c0, 128, hi, lo);
-    }
+    um_hidden_bwd(th, mask1, ln, rs1, H1h, H1l, D1h, D1l, false, accB);
     um_fence_before();
     um_fence_proxy_async();                    // scratch written by the generic proxy -> bulk-copy (async proxy) reads
     __syncthreads();
@@ -505,9 +644,9 @@ __device__ __noinline__ void ppo_umma_stage(Cta& c, float* user, const frl_ppo_a
         }
         if (st > 0) {
           const int g = (st - 1) >> 2, j = (st - 1) & 3;
-          if (g == 0) um_consume_ss(p, 0, 128, 32, 16, j == 0, -1, false, ones_addr);
-          else if (g == 1) um_consume_ss(p, 384, 128, 128, 128, j == 0 && it == 0, 16, j == 0, ones_addr);
-          else um_consume_ss(p, 64, 128, Cx, K0, j == 0, 32, j == 0, ones_addr);
+          if (g == 0) um_consume_ss(p, 0, 128, 32, 16, j == 0);
+          else if (g == 1) um_consume_ss(p, 384, 128, 128, 128, j == 0 && it == 0);
+          else um_consume_ss(p, 64, 128, Cx, K0, j == 0);
         }
       }
       um_commit(p.acc);
@@ -519,10 +658,6 @@ __device__ __noinline__ void ppo_umma_stage(Cta& c, float* user, const frl_ppo_a
       um_ld16(tm + lane_base, v);
 #pragma unroll
       for (int i = 0; i < 16; ++i) accW3[i * 128 + row] += v[i];
-      um_ld16(tm + lane_base + 16, v);
-      accB[128 + row] += v[0];
-      um_ld16(tm + lane_base + 32, v);
-      accB[row] += v[0];
       for (int c0 = 0; c0 < K0; c0 += 16) {
         um_ld16(tm + lane_base + 64 + c0, v);
 #pragma unroll
@@ -556,28 +691,22 @@ __device__ __noinline__ void ppo_umma_stage(Cta& c, float* user, const frl_ppo_a
     const int n = e / L2.in_pad, k = e % L2.in_pad;
     gp[L2.w_off + e] = (n < L2.out && k < L2.in) ? accW3[n * 128 + k] : 0.f;
   }
-  if (tid < L0.out_pad) gp[L0.b_off + tid] = tid < L0.out ? accB[tid] : 0.f;
-  if (tid < L1.out_pad) gp[L1.b_off + tid] = tid < L1.out ? accB[128 + tid] : 0.f;
+  __syncthreads();
+  if (tid < L0.out_pad) gp[L0.b_off + tid] = tid < L0.out ? ((accB[tid] + accB[128 + tid]) + accB[256 + tid]) + accB[384 + tid] : 0.f;
+  if (tid < L1.out_pad) gp[L1.b_off + tid] = tid < L1.out ? ((accB[512 + tid] + accB[640 + tid]) + accB[768 + tid]) + accB[896 + tid] : 0.f;
   if (tid < L2.out_pad) gp[L2.b_off + tid] = tid < L2.out ? accX[tid] : 0.f;
   if (role == 0 && a.continuous && tid < L2.out_pad) gp[N.x_off + tid] = tid < nout ? accX[16 + tid] : 0.f;
-  // loss partials, folded in thread order
+  // loss partials (fixed shuffle-tree association of block_sum)
   __syncthreads();
   red[tid] = role ? lc : la;
   __syncthreads();
-  if (tid == 0) {
-    float s = 0.f;
-    for (int i = 0; i < FRL_NT; ++i) s += red[i];
-    a.stats[ci * 8 + (role ? 1 : 0)] = s;
-  }
+  const float l0s = block_sum(red);
+  red[tid] = le;
   __syncthreads();
-  if (role == 0) {
-    red[tid] = le;
-    __syncthreads();
-    if (tid == 0) {
-      float s = 0.f;
-      for (int i = 0; i < FRL_NT; ++i) s += red[i];
-      a.stats[ci * 8 + 2] = s;
-    }
+  const float l2s = block_sum(red);
+  if (tid == 0) {
+    a.stats[ci * 8 + (role ? 1 : 0)] = l0s;
+    if (role == 0) a.stats[ci * 8 + 2] = l2s;
   }
   um_fence_before();
   __syncthreads();

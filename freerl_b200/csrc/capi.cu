@@ -26,7 +26,7 @@ extern "C" void frl_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 extern "C" const char* frl_last_error(void) { return g_err; }
-extern "C" int frl_abi_version(void) { return 7; }
+extern "C" int frl_abi_version(void) { return 8; }
 // sizeof() of the argument structs, so a binding can verify its mirror of the layout before the first call
 extern "C" int frl_struct_size(int which) {
   switch (which) {
@@ -430,6 +430,18 @@ extern "C" int frl_net_sync_mirror(const frl_net_t* net, void* stream) {
   return frl_for(net->n_p, b, (cudaStream_t)stream);
 }
 
+// audit hook for fast mode: the N(0,1) values the learn kernels draw for (seed, stream, counter), element idx = 0 .. n-1 — the same
+// randn_ni call, so a test can hand the exact noise of a fast-mode learn to the oracle (tests/test_parity_ac.py)
+struct RandnBody {
+  uint64_t seed; uint32_t stream, ctr; float* out;
+  FRL_DEVM void operator()(long i) const { out[i] = frl_randn(seed, stream, ctr, (uint32_t)i); }
+};
+extern "C" int frl_debug_randn(uint64_t seed, uint32_t stream, uint32_t ctr, long long n, float* out, void* cuda_stream) {
+  if (!out || n <= 0) { frl_set_error("frl_debug_randn: bad arguments"); return -1; }
+  RandnBody b = {seed, stream, ctr, out};
+  return frl_for((long)n, b, (cudaStream_t)cuda_stream);
+}
+
 struct PolyakBody {
   frl_net_t src, tgt; float tau, omt;
   FRL_DEVM void operator()(long p) const {
@@ -661,6 +673,55 @@ extern "C" int frl_gae(const float* reward, const float* done, const float* adv_
 
 }
 
+// ---- peer-memory blocks for the in-kernel data-parallel gradient exchange (frl_dp_peers_t) ----
+extern "C" int frl_dp_alloc(long long bytes, void** dev_ptr, unsigned char* ipc_handle_64) {
+#ifndef FRL_EMUL
+  if (bytes <= 0 || !dev_ptr || !ipc_handle_64) { frl_set_error("frl_dp_alloc: bad arguments"); return -1; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* p = nullptr;
+  FRL_CUDA_OK(cudaMalloc(&p, (size_t)bytes));
+  FRL_CUDA_OK(cudaMemset(p, 0, (size_t)bytes));
+  cudaIpcMemHandle_t h;
+  FRL_CUDA_OK(cudaIpcGetMemHandle(&h, p));
+  memcpy(ipc_handle_64, &h, 64);
+  *dev_ptr = p;
+  return 0;
+#else
+  (void)bytes; (void)dev_ptr; (void)ipc_handle_64;
+  frl_set_error("frl_dp_alloc: peer memory needs the CUDA library");
+  return -1;
+#endif
+}
+extern "C" int frl_dp_open(const unsigned char* ipc_handle_64, void** dev_ptr) {
+#ifndef FRL_EMUL
+  if (!ipc_handle_64 || !dev_ptr) { frl_set_error("frl_dp_open: bad arguments"); return -1; }
+  cudaIpcMemHandle_t h;
+  memcpy(&h, ipc_handle_64, 64);
+  FRL_CUDA_OK(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+#else
+  (void)ipc_handle_64; (void)dev_ptr;
+  frl_set_error("frl_dp_open: peer memory needs the CUDA library");
+  return -1;
+#endif
+}
+extern "C" int frl_dp_close(void* peer_ptr) {
+#ifndef FRL_EMUL
+  if (peer_ptr) FRL_CUDA_OK(cudaIpcCloseMemHandle(peer_ptr));
+#else
+  (void)peer_ptr;
+#endif
+  return 0;
+}
+extern "C" int frl_dp_free(void* dev_ptr) {
+#ifndef FRL_EMUL
+  if (dev_ptr) FRL_CUDA_OK(cudaFree(dev_ptr));
+#else
+  (void)dev_ptr;
+#endif
+  return 0;
+}
+
 // floats of frl_ppo_args_t.umma_ws: 6 split-weight blocks + one activation scratch per CTA of the largest grid
 extern "C" long long frl_ppo_umma_ws_floats(void) {
 #ifndef FRL_EMUL
@@ -678,6 +739,16 @@ extern "C" int frl_ppo_update(const frl_ppo_args_t* a, void* stream) {
   }
   if (check_net(a->net, true, "frl_ppo_update(net)")) return -1;
   if (a->hidden_tanh && a->layer_norm) { frl_set_error("frl_ppo_update: hidden_tanh is not available with layer_norm"); return -1; }
+  if (a->dp.world > 1) {
+    if (a->dp.world > FRL_DP_MAX_RANKS || a->dp.rank < 0 || a->dp.rank >= a->dp.world) { frl_set_error("frl_ppo_update: bad dp rank / world"); return -1; }
+    for (int r = 0; r < a->dp.world; ++r)
+      if (!a->dp.g[r] || !a->dp.flags[r]) { frl_set_error("frl_ppo_update: dp peer block %d missing", r); return -1; }
+    if (a->stage_hi > 0) { frl_set_error("frl_ppo_update: the peer-memory exchange runs whole updates (stage_lo / stage_hi must be 0)"); return -1; }
+#ifdef FRL_EMUL
+    frl_set_error("frl_ppo_update: the peer-memory exchange needs the CUDA library");
+    return -1;
+#endif
+  }
   if (a->net.n_layers != 6 || (a->continuous && a->net.x_len <= 0)) {
     frl_set_error("frl_ppo_update: net must hold actor (layers 0-2) + critic (layers 3-5)");
     return -1;

@@ -162,6 +162,19 @@ typedef struct {
   int hidden_tanh;          /* 1: tanh hidden activations (the `tanh` trick of PPO_file/PPO_with_tricks.py:95,172); 0: ReLU */
 } frl_infer_args_t;
 
+/* Data-parallel gradient exchange over peer memory (one process per GPU, NVLink): rank r owns a device block
+ *   [ flags: FRL_DP_MAX_RANKS x uint32 (padded to 256 B) | g: 2 x n_p floats ]   allocated by frl_dp_alloc and opened by every peer with
+ * frl_dp_open (CUDA IPC).  After the in-kernel cross-CTA reduction of update number e (= epoch0 + u + 1) a rank writes its gradient to
+ * g[e & 1], publishes e into slot `rank` of every peer's flags, waits until its own flags hold e for every rank and sums the world's
+ * gradients in rank order (bit-identical on every rank) — inside the one persistent launch, no NCCL call per step. */
+#define FRL_DP_MAX_RANKS 8
+typedef struct {
+  float* g[FRL_DP_MAX_RANKS];           /* dev: rank r's g block (peer-mapped for r != rank) */
+  unsigned* flags[FRL_DP_MAX_RANKS];    /* dev: rank r's flag block */
+  int rank, world;                      /* world <= 1: exchange disabled */
+  unsigned epoch0;                      /* exchanges completed before this launch (identical on all ranks) */
+} frl_dp_peers_t;
+
 /* On-policy (PPO.py) minibatch update.  `net` holds actor (layers 0-2, + log_std extra when continuous) and critic
  * (layers 3-5) in ONE parameter block with ONE optimiser, like the reference's merged `ac_optimizer`. */
 enum { FRL_OPT_CAUTIOUS_ADAMW = 0, FRL_OPT_ADAM = 1 };
@@ -203,6 +216,7 @@ typedef struct {
   /* ---- tensor-core path (csrc/algo_ppo_umma.cuh): taken for minibatches of >= 1024 rows over in->128->128->out networks when
    * umma_ws = dev scratch of frl_ppo_umma_ws_floats() floats (512-B aligned; split weights + per-CTA activation scratch) is given */
   float* umma_ws;
+  frl_dp_peers_t dp;        /* in-kernel data-parallel gradient exchange (world > 1); then grad_scale should be 1 / world */
 } frl_ppo_args_t;
 
 /* Rainbow (DQN_with_tricks.py): Categorical + Dueling + Noisy net.  The trainable block holds the torch tensors;
@@ -266,7 +280,14 @@ typedef struct {
 const char* frl_last_error(void);
 int frl_is_emulation(void);          /* 0 for the CUDA library (the only one the product path accepts) */
 int frl_device_sm_count(void);
+/* audit of fast mode: out[i] = the standard normal the learn kernels draw for (seed, stream, counter, element i) */
+int frl_debug_randn(uint64_t seed, uint32_t stream, uint32_t counter, long long n, float* out, void* cuda_stream);
 long long frl_launch_count(void);    /* kernels launched by the library since load (bench.py's gpu_launches) */
+/* peer-memory blocks of frl_dp_peers_t: cudaMalloc + zero + IPC handle (64 bytes) / open a peer's handle / release */
+int frl_dp_alloc(long long bytes, void** dev_ptr, unsigned char* ipc_handle_64);
+int frl_dp_open(const unsigned char* ipc_handle_64, void** dev_ptr);
+int frl_dp_close(void* peer_ptr);
+int frl_dp_free(void* dev_ptr);
 long long frl_ppo_umma_ws_floats(void);   /* size of frl_ppo_args_t.umma_ws (0 from the test-only emulation) */
 int frl_wt_ld(int out_pad);          /* row stride (floats) of a transposed-mirror layer image with this padded width */
 int frl_abi_version(void);

@@ -118,3 +118,62 @@ def test_offpolicy_replica_sync_gloo(tmp_path, emul):
         np.testing.assert_allclose(a["synced" + n], (a["local" + n] + b["local" + n]) / 2, rtol=1e-6, atol=1e-8)
     np.testing.assert_allclose(a["la"], (a["la_local"] + b["la_local"]) / 2, rtol=1e-6)
     assert np.array_equal(a["mirror"], b["mirror"])
+
+
+MAPPO_WORKER = r'''
+import os, sys
+import numpy as np, torch
+import torch.distributed as dist
+sys.path.insert(0, os.environ["FRL_ROOT"]); sys.path.insert(0, os.path.join(os.environ["FRL_ROOT"], "tests"))
+from freerl_b200.MAPPO import MAPPO
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+trick = {'adv_norm': True, 'ObsNorm': True, 'reward_norm': False, 'reward_scaling': True, 'orthogonal_init': True,
+         'adam_eps': True, 'lr_decay': False, 'ValueClip': True, 'huber_loss': True, 'LayerNorm': True, 'feature_norm': True}
+ids = ["agent_%d" % i for i in range(2)]
+H, E = 8, 2
+torch.manual_seed(3 + rank)                      # different initial replicas: enable_data_parallel must broadcast rank 0's
+pol = MAPPO({k: [6, 3] for k in ids}, True, 1e-3, 1e-3, H * E, torch.device("cpu"), dict(trick))
+pol.enable_data_parallel()
+rng = np.random.default_rng(40 + rank)           # every rank steps its own envs
+for t in range(H):
+    obs = {k: rng.standard_normal((E, 6), dtype=np.float32) for k in ids}
+    act = {k: rng.uniform(-1, 1, (E, 3)).astype(np.float32) for k in ids}
+    lp = {k: (-np.abs(rng.standard_normal((E, 3))) - 0.5).astype(np.float32) for k in ids}
+    rew = {k: rng.standard_normal(E).astype(np.float32) * (1 + 2 * rank) for k in ids}
+    nobs = {k: rng.standard_normal((E, 6), dtype=np.float32) for k in ids}
+    pol.add(obs, act, rew, nobs, {k: np.zeros(E, bool) for k in ids}, lp, {k: np.full(E, t == H - 1) for k in ids})
+pol.trick['adv_norm'] = False
+raw, _, _ = pol.compute_advantages(0.95, 0.95)
+pol.trick['adv_norm'] = True
+adv, _, _ = pol.compute_advantages(0.95, 0.95)
+prng = np.random.default_rng(9)
+perms = {k: [prng.permutation(H * E) for _ in range(2)] for k in ids}      # same local permutations on both ranks
+pol.learn(8, 0.95, 0.95, 0.2, 2, 0.01, 10.0, permutations=perms)
+out = {"raw": raw.cpu().numpy(), "adv": adv.cpu().numpy()}
+for k in ids:
+    out["p." + k] = pol.agents[k]._net.p.cpu().numpy()
+np.savez(os.path.join(os.environ["FRL_OUT"], "mappo_rank%d.npz" % rank), **out)
+dist.destroy_process_group()
+'''
+
+
+def test_mappo_data_parallel_adv_norm_gloo(tmp_path, emul):
+    """MAPPO under data parallel with the adv_norm trick (the class default): the advantages are normalised with the statistics of the
+    UNION of the ranks' rollouts (all-reduced sum / sum of squares / count), and the replicas stay bit-identical through the learn."""
+    (tmp_path / "worker.py").write_text(MAPPO_WORKER)
+    env = dict(os.environ, FRL_ROOT=ROOT, FRL_OUT=str(tmp_path), FREERL_B200_LIB=os.environ["FREERL_B200_LIB"], OMP_NUM_THREADS="2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", str(tmp_path / "worker.py")]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    r0, r1 = np.load(tmp_path / "mappo_rank0.npz"), np.load(tmp_path / "mappo_rank1.npz")
+    union = torch.from_numpy(np.concatenate([r0["raw"], r1["raw"]]))
+    want = ((union - union.mean()) / (union.std() + 1e-8)).numpy()          # MAPPO.py:386-388 over the whole (union) rollout
+    n = r0["raw"].shape[0]
+    np.testing.assert_allclose(r0["adv"], want[:n], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(r1["adv"], want[n:], rtol=1e-5, atol=1e-6)
+    assert abs(float(r0["adv"].mean())) > 1e-3                               # a per-shard normalisation would have centred each shard
+    for k in r0.files:
+        if k.startswith("p."):
+            assert np.array_equal(r0[k], r1[k]), "replicas diverged: " + k

@@ -18,14 +18,17 @@ NCCL_WORKER = (WORKER.replace('dist.init_process_group("gloo")',
 
 
 @pytest.mark.gpu
-def test_ppo_data_parallel_nccl(tmp_path):
+@pytest.mark.parametrize("peer", ["1", "0"])
+def test_ppo_data_parallel_nccl(tmp_path, peer):
+    """peer = 1: gradients summed inside the one persistent launch over peer-mapped NVLink memory (the default on CUDA);
+    peer = 0: host-driven launch / dist.all_reduce(net.g) / launch per optimiser step."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     (tmp_path / "worker.py").write_text(NCCL_WORKER)
-    env = dict(os.environ, FRL_ROOT=ROOT, FRL_OUT=str(tmp_path))
+    env = dict(os.environ, FRL_ROOT=ROOT, FRL_OUT=str(tmp_path), FREERL_B200_DP_PEER=peer)
     env.pop("FREERL_B200_LIB", None)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29541", str(tmp_path / "worker.py")]
+           "--master-port", "29541" if peer == "1" else "29542", str(tmp_path / "worker.py")]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")

@@ -280,3 +280,56 @@ def test_fused_equals_sequential_emulated(emul):
 def test_fused_equals_sequential_gpu():
     _fused_equals_sequential(torch.device("cuda"), "sac", 256, 8)
     _fused_equals_sequential(torch.device("cuda"), "td3", 256, 8)
+
+
+# ---- the mode the bench times (mode="fast": device sampler + in-kernel Philox noise, K learns per launch) against the oracle:
+#      the indices the launch sampled are read back, the noise it drew is regenerated by the library's audit hook
+#      (frl_debug_randn: the same randn call, streams 1 = eps of a', 2 = eps of the new action, counter = learn number) and both
+#      are handed to the oracle — B = 256, 8 fused updates, the bench's batch shape ----
+def _fast_mode_audit(device, B=256, K=8, n=4096):
+    import ctypes
+    from collections import OrderedDict
+    from freerl_b200 import _lib
+    from freerl_b200.SAC import SAC
+    torch.manual_seed(21)
+    np.random.seed(21)
+    pol = SAC([17, 6], True, 1e-3, 1e-3, n, device, trick={}, mode="fast")
+    rng = np.random.default_rng(8)
+    obs, act = rng.standard_normal((n, 17), dtype=np.float32), rng.uniform(-1, 1, (n, 6)).astype(np.float32)
+    rew, nobs = rng.standard_normal(n).astype(np.float32), rng.standard_normal((n, 17), dtype=np.float32)
+    done = rng.random(n) < 0.05
+    pol.add(obs, act, rew, nobs, done)
+    sd = lambda m: OrderedDict((k, v.detach().cpu().clone()) for k, v in m.state_dict().items())
+    orc = algos.SACOracle(sd(pol.agent.actor), sd(pol.agent.critic), 1e-3, 1e-3, act_dim=6)
+    seed, it0 = pol._seed, pol._n_learn
+    pol.learn(B, 0.99, 0.01, n_updates=K)
+    idx = pol._keepalive[0].cpu().numpy()
+    assert idx.shape == (K, B) and pol._keepalive[1] is None and pol._keepalive[2] is None       # nothing was injected
+    m = pol.last_metrics.cpu().numpy()
+    for u in range(K):
+        assert len(set(idx[u].tolist())) == B and idx[u].min() >= 0 and idx[u].max() < n       # without replacement, in range
+        nz = []
+        for stream in (1, 2):
+            t = torch.empty(B * 6, dtype=torch.float32, device=device)
+            _lib.check(_lib.lib().frl_debug_randn(ctypes.c_uint64(seed), stream, it0 + u, B * 6, _lib.ptr(t), _lib.stream_ptr(device)), "frl_debug_randn")
+            nz.append(t.cpu().reshape(B, 6))
+        i = idx[u]
+        batch = (torch.from_numpy(obs[i]), torch.from_numpy(act[i]), torch.from_numpy(rew[i]).reshape(-1, 1), torch.from_numpy(nobs[i]),
+                 torch.from_numpy(done[i].astype(np.float32)).reshape(-1, 1))
+        r = orc.learn(batch, nz[0], nz[1], 0.99, 0.01)
+        assert _rel(m[u, 0], r["critic_loss"]) < 1e-5, (u, m[u, 0], r["critic_loss"])
+        assert _rel(m[u, 1], r["actor_loss"]) < 2e-5, (u, m[u, 1], r["actor_loss"])
+    z = torch.cat(nz).numpy()                                  # the regenerated draws are standard normals
+    assert abs(z.mean()) < 0.08 and abs(z.std() - 1.0) < 0.05
+    for name in NETS:
+        assert_module_close(getattr(pol.agent, name), getattr(orc, name), "fast mode, %s after %d fused learns" % (name, K))
+    assert _rel(float(pol.alphas.log_alpha), orc.log_alpha.item()) < 1e-5
+
+
+def test_fast_mode_audit_emulated(emul):
+    _fast_mode_audit(torch.device("cpu"), B=64, K=3, n=512)
+
+
+@pytest.mark.gpu
+def test_fast_mode_audit_gpu():
+    _fast_mode_audit(torch.device("cuda"))

@@ -99,7 +99,54 @@ def vs_oracle(is_continue, mb=1024, T=16, N=128):
             print("  %-6s %-12s max|diff| %.3e  max|ref| %.3e" % (name, k, np.abs(x - y).max(), np.abs(y).max()))
 
 
+def mappo_ab(is_continue=True):
+    """MAPPO (LayerNorm nets, centralised critic on the joint observation, huber value loss): one 2048-row full-batch update per
+    agent, tensor-core path vs FFMA tile path from identical parameters."""
+    from freerl_b200.MAPPO import MAPPO
+    from oracle.make_golden_marl import MAPPO_TRICK          # the trick dict only
+    H, E = 32, 64
+    ids = ["agent_%d" % i for i in range(3)]
+    res = {}
+    for umma in (False, True):
+        if umma:
+            os.environ.pop("FREERL_B200_NO_UMMA", None)
+        else:
+            os.environ["FREERL_B200_NO_UMMA"] = "1"
+        torch.manual_seed(7)
+        np.random.seed(7)
+        pol = MAPPO({k: [18, 5] for k in ids}, is_continue, 1e-3, 1e-3, H * E, dev, dict(MAPPO_TRICK))
+        rng = np.random.default_rng(3)
+        for t in range(H):
+            obs = {k: rng.standard_normal((E, 18), dtype=np.float32) for k in ids}
+            act, lp = {}, {}
+            for k in ids:
+                if is_continue:
+                    act[k] = rng.uniform(-1, 1, (E, 5)).astype(np.float32)
+                    lp[k] = (-np.abs(rng.standard_normal((E, 5))) * 0.1 - 0.9).astype(np.float32)
+                else:
+                    act[k] = rng.integers(0, 5, (E, 1)).astype(np.float32)
+                    lp[k] = (-np.abs(rng.standard_normal((E, 1))) * 0.1 - 1.5).astype(np.float32)
+            rew = {k: rng.standard_normal(E).astype(np.float32) for k in ids}
+            nobs = {k: rng.standard_normal((E, 18), dtype=np.float32) for k in ids}
+            done = {k: np.zeros(E, bool) for k in ids}
+            trunc = np.full(E, (t % 25) == 24)
+            pol.add(obs, act, rew, nobs, done, lp, {k: trunc for k in ids})
+        pol.learn(H * E, 0.95, 0.95, 0.2, 1, 0.01, 10.0)
+        torch.cuda.synchronize()
+        res[umma] = (pol, pol.last_metrics.cpu().numpy().copy())
+    print("MAPPO A/B one 2048-row update per agent,", "continuous" if is_continue else "discrete")
+    print("  metrics FFMA", res[False][1][:, :5].tolist())
+    print("  metrics UMMA", res[True][1][:, :5].tolist())
+    for k in ids:
+        nu, nf = res[True][0].agents[k]._net, res[False][0].agents[k]._net
+        seg_report(nu, nu.g, nf.g, "%s gradient UMMA vs FFMA" % k)
+        print("  %s parameters after the update: max|diff| %.3e" % (k, (nu.p - nf.p).abs().max().item()))
+
+
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
+if which in ("all", "mappo"):
+    mappo_ab(True)
+    mappo_ab(False)
 for cont in (False, True):
     if which in ("all", "ab"):
         ab(cont)

@@ -24,7 +24,7 @@
 // mode 2: D[m][n] = sum_k A[k][m] B[k][n]     SS: A stored [K x M], B stored [K x N], layout S (MN-major)  (dW = dZ^T . H over tile rows)
 // M = 128, N = 128, K = 64.  terms: 1 = TF32, 3 = 3xTF32.
 __global__ void __launch_bounds__(128, 1) umma_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int mode,
-                                                      int terms, int reps, long long* clk) {
+                                                      int terms, int reps, long long* clk, int n_issue = 128) {
   constexpr int M = 128, N = 128, K = 64;
   extern __shared__ __align__(1024) unsigned char smraw[];
   float* a_hi = (float*)smraw;
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(128, 1) umma_kernel(const float* __restrict__ 
   }
   if (t == 0) {
     const int mn = mode == 2;
-    const uint32_t idesc = um_idesc_tf32(M, N, mn, mn);
+    const uint32_t idesc = um_idesc_tf32(M, n_issue, mn, mn);      // n_issue < N: timing of narrow MMAs (results unused)
     const uint32_t a_step = mn ? 32 * M : 32 * M, b_step = mn ? 32 * N : 32 * N;   // bytes per K = 8 step (both layouts: 32 x rows-or-cols)
     long long t0 = clock64();
     for (int rep = 0; rep < reps; ++rep)
@@ -235,6 +235,16 @@ int main(int argc, char** argv) {
       int n = reps * (K / 8) * terms;
       printf("timing mode %d terms %d: %d MMAs (128x128x8 tf32) in %lld clk = %.1f clk / MMA = %.2f TFLOP/s/SM-equivalent at 1.965 GHz\n", mode, terms, n, c,
              (double)c / n, 2.0 * 128 * 128 * 8 / ((double)c / n) * 1.965e9 / 1e12);
+    }
+  for (int nn = 16; nn <= 64; nn *= 2)
+    for (int mode = 0; mode < 3; ++mode) {
+      const int reps = 64;
+      umma_kernel<<<1, 128, smem>>>(dA, dB, dD, mode, 3, reps, dclk, nn);
+      CK(cudaDeviceSynchronize());
+      long long c;
+      CK(cudaMemcpy(&c, dclk, 8, cudaMemcpyDeviceToHost));
+      int n = reps * (K / 8) * 3;
+      printf("timing N = %d mode %d: %d MMAs (128x%dx8 tf32) in %lld clk = %.1f clk / MMA\n", nn, mode, n, nn, c, (double)c / n);
     }
   printf(bad ? "FAILED (%d)\n" : "ALL OK\n", bad);
   return bad != 0;
