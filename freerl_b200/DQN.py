@@ -38,7 +38,10 @@ class Agent:
         self.step = 0                                    # torch.optim.Adam step counter (DQN.py:54)
 
 
-class DQN:
+class DQN(_common.ReplicaSyncMixin):
+    def _replica_pairs(self):
+        return [(self.agent._q.p, self.agent._q.sync_mirror), (self.agent._qt.p, self.agent._qt.sync_mirror)]
+
     def __init__(self, dim_info, is_continue, Qnet_lr, buffer_size, device, trick=None, mode=None):
         obs_dim, action_dim = dim_info
         self.device = _lib.require_device(device)

@@ -154,8 +154,14 @@ class Agent:
 TRICKS = ("Double", "Dueling", "PER", "Noisy", "N_Step", "Categorical")
 
 
-class DQN:
+class DQN(_common.ReplicaSyncMixin):
     """Dispatches on the trick set like the reference's ``Agent.__init__`` (``DQN_with_tricks.py:163-172``)."""
+
+    def _replica_pairs(self):
+        ag = self.agent
+        if hasattr(ag, "online"):                 # Rainbow: flat parameter blocks (the noisy effective weights are rebuilt by every learn)
+            return [(ag.online.p, None), (ag.target.p, None)]
+        return [(ag._q.p, ag._q.sync_mirror), (ag._qt.p, ag._qt.sync_mirror)]
 
     def __new__(cls, dim_info=None, is_continue=None, Qnet_lr=None, buffer_size=None, device=None, trick=None, *args, **kw):
         if cls is DQN:

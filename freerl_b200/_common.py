@@ -181,3 +181,31 @@ class DpPeers:
             a.dp.g[r] = self.base[r] + 256
         a.dp.rank, a.dp.world, a.dp.epoch0 = self.rank, self.world, self.epoch & 0xFFFFFFFF
         self.epoch += n_updates
+
+
+class ReplicaSyncMixin:
+    """Multi-GPU mode of the off-policy value learners (SURVEY §8e "replicas + sharded replay"; DQN / Rainbow = BASELINE config 4):
+    one process per GPU, each with its own env shard and its own replay shard — for PER its own sum-tree, priorities never leave the
+    GPU that sampled them — and no data-path collective.  The replicas are kept ONE policy by a parameter average over
+    ``torch.distributed`` (NCCL over NVLink): ``enable_replica_sync()`` broadcasts rank 0's parameters, ``sync_replicas()`` averages
+    online and target parameters (call it every K learns; Adam moments stay local, the standard local-SGD scheme).
+    A class provides ``_replica_pairs() -> [(parameter block tensor, refresh callable or None), ...]``."""
+
+    def enable_replica_sync(self, group=None):
+        import torch.distributed as dist
+        self._rs = (dist, group, dist.get_world_size(group))
+        for t, refresh in self._replica_pairs():
+            dist.broadcast(t, src=0, group=group)
+            if refresh:
+                refresh()
+
+    def sync_replicas(self):
+        rs = getattr(self, "_rs", None)
+        if rs is None or rs[2] == 1:
+            return
+        dist, group, world = rs
+        for t, refresh in self._replica_pairs():
+            dist.all_reduce(t, group=group)
+            t.div_(world)
+            if refresh:
+                refresh()

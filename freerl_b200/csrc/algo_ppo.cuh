@@ -150,12 +150,15 @@ FRL_DEV void dp_exchange(Cta& c, const frl_ppo_args_t& a, int u) {
   __syncthreads();
   const size_t par = (size_t)(epoch & 1u) * N.n_p;
   for (int p = (c.cta * FRL_NT + tid) * 4; p < N.n_p; p += c.ncta * FRL_NT * 4) {
+    float4 v[FRL_DP_MAX_RANKS];                    // all peers' loads in flight together (NVLink latency once, not world times)
+#pragma unroll
+    for (int r = 0; r < FRL_DP_MAX_RANKS; ++r)
+      if (r < world)
+        asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[r].x), "=f"(v[r].y), "=f"(v[r].z), "=f"(v[r].w) : "l"(a.dp.g[r] + par + p) : "memory");
     float4 sgm = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < world; ++r) {
-      float4 v;
-      asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(a.dp.g[r] + par + p) : "memory");
-      sgm = f4add(sgm, v);
-    }
+#pragma unroll
+    for (int r = 0; r < FRL_DP_MAX_RANKS; ++r)
+      if (r < world) sgm = f4add(sgm, v[r]);       // rank order: bit-identical on every rank
     st4(N.g + p, sgm);
   }
   __syncthreads();
@@ -560,10 +563,17 @@ struct PpoAlgoT {
         FRL_SYNC();
       } else {
         // pass 2: p += -step * (m * mask / max(mean(mask), 1e-3)) / (sqrt(v) + eps)
+        // per-tensor mask counts of all CTAs: staged into shared memory by the whole CTA (one coalesced sweep instead of 13 threads
+        // each waiting on ncta / 16 rounds of L2 latency), then folded in CTA order — the same association as before
         float* segmean = red0;
+        float* stg = c.red + 64;                 // c.red[0..5] still hold the optimiser scalars
+        FRL_PAR(t) { for (int i = t; i < c.ncta * FRL_NSEG; i += FRL_NT) stg[i] = a.segcnt[i]; }
+        FRL_SYNC();
         FRL_PAR(t) {
           if (t < FRL_NSEG) {
-            segmean[t] = strided_sum(a.segcnt + t, FRL_NSEG, c.ncta);
+            float tot = 0.f;
+            for (int cc = 0; cc < c.ncta; ++cc) tot += stg[cc * FRL_NSEG + t];
+            segmean[t] = tot;
           }
         }
         FRL_SYNC();

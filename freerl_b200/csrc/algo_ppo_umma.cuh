@@ -104,16 +104,56 @@ UM_DEV void um_split_one(const frl_ppo_args_t& a, int p, float w) {
   }
 }
 
-// 16 consecutive columns of row `r` -> layout S scratch (two 8-float groups, float4 stores)
-UM_DEV void um_s_store16(float* bh, float* bl, int r, int c0, int C, const float* hi, const float* lo) {
+// 4 x 4 transpose of float4 pieces among the four lanes of an aligned lane group (butterfly, an involution): afterwards
+// v[i] of lane l = the former v[l & 3] of lane (l & ~3) + i
+UM_DEV void um_xpose4(float4* v, int lane) {
+  const bool b0 = lane & 1, b1 = lane & 2;
 #pragma unroll
-  for (int g = 0; g < 2; ++g) {
-    const int o = um_s_off(r, c0 + 8 * g, C);
-    st4(bh + o, make_float4(hi[8 * g], hi[8 * g + 1], hi[8 * g + 2], hi[8 * g + 3]));
-    st4(bh + o + 4, make_float4(hi[8 * g + 4], hi[8 * g + 5], hi[8 * g + 6], hi[8 * g + 7]));
-    st4(bl + o, make_float4(lo[8 * g], lo[8 * g + 1], lo[8 * g + 2], lo[8 * g + 3]));
-    st4(bl + o + 4, make_float4(lo[8 * g + 4], lo[8 * g + 5], lo[8 * g + 6], lo[8 * g + 7]));
+  for (int p = 0; p < 4; p += 2) {
+    float4 s_ = b0 ? v[p] : v[p + 1], r_;
+    r_.x = __shfl_xor_sync(0xffffffffu, s_.x, 1); r_.y = __shfl_xor_sync(0xffffffffu, s_.y, 1);
+    r_.z = __shfl_xor_sync(0xffffffffu, s_.z, 1); r_.w = __shfl_xor_sync(0xffffffffu, s_.w, 1);
+    if (b0) v[p] = r_; else v[p + 1] = r_;
   }
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    float4 s_ = b1 ? v[p] : v[p + 2], r_;
+    r_.x = __shfl_xor_sync(0xffffffffu, s_.x, 2); r_.y = __shfl_xor_sync(0xffffffffu, s_.y, 2);
+    r_.z = __shfl_xor_sync(0xffffffffu, s_.z, 2); r_.w = __shfl_xor_sync(0xffffffffu, s_.w, 2);
+    if (b1) v[p] = r_; else v[p + 2] = r_;
+  }
+}
+
+// 16 consecutive columns (c0 ..) of this thread's row -> hi / lo copies in the layout-S scratch.  A thread owns a ROW (TMEM lane), and
+// rows are 128 B apart in layout S: storing its own 16-byte pieces would touch 32 lines per warp instruction (measured: the stores,
+// not the MMAs, bounded the epilogues).  The four lanes of a row group first transpose their pieces, so that every instruction
+// writes, per group, the 64 contiguous bytes of ONE row (8 lines per instruction).  All 32 lanes of the warp must call it.
+UM_DEV void um_s_store16(float* bh, float* bl, int row, int c0, int C, const float* x) {
+  const int lane = (int)threadIdx.x & 31, l = lane & 3, rb = row & ~3;
+  float4 v[4] = {make_float4(x[0], x[1], x[2], x[3]), make_float4(x[4], x[5], x[6], x[7]), make_float4(x[8], x[9], x[10], x[11]),
+                 make_float4(x[12], x[13], x[14], x[15])};
+  um_xpose4(v, lane);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int o = um_s_off(rb + i, c0 + 4 * l, C);
+    const float4 h = make_float4(um_hi(v[i].x), um_hi(v[i].y), um_hi(v[i].z), um_hi(v[i].w));
+    st4(bh + o, h);
+    st4(bl + o, make_float4(v[i].x - h.x, v[i].y - h.y, v[i].z - h.z, v[i].w - h.w));
+  }
+}
+// the inverse: 16 columns of this thread's row, hi + lo (= the exact fp32 value), read back with the same coalescing
+UM_DEV void um_s_load16(const float* bh, const float* bl, int row, int c0, int C, float* y) {
+  const int lane = (int)threadIdx.x & 31, l = lane & 3, rb = row & ~3;
+  float4 v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int o = um_s_off(rb + i, c0 + 4 * l, C);
+    const float4 h = ld4(bh + o), lo = ld4(bl + o);
+    v[i] = make_float4(h.x + lo.x, h.y + lo.y, h.z + lo.z, h.w + lo.w);
+  }
+  um_xpose4(v, lane);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { y[4 * i] = v[i].x; y[4 * i + 1] = v[i].y; y[4 * i + 2] = v[i].z; y[4 * i + 3] = v[i].w; }
 }
 
 // ring + barriers, driven by thread 0 only
@@ -178,8 +218,9 @@ struct UmThr {
 
 // Forward epilogue of a hidden layer: acc -> +bias -> ReLU [-> F.layer_norm over the 128 features, MAPPO.py:145-151] -> TMEM A
 // operand (hi | lo) + layout-S scratch.  Returns the ReLU mask of the thread's 64 columns; *rstd = 1 / sqrt(var + 1e-5) of the row.
+template <int NO>      // NO = 0: no output layer; 4 / 8 / 16: register accumulators for that many output columns
 UM_DEV uint64_t um_hidden_fwd(const UmThr& th, const float* bias, bool ln, float* Sh, float* Sl, float* rstd, const float* W3s = nullptr,
-                              int nout = 0, float* lgp = nullptr) {
+                              float* lgp = nullptr) {
   uint64_t mask = 0;
   float mean = 0.f, rs = 1.f;
   if (ln) {
@@ -212,28 +253,34 @@ UM_DEV uint64_t um_hidden_fwd(const UmThr& th, const float* bias, bool ln, float
   for (int j = 0; j < 4; ++j) {
     const int c0 = th.hh * 64 + j * 16;
     float v[16], hi[16], lo[16];
+    trace(2100 + j, 32);
     um_ld16(th.tm + th.lane_base + c0, v);
+    trace(2110 + j, 32);
 #pragma unroll
+    uint32_t m16 = 0;
     for (int i = 0; i < 16; ++i) {
       float x = v[i] + bias[c0 + i];
-      if (x > 0.f) mask |= 1ull << (j * 16 + i); else x = 0.f;
+      if (x > 0.f) m16 |= 1u << i; else x = 0.f;
       if (ln) x = (x - mean) * rs;
       hi[i] = um_hi(x);
       lo[i] = x - hi[i];
       v[i] = x;
     }
+    mask |= (uint64_t)m16 << (j * 16);
+    trace(2120 + j, 32);
     um_st16(th.tm + th.lane_base + 128 + c0, hi);
     um_st16(th.tm + th.lane_base + 256 + c0, lo);
-    um_s_store16(Sh, Sl, th.row, c0, 128, hi, lo);
-    if (W3s) {                                 // output layer on the CUDA cores (out <= 16): partial dot products over this thread's columns
+    trace(2130 + j, 32);
+    um_s_store16(Sh, Sl, th.row, c0, 128, v);
+    trace(2140 + j, 32);
+    if (NO > 0) {                              // output layer on the CUDA cores (out <= 16): partial dot products over this thread's columns
 #pragma unroll
-      for (int n = 0; n < 16; ++n)
-        if (n < nout) {
-          float acc = lgp[n];
+      for (int n = 0; n < NO; ++n) {
+        float acc = lgp[n];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) acc = fmaf(v[i], W3s[n * 128 + c0 + i], acc);
-          lgp[n] = acc;
-        }
+        for (int i = 0; i < 16; ++i) acc = fmaf(v[i], W3s[n * 128 + c0 + i], acc);
+        lgp[n] = acc;
+      }
     }
   }
   *rstd = rs;
@@ -264,12 +311,12 @@ UM_DEV void um_dy16(const UmThr& th, int c0, const float* W3s, const float* dz, 
   if (!W3s) { um_ld16(th.tm + th.lane_base + c0, v); return; }
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = 0.f;
+#pragma unroll 1
+  for (int n = 0; n < nout; ++n) {           // dz: this row's dZ3 in shared memory
+    const float d = dz[n];
 #pragma unroll
-  for (int n = 0; n < 16; ++n)
-    if (n < nout) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = fmaf(dz[n], W3s[n * 128 + c0 + i], v[i]);
-    }
+    for (int i = 0; i < 16; ++i) v[i] = fmaf(d, W3s[n * 128 + c0 + i], v[i]);
+  }
 }
 
 UM_DEV void um_hidden_bwd(const UmThr& th, uint64_t mask, bool ln, float rs, const float* Yh, const float* Yl, float* Dh, float* Dl,
@@ -282,14 +329,10 @@ UM_DEV void um_hidden_bwd(const UmThr& th, uint64_t mask, bool ln, float rs, con
       const int c0 = th.hh * 64 + j * 16;
       float v[16];
       um_dy16(th, c0, W3s, dz, nout, v);
+      float y[16];
+      um_s_load16(Yh, Yl, th.row, c0, 128, y);
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        const int o = um_s_off(th.row, c0 + 8 * g, 128);
-        const float4 a0 = ld4(Yh + o), a1 = ld4(Yh + o + 4), b0 = ld4(Yl + o), b1 = ld4(Yl + o + 4);
-        const float y[8] = {a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w, a1.x + b1.x, a1.y + b1.y, a1.z + b1.z, a1.w + b1.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { s1 += v[8 * g + i]; s2 += v[8 * g + i] * y[i]; }
-      }
+      for (int i = 0; i < 16; ++i) { s1 += v[i]; s2 += v[i] * y[i]; }
     }
     th.xs[512 + th.hh * 128 + th.row] = s1;
     th.xs[768 + th.hh * 128 + th.row] = s2;
@@ -303,18 +346,15 @@ UM_DEV void um_hidden_bwd(const UmThr& th, uint64_t mask, bool ln, float rs, con
     float v[16], hi[16], lo[16];
     um_dy16(th, c0, W3s, dz, nout, v);
     if (ln) {
+      float y[16];
+      um_s_load16(Yh, Yl, th.row, c0, 128, y);
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        const int o = um_s_off(th.row, c0 + 8 * g, 128);
-        const float4 a0 = ld4(Yh + o), a1 = ld4(Yh + o + 4), b0 = ld4(Yl + o), b1 = ld4(Yl + o + 4);
-        const float y[8] = {a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w, a1.x + b1.x, a1.y + b1.y, a1.z + b1.z, a1.w + b1.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[8 * g + i] = rs * (v[8 * g + i] - m1 - y[i] * m2);
-      }
+      for (int i = 0; i < 16; ++i) v[i] = rs * (v[i] - m1 - y[i] * m2);
     }
 #pragma unroll
+    const uint32_t m16 = (uint32_t)(mask >> (j * 16));
     for (int i = 0; i < 16; ++i) {
-      const float x = ((mask >> (j * 16 + i)) & 1ull) ? v[i] : 0.f;
+      const float x = ((m16 >> i) & 1u) ? v[i] : 0.f;
       hi[i] = um_hi(x);
       lo[i] = x - hi[i];
       v[i] = x;
@@ -328,7 +368,7 @@ UM_DEV void um_hidden_bwd(const UmThr& th, uint64_t mask, bool ln, float rs, con
       um_st16(th.tm + th.lane_base + 128 + c0, hi);
       um_st16(th.tm + th.lane_base + 256 + c0, lo);
     }
-    um_s_store16(Dh, Dl, th.row, c0, 128, hi, lo);
+    um_s_store16(Dh, Dl, th.row, c0, 128, v);
   }
 }
 
@@ -419,17 +459,18 @@ __device__ __noinline__ void ppo_umma_stage(Cta& c, float* user, const frl_ppo_a
         rs = 1.0f / sqrtf(q_ / (float)in + 1e-5f);
       }
       for (int c0 = 0; c0 < K0; c0 += 16) {
-        float hi[16], lo[16];
+        float xv[16], hi[16], lo[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           float x = (valid && c0 + i < in) ? src[c0 + i] : 0.f;
           if (ln && valid && c0 + i < in) x = (x - mean) * rs;
+          xv[i] = x;
           hi[i] = um_hi(x);
           lo[i] = x - hi[i];
         }
         um_st16(tm + lane_base + 128 + c0, hi);
         um_st16(tm + lane_base + 256 + c0, lo);
-        um_s_store16(Xh, Xl, row, c0, Cx, hi, lo);
+        um_s_store16(Xh, Xl, row, c0, Cx, xv);
       }
     }
     um_wait_st();
@@ -437,82 +478,91 @@ __device__ __noinline__ void ppo_umma_stage(Cta& c, float* user, const frl_ppo_a
     __syncthreads();
     stamp(c, 301);
     // ---- layer 1: acc = x W1^T ----
+    trace(2001, 32);
     if (tid == 0) {
+      trace(2200, 0);
       um_fence_after();
       for (int c0 = 0; c0 < K0; c0 += 32) um_consume_ts(p, 0, c0, 128, (K0 - c0) < 32 ? (K0 - c0) : 32, c0 == 0);
       um_commit(p.acc);
+      trace(2201, 0);
     }
-    um_mbar_wait(p.acc, accn & 1u); ++accn;
+    if (warp == 0) um_mbar_wait(p.acc, accn & 1u);      // one polling warp: seven more would contend with the operand reads of the running MMAs
+    ++accn;
+    __syncthreads();
     um_fence_after();
+    trace(2002, 32);
+    trace(2202, 0);
     if (tid == 0)
       for (int c0 = 0; c0 < 128; c0 += 32) um_fill(p, UM_W(l0 + 1, 0) + c0 * 128, UM_W(l0 + 1, 1) + c0 * 128, 16384u);
     float rs1 = 1.f, rs2 = 1.f;
-    const uint64_t mask1 = um_hidden_fwd(th, bias, ln, H1h, H1l, &rs1);
+    const uint64_t mask1 = um_hidden_fwd<0>(th, bias, ln, H1h, H1l, &rs1);
     um_wait_st();
     um_fence_before();
     __syncthreads();
     stamp(c, 302);
     // ---- layer 2: acc = h1 W2^T ----
+    trace(2003, 32);
     if (tid == 0) {
+      trace(2210, 0);
       um_fence_after();
       for (int c0 = 0; c0 < 128; c0 += 32) um_consume_ts(p, 0, c0, 128, 32, c0 == 0);
+      trace(2211, 0);
       um_commit(p.acc);
     }
-    um_mbar_wait(p.acc, accn & 1u); ++accn;
+    if (warp == 0) um_mbar_wait(p.acc, accn & 1u);      // one polling warp: seven more would contend with the operand reads of the running MMAs
+    ++accn;
+    __syncthreads();
     um_fence_after();
+    trace(2004, 32);
+    trace(2212, 0);
     if (tid == 0)                              // W2 backward operand for dH1, one GEMM ahead
       for (int c0 = 0; c0 < 128; c0 += 32) um_fill(p, UM_W(l0 + 1, 2) + c0 * 128, UM_W(l0 + 1, 3) + c0 * 128, 16384u);
     // layer-2 epilogue; the output layer (out <= 16 columns) runs on the CUDA cores from the registers of the same pass
     float lgp[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) lgp[i] = 0.f;
-    const uint64_t mask2 = um_hidden_fwd(th, bias + 128, ln, H2h, H2l, &rs2, W3s, nout, lgp);
+    const uint64_t mask2 = nout <= 4 ? um_hidden_fwd<4>(th, bias + 128, ln, H2h, H2l, &rs2, W3s, lgp)
+                         : nout <= 8 ? um_hidden_fwd<8>(th, bias + 128, ln, H2h, H2l, &rs2, W3s, lgp)
+                                     : um_hidden_fwd<16>(th, bias + 128, ln, H2h, H2l, &rs2, W3s, lgp);
     if (hh == 1) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) cs[row * 17 + i] = lgp[i];
     }
+    trace(2005, 32);
     um_wait_st();
+    trace(2006, 32);
     __syncthreads();
+    trace(2007, 32);
     stamp(c, 303);
-    // ---- heads: losses and dL/d(output) per row (PPO.py:256-279) ----
-    float lsg[16];                             // d/dlog_std through the log-prob, per action dim (continuous actor)
-#pragma unroll
-    for (int i = 0; i < 16; ++i) lsg[i] = 0.f;
+    // ---- heads: losses and dL/d(output) per row (PPO.py:256-279); the row's logits / dZ3 live in shared memory (runtime-bounded
+    //      loops over out <= 16 columns: the 16-wide predicated register version was 20 k clk of mostly dead code per tile) ----
     if (hh == 0) {
-      float v[16], dz[16];
+      float* lg = cs + row * 17;               // logits, then (continuous actor) d/dlog_std per action dim
+      float* dz = dzs + row * 17;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) { v[i] = (lgp[i] + cs[row * 17 + i]) + bias[256 + i]; dz[i] = 0.f; }
+      for (int j = 0; j < 16; ++j) { lg[j] = j < nout ? (lgp[j] + lg[j]) + bias[256 + j] : 0.f; dz[j] = 0.f; }
       if (valid && role == 0) {
         float lp_now = 0.f, lp_old = 0.f, ent = 0.f, lse = 0.f;
         int act = 0;
         if (a.continuous) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < nout) {
-              const float mean = tanhf(v[j]);
-              const float ls = fminf(fmaxf(N.p[N.x_off + j], -20.f), 2.f);
-              const float sd = expf(ls);
-              const float diff = a.action[(size_t)gi * a.act_cols + j] - mean;
-              lp_now += -(diff * diff) / (2.f * (sd * sd)) - logf(sd) - FRL_HALF_LOG_2PI;
-              ent += 0.5f + FRL_HALF_LOG_2PI + logf(sd);
-            }
+          for (int j = 0; j < nout; ++j) {
+            const float mean = tanhf(lg[j]);
+            const float ls = fminf(fmaxf(N.p[N.x_off + j], -20.f), 2.f);
+            const float sd = expf(ls);
+            const float diff = a.action[(size_t)gi * a.act_cols + j] - mean;
+            lp_now += -(diff * diff) / (2.f * (sd * sd)) - logf(sd) - FRL_HALF_LOG_2PI;
+            ent += 0.5f + FRL_HALF_LOG_2PI + logf(sd);
+          }
           for (int j = 0; j < a.logp_cols; ++j) lp_old += a.logp_old[(size_t)gi * a.logp_cols + j];
         } else {
-          float mx = v[0];
-#pragma unroll
-          for (int j = 1; j < 16; ++j) if (j < nout) mx = fmaxf(mx, v[j]);
+          float mx = lg[0];
+          for (int j = 1; j < nout; ++j) mx = fmaxf(mx, lg[j]);
           float se_ = 0.f;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) if (j < nout) se_ += expf(v[j] - mx);
+          for (int j = 0; j < nout; ++j) se_ += expf(lg[j] - mx);
           lse = mx + logf(se_);
           act = (int)a.action[(size_t)gi * a.act_cols];
-          float oa_act = 0.f;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (j == act) oa_act = v[j];
-            if (j < nout) { const float lg = v[j] - lse; ent -= expf(lg) * lg; }
-          }
-          lp_now = oa_act - lse;
+          for (int j = 0; j < nout; ++j) { const float l_ = lg[j] - lse; ent -= expf(l_) * l_; }
+          lp_now = lg[act] - lse;
           lp_old = a.logp_old[(size_t)gi * a.logp_cols];
         }
         const float ratio = expf(lp_now - lp_old);
@@ -529,31 +579,27 @@ __device__ __noinline__ void ppo_umma_stage(Cta& c, float* user, const frl_ppo_a
         la += -surr * inv_rn;
         le += ent;
         if (a.continuous) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < nout) {
-              const float mean = tanhf(v[j]);
-              const float lsr = N.p[N.x_off + j];
-              const float ls = fminf(fmaxf(lsr, -20.f), 2.f);
-              const float sd = expf(ls);
-              const float diff = a.action[(size_t)gi * a.act_cols + j] - mean;
-              dz[j] = dlp * (diff / (sd * sd)) * (1.f - mean * mean);
-              if (lsr >= -20.f && lsr <= 2.f) lsg[j] = dlp * ((diff * diff) / (sd * sd) - 1.f) - a.entropy_coef * inv_rows;
-            }
+          for (int j = 0; j < nout; ++j) {
+            const float mean = tanhf(lg[j]);
+            const float lsr = N.p[N.x_off + j];
+            const float ls = fminf(fmaxf(lsr, -20.f), 2.f);
+            const float sd = expf(ls);
+            const float diff = a.action[(size_t)gi * a.act_cols + j] - mean;
+            dz[j] = dlp * (diff / (sd * sd)) * (1.f - mean * mean);
+            lg[j] = (lsr >= -20.f && lsr <= 2.f) ? dlp * ((diff * diff) / (sd * sd) - 1.f) - a.entropy_coef * inv_rows : 0.f;
+          }
         } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < nout) {
-              const float lg = v[j] - lse, pj = expf(lg);
-              float g = dlp * ((j == act ? 1.f : 0.f) - pj);
-              g += -a.entropy_coef * inv_rows * (-pj * (lg + ent));
-              dz[j] = g;
-            }
+          for (int j = 0; j < nout; ++j) {
+            const float l_ = lg[j] - lse, pj = expf(l_);
+            float g = dlp * ((j == act ? 1.f : 0.f) - pj);
+            g += -a.entropy_coef * inv_rows * (-pj * (l_ + ent));
+            dz[j] = g;
+          }
         }
       } else if (valid) {
         float g = 0.f, l = 0.f;
         for (int k = 0; k < a.n_adv; ++k) {
-          const float d = v[0] - a.v_target[(size_t)gi * a.n_adv + k];
+          const float d = lg[0] - a.v_target[(size_t)gi * a.n_adv + k];
           if (a.value_loss == 1) {
             const float e = -d, ae = fabsf(e), dl = a.huber_delta;
             l += (ae <= dl) ? 0.5f * e * e : dl * (ae - 0.5f * dl);
@@ -565,13 +611,17 @@ __device__ __noinline__ void ppo_umma_stage(Cta& c, float* user, const frl_ppo_a
         }
         lc += l;
         dz[0] = g;
+      } else if (role == 0 && a.continuous) {
+        for (int j = 0; j < 16; ++j) lg[j] = 0.f;      // padded rows add nothing to d/dlog_std
       }
-      float hi[16], lo[16];
+      float d16[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) { hi[i] = um_hi(dz[i]); lo[i] = dz[i] - hi[i]; dzs[row * 17 + i] = dz[i]; }
-      um_s_store16(D3h, D3l, row, 0, 32, hi, lo);
+      for (int i = 0; i < 16; ++i) d16[i] = dz[i];
+      um_s_store16(D3h, D3l, row, 0, 32, d16);
     }
+    trace(2008, 32);
     __syncthreads();
+    trace(2009, 32);
     stamp(c, 304);
     {                                          // db3: column sums of dZ3 — 16 segments of 8 rows, then the segments in order
       float s = 0.f;
@@ -586,12 +636,7 @@ __device__ __noinline__ void ppo_umma_stage(Cta& c, float* user, const frl_ppo_a
     }
     if (role == 0 && a.continuous) {
       __syncthreads();
-      if (hh == 0) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) cs[row * 17 + i] = lsg[i];
-      }
-      __syncthreads();
-      {
+      {                                        // cs rows hold d/dlog_std per action dim since the head
         float s = 0.f;
         for (int r = 0; r < 8; ++r) s += cs[((tid >> 4) * 8 + r) * 17 + (tid & 15)];
         red[tid] = s;
@@ -604,12 +649,7 @@ __device__ __noinline__ void ppo_umma_stage(Cta& c, float* user, const frl_ppo_a
       }
     }
     // dH2 = dZ3 W3 on the CUDA cores, straight into the layer-2 backward epilogue
-    {
-      float dz[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) dz[i] = dzs[row * 17 + i];
-      um_hidden_bwd(th, mask2, ln, rs2, H2h, H2l, D2h, D2l, true, accB + 512, W3s, dz, nout);
-    }
+    um_hidden_bwd(th, mask2, ln, rs2, H2h, H2l, D2h, D2l, true, accB + 512, W3s, dzs + row * 17, nout);
     um_wait_st();
     um_fence_before();
     um_fence_proxy_async();
@@ -621,7 +661,9 @@ __device__ __noinline__ void ppo_umma_stage(Cta& c, float* user, const frl_ppo_a
       for (int c0 = 0; c0 < 128; c0 += 32) um_consume_ts(p, 0, c0, 128, 32, c0 == 0);
       um_commit(p.acc);
     }
-    um_mbar_wait(p.acc, accn & 1u); ++accn;
+    if (warp == 0) um_mbar_wait(p.acc, accn & 1u);      // one polling warp: seven more would contend with the operand reads of the running MMAs
+    ++accn;
+    __syncthreads();
     um_fence_after();
     um_hidden_bwd(th, mask1, ln, rs1, H1h, H1l, D1h, D1l, false, accB);
     um_fence_before();
@@ -651,7 +693,9 @@ __device__ __noinline__ void ppo_umma_stage(Cta& c, float* user, const frl_ppo_a
       }
       um_commit(p.acc);
     }
-    um_mbar_wait(p.acc, accn & 1u); ++accn;
+    if (warp == 0) um_mbar_wait(p.acc, accn & 1u);      // one polling warp: seven more would contend with the operand reads of the running MMAs
+    ++accn;
+    __syncthreads();
     um_fence_after();
     if (hh == 0) {
       float v[16];

@@ -58,6 +58,14 @@ def build_policy(algo, obs_dim, act_dim, n_actions, args, device):
     raise ValueError("algo must be SAC, TD3, DQN or RAINBOW")
 
 
+def _save_obs_norm(args, norm):
+    """The reference mains store the running observation statistics next to the model (``SAC.py:583-584``,
+    ``PPO_with_tricks.py:581-582``: ``np.array([mean, std])``) — evaluate.py and a resumed run need them."""
+    if norm is not None:
+        ms = norm.running_ms
+        np.save(os.path.join(args.save_dir, "%s_running_mean_std.npy" % args.algo), np.array([ms.mean.cpu().numpy(), ms.std.cpu().numpy()]))
+
+
 def _ppo_loop(args, envs, obs_dim, action_dim, discrete, device, world=1, rank=0):
     from .PPO import PPO
     N, T = args.n_envs, args.horizon
@@ -96,6 +104,7 @@ def _ppo_loop(args, envs, obs_dim, action_dim, discrete, device, world=1, rank=0
     if args.save_dir and rank == 0:
         os.makedirs(args.save_dir, exist_ok=True)
         policy.save(args.save_dir)
+        _save_obs_norm(args, norm)
     return {"policy": policy, "steps": steps, "learns": n_learn, "returns": returns, "rank": rank, "world": world}
 
 
@@ -111,7 +120,7 @@ def _mpe(name, **kw):
     return envshim.mpe_modules()["pettingzoo.mpe." + name].parallel_env(**kw)
 
 
-def _mappo_loop(args, device):
+def _mappo_loop(args, device, world=1, rank=0):
     """``MAPPO_file/MAPPO.py:640-742`` over N parallel envs (BASELINE config C5: simple_spread_v3, 3 agents, continuous actions)."""
     from .MAPPO import MAPPO
     N, T = args.n_envs, args.horizon
@@ -122,6 +131,8 @@ def _mappo_loop(args, device):
     trick = {'adv_norm': True, 'ObsNorm': False, 'reward_norm': False, 'reward_scaling': False, 'orthogonal_init': True, 'adam_eps': True,
              'lr_decay': False, 'ValueClip': False, 'huber_loss': False, 'LayerNorm': True, 'feature_norm': True}
     policy = MAPPO(dim_info, True, args.actor_lr, args.critic_lr, T * N, device, trick, mode=args.mode)
+    if world > 1:      # synchronous data parallel (BASELINE config 5 at 8 GPUs): every rank steps its own N envs; per optimiser step the flat
+        policy.enable_data_parallel()       # gradient of the agent is summed over the ranks, advantages are normalised over the union rollout
     stack = lambda dicts: {a: np.stack([d[a] for d in dicts]).astype(np.float32) for a in ids}
     obs = stack(first)
     ep_ret, returns, steps, n_learn, t0 = np.zeros(N), [], 0, 0, time.perf_counter()
@@ -151,10 +162,10 @@ def _mappo_loop(args, device):
         if args.log_every:
             print("steps %d  rollouts %d  %.0f env-steps/s  mean return(last 20) %s" % (
                 steps, n_learn, steps / (time.perf_counter() - t0), "%.2f" % np.mean(returns[-20:]) if returns else "n/a"), flush=True)
-    if args.save_dir:
+    if args.save_dir and rank == 0:
         os.makedirs(args.save_dir, exist_ok=True)
         policy.save(args.save_dir)
-    return {"policy": policy, "steps": steps, "learns": n_learn, "returns": returns}
+    return {"policy": policy, "steps": steps, "learns": n_learn, "returns": returns, "rank": rank, "world": world}
 
 
 def main(argv=None):
@@ -192,12 +203,15 @@ def main(argv=None):
     ap.add_argument("--log_every", type=int, default=50, help="vector steps between progress lines (0: quiet)")
     args = ap.parse_args(argv)
 
-    # one process per GPU (torchrun): every rank steps its own n_envs envs into its own replay shard — no data-path collective —
-    # and the SAC / TD3 replicas are kept one policy by a parameter average per vector step (ACBase.sync_replicas)
+    # one process per GPU (torchrun): every rank steps its own n_envs envs into its own replay shard (PER: its own sum-tree) — no
+    # data-path collective — and the SAC / TD3 / DQN / Rainbow replicas are kept one policy by a parameter average per vector step
+    # (sync_replicas); PPO / MAPPO train synchronously data parallel (gradient sum per optimiser step)
     world, rank, dist = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), None
     if world > 1:
-        if args.algo not in ("SAC", "TD3", "PPO"):
-            raise ValueError("multi-process train_vec supports SAC / TD3 (replica sync) and PPO (gradient all-reduce)")
+        if args.obs_norm:
+            # per-rank running statistics would feed differently normalised observations to replicas that are then averaged /
+            # gradient-summed as one policy; a merged (Chan) statistic per vector step is not implemented
+            raise ValueError("--obs_norm is single-process only (the running statistics are per process)")
         import torch.distributed as dist
         if args.device.startswith("cuda"):
             torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
@@ -210,7 +224,7 @@ def main(argv=None):
     np.random.seed(args.seed)
     torch.manual_seed(args.seed)
     if args.algo == "MAPPO":
-        return _mappo_loop(args, device)
+        return _mappo_loop(args, device, world, rank)
     gym = _gym()
     N = args.n_envs
     envs = [gym.make(args.env_name) for _ in range(N)]
@@ -297,6 +311,7 @@ def main(argv=None):
     if args.save_dir and rank == 0:
         os.makedirs(args.save_dir, exist_ok=True)
         policy.save(args.save_dir)
+        _save_obs_norm(args, norm)
         np.save(os.path.join(args.save_dir, "%s_seed_%d.npy" % (args.algo, args.seed)), np.array(returns))
     return {"policy": policy, "steps": steps, "learns": n_learn, "returns": returns, "rank": rank, "world": world}
 

@@ -67,13 +67,13 @@ def rng_restore(s):
 
 
 def gen_offpolicy(name, make_policy, learn_call, n_learn, B, obs_dim, act_dim, noise_draws, nets, discrete=None,
-                  extra=None, seed=3, bon=False):
+                  extra=None, seed=3, bon=False, n_fill=400):
     np.random.seed(seed)
     torch.manual_seed(seed)
     policy = make_policy()
     rng = np.random.default_rng(seed)
     offset = rng.uniform(1.0, 3.0, obs_dim).astype(np.float32) if bon else None
-    fill(policy, 400, obs_dim, act_dim, rng, discrete, offset)
+    fill(policy, n_fill, obs_dim, act_dim, rng, discrete, offset)
     tap = LossTap(policy.agent, [n for n in ("update_critic", "update_actor", "update_Qnet") if hasattr(policy.agent, n)])
     rec = {}
     for nm, getter in nets.items():
@@ -105,6 +105,11 @@ def gen_offpolicy(name, make_policy, learn_call, n_learn, B, obs_dim, act_dim, n
         rec["act/obs"] = o
         if name.startswith("ddpg"):
             rec["act/action"] = np.asarray(policy.select_action(o))
+    if name == "sac":     # stochastic select_action (SAC.py:192-198: tanh(rsample)) after the learns, with the generator state it starts from
+        o = rng.standard_normal((8, obs_dim)).astype(np.float32)
+        rec["sel/obs"] = o
+        rec["sel/rng_state"] = torch.get_rng_state().numpy().copy()
+        rec["sel/action"] = np.stack([np.asarray(policy.select_action(o[i])) for i in range(8)])
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
     print(name, "ok:", len(rec), "arrays;", [(n, v) for n, v in tap.log[:3]])
 
@@ -124,6 +129,17 @@ def gen_sac():
                   {"actor": lambda p: p.agent.actor, "critic": lambda p: p.agent.critic,
                    "actor_target": lambda p: p.agent.actor_target, "critic_target": lambda p: p.agent.critic_target},
                   extra=lambda p: {"final/log_alpha": np.array(p.alphas.log_alpha.item(), np.float64)})
+
+
+def gen_sac_b256():
+    """The bench's batch shape: SAC, B = 256, ten chained learns (the other fixtures are B = 64, k <= 4)."""
+    m = refload.load("SAC_file", "SAC")
+    trick = {"ObsNorm": False, "Batch_ObsNorm": False, "OUNoise": True, "GaussNoise": False}
+    gen_offpolicy("sac_b256", lambda: m.SAC([17, 6], True, 1e-3, 1e-3, 2000, torch.device("cpu"), trick=trick),
+                  lambda p, B: p.learn(B, 0.99, 0.01), 10, 256, 17, 6, 2,
+                  {"actor": lambda p: p.agent.actor, "critic": lambda p: p.agent.critic, "actor_target": lambda p: p.agent.actor_target,
+                   "critic_target": lambda p: p.agent.critic_target},
+                  extra=lambda p: {"final/log_alpha": p.alphas.log_alpha.detach().numpy().copy()}, seed=13, n_fill=1200)
 
 
 def gen_sac_bon():
@@ -178,6 +194,7 @@ def gen_ppo(is_continue):
     rec.update(sd_np(policy.agent.actor, "init/actor/"))
     rec.update(sd_np(policy.agent.critic, "init/critic/"))
     obs = rng.standard_normal(obs_dim).astype(np.float32)
+    rec["rng/before_rollout"] = torch.get_rng_state().numpy().copy()     # CPU generator state the 256 select_action calls start from
     for t in range(horizon):
         a, logp = policy.select_action(obs)
         o2 = rng.standard_normal(obs_dim).astype(np.float32)
@@ -283,6 +300,8 @@ if __name__ == "__main__":
         gen_dqn()
     if "sac" in which:
         gen_sac()
+    if "sac_b256" in which:
+        gen_sac_b256()
     if "td3" in which:
         gen_td3()
     if "ddpg" in which:

@@ -333,3 +333,76 @@ def test_fast_mode_audit_emulated(emul):
 @pytest.mark.gpu
 def test_fast_mode_audit_gpu():
     _fast_mode_audit(torch.device("cuda"))
+
+
+# ---- the bench's batch shape against the REFERENCE: B = 256, ten chained learns (fixture sac_b256.npz, generated from the unmodified
+#      SAC_file/SAC.py by oracle/make_golden.py::gen_sac_b256); losses of every learn vs the reference's own numbers ----
+def _sac_b256(golden, device):
+    from freerl_b200.SAC import SAC
+    g = golden("sac_b256")
+    trick = {"ObsNorm": False, "Batch_ObsNorm": False, "OUNoise": True, "GaussNoise": False}
+    pol = SAC([17, 6], True, 1e-3, 1e-3, 4096, device, trick=trick)
+    _load(pol, g)
+    orc = algos.SACOracle(net_from_golden(g, "init/actor/"), net_from_golden(g, "init/critic/"), 1e-3, 1e-3, act_dim=6)
+    idxs = fill_buffer_from_batches(pol.buffer, g, 10)
+    for it in range(10):
+        n0, n1 = g["noise/%d/0" % it], g["noise/%d/1" % it]
+        r = orc.learn(golden_batch(g, it), torch.from_numpy(n0), torch.from_numpy(n1), 0.99, 0.01)
+        pol.learn(256, 0.99, 0.01, indices=idxs[it][None], noise_next=n0[None], noise_new=n1[None])
+        m = pol.last_metrics[0].cpu().numpy()
+        ref_c, ref_a = float(g["loss/%03d/update_critic" % (2 * it)][0]), float(g["loss/%03d/update_actor" % (2 * it + 1)][0])
+        assert _rel(r["critic_loss"], ref_c) < 1e-6 and _rel(r["actor_loss"], ref_a) < 2e-6      # the oracle IS the reference here
+        assert _rel(m[0], ref_c) < 1e-5, (it, m[0], ref_c)
+        assert _rel(m[1], ref_a) < 2e-5, (it, m[1], ref_a)
+    for n in NETS:
+        assert_module_close(getattr(pol.agent, n), net_from_golden(g, "final/%s/" % n), "final " + n)
+    assert _rel(float(pol.alphas.log_alpha), float(g["final/log_alpha"])) < 1e-5
+
+
+def test_sac_b256_k10_vs_reference_emulated(golden, emul):
+    _sac_b256(golden, torch.device("cpu"))
+
+
+@pytest.mark.gpu
+def test_sac_b256_k10_vs_reference_gpu(golden):
+    _sac_b256(golden, torch.device("cuda"))
+
+
+# ---- k = 100 chained learns at B = 256, ONE fused launch, vs the oracle fed the same indices / noise: the loss trajectory may
+#      not drift (Adam has no sign masks: two fp32 implementations stay within rounding of each other) ----
+def _sac_k100(device, K=100, B=256, n=4096):
+    from collections import OrderedDict
+    from freerl_b200.SAC import SAC
+    torch.manual_seed(33)
+    np.random.seed(33)
+    pol = SAC([17, 6], True, 1e-3, 1e-3, n, device, trick={})
+    rng = np.random.default_rng(17)
+    obs, act = rng.standard_normal((n, 17), dtype=np.float32), rng.uniform(-1, 1, (n, 6)).astype(np.float32)
+    rew, nobs = rng.standard_normal(n).astype(np.float32), rng.standard_normal((n, 17), dtype=np.float32)
+    done = rng.random(n) < 0.05
+    pol.add(obs, act, rew, nobs, done)
+    sd = lambda m: OrderedDict((k, v.detach().cpu().clone()) for k, v in m.state_dict().items())
+    orc = algos.SACOracle(sd(pol.agent.actor), sd(pol.agent.critic), 1e-3, 1e-3, act_dim=6)
+    idx = np.stack([rng.choice(n, B, replace=False) for _ in range(K)])
+    nz0, nz1 = rng.standard_normal((K, B, 6)).astype(np.float32), rng.standard_normal((K, B, 6)).astype(np.float32)
+    pol.learn(B, 0.99, 0.01, n_updates=K, indices=idx, noise_next=nz0, noise_new=nz1)
+    m = pol.last_metrics.cpu().numpy()
+    worst_c = worst_a = 0.0
+    for u in range(K):
+        i = idx[u]
+        batch = (torch.from_numpy(obs[i]), torch.from_numpy(act[i]), torch.from_numpy(rew[i]).reshape(-1, 1), torch.from_numpy(nobs[i]),
+                 torch.from_numpy(done[i].astype(np.float32)).reshape(-1, 1))
+        r = orc.learn(batch, torch.from_numpy(nz0[u]), torch.from_numpy(nz1[u]), 0.99, 0.01)
+        worst_c, worst_a = max(worst_c, _rel(m[u, 0], r["critic_loss"])), max(worst_a, _rel(m[u, 1], r["actor_loss"]))
+    assert worst_c < 1e-5 and worst_a < 2e-5, (worst_c, worst_a)
+    for name in NETS:
+        assert_module_close(getattr(pol.agent, name), getattr(orc, name), "%s after %d chained learns" % (name, K), dict(rtol=2e-5, atol=4e-6))
+
+
+def test_sac_k100_emulated(emul):
+    _sac_k100(torch.device("cpu"), K=40, B=64, n=1024)
+
+
+@pytest.mark.gpu
+def test_sac_k100_gpu():
+    _sac_k100(torch.device("cuda"))

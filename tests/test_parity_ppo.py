@@ -258,3 +258,86 @@ def test_device_minibatch_plan(emul):
     pol.learn(32, 0.99, 0.95, 0.2, 2, 0.01)
     m = pol.last_metrics.numpy()
     assert m.shape[0] == 8 and np.isfinite(m).all() and not torch.equal(before, pol.agent._net.p)
+
+
+# ---- teacher-forced chain: sixteen 1024-row minibatch updates, each STARTED FROM THE ORACLE'S STATE (parameters,
+#      cautious-AdamW moments, step count), so the per-step agreement is measured without the exponential separation that one flipped
+#      sign-mask bit causes in a free-running chain (tests/test_full_size.py).  mb = 1024 takes the tensor-core path on the GPU. ----
+def _push_oracle_state(pol, orc, is_continue):
+    net = pol.agent._net
+    a_items, c_items = list(orc.actor.items()), list(orc.critic.items())
+    names = [k for k, _ in a_items] + ["critic." + k for k, _ in c_items]
+    tensors = [v for _, v in a_items] + [v for _, v in c_items]
+    li_of = {"l1": 0, "l2": 1, "l3": 2, "mean_layer": 2}
+    with torch.no_grad():
+        for i, (nm, t) in enumerate(zip(names, tensors)):
+            crit = nm.startswith("critic.")
+            base = nm[7:] if crit else nm
+            for buf, src in ((net.p, t), (net.m, orc.opt.m[i]), (net.v, orc.opt.v[i])):
+                src = src.detach().to(buf.device)
+                if base == "log_std":
+                    buf[net.x_off:net.x_off + net.x_len].copy_(src.reshape(-1))
+                    continue
+                lname, kind = base.rsplit(".", 1)
+                li = li_of[lname] + (3 if crit else 0)
+                L = net.layers[li]
+                if kind == "weight":
+                    net._state_like(buf, li).copy_(src)
+                else:
+                    buf[L["b_off"]:L["b_off"] + L["out"]].copy_(src)
+    net.sync_mirror()
+    pol.agent.step = orc.opt.step
+
+
+def _ppo_teacher_forced(device, is_continue, T=16, N=1024, mb=1024):
+    from collections import OrderedDict
+    from freerl_b200.PPO import PPO
+    torch.manual_seed(9)
+    ad = 2 if is_continue else 4
+    H = T * N
+    pol = PPO([8, ad], is_continue, 1e-3, 1e-3, H, device)
+    rng = np.random.default_rng(21)
+    cols = []
+    for t in range(T):
+        o, o2 = rng.standard_normal((N, 8), dtype=np.float32), rng.standard_normal((N, 8), dtype=np.float32)
+        act, lp = pol.select_action(o)
+        act, lp = np.asarray(act, dtype=np.float32).reshape(N, -1), np.asarray(lp, dtype=np.float32).reshape(N, -1)
+        r = rng.standard_normal(N).astype(np.float32)
+        d = rng.random(N) < 0.02
+        adn = d | (rng.random(N) < 0.02)
+        pol.add(o, act, r, o2, d, lp, adn)
+        cols.append((o, act, r.reshape(N, 1), o2, d.reshape(N, 1).astype(np.float32), lp, adn.reshape(N, 1).astype(np.float32)))
+    data = tuple(torch.from_numpy(np.concatenate([c[k] for c in cols])) for k in range(7))
+    sd = lambda m: OrderedDict((k, v.detach().cpu().clone()) for k, v in m.state_dict().items())
+    orc = algos.PPOOracle(sd(pol.agent.actor), sd(pol.agent.critic), 1e-3, is_continue)
+    adv, vt = pol.compute_gae(0.99, 0.95)
+    adv_o, vt_o = adv.cpu(), vt.cpu()
+    perm = rng.permutation(H)
+    nmb = H // mb
+    worst = [0.0, 0.0]
+    for u in range(nmb):
+        _push_oracle_state(pol, orc, is_continue)
+        index = perm[u * mb:(u + 1) * mb]
+        want = orc.minibatch(data, adv_o, vt_o, index, 0.2, 0.01)
+        idx = torch.from_numpy(index.astype(np.int64))[None].to(device)
+        rows = torch.tensor([mb], dtype=torch.int32, device=device)
+        pol._minibatch_plan = lambda *a, **k: (idx, rows, 1)
+        pol._update(adv, vt, mb, 1, 0.2, 0.01, None)
+        m = pol.last_metrics.cpu().numpy()[0]
+        for j in range(2):
+            worst[j] = max(worst[j], abs(m[j] - float(want[j])) / max(abs(float(want[j])), 1e-12))
+        # one step from identical state: parameters agree to rounding, except where a sign-mask element flips (|m g| ~ 0)
+        tol = dict(rtol=1e-5, atol=2e-6)
+        assert_module_close(pol.agent.actor, orc.actor, "actor after teacher-forced step %d" % u, tol)
+        assert_module_close(pol.agent.critic, orc.critic, "critic after teacher-forced step %d" % u, tol)
+    assert worst[0] < 2e-5 and worst[1] < 1e-5, worst
+
+
+def test_ppo_teacher_forced_emulated(emul):
+    _ppo_teacher_forced(torch.device("cpu"), True, T=4, N=64, mb=64)
+
+
+@pytest.mark.gpu
+def test_ppo_teacher_forced_gpu():
+    _ppo_teacher_forced(torch.device("cuda"), False)
+    _ppo_teacher_forced(torch.device("cuda"), True)
