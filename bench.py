@@ -435,10 +435,17 @@ def main():
                                      "sample": "12 steps x %d single-env iterations; numpy replay on the host, networks + learn on cuda:0" % tps}
         except Exception as e:
             out["reference_cuda"] = {"error": "%s: %s" % (type(e).__name__, e)}
-        try:
-            sys.path.insert(0, os.path.join(ROOT, "tools"))
-            import configbench
-            extra["configs"] = configbench.run(("C1", "C3", "C4", "C5"), log=lambda *a: print(*a, file=sys.stderr))
+        try:       # the other BASELINE configurations (learn() only), in a fresh process: tools/configbench.py, one GPU, after this one is idle
+            del pol, obs_pool, rew_pool
+            torch.cuda.empty_cache()
+            tmp = os.path.join(ROOT, "gpurun_out", "bench_configs.json")
+            os.makedirs(os.path.dirname(tmp), exist_ok=True)
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "configbench.py"), "--only", "C1,C3,C4,C5", "--json", tmp],
+                               stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, timeout=600,
+                               env=dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(local))))
+            if r.returncode != 0:
+                raise RuntimeError(r.stderr[-300:])
+            extra["configs"] = json.load(open(tmp))["rows"]
         except Exception as e:
             extra["configs_error"] = "%s: %s" % (type(e).__name__, e)
         out["extra"] = extra

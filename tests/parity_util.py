@@ -52,3 +52,20 @@ def fill_buffer_from_batches(buf, g, n_iter):
         idxs.append(np.arange(start, start + B))
         start += B
     return idxs
+
+
+def push_block_state(net, module, params, moments_m=None, moments_v=None):
+    """Teacher forcing: copy an oracle's tensors INTO the device blocks of ``net`` — ``params`` (OrderedDict, the module's state-dict
+    names) into ``net.p`` and, when given, the optimiser moments (lists in the same order) into ``net.m`` / ``net.v``.  The module's
+    parameters are views of ``net.p``; the same (offset, shape, stride) addresses the moment blocks."""
+    sd = module.state_dict()
+    with torch.no_grad():
+        for i, (k, src) in enumerate(params.items()):
+            view = sd[k]
+            off = (view.data_ptr() - net.p.data_ptr()) // 4
+            for buf, t in ((net.p, src), (net.m if moments_m is not None else None, moments_m[i] if moments_m is not None else None),
+                           (net.v if moments_v is not None else None, moments_v[i] if moments_v is not None else None)):
+                if buf is None:
+                    continue
+                torch.as_strided(buf, tuple(view.shape), tuple(view.stride()), off).copy_(t.detach().reshape(view.shape).to(buf.device))
+    net.sync_mirror()

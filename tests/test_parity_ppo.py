@@ -324,8 +324,8 @@ def _ppo_teacher_forced(device, is_continue, T=16, N=1024, mb=1024):
         pol._minibatch_plan = lambda *a, **k: (idx, rows, 1)
         pol._update(adv, vt, mb, 1, 0.2, 0.01, None)
         m = pol.last_metrics.cpu().numpy()[0]
-        for j in range(2):
-            worst[j] = max(worst[j], abs(m[j] - float(want[j])) / max(abs(float(want[j])), 1e-12))
+        for j in range(2):      # the surrogate loss is a mean of signed O(1) terms and sits near zero: allclose form, atol = 2e-6 of that scale
+            worst[j] = max(worst[j], abs(m[j] - float(want[j])) / (abs(float(want[j])) + (0.1 if j == 0 else 0.0)))
         # one step from identical state: parameters agree to rounding, except where a sign-mask element flips (|m g| ~ 0)
         tol = dict(rtol=1e-5, atol=2e-6)
         assert_module_close(pol.agent.actor, orc.actor, "actor after teacher-forced step %d" % u, tol)
