@@ -12,7 +12,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 FRL_MAX_LAYERS = 6
 FRL_MAX_AGENTS = 6
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 
 class Layer(C.Structure):
@@ -85,6 +85,15 @@ class PpoArgs(C.Structure):
                 ("gpart", C.c_void_p),
                 ("sumsq", C.c_void_p), ("segcnt", C.c_void_p), ("stats", C.c_void_p), ("out", C.c_void_p),
                 ("lr_critic", C.c_double), ("hidden_tanh", C.c_int), ("umma_ws", C.c_void_p), ("dp", DpPeers)]
+
+
+class SacdArgs(C.Structure):
+    _fields_ = [("actor", Net), ("actor_target", Net), ("critic", Net), ("critic_target", Net), ("replay", Replay),
+                ("indices", C.c_void_p), ("B", C.c_int), ("n_updates", C.c_int), ("gamma", C.c_float), ("tau", C.c_float),
+                ("lr_actor", C.c_double), ("lr_critic", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
+                ("max_norm", C.c_float), ("step_actor0", C.c_int64), ("step_critic0", C.c_int64), ("alpha_state", C.c_void_p),
+                ("adaptive_alpha", C.c_int), ("alpha_lr", C.c_double), ("target_entropy", C.c_float), ("step_alpha0", C.c_int64),
+                ("gpart", C.c_void_p), ("sumsq", C.c_void_p), ("stats", C.c_void_p), ("out", C.c_void_p)]
 
 
 class NoisyMap(C.Structure):
@@ -168,6 +177,8 @@ def _declare(lib):
     lib.frl_ppo_umma_ws_floats.argtypes = []
     lib.frl_adv_norm.restype = ci
     lib.frl_rainbow_learn.restype = ci
+    lib.frl_sacd_learn.argtypes = [C.POINTER(SacdArgs), vp]
+    lib.frl_sacd_learn.restype = ci
     lib.frl_rainbow_act.restype = ci
     for name in ("frl_replay_add_batch", "frl_replay_gather", "frl_sample_uniform", "frl_net_sync_mirror",
                  "frl_dqn_learn", "frl_ac_learn", "frl_policy_infer", "frl_gae", "frl_ppo_update", "frl_sumtree_update", "frl_sumtree_update_td", "frl_sumtree_sample", "frl_sumtree_max",
@@ -196,7 +207,7 @@ def lib():
                                % (path, l.frl_abi_version(), ABI_VERSION))
         l.frl_struct_size.restype = C.c_int
         l.frl_struct_size.argtypes = [C.c_int]
-        for which, mirror in enumerate((Layer, Net, Replay, DqnArgs, AcArgs, InferArgs, PpoArgs, NoisyMap, RainbowArgs, ExploreArgs)):
+        for which, mirror in enumerate((Layer, Net, Replay, DqnArgs, AcArgs, InferArgs, PpoArgs, NoisyMap, RainbowArgs, ExploreArgs, SacdArgs)):
             if l.frl_struct_size(which) != C.sizeof(mirror):
                 raise RuntimeError("freerl_b200: ctypes mirror %s is %d bytes, the library's struct is %d"
                                    % (mirror.__name__, C.sizeof(mirror), l.frl_struct_size(which)))

@@ -137,14 +137,16 @@ FRL_DEV void dp_exchange(Cta& c, const frl_ppo_args_t& a, int u) {
   }
   if (tid < world && tid != rank) {
     const unsigned* f = a.dp.flags[rank] + tid;
+    unsigned* dead = a.dp.flags[rank] + 32;        // sticky: a peer timed out once -> later exchanges do not wait again
     long long t0, t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     for (;;) {
       unsigned v;
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
       if ((int)(v - epoch) >= 0) break;
+      if (*(volatile unsigned*)dead) { if (c.cta == 0) a.out[u * 8 + 7] = -1.f; break; }
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t1 - t0 > 2000000000ll) { if (c.cta == 0) a.out[u * 8 + 7] = -1.f; break; }
+      if (t1 - t0 > 2000000000ll) { *(volatile unsigned*)dead = 1u; if (c.cta == 0) a.out[u * 8 + 7] = -1.f; break; }
     }
   }
   __syncthreads();

@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include "algo_ppo.cuh"
+#include "algo_sacd.cuh"
 #include "algo_acfx.cuh"
 #include "algo_per.cuh"
 #include "algo_rainbow.cuh"
@@ -26,7 +27,7 @@ extern "C" void frl_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 extern "C" const char* frl_last_error(void) { return g_err; }
-extern "C" int frl_abi_version(void) { return 8; }
+extern "C" int frl_abi_version(void) { return 9; }
 // sizeof() of the argument structs, so a binding can verify its mirror of the layout before the first call
 extern "C" int frl_struct_size(int which) {
   switch (which) {
@@ -39,6 +40,7 @@ extern "C" int frl_struct_size(int which) {
     case 6: return (int)sizeof(frl_ppo_args_t);
     case 7: return (int)sizeof(frl_noisy_map_t);
     case 8: return (int)sizeof(frl_rainbow_args_t);
+    case 10: return (int)sizeof(frl_sacd_args_t);
     case 9: return (int)sizeof(frl_explore_args_t);
     default: return -1;
   }
@@ -614,6 +616,22 @@ extern "C" int frl_dqn_learn(const frl_dqn_args_t* a, void* stream) {
   }
   if (check_net(a->q, true, "frl_dqn_learn(q)") || check_net(a->q_target, false, "frl_dqn_learn(q_target)")) return -1;
   return frl_launch<DqnAlgo>(*a, (cudaStream_t)stream);
+}
+
+extern "C" int frl_sacd_learn(const frl_sacd_args_t* a, void* stream) {
+  if (!a || a->B <= 0 || a->n_updates <= 0 || !a->indices || !a->gpart || !a->sumsq || !a->stats || !a->out || !a->alpha_state) {
+    frl_set_error("frl_sacd_learn: bad arguments");
+    return -1;
+  }
+  if (check_net(a->actor, true, "frl_sacd_learn(actor)") || check_net(a->critic, true, "frl_sacd_learn(critic)") ||
+      check_net(a->actor_target, false, "frl_sacd_learn(actor_target)") || check_net(a->critic_target, false, "frl_sacd_learn(critic_target)"))
+    return -1;
+  if (a->actor.n_layers != 3 || a->critic.n_layers != 6 || a->actor.L[2].out != a->critic.L[2].out || a->critic.L[2].out != a->critic.L[5].out ||
+      a->replay.act_dim != 1) {
+    frl_set_error("frl_sacd_learn: actor obs->h->h->n_actions, twin critic heads obs->h->h->n_actions, 1-column action index expected");
+    return -1;
+  }
+  return frl_launch<SacdAlgo>(*a, (cudaStream_t)stream);
 }
 
 // FREERL_B200_AC_PATH=generic forces the generic kernel (A/B timing, tests of the fallback)

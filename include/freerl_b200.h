@@ -140,6 +140,29 @@ typedef struct {
   unsigned* sync;
 } frl_ac_args_t;
 
+/* Discrete-action SAC, the `hands_on` variant of SAC_file/SAC_add_discrete.py:137-177, 299-360: softmax actor (obs -> n_actions), twin
+ * critic heads obs -> Q(s, .) in ONE 6-layer net (head h = layers 3h .. 3h+2), replay rows with a 1-column action index. */
+typedef struct {
+  frl_net_t actor, actor_target, critic, critic_target;
+  frl_replay_t replay;
+  const int64_t* indices;   /* dev [n_updates][B] */
+  int B, n_updates;
+  float gamma, tau;
+  double lr_actor, lr_critic, beta1, beta2, eps;
+  float max_norm;           /* clip_grad_norm_ max (0.5 upstream) */
+  int64_t step_actor0, step_critic0;
+  float* alpha_state;       /* dev {log_alpha, exp_avg, exp_avg_sq, unused} */
+  int adaptive_alpha;
+  double alpha_lr;
+  float target_entropy;     /* 0.6 * log(n_actions)  (SAC_add_discrete.py:214) */
+  int64_t step_alpha0;
+  float* gpart;             /* dev scratch [sm_count][max(actor.n_p, critic.n_p)] */
+  float* sumsq;             /* dev scratch [sm_count] */
+  float* stats;             /* dev scratch [sm_count][8] */
+  float* out;               /* dev [n_updates][8]: critic_loss, actor_loss, alpha, alpha_loss, critic_gnorm, actor_gnorm, mean_entropy, 0 */
+} frl_sacd_args_t;
+int frl_sacd_learn(const frl_sacd_args_t* args, void* cuda_stream);
+
 /* FRL_INFER_ARGMAX_DUELING (7): argmax_a of V + A_a - mean(A) for a [V | A] head (Dueling.forward, DQN_with_tricks.py:75-79) */
 enum { FRL_INFER_ARGMAX_DUELING = 7 };
 enum { FRL_INFER_ARGMAX = 0, FRL_INFER_TANH = 1, FRL_INFER_SAC_SAMPLE = 2, FRL_INFER_SAC_MEAN = 3, FRL_INFER_RAW = 4,

@@ -265,6 +265,69 @@ class SACOracle:
         return out
 
 
+class SACDiscreteOracle:
+    """The ``hands_on`` discrete branch of ``SAC_file/SAC_add_discrete.py`` (:137-177 nets, :299-348 learn, :350-360 targets,
+    :206-223 Alpha with target entropy ``0.6 * -log(1 / n_actions)``): softmax actor, twin critic heads ``obs -> Q(s, .)``,
+    next-state probabilities from the ONLINE actor, ``log(p + 1e-8)``."""
+
+    def __init__(self, actor, critic, actor_lr, critic_lr, n_actions, alpha0=0.01, alpha_lr=1e-4):
+        self.actor, self.critic = _leaf(actor), _leaf(critic)
+        self.actor_target, self.critic_target = clone_net(actor), clone_net(critic)
+        self.opt_a = AdamState(list(self.actor.values()), actor_lr)
+        self.opt_c = AdamState(list(self.critic.values()), critic_lr)
+        self.log_alpha = torch.tensor(np.log(alpha0), dtype=torch.float32, requires_grad=True)
+        self.opt_alpha = AdamState([self.log_alpha], alpha_lr)
+        self.alpha = self.log_alpha.exp()
+        self.target_entropy = 0.6 * (-torch.log(torch.tensor(1.0 / n_actions)))
+
+    @staticmethod
+    def probs(net, obs):
+        return torch.softmax(mlp2(net, obs), dim=1)
+
+    @staticmethod
+    def heads(net, obs):
+        return mlp2(net, obs, ("l1", "l2", "l3")), mlp2(net, obs, ("l4", "l5", "l6"))
+
+    def learn(self, batch, gamma, tau):
+        obs, act, rew, nobs, done = batch
+        alpha = self.alpha.detach()
+        with torch.no_grad():
+            npb = self.probs(self.actor, nobs)
+            nlog = torch.log(npb + 1e-8)
+            v1t, v2t = self.heads(self.critic_target, nobs)
+            next_q = torch.sum(npb * torch.min(v1t, v2t), dim=1, keepdim=True)
+            ent_next = -torch.sum(npb * nlog, dim=1, keepdim=True)
+            target = rew + gamma * (1 - done) * (next_q + alpha * ent_next)
+        v1, v2 = self.heads(self.critic, obs)
+        q1, q2 = v1.gather(1, act.long()), v2.gather(1, act.long())
+        critic_loss = F.mse_loss(q1, target) + F.mse_loss(q2, target)
+        cp = list(self.critic.values())
+        g = torch.autograd.grad(critic_loss, cp)
+        g, cnorm = clip_grad_norm(g, 0.5)
+        adam_step(cp, g, self.opt_c)
+
+        pb = self.probs(self.actor, obs)
+        logp = torch.log(pb + 1e-8)
+        entropy = -torch.sum(pb * logp, dim=1, keepdim=True)
+        with torch.no_grad():
+            v1p, v2p = self.heads(self.critic, obs)                          # UPDATED critic
+        q_pi = torch.sum(pb * torch.min(v1p, v2p), dim=1, keepdim=True)
+        actor_loss = (-q_pi - alpha * entropy).mean()
+        ap = list(self.actor.values())
+        ga = torch.autograd.grad(actor_loss, ap)
+        ga, anorm = clip_grad_norm(ga, 0.5)
+        adam_step(ap, ga, self.opt_a)
+
+        polyak(self.critic_target, self.critic, tau)
+        polyak(self.actor_target, self.actor, tau)
+        alpha_loss = (self.log_alpha.exp() * (entropy - self.target_entropy).detach()).mean()
+        (ga_,) = torch.autograd.grad(alpha_loss, [self.log_alpha])
+        adam_step([self.log_alpha], [ga_], self.opt_alpha)
+        self.alpha = self.log_alpha.exp()
+        return {"critic_loss": critic_loss.item(), "actor_loss": actor_loss.item(), "critic_gnorm": cnorm.item(), "actor_gnorm": anorm.item(),
+                "alpha_loss": alpha_loss.item(), "alpha": self.alpha.item()}
+
+
 # --------------------------------------------------------------------------------------------------
 # TD3  (TD3_file/TD3.py:189-244)  and DDPG  (DDPG_file/DDPG.py:203-233)
 # --------------------------------------------------------------------------------------------------

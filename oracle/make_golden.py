@@ -142,6 +142,27 @@ def gen_sac_b256():
                   extra=lambda p: {"final/log_alpha": p.alphas.log_alpha.detach().numpy().copy()}, seed=13, n_fill=1200)
 
 
+def gen_sac_discrete():
+    """``SAC_add_discrete.py`` with ``is_continue=False`` (the ``hands_on`` branch): obs 8, 4 actions, B = 64, three learns, plus
+    stochastic ``select_action`` calls (Categorical sampling) with the generator state they start from."""
+    m = refload.load("SAC_file", "SAC_add_discrete")
+    m.is_continue = False       # learn() reads the module global its __main__ block defines (SAC_add_discrete.py:325 <- :494)
+    trick = {"ObsNorm": False, "Batch_ObsNorm": False, "OUNoise": True, "GaussNoise": False}
+
+    def extra(p):
+        rng = np.random.default_rng(77)
+        o = rng.standard_normal((8, 8)).astype(np.float32)
+        rec = {"final/log_alpha": np.array(p.alphas.log_alpha.item(), np.float64), "sel/obs": o,
+               "sel/rng_state": torch.get_rng_state().numpy().copy()}
+        rec["sel/action"] = np.stack([np.asarray(p.select_action(o[i])) for i in range(8)])
+        rec["sel/greedy"] = np.stack([np.asarray(p.evaluate_action(torch.as_tensor(o[i]).reshape(1, -1))) for i in range(8)])
+        return rec
+    gen_offpolicy("sac_discrete", lambda: m.SAC([8, 4], False, 1e-3, 1e-3, 1000, torch.device("cpu"), trick=trick),
+                  lambda p, B: p.learn(B, 0.99, 0.01), 3, 64, 8, 1, 0,
+                  {"actor": lambda p: p.agent.actor, "critic": lambda p: p.agent.critic, "actor_target": lambda p: p.agent.actor_target,
+                   "critic_target": lambda p: p.agent.critic_target}, discrete=4, extra=extra, seed=23)
+
+
 def gen_sac_bon():
     """SAC with trick Batch_ObsNorm (SAC.py:181-182, 215-217)."""
     m = refload.load("SAC_file", "SAC")
@@ -300,6 +321,8 @@ if __name__ == "__main__":
         gen_dqn()
     if "sac" in which:
         gen_sac()
+    if "sac_discrete" in which:
+        gen_sac_discrete()
     if "sac_b256" in which:
         gen_sac_b256()
     if "td3" in which:
