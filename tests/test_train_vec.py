@@ -32,6 +32,14 @@ def _run(device, tmp_path):
 
 def test_train_vec_emulated(emul, tmp_path):
     _run(torch.device("cpu"), tmp_path)
+    ms = np.load(tmp_path / "sac" / "SAC_running_mean_std.npy")          # --obs_norm statistics in the reference's layout (SAC.py:583-584)
+    assert ms.shape == (2, 3) and np.isfinite(ms).all()
+
+
+@pytest.mark.gpu
+def test_train_vec_gpu(tmp_path):
+    """the same loops through the CUDA kernels (SAC / TD3 / DQN / Rainbow / PPO both heads / MAPPO) on the device"""
+    _run(torch.device("cuda"), tmp_path)
 
 
 WORKER = r'''
