@@ -176,6 +176,17 @@ FRL_HD void replay_field(const frl_replay_t& rb, int f, int* width, int* off) {
   else if (f == 3) { *width = 1; *off = od + ad + 1; }
   else { *width = od; *off = od + ad + 2; }
 }
+// Index arithmetic of the tile walkers: a thread visits elements e = e0, e0 + S, e0 + 2S, ... of a [rows][w] field; (row, col) advance by
+// the constant (S / w, S % w) with one carry — two divisions per field and tile instead of one per visited element (ncu of the first tile
+// kernels: issue-active 62 % / 57 % for what is a copy; the per-element divisions and address products were most of it).
+struct FieldWalk {
+  unsigned row, col, drow, dcol, w;
+  FRL_DEVM void init(unsigned e0, unsigned step, unsigned w_) {
+    w = w_; row = e0 / w_; col = e0 - row * w_; drow = step / w_; dcol = step - drow * w_;
+  }
+  FRL_DEVM void next() { row += drow; col += dcol; if (col >= w) { col -= w; ++row; } }
+};
+
 struct ReplayAddTiles {
   typedef ReplayTileArgs Args;
   static const int MIN_CTAS = 8;
@@ -191,14 +202,17 @@ struct ReplayAddTiles {
           replay_field(a.rb, f, &w, &off);
           const float* p = src[f] + (size_t)r0 * w;
           const int ne = nr * w, n4 = (((size_t)p & 15) == 0) ? (ne >> 2) : 0;
-          for (int q = t; q < n4; q += FRL_NT) {
+          FieldWalk fw;
+          fw.init(4u * (unsigned)t, 4u * FRL_NT, (unsigned)w);
+          for (int q = t; q < n4; q += FRL_NT, fw.next()) {
             const float4 v = ld4(p + 4 * q);
             const float e4[4] = {v.x, v.y, v.z, v.w};
-            unsigned row = (unsigned)(4 * q) / (unsigned)w, col = (unsigned)(4 * q) - row * (unsigned)w;
+            unsigned col = fw.col, addr = fw.row * RF + off + fw.col;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              sm[row * RF + off + col] = e4[k];
-              if (++col == (unsigned)w) { col = 0; ++row; }
+              sm[addr] = e4[k];
+              ++addr;
+              if (++col == (unsigned)w) { col = 0; addr += RF - w; }
             }
           }
           for (int e = 4 * n4 + t; e < ne; e += FRL_NT) {
@@ -213,11 +227,13 @@ struct ReplayAddTiles {
       }
       FRL_SYNC();
       FRL_PAR(t) {
-        for (int q = t; q < nr * nq; q += FRL_NT) {
-          const int row = (unsigned)q / (unsigned)nq, c4 = (q - row * nq) * 4;
-          int64_t slot = a.index + r0 + row;
+        FieldWalk rw;                                              // (row, 16-byte column) of the ring rows, nq quads per row
+        rw.init((unsigned)t, FRL_NT, (unsigned)nq);
+        int64_t slot0 = a.index + r0;
+        for (int q = t; q < nr * nq; q += FRL_NT, rw.next()) {
+          int64_t slot = slot0 + rw.row;
           if (slot >= a.rb.capacity) slot %= a.rb.capacity;
-          st4(a.rb.storage + slot * RF + c4, lds4(sm + row * RF + c4));
+          st4(a.rb.storage + slot * RF + 4 * rw.col, lds4(sm + q * 4));
         }
       }
       FRL_SYNC();
@@ -234,10 +250,10 @@ struct ReplayGatherTiles {
     for (int tile = cta; tile < ntiles; tile += ncta) {
       const int r0 = tile * FRL_RT_ROWS, nr = (a.n - r0 < FRL_RT_ROWS) ? a.n - r0 : FRL_RT_ROWS;
       FRL_PAR(t) {
-        for (int q = t; q < nr * nq; q += FRL_NT) {
-          const int row = (unsigned)q / (unsigned)nq, c4 = (q - row * nq) * 4;
-          sts4(sm + row * RF + c4, ld4(a.rb.storage + a.idx[r0 + row] * RF + c4));
-        }
+        FieldWalk rw;
+        rw.init((unsigned)t, FRL_NT, (unsigned)nq);
+        for (int q = t; q < nr * nq; q += FRL_NT, rw.next())
+          sts4(sm + q * 4, ld4(a.rb.storage + a.idx[r0 + rw.row] * RF + 4 * rw.col));
       }
       FRL_SYNC();
       FRL_PAR(t) {
@@ -246,13 +262,16 @@ struct ReplayGatherTiles {
           replay_field(a.rb, f, &w, &off);
           float* p = dst[f] + (size_t)r0 * w;
           const int ne = nr * w, n4 = (((size_t)p & 15) == 0) ? (ne >> 2) : 0;
-          for (int q = t; q < n4; q += FRL_NT) {
+          FieldWalk fw;
+          fw.init(4u * (unsigned)t, 4u * FRL_NT, (unsigned)w);
+          for (int q = t; q < n4; q += FRL_NT, fw.next()) {
             float e4[4];
-            unsigned row = (unsigned)(4 * q) / (unsigned)w, col = (unsigned)(4 * q) - row * (unsigned)w;
+            unsigned col = fw.col, addr = fw.row * RF + off + fw.col;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              e4[k] = sm[row * RF + off + col];
-              if (++col == (unsigned)w) { col = 0; ++row; }
+              e4[k] = sm[addr];
+              ++addr;
+              if (++col == (unsigned)w) { col = 0; addr += RF - w; }
             }
             st4(p + 4 * q, make_float4(e4[0], e4[1], e4[2], e4[3]));
           }
