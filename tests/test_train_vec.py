@@ -51,9 +51,15 @@ r = train_vec.main(["--algo", "SAC", "--env_name", "Pendulum-v1", "--n_envs", "4
 pol = r["policy"]
 q = train_vec.main(["--algo", "PPO", "--env_name", "Pendulum-v1", "--n_envs", "4", "--horizon", "16", "--total_steps", "128", "--minibatch_size", "16",
                     "--K_epochs", "2", "--log_every", "0", "--device", "cpu"])
+rb = train_vec.main(["--algo", "RAINBOW", "--env_name", "CartPole-v1", "--n_envs", "4", "--total_steps", "96", "--random_steps", "16", "--start_steps", "48",
+                     "--batch_size", "8", "--buffer_size", "300", "--updates_per_step", "0.25", "--log_every", "0", "--device", "cpu"])
+mp = train_vec.main(["--algo", "MAPPO", "--env_name", "simple_spread_v3", "--n_agents", "3", "--n_envs", "2", "--horizon", "30", "--total_steps", "120",
+                     "--minibatch_size", "30", "--K_epochs", "2", "--log_every", "0", "--device", "cpu"])
 np.savez(os.path.join(os.environ["FRL_OUT"], "tv%d.npz" % r["rank"]), actor=pol.agent._actor.p.numpy(), critic=pol.agent._critic.p.numpy(),
          first_obs=pol.buffer.obs[0].numpy(), learns=r["learns"], world=r["world"], ppo=q["policy"].agent._net.p.numpy(),
-         ppo_steps=q["policy"].agent.step)
+         ppo_steps=q["policy"].agent.step, rainbow=rb["policy"].agent.online.p.numpy(), rainbow_target=rb["policy"].agent.target.p.numpy(),
+         rainbow_learns=rb["learns"], rainbow_tree_total=float(rb["policy"].buffer.tree.total_priority) if hasattr(rb["policy"].buffer, "tree") else 0.0,
+         mappo=np.concatenate([ag._net.p.numpy() for ag in mp["policy"].agents.values()]), mappo_learns=mp["learns"])
 dist.destroy_process_group()
 '''
 
@@ -77,3 +83,8 @@ def test_train_vec_two_processes_gloo(tmp_path, emul):
     assert np.array_equal(a["actor"], b["actor"]) and np.array_equal(a["critic"], b["critic"])
     # PPO: gradient all-reduce inside every minibatch step -> bit-identical replicas although the rollouts differ
     assert int(a["ppo_steps"]) == 2 * 2 * 4 and np.array_equal(a["ppo"], b["ppo"])
+    # Rainbow (BASELINE config 4): replicas with their own env / PER shards (sum-trees differ), parameters averaged per vector step
+    assert int(a["rainbow_learns"]) == int(b["rainbow_learns"]) > 0
+    assert np.array_equal(a["rainbow"], b["rainbow"]) and np.array_equal(a["rainbow_target"], b["rainbow_target"])
+    # MAPPO (config 5): synchronous data parallel over the ranks' env shards -> bit-identical replicas of every agent
+    assert int(a["mappo_learns"]) == 2 and np.array_equal(a["mappo"], b["mappo"])
