@@ -114,7 +114,8 @@ class PPO:
             elif noise is not None:
                 noise = torch.as_tensor(noise, dtype=torch.float32).to(self.device).reshape(n, self.action_dim).contiguous()
             out = _common.infer(net, x, _lib.INFER_PPO_GAUSS, self.device, 2 * self.action_dim, noise=noise, seed=self._seed,
-                                counter=self._n_act, l0=0, nl=3, hidden_tanh=bool(self.hidden_tanh & 1)).cpu().numpy()
+                                counter=self._n_act, l0=0, nl=3, hidden_tanh=bool(self.hidden_tanh & 1),
+                                obs_norm=getattr(self, "batch_size_obs_norm", None)).cpu().numpy()
             action, logp = out[:, :self.action_dim], out[:, self.action_dim:]
             return (action[0], logp[0]) if single else (action, logp)
         if noise is None and self.mode == "parity":
@@ -123,7 +124,7 @@ class PPO:
         elif noise is not None:
             noise = torch.as_tensor(noise, dtype=torch.float32).to(self.device).reshape(n, self.action_dim).contiguous()
         out = _common.infer(net, x, _lib.INFER_PPO_CAT, self.device, 2, noise=noise, seed=self._seed, counter=self._n_act,
-                            l0=0, nl=3, hidden_tanh=bool(self.hidden_tanh & 1)).cpu().numpy()
+                            l0=0, nl=3, hidden_tanh=bool(self.hidden_tanh & 1), obs_norm=getattr(self, "batch_size_obs_norm", None)).cpu().numpy()
         action, logp = out[:, 0].astype(np.int64), out[:, 1]
         return (action[0], logp[0]) if single else (action, logp)
 

@@ -14,7 +14,11 @@ executed with that one call patched (``oracle/make_golden_ppo_tricks.py``):
 * ``tanh``            tanh instead of ReLU hidden activations in actor and critic (``:95,172``; continuous actor and critic — the
                       discrete actor takes no trick argument upstream and keeps ReLU and the default init, ``:106-118``) -> ``frl_ppo_args_t.hidden_tanh`` / ``frl_infer_args_t.hidden_tanh``
 
-Not provided (raise ``NotImplementedError``): ``Batch_ObsNorm`` inside ``learn`` and the Beta policy (``beta=True``).
+* ``Batch_ObsNorm``   running statistics over the MEAN of each rollout (``Normalization_batch_size``, ``:227-228``): ``learn`` folds the rollout's
+                      observations in and trains on the normalised ``obs`` / ``next_obs`` (``:296-298``), ``select_action`` applies them with
+                      ``update=False`` (``:235-236``); like upstream ``evaluate_action`` does not normalise
+
+Not provided (raises ``NotImplementedError``): the Beta policy (``beta=True``).
 """
 import os
 
@@ -39,8 +43,6 @@ class PPO(_PPOAdvance):
         t.update(trick or {})
         if beta:
             raise NotImplementedError("PPO_with_tricks: the Beta policy head (beta=True) is not implemented on the fused kernel")
-        if t['Batch_ObsNorm']:
-            raise NotImplementedError("PPO_with_tricks: trick 'Batch_ObsNorm' is not implemented on the fused kernel")
         # Actor_discrete takes no trick argument upstream (:106-118, :187): ReLU body and default init whatever the switches say
         self.hidden_tanh = (3 if is_continue else 2) if t['tanh'] else 0
         self.adam_eps = 1e-5 if t['adam_eps'] else 1e-8
@@ -55,8 +57,24 @@ class PPO(_PPOAdvance):
             self._init_hook = hook
         super().__init__(dim_info, is_continue, actor_lr, critic_lr, horizon, device, trick=t, mode=mode)
         self.actor_lr, self.critic_lr = actor_lr, critic_lr
+        if t['Batch_ObsNorm']:
+            from .normalization import Normalization_batch_size
+            self.batch_size_obs_norm = Normalization_batch_size(shape=self.obs_dim, device=self.device)       # read by select_action
 
     def learn(self, minibatch_size, gamma, lmbda, clip_param, K_epochs, entropy_coefficient, *, permutations=None):
+        b = self.buffer
+        raw = None
+        if self.trick['Batch_ObsNorm']:          # :296-298 — statistics updated with this rollout's mean, next_obs normalised without update
+            raw = (b.obs, b.next_obs)
+            b.obs = self.batch_size_obs_norm(raw[0]).contiguous()
+            b.next_obs = self.batch_size_obs_norm(raw[1], update=False).contiguous()
+        try:
+            self._learn_normalised(minibatch_size, gamma, lmbda, clip_param, K_epochs, entropy_coefficient, permutations)
+        finally:
+            if raw is not None:
+                b.obs, b.next_obs = raw
+
+    def _learn_normalised(self, minibatch_size, gamma, lmbda, clip_param, K_epochs, entropy_coefficient, permutations):
         adv, v_target = self.compute_gae(gamma, lmbda)
         if self.trick['adv_norm']:
             _lib.check(_lib.lib().frl_adv_norm(_lib.ptr(adv), adv.numel(), 1e-8, _lib.ptr(adv), _lib.stream_ptr(self.device)), "frl_adv_norm")

@@ -147,9 +147,57 @@ def _ppo_tricks(golden, device, name, is_continue, tanh=False):
         assert_module_close(pol.agent.actor, net_from_golden(g, "after%d/actor/" % r), "actor vs reference", tol)
         assert_module_close(pol.agent.critic, net_from_golden(g, "after%d/critic/" % r), "critic vs reference", tol)
     with pytest.raises(NotImplementedError):
-        PPO([8, act_dim], is_continue, 1e-3, 5e-4, 256, device, trick=dict(TRICKS, Batch_ObsNorm=True))
-    with pytest.raises(NotImplementedError):
         PPO([8, act_dim], is_continue, 1e-3, 5e-4, 256, device, trick=dict(TRICKS), beta=True)
+
+
+def _ppo_tricks_bon(golden, device, is_continue, inject):
+    """PPO_with_tricks with the Batch_ObsNorm switch (``PPO_with_tricks.py:227-228, 235-236, 296-298``) against the fixture generated from
+    the reference (oracle/make_golden_ppo_tricks.py bon): two rollouts of offset observations; the SECOND rollout's sampled actions and
+    log-probabilities go through the normalisation the first learn installed (select_action, update=False), every minibatch loss, the
+    parameters after each learn and the running statistics are the reference's own numbers."""
+    from freerl_b200.PPO_with_tricks import PPO
+    g = golden("ppo_tricks_bon_cont" if is_continue else "ppo_tricks_bon_disc")
+    ad = 2 if is_continue else 4
+    pol = PPO([8, ad], is_continue, 1e-3, 5e-4, 256, device, trick=dict(TRICKS, Batch_ObsNorm=True))
+    load_into(pol.agent.actor, net_from_golden(g, "init/actor/"))
+    load_into(pol.agent.critic, net_from_golden(g, "init/critic/"))
+    tol = dict(rtol=5e-5, atol=6e-6)
+    for r in range(2):
+        d = [g["data%d/%s" % (r, k)] for k in ("obs", "act", "rew", "nobs", "done", "logp", "adv_done")]
+        torch.set_rng_state(torch.from_numpy(g["rng%d/before_rollout" % r].copy()))
+        for t in range(256):
+            if inject:
+                z = torch.empty((1, ad)).normal_() if is_continue else torch.empty((1, ad)).exponential_(1)
+                a, lp = pol.select_action(d[0][t], noise=z)
+            else:
+                a, lp = pol.select_action(d[0][t])
+            if is_continue:
+                np.testing.assert_allclose(a, d[1][t], rtol=2e-5, atol=4e-6, err_msg="rollout %d action %d" % (r, t))
+            else:
+                assert int(a) == int(d[1][t].reshape(-1)[0]), (r, t)
+            np.testing.assert_allclose(np.asarray(lp).reshape(-1), d[5][t].reshape(-1), rtol=5e-5, atol=5e-6, err_msg="rollout %d log-prob %d" % (r, t))
+            pol.add(d[0][t], d[1][t], float(d[2][t, 0]), d[3][t], bool(d[4][t, 0]), d[5][t], bool(d[6][t, 0]))
+        perms = [g["perm%d/%d" % (r, k)] for k in range(2)]
+        pol.learn(64, 0.99, 0.95, 0.2, 2, 0.01, permutations=perms)
+        m = pol.last_metrics.cpu().numpy()
+        np.testing.assert_allclose(m[:, :2], g["losses"][8 * r:8 * r + 8], rtol=6e-5, atol=6e-6)
+        pol.lr_decay(10, 100)
+        assert_module_close(pol.agent.actor, net_from_golden(g, "after%d/actor/" % r), "actor vs reference", tol)
+        assert_module_close(pol.agent.critic, net_from_golden(g, "after%d/critic/" % r), "critic vs reference", tol)
+        ms = pol.batch_size_obs_norm.running_ms
+        np.testing.assert_allclose(ms.mean.cpu().numpy(), g["after%d/norm/mean" % r], rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(ms.std.cpu().numpy(), g["after%d/norm/std" % r], rtol=1e-5, atol=1e-6)
+
+
+def test_ppo_with_tricks_batch_obs_norm_emulated(golden, emul):
+    _ppo_tricks_bon(golden, torch.device("cpu"), True, False)
+    _ppo_tricks_bon(golden, torch.device("cpu"), False, False)
+
+
+@pytest.mark.gpu
+def test_ppo_with_tricks_batch_obs_norm_gpu(golden):
+    _ppo_tricks_bon(golden, torch.device("cuda"), True, True)
+    _ppo_tricks_bon(golden, torch.device("cuda"), False, True)
 
 
 def test_ppo_with_tricks_continuous_emulated(golden, emul):
