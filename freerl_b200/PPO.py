@@ -54,9 +54,14 @@ class Agent:
     """``PPO.py:109-152``: actor + critic with ONE merged optimiser -> ONE device parameter block (layers 0-2 actor,
     3-5 critic, extra = log_std)."""
 
-    def __init__(self, obs_dim, action_dim, actor_lr, critic_lr, is_continue, device, critic_in=None, init_hook=None):
+    def __init__(self, obs_dim, action_dim, actor_lr, critic_lr, is_continue, device, critic_in=None, init_hook=None, beta=False):
         head = "mean_layer" if is_continue else "l3"
         critic_in = obs_dim if critic_in is None else critic_in
+        self.beta = bool(beta and is_continue)
+        if self.beta:
+            self._init_beta(obs_dim, action_dim, critic_in, device, init_hook)
+            self.lr, self.step = actor_lr, 0
+            return
         dims = [(obs_dim, 128), (128, 128), (128, action_dim), (critic_in, 128), (128, 128), (128, 1)]
         self._net = DeviceNet(dims, device, True, x_len=action_dim if is_continue else 0)
         a_init = _ActorInit(obs_dim, action_dim, head)          # same RNG consumption as Actor / Actor_discrete
@@ -76,6 +81,38 @@ class Agent:
         self.lr = actor_lr                                       # AdamW(actor+critic params, lr=actor_lr)  PPO.py:121
         self.step = 0
 
+    def _init_beta(self, obs_dim, action_dim, critic_in, device, init_hook):
+        """``Actor_Beta`` (``PPO_with_tricks.py:120-150``): l1, l2, alpha_layer, beta_layer.  The two heads are ONE device layer of width
+        2 * action_dim (rows [alpha | beta]); the shim exposes them as ``alpha_layer`` / ``beta_layer`` row slices, in the reference's
+        state-dict order.  No ``log_std``."""
+        A = action_dim
+        dims = [(obs_dim, 128), (128, 128), (128, 2 * A), (critic_in, 128), (128, 128), (128, 1)]
+        self._net = net = DeviceNet(dims, device, True, x_len=0)
+        a_init = nn.Module()
+        a_init.l1, a_init.l2 = nn.Linear(obs_dim, 128), nn.Linear(128, 128)
+        a_init.alpha_layer, a_init.beta_layer = nn.Linear(128, A), nn.Linear(128, A)
+        if init_hook:
+            init_hook(a_init, ("l1", "l2", "alpha_layer", "beta_layer"), "actor")
+        c_init = _CriticInit(critic_in)
+        if init_hook:
+            init_hook(c_init, ("l1", "l2", "l3"), "critic")
+        with torch.no_grad():
+            for li, lay in ((0, a_init.l1), (1, a_init.l2), (3, c_init.l1), (4, c_init.l2), (5, c_init.l3)):
+                net.weight(li).copy_(lay.weight.to(device))
+                net.bias(li).copy_(lay.bias.to(device))
+            net.weight(2)[:A].copy_(a_init.alpha_layer.weight.to(device)); net.weight(2)[A:].copy_(a_init.beta_layer.weight.to(device))
+            net.bias(2)[:A].copy_(a_init.alpha_layer.bias.to(device)); net.bias(2)[A:].copy_(a_init.beta_layer.bias.to(device))
+        net.sync_mirror()
+        self.actor_names = ("l1", "l2", "alpha_layer", "beta_layer")
+        shim = _shim(net, (0, 1), ("l1", "l2"))
+        for name, sl in (("alpha_layer", slice(0, A)), ("beta_layer", slice(A, 2 * A))):
+            lin = nn.Module()
+            lin.weight = nn.Parameter(net.weight(2)[sl], requires_grad=False)
+            lin.bias = nn.Parameter(net.bias(2)[sl], requires_grad=False)
+            shim.add_module(name, lin)
+        self.actor = shim
+        self.critic = _shim(net, (3, 4, 5), ("l1", "l2", "l3"))
+
 
 class PPO:
     optimizer = _lib.OPT_CAUTIOUS_ADAMW
@@ -87,7 +124,8 @@ class PPO:
         obs_dim, action_dim = dim_info
         self.device = _lib.require_device(device)
         self.obs_dim, self.action_dim = obs_dim, action_dim
-        self.agent = Agent(obs_dim, action_dim, actor_lr, critic_lr, is_continue, self.device, init_hook=getattr(self, "_init_hook", None))
+        self.agent = Agent(obs_dim, action_dim, actor_lr, critic_lr, is_continue, self.device, init_hook=getattr(self, "_init_hook", None),
+                           beta=getattr(self, "_beta", False))
         self.buffer = Buffer_for_PPO(horizon, obs_dim, act_dim=action_dim if is_continue else 1, device=self.device)
         self.is_continue = is_continue
         print('actor_type:continue') if self.is_continue else print('actor_type:discrete')
@@ -108,6 +146,20 @@ class PPO:
         n = x.shape[0]
         net = self.agent._net
         self._n_act += 1
+        if self.is_continue and getattr(self.agent, "beta", False):
+            # Beta(alpha, beta).sample() (PPO_with_tricks.py:238-240, 246-247): the kernel evaluates the network, the draw and its
+            # log-prob are torch's own (Dirichlet / gamma sampler — on the CPU generator in parity mode, like the reference)
+            z = _common.infer(net, x, _lib.INFER_RAW, self.device, 2 * self.action_dim, l0=0, nl=3, hidden_tanh=bool(self.hidden_tanh & 1),
+                              obs_norm=getattr(self, "batch_size_obs_norm", None))
+            if self.mode == "parity":
+                z = z.cpu()
+            al = torch.nn.functional.softplus(z[:, :self.action_dim]) + 1.0
+            be = torch.nn.functional.softplus(z[:, self.action_dim:]) + 1.0
+            dist = torch.distributions.Beta(al, be)
+            action = dist.sample() if noise is None else torch.as_tensor(noise, dtype=torch.float32).reshape(n, self.action_dim).to(al.device)
+            logp = dist.log_prob(action)
+            action, logp = action.cpu().numpy(), logp.cpu().numpy()
+            return (action[0], logp[0]) if single else (action, logp)
         if self.is_continue:
             if noise is None and self.mode == "parity":
                 noise = _common.reference_randn((n, self.action_dim), self.device)    # dist.sample() (PPO.py:173)
@@ -131,6 +183,12 @@ class PPO:
     def evaluate_action(self, obs):
         x, single = _common.as_obs_batch(obs, self.obs_dim)
         net = self.agent._net
+        if self.is_continue and getattr(self.agent, "beta", False):          # 2 (alpha / (alpha + beta) - 0.5)   PPO_with_tricks.py:259-262
+            z = _common.infer(net, x, _lib.INFER_RAW, self.device, 2 * self.action_dim, l0=0, nl=3, hidden_tanh=bool(self.hidden_tanh & 1))
+            al = torch.nn.functional.softplus(z[:, :self.action_dim]) + 1.0
+            be = torch.nn.functional.softplus(z[:, self.action_dim:]) + 1.0
+            a = (2.0 * (al / (al + be) - 0.5)).cpu().numpy()
+            return a[0] if single else a
         if self.is_continue:
             a = _common.infer(net, x, _lib.INFER_TANH, self.device, self.action_dim, l0=0, nl=3, hidden_tanh=bool(self.hidden_tanh & 1)).cpu().numpy()
             return a[0] if single else a
@@ -186,7 +244,7 @@ class PPO:
         out = torch.zeros((n_updates, 8), dtype=torch.float32, device=self.device)
         a = _lib.PpoArgs()
         a.net = ag._net.c_struct()
-        a.continuous = int(self.is_continue)
+        a.continuous = 2 if getattr(self.agent, "beta", False) else int(self.is_continue)
         a.obs, a.action, a.logp_old = b.obs.data_ptr(), b.actions.data_ptr(), b.action_log_probs.data_ptr()
         a.adv, a.v_target = adv.data_ptr(), v_target.data_ptr()
         a.M, a.obs_dim, a.act_cols, a.logp_cols, a.n_adv = b.capacity, self.obs_dim, b.act_dim, b.logp_dim, n_adv

@@ -18,7 +18,9 @@ executed with that one call patched (``oracle/make_golden_ppo_tricks.py``):
                       observations in and trains on the normalised ``obs`` / ``next_obs`` (``:296-298``), ``select_action`` applies them with
                       ``update=False`` (``:235-236``); like upstream ``evaluate_action`` does not normalise
 
-Not provided (raises ``NotImplementedError``): the Beta policy (``beta=True``).
+* ``beta=True``       the Beta policy head (``Actor_Beta``, ``:120-150``): ``alpha, beta = softplus(.) + 1`` from two heads stored as one device layer,
+                      ``Beta.log_prob`` / ``.entropy`` and their gradients (digamma / trigamma) inside the fused update (``frl_ppo_args_t.continuous = 2``);
+                      sampling in ``select_action`` is torch's own gamma sampler on the kernel's network output; ``evaluate_action`` = ``2 (mean - 0.5)``
 """
 import os
 
@@ -41,19 +43,18 @@ class PPO(_PPOAdvance):
     def __init__(self, dim_info, is_continue, actor_lr, critic_lr, horizon, device, trick=None, beta=False, mode=None):
         t = {k: False for k in _TRICKS}
         t.update(trick or {})
-        if beta:
-            raise NotImplementedError("PPO_with_tricks: the Beta policy head (beta=True) is not implemented on the fused kernel")
+        self._beta = bool(beta and is_continue)          # Actor_Beta exists for continuous actions only (:187-192)
         # Actor_discrete takes no trick argument upstream (:106-118, :187): ReLU body and default init whatever the switches say
         self.hidden_tanh = (3 if is_continue else 2) if t['tanh'] else 0
         self.adam_eps = 1e-5 if t['adam_eps'] else 1e-8
-        self.actor_dist = {'Beta': False}
-        print('actor_dist:Gaussian')
+        self.actor_dist = {'Beta': self._beta}
+        print('actor_dist:Beta' if self._beta else 'actor_dist:Gaussian')
         if t['orthogonal_init']:
             def hook(module, names, which):
                 if which == "actor" and not is_continue:
                     return
                 for n in names:
-                    orthogonal_init(getattr(module, n), gain=0.01 if (which == "actor" and n == "mean_layer") else 1.0)
+                    orthogonal_init(getattr(module, n), gain=0.01 if (which == "actor" and n in ("mean_layer", "alpha_layer", "beta_layer")) else 1.0)
             self._init_hook = hook
         super().__init__(dim_info, is_continue, actor_lr, critic_lr, horizon, device, trick=t, mode=mode)
         self.actor_lr, self.critic_lr = actor_lr, critic_lr

@@ -12,6 +12,22 @@
 #define FRL_HALF_LOG_2PI 0.91893853320467274178f
 #include "algo_ppo_umma.cuh"
 
+// digamma / trigamma for x >= 1 (recurrence up to x >= 6, then the asymptotic series; evaluated in double: the Beta head calls them
+// a few times per row) — torch.distributions.Beta.entropy / log_prob gradients, PPO_with_tricks.py:120-150, 327-333
+FRL_HD double frl_digamma(double x) {
+  double r = 0.0;
+  while (x < 6.0) { r -= 1.0 / x; x += 1.0; }
+  const double f = 1.0 / (x * x);
+  return r + log(x) - 0.5 / x - f * (1.0 / 12.0 - f * (1.0 / 120.0 - f * (1.0 / 252.0 - f * (1.0 / 240.0 - f * (1.0 / 132.0)))));
+}
+FRL_HD double frl_trigamma(double x) {
+  double r = 0.0;
+  while (x < 6.0) { r += 1.0 / (x * x); x += 1.0; }
+  const double f = 1.0 / (x * x);
+  return r + 1.0 / x + 0.5 * f + (1.0 / x) * f * (1.0 / 6.0 - f * (1.0 / 30.0 - f * (1.0 / 42.0 - f * (1.0 / 30.0))));
+}
+FRL_HD float frl_softplus(float z) { return z > 20.f ? z : log1pf(expf(z)); }       // F.softplus (beta 1, threshold 20)
+
 // tensor (segment) id of parameter index p and that tensor's logical element count
 FRL_DEV int seg_of(const frl_net_t& n, int p, int* numel) {
   for (int li = 0; li < n.n_layers; ++li) {
@@ -307,7 +323,19 @@ struct PpoAlgoT {
             for (int j = 0; j < ap; ++j) dOA[r * ap + j] = 0.f;
             if (r < nvalid) {
               float lp_now = 0.f, lp_old = 0.f, ent = 0.f;
-              if (a.continuous) {
+              if (a.continuous == 2) {
+                // Beta head (Actor_Beta, PPO_with_tricks.py:120-150): output columns [alpha logits (A) | beta logits (A)],
+                // alpha = softplus(.) + 1, beta likewise; Beta(alpha, beta).log_prob(x), .entropy() as torch's Dirichlet computes them
+                const int A = nout >> 1;
+                for (int j = 0; j < A; ++j) {
+                  const double al = (double)frl_softplus(OA[r * ap + j]) + 1.0, be = (double)frl_softplus(OA[r * ap + A + j]) + 1.0;
+                  const double x = (double)ACT[r * ap + j];
+                  const double lnB = lgamma(al) + lgamma(be) - lgamma(al + be);
+                  lp_now += (float)((al - 1.0) * log(x) + (be - 1.0) * log(1.0 - x) - lnB);
+                  ent += (float)(lnB + (al + be - 2.0) * frl_digamma(al + be) - (al - 1.0) * frl_digamma(al) - (be - 1.0) * frl_digamma(be));
+                }
+                for (int j = 0; j < a.logp_cols; ++j) lp_old += LPO[r * ap + j];
+              } else if (a.continuous) {
                 for (int j = 0; j < nout; ++j) {
                   const float mean = tanhf(OA[r * ap + j]);
                   const float ls = fminf(fmaxf(N.p[N.x_off + j], -20.f), 2.f);
@@ -343,7 +371,21 @@ struct PpoAlgoT {
               sa = -surr * inv_rn;
               se = ent;
               // chain to the actor output
-              if (a.continuous) {
+              if (a.continuous == 2) {
+                const int A = nout >> 1;
+                const float dent = -a.entropy_coef * inv_rows;                       // d(loss) / d(entropy of this row)
+                for (int j = 0; j < A; ++j) {
+                  const float za = OA[r * ap + j], zb = OA[r * ap + A + j];
+                  const double al = (double)frl_softplus(za) + 1.0, be = (double)frl_softplus(zb) + 1.0, x = (double)ACT[r * ap + j];
+                  const double psi0 = frl_digamma(al + be), tri0 = frl_trigamma(al + be);
+                  const double dlp_a = log(x) + psi0 - frl_digamma(al), dlp_b = log(1.0 - x) + psi0 - frl_digamma(be);
+                  const double dh_a = -(al - 1.0) * frl_trigamma(al) + (al + be - 2.0) * tri0;
+                  const double dh_b = -(be - 1.0) * frl_trigamma(be) + (al + be - 2.0) * tri0;
+                  const float sa_ = 1.f / (1.f + expf(-za)), sb_ = 1.f / (1.f + expf(-zb));        // d softplus / dz (1 beyond the threshold)
+                  dOA[r * ap + j] = (float)((double)dlp * dlp_a + (double)dent * dh_a) * (za > 20.f ? 1.f : sa_);
+                  dOA[r * ap + A + j] = (float)((double)dlp * dlp_b + (double)dent * dh_b) * (zb > 20.f ? 1.f : sb_);
+                }
+              } else if (a.continuous) {
                 for (int j = 0; j < nout; ++j) {
                   const float mean = tanhf(OA[r * ap + j]);
                   const float ls = fminf(fmaxf(N.p[N.x_off + j], -20.f), 2.f);
@@ -367,7 +409,7 @@ struct PpoAlgoT {
                   dOA[r * ap + j] = g;
                 }
               }
-            } else if (a.continuous) {
+            } else if (a.continuous == 1) {
               for (int j = 0; j < ap; ++j) LPO[r * ap + j] = 0.f;
             }
           }
@@ -402,7 +444,7 @@ struct PpoAlgoT {
         }
         FRL_SYNC();
         lc += block_sum(red0);
-        if (a.continuous) {
+        if (a.continuous == 1) {
           // log_std gradient: log-prob path (stored in LPO) + entropy bonus  -c * mean_rows(sum_j 1)
           FRL_PAR(t) {
             if (t < ap) {

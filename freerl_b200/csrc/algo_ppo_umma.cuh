@@ -29,7 +29,7 @@ FRL_HD int um_pad32(int x) { return (x + 31) & ~31; }
 
 // host + device: can this update take the tensor-core path?
 FRL_HD bool um_eligible(const frl_ppo_args_t& a) {
-  if (!a.umma_ws || a.mb < 1024 || a.hidden_tanh || a.net.n_layers != 6) return false;
+  if (!a.umma_ws || a.mb < 1024 || a.hidden_tanh || a.net.n_layers != 6 || a.continuous == 2) return false;
   for (int r = 0; r < 2; ++r) {
     const frl_layer_t &L0 = a.net.L[3 * r], &L1 = a.net.L[3 * r + 1], &L2 = a.net.L[3 * r + 2];
     if (L0.out != 128 || L1.in != 128 || L1.out != 128 || L2.in != 128 || L0.in > 64 || L2.out > 16) return false;

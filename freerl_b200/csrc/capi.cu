@@ -786,7 +786,7 @@ extern "C" int frl_ppo_update(const frl_ppo_args_t* a, void* stream) {
     return -1;
 #endif
   }
-  if (a->net.n_layers != 6 || (a->continuous && a->net.x_len <= 0)) {
+  if (a->net.n_layers != 6 || (a->continuous == 1 && a->net.x_len <= 0) || (a->continuous == 2 && (a->net.L[2].out & 1))) {
     frl_set_error("frl_ppo_update: net must hold actor (layers 0-2) + critic (layers 3-5)");
     return -1;
   }

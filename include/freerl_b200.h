@@ -203,7 +203,8 @@ typedef struct {
 enum { FRL_OPT_CAUTIOUS_ADAMW = 0, FRL_OPT_ADAM = 1 };
 typedef struct {
   frl_net_t net;
-  int continuous;           /* 1: Normal(tanh(mean), exp(clamp(log_std))), 0: Categorical(logits) */
+  int continuous;           /* 1: Normal(tanh(mean), exp(clamp(log_std))), 0: Categorical(logits), 2: Beta(softplus + 1) with the actor's last layer
+                             *    = [alpha logits (A) | beta logits (A)] (Actor_Beta, PPO_with_tricks.py:120-150; FFMA tile kernels only) */
   const float* obs;         /* dev [M][obs_dim] rollout arrays (Buffer_for_PPO.all()) */
   const float* action;      /* dev [M][act_cols]  (discrete: 1 column holding the index) */
   const float* logp_old;    /* dev [M][logp_cols] */

@@ -524,8 +524,9 @@ class PPOTricksOracle(PPOAdvanceOracle):
     ``PPOAdvanceOracle`` plus ``adam_eps`` (both Adams eps 1e-5, ``:198-200``), ``adv_norm`` (``:314-315``) and ``lr_decay``
     (``:356-362``)."""
 
-    def __init__(self, actor, critic, actor_lr, critic_lr, is_continue, adam_eps=False, adv_norm=False, tanh=False):
+    def __init__(self, actor, critic, actor_lr, critic_lr, is_continue, adam_eps=False, adv_norm=False, tanh=False, beta=False):
         super().__init__(actor, critic, actor_lr, critic_lr, is_continue)
+        self.beta = bool(beta and is_continue)          # Actor_Beta (``:120-150``): alpha, beta = softplus(head) + 1
         if tanh:
             self.act = torch.tanh
             if is_continue:
@@ -543,4 +544,33 @@ class PPOTricksOracle(PPOAdvanceOracle):
     def lr_decay(self, episode_num, max_episodes):
         self.opt_a.lr = self.actor_lr * (1 - episode_num / max_episodes)
         self.opt_c.lr = self.critic_lr * (1 - episode_num / max_episodes)
+
+    def beta_params(self, obs):
+        h = self.act_actor(F.linear(obs, self.actor["l1.weight"], self.actor["l1.bias"]))
+        h = self.act_actor(F.linear(h, self.actor["l2.weight"], self.actor["l2.bias"]))
+        alpha = F.softplus(F.linear(h, self.actor["alpha_layer.weight"], self.actor["alpha_layer.bias"])) + 1.0
+        beta = F.softplus(F.linear(h, self.actor["beta_layer.weight"], self.actor["beta_layer.bias"])) + 1.0
+        return alpha, beta
+
+    def minibatch(self, data, adv, v_target, index, clip_param, entropy_coefficient):
+        if not self.beta:
+            return super().minibatch(data, adv, v_target, index, clip_param, entropy_coefficient)
+        obs, action, reward, next_obs, done, logp_old, adv_dones = data
+        alpha, beta = self.beta_params(obs[index])                      # ``:326-333``
+        dist = torch.distributions.Beta(alpha, beta)
+        ent = dist.entropy().sum(dim=1, keepdim=True)
+        logp = dist.log_prob(action[index])
+        ratios = torch.exp(logp.sum(dim=1, keepdim=True) - logp_old[index].sum(dim=1, keepdim=True))
+        surr1 = ratios * adv[index]
+        surr2 = torch.clamp(ratios, 1 - clip_param, 1 + clip_param) * adv[index]
+        actor_loss = -torch.min(surr1, surr2).mean() - entropy_coefficient * ent.mean()
+        ap = list(self.actor.values())
+        ga, _ = clip_grad_norm(torch.autograd.grad(actor_loss, ap), 0.5)
+        adam_step(ap, list(ga), self.opt_a)
+        v_s = mlp2(self.critic, obs[index], act=self.act)
+        critic_loss = F.mse_loss(v_target[index], v_s)
+        cp = list(self.critic.values())
+        gc, _ = clip_grad_norm(torch.autograd.grad(critic_loss, cp), 0.5)
+        adam_step(cp, list(gc), self.opt_c)
+        return actor_loss.item(), critic_loss.item()
 

@@ -33,14 +33,14 @@ class _NpProxy:
         return np.zeros(shape, dtype=dtype)
 
 
-def gen(is_continue, tanh=False, bon=False):
+def gen(is_continue, tanh=False, bon=False, beta=False):
     m = refload.load("PPO_file", "PPO_with_tricks")
     m.np = _NpProxy()
     seed, horizon, mb, K = 13, 256, 64, 2
     obs_dim, act_dim = 8, (2 if is_continue else 4)
     np.random.seed(seed)
     torch.manual_seed(seed)
-    policy = m.PPO([obs_dim, act_dim], is_continue, 1e-3, 5e-4, horizon, torch.device("cpu"), trick=dict(TRICK, tanh=tanh, Batch_ObsNorm=bon))
+    policy = m.PPO([obs_dim, act_dim], is_continue, 1e-3, 5e-4, horizon, torch.device("cpu"), trick=dict(TRICK, tanh=tanh, Batch_ObsNorm=bon), beta=beta)
     rng = np.random.default_rng(seed)
     offset = rng.uniform(1.0, 3.0, obs_dim).astype(np.float32) if bon else 0.0      # Batch_ObsNorm fixture: observations with a non-zero mean
     rec = {}
@@ -49,7 +49,7 @@ def gen(is_continue, tanh=False, bon=False):
     tap = LossTap(policy.agent, ["update_actor", "update_critic"])
     obs = rng.standard_normal(obs_dim).astype(np.float32) + offset
     for r in range(2):
-        if bon:
+        if bon or beta:
             rec["rng%d/before_rollout" % r] = torch.get_rng_state().numpy().copy()
         for t in range(horizon):
             a, logp = policy.select_action(obs)
@@ -75,13 +75,16 @@ def gen(is_continue, tanh=False, bon=False):
         rec.update(sd_np(policy.agent.critic, "after%d/critic/" % r))
     log = [v[0] for _, v in tap.log]
     rec["losses"] = np.array(list(zip(log[0::2], log[1::2])), np.float64)          # (actor, critic) per minibatch, both learns
-    name = ("ppo_tricks_bon_" if bon else "ppo_tricks_tanh_" if tanh else "ppo_tricks_") + ("cont" if is_continue else "disc")
+    name = ("ppo_tricks_beta_" if beta else "ppo_tricks_bon_" if bon else "ppo_tricks_tanh_" if tanh else "ppo_tricks_") + ("cont" if is_continue else "disc")
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
     print(name, "ok", rec["losses"][:2], rec["losses"].shape)
 
 
 if __name__ == "__main__":
     torch.set_num_threads(1)
+    if "beta" in sys.argv[1:]:
+        gen(True, beta=True)
+        sys.exit(0)
     if "bon" in sys.argv[1:]:
         gen(True, bon=True)
         gen(False, bon=True)

@@ -146,8 +146,57 @@ def _ppo_tricks(golden, device, name, is_continue, tanh=False):
         assert_module_close(pol.agent.critic, orc.critic, "critic", tol)
         assert_module_close(pol.agent.actor, net_from_golden(g, "after%d/actor/" % r), "actor vs reference", tol)
         assert_module_close(pol.agent.critic, net_from_golden(g, "after%d/critic/" % r), "critic vs reference", tol)
-    with pytest.raises(NotImplementedError):
-        PPO([8, act_dim], is_continue, 1e-3, 5e-4, 256, device, trick=dict(TRICKS), beta=True)
+
+
+def _ppo_tricks_beta(golden, device):
+    """PPO_with_tricks(beta=True): the Beta policy head (``Actor_Beta``, ``PPO_with_tricks.py:120-150, 238-247, 326-333``) vs the oracle and
+    the fixture generated from the reference (oracle/make_golden_ppo_tricks.py beta).  ``select_action`` on the emulation restores the
+    reference's generator state and must reproduce its sampled actions / log-probs (torch's gamma sampler on the kernel's network
+    output); on the GPU the reference's actions are injected and the log-probs compared."""
+    from freerl_b200.PPO_with_tricks import PPO
+    g = golden("ppo_tricks_beta_cont")
+    pol = PPO([8, 2], True, 1e-3, 5e-4, 256, device, trick=dict(TRICKS), beta=True)
+    assert list(pol.agent.actor.state_dict().keys()) == [k[len("init/actor/"):] for k in g.files if k.startswith("init/actor/")]
+    w = pol.agent.actor.state_dict()["alpha_layer.weight"].cpu().double()                      # orthogonal init, gain 0.01
+    assert torch.allclose(w @ w.T, 1e-4 * torch.eye(2, dtype=torch.float64), atol=1e-7)
+    load_into(pol.agent.actor, net_from_golden(g, "init/actor/"))
+    load_into(pol.agent.critic, net_from_golden(g, "init/critic/"))
+    orc = algos.PPOTricksOracle(net_from_golden(g, "init/actor/"), net_from_golden(g, "init/critic/"), 1e-3, 5e-4, True, adam_eps=True,
+                                adv_norm=True, beta=True)
+    tol = dict(rtol=3e-5, atol=4e-6)
+    on_cpu = device.type == "cpu"
+    for r in range(2):
+        data = tuple(torch.from_numpy(g["data%d/%s" % (r, k)]) for k in ("obs", "act", "rew", "nobs", "done", "logp", "adv_done"))
+        d = [x.numpy() for x in data]
+        torch.set_rng_state(torch.from_numpy(g["rng%d/before_rollout" % r].copy()))
+        for t in range(256):
+            a, lp = pol.select_action(d[0][t]) if on_cpu else pol.select_action(d[0][t], noise=d[1][t])
+            np.testing.assert_allclose(a, d[1][t], rtol=2e-5, atol=2e-6, err_msg="rollout %d action %d" % (r, t))
+            np.testing.assert_allclose(lp, d[5][t], rtol=5e-5, atol=5e-6, err_msg="rollout %d log-prob %d" % (r, t))
+            pol.add(d[0][t], d[1][t], float(d[2][t, 0]), d[3][t], bool(d[4][t, 0]), d[5][t], bool(d[6][t, 0]))
+        perms = [g["perm%d/%d" % (r, k)] for k in range(2)]
+        ref = np.array(orc.learn(data, perms, 64, 0.99, 0.95, 0.2, 0.01)["losses"])
+        np.testing.assert_allclose(ref, g["losses"][8 * r:8 * r + 8], rtol=2e-6, atol=2e-7)      # the oracle is the reference here
+        pol.learn(64, 0.99, 0.95, 0.2, 2, 0.01, permutations=perms)
+        m = pol.last_metrics.cpu().numpy()
+        np.testing.assert_allclose(m[:, :2], ref, rtol=3e-5, atol=3e-6)
+        orc.lr_decay(10, 100)
+        pol.lr_decay(10, 100)
+        assert_module_close(pol.agent.actor, orc.actor, "actor", tol)
+        assert_module_close(pol.agent.critic, orc.critic, "critic", tol)
+        assert_module_close(pol.agent.actor, net_from_golden(g, "after%d/actor/" % r), "actor vs reference", tol)
+    ev = pol.evaluate_action(g["data1/obs"][0])
+    al, be = orc.beta_params(torch.from_numpy(g["data1/obs"][:1]))
+    np.testing.assert_allclose(ev, (2 * (al / (al + be) - 0.5)).detach().numpy()[0], rtol=1e-5, atol=1e-6)
+
+
+def test_ppo_with_tricks_beta_emulated(golden, emul):
+    _ppo_tricks_beta(golden, torch.device("cpu"))
+
+
+@pytest.mark.gpu
+def test_ppo_with_tricks_beta_gpu(golden):
+    _ppo_tricks_beta(golden, torch.device("cuda"))
 
 
 def _ppo_tricks_bon(golden, device, is_continue, inject):
