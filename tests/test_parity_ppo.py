@@ -210,7 +210,11 @@ def _ppo_tricks_bon(golden, device, is_continue, inject):
     pol = PPO([8, ad], is_continue, 1e-3, 5e-4, 256, device, trick=dict(TRICKS, Batch_ObsNorm=True))
     load_into(pol.agent.actor, net_from_golden(g, "init/actor/"))
     load_into(pol.agent.critic, net_from_golden(g, "init/critic/"))
-    tol = dict(rtol=5e-5, atol=6e-6)
+    # On the GPU the rollout mean that feeds the running statistics is reduced by torch's CUDA kernel in another order than the reference's
+    # CPU reduction; the first update's quirk (mean = std = x_bar) divides by that mean, and the critic targets of this fixture are in the
+    # hundreds: measured 1.3e-4 relative on one actor loss (B200).  The emulation run (CPU torch, same reduction) holds the tight numbers.
+    tol = dict(rtol=5e-5, atol=6e-6) if not inject else dict(rtol=5e-4, atol=5e-5)
+    ltol = dict(rtol=6e-5, atol=6e-6) if not inject else dict(rtol=5e-4, atol=5e-5)
     for r in range(2):
         d = [g["data%d/%s" % (r, k)] for k in ("obs", "act", "rew", "nobs", "done", "logp", "adv_done")]
         torch.set_rng_state(torch.from_numpy(g["rng%d/before_rollout" % r].copy()))
@@ -221,15 +225,16 @@ def _ppo_tricks_bon(golden, device, is_continue, inject):
             else:
                 a, lp = pol.select_action(d[0][t])
             if is_continue:
-                np.testing.assert_allclose(a, d[1][t], rtol=2e-5, atol=4e-6, err_msg="rollout %d action %d" % (r, t))
+                np.testing.assert_allclose(a, d[1][t], err_msg="rollout %d action %d" % (r, t), **(dict(rtol=2e-5, atol=4e-6) if not inject else tol))
             else:
                 assert int(a) == int(d[1][t].reshape(-1)[0]), (r, t)
-            np.testing.assert_allclose(np.asarray(lp).reshape(-1), d[5][t].reshape(-1), rtol=5e-5, atol=5e-6, err_msg="rollout %d log-prob %d" % (r, t))
+            np.testing.assert_allclose(np.asarray(lp).reshape(-1), d[5][t].reshape(-1), err_msg="rollout %d log-prob %d" % (r, t),
+                                       **(dict(rtol=5e-5, atol=5e-6) if not inject else tol))
             pol.add(d[0][t], d[1][t], float(d[2][t, 0]), d[3][t], bool(d[4][t, 0]), d[5][t], bool(d[6][t, 0]))
         perms = [g["perm%d/%d" % (r, k)] for k in range(2)]
         pol.learn(64, 0.99, 0.95, 0.2, 2, 0.01, permutations=perms)
         m = pol.last_metrics.cpu().numpy()
-        np.testing.assert_allclose(m[:, :2], g["losses"][8 * r:8 * r + 8], rtol=6e-5, atol=6e-6)
+        np.testing.assert_allclose(m[:, :2], g["losses"][8 * r:8 * r + 8], **ltol)
         pol.lr_decay(10, 100)
         assert_module_close(pol.agent.actor, net_from_golden(g, "after%d/actor/" % r), "actor vs reference", tol)
         assert_module_close(pol.agent.critic, net_from_golden(g, "after%d/critic/" % r), "critic vs reference", tol)
