@@ -21,9 +21,6 @@ class HAPPO(_MAPPO):
     max_norm = 0.5
 
     def __init__(self, dim_info, is_continue, actor_lr, critic_lr, horizon, device, trick=None, mode=None):
-        if not is_continue:
-            raise NotImplementedError("HAPPO: the reference's discrete factor update (HAPPO.py:443-444) mixes minibatch and horizon "
-                                      "rows; only the continuous-action path is provided")
         super().__init__(dim_info, is_continue, actor_lr, critic_lr, horizon, device, trick=trick, mode=mode)
         for ag in self.agents.values():
             ag.lr_critic = critic_lr
@@ -35,10 +32,13 @@ class HAPPO(_MAPPO):
         self._lr_decay_two_optimisers(episode_num, max_episodes)
 
     def _full_logp(self, agent_id):
-        """sum_j log N(action_j | mean_j, std_j) of the STORED actions over the whole horizon with the agent's current actor"""
+        """log-probability of the STORED actions over the whole horizon with the agent's current actor: sum_j log N(action_j | mean_j, std_j),
+        or log p(action) of the categorical head"""
         ag, b = self.agents[agent_id], self.buffers[agent_id]
         ad = self.dim_info[agent_id][1]
         raw = _common.infer(ag._net, b.obs, _lib.INFER_RAW, self.device, ad, l0=0, nl=3, layer_norm=self.layer_norm)
+        if not self.is_continue:
+            return torch.log_softmax(raw, dim=1).gather(1, b.actions.long())
         mean = torch.tanh(raw)
         std = torch.exp(torch.clamp(ag._net.extra().view(1, -1).expand_as(mean), -20, 2))
         return torch.distributions.Normal(mean, std).log_prob(b.actions).sum(dim=1, keepdim=True)
@@ -50,6 +50,11 @@ class HAPPO(_MAPPO):
         N = self.num_agents
         if order is None:
             order = torch.randperm(N).numpy()                                  # HAPPO.py:364 (CPU generator)
+        if not self.is_continue and minibatch_size != self.horizon:
+            # upstream the discrete factor update evaluates the new log-probs on the rows of the LAST minibatch only (HAPPO.py:449-450) and
+            # then subtracts the full-horizon old ones: the shapes only broadcast when one minibatch covers the horizon
+            raise RuntimeError("HAPPO (discrete): the size of tensor a (%d) must match the size of tensor b (%d) at non-singleton dimension 0 "
+                               "— the reference's discrete factor update needs minibatch_size == horizon" % (minibatch_size, self.horizon))
         factor = torch.ones((self.horizon, 1), dtype=torch.float32, device=self.device)
         outs = []
         for pos, ai in enumerate(order):
@@ -62,7 +67,12 @@ class HAPPO(_MAPPO):
             outs.append(self._agent_update(agent_id, adv_f, v_target, joint, minibatch_size, K_epochs, clip_param, entropy_coefficient,
                                            huber_delta, perms))
             if not last:
-                factor = factor * torch.exp(self._full_logp(agent_id) - old)
+                new = self._full_logp(agent_id)
+                if not self.is_continue:
+                    # reference quirk kept: the new log-probs are in the order of the last minibatch's permutation, the old ones in time order
+                    idx_last = self._keep[0][-1]
+                    new = new[idx_last]
+                factor = factor * torch.exp(new - old)
         self.last_factor = factor
         self.last_metrics = torch.cat(outs)               # rows in VISITING order
         for buffer in self.buffers.values():

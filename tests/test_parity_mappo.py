@@ -164,6 +164,44 @@ def _happo(golden, device):
         assert_module_close(pol.agents[k].critic, maddpg_nets(g, "final", "critic")[k], "final critic " + k, tol)
 
 
+def _happo_discrete(golden, device):
+    """HAPPO with Categorical actors against the fixture generated from MAPPO_file/HAPPO.py (happo_disc.npz, minibatch == horizon — the
+    only setting in which the reference's discrete factor update broadcasts, HAPPO.py:449-450): losses of every update of every agent in
+    visiting order and the final networks are the reference's own numbers; any other minibatch size raises like upstream."""
+    from freerl_b200.HAPPO import HAPPO
+    g = golden("happo_disc")
+    pol = HAPPO({k: [18, 5] for k in IDS}, False, 1e-3, 5e-4, 64, device, dict(MAPPO_TRICK))
+    ia, ic = maddpg_nets(g, "init", "actor"), maddpg_nets(g, "init", "critic")
+    for k in IDS:
+        load_into(pol.agents[k].actor, ia[k])
+        load_into(pol.agents[k].critic, ic[k])
+    d = {k: [g["data/%s/%s" % (k, n)] for n in ("obs", "act", "rew", "nobs", "done", "logp", "adv_done")] for k in IDS}
+    for t in range(64):
+        pol.add({k: d[k][0][t] for k in IDS}, {k: d[k][1][t] for k in IDS}, {k: float(d[k][2][t, 0]) for k in IDS},
+                {k: d[k][3][t] for k in IDS}, {k: bool(d[k][4][t, 0]) for k in IDS}, {k: d[k][5][t] for k in IDS},
+                {k: bool(d[k][6][t, 0]) for k in IDS})
+    with pytest.raises(RuntimeError, match="minibatch_size == horizon"):
+        pol.learn(32, 0.95, 0.95, 0.2, 2, 0.01, 10.0)
+    perms = {k: [g["perm/%s/%d" % (k, e)] for e in range(2)] for k in IDS}
+    pol.learn(64, 0.95, 0.95, 0.2, 2, 0.01, 10.0, permutations=perms, order=g["order"])
+    m = pol.last_metrics.cpu().numpy()
+    np.testing.assert_allclose(m[:, :2], g["losses"], rtol=1e-4, atol=1e-5)
+    assert not np.allclose(pol.last_factor.cpu().numpy(), 1.0)                     # the sequential factor did move
+    tol = dict(rtol=1e-4, atol=1e-5)
+    for k in IDS:
+        assert_module_close(pol.agents[k].actor, maddpg_nets(g, "final", "actor")[k], "final actor " + k, tol)
+        assert_module_close(pol.agents[k].critic, maddpg_nets(g, "final", "critic")[k], "final critic " + k, tol)
+
+
+def test_happo_discrete_emulated(golden, emul):
+    _happo_discrete(golden, torch.device("cpu"))
+
+
+@pytest.mark.gpu
+def test_happo_discrete_gpu(golden):
+    _happo_discrete(golden, torch.device("cuda"))
+
+
 def test_happo_emulated(golden, emul):
     _happo(golden, torch.device("cpu"))
 
