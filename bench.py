@@ -237,9 +237,120 @@ def ppo_dp_block(dev, rank, world, dist, learns=3):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     updates = K * (T * N // mb)
+    # end to end through the public API with HOST buffers: T vector steps of select_action(host obs) + add(host arrays), then learn()
+    torch.cuda.synchronize()
+    e0.record()
+    for o, a, r, o2, d, lp in data:
+        act, logp = pol.select_action(o)                          # H2D obs, kernel, D2H actions + log-probs
+        pol.add(o, act.reshape(N, 1), r, o2, d, logp.reshape(N, 1), d)
+    pol.learn(mb, 0.99, 0.95, 0.2, K, 0.01)
+    loss = float(pol.last_metrics[-1, 0].item())
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+    ms_e2e = float(ms_e2e.item())
     return {"workload": "ppo_lunarlander_1024env_x128_mb8192_k10", "ms_per_learn": ms, "updates_per_learn": updates,
+            "e2e_env_steps_per_sec": world * T * N / ms_e2e * 1e3, "e2e_ms_per_rollout_and_learn": ms_e2e, "e2e_last_loss": loss,
             "updates_per_sec": updates / ms * 1e3, "env_steps_per_sec": world * T * N / ms * 1e3, "us_per_update": ms * 1e3 / updates,
             "scaling": "weak", "collective": "none (1 rank)" if world == 1 else getattr(pol, "dp_collective", "nccl all_reduce of net.g per optimiser step"),
+            "loss_finite": bool(torch.isfinite(pol.last_metrics).all().item())}
+
+
+def rainbow_block(dev, rank, world, dist, vsteps=6):
+    """BASELINE config 4 on every rank: Rainbow (PER + Noisy + C51 + N-step + Double + Dueling), LunarLander dims, 512 envs per GPU,
+    PER capacity 1e6 per GPU (its own sum-tree), batch 256, one learn per env step (512 per vector step).  Multi-GPU = replicas with
+    per-GPU env / PER shards and a parameter average per vector step (ReplicaSyncMixin), weak scaling."""
+    import contextlib
+    import torch
+    from freerl_b200.DQN_with_tricks import DQN as Rainbow
+    NE = 512
+    trick = {"Double": True, "Dueling": True, "PER": True, "Noisy": True, "N_Step": True, "Categorical": True}
+    rng = np.random.default_rng(200 + rank)
+    with contextlib.redirect_stdout(sys.stderr):
+        pol = Rainbow([8, 4], False, 1e-3, 1e6, dev, trick=trick, gamma=0.99, batch_size=256, mode="fast")
+    if world > 1:
+        pol.enable_replica_sync()
+    obs = rng.standard_normal((NE, 8))
+
+    def vstep():
+        nonlocal obs
+        act = pol.select_action(obs)
+        nxt = rng.standard_normal((NE, 8))
+        pol.add(obs, np.asarray(act).reshape(NE, 1), rng.standard_normal(NE), nxt, rng.random(NE) < 0.01)
+        obs = nxt
+        for _ in range(NE):
+            pol.learn(256, 0.99, 0.01)
+        pol.sync_replicas()
+    for _ in range(8):                      # fill past the n-step windows and the first batch
+        act = pol.select_action(obs)
+        nxt = rng.standard_normal((NE, 8))
+        pol.add(obs, np.asarray(act).reshape(NE, 1), rng.standard_normal(NE), nxt, rng.random(NE) < 0.01)
+        obs = nxt
+    vstep()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(vsteps):
+        vstep()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / vsteps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    return {"workload": "rainbow_lunarlander_512env_per1e6_b256_utd1", "ms_per_vector_step": ms, "env_steps_per_sec": world * NE / ms * 1e3,
+            "updates_per_sec": world * NE / ms * 1e3, "scaling": "weak", "e2e": "host observations / transitions in, actions out, every step",
+            "parallelism": "replicas, env + PER shard per GPU, parameter average per vector step" if world > 1 else "1 rank"}
+
+
+def mappo_block(dev, rank, world, dist, learns=2):
+    """BASELINE config 5 on every rank: MAPPO, simple_spread dims (3 agents, obs 18, act 5), 512 envs x 256 steps per GPU, full-batch
+    minibatch (131 072 rows), K = 15.  Multi-GPU = synchronous data parallel over the in-kernel peer exchange, weak scaling."""
+    import contextlib
+    import torch
+    from freerl_b200.MAPPO import MAPPO
+    H, E, K5 = 256, 512, 15
+    trick = {'adv_norm': True, 'ObsNorm': True, 'reward_norm': False, 'reward_scaling': True, 'orthogonal_init': True,
+             'adam_eps': True, 'lr_decay': False, 'ValueClip': True, 'huber_loss': True, 'LayerNorm': True, 'feature_norm': True}
+    ids = ["agent_%d" % i for i in range(3)]
+    rng = np.random.default_rng(300 + rank)
+    with contextlib.redirect_stdout(sys.stderr):
+        pol = MAPPO({k: [18, 5] for k in ids}, True, 1e-3, 1e-3, H * E, dev, dict(trick), mode="fast")
+    if world > 1:
+        pol.enable_data_parallel()
+    step = {k: (rng.standard_normal((E, 18), dtype=np.float32), rng.uniform(-1, 1, (E, 5)).astype(np.float32), rng.standard_normal(E).astype(np.float32),
+                rng.standard_normal((E, 18), dtype=np.float32), np.zeros(E, bool), (-np.abs(rng.standard_normal((E, 5))) * 0.1 - 0.9).astype(np.float32))
+            for k in ids}
+    for t in range(H):
+        trunc = np.full(E, (t % 25) == 24)
+        pol.add({k: step[k][0] for k in ids}, {k: step[k][1] for k in ids}, {k: step[k][2] for k in ids}, {k: step[k][3] for k in ids},
+                {k: step[k][4] for k in ids}, {k: step[k][5] for k in ids}, {k: trunc for k in ids})
+
+    def learn():
+        for b in pol.buffers.values():
+            b._index, b._size, b.n_envs = 0, H * E, E
+        pol.learn(H * E, 0.95, 0.95, 0.2, K5, 0.01, 10.0)
+    learn()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(learns):
+        learn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / learns], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    return {"workload": "mappo_simple_spread_3agents_512env_x256_fullbatch_k15", "ms_per_learn": ms, "updates_per_learn": 3 * K5,
+            "env_steps_per_sec": world * H * E / ms * 1e3, "scaling": "weak",
+            "collective": "none (1 rank)" if world == 1 else getattr(pol, "dp_collective", "?"),
             "loss_finite": bool(torch.isfinite(pol.last_metrics).all().item())}
 
 
@@ -392,11 +503,17 @@ def main():
 
     # ---- on-policy data parallel (config 3 shape) at this N: every rank runs it, rank 0 reports ------------------------
     ppo_dp = None
+    multi = {}
     if not args.no_extras:
         try:
             ppo_dp = ppo_dp_block(dev, rank, world, dist)
         except Exception as e:                                   # the headline line must survive a failure of an extra
             ppo_dp = {"error": "%s: %s" % (type(e).__name__, e)}
+        for name, fn in (("rainbow_replicas", rainbow_block), ("mappo_dp", mappo_block)):      # configs 4 and 5 at this N
+            try:
+                multi[name] = fn(dev, rank, world, dist)
+            except Exception as e:
+                multi[name] = {"error": "%s: %s" % (type(e).__name__, e)}
 
     if rank != 0:
         if world > 1:
@@ -426,6 +543,7 @@ def main():
                                "sample": "150 steps x %d single-env iterations of the oracle port (np.random.choice over the full 1e6 replay + SAC learn B=256)" % tps}
     if ppo_dp is not None:
         out["ppo_dp"] = ppo_dp
+    out.update(multi)
     if not args.no_extras and world == 1:
         extra = {}
         try:       # stock PyTorch on this same B200: the oracle port's torch code with the networks on cuda
