@@ -234,7 +234,13 @@ def require_device(device):
 
 
 def stream_ptr(device):
+    """Stream every library call launches on.  The library launches on the CURRENT CUDA device, so a policy that lives on another device
+    than the current one (cuda:1 without torch.cuda.set_device(1), or one process driving two GPUs) first makes its device current —
+    otherwise its kernels would run on the wrong GPU with pointers of another one."""
     if device.type == "cuda":
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        if torch.cuda.current_device() != idx:
+            torch.cuda.set_device(idx)
         return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
     return C.c_void_p(0)
 
