@@ -286,6 +286,10 @@ struct ReplayGatherTiles {
   }
 };
 
+#ifndef FRL_EMUL
+#include "replay_bulk.cuh"
+#endif
+
 extern "C" int frl_replay_add_batch(const frl_replay_t* rb, int64_t index, const float* obs, const float* act, const float* rew,
                                     const float* next_obs, const float* done, int n, void* stream) {
   if (!rb || !rb->storage || n < 0 || rb->row_floats % 4 || rb->row_floats < 2 * rb->obs_dim + rb->act_dim + 2) {
@@ -294,6 +298,12 @@ extern "C" int frl_replay_add_batch(const frl_replay_t* rb, int64_t index, const
   }
   if (n == 0) return 0;
   ReplayTileArgs a = {*rb, index, nullptr, obs, act, rew, next_obs, done, n};
+#ifndef FRL_EMUL
+  if (rb_bulk_ok(a)) {                                   // copy-engine path (replay_bulk.cuh); 1 = rows too wide for its two stages
+    const int rc = rb_launch_add(a, (cudaStream_t)stream);
+    if (rc <= 0) return rc;
+  }
+#endif
   return frl_launch_simple<ReplayAddTiles>(a, replay_tile_grid(n), FRL_RT_ROWS * rb->row_floats, (cudaStream_t)stream);
 }
 
@@ -697,6 +707,10 @@ extern "C" int frl_ac_learn(const frl_ac_args_t* a, void* stream) {
   return frl_launch<AcAlgo>(*a, (cudaStream_t)stream);
 }
 
+#ifndef FRL_EMUL
+#include "gae_stream.cuh"
+#endif
+
 extern "C" int frl_gae(const float* reward, const float* done, const float* adv_done, const float* vs, const float* vs_next, int T,
                        int N, double gamma, double lmbda, float* adv_out, float* v_target_out, void* stream) {
   if (!reward || !done || !adv_done || !vs || !vs_next || !adv_out || !v_target_out || T <= 0 || N <= 0) {
@@ -704,6 +718,9 @@ extern "C" int frl_gae(const float* reward, const float* done, const float* adv_
     return -1;
   }
   GaeArgs a = {reward, done, adv_done, vs, vs_next, T, N, gamma, lmbda, adv_out, v_target_out};
+#ifndef FRL_EMUL
+  if (gae_stream_ok(a)) return gae_stream_launch(a, (cudaStream_t)stream);       // inputs streamed through shared memory (gae_stream.cuh)
+#endif
   if (N >= 32)                                                                     // vectorised envs: coalesced column tiles
     return frl_launch_simple<GaeTileAlgo>(a, GaeTileAlgo::grid(a), GaeTileAlgo::smem_floats(a), (cudaStream_t)stream);
   return frl_launch_tiles<GaeAlgo>(a, (cudaStream_t)stream);                       // few columns: one warp per column

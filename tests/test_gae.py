@@ -61,3 +61,22 @@ def test_gae_round_boundaries_emulated(emul):
     for seed, (T, N) in enumerate(((127, 32), (128, 33), (129, 64), (255, 40), (256, 32), (257, 65), (16, 32), (17, 47), (9, 32), (8, 96),
                                    (383, 32), (640, 34))):
         _gae_case(emul, torch.device("cpu"), T, N, 100 + seed)
+
+
+@pytest.mark.gpu
+def test_gae_stream_round_boundaries_gpu():
+    """The streamed kernel (gae_stream.cuh: N % 4 == 0, rounds of 8 warps x 4 steps aligned to the END of the rollout): horizons around the
+    round size (32) and its multiples, a front round shorter than one warp's chunk, ragged column tiles, and the tile kernel for N % 4 != 0."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("FREERL_B200_GAE_STREAM") is None:            # the library reads the switch once: run the cases in a child with it set
+        env = dict(os.environ, FREERL_B200_GAE_STREAM="1")
+        r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", __file__ + "::test_gae_stream_round_boundaries_gpu"],
+                           env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        return
+    from freerl_b200 import _lib
+    for seed, (T, N) in enumerate(((31, 32), (32, 36), (33, 64), (63, 40), (64, 32), (65, 68), (3, 32), (4, 44), (5, 32), (1, 96),
+                                   (95, 32), (640, 36), (1024, 256), (127, 33), (130, 47), (40, 4800))):
+        _gae_case(_lib, torch.device("cuda"), T, N, 200 + seed)

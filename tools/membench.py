@@ -65,6 +65,11 @@ def main():
     r = torch.randn(n, device=dev, generator=g); o2 = torch.randn((n, OBS), device=dev, generator=g); d = torch.zeros(n, device=dev)
     ms = timeit(lambda: buf.add_device(o, a_, r, o2, d), reps=8)
     rec("frl_replay_add_batch n=1e6 (C2 rows)", ms, n * (168 + 176), "read SoA 168 B + write row 176 B per transition")
+    rep4 = lambda x: x.repeat(*([4] + [1] * (x.dim() - 1)))
+    o4, a4, r4, o24, d4 = rep4(o), rep4(a_), rep4(r), rep4(o2), rep4(d)
+    ms = timeit(lambda: buf.add_device(o4, a4, r4, o24, d4), reps=4)
+    rec("frl_replay_add_batch n=4e6 (C2 rows)", ms, 4 * n * (168 + 176), "the whole 704 MB ring in one launch (fixed launch / ramp cost amortised)")
+    del o4, a4, r4, o24, d4
     # ---- replay gather: B rows sampled uniformly from the 704 MB ring ----
     for B in (65536, 1 << 20):
         idx = torch.randint(0, cap, (8, B), device=dev, generator=g)
