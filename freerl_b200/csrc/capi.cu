@@ -1022,8 +1022,21 @@ static double* frl_reduce_scratch(int doubles) {
   return buf;
 }
 
+#ifndef FRL_EMUL
+#include "adv_norm_resident.cuh"
+#endif
+
 extern "C" int frl_adv_norm(const float* x, int n, float eps, float* out, void* stream) {
   if (!x || !out || n < 2) { frl_set_error("frl_adv_norm: bad arguments"); return -1; }
+#ifndef FRL_EMUL
+  {                                                  // data resident in shared memory across the grid-wide mean / std: one read, one launch
+    double* part1 = frl_reduce_scratch(4096);
+    if (!part1) { frl_set_error("frl_adv_norm: scratch allocation failed"); return -2; }
+    AdvNormArgs a1 = {x, n, eps, out, part1, 0, 0};
+    const int rc1 = adv_norm_resident_launch(a1, (cudaStream_t)stream);
+    if (rc1 <= 0) return rc1;
+  }
+#endif
   int ncta = (n / 16 + FRL_NT - 1) / FRL_NT;      // >= 4 quads per thread before the grid grows
   const int cap = 6 * frl_device_max_ctas();
   if (ncta > cap) ncta = cap;

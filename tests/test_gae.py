@@ -80,3 +80,23 @@ def test_gae_stream_round_boundaries_gpu():
     for seed, (T, N) in enumerate(((31, 32), (32, 36), (33, 64), (63, 40), (64, 32), (65, 68), (3, 32), (4, 44), (5, 32), (1, 96),
                                    (95, 32), (640, 36), (1024, 256), (127, 33), (130, 47), (40, 4800))):
         _gae_case(_lib, torch.device("cuda"), T, N, 200 + seed)
+
+
+@pytest.mark.gpu
+def test_adv_norm_resident_gpu():
+    """The single-launch kernel that keeps the data in shared memory across the grid-wide statistics (adv_norm_resident.cuh: n % 4 == 0,
+    aligned, n <= 2 M) against torch in float64, from one quad to the largest size it takes, with a mean far from zero; and the
+    same input through the two-launch kernel (a 4-byte offset view) gives the same statistics."""
+    from freerl_b200 import _lib
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev); g.manual_seed(5)
+    for n in (4, 8, 1024, 1028, 393216, 1 << 21, 4_000_000):
+        x = torch.randn(n + 4, device=dev, generator=g) * 3 + 7
+        out = torch.empty(n + 4, device=dev)
+        for off in (0, 1):
+            xs, os_ = x[off:off + n], out[off:off + n]
+            _lib.check(_lib.lib().frl_adv_norm(_lib.ptr(xs), n, ctypes.c_float(1e-8), _lib.ptr(os_), _lib.stream_ptr(dev)), "frl_adv_norm")
+            x64 = xs.double()
+            want = ((x64 - x64.mean()) / (x64.std() + 1e-8)).float()
+            err = (os_ - want).abs().max().item()
+            assert err < 5e-6, (n, off, err)

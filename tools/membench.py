@@ -103,7 +103,7 @@ def main():
     for n_ in (256 * 3, 256 * 512 * 3, 1 << 24):
         x = torch.randn(n_, device=dev, generator=g); y = torch.empty_like(x)
         ms = timeit(lambda: L.frl_adv_norm(_lib.ptr(x), n_, ctypes.c_float(1e-8), _lib.ptr(y), st), reps=20)
-        rec("frl_adv_norm n=%d" % n_, ms, n_ * 8, "4 B read (+ re-reads for the two statistics passes) + 4 B written")
+        rec("frl_adv_norm n=%d" % n_, ms, n_ * 8, "4 B read + 4 B written" + (" (two launches: + one re-read)" if n_ > (1 << 21) else " (resident: one launch)"))
     # ---- PER sum-tree (cap 1e6 like the reference default, non power of two) ----
     capt = 1_000_000
     tree = torch.zeros(2 * capt - 1, dtype=torch.float64, device=dev)
