@@ -309,3 +309,39 @@ def test_gae_adv_norm_mappo_full_shape():
     want_n = (x.double() - x.double().mean()) / (x.double().std() + 1e-8)
     np.testing.assert_allclose(out.cpu().numpy(), want_n.float().numpy(), rtol=1e-5, atol=2e-6)
     assert abs(float(out.mean())) < 1e-5 and abs(float(out.std()) - 1.0) < 1e-5
+
+
+def test_gae_streamed_kernel_long_wide_rollout():
+    """[1024, 16384] — the size `tools/membench.py` streams from HBM, taken by the LDGSTS kernel of csrc/gae_stream.cuh (one CTA per SM and more).
+    Against the float64 column scan of PPO_file/PPO.py:222-233 vectorised over the env axis, with done / adv_done episodes, plus the
+    size-independent properties of the scan: A_t = td_t at every adv_done step (segments are independent), v_target - adv = V(s) bit for
+    bit, and linearity in the rewards (scaling rewards and both value tensors by 2 scales adv by exactly 2: powers of two are exact)."""
+    from freerl_b200 import _lib
+    dev = torch.device("cuda")
+    T, N = 1024, 16384
+    g = torch.Generator(device=dev); g.manual_seed(11)
+    f = lambda: torch.randn((T, N), device=dev, generator=g)
+    rew, vs, vn = f(), f(), f()
+    done = (torch.rand((T, N), device=dev, generator=g) < 0.01).float()
+    adone = torch.maximum(done, (torch.rand((T, N), device=dev, generator=g) < 0.01).float())
+
+    def run(r_, vs_, vn_):
+        adv, vt = torch.empty((T, N), device=dev), torch.empty((T, N), device=dev)
+        _lib.check(_lib.lib().frl_gae(_lib.ptr(r_), _lib.ptr(done), _lib.ptr(adone), _lib.ptr(vs_), _lib.ptr(vn_), T, N, 0.99, 0.95,
+                                      _lib.ptr(adv), _lib.ptr(vt), _lib.stream_ptr(dev)), "frl_gae")
+        return adv, vt
+    adv, vt = run(rew, vs, vn)
+    td = (rew + 0.99 * (1.0 - done) * vn - vs)                        # fp32, the reference's expression order (PPO.py:226)
+    td64, keep = td.double(), (1.0 - adone).double()
+    want = torch.empty((T, N), dtype=torch.float64, device=dev)
+    acc = torch.zeros(N, dtype=torch.float64, device=dev)
+    for t in reversed(range(T)):
+        acc = td64[t] + 0.99 * 0.95 * acc * keep[t]
+        want[t] = acc
+    err = (adv.double() - want).abs().max().item()
+    assert err < 4e-6, err
+    m = adone.bool()
+    assert torch.equal(adv[m], td[m])
+    assert torch.equal(vt, adv + vs)
+    adv2, _ = run(2 * rew, 2 * vs, 2 * vn)
+    assert torch.equal(adv2, 2 * adv)
