@@ -84,7 +84,8 @@ class PpoArgs(C.Structure):
                 ("huber_delta", C.c_float), ("stage_lo", C.c_int), ("stage_hi", C.c_int), ("grad_scale", C.c_float),
                 ("gpart", C.c_void_p),
                 ("sumsq", C.c_void_p), ("segcnt", C.c_void_p), ("stats", C.c_void_p), ("out", C.c_void_p),
-                ("lr_critic", C.c_double), ("hidden_tanh", C.c_int), ("umma_ws", C.c_void_p), ("dp", DpPeers)]
+                ("lr_critic", C.c_double), ("hidden_tanh", C.c_int), ("umma_ws", C.c_void_p), ("dp", DpPeers),
+                ("max_norm_joint", C.c_float), ("opt_repeat", C.c_int), ("v_old", C.c_void_p)]
 
 
 class SacdArgs(C.Structure):

@@ -271,6 +271,7 @@ struct PpoAlgoT {
     float* dV = sb.take(R * 4);
     float* ADV = sb.take(R * a.n_adv);
     float* VT = sb.take(R * a.n_adv);
+    float* VO = sb.take(R * a.n_adv);   // rollout values of the clipped value loss (value_loss 2); user_floats counts 4 n_adv columns
     float* red0 = sb.take(FRL_NT);
     float* red1 = sb.take(FRL_NT);
     int* segc = (int*)sb.take(FRL_NSEG + 3);
@@ -309,6 +310,7 @@ struct PpoAlgoT {
             const int r = e / a.n_adv, j = e % a.n_adv;
             ADV[e] = (r < nvalid) ? a.adv[(size_t)idx[r] * a.n_adv + j] : 0.f;
             VT[e] = (r < nvalid) ? a.v_target[(size_t)idx[r] * a.n_adv + j] : 0.f;
+            VO[e] = (r < nvalid && a.value_loss == 2) ? a.v_old[(size_t)idx[r] * a.n_adv + j] : 0.f;
           }
         }
         FRL_SYNC();
@@ -432,6 +434,15 @@ struct PpoAlgoT {
                   const float e = -d, ae = fabsf(e), dl = a.huber_delta;
                   l += (ae <= dl) ? 0.5f * e * e : dl * (ae - 0.5f * dl);
                   g += -((ae <= dl) ? e : (e > 0.f ? dl : -dl)) * inv_rn;
+                } else if (a.value_loss == 2) {
+                  // max(e_clip^2, e_orig^2), e_clip = clamp(V - v_old, +-c) + v_old - v_target (MAPPO_discrete.py:350-357); inside the
+                  // clip range both are the same number and torch.max's tie shares the gradient between two equal halves
+                  const float vo = VO[t * a.n_adv + k], dv = V[t * 4] - vo;
+                  const float ec = fminf(fmaxf(dv, -a.clip_param), a.clip_param) + vo - VT[t * a.n_adv + k];
+                  const bool inside = dv >= -a.clip_param && dv <= a.clip_param;
+                  const float qo = d * d, qc = ec * ec;
+                  if (qo >= qc) { l += qo; g += 2.f * d * inv_rn; }
+                  else { l += qc; if (inside) g += 2.f * ec * inv_rn; }
                 } else {
                   g += 2.f * d * inv_rn;
                   l += d * d;
@@ -525,6 +536,7 @@ struct PpoAlgoT {
       // cost 7 us per sum while its CTA, and with it the whole grid, waited at the next barrier).
       float* sh = c.red;
       float nrm[3], met[3] = {0.f, 0.f, 0.f};
+      const int rep = (a.optimizer == FRL_OPT_ADAM && a.opt_repeat > 1) ? 2 : 1;
       cta_sums(sh, a.sumsq, 2, a.sumsq + 1, 2, nullptr, 0, c.ncta, nrm);
       if (s == 3 && c.cta == 0) cta_sums(sh, a.stats, 8, a.stats + 1, 8, a.stats + 2, 8, ncontrib, met);
       FRL_PAR(t) {
@@ -533,17 +545,21 @@ struct PpoAlgoT {
           float ca = 1.f, cc = 1.f;
           if (a.max_norm_actor > 0.f) ca = fminf(a.max_norm_actor / (sqrtf(ta) + 1e-6f), 1.f);
           if (a.max_norm_critic > 0.f) cc = fminf(a.max_norm_critic / (sqrtf(tc) + 1e-6f), 1.f);
+          if (a.max_norm_joint > 0.f) ca = cc = fminf(a.max_norm_joint / (sqrtf(ta + tc) + 1e-6f), 1.f);   // one clip over both nets
           sh[0] = ca; sh[1] = cc;
-          double p1 = 1.0, p2 = 1.0, q1 = a.beta1, q2 = a.beta2;          // beta^step by squaring (as make_adam_hp)
-          for (unsigned long e = (unsigned long)(a.step0 + u + 1); e; e >>= 1) {
-            if (e & 1) { p1 *= q1; p2 *= q2; }
-            q1 *= q1; q2 *= q2;
+          // optimiser step k of this update is step number step0 + u * rep + k + 1 (rep = 2: MAPPO_discrete's second step())
+          for (int k = 0; k < rep; ++k) {
+            double p1 = 1.0, p2 = 1.0, q1 = a.beta1, q2 = a.beta2;          // beta^step by squaring (as make_adam_hp)
+            for (unsigned long e = (unsigned long)(a.step0 + (int64_t)u * rep + k + 1); e; e >>= 1) {
+              if (e & 1) { p1 *= q1; p2 *= q2; }
+              q1 *= q1; q2 *= q2;
+            }
+            const double bc1 = 1.0 - p1, bc2 = 1.0 - p2;
+            if (k == 0) sh[2] = (float)(a.lr * sqrt(bc2) / bc1);         // c_adamw step_size
+            sh[3 + 3 * k] = (float)(-(a.lr / bc1));                   // torch Adam: -lr/bc1
+            sh[4 + 3 * k] = (float)sqrt(bc2);
+            sh[5 + 3 * k] = (float)(-((a.lr_critic > 0.0 ? a.lr_critic : a.lr) / bc1));
           }
-          const double bc1 = 1.0 - p1, bc2 = 1.0 - p2;
-          sh[2] = (float)(a.lr * sqrt(bc2) / bc1);         // c_adamw step_size
-          sh[3] = (float)(-(a.lr / bc1));                   // torch Adam: -lr/bc1
-          sh[4] = (float)sqrt(bc2);
-          sh[5] = (float)(-((a.lr_critic > 0.0 ? a.lr_critic : a.lr) / bc1));
           if (s == 3 && c.cta == 0) {
             const float l0 = met[0], l1 = met[1], l2 = met[2];
             const float ent_mean = l2 / (float)rows;
@@ -558,6 +574,7 @@ struct PpoAlgoT {
       }
       FRL_SYNC();
       const float coef_a = sh[0], coef_c = sh[1], step_size = sh[2], adam_step = sh[3], bc2s = sh[4], adam_step_c = sh[5];
+      const float adam_step1 = sh[6], bc2s1 = sh[7], adam_step_c1 = sh[8];      // second step of opt_repeat 2 (unset otherwise, unused)
       const float b1 = (float)a.beta1, b2 = (float)a.beta2, omb1 = (float)(1.0 - a.beta1), omb2 = (float)(1.0 - a.beta2);
       const float eps = (float)a.eps;
       if (a.optimizer == FRL_OPT_ADAM) {
@@ -567,10 +584,12 @@ struct PpoAlgoT {
             const bool crit = is_critic(N, p);
             const float g = N.g[p] * (crit ? coef_c : coef_a);
             float m = N.m[p], v = N.v[p], w = N.p[p];
-            m = fmaf(omb1, g - m, m);
-            v = fadd(fmul(v, b2), fmul(fmul(omb2, g), g));
-            const float denom = fadd(fdiv(fsqrt(v), bc2s), eps);
-            w = fadd(w, fdiv(fmul(crit ? adam_step_c : adam_step, m), denom));
+            for (int k = 0; k < rep; ++k) {
+              m = fmaf(omb1, g - m, m);
+              v = fadd(fmul(v, b2), fmul(fmul(omb2, g), g));
+              const float denom = fadd(fdiv(fsqrt(v), k ? bc2s1 : bc2s), eps);
+              w = fadd(w, fdiv(fmul(crit ? (k ? adam_step_c1 : adam_step_c) : (k ? adam_step1 : adam_step), m), denom));
+            }
             N.m[p] = m; N.v[p] = v; N.p[p] = w;
             const int mi = mirror_index(N, p);
             if (mi >= 0) N.pt[mi] = w;

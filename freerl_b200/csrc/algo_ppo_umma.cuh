@@ -604,6 +604,13 @@ __device__ __noinline__ void ppo_umma_stage(Cta& c, float* user, const frl_ppo_a
             const float e = -d, ae = fabsf(e), dl = a.huber_delta;
             l += (ae <= dl) ? 0.5f * e * e : dl * (ae - 0.5f * dl);
             g += -((ae <= dl) ? e : (e > 0.f ? dl : -dl)) * inv_rn;
+          } else if (a.value_loss == 2) {                 // clipped value loss, as in algo_ppo.cuh (MAPPO_discrete.py:350-357)
+            const float vo = a.v_old[(size_t)gi * a.n_adv + k], dv = lg[0] - vo;
+            const float ec = fminf(fmaxf(dv, -a.clip_param), a.clip_param) + vo - a.v_target[(size_t)gi * a.n_adv + k];
+            const bool inside = dv >= -a.clip_param && dv <= a.clip_param;
+            const float qo = d * d, qc = ec * ec;
+            if (qo >= qc) { l += qo; g += 2.f * d * inv_rn; }
+            else { l += qc; if (inside) g += 2.f * ec * inv_rn; }
           } else {
             g += 2.f * d * inv_rn;
             l += d * d;

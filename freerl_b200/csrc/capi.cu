@@ -792,6 +792,9 @@ extern "C" int frl_ppo_update(const frl_ppo_args_t* a, void* stream) {
     return -1;
   }
   if (check_net(a->net, true, "frl_ppo_update(net)")) return -1;
+  if (a->value_loss == 2 && !a->v_old) { frl_set_error("frl_ppo_update: value_loss 2 needs v_old"); return -1; }
+  if (a->opt_repeat > 1 && a->optimizer != FRL_OPT_ADAM) { frl_set_error("frl_ppo_update: opt_repeat is for FRL_OPT_ADAM"); return -1; }
+  if (a->opt_repeat > 2) { frl_set_error("frl_ppo_update: opt_repeat is 0, 1 or 2"); return -1; }
   if (a->hidden_tanh && a->layer_norm) { frl_set_error("frl_ppo_update: hidden_tanh is not available with layer_norm"); return -1; }
   if (a->dp.world > 1) {
     if (a->dp.world > FRL_DP_MAX_RANKS || a->dp.rank < 0 || a->dp.rank >= a->dp.world) { frl_set_error("frl_ppo_update: bad dp rank / world"); return -1; }

@@ -31,14 +31,16 @@ _ALGOS = {            # script file name -> (class name in the script, our modul
     "MATD3_simple.py": ("MATD3", "freerl_b200.MATD3_simple", "MATD3"),
     "DDPG_simple.py": ("DDPG", "freerl_b200.DDPG_simple", "DDPG"),
     "MAPPO.py": ("MAPPO", "freerl_b200.MAPPO", "MAPPO"),
+    "MAPPO_discrete.py": ("MAPPO", "freerl_b200.MAPPO_discrete", "MAPPO"),  # shared nets + episode ReplayBuffer (--policy_name MAPPO_simple)
     "IPPO.py": ("IPPO", "freerl_b200.IPPO", "IPPO"),
     "HAPPO.py": ("HAPPO", "freerl_b200.HAPPO", "HAPPO"),
 }
 
 
 def buffer_module():
-    from . import Buffer as B, per
+    from . import Buffer as B, MAPPO_discrete, per
     m = types.ModuleType("Buffer")
+    m.ReplayBuffer = MAPPO_discrete.ReplayBuffer
     m.Buffer, m.Buffer_for_PPO = B.Buffer, B.Buffer_for_PPO
     m.SumTree, m.PER_Buffer = per.SumTree, per.PER_Buffer
     m.N_Step_Buffer, m.N_Step_PER_Buffer = per.N_Step_Buffer, per.N_Step_PER_Buffer

@@ -223,7 +223,7 @@ typedef struct {
   int layer_norm;           /* F.layer_norm (no affine, eps 1e-5) on the input and after each hidden ReLU, actor and critic */
   const float* critic_obs;  /* dev [M][critic_obs_dim] joint observation for the centralised critic (NULL: critic sees `obs`) */
   int critic_obs_dim;
-  int value_loss;           /* 0: mse(v_target, V);  1: huber(v_target - V, huber_delta).mean()  (MAPPO.py:273-276,426-433) */
+  int value_loss;           /* 0: mse(v_target, V);  1: huber(v_target - V, huber_delta).mean()  (MAPPO.py:273-276,426-433);  2: clipped, see v_old */
   float huber_delta;
   /* ---- data-parallel split (one process per GPU): stages are 0 fwd/bwd, 1 cross-CTA reduce -> net.g, 2 grad scale + norms,
    * 3/4 optimiser.  A DP step launches [0,2), all-reduces net.g over NCCL, then launches [2,5) with grad_scale = 1/world. */
@@ -241,6 +241,12 @@ typedef struct {
    * umma_ws = dev scratch of frl_ppo_umma_ws_floats() floats (512-B aligned; split weights + per-CTA activation scratch) is given */
   float* umma_ws;
   frl_dp_peers_t dp;        /* in-kernel data-parallel gradient exchange (world > 1); then grad_scale should be 1 / world */
+  /* ---- MAPPO_discrete options (MAPPO_file/MAPPO_discrete.py:188-192, 336-371): shared actor / critic under ONE Adam ---- */
+  float max_norm_joint;     /* > 0: clip_grad_norm_ over actor AND critic gradients together (update_ac, :191); replaces the two above */
+  int opt_repeat;           /* 2: the optimiser steps twice on the same clipped gradient (update_ac's step() then :371's second step());
+                             *    the step counter advances by opt_repeat per update (FRL_OPT_ADAM only); 0 / 1: once */
+  const float* v_old;       /* dev [M][n_adv] rollout values for value_loss 2: max((clamp(V - v_old, +-clip_param) + v_old - v_target)^2,
+                             *    (V - v_target)^2) element-wise (the ValueClip branch without huber_loss, :350-357) */
 } frl_ppo_args_t;
 
 /* Rainbow (DQN_with_tricks.py): Categorical + Dueling + Noisy net.  The trainable block holds the torch tensors;

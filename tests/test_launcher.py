@@ -56,6 +56,13 @@ def test_reference_multi_agent_scripts_unchanged(tmp_path, emul):
         ns = launcher.run_reference_script(os.path.join(REF, "MAPPO_file", sub), on + extra, results_root=str(tmp_path))
         pol = ns["policy"]
         assert type(pol).__module__ == "freerl_b200." + cls and all(a.step > 0 for a in pol.agents.values()), sub
+    # MAPPO_discrete.py: shared networks + episode ReplayBuffer; `horizon` counts EPISODES; the all-False trick set is reachable from the CLI
+    ns = launcher.run_reference_script(os.path.join(REF, "MAPPO_file", "MAPPO_discrete.py"),
+                                       ["--env_name", "simple_spread_v3", "--N", "3", "--max_episodes", "4", "--horizon", "2", "--minibatch_size", "1",
+                                        "--K_epochs", "2", "--policy_name", "MAPPO_simple", "--device", "cpu"], results_root=str(tmp_path))
+    pol = ns["policy"]
+    assert type(pol).__module__ == "freerl_b200.MAPPO_discrete" and pol.agent.step == 2 * 2 * 2 * 2      # 2 learns x 2 epochs x 2 minibatches x 2 steps
+    assert os.path.exists(os.path.join(ns["model_dir"], "MAPPO_discrete.pth"))
 
 
 def test_reference_single_agent_siblings_unchanged(tmp_path, emul):
