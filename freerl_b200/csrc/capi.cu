@@ -930,7 +930,7 @@ FRL_NI_MISC double block_sum_f64(double* slot /*[FRL_NT] smem*/) {
   FRL_SYNC();
   return r;
 }
-struct AdvNormArgs { const float* x; int n; float eps; float* out; double* part; int phase; int ncta; };
+struct AdvNormArgs { const float* x; int n; float eps; float* out; double* part; int phase; int ncta; int nohint; };
 // Two launches (a grid-wide mean / std sits between them).  Launch 0: every thread streams float4 quads with four
 // independent loads in flight and accumulates sum / sum of squares in float64; per-CTA partials go to `part`.  Launch 1:
 // every CTA folds the partials in the same order (identical statistics on all CTAs), then streams the input a second time
@@ -948,9 +948,10 @@ struct AdvNormAlgo {
       FRL_PAR(t) {
         double s = 0.0, q = 0.0;
         int i = cta * FRL_NT + t;
+        const unsigned long long keep = a.nohint ? 0ull : l2_policy_evict_last();          // launch 1 reads x again: ask L2 to hold on to it
         for (; i + 3 * stride < n4; i += 4 * stride) {
-          const float4 v0 = ld4(a.x + 4 * (size_t)i), v1 = ld4(a.x + 4 * (size_t)(i + stride));
-          const float4 v2 = ld4(a.x + 4 * (size_t)(i + 2 * stride)), v3 = ld4(a.x + 4 * (size_t)(i + 3 * stride));
+          const float4 v0 = ld4_hint(a.x + 4 * (size_t)i, keep), v1 = ld4_hint(a.x + 4 * (size_t)(i + stride), keep);
+          const float4 v2 = ld4_hint(a.x + 4 * (size_t)(i + 2 * stride), keep), v3 = ld4_hint(a.x + 4 * (size_t)(i + 3 * stride), keep);
           const float4 vv[4] = {v0, v1, v2, v3};
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -986,15 +987,16 @@ struct AdvNormAlgo {
       FRL_PAR(t) {
         for (int j = 4 * n4 + cta * FRL_NT + t; j < a.n; j += stride) a.out[j] = fdiv(a.x[j] - mf, den);
         int i = n4 - 1 - (cta * FRL_NT + t);
+        const unsigned long long drop = a.nohint ? 0ull : l2_policy_evict_first();         // last use of x; the output must not evict what is still unread
         for (; i - 3 * stride >= 0; i -= 4 * stride) {
           float4 vv[4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) vv[k] = ld4(a.x + 4 * (size_t)(i - k * stride));
+          for (int k = 0; k < 4; ++k) vv[k] = ld4_hint(a.x + 4 * (size_t)(i - k * stride), drop);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             float4 v = vv[k];
             v.x = fdiv(v.x - mf, den); v.y = fdiv(v.y - mf, den); v.z = fdiv(v.z - mf, den); v.w = fdiv(v.w - mf, den);
-            st4(a.out + 4 * (size_t)(i - k * stride), v);
+            st4_hint(a.out + 4 * (size_t)(i - k * stride), v, drop);
           }
         }
         for (; i >= 0; i -= stride) {
@@ -1046,7 +1048,8 @@ extern "C" int frl_adv_norm(const float* x, int n, float eps, float* out, void* 
   if (ncta < 1) ncta = 1;
   double* part = frl_reduce_scratch(2 * cap > 4096 ? 2 * cap : 4096);
   if (!part) { frl_set_error("frl_adv_norm: scratch allocation failed"); return -2; }
-  AdvNormArgs a = {x, n, eps, out, part, 0, ncta};
+  static const bool nohint = getenv("FREERL_B200_ADVNORM_NO_HINT") != nullptr;      // A/B switch: plain loads / stores
+  AdvNormArgs a = {x, n, eps, out, part, 0, ncta, nohint ? 1 : 0};
   int rc = frl_launch_simple<AdvNormAlgo>(a, ncta, AdvNormAlgo::smem_floats(a), (cudaStream_t)stream);
   if (rc) return rc;
   a.phase = 1;

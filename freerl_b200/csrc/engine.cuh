@@ -315,6 +315,27 @@ FRL_DEV void stage_reset(Cta& c) {
 // ------------------------------------------------------------------------------------------------
 FRL_DEV float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 FRL_DEV void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// L2 residency hints for streaming kernels that read an array twice (frl_adv_norm): the first pass loads with evict_last so that the
+// array stays in the 126 MB L2, the second pass loads and stores with evict_first so that the output does not push the unread part out
+#ifndef FRL_EMUL
+FRL_DEV unsigned long long l2_policy_evict_last() { unsigned long long p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+FRL_DEV unsigned long long l2_policy_evict_first() { unsigned long long p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+FRL_DEV float4 ld4_hint(const float* p, unsigned long long pol) {
+  if (pol == 0ull) return ld4(p);
+  float4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+FRL_DEV void st4_hint(float* p, float4 v, unsigned long long pol) {
+  if (pol == 0ull) { st4(p, v); return; }
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+#else
+FRL_DEV unsigned long long l2_policy_evict_last() { return 0; }
+FRL_DEV unsigned long long l2_policy_evict_first() { return 0; }
+FRL_DEV float4 ld4_hint(const float* p, unsigned long long) { return ld4(p); }
+FRL_DEV void st4_hint(float* p, float4 v, unsigned long long) { st4(p, v); }
+#endif
 // shared-memory flavours: explicit ld.shared / st.shared (the address-space is not always inferable once the
 // hot loops live in non-inlined functions; `__builtin_assume(__isShared(p))` proved fragile — the optimiser used it
 // to delete the K loop of the de-inlined gemm — so the space is spelled out in PTX instead).

@@ -41,6 +41,25 @@ def timeit(fn, reps=20, warm=3):
     return e0.elapsed_time(e1) / reps
 
 
+def timeit_flushed(fn, reps=10, warm=2, flush_mb=512):
+    """every iteration timed alone with the L2 flushed first (a buffer of flush_mb > 126 MB is overwritten before each call): nothing of the
+    previous iteration's input or output can be served by L2"""
+    junk = torch.empty(flush_mb << 18, dtype=torch.float32, device=dev)
+    for _ in range(warm):
+        fn()
+    tot = 0.0
+    for i in range(reps):
+        junk.fill_(float(i))
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / reps
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--json", default=None)
@@ -104,6 +123,10 @@ def main():
         x = torch.randn(n_, device=dev, generator=g); y = torch.empty_like(x)
         ms = timeit(lambda: L.frl_adv_norm(_lib.ptr(x), n_, ctypes.c_float(1e-8), _lib.ptr(y), st), reps=20)
         rec("frl_adv_norm n=%d" % n_, ms, n_ * 8, "4 B read + 4 B written" + (" (two launches: + one re-read)" if n_ > (1 << 21) else " (resident: one launch)"))
+    x = torch.randn(1 << 24, device=dev, generator=g); y = torch.empty_like(x)
+    ms = timeit_flushed(lambda: L.frl_adv_norm(_lib.ptr(x), 1 << 24, ctypes.c_float(1e-8), _lib.ptr(y), st))
+    rec("frl_adv_norm n=16777216, L2 flushed before every call", ms, (1 << 24) * 8, "4 B read + 4 B written; cold caches, each call timed alone (includes both launches' ramp)")
+    del x, y
     # ---- PER sum-tree (cap 1e6 like the reference default, non power of two) ----
     capt = 1_000_000
     tree = torch.zeros(2 * capt - 1, dtype=torch.float64, device=dev)
