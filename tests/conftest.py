@@ -69,3 +69,15 @@ def dev(request):
     """Device for parity tests: cuda under -m gpu, cpu (emulation) otherwise."""
     import torch
     return torch.device("cuda" if torch.cuda.is_available() else "cpu")
+
+
+@pytest.fixture(autouse=True)
+def _pin_fast_seed_counter():
+    """The seed of the on-device generators (fast mode) counts the policies built in the process (``_common.default_seed``); reset the
+    counter before every test so that a test's draws do not depend on which tests ran before it."""
+    try:
+        from freerl_b200 import _common
+        _common._fast_seed_counter[0] = 0
+    except Exception:
+        pass
+    yield

@@ -291,8 +291,11 @@ def _fast_mode_audit(device, B=256, K=8, n=4096):
     from collections import OrderedDict
     from freerl_b200 import _lib
     from freerl_b200.SAC import SAC
+    from freerl_b200 import _common
     torch.manual_seed(21)
     np.random.seed(21)
+    _common._fast_seed_counter[0] = 0      # the device generators' seed counts the policies built in this process: pin it, so that the
+    #                                        draws (and the margins below) do not depend on which tests ran before this one
     pol = SAC([17, 6], True, 1e-3, 1e-3, n, device, trick={}, mode="fast")
     rng = np.random.default_rng(8)
     obs, act = rng.standard_normal((n, 17), dtype=np.float32), rng.uniform(-1, 1, (n, 6)).astype(np.float32)
@@ -318,7 +321,10 @@ def _fast_mode_audit(device, B=256, K=8, n=4096):
                  torch.from_numpy(done[i].astype(np.float32)).reshape(-1, 1))
         r = orc.learn(batch, nz[0], nz[1], 0.99, 0.01)
         assert _rel(m[u, 0], r["critic_loss"]) < 1e-5, (u, m[u, 0], r["critic_loss"])
-        assert _rel(m[u, 1], r["actor_loss"]) < 2e-5, (u, m[u, 1], r["actor_loss"])
+        # the actor loss is a mean of signed O(1) terms (-Q - alpha * entropy) that sits near -0.17 here, and this is a FREE-running chain
+        # (update u starts from the kernel's own parameters after u fused updates): allclose form.  Measured on B200 over seeds: <= 2e-7
+        # relative on the first update, 3.4e-6 absolute at worst by update 2 (tools/parity_margin.py, profiles/r4_parity_margin.txt)
+        np.testing.assert_allclose(m[u, 1], r["actor_loss"], rtol=2e-5, atol=2e-6 if u == 0 else 5e-6, err_msg="actor loss, update %d" % u)
     z = torch.cat(nz).numpy()                                  # the regenerated draws are standard normals
     assert abs(z.mean()) < 0.08 and abs(z.std() - 1.0) < 0.05
     for name in NETS:
