@@ -32,9 +32,9 @@ def _run(golden, device, is_continue=True):
     np.testing.assert_allclose(pol.last_v_target.cpu().numpy(), r["v_target"].numpy(), rtol=1e-5, atol=2e-6)
     m = pol.last_metrics.cpu().numpy()
     ref = np.array(r["losses"])
-    np.testing.assert_allclose(m[:, 0], ref[:, 0], rtol=3e-5, atol=3e-6)
-    np.testing.assert_allclose(m[:, 1], ref[:, 1], rtol=2e-5, atol=2e-6)
-    np.testing.assert_allclose(m[:, :2], g["losses"], rtol=5e-5, atol=5e-6)
+    np.testing.assert_allclose(m[:, 0], ref[:, 0], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(m[:, 1], ref[:, 1], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(m[:, :2], g["losses"], rtol=1e-5, atol=2e-6)
     tol = dict(rtol=1e-4, atol=1e-5)
     for k in IDS:
         assert_module_close(pol.agents[k].actor, orc.actor[k], "actor " + k, tol)
@@ -93,8 +93,8 @@ def _ippo(golden, device, name, is_continue):
         np.testing.assert_allclose(pol.last_v_target[k].cpu().numpy(), r["v_target"][k].numpy(), rtol=1e-5, atol=2e-6)
     m = pol.last_metrics.cpu().numpy()
     ref = np.array(r["losses"])
-    np.testing.assert_allclose(m[:, 0], ref[:, 0], rtol=3e-5, atol=3e-6)
-    np.testing.assert_allclose(m[:, 1], ref[:, 1], rtol=3e-5, atol=3e-6)
+    np.testing.assert_allclose(m[:, 0], ref[:, 0], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(m[:, 1], ref[:, 1], rtol=1e-5, atol=2e-6)
     np.testing.assert_allclose(m[:, :2], g["losses"], rtol=1e-4, atol=1e-5)
     tol = dict(rtol=5e-5, atol=5e-6)
     for k in IDS:
@@ -153,8 +153,8 @@ def _happo(golden, device):
     np.testing.assert_allclose(pol.last_factor.cpu().numpy(), r["factor"], rtol=5e-5, atol=1e-6)
     m = pol.last_metrics.cpu().numpy()
     ref = np.array(r["losses"])
-    np.testing.assert_allclose(m[:, 0], ref[:, 0], rtol=5e-5, atol=3e-6)
-    np.testing.assert_allclose(m[:, 1], ref[:, 1], rtol=3e-5, atol=3e-6)
+    np.testing.assert_allclose(m[:, 0], ref[:, 0], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(m[:, 1], ref[:, 1], rtol=1e-5, atol=2e-6)
     np.testing.assert_allclose(m[:, :2], g["losses"], rtol=1e-4, atol=1e-5)
     tol = dict(rtol=1e-4, atol=1e-5)
     for k in IDS:

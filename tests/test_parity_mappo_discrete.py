@@ -73,9 +73,9 @@ def _run(golden, device, name, parity_draws):
     np.testing.assert_allclose(tm(pol.last_v_target), r["v_target"].numpy(), rtol=1e-5, atol=2e-6)
     m = pol.last_metrics.cpu().numpy()
     ref = np.array(r["losses"])
-    np.testing.assert_allclose(m[:, 0], ref[:, 0], rtol=3e-5, atol=3e-6)
-    np.testing.assert_allclose(m[:, 1], ref[:, 1], rtol=2e-5, atol=2e-6)
-    np.testing.assert_allclose(m[:, 0] + m[:, 1], g["losses"], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(m[:, 0], ref[:, 0], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(m[:, 1], ref[:, 1], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(m[:, 0] + m[:, 1], g["losses"], rtol=1e-5, atol=2e-6)
     tol = dict(rtol=5e-5, atol=5e-6)
     assert_module_close(pol.agent.actor, orc.actor.state_dict(), "actor vs oracle", tol)
     assert_module_close(pol.agent.critic, orc.critic.state_dict(), "critic vs oracle", tol)
@@ -130,8 +130,8 @@ def _big(device, seed=5):
     pol.learn(MB_, 0.95, 0.95, 0.2, 2, 0.01, 10.0)
     m = pol.last_metrics.cpu().numpy()
     ref = np.array(r["losses"])
-    np.testing.assert_allclose(m[:, 0], ref[:, 0], rtol=3e-5, atol=3e-6)
-    np.testing.assert_allclose(m[:, 1], ref[:, 1], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(m[:, 0], ref[:, 0], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(m[:, 1], ref[:, 1], rtol=1e-5, atol=2e-6)
     tol = dict(rtol=1e-4, atol=1e-5)
     assert_module_close(pol.agent.actor, orc.actor.state_dict(), "actor vs oracle", tol)
     assert_module_close(pol.agent.critic, orc.critic.state_dict(), "critic vs oracle", tol)

@@ -27,9 +27,9 @@ def _ppo(golden, device, name, is_continue):
     np.testing.assert_allclose(pol.last_v_target.cpu().numpy(), r["v_target"].numpy(), rtol=1e-5, atol=1e-6)
     m = pol.last_metrics.cpu().numpy()
     ref = np.array(r["losses"])
-    np.testing.assert_allclose(m[:, 0], ref[:, 0], rtol=2e-5, atol=2e-6)
-    np.testing.assert_allclose(m[:, 1], ref[:, 1], rtol=2e-5, atol=2e-6)
-    np.testing.assert_allclose(m[:, :2], g["losses"], rtol=5e-5, atol=5e-6)
+    np.testing.assert_allclose(m[:, 0], ref[:, 0], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(m[:, 1], ref[:, 1], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(m[:, :2], g["losses"], rtol=1e-5, atol=2e-6)
     tol = dict(rtol=2e-4, atol=2e-5)     # 8 chained cautious-AdamW steps: sign masks amplify last-ulp differences
     assert_module_close(pol.agent.actor, orc.actor, "actor", tol)
     assert_module_close(pol.agent.critic, orc.critic, "critic", tol)
@@ -73,9 +73,9 @@ def _ppo_advance(golden, device, name, is_continue):
     pol.learn(64, 0.99, 0.95, 0.2, 2, 0.01, permutations=perms)
     m = pol.last_metrics.cpu().numpy()
     ref = np.array(r["losses"])
-    np.testing.assert_allclose(m[:, 0], ref[:, 0], rtol=2e-5, atol=2e-6)
-    np.testing.assert_allclose(m[:, 1], ref[:, 1], rtol=2e-5, atol=2e-6)
-    np.testing.assert_allclose(m[:, :2], g["losses"], rtol=5e-5, atol=5e-6)
+    np.testing.assert_allclose(m[:, 0], ref[:, 0], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(m[:, 1], ref[:, 1], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(m[:, :2], g["losses"], rtol=1e-5, atol=2e-6)
     tol = dict(rtol=2e-5, atol=3e-6)      # plain Adam: no sign masks, 8 chained steps stay inside the fp32 band
     assert_module_close(pol.agent.actor, orc.actor, "actor", tol)
     assert_module_close(pol.agent.critic, orc.critic, "critic", tol)
@@ -138,7 +138,7 @@ def _ppo_tricks(golden, device, name, is_continue, tanh=False):
         ref = np.array(orc.learn(data, perms, 64, 0.99, 0.95, 0.2, 0.01)["losses"])
         pol.learn(64, 0.99, 0.95, 0.2, 2, 0.01, permutations=perms)
         m = pol.last_metrics.cpu().numpy()
-        np.testing.assert_allclose(m[:, :2], ref, rtol=3e-5, atol=3e-6)
+        np.testing.assert_allclose(m[:, :2], ref, rtol=1e-5, atol=2e-6)
         np.testing.assert_allclose(m[:, :2], g["losses"][8 * r:8 * r + 8], rtol=6e-5, atol=6e-6)
         orc.lr_decay(10, 100)
         pol.lr_decay(10, 100)
@@ -179,7 +179,7 @@ def _ppo_tricks_beta(golden, device):
         np.testing.assert_allclose(ref, g["losses"][8 * r:8 * r + 8], rtol=2e-6, atol=2e-7)      # the oracle is the reference here
         pol.learn(64, 0.99, 0.95, 0.2, 2, 0.01, permutations=perms)
         m = pol.last_metrics.cpu().numpy()
-        np.testing.assert_allclose(m[:, :2], ref, rtol=3e-5, atol=3e-6)
+        np.testing.assert_allclose(m[:, :2], ref, rtol=1e-5, atol=2e-6)
         orc.lr_decay(10, 100)
         pol.lr_decay(10, 100)
         assert_module_close(pol.agent.actor, orc.actor, "actor", tol)
@@ -314,8 +314,8 @@ def _ppo_large_minibatch(device, is_continue):
     ref = [orc.minibatch(data, adv_o, adv_o + vs, perm[s:s + mb], 0.2, 0.01) for s in range(0, T * N, mb)]
     pol.learn(mb, 0.99, 0.95, 0.2, 1, 0.01, permutations=[perm])
     m = pol.last_metrics.cpu().numpy()
-    np.testing.assert_allclose(m[:, 0], [x[0] for x in ref], rtol=3e-5, atol=2e-6)
-    np.testing.assert_allclose(m[:, 1], [x[1] for x in ref], rtol=3e-5, atol=2e-6)
+    np.testing.assert_allclose(m[:, 0], [x[0] for x in ref], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(m[:, 1], [x[1] for x in ref], rtol=1e-5, atol=2e-6)
     tol = dict(rtol=2e-4, atol=2e-5)
     assert_module_close(pol.agent.actor, orc.actor, "actor", tol)
     assert_module_close(pol.agent.critic, orc.critic, "critic", tol)
