@@ -16,15 +16,18 @@ Reference behaviour kept:
     ``adv_done = 0`` (float64 per-column scan, rounded once); ``adv_norm`` over the whole [B, T, N] block (``frl_adv_norm``);
   * minibatches are consecutive blocks of ``minibatch_size`` EPISODES in storage order, every epoch the same (``SequentialSampler``, ``:326``);
   * ``ValueClip`` without ``huber_loss``: element-wise ``max((clamp(V - v_old, +-clip) + v_old - v_target)^2, (V - v_target)^2)``
-    (``value_loss = 2``); ``huber_loss`` alone changes nothing upstream (it is only read inside the ``ValueClip`` branch).
+    (``value_loss = 2``); with ``huber_loss`` the squared maximum of the two batch-mean huber SCALARS (``:353-357``; ``value_loss = 3``:
+    a forward-only pre-pass launch leaves the two sums, the update launch folds them); ``huber_loss`` alone changes nothing upstream
+    (it is only read inside the ``ValueClip`` branch);
+  * ``LayerNorm`` / ``feature_norm`` are ``F.layer_norm(x, x.size()[1:])``: per row when acting (2-D inputs) but, inside ``learn``, jointly
+    over the (step, agent, feature) axes of each EPISODE (4-D inputs) — the group mode of ``frl_ppo_update`` (csrc/algo_ppo_group.cuh: a CTA
+    owns whole episodes and recomputes the forward pass once per statistic).  The discrete actor overwrites its normalised input
+    (``:113-115``), so ``feature_norm`` only reaches the critic.  The script's default trick set therefore runs as upstream.
 Device layout: TIME-MAJOR rows ``r = (t * B + b) * N + n`` so that one ``frl_gae`` call scans all B*N columns; the host-side staging
 arrays keep the reference's ``[B, T, N, ...]`` shapes (``ReplayBuffer.buffer``), uploaded once per ``learn`` like the reference's
 ``get_training_data``.
 
-Not reproduced (raise ``NotImplementedError``): ``LayerNorm`` / ``feature_norm`` — inside ``learn`` the reference
-normalises ``F.layer_norm(x, x.size()[1:])`` of a 4-D ``[mb, T, N, h]`` tensor, i.e. jointly over (step, agent, feature), while
-``select_action`` / ``get_value`` normalise per row: train and act see different networks; ``ValueClip`` + ``huber_loss`` — the squared
-maximum of two batch-mean SCALARS (``:353-357``); ``is_continue=True`` — upstream ``learn`` builds ``Categorical(actor(x))`` from the
+Not reproduced (raises ``NotImplementedError``): ``is_continue=True`` — upstream ``learn`` builds ``Categorical(actor(x))`` from the
 Gaussian actor's ``(mean, std)`` tuple and fails.
 """
 import ctypes
@@ -85,11 +88,6 @@ class MAPPO:
         self.device = _lib.require_device(device)
         if is_continue:
             raise NotImplementedError("MAPPO_discrete.learn is Categorical-only upstream (MAPPO_discrete.py:337); use MAPPO.py for Gaussian actors")
-        if trick['LayerNorm'] or trick['feature_norm']:
-            raise NotImplementedError("LayerNorm / feature_norm of MAPPO_discrete.py normalise jointly over (step, agent, feature) inside learn "
-                                      "but per row when acting (x.size()[1:] of a 4-D tensor); not reproduced")
-        if trick['ValueClip'] and trick['huber_loss']:
-            raise NotImplementedError("ValueClip + huber_loss (squared maximum of two batch-mean scalars, MAPPO_discrete.py:353-357) is not reproduced")
         if len({tuple(v) for v in dim_info.values()}) != 1:
             raise ValueError("MAPPO_discrete shares one actor: every agent needs the same (obs_dim, action_dim)")
         self.agent_x = list(dim_info.keys())[0]
@@ -105,6 +103,12 @@ class MAPPO:
         self.horizon = int(horizon)
         self.trick = trick
         self.actor_lr, self.critic_lr = actor_lr, critic_lr
+        ln, fn = bool(trick['LayerNorm']), bool(trick['feature_norm'])
+        # acting networks normalise per row (frl_infer_args_t.layer_norm: 1 input + hidden, 2 hidden only, 3 input only)
+        self._ln_actor = 2 if ln else 0
+        self._ln_critic = (1 if fn else 2) if ln else (3 if fn else 0)
+        self._group_norm = (1 if ln else 0) | (2 if fn else 0)
+        self._scalar_vloss = bool(trick['ValueClip'] and trick['huber_loss'])
         self.mode = _common.resolve_mode(None)
         self._seed = _common.default_seed()
         self._n_act = 0
@@ -126,18 +130,19 @@ class MAPPO:
         elif self.mode == "parity":
             noise = torch.empty((n, self.action_dim), dtype=torch.float32, device=self.device).exponential_(1)
         out = _common.infer(self.agent._net, x, _lib.INFER_PPO_CAT, self.device, 2, noise=noise, seed=self._seed, counter=self._n_act,
-                            l0=0, nl=3).cpu().numpy()
+                            l0=0, nl=3, layer_norm=self._ln_actor).cpu().numpy()
         return out[:, 0].astype(np.int64), out[:, 1]
 
     def evaluate_action(self, obs):
         x = np.asarray(obs, dtype=np.float32).reshape(-1, self.obs_dim)
-        return _common.infer(self.agent._net, x, _lib.INFER_ARGMAX, self.device, 1, l0=0, nl=3).reshape(-1).to(torch.int64).cpu().numpy()
+        return _common.infer(self.agent._net, x, _lib.INFER_ARGMAX, self.device, 1, l0=0, nl=3,
+                             layer_norm=self._ln_actor).reshape(-1).to(torch.int64).cpu().numpy()
 
     # ---- buffer ------------------------------------------------------------------------------------
     def get_value(self, s):
         """every agent sees the same joint state, so the N critic rows of ``:252-260`` are one value repeated"""
         x = np.asarray(s, dtype=np.float32).reshape(1, -1)
-        v = _common.infer(self.agent._net, x, _lib.INFER_RAW, self.device, 1, l0=3, nl=3).cpu().numpy().reshape(-1)
+        v = _common.infer(self.agent._net, x, _lib.INFER_RAW, self.device, 1, l0=3, nl=3, layer_norm=self._ln_critic).cpu().numpy().reshape(-1)
         return np.repeat(v, self.N)
 
     def add(self, obs, action, reward, next_obs, done, action_log_pi, adv_dones, episode_step):
@@ -178,16 +183,17 @@ class MAPPO:
         obs, s, v, act, logp, rew, done = self._time_major(self.buffer.get_training_data())
         adv, v_target, v_old = self.compute_advantages(v, rew, done, gamma, lmbda)
         self.last_adv, self.last_v_target = adv, v_target
-        # one epoch's plan: consecutive blocks of minibatch_size episodes; rows of episode b are {(t * B + b) * N + n}
+        # one epoch's plan: consecutive blocks of minibatch_size episodes; rows of episode b are {(t * B + b) * N + n}, listed episode by
+        # episode (the T * N rows of an episode are one LayerNorm group of the kernel's group mode)
         nmb = (B + minibatch_size - 1) // minibatch_size
         mb = minibatch_size * T * N
         ar = torch.arange
-        base = (ar(T, device=self.device).view(T, 1, 1) * B) * N + ar(N, device=self.device).view(1, 1, N)          # + b * N
+        base = (ar(T, device=self.device).view(1, T, 1) * B) * N + ar(N, device=self.device).view(1, 1, N)          # + b * N
         idx = torch.zeros((nmb, mb), dtype=torch.int64, device=self.device)
         rows = torch.zeros(nmb, dtype=torch.int32, device=self.device)
         for j in range(nmb):
             eps = ar(j * minibatch_size, min((j + 1) * minibatch_size, B), device=self.device)
-            r = (base + eps.view(1, -1, 1) * N).reshape(-1)
+            r = (base + eps.view(-1, 1, 1) * N).reshape(-1)
             idx[j, :r.numel()] = r
             rows[j] = r.numel()
         idx_d, rows_d = idx.repeat(K_epochs, 1).contiguous(), rows.repeat(K_epochs).contiguous()
@@ -208,11 +214,28 @@ class MAPPO:
         a.step0 = ag.step
         a.critic_obs, a.critic_obs_dim = s.data_ptr(), s.shape[1]
         if self.trick['ValueClip']:
-            a.value_loss, a.v_old = 2, v_old.data_ptr()
+            a.value_loss, a.v_old = (3 if self._scalar_vloss else 2), v_old.data_ptr()
+            a.huber_delta = float(huber_delta) if huber_delta is not None else 0.0
         a.gpart, a.sumsq, a.segcnt = self._gpart.data_ptr(), self._sumsq.data_ptr(), self._segcnt.data_ptr()
-        a.umma_ws = _common.umma_ws_ptr(self.device, int(mb))
         a.stats, a.out = self._stats.data_ptr(), out.data_ptr()
-        _lib.check(_lib.lib().frl_ppo_update(ctypes.byref(a), _lib.stream_ptr(self.device)), "frl_ppo_update")
+        if self._group_norm or self._scalar_vloss:
+            a.group_rows, a.group_norm = T * N, self._group_norm
+        else:
+            a.umma_ws = _common.umma_ws_ptr(self.device, int(mb))
+        launch = lambda: _lib.check(_lib.lib().frl_ppo_update(ctypes.byref(a), _lib.stream_ptr(self.device)), "frl_ppo_update")
+        if not self._scalar_vloss:
+            launch()                              # every minibatch of every epoch in one persistent launch
+        else:
+            # the scalar value loss needs the whole minibatch's critic outputs before any gradient: per update, a forward-only
+            # pre-pass launch (per-CTA huber sums) and the update launch that folds them
+            idx0, rows0, out0, step0 = a.indices, a.mb_rows, a.out, a.step0
+            a.n_updates = 1
+            for u in range(n_updates):
+                a.indices, a.mb_rows, a.out, a.step0 = idx0 + u * mb * 8, rows0 + u * 4, out0 + u * 8 * 4, step0 + 2 * u
+                a.group_prepass, a.stage_lo, a.stage_hi = 1, 0, 1
+                launch()
+                a.group_prepass, a.stage_lo, a.stage_hi = 0, 0, 0
+                launch()
         ag.step += 2 * n_updates
         self._keep = (obs, s, v, act, logp, rew, done, adv, v_target, v_old, idx_d, rows_d)
         self.last_metrics = out

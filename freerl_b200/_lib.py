@@ -85,7 +85,8 @@ class PpoArgs(C.Structure):
                 ("gpart", C.c_void_p),
                 ("sumsq", C.c_void_p), ("segcnt", C.c_void_p), ("stats", C.c_void_p), ("out", C.c_void_p),
                 ("lr_critic", C.c_double), ("hidden_tanh", C.c_int), ("umma_ws", C.c_void_p), ("dp", DpPeers),
-                ("max_norm_joint", C.c_float), ("opt_repeat", C.c_int), ("v_old", C.c_void_p)]
+                ("max_norm_joint", C.c_float), ("opt_repeat", C.c_int), ("v_old", C.c_void_p),
+                ("group_rows", C.c_int), ("group_norm", C.c_int), ("group_prepass", C.c_int)]
 
 
 class SacdArgs(C.Structure):

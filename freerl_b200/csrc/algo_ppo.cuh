@@ -113,15 +113,25 @@ FRL_NI_MISC void ln_bwd(const float* dY, const float* Y, const float* rstd, cons
 // activations kept by one 3-layer net pass (layer-norm variant keeps both the ReLU outputs and their normalised copies)
 struct NetBufs { float *X0, *H1, *H1n, *H2, *H2n, *rs1, *rs2, *scratch; };
 
+template <int R>
+FRL_NI_MISC void tile_copy(const float* X, float* Y, int n) {
+  FRL_PAR(t) { for (int e = t; e < n; e += FRL_NT) Y[e] = X[e]; }
+  FRL_SYNC();
+}
+// ln: 0 none, 1 input + hidden (MAPPO.py), 2 hidden only, 3 input only (the acting networks of MAPPO_discrete.py: its discrete actor
+// drops the normalised input, and LayerNorm / feature_norm are separate switches); the backward (net_bwd) exists for 0 / 1
 template <int R, int HM = 0>
-FRL_DEV void net_fwd(Cta& c, const frl_net_t& N, int l0, bool ln, const float* Xin, int ip, int n_in, const NetBufs& b, int ldh,
+FRL_DEV void net_fwd(Cta& c, const frl_net_t& N, int l0, int ln, const float* Xin, int ip, int n_in, const NetBufs& b, int ldh,
                      float* OUT, int ldo, Hint next) {
   if (!ln) { mlp_fwd<R, HM>(c, N, l0, 3, Xin, ip, b.H1, b.H2, ldh, OUT, ldo, FRL_ACT_NONE, next); return; }
-  ln_fwd<R>(Xin, ip, n_in, b.X0, b.rs1, b.scratch);                       // feature_norm (rstd not needed later)
+  if (ln != 2) ln_fwd<R>(Xin, ip, n_in, b.X0, b.rs1, b.scratch);          // feature_norm (rstd not needed later)
+  else tile_copy<R>(Xin, b.X0, R * ip);
   layer_fwd<R>(c, N, l0, b.X0, ip, b.H1, ldh, FRL_ACT_RELU, fwd_hint(N, l0 + 1));
-  ln_fwd<R>(b.H1, ldh, N.L[l0].out, b.H1n, b.rs1, b.scratch);
+  if (ln != 3) ln_fwd<R>(b.H1, ldh, N.L[l0].out, b.H1n, b.rs1, b.scratch);
+  else tile_copy<R>(b.H1, b.H1n, R * ldh);
   layer_fwd<R>(c, N, l0 + 1, b.H1n, ldh, b.H2, ldh, FRL_ACT_RELU, fwd_hint(N, l0 + 2));
-  ln_fwd<R>(b.H2, ldh, N.L[l0 + 1].out, b.H2n, b.rs2, b.scratch);
+  if (ln != 3) ln_fwd<R>(b.H2, ldh, N.L[l0 + 1].out, b.H2n, b.rs2, b.scratch);
+  else tile_copy<R>(b.H2, b.H2n, R * ldh);
   layer_fwd<R>(c, N, l0 + 2, b.H2n, ldh, OUT, ldo, FRL_ACT_NONE, next);
 }
 
@@ -189,7 +199,9 @@ FRL_DEV void dp_exchange(Cta& c, const frl_ppo_args_t& a, int u) {
 // kernel every other PPO-family class launches; the tanh instantiations exist for 8-row tiles only.
 // UM = 1 (GPU only): the tensor-core variant of algo_ppo_umma.cuh — one more stage in front (split the weights into hi / lo TF32
 // operands), stage "fwd/bwd" runs on tcgen05 over 128-row tiles, the reduce / clip / optimiser stages below are shared.
-template <int R, int HM = 0, int UM = 0>
+// GRP = 1: group mode (algo_ppo_group.cuh, MAPPO_discrete.py's episode-wide LayerNorm): stage "fwd/bwd" walks whole groups per CTA.
+#include "algo_ppo_group.cuh"
+template <int R, int HM = 0, int UM = 0, int GRP = 0>
 struct PpoAlgoT {
   typedef frl_ppo_args_t Args;
   static const int NSTAGES = UM ? 7 : 6;      // [split,] fwd/bwd, reduce, exchange (data-parallel peers only), norms, optimiser x 2
@@ -206,13 +218,15 @@ struct PpoAlgoT {
     const int ldh = act_ld(a.net.L[0].out_pad), ip = a.net.L[0].in_pad, cip = a.net.L[3].in_pad, ap = a.net.L[2].out_pad;
     // the LayerNorm variant keeps the normalised copies of the input and of both hidden activations, per net
     const int ln_extra = a.layer_norm ? (ip + cip + 4 * ldh) : 0;
-    return R * (ip + cip + ln_extra + 6 * ldh + 4 * ap + 8 + 4 * a.n_adv + 8 + 4 + 64) + 2 * FRL_NT + 64 + FRL_NSEG + 3;
+    const int std_floats = R * (ip + cip + ln_extra + 6 * ldh + 4 * ap + 8 + 4 * a.n_adv + 8 + 4 + 64) + 2 * FRL_NT + 64 + FRL_NSEG + 3;
+    if (GRP) { const int gf = ppo_group_user_floats(a); return gf > std_floats ? gf : std_floats; }
+    return std_floats;
   }
   FRL_SHD int grid(const Args& a, int max_ctas) {
 #ifndef FRL_EMUL
     if (UM) return um_grid(a, max_ctas);
 #endif
-    int tiles = (a.mb + R - 1) / R;
+    int tiles = GRP ? a.mb / a.group_rows : (a.mb + R - 1) / R;
     return tiles < max_ctas ? tiles : max_ctas;
   }
   FRL_SHD int n_updates(const Args& a) { return a.n_updates; }
@@ -239,7 +253,7 @@ struct PpoAlgoT {
     if (UM && phys == 1) { ppo_umma_stage(c, user, a, u); return; }
 #endif
     const int rows = a.mb_rows[u];
-    const int ntile = (rows + R - 1) / R;
+    const int ntile = GRP ? rows / a.group_rows : (rows + R - 1) / R;        // work items of stage 0 = gradient partials to reduce
 #ifndef FRL_EMUL
     const int ncontrib = UM ? um_ncontrib(rows, c.ncta) : (ntile < c.ncta ? ntile : c.ncta);
 #else
@@ -277,6 +291,7 @@ struct PpoAlgoT {
     int* segc = (int*)sb.take(FRL_NSEG + 3);
     float* gp = a.gpart + (size_t)c.cta * N.n_p;
 
+    if (GRP && s == 0) { ppo_group_stage(c, user, a, u); return; }
     if (s == 0) {
       if (c.cta >= ntile) return;
       float la = 0.f, lc = 0.f, le = 0.f;
@@ -315,8 +330,8 @@ struct PpoAlgoT {
         }
         FRL_SYNC();
         const int c_in = a.critic_obs ? a.critic_obs_dim : a.obs_dim;
-        net_fwd<R, (HM & 1)>(c, N, 0, ln, X, ip, a.obs_dim, ba, ldh, OA, ap, fwd_hint(N, 3));
-        net_fwd<R, ((HM >> 1) & 1)>(c, N, 3, ln, XC, cip, c_in, bc, ldh, V, 4, bwd_hint(N, 2));
+        net_fwd<R, (HM & 1)>(c, N, 0, ln ? 1 : 0, X, ip, a.obs_dim, ba, ldh, OA, ap, fwd_hint(N, 3));
+        net_fwd<R, ((HM >> 1) & 1)>(c, N, 3, ln ? 1 : 0, XC, cip, c_in, bc, ldh, V, 4, bwd_hint(N, 2));
         // policy head: log-prob, entropy, ratio, clipped surrogate and its gradient w.r.t. the actor output
         FRL_PAR(t) {
           float sa = 0.f, se = 0.f;

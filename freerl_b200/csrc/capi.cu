@@ -537,7 +537,7 @@ struct InferAlgoT {
       }
     }
     FRL_SYNC();
-    if (a.layer_norm && nl == 3) net_fwd<FRL_R>(c, n, l0, true, X, in_pad, a.obs_dim, nb, ldh, O, op, no_hint());
+    if (a.layer_norm && nl == 3) net_fwd<FRL_R>(c, n, l0, a.layer_norm, X, in_pad, a.obs_dim, nb, ldh, O, op, no_hint());
     else mlp_fwd<FRL_R, HM>(c, n, l0, nl, X, in_pad, H1, H2, ldh, O, op, FRL_ACT_NONE, no_hint());
     FRL_PAR(t) {
       if (a.mode == FRL_INFER_ARGMAX) {
@@ -810,6 +810,17 @@ extern "C" int frl_ppo_update(const frl_ppo_args_t* a, void* stream) {
     frl_set_error("frl_ppo_update: net must hold actor (layers 0-2) + critic (layers 3-5)");
     return -1;
   }
+  if (a->group_rows > 0) {       // MAPPO_discrete.py's episode-wide LayerNorm / scalar value loss: group mode (csrc/algo_ppo_group.cuh)
+    if (a->continuous != 0 || a->n_adv != 1 || a->hidden_tanh || a->layer_norm || a->value_loss == 1 || a->dp.world > 1 ||
+        a->mb % a->group_rows != 0 || a->act_cols < 1 || a->logp_cols < 1) {
+      frl_set_error("frl_ppo_update: group mode is Categorical, n_adv 1, value_loss 0 / 2 / 3, single rank, minibatches of whole groups");
+      return -1;
+    }
+    if (a->value_loss == 3 && (a->n_updates != 1 || !a->v_old)) { frl_set_error("frl_ppo_update: value_loss 3 runs one update per launch and needs v_old"); return -1; }
+    if (a->group_prepass && (a->value_loss != 3 || a->stage_lo != 0 || a->stage_hi != 1)) { frl_set_error("frl_ppo_update: group_prepass needs value_loss 3 and stages [0, 1)"); return -1; }
+    return frl_launch<PpoAlgoT<8, 0, 0, 1> >(*a, (cudaStream_t)stream);
+  }
+  if (a->value_loss == 3 || a->group_prepass) { frl_set_error("frl_ppo_update: value_loss 3 / group_prepass need group mode (group_rows)"); return -1; }
   if (a->hidden_tanh) {          // tanh hidden activations (PPO_with_tricks): compile-time variants of the 8-row-tile kernel
     if ((a->hidden_tanh & 3) == 3) return frl_launch<PpoAlgoT<8, 3> >(*a, (cudaStream_t)stream);
     if (a->hidden_tanh & 2) return frl_launch<PpoAlgoT<8, 2> >(*a, (cudaStream_t)stream);

@@ -180,7 +180,7 @@ typedef struct {
   uint32_t counter;
   float* out;               /* dev [n][out_cols]: actions (ARGMAX: 1 column holding the index as float; RAW: net output) */
   int out_cols;
-  int layer_norm;           /* MAPPO nets: F.layer_norm on the input and after each hidden ReLU */
+  int layer_norm;           /* 1: MAPPO nets, F.layer_norm on the input and after each hidden ReLU; 2: hidden only; 3: input only (MAPPO_discrete.py's acting nets) */
   const float* obs_norm;    /* dev [3][obs_dim] {mean, S, std} Batch_ObsNorm state applied with update=False, or NULL */
   int hidden_tanh;          /* 1: tanh hidden activations (the `tanh` trick of PPO_file/PPO_with_tricks.py:95,172); 0: ReLU */
 } frl_infer_args_t;
@@ -220,7 +220,7 @@ typedef struct {
   double lr, beta1, beta2, eps;
   int64_t step0;
   /* ---- MAPPO options (MAPPO_file/MAPPO.py:127-218, 357-482) ---- */
-  int layer_norm;           /* F.layer_norm (no affine, eps 1e-5) on the input and after each hidden ReLU, actor and critic */
+  int layer_norm;           /* F.layer_norm (no affine, eps 1e-5) on the input and after each hidden ReLU, actor and critic (per row; group mode below ignores it) */
   const float* critic_obs;  /* dev [M][critic_obs_dim] joint observation for the centralised critic (NULL: critic sees `obs`) */
   int critic_obs_dim;
   int value_loss;           /* 0: mse(v_target, V);  1: huber(v_target - V, huber_delta).mean()  (MAPPO.py:273-276,426-433);  2: clipped, see v_old */
@@ -247,6 +247,18 @@ typedef struct {
                              *    the step counter advances by opt_repeat per update (FRL_OPT_ADAM only); 0 / 1: once */
   const float* v_old;       /* dev [M][n_adv] rollout values for value_loss 2: max((clamp(V - v_old, +-clip_param) + v_old - v_target)^2,
                              *    (V - v_target)^2) element-wise (the ValueClip branch without huber_loss, :350-357) */
+  /* ---- group mode (csrc/algo_ppo_group.cuh; Categorical actor, FFMA tiles): MAPPO_discrete.py's networks normalise
+   * F.layer_norm(x, x.size()[1:]) of a 4-D [minibatch, T, N, features] tensor inside learn (:81-87,114-120,141-149), i.e. jointly over
+   * the T*N rows of an EPISODE.  group_rows = T*N rows that form one group; the rows of a group are consecutive in `indices` and every
+   * minibatch holds whole groups (mb and mb_rows multiples of group_rows).  A CTA owns whole groups and recomputes the forward pass once
+   * per statistic it needs (5 sweeps over the group's 8-row tiles), so no activation of more than one tile is ever kept. */
+  int group_rows;
+  int group_norm;           /* bit 0: layer_norm after both hidden ReLUs (actor and critic); bit 1: the critic's input (feature_norm; the
+                             *    reference's Actor_discrete overwrites its normalised input, :113-115, so the actor has none) */
+  /* value_loss 3 (group mode, n_updates = 1): ValueClip + huber_loss, critic loss = max(a, b)^2 with the batch-mean SCALARS
+   * a = mean huber(e_clip), b = mean huber(e_orig) (:350-357).  Two launches per update: group_prepass = 1 with stage_lo, stage_hi =
+   * 0, 1 leaves each CTA's sums of huber(e_clip) / huber(e_orig) in stats[cta][5..6]; the update launch (group_prepass = 0) folds them. */
+  int group_prepass;
 } frl_ppo_args_t;
 
 /* Rainbow (DQN_with_tricks.py): Categorical + Dueling + Noisy net.  The trainable block holds the torch tensors;

@@ -5,46 +5,70 @@ Pinned against fixtures generated from the unmodified reference (``oracle/make_g
 
 What the reference does (and this file restates, plain torch + autograd):
   * nets ``MAPPO_discrete.py:95-153``: actor obs->128->128->A with softmax head, critic (N*obs)->128->128->1; ReLU bodies.
-    ``LayerNorm`` / ``feature_norm`` are NOT restated: inside ``learn`` they normalise over ``x.size()[1:]`` of a 4-D tensor, i.e. jointly
-    over (episode step, agent, feature), while acting normalises per row — see DESIGN.md, out of scope.
+    ``LayerNorm`` / ``feature_norm`` call ``F.layer_norm(x, x.size()[1:])``: inside ``learn`` the tensors are 4-D, so the statistics run
+    jointly over (episode step, agent, feature) of each episode, while acting normalises per row.  The discrete actor computes the
+    normalised input and then overwrites it (``:113-115``): ``feature_norm`` only reaches the critic.
   * ONE Adam over actor + critic, lr = actor_lr, eps 1e-5 with ``adam_eps`` (``:160-166``); ``update_ac`` clips the JOINT gradient norm
     to 10 and steps (``:188-192``), and ``learn`` then calls ``ac_optimizer.step()`` AGAIN on the same gradients (``:371``).
   * GAE ``:302-315``: float32 tensors, ``delta = r + gamma v[t+1] (1 - done) - v[t]``, ``gae = delta + gamma lmbda gae`` with NO done mask on
     the recursion, zero tail per episode; ``v_target = adv + v[:-1]``; ``adv_norm`` over the whole [B, T, N] block (unbiased std, + 1e-8).
   * minibatches ``:326``: ``BatchSampler(SequentialSampler(range(batch_size)), minibatch_size, False)`` over EPISODES — no shuffling.
-  * losses ``:333-361``: ``-min(ratio adv, clamp(ratio) adv) - c entropy`` and ``(V - v_target)^2`` (or the ``ValueClip`` maximum), each
-    averaged over (episodes, steps, agents), summed.
+  * losses ``:333-361``: ``-min(ratio adv, clamp(ratio) adv) - c entropy`` and ``(V - v_target)^2`` (or the ``ValueClip`` maximum; with ``huber_loss`` the
+    squared maximum of the two batch-mean huber SCALARS), each averaged over (episodes, steps, agents), summed.
 """
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
 
+def _ln(x):
+    return F.layer_norm(x, x.size()[1:])          # every axis but the first: (T, N, features) inside learn, (features,) when acting
+
+
 class _Actor(nn.Module):
-    def __init__(self, od, ad):
+    def __init__(self, od, ad, trick):
         super().__init__()
         self.l1, self.l2, self.l3 = nn.Linear(od, 128), nn.Linear(128, 128), nn.Linear(128, ad)
+        self.ln = bool(trick["LayerNorm"])
 
-    def forward(self, x):
-        return torch.softmax(self.l3(F.relu(self.l2(F.relu(self.l1(x))))), dim=-1)
+    def forward(self, obs):
+        x = F.relu(self.l1(obs))                   # :113-115: the feature_norm result is overwritten — the actor reads the raw observation
+        if self.ln:
+            x = _ln(x)
+        x = F.relu(self.l2(x))
+        if self.ln:
+            x = _ln(x)
+        return torch.softmax(self.l3(x), dim=-1)
 
 
 class _Critic(nn.Module):
-    def __init__(self, sd):
+    def __init__(self, sd, trick):
         super().__init__()
         self.l1, self.l2, self.l3 = nn.Linear(sd, 128), nn.Linear(128, 128), nn.Linear(128, 1)
+        self.ln, self.fn = bool(trick["LayerNorm"]), bool(trick["feature_norm"])
 
     def forward(self, s):
-        return self.l3(F.relu(self.l2(F.relu(self.l1(s)))))
+        if self.fn:
+            s = _ln(s)
+        q = F.relu(self.l1(s))
+        if self.ln:
+            q = _ln(q)
+        q = F.relu(self.l2(q))
+        if self.ln:
+            q = _ln(q)
+        return self.l3(q)
+
+
+def huber_loss(e, d):                              # :197-200
+    a = (abs(e) <= d).float()
+    b = (abs(e) > d).float()
+    return a * e ** 2 / 2 + b * d * (abs(e) - d / 2)
 
 
 class MAPPODiscreteOracle:
     def __init__(self, actor_sd, critic_sd, n_agents, obs_dim, act_dim, actor_lr, trick):
-        for k in ("LayerNorm", "feature_norm"):
-            assert not trick[k], "not restated (see module docstring)"
-        assert not (trick["ValueClip"] and trick["huber_loss"]), "scalar huber / ValueClip form not restated"
         self.N, self.trick = n_agents, trick
-        self.actor, self.critic = _Actor(obs_dim, act_dim), _Critic(n_agents * obs_dim)
+        self.actor, self.critic = _Actor(obs_dim, act_dim, trick), _Critic(n_agents * obs_dim, trick)
         self.actor.load_state_dict(actor_sd)
         self.critic.load_state_dict(critic_sd)
         self.params = list(self.actor.parameters()) + list(self.critic.parameters())
@@ -64,7 +88,7 @@ class MAPPODiscreteOracle:
             adv = (adv - adv.mean()) / (adv.std() + 1e-8)                                                       # :316
         return adv, v_target
 
-    def learn(self, batch, minibatch_size, gamma, lmbda, clip_param, K_epochs, entropy_coefficient):
+    def learn(self, batch, minibatch_size, gamma, lmbda, clip_param, K_epochs, entropy_coefficient, huber_delta=None):
         """batch: dict of tensors in the reference's layout ([B, T, N, ...], ``a_n`` long).  Returns adv, v_target and, per
         minibatch update, (actor loss incl. entropy term, critic loss)."""
         with torch.no_grad():
@@ -87,7 +111,11 @@ class MAPPODiscreteOracle:
                 if self.trick["ValueClip"]:                                                                     # :350-357
                     v_old = batch["v_n"][idx, :-1]
                     e_clip = torch.clamp(values - v_old, -clip_param, clip_param) + v_old - v_target[idx]
-                    e_orig = values - v_target[idx]
+                    if self.trick["huber_loss"]:                                                                # :353-355: two batch-mean SCALARS
+                        e_clip = huber_loss(e_clip, huber_delta).mean()
+                        e_orig = huber_loss(values - v_target[idx], huber_delta).mean()
+                    else:
+                        e_orig = values - v_target[idx]
                     critic_loss = torch.max(e_clip ** 2, e_orig ** 2)
                 else:
                     critic_loss = (values - v_target[idx]) ** 2

@@ -56,13 +56,17 @@ def test_reference_multi_agent_scripts_unchanged(tmp_path, emul):
         ns = launcher.run_reference_script(os.path.join(REF, "MAPPO_file", sub), on + extra, results_root=str(tmp_path))
         pol = ns["policy"]
         assert type(pol).__module__ == "freerl_b200." + cls and all(a.step > 0 for a in pol.agents.values()), sub
-    # MAPPO_discrete.py: shared networks + episode ReplayBuffer; `horizon` counts EPISODES; the all-False trick set is reachable from the CLI
-    ns = launcher.run_reference_script(os.path.join(REF, "MAPPO_file", "MAPPO_discrete.py"),
-                                       ["--env_name", "simple_spread_v3", "--N", "3", "--max_episodes", "4", "--horizon", "2", "--minibatch_size", "1",
-                                        "--K_epochs", "2", "--policy_name", "MAPPO_simple", "--device", "cpu"], results_root=str(tmp_path))
-    pol = ns["policy"]
-    assert type(pol).__module__ == "freerl_b200.MAPPO_discrete" and pol.agent.step == 2 * 2 * 2 * 2      # 2 learns x 2 epochs x 2 minibatches x 2 steps
-    assert os.path.exists(os.path.join(ns["model_dir"], "MAPPO_discrete.pth"))
+    # MAPPO_discrete.py: shared networks + episode ReplayBuffer; `horizon` counts EPISODES.  The script's DEFAULT switches (policy_name
+    # MAPPO: ObsNorm, reward_scaling, adv_norm, orthogonal init, adam_eps, ValueClip + huber_loss, LayerNorm, feature_norm) and the
+    # all-False set (MAPPO_simple) both run
+    for extra in ([], ["--policy_name", "MAPPO_simple"]):
+        ns = launcher.run_reference_script(os.path.join(REF, "MAPPO_file", "MAPPO_discrete.py"),
+                                           ["--env_name", "simple_spread_v3", "--N", "3", "--max_episodes", "4", "--horizon", "2", "--minibatch_size", "1",
+                                            "--K_epochs", "2", "--device", "cpu"] + extra, results_root=str(tmp_path))
+        pol = ns["policy"]
+        assert type(pol).__module__ == "freerl_b200.MAPPO_discrete" and pol.agent.step == 2 * 2 * 2 * 2      # 2 learns x 2 epochs x 2 minibatches x 2 steps
+        assert bool(pol.trick["LayerNorm"]) == (not extra) and np.isfinite(pol.last_metrics.cpu().numpy()).all()
+        assert os.path.exists(os.path.join(ns["model_dir"], "MAPPO_discrete.pth"))
 
 
 def test_reference_single_agent_siblings_unchanged(tmp_path, emul):

@@ -17,11 +17,11 @@ def _batch(g):
 
 def _oracle(g, name):
     orc = MAPPODiscreteOracle(net_from_golden(g, "init/actor/"), net_from_golden(g, "init/critic/"), N, OD, AD, 1e-3, TRICKS[name])
-    r = orc.learn(_batch(g), MB, HP["gamma"], HP["lmbda"], HP["clip_param"], K, HP["entropy_coefficient"])
+    r = orc.learn(_batch(g), MB, HP["gamma"], HP["lmbda"], HP["clip_param"], K, HP["entropy_coefficient"], HP["huber_delta"])
     return orc, r
 
 
-@pytest.mark.parametrize("name", ["simple", "clip"])
+@pytest.mark.parametrize("name", ["simple", "clip", "full"])
 def test_oracle_vs_reference_fixture(golden, name):
     """pins the restatement: losses 1e-6, final parameters 1e-6 of the reference's, Adam stepped twice per minibatch"""
     g = golden("mappo_discrete_" + name)
@@ -93,25 +93,26 @@ def _run(golden, device, name, parity_draws):
         assert back.evaluate_action(g["eval/obs"]).tolist() == g["eval/action"].tolist()
 
 
-@pytest.mark.parametrize("name", ["simple", "clip"])
+@pytest.mark.parametrize("name", ["simple", "clip", "full"])
 def test_mappo_discrete_shared_emulated(golden, emul, name):
     _run(golden, torch.device("cpu"), name, True)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["simple", "clip"])
+@pytest.mark.parametrize("name", ["simple", "clip", "full"])
 def test_mappo_discrete_shared_gpu(golden, name):
     _run(golden, torch.device("cuda"), name, False)
 
 
-def _big(device, seed=5):
-    """MPE-sized learn (25 steps, 3 agents, 32 episodes, minibatches of 16 episodes = 1200 rows: the tensor-core path on a GPU) on a
-    synthetic rollout, product vs oracle"""
+def _big(device, name="clip", seed=5):
+    """MPE-sized learn (25 steps, 3 agents, 32 episodes, minibatches of 16 episodes = 1200 rows) on a synthetic rollout, product vs
+    oracle.  "clip": the tensor-core path on a GPU; "full" (the script's default switches): group mode with 75-row LayerNorm groups —
+    nine full 8-row tiles and one of three rows — and the scalar huber / ValueClip loss"""
     from freerl_b200.MAPPO_discrete import MAPPO, ReplayBuffer
     T_, B_, MB_ = 25, 32, 16
     torch.manual_seed(seed)
     rng = np.random.default_rng(seed)
-    trick = dict(TRICKS["clip"])
+    trick = dict(TRICKS[name])
     buf = ReplayBuffer(N=N, obs_dim=OD, state_dim=N * OD, episode_limit=T_, batch_size=B_, device=device)
     pol = MAPPO({k: [OD, AD] for k in IDS}, False, 1e-3, 5e-4, B_, device, trick, buf)
     sd = lambda mod: {k: v.detach().cpu().clone() for k, v in mod.state_dict().items()}
@@ -126,8 +127,8 @@ def _big(device, seed=5):
     b["done_n"][...] = rng.random(b["done_n"].shape) < 0.05
     buf.episode_num = B_
     batch = {k: torch.from_numpy(v.copy()) for k, v in b.items()}
-    r = orc.learn(batch, MB_, 0.95, 0.95, 0.2, 2, 0.01)
-    pol.learn(MB_, 0.95, 0.95, 0.2, 2, 0.01, 10.0)
+    r = orc.learn(batch, MB_, 0.95, 0.95, 0.2, 2, 0.01, 1.0)
+    pol.learn(MB_, 0.95, 0.95, 0.2, 2, 0.01, 1.0)          # huber_delta 1: both huber branches occur
     m = pol.last_metrics.cpu().numpy()
     ref = np.array(r["losses"])
     np.testing.assert_allclose(m[:, 0], ref[:, 0], rtol=1e-5, atol=2e-6)
@@ -137,21 +138,20 @@ def _big(device, seed=5):
     assert_module_close(pol.agent.critic, orc.critic.state_dict(), "critic vs oracle", tol)
 
 
-def test_mappo_discrete_mpe_size_emulated(emul):
-    _big(torch.device("cpu"))
+@pytest.mark.parametrize("name", ["clip", "full"])
+def test_mappo_discrete_mpe_size_emulated(emul, name):
+    _big(torch.device("cpu"), name)
 
 
 @pytest.mark.gpu
-def test_mappo_discrete_mpe_size_gpu():
-    _big(torch.device("cuda"))
+@pytest.mark.parametrize("name", ["clip", "full"])
+def test_mappo_discrete_mpe_size_gpu(name):
+    _big(torch.device("cuda"), name)
 
 
 def test_unreproduced_switches_raise(emul):
     from freerl_b200.MAPPO_discrete import MAPPO, ReplayBuffer
     dev = torch.device("cpu")
     buf = ReplayBuffer(N=N, obs_dim=OD, state_dim=N * OD, episode_limit=T, batch_size=B, device=dev)
-    for bad in ({"LayerNorm": True}, {"feature_norm": True}, {"ValueClip": True, "huber_loss": True}):
-        with pytest.raises(NotImplementedError):
-            MAPPO({k: [OD, AD] for k in IDS}, False, 1e-3, 5e-4, B, dev, dict(TRICKS["simple"], **bad), buf)
     with pytest.raises(NotImplementedError):
         MAPPO({k: [OD, AD] for k in IDS}, True, 1e-3, 5e-4, B, dev, dict(TRICKS["simple"]), buf)
