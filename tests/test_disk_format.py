@@ -139,3 +139,34 @@ def test_rainbow_checkpoint_schema_matches_the_reference(tmp_path, emul):
     r.save(str(d2))
     b = DQN.load([8, 4], False, str(d2), trick=dict(trick), device=dev, gamma=0.99, batch_size=32)
     assert [int(b.evaluate_action(o)) for o in obs] == [int(r.evaluate_action(o)) for o in obs]
+
+
+@pytest.mark.parametrize("tricks", ["simple", "full"])
+def test_mappo_discrete_checkpoint_schema_matches_the_reference(tmp_path, emul, tricks):
+    """MAPPO_discrete.pth (MAPPO_file/MAPPO_discrete.py:389-393) = the shared actor's state dict.  Upstream ``MAPPO.load`` cannot run (it
+    builds ``MAPPO(...)`` without a buffer and dereferences ``buffer.batch_size``), so the file written by us is loaded with a strict
+    ``load_state_dict`` into a reference policy built by the reference constructor, and the reverse through ours; greedy actions agree
+    (``full``: per-row LayerNorm in the acting network, hidden layers only — the discrete actor drops its normalised input)."""
+    import sys
+    from freerl_b200.MAPPO_discrete import MAPPO, ReplayBuffer
+    from oracle import refload
+    from oracle.make_golden_mappo_discrete import TRICKS
+    refmod = refload.load("MAPPO_file", "MAPPO_discrete")
+    ref_buffer = sys.modules["Buffer"].ReplayBuffer
+    dim_info = {"agent_%d" % i: [9, 4] for i in range(3)}
+    trick = dict(TRICKS[tricks])
+    dev = torch.device("cpu")
+    obs = np.random.default_rng(2).standard_normal((5, 3, 9)).astype(np.float32)
+    torch.manual_seed(11)
+    a = MAPPO(dim_info, False, 1e-3, 5e-4, 4, dev, dict(trick), ReplayBuffer(3, 9, 27, 5, 4, dev))
+    d1 = tmp_path / "ours"; d1.mkdir()
+    a.save(str(d1))
+    r = refmod.MAPPO(dim_info, False, 1e-3, 5e-4, 4, dev, dict(trick), ref_buffer(N=3, obs_dim=9, state_dim=27, episode_limit=5, batch_size=4, device="cpu"))
+    sd = torch.load(d1 / "MAPPO_discrete.pth")
+    r.agent.actor.load_state_dict(sd, strict=True)
+    assert list(sd) == list(r.agent.actor.state_dict())
+    assert [a.evaluate_action(o).tolist() for o in obs] == [r.evaluate_action(o).tolist() for o in obs]
+    d2 = tmp_path / "ref"; d2.mkdir()
+    r.save(str(d2))
+    b = MAPPO.load(dim_info, False, str(d2), trick=dict(trick), device=dev)
+    assert [b.evaluate_action(o).tolist() for o in obs] == [r.evaluate_action(o).tolist() for o in obs]
