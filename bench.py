@@ -304,7 +304,7 @@ def rainbow_block(dev, rank, world, dist, vsteps=6):
     ms = float(ms.item())
     return {"workload": "rainbow_lunarlander_512env_per1e6_b256_utd1", "ms_per_vector_step": ms, "env_steps_per_sec": world * NE / ms * 1e3,
             "updates_per_sec": world * NE / ms * 1e3, "scaling": "weak", "e2e": "host observations / transitions in, actions out, every step",
-            "parallelism": "replicas, env + PER shard per GPU, parameter average per vector step" if world > 1 else "1 rank"}
+            "parallelism": ("replicas, env + PER shard per GPU, parameter average per vector step: " + getattr(pol, "replica_collective", "?")) if world > 1 else "1 rank"}
 
 
 def mappo_block(dev, rank, world, dist, learns=2):
@@ -376,7 +376,7 @@ def main():
               "envs_per_gpu": NENV, "replay_capacity_per_gpu": CAP, "batch": BATCH, "updates_per_env_step": 1,
               "vector_steps_per_step": VSTEPS,
               "l2_note": "batches are uniform random rows of a 176 MB replay (> 126 MB L2)",
-              "parallelism": "dp%d (env+replay shards per GPU, parameter all-reduce per vector step)" % max(world, 1)}
+              "parallelism": "dp%d (env+replay shards per GPU, parameter average per vector step)" % max(world, 1)}
 
     if args.impl == "reference":
         if rank != 0:
@@ -422,6 +422,7 @@ def main():
     from freerl_b200 import _common, _lib
     if world > 1:
         pol.enable_replica_sync()             # broadcast rank 0's parameters; sync_replicas() averages them afterwards
+        config["parallelism"] += ": " + pol.replica_collective
 
     def sync_params():
         pol.sync_replicas()                   # no-op at world 1

@@ -192,6 +192,15 @@ class ACBase:
             n_.sync_mirror()
         if self.sac:
             dist.broadcast(self.alphas.state, src=0, group=group)
+        self._rs_peers = _common.replica_peers(dist, group, self.device, self._replica_tensors())
+        self.replica_collective = ("in-kernel peer-memory average (frl_replica_average), one launch per sync" if self._rs_peers
+                                   else "dist.all_reduce + divide per parameter block")
+
+    def _replica_tensors(self):
+        ts = [n_.p for n_ in self._replica_nets()]
+        if self.sac:
+            ts.append(self.alphas.state[:1])          # log_alpha (the Adam moments of alpha stay local like the others)
+        return ts
 
     def _replica_nets(self):
         ag = self.agent
@@ -203,6 +212,11 @@ class ACBase:
         if rs is None or rs[2] == 1:
             return
         dist, group, world = rs
+        if getattr(self, "_rs_peers", None) is not None:        # one cooperative launch over NVLink peer memory, then the mirrors
+            _common.replica_average(self._rs_peers, self._replica_tensors(), self.device)
+            for n_ in self._replica_nets():
+                n_.sync_mirror()
+            return
         for n_ in self._replica_nets():
             dist.all_reduce(n_.p, group=group)
             n_.p.div_(world)

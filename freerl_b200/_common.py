@@ -183,6 +183,31 @@ class DpPeers:
         self.epoch += n_updates
 
 
+def replica_peers(dist, group, device, tensors):
+    """Exchange blocks for the in-kernel replica average (``frl_replica_average``) of these tensors, or None where the peer path does
+    not apply (one rank, CPU / the test-only emulation, more ranks than a node holds, ``FREERL_B200_DP_PEER=0``): the callers then keep the
+    ``dist.all_reduce`` + divide pairs."""
+    world = dist.get_world_size(group)
+    if (world < 2 or world > _lib.FRL_DP_MAX_RANKS or len(tensors) > _lib.FRL_RA_MAX_TENSORS or device.type != "cuda"
+            or _lib.lib().frl_is_emulation() or os.environ.get("FREERL_B200_DP_PEER", "1") == "0"):
+        return None
+    total = sum((t.numel() + 3) & ~3 for t in tensors)
+    peers = DpPeers(dist, group, device, total)
+    peers.status = torch.zeros(1, dtype=torch.float32, device=device)
+    return peers
+
+
+def replica_average(peers, tensors, device):
+    """tensors[i] <- mean over the ranks (rank-ordered sum / world), ONE cooperative launch over peer-mapped NVLink memory"""
+    import ctypes
+    a = _lib.ReplicaAvgArgs()
+    peers.fill(a, sum((t.numel() + 3) & ~3 for t in tensors), 1)
+    for i, t in enumerate(tensors):
+        a.tensor[i], a.n[i] = t.data_ptr(), t.numel()
+    a.n_tensors, a.block_floats, a.status = len(tensors), peers.n_floats, peers.status.data_ptr()
+    _lib.check(_lib.lib().frl_replica_average(ctypes.byref(a), _lib.stream_ptr(device)), "frl_replica_average")
+
+
 class ReplicaSyncMixin:
     """Multi-GPU mode of the off-policy value learners (SURVEY §8e "replicas + sharded replay"; DQN / Rainbow = BASELINE config 4):
     one process per GPU, each with its own env shard and its own replay shard — for PER its own sum-tree, priorities never leave the
@@ -198,13 +223,23 @@ class ReplicaSyncMixin:
             dist.broadcast(t, src=0, group=group)
             if refresh:
                 refresh()
+        self._rs_peers = replica_peers(dist, group, self.device, [t for t, _ in self._replica_pairs()])
+        self.replica_collective = ("in-kernel peer-memory average (frl_replica_average), one launch per sync" if self._rs_peers
+                                   else "dist.all_reduce + divide per parameter block")
 
     def sync_replicas(self):
         rs = getattr(self, "_rs", None)
         if rs is None or rs[2] == 1:
             return
         dist, group, world = rs
-        for t, refresh in self._replica_pairs():
+        pairs = self._replica_pairs()
+        if getattr(self, "_rs_peers", None) is not None:
+            replica_average(self._rs_peers, [t for t, _ in pairs], self.device)
+            for _, refresh in pairs:
+                if refresh:
+                    refresh()
+            return
+        for t, refresh in pairs:
             dist.all_reduce(t, group=group)
             t.div_(world)
             if refresh:

@@ -12,7 +12,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 FRL_MAX_LAYERS = 6
 FRL_MAX_AGENTS = 6
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 
 class Layer(C.Structure):
@@ -87,6 +87,14 @@ class PpoArgs(C.Structure):
                 ("lr_critic", C.c_double), ("hidden_tanh", C.c_int), ("umma_ws", C.c_void_p), ("dp", DpPeers),
                 ("max_norm_joint", C.c_float), ("opt_repeat", C.c_int), ("v_old", C.c_void_p),
                 ("group_rows", C.c_int), ("group_norm", C.c_int), ("group_prepass", C.c_int)]
+
+
+FRL_RA_MAX_TENSORS = 8
+
+
+class ReplicaAvgArgs(C.Structure):
+    _fields_ = [("dp", DpPeers), ("tensor", C.c_void_p * FRL_RA_MAX_TENSORS), ("n", C.c_int * FRL_RA_MAX_TENSORS), ("n_tensors", C.c_int),
+                ("block_floats", C.c_longlong), ("status", C.c_void_p)]
 
 
 class SacdArgs(C.Structure):
@@ -181,6 +189,8 @@ def _declare(lib):
     lib.frl_rainbow_learn.restype = ci
     lib.frl_sacd_learn.argtypes = [C.POINTER(SacdArgs), vp]
     lib.frl_sacd_learn.restype = ci
+    lib.frl_replica_average.argtypes = [C.POINTER(ReplicaAvgArgs), vp]
+    lib.frl_replica_average.restype = ci
     lib.frl_rainbow_act.restype = ci
     for name in ("frl_replay_add_batch", "frl_replay_gather", "frl_sample_uniform", "frl_net_sync_mirror",
                  "frl_dqn_learn", "frl_ac_learn", "frl_policy_infer", "frl_gae", "frl_ppo_update", "frl_sumtree_update", "frl_sumtree_update_td", "frl_sumtree_sample", "frl_sumtree_max",
@@ -209,7 +219,7 @@ def lib():
                                % (path, l.frl_abi_version(), ABI_VERSION))
         l.frl_struct_size.restype = C.c_int
         l.frl_struct_size.argtypes = [C.c_int]
-        for which, mirror in enumerate((Layer, Net, Replay, DqnArgs, AcArgs, InferArgs, PpoArgs, NoisyMap, RainbowArgs, ExploreArgs, SacdArgs)):
+        for which, mirror in enumerate((Layer, Net, Replay, DqnArgs, AcArgs, InferArgs, PpoArgs, NoisyMap, RainbowArgs, ExploreArgs, SacdArgs, ReplicaAvgArgs)):
             if l.frl_struct_size(which) != C.sizeof(mirror):
                 raise RuntimeError("freerl_b200: ctypes mirror %s is %d bytes, the library's struct is %d"
                                    % (mirror.__name__, C.sizeof(mirror), l.frl_struct_size(which)))

@@ -27,7 +27,7 @@ extern "C" void frl_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 extern "C" const char* frl_last_error(void) { return g_err; }
-extern "C" int frl_abi_version(void) { return 9; }
+extern "C" int frl_abi_version(void) { return 10; }
 // sizeof() of the argument structs, so a binding can verify its mirror of the layout before the first call
 extern "C" int frl_struct_size(int which) {
   switch (which) {
@@ -42,6 +42,7 @@ extern "C" int frl_struct_size(int which) {
     case 8: return (int)sizeof(frl_rainbow_args_t);
     case 10: return (int)sizeof(frl_sacd_args_t);
     case 9: return (int)sizeof(frl_explore_args_t);
+    case 11: return (int)sizeof(frl_replica_avg_args_t);
     default: return -1;
   }
 }
@@ -774,6 +775,26 @@ extern "C" int frl_dp_free(void* dev_ptr) {
   (void)dev_ptr;
 #endif
   return 0;
+}
+
+#include "replica_avg.cuh"
+extern "C" int frl_replica_average(const frl_replica_avg_args_t* a, void* stream) {
+  if (!a || a->n_tensors < 1 || a->n_tensors > FRL_RA_MAX_TENSORS) { frl_set_error("frl_replica_average: 1..%d tensors", FRL_RA_MAX_TENSORS); return -1; }
+  if (a->dp.world < 2 || a->dp.world > FRL_DP_MAX_RANKS || a->dp.rank < 0 || a->dp.rank >= a->dp.world) { frl_set_error("frl_replica_average: bad rank / world"); return -1; }
+  long long tot = 0;
+  for (int i = 0; i < a->n_tensors; ++i) {
+    if (!a->tensor[i] || a->n[i] <= 0) { frl_set_error("frl_replica_average: tensor %d missing", i); return -1; }
+    tot += (a->n[i] + 3) & ~3;
+  }
+  if (tot > a->block_floats) { frl_set_error("frl_replica_average: tensors (%lld floats) exceed the exchange block (%lld)", tot, a->block_floats); return -1; }
+  for (int r = 0; r < a->dp.world; ++r)
+    if (!a->dp.g[r] || !a->dp.flags[r]) { frl_set_error("frl_replica_average: peer block %d missing", r); return -1; }
+#ifdef FRL_EMUL
+  frl_set_error("frl_replica_average: the peer-memory exchange needs the CUDA library");
+  return -1;
+#else
+  return frl_launch<ReplicaAvgAlgo>(*a, (cudaStream_t)stream);
+#endif
 }
 
 // floats of frl_ppo_args_t.umma_ws: 6 split-weight blocks + one activation scratch per CTA of the largest grid

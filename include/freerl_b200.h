@@ -198,6 +198,20 @@ typedef struct {
   unsigned epoch0;                      /* exchanges completed before this launch (identical on all ranks) */
 } frl_dp_peers_t;
 
+/* Parameter average of the off-policy replicas over the same peer blocks (csrc/replica_avg.cuh): tensor[i] (n[i] floats, this rank's
+ * parameter blocks) <- (sum over the ranks, in rank order) / world, one cooperative launch per sync instead of an all-reduce + divide
+ * per tensor.  The exchange block of every rank holds 2 x block_floats floats behind its flags (block_floats >= sum of n[i] rounded up
+ * to 4 each).  status (dev [1] or NULL) is set to -1 if a peer did not arrive within 30 s. */
+#define FRL_RA_MAX_TENSORS 8
+typedef struct {
+  frl_dp_peers_t dp;                    /* epoch0 = syncs completed before this one (identical on all ranks) */
+  float* tensor[FRL_RA_MAX_TENSORS];
+  int n[FRL_RA_MAX_TENSORS];
+  int n_tensors;
+  long long block_floats;
+  float* status;
+} frl_replica_avg_args_t;
+
 /* On-policy (PPO.py) minibatch update.  `net` holds actor (layers 0-2, + log_std extra when continuous) and critic
  * (layers 3-5) in ONE parameter block with ONE optimiser, like the reference's merged `ac_optimizer`. */
 enum { FRL_OPT_CAUTIOUS_ADAMW = 0, FRL_OPT_ADAM = 1 };
@@ -330,11 +344,13 @@ int frl_dp_alloc(long long bytes, void** dev_ptr, unsigned char* ipc_handle_64);
 int frl_dp_open(const unsigned char* ipc_handle_64, void** dev_ptr);
 int frl_dp_close(void* peer_ptr);
 int frl_dp_free(void* dev_ptr);
+int frl_replica_average(const frl_replica_avg_args_t* args, void* stream);
 long long frl_ppo_umma_ws_floats(void);   /* size of frl_ppo_args_t.umma_ws (0 from the test-only emulation) */
 int frl_wt_ld(int out_pad);          /* row stride (floats) of a transposed-mirror layer image with this padded width */
 int frl_abi_version(void);
 /* sizeof the argument structs as compiled: 0 frl_layer_t, 1 frl_net_t, 2 frl_replay_t, 3 frl_dqn_args_t, 4 frl_ac_args_t,
- * 5 frl_infer_args_t, 6 frl_ppo_args_t, 7 frl_noisy_map_t, 8 frl_rainbow_args_t, 9 frl_explore_args_t; -1 otherwise.  A binding checks its mirror
+ * 5 frl_infer_args_t, 6 frl_ppo_args_t, 7 frl_noisy_map_t, 8 frl_rainbow_args_t, 9 frl_explore_args_t, 10 frl_sacd_args_t,
+ * 11 frl_replica_avg_args_t; -1 otherwise.  A binding checks its mirror
  * of the layout against these before the first call (freerl_b200/_lib.py does, at load time). */
 int frl_struct_size(int which);
 

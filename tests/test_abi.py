@@ -32,7 +32,7 @@ def test_header_symbols_exported():
     # the ctypes mirrors have the byte size of the compiled structs (also enforced by _lib.lib() at load time)
     lib.frl_struct_size.restype = ctypes.c_int
     mirrors = (_lib.Layer, _lib.Net, _lib.Replay, _lib.DqnArgs, _lib.AcArgs, _lib.InferArgs, _lib.PpoArgs, _lib.NoisyMap, _lib.RainbowArgs, _lib.ExploreArgs,
-               _lib.SacdArgs)
+               _lib.SacdArgs, _lib.ReplicaAvgArgs)
     for which, m in enumerate(mirrors):
         assert lib.frl_struct_size(which) == ctypes.sizeof(m), m.__name__
     assert lib.frl_struct_size(len(mirrors)) == -1

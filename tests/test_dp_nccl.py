@@ -70,6 +70,7 @@ dev = torch.device("cuda", rank)
 with contextlib.redirect_stdout(io.StringIO()):
     pol = SAC([2, 1], True, 1e-3, 1e-3, 100_000, dev, trick={}, mode="fast")
 pol.enable_replica_sync()
+assert pol._rs_peers is not None, pol.replica_collective      # the in-kernel peer-memory average, not the all-reduce fallback
 env = PointEnv(64, 100 + rank)              # every rank steps its OWN env shard and fills its OWN replay shard
 obs, rets = env.obs(), []
 for step in range(500):
@@ -81,6 +82,7 @@ for step in range(500):
     if step >= 20:
         pol.learn(256, 0.95, 0.01, n_updates=16)
         pol.sync_replicas()                 # parameter average per vector step, like bench.py / train_vec
+assert float(pol._rs_peers.status.item()) == 0.0             # no peer ever timed out
 sd = {k: v.detach().cpu().numpy() for k, v in pol.agent.actor.state_dict().items()}
 np.savez(os.path.join(os.environ["FRL_OUT"], "replica%d.npz" % rank), rets=np.array(rets), **sd)
 dist.barrier()
@@ -111,3 +113,55 @@ def test_sac_replicas_learn_point_env_nccl(tmp_path):
         random_phase, late = rets[:20].mean(), rets[-100:].mean()
         print("rank %d: random phase %.3f, last 100 steps %.3f" % (rk, random_phase, late))
         assert late > random_phase + 0.3 and late > -0.2, (rk, random_phase, late)
+
+
+AVG_WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["FRL_ROOT"])
+rank = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(rank)
+dev = torch.device("cuda", rank)
+dist.init_process_group("nccl", device_id=dev)
+from freerl_b200 import _common
+sizes = [36868, 39426, 3, 1, 130]                   # parameter-block sized tensors, odd tails, a scalar
+g = torch.Generator().manual_seed(100 + rank)
+ts = [torch.randn(n, generator=g).to(dev) for n in sizes]
+peers = _common.replica_peers(dist, None, dev, ts)
+assert peers is not None
+outs = {}
+for it in range(3):                                 # three syncs: both halves of the double buffer and the epoch hand-off
+    before = [t.cpu().numpy().copy() for t in ts]
+    _common.replica_average(peers, ts, dev)
+    torch.cuda.synchronize()
+    for i, t in enumerate(ts):
+        outs["in%d_%d" % (it, i)] = before[i]
+        outs["out%d_%d" % (it, i)] = t.cpu().numpy().copy()
+    for t in ts:                                    # drift apart again before the next sync
+        t.add_(torch.randn(t.shape, generator=g).to(dev) * 0.1)
+assert float(peers.status.item()) == 0.0
+np.savez(os.path.join(os.environ["FRL_OUT"], "avg%d.npz" % rank), **outs)
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.gpu
+def test_replica_average_peer_memory_nccl(tmp_path):
+    """frl_replica_average on two GPUs: every rank ends with (x_0 + x_1) * 0.5 in rank order — bit-identical across the ranks and equal
+    to the host computation, over three successive syncs (both buffer halves)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    (tmp_path / "worker.py").write_text(AVG_WORKER)
+    env = dict(os.environ, FRL_ROOT=ROOT, FRL_OUT=str(tmp_path))
+    env.pop("FREERL_B200_LIB", None)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29544", str(tmp_path / "worker.py")]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    r0, r1 = np.load(tmp_path / "avg0.npz"), np.load(tmp_path / "avg1.npz")
+    for it in range(3):
+        for i in range(5):
+            want = (r0["in%d_%d" % (it, i)] + r1["in%d_%d" % (it, i)]) * np.float32(0.5)
+            assert np.array_equal(r0["out%d_%d" % (it, i)], want), (it, i)
+            assert np.array_equal(r1["out%d_%d" % (it, i)], want), (it, i)
