@@ -107,7 +107,7 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-NCU_CAPTURE = "profiles/r2_bench_sac_learn_ncu_full.json"
+NCU_CAPTURE = "profiles/r6_bench_sac_learn_ncu_full.json"
 
 
 def ncu_traffic():

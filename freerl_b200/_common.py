@@ -172,6 +172,22 @@ class DpPeers:
         self.epoch = 0
         dist.barrier(group=group)
 
+    def close(self, dist=None, group=None):
+        """Unmap the peers' blocks and free this rank's own.  Call it on every rank at the same point (pass ``dist`` to put the barriers
+        in: nobody may still be reading a block that is being freed).  Not called implicitly — at interpreter exit the driver
+        reclaims the blocks."""
+        lib = _lib.lib()
+        if dist is not None:
+            dist.barrier(group=group)
+        for r, base in enumerate(self.base):
+            if r != self.rank and base:
+                _lib.check(lib.frl_dp_close(base), "frl_dp_close")
+        if dist is not None:
+            dist.barrier(group=group)
+        if self.base[self.rank]:
+            _lib.check(lib.frl_dp_free(self.base[self.rank]), "frl_dp_free")
+        self.base = [0] * self.world
+
     def fill(self, a, n_floats, n_updates):
         """Point ``a.dp`` (a ``PpoArgs``) at the blocks for a launch of ``n_updates`` exchanges of ``n_floats`` gradients each."""
         if n_floats > self.n_floats:

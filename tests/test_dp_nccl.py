@@ -141,6 +141,7 @@ for it in range(3):                                 # three syncs: both halves o
         t.add_(torch.randn(t.shape, generator=g).to(dev) * 0.1)
 assert float(peers.status.item()) == 0.0
 np.savez(os.path.join(os.environ["FRL_OUT"], "avg%d.npz" % rank), **outs)
+peers.close(dist)                                   # unmap the peers' blocks, free the own one (barriers inside)
 dist.barrier()
 dist.destroy_process_group()
 '''
