@@ -209,7 +209,12 @@ struct PpoAlgoT {
   FRL_SHD bool writes_params(int) { return true; }
   // the exchange stage exists for data-parallel peers only; the weight split of the tensor-core variant runs on the first update of
   // a launch (the optimiser stages keep the split copies current afterwards)
-  FRL_SHD bool stage_enabled(int s, int u, const Args& a) { return (s != XCHG || a.dp.world > 1) && !(UM && s == 0 && u > 0); }
+  // single rank, gradient used as reduced: the reduce stage also leaves the per-CTA sums of squares, the norms stage is skipped
+  FRL_SHD bool norms_in_reduce(const Args& a) { return a.dp.world <= 1 && a.stage_hi == 0 && (a.grad_scale == 0.f || a.grad_scale == 1.f); }
+  FRL_SHD bool stage_enabled(int s, int u, const Args& a) {
+    return (s != XCHG || a.dp.world > 1) && !(UM && s == 0 && u > 0) && !(s == XCHG + 1 && norms_in_reduce(a)) &&
+           !(s == XCHG + 3 && a.optimizer == FRL_OPT_ADAM);      // plain Adam is one sweep: no second optimiser stage, no barrier for it
+  }
   FRL_SHD int wbuf_floats(const Args& a) { return UM ? 32 : ((AcAlgo::max_layer_floats(a.net) + 31) & ~31); }      // UM: no weight stager, its ring lives in `user`
   FRL_SHD int user_floats(const Args& a) {
 #ifndef FRL_EMUL
@@ -502,6 +507,11 @@ struct PpoAlgoT {
       float* r4 = c.red;                                     // [FRL_NT] float4
       // data-parallel peers: the rank's sum goes to its exchange block g[epoch & 1]; the exchange stage writes net.g
       float* gdst = a.dp.world > 1 ? a.dp.g[a.dp.rank] + (size_t)((a.dp.epoch0 + (unsigned)u + 1u) & 1u) * N.n_p : N.g;
+      // the clip norms ride along (single rank, unscaled gradient): the thread that writes a quad of net.g also squares it, so the
+      // separate "norms" stage and its grid barrier are skipped (stage_enabled)
+      const bool fold_norms = norms_in_reduce(a);
+      FRL_PAR(t) { red0[t] = 0.f; red1[t] = 0.f; }
+      FRL_SYNC();
       for (int q0 = c.cta * (FRL_NT / 8); q0 < nq; q0 += c.ncta * (FRL_NT / 8)) {
         FRL_PAR(t) {
           const int sub = t & 7, q = q0 + (t >> 3);
@@ -521,8 +531,17 @@ struct PpoAlgoT {
             float4 sgm = ld4(r4 + 4 * t);
             for (int l = 1; l < 8; ++l) sgm = f4add(sgm, ld4(r4 + 4 * (t + l)));
             st4(gdst + 4 * q, sgm);
+            if (fold_norms) {
+              const float qq = sgm.x * sgm.x + sgm.y * sgm.y + sgm.z * sgm.z + sgm.w * sgm.w;
+              if (is_critic(N, 4 * q)) red1[t] += qq; else red0[t] += qq;
+            }
           }
         }
+        FRL_SYNC();
+      }
+      if (fold_norms) {
+        const float ta = block_sum(red0), tc = block_sum(red1);
+        FRL_PAR(t) { if (t == 0) { a.sumsq[c.cta * 2] = ta; a.sumsq[c.cta * 2 + 1] = tc; } }
         FRL_SYNC();
       }
 #ifndef FRL_EMUL
@@ -550,12 +569,39 @@ struct PpoAlgoT {
       // order from shared memory (same association as a serial walk; a single thread walking 148 partials in global memory
       // cost 7 us per sum while its CTA, and with it the whole grid, waited at the next barrier).
       float* sh = c.red;
-      float nrm[3], met[3] = {0.f, 0.f, 0.f};
+      float nrm[3] = {0.f, 0.f, 0.f}, met[3] = {0.f, 0.f, 0.f};
       const int rep = (a.optimizer == FRL_OPT_ADAM && a.opt_repeat > 1) ? 2 : 1;
-      cta_sums(sh, a.sumsq, 2, a.sumsq + 1, 2, nullptr, 0, c.ncta, nrm);
-      if (s == 3 && c.cta == 0) cta_sums(sh, a.stats, 8, a.stats + 1, 8, a.stats + 2, 8, ncontrib, met);
+      // pass 2 of the cautious optimiser runs right after pass 1 in the same launch: the scalars pass 1 left in sh[0..8] are still there
+      const bool reuse = s == 4 && (a.stage_hi == 0 || a.stage_lo <= 3);
+      if (!reuse) {
+        // the per-CTA sums of squares, folded by 2 x 8 threads (contiguous eighths in CTA order, then the eighths in order)
+        float* stg2 = c.red + 64;
+        FRL_PAR(t) { for (int i = t; i < 2 * c.ncta; i += FRL_NT) stg2[i] = a.sumsq[i]; }
+        FRL_SYNC();
+        FRL_PAR(t) {
+          if (t < 16) {
+            const int k = t >> 3, sub = t & 7, per8 = (c.ncta + 7) >> 3;
+            const int i0 = sub * per8, i1 = (i0 + per8) < c.ncta ? (i0 + per8) : c.ncta;
+            float acc = 0.f;
+            for (int i = i0; i < i1; ++i) acc += stg2[2 * i + k];
+            sh[16 + t] = acc;
+          }
+        }
+        FRL_SYNC();
+        FRL_PAR(t) {
+          if (t < 2) {
+            float acc = 0.f;
+            for (int l = 0; l < 8; ++l) acc += sh[16 + t * 8 + l];
+            sh[32 + t] = acc;
+          }
+        }
+        FRL_SYNC();
+        nrm[0] = sh[32]; nrm[1] = sh[33];
+        FRL_SYNC();
+      }
+      if (s == 3 && c.cta == 0) cta_sums(sh + 64, a.stats, 8, a.stats + 1, 8, a.stats + 2, 8, ncontrib, met);
       FRL_PAR(t) {
-        if (t == 0) {
+        if (t == 0 && !reuse) {
           const float ta = nrm[0], tc = nrm[1];
           float ca = 1.f, cc = 1.f;
           if (a.max_norm_actor > 0.f) ca = fminf(a.max_norm_actor / (sqrtf(ta) + 1e-6f), 1.f);
@@ -647,10 +693,22 @@ struct PpoAlgoT {
         float* stg = c.red + 64;                 // c.red[0..5] still hold the optimiser scalars
         FRL_PAR(t) { for (int i = t; i < c.ncta * FRL_NSEG; i += FRL_NT) stg[i] = a.segcnt[i]; }
         FRL_SYNC();
+        // the counts are small integers held in floats: any association gives the same sum, so eight threads share a tensor
+        float* part8 = red1;
+        FRL_PAR(t) {
+          if (t < FRL_NSEG * 8) {
+            const int sg = t >> 3, sub = t & 7, per8 = (c.ncta + 7) >> 3;
+            const int i0 = sub * per8, i1 = (i0 + per8) < c.ncta ? (i0 + per8) : c.ncta;
+            float tot = 0.f;
+            for (int cc = i0; cc < i1; ++cc) tot += stg[cc * FRL_NSEG + sg];
+            part8[t] = tot;
+          }
+        }
+        FRL_SYNC();
         FRL_PAR(t) {
           if (t < FRL_NSEG) {
             float tot = 0.f;
-            for (int cc = 0; cc < c.ncta; ++cc) tot += stg[cc * FRL_NSEG + t];
+            for (int l = 0; l < 8; ++l) tot += part8[t * 8 + l];
             segmean[t] = tot;
           }
         }
