@@ -81,6 +81,7 @@ def test_entry_points_reject_bad_arguments_without_touching_the_gpu():
         "frl_masked_reset": lambda: lib.frl_masked_reset(N, N, 4, 1, 0.0, N),
         "frl_epsilon_greedy": lambda: lib.frl_epsilon_greedy(N, 4, 2, 0.1, N, N, 0, 0, N, N),
         "frl_dis_to_con": lambda: lib.frl_dis_to_con(N, 4, 11, 1, 0, N, N, N, N, N),
+        "frl_replica_average": lambda: lib.frl_replica_average(N, N),
     }
     for name, call in calls.items():
         rc = call()
@@ -88,6 +89,15 @@ def test_entry_points_reject_bad_arguments_without_touching_the_gpu():
         msg = lib.frl_last_error().decode()
         assert name.replace("frl_", "").split("_")[0] in msg or name in msg, (name, msg)
     # a struct with inconsistent fields is refused too (PPO tanh + layer_norm; unknown explore kind)
+    g = _lib.PpoArgs()                       # group mode (MAPPO_discrete.py) is Categorical-only; the scalar value loss needs group mode
+    g.mb = g.n_updates = g.n_adv = 1
+    for k in ("indices", "mb_rows", "gpart", "sumsq", "segcnt", "stats", "out"):
+        setattr(g, k, 8)
+    g.value_loss = 3
+    assert lib.frl_ppo_update(ctypes.byref(g), None) < 0 and "frl_ppo_update" in lib.frl_last_error().decode()
+    r = _lib.ReplicaAvgArgs()                # a world of one has nothing to average
+    r.n_tensors, r.dp.world = 1, 1
+    assert lib.frl_replica_average(ctypes.byref(r), None) < 0 and "frl_replica_average" in lib.frl_last_error().decode()
     a = _lib.ExploreArgs()
     a.kind, a.N, a.A = 7, 4, 2
     assert lib.frl_explore(ctypes.byref(a), None) < 0 and "frl_explore" in lib.frl_last_error().decode()
