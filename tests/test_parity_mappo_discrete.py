@@ -104,12 +104,13 @@ def test_mappo_discrete_shared_gpu(golden, name):
     _run(golden, torch.device("cuda"), name, False)
 
 
-def _big(device, name="clip", seed=5):
+def _big(device, name="clip", seed=5, dims=None):
     """MPE-sized learn (25 steps, 3 agents, 32 episodes, minibatches of 16 episodes = 1200 rows) on a synthetic rollout, product vs
     oracle.  "clip": the tensor-core path on a GPU; "full" (the script's default switches): group mode with 75-row LayerNorm groups —
     nine full 8-row tiles and one of three rows — and the scalar huber / ValueClip loss"""
     from freerl_b200.MAPPO_discrete import MAPPO, ReplayBuffer
-    T_, B_, MB_ = 25, 32, 16
+    N, OD, AD, T_, B_, MB_ = dims or (3, 18, 5, 25, 32, 16)          # agents, obs, actions, episode_limit, episodes, minibatch (episodes)
+    IDS = ["agent_%d" % i for i in range(N)]
     torch.manual_seed(seed)
     rng = np.random.default_rng(seed)
     trick = dict(TRICKS[name])
@@ -147,6 +148,24 @@ def test_mappo_discrete_mpe_size_emulated(emul, name):
 @pytest.mark.parametrize("name", ["clip", "full"])
 def test_mappo_discrete_mpe_size_gpu(name):
     _big(torch.device("cuda"), name)
+
+
+# odd shapes: two agents / 10-row groups (one full tile + two rows) with a ragged last minibatch; five agents with a 150-wide joint
+# observation (wider than the tensor-core path takes) and 35-row groups; a group of exactly one tile
+ODD = [(2, 7, 3, 5, 6, 4), (5, 30, 4, 7, 8, 3), (2, 6, 2, 4, 5, 5)]
+
+
+@pytest.mark.parametrize("dims", ODD, ids=["n2_g10", "n5_g35", "n2_g8"])
+@pytest.mark.parametrize("name", ["clip", "full"])
+def test_mappo_discrete_odd_shapes_emulated(emul, name, dims):
+    _big(torch.device("cpu"), name, seed=9, dims=dims)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dims", ODD, ids=["n2_g10", "n5_g35", "n2_g8"])
+@pytest.mark.parametrize("name", ["clip", "full"])
+def test_mappo_discrete_odd_shapes_gpu(name, dims):
+    _big(torch.device("cuda"), name, seed=9, dims=dims)
 
 
 def test_unreproduced_switches_raise(emul):
