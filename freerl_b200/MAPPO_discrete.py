@@ -78,7 +78,9 @@ class ReplayBuffer:
         self.episode_num += 1
 
     def get_training_data(self):
-        return {k: v.to(self.device, non_blocking=True) for k, v in self._host.items()}
+        # read through `buffer` (the reference's attribute): normally views of the pinned staging tensors (asynchronous copies); arrays
+        # assigned from outside — a restored checkpoint, a test — are uploaded just the same
+        return {k: torch.from_numpy(np.ascontiguousarray(self.buffer[k])).to(self.device, non_blocking=True) for k in self.KEYS}
 
 
 class MAPPO:

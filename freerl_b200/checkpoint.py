@@ -17,7 +17,8 @@ import torch
 # results of the last call, keep-alive references of in-flight launches, cached C descriptors, process-group handles, and the
 # scratch of the small-batch actor-critic schedule (rewritten by every launch)
 _SKIP = frozenset(("last_adv", "last_error", "last_factor", "last_indices", "last_metrics", "last_path", "last_v_target", "_last_eps",
-                   "_keep", "_keep_noise", "_keepalive", "_c", "_dp", "_dp_peers", "_rs", "_rs_peers", "_fx_ws", "_fx_sync"))
+                   "_keep", "_keep_noise", "_keepalive", "_c", "_dp", "_dp_peers", "_rs", "_rs_peers", "_fx_ws", "_fx_sync",
+                   "_host"))        # pinned staging tensors of MAPPO_discrete.ReplayBuffer: `buffer` (numpy views of them) is the state
 _SCALARS = (int, float, bool, str, type(None), np.integer, np.floating, np.bool_)
 
 

@@ -84,6 +84,32 @@ def _run(device, tmp_path):
               {k: rng.standard_normal((n, 4)) for k in ids}, {k: rng.random(n) < 0.1 for k in ids})
     _case(lambda: MADDPG({k: [4, 2] for k in ids}, True, 1e-3, 1e-3, 256, device, None, sup), feed_ma, lambda p: p.learn(16, 0.95, 0.01), tmp_path)
 
+    # MAPPO_discrete (shared nets, episode ReplayBuffer, the script's default switches): the checkpoint is taken in the MIDDLE of a
+    # rollout — three of four episodes stored — so the host-side episode arrays and the episode counter are part of the state
+    from freerl_b200.MAPPO_discrete import MAPPO as MAPPOd, ReplayBuffer
+    from oracle.make_golden_mappo_discrete import TRICKS          # the switch sets only
+    Nn, OD, AD, T, B = 2, 6, 3, 4, 4
+
+    def episode(p, rng):
+        for t in range(T):
+            obs = [rng.standard_normal(OD).astype(np.float32) for _ in range(Nn)]
+            a, lp = p.select_action(obs)
+            p.add(obs, a, {k: float(rng.standard_normal()) for k in ids}, None, {k: t == T - 1 for k in ids}, lp, None, t)
+        p.buffer.store_last_value(T, p.get_value(rng.standard_normal(Nn * OD).astype(np.float32)))
+
+    def feed_md(p, rng):
+        while p.buffer.episode_num < B - 1:
+            episode(p, rng)
+
+    def learn_md(p):
+        rng = np.random.default_rng(p.agent.step)
+        episode(p, rng)
+        p.learn(2, 0.95, 0.95, 0.2, 2, 0.01, 10.0)
+        feed_md(p, rng)
+    _case(lambda: MAPPOd({k: [OD, AD] for k in ids}, False, 1e-3, 5e-4, B, device, dict(TRICKS["full"]),
+                         ReplayBuffer(N=Nn, obs_dim=OD, state_dim=Nn * OD, episode_limit=T, batch_size=B, device=device)),
+          feed_md, learn_md, tmp_path, rounds=1)
+
 
 def test_checkpoint_resume_emulated(emul, tmp_path):
     _run(torch.device("cpu"), tmp_path)
