@@ -18,7 +18,8 @@ import torch
 # scratch of the small-batch actor-critic schedule (rewritten by every launch)
 _SKIP = frozenset(("last_adv", "last_error", "last_factor", "last_indices", "last_metrics", "last_path", "last_v_target", "_last_eps",
                    "_keep", "_keep_noise", "_keepalive", "_c", "_dp", "_dp_peers", "_rs", "_rs_peers", "_fx_ws", "_fx_sync",
-                   "_host"))        # pinned staging tensors of MAPPO_discrete.ReplayBuffer: `buffer` (numpy views of them) is the state
+                   "_host",         # pinned staging tensors of MAPPO_discrete.ReplayBuffer: `buffer` (numpy views of them) is the state
+                   "_stage_buf", "_stage_idx"))     # per-learn staging replay of the discrete SAC's Batch_ObsNorm (refilled by every learn)
 _SCALARS = (int, float, bool, str, type(None), np.integer, np.floating, np.bool_)
 
 

@@ -128,3 +128,62 @@ def test_checkpoint_rejects_other_class(emul, tmp_path):
     b = _quiet(lambda: DDPG([5, 2], True, 1e-3, 1e-3, 64, torch.device("cpu")))
     with pytest.raises(ValueError):
         load_checkpoint(b, str(tmp_path / "x.pt"))
+
+
+def _run_more(device, tmp_path):
+    """the classes added after the first slice: MAPPO (both heads), IPPO, HAPPO, discrete SAC with its per-learn staging replay,
+    PPO_with_tricks (Batch_ObsNorm, Beta head), MATD3"""
+    import importlib
+    ids = ["a", "b"]
+    mt = {"adv_norm": True, "ObsNorm": False, "reward_norm": False, "reward_scaling": False, "orthogonal_init": True, "adam_eps": True,
+          "lr_decay": False, "ValueClip": True, "huber_loss": True, "LayerNorm": True, "feature_norm": True}
+
+    def feed_on(p, rng):
+        while len(p.buffers["a"]) < 32:
+            obs = {k: rng.standard_normal(5).astype(np.float32) for k in ids}
+            a, lp = p.select_action(obs)
+            p.add(obs, a, {k: float(rng.standard_normal()) for k in ids}, {k: rng.standard_normal(5).astype(np.float32) for k in ids},
+                  {k: bool(rng.random() < 0.05) for k in ids}, lp, {k: bool(rng.random() < 0.1) for k in ids})
+
+    def learn_on(p):
+        p.learn(16, 0.95, 0.95, 0.2, 2, 0.01, 10.0)
+        feed_on(p, np.random.default_rng(sum(a.step for a in p.agents.values())))
+    for mod, cls, cont in (("MAPPO", "MAPPO", True), ("MAPPO", "MAPPO", False), ("IPPO", "IPPO", True), ("HAPPO", "HAPPO", True)):
+        C = getattr(importlib.import_module("freerl_b200." + mod), cls)
+        _case(lambda: C({k: [5, 3] for k in ids}, cont, 1e-3, 5e-4, 32, device, dict(mt)), feed_on, learn_on, tmp_path, rounds=1)
+
+    from freerl_b200.SAC_add_discrete import SAC as SACd
+
+    def feed_sd(p, rng, n=80):
+        p.add(rng.standard_normal((n, 4)), rng.integers(0, 3, (n, 1)), rng.standard_normal(n), rng.standard_normal((n, 4)), rng.random(n) < 0.1)
+    _case(lambda: SACd([4, 3], False, 1e-3, 1e-3, 256, device, trick={"Batch_ObsNorm": True}), feed_sd, lambda p: p.learn(32, 0.99, 0.01), tmp_path)
+
+    from freerl_b200.PPO_with_tricks import PPO as PPOt
+    pt = {"adv_norm": True, "ObsNorm": False, "reward_norm": False, "reward_scaling": False, "orthogonal_init": True, "adam_eps": True,
+          "lr_decay": False, "tanh": False, "Batch_ObsNorm": True}
+
+    def feed_pt(p, rng):
+        for _ in range(64 - len(p.buffer)):
+            o = rng.standard_normal(6).astype(np.float32)
+            act, lp = p.select_action(o)
+            p.add(o, act, float(rng.standard_normal()), rng.standard_normal(6).astype(np.float32), bool(rng.random() < 0.05), lp, bool(rng.random() < 0.1))
+    for kw in ({}, {"beta": True}):
+        _case(lambda: PPOt([6, 2], True, 1e-3, 1e-3, 64, device, trick=dict(pt), **kw), feed_pt,
+              lambda p: (p.learn(32, 0.99, 0.95, 0.2, 2, 0.01), feed_pt(p, np.random.default_rng(p.agent.step))), tmp_path, rounds=1)
+
+    from freerl_b200.MATD3_simple import MATD3
+
+    def feed_ma(p, rng, n=60):
+        p.add({k: rng.standard_normal((n, 4)) for k in ids}, {k: rng.uniform(-1, 1, (n, 2)) for k in ids}, {k: rng.standard_normal(n) for k in ids},
+              {k: rng.standard_normal((n, 4)) for k in ids}, {k: rng.random(n) < 0.1 for k in ids})
+    _case(lambda: MATD3({k: [4, 2] for k in ids}, True, 1e-3, 1e-3, 256, device, trick=None), feed_ma,
+          lambda p: p.learn(16, 0.95, 0.01, 0.1, 0.5, 1.0, 2, 1.0), tmp_path, rounds=3)
+
+
+def test_checkpoint_resume_more_classes_emulated(emul, tmp_path):
+    _run_more(torch.device("cpu"), tmp_path)
+
+
+@pytest.mark.gpu
+def test_checkpoint_resume_more_classes_gpu(tmp_path):
+    _run_more(torch.device("cuda"), tmp_path)
