@@ -12,6 +12,9 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "DQN_file"))
 
 SAC_TRICK = {"ObsNorm": False, "Batch_ObsNorm": False, "OUNoise": True, "GaussNoise": False}
 TD3_TRICK = {"Batch_ObsNorm": False}
+DDPG_SUP = {"weight_decay": True, "OUNoise": True, "ObsNorm": False, "net_init": True, "Batch_ObsNorm": False}
+PPO_TRICKS = {"adv_norm": True, "ObsNorm": False, "reward_norm": False, "reward_scaling": False, "orthogonal_init": True, "adam_eps": True,
+              "lr_decay": False, "tanh": False, "Batch_ObsNorm": False}
 CASES = [
     # name, reference dir, module, class, our module, dim_info, is_continue, ctor args after (dim_info, is_continue), kwargs, file
     ("dqn", "DQN_file", "DQN", "DQN", "freerl_b200.DQN", [4, 3], False, (1e-3, 100), {}, "DQN.pt"),
@@ -21,6 +24,14 @@ CASES = [
     ("ppo_advance", "PPO_advance", "PPO", "PPO", "freerl_b200.PPO_advance", [6, 2], True, (1e-3, 1e-3, 32), {"trick": {"adv_norm": False}}, "PPO.pt"),
     ("td3", "TD3_file", "TD3", "TD3", "freerl_b200.TD3", [5, 2], True, (1e-3, 1e-3, 100),
      {"trick": None, "realize": {"clip_double": True, "policy_noise": True, "twin_delay": True}}, "TD3.pt"),
+    ("ddpg", "DDPG_file", "DDPG", "DDPG", "freerl_b200.DDPG", [5, 2], True, (1e-3, 1e-3, 100), {"trick": None, "supplement": DDPG_SUP}, "DDPG.pt"),
+    ("ddpg_simple", "DDPG_file", "DDPG_simple", "DDPG", "freerl_b200.DDPG_simple", [5, 2], True, (1e-3, 1e-3, 100), {"trick": None}, "DDPG.pt"),
+    ("ppo_tricks", "PPO_file", "PPO_with_tricks", "PPO", "freerl_b200.PPO_with_tricks", [6, 2], True, (1e-3, 1e-3, 32),
+     {"trick": PPO_TRICKS, "beta": False}, "PPO.pt"),
+    ("ppo_tricks_beta", "PPO_file", "PPO_with_tricks", "PPO", "freerl_b200.PPO_with_tricks", [6, 2], True, (1e-3, 1e-3, 32),
+     {"trick": PPO_TRICKS, "beta": True}, "PPO.pt"),          # alpha_layer / beta_layer keys: two row slices of one device layer
+    ("ppo_tricks_disc", "PPO_file", "PPO_with_tricks", "PPO", "freerl_b200.PPO_with_tricks", [6, 3], False, (1e-3, 1e-3, 32),
+     {"trick": PPO_TRICKS, "beta": False}, "PPO.pt"),
 ]
 
 
