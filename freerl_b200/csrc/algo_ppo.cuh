@@ -42,30 +42,31 @@ FRL_DEV int seg_of(const frl_net_t& n, int p, int* numel) {
 // ---- F.layer_norm(x, x.size()[1:]) without affine, eps 1e-5 (MAPPO.py:145-151), rows of a [R][ld] smem tile ----------
 template <int R>
 FRL_NI_MISC void ln_fwd(const float* X, int ld, int n, float* Y, float* rstd, float* scratch /*[R*32*2]*/) {
+  // one warp per row; R > FRL_NT / 32 rows (the 16-row inference tile) take the rows in rounds of FRL_NT / 32
   FRL_PAR(t) {
-    if (t < R * 32) {
-      const int r = t >> 5, l = t & 31;
+    for (int r = t >> 5; r < R; r += FRL_NT / 32) {
+      const int l = t & 31;
       float s = 0.f;
       for (int k = l; k < n; k += 32) s += X[r * ld + k];
-      scratch[t] = s;
+      scratch[r * 32 + l] = s;
     }
   }
   FRL_SYNC();
   FRL_PAR(t) {
-    if (t < R * 32) {
-      const int r = t >> 5, l = t & 31;
+    for (int r = t >> 5; r < R; r += FRL_NT / 32) {
+      const int l = t & 31;
       float mean = 0.f;
       for (int i = 0; i < 32; ++i) mean += scratch[r * 32 + i];
       mean = mean / (float)n;
       float s = 0.f;
       for (int k = l; k < n; k += 32) { const float d = X[r * ld + k] - mean; s += d * d; }
-      scratch[R * 32 + t] = s;
+      scratch[R * 32 + r * 32 + l] = s;
     }
   }
   FRL_SYNC();
   FRL_PAR(t) {
-    if (t < R * 32) {
-      const int r = t >> 5, l = t & 31;
+    for (int r = t >> 5; r < R; r += FRL_NT / 32) {
+      const int l = t & 31;
       float mean = 0.f, var = 0.f;
       for (int i = 0; i < 32; ++i) { mean += scratch[r * 32 + i]; var += scratch[R * 32 + r * 32 + i]; }
       mean = mean / (float)n;

@@ -501,35 +501,38 @@ extern "C" int frl_polyak(const frl_net_t* src, const frl_net_t* target, float t
 // ------------------------------------------------------------------------------------------------
 // batched policy inference (select_action / evaluate_action for N vectorised envs)
 // ------------------------------------------------------------------------------------------------
-template <int HM>      // HM = 1: tanh hidden activations (frl_infer_args_t.hidden_tanh); 0: the kernel every other caller launches
+// HM = 1: tanh hidden activations (frl_infer_args_t.hidden_tanh); 0: the kernel every other caller launches.  RT = rows per CTA tile:
+// 8, or 16 for batches of thousands of rows (every tile streams the whole network out of L2 — 16-row tiles halve that traffic; taken
+// for n >= 2048 when the head is at most 16 wide, one output element per thread)
+template <int HM, int RT = FRL_R>
 struct InferAlgoT {
   typedef frl_infer_args_t Args;
   static const int NSTAGES = 1;
   FRL_SHD int nl_of(const Args& a) { return a.nl > 0 ? a.nl : a.net.n_layers; }
   FRL_SHD int wbuf_floats(const Args& a) { return (AcAlgo::max_layer_floats(a.net) + 31) & ~31; }
   FRL_SHD int user_floats(const Args& a) {
-    return FRL_R * (2 * a.net.L[a.l0].in_pad + 4 * act_ld(a.net.L[a.l0].out_pad) + a.net.L[a.l0 + nl_of(a) - 1].out_pad + 2 + 64) + 64;
+    return RT * (2 * a.net.L[a.l0].in_pad + 4 * act_ld(a.net.L[a.l0].out_pad) + a.net.L[a.l0 + nl_of(a) - 1].out_pad + 2 + 64) + 64;
   }
-  FRL_SHD int grid(const Args& a, int) { return (a.n + FRL_R - 1) / FRL_R; }
+  FRL_SHD int grid(const Args& a, int) { return (a.n + RT - 1) / RT; }
   FRL_SHD int n_updates(const Args&) { return 1; }
   FRL_SDEV void stage(int, int, Cta& c, float* user, const Args& a) {
     const frl_net_t& n = a.net;
     const int nl = nl_of(a), l0 = a.l0;
     const int in_pad = n.L[l0].in_pad, ldh = act_ld(n.L[l0].out_pad), op = n.L[l0 + nl - 1].out_pad, nout = n.L[l0 + nl - 1].out;
     SmemBump sb; sb.p = user;
-    float* X = sb.take(FRL_R * in_pad);
-    float* H1 = sb.take(FRL_R * ldh);
-    float* H2 = sb.take(FRL_R * ldh);
-    float* O = sb.take(FRL_R * op);
+    float* X = sb.take(RT * in_pad);
+    float* H1 = sb.take(RT * ldh);
+    float* H2 = sb.take(RT * ldh);
+    float* O = sb.take(RT * op);
     NetBufs nb;
     nb.H1 = H1; nb.H2 = H2;
-    nb.X0 = sb.take(FRL_R * in_pad); nb.H1n = sb.take(FRL_R * ldh); nb.H2n = sb.take(FRL_R * ldh);
-    nb.rs1 = sb.take(FRL_R); nb.rs2 = sb.take(FRL_R); nb.scratch = sb.take(FRL_R * 64);
-    const int row0 = c.cta * FRL_R;
-    const int nvalid = (a.n - row0) < FRL_R ? (a.n - row0) : FRL_R;
+    nb.X0 = sb.take(RT * in_pad); nb.H1n = sb.take(RT * ldh); nb.H2n = sb.take(RT * ldh);
+    nb.rs1 = sb.take(RT); nb.rs2 = sb.take(RT); nb.scratch = sb.take(RT * 64);
+    const int row0 = c.cta * RT;
+    const int nvalid = (a.n - row0) < RT ? (a.n - row0) : RT;
     stage_prefetch(c, layer_fwd_src(n, l0), layer_fwd_bytes(n.L[l0]));
     FRL_PAR(t) {
-      for (int e = t; e < FRL_R * in_pad; e += FRL_NT) {
+      for (int e = t; e < RT * in_pad; e += FRL_NT) {
         const int r = e / in_pad, j = e % in_pad;
         float x = (r < nvalid && j < a.obs_dim) ? a.obs[(size_t)(row0 + r) * a.obs_dim + j] : 0.f;
         if (a.obs_norm && r < nvalid && j < a.obs_dim)       // Batch_ObsNorm with update=False (e.g. DDPG.py:168-169)
@@ -538,8 +541,8 @@ struct InferAlgoT {
       }
     }
     FRL_SYNC();
-    if (a.layer_norm && nl == 3) net_fwd<FRL_R>(c, n, l0, a.layer_norm, X, in_pad, a.obs_dim, nb, ldh, O, op, no_hint());
-    else mlp_fwd<FRL_R, HM>(c, n, l0, nl, X, in_pad, H1, H2, ldh, O, op, FRL_ACT_NONE, no_hint());
+    if (a.layer_norm && nl == 3) net_fwd<RT>(c, n, l0, a.layer_norm, X, in_pad, a.obs_dim, nb, ldh, O, op, no_hint());
+    else mlp_fwd<RT, HM>(c, n, l0, nl, X, in_pad, H1, H2, ldh, O, op, FRL_ACT_NONE, no_hint());
     FRL_PAR(t) {
       if (a.mode == FRL_INFER_ARGMAX) {
         if (t < nvalid) {
@@ -583,7 +586,7 @@ struct InferAlgoT {
           a.out[(size_t)(row0 + t) * a.out_cols] = (float)best;
           a.out[(size_t)(row0 + t) * a.out_cols + 1] = O[t * op + best] - lse;
         }
-      } else if (t < FRL_R * nout) {
+      } else if (t < RT * nout) {
         const int r = t / nout, j = t % nout;
         if (r < nvalid) {
           float v = O[r * op + j];
@@ -619,6 +622,10 @@ extern "C" int frl_policy_infer(const frl_infer_args_t* a, void* stream) {
   if (a->hidden_tanh) {
     if (a->layer_norm) { frl_set_error("frl_policy_infer: hidden_tanh is not available with layer_norm"); return -1; }
     return frl_launch_tiles<InferAlgoT<1> >(*a, (cudaStream_t)stream);
+  }
+  {
+    const int nl = a->nl > 0 ? a->nl : a->net.n_layers;
+    if (a->n >= 2048 && a->net.L[a->l0 + nl - 1].out <= 16) return frl_launch_tiles<InferAlgoT<0, 16> >(*a, (cudaStream_t)stream);
   }
   return frl_launch_tiles<InferAlgo>(*a, (cudaStream_t)stream);
 }
