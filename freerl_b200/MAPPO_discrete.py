@@ -80,7 +80,14 @@ class ReplayBuffer:
     def get_training_data(self):
         # read through `buffer` (the reference's attribute): normally views of the pinned staging tensors (asynchronous copies); arrays
         # assigned from outside — a restored checkpoint, a test — are uploaded just the same
-        return {k: torch.from_numpy(np.ascontiguousarray(self.buffer[k])).to(self.device, non_blocking=True) for k in self.KEYS}
+        out = {}
+        for k in self.KEYS:
+            arr, h = self.buffer[k], self._host.get(k)
+            if h is not None and arr.shape == tuple(h.shape) and arr.__array_interface__["data"][0] == h.data_ptr():
+                out[k] = h.to(self.device, non_blocking=True)       # the pinned tensor itself: its allocator tracks the copy in flight
+            else:
+                out[k] = torch.from_numpy(np.ascontiguousarray(arr)).to(self.device)
+        return out
 
 
 class MAPPO:
