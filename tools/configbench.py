@@ -131,7 +131,9 @@ def _c4(rec, rng, Rainbow):
 
 def _c5(rec, rng, MAPPO):
     # ---- C5: MAPPO ----
-    from oracle.make_golden_marl import MAPPO_TRICK          # the trick dict only (no reference code involved)
+    # the switch set the reference's default policy_name 'MAPPO' forces (MAPPO.py:616-622)
+    MAPPO_TRICK = {'adv_norm': True, 'ObsNorm': True, 'reward_norm': False, 'reward_scaling': True, 'orthogonal_init': True,
+                   'adam_eps': True, 'lr_decay': False, 'ValueClip': True, 'huber_loss': True, 'LayerNorm': True, 'feature_norm': True}
     H, E, K5 = 256, 512, 15
     ids = ["agent_%d" % i for i in range(3)]
     with contextlib.redirect_stdout(sys.stderr):

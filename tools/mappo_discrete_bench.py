@@ -8,7 +8,13 @@ import contextlib, io, sys
 import numpy as np, torch
 sys.path.insert(0, '.')
 from freerl_b200.MAPPO_discrete import MAPPO, ReplayBuffer
-from oracle.make_golden_mappo_discrete import TRICKS          # the switch sets only
+OFF = dict(adv_norm=False, ObsNorm=False, reward_norm=False, reward_scaling=False, orthogonal_init=False, adam_eps=False, lr_decay=False,
+           ValueClip=False, huber_loss=False, LayerNorm=False, feature_norm=False)
+TRICKS = {"simple": OFF,
+          "clip": dict(OFF, adv_norm=True, orthogonal_init=True, adam_eps=True, ValueClip=True),
+          # the script's default (`--policy_name MAPPO`, MAPPO_discrete.py:520-527): every switch on except reward_norm / lr_decay
+          "full": dict(OFF, adv_norm=True, ObsNorm=True, reward_scaling=True, orthogonal_init=True, adam_eps=True, ValueClip=True,
+                       huber_loss=True, LayerNorm=True, feature_norm=True)}
 
 dev = torch.device("cuda")
 N, OD, AD, T, B, K = 3, 18, 5, 25, 256, 15
