@@ -298,7 +298,7 @@ struct PpoAlgoT {
     float* gp = a.gpart + (size_t)c.cta * N.n_p;
 
     if (GRP && s == 0) { ppo_group_stage(c, user, a, u); return; }
-    if (s == 0) {
+    if (!UM && !GRP && s == 0) {        // (compile-time guard: the tensor-core and group kernels never reach this stage body — keep it out of their code)
       if (c.cta >= ntile) return;
       float la = 0.f, lc = 0.f, le = 0.f;
       bool first = true;
