@@ -198,7 +198,26 @@ def cpu_reference_arm(steps, warmup, transitions_per_step=4, fill=CAP, threads=N
 
 
 # --------------------------------------------------------------------------------------------------
-def ppo_dp_block(dev, rank, world, dist, learns=3):
+def _timed_learns(learn, learns, dev, world, dist):
+    """every learn timed on its own with CUDA events (max over ranks per learn); returns (median, all) in ms — single learns of these
+    long cooperative launches occasionally run 10-30 % slow, which an average of two or three would carry into the record"""
+    import torch
+    each = []
+    for _ in range(learns):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        learn()
+        e1.record()
+        torch.cuda.synchronize()
+        each.append(e0.elapsed_time(e1))
+    t = torch.tensor(each, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    each = [float(x) for x in t.tolist()]
+    return float(np.median(each)), each
+
+
+def ppo_dp_block(dev, rank, world, dist, learns=5):
     """BASELINE config 3 on every rank: PPO (LunarLander dims: obs 8, 4 actions), 1024 envs x 128 steps per GPU, minibatch
     8192 rows per GPU, K = 10 epochs = 160 optimiser steps per learn.  At world > 1 the replicas train data-parallel
     (PPO.enable_data_parallel: the flat gradient is summed across ranks between the in-kernel reduction and the clip /
@@ -227,15 +246,7 @@ def ppo_dp_block(dev, rank, world, dist, learns=3):
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(learns):
-        learn()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1) / learns], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item())
+    ms, ms_each = _timed_learns(learn, learns, dev, world, dist)
     updates = K * (T * N // mb)
     # end to end through the public API with HOST buffers: T vector steps of select_action(host obs) + add(host arrays), then learn()
     torch.cuda.synchronize()
@@ -251,7 +262,7 @@ def ppo_dp_block(dev, rank, world, dist, learns=3):
     if world > 1:
         dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
     ms_e2e = float(ms_e2e.item())
-    return {"workload": "ppo_lunarlander_1024env_x128_mb8192_k10", "ms_per_learn": ms, "updates_per_learn": updates,
+    return {"workload": "ppo_lunarlander_1024env_x128_mb8192_k10", "ms_per_learn": ms, "ms_per_learn_each": ms_each, "updates_per_learn": updates,
             "e2e_env_steps_per_sec": world * T * N / ms_e2e * 1e3, "e2e_ms_per_rollout_and_learn": ms_e2e, "e2e_last_loss": loss,
             "updates_per_sec": updates / ms * 1e3, "env_steps_per_sec": world * T * N / ms * 1e3, "us_per_update": ms * 1e3 / updates,
             "scaling": "weak", "collective": "none (1 rank)" if world == 1 else getattr(pol, "dp_collective", "nccl all_reduce of net.g per optimiser step"),
@@ -307,7 +318,7 @@ def rainbow_block(dev, rank, world, dist, vsteps=6):
             "parallelism": ("replicas, env + PER shard per GPU, parameter average per vector step: " + getattr(pol, "replica_collective", "?")) if world > 1 else "1 rank"}
 
 
-def mappo_block(dev, rank, world, dist, learns=2):
+def mappo_block(dev, rank, world, dist, learns=3):
     """BASELINE config 5 on every rank: MAPPO, simple_spread dims (3 agents, obs 18, act 5), 512 envs x 256 steps per GPU, full-batch
     minibatch (131 072 rows), K = 15.  Multi-GPU = synchronous data parallel over the in-kernel peer exchange, weak scaling."""
     import contextlib
@@ -338,17 +349,8 @@ def mappo_block(dev, rank, world, dist, learns=2):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(learns):
-        learn()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1) / learns], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item())
-    return {"workload": "mappo_simple_spread_3agents_512env_x256_fullbatch_k15", "ms_per_learn": ms, "updates_per_learn": 3 * K5,
+    ms, ms_each = _timed_learns(learn, learns, dev, world, dist)
+    return {"workload": "mappo_simple_spread_3agents_512env_x256_fullbatch_k15", "ms_per_learn": ms, "ms_per_learn_each": ms_each, "updates_per_learn": 3 * K5,
             "env_steps_per_sec": world * H * E / ms * 1e3, "scaling": "weak",
             "collective": "none (1 rank)" if world == 1 else getattr(pol, "dp_collective", "?"),
             "loss_finite": bool(torch.isfinite(pol.last_metrics).all().item())}
