@@ -22,17 +22,30 @@ sys.path.insert(0, ROOT)
 dev = torch.device("cuda")
 
 
-def timeit(fn, reps, warm=2):
+def timeit(fn, reps, warm=2, median=False):
+    """mean over `reps` back-to-back calls (short calls: host launch work overlaps the previous call, as in a training loop), or with
+    median=True the median over calls bracketed one by one (the 20-70 ms cooperative launches occasionally run 10-30 % slow; a mean of
+    a few calls would carry that into the table)"""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    if not median:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    each = []
     for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         fn()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / reps
+        e1.record()
+        torch.cuda.synchronize()
+        each.append(e0.elapsed_time(e1))
+    return float(np.median(each))
 
 
 def run(which=("C1", "C2", "C3", "C4", "C5"), log=print):
@@ -107,7 +120,7 @@ def _c3(rec, rng, PPO):
         pol.buffer._index, pol.buffer._size, pol.buffer.n_envs = 0, T * N, N          # rollout already resident (learn() clears it)
         pol.learn(mb, 0.99, 0.95, 0.2, K, 0.01)
     fill_ppo()
-    ms = timeit(ppo_learn, 3, warm=1)
+    ms = timeit(ppo_learn, 5, warm=1, median=True)
     rec("C3 PPO 1024 envs x 128, mb 8192, K 10", ms, K * (T * N // mb), T * N, "GAE scan + 160 minibatch updates in one launch; transitions/s = rollout rows consumed")
     adv_ms = timeit(lambda: pol.compute_gae(0.99, 0.95), 10)
     rec("C3 PPO critic(obs), critic(obs') + GAE", adv_ms, 1, T * N, "2 batched value inferences + frl_gae over [128, 1024]")
@@ -150,7 +163,7 @@ def _c5(rec, rng, MAPPO):
         for b in pol.buffers.values():
             b._index, b._size, b.n_envs = 0, H * E, E
         pol.learn(H * E, 0.95, 0.95, 0.2, K5, 0.01, 10.0)
-    ms = timeit(mappo_learn, 2, warm=1)
+    ms = timeit(mappo_learn, 3, warm=1, median=True)
     rec("C5 MAPPO 3 agents, 512 envs x 256, K 15", ms, 3 * K5, H * E, "joint GAE + adv-norm + 15 full-batch updates per agent (minibatch = horizon x envs)")
 
 
